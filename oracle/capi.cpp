@@ -1,0 +1,399 @@
+// ORACLE (test infrastructure, NOT product code): C API over the C++ restatement so that
+// tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg can drive it through ctypes.
+#include <cstring>
+#include <string>
+#include <thread>
+#include <chrono>
+#include "system.hpp"
+#include "rng.hpp"
+#include "excit_gen.hpp"
+#include "fciqmc.hpp"
+
+using namespace oracle;
+
+static thread_local std::string g_err;
+
+#define ORC_TRY try {
+#define ORC_CATCH(rv)                     \
+    }                                     \
+    catch (const std::exception& e) {     \
+        g_err = e.what();                 \
+        return rv;                        \
+    }
+
+extern "C" {
+
+struct orc_qmc_in {
+    double tau;
+    int seed;
+    double D0_population;
+    int ncycles, nreport;
+    double target_particles, initial_shift, shift_damping, vary_shift_from;
+    int vary_shift_from_proje;
+    int initiator_approx;
+    double initiator_pop;
+    int real_amplitudes;
+    double spawn_cutoff;
+    int excit_gen;
+    double pattempt_single, pattempt_double;
+    int64_t walker_length, spawned_walker_length;
+    int ex_level;
+    int nprocs, nslots;
+    int rng_kind;
+    int literal_event_int32;
+};
+
+const char* orc_last_error() { return g_err.c_str(); }
+
+int orc_set_ref_lib(const char* path) {
+    ORC_TRY
+    DsfmtLib::get(path);
+    return 0;
+    ORC_CATCH(-1)
+}
+
+void* orc_create() { return new Oracle(); }
+void orc_destroy(void* h) { delete (Oracle*)h; }
+
+int orc_read_fcidump(void* h, const char* path, int nel, int ms, int sym, int cas_nel, int cas_norb) {
+    ORC_TRY
+    Oracle* o = (Oracle*)h;
+    ReadInOpts opt;
+    opt.nel = nel; opt.ms = ms; opt.sym = sym; opt.cas[0] = cas_nel; opt.cas[1] = cas_norb;
+    o->sys = System();
+    read_in_file(o->sys, path, opt);
+    return 0;
+    ORC_CATCH(-1)
+}
+
+// info[0..]: nbasis, nel, W, nsym_tot, sym0, sym_max, nalpha, nbeta, uhf, pg_mask, Lz_mask, Lz_offset,
+//            gamma_sym, max_nbss, nvirt, nvirt_alpha, nvirt_beta, symmetry, int_err, n_two_body_channels
+void orc_sys_info(void* h, int64_t* info) {
+    const System& s = ((Oracle*)h)->sys;
+    int64_t v[] = {s.nbasis, s.nel, s.W, s.nsym_tot, s.sym0, s.sym_max, s.nalpha, s.nbeta, s.uhf, s.pg_mask,
+                   s.Lz_mask, s.Lz_offset, s.gamma_sym, s.max_nbss, s.nvirt, s.nvirt_alpha, s.nvirt_beta,
+                   s.symmetry, s.int_err, (int64_t)s.two_body.size(), s.nintgrls};
+    memcpy(info, v, sizeof(v));
+}
+double orc_ecore(void* h) { return ((Oracle*)h)->sys.Ecore; }
+
+// arrays of length nbasis (0-based storage of the 1-based functions)
+void orc_basis(void* h, int* sym, int* ms, int* spatial, int* sym_index, int* sym_spin_index, double* sp_eigv) {
+    const System& s = ((Oracle*)h)->sys;
+    for (int i = 1; i <= s.nbasis; ++i) {
+        sym[i - 1] = s.bf[i].sym; ms[i - 1] = s.bf[i].ms; spatial[i - 1] = s.bf[i].spatial_index;
+        sym_index[i - 1] = s.bf[i].sym_index; sym_spin_index[i - 1] = s.bf[i].sym_spin_index;
+        sp_eigv[i - 1] = s.bf[i].sp_eigv;
+    }
+}
+// nbasis_sym_spin: [2*nsym_tot]; sym_spin_basis_fns: [max_nbss*2*nsym_tot]
+void orc_sym_tables(void* h, int* nbss, int* ssbf) {
+    const System& s = ((Oracle*)h)->sys;
+    memcpy(nbss, s.nbasis_sym_spin.data(), s.nbasis_sym_spin.size() * sizeof(int));
+    memcpy(ssbf, s.sym_spin_basis_fns.data(), s.sym_spin_basis_fns.size() * sizeof(int));
+}
+double orc_get_one_body(void* h, int i, int j) { return ((Oracle*)h)->sys.get_one_body_real(i, j); }
+double orc_get_two_body(void* h, int i, int j, int a, int b) { return ((Oracle*)h)->sys.get_two_body_real(i, j, a, b); }
+const double* orc_two_body_store(void* h, int chan) { return ((Oracle*)h)->sys.two_body[chan].data(); }
+
+static Det mkdet(const System& s, const uint64_t* f) {
+    Det d;
+    for (int k = 0; k < s.W; ++k) d.w[k] = f[k];
+    return d;
+}
+
+double orc_sc0(void* h, const uint64_t* f) {
+    const System& s = ((Oracle*)h)->sys;
+    return s.slater_condon0(mkdet(s, f));
+}
+// Slater-Condon single: matrix element <D|H|D_i^a> incl. permutation sign
+double orc_sc1(void* h, const uint64_t* f, int i, int a) {
+    const System& s = ((Oracle*)h)->sys;
+    Det d = mkdet(s, f);
+    int occ[MAXNEL];
+    s.decode(d, occ);
+    Excit e; e.nexcit = 1; e.from_orb[0] = i; e.to_orb[0] = a;
+    s.find_excitation_permutation1(d, e);
+    return s.slater_condon1_excit(occ, i, a, e.perm);
+}
+double orc_sc2(void* h, const uint64_t* f, int i, int j, int a, int b) {
+    const System& s = ((Oracle*)h)->sys;
+    Det d = mkdet(s, f);
+    Excit e; e.nexcit = 2; e.from_orb[0] = i; e.from_orb[1] = j; e.to_orb[0] = a; e.to_orb[1] = b;
+    s.find_excitation_permutation2(d, e);
+    return s.slater_condon2_excit(i, j, a, b, e.perm);
+}
+// symmetry/spin-checked variants used to enumerate the full Hamiltonian row in tests
+double orc_sc1_checked(void* h, const uint64_t* f, int i, int a) {
+    const System& s = ((Oracle*)h)->sys;
+    Det d = mkdet(s, f);
+    if (s.bf[i].ms != s.bf[a].ms) return 0.0;
+    int occ[MAXNEL];
+    s.decode(d, occ);
+    Excit e; e.nexcit = 1; e.from_orb[0] = i; e.to_orb[0] = a;
+    s.find_excitation_permutation1(d, e);
+    return s.slater_condon1(occ, i, a, e.perm);
+}
+double orc_sc2_checked(void* h, const uint64_t* f, int i, int j, int a, int b) {
+    const System& s = ((Oracle*)h)->sys;
+    Det d = mkdet(s, f);
+    Excit e; e.nexcit = 2; e.from_orb[0] = i; e.from_orb[1] = j; e.to_orb[0] = a; e.to_orb[1] = b;
+    s.find_excitation_permutation2(d, e);
+    return s.slater_condon2(i, j, a, b, e.perm);
+}
+
+int32_t orc_murmur_bit_string(void* h, const uint64_t* f, uint32_t seed) {
+    const System& s = ((Oracle*)h)->sys;
+    return murmurhash_bit_string(mkdet(s, f), s.nbasis, seed);
+}
+uint32_t orc_murmur2(const void* key, int len, uint32_t seed) { return murmurhash2(key, len, seed); }
+uint32_t orc_ref_murmur2(const void* key, int len, uint32_t seed) {
+    ORC_TRY
+    return DsfmtLib::get().murmur2(key, len, seed);
+    ORC_CATCH(0)
+}
+int orc_owner(void* h, const uint64_t* f) {
+    Oracle* o = (Oracle*)h;
+    return o->owner(mkdet(o->sys, f));
+}
+
+// Fill n doubles from the reference dSFMT stream through the 50,000-element buffer.
+int orc_dsfmt_stream(int seed, int n, double* out) {
+    ORC_TRY
+    DsfmtRng r(seed, 50000);
+    for (int i = 0; i < n; ++i) out[i] = r.next();
+    return 0;
+    ORC_CATCH(-1)
+}
+// Philox stream sample: n draws for (seed, cycle, purpose, f, attempt)
+void orc_philox_stream(uint32_t seed, uint32_t cycle, uint32_t purpose, const uint64_t* f, int W, uint32_t attempt,
+                       int n, double* out) {
+    PhiloxRng r(seed);
+    r.set_cycle(cycle);
+    Det d;
+    for (int k = 0; k < W; ++k) d.w[k] = f[k];
+    r.begin(purpose, d, W, attempt);
+    for (int i = 0; i < n; ++i) out[i] = r.next();
+}
+
+int orc_set_qmc(void* h, const orc_qmc_in* q) {
+    Oracle* o = (Oracle*)h;
+    QmcIn& in = o->in;
+    in.tau = q->tau; in.seed = q->seed; in.D0_population = q->D0_population;
+    in.ncycles = q->ncycles; in.nreport = q->nreport; in.target_particles = q->target_particles;
+    in.initial_shift = q->initial_shift; in.shift_damping = q->shift_damping;
+    in.vary_shift_from = q->vary_shift_from; in.vary_shift_from_proje = q->vary_shift_from_proje;
+    in.initiator_approx = q->initiator_approx; in.initiator_pop = q->initiator_pop;
+    in.real_amplitudes = q->real_amplitudes; in.spawn_cutoff = q->spawn_cutoff;
+    in.excit_gen = q->excit_gen; in.pattempt_single = q->pattempt_single; in.pattempt_double = q->pattempt_double;
+    in.walker_length = q->walker_length; in.spawned_walker_length = q->spawned_walker_length;
+    in.ex_level = q->ex_level; in.nprocs = q->nprocs; in.nslots = q->nslots; in.rng_kind = q->rng_kind;
+    in.literal_event_int32 = q->literal_event_int32;
+    return 0;
+}
+int orc_init(void* h) {
+    ORC_TRY
+    ((Oracle*)h)->init();
+    return 0;
+    ORC_CATCH(-1)
+}
+int orc_run(void* h) {
+    ORC_TRY
+    ((Oracle*)h)->run();
+    return 0;
+    ORC_CATCH(-1)
+}
+int orc_nrows(void* h) { return (int)((Oracle*)h)->rows.size(); }
+// rows[nrows][8]: iter, shift, proj_energy, D0, nparticles, nstates, nspawn_events, rspawn
+void orc_get_rows(void* h, double* out) {
+    Oracle* o = (Oracle*)h;
+    for (size_t i = 0; i < o->rows.size(); ++i) {
+        const ReportRow& r = o->rows[i];
+        double* p = out + 8 * i;
+        p[0] = r.iter; p[1] = r.shift; p[2] = r.proj_energy; p[3] = r.D0_population; p[4] = r.nparticles;
+        p[5] = (double)r.nstates; p[6] = (double)r.nspawn_events; p[7] = r.rspawn;
+    }
+}
+// ref[0]=H00, ref[1]=pattempt_single, ref[2]=pattempt_double; occ0[nel]; f0[W]
+void orc_reference(void* h, double* ref, int* occ0, uint64_t* f0) {
+    Oracle* o = (Oracle*)h;
+    ref[0] = o->H00; ref[1] = o->eg.pattempt_single; ref[2] = o->eg.pattempt_double;
+    for (int i = 0; i < o->sys.nel; ++i) occ0[i] = o->occ_list0[i];
+    for (int k = 0; k < o->sys.W; ++k) f0[k] = o->f0.w[k];
+}
+int64_t orc_nstates(void* h, int rank) { return ((Oracle*)h)->ranks[rank].nstates; }
+double orc_nparticles(void* h, int rank) { return ((Oracle*)h)->ranks[rank].nparticles; }
+void orc_get_psips(void* h, int rank, uint64_t* states, int64_t* pops, double* dat) {
+    Oracle* o = (Oracle*)h;
+    RankState& r = o->ranks[rank];
+    int W = o->sys.W;
+    for (int64_t i = 0; i < r.nstates; ++i) {
+        for (int k = 0; k < W; ++k) states[i * W + k] = r.states[i].w[k];
+        pops[i] = r.pops[i];
+        dat[i] = r.dat[i];
+    }
+}
+void orc_set_psips(void* h, int rank, int64_t n, const uint64_t* states, const int64_t* pops, const double* dat) {
+    Oracle* o = (Oracle*)h;
+    RankState& r = o->ranks[rank];
+    int W = o->sys.W;
+    r.states.resize(n); r.pops.resize(n); r.dat.resize(n);
+    for (int64_t i = 0; i < n; ++i) {
+        r.states[i] = Det();
+        for (int k = 0; k < W; ++k) r.states[i].w[k] = states[i * W + k];
+        r.pops[i] = pops[i];
+        r.dat[i] = dat[i];
+    }
+    r.nstates = n;
+    o->recompute_nparticles(r);
+}
+void orc_set_reference_det(void* h, const uint64_t* f0) {
+    Oracle* o = (Oracle*)h;
+    o->f0 = mkdet(o->sys, f0);
+    o->occ_list0.resize(o->sys.nel);
+    o->sys.decode(o->f0, o->occ_list0.data());
+    o->H00 = o->sys.slater_condon0(o->f0);
+}
+
+// Run ncycles MC cycles with fixed shift / proj_energy_old / tau (what hb200_iterate does).
+// out[0]=sum proj_energy, out[1]=sum D0, out[2]=nparticles(total), out[3]=nstates(total),
+// out[4]=nspawn_events(last cycle, total), out[5]=ndeath(last cycle, total), out[6]=rspawn sum,
+// out[7]=error flag, out[8]=nattempts(last cycle), out[9]=total rng draws
+int orc_iterate(void* h, int ncycles, uint32_t first_cycle_id, double tau, double shift, double proj_energy_old,
+                double* out) {
+    ORC_TRY
+    Oracle* o = (Oracle*)h;
+    o->tau = tau; o->shift = shift; o->est.proj_energy_old = proj_energy_old;
+    for (auto& r : o->ranks) { r.rspawn = 0.0; r.proj_energy = 0.0; r.D0_population = 0.0; }
+    for (int c = 0; c < ncycles; ++c) o->mc_cycle(first_cycle_id + c);
+    double pe = 0, d0 = 0, np = 0, rs = 0;
+    int64_t ns = 0, nev = 0, nd = 0, na = 0;
+    uint64_t draws = 0;
+    bool err = false;
+    for (auto& r : o->ranks) {
+        pe += r.proj_energy; d0 += r.D0_population; np += r.nparticles; ns += r.nstates;
+        nev += r.nspawn_events; nd += r.ndeath; rs += r.rspawn; na += r.nattempts;
+        err = err || r.spawn_error || r.psip_error;
+        draws += r.rng->ndraws;
+    }
+    out[0] = pe; out[1] = d0; out[2] = np; out[3] = (double)ns; out[4] = (double)nev; out[5] = (double)nd;
+    out[6] = rs; out[7] = err ? 1.0 : 0.0; out[8] = (double)na; out[9] = (double)draws;
+    return 0;
+    ORC_CATCH(-1)
+}
+
+// One excitation-generation + spawn attempt with the Philox stream (kernel parity probe).
+// iout: nexcit, from1, from2, to1, to2, perm, allowed ; dout: pgen, hmatel ; nspawn: encoded spawn
+int orc_gen_excit_philox(void* h, const uint64_t* f, uint32_t cycle, uint32_t attempt, int64_t parent_pop,
+                         double tau, int* iout, double* dout, int64_t* nspawn) {
+    ORC_TRY
+    Oracle* o = (Oracle*)h;
+    PhiloxRng rng((uint32_t)o->in.seed);
+    rng.set_cycle(cycle);
+    DetInfo d;
+    Det fd = mkdet(o->sys, f);
+    decode_for(o->sys, o->eg, fd, d);
+    rng.begin(RNG_SPAWN, fd, o->sys.W, attempt);
+    GenResult g = gen_excit(rng, o->sys, o->eg, d);
+    double save_tau = o->tau;
+    o->tau = tau;
+    *nspawn = o->attempt_to_spawn(rng, g.hmatel, g.pgen, parent_pop);
+    o->tau = save_tau;
+    iout[0] = g.conn.nexcit; iout[1] = g.conn.from_orb[0]; iout[2] = g.conn.from_orb[1];
+    iout[3] = g.conn.to_orb[0]; iout[4] = g.conn.to_orb[1]; iout[5] = g.conn.perm; iout[6] = g.allowed;
+    dout[0] = g.pgen; dout[1] = g.hmatel;
+    return 0;
+    ORC_CATCH(-1)
+}
+
+// Exact pgen check helper: sample one excitation with an arbitrary caller-provided stream
+// (list of doubles in [0,1)); returns number of randoms consumed.
+struct ListRng : Rng {
+    const double* v; int n; int k = 0;
+    ListRng(const double* v_, int n_) : v(v_), n(n_) {}
+    void begin(uint32_t, const Det&, int, uint32_t) override {}
+    void set_cycle(uint32_t) override {}
+    double next() override { if (k >= n) throw std::runtime_error("ListRng exhausted"); ndraws++; return v[k++]; }
+};
+int orc_gen_excit_list(void* h, const uint64_t* f, const double* rn, int nrn, int* iout, double* dout) {
+    ORC_TRY
+    Oracle* o = (Oracle*)h;
+    ListRng rng(rn, nrn);
+    DetInfo d;
+    Det fd = mkdet(o->sys, f);
+    decode_for(o->sys, o->eg, fd, d);
+    GenResult g = gen_excit(rng, o->sys, o->eg, d);
+    iout[0] = g.conn.nexcit; iout[1] = g.conn.from_orb[0]; iout[2] = g.conn.from_orb[1];
+    iout[3] = g.conn.to_orb[0]; iout[4] = g.conn.to_orb[1]; iout[5] = g.conn.perm; iout[6] = g.allowed;
+    dout[0] = g.pgen; dout[1] = g.hmatel;
+    return rng.k;
+    ORC_CATCH(-1)
+}
+
+// Heat-bath tables (column-major, Fortran order), for comparison with the device builder.
+int64_t orc_hb_nb(void* h) { return ((Oracle*)h)->eg.hb.nb; }
+const double* orc_hb_ptr_d(void* h, int which) {
+    HeatBath& hb = ((Oracle*)h)->eg.hb;
+    switch (which) {
+        case 0: return hb.i_weights.data();
+        case 1: return hb.ij_weights.data();
+        case 2: return hb.ija_w.data();
+        case 3: return hb.ija_U.data();
+        case 4: return hb.ija_tot.data();
+        case 5: return hb.ijab_w.data();
+        case 6: return hb.ijab_U.data();
+        case 7: return hb.ijab_tot.data();
+    }
+    return nullptr;
+}
+const int* orc_hb_ptr_i(void* h, int which) {
+    HeatBath& hb = ((Oracle*)h)->eg.hb;
+    return which == 0 ? hb.ija_K.data() : hb.ijab_K.data();
+}
+
+// CPU baseline: run `ncycles` MC cycles on `nthreads` independent replicas of the current state
+// (one emulated MPI rank per core, as the reference would be run with mpiexec -np <cores>), each
+// with its own stream; returns wall seconds and the attempts/walker-iterations processed.
+int orc_cpu_baseline(void* h, int nthreads, int ncycles, double tau, double shift, double proj_energy_old,
+                     double* out) {
+    ORC_TRY
+    Oracle* o = (Oracle*)h;
+    std::vector<std::unique_ptr<Oracle>> reps(nthreads);
+    for (int t = 0; t < nthreads; ++t) {
+        reps[t].reset(new Oracle());
+        Oracle& r = *reps[t];
+        r.sys = o->sys; r.in = o->in; r.eg = o->eg; r.occ_list0 = o->occ_list0; r.f0 = o->f0; r.H00 = o->H00;
+        r.ref_ex_level = o->ref_ex_level; r.pop_real_factor = o->pop_real_factor; r.spawn_cutoff = o->spawn_cutoff;
+        r.proc_map = o->proc_map; r.tau = tau; r.shift = shift; r.est.proj_energy_old = proj_energy_old;
+        r.ranks.resize(1);
+        r.ranks[0].iproc = 0;
+        r.ranks[0].send.assign(1, {});
+        r.in.nprocs = 1; r.in.nslots = 1; r.proc_map.assign(1, 0);
+        r.ranks[0].states = o->ranks[0].states; r.ranks[0].pops = o->ranks[0].pops; r.ranks[0].dat = o->ranks[0].dat;
+        r.ranks[0].nstates = o->ranks[0].nstates; r.ranks[0].nparticles = o->ranks[0].nparticles;
+        r.ranks[0].rng.reset(new PhiloxRng((uint32_t)(o->in.seed + 1000 * (t + 1))));
+    }
+    std::vector<double> walker_iters(nthreads, 0.0), attempts(nthreads, 0.0);
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t) {
+        th.emplace_back([&, t]() {
+            Oracle& r = *reps[t];
+            for (int c = 0; c < ncycles; ++c) {
+                walker_iters[t] += r.ranks[0].nparticles;
+                r.mc_cycle(1 + c);
+                attempts[t] += (double)r.ranks[0].nattempts / 2.0;
+            }
+        });
+    }
+    for (auto& x : th) x.join();
+    auto t1 = std::chrono::steady_clock::now();
+    double wi = 0, at = 0;
+    for (int t = 0; t < nthreads; ++t) { wi += walker_iters[t]; at += attempts[t]; }
+    out[0] = std::chrono::duration<double>(t1 - t0).count();
+    out[1] = wi; out[2] = at;
+    return 0;
+    ORC_CATCH(-1)
+}
+
+}  // extern "C"

@@ -1,0 +1,628 @@
+// ORACLE (test infrastructure, NOT product code).
+//
+// CPU restatement of the reference's molecular excitation generators:
+//   renorm      src/excit_gen_mol.f90:16-101,384-448,521-682,802-946,1140-1327
+//   no_renorm   src/excit_gen_mol.f90:195-284,450-517,950-1136,1329-1445
+//   heat_bath   src/excit_gen_heat_bath_mol.F90:14-548, src/excit_gen_utils.f90:9-66,142-160,
+//               lib/local/alias.f90:13-184
+// Random numbers are consumed in exactly the reference's order.
+#pragma once
+#include "system.hpp"
+#include "rng.hpp"
+
+namespace oracle {
+
+constexpr int MAXNEL = 64;
+
+enum ExcitGenKind {  // values of src/qmc_data.f90:31-69
+    EXCIT_GEN_NO_RENORM = 0,
+    EXCIT_GEN_RENORM = 1,
+    EXCIT_GEN_HEAT_BATH = 4,
+    EXCIT_GEN_HEAT_BATH_UNIFORM = 5,
+    EXCIT_GEN_HEAT_BATH_SINGLE = 6,
+};
+
+struct DetInfo {
+    Det f;
+    int occ[MAXNEL];
+    std::vector<int> symunocc;  // [(ims-1) + 2*sym]
+    int initiator_flag = 0;
+    // heat-bath per-determinant cache (det_info_t%i_d_occ, src/determinant_data.f90:22-70)
+    bool double_precalc = false;
+    double i_d_weights[MAXNEL];
+    double i_d_weights_tot = 0.0;
+    inline int su(int ims, int sym) const { return symunocc[(ims - 1) + 2 * sym]; }
+};
+
+// decode_det_occ / decode_det_occ_symunocc (src/determinant_decoders.f90:15-35,166-206)
+inline void decode_det_occ(const System& sys, const Det& f, DetInfo& d) {
+    d.f = f;
+    sys.decode(f, d.occ);
+    d.double_precalc = false;
+}
+inline void decode_det_occ_symunocc(const System& sys, const Det& f, DetInfo& d) {
+    decode_det_occ(sys, f, d);
+    d.symunocc = sys.nbasis_sym_spin;
+    for (int i = 0; i < sys.nel; ++i) {
+        const BasisFn& b = sys.bf[d.occ[i]];
+        d.symunocc[((b.ms + 3) / 2 - 1) + 2 * b.sym]--;
+    }
+}
+
+struct GenResult {
+    Excit conn;
+    double pgen = 1.0;
+    double hmatel = 0.0;
+    bool allowed = false;
+};
+
+// ------------------------------------------------------------------------ alias method
+// lib/local/alias.f90:101-184.  Arrays are 0-based here; returned/stored indices 1-based.
+inline void generate_alias_tables(int N, const double* weights, double totweight, double* aliasU, int* aliasK) {
+    std::vector<int> underfull(N), overfull(N);
+    int nunder = 0, nover = 0;
+    double scale = N / totweight;
+    for (int i = 0; i < N; ++i) aliasU[i] = weights[i] * scale;
+    for (int i = 0; i < N; ++i) {
+        if (aliasU[i] <= 1.0) underfull[nunder++] = i; else overfull[nover++] = i;
+        aliasK[i] = i + 1;
+    }
+    while (nover > 0 && nunder > 0) {
+        int ov = overfull[nover - 1];
+        int un = underfull[nunder - 1];
+        aliasK[un] = ov + 1;
+        nunder--;
+        aliasU[ov] = aliasU[ov] - (1 - aliasU[un]);
+        if (aliasU[ov] < 1.0) {
+            underfull[nunder++] = overfull[nover - 1];
+            nover--;
+        }
+    }
+}
+// lib/local/alias.f90:13-66
+inline int select_weighted_value_precalc(Rng& rng, int N, const double* aliasU, const int* aliasK) {
+    double x = rng.next() * N;
+    int K = (int)std::floor(x);
+    x = x - K;
+    if (x < aliasU[K]) return K + 1;
+    return aliasK[K];
+}
+// lib/local/alias.f90:68-99
+inline int select_weighted_value(Rng& rng, int N, const double* weights, double totweight) {
+    double aliasU[MAXNEL * 4];
+    int aliasK[MAXNEL * 4];
+    generate_alias_tables(N, weights, totweight, aliasU, aliasK);
+    return select_weighted_value_precalc(rng, N, aliasU, aliasK);
+}
+
+// ------------------------------------------------------------------------ heat-bath tables
+struct HeatBath {
+    int nb = 0;
+    std::vector<double> i_weights;      // (nb)
+    std::vector<double> ij_weights;     // (j,i)
+    std::vector<double> ija_w, ija_U;   // (a,j,i)
+    std::vector<int> ija_K;
+    std::vector<double> ija_tot;        // (j,i)
+    std::vector<double> ijab_w, ijab_U; // (b,a,j,i)
+    std::vector<int> ijab_K;
+    std::vector<double> ijab_tot;       // (a,j,i)
+    inline size_t i2(int j, int i) const { return (size_t)(j - 1) + (size_t)nb * (i - 1); }
+    inline size_t i3(int a, int j, int i) const { return (size_t)(a - 1) + (size_t)nb * ((j - 1) + (size_t)nb * (i - 1)); }
+    inline size_t i4(int b, int a, int j, int i) const {
+        return (size_t)(b - 1) + (size_t)nb * ((a - 1) + (size_t)nb * ((j - 1) + (size_t)nb * (i - 1)));
+    }
+};
+
+// init_excit_mol_heat_bath (src/excit_gen_heat_bath_mol.F90:14-256).  Returns false if the
+// "not all single excitations can be accounted for" check (:171-182) fails for original=true.
+inline bool init_excit_mol_heat_bath(const System& sys, HeatBath& hb, bool original) {
+    int nb = sys.nbasis;
+    hb.nb = nb;
+    size_t n2 = (size_t)nb * nb, n3 = n2 * nb, n4 = n3 * nb;
+    hb.i_weights.assign(nb, 0.0);
+    hb.ij_weights.assign(n2, 0.0);
+    hb.ija_w.assign(n3, 0.0); hb.ija_U.assign(n3, 0.0); hb.ija_K.assign(n3, 0);
+    hb.ija_tot.assign(n2, 0.0);
+    hb.ijab_w.assign(n4, 0.0); hb.ijab_U.assign(n4, 0.0); hb.ijab_K.assign(n4, 0);
+    hb.ijab_tot.assign(n3, 0.0);
+    std::vector<int> j_nonzero(n2, 0);  // (a,i)
+    bool ok = true;
+    for (int i = 1; i <= nb; ++i) {
+        double i_weight = 0.0;
+        for (int j = 1; j <= nb; ++j) {
+            double ij_weight = 0.0;
+            hb.ija_tot[hb.i2(j, i)] = 0.0;
+            if (i != j) {
+                int i_tmp = std::min(i, j), j_tmp = std::max(i, j);
+                int ij_sym = sys.sym_conj(sys.cross_product_basis(i_tmp, j_tmp));
+                double ija_weights_tot = 0.0, i_weight_extra = 0.0;
+                for (int a = 1; a <= nb; ++a) {
+                    double ija_weight = 0.0;
+                    hb.ijab_tot[hb.i3(a, j, i)] = 0.0;
+                    if (a != i && a != j) {
+                        int isymb = sys.sym_conj(sys.cross_product(ij_sym, sys.bf[a].sym));
+                        for (int b = 1; b <= nb; ++b) {
+                            double ijab_weight = 0.0;
+                            bool spin_ok = (sys.bf[i_tmp].ms == sys.bf[a].ms && sys.bf[j_tmp].ms == sys.bf[b].ms) ||
+                                           (sys.bf[i_tmp].ms == sys.bf[b].ms && sys.bf[j_tmp].ms == sys.bf[a].ms);
+                            if (spin_ok && sys.bf[b].sym == isymb && b != a && b != i && b != j) {
+                                int a_tmp = std::min(a, b), b_tmp = std::max(a, b);
+                                double h = std::fabs(sys.slater_condon2_excit(i_tmp, j_tmp, a_tmp, b_tmp, false));
+                                i_weight_extra = i_weight_extra + h;
+                                ij_weight = ij_weight + h;
+                                ija_weight = ija_weight + h;
+                                ijab_weight = ijab_weight + h;
+                            }
+                            hb.ijab_w[hb.i4(b, a, j, i)] = ijab_weight;
+                            hb.ijab_tot[hb.i3(a, j, i)] = hb.ijab_tot[hb.i3(a, j, i)] + ijab_weight;
+                        }
+                    }
+                    hb.ija_w[hb.i3(a, j, i)] = ija_weight;
+                    ija_weights_tot = ija_weights_tot + ija_weight;
+                    if (ija_weight > depsilon) j_nonzero[(size_t)(a - 1) + (size_t)nb * (i - 1)]++;
+                }
+                i_weight = i_weight + i_weight_extra;
+                hb.ija_tot[hb.i2(j, i)] = hb.ija_tot[hb.i2(j, i)] + ija_weights_tot;
+            }
+            hb.ij_weights[hb.i2(j, i)] = ij_weight;
+        }
+        hb.i_weights[i - 1] = i_weight;
+        for (int a = 1; a <= nb; ++a) {
+            if (j_nonzero[(size_t)(a - 1) + (size_t)nb * (i - 1)] < (nb - sys.nel) && original && i != a) {
+                int isyma = sys.cross_product(sys.bf[i].sym, sys.gamma_sym);
+                if (sys.bf[a].sym == isyma && sys.bf[a].ms == sys.bf[i].ms) ok = false;
+            }
+        }
+    }
+    for (int i = 1; i <= nb; ++i)
+        for (int j = 1; j <= nb; ++j)
+            if (std::fabs(hb.ija_tot[hb.i2(j, i)]) > 0.0) {
+                size_t o3 = hb.i3(1, j, i);
+                generate_alias_tables(nb, &hb.ija_w[o3], hb.ija_tot[hb.i2(j, i)], &hb.ija_U[o3], &hb.ija_K[o3]);
+                for (int a = 1; a <= nb; ++a)
+                    if (std::fabs(hb.ijab_tot[hb.i3(a, j, i)]) > 0.0) {
+                        size_t o4 = hb.i4(1, a, j, i);
+                        generate_alias_tables(nb, &hb.ijab_w[o4], hb.ijab_tot[hb.i3(a, j, i)], &hb.ijab_U[o4],
+                                              &hb.ijab_K[o4]);
+                    }
+            }
+    return ok;
+}
+
+struct ExcitGenData {
+    int excit_gen = EXCIT_GEN_RENORM;
+    double pattempt_single = 0.0, pattempt_double = 1.0;
+    HeatBath hb;
+};
+
+// find_single_double_prob (src/qmc_common.F90:152-260), read_in branch
+inline void find_single_double_prob(const System& sys, const int* occ, double& psingle, double& pdouble) {
+    std::vector<int> virt = sys.nbasis_sym_spin;
+    auto V = [&](int ims, int sym) -> int& { return virt[(ims - 1) + 2 * sym]; };
+    for (int i = 0; i < sys.nel; ++i) V((sys.bf[occ[i]].ms + 3) / 2, sys.bf[occ[i]].sym)--;
+    int nsingles = 0;
+    for (int i = 0; i < sys.nel; ++i) nsingles += V((sys.bf[occ[i]].ms + 3) / 2, sys.bf[occ[i]].sym);
+    int ndoubles = 0;
+    for (int i = 0; i < sys.nel; ++i) {
+        int ims1 = (sys.bf[occ[i]].ms + 3) / 2;
+        for (int j = i + 1; j < sys.nel; ++j) {
+            int ims2 = (sys.bf[occ[j]].ms + 3) / 2;
+            for (int isyma = sys.sym0; isyma <= sys.sym_max; ++isyma) {
+                int isymb = sys.cross_product(sys.bf[occ[i]].sym, sys.bf[occ[j]].sym);
+                isymb = sys.cross_product(isyma, isymb);
+                if (isyma == isymb) {
+                    if (ims1 == ims2) ndoubles += (V(ims1, isyma) * (V(ims2, isymb) - 1)) / 2;
+                    else ndoubles += V(ims1, isyma) * V(ims2, isymb);
+                } else if (isyma < isymb) {
+                    ndoubles += V(ims1, isyma) * V(ims2, isymb);
+                    if (ims1 != ims2) ndoubles += V(ims2, isyma) * V(ims1, isymb);
+                }
+            }
+        }
+    }
+    psingle = (double)nsingles / (nsingles + ndoubles);
+    pdouble = (double)ndoubles / (nsingles + ndoubles);
+}
+
+// ------------------------------------------------------------------------ renorm pieces
+// choose_ij_mol (src/excit_gen_mol.f90:620-682)
+inline void choose_ij_mol(Rng& rng, const System& sys, const int* occ, int& i, int& j, int& ij_sym, int& ij_spin,
+                          double& pgen_ij) {
+    int nel = sys.nel;
+    int ind = (int)(rng.next() * nel * (nel - 1) / 2) + 1;
+    int j_ind = (int)(1.50 + std::sqrt(2 * ind - 1.750));
+    int i_ind = ind - ((j_ind - 1) * (j_ind - 2)) / 2;
+    i = occ[i_ind - 1];
+    j = occ[j_ind - 1];
+    ij_sym = sys.sym_conj(sys.cross_product_basis(i, j));
+    ij_spin = sys.bf[i].ms + sys.bf[j].ms;
+    pgen_ij = 2.0 / (nel * (nel - 1));
+}
+
+// choose_ia_mol (src/excit_gen_mol.f90:521-616)
+inline void choose_ia_mol(Rng& rng, const System& sys, int op_sym, const DetInfo& d, int& i, int& a, bool& allowed) {
+    allowed = false;
+    for (int k = 0; k < sys.nel; ++k) {
+        int imsa = (sys.bf[d.occ[k]].ms + 3) / 2;
+        int isyma = sys.cross_product(sys.bf[d.occ[k]].sym, op_sym);
+        if (d.su(imsa, isyma) != 0) { allowed = true; break; }
+    }
+    if (allowed) {
+        for (;;) {
+            i = d.occ[(int)(rng.next() * sys.nel)];
+            int imsa = (sys.bf[i].ms + 3) / 2;
+            int isyma = sys.cross_product(sys.bf[i].sym, op_sym);
+            if (d.su(imsa, isyma) != 0) {
+                for (;;) {
+                    int ind = (int)(sys.nbss(imsa, isyma) * rng.next()) + 1;
+                    a = sys.ssbf(ind, imsa, isyma);
+                    if (!det_test(d.f, a)) break;
+                }
+                break;
+            }
+        }
+    }
+}
+
+// choose_ab_mol (src/excit_gen_mol.f90:802-946)
+inline void choose_ab_mol(Rng& rng, const System& sys, const DetInfo& d, int sym, int spin, int& a, int& b,
+                          bool& allowed) {
+    allowed = false;
+    int fac = 1, shift = 0, na = sys.nbasis;
+    if (spin == -2) {
+        for (int isyma = sys.sym0; isyma <= sys.sym_max; ++isyma) {
+            int isymb = sys.sym_conj(sys.cross_product(isyma, sym));
+            if (d.su(1, isyma) > 0 && (d.su(1, isymb) > 1 || (d.su(1, isymb) == 1 && isyma != isymb))) {
+                allowed = true; break;
+            }
+        }
+        fac = 2; shift = 0; na = sys.nbasis / 2;
+    } else if (spin == 0) {
+        for (int isyma = sys.sym0; isyma <= sys.sym_max; ++isyma) {
+            int isymb = sys.sym_conj(sys.cross_product(isyma, sym));
+            if ((d.su(1, isyma) > 0 && d.su(2, isymb) > 0) || (d.su(2, isyma) > 0 && d.su(1, isymb) > 0)) {
+                allowed = true; break;
+            }
+        }
+        fac = 1; shift = 0; na = sys.nbasis;
+    } else {
+        for (int isyma = sys.sym0; isyma <= sys.sym_max; ++isyma) {
+            int isymb = sys.sym_conj(sys.cross_product(isyma, sym));
+            if (d.su(2, isyma) > 0 && (d.su(2, isymb) > 1 || (d.su(2, isymb) == 1 && isyma != isymb))) {
+                allowed = true; break;
+            }
+        }
+        fac = 2; shift = 1; na = sys.nbasis / 2;
+    }
+    if (allowed) {
+        for (;;) {
+            a = (int)(rng.next() * na) + 1;
+            a = fac * a - shift;
+            if (!det_test(d.f, a)) {
+                int imsb = (spin - sys.bf[a].ms + 3) / 2;
+                int isymb = sys.sym_conj(sys.cross_product(sym, sys.bf[a].sym));
+                if (d.su(imsb, isymb) > 1 || (d.su(imsb, isymb) == 1 && (isymb != sys.bf[a].sym || spin == 0))) {
+                    for (;;) {
+                        int ind = (int)(sys.nbss(imsb, isymb) * rng.next()) + 1;
+                        b = sys.ssbf(ind, imsb, isymb);
+                        if (b != a && !det_test(d.f, b)) break;
+                    }
+                    break;
+                }
+            }
+        }
+        if (a > b) std::swap(a, b);
+    }
+}
+
+// calc_pgen_single_mol (src/excit_gen_mol.f90:1140-1190)
+inline double calc_pgen_single_mol(const System& sys, int op_sym, const DetInfo& d, int a) {
+    int ni = sys.nel;
+    for (int k = 0; k < sys.nel; ++k) {
+        int imsa = (sys.bf[d.occ[k]].ms + 3) / 2;
+        int isyma = sys.cross_product(sys.bf[d.occ[k]].sym, op_sym);
+        if (d.su(imsa, isyma) == 0) ni--;
+    }
+    int imsi = (sys.bf[a].ms + 3) / 2, isymi = sys.bf[a].sym;
+    return 1.0 / (ni * d.su(imsi, isymi));
+}
+
+// calc_pgen_double_mol (src/excit_gen_mol.f90:1192-1327)
+inline double calc_pgen_double_mol(const System& sys, int ij_sym, int a, int b, int spin, const DetInfo& d) {
+    int imsa = (sys.bf[a].ms + 3) / 2, imsb = (sys.bf[b].ms + 3) / 2;
+    int n_aij;
+    double p_aijb, p_bija;
+    if (spin == -2 || spin == 2) {
+        int s = (spin == -2) ? 1 : 2;
+        n_aij = (spin == -2) ? sys.nvirt_beta : sys.nvirt_alpha;
+        for (int isyma = sys.sym0; isyma <= sys.sym_max; ++isyma) {
+            int isymb = sys.sym_conj(sys.cross_product(isyma, ij_sym));
+            if (d.su(s, isymb) == 0) n_aij -= d.su(s, isyma);
+            else if (isyma == isymb && d.su(s, isymb) == 1) n_aij -= d.su(s, isyma);
+        }
+        if (sys.bf[a].sym == sys.bf[b].sym) {
+            p_aijb = 1.0 / (d.su(imsa, sys.bf[a].sym) - 1);
+            p_bija = 1.0 / (d.su(imsb, sys.bf[b].sym) - 1);
+        } else {
+            p_aijb = 1.0 / d.su(imsa, sys.bf[a].sym);
+            p_bija = 1.0 / d.su(imsb, sys.bf[b].sym);
+        }
+    } else {
+        n_aij = sys.nvirt;
+        for (int isyma = sys.sym0; isyma <= sys.sym_max; ++isyma) {
+            int isymb = sys.sym_conj(sys.cross_product(isyma, ij_sym));
+            if (d.su(1, isymb) == 0) n_aij -= d.su(2, isyma);
+            if (d.su(2, isymb) == 0) n_aij -= d.su(1, isyma);
+        }
+        p_aijb = 1.0 / d.su(imsa, sys.bf[a].sym);
+        p_bija = 1.0 / d.su(imsb, sys.bf[b].sym);
+    }
+    return (1.0 / n_aij) * (p_bija + p_aijb);
+}
+
+// gen_excit_mol (src/excit_gen_mol.f90:16-101)
+inline GenResult gen_excit_mol(Rng& rng, const System& sys, const ExcitGenData& eg, const DetInfo& d) {
+    GenResult r;
+    if (rng.next() < eg.pattempt_single) {
+        choose_ia_mol(rng, sys, sys.gamma_sym, d, r.conn.from_orb[0], r.conn.to_orb[0], r.allowed);
+        r.conn.nexcit = 1;
+        if (r.allowed) {
+            r.pgen = eg.pattempt_single * calc_pgen_single_mol(sys, sys.gamma_sym, d, r.conn.to_orb[0]);
+            sys.find_excitation_permutation1(d.f, r.conn);
+            r.hmatel = sys.slater_condon1_excit(d.occ, r.conn.from_orb[0], r.conn.to_orb[0], r.conn.perm);
+        } else { r.hmatel = 0.0; r.pgen = 1.0; }
+    } else {
+        int ij_sym, ij_spin;
+        double pgen_ij;
+        choose_ij_mol(rng, sys, d.occ, r.conn.from_orb[0], r.conn.from_orb[1], ij_sym, ij_spin, pgen_ij);
+        choose_ab_mol(rng, sys, d, ij_sym, ij_spin, r.conn.to_orb[0], r.conn.to_orb[1], r.allowed);
+        r.conn.nexcit = 2;
+        if (r.allowed) {
+            r.pgen = eg.pattempt_double * pgen_ij *
+                     calc_pgen_double_mol(sys, ij_sym, r.conn.to_orb[0], r.conn.to_orb[1], ij_spin, d);
+            sys.find_excitation_permutation2(d.f, r.conn);
+            r.hmatel = sys.slater_condon2_excit(r.conn.from_orb[0], r.conn.from_orb[1], r.conn.to_orb[0],
+                                                r.conn.to_orb[1], r.conn.perm);
+        } else { r.hmatel = 0.0; r.pgen = 1.0; }
+    }
+    return r;
+}
+
+// ------------------------------------------------------------------------ no_renorm
+// find_ia_mol (src/excit_gen_mol.f90:950-1010)
+inline void find_ia_mol(Rng& rng, const System& sys, int op_sym, const DetInfo& d, int& i, int& a, bool& allowed) {
+    i = d.occ[(int)(rng.next() * sys.nel)];
+    int imsa = (sys.bf[i].ms + 3) / 2;
+    int isyma = sys.cross_product(sys.bf[i].sym, op_sym);
+    int ind = (int)(sys.nbss(imsa, isyma) * rng.next()) + 1;
+    if (sys.nbss(imsa, isyma) == 0) {
+        allowed = false;
+    } else {
+        a = sys.ssbf(ind, imsa, isyma);
+        allowed = !det_test(d.f, a);
+    }
+}
+// find_ab_mol (src/excit_gen_mol.f90:1012-1136)
+inline void find_ab_mol(Rng& rng, const System& sys, const DetInfo& d, int sym, int spin, int& a, int& b,
+                        bool& allowed) {
+    int fac = 1, shift = 0, na = sys.nbasis;
+    if (spin == -2) { fac = 2; shift = 0; na = sys.nbasis / 2; }
+    else if (spin == 2) { fac = 2; shift = 1; na = sys.nbasis / 2; }
+    for (;;) {
+        a = (int)(rng.next() * na) + 1;
+        a = fac * a - shift;
+        if (!det_test(d.f, a)) break;
+    }
+    int imsb = (spin - sys.bf[a].ms + 3) / 2;
+    int isymb = sys.sym_conj(sys.cross_product(sym, sys.bf[a].sym));
+    if (sys.nbss(imsb, isymb) == 0) {
+        allowed = false;
+    } else if (spin != 0 && isymb == sys.bf[a].sym && sys.nbss(imsb, isymb) == 1) {
+        allowed = false;
+    } else {
+        for (;;) {
+            int ind = (int)(sys.nbss(imsb, isymb) * rng.next()) + 1;
+            b = sys.ssbf(ind, imsb, isymb);
+            if (b != a) break;
+        }
+        allowed = !det_test(d.f, b);
+        if (a > b) std::swap(a, b);
+    }
+}
+// src/excit_gen_mol.f90:1329-1445
+inline double calc_pgen_single_mol_no_renorm(const System& sys, int a) {
+    return 1.0 / (sys.nel * sys.nbss((sys.bf[a].ms + 3) / 2, sys.bf[a].sym));
+}
+inline double calc_pgen_double_mol_no_renorm(const System& sys, int a, int b, int spin) {
+    int n_aij = (spin == -2) ? sys.nvirt_beta : (spin == 0 ? sys.nvirt : sys.nvirt_alpha);
+    int imsa = (sys.bf[a].ms + 3) / 2, isyma = sys.bf[a].sym;
+    int imsb = (sys.bf[b].ms + 3) / 2, isymb = sys.bf[b].sym;
+    double p_aijb, p_bija;
+    if (isyma == isymb && imsa == imsb) {
+        p_aijb = 1.0 / (sys.nbss(imsa, isyma) - 1);
+        p_bija = 1.0 / (sys.nbss(imsb, isymb) - 1);
+    } else {
+        p_aijb = 1.0 / sys.nbss(imsa, isyma);
+        p_bija = 1.0 / sys.nbss(imsb, isymb);
+    }
+    return (1.0 / n_aij) * (p_bija + p_aijb);
+}
+// gen_excit_mol_no_renorm (src/excit_gen_mol.f90:195-284)
+inline GenResult gen_excit_mol_no_renorm(Rng& rng, const System& sys, const ExcitGenData& eg, const DetInfo& d) {
+    GenResult r;
+    if (rng.next() < eg.pattempt_single) {
+        find_ia_mol(rng, sys, sys.gamma_sym, d, r.conn.from_orb[0], r.conn.to_orb[0], r.allowed);
+        r.conn.nexcit = 1;
+        if (r.allowed) {
+            r.pgen = eg.pattempt_single * calc_pgen_single_mol_no_renorm(sys, r.conn.to_orb[0]);
+            sys.find_excitation_permutation1(d.f, r.conn);
+            r.hmatel = sys.slater_condon1_excit(d.occ, r.conn.from_orb[0], r.conn.to_orb[0], r.conn.perm);
+        } else { r.hmatel = 0.0; r.pgen = 1.0; }
+    } else {
+        int ij_sym, ij_spin;
+        double pgen_ij;
+        choose_ij_mol(rng, sys, d.occ, r.conn.from_orb[0], r.conn.from_orb[1], ij_sym, ij_spin, pgen_ij);
+        find_ab_mol(rng, sys, d, ij_sym, ij_spin, r.conn.to_orb[0], r.conn.to_orb[1], r.allowed);
+        r.conn.nexcit = 2;
+        if (r.allowed) {
+            r.pgen = eg.pattempt_double * pgen_ij *
+                     calc_pgen_double_mol_no_renorm(sys, r.conn.to_orb[0], r.conn.to_orb[1], ij_spin);
+            sys.find_excitation_permutation2(d.f, r.conn);
+            r.hmatel = sys.slater_condon2_excit(r.conn.from_orb[0], r.conn.from_orb[1], r.conn.to_orb[0],
+                                                r.conn.to_orb[1], r.conn.perm);
+        } else { r.hmatel = 0.0; r.pgen = 1.0; }
+    }
+    return r;
+}
+
+// ------------------------------------------------------------------------ heat bath (original)
+// gen_excit_mol_heat_bath (src/excit_gen_heat_bath_mol.F90:258-548)
+inline GenResult gen_excit_mol_heat_bath(Rng& rng, const System& sys, const ExcitGenData& eg, DetInfo& d) {
+    GenResult r;
+    const HeatBath& hb = eg.hb;
+    const int nel = sys.nel, nb = sys.nbasis;
+    double ij_w[MAXNEL], ji_w[MAXNEL];
+    double ij_tot = 0.0, ji_tot = 0.0;
+    if (!d.double_precalc) {
+        // find_i_d_weights (src/excit_gen_utils.f90:142-160)
+        d.i_d_weights_tot = 0.0;
+        for (int p = 0; p < nel; ++p) {
+            d.i_d_weights[p] = hb.i_weights[d.occ[p] - 1];
+            d.i_d_weights_tot = d.i_d_weights_tot + d.i_d_weights[p];
+        }
+        d.double_precalc = true;
+    }
+    // select_ij_heat_bath (src/excit_gen_utils.f90:9-66)
+    int i_ind = select_weighted_value(rng, nel, d.i_d_weights, d.i_d_weights_tot);
+    int i = d.occ[i_ind - 1];
+    int j_ind = 0, j = 0;
+    for (int p = 0; p < nel; ++p) {
+        ij_w[p] = hb.ij_weights[hb.i2(d.occ[p], i)];
+        ij_tot = ij_tot + ij_w[p];
+    }
+    bool allowed;
+    if (ij_tot > 0.0) {
+        j_ind = select_weighted_value(rng, nel, ij_w, ij_tot);
+        j = d.occ[j_ind - 1];
+        for (int p = 0; p < nel; ++p) {
+            ji_w[p] = hb.ij_weights[hb.i2(d.occ[p], j)];
+            ji_tot = ji_tot + ji_w[p];
+        }
+        allowed = true;
+    } else {
+        allowed = false;
+    }
+    allowed = allowed && (std::fabs(hb.ija_tot[hb.i2(j > 0 ? j : 1, i)]) > 0.0) && j > 0;
+
+    int a = 0, b = 0;
+    bool dbl = true;
+    double psingle = 0.0, hmatel_mod_ia = 0.0;
+    if (allowed) {
+        size_t o3 = hb.i3(1, j, i);
+        a = select_weighted_value_precalc(rng, nb, &hb.ija_U[o3], &hb.ija_K[o3]);
+        if (!det_test(d.f, a)) {
+            int ims = sys.bf[i].ms;
+            int isyma = sys.cross_product(sys.bf[i].sym, sys.gamma_sym);
+            if (sys.bf[a].sym == isyma && sys.bf[a].ms == ims) {
+                r.conn.from_orb[0] = i; r.conn.to_orb[0] = a; r.conn.nexcit = 1;
+                sys.find_excitation_permutation1(d.f, r.conn);
+                double hs = sys.slater_condon1_excit(d.occ, i, a, r.conn.perm);
+                hmatel_mod_ia = std::fabs(hs);
+                double x = rng.next();
+                double wt = hb.ijab_tot[hb.i3(a, j, i)];
+                if (hmatel_mod_ia < wt) psingle = hmatel_mod_ia / (wt + hmatel_mod_ia);
+                else psingle = 0.5;
+                dbl = !(x < psingle);
+            } else {
+                dbl = true;
+                psingle = 0.0;
+            }
+        } else {
+            allowed = false;
+        }
+    }
+    if (allowed) {
+        if (dbl) {
+            size_t o4 = hb.i4(1, a, j, i);
+            b = select_weighted_value_precalc(rng, nb, &hb.ijab_U[o4], &hb.ijab_K[o4]);
+            if (!det_test(d.f, b)) {
+                const double pi_ = d.i_d_weights[i_ind - 1] / d.i_d_weights_tot;
+                const double pj_ = d.i_d_weights[j_ind - 1] / d.i_d_weights_tot;
+                auto psingle_of = [&](int from, int to, int other) -> double {
+                    // single-vs-double coin for ordering (from -> to | other)
+                    int ims = sys.bf[from].ms;
+                    int isyma = sys.cross_product(sys.bf[from].sym, sys.gamma_sym);
+                    if (sys.bf[to].sym == isyma && sys.bf[to].ms == ims) {
+                        Excit e; e.from_orb[0] = from; e.to_orb[0] = to; e.nexcit = 1;
+                        sys.find_excitation_permutation1(d.f, e);
+                        double hm = std::fabs(sys.slater_condon1_excit(d.occ, from, to, e.perm));
+                        double wt = hb.ijab_tot[hb.i3(to, other, from)];
+                        if (hm < wt) return hm / (wt + hm);
+                        return 0.5;
+                    }
+                    return 0.0;
+                };
+                double pgen_ija = ((pi_) * (ij_w[j_ind - 1] / ij_tot)) *
+                                  (hb.ija_w[hb.i3(a, j, i)] / hb.ija_tot[hb.i2(j, i)]) * (1.0 - psingle) *
+                                  (hb.ijab_w[hb.i4(b, a, j, i)] / hb.ijab_tot[hb.i3(a, j, i)]);
+                double ps = psingle_of(i, b, j);
+                double pgen_ijb = ((pi_) * (ij_w[j_ind - 1] / ij_tot)) *
+                                  (hb.ija_w[hb.i3(b, j, i)] / hb.ija_tot[hb.i2(j, i)]) * (1.0 - ps) *
+                                  (hb.ijab_w[hb.i4(a, b, j, i)] / hb.ijab_tot[hb.i3(b, j, i)]);
+                ps = psingle_of(j, a, i);
+                double pgen_jia = ((pj_) * (ji_w[i_ind - 1] / ji_tot)) *
+                                  (hb.ija_w[hb.i3(a, i, j)] / hb.ija_tot[hb.i2(i, j)]) * (1.0 - ps) *
+                                  (hb.ijab_w[hb.i4(b, a, i, j)] / hb.ijab_tot[hb.i3(a, i, j)]);
+                ps = psingle_of(j, b, i);
+                double pgen_jib = ((pj_) * (ji_w[i_ind - 1] / ji_tot)) *
+                                  (hb.ija_w[hb.i3(b, i, j)] / hb.ija_tot[hb.i2(i, j)]) * (1.0 - ps) *
+                                  (hb.ijab_w[hb.i4(a, b, i, j)] / hb.ijab_tot[hb.i3(b, i, j)]);
+                r.pgen = pgen_ija + pgen_ijb + pgen_jia + pgen_jib;
+                r.conn.from_orb[0] = std::min(i, j); r.conn.from_orb[1] = std::max(i, j);
+                r.conn.to_orb[0] = std::min(a, b); r.conn.to_orb[1] = std::max(a, b);
+                r.conn.nexcit = 2;
+                sys.find_excitation_permutation2(d.f, r.conn);
+                r.hmatel = sys.slater_condon2_excit(r.conn.from_orb[0], r.conn.from_orb[1], r.conn.to_orb[0],
+                                                    r.conn.to_orb[1], r.conn.perm);
+                r.allowed = true;
+            } else {
+                r.allowed = false; r.hmatel = 0.0; r.pgen = 1.0;
+                r.conn.nexcit = 2;
+            }
+        } else {
+            r.conn.from_orb[0] = i; r.conn.to_orb[0] = a; r.conn.nexcit = 1;
+            r.hmatel = sys.slater_condon1_excit(d.occ, i, a, r.conn.perm);
+            double pgen = 0.0;
+            for (int q = 0; q < nel; ++q) {
+                int oq = d.occ[q];
+                if (i != oq && a != oq) {
+                    double wt = hb.ijab_tot[hb.i3(a, oq, i)];
+                    double psq;
+                    if (hmatel_mod_ia < wt) psq = hmatel_mod_ia / (wt + hmatel_mod_ia);
+                    else psq = 0.5;
+                    pgen = pgen + (psq * (ij_w[q] / ij_tot) * (hb.ija_w[hb.i3(a, oq, i)] / hb.ija_tot[hb.i2(oq, i)]));
+                }
+            }
+            r.pgen = pgen * (d.i_d_weights[i_ind - 1] / d.i_d_weights_tot);
+            r.allowed = true;
+        }
+    } else {
+        r.allowed = false; r.hmatel = 0.0; r.pgen = 1.0;
+    }
+    return r;
+}
+
+inline GenResult gen_excit(Rng& rng, const System& sys, const ExcitGenData& eg, DetInfo& d) {
+    switch (eg.excit_gen) {
+        case EXCIT_GEN_RENORM: return gen_excit_mol(rng, sys, eg, d);
+        case EXCIT_GEN_NO_RENORM: return gen_excit_mol_no_renorm(rng, sys, eg, d);
+        case EXCIT_GEN_HEAT_BATH: return gen_excit_mol_heat_bath(rng, sys, eg, d);
+        default: throw std::runtime_error("oracle: excitation generator not implemented");
+    }
+}
+inline void decode_for(const System& sys, const ExcitGenData& eg, const Det& f, DetInfo& d) {
+    if (eg.excit_gen == EXCIT_GEN_RENORM) decode_det_occ_symunocc(sys, f, d);
+    else decode_det_occ(sys, f, d);
+}
+
+}  // namespace oracle

@@ -1,0 +1,710 @@
+// ORACLE (test infrastructure, NOT product code).
+//
+// CPU restatement of the reference's FCIQMC / iFCIQMC propagation loop:
+//   do_fciqmc main loop               src/fciqmc.f90:276-407, 635-769
+//   spawn_standard / attempt_to_spawn src/spawning.F90:34-124, 711-766
+//   create_spawned_particle*          src/spawning.F90:907-1319
+//   stochastic_round*                 src/stoch_utils.f90:15-136
+//   stochastic_death                  src/death.f90:11-130
+//   set_parent_flag                   src/ifciqmc.f90:13-57
+//   direct_annihilation and friends   src/annihilation.f90:9-901
+//   spawn_t store / sort / merge      src/spawn_data.F90:156-248, 359-465, 624-739, 859-1101
+//   qsort                             src/sort.f90:213-395
+//   binary_search                     src/search.f90:47-170
+//   estimators / shift                src/energy_evaluation.F90:126-201, 320-711, 906-986, 1433-1456
+//   cycle bookkeeping                 src/qmc_common.F90:379-406, 697-797, 929-1017, 1240-1304
+//   initial distribution              src/qmc.F90:1507-1646
+// Several MPI ranks are emulated in-process (one RankState each, own RNG seed+iproc) so the
+// np2/np4 golden trajectories can be followed too.
+#pragma once
+#include <memory>
+#include <cmath>
+#include "system.hpp"
+#include "rng.hpp"
+#include "excit_gen.hpp"
+
+namespace oracle {
+
+struct QmcIn {
+    double tau = 0.001;
+    int seed = 7;
+    double D0_population = 10.0;
+    int ncycles = 20;
+    int nreport = 10;
+    double target_particles = 1.e7;
+    double initial_shift = 0.0;
+    double shift_damping = 0.05;
+    double vary_shift_from = 0.0;
+    bool vary_shift_from_proje = false;
+    bool initiator_approx = false;
+    double initiator_pop = 3.0;
+    bool real_amplitudes = false;
+    double spawn_cutoff = 0.01;
+    int excit_gen = EXCIT_GEN_RENORM;
+    double pattempt_single = -1.0, pattempt_double = -1.0;
+    int64_t walker_length = 1 << 20;          // elements per rank
+    int64_t spawned_walker_length = 1 << 18;  // elements per rank
+    int ex_level = -1;                        // truncation level (reference%ex_level); -1 => none
+    int nprocs = 1;
+    int nslots = 1;
+    int rng_kind = 0;  // 0 dSFMT (reference stream), 1 Philox (engine stream)
+    // Literal int32 truncation of the first event in annihilate_spawn_t_initiator
+    // (src/spawn_data.F90:1019, sign(1,int(spawn_parts))).  true = as the reference (gfortran wraps),
+    // false = mathematically intended symmetric rule (what the GPU engine implements).
+    bool literal_event_int32 = true;
+};
+
+struct SpawnElem {
+    Det f;
+    int64_t pop = 0;
+    int64_t flag = 0;
+};
+
+struct Estimators {
+    double proj_energy = 0.0, D0_population = 0.0;
+    double proj_energy_old = 0.0, D0_population_old = 0.0;
+    int64_t tot_nstates = 0, tot_nspawn_events = 0;
+};
+
+struct RankState {
+    int iproc = 0;
+    std::vector<Det> states;
+    std::vector<int64_t> pops;
+    std::vector<double> dat;
+    int64_t nstates = 0;
+    double nparticles = 0.0;
+    std::vector<std::vector<SpawnElem>> send;  // per destination rank (block of sdata)
+    std::vector<SpawnElem> recv;               // after comm: concatenated by source rank
+    std::unique_ptr<Rng> rng;
+    bool spawn_error = false, psip_error = false;
+    double rspawn = 0.0;
+    double proj_energy = 0.0, D0_population = 0.0;  // per-rank accumulators within a report loop
+    int nspawn_events = 0;
+    int64_t ndeath = 0;
+    int64_t nattempts = 0;
+};
+
+struct ReportRow {
+    int iter;
+    double shift, proj_energy, D0_population, nparticles;
+    int64_t nstates, nspawn_events;
+    double rspawn;
+};
+
+// qsort_int_64_list (src/sort.f90:213-395) for spawn elements keyed on the bit string, ascending.
+inline void qsort_spawn(std::vector<SpawnElem>& list, int head, int W) {
+    auto gt = [&](const SpawnElem& a, const SpawnElem& b) { return det_less(b.f, a.f, W); };
+    auto ge = [&](const SpawnElem& a, const SpawnElem& b) { return !det_less(a.f, b.f, W); };
+    const int switch_threshold = 7;
+    std::vector<std::pair<int, int>> stack;
+    int lo = 1, hi = head;
+    auto L = [&](int k) -> SpawnElem& { return list[k - 1]; };
+    for (;;) {
+        if (hi - lo < switch_threshold) {
+            for (int j = lo + 1; j <= hi; ++j) {
+                SpawnElem tmp = L(j);
+                int i;
+                for (i = j - 1; i >= 1; --i) {
+                    if (ge(tmp, L(i))) break;
+                    L(i + 1) = L(i);
+                }
+                L(i + 1) = tmp;
+            }
+            if (stack.empty()) break;
+            lo = stack.back().first; hi = stack.back().second;
+            stack.pop_back();
+        } else {
+            int pivot = (lo + hi) / 2;
+            std::swap(L(pivot), L(lo + 1));
+            if (gt(L(lo), L(hi))) std::swap(L(lo), L(hi));
+            if (gt(L(lo + 1), L(hi))) std::swap(L(lo + 1), L(hi));
+            if (gt(L(lo), L(lo + 1))) std::swap(L(lo), L(lo + 1));
+            int i = lo + 1, j = hi;
+            SpawnElem tmp = L(lo + 1);
+            for (;;) {
+                i++;
+                while (gt(tmp, L(i))) i++;
+                j--;
+                while (gt(L(j), tmp)) j--;
+                if (j < i) break;
+                std::swap(L(i), L(j));
+            }
+            L(lo + 1) = L(j);
+            L(j) = tmp;
+            if (hi - i + 1 >= j - lo) {
+                stack.push_back({i, hi});
+                hi = j - 1;
+            } else {
+                stack.push_back({lo, j - 1});
+                lo = i;
+            }
+        }
+    }
+}
+
+// binary_search_i0_list (src/search.f90:47-170), ascending order; 1-based positions.
+inline void binary_search(const std::vector<Det>& list, const Det& item, int istart, int iend, int W, bool& hit,
+                          int& pos) {
+    auto cmp = [&](const Det& b1, const Det& b2) -> int {  // bit_str_cmp(b1,b2): 1 if b1<b2, -1 if b1>b2
+        if (det_less(b1, b2, W)) return 1;
+        if (det_less(b2, b1, W)) return -1;
+        return 0;
+    };
+    if (istart > iend) { pos = istart; hit = false; return; }
+    int lo = istart, hi = iend;
+    hit = false;
+    pos = istart;
+    while (hi != lo) {
+        pos = (hi + lo) / 2;
+        int c = cmp(list[pos - 1], item);
+        if (c == 0) { hit = true; break; }
+        else if (c == 1) lo = pos + 1;
+        else hi = pos;
+    }
+    if (hi == lo) {
+        int c = cmp(list[hi - 1], item);
+        if (c == 0) { hit = true; pos = hi; }
+        else if (c == 1) pos = hi + 1;
+        else pos = hi;
+    }
+}
+
+struct Oracle {
+    System sys;
+    QmcIn in;
+    ExcitGenData eg;
+    // reference_t
+    std::vector<int> occ_list0;
+    Det f0;
+    double H00 = 0.0;
+    int ref_ex_level = 0;
+    // qmc_state_t
+    double tau = 0.0, shift = 0.0;
+    bool vary_shift = false;
+    int64_t pop_real_factor = 1;
+    int64_t spawn_cutoff = 0;
+    std::vector<int> proc_map;
+    int mc_cycles_done = 0;
+    Estimators est;
+    double rspawn_report = 0.0;
+    double ntot_particles_old = 0.0;
+    std::vector<RankState> ranks;
+    std::vector<ReportRow> rows;
+    bool error = false;
+    uint32_t hash_seed = 7;  // src/qmc.F90:1497
+
+    // ---------------------------------------------------------------- setup (init_qmc)
+    void init() {
+        // init_reference (src/qmc.F90:1162-1226)
+        occ_list0 = set_reference_det(sys, sys.symmetry);
+        f0 = sys.encode(occ_list0.data(), sys.nel);
+        H00 = sys.slater_condon0(f0);
+        ref_ex_level = (in.ex_level < 0) ? sys.nel : in.ex_level;
+        pop_real_factor = in.real_amplitudes ? (1ll << 31) : 1;  // src/particle_t_utils.f90 (POP_SIZE=64)
+        double cutoff = in.real_amplitudes ? in.spawn_cutoff : 0.0;
+        spawn_cutoff = (int64_t)std::ceil(cutoff * (double)pop_real_factor);  // src/spawn_data.F90:215
+        if (in.spawned_walker_length % in.nprocs != 0)
+            in.spawned_walker_length = (int64_t)std::ceil((float)in.spawned_walker_length / in.nprocs) * in.nprocs;
+        proc_map.resize((size_t)in.nprocs * in.nslots);
+        for (size_t i = 0; i < proc_map.size(); ++i) proc_map[i] = (int)(i % in.nprocs);  // src/load_balancing.F90:170
+        tau = in.tau;
+        shift = in.initial_shift;
+        vary_shift = false;
+        // init_excit_gen (src/qmc.F90:910-1010)
+        eg.excit_gen = in.excit_gen;
+        if (in.pattempt_single < 0 || in.pattempt_double < 0) {
+            find_single_double_prob(sys, occ_list0.data(), eg.pattempt_single, eg.pattempt_double);
+        } else {
+            eg.pattempt_single = in.pattempt_single / (in.pattempt_single + in.pattempt_double);
+            eg.pattempt_double = 1.0 - in.pattempt_single;
+        }
+        if (in.excit_gen == EXCIT_GEN_HEAT_BATH) {
+            if (!init_excit_mol_heat_bath(sys, eg.hb, true))
+                throw std::runtime_error("heat_bath: not all single excitations can be accounted for");
+        }
+        ranks.clear();
+        ranks.resize(in.nprocs);
+        for (int ip = 0; ip < in.nprocs; ++ip) {
+            RankState& r = ranks[ip];
+            r.iproc = ip;
+            r.send.assign(in.nprocs, {});
+            if (in.rng_kind == 0) r.rng.reset(new DsfmtRng(in.seed + ip, 50000));
+            else r.rng.reset(new PhiloxRng((uint32_t)in.seed));
+        }
+        initial_distribution();
+        for (auto& r : ranks) recompute_nparticles(r);
+        mc_cycles_done = 0;
+        rows.clear();
+        est = Estimators();
+    }
+
+    int owner(const Det& f) const {
+        return assign_particle_processor(f, sys.nbasis, hash_seed, 0, 0, in.nprocs, proc_map.data(), in.nslots);
+    }
+
+    // initial_distribution (src/qmc.F90:1507-1646), single reference, no spin-inverse
+    void initial_distribution() {
+        int D0_proc = owner(f0);
+        for (auto& r : ranks) {
+            r.states.clear(); r.pops.clear(); r.dat.clear();
+            r.nstates = 0;
+            if (r.iproc == D0_proc) {
+                r.states.push_back(f0);
+                r.pops.push_back((int64_t)std::llround(in.D0_population) * pop_real_factor);
+                r.dat.push_back(0.0);
+                r.nstates = 1;
+            }
+        }
+    }
+    void recompute_nparticles(RankState& r) {
+        // init_estimators (src/qmc.F90:845-850)
+        double s = 0.0;
+        for (int64_t k = 0; k < r.nstates; ++k) s += std::fabs((double)r.pops[k] / (double)pop_real_factor);
+        r.nparticles = s;
+    }
+
+    // ---------------------------------------------------------------- per-determinant pieces
+    // update_proj_energy_mol (src/energy_evaluation.F90:906-986); returns contribution pieces.
+    void update_proj_energy(const DetInfo& d, double pop, double& D0_acc, double& pe_acc) const {
+        Excit ex = sys.get_excitation(d.f, f0);
+        if (ex.nexcit == 0) {
+            // any(f1/=f2) false => nexcit 0
+            bool same = true;
+            for (int k = 0; k < sys.W; ++k) if (d.f.w[k] != f0.w[k]) same = false;
+            if (same) D0_acc = D0_acc + pop;
+        } else if (ex.nexcit == 1) {
+            if (sys.bf[ex.from_orb[0]].ms == sys.bf[ex.to_orb[0]].ms &&
+                sys.bf[ex.from_orb[0]].sym == sys.bf[ex.to_orb[0]].sym) {
+                double h = sys.slater_condon1_excit(d.occ, ex.from_orb[0], ex.to_orb[0], ex.perm);
+                pe_acc = pe_acc + h * pop;
+            }
+        } else if (ex.nexcit == 2) {
+            if (sys.bf[ex.from_orb[0]].ms + sys.bf[ex.from_orb[1]].ms ==
+                sys.bf[ex.to_orb[0]].ms + sys.bf[ex.to_orb[1]].ms) {
+                int ij_sym = sys.cross_product_basis(ex.from_orb[0], ex.from_orb[1]);
+                int ab_sym = sys.cross_product_basis(ex.to_orb[0], ex.to_orb[1]);
+                if (ij_sym == ab_sym) {
+                    double h = sys.slater_condon2_excit(ex.from_orb[0], ex.from_orb[1], ex.to_orb[0], ex.to_orb[1],
+                                                        ex.perm);
+                    pe_acc = pe_acc + h * pop;
+                }
+            }
+        }
+    }
+
+    // decide_nattempts (src/qmc_common.F90:379-406)
+    static int decide_nattempts(Rng& rng, double population) {
+        int nattempts = std::abs((int)population);
+        double pextra = std::fabs(population) - nattempts;
+        if (std::fabs(pextra) > depsilon) {
+            if (pextra > rng.next()) nattempts++;
+        }
+        return nattempts;
+    }
+
+    // stochastic_round_spawned_particle (src/stoch_utils.f90:87-136)
+    static int64_t stochastic_round_spawned_particle(int64_t cutoff, double pspawn, Rng& rng) {
+        int64_t nspawn;
+        if (pspawn < (double)cutoff) {
+            if (pspawn > rng.next() * (double)cutoff) nspawn = cutoff; else nspawn = 0;
+        } else {
+            nspawn = (int64_t)pspawn;
+            double padd = pspawn - (double)nspawn;
+            if (padd > rng.next()) nspawn++;
+        }
+        return nspawn;
+    }
+    // attempt_to_spawn (src/spawning.F90:711-766)
+    int64_t attempt_to_spawn(Rng& rng, double hmatel, double pgen, int64_t parent_sign) const {
+        double pspawn = tau * std::fabs(hmatel) / pgen;
+        pspawn = pspawn * (double)pop_real_factor;
+        int64_t nspawn = stochastic_round_spawned_particle(spawn_cutoff, pspawn, rng);
+        if (nspawn > 0) {
+            int64_t mag = nspawn;
+            int64_t signed_n = (parent_sign >= 0) ? mag : -mag;  // sign(nspawn, parent_sign)
+            nspawn = (hmatel > 0.0) ? -signed_n : signed_n;
+        }
+        return nspawn;
+    }
+    // stochastic_round (src/stoch_utils.f90:51-85), one population
+    static void stochastic_round(Rng& rng, int64_t& pop, int64_t cutoff) {
+        int64_t ap = pop < 0 ? -pop : pop;
+        if (ap < cutoff && pop != 0) {
+            double r = rng.next() * (double)cutoff;
+            if ((double)ap > r) pop = (pop < 0) ? -cutoff : cutoff; else pop = 0;
+        }
+    }
+
+    // ---------------------------------------------------------------- one MC cycle, one rank: spawn+death
+    void spawn_death_rank(RankState& r, uint32_t cycle_id) {
+        Rng& rng = *r.rng;
+        rng.set_cycle(cycle_id);
+        // init_mc_cycle (src/qmc_common.F90:950-1017)
+        for (auto& b : r.send) b.clear();
+        r.ndeath = 0;
+        r.nattempts = (int64_t)std::llround(2 * r.nparticles);
+        const int64_t block_size = in.spawned_walker_length / in.nprocs;
+        DetInfo d;
+        for (int64_t idet = 0; idet < r.nstates; ++idet) {
+            decode_for(sys, eg, r.states[idet], d);
+            double real_population = (double)r.pops[idet] / (double)pop_real_factor;
+            // set_parent_flag (src/ifciqmc.f90:13-57), nspaces=1, no deterministic space (determ_flag=1)
+            d.initiator_flag = (std::fabs(real_population) > in.initiator_pop) ? 0 : 1;
+            update_proj_energy(d, real_population, r.D0_population, r.proj_energy);
+            rng.begin(RNG_NATTEMPTS, d.f, sys.W, 0);
+            int nattempts_det = decide_nattempts(rng, real_population);
+            int64_t pop = r.pops[idet];
+            for (int ip = 0; ip < nattempts_det; ++ip) {
+                rng.begin(RNG_SPAWN, d.f, sys.W, (uint32_t)ip);
+                GenResult g = gen_excit(rng, sys, eg, d);
+                int64_t nspawned = attempt_to_spawn(rng, g.hmatel, g.pgen, pop);
+                if (nspawned != 0) {
+                    Det fnew = sys.create_excited_det(d.f, g.conn);
+                    // create_spawned_particle[_initiator][_truncated] (src/spawning.F90:1074-1319)
+                    if (in.ex_level >= 0 && sys.excitation_level(f0, fnew) > ref_ex_level) continue;
+                    int dest = owner(fnew);
+                    // add_[flagged_]spawned_particle (src/spawning.F90:907-1018)
+                    if ((int64_t)r.send[dest].size() + 1 > block_size) {
+                        r.spawn_error = true;
+                    } else {
+                        SpawnElem e;
+                        e.f = fnew; e.pop = nspawned;
+                        e.flag = in.initiator_approx ? d.initiator_flag : 0;
+                        r.send[dest].push_back(e);
+                    }
+                }
+            }
+            // stochastic_death (src/death.f90:11-130)
+            {
+                rng.begin(RNG_DEATH, d.f, sys.W, 0);
+                double Kii = r.dat[idet];
+                double weight = 1.0;
+                double pd = tau * ((Kii - est.proj_energy_old) * weight + (est.proj_energy_old - shift) * 1.0) * 1.0;
+                pd = pd * 1.0;
+                int64_t& population = r.pops[idet];
+                int64_t apop = population < 0 ? -population : population;
+                pd = pd * (double)apop;
+                int64_t kill = (int64_t)pd;
+                pd = pd - (double)kill;
+                double rr = rng.next();
+                if (std::fabs(pd) > rr) {
+                    if (pd > 0.0) kill++; else kill--;
+                }
+                int64_t old_population = population;
+                if (population < 0) population += kill; else population -= kill;
+                int64_t anew = population < 0 ? -population : population;
+                int64_t aold = old_population < 0 ? -old_population : old_population;
+                r.nparticles = r.nparticles + (double)(anew - aold) / (double)pop_real_factor;
+                r.ndeath += (kill < 0 ? -kill : kill);
+            }
+        }
+        // calc_events_spawn_t (src/spawn_data.F90:445-465)
+        int ev = 0;
+        for (auto& b : r.send) ev += (int)b.size();
+        r.nspawn_events = ev;
+    }
+
+    // comm_spawn_t (src/spawn_data.F90:624-739): personalised all-to-all between emulated ranks
+    void comm_spawn() {
+        for (auto& r : ranks) r.recv.clear();
+        for (int dst = 0; dst < in.nprocs; ++dst)
+            for (int src = 0; src < in.nprocs; ++src)
+                for (auto& e : ranks[src].send[dst]) ranks[dst].recv.push_back(e);
+    }
+
+    // annihilate_spawn_t (src/spawn_data.F90:859-935)
+    void annihilate_spawn_t(std::vector<SpawnElem>& s) const {
+        int head = (int)s.size();
+        if (head == 0) return;
+        int islot = 1, k = 1;
+        const int upper = head;
+        auto S = [&](int i) -> SpawnElem& { return s[i - 1]; };
+        for (;;) {
+            S(islot) = S(k);
+            bool done = false;
+            for (;;) {
+                k++;
+                if (k > upper) { done = true; break; }
+                if (S(k).f == S(islot).f) {
+                    S(islot).pop += S(k).pop;
+                    S(islot).flag += S(k).flag;  // sdata(bit_str_len+1:) sums everything after the string
+                } else break;
+            }
+            if (done) break;
+            if (islot == upper) break;
+            if (S(islot).pop != 0 || S(islot).flag != 0) islot++;
+        }
+        if (S(islot).pop == 0 && S(islot).flag == 0) islot--;
+        s.resize(islot);
+    }
+
+    // annihilate_spawn_t_initiator (src/spawn_data.F90:937-1101), ntypes = 1
+    void annihilate_spawn_t_initiator(std::vector<SpawnElem>& s) const {
+        int head = (int)s.size();
+        if (head == 0) return;
+        int islot = 1, k = 1;
+        const int upper = head;
+        auto S = [&](int i) -> SpawnElem& { return s[i - 1]; };
+        int64_t events = 0, initiator_pop = 0;
+        for (;;) {
+            S(islot) = S(k);
+            if (!(S(k).flag & 1)) {
+                initiator_pop = S(k).pop;
+                events = 0;
+            } else {
+                initiator_pop = 0;
+                if (in.literal_event_int32) {
+                    int32_t t = (int32_t)(uint32_t)(uint64_t)S(k).pop;  // int(spawn_parts) default integer
+                    events = (t >= 0) ? 1 : -1;                         // sign(1, .)
+                } else {
+                    events = (S(k).pop >= 0) ? 1 : -1;
+                }
+            }
+            for (;;) {
+                k++;
+                bool same_slot = k <= head;
+                if (same_slot) same_slot = (S(k).f == S(islot).f);
+                if (same_slot) {
+                    if (!(S(k).flag & 1)) initiator_pop += S(k).pop;
+                    else if (S(k).pop < 0) events -= 1;
+                    else if (S(k).pop > 0) events += 1;
+                    S(islot).pop += S(k).pop;
+                } else {
+                    S(islot).flag = 0;
+                    int64_t sgn_tot = (S(islot).pop >= 0) ? 1 : -1;
+                    int64_t sgn_ini = (initiator_pop >= 0) ? 1 : -1;
+                    if (initiator_pop != 0 && sgn_tot == sgn_ini) {
+                        // keep
+                    } else if ((events < 0 ? -events : events) > 1) {
+                        // keep
+                    } else {
+                        S(islot).flag += 1;
+                    }
+                    break;
+                }
+            }
+            if (islot == upper || k > upper) break;
+            if (S(islot).pop != 0) islot++;
+        }
+        if (S(islot).pop == 0) islot--;
+        s.resize(islot);
+    }
+
+    // annihilate_main_list[_initiator] (src/annihilation.f90:294-486)
+    void annihilate_main_list(RankState& r, std::vector<SpawnElem>& s) const {
+        int nannihilate = 0;
+        int istart = 1, iend = (int)r.nstates;
+        int head = (int)s.size();
+        for (int i = 1; i <= head; ++i) {
+            bool hit; int pos;
+            binary_search(r.states, s[i - 1].f, istart, iend, sys.W, hit, pos);
+            if (hit) {
+                int64_t old_pop = r.pops[pos - 1];
+                if (!in.initiator_approx) {
+                    r.pops[pos - 1] += s[i - 1].pop;
+                } else {
+                    if (r.pops[pos - 1] != 0) r.pops[pos - 1] += s[i - 1].pop;
+                    else if (!(s[i - 1].flag & 1)) r.pops[pos - 1] = s[i - 1].pop;
+                }
+                int64_t an = std::llabs(r.pops[pos - 1]), ao = std::llabs(old_pop);
+                r.nparticles = r.nparticles + (double)(an - ao) / (double)pop_real_factor;
+                nannihilate++;
+                istart = pos + 1;
+            } else {
+                if (!in.initiator_approx) {
+                    s[i - 1 - nannihilate] = s[i - 1];
+                } else {
+                    if (s[i - 1].flag & 1) {
+                        nannihilate++;  // discard: spawned from a non-initiator onto an unoccupied det
+                    } else {
+                        SpawnElem e = s[i - 1];
+                        s[i - 1 - nannihilate] = e;
+                    }
+                }
+            }
+        }
+        s.resize(head - nannihilate);
+    }
+
+    // remove_unoccupied_dets (src/annihilation.f90:537-598)
+    void remove_unoccupied_dets(RankState& r) const {
+        Rng& rng = *r.rng;
+        int64_t nzero = 0;
+        for (int64_t i = 0; i < r.nstates; ++i) {
+            if (in.real_amplitudes) {
+                int64_t old_pop = r.pops[i];
+                rng.begin(RNG_ROUND_MAIN, r.states[i], sys.W, 0);
+                stochastic_round(rng, r.pops[i], pop_real_factor);
+                r.nparticles = r.nparticles + (double)(std::llabs(r.pops[i]) - std::llabs(old_pop)) / (double)pop_real_factor;
+            }
+            if (r.pops[i] == 0) {
+                nzero++;
+            } else if (nzero > 0) {
+                int64_t k = i - nzero;
+                r.states[k] = r.states[i]; r.pops[k] = r.pops[i]; r.dat[k] = r.dat[i];
+            }
+        }
+        r.nstates -= nzero;
+        r.states.resize(r.nstates); r.pops.resize(r.nstates); r.dat.resize(r.nstates);
+    }
+
+    // round_low_population_spawns (src/annihilation.f90:600-675)
+    void round_low_population_spawns(RankState& r, std::vector<SpawnElem>& s) const {
+        Rng& rng = *r.rng;
+        int nremoved = 0;
+        int head = (int)s.size();
+        for (int i = 0; i < head; ++i) {
+            rng.begin(RNG_ROUND_SPAWN, s[i].f, sys.W, 0);
+            stochastic_round(rng, s[i].pop, pop_real_factor);
+            if (s[i].pop == 0) nremoved++;
+            else s[i - nremoved] = s[i];
+        }
+        s.resize(head - nremoved);
+    }
+
+    // insert_new_walkers (src/annihilation.f90:677-818)
+    void insert_new_walkers(RankState& r, std::vector<SpawnElem>& s) const {
+        int head = (int)s.size();
+        if (!r.psip_error) {
+            float fill = (float)(r.nstates + head) / (float)in.walker_length;
+            if (fill > 1.00f) r.psip_error = true;
+        }
+        if (r.psip_error) return;
+        int64_t nold = r.nstates;
+        r.states.resize(nold + head); r.pops.resize(nold + head); r.dat.resize(nold + head);
+        int istart = 1, iend = (int)nold;
+        for (int i = head; i >= 1; --i) {
+            bool hit; int pos;
+            binary_search(r.states, s[i - 1].f, istart, iend, sys.W, hit, pos);
+            for (int j = iend; j >= pos; --j) {
+                int k = j + i;
+                r.states[k - 1] = r.states[j - 1]; r.pops[k - 1] = r.pops[j - 1]; r.dat[k - 1] = r.dat[j - 1];
+            }
+            int k = pos + i - 1;
+            // insert_new_walker (src/annihilation.f90:820-901)
+            r.states[k - 1] = s[i - 1].f;
+            r.pops[k - 1] = s[i - 1].pop;
+            r.dat[k - 1] = sys.slater_condon0(s[i - 1].f) - H00;
+            double real_population = (double)s[i - 1].pop / (double)pop_real_factor;
+            r.nparticles = r.nparticles + std::fabs(real_population);
+            iend = pos - 1;
+        }
+        r.nstates = nold + head;
+    }
+
+    // direct_annihilation (src/annihilation.f90:9-79) for one rank, after comm
+    void annihilate_rank(RankState& r) {
+        std::vector<SpawnElem>& s = r.recv;
+        if (!s.empty()) {
+            qsort_spawn(s, (int)s.size(), sys.W);
+            if (in.initiator_approx) annihilate_spawn_t_initiator(s); else annihilate_spawn_t(s);
+        }
+        if (!s.empty()) {
+            annihilate_main_list(r, s);
+            remove_unoccupied_dets(r);
+            if (in.real_amplitudes) round_low_population_spawns(r, s);
+            insert_new_walkers(r, s);
+        } else {
+            remove_unoccupied_dets(r);
+        }
+    }
+
+    void mc_cycle(uint32_t cycle_id) {
+        for (auto& r : ranks) spawn_death_rank(r, cycle_id);
+        comm_spawn();
+        for (auto& r : ranks) {
+            annihilate_rank(r);
+            // end_mc_cycle / spawning_rate (src/qmc_common.F90:1240-1304)
+            double ndeath_real = (double)r.ndeath / (double)pop_real_factor;
+            double rate = (r.nattempts > 0) ? (r.nspawn_events + ndeath_real) / (double)r.nattempts : 0.0;
+            r.rspawn = r.rspawn + rate;
+        }
+    }
+
+    // initial_ci_projected_energy (src/qmc_common.F90:697-797)
+    void initial_ci_projected_energy() {
+        double pe = 0.0, d0 = 0.0, ntot = 0.0;
+        int64_t nst = 0;
+        for (auto& r : ranks) {
+            double pe_r = 0.0, d0_r = 0.0;
+            DetInfo d;
+            for (int64_t i = 0; i < r.nstates; ++i) {
+                decode_det_occ(sys, r.states[i], d);
+                update_proj_energy(d, (double)r.pops[i] / (double)pop_real_factor, d0_r, pe_r);
+            }
+            pe += pe_r; d0 += d0_r; ntot += r.nparticles; nst += r.nstates;
+        }
+        est.proj_energy = pe; est.D0_population = d0; est.tot_nstates = nst;
+        ntot_particles_old = ntot;
+    }
+
+    // update_shift (src/energy_evaluation.F90:659-711), target_particles > 0 branch with
+    // shift_harmonic_forcing = 0 (default)
+    void update_shift(double nparticles_old, double nparticles, int nupdate_steps) {
+        if (in.target_particles <= 0.0) {
+            shift = shift - std::log(nparticles / nparticles_old) * in.shift_damping / (1.0 * tau * nupdate_steps);
+        } else {
+            shift = shift - std::log(nparticles / nparticles_old) * in.shift_damping / (1.0 * tau * nupdate_steps) -
+                    std::log(nparticles / in.target_particles) * (0.0) / (1.0 * tau * nupdate_steps);
+        }
+    }
+
+    // One report loop (src/fciqmc.f90:276-407 + end_report_loop)
+    void report_loop(int ireport) {
+        // get_sanitized_projected_energy (src/energy_evaluation.F90:1433-1456)
+        est.proj_energy_old = (std::fabs(est.D0_population) < std::numeric_limits<double>::min())
+                                  ? 0.0 : est.proj_energy / est.D0_population;
+        // init_report_loop (src/qmc_common.F90:929-948)
+        est.D0_population_old = est.D0_population;
+        for (auto& r : ranks) { r.rspawn = 0.0; r.proj_energy = 0.0; r.D0_population = 0.0; }
+        for (int icycle = 1; icycle <= in.ncycles; ++icycle) {
+            int iter = mc_cycles_done + (ireport - 1) * in.ncycles + icycle;
+            mc_cycle((uint32_t)iter);
+        }
+        // update_energy_estimators (src/energy_evaluation.F90:126-201, 320-655)
+        double pe = 0.0, d0 = 0.0, rsp = 0.0, ntot = 0.0;
+        int64_t nst = 0, nev = 0;
+        bool err = false;
+        for (auto& r : ranks) {
+            pe += r.proj_energy; d0 += r.D0_population; rsp += r.rspawn; ntot += r.nparticles;
+            nst += r.nstates; nev += r.nspawn_events;
+            err = err || r.spawn_error || r.psip_error;
+        }
+        est.proj_energy = pe / (in.ncycles * 1);
+        est.D0_population = d0 / (in.ncycles * 1);
+        rspawn_report = rsp / (in.ncycles * 1 * in.nprocs);
+        est.tot_nstates = nst; est.tot_nspawn_events = nev;
+        if (vary_shift) update_shift(ntot_particles_old, ntot, in.ncycles);
+        est.D0_population_old = est.D0_population;
+        ntot_particles_old = ntot;
+        if (!vary_shift && ntot > in.target_particles) {
+            vary_shift = true;
+            if (in.vary_shift_from_proje) shift = est.proj_energy / est.D0_population;
+            else shift = in.vary_shift_from;
+        }
+        error = err;
+        ReportRow row;
+        row.iter = mc_cycles_done + ireport * in.ncycles;
+        row.shift = shift; row.proj_energy = est.proj_energy; row.D0_population = est.D0_population;
+        row.nparticles = ntot_particles_old; row.nstates = est.tot_nstates; row.nspawn_events = est.tot_nspawn_events;
+        row.rspawn = rspawn_report;
+        rows.push_back(row);
+    }
+
+    void run() {
+        initial_ci_projected_energy();
+        // initial_qmc_status row (iteration 0)
+        ReportRow row0;
+        row0.iter = mc_cycles_done; row0.shift = shift; row0.proj_energy = est.proj_energy;
+        row0.D0_population = est.D0_population; row0.nparticles = ntot_particles_old;
+        row0.nstates = est.tot_nstates; row0.nspawn_events = 0; row0.rspawn = 0.0;
+        rows.push_back(row0);
+        for (int ireport = 1; ireport <= in.nreport; ++ireport) {
+            report_loop(ireport);
+            if (error) break;
+        }
+        mc_cycles_done += in.ncycles * in.nreport;
+    }
+};
+
+}  // namespace oracle

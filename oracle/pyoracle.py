@@ -1,0 +1,323 @@
+"""ORACLE (test infrastructure, NOT product code): ctypes driver for oracle/liboracle.so.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "liboracle.so")
+REF_LIB = os.path.join(HERE, "_ref", "libhande_ref_c.so")
+HUGE = 2**31 - 1
+
+EXCIT_GEN = {"no_renorm": 0, "renorm": 1, "heat_bath": 4, "heat_bath_uniform": 5, "heat_bath_single": 6}
+
+
+class QmcIn(C.Structure):
+    _fields_ = [
+        ("tau", C.c_double), ("seed", C.c_int), ("D0_population", C.c_double),
+        ("ncycles", C.c_int), ("nreport", C.c_int),
+        ("target_particles", C.c_double), ("initial_shift", C.c_double), ("shift_damping", C.c_double),
+        ("vary_shift_from", C.c_double), ("vary_shift_from_proje", C.c_int),
+        ("initiator_approx", C.c_int), ("initiator_pop", C.c_double),
+        ("real_amplitudes", C.c_int), ("spawn_cutoff", C.c_double),
+        ("excit_gen", C.c_int), ("pattempt_single", C.c_double), ("pattempt_double", C.c_double),
+        ("walker_length", C.c_int64), ("spawned_walker_length", C.c_int64),
+        ("ex_level", C.c_int), ("nprocs", C.c_int), ("nslots", C.c_int), ("rng_kind", C.c_int),
+        ("literal_event_int32", C.c_int),
+    ]
+
+
+def build(force=False):
+    """Compile the oracle (and oracle/_ref when the reference tree is present)."""
+    if force or not os.path.exists(LIB) or any(
+            os.path.getmtime(os.path.join(HERE, f)) > os.path.getmtime(LIB)
+            for f in ("capi.cpp", "system.hpp", "rng.hpp", "excit_gen.hpp", "fciqmc.hpp")):
+        subprocess.check_call(["make", "-C", HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    if not os.path.exists(REF_LIB) and os.path.isdir("/root/reference/lib/dSFMT-src-2.2.3"):
+        subprocess.check_call(["make", "-C", HERE, "ref"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB)
+        L.orc_last_error.restype = C.c_char_p
+        L.orc_create.restype = C.c_void_p
+        L.orc_destroy.argtypes = [C.c_void_p]
+        L.orc_ecore.restype = C.c_double
+        L.orc_ecore.argtypes = [C.c_void_p]
+        for name in ("orc_sc0",):
+            getattr(L, name).restype = C.c_double
+            getattr(L, name).argtypes = [C.c_void_p, C.c_void_p]
+        for name in ("orc_sc1", "orc_sc1_checked"):
+            getattr(L, name).restype = C.c_double
+            getattr(L, name).argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        for name in ("orc_sc2", "orc_sc2_checked"):
+            getattr(L, name).restype = C.c_double
+            getattr(L, name).argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_get_one_body.restype = C.c_double
+        L.orc_get_one_body.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc_get_two_body.restype = C.c_double
+        L.orc_get_two_body.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_two_body_store.restype = C.POINTER(C.c_double)
+        L.orc_two_body_store.argtypes = [C.c_void_p, C.c_int]
+        L.orc_read_fcidump.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_sys_info.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_basis.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+        L.orc_sym_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_murmur_bit_string.restype = C.c_int32
+        L.orc_murmur_bit_string.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.orc_murmur2.restype = C.c_uint32
+        L.orc_murmur2.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
+        L.orc_ref_murmur2.restype = C.c_uint32
+        L.orc_ref_murmur2.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
+        L.orc_owner.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_dsfmt_stream.argtypes = [C.c_int, C.c_int, C.c_void_p]
+        L.orc_philox_stream.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_uint32,
+                                        C.c_int, C.c_void_p]
+        L.orc_set_qmc.argtypes = [C.c_void_p, C.POINTER(QmcIn)]
+        L.orc_init.argtypes = [C.c_void_p]
+        L.orc_run.argtypes = [C.c_void_p]
+        L.orc_nrows.argtypes = [C.c_void_p]
+        L.orc_get_rows.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_reference.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_nstates.restype = C.c_int64
+        L.orc_nstates.argtypes = [C.c_void_p, C.c_int]
+        L.orc_nparticles.restype = C.c_double
+        L.orc_nparticles.argtypes = [C.c_void_p, C.c_int]
+        L.orc_get_psips.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_set_psips.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_set_reference_det.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_iterate.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_void_p]
+        L.orc_gen_excit_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int64, C.c_double,
+                                           C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_gen_excit_list.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_hb_nb.restype = C.c_int64
+        L.orc_hb_nb.argtypes = [C.c_void_p]
+        L.orc_hb_ptr_d.restype = C.POINTER(C.c_double)
+        L.orc_hb_ptr_d.argtypes = [C.c_void_p, C.c_int]
+        L.orc_hb_ptr_i.restype = C.POINTER(C.c_int)
+        L.orc_hb_ptr_i.argtypes = [C.c_void_p, C.c_int]
+        L.orc_cpu_baseline.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def have_ref_lib():
+    return os.path.exists(REF_LIB)
+
+
+def use_ref_lib():
+    if lib().orc_set_ref_lib(REF_LIB.encode()) != 0:
+        raise RuntimeError(lib().orc_last_error().decode())
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    """One restated HANDE calculation (system + FCIQMC state)."""
+
+    def __init__(self):
+        self.L = lib()
+        self.h = C.c_void_p(self.L.orc_create())
+
+    def __del__(self):
+        try:
+            self.L.orc_destroy(self.h)
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc < 0:
+            raise RuntimeError(self.L.orc_last_error().decode())
+        return rc
+
+    def read_fcidump(self, path, nel=0, ms=HUGE, sym=HUGE, cas=(-1, -1)):
+        self._chk(self.L.orc_read_fcidump(self.h, str(path).encode(), nel, ms, sym, cas[0], cas[1]))
+        info = np.zeros(32, dtype=np.int64)
+        self.L.orc_sys_info(self.h, _p(info))
+        keys = ["nbasis", "nel", "W", "nsym_tot", "sym0", "sym_max", "nalpha", "nbeta", "uhf", "pg_mask", "Lz_mask",
+                "Lz_offset", "gamma_sym", "max_nbss", "nvirt", "nvirt_alpha", "nvirt_beta", "symmetry", "int_err",
+                "nchan", "nintgrls"]
+        self.info = {k: int(v) for k, v in zip(keys, info)}
+        self.nbasis, self.nel, self.W = self.info["nbasis"], self.info["nel"], self.info["W"]
+        return self.info
+
+    @property
+    def ecore(self):
+        return self.L.orc_ecore(self.h)
+
+    def basis(self):
+        nb = self.nbasis
+        out = {k: np.zeros(nb, dtype=np.int32) for k in ("sym", "ms", "spatial", "sym_index", "sym_spin_index")}
+        eig = np.zeros(nb)
+        self.L.orc_basis(self.h, _p(out["sym"]), _p(out["ms"]), _p(out["spatial"]), _p(out["sym_index"]),
+                         _p(out["sym_spin_index"]), _p(eig))
+        out["sp_eigv"] = eig
+        return out
+
+    def sym_tables(self):
+        ns, mx = self.info["nsym_tot"], self.info["max_nbss"]
+        nbss = np.zeros(2 * ns, dtype=np.int32)
+        ssbf = np.zeros(mx * 2 * ns, dtype=np.int32)
+        self.L.orc_sym_tables(self.h, _p(nbss), _p(ssbf))
+        return nbss, ssbf
+
+    def two_body_store(self, chan=0):
+        n = self.info["nintgrls"]
+        return np.ctypeslib.as_array(self.L.orc_two_body_store(self.h, chan), shape=(n,)).copy()
+
+    def one_body(self, i, j):
+        return self.L.orc_get_one_body(self.h, i, j)
+
+    def two_body(self, i, j, a, b):
+        return self.L.orc_get_two_body(self.h, i, j, a, b)
+
+    def det(self, occ):
+        f = np.zeros(self.W, dtype=np.uint64)
+        for o in occ:
+            f[(o - 1) // 64] |= np.uint64(1) << np.uint64((o - 1) % 64)
+        return f
+
+    def sc0(self, f):
+        f = np.ascontiguousarray(f, dtype=np.uint64)
+        return self.L.orc_sc0(self.h, _p(f))
+
+    def sc1(self, f, i, a, checked=False):
+        f = np.ascontiguousarray(f, dtype=np.uint64)
+        fn = self.L.orc_sc1_checked if checked else self.L.orc_sc1
+        return fn(self.h, _p(f), i, a)
+
+    def sc2(self, f, i, j, a, b, checked=False):
+        f = np.ascontiguousarray(f, dtype=np.uint64)
+        fn = self.L.orc_sc2_checked if checked else self.L.orc_sc2
+        return fn(self.h, _p(f), i, j, a, b)
+
+    def owner(self, f):
+        f = np.ascontiguousarray(f, dtype=np.uint64)
+        return self.L.orc_owner(self.h, _p(f))
+
+    def murmur_bit_string(self, f, seed=7):
+        f = np.ascontiguousarray(f, dtype=np.uint64)
+        return self.L.orc_murmur_bit_string(self.h, _p(f), seed)
+
+    def set_qmc(self, **kw):
+        q = QmcIn(tau=0.001, seed=7, D0_population=10.0, ncycles=20, nreport=10, target_particles=1e7,
+                  initial_shift=0.0, shift_damping=0.05, vary_shift_from=0.0, vary_shift_from_proje=0,
+                  initiator_approx=0, initiator_pop=3.0, real_amplitudes=0, spawn_cutoff=0.01, excit_gen=1,
+                  pattempt_single=-1.0, pattempt_double=-1.0, walker_length=1 << 20,
+                  spawned_walker_length=1 << 18, ex_level=-1, nprocs=1, nslots=1, rng_kind=0,
+                  literal_event_int32=1)
+        for k, v in kw.items():
+            if k == "excit_gen" and isinstance(v, str):
+                v = EXCIT_GEN[v]
+            if not hasattr(q, k):
+                raise KeyError(k)
+            setattr(q, k, v)
+        self.qmc = q
+        self.L.orc_set_qmc(self.h, C.byref(q))
+        if q.rng_kind == 0:
+            use_ref_lib()
+
+    def init(self):
+        self._chk(self.L.orc_init(self.h))
+
+    def run(self):
+        self._chk(self.L.orc_run(self.h))
+        return self.rows()
+
+    def rows(self):
+        n = self.L.orc_nrows(self.h)
+        out = np.zeros((n, 8))
+        self.L.orc_get_rows(self.h, _p(out))
+        return out
+
+    def reference(self):
+        ref = np.zeros(3)
+        occ0 = np.zeros(self.nel, dtype=np.int32)
+        f0 = np.zeros(self.W, dtype=np.uint64)
+        self.L.orc_reference(self.h, _p(ref), _p(occ0), _p(f0))
+        return {"H00": ref[0], "pattempt_single": ref[1], "pattempt_double": ref[2], "occ": occ0, "f0": f0}
+
+    def get_psips(self, rank=0):
+        n = self.L.orc_nstates(self.h, rank)
+        states = np.zeros((n, self.W), dtype=np.uint64)
+        pops = np.zeros(n, dtype=np.int64)
+        dat = np.zeros(n)
+        self.L.orc_get_psips(self.h, rank, _p(states), _p(pops), _p(dat))
+        return states, pops, dat
+
+    def set_psips(self, states, pops, dat, rank=0):
+        states = np.ascontiguousarray(states, dtype=np.uint64)
+        pops = np.ascontiguousarray(pops, dtype=np.int64)
+        dat = np.ascontiguousarray(dat, dtype=np.float64)
+        self.L.orc_set_psips(self.h, rank, len(pops), _p(states), _p(pops), _p(dat))
+
+    def set_reference_det(self, f0):
+        f0 = np.ascontiguousarray(f0, dtype=np.uint64)
+        self.L.orc_set_reference_det(self.h, _p(f0))
+
+    def iterate(self, ncycles, first_cycle, tau, shift, proj_energy_old):
+        out = np.zeros(16)
+        self._chk(self.L.orc_iterate(self.h, ncycles, first_cycle, tau, shift, proj_energy_old, _p(out)))
+        keys = ["proj_energy", "D0_population", "nparticles", "nstates", "nspawn_events", "ndeath", "rspawn", "error",
+                "nattempts", "ndraws"]
+        return dict(zip(keys, out))
+
+    def gen_excit_philox(self, f, cycle, attempt, parent_pop, tau):
+        f = np.ascontiguousarray(f, dtype=np.uint64)
+        io = np.zeros(8, dtype=np.int32)
+        do = np.zeros(2)
+        ns = np.zeros(1, dtype=np.int64)
+        self._chk(self.L.orc_gen_excit_philox(self.h, _p(f), cycle, attempt, parent_pop, tau, _p(io), _p(do), _p(ns)))
+        return io, do, int(ns[0])
+
+    def gen_excit_list(self, f, rn):
+        f = np.ascontiguousarray(f, dtype=np.uint64)
+        rn = np.ascontiguousarray(rn, dtype=np.float64)
+        io = np.zeros(8, dtype=np.int32)
+        do = np.zeros(2)
+        k = self._chk(self.L.orc_gen_excit_list(self.h, _p(f), _p(rn), len(rn), _p(io), _p(do)))
+        return io, do, k
+
+    def heat_bath_tables(self):
+        nb = self.L.orc_hb_nb(self.h)
+        shp = {0: (nb,), 1: (nb, nb), 2: (nb,) * 3, 3: (nb,) * 3, 4: (nb, nb), 5: (nb,) * 4, 6: (nb,) * 4,
+               7: (nb,) * 3}
+        names = ["i_weights", "ij_weights", "ija_w", "ija_U", "ija_tot", "ijab_w", "ijab_U", "ijab_tot"]
+        out = {}
+        for k, nm in enumerate(names):
+            n = int(np.prod(shp[k]))
+            out[nm] = np.ctypeslib.as_array(self.L.orc_hb_ptr_d(self.h, k), shape=(n,))
+        out["ija_K"] = np.ctypeslib.as_array(self.L.orc_hb_ptr_i(self.h, 0), shape=(nb ** 3,))
+        out["ijab_K"] = np.ctypeslib.as_array(self.L.orc_hb_ptr_i(self.h, 1), shape=(nb ** 4,))
+        out["nb"] = nb
+        return out
+
+    def cpu_baseline(self, nthreads, ncycles, tau, shift, proj_energy_old):
+        out = np.zeros(4)
+        self._chk(self.L.orc_cpu_baseline(self.h, nthreads, ncycles, tau, shift, proj_energy_old, _p(out)))
+        return {"seconds": out[0], "walker_iters": out[1], "attempts": out[2]}
+
+
+def dsfmt_stream(seed, n):
+    use_ref_lib()
+    out = np.zeros(n)
+    lib().orc_dsfmt_stream(seed, n, _p(out))
+    return out
+
+
+def philox_stream(seed, cycle, purpose, f, attempt, n):
+    f = np.ascontiguousarray(f, dtype=np.uint64)
+    out = np.zeros(n)
+    lib().orc_philox_stream(seed, cycle, purpose, _p(f), len(f), attempt, n, _p(out))
+    return out

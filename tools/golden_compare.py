@@ -1,0 +1,95 @@
+"""Compare the oracle (dSFMT back-end) with a HANDE test_suite benchmark table.
+
+Test-infrastructure helper: reads /root/reference (only available in the build container).
+Usage: python tools/golden_compare.py <case> [max_rows]
+"""
+import re
+import sys
+import time
+import os
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle.pyoracle import Oracle, HUGE  # noqa: E402
+
+TS = "/root/reference/test_suite/"
+CASES = {
+    "h2o": dict(dir="fciqmc/np1/H2O-RHF-cc-pVTZ", bench="benchmark.out.9712b5a3.inp=h2o.in", int_file="INTDUMP",
+                sys=dict(nel=10, ms=0, sym=0, cas=(8, 13)),
+                qmc=dict(tau=0.003, seed=7, D0_population=10, ncycles=20, nreport=250, target_particles=1e7,
+                         walker_length=178571, spawned_walker_length=31250)),
+    "ne_init": dict(dir="ifciqmc/np1/Ne-RHF-aug-cc-pVDZ", bench="benchmark.out.9712b5a3.inp=hande_dump.in",
+                    int_file="INTDUMP", sys=dict(nel=10, ms=0, sym=0),
+                    qmc=dict(tau=0.005, seed=7, D0_population=10, ncycles=20, nreport=320, target_particles=80000,
+                             initiator_approx=1, walker_length=5 * 10**6 // 32, spawned_walker_length=10**6 // 32)),
+    "cn_uhf": dict(dir="fciqmc/np1/CN-UHF-cc-pVDZ", bench="benchmark.out.9712b5a3.inp=cn.in", int_file="INTDUMP",
+                   sys=dict(nel=13, ms=1, cas=(9, 12)),
+                   qmc=dict(tau=0.005, seed=7, D0_population=10, ncycles=10, nreport=200, target_particles=77000,
+                            walker_length=500 * 10**6 // 32, spawned_walker_length=100 * 10**6 // 48)),
+    "ne_ci6_np2": dict(dir="fciqmc/np2/Ne-aug-cc-pVDZ-ci6qmc", bench="benchmark.out.9712b5a3.inp=ne.ciqmc.in",
+                       int_file="INTDUMP", sys=dict(nel=10, ms=0, sym=0, cas=(8, 22)),
+                       qmc=dict(tau=0.002, seed=18, D0_population=10, ncycles=10, nreport=1200,
+                                target_particles=50000, walker_length=50000, spawned_walker_length=5000,
+                                ex_level=5, nprocs=2)),
+    "ne_ci6_real64_np2": dict(dir="fciqmc_real_64/np2/Ne-aug-cc-pVDZ-ci6qmc_real_64",
+                              bench="benchmark.out.9712b5a3.inp=ne.ciqmc.in", int_file="INTDUMP",
+                              sys=dict(nel=10, ms=0, sym=0, cas=(8, 22)),
+                              qmc=dict(tau=0.002, seed=18, D0_population=10, ncycles=10, nreport=1200,
+                                       target_particles=50000, walker_length=50000, spawned_walker_length=50000,
+                                       ex_level=5, nprocs=2, real_amplitudes=1, spawn_cutoff=0.01)),
+    "ne_ci6_np4": dict(dir="fciqmc/np4/Ne-aug-cc-pVDZ-ci6qmc", bench="benchmark.out.9712b5a3.inp=ne.ciqmc.in",
+                       int_file="INTDUMP", sys=dict(nel=10, ms=0, sym=0, cas=(8, 22)),
+                       qmc=dict(tau=0.002, seed=18, D0_population=10, ncycles=10, nreport=1200,
+                                target_particles=50000, walker_length=50000, spawned_walker_length=5000,
+                                ex_level=5, nprocs=4)),
+}
+
+ROW = re.compile(r"^\s*#?\s+(\d+)\s+(-?\d\.\d+E[+-]\d+)\s+(-?\d\.\d+E[+-]\d+)\s+(-?\d\.\d+E[+-]\d+)\s+"
+                 r"(-?\d\.\d+E[+-]\d+)\s+(\d+)\s+(\d+)\s+(\d\.\d+)\s+(\d+\.\d+)\s*$")
+
+
+def parse_table(path):
+    rows = []
+    for line in open(path):
+        m = ROW.match(line)
+        if m:
+            rows.append([float(x) for x in m.groups()[:8]])
+    return np.array(rows)
+
+
+def row_matches(g, r):
+    """testcode tolerance is (1e-10 abs, 1e-10 rel) on printed values; the table prints es17.10."""
+    def pr(x):
+        return float("%.10E" % x)
+    return (g[0] == r[0] and g[1] == pr(r[1]) and g[2] == pr(r[2]) and g[3] == pr(r[3]) and g[4] == pr(r[4])
+            and g[5] == r[5] and g[6] == r[6] and abs(g[7] - r[7]) < 0.6e-4)
+
+
+def run_case(name, max_rows=None, quiet=False):
+    c = CASES[name]
+    d = TS + c["dir"] + "/"
+    gold = parse_table(d + c["bench"])
+    o = Oracle()
+    s = dict(c["sys"])
+    o.read_fcidump(d + c["int_file"], nel=s.get("nel", 0), ms=s.get("ms", HUGE), sym=s.get("sym", HUGE),
+                   cas=s.get("cas", (-1, -1)))
+    q = dict(c["qmc"])
+    if max_rows is not None:
+        q["nreport"] = min(q["nreport"], max_rows)
+    o.set_qmc(**q)
+    o.init()
+    t = time.time()
+    rows = o.run()
+    dt = time.time() - t
+    n = min(len(gold), len(rows))
+    bad = [i for i in range(n) if not row_matches(gold[i], rows[i])]
+    if not quiet:
+        print(f"{name}: compared {n} rows, mismatches {len(bad)}, oracle time {dt:.1f}s, ref {o.reference()}")
+        for i in bad[:3]:
+            print("  gold", gold[i])
+            print("  orcl", rows[i])
+    return gold, rows, bad
+
+
+if __name__ == "__main__":
+    run_case(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else None)

@@ -1,0 +1,37 @@
+"""Generate tests/golden/ fixtures from the reference's own test_suite (run in the build container).
+
+  * tests/golden/fcidump/{h2o,ne}.INTDUMP.gz   - the FCIDUMP inputs of the reference fixtures (data, not source)
+  * tests/golden/<case>.json                   - every report-loop row of the reference's benchmark.out.* table
+                                                 plus the system/qmc options of the corresponding *.in file
+
+The tables are the reference's golden vectors for the hot path; the oracle must
+reproduce them with the reference dSFMT stream before it is trusted as the checker for the CUDA path.
+"""
+import gzip
+import json
+import os
+import shutil
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tools.golden_compare import CASES, TS, parse_table  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+FCIDUMP_NAME = {"h2o": "h2o", "ne_init": "ne", "ne_ci6_np2": "ne", "ne_ci6_np4": "ne", "ne_ci6_real64_np2": "ne"}
+
+os.makedirs(os.path.join(OUT, "fcidump"), exist_ok=True)
+for name, c in CASES.items():
+    if name not in FCIDUMP_NAME:
+        continue
+    d = TS + c["dir"] + "/"
+    dst = os.path.join(OUT, "fcidump", FCIDUMP_NAME[name] + ".INTDUMP.gz")
+    if not os.path.exists(dst):
+        with open(d + c["int_file"], "rb") as fi, gzip.GzipFile(dst, "wb", compresslevel=9, mtime=0) as fo:
+            shutil.copyfileobj(fi, fo)
+    rows = parse_table(d + c["bench"]).tolist()
+    json.dump({"source": "test_suite/" + c["dir"] + "/" + c["bench"], "fcidump": FCIDUMP_NAME[name], "sys": c["sys"],
+               "qmc": c["qmc"],
+               "columns": ["iterations", "shift", "proj_energy", "D0_population", "nparticles", "nstates",
+                           "nspawn_events", "rspawn"],
+               "rows": rows}, open(os.path.join(OUT, name + ".json"), "w"))
+    print(name, len(rows), "rows")

@@ -1,0 +1,878 @@
+// hande_b200: per-determinant / per-attempt device logic of the FCIQMC propagation hot path.
+//
+// Everything here is __host__ __device__ so that the same source is compiled (a) by nvcc into the
+// sm_100a kernels of libhande_b200.so and (b) by g++ into tests/hdcheck (a CPU harness that checks
+// these functions against the oracle without a GPU).  The product never runs the host versions.
+//
+// Semantics follow the reference (hande-qmc/hande); each function cites the routine it replaces.
+// Orbital indices are 1-based as in the reference; orbital i is bit (i-1)%64 of word (i-1)/64
+// (src/basis_types.f90:134-185); odd = alpha (ms=+1), even = beta (ms=-1); ims = (ms+3)/2.
+//
+// Floating point: compile with -fmad=false (nvcc) / -ffp-contract=off (g++): sums must be evaluated
+// in the reference's order without FMA contraction so that excitation choice, nspawn and death
+// counts are bit-exact against the oracle.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define HB_HD __host__ __device__ __forceinline__
+#define HB_HDN __host__ __device__
+#else
+#define HB_HD inline
+#define HB_HDN inline
+#endif
+
+#ifndef HB_MAXW
+#define HB_MAXW 4
+#endif
+#define HB_MAXNEL 64
+
+namespace hb {
+
+// ------------------------------------------------------------------------------------------------
+// System tables resident in HBM/L2 (plain pointers; filled by hb200_set_system_read_in).
+// ------------------------------------------------------------------------------------------------
+struct Sys {
+    int nbasis, nel, W;
+    int nsym_tot, sym0, sym_max, pg_mask, Lz_mask, Lz_offset, gamma_sym;
+    int uhf, nvirt, nvirt_alpha, nvirt_beta, max_nbss;
+    double Ecore;
+    // basis (1-based: entry 0 unused)
+    const uint8_t* bf_sym;      // [nbasis+1]
+    const int8_t* bf_ms;        // [nbasis+1]
+    const uint16_t* bf_spatial; // [nbasis+1]
+    // symmetry tables (src/point_group_symmetry.f90:82-229)
+    const int* nbss;            // nbasis_sym_spin[(ims-1) + 2*sym]
+    const int* ssbf;            // sym_spin_basis_fns[(ind-1) + max_nbss*((ims-1)+2*sym)]
+    // integrals (src/molecular_integrals.F90): dense one-body <i|h|j> (0 where symmetry forbids),
+    // two-body store v[indx-1] per spin channel exactly as two_body_t%integrals(chan)%v
+    const double* h1;           // [(i-1)*nbasis + (j-1)]
+    const double* v2[4];
+    // diagonal helper tables built on device from v2: J(i,j)=<ij|ij>, K(i,j)=<ij|ji>, spin-orbital indexed
+    const double* Jd;           // [(i-1)*nbasis + (j-1)]
+    const double* Kd;
+    // heat-bath tables (src/excit_gens.f90:143-153), column-major as in the reference
+    const double* hb_i_w;       // (nb)
+    const double* hb_ij_w;      // (j,i)
+    const double* hb_ija_w;     // (a,j,i)
+    const double* hb_ija_U;
+    const int* hb_ija_K;
+    const double* hb_ija_tot;   // (j,i)
+    const double* hb_ijab_w;    // (b,a,j,i)
+    const double* hb_ijab_U;
+    const int* hb_ijab_K;
+    const double* hb_ijab_tot;  // (a,j,i)
+};
+
+// Per-calculation parameters (qmc_in_t / qmc_state_t scalars the kernels need).
+struct Params {
+    int excit_gen;              // src/qmc_data.f90:31-69 values: 0 no_renorm, 1 renorm, 4 heat_bath
+    double pattempt_single, pattempt_double;
+    double tau, shift, proj_energy_old;
+    int64_t real_factor;        // pop_real_factor (1 or 2^31)
+    int64_t spawn_cutoff;       // encoded (src/spawn_data.F90:215)
+    int initiator;              // initiator approximation on
+    double initiator_pop;
+    int real_amplitudes;
+    int trunc_level;            // max excitation level from f0 allowed (-1: none)
+    uint32_t seed, cycle;
+    uint32_t hash_seed;         // 7 (src/qmc.F90:1497)
+    int nprocs, iproc, nslots;
+    uint64_t f0[HB_MAXW];
+    double H00;
+};
+
+enum { EXCIT_GEN_NO_RENORM = 0, EXCIT_GEN_RENORM = 1, EXCIT_GEN_HEAT_BATH = 4 };
+enum { RNG_NATTEMPTS = 0, RNG_SPAWN = 1, RNG_DEATH = 2, RNG_ROUND_MAIN = 3, RNG_ROUND_SPAWN = 4 };
+
+// ------------------------------------------------------------------------------------------------
+// Counter-based random stream: Philox4x32-10 keyed by (seed, cycle); counter
+// (purpose<<24 | draw/2, attempt, hash64(det)).  Identical to oracle/rng.hpp PhiloxRng.
+// ------------------------------------------------------------------------------------------------
+HB_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
+HB_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                         uint32_t* out) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+template <int W>
+HB_HD uint64_t det_hash64(const uint64_t* f) {
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        uint64_t z = f[i] + h;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z = z ^ (z >> 31);
+        h = z + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1);
+    }
+    return h;
+}
+
+struct PhiloxStream {
+    uint32_t k0, k1, c1, c2, c3, purpose, draw;
+    uint32_t buf[4];
+    HB_HD void begin(uint32_t seed, uint32_t cycle, uint32_t purpose_, uint64_t dethash, uint32_t attempt) {
+        k0 = seed; k1 = cycle; purpose = purpose_; c1 = attempt;
+        c2 = (uint32_t)dethash; c3 = (uint32_t)(dethash >> 32); draw = 0;
+    }
+    HB_HD double next() {
+        if ((draw & 1u) == 0) philox4x32_10((purpose << 24) | (draw >> 1), c1, c2, c3, k0, k1, buf);
+        uint32_t lo = (draw & 1u) ? buf[2] : buf[0];
+        uint32_t hi = (draw & 1u) ? buf[3] : buf[1];
+        draw++;
+        uint64_t u = ((uint64_t)hi << 32) | lo;
+        return (double)(u >> 11) * (1.0 / 9007199254740992.0);
+    }
+};
+
+// Test stream: a caller-provided list of uniforms (hdcheck only).
+struct ListStream {
+    const double* v; int n; int k;
+    HB_HD double next() { return (k < n) ? v[k++] : 0.0; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// MurmurHash2 (public-domain algorithm; lib/external/MurmurHash2.c:16) over the first
+// ceil(nbits/32)*4 bytes of the bit string (lib/local/hash.f90:29-60), and the owner rule
+// (assign_particle_processor, src/spawning.F90:770-838, shift == 0 branch).
+// ------------------------------------------------------------------------------------------------
+HB_HD uint32_t murmur2_words(const uint64_t* f, int nbits, uint32_t seed) {
+    const uint32_t m = 0x5bd1e995u;
+    int nwords32 = (nbits + 31) / 32;
+    uint32_t h = seed ^ (uint32_t)(nwords32 * 4);
+    for (int i = 0; i < nwords32; ++i) {
+        uint32_t k = (uint32_t)(f[i >> 1] >> ((i & 1) * 32));
+        k *= m; k ^= k >> 24; k *= m;
+        h *= m; h ^= k;
+    }
+    h ^= h >> 13; h *= m; h ^= h >> 15;
+    return h;
+}
+HB_HD int owner_slot(const uint64_t* f, int nbits, uint32_t seed, int nprocs, int nslots) {
+    int32_t hash = (int32_t)murmur2_words(f, nbits, seed);
+    int64_t p = (int64_t)nprocs * nslots;
+    int64_t r = (int64_t)hash % p;
+    if (r < 0) r += p;  // Fortran modulo
+    return (int)r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bit-string helpers
+// ------------------------------------------------------------------------------------------------
+HB_HD int popc64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return __popcll(x);
+#else
+    return __builtin_popcountll(x);
+#endif
+}
+HB_HD int ctz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)x) - 1;
+#else
+    return __builtin_ctzll(x);
+#endif
+}
+HB_HD bool det_test(const uint64_t* f, int orb) { return (f[(orb - 1) >> 6] >> ((orb - 1) & 63)) & 1ull; }
+
+// decode_det (src/determinants.f90:243-297): occupied orbitals ascending.
+template <int W>
+HB_HD int decode_det(const uint64_t* f, uint8_t* occ) {
+    int n = 0;
+#pragma unroll
+    for (int iw = 0; iw < W; ++iw) {
+        uint64_t x = f[iw];
+        while (x) {
+            int b = ctz64(x);
+            occ[n++] = (uint8_t)(iw * 64 + b + 1);
+            x &= x - 1;
+        }
+    }
+    return n;
+}
+// bit_str_cmp order (src/bit_utils.F90:452-479): unsigned, last word most significant.
+template <int W>
+HB_HD bool det_less(const uint64_t* a, const uint64_t* b) {
+#pragma unroll
+    for (int i = W - 1; i >= 0; --i) {
+        if (a[i] < b[i]) return true;
+        if (a[i] > b[i]) return false;
+    }
+    return false;
+}
+template <int W>
+HB_HD bool det_eq(const uint64_t* a, const uint64_t* b) {
+    bool e = true;
+#pragma unroll
+    for (int i = 0; i < W; ++i) e = e && (a[i] == b[i]);
+    return e;
+}
+
+// Number of set bits of f strictly above orbital `orb` (excit_mask, src/excitations.F90:25-58).
+template <int W>
+HB_HD int popc_above(const uint64_t* f, int orb) {
+    int iw = (orb - 1) >> 6, ib = (orb - 1) & 63;
+    int n = 0;
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+        uint64_t m = (k < iw) ? 0ull : ((k > iw) ? ~0ull : ((ib == 63) ? 0ull : (~0ull << (ib + 1))));
+        n += popc64(f[k] & m);
+    }
+    return n;
+}
+// popcount( f & (mask_i ^ mask_a) ): occupied orbitals between the two positions (incl. the lower...)
+template <int W>
+HB_HD int popc_between(const uint64_t* f, int i, int a) {
+    int n = 0;
+    int iw = (i - 1) >> 6, ib = (i - 1) & 63, aw = (a - 1) >> 6, ab = (a - 1) & 63;
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+        uint64_t mi = (k < iw) ? 0ull : ((k > iw) ? ~0ull : ((ib == 63) ? 0ull : (~0ull << (ib + 1))));
+        uint64_t ma = (k < aw) ? 0ull : ((k > aw) ? ~0ull : ((ab == 63) ? 0ull : (~0ull << (ab + 1))));
+        n += popc64(f[k] & (mi ^ ma));
+    }
+    return n;
+}
+// find_excitation_permutation1 (src/excitations.F90:247-280)
+template <int W>
+HB_HD bool excit_perm1(const uint64_t* f, int i, int a) {
+    int perm = popc_between<W>(f, i, a);
+    if (i > a) perm -= 1;
+    return (perm & 1) != 0;
+}
+// find_excitation_permutation2 (src/excitations.F90:282-363); i<j, a<b as produced by the generators
+template <int W>
+HB_HD bool excit_perm2(const uint64_t* f, int i, int j, int a, int b) {
+    int perm = 0;
+    int iw = (i - 1) >> 6, ib = (i - 1) & 63, aw = (a - 1) >> 6, ab = (a - 1) & 63;
+    int jw = (j - 1) >> 6, jb = (j - 1) & 63, bw = (b - 1) >> 6, bb = (b - 1) & 63;
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+        uint64_t mi = (k < iw) ? 0ull : ((k > iw) ? ~0ull : ((ib == 63) ? 0ull : (~0ull << (ib + 1))));
+        uint64_t ma = (k < aw) ? 0ull : ((k > aw) ? ~0ull : ((ab == 63) ? 0ull : (~0ull << (ab + 1))));
+        uint64_t mj = (k < jw) ? 0ull : ((k > jw) ? ~0ull : ((jb == 63) ? 0ull : (~0ull << (jb + 1))));
+        uint64_t mb = (k < bw) ? 0ull : ((k > bw) ? ~0ull : ((bb == 63) ? 0ull : (~0ull << (bb + 1))));
+        perm += popc64((f[k] & (mi ^ ma)) ^ (f[k] & (mj ^ mb)));
+    }
+    if (i > a) perm += 1;
+    if (i > b) perm += 1;
+    if (j > b || j < a) perm += 1;
+    return (perm & 1) != 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Symmetry algebra (src/point_group_symmetry.f90:297-346)
+// ------------------------------------------------------------------------------------------------
+HB_HD int cross_product(const Sys& s, int a, int b) {
+    return ((a ^ b) & s.pg_mask) | ((a & s.Lz_mask) + (b & s.Lz_mask) - s.Lz_offset);
+}
+HB_HD int sym_conj(const Sys& s, int a) {
+    return (a & s.pg_mask) | ((2 * s.Lz_offset - (a & s.Lz_mask)) & s.Lz_mask);
+}
+HB_HD int nbss(const Sys& s, int ims, int sym) { return s.nbss[(ims - 1) + 2 * sym]; }
+HB_HD int ssbf(const Sys& s, int ind, int ims, int sym) {
+    return s.ssbf[(ind - 1) + s.max_nbss * ((ims - 1) + 2 * sym)];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Integral store lookups (src/molecular_integrals.F90:685-845,1217-1257; lib/local/utils.F90:449-480)
+// ------------------------------------------------------------------------------------------------
+HB_HD int64_t tri_ind(int64_t i, int64_t j) { return (i * (i - 1)) / 2 + j; }
+
+HB_HD double two_body(const Sys& s, int i, int j, int a, int b) {
+    int ii, jj, aa, bb;
+    if (i < a) { ii = a; aa = i; } else { ii = i; aa = a; }
+    if (j < b) { jj = b; bb = j; } else { jj = j; bb = b; }
+    int64_t ia = tri_ind(s.bf_spatial[ii], s.bf_spatial[aa]);
+    int64_t jb = tri_ind(s.bf_spatial[jj], s.bf_spatial[bb]);
+    int64_t indx = (ia < jb) ? tri_ind(jb, ia) : tri_ind(ia, jb);
+    int chan = 0;
+    if (s.uhf) {
+        if (ia < jb || (ia == jb && ii < jj)) { int t = ii; ii = jj; jj = t; }
+        if (s.bf_ms[ii] == -1) chan = (s.bf_ms[jj] == -1) ? 0 : 2;
+        else chan = (s.bf_ms[jj] == 1) ? 1 : 3;
+    }
+    return s.v2[chan][indx - 1];
+}
+HB_HD double one_body(const Sys& s, int i, int j) { return s.h1[(i - 1) * s.nbasis + (j - 1)]; }
+
+// slater_condon0_mol_orb_list (src/hamiltonian_molecular.f90:99-139) through the J/K tables.
+HB_HDN double slater_condon0(const Sys& s, const uint8_t* occ) {
+    double h = s.Ecore;
+    const int nb = s.nbasis;
+    for (int iel = 0; iel < s.nel; ++iel) {
+        int i = occ[iel];
+        h = h + one_body(s, i, i);
+        for (int jel = iel + 1; jel < s.nel; ++jel) {
+            int j = occ[jel];
+            h = h + s.Jd[(i - 1) * nb + (j - 1)];
+            if (s.bf_ms[i] == s.bf_ms[j]) h = h - s.Kd[(i - 1) * nb + (j - 1)];
+        }
+    }
+    return h;
+}
+// slater_condon1_mol_excit (src/hamiltonian_molecular.f90:199-259)
+HB_HDN double slater_condon1_excit(const Sys& s, const uint8_t* occ, int i, int a, bool perm) {
+    double h = one_body(s, i, a);
+    const int msi = s.bf_ms[i];
+    for (int iel = 0; iel < s.nel; ++iel) {
+        int j = occ[iel];
+        if (j != i) {
+            h = h + two_body(s, i, j, a, j);
+            if (s.bf_ms[j] == msi) h = h - two_body(s, i, j, j, a);
+        }
+    }
+    return perm ? -h : h;
+}
+// slater_condon2_mol_excit (src/hamiltonian_molecular.f90:300-346)
+HB_HD double slater_condon2_excit(const Sys& s, int i, int j, int a, int b, bool perm) {
+    double h = 0.0;
+    if (s.bf_ms[i] == s.bf_ms[a]) h = two_body(s, i, j, a, b);
+    if (s.bf_ms[i] == s.bf_ms[b]) h = h - two_body(s, i, j, b, a);
+    return perm ? -h : h;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Excitation result
+// ------------------------------------------------------------------------------------------------
+struct Gen {
+    int nexcit, from1, from2, to1, to2;
+    bool perm, allowed;
+    double pgen, hmatel;
+};
+
+// symunocc(ims, sym) = nbasis_sym_spin - occupied (decode_det_occ_symunocc,
+// src/determinant_decoders.f90:166-206); stored as uint8 [(ims-1)+2*sym]
+HB_HD void build_symunocc(const Sys& s, const uint8_t* occ, uint8_t* su) {
+    for (int k = 0; k < 2 * s.nsym_tot; ++k) su[k] = (uint8_t)s.nbss[k];
+    for (int i = 0; i < s.nel; ++i) {
+        int o = occ[i];
+        su[((s.bf_ms[o] + 3) / 2 - 1) + 2 * s.bf_sym[o]]--;
+    }
+}
+#define HB_SU(ims, sym) ((int)su[((ims) - 1) + 2 * (sym)])
+
+// choose_ij_mol (src/excit_gen_mol.f90:620-682)
+template <class R>
+HB_HD void choose_ij(R& rng, const Sys& s, const uint8_t* occ, int& i, int& j, int& ij_sym, int& ij_spin) {
+    int nel = s.nel;
+    int ind = (int)(rng.next() * nel * (nel - 1) / 2) + 1;
+    int j_ind = (int)(1.50 + sqrt(2 * ind - 1.750));
+    int i_ind = ind - ((j_ind - 1) * (j_ind - 2)) / 2;
+    i = occ[i_ind - 1];
+    j = occ[j_ind - 1];
+    ij_sym = sym_conj(s, cross_product(s, s.bf_sym[i], s.bf_sym[j]));
+    ij_spin = s.bf_ms[i] + s.bf_ms[j];
+}
+
+// gen_excit_mol: renormalised uniform generator (src/excit_gen_mol.f90:16-101,384-448,521-616,
+// 802-946,1140-1327)
+template <int W, class R>
+HB_HDN void gen_excit_renorm(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ,
+                             const uint8_t* su, Gen& g) {
+    const int nel = s.nel;
+    g.from2 = 0; g.to2 = 0; g.perm = false;
+    if (rng.next() < p.pattempt_single) {
+        // choose_ia_mol
+        g.nexcit = 1;
+        bool allowed = false;
+        int ni = nel;
+        for (int k = 0; k < nel; ++k) {
+            int o = occ[k];
+            int imsa = (s.bf_ms[o] + 3) / 2;
+            int isyma = cross_product(s, s.bf_sym[o], s.gamma_sym);
+            if (HB_SU(imsa, isyma) != 0) allowed = true; else ni--;
+        }
+        g.allowed = allowed;
+        if (allowed) {
+            int i, a;
+            for (;;) {
+                i = occ[(int)(rng.next() * nel)];
+                int imsa = (s.bf_ms[i] + 3) / 2;
+                int isyma = cross_product(s, s.bf_sym[i], s.gamma_sym);
+                if (HB_SU(imsa, isyma) != 0) {
+                    int n = nbss(s, imsa, isyma);
+                    for (;;) {
+                        int ind = (int)(n * rng.next()) + 1;
+                        a = ssbf(s, ind, imsa, isyma);
+                        if (!det_test(f, a)) break;
+                    }
+                    break;
+                }
+            }
+            g.from1 = i; g.to1 = a;
+            // calc_pgen_single_mol
+            g.pgen = p.pattempt_single * (1.0 / (ni * HB_SU((s.bf_ms[a] + 3) / 2, s.bf_sym[a])));
+            g.perm = excit_perm1<W>(f, i, a);
+            g.hmatel = slater_condon1_excit(s, occ, i, a, g.perm);
+        } else {
+            g.hmatel = 0.0; g.pgen = 1.0; g.from1 = 0; g.to1 = 0;
+        }
+    } else {
+        g.nexcit = 2;
+        int i, j, ij_sym, spin;
+        choose_ij(rng, s, occ, i, j, ij_sym, spin);
+        g.from1 = i; g.from2 = j;
+        // choose_ab_mol
+        bool allowed = false;
+        int fac = 1, shift = 0, na = s.nbasis;
+        if (spin == 0) {
+            for (int isyma = s.sym0; isyma <= s.sym_max; ++isyma) {
+                int isymb = sym_conj(s, cross_product(s, isyma, ij_sym));
+                if ((HB_SU(1, isyma) > 0 && HB_SU(2, isymb) > 0) || (HB_SU(2, isyma) > 0 && HB_SU(1, isymb) > 0)) {
+                    allowed = true; break;
+                }
+            }
+        } else {
+            const int sp = (spin == -2) ? 1 : 2;
+            for (int isyma = s.sym0; isyma <= s.sym_max; ++isyma) {
+                int isymb = sym_conj(s, cross_product(s, isyma, ij_sym));
+                if (HB_SU(sp, isyma) > 0 && (HB_SU(sp, isymb) > 1 || (HB_SU(sp, isymb) == 1 && isyma != isymb))) {
+                    allowed = true; break;
+                }
+            }
+            fac = 2; shift = (spin == -2) ? 0 : 1; na = s.nbasis / 2;
+        }
+        g.allowed = allowed;
+        if (allowed) {
+            int a, b;
+            for (;;) {
+                a = (int)(rng.next() * na) + 1;
+                a = fac * a - shift;
+                if (!det_test(f, a)) {
+                    int imsb = (spin - s.bf_ms[a] + 3) / 2;
+                    int isymb = sym_conj(s, cross_product(s, ij_sym, s.bf_sym[a]));
+                    int nu = HB_SU(imsb, isymb);
+                    if (nu > 1 || (nu == 1 && (isymb != s.bf_sym[a] || spin == 0))) {
+                        int n = nbss(s, imsb, isymb);
+                        for (;;) {
+                            int ind = (int)(n * rng.next()) + 1;
+                            b = ssbf(s, ind, imsb, isymb);
+                            if (b != a && !det_test(f, b)) break;
+                        }
+                        break;
+                    }
+                }
+            }
+            if (a > b) { int t = a; a = b; b = t; }
+            g.to1 = a; g.to2 = b;
+            // calc_pgen_double_mol
+            int imsa = (s.bf_ms[a] + 3) / 2, imsb = (s.bf_ms[b] + 3) / 2;
+            int n_aij;
+            double p_aijb, p_bija;
+            if (spin != 0) {
+                const int sp = (spin == -2) ? 1 : 2;
+                n_aij = (spin == -2) ? s.nvirt_beta : s.nvirt_alpha;
+                for (int isyma = s.sym0; isyma <= s.sym_max; ++isyma) {
+                    int isymb = sym_conj(s, cross_product(s, isyma, ij_sym));
+                    if (HB_SU(sp, isymb) == 0) n_aij -= HB_SU(sp, isyma);
+                    else if (isyma == isymb && HB_SU(sp, isymb) == 1) n_aij -= HB_SU(sp, isyma);
+                }
+                if (s.bf_sym[a] == s.bf_sym[b]) {
+                    p_aijb = 1.0 / (HB_SU(imsa, s.bf_sym[a]) - 1);
+                    p_bija = 1.0 / (HB_SU(imsb, s.bf_sym[b]) - 1);
+                } else {
+                    p_aijb = 1.0 / HB_SU(imsa, s.bf_sym[a]);
+                    p_bija = 1.0 / HB_SU(imsb, s.bf_sym[b]);
+                }
+            } else {
+                n_aij = s.nvirt;
+                for (int isyma = s.sym0; isyma <= s.sym_max; ++isyma) {
+                    int isymb = sym_conj(s, cross_product(s, isyma, ij_sym));
+                    if (HB_SU(1, isymb) == 0) n_aij -= HB_SU(2, isyma);
+                    if (HB_SU(2, isymb) == 0) n_aij -= HB_SU(1, isyma);
+                }
+                p_aijb = 1.0 / HB_SU(imsa, s.bf_sym[a]);
+                p_bija = 1.0 / HB_SU(imsb, s.bf_sym[b]);
+            }
+            double pgen_ij = 2.0 / (nel * (nel - 1));
+            g.pgen = p.pattempt_double * pgen_ij * ((1.0 / n_aij) * (p_bija + p_aijb));
+            g.perm = excit_perm2<W>(f, i, j, a, b);
+            g.hmatel = slater_condon2_excit(s, i, j, a, b, g.perm);
+        } else {
+            g.hmatel = 0.0; g.pgen = 1.0; g.to1 = 0; g.to2 = 0;
+        }
+    }
+}
+
+// gen_excit_mol_no_renorm (src/excit_gen_mol.f90:195-284,450-517,950-1136,1329-1445)
+template <int W, class R>
+HB_HDN void gen_excit_no_renorm(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ,
+                                Gen& g) {
+    const int nel = s.nel;
+    g.from2 = 0; g.to2 = 0; g.perm = false; g.to1 = 0;
+    if (rng.next() < p.pattempt_single) {
+        g.nexcit = 1;
+        int i = occ[(int)(rng.next() * nel)];
+        int imsa = (s.bf_ms[i] + 3) / 2;
+        int isyma = cross_product(s, s.bf_sym[i], s.gamma_sym);
+        int n = nbss(s, imsa, isyma);
+        int ind = (int)(n * rng.next()) + 1;
+        g.from1 = i;
+        int a = 0;
+        if (n == 0) {
+            g.allowed = false;
+        } else {
+            a = ssbf(s, ind, imsa, isyma);
+            g.allowed = !det_test(f, a);
+        }
+        if (g.allowed) {
+            g.to1 = a;
+            g.pgen = p.pattempt_single * (1.0 / (nel * nbss(s, (s.bf_ms[a] + 3) / 2, s.bf_sym[a])));
+            g.perm = excit_perm1<W>(f, i, a);
+            g.hmatel = slater_condon1_excit(s, occ, i, a, g.perm);
+        } else {
+            g.hmatel = 0.0; g.pgen = 1.0;
+        }
+    } else {
+        g.nexcit = 2;
+        int i, j, ij_sym, spin;
+        choose_ij(rng, s, occ, i, j, ij_sym, spin);
+        g.from1 = i; g.from2 = j;
+        int fac = 1, shift = 0, na = s.nbasis;
+        if (spin == -2) { fac = 2; shift = 0; na = s.nbasis / 2; }
+        else if (spin == 2) { fac = 2; shift = 1; na = s.nbasis / 2; }
+        int a, b = 0;
+        for (;;) {
+            a = (int)(rng.next() * na) + 1;
+            a = fac * a - shift;
+            if (!det_test(f, a)) break;
+        }
+        int imsb = (spin - s.bf_ms[a] + 3) / 2;
+        int isymb = sym_conj(s, cross_product(s, ij_sym, s.bf_sym[a]));
+        int n = nbss(s, imsb, isymb);
+        if (n == 0) {
+            g.allowed = false;
+        } else if (spin != 0 && isymb == s.bf_sym[a] && n == 1) {
+            g.allowed = false;
+        } else {
+            for (;;) {
+                int ind = (int)(n * rng.next()) + 1;
+                b = ssbf(s, ind, imsb, isymb);
+                if (b != a) break;
+            }
+            g.allowed = !det_test(f, b);
+            if (a > b) { int t = a; a = b; b = t; }
+        }
+        if (g.allowed) {
+            g.to1 = a; g.to2 = b;
+            int n_aij = (spin == -2) ? s.nvirt_beta : (spin == 0 ? s.nvirt : s.nvirt_alpha);
+            int imsa = (s.bf_ms[a] + 3) / 2, isyma = s.bf_sym[a];
+            int imsb2 = (s.bf_ms[b] + 3) / 2, isymb2 = s.bf_sym[b];
+            double p_aijb, p_bija;
+            if (isyma == isymb2 && imsa == imsb2) {
+                p_aijb = 1.0 / (nbss(s, imsa, isyma) - 1);
+                p_bija = 1.0 / (nbss(s, imsb2, isymb2) - 1);
+            } else {
+                p_aijb = 1.0 / nbss(s, imsa, isyma);
+                p_bija = 1.0 / nbss(s, imsb2, isymb2);
+            }
+            double pgen_ij = 2.0 / (nel * (nel - 1));
+            g.pgen = p.pattempt_double * pgen_ij * ((1.0 / n_aij) * (p_bija + p_aijb));
+            g.perm = excit_perm2<W>(f, i, j, a, b);
+            g.hmatel = slater_condon2_excit(s, i, j, a, b, g.perm);
+        } else {
+            g.hmatel = 0.0; g.pgen = 1.0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Alias method (lib/local/alias.f90:13-184).  N <= HB_MAXNEL for the on-the-fly tables.
+// ------------------------------------------------------------------------------------------------
+HB_HDN void generate_alias_tables(int N, const double* weights, double totweight, double* aliasU, int* aliasK,
+                                  int* underfull, int* overfull) {
+    int nunder = 0, nover = 0;
+    double scale = N / totweight;
+    for (int i = 0; i < N; ++i) aliasU[i] = weights[i] * scale;
+    for (int i = 0; i < N; ++i) {
+        if (aliasU[i] <= 1.0) underfull[nunder++] = i; else overfull[nover++] = i;
+        aliasK[i] = i + 1;
+    }
+    while (nover > 0 && nunder > 0) {
+        int ov = overfull[nover - 1];
+        int un = underfull[nunder - 1];
+        aliasK[un] = ov + 1;
+        nunder--;
+        aliasU[ov] = aliasU[ov] - (1 - aliasU[un]);
+        if (aliasU[ov] < 1.0) {
+            underfull[nunder++] = overfull[nover - 1];
+            nover--;
+        }
+    }
+}
+template <class R>
+HB_HD int select_precalc(R& rng, int N, const double* aliasU, const int* aliasK) {
+    double x = rng.next() * N;
+    int K = (int)floor(x);
+    x = x - K;
+    if (x < aliasU[K]) return K + 1;
+    return aliasK[K];
+}
+template <class R>
+HB_HDN int select_weighted_value(R& rng, int N, const double* weights, double totweight) {
+    double aliasU[HB_MAXNEL];
+    int aliasK[HB_MAXNEL], under[HB_MAXNEL], over[HB_MAXNEL];
+    generate_alias_tables(N, weights, totweight, aliasU, aliasK, under, over);
+    return select_precalc(rng, N, aliasU, aliasK);
+}
+
+// gen_excit_mol_heat_bath (src/excit_gen_heat_bath_mol.F90:258-548; src/excit_gen_utils.f90:9-66,142-160)
+template <int W, class R>
+HB_HDN void gen_excit_heat_bath(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ,
+                                Gen& g) {
+    const int nel = s.nel;
+    const int64_t nb = s.nbasis;
+#define HB_I2(j, i) ((int64_t)((j) - 1) + nb * ((i) - 1))
+#define HB_I3(a, j, i) ((int64_t)((a) - 1) + nb * (((j) - 1) + nb * ((i) - 1)))
+#define HB_I4(b, a, j, i) ((int64_t)((b) - 1) + nb * (((a) - 1) + nb * (((j) - 1) + nb * ((i) - 1))))
+    double i_w[HB_MAXNEL], ij_w[HB_MAXNEL], ji_w[HB_MAXNEL];
+    double i_tot = 0.0, ij_tot = 0.0, ji_tot = 0.0;
+    g.from2 = 0; g.to2 = 0; g.perm = false; g.from1 = 0; g.to1 = 0; g.nexcit = 2;
+    for (int q = 0; q < nel; ++q) {
+        i_w[q] = s.hb_i_w[occ[q] - 1];
+        i_tot = i_tot + i_w[q];
+    }
+    int i_ind = select_weighted_value(rng, nel, i_w, i_tot);
+    int i = occ[i_ind - 1];
+    for (int q = 0; q < nel; ++q) {
+        ij_w[q] = s.hb_ij_w[HB_I2(occ[q], i)];
+        ij_tot = ij_tot + ij_w[q];
+    }
+    bool allowed = false;
+    int j_ind = 0, j = 0;
+    if (ij_tot > 0.0) {
+        j_ind = select_weighted_value(rng, nel, ij_w, ij_tot);
+        j = occ[j_ind - 1];
+        for (int q = 0; q < nel; ++q) {
+            ji_w[q] = s.hb_ij_w[HB_I2(occ[q], j)];
+            ji_tot = ji_tot + ji_w[q];
+        }
+        allowed = fabs(s.hb_ija_tot[HB_I2(j, i)]) > 0.0;
+    }
+    int a = 0, b = 0;
+    bool dbl = true;
+    double psingle = 0.0, hmod_ia = 0.0;
+    bool perm_ia = false;
+    if (allowed) {
+        a = select_precalc(rng, (int)nb, s.hb_ija_U + HB_I3(1, j, i), s.hb_ija_K + HB_I3(1, j, i));
+        if (!det_test(f, a)) {
+            int isyma = cross_product(s, s.bf_sym[i], s.gamma_sym);
+            if (s.bf_sym[a] == isyma && s.bf_ms[a] == s.bf_ms[i]) {
+                perm_ia = excit_perm1<W>(f, i, a);
+                hmod_ia = fabs(slater_condon1_excit(s, occ, i, a, perm_ia));
+                double x = rng.next();
+                double wt = s.hb_ijab_tot[HB_I3(a, j, i)];
+                if (hmod_ia < wt) psingle = hmod_ia / (wt + hmod_ia); else psingle = 0.5;
+                dbl = !(x < psingle);
+            } else {
+                dbl = true; psingle = 0.0;
+            }
+        } else {
+            allowed = false;
+        }
+    }
+    if (!allowed) {
+        g.allowed = false; g.hmatel = 0.0; g.pgen = 1.0;
+        return;
+    }
+    if (dbl) {
+        b = select_precalc(rng, (int)nb, s.hb_ijab_U + HB_I4(1, a, j, i), s.hb_ijab_K + HB_I4(1, a, j, i));
+        if (det_test(f, b)) {
+            g.allowed = false; g.hmatel = 0.0; g.pgen = 1.0;
+            return;
+        }
+        const double pi_ = i_w[i_ind - 1] / i_tot;
+        const double pj_ = i_w[j_ind - 1] / i_tot;
+        double ps[3];
+        const int fr[3] = {i, j, j}, to[3] = {b, a, b}, ot[3] = {j, i, i};
+        for (int k = 0; k < 3; ++k) {
+            int isyma = cross_product(s, s.bf_sym[fr[k]], s.gamma_sym);
+            if (s.bf_sym[to[k]] == isyma && s.bf_ms[to[k]] == s.bf_ms[fr[k]]) {
+                bool pm = excit_perm1<W>(f, fr[k], to[k]);
+                double hm = fabs(slater_condon1_excit(s, occ, fr[k], to[k], pm));
+                double wt = s.hb_ijab_tot[HB_I3(to[k], ot[k], fr[k])];
+                if (hm < wt) ps[k] = hm / (wt + hm); else ps[k] = 0.5;
+            } else {
+                ps[k] = 0.0;
+            }
+        }
+        double pgen_ija = ((pi_) * (ij_w[j_ind - 1] / ij_tot)) * (s.hb_ija_w[HB_I3(a, j, i)] / s.hb_ija_tot[HB_I2(j, i)]) *
+                          (1.0 - psingle) * (s.hb_ijab_w[HB_I4(b, a, j, i)] / s.hb_ijab_tot[HB_I3(a, j, i)]);
+        double pgen_ijb = ((pi_) * (ij_w[j_ind - 1] / ij_tot)) * (s.hb_ija_w[HB_I3(b, j, i)] / s.hb_ija_tot[HB_I2(j, i)]) *
+                          (1.0 - ps[0]) * (s.hb_ijab_w[HB_I4(a, b, j, i)] / s.hb_ijab_tot[HB_I3(b, j, i)]);
+        double pgen_jia = ((pj_) * (ji_w[i_ind - 1] / ji_tot)) * (s.hb_ija_w[HB_I3(a, i, j)] / s.hb_ija_tot[HB_I2(i, j)]) *
+                          (1.0 - ps[1]) * (s.hb_ijab_w[HB_I4(b, a, i, j)] / s.hb_ijab_tot[HB_I3(a, i, j)]);
+        double pgen_jib = ((pj_) * (ji_w[i_ind - 1] / ji_tot)) * (s.hb_ija_w[HB_I3(b, i, j)] / s.hb_ija_tot[HB_I2(i, j)]) *
+                          (1.0 - ps[2]) * (s.hb_ijab_w[HB_I4(a, b, i, j)] / s.hb_ijab_tot[HB_I3(b, i, j)]);
+        g.pgen = pgen_ija + pgen_ijb + pgen_jia + pgen_jib;
+        g.from1 = (i < j) ? i : j; g.from2 = (i < j) ? j : i;
+        g.to1 = (a < b) ? a : b; g.to2 = (a < b) ? b : a;
+        g.nexcit = 2;
+        g.perm = excit_perm2<W>(f, g.from1, g.from2, g.to1, g.to2);
+        g.hmatel = slater_condon2_excit(s, g.from1, g.from2, g.to1, g.to2, g.perm);
+        g.allowed = true;
+    } else {
+        g.nexcit = 1; g.from1 = i; g.to1 = a; g.perm = perm_ia;
+        g.hmatel = slater_condon1_excit(s, occ, i, a, perm_ia);
+        double pgen = 0.0;
+        for (int q = 0; q < nel; ++q) {
+            int oq = occ[q];
+            if (i != oq && a != oq) {
+                double wt = s.hb_ijab_tot[HB_I3(a, oq, i)];
+                double psq;
+                if (hmod_ia < wt) psq = hmod_ia / (wt + hmod_ia); else psq = 0.5;
+                pgen = pgen + (psq * (ij_w[q] / ij_tot) * (s.hb_ija_w[HB_I3(a, oq, i)] / s.hb_ija_tot[HB_I2(oq, i)]));
+            }
+        }
+        g.pgen = pgen * (i_w[i_ind - 1] / i_tot);
+        g.allowed = true;
+    }
+}
+
+template <int W, class R>
+HB_HD void gen_excit(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ, const uint8_t* su,
+                     Gen& g) {
+    if (p.excit_gen == EXCIT_GEN_RENORM) gen_excit_renorm<W>(rng, s, p, f, occ, su, g);
+    else if (p.excit_gen == EXCIT_GEN_NO_RENORM) gen_excit_no_renorm<W>(rng, s, p, f, occ, g);
+    else gen_excit_heat_bath<W>(rng, s, p, f, occ, g);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Spawning / death arithmetic
+// ------------------------------------------------------------------------------------------------
+// attempt_to_spawn + stochastic_round_spawned_particle (src/spawning.F90:711-766,
+// src/stoch_utils.f90:87-136).  Always draws exactly one random number.
+template <class R>
+HB_HD int64_t attempt_to_spawn(R& rng, const Params& p, double hmatel, double pgen, int64_t parent_pop) {
+    double pspawn = p.tau * fabs(hmatel) / pgen;
+    pspawn = pspawn * (double)p.real_factor;
+    int64_t nspawn;
+    if (pspawn < (double)p.spawn_cutoff) {
+        nspawn = (pspawn > rng.next() * (double)p.spawn_cutoff) ? p.spawn_cutoff : 0;
+    } else {
+        nspawn = (int64_t)pspawn;
+        double padd = pspawn - (double)nspawn;
+        if (padd > rng.next()) nspawn++;
+    }
+    if (nspawn > 0) {
+        int64_t sg = (parent_pop >= 0) ? nspawn : -nspawn;
+        nspawn = (hmatel > 0.0) ? -sg : sg;
+    }
+    return nspawn;
+}
+// decide_nattempts (src/qmc_common.F90:379-406)
+template <class R>
+HB_HD int decide_nattempts(R& rng, double population) {
+    int n = (int)population;
+    if (n < 0) n = -n;
+    double pextra = fabs(population) - n;
+    if (fabs(pextra) > 1.e-12) {
+        if (pextra > rng.next()) n++;
+    }
+    return n;
+}
+// stochastic_death (src/death.f90:11-130), no quasi-Newton / Chebyshev weights.  Returns the new
+// population; kill_abs receives |kill| (ndeath contribution).
+template <class R>
+HB_HD int64_t stochastic_death(R& rng, const Params& p, double Kii, int64_t population, int64_t& kill_abs) {
+    double pd = p.tau * ((Kii - p.proj_energy_old) * 1.0 + (p.proj_energy_old - p.shift) * 1.0) * 1.0;
+    pd = pd * 1.0;
+    int64_t apop = population < 0 ? -population : population;
+    pd = pd * (double)apop;
+    int64_t kill = (int64_t)pd;
+    pd = pd - (double)kill;
+    double r = rng.next();
+    if (fabs(pd) > r) {
+        if (pd > 0.0) kill++; else kill--;
+    }
+    kill_abs = kill < 0 ? -kill : kill;
+    return (population < 0) ? population + kill : population - kill;
+}
+// stochastic_round (src/stoch_utils.f90:51-85)
+template <class R>
+HB_HD int64_t stochastic_round(R& rng, int64_t pop, int64_t cutoff) {
+    int64_t ap = pop < 0 ? -pop : pop;
+    if (ap < cutoff && pop != 0) {
+        double r = rng.next() * (double)cutoff;
+        if ((double)ap > r) return (pop < 0) ? -cutoff : cutoff;
+        return 0;
+    }
+    return pop;
+}
+
+// Projected-energy contribution of one determinant (get_excitation src/excitations.F90:75-200 +
+// update_proj_energy_mol src/energy_evaluation.F90:906-986).  Returns H_0j (incl. sign) or 0; sets
+// is_ref when f == f0.
+template <int W>
+HB_HDN double proj_energy_hmatel(const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ, bool& is_ref) {
+    int nx = 0;
+#pragma unroll
+    for (int k = 0; k < W; ++k) nx += popc64(f[k] ^ p.f0[k]);
+    is_ref = (nx == 0);
+    if (nx == 0 || nx > 4) return 0.0;
+    const int nexcit = nx / 2;
+    const int shift = s.nel - nexcit;
+    int from[2] = {0, 0}, to[2] = {0, 0};
+    int iexcit1 = 0, iexcit2 = 0, iel1 = 0, iel2 = 0, perm = 0;
+    for (int i = 0; i < W; ++i) {
+        uint64_t f1 = f[i], f2 = p.f0[i];
+        if (f1 == f2) {
+            if (((iexcit1 - iexcit2) & 1) != 0) {
+                int n = popc64(f1);
+                iel1 += n; iel2 += n;
+            }
+            continue;
+        }
+        for (int jb = 0; jb < 64; ++jb) {
+            bool t1 = (f1 >> jb) & 1ull, t2 = (f2 >> jb) & 1ull;
+            if (t2) iel2++;
+            if (t1) {
+                iel1++;
+                if (!t2) { iexcit1++; from[iexcit1 - 1] = i * 64 + jb + 1; perm += (shift - iel1 + iexcit1); }
+            } else if (t2) {
+                iexcit2++; to[iexcit2 - 1] = i * 64 + jb + 1; perm += (shift - iel2 + iexcit2);
+            }
+        }
+    }
+    bool pm = (((perm % 2) + 2) % 2) == 1;
+    if (nexcit == 1) {
+        if (s.bf_ms[from[0]] == s.bf_ms[to[0]] && s.bf_sym[from[0]] == s.bf_sym[to[0]])
+            return slater_condon1_excit(s, occ, from[0], to[0], pm);
+        return 0.0;
+    }
+    if (s.bf_ms[from[0]] + s.bf_ms[from[1]] == s.bf_ms[to[0]] + s.bf_ms[to[1]]) {
+        int ij = cross_product(s, s.bf_sym[from[0]], s.bf_sym[from[1]]);
+        int ab = cross_product(s, s.bf_sym[to[0]], s.bf_sym[to[1]]);
+        if (ij == ab) return slater_condon2_excit(s, from[0], from[1], to[0], to[1], pm);
+    }
+    return 0.0;
+}
+
+// Excitation level of f relative to f0 (get_excitation_level)
+template <int W>
+HB_HD int excit_level(const uint64_t* f, const uint64_t* f0) {
+    int nx = 0;
+#pragma unroll
+    for (int k = 0; k < W; ++k) nx += popc64(f[k] ^ f0[k]);
+    return nx / 2;
+}
+
+}  // namespace hb

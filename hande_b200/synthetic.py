@@ -1,0 +1,108 @@
+"""Synthetic inputs for benchmarks and tests.
+
+* `synthetic_fcidump(norb, nelec)`: an 8-fold-symmetric, C1-symmetry RHF FCIDUMP in the text format the
+  reference reads (`read (ir,*) x, i, a, j, b`, src/read_in.F90:535), so one file feeds the oracle, this engine
+  and (elsewhere) a real HANDE binary.  S50 = (50, 20), S40 = (40, 16).
+* `random_walkers(...)`: distinct random determinants with unit (distribution A) or 1+Exp(1) (distribution B)
+  populations, sorted in the reference's list order.
+"""
+from __future__ import annotations
+
+import io
+
+import numpy as np
+
+SEED = 20261017
+
+
+def synthetic_integrals(norb, seed=SEED):
+    """Return (eps[norb], h[norb,norb], eri dict arrays) for the canonical 8-fold unique (pq|rs), chemists' notation."""
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    p = np.arange(1, norb + 1)
+    eps = -2.0 + 0.1 * p
+    g1 = rng.standard_normal((norb, norb))
+    g1 = np.tril(g1) + np.tril(g1, -1).T
+    h = 0.02 * g1 * np.exp(-np.abs(p[:, None] - p[None, :]) / 5.0)
+    h[np.diag_indices(norb)] = 0.0
+    h = h + np.diag(eps)
+    # canonical pairs pq (p>=q), ordered by tri index
+    pp, qq = np.tril_indices(norb)
+    pp, qq = pp + 1, qq + 1
+    npair = len(pp)
+    a, b = np.tril_indices(npair)          # pair index pq >= rs
+    P, Q, R, S = pp[a], qq[a], pp[b], qq[b]
+    g = rng.standard_normal(len(a))
+    val = 0.5 * np.exp(-(np.abs(P - Q) + np.abs(R - S)) / 4.0) * np.exp(-np.abs((P + Q) / 2.0 - (R + S) / 2.0) / 10.0) \
+        * (1.0 + 0.1 * g)
+    return eps, h, (P, Q, R, S, val)
+
+
+def synthetic_fcidump(norb, nelec, ms2=0, seed=SEED, path=None):
+    eps, h, (P, Q, R, S, val) = synthetic_integrals(norb, seed)
+    out = io.StringIO()
+    out.write(f" &FCI NORB={norb},NELEC={nelec},MS2={ms2},\n  ORBSYM=" + ",".join(["1"] * norb) + ",\n  ISYM=1 UHF=.FALSE.\n &END\n")
+    body = np.column_stack([val, P, Q, R, S])
+    np.savetxt(out, body, fmt="%23.16e %3d %3d %3d %3d")
+    pp, qq = np.tril_indices(norb)
+    np.savetxt(out, np.column_stack([h[pp, qq], pp + 1, qq + 1, 0 * pp, 0 * pp]), fmt="%23.16e %3d %3d %3d %3d")
+    np.savetxt(out, np.column_stack([eps, np.arange(1, norb + 1), 0 * eps, 0 * eps, 0 * eps]),
+               fmt="%23.16e %3d %3d %3d %3d")
+    out.write("%23.16e %3d %3d %3d %3d\n" % (0.0, 0, 0, 0, 0))
+    text = out.getvalue()
+    if path is not None:
+        with open(path, "w") as f:
+            f.write(text)
+    return text
+
+
+def random_dets(n, nbasis, nalpha, nbeta, seed=1):
+    """n distinct random determinants (alpha = odd orbitals, beta = even), sorted ascending in the reference order
+    (unsigned compare, last word most significant).  Returns uint64 array (n, W)."""
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    norb = nbasis // 2
+    W = (nbasis + 63) // 64
+    need = n
+    chunks = []
+    total = None
+    while True:
+        m = int(need * 1.1) + 16
+        f = np.zeros((m, W), dtype=np.uint64)
+        for nocc, off in ((nalpha, 0), (nbeta, 1)):
+            # choose nocc of norb spatial orbitals per row: argsort of random keys
+            keys = rng.random((m, norb))
+            sel = np.argpartition(keys, nocc - 1, axis=1)[:, :nocc]
+            orb0 = 2 * sel + off                      # 0-based spin-orbital = bit position
+            for k in range(nocc):
+                w = orb0[:, k] // 64
+                bit = (orb0[:, k] % 64).astype(np.uint64)
+                for iw in range(W):
+                    msk = w == iw
+                    f[msk, iw] |= (np.uint64(1) << bit[msk])
+        chunks.append(f)
+        total = np.unique(np.concatenate(chunks), axis=0)
+        if len(total) >= n:
+            break
+        need = n - len(total)
+    total = total[:n] if len(total) > n else total
+    return sort_dets(total)
+
+
+def sort_dets(f):
+    """Sort rows in the reference's list order (bit_str_cmp, src/bit_utils.F90:452-479)."""
+    W = f.shape[1]
+    order = np.lexsort(tuple(f[:, k] for k in range(W)))   # last key (highest word) is primary
+    return np.ascontiguousarray(f[order])
+
+
+def random_walkers(n, nbasis, nalpha, nbeta, real_factor=1, dist="A", seed=1):
+    """(states, pops) for walker distribution A (|pop| = 1) or B (|pop| = 1 + Exp(1)), sign Bernoulli(1/2)."""
+    f = random_dets(n, nbasis, nalpha, nbeta, seed)
+    rng = np.random.Generator(np.random.Philox(key=seed + 7919))
+    sign = np.where(rng.random(len(f)) < 0.5, -1, 1).astype(np.int64)
+    if dist == "A":
+        mag = np.full(len(f), real_factor, dtype=np.int64)
+    else:
+        mag = np.floor((1.0 + rng.exponential(1.0, len(f))) * real_factor).astype(np.int64)
+        if real_factor == 1:
+            mag = np.maximum(mag, 1)
+    return f, sign * mag

@@ -1,0 +1,135 @@
+// TEST HARNESS (not product code): compiles the __host__ __device__ core of the CUDA engine
+// (hande_b200/csrc/hb_core.cuh) with g++ so that the per-attempt logic - excitation generators,
+// Slater-Condon rules, Philox stream, owner hash, death/spawn arithmetic - can be compared with the
+// oracle on a machine without a GPU.  The product library never uses these host instantiations.
+#include <cstring>
+#include <vector>
+#include "../../hande_b200/csrc/hb_core.cuh"
+
+using namespace hb;
+
+static Sys g_sys;
+static Params g_par;
+static std::vector<uint8_t> g_sym;
+static std::vector<int8_t> g_ms;
+static std::vector<uint16_t> g_spatial;
+static std::vector<double> g_J, g_K;
+
+template <int W, class R>
+static void gen_one(R& rng, const uint64_t* f, int64_t parent_pop, int* iout, double* dout, int64_t* nspawn) {
+    uint8_t occ[HB_MAXNEL], su[64];
+    decode_det<W>(f, occ);
+    build_symunocc(g_sys, occ, su);
+    Gen g;
+    gen_excit<W>(rng, g_sys, g_par, f, occ, su, g);
+    *nspawn = attempt_to_spawn(rng, g_par, g.hmatel, g.pgen, parent_pop);
+    iout[0] = g.nexcit; iout[1] = g.from1; iout[2] = g.from2; iout[3] = g.to1; iout[4] = g.to2; iout[5] = g.perm;
+    iout[6] = g.allowed;
+    dout[0] = g.pgen; dout[1] = g.hmatel;
+}
+
+extern "C" {
+
+void hd_set_sys(int nbasis, int nel, int nsym_tot, int sym0, int sym_max, int pg_mask, int Lz_mask, int Lz_offset,
+                int gamma_sym, int uhf, int nvirt, int nvirt_alpha, int nvirt_beta, int max_nbss, double Ecore,
+                const int* sym, const int* ms, const int* spatial, const int* nbss, const int* ssbf, const double* h1,
+                const double* const* v2) {
+    Sys& s = g_sys;
+    memset(&s, 0, sizeof(s));
+    s.nbasis = nbasis; s.nel = nel; s.W = (nbasis + 63) / 64;
+    s.nsym_tot = nsym_tot; s.sym0 = sym0; s.sym_max = sym_max; s.pg_mask = pg_mask; s.Lz_mask = Lz_mask;
+    s.Lz_offset = Lz_offset; s.gamma_sym = gamma_sym; s.uhf = uhf; s.nvirt = nvirt; s.nvirt_alpha = nvirt_alpha;
+    s.nvirt_beta = nvirt_beta; s.max_nbss = max_nbss; s.Ecore = Ecore;
+    g_sym.assign(nbasis + 1, 0); g_ms.assign(nbasis + 1, 0); g_spatial.assign(nbasis + 1, 0);
+    for (int i = 1; i <= nbasis; ++i) { g_sym[i] = (uint8_t)sym[i]; g_ms[i] = (int8_t)ms[i]; g_spatial[i] = (uint16_t)spatial[i]; }
+    s.bf_sym = g_sym.data(); s.bf_ms = g_ms.data(); s.bf_spatial = g_spatial.data();
+    s.nbss = nbss; s.ssbf = ssbf; s.h1 = h1;
+    for (int c = 0; c < (uhf ? 4 : 1); ++c) s.v2[c] = v2[c];
+    g_J.assign((size_t)nbasis * nbasis, 0.0); g_K.assign((size_t)nbasis * nbasis, 0.0);
+    for (int i = 1; i <= nbasis; ++i)
+        for (int j = 1; j <= nbasis; ++j) {
+            g_J[(size_t)(i - 1) * nbasis + (j - 1)] = two_body(s, i, j, i, j);
+            g_K[(size_t)(i - 1) * nbasis + (j - 1)] = two_body(s, i, j, j, i);
+        }
+    s.Jd = g_J.data(); s.Kd = g_K.data();
+}
+void hd_set_heat_bath(const double* i_w, const double* ij_w, const double* ija_w, const double* ija_U, const int* ija_K,
+                      const double* ija_tot, const double* ijab_w, const double* ijab_U, const int* ijab_K,
+                      const double* ijab_tot) {
+    Sys& s = g_sys;
+    s.hb_i_w = i_w; s.hb_ij_w = ij_w; s.hb_ija_w = ija_w; s.hb_ija_U = ija_U; s.hb_ija_K = ija_K; s.hb_ija_tot = ija_tot;
+    s.hb_ijab_w = ijab_w; s.hb_ijab_U = ijab_U; s.hb_ijab_K = ijab_K; s.hb_ijab_tot = ijab_tot;
+}
+void hd_set_params(int excit_gen, double ps, double pd, double tau, double shift, double pe_old, int64_t real_factor,
+                   int64_t spawn_cutoff, uint32_t seed, const uint64_t* f0, double H00) {
+    Params& p = g_par;
+    memset(&p, 0, sizeof(p));
+    p.excit_gen = excit_gen; p.pattempt_single = ps; p.pattempt_double = pd; p.tau = tau; p.shift = shift;
+    p.proj_energy_old = pe_old; p.real_factor = real_factor; p.spawn_cutoff = spawn_cutoff; p.seed = seed;
+    p.hash_seed = 7; p.nprocs = 1; p.nslots = 1; p.H00 = H00; p.trunc_level = -1;
+    for (int k = 0; k < g_sys.W; ++k) p.f0[k] = f0[k];
+}
+
+void hd_gen_excit_philox(const uint64_t* f, uint32_t cycle, uint32_t attempt, int64_t parent_pop, int* iout,
+                         double* dout, int64_t* nspawn) {
+    PhiloxStream rng;
+    switch (g_sys.W) {
+        case 1: rng.begin(g_par.seed, cycle, RNG_SPAWN, det_hash64<1>(f), attempt); gen_one<1>(rng, f, parent_pop, iout, dout, nspawn); break;
+        case 2: rng.begin(g_par.seed, cycle, RNG_SPAWN, det_hash64<2>(f), attempt); gen_one<2>(rng, f, parent_pop, iout, dout, nspawn); break;
+        case 3: rng.begin(g_par.seed, cycle, RNG_SPAWN, det_hash64<3>(f), attempt); gen_one<3>(rng, f, parent_pop, iout, dout, nspawn); break;
+        default: rng.begin(g_par.seed, cycle, RNG_SPAWN, det_hash64<4>(f), attempt); gen_one<4>(rng, f, parent_pop, iout, dout, nspawn); break;
+    }
+}
+int hd_gen_excit_list(const uint64_t* f, const double* rn, int nrn, int* iout, double* dout) {
+    ListStream rng{rn, nrn, 0};
+    int64_t ns;
+    switch (g_sys.W) {
+        case 1: gen_one<1>(rng, f, 1, iout, dout, &ns); break;
+        case 2: gen_one<2>(rng, f, 1, iout, dout, &ns); break;
+        case 3: gen_one<3>(rng, f, 1, iout, dout, &ns); break;
+        default: gen_one<4>(rng, f, 1, iout, dout, &ns); break;
+    }
+    return rng.k - 1;  // attempt_to_spawn consumed one more
+}
+double hd_sc0(const uint64_t* f) {
+    uint8_t occ[HB_MAXNEL];
+    switch (g_sys.W) { case 1: decode_det<1>(f, occ); break; case 2: decode_det<2>(f, occ); break;
+                       case 3: decode_det<3>(f, occ); break; default: decode_det<4>(f, occ); }
+    return slater_condon0(g_sys, occ);
+}
+double hd_sc1(const uint64_t* f, int i, int a) {
+    uint8_t occ[HB_MAXNEL];
+    bool pm;
+    switch (g_sys.W) { case 1: decode_det<1>(f, occ); pm = excit_perm1<1>(f, i, a); break;
+                       case 2: decode_det<2>(f, occ); pm = excit_perm1<2>(f, i, a); break;
+                       case 3: decode_det<3>(f, occ); pm = excit_perm1<3>(f, i, a); break;
+                       default: decode_det<4>(f, occ); pm = excit_perm1<4>(f, i, a); }
+    return slater_condon1_excit(g_sys, occ, i, a, pm);
+}
+double hd_sc2(const uint64_t* f, int i, int j, int a, int b) {
+    bool pm;
+    switch (g_sys.W) { case 1: pm = excit_perm2<1>(f, i, j, a, b); break; case 2: pm = excit_perm2<2>(f, i, j, a, b); break;
+                       case 3: pm = excit_perm2<3>(f, i, j, a, b); break; default: pm = excit_perm2<4>(f, i, j, a, b); }
+    return slater_condon2_excit(g_sys, i, j, a, b, pm);
+}
+int32_t hd_murmur(const uint64_t* f, uint32_t seed) { return (int32_t)murmur2_words(f, g_sys.nbasis, seed); }
+int hd_owner(const uint64_t* f, int nprocs, int nslots) { return owner_slot(f, g_sys.nbasis, 7, nprocs, nslots); }
+void hd_philox_stream(uint32_t seed, uint32_t cycle, uint32_t purpose, const uint64_t* f, int W, uint32_t attempt, int n,
+                      double* out) {
+    PhiloxStream r;
+    uint64_t h = (W == 1) ? det_hash64<1>(f) : (W == 2) ? det_hash64<2>(f) : (W == 3) ? det_hash64<3>(f) : det_hash64<4>(f);
+    r.begin(seed, cycle, purpose, h, attempt);
+    for (int i = 0; i < n; ++i) out[i] = r.next();
+}
+// proj-energy contribution and death for one determinant (Philox stream)
+double hd_proj_hmatel(const uint64_t* f, int* is_ref) {
+    uint8_t occ[HB_MAXNEL];
+    bool r; double h;
+    switch (g_sys.W) { case 1: decode_det<1>(f, occ); h = proj_energy_hmatel<1>(g_sys, g_par, f, occ, r); break;
+                       case 2: decode_det<2>(f, occ); h = proj_energy_hmatel<2>(g_sys, g_par, f, occ, r); break;
+                       case 3: decode_det<3>(f, occ); h = proj_energy_hmatel<3>(g_sys, g_par, f, occ, r); break;
+                       default: decode_det<4>(f, occ); h = proj_energy_hmatel<4>(g_sys, g_par, f, occ, r); }
+    *is_ref = r;
+    return h;
+}
+}  // extern "C"

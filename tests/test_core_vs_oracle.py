@@ -1,0 +1,148 @@
+"""CPU parity of the engine's __host__ __device__ core (hb_core.cuh, built for the host by tests/hdcheck) against
+the oracle: identical Philox stream -> bit-exact excitation choice, pgen, H_ij and nspawn; Slater-Condon rules,
+owner hash and the heat-bath generator's normalisation (sum of pgen over all sampled excitations)."""
+import numpy as np
+import pytest
+
+from hande_b200 import read_in as R
+from hande_b200 import synthetic
+from oracle.pyoracle import Oracle, philox_stream, EXCIT_GEN
+from tests.hdcheck.harness import HdCheck
+
+
+def _setup(path, kw, excit_gen, tau=0.01, real=False, seed=11):
+    s = R.read_in(path, **kw)
+    o = Oracle()
+    o.read_fcidump(path, **kw)
+    o.set_qmc(tau=tau, seed=seed, excit_gen=excit_gen, rng_kind=1, real_amplitudes=int(real), spawn_cutoff=0.01)
+    o.init()
+    ref = o.reference()
+    hb = o.heat_bath_tables() if excit_gen == "heat_bath" else None
+    rf = 2**31 if real else 1
+    cutoff = int(np.ceil(0.01 * rf)) if real else 0
+    h = HdCheck(s, EXCIT_GEN[excit_gen], ref["pattempt_single"], ref["pattempt_double"], tau, 0.0, 0.0, rf, cutoff,
+                seed, ref["f0"], ref["H00"], hb=hb)
+    return s, o, h
+
+
+def _compare_attempts(s, o, h, dets, pops, tau, ncycle=2, nattempt=6):
+    nchecked = 0
+    for f, pop in zip(dets, pops):
+        for cyc in range(1, 1 + ncycle):
+            for att in range(nattempt):
+                io_o, do_o, ns_o = o.gen_excit_philox(f, cyc, att, int(pop), tau)
+                io_h, do_h, ns_h = h.gen_excit_philox(f, cyc, att, int(pop))
+                assert io_o[6] == io_h[6], (f, cyc, att, io_o, io_h)
+                if io_o[6]:
+                    assert list(io_o[:6]) == list(io_h[:6]), (f, cyc, att, io_o, io_h)
+                assert do_o[0] == do_h[0] and do_o[1] == do_h[1], (f, cyc, att, do_o, do_h)   # bit-exact doubles
+                assert ns_o == ns_h
+                nchecked += 1
+    return nchecked
+
+
+@pytest.mark.parametrize("gen", ["renorm", "no_renorm"])
+def test_uniform_generators_h2o(fcidump_path, gen):
+    kw = dict(nel=10, ms=0, sym=0, cas=(8, 13))
+    s, o, h = _setup(fcidump_path("h2o"), kw, gen, tau=0.003)
+    dets = synthetic.random_dets(150, s.nbasis, s.nalpha, s.nbeta, seed=3)
+    pops = np.where(np.arange(len(dets)) % 2 == 0, 3, -2)
+    n = _compare_attempts(s, o, h, dets, pops, 0.003)
+    assert n > 1000
+    for f in dets[:40]:
+        assert h.sc0(f) == o.sc0(f)
+        assert h.murmur(f) == o.murmur_bit_string(f)
+        hm, isref = h.proj_hmatel(f)
+        assert isref == int((f == o.reference()["f0"]).all())
+
+
+def test_ne_large_basis_two_sym(fcidump_path):
+    kw = dict(nel=10, ms=0, sym=0)
+    s, o, h = _setup(fcidump_path("ne"), kw, "renorm", tau=0.005, real=True)
+    dets = synthetic.random_dets(60, s.nbasis, s.nalpha, s.nbeta, seed=5)
+    pops = np.full(len(dets), 2**31 + 12345)
+    _compare_attempts(s, o, h, dets, pops, 0.005)
+
+
+@pytest.fixture(scope="module")
+def s10(tmp_path_factory):
+    p = tmp_path_factory.mktemp("syn") / "s10.fcidump"
+    synthetic.synthetic_fcidump(10, 8, path=str(p))
+    return str(p)
+
+
+def test_heat_bath_generator_synthetic(s10):
+    s, o, h = _setup(s10, {}, "heat_bath", tau=0.01, real=True)
+    dets = synthetic.random_dets(120, s.nbasis, s.nalpha, s.nbeta, seed=9)
+    pops = np.where(np.arange(len(dets)) % 3 == 0, -(2**31), 2**32 + 17)
+    n = _compare_attempts(s, o, h, dets, pops, 0.01, ncycle=2, nattempt=8)
+    assert n > 1500
+
+
+def test_slater_condon_two_word_bitstrings(tmp_path):
+    # 40 spatial orbitals -> 80 spin orbitals -> W = 2 words
+    p = tmp_path / "s40.fcidump"
+    synthetic.synthetic_fcidump(40, 10, path=str(p))
+    s, o, h = _setup(str(p), {}, "renorm")
+    assert s.W == 2
+    dets = synthetic.random_dets(40, s.nbasis, s.nalpha, s.nbeta, seed=2)
+    rng = np.random.default_rng(0)
+    for f in dets:
+        assert h.sc0(f) == o.sc0(f)
+        occ = s.decode(f)
+        virt = [v for v in range(1, s.nbasis + 1) if v not in occ]
+        for _ in range(6):
+            i = int(rng.choice(occ))
+            a = int(rng.choice([v for v in virt if s.ms[v] == s.ms[i]]))
+            assert h.sc1(f, i, a) == o.sc1(f, i, a)
+            i, j = sorted(int(x) for x in rng.choice(occ, 2, replace=False))
+            cand = [(a, b) for a in virt for b in virt if a < b and s.ms[a] + s.ms[b] == s.ms[i] + s.ms[j]]
+            a, b = cand[int(rng.integers(len(cand)))]
+            assert h.sc2(f, i, j, a, b) == o.sc2(f, i, j, a, b)
+        assert h.murmur(f) == o.murmur_bit_string(f)
+    _compare_attempts(s, o, h, dets[:20], np.ones(20, dtype=np.int64), 0.01)
+
+
+def test_philox_stream_matches_oracle():
+    f = np.array([0x123456789ABCDEF, 0xFEDCBA98], dtype=np.uint64)
+    from tests.hdcheck import harness
+    harness.build()
+    import ctypes as C
+    L = C.CDLL(harness.LIB)
+    L.hd_philox_stream.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int, C.c_uint32, C.c_int,
+                                   C.c_void_p]
+    for purpose in range(5):
+        out = np.zeros(9)
+        L.hd_philox_stream(77, 123, purpose, f.ctypes.data, 2, 5, 9, out.ctypes.data)
+        ref = philox_stream(77, 123, purpose, f, 5, 9)
+        assert (out == ref).all()
+        assert ((out >= 0) & (out < 1)).all()
+
+
+def test_heat_bath_pgen_normalisation(s10):
+    """SURVEY 8c gap-filler: heat-bath has no single-rank golden trajectory, so pin it statistically.  The
+    generator reports pgen for the excitation it produced; over many samples each excitation must appear with
+    that frequency, and the reported pgen of all distinct excitations plus the null fraction must sum to one."""
+    s, o, h = _setup(s10, {}, "heat_bath", tau=0.01)
+    dets = synthetic.random_dets(3, s.nbasis, s.nalpha, s.nbeta, seed=4)
+    rng = np.random.default_rng(5)
+    n = 150000
+    for f in [o.reference()["f0"], dets[1]]:
+        counts, pg = {}, {}
+        nnull = 0
+        for _ in range(n):
+            io, do, k = o.gen_excit_list(f, rng.random(12))
+            if not io[6]:
+                nnull += 1
+                continue
+            key = tuple(io[:5])
+            counts[key] = counts.get(key, 0) + 1
+            if key in pg:
+                assert abs(pg[key] - do[0]) <= 4e-16 * do[0]   # function of the excitation only (sum order may differ)
+            pg[key] = do[0]
+        tot = sum(pg.values()) + nnull / n
+        assert abs(tot - 1.0) < 0.02, tot
+        for key, c in counts.items():
+            e = n * pg[key]
+            if e > 50:
+                assert abs(c - e) < 5.5 * np.sqrt(e), (key, c, e)

@@ -8,7 +8,7 @@ here a leading slice of each table keeps the CPU suite to a few minutes.
 import numpy as np
 import pytest
 
-from conftest import load_golden
+from tests.conftest import load_golden
 from oracle import pyoracle
 from oracle.pyoracle import Oracle, HUGE
 

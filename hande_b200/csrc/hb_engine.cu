@@ -1,0 +1,1538 @@
+// hande_b200: CUDA engine (sm_100a) for the FCIQMC propagation hot path + its C ABI.
+//
+// One engine = one GPU = one MPI rank of the reference.  Data layout in HBM:
+//   main walker list (particle_t, src/qmc_data.f90:615-682), double-buffered:
+//       states[N][W] uint64 (sorted ascending, bit_str_cmp order), pops[N] int64 (encoded), dat[N] double
+//   spawn store (spawn_t, src/spawn_data.F90:35-145): two buffers of `spawned_walker_length` elements,
+//       element = [f(0..W-1), population, flag] int64  (32 B for W=2), partitioned in nprocs blocks
+//   system tables (integral store, symmetry tables, heat-bath alias tables): replicated per GPU, L2-resident
+//       except the nb^4 heat-bath tables.
+//
+// Kernels (all HBM/L2-bound integer + fp64 scalar work; no tensor cores - nothing is a dense contraction):
+//   k_spawn_death     fused: decode, initiator flag, projected energy, decide_nattempts, spawning attempts
+//                     (load-balanced over a 256-state tile), stochastic death; warp-aggregated append
+//   k_radix_*         LSD radix sort of the spawn list on the bit-string key (8-bit digits)
+//   k_annihilate      segmented sum of equal keys + initiator flag algebra + binary search into the main list
+//   k_round_count     stochastic rounding of main-list populations + per-tile survivor counts
+//   k_merge           single pass merge of survivors and new determinants into the other main-list buffer
+//   k_sc0             <D|H|D> - H00 for new determinants
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/hande_b200.h"
+#include "hb_core.cuh"
+
+using namespace hb;
+
+static thread_local std::string g_err;
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(_e) + " @" + std::to_string(__LINE__); \
+            return 1;                                                                              \
+        }                                                                                          \
+    } while (0)
+#define NCK(call)                                                                                  \
+    do {                                                                                           \
+        ncclResult_t _e = (call);                                                                  \
+        if (_e != ncclSuccess) {                                                                   \
+            g_err = std::string(#call) + ": " + ncclGetErrorString(_e) + " @" + std::to_string(__LINE__); \
+            return 1;                                                                              \
+        }                                                                                          \
+    } while (0)
+#define FAIL(msg)        \
+    do {                 \
+        g_err = (msg);   \
+        return 1;        \
+    } while (0)
+
+constexpr int TILE = 256;  // states per block in the fused spawn kernel and in the merge passes
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int warp_incl_scan(int v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+// exclusive scan over a block of TILE threads; returns exclusive prefix, total in *total.  warp_sums: >= 8 ints smem
+__device__ __forceinline__ int block_excl_scan(int v, int* warp_sums, int* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = warp_incl_scan(v);
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    int off = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < TILE / 32; ++w) {
+        int s = warp_sums[w];
+        if (w < warp) off += s;
+        tot += s;
+    }
+    __syncthreads();
+    *total = tot;
+    return off + incl - v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int W>
+__device__ __forceinline__ void load_det(const uint64_t* p, uint64_t* f) {
+    if (W == 2) {
+        ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p);
+        f[0] = v.x; f[1] = v.y;
+    } else {
+#pragma unroll
+        for (int k = 0; k < W; ++k) f[k] = p[k];
+    }
+}
+template <int W>
+__device__ __forceinline__ void store_det(uint64_t* p, const uint64_t* f) {
+    if (W == 2) {
+        *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2(f[0], f[1]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < W; ++k) p[k] = f[k];
+    }
+}
+
+// lower_bound in the sorted main list: first index with states[idx] >= key
+template <int W>
+__device__ __forceinline__ long long lower_bound_det(const uint64_t* states, long long n, const uint64_t* key) {
+    long long lo = 0, hi = n;
+    while (lo < hi) {
+        long long mid = (lo + hi) >> 1;
+        uint64_t f[W];
+        load_det<W>(states + mid * W, f);
+        if (det_less<W>(f, key)) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel: fused spawn + death + estimators  (src/fciqmc.f90:315-371, 635-769)
+// ------------------------------------------------------------------------------------------------
+struct SpawnPartials {  // one per block; reduced in fixed order by k_reduce_partials
+    double pe, d0;
+    long long ndeath, npart, nattempts;
+};
+
+template <int W>
+__global__ void __launch_bounds__(TILE)
+k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __restrict__ pops,
+              const double* __restrict__ dat, long long nstates, int64_t* __restrict__ spawn,
+              unsigned long long* __restrict__ head, long long block_size, const int* __restrict__ proc_map,
+              SpawnPartials* __restrict__ partials, int* __restrict__ err) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nel = s.nel;
+    const int nsu = (p.excit_gen == EXCIT_GEN_RENORM) ? 2 * s.nsym_tot : 0;
+    uint64_t* sf = reinterpret_cast<uint64_t*>(smem_raw);                 // [TILE*W]
+    uint64_t* shash = sf + TILE * W;                                      // [TILE]
+    int64_t* spop = reinterpret_cast<int64_t*>(shash + TILE);             // [TILE]
+    int* sscan = reinterpret_cast<int*>(spop + TILE);                     // [TILE+1]
+    int* swarp = sscan + TILE + 1;                                        // [8]
+    double* sred = reinterpret_cast<double*>(swarp + 8 + ((TILE + 1 + 8) & 1)); // [5*8] (8-byte aligned)
+    uint8_t* sflag = reinterpret_cast<uint8_t*>(sred + 40);               // [TILE]
+    uint8_t* socc = sflag + TILE;                                         // [TILE*nel]
+    uint8_t* ssu = socc + TILE * nel;                                     // [TILE*nsu]
+
+    const int tid = threadIdx.x;
+    const long long idx = (long long)blockIdx.x * TILE + tid;
+    const int E = W + 2;
+
+    double pe = 0.0, d0 = 0.0;
+    long long ndeath = 0, npart = 0;
+    int natt = 0;
+    if (idx < nstates) {
+        uint64_t f[W];
+        load_det<W>(states + idx * W, f);
+        const int64_t pop = pops[idx];
+        const double Kii = dat[idx];
+#pragma unroll
+        for (int k = 0; k < W; ++k) sf[tid * W + k] = f[k];
+        spop[tid] = pop;
+        uint8_t* occ = socc + tid * nel;
+        decode_det<W>(f, occ);
+        if (nsu) build_symunocc(s, occ, ssu + tid * nsu);
+        const uint64_t h = det_hash64<W>(f);
+        shash[tid] = h;
+        const double real_pop = (double)pop / (double)p.real_factor;
+        // set_parent_flag (src/ifciqmc.f90:13-57)
+        sflag[tid] = (fabs(real_pop) > p.initiator_pop) ? 0 : 1;
+        // update_proj_energy_mol (src/energy_evaluation.F90:906-986)
+        bool is_ref;
+        double hm = proj_energy_hmatel<W>(s, p, f, occ, is_ref);
+        if (is_ref) d0 = real_pop; else pe = hm * real_pop;
+        PhiloxStream rng;
+        rng.begin(p.seed, p.cycle, RNG_NATTEMPTS, h, 0);
+        natt = decide_nattempts(rng, real_pop);
+        rng.begin(p.seed, p.cycle, RNG_DEATH, h, 0);
+        int64_t kill_abs;
+        const int64_t newpop = stochastic_death(rng, p, Kii, pop, kill_abs);
+        pops[idx] = newpop;
+        ndeath = kill_abs;
+        npart = newpop < 0 ? -newpop : newpop;
+    }
+    int T;
+    const int excl = block_excl_scan(natt, swarp, &T);
+    sscan[tid] = excl;
+    if (tid == 0) sscan[TILE] = T;
+    __syncthreads();
+
+    for (int base = 0; base < T; base += TILE) {
+        const int a = base + tid;
+        int64_t nspawn = 0;
+        uint64_t child[W];
+        int dest = 0, pflag = 0;
+        if (a < T) {
+            int lo = 0, hi = TILE;
+            while (hi - lo > 1) {
+                int mid = (lo + hi) >> 1;
+                if (sscan[mid] <= a) lo = mid; else hi = mid;
+            }
+            const int att = a - sscan[lo];
+            uint64_t f[W];
+#pragma unroll
+            for (int k = 0; k < W; ++k) f[k] = sf[lo * W + k];
+            PhiloxStream rng;
+            rng.begin(p.seed, p.cycle, RNG_SPAWN, shash[lo], (uint32_t)att);
+            Gen g;
+            gen_excit<W>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, g);
+            nspawn = attempt_to_spawn(rng, p, g.hmatel, g.pgen, spop[lo]);
+            if (nspawn != 0) {
+                // create_excited_det (src/excitations.F90:365-406)
+#pragma unroll
+                for (int k = 0; k < W; ++k) child[k] = f[k];
+                child[(g.from1 - 1) >> 6] &= ~(1ull << ((g.from1 - 1) & 63));
+                child[(g.to1 - 1) >> 6] |= (1ull << ((g.to1 - 1) & 63));
+                if (g.nexcit == 2) {
+                    child[(g.from2 - 1) >> 6] &= ~(1ull << ((g.from2 - 1) & 63));
+                    child[(g.to2 - 1) >> 6] |= (1ull << ((g.to2 - 1) & 63));
+                }
+                // create_spawned_particle[_initiator]_truncated (src/spawning.F90:1186-1319)
+                if (p.trunc_level >= 0 && excit_level<W>(child, p.f0) > p.trunc_level) {
+                    nspawn = 0;
+                } else {
+                    // assign_particle_processor (src/spawning.F90:770-838)
+                    dest = (p.nprocs > 1) ? proc_map[owner_slot(child, s.nbasis, p.hash_seed, p.nprocs, p.nslots)] : 0;
+                    pflag = p.initiator ? sflag[lo] : 0;
+                }
+            }
+        }
+        __syncwarp();
+        const unsigned has = __ballot_sync(0xffffffffu, nspawn != 0);
+        if (nspawn != 0) {
+            // add_[flagged_]spawned_particle (src/spawning.F90:907-1018): warp-aggregated pointer bump per destination
+            const unsigned peers = (p.nprocs > 1) ? __match_any_sync(has, dest) : has;
+            const int lane = tid & 31;
+            const int leader = __ffs(peers) - 1;
+            const int rank = __popc(peers & ((1u << lane) - 1u));
+            unsigned long long slot0 = 0;
+            if (lane == leader) slot0 = atomicAdd(&head[dest], (unsigned long long)__popc(peers));
+            slot0 = __shfl_sync(peers, slot0, leader);
+            const long long slot = (long long)slot0 + rank;
+            if (slot < block_size) {
+                int64_t* dst = spawn + ((long long)dest * block_size + slot) * E;
+                if (W == 2) {
+                    reinterpret_cast<ulonglong2*>(dst)[0] = make_ulonglong2(child[0], child[1]);
+                    reinterpret_cast<longlong2*>(dst)[1] = make_longlong2((long long)nspawn, (long long)pflag);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < W; ++k) dst[k] = (int64_t)child[k];
+                    dst[W] = nspawn;
+                    dst[W + 1] = pflag;
+                }
+            } else {
+                atomicOr(err, 1);  // spawn%error: no space left in the spawning array
+            }
+        }
+    }
+
+    // deterministic block reduction of the estimators
+    const int lane = tid & 31, warp = tid >> 5;
+    double r0 = warp_sum_d(pe), r1 = warp_sum_d(d0);
+    long long r2 = warp_sum_ll(ndeath), r3 = warp_sum_ll(npart);
+    __syncthreads();
+    if (lane == 0) {
+        sred[warp] = r0; sred[8 + warp] = r1;
+        reinterpret_cast<long long*>(sred)[16 + warp] = r2;
+        reinterpret_cast<long long*>(sred)[24 + warp] = r3;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        SpawnPartials out;
+        out.pe = 0.0; out.d0 = 0.0; out.ndeath = 0; out.npart = 0;
+        for (int w = 0; w < TILE / 32; ++w) {
+            out.pe += sred[w]; out.d0 += sred[8 + w];
+            out.ndeath += reinterpret_cast<long long*>(sred)[16 + w];
+            out.npart += reinterpret_cast<long long*>(sred)[24 + w];
+        }
+        out.nattempts = T;
+        partials[blockIdx.x] = out;
+    }
+}
+
+struct CycleStats {
+    double pe, d0;              // this cycle
+    long long ndeath, npart_after_death, nattempts_spawn;
+    long long nkept, npart_new; // after merge
+};
+
+__global__ void k_reduce_partials(const SpawnPartials* __restrict__ partials, int n, CycleStats* st) {
+    __shared__ double sd[2][32];
+    __shared__ long long sl[3][32];
+    double pe = 0.0, d0 = 0.0;
+    long long nd = 0, np = 0, na = 0;
+    // fixed assignment of partials to threads + fixed-order tree => run-to-run deterministic
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        pe += partials[i].pe; d0 += partials[i].d0;
+        nd += partials[i].ndeath; np += partials[i].npart; na += partials[i].nattempts;
+    }
+    pe = warp_sum_d(pe); d0 = warp_sum_d(d0);
+    nd = warp_sum_ll(nd); np = warp_sum_ll(np); na = warp_sum_ll(na);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { sd[0][warp] = pe; sd[1][warp] = d0; sl[0][warp] = nd; sl[1][warp] = np; sl[2][warp] = na; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0; long long c = 0, d = 0, e = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += sd[0][w]; b += sd[1][w]; c += sl[0][w]; d += sl[1][w]; e += sl[2][w]; }
+        st->pe = a; st->d0 = b; st->ndeath = c; st->npart_after_death = d; st->nattempts_spawn = e;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LSD radix sort of spawn elements (replaces qsort, src/sort.f90:213-395) on the key words
+// ------------------------------------------------------------------------------------------------
+constexpr int SORT_THREADS = 256;
+
+template <int E>
+__global__ void __launch_bounds__(SORT_THREADS)
+k_radix_hist(const int64_t* __restrict__ in, long long n, int word, int shift, unsigned* __restrict__ hist, int nblk,
+             long long chunk) {
+    __shared__ unsigned sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    const long long start = (long long)blockIdx.x * chunk;
+    const long long end = min(n, start + chunk);
+    for (long long i = start + threadIdx.x; i < end; i += SORT_THREADS) {
+        unsigned d = (unsigned)(((uint64_t)in[i * E + word] >> shift) & 0xFFu);
+        atomicAdd(&sh[d], 1u);
+    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * nblk + blockIdx.x] = sh[threadIdx.x];
+}
+
+// exclusive scan of m unsigned values in place, single block
+__global__ void k_scan_u32_single(unsigned* data, long long m) {
+    __shared__ unsigned swarp[32];
+    __shared__ unsigned carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (long long base = 0; base < m; base += blockDim.x) {
+        long long i = base + threadIdx.x;
+        unsigned v = (i < m) ? data[i] : 0u;
+        unsigned incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) swarp[warp] = incl;
+        __syncthreads();
+        unsigned off = 0, tot = 0;
+        for (int w = 0; w < nw; ++w) { unsigned sv = swarp[w]; if (w < warp) off += sv; tot += sv; }
+        unsigned c = carry;
+        if (i < m) data[i] = c + off + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry = c + tot;
+        __syncthreads();
+    }
+}
+
+template <int E>
+__global__ void __launch_bounds__(SORT_THREADS)
+k_radix_scatter(const int64_t* __restrict__ in, int64_t* __restrict__ out, long long n, int word, int shift,
+                const unsigned* __restrict__ hist, int nblk, long long chunk) {
+    __shared__ unsigned sbase[256];
+    __shared__ unsigned swc[SORT_THREADS / 32][256];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    sbase[tid] = hist[(size_t)tid * nblk + blockIdx.x];
+    const long long start = (long long)blockIdx.x * chunk;
+    const long long end = min(n, start + chunk);
+    for (long long t0 = start; t0 < end; t0 += SORT_THREADS) {
+#pragma unroll
+        for (int w = 0; w < SORT_THREADS / 32; ++w) swc[w][tid] = 0;
+        __syncthreads();
+        const long long i = t0 + tid;
+        const bool valid = i < end;
+        int64_t el[E];
+        unsigned d = 256u + (unsigned)lane;  // invalid lanes never match a real digit nor each other
+        if (valid) {
+#pragma unroll
+            for (int k = 0; k < E; ++k) el[k] = in[i * E + k];
+            d = (unsigned)(((uint64_t)el[word] >> shift) & 0xFFu);
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        if (valid && rank == 0) swc[warp][d] = __popc(peers);
+        __syncthreads();
+        {   // digit `tid`: exclusive prefix over warps on top of the running base (stable order)
+            unsigned run = sbase[tid];
+#pragma unroll
+            for (int w = 0; w < SORT_THREADS / 32; ++w) {
+                unsigned c = swc[w][tid];
+                swc[w][tid] = run;
+                run += c;
+            }
+            sbase[tid] = run;
+        }
+        __syncthreads();
+        if (valid) {
+            const long long pos = (long long)swc[warp][d] + rank;
+            int64_t* dst = out + pos * E;
+            if (E == 4) {
+                reinterpret_cast<longlong2*>(dst)[0] = make_longlong2(el[0], el[1]);
+                reinterpret_cast<longlong2*>(dst)[1] = make_longlong2(el[2], el[3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < E; ++k) dst[k] = el[k];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic exclusive scan of int32 (two-level recursion): used for the insert flags and tile counts
+// ------------------------------------------------------------------------------------------------
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_BLOCK = TILE * SCAN_ITEMS;
+
+__global__ void __launch_bounds__(TILE) k_scan_block(const int* __restrict__ in, int* __restrict__ out, long long n,
+                                                     int* __restrict__ block_sums) {
+    __shared__ int swarp[8];
+    const long long base = (long long)blockIdx.x * SCAN_BLOCK + (long long)threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = (base + k < n) ? in[base + k] : 0;
+        sum += v[k];
+    }
+    int tot;
+    int excl = block_excl_scan(sum, swarp, &tot);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < n) out[base + k] = excl;
+        excl += v[k];
+    }
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(TILE) k_scan_add(int* __restrict__ out, long long n, const int* __restrict__ block_offs) {
+    const long long base = (long long)blockIdx.x * SCAN_BLOCK + (long long)threadIdx.x * SCAN_ITEMS;
+    const int off = block_offs[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (base + k < n) out[base + k] += off;
+}
+// single-block scan for small arrays; also writes the total to *total
+__global__ void k_scan_small(const int* __restrict__ in, int* __restrict__ out, long long n, int* total) {
+    __shared__ int swarp[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (long long base = 0; base < n; base += blockDim.x) {
+        long long i = base + threadIdx.x;
+        int v = (i < n) ? in[i] : 0;
+        int incl = warp_incl_scan(v);
+        if (lane == 31) swarp[warp] = incl;
+        __syncthreads();
+        int off = 0, tot = 0;
+        for (int w = 0; w < nw; ++w) { int sv = swarp[w]; if (w < warp) off += sv; tot += sv; }
+        int c = carry;
+        if (i < n) out[i] = c + off + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry = c + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total) *total = carry;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel: annihilate_spawn_t[_initiator] + annihilate_main_list[_initiator] + round_low_population_spawns
+// (src/spawn_data.F90:859-1101, src/annihilation.f90:294-486, 600-675) on the sorted spawn list.
+// ------------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(256)
+k_annihilate(Params p, int64_t* __restrict__ sp, long long n, const uint64_t* __restrict__ states,
+             int64_t* __restrict__ pops, long long nstates, int* __restrict__ ins_flag, long long* __restrict__ ins_pos) {
+    constexpr int E = W + 2;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ins_flag[i] = 0;
+    uint64_t key[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) key[k] = (uint64_t)sp[i * E + k];
+    if (i > 0) {
+        bool same = true;
+#pragma unroll
+        for (int k = 0; k < W; ++k) same = same && ((uint64_t)sp[(i - 1) * E + k] == key[k]);
+        if (same) return;  // not the head of its segment
+    }
+    long long pop = 0, initiator_pop = 0, events = 0;
+    for (long long j = i; j < n; ++j) {
+        if (j > i) {
+            bool same = true;
+#pragma unroll
+            for (int k = 0; k < W; ++k) same = same && ((uint64_t)sp[j * E + k] == key[k]);
+            if (!same) break;
+        }
+        const long long pj = sp[j * E + W];
+        pop += pj;
+        if (p.initiator) {
+            if (!(sp[j * E + W + 1] & 1)) initiator_pop += pj;
+            else events += (pj < 0) ? -1 : ((pj > 0) ? 1 : 0);
+        }
+    }
+    int flag = 0;
+    if (p.initiator) {
+        const bool sgn_tot = pop >= 0, sgn_ini = initiator_pop >= 0;  // Fortran sign(1,0) = +1
+        const bool keep = (initiator_pop != 0 && sgn_tot == sgn_ini) || ((events < 0 ? -events : events) > 1);
+        flag = keep ? 0 : 1;
+    }
+    if (pop == 0) return;
+    const long long pos = lower_bound_det<W>(states, nstates, key);
+    bool hit = false;
+    if (pos < nstates) {
+        uint64_t f[W];
+        load_det<W>(states + pos * W, f);
+        hit = det_eq<W>(f, key);
+    }
+    if (hit) {
+        const long long cur = pops[pos];
+        if (!p.initiator) pops[pos] = cur + pop;
+        else if (cur != 0) pops[pos] = cur + pop;
+        else if (!flag) pops[pos] = pop;
+        return;
+    }
+    if (p.initiator && flag) return;  // spawned by non-initiators onto an unoccupied determinant
+    if (p.real_amplitudes) {
+        PhiloxStream rng;
+        rng.begin(p.seed, p.cycle, RNG_ROUND_SPAWN, det_hash64<W>(key), 0);
+        pop = stochastic_round(rng, (int64_t)pop, p.real_factor);
+        if (pop == 0) return;
+    }
+    sp[i * E + W] = pop;
+    ins_flag[i] = 1;
+    ins_pos[i] = pos;
+}
+
+// compaction of the surviving new determinants: ins[k] = [f, pop, pos]
+template <int W>
+__global__ void __launch_bounds__(256)
+k_compact_inserts(const int64_t* __restrict__ sp, long long n, const int* __restrict__ ins_flag,
+                  const int* __restrict__ ins_idx, const long long* __restrict__ ins_pos, int64_t* __restrict__ ins) {
+    constexpr int E = W + 2;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !ins_flag[i]) return;
+    const long long k = ins_idx[i];
+#pragma unroll
+    for (int w = 0; w < W; ++w) ins[k * E + w] = sp[i * E + w];
+    ins[k * E + W] = sp[i * E + W];
+    ins[k * E + W + 1] = ins_pos[i];
+}
+
+// insert_new_walker: dat(1) = sc0_ptr(f) - H00 (src/annihilation.f90:820-901)
+template <int W>
+__global__ void __launch_bounds__(256)
+k_sc0(Sys s, double H00, const uint64_t* __restrict__ dets, long long stride_words, long long n, double* __restrict__ out) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint64_t f[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) f[w] = dets[k * stride_words + w];
+    uint8_t occ[HB_MAXNEL];
+    decode_det<W>(f, occ);
+    out[k] = slater_condon0(s, occ) - H00;
+}
+
+// remove_unoccupied_dets, first half (src/annihilation.f90:537-598): stochastic rounding of main-list
+// populations (real amplitudes) and per-tile survivor counts.
+template <int W>
+__global__ void __launch_bounds__(TILE)
+k_round_count(Params p, const uint64_t* __restrict__ states, int64_t* __restrict__ pops, long long nstates,
+              int* __restrict__ tile_keep) {
+    __shared__ int swarp[8];
+    const long long i = (long long)blockIdx.x * TILE + threadIdx.x;
+    int keep = 0;
+    if (i < nstates) {
+        int64_t pop = pops[i];
+        if (p.real_amplitudes) {
+            const int64_t ap = pop < 0 ? -pop : pop;
+            if (pop != 0 && ap < p.real_factor) {
+                uint64_t f[W];
+                load_det<W>(states + i * W, f);
+                PhiloxStream rng;
+                rng.begin(p.seed, p.cycle, RNG_ROUND_MAIN, det_hash64<W>(f), 0);
+                pop = stochastic_round(rng, pop, p.real_factor);
+                pops[i] = pop;
+            }
+        }
+        keep = pop != 0;
+    }
+    int tot;
+    block_excl_scan(keep, swarp, &tot);
+    if (threadIdx.x == 0) tile_keep[blockIdx.x] = tot;
+}
+
+// remove_unoccupied_dets (compaction) + insert_new_walkers (src/annihilation.f90:537-598, 677-818) as ONE
+// out-of-place merge: tile of TILE old states + the new determinants whose insertion point falls in the tile.
+template <int W>
+__global__ void __launch_bounds__(TILE)
+k_merge(const uint64_t* __restrict__ states, const int64_t* __restrict__ pops, const double* __restrict__ dat,
+        long long nstates, const int* __restrict__ tile_off, const int64_t* __restrict__ ins,
+        const double* __restrict__ ins_dat, long long nins, uint64_t* __restrict__ ostates, int64_t* __restrict__ opops,
+        double* __restrict__ odat, long long* __restrict__ part_npart, int ntiles) {
+    constexpr int E = W + 2;
+    __shared__ int swarp[8];
+    __shared__ int skept[TILE + 1];
+    __shared__ long long sk[2];
+    __shared__ long long sred[8];
+    const int tid = threadIdx.x;
+    const long long t0 = (long long)blockIdx.x * TILE;
+    const long long t1 = min(nstates, t0 + TILE);
+    const bool last = (blockIdx.x == ntiles - 1);
+    if (tid < 2) {
+        // inserts with pos in [t0, t1) (last tile: also pos == nstates) are a contiguous range [k_lo, k_hi)
+        const long long target = (tid == 0) ? t0 : t1;
+        long long lo = 0, hi = nins;
+        if (tid == 1 && last) lo = nins;
+        while (lo < hi) {
+            long long mid = (lo + hi) >> 1;
+            if (ins[mid * E + W + 1] < target) lo = mid + 1; else hi = mid;
+        }
+        sk[tid] = lo;
+    }
+    const long long m = t0 + tid;
+    int keep = 0;
+    int64_t pop = 0;
+    if (m < t1) { pop = pops[m]; keep = pop != 0; }
+    int tot;
+    const int kb = block_excl_scan(keep, swarp, &tot);
+    skept[tid] = kb;
+    if (tid == 0) skept[TILE] = tot;
+    __syncthreads();
+    const long long k_lo = sk[0], k_hi = sk[1];
+    const long long ns = k_hi - k_lo;
+    const long long out_base = (long long)tile_off[blockIdx.x] + k_lo;
+    long long npart = 0;
+    if (keep) {
+        // number of new determinants in this tile inserted at or before old state m
+        long long lo = 0, hi = ns;
+        while (lo < hi) {
+            long long mid = (lo + hi) >> 1;
+            if (ins[(k_lo + mid) * E + W + 1] <= m) lo = mid + 1; else hi = mid;
+        }
+        const long long o = out_base + kb + lo;
+        uint64_t f[W];
+        load_det<W>(states + m * W, f);
+        store_det<W>(ostates + o * W, f);
+        opops[o] = pop;
+        odat[o] = dat[m];
+        npart += pop < 0 ? -pop : pop;
+    }
+    for (long long j = tid; j < ns; j += TILE) {
+        const long long k = k_lo + j;
+        const long long pos = ins[k * E + W + 1];
+        const int loc = (int)(pos - t0);  // 0..TILE (TILE only for pos == nstates in the last tile)
+        const long long o = out_base + skept[loc] + j;
+        uint64_t f[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) f[w] = (uint64_t)ins[k * E + w];
+        store_det<W>(ostates + o * W, f);
+        const int64_t ip = ins[k * E + W];
+        opops[o] = ip;
+        odat[o] = ins_dat[k];
+        npart += ip < 0 ? -ip : ip;
+    }
+    npart = warp_sum_ll(npart);
+    if ((tid & 31) == 0) sred[tid >> 5] = npart;
+    __syncthreads();
+    if (tid == 0) {
+        long long t = 0;
+        for (int w = 0; w < TILE / 32; ++w) t += sred[w];
+        part_npart[blockIdx.x] = t;
+    }
+}
+
+__global__ void k_reduce_ll(const long long* __restrict__ in, int n, long long* out) {
+    __shared__ long long sl[32];
+    long long v = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) v += in[i];
+    v = warp_sum_ll(v);
+    if ((threadIdx.x & 31) == 0) sl[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long t = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sl[w];
+        *out = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// System-table kernels: J/K diagonal tables and the heat-bath builder
+// (init_excit_mol_heat_bath, src/excit_gen_heat_bath_mol.F90:14-256; sums in the reference's order)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_build_JK(Sys s, double* J, double* K) {
+    const int nb = s.nbasis;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nb * nb) return;
+    const int i = t / nb + 1, j = t % nb + 1;
+    J[t] = two_body(s, i, j, i, j);
+    K[t] = two_body(s, i, j, j, i);
+}
+
+// ijab_w(b,a,j,i) = |<ij||ab>| for allowed (spin, symmetry, distinct) index quadruples, else 0
+__global__ void k_hb_ijab_w(Sys s, double* __restrict__ w) {
+    const long long nb = s.nbasis;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nb * nb * nb * nb) return;
+    const int b = (int)(t % nb) + 1, a = (int)((t / nb) % nb) + 1, j = (int)((t / (nb * nb)) % nb) + 1,
+              i = (int)(t / (nb * nb * nb)) + 1;
+    double val = 0.0;
+    if (i != j && a != i && a != j) {
+        const int it = min(i, j), jt = max(i, j);
+        const int ij_sym = sym_conj(s, cross_product(s, s.bf_sym[it], s.bf_sym[jt]));
+        const int isymb = sym_conj(s, cross_product(s, ij_sym, s.bf_sym[a]));
+        const bool spin_ok = (s.bf_ms[it] == s.bf_ms[a] && s.bf_ms[jt] == s.bf_ms[b]) ||
+                             (s.bf_ms[it] == s.bf_ms[b] && s.bf_ms[jt] == s.bf_ms[a]);
+        if (spin_ok && s.bf_sym[b] == isymb && b != a && b != i && b != j) {
+            const int at = min(a, b), bt = max(a, b);
+            val = fabs(slater_condon2_excit(s, it, jt, at, bt, false));
+        }
+    }
+    w[t] = val;
+}
+// ijab_tot(a,j,i) = sum_b ijab_w (sequential in b) ; ija_w(a,j,i) is the same sum
+__global__ void k_hb_ijab_tot(int nb_, const double* __restrict__ w, double* __restrict__ tot, double* __restrict__ ija_w) {
+    const long long nb = nb_;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nb * nb * nb) return;
+    double sum = 0.0;
+    const double* row = w + t * nb;
+    for (int b = 0; b < nb; ++b) sum = sum + row[b];
+    tot[t] = sum;
+    ija_w[t] = sum;
+}
+// ija_tot(j,i) = sum_a ija_w (sequential) ; ij_w(j,i) = flat sequential sum over (a,b) of ijab_w
+__global__ void k_hb_ij(int nb_, const double* __restrict__ ijab_w, const double* __restrict__ ija_w,
+                        double* __restrict__ ija_tot, double* __restrict__ ij_w) {
+    const long long nb = nb_;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nb * nb) return;
+    double sum = 0.0;
+    for (int a = 0; a < nb; ++a) sum = sum + ija_w[t * nb + a];
+    ija_tot[t] = sum;
+    double flat = 0.0;
+    const double* base = ijab_w + t * nb * nb;
+    for (long long ab = 0; ab < nb * nb; ++ab) {
+        const double v = base[ab];
+        if (v != 0.0) flat = flat + v;  // the reference only adds allowed terms; adding 0.0 would be identical
+    }
+    ij_w[t] = flat;
+}
+__global__ void k_hb_i(int nb, const double* __restrict__ ij_w, double* __restrict__ i_w) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    double sum = 0.0;
+    for (int j = 0; j < nb; ++j)
+        if (j != i) sum = sum + ij_w[(long long)i * nb + j];
+    i_w[i] = sum;
+}
+// alias tables per row of length nb: rows = nb^2 (ija) or nb^3 (ijab); scratch: 2 ints per element
+__global__ void k_hb_alias(int nb, long long nrows, const double* __restrict__ w, const double* __restrict__ tot,
+                           double* __restrict__ U, int* __restrict__ K, int* __restrict__ scratch) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    if (!(fabs(tot[r]) > 0.0)) return;
+    generate_alias_tables(nb, w + r * nb, tot[r], U + r * nb, K + r * nb, scratch + 2 * r * nb, scratch + 2 * r * nb + nb);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Probe kernels (parity tests through the C ABI)
+// ------------------------------------------------------------------------------------------------
+template <int W>
+__global__ void k_gen_excit_batch(Sys s, Params p, const uint64_t* __restrict__ states, const int64_t* __restrict__ pops,
+                                  const uint32_t* __restrict__ attempt, long long n, const int* __restrict__ proc_map,
+                                  int* __restrict__ iout, double* __restrict__ dout, int64_t* __restrict__ nspawn) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    uint64_t f[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) f[k] = states[t * W + k];
+    uint8_t occ[HB_MAXNEL], su[64];
+    decode_det<W>(f, occ);
+    build_symunocc(s, occ, su);
+    PhiloxStream rng;
+    rng.begin(p.seed, p.cycle, RNG_SPAWN, det_hash64<W>(f), attempt[t]);
+    Gen g;
+    gen_excit<W>(rng, s, p, f, occ, su, g);
+    const int64_t ns = attempt_to_spawn(rng, p, g.hmatel, g.pgen, pops[t]);
+    int own = -1;
+    if (g.allowed) {
+        uint64_t child[W];
+#pragma unroll
+        for (int k = 0; k < W; ++k) child[k] = f[k];
+        child[(g.from1 - 1) >> 6] &= ~(1ull << ((g.from1 - 1) & 63));
+        child[(g.to1 - 1) >> 6] |= (1ull << ((g.to1 - 1) & 63));
+        if (g.nexcit == 2) {
+            child[(g.from2 - 1) >> 6] &= ~(1ull << ((g.from2 - 1) & 63));
+            child[(g.to2 - 1) >> 6] |= (1ull << ((g.to2 - 1) & 63));
+        }
+        own = proc_map[owner_slot(child, s.nbasis, p.hash_seed, p.nprocs, p.nslots)];
+    }
+    int* io = iout + t * 8;
+    io[0] = g.nexcit; io[1] = g.from1; io[2] = g.from2; io[3] = g.to1; io[4] = g.to2; io[5] = g.perm; io[6] = g.allowed;
+    io[7] = own;
+    dout[t * 2] = g.pgen; dout[t * 2 + 1] = g.hmatel;
+    nspawn[t] = ns;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Engine
+// ------------------------------------------------------------------------------------------------
+struct hb200_engine {
+    hb200_config cfg;
+    int W = 1, E = 3;
+    cudaStream_t stream = nullptr;
+    Sys sys;
+    Params par;
+    bool have_sys = false, have_hb = false;
+    // owned device buffers for system tables
+    std::vector<void*> owned;
+    int* d_proc_map = nullptr;
+    // main list (double buffered)
+    uint64_t* d_states[2] = {nullptr, nullptr};
+    int64_t* d_pops[2] = {nullptr, nullptr};
+    double* d_dat[2] = {nullptr, nullptr};
+    int cur = 0;
+    long long nstates = 0;
+    long long nparticles_enc = 0;  // sum |pop| (encoded) of the current list
+    // spawn store
+    int64_t* d_spawn[2] = {nullptr, nullptr};
+    int sp_cur = 0;      // buffer holding the current stage's list
+    long long sp_n = 0;  // number of elements in it (contiguous from 0) after comm
+    bool sp_blocked = true;  // true: still partitioned in per-destination blocks (before comm)
+    long long block_size = 0;
+    unsigned long long* d_head = nullptr;
+    std::vector<unsigned long long> h_head;
+    int* d_err = nullptr;
+    // scratch
+    SpawnPartials* d_partials = nullptr;
+    long long max_tiles = 0;
+    CycleStats* d_stats = nullptr;
+    unsigned* d_hist = nullptr;
+    long long hist_cap = 0;
+    int* d_ins_flag = nullptr;
+    int* d_ins_idx = nullptr;
+    long long* d_ins_pos = nullptr;
+    double* d_ins_dat = nullptr;
+    int* d_tile_keep = nullptr;
+    int* d_tile_off = nullptr;
+    int* d_scan_l1 = nullptr;
+    int* d_scan_l1o = nullptr;
+    int* d_total = nullptr;   // [4] small ints
+    long long* d_part_ll = nullptr;
+    long long* d_ll = nullptr;  // [4]
+    // NCCL
+    ncclComm_t comm = nullptr;
+    long long* d_counts = nullptr;  // [nprocs*nprocs]
+    // timing / counters
+    cudaEvent_t ev[6];
+    double ms[8] = {0};
+    long long launches = 0, spawn_launches = 0;
+};
+
+template <class T>
+static int dalloc(hb200_engine* e, T** p, size_t n) {
+    void* q = nullptr;
+    CK(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
+    *p = (T*)q;
+    e->owned.push_back(q);
+    return 0;
+}
+template <class T>
+static int dupload(hb200_engine* e, const T** dst, const T* src, size_t n) {
+    T* q = nullptr;
+    if (dalloc(e, &q, n)) return 1;
+    if (n) CK(cudaMemcpy(q, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    *dst = q;
+    return 0;
+}
+
+static size_t spawn_smem_bytes(const hb200_engine* e) {
+    const int W = e->W;
+    const int nsu = (e->cfg.excit_gen == HB200_EXCIT_GEN_RENORM) ? 2 * e->sys.nsym_tot : 0;
+    size_t b = 0;
+    b += (size_t)TILE * W * 8;  // sf
+    b += (size_t)TILE * 8;      // shash
+    b += (size_t)TILE * 8;      // spop
+    b += (size_t)(TILE + 1 + 8 + ((TILE + 1 + 8) & 1)) * 4;  // sscan + swarp (+pad to 8 bytes)
+    b += 40 * 8;                // sred
+    b += TILE;                  // sflag
+    b += (size_t)TILE * e->sys.nel;
+    b += (size_t)TILE * nsu;
+    return (b + 15) & ~(size_t)15;
+}
+
+extern "C" {
+
+const char* hb200_last_error(void) { return g_err.c_str(); }
+
+hb200_engine* hb200_create(const hb200_config* cfg) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        g_err = "hb200_create: no CUDA device (the engine has no CPU fallback)";
+        return nullptr;
+    }
+    if (cfg->nel > HB_MAXNEL || cfg->nbasis > 64 * HB_MAXW || cfg->nbasis > 255) {
+        g_err = "hb200_create: nel/nbasis beyond compiled limits (HB_MAXNEL, HB_MAXW)";
+        return nullptr;
+    }
+    hb200_engine* e = new hb200_engine();
+    e->cfg = *cfg;
+    e->W = (cfg->nbasis + 63) / 64;
+    e->E = e->W + 2;
+    auto fail = [&](const char* what) -> hb200_engine* {
+        if (g_err.empty()) g_err = what;
+        hb200_destroy(e);
+        return nullptr;
+    };
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return fail("cudaSetDevice failed");
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return fail("stream");
+    for (int i = 0; i < 6; ++i) cudaEventCreate(&e->ev[i]);
+    memset(&e->sys, 0, sizeof(Sys));
+    memset(&e->par, 0, sizeof(Params));
+    Params& p = e->par;
+    p.excit_gen = cfg->excit_gen;
+    p.pattempt_single = cfg->pattempt_single;
+    p.pattempt_double = cfg->pattempt_double;
+    p.real_amplitudes = cfg->real_amplitudes;
+    p.real_factor = cfg->real_amplitudes ? (1ll << 31) : 1;  // particle_t_utils.f90 (POP_SIZE=64)
+    {
+        double c = cfg->real_amplitudes ? cfg->spawn_cutoff : 0.0;
+        p.spawn_cutoff = (int64_t)ceil(c * (double)p.real_factor);  // src/spawn_data.F90:215
+    }
+    p.initiator = cfg->initiator_approx;
+    p.initiator_pop = cfg->initiator_pop;
+    p.trunc_level = cfg->trunc_level;
+    p.seed = cfg->rng_seed;
+    p.hash_seed = (uint32_t)cfg->hash_seed;
+    p.nprocs = std::max(1, cfg->nprocs);
+    p.iproc = cfg->iproc;
+    p.nslots = std::max(1, cfg->nslots);
+    const long long cap = cfg->walker_length;
+    long long scap = cfg->spawned_walker_length;
+    if (scap % p.nprocs != 0) scap = ((scap + p.nprocs - 1) / p.nprocs) * p.nprocs;  // src/qmc.F90:1461-1468
+    e->cfg.spawned_walker_length = scap;
+    e->block_size = scap / p.nprocs;
+    const int W = e->W, E = e->E;
+    for (int b = 0; b < 2; ++b) {
+        if (dalloc(e, &e->d_states[b], (size_t)cap * W)) return fail("alloc states");
+        if (dalloc(e, &e->d_pops[b], (size_t)cap)) return fail("alloc pops");
+        if (dalloc(e, &e->d_dat[b], (size_t)cap)) return fail("alloc dat");
+        if (dalloc(e, &e->d_spawn[b], (size_t)scap * E)) return fail("alloc spawn");
+    }
+    e->max_tiles = (cap + TILE - 1) / TILE + 1;
+    if (dalloc(e, &e->d_head, (size_t)p.nprocs)) return fail("alloc");
+    e->h_head.assign(p.nprocs, 0);
+    if (dalloc(e, &e->d_err, 4)) return fail("alloc");
+    if (dalloc(e, &e->d_partials, (size_t)e->max_tiles)) return fail("alloc");
+    if (dalloc(e, &e->d_stats, 1)) return fail("alloc");
+    e->hist_cap = 256ll * ((scap + 2047) / 2048 + 1);
+    if (dalloc(e, &e->d_hist, (size_t)e->hist_cap)) return fail("alloc");
+    if (dalloc(e, &e->d_ins_flag, (size_t)scap)) return fail("alloc");
+    if (dalloc(e, &e->d_ins_idx, (size_t)scap)) return fail("alloc");
+    if (dalloc(e, &e->d_ins_pos, (size_t)scap)) return fail("alloc");
+    if (dalloc(e, &e->d_ins_dat, (size_t)scap)) return fail("alloc");
+    if (dalloc(e, &e->d_tile_keep, (size_t)e->max_tiles)) return fail("alloc");
+    if (dalloc(e, &e->d_tile_off, (size_t)e->max_tiles)) return fail("alloc");
+    const long long l1 = std::max(scap, e->max_tiles) / SCAN_BLOCK + 2;
+    if (dalloc(e, &e->d_scan_l1, (size_t)l1)) return fail("alloc");
+    if (dalloc(e, &e->d_scan_l1o, (size_t)l1)) return fail("alloc");
+    if (dalloc(e, &e->d_total, 4)) return fail("alloc");
+    if (dalloc(e, &e->d_part_ll, (size_t)e->max_tiles)) return fail("alloc");
+    if (dalloc(e, &e->d_ll, 4)) return fail("alloc");
+    if (dalloc(e, &e->d_counts, (size_t)p.nprocs * p.nprocs)) return fail("alloc");
+    {
+        std::vector<int> map((size_t)p.nprocs * p.nslots);
+        for (size_t i = 0; i < map.size(); ++i) map[i] = (int)(i % p.nprocs);  // src/load_balancing.F90:170
+        if (dalloc(e, &e->d_proc_map, map.size())) return fail("alloc");
+        if (cudaMemcpy(e->d_proc_map, map.data(), map.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess)
+            return fail("memcpy proc_map");
+    }
+    if (cudaMemset(e->d_err, 0, 4 * sizeof(int)) != cudaSuccess) return fail("memset");
+    return e;
+}
+
+void hb200_destroy(hb200_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    if (e->comm) ncclCommDestroy(e->comm);
+    for (void* q : e->owned) cudaFree(q);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int hb200_set_system_read_in(hb200_engine* e, const hb200_system_read_in* in) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (in->nbasis != e->cfg.nbasis || in->nel != e->cfg.nel) FAIL("set_system: nbasis/nel differ from hb200_create");
+    Sys& s = e->sys;
+    s.nbasis = in->nbasis; s.nel = in->nel; s.W = e->W;
+    s.nsym_tot = in->nsym_tot; s.sym0 = in->sym0; s.sym_max = in->sym_max; s.pg_mask = in->pg_mask;
+    s.Lz_mask = in->Lz_mask; s.Lz_offset = in->Lz_offset; s.gamma_sym = in->gamma_sym; s.uhf = in->uhf;
+    s.nvirt = in->nvirt; s.nvirt_alpha = in->nvirt_alpha; s.nvirt_beta = in->nvirt_beta; s.max_nbss = in->max_nbss;
+    s.Ecore = in->Ecore;
+    if (2 * s.nsym_tot > 64) FAIL("set_system: too many irreps for the symunocc scratch");
+    const int nb = s.nbasis;
+    std::vector<uint8_t> sym(nb + 1, 0);
+    std::vector<int8_t> ms(nb + 1, 0);
+    std::vector<uint16_t> sp(nb + 1, 0);
+    for (int i = 1; i <= nb; ++i) { sym[i] = (uint8_t)in->bf_sym[i]; ms[i] = (int8_t)in->bf_ms[i]; sp[i] = (uint16_t)in->bf_spatial[i]; }
+    if (dupload(e, &s.bf_sym, sym.data(), sym.size())) return 1;
+    if (dupload(e, &s.bf_ms, ms.data(), ms.size())) return 1;
+    if (dupload(e, &s.bf_spatial, sp.data(), sp.size())) return 1;
+    if (dupload(e, &s.nbss, in->nbasis_sym_spin, (size_t)2 * s.nsym_tot)) return 1;
+    if (dupload(e, &s.ssbf, in->sym_spin_basis_fns, (size_t)s.max_nbss * 2 * s.nsym_tot)) return 1;
+    if (dupload(e, &s.h1, in->one_body, (size_t)nb * nb)) return 1;
+    for (int c = 0; c < (s.uhf ? 4 : 1); ++c)
+        if (dupload(e, &s.v2[c], in->two_body[c], (size_t)in->nintgrls)) return 1;
+    double *J = nullptr, *K = nullptr;
+    if (dalloc(e, &J, (size_t)nb * nb) || dalloc(e, &K, (size_t)nb * nb)) return 1;
+    k_build_JK<<<(nb * nb + 255) / 256, 256, 0, e->stream>>>(s, J, K);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+    s.Jd = J; s.Kd = K;
+    e->have_sys = true;
+    return 0;
+}
+
+int hb200_build_heat_bath(hb200_engine* e) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (!e->have_sys) FAIL("build_heat_bath: system not set");
+    Sys& s = e->sys;
+    const long long nb = s.nbasis;
+    const long long n2 = nb * nb, n3 = n2 * nb, n4 = n3 * nb;
+    double *i_w, *ij_w, *ija_w, *ija_U, *ija_tot, *ijab_w, *ijab_U, *ijab_tot;
+    int *ija_K, *ijab_K, *scratch;
+    if (dalloc(e, &i_w, nb) || dalloc(e, &ij_w, n2) || dalloc(e, &ija_w, n3) || dalloc(e, &ija_U, n3) ||
+        dalloc(e, &ija_K, n3) || dalloc(e, &ija_tot, n2) || dalloc(e, &ijab_w, n4) || dalloc(e, &ijab_U, n4) ||
+        dalloc(e, &ijab_K, n4) || dalloc(e, &ijab_tot, n3))
+        return 1;
+    void* sc = nullptr;
+    CK(cudaMalloc(&sc, (size_t)2 * n4 * sizeof(int)));
+    scratch = (int*)sc;
+    cudaStream_t st = e->stream;
+    CK(cudaMemsetAsync(ija_U, 0, n3 * sizeof(double), st));
+    CK(cudaMemsetAsync(ija_K, 0, n3 * sizeof(int), st));
+    CK(cudaMemsetAsync(ijab_U, 0, n4 * sizeof(double), st));
+    CK(cudaMemsetAsync(ijab_K, 0, n4 * sizeof(int), st));
+    k_hb_ijab_w<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(s, ijab_w);
+    k_hb_ijab_tot<<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>((int)nb, ijab_w, ijab_tot, ija_w);
+    k_hb_ij<<<(unsigned)((n2 + 127) / 128), 128, 0, st>>>((int)nb, ijab_w, ija_w, ija_tot, ij_w);
+    k_hb_i<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>((int)nb, ij_w, i_w);
+    k_hb_alias<<<(unsigned)((n2 + 127) / 128), 128, 0, st>>>((int)nb, n2, ija_w, ija_tot, ija_U, ija_K, scratch);
+    k_hb_alias<<<(unsigned)((n3 + 127) / 128), 128, 0, st>>>((int)nb, n3, ijab_w, ijab_tot, ijab_U, ijab_K, scratch);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    CK(cudaFree(sc));
+    s.hb_i_w = i_w; s.hb_ij_w = ij_w; s.hb_ija_w = ija_w; s.hb_ija_U = ija_U; s.hb_ija_K = ija_K; s.hb_ija_tot = ija_tot;
+    s.hb_ijab_w = ijab_w; s.hb_ijab_U = ijab_U; s.hb_ijab_K = ijab_K; s.hb_ijab_tot = ijab_tot;
+    e->have_hb = true;
+    return 0;
+}
+
+int hb200_download_heat_bath(hb200_engine* e, int which, void* out, int64_t n) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (!e->have_hb) FAIL("heat-bath tables not built");
+    const Sys& s = e->sys;
+    const void* src[10] = {s.hb_i_w, s.hb_ij_w, s.hb_ija_w, s.hb_ija_U, s.hb_ija_tot, s.hb_ijab_w, s.hb_ijab_U,
+                           s.hb_ijab_tot, s.hb_ija_K, s.hb_ijab_K};
+    if (which < 0 || which > 9) FAIL("download_heat_bath: bad table id");
+    const size_t esz = which >= 8 ? sizeof(int) : sizeof(double);
+    CK(cudaMemcpy(out, src[which], (size_t)n * esz, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int hb200_set_reference(hb200_engine* e, const uint64_t* f0, double H00) {
+    for (int k = 0; k < HB_MAXW; ++k) e->par.f0[k] = (k < e->W) ? f0[k] : 0;
+    e->par.H00 = H00;
+    return 0;
+}
+
+int hb200_set_proc_map(hb200_engine* e, const int32_t* map, int32_t n) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (n != e->par.nprocs * e->par.nslots) FAIL("set_proc_map: wrong length");
+    CK(cudaMemcpy(e->d_proc_map, map, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int hb200_upload_psips(hb200_engine* e, const uint64_t* states, const int64_t* pops, const double* dat, int64_t n) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (n > e->cfg.walker_length) FAIL("upload_psips: more states than walker_length");
+    const int c = e->cur;
+    if (n) {
+        CK(cudaMemcpy(e->d_states[c], states, (size_t)n * e->W * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(e->d_pops[c], pops, (size_t)n * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(e->d_dat[c], dat, (size_t)n * 8, cudaMemcpyHostToDevice));
+    }
+    e->nstates = n;
+    long long s = 0;
+    for (int64_t i = 0; i < n; ++i) s += pops[i] < 0 ? -pops[i] : pops[i];
+    e->nparticles_enc = s;
+    return 0;
+}
+
+int hb200_download_psips(hb200_engine* e, uint64_t* states, int64_t* pops, double* dat, int64_t capacity, int64_t* nstates) {
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaStreamSynchronize(e->stream));
+    const long long n = e->nstates;
+    *nstates = n;
+    if (n > capacity) FAIL("download_psips: capacity too small");
+    const int c = e->cur;
+    if (n) {
+        CK(cudaMemcpy(states, e->d_states[c], (size_t)n * e->W * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(pops, e->d_pops[c], (size_t)n * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(dat, e->d_dat[c], (size_t)n * 8, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+int64_t hb200_nstates(hb200_engine* e) { return e->nstates; }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// stage drivers
+// ------------------------------------------------------------------------------------------------
+#define DISPATCH_W(e, ...)                                    \
+    switch ((e)->W) {                                         \
+        case 1: { constexpr int WW = 1; __VA_ARGS__; } break; \
+        case 2: { constexpr int WW = 2; __VA_ARGS__; } break; \
+        case 3: { constexpr int WW = 3; __VA_ARGS__; } break; \
+        default: { constexpr int WW = 4; __VA_ARGS__; } break; \
+    }
+
+static int stage_spawn_death(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, CycleStats* hst) {
+    Params& p = e->par;
+    p.tau = in->tau; p.shift = in->shift; p.proj_energy_old = in->proj_energy_old; p.cycle = cycle;
+    cudaStream_t st = e->stream;
+    CK(cudaMemsetAsync(e->d_head, 0, sizeof(unsigned long long) * p.nprocs, st));
+    const long long n = e->nstates;
+    const int ntiles = (int)((n + TILE - 1) / TILE);
+    if (ntiles > 0) {
+        const size_t smem = spawn_smem_bytes(e);
+        const int c = e->cur;
+        DISPATCH_W(e, {
+            static bool attr_set[5] = {false, false, false, false, false};
+            if (!attr_set[WW]) {
+                CK(cudaFuncSetAttribute(k_spawn_death<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+                attr_set[WW] = true;
+            }
+            k_spawn_death<WW><<<ntiles, TILE, smem, st>>>(e->sys, p, e->d_states[c], e->d_pops[c], e->d_dat[c], n,
+                                                           e->d_spawn[0], e->d_head, e->block_size, e->d_proc_map,
+                                                           e->d_partials, e->d_err);
+        });
+        CK(cudaGetLastError());
+        e->launches++; e->spawn_launches++;
+    }
+    k_reduce_partials<<<1, 1024, 0, st>>>(e->d_partials, ntiles, e->d_stats);
+    CK(cudaGetLastError());
+    e->launches++;
+    CK(cudaMemcpyAsync(e->h_head.data(), e->d_head, sizeof(unsigned long long) * p.nprocs, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hst, e->d_stats, sizeof(CycleStats), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int d = 0; d < p.nprocs; ++d)
+        if ((long long)e->h_head[d] > e->block_size) e->h_head[d] = (unsigned long long)e->block_size;  // overflow: dropped
+    e->sp_cur = 0;
+    e->sp_blocked = true;
+    e->sp_n = (p.nprocs == 1) ? (long long)e->h_head[0] : 0;
+    if (p.nprocs == 1) e->sp_blocked = false;
+    return 0;
+}
+
+static int stage_comm(hb200_engine* e) {
+    Params& p = e->par;
+    if (p.nprocs == 1) { e->sp_blocked = false; e->sp_n = (long long)e->h_head[0]; e->sp_cur = 0; return 0; }
+    if (!e->comm) FAIL("comm_spawn: nprocs > 1 but hb200_comm_init was not called");
+    cudaStream_t st = e->stream;
+    const int np = p.nprocs, me = p.iproc, E = e->E;
+    // MPI_Alltoall of the counts (src/spawn_data.F90:693) as an all-gather of each rank's row
+    std::vector<long long> row(np);
+    for (int d = 0; d < np; ++d) row[d] = (long long)e->h_head[d];
+    CK(cudaMemcpyAsync(e->d_counts + (size_t)me * np, row.data(), sizeof(long long) * np, cudaMemcpyHostToDevice, st));
+    NCK(ncclAllGather(e->d_counts + (size_t)me * np, e->d_counts, np, ncclInt64, e->comm, st));
+    std::vector<long long> counts((size_t)np * np);
+    CK(cudaMemcpyAsync(counts.data(), e->d_counts, sizeof(long long) * np * np, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    // MPI_Alltoallv (src/spawn_data.F90:721): receive blocks ordered by source rank
+    long long off = 0;
+    NCK(ncclGroupStart());
+    for (int r = 0; r < np; ++r) {
+        const long long nsend = counts[(size_t)me * np + r], nrecv = counts[(size_t)r * np + me];
+        if (r == me) {
+            if (nsend) CK(cudaMemcpyAsync(e->d_spawn[1] + off * E, e->d_spawn[0] + (long long)r * e->block_size * E,
+                                          (size_t)nsend * E * 8, cudaMemcpyDeviceToDevice, st));
+        } else {
+            if (nsend) NCK(ncclSend(e->d_spawn[0] + (long long)r * e->block_size * E, (size_t)nsend * E, ncclInt64, r, e->comm, st));
+            if (nrecv) NCK(ncclRecv(e->d_spawn[1] + off * E, (size_t)nrecv * E, ncclInt64, r, e->comm, st));
+        }
+        off += nrecv;
+    }
+    NCK(ncclGroupEnd());
+    if (off > e->cfg.spawned_walker_length) FAIL("comm_spawn: received more than spawned_walker_length");
+    e->sp_cur = 1;
+    e->sp_n = off;
+    e->sp_blocked = false;
+    return 0;
+}
+
+static int stage_sort(hb200_engine* e) {
+    const long long n = e->sp_n;
+    if (n <= 1) return 0;
+    cudaStream_t st = e->stream;
+    const int E = e->E;
+    const long long chunk = std::max<long long>(2048, ((n + 1183) / 1184 + SORT_THREADS - 1) / SORT_THREADS * SORT_THREADS);
+    const int nblk = (int)((n + chunk - 1) / chunk);
+    if (256ll * nblk > e->hist_cap) FAIL("sort: histogram scratch too small");
+    const int npass = (e->cfg.nbasis + 7) / 8;
+    for (int ps = 0; ps < npass; ++ps) {
+        const int word = (8 * ps) / 64, shift = (8 * ps) % 64;
+        const int64_t* src = e->d_spawn[e->sp_cur];
+        int64_t* dst = e->d_spawn[e->sp_cur ^ 1];
+        switch (E) {
+            case 3: k_radix_hist<3><<<nblk, SORT_THREADS, 0, st>>>(src, n, word, shift, e->d_hist, nblk, chunk); break;
+            case 4: k_radix_hist<4><<<nblk, SORT_THREADS, 0, st>>>(src, n, word, shift, e->d_hist, nblk, chunk); break;
+            case 5: k_radix_hist<5><<<nblk, SORT_THREADS, 0, st>>>(src, n, word, shift, e->d_hist, nblk, chunk); break;
+            default: k_radix_hist<6><<<nblk, SORT_THREADS, 0, st>>>(src, n, word, shift, e->d_hist, nblk, chunk); break;
+        }
+        k_scan_u32_single<<<1, 1024, 0, st>>>(e->d_hist, 256ll * nblk);
+        switch (E) {
+            case 3: k_radix_scatter<3><<<nblk, SORT_THREADS, 0, st>>>(src, dst, n, word, shift, e->d_hist, nblk, chunk); break;
+            case 4: k_radix_scatter<4><<<nblk, SORT_THREADS, 0, st>>>(src, dst, n, word, shift, e->d_hist, nblk, chunk); break;
+            case 5: k_radix_scatter<5><<<nblk, SORT_THREADS, 0, st>>>(src, dst, n, word, shift, e->d_hist, nblk, chunk); break;
+            default: k_radix_scatter<6><<<nblk, SORT_THREADS, 0, st>>>(src, dst, n, word, shift, e->d_hist, nblk, chunk); break;
+        }
+        CK(cudaGetLastError());
+        e->launches += 3;
+        e->sp_cur ^= 1;
+    }
+    return 0;
+}
+
+// exclusive scan of n ints (d_in -> d_out), total to d_total[slot]
+static int device_scan(hb200_engine* e, const int* d_in, int* d_out, long long n, int slot) {
+    cudaStream_t st = e->stream;
+    if (n <= 0) { CK(cudaMemsetAsync(e->d_total + slot, 0, sizeof(int), st)); return 0; }
+    if (n <= 4 * SCAN_BLOCK) {
+        k_scan_small<<<1, 1024, 0, st>>>(d_in, d_out, n, e->d_total + slot);
+        e->launches++;
+    } else {
+        const long long nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+        k_scan_block<<<(unsigned)nb, TILE, 0, st>>>(d_in, d_out, n, e->d_scan_l1);
+        k_scan_small<<<1, 1024, 0, st>>>(e->d_scan_l1, e->d_scan_l1o, nb, e->d_total + slot);
+        k_scan_add<<<(unsigned)nb, TILE, 0, st>>>(d_out, n, e->d_scan_l1o);
+        e->launches += 3;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int stage_annihilate_main(hb200_engine* e, uint32_t cycle, CycleStats* hst) {
+    Params& p = e->par;
+    p.cycle = cycle;
+    cudaStream_t st = e->stream;
+    const long long n = e->sp_n, ns = e->nstates;
+    const int c = e->cur, o = c ^ 1;
+    int64_t* sp = e->d_spawn[e->sp_cur];
+    int64_t* ins = e->d_spawn[e->sp_cur ^ 1];
+    int h_tot[2] = {0, 0};
+    if (n > 0) {
+        DISPATCH_W(e, k_annihilate<WW><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, sp, n, e->d_states[c], e->d_pops[c], ns,
+                                                                                   e->d_ins_flag, e->d_ins_pos));
+        CK(cudaGetLastError());
+        e->launches++;
+        if (device_scan(e, e->d_ins_flag, e->d_ins_idx, n, 0)) return 1;
+        DISPATCH_W(e, k_compact_inserts<WW><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sp, n, e->d_ins_flag, e->d_ins_idx,
+                                                                                        e->d_ins_pos, ins));
+        CK(cudaGetLastError());
+        e->launches++;
+    } else {
+        CK(cudaMemsetAsync(e->d_total, 0, sizeof(int), st));
+    }
+    const int ntiles = std::max<int>(1, (int)((ns + TILE - 1) / TILE));
+    DISPATCH_W(e, k_round_count<WW><<<ntiles, TILE, 0, st>>>(p, e->d_states[c], e->d_pops[c], ns, e->d_tile_keep));
+    CK(cudaGetLastError());
+    e->launches++;
+    if (device_scan(e, e->d_tile_keep, e->d_tile_off, ntiles, 1)) return 1;
+    CK(cudaMemcpyAsync(h_tot, e->d_total, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    long long nins = h_tot[0];
+    const long long nkept = h_tot[1];
+    // insert_new_walkers capacity check (src/annihilation.f90:750-771)
+    if (nkept + nins > e->cfg.walker_length) {
+        int one = 1;
+        CK(cudaMemcpyAsync(e->d_err + 1, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+        nins = 0;
+    }
+    if (nins > 0) {
+        DISPATCH_W(e, k_sc0<WW><<<(unsigned)((nins + 255) / 256), 256, 0, st>>>(e->sys, p.H00, (const uint64_t*)ins, e->E, nins,
+                                                                               e->d_ins_dat));
+        CK(cudaGetLastError());
+        e->launches++;
+    }
+    DISPATCH_W(e, k_merge<WW><<<ntiles, TILE, 0, st>>>(e->d_states[c], e->d_pops[c], e->d_dat[c], ns, e->d_tile_off, ins,
+                                                        e->d_ins_dat, nins, e->d_states[o], e->d_pops[o], e->d_dat[o],
+                                                        e->d_part_ll, ntiles));
+    CK(cudaGetLastError());
+    k_reduce_ll<<<1, 1024, 0, st>>>(e->d_part_ll, ntiles, e->d_ll);
+    CK(cudaGetLastError());
+    e->launches += 2;
+    long long npart = 0;
+    CK(cudaMemcpyAsync(&npart, e->d_ll, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    e->cur = o;
+    e->nstates = nkept + nins;
+    e->nparticles_enc = npart;
+    hst->nkept = nkept;
+    hst->npart_new = npart;
+    e->sp_n = 0;
+    return 0;
+}
+
+static void fill_out(hb200_engine* e, hb200_iter_out* out, const CycleStats& st, long long nattempts) {
+    out->nparticles = (double)e->nparticles_enc / (double)e->par.real_factor;
+    out->nstates = e->nstates;
+    out->ndeath = st.ndeath;
+    out->nattempts = nattempts;
+    int herr[2] = {0, 0};
+    cudaMemcpy(herr, e->d_err, 2 * sizeof(int), cudaMemcpyDeviceToHost);
+    out->spawn_error = herr[0];
+    out->psip_error = herr[1];
+}
+
+extern "C" {
+
+int hb200_spawn_death(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, hb200_iter_out* out) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (!e->have_sys) FAIL("spawn_death: system not set");
+    if (e->cfg.excit_gen == HB200_EXCIT_GEN_HEAT_BATH && !e->have_hb) FAIL("spawn_death: heat-bath tables not built");
+    CycleStats st;
+    memset(&st, 0, sizeof(st));
+    const long long nattempts = llround(2.0 * ((double)e->nparticles_enc / (double)e->par.real_factor));
+    if (stage_spawn_death(e, in, cycle, &st)) return 1;
+    e->nparticles_enc = st.npart_after_death;
+    if (out) {
+        memset(out, 0, sizeof(*out));
+        out->proj_energy = st.pe; out->D0_population = st.d0;
+        long long ev = 0;
+        for (int d = 0; d < e->par.nprocs; ++d) ev += (long long)e->h_head[d];
+        out->nspawn_events = ev;
+        out->nattempts_spawn = st.nattempts_spawn;
+        fill_out(e, out, st, nattempts);
+    }
+    return 0;
+}
+
+int hb200_comm_spawn(hb200_engine* e) {
+    CK(cudaSetDevice(e->cfg.device));
+    return stage_comm(e);
+}
+
+int hb200_annihilate_spawn(hb200_engine* e) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (e->sp_blocked) FAIL("annihilate_spawn: call hb200_comm_spawn first");
+    if (stage_sort(e)) return 1;
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int hb200_annihilate_main(hb200_engine* e, uint32_t cycle, hb200_iter_out* out) {
+    CK(cudaSetDevice(e->cfg.device));
+    CycleStats st;
+    memset(&st, 0, sizeof(st));
+    if (stage_annihilate_main(e, cycle, &st)) return 1;
+    if (out) fill_out(e, out, st, 0);
+    return 0;
+}
+
+int hb200_download_spawn(hb200_engine* e, int64_t* sdata, int64_t capacity, int64_t* n) {
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaStreamSynchronize(e->stream));
+    const int E = e->E;
+    if (e->sp_blocked) {
+        // still partitioned by destination: concatenate the blocks
+        long long tot = 0;
+        for (int d = 0; d < e->par.nprocs; ++d) tot += (long long)e->h_head[d];
+        *n = tot;
+        if (tot > capacity) FAIL("download_spawn: capacity too small");
+        long long off = 0;
+        for (int d = 0; d < e->par.nprocs; ++d) {
+            const long long c = (long long)e->h_head[d];
+            if (c) CK(cudaMemcpy(sdata + off * E, e->d_spawn[0] + (long long)d * e->block_size * E, (size_t)c * E * 8,
+                                 cudaMemcpyDeviceToHost));
+            off += c;
+        }
+        return 0;
+    }
+    *n = e->sp_n;
+    if (e->sp_n > capacity) FAIL("download_spawn: capacity too small");
+    if (e->sp_n) CK(cudaMemcpy(sdata, e->d_spawn[e->sp_cur], (size_t)e->sp_n * E * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int hb200_upload_spawn(hb200_engine* e, const int64_t* sdata, int64_t n) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (n > e->cfg.spawned_walker_length) FAIL("upload_spawn: too many elements");
+    if (n) CK(cudaMemcpy(e->d_spawn[0], sdata, (size_t)n * e->E * 8, cudaMemcpyHostToDevice));
+    e->sp_cur = 0; e->sp_n = n; e->sp_blocked = false;
+    return 0;
+}
+
+int hb200_iterate(hb200_engine* e, int32_t ncycles, const hb200_iter_in* in, hb200_iter_out* out) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (!e->have_sys) FAIL("iterate: system not set");
+    if (e->cfg.excit_gen == HB200_EXCIT_GEN_HEAT_BATH && !e->have_hb) FAIL("iterate: heat-bath tables not built");
+    memset(out, 0, sizeof(*out));
+    cudaStream_t st = e->stream;
+    float acc[4] = {0, 0, 0, 0};
+    CycleStats cs;
+    memset(&cs, 0, sizeof(cs));
+    long long nattempts = 0;
+    CK(cudaEventRecord(e->ev[5], st));
+    for (int c = 0; c < ncycles; ++c) {
+        const uint32_t cycle = in->first_cycle + (uint32_t)c;
+        // init_mc_cycle (src/qmc_common.F90:950-1017)
+        nattempts = llround(2.0 * ((double)e->nparticles_enc / (double)e->par.real_factor));
+        CK(cudaEventRecord(e->ev[0], st));
+        if (stage_spawn_death(e, in, cycle, &cs)) return 1;
+        CK(cudaEventRecord(e->ev[1], st));
+        out->proj_energy += cs.pe;
+        out->D0_population += cs.d0;
+        out->nattempts_spawn += cs.nattempts_spawn;
+        long long ev = 0;
+        for (int d = 0; d < e->par.nprocs; ++d) ev += (long long)e->h_head[d];
+        out->nspawn_events = ev;
+        if (stage_comm(e)) return 1;
+        CK(cudaEventRecord(e->ev[2], st));
+        if (stage_sort(e)) return 1;
+        CK(cudaEventRecord(e->ev[3], st));
+        if (stage_annihilate_main(e, cycle, &cs)) return 1;
+        CK(cudaEventRecord(e->ev[4], st));
+        CK(cudaEventSynchronize(e->ev[4]));
+        for (int k = 0; k < 4; ++k) {
+            float t = 0;
+            cudaEventElapsedTime(&t, e->ev[k], e->ev[k + 1]);
+            acc[k] += t;
+        }
+        // end_mc_cycle / spawning_rate (src/qmc_common.F90:1240-1304)
+        const double ndeath_real = (double)cs.ndeath / (double)e->par.real_factor;
+        if (nattempts > 0) out->rspawn += ((double)ev + ndeath_real) / (double)nattempts;
+    }
+    float tot = 0;
+    cudaEventElapsedTime(&tot, e->ev[5], e->ev[4]);
+    for (int k = 0; k < 4; ++k) e->ms[k] = acc[k];
+    e->ms[4] = tot;
+    fill_out(e, out, cs, nattempts);
+    return 0;
+}
+
+int hb200_sc0_batch(hb200_engine* e, const uint64_t* states, int64_t n, double* out) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (!e->have_sys) FAIL("sc0_batch: system not set");
+    if (n == 0) return 0;
+    uint64_t* d_f = nullptr;
+    double* d_o = nullptr;
+    CK(cudaMalloc((void**)&d_f, (size_t)n * e->W * 8));
+    CK(cudaMalloc((void**)&d_o, (size_t)n * 8));
+    CK(cudaMemcpy(d_f, states, (size_t)n * e->W * 8, cudaMemcpyHostToDevice));
+    DISPATCH_W(e, k_sc0<WW><<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->sys, 0.0, d_f, e->W, n, d_o));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(out, d_o, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    cudaFree(d_f); cudaFree(d_o);
+    return 0;
+}
+
+int hb200_gen_excit_batch(hb200_engine* e, const uint64_t* states, const int64_t* pops, const uint32_t* attempt,
+                          int64_t n, uint32_t cycle, double tau, int32_t* iout, double* dout, int64_t* nspawn) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (!e->have_sys) FAIL("gen_excit_batch: system not set");
+    if (n == 0) return 0;
+    Params p = e->par;
+    p.cycle = cycle; p.tau = tau;
+    uint64_t* d_f; int64_t* d_p; uint32_t* d_a; int* d_io; double* d_do; int64_t* d_ns;
+    CK(cudaMalloc((void**)&d_f, (size_t)n * e->W * 8));
+    CK(cudaMalloc((void**)&d_p, (size_t)n * 8));
+    CK(cudaMalloc((void**)&d_a, (size_t)n * 4));
+    CK(cudaMalloc((void**)&d_io, (size_t)n * 8 * 4));
+    CK(cudaMalloc((void**)&d_do, (size_t)n * 2 * 8));
+    CK(cudaMalloc((void**)&d_ns, (size_t)n * 8));
+    CK(cudaMemcpy(d_f, states, (size_t)n * e->W * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_p, pops, (size_t)n * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_a, attempt, (size_t)n * 4, cudaMemcpyHostToDevice));
+    DISPATCH_W(e, k_gen_excit_batch<WW><<<(unsigned)((n + 127) / 128), 128, 0, e->stream>>>(e->sys, p, d_f, d_p, d_a, n,
+                                                                                           e->d_proc_map, d_io, d_do, d_ns));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(iout, d_io, (size_t)n * 8 * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(dout, d_do, (size_t)n * 2 * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(nspawn, d_ns, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    cudaFree(d_f); cudaFree(d_p); cudaFree(d_a); cudaFree(d_io); cudaFree(d_do); cudaFree(d_ns);
+    return 0;
+}
+
+int hb200_get_unique_id(uint8_t id[128]) {
+    ncclUniqueId uid;
+    NCK(ncclGetUniqueId(&uid));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    memcpy(id, &uid, 128);
+    return 0;
+}
+
+int hb200_comm_init(hb200_engine* e, const uint8_t id[128]) {
+    CK(cudaSetDevice(e->cfg.device));
+    ncclUniqueId uid;
+    memcpy(&uid, id, 128);
+    NCK(ncclCommInitRank(&e->comm, e->par.nprocs, uid, e->par.iproc));
+    return 0;
+}
+
+int hb200_last_timing(hb200_engine* e, double ms[8], int64_t cnt[4]) {
+    for (int k = 0; k < 8; ++k) ms[k] = e->ms[k];
+    cnt[0] = e->spawn_launches; cnt[1] = e->launches; cnt[2] = 0; cnt[3] = 0;
+    return 0;
+}
+
+}  // extern "C"

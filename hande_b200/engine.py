@@ -1,0 +1,283 @@
+"""ctypes binding of libhande_b200.so (include/hande_b200.h): the only way this package computes anything.
+
+There is no CPU fallback: if the CUDA library is missing or no GPU is visible, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+EXCIT_GEN = {"no_renorm": 0, "renorm": 1, "heat_bath": 4}
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("device", C.c_int32), ("nbasis", C.c_int32), ("nel", C.c_int32), ("excit_gen", C.c_int32),
+        ("pattempt_single", C.c_double), ("pattempt_double", C.c_double),
+        ("real_amplitudes", C.c_int32), ("spawn_cutoff", C.c_double),
+        ("initiator_approx", C.c_int32), ("initiator_pop", C.c_double),
+        ("trunc_level", C.c_int32),
+        ("walker_length", C.c_int64), ("spawned_walker_length", C.c_int64),
+        ("rng_seed", C.c_uint32), ("nprocs", C.c_int32), ("iproc", C.c_int32), ("nslots", C.c_int32),
+        ("hash_seed", C.c_int32),
+    ]
+
+
+class SystemReadIn(C.Structure):
+    _fields_ = [
+        ("nbasis", C.c_int32), ("nel", C.c_int32), ("uhf", C.c_int32),
+        ("nsym_tot", C.c_int32), ("sym0", C.c_int32), ("sym_max", C.c_int32), ("pg_mask", C.c_int32),
+        ("Lz_mask", C.c_int32), ("Lz_offset", C.c_int32), ("gamma_sym", C.c_int32),
+        ("nvirt", C.c_int32), ("nvirt_alpha", C.c_int32), ("nvirt_beta", C.c_int32), ("max_nbss", C.c_int32),
+        ("Ecore", C.c_double),
+        ("bf_sym", C.c_void_p), ("bf_ms", C.c_void_p), ("bf_spatial", C.c_void_p),
+        ("nbasis_sym_spin", C.c_void_p), ("sym_spin_basis_fns", C.c_void_p),
+        ("one_body", C.c_void_p), ("two_body", C.c_void_p * 4), ("nintgrls", C.c_int64),
+    ]
+
+
+class IterIn(C.Structure):
+    _fields_ = [("tau", C.c_double), ("shift", C.c_double), ("proj_energy_old", C.c_double),
+                ("first_cycle", C.c_uint32)]
+
+
+class IterOut(C.Structure):
+    _fields_ = [
+        ("proj_energy", C.c_double), ("D0_population", C.c_double), ("nparticles", C.c_double),
+        ("nstates", C.c_int64), ("nspawn_events", C.c_int64), ("ndeath", C.c_int64), ("nattempts", C.c_int64),
+        ("rspawn", C.c_double), ("nattempts_spawn", C.c_int64), ("spawn_error", C.c_int32), ("psip_error", C.c_int32),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_LIB = None
+
+
+def load_library():
+    """Load (building if stale) the CUDA engine.  Raises if it cannot be built/loaded - never falls back."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB
+    if _build.needs_build():
+        if os.path.exists("/usr/local/cuda/bin/nvcc"):
+            _build.build()
+        elif not os.path.exists(path):
+            raise RuntimeError("libhande_b200.so is missing and nvcc is unavailable: the engine has no CPU fallback")
+    L = C.CDLL(path)
+    L.hb200_last_error.restype = C.c_char_p
+    L.hb200_create.restype = C.c_void_p
+    L.hb200_create.argtypes = [C.POINTER(Config)]
+    L.hb200_destroy.argtypes = [C.c_void_p]
+    L.hb200_set_system_read_in.argtypes = [C.c_void_p, C.POINTER(SystemReadIn)]
+    L.hb200_build_heat_bath.argtypes = [C.c_void_p]
+    L.hb200_download_heat_bath.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]
+    L.hb200_set_reference.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
+    L.hb200_set_proc_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    L.hb200_upload_psips.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    L.hb200_download_psips.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    L.hb200_nstates.restype = C.c_int64
+    L.hb200_nstates.argtypes = [C.c_void_p]
+    L.hb200_iterate.argtypes = [C.c_void_p, C.c_int32, C.POINTER(IterIn), C.POINTER(IterOut)]
+    L.hb200_spawn_death.argtypes = [C.c_void_p, C.POINTER(IterIn), C.c_uint32, C.POINTER(IterOut)]
+    L.hb200_comm_spawn.argtypes = [C.c_void_p]
+    L.hb200_annihilate_spawn.argtypes = [C.c_void_p]
+    L.hb200_annihilate_main.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(IterOut)]
+    L.hb200_download_spawn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    L.hb200_upload_spawn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    L.hb200_sc0_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    L.hb200_gen_excit_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32,
+                                        C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hb200_get_unique_id.argtypes = [C.c_void_p]
+    L.hb200_comm_init.argtypes = [C.c_void_p, C.c_void_p]
+    L.hb200_last_timing.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    _LIB = L
+    return L
+
+
+ABI_SYMBOLS = [
+    "hb200_last_error", "hb200_create", "hb200_destroy", "hb200_set_system_read_in", "hb200_build_heat_bath",
+    "hb200_download_heat_bath", "hb200_set_reference", "hb200_set_proc_map", "hb200_upload_psips",
+    "hb200_download_psips", "hb200_nstates", "hb200_iterate", "hb200_spawn_death", "hb200_comm_spawn",
+    "hb200_annihilate_spawn", "hb200_annihilate_main", "hb200_download_spawn", "hb200_upload_spawn",
+    "hb200_sc0_batch", "hb200_gen_excit_batch", "hb200_get_unique_id", "hb200_comm_init", "hb200_last_timing",
+]
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class Engine:
+    """One GPU's share of the walker population (one MPI rank of the reference)."""
+
+    def __init__(self, sys, *, excit_gen="renorm", pattempt_single, pattempt_double, real_amplitudes=False,
+                 spawn_cutoff=0.01, initiator_approx=False, initiator_pop=3.0, trunc_level=-1, walker_length=1 << 20,
+                 spawned_walker_length=1 << 18, seed=7, nprocs=1, iproc=0, nslots=1, device=0, hash_seed=7):
+        self.L = load_library()
+        self.sys = sys
+        self.W = sys.W
+        self.E = sys.W + 2
+        self.real_factor = (1 << 31) if real_amplitudes else 1
+        eg = EXCIT_GEN[excit_gen] if isinstance(excit_gen, str) else int(excit_gen)
+        self.cfg = Config(device=device, nbasis=sys.nbasis, nel=sys.nel, excit_gen=eg,
+                          pattempt_single=pattempt_single, pattempt_double=pattempt_double,
+                          real_amplitudes=int(real_amplitudes), spawn_cutoff=spawn_cutoff,
+                          initiator_approx=int(initiator_approx), initiator_pop=initiator_pop, trunc_level=trunc_level,
+                          walker_length=walker_length, spawned_walker_length=spawned_walker_length, rng_seed=seed,
+                          nprocs=nprocs, iproc=iproc, nslots=nslots, hash_seed=hash_seed)
+        h = self.L.hb200_create(C.byref(self.cfg))
+        if not h:
+            raise EngineError(self.L.hb200_last_error().decode())
+        self.h = C.c_void_p(h)
+        self._set_system(sys)
+        if eg == EXCIT_GEN["heat_bath"]:
+            self._chk(self.L.hb200_build_heat_bath(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.hb200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise EngineError(self.L.hb200_last_error().decode())
+
+    def _set_system(self, s):
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)  # noqa: E731
+        keep = [i32(s.sym), i32(s.ms), i32(s.spatial), i32(s.nbasis_sym_spin), i32(s.sym_spin_basis_fns),
+                np.ascontiguousarray(s.h1, dtype=np.float64)]
+        v2 = [np.ascontiguousarray(v, dtype=np.float64) for v in s.v2]
+        tb = (C.c_void_p * 4)(*[v.ctypes.data for v in v2] + [None] * (4 - len(v2)))
+        si = SystemReadIn(nbasis=s.nbasis, nel=s.nel, uhf=int(s.uhf), nsym_tot=s.nsym_tot, sym0=s.sym0,
+                          sym_max=s.sym_max, pg_mask=s.pg_mask, Lz_mask=s.Lz_mask, Lz_offset=s.Lz_offset,
+                          gamma_sym=s.gamma_sym, nvirt=s.nvirt, nvirt_alpha=s.nvirt_alpha, nvirt_beta=s.nvirt_beta,
+                          max_nbss=s.max_nbss, Ecore=s.Ecore, bf_sym=keep[0].ctypes.data, bf_ms=keep[1].ctypes.data,
+                          bf_spatial=keep[2].ctypes.data, nbasis_sym_spin=keep[3].ctypes.data,
+                          sym_spin_basis_fns=keep[4].ctypes.data, one_body=keep[5].ctypes.data, two_body=tb,
+                          nintgrls=s.nintgrls)
+        self._chk(self.L.hb200_set_system_read_in(self.h, C.byref(si)))
+
+    # ---- reference / lists
+    def set_reference(self, f0, H00):
+        f0 = np.ascontiguousarray(f0, dtype=np.uint64)
+        self._chk(self.L.hb200_set_reference(self.h, _p(f0), float(H00)))
+
+    def set_proc_map(self, pmap):
+        pmap = np.ascontiguousarray(pmap, dtype=np.int32)
+        self._chk(self.L.hb200_set_proc_map(self.h, _p(pmap), len(pmap)))
+
+    def upload_psips(self, states, pops, dat):
+        states = np.ascontiguousarray(states, dtype=np.uint64).reshape(-1, self.W)
+        pops = np.ascontiguousarray(pops, dtype=np.int64)
+        dat = np.ascontiguousarray(dat, dtype=np.float64)
+        assert len(states) == len(pops) == len(dat)
+        self._chk(self.L.hb200_upload_psips(self.h, _p(states), _p(pops), _p(dat), len(pops)))
+
+    @property
+    def nstates(self):
+        return int(self.L.hb200_nstates(self.h))
+
+    def download_psips(self):
+        n = self.nstates
+        states = np.zeros((n, self.W), dtype=np.uint64)
+        pops = np.zeros(n, dtype=np.int64)
+        dat = np.zeros(n)
+        nn = C.c_int64(0)
+        self._chk(self.L.hb200_download_psips(self.h, _p(states), _p(pops), _p(dat), n, C.byref(nn)))
+        return states, pops, dat
+
+    # ---- propagation
+    def iterate(self, ncycles, tau, shift, proj_energy_old, first_cycle):
+        i = IterIn(tau=tau, shift=shift, proj_energy_old=proj_energy_old, first_cycle=first_cycle)
+        o = IterOut()
+        self._chk(self.L.hb200_iterate(self.h, ncycles, C.byref(i), C.byref(o)))
+        return o.as_dict()
+
+    def spawn_death(self, tau, shift, proj_energy_old, cycle):
+        i = IterIn(tau=tau, shift=shift, proj_energy_old=proj_energy_old, first_cycle=cycle)
+        o = IterOut()
+        self._chk(self.L.hb200_spawn_death(self.h, C.byref(i), cycle, C.byref(o)))
+        return o.as_dict()
+
+    def comm_spawn(self):
+        self._chk(self.L.hb200_comm_spawn(self.h))
+
+    def annihilate_spawn(self):
+        self._chk(self.L.hb200_annihilate_spawn(self.h))
+
+    def annihilate_main(self, cycle):
+        o = IterOut()
+        self._chk(self.L.hb200_annihilate_main(self.h, cycle, C.byref(o)))
+        return o.as_dict()
+
+    def download_spawn(self):
+        cap = int(self.cfg.spawned_walker_length)
+        buf = np.zeros((cap, self.E), dtype=np.int64)
+        n = C.c_int64(0)
+        self._chk(self.L.hb200_download_spawn(self.h, _p(buf), cap, C.byref(n)))
+        return buf[: n.value].copy()
+
+    def upload_spawn(self, sdata):
+        sdata = np.ascontiguousarray(sdata, dtype=np.int64).reshape(-1, self.E)
+        self._chk(self.L.hb200_upload_spawn(self.h, _p(sdata), len(sdata)))
+
+    # ---- pure-function batches
+    def sc0_batch(self, states):
+        states = np.ascontiguousarray(states, dtype=np.uint64).reshape(-1, self.W)
+        out = np.zeros(len(states))
+        self._chk(self.L.hb200_sc0_batch(self.h, _p(states), len(states), _p(out)))
+        return out
+
+    def gen_excit_batch(self, states, pops, attempts, cycle, tau):
+        states = np.ascontiguousarray(states, dtype=np.uint64).reshape(-1, self.W)
+        pops = np.ascontiguousarray(pops, dtype=np.int64)
+        attempts = np.ascontiguousarray(attempts, dtype=np.uint32)
+        n = len(pops)
+        io = np.zeros((n, 8), dtype=np.int32)
+        do = np.zeros((n, 2))
+        ns = np.zeros(n, dtype=np.int64)
+        self._chk(self.L.hb200_gen_excit_batch(self.h, _p(states), _p(pops), _p(attempts), n, cycle, tau, _p(io), _p(do),
+                                               _p(ns)))
+        return io, do, ns
+
+    def heat_bath_table(self, which, n):
+        out = np.zeros(n, dtype=np.int32 if which >= 8 else np.float64)
+        self._chk(self.L.hb200_download_heat_bath(self.h, which, _p(out), n))
+        return out
+
+    # ---- multi-GPU
+    @staticmethod
+    def get_unique_id():
+        L = load_library()
+        buf = np.zeros(128, dtype=np.uint8)
+        if L.hb200_get_unique_id(_p(buf)) != 0:
+            raise EngineError(L.hb200_last_error().decode())
+        return buf
+
+    def comm_init(self, uid):
+        uid = np.ascontiguousarray(uid, dtype=np.uint8)
+        self._chk(self.L.hb200_comm_init(self.h, _p(uid)))
+
+    def last_timing(self):
+        ms = np.zeros(8)
+        cnt = np.zeros(4, dtype=np.int64)
+        self.L.hb200_last_timing(self.h, _p(ms), _p(cnt))
+        return {"spawn_ms": ms[0], "comm_ms": ms[1], "sort_ms": ms[2], "annihilate_ms": ms[3], "total_ms": ms[4],
+                "spawn_launches": int(cnt[0]), "launches": int(cnt[1])}

@@ -1,0 +1,253 @@
+"""Host-side FCIQMC driver: the stand-in for the part of `do_fciqmc` (reference src/fciqmc.f90:12-521) that
+stays on the host.  Per report loop it calls the engine once (`hb200_iterate`, ncycles MC cycles on the GPU), then
+does what `end_report_loop` does on the CPU: sum the rep_loop buffer over ranks
+(`update_energy_estimators`, src/energy_evaluation.F90:126-201), average the estimators, update the shift
+(`update_shift`, :659-711), switch on variable shift (:637-651) and print one row in HANDE's table format
+(`write_qmc_report`, src/qmc_io.f90:412-508) so pyhande/pyblock parse the output unchanged.
+
+Option names follow the Lua `fciqmc{ qmc = {...} }` table (src/lua_hande_calc.f90:1244-1503).
+"""
+from __future__ import annotations
+
+import math
+import sys as _sys
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import read_in as _ri
+from .engine import Engine
+
+HUGE = _ri.HUGE
+
+
+@dataclass
+class QmcIn:
+    """qmc_in_t (src/qmc_data.f90:121-330); names = Lua keys."""
+    tau: float = 0.001
+    rng_seed: int = 7
+    init_pop: float = 10.0
+    mc_cycles: int = 20
+    nreports: int = 10
+    target_population: float = 1.0e7
+    initial_shift: float = 0.0
+    shift_damping: float = 0.05
+    vary_shift_from: float = 0.0
+    vary_shift_from_proje: bool = False
+    initiator: bool = False
+    initiator_population: float = 3.0
+    real_amplitudes: bool = False
+    spawn_cutoff: float = 0.01
+    excit_gen: str = "renorm"
+    pattempt_single: float = -1.0
+    pattempt_double: float = -1.0
+    state_size: int = -5            # <0: MB (src/particle_t_utils.f90), >0: elements
+    spawned_state_size: int = -1
+    ex_level: int = -1              # reference = {ex_level = ...}: truncation level, -1 = none
+    nslots: int = 1
+
+
+def murmurhash2(data: bytes, seed: int) -> int:
+    """MurmurHash2 (public-domain algorithm; lib/external/MurmurHash2.c) - host copy for the owner of f0."""
+    m, r = 0x5BD1E995, 24
+    n = len(data)
+    h = (seed ^ n) & 0xFFFFFFFF
+    i = 0
+    while n >= 4:
+        k = int.from_bytes(data[i:i + 4], "little")
+        k = (k * m) & 0xFFFFFFFF
+        k ^= k >> r
+        k = (k * m) & 0xFFFFFFFF
+        h = (h * m) & 0xFFFFFFFF
+        h ^= k
+        i += 4
+        n -= 4
+    if n == 3:
+        h ^= data[i + 2] << 16
+    if n >= 2:
+        h ^= data[i + 1] << 8
+    if n >= 1:
+        h ^= data[i]
+        h = (h * m) & 0xFFFFFFFF
+    h ^= h >> 13
+    h = (h * m) & 0xFFFFFFFF
+    h ^= h >> 15
+    return h
+
+
+def owner_of(f, nbasis, nprocs, nslots, proc_map=None, seed=7):
+    """assign_particle_processor (src/spawning.F90:770-838), shift == 0."""
+    nbytes = ((nbasis + 31) // 32) * 4
+    h = murmurhash2(np.ascontiguousarray(f, dtype=np.uint64).tobytes()[:nbytes], seed)
+    if h >= 2**31:
+        h -= 2**32
+    slot = h % (nprocs * nslots)          # Python % == Fortran modulo for positive divisor
+    return (slot % nprocs) if proc_map is None else int(proc_map[slot])
+
+
+def list_sizes(qmc: QmcIn, W, nprocs):
+    """init_particle_t / init_spawn_store sizing (src/particle_t_utils.f90, src/qmc.F90:1418-1505)."""
+    size_main = W * 8 + 8 + 4 + 8
+    wl = qmc.state_size
+    if wl < 0:
+        wl = int((-float(wl) * 10**6) / size_main)
+    size_sp = (W + 1 + (1 if qmc.initiator else 0)) * 8
+    sl = qmc.spawned_state_size
+    if sl < 0:
+        sl = int((-float(sl) * 10**6) / (2 * size_sp))
+    if sl % nprocs != 0:
+        sl = int(math.ceil(np.float32(sl) / nprocs)) * nprocs
+    return wl, sl
+
+
+class _SingleProcess:
+    """Collective layer for one rank (the serial build of the reference)."""
+    rank, size = 0, 1
+
+    def allreduce_sum(self, buf):
+        return buf
+
+    def broadcast_bytes(self, arr, src=0):
+        return arr
+
+
+class TorchDist:
+    """Collective layer over torch.distributed (gloo on CPU tests, nccl on GPUs) - replaces MPI_Allreduce of rep_loop."""
+
+    def __init__(self, device=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.device = torch, dist, device
+        self.rank, self.size = dist.get_rank(), dist.get_world_size()
+
+    def allreduce_sum(self, buf):
+        t = self.torch.tensor(buf, dtype=self.torch.float64, device=self.device)
+        self.dist.all_reduce(t)
+        return t.cpu().numpy()
+
+    def broadcast_bytes(self, arr, src=0):
+        t = self.torch.tensor(np.asarray(arr, dtype=np.uint8), device=self.device)
+        self.dist.broadcast(t, src=src)
+        return t.cpu().numpy()
+
+
+HEADER = (" #     iterations   Shift                 \\sum H_0j N_j         N_0                   # H psips"
+          "                  # states  # spawn_events   R_spawn    time    ")
+
+
+def format_row(it, shift, pe, d0, npart, nstates, nev, rspawn, t, comment=False):
+    """write_qmc_report (src/qmc_io.f90:412-508)."""
+    lead = " # " if comment else "   "
+    return (f"{lead}{it:11d}  {shift:17.10E}    {pe:18.10E}    {d0:18.10E}    {npart:18.10E}"
+            f"  {nstates:17d}  {nev:14d}  {rspawn:8.4f}  {t:8.4f}  ")
+
+
+@dataclass
+class FciqmcResult:
+    rows: list = field(default_factory=list)   # iterations, shift, proj_energy, D0, nparticles, nstates, nspawn_events, rspawn
+    shift: float = 0.0
+    vary_shift: bool = False
+    H00: float = 0.0
+    occ0: list = None
+    engine: object = None
+    error: bool = False
+    timings: list = field(default_factory=list)
+
+
+def do_fciqmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, keep_engine=False, psips=None):
+    """fciqmc{sys=sys, qmc={...}} on the GPU engine.  `psips` = (states, pops, dat) restarts from a given list
+    (this rank's share), else the initial distribution puts init_pop on the reference determinant."""
+    comm = comm or _SingleProcess()
+    nprocs, iproc = comm.size, comm.rank
+    out = io if io is not None else None
+    # init_reference (src/qmc.F90:1162-1226)
+    occ0 = _ri.set_reference_det(sys)
+    f0 = sys.encode(occ0)
+    H00 = sys.slater_condon0(occ0)
+    # init_excit_gen (src/qmc.F90:910-1010)
+    if qmc.pattempt_single < 0 or qmc.pattempt_double < 0:
+        ps, pd = _ri.find_single_double_prob(sys, occ0)
+    else:
+        ps = qmc.pattempt_single / (qmc.pattempt_single + qmc.pattempt_double)
+        pd = 1.0 - qmc.pattempt_single
+    wl, sl = list_sizes(qmc, sys.W, nprocs)
+    eng = engine_cls(sys, excit_gen=qmc.excit_gen, pattempt_single=ps, pattempt_double=pd,
+                     real_amplitudes=qmc.real_amplitudes, spawn_cutoff=qmc.spawn_cutoff,
+                     initiator_approx=qmc.initiator, initiator_pop=qmc.initiator_population,
+                     trunc_level=qmc.ex_level, walker_length=wl, spawned_walker_length=sl, seed=qmc.rng_seed,
+                     nprocs=nprocs, iproc=iproc, nslots=qmc.nslots, device=device)
+    eng.set_reference(f0, H00)
+    if nprocs > 1:
+        uid = eng.get_unique_id() if iproc == 0 else np.zeros(128, dtype=np.uint8)
+        uid = comm.broadcast_bytes(uid, src=0)
+        eng.comm_init(uid)
+    real_factor = (1 << 31) if qmc.real_amplitudes else 1
+    # initial_distribution (src/qmc.F90:1507-1646)
+    if psips is None:
+        if owner_of(f0, sys.nbasis, nprocs, qmc.nslots) == iproc:
+            eng.upload_psips(f0.reshape(1, -1), np.array([int(round(qmc.init_pop)) * real_factor], dtype=np.int64),
+                             np.zeros(1))
+            nparticles_loc, d0_loc = float(int(round(qmc.init_pop))), float(int(round(qmc.init_pop)))
+        else:
+            eng.upload_psips(np.zeros((0, sys.W), dtype=np.uint64), np.zeros(0, dtype=np.int64), np.zeros(0))
+            nparticles_loc, d0_loc = 0.0, 0.0
+        pe_loc = 0.0
+    else:
+        eng.upload_psips(*psips)
+        nparticles_loc = float(np.abs(psips[1]).sum()) / real_factor
+        hit = np.nonzero((np.asarray(psips[0]).reshape(-1, sys.W) == f0).all(axis=1))[0]
+        d0_loc = float(psips[1][hit[0]]) / real_factor if len(hit) else 0.0
+        pe_loc = 0.0   # initial_ci_projected_energy: first-loop proj_energy_old uses D0 only if pe unknown
+    # initial_ci_projected_energy (src/qmc_common.F90:697-797): allreduce of the starting estimators
+    buf = comm.allreduce_sum(np.array([pe_loc, d0_loc, nparticles_loc, float(eng.nstates)]))
+    proj_energy, D0, ntot_old, tot_nstates = float(buf[0]), float(buf[1]), float(buf[2]), int(round(buf[3]))
+    shift, vary_shift = qmc.initial_shift, False
+    res = FciqmcResult(H00=H00, occ0=occ0)
+    res.rows.append([0, shift, proj_energy, D0, ntot_old, tot_nstates, 0, 0.0])
+    if out is not None and iproc == 0:
+        out.write(HEADER + "\n")
+        out.write(format_row(0, shift, proj_energy, D0, ntot_old, tot_nstates, 0, 0.0, 0.0, comment=True) + "\n")
+    mc_cycles_done = 0
+    for ireport in range(1, qmc.nreports + 1):
+        t0 = time.time()
+        # get_sanitized_projected_energy (src/energy_evaluation.F90:1433-1456)
+        pe_old = 0.0 if abs(D0) < np.finfo(np.float64).tiny else proj_energy / D0
+        first_cycle = mc_cycles_done + (ireport - 1) * qmc.mc_cycles + 1
+        o = eng.iterate(qmc.mc_cycles, qmc.tau, shift, pe_old, first_cycle)
+        res.timings.append(eng.last_timing())
+        # local_energy_estimators + MPI_Allreduce + communicated_energy_estimators
+        # (src/energy_evaluation.F90:126-201, 320-655)
+        loc = np.array([o["proj_energy"], o["D0_population"], o["rspawn"], o["nparticles"], float(o["nstates"]),
+                        float(o["nspawn_events"]), float(bool(o["spawn_error"] or o["psip_error"]))])
+        tot = comm.allreduce_sum(loc)
+        proj_energy = float(tot[0]) / qmc.mc_cycles
+        D0 = float(tot[1]) / qmc.mc_cycles
+        rspawn = float(tot[2]) / (qmc.mc_cycles * nprocs)
+        ntot = float(tot[3])
+        tot_nstates, tot_nev = int(round(tot[4])), int(round(tot[5]))
+        error = tot[6] > 0
+        if vary_shift:
+            # update_shift (src/energy_evaluation.F90:659-711)
+            shift = shift - math.log(ntot / ntot_old) * qmc.shift_damping / (1.0 * qmc.tau * qmc.mc_cycles) \
+                - math.log(ntot / qmc.target_population) * 0.0 / (1.0 * qmc.tau * qmc.mc_cycles) \
+                if qmc.target_population > 0 else \
+                shift - math.log(ntot / ntot_old) * qmc.shift_damping / (1.0 * qmc.tau * qmc.mc_cycles)
+        ntot_old = ntot
+        if not vary_shift and ntot > qmc.target_population:
+            vary_shift = True
+            shift = proj_energy / D0 if qmc.vary_shift_from_proje else qmc.vary_shift_from
+        it = mc_cycles_done + ireport * qmc.mc_cycles
+        res.rows.append([it, shift, proj_energy, D0, ntot, tot_nstates, tot_nev, rspawn])
+        if out is not None and iproc == 0:
+            out.write(format_row(it, shift, proj_energy, D0, ntot, tot_nstates, tot_nev, rspawn,
+                                 (time.time() - t0) / qmc.mc_cycles) + "\n")
+        if error:
+            res.error = True
+            break
+    res.shift, res.vary_shift = shift, vary_shift
+    if keep_engine:
+        res.engine = eng
+    else:
+        eng.close()
+    return res

@@ -1,0 +1,158 @@
+/* hande_b200 - B200-native FCIQMC walker-propagation engine behind HANDE's hot-path seams.
+ *
+ * C ABI of libhande_b200.so.  The reference (hande-qmc/hande) has no C plugin interface for this
+ * path: its seams are Fortran procedure pointers bound in init_proc_pointers (src/qmc.F90:217-703;
+ * interfaces src/proc_pointers.f90:15-343) and the particle_t / spawn_t layouts.  Those are
+ * per-walker scalar callbacks; this ABI is the batch-granular equivalent a ~100-line
+ * iso_c_binding shim in do_fciqmc would call (INTEGRATION.md shows the Fortran side).
+ * Every entry point names the reference routine(s) it replaces.
+ *
+ * Conventions: plain pointers and sizes only; host memory unless noted; orbital indices 1-based
+ * as in the reference; arrays are in the reference's (Fortran, column-major) order; all functions
+ * return 0 on success and non-zero on CUDA/NCCL/usage errors (message via hb200_last_error()).
+ * Soft errors of the algorithm (spawn list / main list overflow) never abort: they set the
+ * spawn_error / psip_error flags of hb200_iter_out exactly like spawn%error / psip_list%error
+ * (src/spawning.F90:938-947, src/annihilation.f90:750-771) and the host exits at the end of the
+ * report loop.
+ */
+#ifndef HANDE_B200_H
+#define HANDE_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hb200_engine hb200_engine;
+
+/* Values of qmc_in%excit_gen (src/qmc_data.f90:31-69) that the engine implements. */
+enum { HB200_EXCIT_GEN_NO_RENORM = 0, HB200_EXCIT_GEN_RENORM = 1, HB200_EXCIT_GEN_HEAT_BATH = 4 };
+
+/* qmc_in_t / fciqmc options that size and configure the device state
+ * (src/qmc_data.f90:121-512; lua keys src/lua_hande_calc.f90:1244-1503). */
+typedef struct hb200_config {
+    int32_t device;                /* CUDA device ordinal (one engine = one MPI rank = one GPU) */
+    int32_t nbasis, nel;           /* spin-orbitals, electrons (after CAS freezing) */
+    int32_t excit_gen;             /* HB200_EXCIT_GEN_* */
+    double pattempt_single, pattempt_double; /* excit_gen_data%pattempt_* (find_single_double_prob) */
+    int32_t real_amplitudes;       /* qmc_in%real_amplitudes: pops encoded * 2^31 (POP_SIZE=64) */
+    double spawn_cutoff;           /* qmc_in%spawn_cutoff (only with real amplitudes) */
+    int32_t initiator_approx;      /* qmc_in%initiator_approx */
+    double initiator_pop;          /* qmc_in%initiator_pop (default 3.0) */
+    int32_t trunc_level;           /* reference%ex_level when truncating the space, else -1 */
+    int64_t walker_length;         /* main list capacity (states), particle_t */
+    int64_t spawned_walker_length; /* spawn_t%array_len (elements, all destinations together) */
+    uint32_t rng_seed;             /* qmc_in%seed: key of the Philox stream */
+    int32_t nprocs, iproc, nslots; /* hash-owner sharding (src/spawning.F90:770-838; load_bal nslots) */
+    int32_t hash_seed;             /* 7 (src/qmc.F90:1497) */
+} hb200_config;
+
+/* sys_t / basis_t / pg_sym / integral stores for read_in systems
+ * (src/system.f90:366-457, src/basis_types.f90:58-130, src/point_group_symmetry.f90,
+ *  src/molecular_integral_types.f90:19-72).  Basis arrays have nbasis+1 entries (entry 0 unused). */
+typedef struct hb200_system_read_in {
+    int32_t nbasis, nel, uhf;
+    int32_t nsym_tot, sym0, sym_max, pg_mask, Lz_mask, Lz_offset, gamma_sym;
+    int32_t nvirt, nvirt_alpha, nvirt_beta, max_nbss;
+    double Ecore;
+    const int32_t* bf_sym;         /* basis_fns(:)%sym */
+    const int32_t* bf_ms;          /* basis_fns(:)%ms (+1 alpha / -1 beta) */
+    const int32_t* bf_spatial;     /* basis_fns(:)%spatial_index */
+    const int32_t* nbasis_sym_spin;    /* (2, nsym_tot) */
+    const int32_t* sym_spin_basis_fns; /* (max_nbss, 2, nsym_tot) */
+    const double* one_body;        /* dense (nbasis, nbasis) of get_one_body_int_mol_real */
+    const double* two_body[4];     /* coulomb_integrals%integrals(chan)%v, 1 (RHF) or 4 (UHF) channels */
+    int64_t nintgrls;              /* length of each two-body channel */
+} hb200_system_read_in;
+
+/* Per-call propagation inputs (qmc_state_t scalars read by the hot loop). */
+typedef struct hb200_iter_in {
+    double tau;                    /* qs%tau */
+    double shift;                  /* qs%shift(1) */
+    double proj_energy_old;        /* qs%estimators(1)%proj_energy_old (src/fciqmc.f90:278) */
+    uint32_t first_cycle;          /* iteration number of the first cycle (Philox key) */
+} hb200_iter_in;
+
+/* Per-call outputs: what end_mc_cycle / update_energy_estimators need
+ * (src/qmc_common.F90:1240-1304, src/energy_evaluation.F90:320-420). */
+typedef struct hb200_iter_out {
+    double proj_energy;            /* sum over cycles of sum_j H_0j N_j (this rank) */
+    double D0_population;          /* sum over cycles of N_0 (this rank) */
+    double nparticles;             /* psip_list%nparticles(1) after the last cycle */
+    int64_t nstates;               /* psip_list%nstates after the last cycle */
+    int64_t nspawn_events;         /* calc_events_spawn_t of the last cycle (this rank) */
+    int64_t ndeath;                /* ndeath of the last cycle (encoded units) */
+    int64_t nattempts;             /* nint(2*nparticles) at the start of the last cycle */
+    double rspawn;                 /* sum over cycles of spawning_rate() */
+    int64_t nattempts_spawn;       /* total spawning attempts made (all cycles; throughput metric) */
+    int32_t spawn_error, psip_error;
+} hb200_iter_out;
+
+const char* hb200_last_error(void);
+
+/* init_qmc sizing (src/qmc.F90:10-215): allocates all device state. NULL on failure. */
+hb200_engine* hb200_create(const hb200_config* cfg);
+void hb200_destroy(hb200_engine* e);
+
+/* Copies the system tables to the device (read_in systems); builds the J/K diagonal tables. */
+int hb200_set_system_read_in(hb200_engine* e, const hb200_system_read_in* sys);
+/* init_excit_mol_heat_bath (src/excit_gen_heat_bath_mol.F90:14-256) evaluated on the device. */
+int hb200_build_heat_bath(hb200_engine* e);
+/* Test/inspection: copy heat-bath table `which` to the host (0 i_w,1 ij_w,2 ija_w,3 ija_U,4 ija_tot,
+ * 5 ijab_w,6 ijab_U,7 ijab_tot as double; 8 ija_K, 9 ijab_K as int32). n = element count expected. */
+int hb200_download_heat_bath(hb200_engine* e, int which, void* out, int64_t n);
+
+/* reference_t: f0 (W words) and H00 (init_reference src/qmc.F90:1162-1226). */
+int hb200_set_reference(hb200_engine* e, const uint64_t* f0, double H00);
+/* proc_map%map(0:nprocs*nslots-1) (src/spawn_data.F90:13-24, src/load_balancing.F90:141-172). */
+int hb200_set_proc_map(hb200_engine* e, const int32_t* map, int32_t n);
+
+/* particle_t upload/download: states(W,N), pops(1,N), dat(1,N), sorted ascending
+ * (src/qmc_data.f90:615-682); used at init, restart read/write (src/restart_hdf5.F90:307,539). */
+int hb200_upload_psips(hb200_engine* e, const uint64_t* states, const int64_t* pops, const double* dat, int64_t nstates);
+int hb200_download_psips(hb200_engine* e, uint64_t* states, int64_t* pops, double* dat, int64_t capacity, int64_t* nstates);
+int64_t hb200_nstates(hb200_engine* e);
+
+/* ncycles full MC cycles: the body of do_fciqmc's icycle loop (src/fciqmc.f90:293-398):
+ * init_mc_cycle, the idet loop (spawn + death + projected energy), direct_annihilation, end_mc_cycle. */
+int hb200_iterate(hb200_engine* e, int32_t ncycles, const hb200_iter_in* in, hb200_iter_out* out);
+
+/* Stage-level entry points (same state machine as hb200_iterate, one stage per call). */
+/* do idet loop: decoder_ptr, set_parent_flag, update_proj_energy_ptr, decide_nattempts,
+ * do_fciqmc_spawning_attempt, stochastic_death (src/fciqmc.f90:315-371). */
+int hb200_spawn_death(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, hb200_iter_out* out);
+/* comm_spawn_t (src/spawn_data.F90:624-739): all-to-all of the per-destination blocks over NCCL. */
+int hb200_comm_spawn(hb200_engine* e);
+/* annihilate_wrapper_spawn_t (sort + annihilate_spawn_t[_initiator], src/spawn_data.F90:359-418,859-1101) */
+int hb200_annihilate_spawn(hb200_engine* e);
+/* annihilate_main_list_wrapper (src/annihilation.f90:214-290): annihilate_main_list[_initiator],
+ * remove_unoccupied_dets, round_low_population_spawns, insert_new_walkers. */
+int hb200_annihilate_main(hb200_engine* e, uint32_t cycle, hb200_iter_out* out);
+/* spawn%sdata(element_len, n) of the current stage (element = W string words, population, flag). */
+int hb200_download_spawn(hb200_engine* e, int64_t* sdata, int64_t capacity, int64_t* n);
+int hb200_upload_spawn(hb200_engine* e, const int64_t* sdata, int64_t n);
+
+/* Pure-function batches evaluated on the device (parity probes; also used by the host for init):
+ * sc0_ptr over a list of determinants (src/hamiltonian_molecular.f90:73-139). */
+int hb200_sc0_batch(hb200_engine* e, const uint64_t* states, int64_t n, double* out);
+/* One spawning attempt per (determinant, attempt index) with the engine's Philox stream:
+ * gen_excit_ptr%full + attempt_to_spawn (src/spawning.F90:34-124).  iout[n][8] = nexcit, from1, from2,
+ * to1, to2, perm, allowed, owner; dout[n][2] = pgen, hmatel; nspawn[n]. */
+int hb200_gen_excit_batch(hb200_engine* e, const uint64_t* states, const int64_t* pops, const uint32_t* attempt,
+                          int64_t n, uint32_t cycle, double tau, int32_t* iout, double* dout, int64_t* nspawn);
+
+/* NCCL bootstrap for nprocs > 1: rank 0 calls hb200_get_unique_id, the host broadcasts the 128 bytes
+ * (MPI_Bcast in the Fortran host, torch.distributed in this repo's harness), every rank calls
+ * hb200_comm_init.  Replaces MPI_COMM_WORLD use in comm_spawn_t. */
+int hb200_get_unique_id(uint8_t id[128]);
+int hb200_comm_init(hb200_engine* e, const uint8_t id[128]);
+
+/* Timing of the stages of the last hb200_iterate call, milliseconds (CUDA events on the engine stream):
+ * ms[0] spawn+death kernel, ms[1] exchange, ms[2] sort+annihilate_spawn, ms[3] main-list annihilation+merge,
+ * ms[4] total.  Counters: cnt[0] = spawn kernel launches, cnt[1] = all kernel launches. */
+int hb200_last_timing(hb200_engine* e, double ms[8], int64_t cnt[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -282,6 +282,50 @@ int orc_iterate(void* h, int ncycles, uint32_t first_cycle_id, double tau, doubl
     ORC_CATCH(-1)
 }
 
+// Stage probes: run only the spawn/death loop of one cycle on every emulated rank (no comm, no annihilation)
+// and read back the per-destination send blocks concatenated by destination (spawn%sdata before comm_spawn_t).
+int orc_stage_spawn(void* h, uint32_t cycle_id, double tau, double shift, double proj_energy_old, double* out) {
+    ORC_TRY
+    Oracle* o = (Oracle*)h;
+    o->tau = tau; o->shift = shift; o->est.proj_energy_old = proj_energy_old;
+    double pe = 0, d0 = 0; int64_t nev = 0, nd = 0;
+    for (auto& r : o->ranks) {
+        r.proj_energy = 0.0; r.D0_population = 0.0;
+        o->spawn_death_rank(r, cycle_id);
+        pe += r.proj_energy; d0 += r.D0_population; nev += r.nspawn_events; nd += r.ndeath;
+    }
+    out[0] = pe; out[1] = d0; out[2] = (double)nev; out[3] = (double)nd;
+    return 0;
+    ORC_CATCH(-1)
+}
+int64_t orc_spawn_count(void* h, int rank) {
+    int64_t n = 0;
+    for (auto& b : ((Oracle*)h)->ranks[rank].send) n += (int64_t)b.size();
+    return n;
+}
+// sdata[n][W+2]: string words, population, flag
+void orc_get_spawn(void* h, int rank, int64_t* sdata) {
+    Oracle* o = (Oracle*)h;
+    int W = o->sys.W, E = W + 2;
+    int64_t k = 0;
+    for (auto& b : o->ranks[rank].send)
+        for (auto& e : b) {
+            for (int w = 0; w < W; ++w) sdata[k * E + w] = (int64_t)e.f.w[w];
+            sdata[k * E + W] = e.pop;
+            sdata[k * E + W + 1] = e.flag;
+            ++k;
+        }
+}
+// finish the cycle started by orc_stage_spawn: comm + annihilation on every rank
+int orc_stage_annihilate(void* h) {
+    ORC_TRY
+    Oracle* o = (Oracle*)h;
+    o->comm_spawn();
+    for (auto& r : o->ranks) o->annihilate_rank(r);
+    return 0;
+    ORC_CATCH(-1)
+}
+
 // One excitation-generation + spawn attempt with the Philox stream (kernel parity probe).
 // iout: nexcit, from1, from2, to1, to2, perm, allowed ; dout: pgen, hmatel ; nspawn: encoded spawn
 int orc_gen_excit_philox(void* h, const uint64_t* f, uint32_t cycle, uint32_t attempt, int64_t parent_pop,

@@ -96,6 +96,11 @@ def lib():
         L.orc_set_psips.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_set_reference_det.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_iterate.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_void_p]
+        L.orc_stage_spawn.argtypes = [C.c_void_p, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_void_p]
+        L.orc_spawn_count.restype = C.c_int64
+        L.orc_spawn_count.argtypes = [C.c_void_p, C.c_int]
+        L.orc_get_spawn.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_stage_annihilate.argtypes = [C.c_void_p]
         L.orc_gen_excit_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int64, C.c_double,
                                            C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_gen_excit_list.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -272,6 +277,18 @@ class Oracle:
         keys = ["proj_energy", "D0_population", "nparticles", "nstates", "nspawn_events", "ndeath", "rspawn", "error",
                 "nattempts", "ndraws"]
         return dict(zip(keys, out))
+
+    def stage_spawn(self, cycle, tau, shift, proj_energy_old, rank=0):
+        """Spawn/death loop of one cycle only; returns (stats, sdata[n][W+2]) of `rank` before the exchange."""
+        out = np.zeros(4)
+        self._chk(self.L.orc_stage_spawn(self.h, cycle, tau, shift, proj_energy_old, _p(out)))
+        n = self.L.orc_spawn_count(self.h, rank)
+        sd = np.zeros((n, self.W + 2), dtype=np.int64)
+        self.L.orc_get_spawn(self.h, rank, _p(sd))
+        return dict(zip(["proj_energy", "D0_population", "nspawn_events", "ndeath"], out)), sd
+
+    def stage_annihilate(self):
+        self._chk(self.L.orc_stage_annihilate(self.h))
 
     def gen_excit_philox(self, f, cycle, attempt, parent_pop, tau):
         f = np.ascontiguousarray(f, dtype=np.uint64)

@@ -1,0 +1,173 @@
+"""GPU parity tests (-m gpu): every call goes through the C ABI of libhande_b200.so and is compared with the
+oracle fed the same Philox stream.  Bit-exact: excitation choice, nspawn, spawn lists, sort, annihilation, merged
+main list (states, pops) and dat (same summation order, no FMA).  1e-12 relative: block-reduced estimators."""
+import numpy as np
+import pytest
+
+from tests.common import make_pair, random_population, sort_rows
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_gen(name, gen, real, tau, n=200, nattempt=4, cycles=(1, 7)):
+    s, o, eng, ref = make_pair(name, excit_gen=gen, tau=tau, real=real)
+    f, pops, dat = random_population(s, o, n, real, seed=3)
+    nd = len(f)
+    for cyc in cycles:
+        att = np.tile(np.arange(nattempt, dtype=np.uint32), nd)
+        ff = np.repeat(f, nattempt, axis=0)
+        pp = np.repeat(pops, nattempt)
+        io, do, ns = eng.gen_excit_batch(ff, pp, att, cyc, tau)
+        for k in range(len(pp)):
+            io_o, do_o, ns_o = o.gen_excit_philox(ff[k], cyc, int(att[k]), int(pp[k]), tau)
+            assert io_o[6] == io[k, 6], (k, io_o, io[k])
+            if io_o[6]:
+                assert list(io_o[:6]) == list(io[k, :6]), (k, io_o, io[k])
+            assert do_o[0] == do[k, 0] and do_o[1] == do[k, 1], (k, do_o, do[k])
+            assert ns_o == ns[k], (k, ns_o, ns[k])
+    sc = eng.sc0_batch(f)
+    for k in range(nd):
+        assert sc[k] == o.sc0(f[k])
+    eng.close()
+
+
+def test_gen_excit_renorm_h2o():
+    _check_gen("h2o", "renorm", False, 0.003)
+
+
+def test_gen_excit_no_renorm_h2o():
+    _check_gen("h2o", "no_renorm", False, 0.003)
+
+
+def test_gen_excit_renorm_ne_real():
+    _check_gen("ne", "renorm", True, 0.005, n=100)
+
+
+def test_gen_excit_renorm_two_words():
+    _check_gen("s40", "renorm", False, 0.01, n=100)
+
+
+def test_gen_excit_heat_bath():
+    _check_gen("s10", "heat_bath", True, 0.01, n=150, nattempt=6)
+
+
+def test_heat_bath_tables_match_oracle():
+    s, o, eng, ref = make_pair("s10", excit_gen="heat_bath")
+    hb = o.heat_bath_tables()
+    nb = hb["nb"]
+    names = ["i_weights", "ij_weights", "ija_w", "ija_U", "ija_tot", "ijab_w", "ijab_U", "ijab_tot", "ija_K", "ijab_K"]
+    for which, nm in enumerate(names):
+        ref_t = np.asarray(hb[nm])
+        got = eng.heat_bath_table(which, len(ref_t))
+        if nm in ("ija_U", "ija_K", "ijab_U", "ijab_K"):
+            # rows with zero total weight are never initialised/used by the reference: compare the used rows only
+            tot = np.asarray(hb["ija_tot"] if nm.startswith("ija_") else hb["ijab_tot"])
+            used = np.repeat(np.abs(tot) > 0, nb)
+            assert (got[used] == ref_t[used]).all(), nm
+        else:
+            assert (got == ref_t).all(), nm
+    eng.close()
+
+
+def test_radix_sort_spawn_list():
+    s, o, eng, ref = make_pair("s40", spawned_walker_length=1 << 16)
+    rng = np.random.default_rng(4)
+    for n in (1, 2, 37, 255, 256, 257, 5000, 40000):
+        keys = rng.integers(0, 2**63 - 1, size=(n, 2), dtype=np.int64)
+        keys[:, 1] &= (1 << (s.nbasis - 64)) - 1
+        keys[rng.integers(0, n, size=n // 3)] = keys[0]          # duplicates
+        sd = np.concatenate([keys, rng.integers(-5, 6, size=(n, 1)), np.arange(n).reshape(-1, 1)], axis=1)
+        eng.upload_spawn(sd)
+        eng.annihilate_spawn()
+        got = eng.download_spawn()
+        # reference order: unsigned compare, word 1 most significant, stable
+        order = np.lexsort((sd[:, 0].astype(np.uint64), sd[:, 1].astype(np.uint64)))
+        assert (got == sd[order]).all(), n
+    eng.close()
+
+
+CASES = [
+    # name, generator, real, initiator, tau, nwalkers, ex_level
+    ("h2o", "renorm", False, False, 0.003, 3000, -1),
+    ("h2o", "no_renorm", False, True, 0.003, 3000, -1),
+    ("ne_cas", "renorm", True, False, 0.004, 4000, 5),
+    ("ne", "renorm", True, True, 0.005, 5000, -1),
+    ("s40", "renorm", False, True, 0.02, 3000, -1),
+    ("s12", "heat_bath", True, True, 0.01, 2500, -1),
+]
+
+
+@pytest.mark.parametrize("name,gen,real,init,tau,n,exl", CASES)
+def test_stage_and_cycle_parity(name, gen, real, init, tau, n, exl):
+    s, o, eng, ref = make_pair(name, excit_gen=gen, tau=tau, real=real, initiator=init, ex_level=exl)
+    f, pops, dat = random_population(s, o, n, real, seed=5)
+    o.set_psips(f, pops, dat)
+    eng.upload_psips(f, pops, dat)
+    shift, pe_old = -0.05, -0.11
+    rf = 2**31 if real else 1
+    for cycle in (1, 2, 3):
+        st_o, sd_o = o.stage_spawn(cycle, tau, shift, pe_old)
+        st_g = eng.spawn_death(tau, shift, pe_old, cycle)
+        sd_g = eng.download_spawn()
+        assert st_g["nspawn_events"] == st_o["nspawn_events"] == len(sd_o)
+        assert (sort_rows(sd_g) == sort_rows(sd_o)).all()
+        assert st_g["ndeath"] == st_o["ndeath"]
+        assert abs(st_g["proj_energy"] - st_o["proj_energy"]) <= 1e-12 * max(1.0, abs(st_o["proj_energy"]))
+        assert abs(st_g["D0_population"] - st_o["D0_population"]) <= 1e-12 * max(1.0, abs(st_o["D0_population"]))
+        eng.comm_spawn()
+        eng.annihilate_spawn()
+        srt = eng.download_spawn()
+        k = srt[:, : s.W].astype(np.uint64)
+        order = np.lexsort(tuple(k[:, w] for w in range(s.W)))
+        assert (order == np.arange(len(srt))).all() or (k[order] == k).all()
+        out = eng.annihilate_main(cycle)
+        o.stage_annihilate()
+        fo, po, do_ = o.get_psips()
+        fg, pg, dg = eng.download_psips()
+        assert len(fg) == len(fo) == out["nstates"]
+        assert (fg == fo).all()
+        assert (pg == po).all()
+        assert (dg == do_).all()
+        assert out["nparticles"] == pytest.approx(np.abs(po).sum() / rf, rel=1e-14)
+    eng.close()
+
+
+@pytest.mark.parametrize("name,gen,real,init,tau", [("h2o", "renorm", False, False, 0.003),
+                                                     ("ne", "renorm", True, True, 0.005),
+                                                     ("s12", "heat_bath", True, True, 0.01)])
+def test_iterate_from_single_determinant(name, gen, real, init, tau):
+    """Population growth from the reference determinant: 60 cycles in blocks of 10 through hb200_iterate."""
+    s, o, eng, ref = make_pair(name, excit_gen=gen, tau=tau, real=real, initiator=init)
+    rf = 2**31 if real else 1
+    f0 = ref["f0"].reshape(1, -1)
+    o.set_psips(f0, [50 * rf], [0.0])
+    eng.upload_psips(f0, [50 * rf], [0.0])
+    cyc = 1
+    for block in range(6):
+        ro = o.iterate(10, cyc, tau, 0.0, -0.02 * block)
+        rg = eng.iterate(10, tau, 0.0, -0.02 * block, cyc)
+        cyc += 10
+        fo, po, do_ = o.get_psips()
+        fg, pg, dg = eng.download_psips()
+        assert len(fg) == len(fo)
+        assert (fg == fo).all() and (pg == po).all() and (dg == do_).all()
+        assert rg["nspawn_events"] == ro["nspawn_events"] and rg["ndeath"] == ro["ndeath"]
+        assert rg["nattempts"] == ro["nattempts"]
+        for key in ("proj_energy", "D0_population", "rspawn", "nparticles"):
+            assert abs(rg[key] - ro[key]) <= 1e-12 * max(1.0, abs(ro[key])), key
+    assert len(fg) > 20
+    eng.close()
+
+
+def test_edge_cases_empty_and_overflow():
+    s, o, eng, ref = make_pair("h2o", tau=0.003, walker_length=64, spawned_walker_length=32)
+    # empty main list
+    eng.upload_psips(np.zeros((0, 1), dtype=np.uint64), [], [])
+    out = eng.iterate(2, 0.003, 0.0, 0.0, 1)
+    assert out["nstates"] == 0 and out["nspawn_events"] == 0 and out["spawn_error"] == 0
+    # a single huge population: spawn list (32) and main list (64) overflow -> flags, no abort
+    eng.upload_psips(ref["f0"].reshape(1, -1), [2000000], [0.0])
+    out = eng.iterate(1, 0.003, 0.0, 0.0, 5)
+    assert out["spawn_error"] == 1
+    assert out["nstates"] <= 64
+    eng.close()

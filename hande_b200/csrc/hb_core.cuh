@@ -52,6 +52,13 @@ struct Sys {
     // diagonal helper tables built on device from v2: J(i,j)=<ij|ij>, K(i,j)=<ij|ji>, spin-orbital indexed
     const double* Jd;           // [(i-1)*nbasis + (j-1)]
     const double* Kd;
+    // single-excitation tables built on device from v2: C(i,a,j)=<ij|aj>, X(i,a,j)=<ij|ja>, stored
+    // [(t(i)*NT + t(a))*NT + t(j)] with t() = spatial index-1 (RHF, NT = nbasis/2) or orbital-1 (UHF, NT = nbasis):
+    // the occupied-orbital sum of slater_condon1_mol_excit then walks two contiguous rows instead of
+    // gathering ~30 scattered entries of the 8-fold store (same values, same summation order).
+    const double* sc1C;
+    const double* sc1X;
+    int NT;
     // heat-bath tables (src/excit_gens.f90:143-153), column-major as in the reference
     const double* hb_i_w;       // (nb)
     const double* hb_ij_w;      // (j,i)
@@ -328,15 +335,31 @@ HB_HDN double slater_condon0(const Sys& s, const uint8_t* occ) {
     }
     return h;
 }
-// slater_condon1_mol_excit (src/hamiltonian_molecular.f90:199-259)
+// slater_condon1_mol_excit (src/hamiltonian_molecular.f90:199-259); integrals through the C/X row tables
+HB_HD int tix(const Sys& s, int i) { return s.uhf ? (i - 1) : ((i - 1) >> 1); }
 HB_HDN double slater_condon1_excit(const Sys& s, const uint8_t* occ, int i, int a, bool perm) {
     double h = one_body(s, i, a);
-    const int msi = s.bf_ms[i];
-    for (int iel = 0; iel < s.nel; ++iel) {
-        int j = occ[iel];
-        if (j != i) {
-            h = h + two_body(s, i, j, a, j);
-            if (s.bf_ms[j] == msi) h = h - two_body(s, i, j, j, a);
+    const long long base = ((long long)tix(s, i) * s.NT + tix(s, a)) * s.NT;
+    const double* __restrict__ C = s.sc1C + base;
+    const double* __restrict__ X = s.sc1X + base;
+    if (!s.uhf) {
+        // RHF: odd orbital = alpha, even = beta -> same spin <=> same parity
+        for (int iel = 0; iel < s.nel; ++iel) {
+            const int j = occ[iel];
+            if (j != i) {
+                const int t = (j - 1) >> 1;
+                h = h + C[t];
+                if (((j ^ i) & 1) == 0) h = h - X[t];
+            }
+        }
+    } else {
+        const int msi = s.bf_ms[i];
+        for (int iel = 0; iel < s.nel; ++iel) {
+            const int j = occ[iel];
+            if (j != i) {
+                h = h + C[j - 1];
+                if (s.bf_ms[j] == msi) h = h - X[j - 1];
+            }
         }
     }
     return perm ? -h : h;
@@ -634,7 +657,50 @@ HB_HDN int select_weighted_value(R& rng, int N, const double* weights, double to
     return select_precalc(rng, N, aliasU, aliasK);
 }
 
-// gen_excit_mol_heat_bath (src/excit_gen_heat_bath_mol.F90:258-548; src/excit_gen_utils.f90:9-66,142-160)
+// On-the-fly alias table over the occupied orbitals (select_weighted_value, lib/local/alias.f90:68-184) with
+// weights w(q) = tab[occ[q]-1], N = nel <= 64.  Equivalent to generate_alias_tables: the overfull stack is only
+// ever popped, so it is a bitmask read from its highest bit; the underfull stack is its initial ascending content
+// (a bitmask) plus at most one element pushed on top (the overfull entry that just dropped below one).
+HB_HD int clz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return __clzll((long long)x);
+#else
+    return __builtin_clzll(x);
+#endif
+}
+template <class R>
+HB_HDN int select_weighted_occ(R& rng, int N, const double* __restrict__ tab, const uint8_t* occ, double totweight) {
+    double U[HB_MAXNEL];
+    uint8_t K[HB_MAXNEL];
+    uint64_t under = 0, over = 0;
+    const double scale = N / totweight;
+    for (int q = 0; q < N; ++q) {
+        const double u = tab[occ[q] - 1] * scale;
+        U[q] = u;
+        if (u <= 1.0) under |= (1ull << q); else over |= (1ull << q);
+        K[q] = (uint8_t)(q + 1);
+    }
+    int pushed = -1;
+    while (over != 0 && (pushed >= 0 || under != 0)) {
+        const int ov = 63 - clz64(over);
+        int un;
+        if (pushed >= 0) { un = pushed; pushed = -1; }
+        else { un = 63 - clz64(under); under &= ~(1ull << un); }
+        K[un] = (uint8_t)(ov + 1);
+        const double v = U[ov] - (1 - U[un]);
+        U[ov] = v;
+        if (v < 1.0) { pushed = ov; over &= ~(1ull << ov); }
+    }
+    double x = rng.next() * N;
+    const int k = (int)floor(x);
+    x = x - k;
+    if (x < U[k]) return k + 1;
+    return K[k];
+}
+
+// gen_excit_mol_heat_bath (src/excit_gen_heat_bath_mol.F90:258-548; src/excit_gen_utils.f90:9-66,142-160).
+// The per-determinant weight lists (i_d_occ%weights, ij_weights_occ, ji_weights_occ) are columns of hb_i_w / hb_ij_w
+// gathered at the occupied orbitals; they are re-read where needed instead of being staged in per-thread arrays.
 template <int W, class R>
 HB_HDN void gen_excit_heat_bath(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ,
                                 Gen& g) {
@@ -643,28 +709,19 @@ HB_HDN void gen_excit_heat_bath(R& rng, const Sys& s, const Params& p, const uin
 #define HB_I2(j, i) ((int64_t)((j) - 1) + nb * ((i) - 1))
 #define HB_I3(a, j, i) ((int64_t)((a) - 1) + nb * (((j) - 1) + nb * ((i) - 1)))
 #define HB_I4(b, a, j, i) ((int64_t)((b) - 1) + nb * (((a) - 1) + nb * (((j) - 1) + nb * ((i) - 1))))
-    double i_w[HB_MAXNEL], ij_w[HB_MAXNEL], ji_w[HB_MAXNEL];
     double i_tot = 0.0, ij_tot = 0.0, ji_tot = 0.0;
     g.from2 = 0; g.to2 = 0; g.perm = false; g.from1 = 0; g.to1 = 0; g.nexcit = 2;
-    for (int q = 0; q < nel; ++q) {
-        i_w[q] = s.hb_i_w[occ[q] - 1];
-        i_tot = i_tot + i_w[q];
-    }
-    int i_ind = select_weighted_value(rng, nel, i_w, i_tot);
-    int i = occ[i_ind - 1];
-    for (int q = 0; q < nel; ++q) {
-        ij_w[q] = s.hb_ij_w[HB_I2(occ[q], i)];
-        ij_tot = ij_tot + ij_w[q];
-    }
+    for (int q = 0; q < nel; ++q) i_tot = i_tot + s.hb_i_w[occ[q] - 1];
+    const int i = occ[select_weighted_occ(rng, nel, s.hb_i_w, occ, i_tot) - 1];
+    const double* __restrict__ ijcol = s.hb_ij_w + nb * (i - 1);
+    for (int q = 0; q < nel; ++q) ij_tot = ij_tot + ijcol[occ[q] - 1];
     bool allowed = false;
-    int j_ind = 0, j = 0;
+    int j = 0;
+    const double* __restrict__ jicol = ijcol;
     if (ij_tot > 0.0) {
-        j_ind = select_weighted_value(rng, nel, ij_w, ij_tot);
-        j = occ[j_ind - 1];
-        for (int q = 0; q < nel; ++q) {
-            ji_w[q] = s.hb_ij_w[HB_I2(occ[q], j)];
-            ji_tot = ji_tot + ji_w[q];
-        }
+        j = occ[select_weighted_occ(rng, nel, ijcol, occ, ij_tot) - 1];
+        jicol = s.hb_ij_w + nb * (j - 1);
+        for (int q = 0; q < nel; ++q) ji_tot = ji_tot + jicol[occ[q] - 1];
         allowed = fabs(s.hb_ija_tot[HB_I2(j, i)]) > 0.0;
     }
     int a = 0, b = 0;
@@ -699,10 +756,13 @@ HB_HDN void gen_excit_heat_bath(R& rng, const Sys& s, const Params& p, const uin
             g.allowed = false; g.hmatel = 0.0; g.pgen = 1.0;
             return;
         }
-        const double pi_ = i_w[i_ind - 1] / i_tot;
-        const double pj_ = i_w[j_ind - 1] / i_tot;
+        const double pi_ = s.hb_i_w[i - 1] / i_tot;
+        const double pj_ = s.hb_i_w[j - 1] / i_tot;
+        const double pij = ijcol[j - 1] / ij_tot;   // ij_weights_occ(j_ind)/ij_weights_occ_tot
+        const double pji = jicol[i - 1] / ji_tot;   // ji_weights_occ(i_ind)/ji_weights_occ_tot
         double ps[3];
         const int fr[3] = {i, j, j}, to[3] = {b, a, b}, ot[3] = {j, i, i};
+#pragma unroll
         for (int k = 0; k < 3; ++k) {
             int isyma = cross_product(s, s.bf_sym[fr[k]], s.gamma_sym);
             if (s.bf_sym[to[k]] == isyma && s.bf_ms[to[k]] == s.bf_ms[fr[k]]) {
@@ -714,13 +774,13 @@ HB_HDN void gen_excit_heat_bath(R& rng, const Sys& s, const Params& p, const uin
                 ps[k] = 0.0;
             }
         }
-        double pgen_ija = ((pi_) * (ij_w[j_ind - 1] / ij_tot)) * (s.hb_ija_w[HB_I3(a, j, i)] / s.hb_ija_tot[HB_I2(j, i)]) *
+        double pgen_ija = ((pi_) * (pij)) * (s.hb_ija_w[HB_I3(a, j, i)] / s.hb_ija_tot[HB_I2(j, i)]) *
                           (1.0 - psingle) * (s.hb_ijab_w[HB_I4(b, a, j, i)] / s.hb_ijab_tot[HB_I3(a, j, i)]);
-        double pgen_ijb = ((pi_) * (ij_w[j_ind - 1] / ij_tot)) * (s.hb_ija_w[HB_I3(b, j, i)] / s.hb_ija_tot[HB_I2(j, i)]) *
+        double pgen_ijb = ((pi_) * (pij)) * (s.hb_ija_w[HB_I3(b, j, i)] / s.hb_ija_tot[HB_I2(j, i)]) *
                           (1.0 - ps[0]) * (s.hb_ijab_w[HB_I4(a, b, j, i)] / s.hb_ijab_tot[HB_I3(b, j, i)]);
-        double pgen_jia = ((pj_) * (ji_w[i_ind - 1] / ji_tot)) * (s.hb_ija_w[HB_I3(a, i, j)] / s.hb_ija_tot[HB_I2(i, j)]) *
+        double pgen_jia = ((pj_) * (pji)) * (s.hb_ija_w[HB_I3(a, i, j)] / s.hb_ija_tot[HB_I2(i, j)]) *
                           (1.0 - ps[1]) * (s.hb_ijab_w[HB_I4(b, a, i, j)] / s.hb_ijab_tot[HB_I3(a, i, j)]);
-        double pgen_jib = ((pj_) * (ji_w[i_ind - 1] / ji_tot)) * (s.hb_ija_w[HB_I3(b, i, j)] / s.hb_ija_tot[HB_I2(i, j)]) *
+        double pgen_jib = ((pj_) * (pji)) * (s.hb_ija_w[HB_I3(b, i, j)] / s.hb_ija_tot[HB_I2(i, j)]) *
                           (1.0 - ps[2]) * (s.hb_ijab_w[HB_I4(a, b, i, j)] / s.hb_ijab_tot[HB_I3(b, i, j)]);
         g.pgen = pgen_ija + pgen_ijb + pgen_jia + pgen_jib;
         g.from1 = (i < j) ? i : j; g.from2 = (i < j) ? j : i;
@@ -739,10 +799,10 @@ HB_HDN void gen_excit_heat_bath(R& rng, const Sys& s, const Params& p, const uin
                 double wt = s.hb_ijab_tot[HB_I3(a, oq, i)];
                 double psq;
                 if (hmod_ia < wt) psq = hmod_ia / (wt + hmod_ia); else psq = 0.5;
-                pgen = pgen + (psq * (ij_w[q] / ij_tot) * (s.hb_ija_w[HB_I3(a, oq, i)] / s.hb_ija_tot[HB_I2(oq, i)]));
+                pgen = pgen + (psq * (ijcol[oq - 1] / ij_tot) * (s.hb_ija_w[HB_I3(a, oq, i)] / s.hb_ija_tot[HB_I2(oq, i)]));
             }
         }
-        g.pgen = pgen * (i_w[i_ind - 1] / i_tot);
+        g.pgen = pgen * (s.hb_i_w[i - 1] / i_tot);
         g.allowed = true;
     }
 }

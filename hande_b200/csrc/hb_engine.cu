@@ -686,6 +686,24 @@ k_merge(const uint64_t* __restrict__ states, const int64_t* __restrict__ pops, c
     }
 }
 
+// sum |pop| over a list: per-block partials (fixed order) -> k_reduce_ll
+__global__ void __launch_bounds__(TILE) k_abs_sum(const int64_t* __restrict__ pops, long long n, long long* __restrict__ part) {
+    __shared__ long long sl[TILE / 32];
+    long long v = 0;
+    for (long long i = (long long)blockIdx.x * TILE + threadIdx.x; i < n; i += (long long)gridDim.x * TILE) {
+        const long long p = pops[i];
+        v += p < 0 ? -p : p;
+    }
+    v = warp_sum_ll(v);
+    if ((threadIdx.x & 31) == 0) sl[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long t = 0;
+        for (int w = 0; w < TILE / 32; ++w) t += sl[w];
+        part[blockIdx.x] = t;
+    }
+}
+
 __global__ void k_reduce_ll(const long long* __restrict__ in, int n, long long* out) {
     __shared__ long long sl[32];
     long long v = 0;
@@ -711,6 +729,16 @@ __global__ void k_build_JK(Sys s, double* J, double* K) {
     const int i = t / nb + 1, j = t % nb + 1;
     J[t] = two_body(s, i, j, i, j);
     K[t] = two_body(s, i, j, j, i);
+}
+
+// single-excitation row tables C(i,a,j) = <ij|aj>, X(i,a,j) = <ij|ja> (see hb_core.cuh Sys::sc1C)
+__global__ void k_build_sc1_tables(Sys s, int NT, double* C, double* X) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)NT * NT * NT) return;
+    const int tj = (int)(t % NT), ta = (int)((t / NT) % NT), ti = (int)(t / ((long long)NT * NT));
+    const int i = s.uhf ? ti + 1 : 2 * ti + 1, a = s.uhf ? ta + 1 : 2 * ta + 1, j = s.uhf ? tj + 1 : 2 * tj + 1;
+    C[t] = two_body(s, i, j, a, j);
+    X[t] = two_body(s, i, j, j, a);
 }
 
 // ijab_w(b,a,j,i) = |<ij||ab>| for allowed (spin, symmetry, distinct) index quadruples, else 0
@@ -870,10 +898,17 @@ struct hb200_engine {
     long long* d_counts = nullptr;  // [nprocs*nprocs]
     // timing / counters
     cudaEvent_t ev[6];
+    cudaEvent_t evk[2];           // brackets the k_spawn_death launch alone (roofline timing)
+    float spawn_kernel_ms = 0.f;  // accumulated over the cycles of the last hb200_iterate
     double ms[8] = {0};
     long long launches = 0, spawn_launches = 0;
 };
 
+
+// All host<->device copies are issued on the engine's own (non-blocking) stream and then synchronised: a plain
+// cudaMemcpy runs on the legacy stream, which is NOT ordered with kernels on a cudaStreamNonBlocking stream, and a
+// pageable H2D copy may return before its DMA has landed.
+static cudaError_t copy_sync(hb200_engine* e, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind);
 template <class T>
 static int dalloc(hb200_engine* e, T** p, size_t n) {
     void* q = nullptr;
@@ -886,9 +921,15 @@ template <class T>
 static int dupload(hb200_engine* e, const T** dst, const T* src, size_t n) {
     T* q = nullptr;
     if (dalloc(e, &q, n)) return 1;
-    if (n) CK(cudaMemcpy(q, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    if (n) CK(copy_sync(e, q, src, n * sizeof(T), cudaMemcpyHostToDevice));
     *dst = q;
     return 0;
+}
+
+static cudaError_t copy_sync(hb200_engine* e, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+    cudaError_t r = cudaMemcpyAsync(dst, src, bytes, kind, e->stream);
+    if (r != cudaSuccess) return r;
+    return cudaStreamSynchronize(e->stream);
 }
 
 static size_t spawn_smem_bytes(const hb200_engine* e) {
@@ -932,6 +973,7 @@ hb200_engine* hb200_create(const hb200_config* cfg) {
     if (cudaSetDevice(cfg->device) != cudaSuccess) return fail("cudaSetDevice failed");
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return fail("stream");
     for (int i = 0; i < 6; ++i) cudaEventCreate(&e->ev[i]);
+    for (int i = 0; i < 2; ++i) cudaEventCreate(&e->evk[i]);
     memset(&e->sys, 0, sizeof(Sys));
     memset(&e->par, 0, sizeof(Params));
     Params& p = e->par;
@@ -989,10 +1031,11 @@ hb200_engine* hb200_create(const hb200_config* cfg) {
         std::vector<int> map((size_t)p.nprocs * p.nslots);
         for (size_t i = 0; i < map.size(); ++i) map[i] = (int)(i % p.nprocs);  // src/load_balancing.F90:170
         if (dalloc(e, &e->d_proc_map, map.size())) return fail("alloc");
-        if (cudaMemcpy(e->d_proc_map, map.data(), map.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess)
+        if (copy_sync(e, e->d_proc_map, map.data(), map.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess)
             return fail("memcpy proc_map");
     }
-    if (cudaMemset(e->d_err, 0, 4 * sizeof(int)) != cudaSuccess) return fail("memset");
+    if (cudaMemsetAsync(e->d_err, 0, 4 * sizeof(int), e->stream) != cudaSuccess) return fail("memset");
+    if (cudaStreamSynchronize(e->stream) != cudaSuccess) return fail("sync");
     return e;
 }
 
@@ -1034,6 +1077,16 @@ int hb200_set_system_read_in(hb200_engine* e, const hb200_system_read_in* in) {
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
     s.Jd = J; s.Kd = K;
+    {
+        const int NT = s.uhf ? nb : nb / 2;
+        const long long n3 = (long long)NT * NT * NT;
+        double *C = nullptr, *X = nullptr;
+        if (dalloc(e, &C, (size_t)n3) || dalloc(e, &X, (size_t)n3)) return 1;
+        k_build_sc1_tables<<<(unsigned)((n3 + 255) / 256), 256, 0, e->stream>>>(s, NT, C, X);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(e->stream));
+        s.sc1C = C; s.sc1X = X; s.NT = NT;
+    }
     e->have_sys = true;
     return 0;
 }
@@ -1081,7 +1134,7 @@ int hb200_download_heat_bath(hb200_engine* e, int which, void* out, int64_t n) {
                            s.hb_ijab_tot, s.hb_ija_K, s.hb_ijab_K};
     if (which < 0 || which > 9) FAIL("download_heat_bath: bad table id");
     const size_t esz = which >= 8 ? sizeof(int) : sizeof(double);
-    CK(cudaMemcpy(out, src[which], (size_t)n * esz, cudaMemcpyDeviceToHost));
+    CK(copy_sync(e, out, src[which], (size_t)n * esz, cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -1094,7 +1147,7 @@ int hb200_set_reference(hb200_engine* e, const uint64_t* f0, double H00) {
 int hb200_set_proc_map(hb200_engine* e, const int32_t* map, int32_t n) {
     CK(cudaSetDevice(e->cfg.device));
     if (n != e->par.nprocs * e->par.nslots) FAIL("set_proc_map: wrong length");
-    CK(cudaMemcpy(e->d_proc_map, map, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+    CK(copy_sync(e, e->d_proc_map, map, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -1102,14 +1155,21 @@ int hb200_upload_psips(hb200_engine* e, const uint64_t* states, const int64_t* p
     CK(cudaSetDevice(e->cfg.device));
     if (n > e->cfg.walker_length) FAIL("upload_psips: more states than walker_length");
     const int c = e->cur;
+    long long s = 0;
+    CK(cudaMemsetAsync(e->d_err, 0, 4 * sizeof(int), e->stream));  // a new list starts a new calculation
     if (n) {
-        CK(cudaMemcpy(e->d_states[c], states, (size_t)n * e->W * 8, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(e->d_pops[c], pops, (size_t)n * 8, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(e->d_dat[c], dat, (size_t)n * 8, cudaMemcpyHostToDevice));
+        cudaStream_t st = e->stream;
+        CK(cudaMemcpyAsync(e->d_states[c], states, (size_t)n * e->W * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(e->d_pops[c], pops, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(e->d_dat[c], dat, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        const int nb = (int)std::min<long long>(1184, (n + TILE - 1) / TILE);
+        k_abs_sum<<<nb, TILE, 0, st>>>(e->d_pops[c], n, e->d_part_ll);
+        k_reduce_ll<<<1, 1024, 0, st>>>(e->d_part_ll, nb, e->d_ll);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&s, e->d_ll, sizeof(long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
     }
     e->nstates = n;
-    long long s = 0;
-    for (int64_t i = 0; i < n; ++i) s += pops[i] < 0 ? -pops[i] : pops[i];
     e->nparticles_enc = s;
     return 0;
 }
@@ -1122,9 +1182,11 @@ int hb200_download_psips(hb200_engine* e, uint64_t* states, int64_t* pops, doubl
     if (n > capacity) FAIL("download_psips: capacity too small");
     const int c = e->cur;
     if (n) {
-        CK(cudaMemcpy(states, e->d_states[c], (size_t)n * e->W * 8, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(pops, e->d_pops[c], (size_t)n * 8, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(dat, e->d_dat[c], (size_t)n * 8, cudaMemcpyDeviceToHost));
+        cudaStream_t st = e->stream;
+        CK(cudaMemcpyAsync(states, e->d_states[c], (size_t)n * e->W * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(pops, e->d_pops[c], (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(dat, e->d_dat[c], (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
     }
     return 0;
 }
@@ -1154,6 +1216,7 @@ static int stage_spawn_death(hb200_engine* e, const hb200_iter_in* in, uint32_t 
     if (ntiles > 0) {
         const size_t smem = spawn_smem_bytes(e);
         const int c = e->cur;
+        CK(cudaEventRecord(e->evk[0], st));
         DISPATCH_W(e, {
             static bool attr_set[5] = {false, false, false, false, false};
             if (!attr_set[WW]) {
@@ -1165,6 +1228,7 @@ static int stage_spawn_death(hb200_engine* e, const hb200_iter_in* in, uint32_t 
                                                            e->d_partials, e->d_err);
         });
         CK(cudaGetLastError());
+        CK(cudaEventRecord(e->evk[1], st));
         e->launches++; e->spawn_launches++;
     }
     k_reduce_partials<<<1, 1024, 0, st>>>(e->d_partials, ntiles, e->d_stats);
@@ -1173,6 +1237,11 @@ static int stage_spawn_death(hb200_engine* e, const hb200_iter_in* in, uint32_t 
     CK(cudaMemcpyAsync(e->h_head.data(), e->d_head, sizeof(unsigned long long) * p.nprocs, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(hst, e->d_stats, sizeof(CycleStats), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (ntiles > 0) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, e->evk[0], e->evk[1]);
+        e->spawn_kernel_ms += t;
+    }
     for (int d = 0; d < p.nprocs; ++d)
         if ((long long)e->h_head[d] > e->block_size) e->h_head[d] = (unsigned long long)e->block_size;  // overflow: dropped
     e->sp_cur = 0;
@@ -1337,7 +1406,7 @@ static void fill_out(hb200_engine* e, hb200_iter_out* out, const CycleStats& st,
     out->ndeath = st.ndeath;
     out->nattempts = nattempts;
     int herr[2] = {0, 0};
-    cudaMemcpy(herr, e->d_err, 2 * sizeof(int), cudaMemcpyDeviceToHost);
+    copy_sync(e, herr, e->d_err, 2 * sizeof(int), cudaMemcpyDeviceToHost);
     out->spawn_error = herr[0];
     out->psip_error = herr[1];
 }
@@ -1400,7 +1469,7 @@ int hb200_download_spawn(hb200_engine* e, int64_t* sdata, int64_t capacity, int6
         long long off = 0;
         for (int d = 0; d < e->par.nprocs; ++d) {
             const long long c = (long long)e->h_head[d];
-            if (c) CK(cudaMemcpy(sdata + off * E, e->d_spawn[0] + (long long)d * e->block_size * E, (size_t)c * E * 8,
+            if (c) CK(copy_sync(e, sdata + off * E, e->d_spawn[0] + (long long)d * e->block_size * E, (size_t)c * E * 8,
                                  cudaMemcpyDeviceToHost));
             off += c;
         }
@@ -1408,14 +1477,14 @@ int hb200_download_spawn(hb200_engine* e, int64_t* sdata, int64_t capacity, int6
     }
     *n = e->sp_n;
     if (e->sp_n > capacity) FAIL("download_spawn: capacity too small");
-    if (e->sp_n) CK(cudaMemcpy(sdata, e->d_spawn[e->sp_cur], (size_t)e->sp_n * E * 8, cudaMemcpyDeviceToHost));
+    if (e->sp_n) CK(copy_sync(e, sdata, e->d_spawn[e->sp_cur], (size_t)e->sp_n * E * 8, cudaMemcpyDeviceToHost));
     return 0;
 }
 
 int hb200_upload_spawn(hb200_engine* e, const int64_t* sdata, int64_t n) {
     CK(cudaSetDevice(e->cfg.device));
     if (n > e->cfg.spawned_walker_length) FAIL("upload_spawn: too many elements");
-    if (n) CK(cudaMemcpy(e->d_spawn[0], sdata, (size_t)n * e->E * 8, cudaMemcpyHostToDevice));
+    if (n) CK(copy_sync(e, e->d_spawn[0], sdata, (size_t)n * e->E * 8, cudaMemcpyHostToDevice));
     e->sp_cur = 0; e->sp_n = n; e->sp_blocked = false;
     return 0;
 }
@@ -1427,6 +1496,7 @@ int hb200_iterate(hb200_engine* e, int32_t ncycles, const hb200_iter_in* in, hb2
     memset(out, 0, sizeof(*out));
     cudaStream_t st = e->stream;
     float acc[4] = {0, 0, 0, 0};
+    e->spawn_kernel_ms = 0.f;
     CycleStats cs;
     memset(&cs, 0, sizeof(cs));
     long long nattempts = 0;
@@ -1435,6 +1505,7 @@ int hb200_iterate(hb200_engine* e, int32_t ncycles, const hb200_iter_in* in, hb2
         const uint32_t cycle = in->first_cycle + (uint32_t)c;
         // init_mc_cycle (src/qmc_common.F90:950-1017)
         nattempts = llround(2.0 * ((double)e->nparticles_enc / (double)e->par.real_factor));
+        out->walker_iterations += (double)e->nparticles_enc / (double)e->par.real_factor;
         CK(cudaEventRecord(e->ev[0], st));
         if (stage_spawn_death(e, in, cycle, &cs)) return 1;
         CK(cudaEventRecord(e->ev[1], st));
@@ -1464,6 +1535,7 @@ int hb200_iterate(hb200_engine* e, int32_t ncycles, const hb200_iter_in* in, hb2
     cudaEventElapsedTime(&tot, e->ev[5], e->ev[4]);
     for (int k = 0; k < 4; ++k) e->ms[k] = acc[k];
     e->ms[4] = tot;
+    e->ms[5] = e->spawn_kernel_ms;
     fill_out(e, out, cs, nattempts);
     return 0;
 }
@@ -1476,11 +1548,11 @@ int hb200_sc0_batch(hb200_engine* e, const uint64_t* states, int64_t n, double* 
     double* d_o = nullptr;
     CK(cudaMalloc((void**)&d_f, (size_t)n * e->W * 8));
     CK(cudaMalloc((void**)&d_o, (size_t)n * 8));
-    CK(cudaMemcpy(d_f, states, (size_t)n * e->W * 8, cudaMemcpyHostToDevice));
+    CK(copy_sync(e, d_f, states, (size_t)n * e->W * 8, cudaMemcpyHostToDevice));
     DISPATCH_W(e, k_sc0<WW><<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->sys, 0.0, d_f, e->W, n, d_o));
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
-    CK(cudaMemcpy(out, d_o, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    CK(copy_sync(e, out, d_o, (size_t)n * 8, cudaMemcpyDeviceToHost));
     cudaFree(d_f); cudaFree(d_o);
     return 0;
 }
@@ -1499,16 +1571,16 @@ int hb200_gen_excit_batch(hb200_engine* e, const uint64_t* states, const int64_t
     CK(cudaMalloc((void**)&d_io, (size_t)n * 8 * 4));
     CK(cudaMalloc((void**)&d_do, (size_t)n * 2 * 8));
     CK(cudaMalloc((void**)&d_ns, (size_t)n * 8));
-    CK(cudaMemcpy(d_f, states, (size_t)n * e->W * 8, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(d_p, pops, (size_t)n * 8, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(d_a, attempt, (size_t)n * 4, cudaMemcpyHostToDevice));
+    CK(copy_sync(e, d_f, states, (size_t)n * e->W * 8, cudaMemcpyHostToDevice));
+    CK(copy_sync(e, d_p, pops, (size_t)n * 8, cudaMemcpyHostToDevice));
+    CK(copy_sync(e, d_a, attempt, (size_t)n * 4, cudaMemcpyHostToDevice));
     DISPATCH_W(e, k_gen_excit_batch<WW><<<(unsigned)((n + 127) / 128), 128, 0, e->stream>>>(e->sys, p, d_f, d_p, d_a, n,
                                                                                            e->d_proc_map, d_io, d_do, d_ns));
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
-    CK(cudaMemcpy(iout, d_io, (size_t)n * 8 * 4, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(dout, d_do, (size_t)n * 2 * 8, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(nspawn, d_ns, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    CK(copy_sync(e, iout, d_io, (size_t)n * 8 * 4, cudaMemcpyDeviceToHost));
+    CK(copy_sync(e, dout, d_do, (size_t)n * 2 * 8, cudaMemcpyDeviceToHost));
+    CK(copy_sync(e, nspawn, d_ns, (size_t)n * 8, cudaMemcpyDeviceToHost));
     cudaFree(d_f); cudaFree(d_p); cudaFree(d_a); cudaFree(d_io); cudaFree(d_do); cudaFree(d_ns);
     return 0;
 }

@@ -50,6 +50,7 @@ class IterOut(C.Structure):
         ("proj_energy", C.c_double), ("D0_population", C.c_double), ("nparticles", C.c_double),
         ("nstates", C.c_int64), ("nspawn_events", C.c_int64), ("ndeath", C.c_int64), ("nattempts", C.c_int64),
         ("rspawn", C.c_double), ("nattempts_spawn", C.c_int64), ("spawn_error", C.c_int32), ("psip_error", C.c_int32),
+        ("walker_iterations", C.c_double),
     ]
 
     def as_dict(self):
@@ -190,6 +191,16 @@ class Engine:
         assert len(states) == len(pops) == len(dat)
         self._chk(self.L.hb200_upload_psips(self.h, _p(states), _p(pops), _p(dat), len(pops)))
 
+    def upload_psips_ptr(self, states_ptr, pops_ptr, dat_ptr, n):
+        """hb200_upload_psips from caller-owned (e.g. pinned) host buffers given as integer addresses."""
+        self._chk(self.L.hb200_upload_psips(self.h, C.c_void_p(states_ptr), C.c_void_p(pops_ptr), C.c_void_p(dat_ptr), n))
+
+    def download_psips_ptr(self, states_ptr, pops_ptr, dat_ptr, capacity):
+        nn = C.c_int64(0)
+        self._chk(self.L.hb200_download_psips(self.h, C.c_void_p(states_ptr), C.c_void_p(pops_ptr),
+                                              C.c_void_p(dat_ptr), capacity, C.byref(nn)))
+        return nn.value
+
     @property
     def nstates(self):
         return int(self.L.hb200_nstates(self.h))
@@ -279,5 +290,5 @@ class Engine:
         ms = np.zeros(8)
         cnt = np.zeros(4, dtype=np.int64)
         self.L.hb200_last_timing(self.h, _p(ms), _p(cnt))
-        return {"spawn_ms": ms[0], "comm_ms": ms[1], "sort_ms": ms[2], "annihilate_ms": ms[3], "total_ms": ms[4],
+        return {"spawn_ms": ms[0], "comm_ms": ms[1], "sort_ms": ms[2], "annihilate_ms": ms[3], "total_ms": ms[4], "spawn_kernel_ms": ms[5],
                 "spawn_launches": int(cnt[0]), "launches": int(cnt[1])}

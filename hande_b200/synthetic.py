@@ -106,3 +106,68 @@ def random_walkers(n, nbasis, nalpha, nbeta, real_factor=1, dist="A", seed=1):
         if real_factor == 1:
             mag = np.maximum(mag, 1)
     return f, sign * mag
+
+
+def murmur_owner_torch(w, nbasis, nprocs, nslots=1, seed=7):
+    """Owner rank of determinants (rows of int64 tensor w[n, W]) by HANDE's rule, evaluated with torch ops:
+    MurmurHash2 over ceil(nbasis/32) 32-bit words, seed 7, Fortran modulo (src/spawning.F90:770-838)."""
+    import torch
+    M32 = 0xFFFFFFFF
+    m = 0x5BD1E995
+    nw = (nbasis + 31) // 32
+    h = torch.full((w.shape[0],), (seed ^ (nw * 4)) & M32, dtype=torch.int64, device=w.device)
+    for i in range(nw):
+        k = (w[:, i // 2] >> (32 * (i % 2))) & M32
+        k = (k * m) & M32
+        k = k ^ (k >> 24)
+        k = (k * m) & M32
+        h = (h * m) & M32
+        h = h ^ k
+    h = h ^ (h >> 13)
+    h = (h * m) & M32
+    h = h ^ (h >> 15)
+    h = torch.where(h >= 2**31, h - 2**32, h)
+    return torch.remainder(h, nprocs * nslots) % nprocs
+
+
+def random_walkers_torch(n, nbasis, nalpha, nbeta, real_factor, device, seed=1, nprocs=1, iproc=0, chunk=4_000_000):
+    """n distinct random determinants owned by rank `iproc`, sorted in the reference's list order, |pop| = 1
+    (distribution A of SURVEY.md 8d), generated on the GPU with torch (data plumbing only).
+    Returns numpy (states[n, W] uint64, pops[n] int64)."""
+    import torch
+    assert nbasis <= 126, "two signed 64-bit words"
+    norb = nbasis // 2
+    W = (nbasis + 63) // 64
+    g = torch.Generator(device=device)
+    g.manual_seed(seed * 1000003 + iproc)
+    parts = []
+    have = 0
+    while have < n:
+        m = chunk
+        w = torch.zeros((m, 2), dtype=torch.int64, device=device)
+        for nocc, off in ((nalpha, 0), (nbeta, 1)):
+            sel = torch.rand((m, norb), device=device, generator=g).topk(nocc, dim=1).indices  # nocc of norb
+            bit = 2 * sel + off
+            for wi in range(W):
+                inw = (bit // 64) == wi
+                contrib = torch.where(inw, torch.ones_like(bit) << (bit % 64), torch.zeros_like(bit)).sum(dim=1)
+                w[:, wi] |= contrib
+        if nprocs > 1:
+            w = w[murmur_owner_torch(w, nbasis, nprocs) == iproc]
+        parts.append(w)
+        have += w.shape[0]
+    w = torch.cat(parts)[: int(n * 1.02) + 16]
+    del parts
+    # sort: unsigned compare, last word most significant (bit_str_cmp): two stable sorts, low word first
+    flip = torch.tensor(-2**63, dtype=torch.int64, device=device)
+    for wi in range(W):
+        key = w[:, wi] ^ flip if wi == 0 or True else w[:, wi]
+        idx = torch.sort(key, stable=True).indices
+        w = w[idx]
+    keep = torch.ones(w.shape[0], dtype=torch.bool, device=device)
+    keep[1:] = (w[1:] != w[:-1]).any(dim=1)
+    w = w[keep][:n]
+    sign = torch.where(torch.rand(w.shape[0], device=device, generator=g) < 0.5, -1, 1).to(torch.int64)
+    pops = sign * int(real_factor)
+    states = w[:, :W].contiguous().cpu().numpy().view(np.uint64)
+    return states, pops.cpu().numpy()

@@ -86,6 +86,7 @@ typedef struct hb200_iter_out {
     double rspawn;                 /* sum over cycles of spawning_rate() */
     int64_t nattempts_spawn;       /* total spawning attempts made (all cycles; throughput metric) */
     int32_t spawn_error, psip_error;
+    double walker_iterations;      /* sum over cycles of nparticles at the start of the cycle (throughput metric) */
 } hb200_iter_out;
 
 const char* hb200_last_error(void);
@@ -149,7 +150,7 @@ int hb200_comm_init(hb200_engine* e, const uint8_t id[128]);
 
 /* Timing of the stages of the last hb200_iterate call, milliseconds (CUDA events on the engine stream):
  * ms[0] spawn+death kernel, ms[1] exchange, ms[2] sort+annihilate_spawn, ms[3] main-list annihilation+merge,
- * ms[4] total.  Counters: cnt[0] = spawn kernel launches, cnt[1] = all kernel launches. */
+ * ms[4] total, ms[5] the k_spawn_death kernel alone.  Counters: cnt[0] = spawn kernel launches, cnt[1] = all kernel launches. */
 int hb200_last_timing(hb200_engine* e, double ms[8], int64_t cnt[4]);
 
 #ifdef __cplusplus

@@ -406,7 +406,7 @@ int orc_cpu_baseline(void* h, int nthreads, int ncycles, double tau, double shif
     for (int t = 0; t < nthreads; ++t) {
         reps[t].reset(new Oracle());
         Oracle& r = *reps[t];
-        r.sys = o->sys; r.in = o->in; r.eg = o->eg; r.occ_list0 = o->occ_list0; r.f0 = o->f0; r.H00 = o->H00;
+        r.sys = o->sys; r.in = o->in; r.eg_shared = &o->eg; r.occ_list0 = o->occ_list0; r.f0 = o->f0; r.H00 = o->H00;
         r.ref_ex_level = o->ref_ex_level; r.pop_real_factor = o->pop_real_factor; r.spawn_cutoff = o->spawn_cutoff;
         r.proc_map = o->proc_map; r.tau = tau; r.shift = shift; r.est.proj_energy_old = proj_energy_old;
         r.ranks.resize(1);

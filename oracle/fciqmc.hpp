@@ -173,6 +173,8 @@ struct Oracle {
     System sys;
     QmcIn in;
     ExcitGenData eg;
+    const ExcitGenData* eg_shared = nullptr;  // replicas of orc_cpu_baseline share the (2 GB) heat-bath tables
+    const ExcitGenData& EG() const { return eg_shared ? *eg_shared : eg; }
     // reference_t
     std::vector<int> occ_list0;
     Det f0;
@@ -346,7 +348,7 @@ struct Oracle {
         const int64_t block_size = in.spawned_walker_length / in.nprocs;
         DetInfo d;
         for (int64_t idet = 0; idet < r.nstates; ++idet) {
-            decode_for(sys, eg, r.states[idet], d);
+            decode_for(sys, EG(), r.states[idet], d);
             double real_population = (double)r.pops[idet] / (double)pop_real_factor;
             // set_parent_flag (src/ifciqmc.f90:13-57), nspaces=1, no deterministic space (determ_flag=1)
             d.initiator_flag = (std::fabs(real_population) > in.initiator_pop) ? 0 : 1;
@@ -356,7 +358,7 @@ struct Oracle {
             int64_t pop = r.pops[idet];
             for (int ip = 0; ip < nattempts_det; ++ip) {
                 rng.begin(RNG_SPAWN, d.f, sys.W, (uint32_t)ip);
-                GenResult g = gen_excit(rng, sys, eg, d);
+                GenResult g = gen_excit(rng, sys, EG(), d);
                 int64_t nspawned = attempt_to_spawn(rng, g.hmatel, g.pgen, pop);
                 if (nspawned != 0) {
                     Det fnew = sys.create_excited_det(d.f, g.conn);

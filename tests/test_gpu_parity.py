@@ -134,7 +134,7 @@ def test_stage_and_cycle_parity(name, gen, real, init, tau, n, exl):
 
 @pytest.mark.parametrize("name,gen,real,init,tau", [("h2o", "renorm", False, False, 0.003),
                                                      ("ne", "renorm", True, True, 0.005),
-                                                     ("s12", "heat_bath", True, True, 0.01)])
+                                                     ("s12", "heat_bath", True, True, 0.002)])
 def test_iterate_from_single_determinant(name, gen, real, init, tau):
     """Population growth from the reference determinant: 60 cycles in blocks of 10 through hb200_iterate."""
     s, o, eng, ref = make_pair(name, excit_gen=gen, tau=tau, real=real, initiator=init)
@@ -147,6 +147,7 @@ def test_iterate_from_single_determinant(name, gen, real, init, tau):
         ro = o.iterate(10, cyc, tau, 0.0, -0.02 * block)
         rg = eng.iterate(10, tau, 0.0, -0.02 * block, cyc)
         cyc += 10
+        assert rg["spawn_error"] == 0 and rg["psip_error"] == 0 and ro["error"] == 0
         fo, po, do_ = o.get_psips()
         fg, pg, dg = eng.download_psips()
         assert len(fg) == len(fo)

@@ -30,6 +30,8 @@
 
 namespace hb {
 
+struct alignas(16) D2 { double x, y; };
+
 // ------------------------------------------------------------------------------------------------
 // System tables resident in HBM/L2 (plain pointers; filled by hb200_set_system_read_in).
 // ------------------------------------------------------------------------------------------------
@@ -56,8 +58,7 @@ struct Sys {
     // [(t(i)*NT + t(a))*NT + t(j)] with t() = spatial index-1 (RHF, NT = nbasis/2) or orbital-1 (UHF, NT = nbasis):
     // the occupied-orbital sum of slater_condon1_mol_excit then walks two contiguous rows instead of
     // gathering ~30 scattered entries of the 8-fold store (same values, same summation order).
-    const double* sc1C;
-    const double* sc1X;
+    const D2* sc1CX;            // {C, X} pairs: one 16-byte load per occupied orbital
     int NT;
     // heat-bath tables (src/excit_gens.f90:143-153), column-major as in the reference
     const double* hb_i_w;       // (nb)
@@ -339,26 +340,24 @@ HB_HDN double slater_condon0(const Sys& s, const uint8_t* occ) {
 HB_HD int tix(const Sys& s, int i) { return s.uhf ? (i - 1) : ((i - 1) >> 1); }
 HB_HDN double slater_condon1_excit(const Sys& s, const uint8_t* occ, int i, int a, bool perm) {
     double h = one_body(s, i, a);
-    const long long base = ((long long)tix(s, i) * s.NT + tix(s, a)) * s.NT;
-    const double* __restrict__ C = s.sc1C + base;
-    const double* __restrict__ X = s.sc1X + base;
-    if (!s.uhf) {
-        // RHF: odd orbital = alpha, even = beta -> same spin <=> same parity
-        for (int iel = 0; iel < s.nel; ++iel) {
-            const int j = occ[iel];
-            if (j != i) {
-                const int t = (j - 1) >> 1;
-                h = h + C[t];
-                if (((j ^ i) & 1) == 0) h = h - X[t];
-            }
+    const D2* __restrict__ row = s.sc1CX + ((long long)tix(s, i) * s.NT + tix(s, a)) * s.NT;
+    const int nel = s.nel;
+    // chunks of 4 occupied orbitals: issue the (independent) loads first, then add in occ_list order
+    for (int q0 = 0; q0 < nel; q0 += 4) {
+        int jj[4];
+        D2 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            jj[k] = (q0 + k < nel) ? occ[q0 + k] : i;
+            v[k] = row[tix(s, jj[k])];
         }
-    } else {
-        const int msi = s.bf_ms[i];
-        for (int iel = 0; iel < s.nel; ++iel) {
-            const int j = occ[iel];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int j = jj[k];
             if (j != i) {
-                h = h + C[j - 1];
-                if (s.bf_ms[j] == msi) h = h - X[j - 1];
+                h = h + v[k].x;
+                const bool same = s.uhf ? (s.bf_ms[j] == s.bf_ms[i]) : (((j ^ i) & 1) == 0);
+                if (same) h = h - v[k].y;
             }
         }
     }
@@ -668,6 +667,18 @@ HB_HD int clz64(uint64_t x) {
     return __builtin_clzll(x);
 #endif
 }
+// sum_q tab[occ[q]-1] in occ_list order; loads issued four at a time (adding the 0.0 padding is exact)
+HB_HD double sum_occ(const double* __restrict__ tab, const uint8_t* occ, int nel) {
+    double tot = 0.0;
+    for (int q0 = 0; q0 < nel; q0 += 4) {
+        double v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (q0 + k < nel) ? tab[occ[q0 + k] - 1] : 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tot = tot + v[k];
+    }
+    return tot;
+}
 template <class R>
 HB_HDN int select_weighted_occ(R& rng, int N, const double* __restrict__ tab, const uint8_t* occ, double totweight) {
     double U[HB_MAXNEL];
@@ -711,17 +722,17 @@ HB_HDN void gen_excit_heat_bath(R& rng, const Sys& s, const Params& p, const uin
 #define HB_I4(b, a, j, i) ((int64_t)((b) - 1) + nb * (((a) - 1) + nb * (((j) - 1) + nb * ((i) - 1))))
     double i_tot = 0.0, ij_tot = 0.0, ji_tot = 0.0;
     g.from2 = 0; g.to2 = 0; g.perm = false; g.from1 = 0; g.to1 = 0; g.nexcit = 2;
-    for (int q = 0; q < nel; ++q) i_tot = i_tot + s.hb_i_w[occ[q] - 1];
+    i_tot = sum_occ(s.hb_i_w, occ, nel);
     const int i = occ[select_weighted_occ(rng, nel, s.hb_i_w, occ, i_tot) - 1];
     const double* __restrict__ ijcol = s.hb_ij_w + nb * (i - 1);
-    for (int q = 0; q < nel; ++q) ij_tot = ij_tot + ijcol[occ[q] - 1];
+    ij_tot = sum_occ(ijcol, occ, nel);
     bool allowed = false;
     int j = 0;
     const double* __restrict__ jicol = ijcol;
     if (ij_tot > 0.0) {
         j = occ[select_weighted_occ(rng, nel, ijcol, occ, ij_tot) - 1];
         jicol = s.hb_ij_w + nb * (j - 1);
-        for (int q = 0; q < nel; ++q) ji_tot = ji_tot + jicol[occ[q] - 1];
+        ji_tot = sum_occ(jicol, occ, nel);
         allowed = fabs(s.hb_ija_tot[HB_I2(j, i)]) > 0.0;
     }
     int a = 0, b = 0;

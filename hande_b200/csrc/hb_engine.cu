@@ -137,7 +137,7 @@ struct SpawnPartials {  // one per block; reduced in fixed order by k_reduce_par
 };
 
 template <int W>
-__global__ void __launch_bounds__(TILE)
+__global__ void __launch_bounds__(TILE, 4)
 k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __restrict__ pops,
               const double* __restrict__ dat, long long nstates, int64_t* __restrict__ spawn,
               unsigned long long* __restrict__ head, long long block_size, const int* __restrict__ proc_map,
@@ -732,13 +732,15 @@ __global__ void k_build_JK(Sys s, double* J, double* K) {
 }
 
 // single-excitation row tables C(i,a,j) = <ij|aj>, X(i,a,j) = <ij|ja> (see hb_core.cuh Sys::sc1C)
-__global__ void k_build_sc1_tables(Sys s, int NT, double* C, double* X) {
+__global__ void k_build_sc1_tables(Sys s, int NT, D2* CX) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)NT * NT * NT) return;
     const int tj = (int)(t % NT), ta = (int)((t / NT) % NT), ti = (int)(t / ((long long)NT * NT));
     const int i = s.uhf ? ti + 1 : 2 * ti + 1, a = s.uhf ? ta + 1 : 2 * ta + 1, j = s.uhf ? tj + 1 : 2 * tj + 1;
-    C[t] = two_body(s, i, j, a, j);
-    X[t] = two_body(s, i, j, j, a);
+    D2 v;
+    v.x = two_body(s, i, j, a, j);
+    v.y = two_body(s, i, j, j, a);
+    CX[t] = v;
 }
 
 // ijab_w(b,a,j,i) = |<ij||ab>| for allowed (spin, symmetry, distinct) index quadruples, else 0
@@ -1080,12 +1082,12 @@ int hb200_set_system_read_in(hb200_engine* e, const hb200_system_read_in* in) {
     {
         const int NT = s.uhf ? nb : nb / 2;
         const long long n3 = (long long)NT * NT * NT;
-        double *C = nullptr, *X = nullptr;
-        if (dalloc(e, &C, (size_t)n3) || dalloc(e, &X, (size_t)n3)) return 1;
-        k_build_sc1_tables<<<(unsigned)((n3 + 255) / 256), 256, 0, e->stream>>>(s, NT, C, X);
+        D2* CX = nullptr;
+        if (dalloc(e, &CX, (size_t)n3)) return 1;
+        k_build_sc1_tables<<<(unsigned)((n3 + 255) / 256), 256, 0, e->stream>>>(s, NT, CX);
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(e->stream));
-        s.sc1C = C; s.sc1X = X; s.NT = NT;
+        s.sc1CX = CX; s.NT = NT;
     }
     e->have_sys = true;
     return 0;

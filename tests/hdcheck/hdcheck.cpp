@@ -13,7 +13,8 @@ static Params g_par;
 static std::vector<uint8_t> g_sym;
 static std::vector<int8_t> g_ms;
 static std::vector<uint16_t> g_spatial;
-static std::vector<double> g_J, g_K, g_C, g_X;
+static std::vector<double> g_J, g_K;
+static std::vector<D2> g_CX;
 
 template <int W, class R>
 static void gen_one(R& rng, const uint64_t* f, int64_t parent_pop, int* iout, double* dout, int64_t* nspawn) {
@@ -54,15 +55,14 @@ void hd_set_sys(int nbasis, int nel, int nsym_tot, int sym0, int sym_max, int pg
     s.Jd = g_J.data(); s.Kd = g_K.data();
     const int NT = uhf ? nbasis : nbasis / 2;
     s.NT = NT;
-    g_C.assign((size_t)NT * NT * NT, 0.0); g_X.assign((size_t)NT * NT * NT, 0.0);
+    g_CX.assign((size_t)NT * NT * NT, D2{0.0, 0.0});
     for (int ti = 0; ti < NT; ++ti)
         for (int ta = 0; ta < NT; ++ta)
             for (int tj = 0; tj < NT; ++tj) {
                 const int i = uhf ? ti + 1 : 2 * ti + 1, a = uhf ? ta + 1 : 2 * ta + 1, j = uhf ? tj + 1 : 2 * tj + 1;
-                g_C[((size_t)ti * NT + ta) * NT + tj] = two_body(s, i, j, a, j);
-                g_X[((size_t)ti * NT + ta) * NT + tj] = two_body(s, i, j, j, a);
+                g_CX[((size_t)ti * NT + ta) * NT + tj] = D2{two_body(s, i, j, a, j), two_body(s, i, j, j, a)};
             }
-    s.sc1C = g_C.data(); s.sc1X = g_X.data();
+    s.sc1CX = g_CX.data();
 }
 void hd_set_heat_bath(const double* i_w, const double* ij_w, const double* ija_w, const double* ija_U, const int* ija_K,
                       const double* ija_tot, const double* ijab_w, const double* ijab_U, const int* ijab_K,

@@ -1,0 +1,74 @@
+"""Worker for the multi-GPU parity test: launched with torchrun (one rank per GPU).  Every rank owns the
+determinants HANDE's hash-owner rule assigns to it, runs MC cycles through hb200_iterate (NCCL all-to-all of the
+spawn blocks inside) and compares its list with the oracle's emulated rank of the same index (test infrastructure)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from hande_b200 import read_in as R
+    from hande_b200.engine import Engine
+    from hande_b200.fciqmc import TorchDist, owner_of
+    from oracle.pyoracle import Oracle
+    from tests.common import system_path, random_population
+
+    name, gen, real, init, tau = sys.argv[1], sys.argv[2], bool(int(sys.argv[3])), bool(int(sys.argv[4])), float(sys.argv[5])
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    comm = TorchDist(device=dev)
+    path, kw = system_path(name) if rank == 0 else (None, None)
+    dist.barrier()
+    path, kw = system_path(name)
+    s = R.read_in(path, **kw)
+    o = Oracle()
+    o.read_fcidump(path, **kw)
+    o.set_qmc(tau=tau, seed=11, excit_gen=gen, rng_kind=1, real_amplitudes=int(real), spawn_cutoff=0.01,
+              initiator_approx=int(init), literal_event_int32=0, walker_length=1 << 17, spawned_walker_length=1 << 16,
+              nprocs=world)
+    o.init()
+    ref = o.reference()
+    eng = Engine(s, excit_gen=gen, pattempt_single=ref["pattempt_single"], pattempt_double=ref["pattempt_double"],
+                 real_amplitudes=real, spawn_cutoff=0.01, initiator_approx=init, walker_length=1 << 17,
+                 spawned_walker_length=1 << 16, seed=11, nprocs=world, iproc=rank, device=local)
+    eng.set_reference(ref["f0"], ref["H00"])
+    uid = eng.get_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)
+    eng.comm_init(comm.broadcast_bytes(uid, src=0))
+    f, pops, dat = random_population(s, o, 4000, real, seed=5)
+    own = np.array([owner_of(x, s.nbasis, world, 1) for x in f])
+    for r in range(world):
+        m = own == r
+        o.set_psips(f[m], pops[m], dat[m], rank=r)
+        assert all(o.owner(x) == r for x in f[m][:50])
+    m = own == rank
+    eng.upload_psips(f[m], pops[m], dat[m])
+    cyc = 1
+    for block in range(3):
+        ro = o.iterate(4, cyc, tau, -0.05, -0.1)
+        rg = eng.iterate(4, tau, -0.05, -0.1, cyc)
+        cyc += 4
+        fo, po, do_ = o.get_psips(rank)
+        fg, pg, dg = eng.download_psips()
+        assert len(fg) == len(fo), (rank, len(fg), len(fo))
+        assert (fg == fo).all() and (pg == po).all() and (dg == do_).all(), rank
+        tot = comm.allreduce_sum(np.array([rg["proj_energy"], rg["D0_population"], float(rg["nspawn_events"]),
+                                           float(rg["ndeath"]), float(rg["nstates"])]))
+        assert abs(tot[0] - ro["proj_energy"]) <= 1e-12 * max(1.0, abs(ro["proj_energy"]))
+        assert abs(tot[1] - ro["D0_population"]) <= 1e-12 * max(1.0, abs(ro["D0_population"]))
+        assert tot[2] == ro["nspawn_events"] and tot[3] == ro["ndeath"] and tot[4] == ro["nstates"]
+    print(f"rank {rank}: OK {len(fg)} states", flush=True)
+    eng.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

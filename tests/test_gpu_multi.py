@@ -1,0 +1,31 @@
+"""Multi-GPU parity (-m gpu, needs >= 2 GPUs): hash-owner sharding + NCCL all-to-all vs the oracle's emulated ranks."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.parametrize("name,gen,real,init,tau", [("h2o", "renorm", 0, 0, 0.003), ("s12", "heat_bath", 1, 1, 0.004)])
+def test_two_rank_parity(name, gen, real, init, tau):
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    nproc = 4 if n >= 4 else 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "multi_gpu_worker.py"),
+           name, gen, str(real), str(init), str(tau)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.stdout.count("OK") == nproc

@@ -17,7 +17,8 @@
 //   k_merge           single pass merge of survivors and new determinants into the other main-list buffer
 //   k_sc0             <D|H|D> - H00 for new determinants
 #include <cuda_runtime.h>
-#include <nccl.h>
+#include <nccl.h>   // types only: the library is bound at run time (see NcclApi below)
+#include <dlfcn.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -39,11 +40,41 @@ static thread_local std::string g_err;
             return 1;                                                                              \
         }                                                                                          \
     } while (0)
+// NCCL is resolved lazily with dlopen/dlsym instead of a link-time dependency: a host process that also uses
+// torch (bench.py, the multi-GPU tests) must end up with ONE libnccl.so.2, and torch's bundled copy (2.28) is newer
+// than the system one (2.27).  Order: a copy already loaded in the process, $HB200_NCCL_LIB, the system library.
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(std::string& err) {
+        if (h) return true;
+        h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+        if (!h) { const char* p = getenv("HB200_NCCL_LIB"); if (p && *p) h = dlopen(p, RTLD_NOW | RTLD_GLOBAL); }
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) { err = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
+#define HB_SYM(field, name) field = (decltype(field))dlsym(h, name); if (!field) { err = std::string("NCCL symbol missing: ") + name; return false; }
+        HB_SYM(GetUniqueId, "ncclGetUniqueId") HB_SYM(CommInitRank, "ncclCommInitRank") HB_SYM(CommDestroy, "ncclCommDestroy")
+        HB_SYM(AllGather, "ncclAllGather") HB_SYM(Send, "ncclSend") HB_SYM(Recv, "ncclRecv")
+        HB_SYM(GroupStart, "ncclGroupStart") HB_SYM(GroupEnd, "ncclGroupEnd") HB_SYM(GetErrorString, "ncclGetErrorString")
+#undef HB_SYM
+        return true;
+    }
+};
+static NcclApi g_nccl;
+
 #define NCK(call)                                                                                  \
     do {                                                                                           \
         ncclResult_t _e = (call);                                                                  \
         if (_e != ncclSuccess) {                                                                   \
-            g_err = std::string(#call) + ": " + ncclGetErrorString(_e) + " @" + std::to_string(__LINE__); \
+            g_err = std::string(#call) + ": " + g_nccl.GetErrorString(_e) + " @" + std::to_string(__LINE__); \
             return 1;                                                                              \
         }                                                                                          \
     } while (0)
@@ -1044,7 +1075,7 @@ hb200_engine* hb200_create(const hb200_config* cfg) {
 void hb200_destroy(hb200_engine* e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
-    if (e->comm) ncclCommDestroy(e->comm);
+    if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     for (void* q : e->owned) cudaFree(q);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -1263,25 +1294,25 @@ static int stage_comm(hb200_engine* e) {
     std::vector<long long> row(np);
     for (int d = 0; d < np; ++d) row[d] = (long long)e->h_head[d];
     CK(cudaMemcpyAsync(e->d_counts + (size_t)me * np, row.data(), sizeof(long long) * np, cudaMemcpyHostToDevice, st));
-    NCK(ncclAllGather(e->d_counts + (size_t)me * np, e->d_counts, np, ncclInt64, e->comm, st));
+    NCK(g_nccl.AllGather(e->d_counts + (size_t)me * np, e->d_counts, np, ncclInt64, e->comm, st));
     std::vector<long long> counts((size_t)np * np);
     CK(cudaMemcpyAsync(counts.data(), e->d_counts, sizeof(long long) * np * np, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     // MPI_Alltoallv (src/spawn_data.F90:721): receive blocks ordered by source rank
     long long off = 0;
-    NCK(ncclGroupStart());
+    NCK(g_nccl.GroupStart());
     for (int r = 0; r < np; ++r) {
         const long long nsend = counts[(size_t)me * np + r], nrecv = counts[(size_t)r * np + me];
         if (r == me) {
             if (nsend) CK(cudaMemcpyAsync(e->d_spawn[1] + off * E, e->d_spawn[0] + (long long)r * e->block_size * E,
                                           (size_t)nsend * E * 8, cudaMemcpyDeviceToDevice, st));
         } else {
-            if (nsend) NCK(ncclSend(e->d_spawn[0] + (long long)r * e->block_size * E, (size_t)nsend * E, ncclInt64, r, e->comm, st));
-            if (nrecv) NCK(ncclRecv(e->d_spawn[1] + off * E, (size_t)nrecv * E, ncclInt64, r, e->comm, st));
+            if (nsend) NCK(g_nccl.Send(e->d_spawn[0] + (long long)r * e->block_size * E, (size_t)nsend * E, ncclInt64, r, e->comm, st));
+            if (nrecv) NCK(g_nccl.Recv(e->d_spawn[1] + off * E, (size_t)nrecv * E, ncclInt64, r, e->comm, st));
         }
         off += nrecv;
     }
-    NCK(ncclGroupEnd());
+    NCK(g_nccl.GroupEnd());
     if (off > e->cfg.spawned_walker_length) FAIL("comm_spawn: received more than spawned_walker_length");
     e->sp_cur = 1;
     e->sp_n = off;
@@ -1589,7 +1620,8 @@ int hb200_gen_excit_batch(hb200_engine* e, const uint64_t* states, const int64_t
 
 int hb200_get_unique_id(uint8_t id[128]) {
     ncclUniqueId uid;
-    NCK(ncclGetUniqueId(&uid));
+    if (!g_nccl.load(g_err)) return 1;
+    NCK(g_nccl.GetUniqueId(&uid));
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
     memcpy(id, &uid, 128);
     return 0;
@@ -1599,7 +1631,8 @@ int hb200_comm_init(hb200_engine* e, const uint8_t id[128]) {
     CK(cudaSetDevice(e->cfg.device));
     ncclUniqueId uid;
     memcpy(&uid, id, 128);
-    NCK(ncclCommInitRank(&e->comm, e->par.nprocs, uid, e->par.iproc));
+    if (!g_nccl.load(g_err)) return 1;
+    NCK(g_nccl.CommInitRank(&e->comm, e->par.nprocs, uid, e->par.iproc));
     return 0;
 }
 

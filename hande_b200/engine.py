@@ -60,11 +60,28 @@ class IterOut(C.Structure):
 _LIB = None
 
 
+def _point_at_bundled_nccl():
+    """Tell the engine where torch's bundled libnccl.so.2 lives (used only if no NCCL is loaded yet when
+    hb200_comm_init runs), so that one process never ends up with two different NCCL builds."""
+    if os.environ.get("HB200_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        if spec and spec.submodule_search_locations:
+            cand = os.path.join(list(spec.submodule_search_locations)[0], "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["HB200_NCCL_LIB"] = cand
+    except Exception:
+        pass
+
+
 def load_library():
     """Load (building if stale) the CUDA engine.  Raises if it cannot be built/loaded - never falls back."""
     global _LIB
     if _LIB is not None:
         return _LIB
+    _point_at_bundled_nccl()
     path = _build.LIB
     if _build.needs_build():
         if os.path.exists("/usr/local/cuda/bin/nvcc"):

@@ -139,7 +139,7 @@ HEADER = (" #     iterations   Shift                 \\sum H_0j N_j         N_0 
 def format_row(it, shift, pe, d0, npart, nstates, nev, rspawn, t, comment=False):
     """write_qmc_report (src/qmc_io.f90:412-508)."""
     lead = " # " if comment else "   "
-    return (f"{lead}{it:11d}  {shift:17.10E}    {pe:18.10E}    {d0:18.10E}    {npart:18.10E}"
+    return (f"{lead}{it:14d}  {shift:17.10E}    {pe:18.10E}    {d0:18.10E}    {npart:18.10E}"
             f"  {nstates:17d}  {nev:14d}  {rspawn:8.4f}  {t:8.4f}  ")
 
 

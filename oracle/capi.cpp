@@ -441,3 +441,48 @@ int orc_cpu_baseline(void* h, int nthreads, int ncycles, double tau, double shif
 }
 
 }  // extern "C"
+
+// ---- per-rank stage API: lets a test drive ONE emulated rank per process (exchange done by the caller),
+// used by the world_size-2 gloo test of the host-side driver.
+extern "C" {
+int orc_rank_spawn(void* h, int rank, uint32_t cycle_id, double tau, double shift, double proj_energy_old, double* out) {
+    ORC_TRY
+    Oracle* o = (Oracle*)h;
+    o->tau = tau; o->shift = shift; o->est.proj_energy_old = proj_energy_old;
+    RankState& r = o->ranks[rank];
+    r.proj_energy = 0.0; r.D0_population = 0.0;
+    o->spawn_death_rank(r, cycle_id);
+    out[0] = r.proj_energy; out[1] = r.D0_population; out[2] = (double)r.nspawn_events; out[3] = (double)r.ndeath;
+    out[4] = (double)r.nattempts;
+    return 0;
+    ORC_CATCH(-1)
+}
+int64_t orc_rank_send_count(void* h, int rank, int dest) { return (int64_t)((Oracle*)h)->ranks[rank].send[dest].size(); }
+void orc_rank_get_send(void* h, int rank, int dest, int64_t* sdata) {
+    Oracle* o = (Oracle*)h;
+    int W = o->sys.W, E = W + 2;
+    int64_t k = 0;
+    for (auto& e : o->ranks[rank].send[dest]) {
+        for (int w = 0; w < W; ++w) sdata[k * E + w] = (int64_t)e.f.w[w];
+        sdata[k * E + W] = e.pop; sdata[k * E + W + 1] = e.flag;
+        ++k;
+    }
+}
+int orc_rank_annihilate(void* h, int rank, const int64_t* sdata, int64_t n, double* out) {
+    ORC_TRY
+    Oracle* o = (Oracle*)h;
+    RankState& r = o->ranks[rank];
+    int W = o->sys.W, E = W + 2;
+    r.recv.clear();
+    for (int64_t k = 0; k < n; ++k) {
+        SpawnElem e;
+        for (int w = 0; w < W; ++w) e.f.w[w] = (uint64_t)sdata[k * E + w];
+        e.pop = sdata[k * E + W]; e.flag = sdata[k * E + W + 1];
+        r.recv.push_back(e);
+    }
+    o->annihilate_rank(r);
+    out[0] = r.nparticles; out[1] = (double)r.nstates; out[2] = (r.spawn_error || r.psip_error) ? 1.0 : 0.0;
+    return 0;
+    ORC_CATCH(-1)
+}
+}

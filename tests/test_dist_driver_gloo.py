@@ -1,0 +1,65 @@
+"""world_size-2 gloo test (CPU) of the multi-rank host path: the product driver hande_b200.fciqmc.do_fciqmc with
+TorchDist collectives, one process per rank, must reproduce the reference's np2 golden trajectory
+(test_suite/fciqmc/np2/Ne-aug-cc-pVDZ-ci6qmc) when each rank's propagation is done by the oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from tests.conftest import load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NROWS = 60
+
+
+def _worker(rank, world, port, fcidump, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from hande_b200 import read_in as R
+    from hande_b200.fciqmc import QmcIn, TorchDist, do_fciqmc
+    from tests.oracle_engine import make_engine_cls
+    g = load_golden("ne_ci6_np2")
+    kw = dict(nel=g["sys"]["nel"], ms=g["sys"]["ms"], sym=g["sys"]["sym"], cas=tuple(g["sys"]["cas"]))
+    s = R.read_in(fcidump, **kw)
+    gq = g["qmc"]
+    qmc = QmcIn(tau=gq["tau"], rng_seed=gq["seed"], init_pop=gq["D0_population"], mc_cycles=gq["ncycles"],
+                nreports=NROWS, target_population=gq["target_particles"], state_size=gq["walker_length"],
+                spawned_state_size=gq["spawned_walker_length"], ex_level=gq["ex_level"])
+    res = do_fciqmc(s, qmc, comm=TorchDist(), engine_cls=make_engine_cls(fcidump, kw, rng_kind=0))
+    if rank == 0:
+        q.put(res.rows)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_np2_driver_reproduces_golden(fcidump_path):
+    from oracle import pyoracle
+    if not pyoracle.have_ref_lib():
+        pytest.skip("oracle/_ref not built")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    path = fcidump_path("ne")
+    procs = [ctx.Process(target=_worker, args=(r, 2, 29577, path, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    rows = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    gold = np.array(load_golden("ne_ci6_np2")["rows"])
+
+    def pr(x):
+        return float("%.10E" % x)
+    assert len(rows) == NROWS + 1
+    for i, r in enumerate(rows):
+        gr = gold[i]
+        assert gr[0] == r[0]
+        for k in (1, 2, 3, 4):
+            assert gr[k] == pr(r[k]), (i, k, gr[k], r[k])
+        assert gr[5] == r[5] and gr[6] == r[6]
+        assert abs(gr[7] - r[7]) < 0.6e-4

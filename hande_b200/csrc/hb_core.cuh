@@ -681,112 +681,178 @@ HB_HD double sum_occ(const double* __restrict__ tab, const uint8_t* occ, int nel
 }
 template <class R>
 HB_HDN int select_weighted_occ(R& rng, int N, const double* __restrict__ tab, const uint8_t* occ, double totweight) {
-    double U[HB_MAXNEL];
-    uint8_t K[HB_MAXNEL];
-    uint64_t under = 0, over = 0;
-    const double scale = N / totweight;
-    for (int q = 0; q < N; ++q) {
-        const double u = tab[occ[q] - 1] * scale;
-        U[q] = u;
-        if (u <= 1.0) under |= (1ull << q); else over |= (1ull << q);
-        K[q] = (uint8_t)(q + 1);
-    }
-    int pushed = -1;
-    while (over != 0 && (pushed >= 0 || under != 0)) {
-        const int ov = 63 - clz64(over);
-        int un;
-        if (pushed >= 0) { un = pushed; pushed = -1; }
-        else { un = 63 - clz64(under); under &= ~(1ull << un); }
-        K[un] = (uint8_t)(ov + 1);
-        const double v = U[ov] - (1 - U[un]);
-        U[ov] = v;
-        if (v < 1.0) { pushed = ov; over &= ~(1ull << ov); }
-    }
+    // The alias construction consumes no random numbers, so the single draw of select_weighted_value_precalc is
+    // taken first: only slot k's final aliasU/aliasK are needed, and no table has to be stored.  Values evolve as
+    // in generate_alias_tables: underfull entries are never modified; an overfull entry is modified only while it
+    // is on top of the overfull stack (carried in a register) and, once it drops below one, is popped as the very
+    // next underfull entry.
     double x = rng.next() * N;
     const int k = (int)floor(x);
     x = x - k;
-    if (x < U[k]) return k + 1;
-    return K[k];
+    const double scale = N / totweight;
+    uint64_t under = 0, over = 0;
+    for (int q = 0; q < N; ++q) {
+        const double u = tab[occ[q] - 1] * scale;
+        if (u <= 1.0) under |= (1ull << q); else over |= (1ull << q);
+    }
+    double Uk = tab[occ[k] - 1] * scale;   // final aliasU(k) unless k is modified as an overfull entry
+    int Kk = k + 1;                        // aliasK(k)
+    int pushed = -1;
+    double pushed_u = 0.0;
+    int ov = -1;
+    double uov = 0.0;
+    while (over != 0 && (pushed >= 0 || under != 0)) {
+        const int top = 63 - clz64(over);
+        if (top != ov) { ov = top; uov = tab[occ[ov] - 1] * scale; }
+        int un;
+        double uun;
+        if (pushed >= 0) { un = pushed; uun = pushed_u; pushed = -1; }
+        else { un = 63 - clz64(under); under &= ~(1ull << un); uun = tab[occ[un] - 1] * scale; }
+        if (un == k) Kk = ov + 1;
+        uov = uov - (1 - uun);
+        if (ov == k) Uk = uov;
+        if (uov < 1.0) { pushed = ov; pushed_u = uov; over &= ~(1ull << ov); ov = -1; }
+    }
+    if (x < Uk) return k + 1;
+    return Kk;
 }
 
-// gen_excit_mol_heat_bath (src/excit_gen_heat_bath_mol.F90:258-548; src/excit_gen_utils.f90:9-66,142-160).
-// The per-determinant weight lists (i_d_occ%weights, ij_weights_occ, ji_weights_occ) are columns of hb_i_w / hb_ij_w
-// gathered at the occupied orbitals; they are re-read where needed instead of being staged in per-thread arrays.
-template <int W, class R>
-HB_HDN void gen_excit_heat_bath(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ,
-                                Gen& g) {
-    const int nel = s.nel;
-    const int64_t nb = s.nbasis;
+// gen_excit_mol_heat_bath (src/excit_gen_heat_bath_mol.F90:258-548; src/excit_gen_utils.f90:9-66,142-160),
+// split into phases so that the kernel can regroup the work of a tile between them (the per-attempt control flow
+// diverges strongly: ~20 % null excitations, spin-conditional slater_condon1 evaluations, a division-heavy pgen
+// loop for singles).  The monolithic gen_excit_heat_bath below chains the phases for one attempt and is what the
+// CPU parity harness and the probe kernel run; k_spawn_death calls the same phase functions with block-level
+// queues in between.  The per-determinant weight lists (i_d_occ%weights, ij_weights_occ, ji_weights_occ) are columns
+// of hb_i_w / hb_ij_w gathered at the occupied orbitals and are re-read where needed.
 #define HB_I2(j, i) ((int64_t)((j) - 1) + nb * ((i) - 1))
 #define HB_I3(a, j, i) ((int64_t)((a) - 1) + nb * (((j) - 1) + nb * ((i) - 1)))
 #define HB_I4(b, a, j, i) ((int64_t)((b) - 1) + nb * (((a) - 1) + nb * (((j) - 1) + nb * ((i) - 1))))
-    double i_tot = 0.0, ij_tot = 0.0, ji_tot = 0.0;
-    g.from2 = 0; g.to2 = 0; g.perm = false; g.from1 = 0; g.to1 = 0; g.nexcit = 2;
-    i_tot = sum_occ(s.hb_i_w, occ, nel);
-    const int i = occ[select_weighted_occ(rng, nel, s.hb_i_w, occ, i_tot) - 1];
-    const double* __restrict__ ijcol = s.hb_ij_w + nb * (i - 1);
-    ij_tot = sum_occ(ijcol, occ, nel);
-    bool allowed = false;
-    int j = 0;
-    const double* __restrict__ jicol = ijcol;
-    if (ij_tot > 0.0) {
-        j = occ[select_weighted_occ(rng, nel, ijcol, occ, ij_tot) - 1];
-        jicol = s.hb_ij_w + nb * (j - 1);
-        ji_tot = sum_occ(jicol, occ, nel);
-        allowed = fabs(s.hb_ija_tot[HB_I2(j, i)]) > 0.0;
+
+struct HbState {
+    int i, j, a, b;
+    double i_tot, ij_tot, ji_tot;
+    double psingle, hmod_ia, h_ia;   // h_ia = signed <D|H|D_i^a> (with permutation) when need_ia
+    bool allowed;                    // still a candidate excitation
+    bool need_ia;                    // i -> a is spin/symmetry allowed: slater_condon1(i,a) required
+    bool dbl;                        // double excitation chosen
+    bool perm_ia;
+    unsigned need_k;                 // bit k set: ordering k (0: i->b, 1: j->a, 2: j->b) needs slater_condon1
+};
+
+// single -> (from,to,other) of ordering k of the pgen sum
+HB_HD void hb_ordering(const HbState& st, int k, int& fr, int& to, int& ot) {
+    fr = (k == 0) ? st.i : st.j;
+    to = (k == 1) ? st.a : st.b;
+    ot = (k == 0) ? st.j : st.i;
+}
+HB_HD bool hb_single_allowed(const Sys& s, int fr, int to) {
+    const int isyma = cross_product(s, s.bf_sym[fr], s.gamma_sym);
+    return s.bf_sym[to] == isyma && s.bf_ms[to] == s.bf_ms[fr];
+}
+
+// Phase A: select i, j (on-the-fly alias tables) and a (precomputed alias table); 2-3 random numbers.
+template <int W, class R>
+HB_HDN void hb_phase_a(R& rng, const Sys& s, const uint64_t* f, const uint8_t* occ, HbState& st) {
+    const int nel = s.nel;
+    const int64_t nb = s.nbasis;
+    st.i_tot = sum_occ(s.hb_i_w, occ, nel);
+    st.ij_tot = 0.0; st.ji_tot = 0.0;
+    st.j = 0; st.a = 0; st.b = 0;
+    st.psingle = 0.0; st.hmod_ia = 0.0; st.h_ia = 0.0; st.perm_ia = false;
+    st.dbl = true; st.need_ia = false; st.need_k = 0; st.allowed = false;
+    st.i = occ[select_weighted_occ(rng, nel, s.hb_i_w, occ, st.i_tot) - 1];
+    const double* __restrict__ ijcol = s.hb_ij_w + nb * (st.i - 1);
+    st.ij_tot = sum_occ(ijcol, occ, nel);
+    if (st.ij_tot > 0.0) {
+        st.j = occ[select_weighted_occ(rng, nel, ijcol, occ, st.ij_tot) - 1];
+        st.ji_tot = sum_occ(s.hb_ij_w + nb * (st.j - 1), occ, nel);
+        st.allowed = fabs(s.hb_ija_tot[HB_I2(st.j, st.i)]) > 0.0;
     }
-    int a = 0, b = 0;
-    bool dbl = true;
-    double psingle = 0.0, hmod_ia = 0.0;
-    bool perm_ia = false;
-    if (allowed) {
-        a = select_precalc(rng, (int)nb, s.hb_ija_U + HB_I3(1, j, i), s.hb_ija_K + HB_I3(1, j, i));
-        if (!det_test(f, a)) {
-            int isyma = cross_product(s, s.bf_sym[i], s.gamma_sym);
-            if (s.bf_sym[a] == isyma && s.bf_ms[a] == s.bf_ms[i]) {
-                perm_ia = excit_perm1<W>(f, i, a);
-                hmod_ia = fabs(slater_condon1_excit(s, occ, i, a, perm_ia));
-                double x = rng.next();
-                double wt = s.hb_ijab_tot[HB_I3(a, j, i)];
-                if (hmod_ia < wt) psingle = hmod_ia / (wt + hmod_ia); else psingle = 0.5;
-                dbl = !(x < psingle);
-            } else {
-                dbl = true; psingle = 0.0;
-            }
-        } else {
-            allowed = false;
+    if (st.allowed) {
+        st.a = select_precalc(rng, (int)nb, s.hb_ija_U + HB_I3(1, st.j, st.i), s.hb_ija_K + HB_I3(1, st.j, st.i));
+        if (det_test(f, st.a)) st.allowed = false;
+        else st.need_ia = hb_single_allowed(s, st.i, st.a);
+    }
+}
+
+// slater_condon1 request of the tile queues: |<D|H|D_fr^to>| with its sign
+template <int W>
+HB_HD double hb_sc1(const Sys& s, const uint64_t* f, const uint8_t* occ, int fr, int to, bool& perm) {
+    perm = excit_perm1<W>(f, fr, to);
+    return slater_condon1_excit(s, occ, fr, to, perm);
+}
+
+// Phase C: single/double coin (1 random number iff need_ia), selection of b (1 random number iff double).
+template <int W, class R>
+HB_HDN void hb_phase_c(R& rng, const Sys& s, const uint64_t* f, HbState& st) {
+    if (!st.allowed) return;
+    const int64_t nb = s.nbasis;
+    if (st.need_ia) {
+        st.hmod_ia = fabs(st.h_ia);
+        const double x = rng.next();
+        const double wt = s.hb_ijab_tot[HB_I3(st.a, st.j, st.i)];
+        if (st.hmod_ia < wt) st.psingle = st.hmod_ia / (wt + st.hmod_ia); else st.psingle = 0.5;
+        st.dbl = !(x < st.psingle);
+    } else {
+        st.dbl = true; st.psingle = 0.0;
+    }
+    if (st.dbl) {
+        st.b = select_precalc(rng, (int)nb, s.hb_ijab_U + HB_I4(1, st.a, st.j, st.i), s.hb_ijab_K + HB_I4(1, st.a, st.j, st.i));
+        if (det_test(f, st.b)) { st.allowed = false; return; }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            int fr, to, ot;
+            hb_ordering(st, k, fr, to, ot);
+            if (hb_single_allowed(s, fr, to)) st.need_k |= (1u << k);
         }
     }
-    if (!allowed) {
+}
+
+// One term of the generation probability of a single excitation (the q-th occupied orbital as spectator j).
+// Returns false when the term is skipped (oq == i or oq == a).
+HB_HD bool hb_single_term(const Sys& s, int i, int a, double hmod_ia, double ij_tot, int oq, double& term) {
+    if (i == oq || a == oq) return false;
+    const int64_t nb = s.nbasis;
+    const double wt = s.hb_ijab_tot[HB_I3(a, oq, i)];
+    double psq;
+    if (hmod_ia < wt) psq = hmod_ia / (wt + hmod_ia); else psq = 0.5;
+    term = (psq * (s.hb_ij_w[HB_I2(oq, i)] / ij_tot) * (s.hb_ija_w[HB_I3(a, oq, i)] / s.hb_ija_tot[HB_I2(oq, i)]));
+    return true;
+}
+
+// Phase F: generation probability, matrix element and excitation.  hm[k] = |slater_condon1| of ordering k (only
+// read where need_k has the bit); pgen_single_sum = sum of hb_single_term over the occupied orbitals (singles).
+template <int W>
+HB_HDN void hb_phase_f(const Sys& s, const uint64_t* f, const HbState& st, const double* hm, double pgen_single_sum,
+                       Gen& g) {
+    const int64_t nb = s.nbasis;
+    g.from1 = 0; g.from2 = 0; g.to1 = 0; g.to2 = 0; g.perm = false; g.nexcit = 2;
+    if (!st.allowed) {
         g.allowed = false; g.hmatel = 0.0; g.pgen = 1.0;
         return;
     }
-    if (dbl) {
-        b = select_precalc(rng, (int)nb, s.hb_ijab_U + HB_I4(1, a, j, i), s.hb_ijab_K + HB_I4(1, a, j, i));
-        if (det_test(f, b)) {
-            g.allowed = false; g.hmatel = 0.0; g.pgen = 1.0;
-            return;
-        }
-        const double pi_ = s.hb_i_w[i - 1] / i_tot;
-        const double pj_ = s.hb_i_w[j - 1] / i_tot;
-        const double pij = ijcol[j - 1] / ij_tot;   // ij_weights_occ(j_ind)/ij_weights_occ_tot
-        const double pji = jicol[i - 1] / ji_tot;   // ji_weights_occ(i_ind)/ji_weights_occ_tot
+    const int i = st.i, j = st.j, a = st.a, b = st.b;
+    if (st.dbl) {
+        const double* __restrict__ ijcol = s.hb_ij_w + nb * (i - 1);
+        const double* __restrict__ jicol = s.hb_ij_w + nb * (j - 1);
+        const double pi_ = s.hb_i_w[i - 1] / st.i_tot;
+        const double pj_ = s.hb_i_w[j - 1] / st.i_tot;
+        const double pij = ijcol[j - 1] / st.ij_tot;   // ij_weights_occ(j_ind)/ij_weights_occ_tot
+        const double pji = jicol[i - 1] / st.ji_tot;   // ji_weights_occ(i_ind)/ji_weights_occ_tot
         double ps[3];
-        const int fr[3] = {i, j, j}, to[3] = {b, a, b}, ot[3] = {j, i, i};
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            int isyma = cross_product(s, s.bf_sym[fr[k]], s.gamma_sym);
-            if (s.bf_sym[to[k]] == isyma && s.bf_ms[to[k]] == s.bf_ms[fr[k]]) {
-                bool pm = excit_perm1<W>(f, fr[k], to[k]);
-                double hm = fabs(slater_condon1_excit(s, occ, fr[k], to[k], pm));
-                double wt = s.hb_ijab_tot[HB_I3(to[k], ot[k], fr[k])];
-                if (hm < wt) ps[k] = hm / (wt + hm); else ps[k] = 0.5;
+            if (st.need_k & (1u << k)) {
+                int fr, to, ot;
+                hb_ordering(st, k, fr, to, ot);
+                const double wt = s.hb_ijab_tot[HB_I3(to, ot, fr)];
+                if (hm[k] < wt) ps[k] = hm[k] / (wt + hm[k]); else ps[k] = 0.5;
             } else {
                 ps[k] = 0.0;
             }
         }
         double pgen_ija = ((pi_) * (pij)) * (s.hb_ija_w[HB_I3(a, j, i)] / s.hb_ija_tot[HB_I2(j, i)]) *
-                          (1.0 - psingle) * (s.hb_ijab_w[HB_I4(b, a, j, i)] / s.hb_ijab_tot[HB_I3(a, j, i)]);
+                          (1.0 - st.psingle) * (s.hb_ijab_w[HB_I4(b, a, j, i)] / s.hb_ijab_tot[HB_I3(a, j, i)]);
         double pgen_ijb = ((pi_) * (pij)) * (s.hb_ija_w[HB_I3(b, j, i)] / s.hb_ija_tot[HB_I2(j, i)]) *
                           (1.0 - ps[0]) * (s.hb_ijab_w[HB_I4(a, b, j, i)] / s.hb_ijab_tot[HB_I3(b, j, i)]);
         double pgen_jia = ((pj_) * (pji)) * (s.hb_ija_w[HB_I3(a, i, j)] / s.hb_ija_tot[HB_I2(i, j)]) *
@@ -801,21 +867,39 @@ HB_HDN void gen_excit_heat_bath(R& rng, const Sys& s, const Params& p, const uin
         g.hmatel = slater_condon2_excit(s, g.from1, g.from2, g.to1, g.to2, g.perm);
         g.allowed = true;
     } else {
-        g.nexcit = 1; g.from1 = i; g.to1 = a; g.perm = perm_ia;
-        g.hmatel = slater_condon1_excit(s, occ, i, a, perm_ia);
-        double pgen = 0.0;
-        for (int q = 0; q < nel; ++q) {
-            int oq = occ[q];
-            if (i != oq && a != oq) {
-                double wt = s.hb_ijab_tot[HB_I3(a, oq, i)];
-                double psq;
-                if (hmod_ia < wt) psq = hmod_ia / (wt + hmod_ia); else psq = 0.5;
-                pgen = pgen + (psq * (ijcol[oq - 1] / ij_tot) * (s.hb_ija_w[HB_I3(a, oq, i)] / s.hb_ija_tot[HB_I2(oq, i)]));
-            }
-        }
-        g.pgen = pgen * (s.hb_i_w[i - 1] / i_tot);
+        g.nexcit = 1; g.from1 = i; g.to1 = a; g.perm = st.perm_ia;
+        g.hmatel = st.h_ia;
+        g.pgen = pgen_single_sum * (s.hb_i_w[i - 1] / st.i_tot);
         g.allowed = true;
     }
+}
+
+template <int W, class R>
+HB_HDN void gen_excit_heat_bath(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ,
+                                Gen& g) {
+    HbState st;
+    hb_phase_a<W>(rng, s, f, occ, st);
+    if (st.allowed && st.need_ia) st.h_ia = hb_sc1<W>(s, f, occ, st.i, st.a, st.perm_ia);
+    hb_phase_c<W>(rng, s, f, st);
+    double hm[3] = {0.0, 0.0, 0.0};
+    double psum = 0.0;
+    if (st.allowed) {
+        if (st.dbl) {
+            for (int k = 0; k < 3; ++k)
+                if (st.need_k & (1u << k)) {
+                    int fr, to, ot;
+                    hb_ordering(st, k, fr, to, ot);
+                    bool pm;
+                    hm[k] = fabs(hb_sc1<W>(s, f, occ, fr, to, pm));
+                }
+        } else {
+            for (int q = 0; q < s.nel; ++q) {
+                double t;
+                if (hb_single_term(s, st.i, st.a, st.hmod_ia, st.ij_tot, occ[q], t)) psum = psum + t;
+            }
+        }
+    }
+    hb_phase_f<W>(s, f, st, hm, psum, g);
 }
 
 template <int W, class R>

@@ -167,6 +167,51 @@ struct SpawnPartials {  // one per block; reduced in fixed order by k_reduce_par
     long long ndeath, npart, nattempts;
 };
 
+constexpr int SINGLES_CHUNK = 64;  // single excitations whose pgen terms are staged in shared memory at a time
+
+// Shared-memory carve-up of k_spawn_death (same arithmetic on host and device).
+struct SpawnSmem {
+    size_t sf, shash, spop, sscan, swarp, sred, sh1, shm, ssp, spsum, sterm, sq, scnt, sflag, slo, sperm, ssq, ssi, sok, socc, ssu, total;
+    __host__ __device__ SpawnSmem(int W, int nel, int nsu, bool heat_bath) {
+        size_t o = 0;
+        sf = o;     o += (size_t)TILE * W * 8;
+        shash = o;  o += (size_t)TILE * 8;
+        spop = o;   o += (size_t)TILE * 8;
+        sred = o;   o += 40 * 8;
+        sh1 = o;    o += heat_bath ? (size_t)TILE * 8 : 0;        // signed slater_condon1(i,a) per attempt slot
+        shm = o;    o += heat_bath ? (size_t)3 * TILE * 8 : 0;    // |slater_condon1| of the three other orderings
+        ssp = o;    o += heat_bath ? (size_t)2 * TILE * 8 : 0;    // singles: hmod_ia, ij_tot
+        spsum = o;  o += heat_bath ? (size_t)TILE * 8 : 0;        // singles: sum of pgen terms
+        sterm = o;  o += heat_bath ? (size_t)SINGLES_CHUNK * nel * 8 : 0;  // singles: pgen terms of one chunk
+        sscan = o;  o += (size_t)(TILE + 1) * 4;
+        swarp = o;  o += 8 * 4;
+        sq = o;     o += heat_bath ? (size_t)4 * TILE * 4 : 0;    // request queues: [TILE] phase B, [3*TILE] phase D
+        scnt = o;   o += 4 * 4;                                    // queue counters
+        sflag = o;  o += TILE;
+        slo = o;    o += heat_bath ? TILE : 0;                     // tile-state index of each attempt slot
+        sperm = o;  o += heat_bath ? TILE : 0;
+        ssq = o;    o += heat_bath ? TILE : 0;                     // queue of single-excitation slots
+        ssi = o;    o += heat_bath ? 2 * TILE : 0;                 // singles: i, a
+        sok = o;    o += heat_bath ? (size_t)SINGLES_CHUNK * nel : 0;
+        socc = o;   o += (size_t)TILE * nel;
+        ssu = o;    o += (size_t)TILE * nsu;
+        total = (o + 15) & ~(size_t)15;
+    }
+};
+
+// create_excited_det (src/excitations.F90:365-406)
+template <int W>
+__device__ __forceinline__ void make_child(const uint64_t* f, const Gen& g, uint64_t* child) {
+#pragma unroll
+    for (int k = 0; k < W; ++k) child[k] = f[k];
+    child[(g.from1 - 1) >> 6] &= ~(1ull << ((g.from1 - 1) & 63));
+    child[(g.to1 - 1) >> 6] |= (1ull << ((g.to1 - 1) & 63));
+    if (g.nexcit == 2) {
+        child[(g.from2 - 1) >> 6] &= ~(1ull << ((g.from2 - 1) & 63));
+        child[(g.to2 - 1) >> 6] |= (1ull << ((g.to2 - 1) & 63));
+    }
+}
+
 template <int W>
 __global__ void __launch_bounds__(TILE, 4)
 k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __restrict__ pops,
@@ -175,18 +220,34 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
               SpawnPartials* __restrict__ partials, int* __restrict__ err) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nel = s.nel;
+    const bool heat_bath = (p.excit_gen == EXCIT_GEN_HEAT_BATH);
     const int nsu = (p.excit_gen == EXCIT_GEN_RENORM) ? 2 * s.nsym_tot : 0;
-    uint64_t* sf = reinterpret_cast<uint64_t*>(smem_raw);                 // [TILE*W]
-    uint64_t* shash = sf + TILE * W;                                      // [TILE]
-    int64_t* spop = reinterpret_cast<int64_t*>(shash + TILE);             // [TILE]
-    int* sscan = reinterpret_cast<int*>(spop + TILE);                     // [TILE+1]
-    int* swarp = sscan + TILE + 1;                                        // [8]
-    double* sred = reinterpret_cast<double*>(swarp + 8 + ((TILE + 1 + 8) & 1)); // [5*8] (8-byte aligned)
-    uint8_t* sflag = reinterpret_cast<uint8_t*>(sred + 40);               // [TILE]
-    uint8_t* socc = sflag + TILE;                                         // [TILE*nel]
-    uint8_t* ssu = socc + TILE * nel;                                     // [TILE*nsu]
+    const SpawnSmem L(W, nel, nsu, heat_bath);
+    uint64_t* sf = reinterpret_cast<uint64_t*>(smem_raw + L.sf);
+    uint64_t* shash = reinterpret_cast<uint64_t*>(smem_raw + L.shash);
+    int64_t* spop = reinterpret_cast<int64_t*>(smem_raw + L.spop);
+    double* sred = reinterpret_cast<double*>(smem_raw + L.sred);
+    double* sh1 = reinterpret_cast<double*>(smem_raw + L.sh1);
+    double* shm = reinterpret_cast<double*>(smem_raw + L.shm);
+    double* ssp = reinterpret_cast<double*>(smem_raw + L.ssp);
+    double* spsum = reinterpret_cast<double*>(smem_raw + L.spsum);
+    double* sterm = reinterpret_cast<double*>(smem_raw + L.sterm);
+    uint8_t* sok = smem_raw + L.sok;
+    int* sscan = reinterpret_cast<int*>(smem_raw + L.sscan);
+    int* swarp = reinterpret_cast<int*>(smem_raw + L.swarp);
+    uint32_t* sq1 = reinterpret_cast<uint32_t*>(smem_raw + L.sq);
+    uint32_t* sq2 = sq1 + TILE;
+    int* scnt = reinterpret_cast<int*>(smem_raw + L.scnt);
+    uint8_t* sflag = smem_raw + L.sflag;
+    uint8_t* slo = smem_raw + L.slo;
+    uint8_t* sperm = smem_raw + L.sperm;
+    uint8_t* ssq = smem_raw + L.ssq;
+    uint8_t* ssi = smem_raw + L.ssi;
+    uint8_t* socc = smem_raw + L.socc;
+    uint8_t* ssu = smem_raw + L.ssu;
 
     const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
     const long long idx = (long long)blockIdx.x * TILE + tid;
     const int E = W + 2;
 
@@ -231,34 +292,131 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
 
     for (int base = 0; base < T; base += TILE) {
         const int a = base + tid;
-        int64_t nspawn = 0;
-        uint64_t child[W];
-        int dest = 0, pflag = 0;
-        if (a < T) {
-            int lo = 0, hi = TILE;
+        const bool active = a < T;
+        int lo = 0, att = 0;
+        if (active) {
+            int hi = TILE;
             while (hi - lo > 1) {
                 int mid = (lo + hi) >> 1;
                 if (sscan[mid] <= a) lo = mid; else hi = mid;
             }
-            const int att = a - sscan[lo];
-            uint64_t f[W];
+            att = a - sscan[lo];
+        }
+        uint64_t f[W];
 #pragma unroll
-            for (int k = 0; k < W; ++k) f[k] = sf[lo * W + k];
-            PhiloxStream rng;
-            rng.begin(p.seed, p.cycle, RNG_SPAWN, shash[lo], (uint32_t)att);
-            Gen g;
+        for (int k = 0; k < W; ++k) f[k] = sf[lo * W + k];
+        PhiloxStream rng;
+        rng.begin(p.seed, p.cycle, RNG_SPAWN, shash[lo], (uint32_t)att);
+        Gen g;
+        if (heat_bath) {
+            // ---- phase A: i, j, a for every attempt of the round
+            if (tid < 4) scnt[tid] = 0;
+            __syncthreads();
+            HbState st;
+            st.allowed = false; st.need_ia = false; st.dbl = true; st.need_k = 0;
+            if (active) {
+                hb_phase_a<W>(rng, s, f, socc + lo * nel, st);
+                slo[tid] = (uint8_t)lo;
+                if (st.allowed && st.need_ia) {
+                    const int q = atomicAdd(&scnt[0], 1);
+                    sq1[q] = (uint32_t)tid | ((uint32_t)st.i << 8) | ((uint32_t)st.a << 16);
+                }
+            }
+            __syncthreads();
+            // ---- phase B: the queued slater_condon1(i,a), one request per thread
+            for (int r = tid; r < scnt[0]; r += TILE) {
+                const uint32_t rq = sq1[r];
+                const int slot = rq & 255, fr = (rq >> 8) & 255, to = (rq >> 16) & 255, l = slo[slot];
+                uint64_t ff[W];
+#pragma unroll
+                for (int k = 0; k < W; ++k) ff[k] = sf[l * W + k];
+                bool pm;
+                sh1[slot] = hb_sc1<W>(s, ff, socc + l * nel, fr, to, pm);
+                sperm[slot] = pm;
+            }
+            __syncthreads();
+            // ---- phase C: single/double coin, b; queue the remaining slater_condon1 and the singles
+            if (active) {
+                if (st.allowed && st.need_ia) { st.h_ia = sh1[tid]; st.perm_ia = sperm[tid] != 0; }
+                hb_phase_c<W>(rng, s, f, st);
+                if (st.allowed) {
+                    if (st.dbl) {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k)
+                            if (st.need_k & (1u << k)) {
+                                int fr, to, ot;
+                                hb_ordering(st, k, fr, to, ot);
+                                const int q = atomicAdd(&scnt[1], 1);
+                                sq2[q] = (uint32_t)tid | ((uint32_t)fr << 8) | ((uint32_t)to << 16) | ((uint32_t)k << 24);
+                            }
+                    } else {
+                        const int q = atomicAdd(&scnt[2], 1);
+                        ssq[q] = (uint8_t)tid;
+                        ssi[tid] = (uint8_t)st.i; ssi[TILE + tid] = (uint8_t)st.a;
+                        ssp[tid] = st.hmod_ia; ssp[TILE + tid] = st.ij_tot;
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- phase D: queued slater_condon1 of the other orderings (dense)
+            for (int r = tid; r < scnt[1]; r += TILE) {
+                const uint32_t rq = sq2[r];
+                const int slot = rq & 255, fr = (rq >> 8) & 255, to = (rq >> 16) & 255, k = rq >> 24, l = slo[slot];
+                uint64_t ff[W];
+#pragma unroll
+                for (int kk = 0; kk < W; ++kk) ff[kk] = sf[l * W + kk];
+                bool pm;
+                shm[k * TILE + slot] = fabs(hb_sc1<W>(s, ff, socc + l * nel, fr, to, pm));
+            }
+            // ---- phase E: singles.  The (division-heavy) pgen terms are evaluated one per thread over all
+            //      (single, occupied orbital) pairs of a chunk, then summed in occ_list order, one single per thread.
+            {
+                const int ns = scnt[2];
+                for (int c0 = 0; c0 < ns; c0 += SINGLES_CHUNK) {
+                    const int nc = min(SINGLES_CHUNK, ns - c0);
+                    for (int w = tid; w < nc * nel; w += TILE) {
+                        const int r = w / nel, q = w - r * nel;
+                        const int slot = ssq[c0 + r], l = slo[slot];
+                        double term = 0.0;
+                        const bool ok = hb_single_term(s, ssi[slot], ssi[TILE + slot], ssp[slot], ssp[TILE + slot],
+                                                       socc[l * nel + q], term);
+                        sterm[w] = term;
+                        sok[w] = ok;
+                    }
+                    __syncthreads();
+                    for (int r = tid; r < nc; r += TILE) {
+                        double psum = 0.0;
+                        for (int q = 0; q < nel; ++q)
+                            if (sok[r * nel + q]) psum = psum + sterm[r * nel + q];
+                        spsum[ssq[c0 + r]] = psum;
+                    }
+                    __syncthreads();
+                }
+            }
+            __syncthreads();
+            // ---- phase F: pgen, H_ij
+            double hmk[3] = {0.0, 0.0, 0.0};
+            double psum = 0.0;
+            if (active && st.allowed) {
+                if (st.dbl) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        if (st.need_k & (1u << k)) hmk[k] = shm[k * TILE + tid];
+                } else {
+                    psum = spsum[tid];
+                }
+            }
+            hb_phase_f<W>(s, f, st, hmk, psum, g);
+        } else if (active) {
             gen_excit<W>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, g);
+        }
+        int64_t nspawn = 0;
+        uint64_t child[W];
+        int dest = 0, pflag = 0;
+        if (active) {
             nspawn = attempt_to_spawn(rng, p, g.hmatel, g.pgen, spop[lo]);
             if (nspawn != 0) {
-                // create_excited_det (src/excitations.F90:365-406)
-#pragma unroll
-                for (int k = 0; k < W; ++k) child[k] = f[k];
-                child[(g.from1 - 1) >> 6] &= ~(1ull << ((g.from1 - 1) & 63));
-                child[(g.to1 - 1) >> 6] |= (1ull << ((g.to1 - 1) & 63));
-                if (g.nexcit == 2) {
-                    child[(g.from2 - 1) >> 6] &= ~(1ull << ((g.from2 - 1) & 63));
-                    child[(g.to2 - 1) >> 6] |= (1ull << ((g.to2 - 1) & 63));
-                }
+                make_child<W>(f, g, child);
                 // create_spawned_particle[_initiator]_truncated (src/spawning.F90:1186-1319)
                 if (p.trunc_level >= 0 && excit_level<W>(child, p.f0) > p.trunc_level) {
                     nspawn = 0;
@@ -274,7 +432,6 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
         if (nspawn != 0) {
             // add_[flagged_]spawned_particle (src/spawning.F90:907-1018): warp-aggregated pointer bump per destination
             const unsigned peers = (p.nprocs > 1) ? __match_any_sync(has, dest) : has;
-            const int lane = tid & 31;
             const int leader = __ffs(peers) - 1;
             const int rank = __popc(peers & ((1u << lane) - 1u));
             unsigned long long slot0 = 0;
@@ -299,7 +456,6 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
     }
 
     // deterministic block reduction of the estimators
-    const int lane = tid & 31, warp = tid >> 5;
     double r0 = warp_sum_d(pe), r1 = warp_sum_d(d0);
     long long r2 = warp_sum_ll(ndeath), r3 = warp_sum_ll(npart);
     __syncthreads();
@@ -966,18 +1122,8 @@ static cudaError_t copy_sync(hb200_engine* e, void* dst, const void* src, size_t
 }
 
 static size_t spawn_smem_bytes(const hb200_engine* e) {
-    const int W = e->W;
     const int nsu = (e->cfg.excit_gen == HB200_EXCIT_GEN_RENORM) ? 2 * e->sys.nsym_tot : 0;
-    size_t b = 0;
-    b += (size_t)TILE * W * 8;  // sf
-    b += (size_t)TILE * 8;      // shash
-    b += (size_t)TILE * 8;      // spop
-    b += (size_t)(TILE + 1 + 8 + ((TILE + 1 + 8) & 1)) * 4;  // sscan + swarp (+pad to 8 bytes)
-    b += 40 * 8;                // sred
-    b += TILE;                  // sflag
-    b += (size_t)TILE * e->sys.nel;
-    b += (size_t)TILE * nsu;
-    return (b + 15) & ~(size_t)15;
+    return SpawnSmem(e->W, e->sys.nel, nsu, e->cfg.excit_gen == HB200_EXCIT_GEN_HEAT_BATH).total;
 }
 
 extern "C" {

@@ -679,8 +679,17 @@ HB_HD double sum_occ(const double* __restrict__ tab, const uint8_t* occ, int nel
     }
     return tot;
 }
-template <class R>
-HB_HDN int select_weighted_occ(R& rng, int N, const double* __restrict__ tab, const uint8_t* occ, double totweight) {
+// weight accessors for select_weighted_acc: w(q), q = position in the occupied list
+struct TabOcc {      // tab[occ[q]-1] gathered from a (global/shared) table
+    const double* tab; const uint8_t* occ;
+    HB_HD double operator()(int q) const { return tab[occ[q] - 1]; }
+};
+struct StridedCol {  // values staged by the caller: base[q*stride]
+    const double* base; int stride;
+    HB_HD double operator()(int q) const { return base[q * stride]; }
+};
+template <class R, class WF>
+HB_HDN int select_weighted_acc(R& rng, int N, const WF w, double totweight) {
     // The alias construction consumes no random numbers, so the single draw of select_weighted_value_precalc is
     // taken first: only slot k's final aliasU/aliasK are needed, and no table has to be stored.  Values evolve as
     // in generate_alias_tables: underfull entries are never modified; an overfull entry is modified only while it
@@ -692,10 +701,10 @@ HB_HDN int select_weighted_occ(R& rng, int N, const double* __restrict__ tab, co
     const double scale = N / totweight;
     uint64_t under = 0, over = 0;
     for (int q = 0; q < N; ++q) {
-        const double u = tab[occ[q] - 1] * scale;
+        const double u = w(q) * scale;
         if (u <= 1.0) under |= (1ull << q); else over |= (1ull << q);
     }
-    double Uk = tab[occ[k] - 1] * scale;   // final aliasU(k) unless k is modified as an overfull entry
+    double Uk = w(k) * scale;              // final aliasU(k) unless k is modified as an overfull entry
     int Kk = k + 1;                        // aliasK(k)
     int pushed = -1;
     double pushed_u = 0.0;
@@ -703,11 +712,11 @@ HB_HDN int select_weighted_occ(R& rng, int N, const double* __restrict__ tab, co
     double uov = 0.0;
     while (over != 0 && (pushed >= 0 || under != 0)) {
         const int top = 63 - clz64(over);
-        if (top != ov) { ov = top; uov = tab[occ[ov] - 1] * scale; }
+        if (top != ov) { ov = top; uov = w(ov) * scale; }
         int un;
         double uun;
         if (pushed >= 0) { un = pushed; uun = pushed_u; pushed = -1; }
-        else { un = 63 - clz64(under); under &= ~(1ull << un); uun = tab[occ[un] - 1] * scale; }
+        else { un = 63 - clz64(under); under &= ~(1ull << un); uun = w(un) * scale; }
         if (un == k) Kk = ov + 1;
         uov = uov - (1 - uun);
         if (ov == k) Uk = uov;
@@ -751,20 +760,40 @@ HB_HD bool hb_single_allowed(const Sys& s, int fr, int to) {
 }
 
 // Phase A: select i, j (on-the-fly alias tables) and a (precomputed alias table); 2-3 random numbers.
+// iw = hb_i_w (or a shared-memory copy); scr/stride = optional staging area for column i of hb_ij_w gathered at the
+// occupied orbitals (the column is needed three times: total, alias classification, alias updates).
 template <int W, class R>
-HB_HDN void hb_phase_a(R& rng, const Sys& s, const uint64_t* f, const uint8_t* occ, HbState& st) {
+HB_HDN void hb_phase_a(R& rng, const Sys& s, const uint64_t* f, const uint8_t* occ, HbState& st,
+                       const double* __restrict__ iw, double* scr, int stride) {
     const int nel = s.nel;
     const int64_t nb = s.nbasis;
-    st.i_tot = sum_occ(s.hb_i_w, occ, nel);
+    st.i_tot = sum_occ(iw, occ, nel);
     st.ij_tot = 0.0; st.ji_tot = 0.0;
     st.j = 0; st.a = 0; st.b = 0;
     st.psingle = 0.0; st.hmod_ia = 0.0; st.h_ia = 0.0; st.perm_ia = false;
     st.dbl = true; st.need_ia = false; st.need_k = 0; st.allowed = false;
-    st.i = occ[select_weighted_occ(rng, nel, s.hb_i_w, occ, st.i_tot) - 1];
+    st.i = occ[select_weighted_acc(rng, nel, TabOcc{iw, occ}, st.i_tot) - 1];
     const double* __restrict__ ijcol = s.hb_ij_w + nb * (st.i - 1);
-    st.ij_tot = sum_occ(ijcol, occ, nel);
+    if (scr) {
+        double tot = 0.0;
+        for (int q0 = 0; q0 < nel; q0 += 4) {
+            double v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = (q0 + k < nel) ? ijcol[occ[q0 + k] - 1] : 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (q0 + k < nel) scr[(q0 + k) * stride] = v[k];
+                tot = tot + v[k];
+            }
+        }
+        st.ij_tot = tot;
+    } else {
+        st.ij_tot = sum_occ(ijcol, occ, nel);
+    }
     if (st.ij_tot > 0.0) {
-        st.j = occ[select_weighted_occ(rng, nel, ijcol, occ, st.ij_tot) - 1];
+        const int jq = scr ? select_weighted_acc(rng, nel, StridedCol{scr, stride}, st.ij_tot)
+                           : select_weighted_acc(rng, nel, TabOcc{ijcol, occ}, st.ij_tot);
+        st.j = occ[jq - 1];
         st.ji_tot = sum_occ(s.hb_ij_w + nb * (st.j - 1), occ, nel);
         st.allowed = fabs(s.hb_ija_tot[HB_I2(st.j, st.i)]) > 0.0;
     }
@@ -878,7 +907,8 @@ template <int W, class R>
 HB_HDN void gen_excit_heat_bath(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ,
                                 Gen& g) {
     HbState st;
-    hb_phase_a<W>(rng, s, f, occ, st);
+    double scr[HB_MAXNEL];
+    hb_phase_a<W>(rng, s, f, occ, st, s.hb_i_w, scr, 1);
     if (st.allowed && st.need_ia) st.h_ia = hb_sc1<W>(s, f, occ, st.i, st.a, st.perm_ia);
     hb_phase_c<W>(rng, s, f, st);
     double hm[3] = {0.0, 0.0, 0.0};

@@ -169,20 +169,33 @@ struct SpawnPartials {  // one per block; reduced in fixed order by k_reduce_par
 
 constexpr int SINGLES_CHUNK = 64;  // single excitations whose pgen terms are staged in shared memory at a time
 
-// Shared-memory carve-up of k_spawn_death (same arithmetic on host and device).
+// Shared-memory carve-up of k_spawn_death (same arithmetic on host and device).  For the heat-bath generator the
+// phase-A staging area (column i of hb_ij_w at the occupied orbitals, [q][thread]) shares its storage with the buffers
+// that are only live in the later phases.
 struct SpawnSmem {
-    size_t sf, shash, spop, sscan, swarp, sred, sh1, shm, ssp, spsum, sterm, sq, scnt, sflag, slo, sperm, ssq, ssi, sok, socc, ssu, total;
-    __host__ __device__ SpawnSmem(int W, int nel, int nsu, bool heat_bath) {
+    size_t sf, shash, spop, sscan, swarp, sred, siw, sw, sh1, shm, ssp, spsum, sterm, sok, sq, scnt, sflag, slo, sperm, ssq,
+        ssi, socc, ssu, total;
+    __host__ __device__ SpawnSmem(int W, int nel, int nsu, int nb, bool heat_bath) {
         size_t o = 0;
         sf = o;     o += (size_t)TILE * W * 8;
         shash = o;  o += (size_t)TILE * 8;
         spop = o;   o += (size_t)TILE * 8;
         sred = o;   o += 40 * 8;
-        sh1 = o;    o += heat_bath ? (size_t)TILE * 8 : 0;        // signed slater_condon1(i,a) per attempt slot
-        shm = o;    o += heat_bath ? (size_t)3 * TILE * 8 : 0;    // |slater_condon1| of the three other orderings
-        ssp = o;    o += heat_bath ? (size_t)2 * TILE * 8 : 0;    // singles: hmod_ia, ij_tot
-        spsum = o;  o += heat_bath ? (size_t)TILE * 8 : 0;        // singles: sum of pgen terms
-        sterm = o;  o += heat_bath ? (size_t)SINGLES_CHUNK * nel * 8 : 0;  // singles: pgen terms of one chunk
+        siw = o;    o += heat_bath ? (size_t)nb * 8 : 0;          // copy of hb_i_w
+        // ---- union: phase A staging | phase B..F buffers
+        const size_t u0 = o;
+        sw = o;
+        size_t v = u0;
+        sh1 = v;    v += heat_bath ? (size_t)TILE * 8 : 0;        // signed slater_condon1(i,a) per attempt slot
+        shm = v;    v += heat_bath ? (size_t)3 * TILE * 8 : 0;    // |slater_condon1| of the three other orderings
+        ssp = v;    v += heat_bath ? (size_t)2 * TILE * 8 : 0;    // singles: hmod_ia, ij_tot
+        spsum = v;  v += heat_bath ? (size_t)TILE * 8 : 0;        // singles: sum of pgen terms
+        sterm = v;  v += heat_bath ? (size_t)SINGLES_CHUNK * nel * 8 : 0;  // singles: pgen terms of one chunk
+        sok = v;    v += heat_bath ? (size_t)SINGLES_CHUNK * nel : 0;
+        const size_t stage = heat_bath ? (size_t)TILE * nel * 8 : 0;
+        o = u0 + (stage > (v - u0) ? stage : (v - u0));
+        o = (o + 7) & ~(size_t)7;
+        // ---- end of union
         sscan = o;  o += (size_t)(TILE + 1) * 4;
         swarp = o;  o += 8 * 4;
         sq = o;     o += heat_bath ? (size_t)4 * TILE * 4 : 0;    // request queues: [TILE] phase B, [3*TILE] phase D
@@ -192,7 +205,6 @@ struct SpawnSmem {
         sperm = o;  o += heat_bath ? TILE : 0;
         ssq = o;    o += heat_bath ? TILE : 0;                     // queue of single-excitation slots
         ssi = o;    o += heat_bath ? 2 * TILE : 0;                 // singles: i, a
-        sok = o;    o += heat_bath ? (size_t)SINGLES_CHUNK * nel : 0;
         socc = o;   o += (size_t)TILE * nel;
         ssu = o;    o += (size_t)TILE * nsu;
         total = (o + 15) & ~(size_t)15;
@@ -213,7 +225,7 @@ __device__ __forceinline__ void make_child(const uint64_t* f, const Gen& g, uint
 }
 
 template <int W>
-__global__ void __launch_bounds__(TILE, 4)
+__global__ void __launch_bounds__(TILE, 3)
 k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __restrict__ pops,
               const double* __restrict__ dat, long long nstates, int64_t* __restrict__ spawn,
               unsigned long long* __restrict__ head, long long block_size, const int* __restrict__ proc_map,
@@ -222,7 +234,7 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
     const int nel = s.nel;
     const bool heat_bath = (p.excit_gen == EXCIT_GEN_HEAT_BATH);
     const int nsu = (p.excit_gen == EXCIT_GEN_RENORM) ? 2 * s.nsym_tot : 0;
-    const SpawnSmem L(W, nel, nsu, heat_bath);
+    const SpawnSmem L(W, nel, nsu, s.nbasis, heat_bath);
     uint64_t* sf = reinterpret_cast<uint64_t*>(smem_raw + L.sf);
     uint64_t* shash = reinterpret_cast<uint64_t*>(smem_raw + L.shash);
     int64_t* spop = reinterpret_cast<int64_t*>(smem_raw + L.spop);
@@ -231,6 +243,8 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
     double* shm = reinterpret_cast<double*>(smem_raw + L.shm);
     double* ssp = reinterpret_cast<double*>(smem_raw + L.ssp);
     double* spsum = reinterpret_cast<double*>(smem_raw + L.spsum);
+    double* siw = reinterpret_cast<double*>(smem_raw + L.siw);
+    double* sw = reinterpret_cast<double*>(smem_raw + L.sw);
     double* sterm = reinterpret_cast<double*>(smem_raw + L.sterm);
     uint8_t* sok = smem_raw + L.sok;
     int* sscan = reinterpret_cast<int*>(smem_raw + L.sscan);
@@ -254,6 +268,8 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
     double pe = 0.0, d0 = 0.0;
     long long ndeath = 0, npart = 0;
     int natt = 0;
+    if (heat_bath)
+        for (int k = tid; k < s.nbasis; k += TILE) siw[k] = s.hb_i_w[k];
     if (idx < nstates) {
         uint64_t f[W];
         load_det<W>(states + idx * W, f);
@@ -315,7 +331,7 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
             HbState st;
             st.allowed = false; st.need_ia = false; st.dbl = true; st.need_k = 0;
             if (active) {
-                hb_phase_a<W>(rng, s, f, socc + lo * nel, st);
+                hb_phase_a<W>(rng, s, f, socc + lo * nel, st, siw, sw + tid, TILE);
                 slo[tid] = (uint8_t)lo;
                 if (st.allowed && st.need_ia) {
                     const int q = atomicAdd(&scnt[0], 1);
@@ -408,7 +424,8 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
             }
             hb_phase_f<W>(s, f, st, hmk, psum, g);
         } else if (active) {
-            gen_excit<W>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, g);
+            if (p.excit_gen == EXCIT_GEN_RENORM) gen_excit_renorm<W>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, g);
+            else gen_excit_no_renorm<W>(rng, s, p, f, socc + lo * nel, g);
         }
         int64_t nspawn = 0;
         uint64_t child[W];
@@ -1123,7 +1140,7 @@ static cudaError_t copy_sync(hb200_engine* e, void* dst, const void* src, size_t
 
 static size_t spawn_smem_bytes(const hb200_engine* e) {
     const int nsu = (e->cfg.excit_gen == HB200_EXCIT_GEN_RENORM) ? 2 * e->sys.nsym_tot : 0;
-    return SpawnSmem(e->W, e->sys.nel, nsu, e->cfg.excit_gen == HB200_EXCIT_GEN_HEAT_BATH).total;
+    return SpawnSmem(e->W, e->sys.nel, nsu, e->sys.nbasis, e->cfg.excit_gen == HB200_EXCIT_GEN_HEAT_BATH).total;
 }
 
 extern "C" {

@@ -1483,6 +1483,8 @@ static int stage_comm(hb200_engine* e) {
     return 0;
 }
 
+static int device_scan(hb200_engine* e, const int* d_in, int* d_out, long long n, int slot);
+
 static int stage_sort(hb200_engine* e) {
     const long long n = e->sp_n;
     if (n <= 1) return 0;
@@ -1502,7 +1504,13 @@ static int stage_sort(hb200_engine* e) {
             case 5: k_radix_hist<5><<<nblk, SORT_THREADS, 0, st>>>(src, n, word, shift, e->d_hist, nblk, chunk); break;
             default: k_radix_hist<6><<<nblk, SORT_THREADS, 0, st>>>(src, n, word, shift, e->d_hist, nblk, chunk); break;
         }
-        k_scan_u32_single<<<1, 1024, 0, st>>>(e->d_hist, 256ll * nblk);
+        if (256ll * nblk <= 8192) {
+            k_scan_u32_single<<<1, 1024, 0, st>>>(e->d_hist, 256ll * nblk);
+        } else {
+            // multi-block exclusive scan (counts < 2^31, so the int scan is bit-identical); in place
+            if (device_scan(e, (const int*)e->d_hist, (int*)e->d_hist, 256ll * nblk, 2)) return 1;
+            e->launches += 2;
+        }
         switch (E) {
             case 3: k_radix_scatter<3><<<nblk, SORT_THREADS, 0, st>>>(src, dst, n, word, shift, e->d_hist, nblk, chunk); break;
             case 4: k_radix_scatter<4><<<nblk, SORT_THREADS, 0, st>>>(src, dst, n, word, shift, e->d_hist, nblk, chunk); break;

@@ -679,51 +679,90 @@ HB_HD double sum_occ(const double* __restrict__ tab, const uint8_t* occ, int nel
     }
     return tot;
 }
-// weight accessors for select_weighted_acc: w(q), q = position in the occupied list
-struct TabOcc {      // tab[occ[q]-1] gathered from a (global/shared) table
-    const double* tab; const uint8_t* occ;
-    HB_HD double operator()(int q) const { return tab[occ[q] - 1]; }
-};
-struct StridedCol {  // values staged by the caller: base[q*stride]
-    const double* base; int stride;
-    HB_HD double operator()(int q) const { return base[q * stride]; }
-};
-template <class R, class WF>
-HB_HDN int select_weighted_acc(R& rng, int N, const WF w, double totweight) {
-    // The alias construction consumes no random numbers, so the single draw of select_weighted_value_precalc is
-    // taken first: only slot k's final aliasU/aliasK are needed, and no table has to be stored.  Values evolve as
-    // in generate_alias_tables: underfull entries are never modified; an overfull entry is modified only while it
-    // is on top of the overfull stack (carried in a register) and, once it drops below one, is popped as the very
-    // next underfull entry.
+// select_weighted_value (lib/local/alias.f90:68-184) for the on-the-fly tables over the occupied orbitals, N <= 64.
+// wq[q*stride] holds the UNSCALED weight of list position q (staged by the caller, who also formed their total in list
+// order); scale = N / totweight.  The alias construction consumes no random numbers, so the single draw of
+// select_weighted_value_precalc is taken first and only slot k's final (aliasU, aliasK) are tracked - no table is stored.
+// Values evolve exactly as in generate_alias_tables: underfull entries are never modified; an overfull entry is modified
+// only while it is on top of the overfull stack (kept in a register) and, once it drops below one, it is pushed on the
+// underfull stack and therefore popped by the very next step (the "carry").  Both stacks start in ascending index order
+// and are only ever popped, so they are bitmasks read from their highest bit.
+template <class Mask>
+HB_HD int mask_top(Mask x);
+template <>
+HB_HD int mask_top<uint32_t>(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return 31 - __clz((int)x);
+#else
+    return 31 - __builtin_clz(x);
+#endif
+}
+template <>
+HB_HD int mask_top<uint64_t>(uint64_t x) { return 63 - clz64(x); }
+
+template <class Mask, class R>
+HB_HD int select_alias_staged_m(R& rng, int N, const double* wq, int stride, double totweight) {
     double x = rng.next() * N;
-    const int k = (int)floor(x);
+    const int k = (int)x;                  // floor: x >= 0
     x = x - k;
     const double scale = N / totweight;
-    uint64_t under = 0, over = 0;
+    Mask under = 0, over = 0;
     for (int q = 0; q < N; ++q) {
-        const double u = w(q) * scale;
-        if (u <= 1.0) under |= (1ull << q); else over |= (1ull << q);
+        const double u = wq[q * stride] * scale;
+        if (u <= 1.0) under |= ((Mask)1 << q); else over |= ((Mask)1 << q);
     }
-    double Uk = w(k) * scale;              // final aliasU(k) unless k is modified as an overfull entry
-    int Kk = k + 1;                        // aliasK(k)
-    int pushed = -1;
-    double pushed_u = 0.0;
-    int ov = -1;
-    double uov = 0.0;
-    while (over != 0 && (pushed >= 0 || under != 0)) {
-        const int top = 63 - clz64(over);
-        if (top != ov) { ov = top; uov = w(ov) * scale; }
-        int un;
-        double uun;
-        if (pushed >= 0) { un = pushed; uun = pushed_u; pushed = -1; }
-        else { un = 63 - clz64(under); under &= ~(1ull << un); uun = w(un) * scale; }
-        if (un == k) Kk = ov + 1;
-        uov = uov - (1 - uun);
-        if (ov == k) Uk = uov;
-        if (uov < 1.0) { pushed = ov; pushed_u = uov; over &= ~(1ull << ov); ov = -1; }
+    double Uk = wq[k * stride] * scale;    // final aliasU(k) unless k is demoted from the overfull stack
+    int Kk = k;                            // aliasK(k) - 1
+    if (over != 0) {
+        int ov = mask_top<Mask>(over);
+        double uov = wq[ov * stride] * scale;
+        bool carry = false;
+        int cq = 0;
+        double cu = 0.0;
+        for (;;) {
+            int un;
+            double uun;
+            if (carry) { un = cq; uun = cu; }
+            else {
+                if (under == 0) break;
+                un = mask_top<Mask>(under);
+                under ^= ((Mask)1 << un);
+                uun = wq[un * stride] * scale;
+            }
+            if (un == k) Kk = ov;
+            uov = uov - (1 - uun);
+            carry = uov < 1.0;
+            if (carry) {
+                if (ov == k) Uk = uov;
+                cq = ov; cu = uov;
+                over ^= ((Mask)1 << ov);
+                if (over == 0) break;
+                ov = mask_top<Mask>(over);
+                uov = wq[ov * stride] * scale;
+            }
+        }
     }
-    if (x < Uk) return k + 1;
-    return Kk;
+    return (x < Uk) ? k + 1 : Kk + 1;
+}
+template <class R>
+HB_HD int select_alias_staged(R& rng, int N, const double* wq, int stride, double totweight) {
+    if (N <= 32) return select_alias_staged_m<uint32_t>(rng, N, wq, stride, totweight);
+    return select_alias_staged_m<uint64_t>(rng, N, wq, stride, totweight);
+}
+// gather tab[occ[q]-1] into wq[q*stride] and return their sum in list order; loads issued four at a time
+HB_HD double stage_occ(const double* __restrict__ tab, const uint8_t* occ, int nel, double* wq, int stride) {
+    double tot = 0.0;
+    for (int q0 = 0; q0 < nel; q0 += 4) {
+        double v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (q0 + k < nel) ? tab[occ[q0 + k] - 1] : 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (q0 + k < nel) wq[(q0 + k) * stride] = v[k];
+            tot = tot + v[k];
+        }
+    }
+    return tot;
 }
 
 // gen_excit_mol_heat_bath (src/excit_gen_heat_bath_mol.F90:258-548; src/excit_gen_utils.f90:9-66,142-160),
@@ -760,40 +799,22 @@ HB_HD bool hb_single_allowed(const Sys& s, int fr, int to) {
 }
 
 // Phase A: select i, j (on-the-fly alias tables) and a (precomputed alias table); 2-3 random numbers.
-// iw = hb_i_w (or a shared-memory copy); scr/stride = optional staging area for column i of hb_ij_w gathered at the
-// occupied orbitals (the column is needed three times: total, alias classification, alias updates).
+// iw = hb_i_w (or a shared-memory copy); scr/stride = staging area of nel doubles for the weight list being selected
+// from (first S_i at the occupied orbitals, then column i of hb_ij_w at the occupied orbitals).
 template <int W, class R>
 HB_HDN void hb_phase_a(R& rng, const Sys& s, const uint64_t* f, const uint8_t* occ, HbState& st,
                        const double* __restrict__ iw, double* scr, int stride) {
     const int nel = s.nel;
     const int64_t nb = s.nbasis;
-    st.i_tot = sum_occ(iw, occ, nel);
     st.ij_tot = 0.0; st.ji_tot = 0.0;
     st.j = 0; st.a = 0; st.b = 0;
     st.psingle = 0.0; st.hmod_ia = 0.0; st.h_ia = 0.0; st.perm_ia = false;
     st.dbl = true; st.need_ia = false; st.need_k = 0; st.allowed = false;
-    st.i = occ[select_weighted_acc(rng, nel, TabOcc{iw, occ}, st.i_tot) - 1];
-    const double* __restrict__ ijcol = s.hb_ij_w + nb * (st.i - 1);
-    if (scr) {
-        double tot = 0.0;
-        for (int q0 = 0; q0 < nel; q0 += 4) {
-            double v[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) v[k] = (q0 + k < nel) ? ijcol[occ[q0 + k] - 1] : 0.0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (q0 + k < nel) scr[(q0 + k) * stride] = v[k];
-                tot = tot + v[k];
-            }
-        }
-        st.ij_tot = tot;
-    } else {
-        st.ij_tot = sum_occ(ijcol, occ, nel);
-    }
+    st.i_tot = stage_occ(iw, occ, nel, scr, stride);
+    st.i = occ[select_alias_staged(rng, nel, scr, stride, st.i_tot) - 1];
+    st.ij_tot = stage_occ(s.hb_ij_w + nb * (st.i - 1), occ, nel, scr, stride);
     if (st.ij_tot > 0.0) {
-        const int jq = scr ? select_weighted_acc(rng, nel, StridedCol{scr, stride}, st.ij_tot)
-                           : select_weighted_acc(rng, nel, TabOcc{ijcol, occ}, st.ij_tot);
-        st.j = occ[jq - 1];
+        st.j = occ[select_alias_staged(rng, nel, scr, stride, st.ij_tot) - 1];
         st.ji_tot = sum_occ(s.hb_ij_w + nb * (st.j - 1), occ, nel);
         st.allowed = fabs(s.hb_ija_tot[HB_I2(st.j, st.i)]) > 0.0;
     }

@@ -66,6 +66,34 @@ int orc_read_fcidump(void* h, const char* path, int nel, int ms, int sym, int ca
     ORC_CATCH(-1)
 }
 
+// sys = ueg { electrons, ms, dim = 3, cutoff, rs } (lua_hande_system / init_system + init_model_basis_fns)
+int orc_init_ueg(void* h, int nel, int ms, double rs, double ecutoff) {
+    ORC_TRY
+    Oracle* o = (Oracle*)h;
+    o->sys = System();
+    init_ueg_system(o->sys, nel, ms, rs, ecutoff);
+    return 0;
+    ORC_CATCH(-1)
+}
+// reference = { det = {...} }: explicit reference determinant used by orc_init (n = 0 clears it)
+void orc_set_ref_det_list(void* h, const int* occ, int n) {
+    Oracle* o = (Oracle*)h;
+    o->in.ref_det.assign(occ, occ + n);
+}
+// UEG tables for the host side of the engine: kvec[3*nbasis] (0-based storage of the 1-based functions),
+// info[0..5] = kmax, offset, offset_inds[3], n_lookup; dinfo[0..2] = L, rs, ecutoff
+void orc_ueg_info(void* h, int* kvec, int64_t* info, double* dinfo) {
+    const System& s = ((Oracle*)h)->sys;
+    const UegData& u = s.ueg;
+    for (int i = 1; i <= s.nbasis; ++i)
+        for (int d = 0; d < 3; ++d) kvec[3 * (i - 1) + d] = u.l[3 * i + d];
+    info[0] = u.kmax; info[1] = u.offset; info[2] = u.offset_inds[0]; info[3] = u.offset_inds[1]; info[4] = u.offset_inds[2];
+    info[5] = (int64_t)u.lookup.size(); info[6] = u.tK; info[7] = u.tD; info[8] = (int64_t)u.ternary.size();
+    dinfo[0] = u.L; dinfo[1] = u.rs; dinfo[2] = u.ecutoff;
+}
+const int* orc_ueg_lookup(void* h) { return ((Oracle*)h)->sys.ueg.lookup.data(); }
+const uint64_t* orc_ueg_ternary(void* h) { return ((Oracle*)h)->sys.ueg.ternary.data(); }
+
 // info[0..]: nbasis, nel, W, nsym_tot, sym0, sym_max, nalpha, nbeta, uhf, pg_mask, Lz_mask, Lz_offset,
 //            gamma_sym, max_nbss, nvirt, nvirt_alpha, nvirt_beta, symmetry, int_err, n_two_body_channels
 void orc_sys_info(void* h, int64_t* info) {
@@ -104,7 +132,7 @@ static Det mkdet(const System& s, const uint64_t* f) {
 
 double orc_sc0(void* h, const uint64_t* f) {
     const System& s = ((Oracle*)h)->sys;
-    return s.slater_condon0(mkdet(s, f));
+    return diag_hmatel(s, mkdet(s, f));
 }
 // Slater-Condon single: matrix element <D|H|D_i^a> incl. permutation sign
 double orc_sc1(void* h, const uint64_t* f, int i, int a) {
@@ -252,7 +280,7 @@ void orc_set_reference_det(void* h, const uint64_t* f0) {
     o->f0 = mkdet(o->sys, f0);
     o->occ_list0.resize(o->sys.nel);
     o->sys.decode(o->f0, o->occ_list0.data());
-    o->H00 = o->sys.slater_condon0(o->f0);
+    o->H00 = diag_hmatel(o->sys, o->f0);
 }
 
 // Run ncycles MC cycles with fixed shift / proj_energy_old / tau (what hb200_iterate does).
@@ -338,7 +366,7 @@ int orc_gen_excit_philox(void* h, const uint64_t* f, uint32_t cycle, uint32_t at
     Det fd = mkdet(o->sys, f);
     decode_for(o->sys, o->eg, fd, d);
     rng.begin(RNG_SPAWN, fd, o->sys.W, attempt);
-    GenResult g = gen_excit(rng, o->sys, o->eg, d);
+    GenResult g = gen_excit_sys(rng, o->sys, o->eg, d);
     double save_tau = o->tau;
     o->tau = tau;
     *nspawn = o->attempt_to_spawn(rng, g.hmatel, g.pgen, parent_pop);
@@ -366,7 +394,7 @@ int orc_gen_excit_list(void* h, const uint64_t* f, const double* rn, int nrn, in
     DetInfo d;
     Det fd = mkdet(o->sys, f);
     decode_for(o->sys, o->eg, fd, d);
-    GenResult g = gen_excit(rng, o->sys, o->eg, d);
+    GenResult g = gen_excit_sys(rng, o->sys, o->eg, d);
     iout[0] = g.conn.nexcit; iout[1] = g.conn.from_orb[0]; iout[2] = g.conn.from_orb[1];
     iout[3] = g.conn.to_orb[0]; iout[4] = g.conn.to_orb[1]; iout[5] = g.conn.perm; iout[6] = g.allowed;
     dout[0] = g.pgen; dout[1] = g.hmatel;

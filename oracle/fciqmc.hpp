@@ -22,6 +22,7 @@
 #include "system.hpp"
 #include "rng.hpp"
 #include "excit_gen.hpp"
+#include "ueg.hpp"
 
 namespace oracle {
 
@@ -52,6 +53,7 @@ struct QmcIn {
     // (src/spawn_data.F90:1019, sign(1,int(spawn_parts))).  true = as the reference (gfortran wraps),
     // false = mathematically intended symmetric rule (what the GPU engine implements).
     bool literal_event_int32 = true;
+    std::vector<int> ref_det;  // explicit reference determinant (reference = { det = {...} }); empty => Aufbau
 };
 
 struct SpawnElem {
@@ -198,9 +200,10 @@ struct Oracle {
     // ---------------------------------------------------------------- setup (init_qmc)
     void init() {
         // init_reference (src/qmc.F90:1162-1226)
-        occ_list0 = set_reference_det(sys, sys.symmetry);
+        if (!in.ref_det.empty()) occ_list0 = in.ref_det;   // reference = { det = {...} } (src/reference_determinant.f90)
+        else occ_list0 = set_reference_det(sys, sys.symmetry);
         f0 = sys.encode(occ_list0.data(), sys.nel);
-        H00 = sys.slater_condon0(f0);
+        H00 = diag_hmatel(sys, f0);
         ref_ex_level = (in.ex_level < 0) ? sys.nel : in.ex_level;
         pop_real_factor = in.real_amplitudes ? (1ll << 31) : 1;  // src/particle_t_utils.f90 (POP_SIZE=64)
         double cutoff = in.real_amplitudes ? in.spawn_cutoff : 0.0;
@@ -215,7 +218,8 @@ struct Oracle {
         // init_excit_gen (src/qmc.F90:910-1010)
         eg.excit_gen = in.excit_gen;
         if (in.pattempt_single < 0 || in.pattempt_double < 0) {
-            find_single_double_prob(sys, occ_list0.data(), eg.pattempt_single, eg.pattempt_double);
+            if (sys.kind == SYS_UEG) { eg.pattempt_single = 0.0; eg.pattempt_double = 1.0; }  // src/qmc_common.F90:178-182
+            else find_single_double_prob(sys, occ_list0.data(), eg.pattempt_single, eg.pattempt_double);
         } else {
             eg.pattempt_single = in.pattempt_single / (in.pattempt_single + in.pattempt_double);
             eg.pattempt_double = 1.0 - in.pattempt_single;
@@ -269,6 +273,18 @@ struct Oracle {
     // update_proj_energy_mol (src/energy_evaluation.F90:906-986); returns contribution pieces.
     void update_proj_energy(const DetInfo& d, double pop, double& D0_acc, double& pe_acc) const {
         Excit ex = sys.get_excitation(d.f, f0);
+        if (sys.kind == SYS_UEG) {
+            // update_proj_energy_ueg (src/energy_evaluation.F90:1072-1127)
+            if (ex.nexcit == 0) {
+                bool same = true;
+                for (int k = 0; k < sys.W; ++k) if (d.f.w[k] != f0.w[k]) same = false;
+                if (same) D0_acc = D0_acc + pop;
+            } else if (ex.nexcit == 2) {
+                double h = slater_condon2_ueg(sys, ex.from_orb[0], ex.from_orb[1], ex.to_orb[0], ex.to_orb[1], ex.perm);
+                pe_acc = pe_acc + h * pop;
+            }
+            return;
+        }
         if (ex.nexcit == 0) {
             // any(f1/=f2) false => nexcit 0
             bool same = true;
@@ -358,7 +374,7 @@ struct Oracle {
             int64_t pop = r.pops[idet];
             for (int ip = 0; ip < nattempts_det; ++ip) {
                 rng.begin(RNG_SPAWN, d.f, sys.W, (uint32_t)ip);
-                GenResult g = gen_excit(rng, sys, EG(), d);
+                GenResult g = gen_excit_sys(rng, sys, EG(), d);
                 int64_t nspawned = attempt_to_spawn(rng, g.hmatel, g.pgen, pop);
                 if (nspawned != 0) {
                     Det fnew = sys.create_excited_det(d.f, g.conn);
@@ -586,7 +602,7 @@ struct Oracle {
             // insert_new_walker (src/annihilation.f90:820-901)
             r.states[k - 1] = s[i - 1].f;
             r.pops[k - 1] = s[i - 1].pop;
-            r.dat[k - 1] = sys.slater_condon0(s[i - 1].f) - H00;
+            r.dat[k - 1] = diag_hmatel(sys, s[i - 1].f) - H00;
             double real_population = (double)s[i - 1].pop / (double)pop_real_factor;
             r.nparticles = r.nparticles + std::fabs(real_population);
             iend = pos - 1;

@@ -34,7 +34,7 @@ def build(force=False):
     """Compile the oracle (and oracle/_ref when the reference tree is present)."""
     if force or not os.path.exists(LIB) or any(
             os.path.getmtime(os.path.join(HERE, f)) > os.path.getmtime(LIB)
-            for f in ("capi.cpp", "system.hpp", "rng.hpp", "excit_gen.hpp", "fciqmc.hpp")):
+            for f in ("capi.cpp", "system.hpp", "rng.hpp", "excit_gen.hpp", "ueg.hpp", "fciqmc.hpp")):
         subprocess.check_call(["make", "-C", HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     if not os.path.exists(REF_LIB) and os.path.isdir("/root/reference/lib/dSFMT-src-2.2.3"):
         subprocess.check_call(["make", "-C", HERE, "ref"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
@@ -70,6 +70,13 @@ def lib():
         L.orc_two_body_store.argtypes = [C.c_void_p, C.c_int]
         L.orc_read_fcidump.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_sys_info.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_init_ueg.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]
+        L.orc_set_ref_det_list.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_ueg_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_ueg_lookup.restype = C.POINTER(C.c_int)
+        L.orc_ueg_lookup.argtypes = [C.c_void_p]
+        L.orc_ueg_ternary.restype = C.POINTER(C.c_uint64)
+        L.orc_ueg_ternary.argtypes = [C.c_void_p]
         L.orc_basis.argtypes = [C.c_void_p] + [C.c_void_p] * 6
         L.orc_sym_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_murmur_bit_string.restype = C.c_int32
@@ -146,8 +153,32 @@ class Oracle:
             raise RuntimeError(self.L.orc_last_error().decode())
         return rc
 
+    def init_ueg(self, nel, ms, rs, cutoff):
+        """sys = ueg { electrons = nel, ms = ms, dim = 3, cutoff = cutoff, rs = rs }"""
+        self._chk(self.L.orc_init_ueg(self.h, nel, ms, float(rs), float(cutoff)))
+        return self._read_info()
+
+    def set_ref_det(self, occ):
+        """reference = { det = {...} } (1-based spin-orbital list); call before init()."""
+        occ = np.ascontiguousarray(sorted(occ), dtype=np.int32)
+        self.L.orc_set_ref_det_list(self.h, _p(occ), len(occ))
+
+    def ueg_tables(self):
+        kvec = np.zeros((self.nbasis, 3), dtype=np.int32)
+        info = np.zeros(16, dtype=np.int64)
+        dinfo = np.zeros(4)
+        self.L.orc_ueg_info(self.h, _p(kvec), _p(info), _p(dinfo))
+        lookup = np.ctypeslib.as_array(self.L.orc_ueg_lookup(self.h), shape=(int(info[5]),)).copy()
+        tern = np.ctypeslib.as_array(self.L.orc_ueg_ternary(self.h), shape=(int(info[8]),)).copy()
+        return {"kvec": kvec, "kmax": int(info[0]), "offset": int(info[1]), "offset_inds": info[2:5].astype(np.int32),
+                "lookup": lookup, "tK": int(info[6]), "tD": int(info[7]), "ternary": tern, "L": dinfo[0],
+                "rs": dinfo[1], "ecutoff": dinfo[2]}
+
     def read_fcidump(self, path, nel=0, ms=HUGE, sym=HUGE, cas=(-1, -1)):
         self._chk(self.L.orc_read_fcidump(self.h, str(path).encode(), nel, ms, sym, cas[0], cas[1]))
+        return self._read_info()
+
+    def _read_info(self):
         info = np.zeros(32, dtype=np.int64)
         self.L.orc_sys_info(self.h, _p(info))
         keys = ["nbasis", "nel", "W", "nsym_tot", "sym0", "sym_max", "nalpha", "nbeta", "uhf", "pg_mask", "Lz_mask",

@@ -78,7 +78,21 @@ struct Excit {
     bool perm = false;
 };
 
+enum SystemKind { SYS_READ_IN = 0, SYS_UEG = 1 };
+
+// sys_ueg_t / ueg_basis_t (src/system.f90:238-264, src/ueg_types.f90) + excit_gen_data_t%ueg_ternary_conserve
+struct UegData {
+    double rs = 0.0, ecutoff = 0.0, L = 0.0;
+    int kmax = 0, offset = 0, offset_inds[3] = {0, 0, 0};
+    std::vector<int> l;        // wavevector of basis function o: l[3*o + d] (1-based o)
+    std::vector<int> lookup;   // 1-based flat index -> alpha basis function or -1
+    int tK = 0, tD = 0;        // ternary_conserve(0:W, -tK:tK, -tK:tK, -tK:tK), tD = 2*tK+1
+    std::vector<uint64_t> ternary;
+};
+
 struct System {
+    int kind = SYS_READ_IN;
+    UegData ueg;
     // --- sizes
     int nbasis = 0, nel = 0, Ms = 0, nalpha = 0, nbeta = 0;
     int nvirt = 0, nvirt_alpha = 0, nvirt_beta = 0;

@@ -23,9 +23,13 @@ def _pr(x):
 def _run(case, fcidump_path, nrows):
     g = load_golden(case)
     o = Oracle()
-    s = g["sys"]
-    o.read_fcidump(fcidump_path(g["fcidump"]), nel=s.get("nel", 0), ms=s.get("ms", HUGE), sym=s.get("sym", HUGE),
-                   cas=tuple(s.get("cas", (-1, -1))))
+    if "ueg" in g:
+        o.init_ueg(**g["ueg"])
+        o.set_ref_det(g["ref_det"])
+    else:
+        s = g["sys"]
+        o.read_fcidump(fcidump_path(g["fcidump"]), nel=s.get("nel", 0), ms=s.get("ms", HUGE), sym=s.get("sym", HUGE),
+                       cas=tuple(s.get("cas", (-1, -1))))
     q = dict(g["qmc"])
     q["nreport"] = min(q["nreport"], nrows)
     o.set_qmc(**q)
@@ -68,6 +72,18 @@ def test_ne_ci6_np4_hash_sharding(fcidump_path):
 
 def test_ne_ci6_real_amplitudes_np2(fcidump_path):
     _run("ne_ci6_real64_np2", fcidump_path, 200)
+
+
+def test_ueg_np2_np4(fcidump_path):
+    # gen_excit_ueg_no_renorm, slater_condon0/2_ueg, update_proj_energy_ueg, plane-wave basis
+    # ordering; the complete 1001-row tables were verified with tools/golden_compare.py (ueg_np2, ueg_np4)
+    for case in ("ueg_np2", "ueg_np4"):
+        o = _run(case, fcidump_path, 300)
+        g = load_golden(case)
+        assert abs(o.reference()["H00"] - g["kat"]["H00"]) < 5e-9     # "H00" of the golden JSON block
+        t = o.ueg_tables()
+        assert abs(t["L"] - g["kat"]["L"]) < 5e-9 and o.nbasis == g["kat"]["nbasis"]
+        assert abs(o.basis()["sp_eigv"][2] - g["kat"]["sp_eigv_3"]) < 5e-10
 
 
 def test_dsfmt_and_murmur_known_answers():

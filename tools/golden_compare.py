@@ -42,6 +42,15 @@ CASES = {
                        qmc=dict(tau=0.002, seed=18, D0_population=10, ncycles=10, nreport=1200,
                                 target_particles=50000, walker_length=50000, spawned_walker_length=5000,
                                 ex_level=5, nprocs=4)),
+    # uniform electron gas: sys = ueg{electrons=6, ms=0, dim=3, cutoff=2, rs=2}, explicit reference
+    "ueg_np2": dict(dir="fciqmc/np2/ueg_n10_rs2_e4_fciqmc", bench="benchmark.out.9712b5a3.inp=ueg.fciqmc.in",
+                    ueg=dict(nel=6, ms=0, rs=2.0, cutoff=2.0), ref_det=[1, 2, 3, 10, 11, 14],
+                    qmc=dict(tau=0.005, seed=122, D0_population=10, ncycles=10, nreport=1000, target_particles=90000,
+                             walker_length=50000, spawned_walker_length=5000, nprocs=2)),
+    "ueg_np4": dict(dir="fciqmc/np4/ueg_n10_rs2_e4_fciqmc", bench="benchmark.out.9712b5a3.inp=ueg.fciqmc.in",
+                    ueg=dict(nel=6, ms=0, rs=2.0, cutoff=2.0), ref_det=[1, 2, 3, 10, 11, 14],
+                    qmc=dict(tau=0.005, seed=122, D0_population=10, ncycles=10, nreport=1000, target_particles=90000,
+                             walker_length=50000, spawned_walker_length=5000, nprocs=4)),
 }
 
 ROW = re.compile(r"^\s*#?\s+(\d+)\s+(-?\d\.\d+E[+-]\d+)\s+(-?\d\.\d+E[+-]\d+)\s+(-?\d\.\d+E[+-]\d+)\s+"
@@ -70,9 +79,13 @@ def run_case(name, max_rows=None, quiet=False):
     d = TS + c["dir"] + "/"
     gold = parse_table(d + c["bench"])
     o = Oracle()
-    s = dict(c["sys"])
-    o.read_fcidump(d + c["int_file"], nel=s.get("nel", 0), ms=s.get("ms", HUGE), sym=s.get("sym", HUGE),
-                   cas=s.get("cas", (-1, -1)))
+    if "ueg" in c:
+        o.init_ueg(**c["ueg"])
+        o.set_ref_det(c["ref_det"])
+    else:
+        s = dict(c["sys"])
+        o.read_fcidump(d + c["int_file"], nel=s.get("nel", 0), ms=s.get("ms", HUGE), sym=s.get("sym", HUGE),
+                       cas=s.get("cas", (-1, -1)))
     q = dict(c["qmc"])
     if max_rows is not None:
         q["nreport"] = min(q["nreport"], max_rows)

@@ -21,9 +21,19 @@ FCIDUMP_NAME = {"h2o": "h2o", "ne_init": "ne", "ne_ci6_np2": "ne", "ne_ci6_np4":
 
 os.makedirs(os.path.join(OUT, "fcidump"), exist_ok=True)
 for name, c in CASES.items():
+    d = TS + c["dir"] + "/"
+    if "ueg" in c:
+        rows = parse_table(d + c["bench"]).tolist()
+        json.dump({"source": "test_suite/" + c["dir"] + "/" + c["bench"], "ueg": c["ueg"], "ref_det": c["ref_det"],
+                   "qmc": c["qmc"],
+                   "columns": ["iterations", "shift", "proj_energy", "D0_population", "nparticles", "nstates",
+                               "nspawn_events", "rspawn"],
+                   "kat": {"H00": 2.02890441, "L": 5.85836755, "nbasis": 66, "sp_eigv_3": 5.75143889E-01},
+                   "rows": rows}, open(os.path.join(OUT, name + ".json"), "w"))
+        print(name, len(rows), "rows")
+        continue
     if name not in FCIDUMP_NAME:
         continue
-    d = TS + c["dir"] + "/"
     dst = os.path.join(OUT, "fcidump", FCIDUMP_NAME[name] + ".INTDUMP.gz")
     if not os.path.exists(dst):
         with open(d + c["int_file"], "rb") as fi, gzip.GzipFile(dst, "wb", compresslevel=9, mtime=0) as fo:

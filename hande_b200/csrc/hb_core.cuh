@@ -31,11 +31,15 @@
 namespace hb {
 
 struct alignas(16) D2 { double x, y; };
+struct alignas(16) K4 { int x, y, z, w; };   // wavevector of a plane-wave basis function (w unused)
+
+enum { SYS_READ_IN = 0, SYS_UEG = 1 };
 
 // ------------------------------------------------------------------------------------------------
 // System tables resident in HBM/L2 (plain pointers; filled by hb200_set_system_read_in).
 // ------------------------------------------------------------------------------------------------
 struct Sys {
+    int kind;                   // SYS_READ_IN (molecular, FCIDUMP) or SYS_UEG (uniform electron gas, 3D)
     int nbasis, nel, W;
     int nsym_tot, sym0, sym_max, pg_mask, Lz_mask, Lz_offset, gamma_sym;
     int uhf, nvirt, nvirt_alpha, nvirt_beta, max_nbss;
@@ -71,6 +75,14 @@ struct Sys {
     const double* hb_ijab_U;
     const int* hb_ijab_K;
     const double* hb_ijab_tot;  // (a,j,i)
+    // uniform electron gas (src/ueg.f90, src/ueg_types.f90): plane-wave basis, analytic integrals
+    const K4* ueg_k;            // [nbasis+1] wavevectors in units of 2 pi / L
+    const double* sp_eigv;      // [nbasis+1] kinetic energies
+    double ueg_piL;             // pi * box_length (coulomb_int_ueg_3d = 1 / (pi L |q|^2))
+    const int* ueg_lookup;      // ueg_basis_t%lookup (1-based flat index -> alpha basis function, -1 if outside)
+    int ueg_kmax, ueg_offset, ueg_oi[3];
+    const uint64_t* ueg_tern;   // ternary_conserve(0:W, -tK:tK, -tK:tK, -tK:tK)
+    int ueg_tK, ueg_tD;
 };
 
 // Per-calculation parameters (qmc_in_t / qmc_state_t scalars the kernels need).
@@ -953,10 +965,115 @@ HB_HDN void gen_excit_heat_bath(R& rng, const Sys& s, const Params& p, const uin
     hb_phase_f<W>(s, f, st, hm, psum, g);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Uniform electron gas (3D): analytic integrals, Slater-Condon rules and the no_renorm generator
+// ------------------------------------------------------------------------------------------------
+// coulomb_int_ueg_3d (src/ueg.f90:250-280): 1 / (pi L |k_i - k_a|^2)
+HB_HD double ueg_coulomb(const Sys& s, int i, int a) {
+    const K4 ki = s.ueg_k[i], ka = s.ueg_k[a];
+    const int qx = ki.x - ka.x, qy = ki.y - ka.y, qz = ki.z - ka.z;
+    return 1.0 / (s.ueg_piL * (qx * qx + qy * qy + qz * qz));
+}
+// get_two_e_int_ueg (src/ueg.f90:176-215): < ij || ab > with momentum and spin checks
+HB_HD double ueg_two_e_int(const Sys& s, int i, int j, int a, int b) {
+    const K4 ki = s.ueg_k[i], kj = s.ueg_k[j], ka = s.ueg_k[a], kb = s.ueg_k[b];
+    double v = 0.0;
+    if (ki.x + kj.x - ka.x - kb.x == 0 && ki.y + kj.y - ka.y - kb.y == 0 && ki.z + kj.z - ka.z - kb.z == 0) {
+        if (s.bf_ms[i] == s.bf_ms[a] && s.bf_ms[j] == s.bf_ms[b]) v = v + ueg_coulomb(s, i, a);
+        if (s.bf_ms[i] == s.bf_ms[b] && s.bf_ms[j] == s.bf_ms[a]) v = v - ueg_coulomb(s, i, b);
+    }
+    return v;
+}
+// slater_condon0_ueg (src/hamiltonian_ueg.f90:71-99,127-156; src/determinants.f90:403-425)
+HB_HDN double slater_condon0_ueg(const Sys& s, const uint8_t* occ) {
+    double spe = 0.0;
+    for (int i = 0; i < s.nel; ++i) spe = spe + s.sp_eigv[occ[i]];
+    double ex = 0.0;
+    for (int i = 0; i < s.nel; ++i)
+        for (int j = i + 1; j < s.nel; ++j)
+            if (((occ[i] ^ occ[j]) & 1) == 0) ex = ex - ueg_coulomb(s, occ[i], occ[j]);
+    return spe + ex;
+}
+// slater_condon2_ueg_excit (src/hamiltonian_ueg.f90:186-223)
+HB_HD double slater_condon2_ueg_excit(const Sys& s, int i, int a, int b, bool perm) {
+    double h = 0.0;
+    if (s.bf_ms[i] == s.bf_ms[a]) h = ueg_coulomb(s, i, a);
+    if (s.bf_ms[i] == s.bf_ms[b]) h = h - ueg_coulomb(s, i, b);
+    return perm ? -h : h;
+}
+// ueg_basis_index (src/ueg.f90:142-172)
+HB_HD int ueg_basis_index(const Sys& s, int kx, int ky, int kz, int spin) {
+    const int mn = kx < ky ? (kx < kz ? kx : kz) : (ky < kz ? ky : kz);
+    const int mx = kx > ky ? (kx > kz ? kx : kz) : (ky > kz ? ky : kz);
+    if (mn < -s.ueg_kmax || mx > s.ueg_kmax) return -1;
+    int indx = s.ueg_lookup[kx * s.ueg_oi[0] + ky * s.ueg_oi[1] + kz * s.ueg_oi[2] + s.ueg_offset];
+    if (spin < 0) indx = indx + 1;
+    return indx;
+}
+// gen_excit_ueg_no_renorm (src/excit_gen_ueg.f90:27-101): choose_ij_k (:105-190), find_ab_ueg (:194-306),
+// calc_pgen_ueg_no_renorm (:310-360).  Two random numbers (the second only if an a exists).
+template <int W, class R>
+HB_HDN void gen_excit_ueg_no_renorm(R& rng, const Sys& s, const uint64_t* f, const uint8_t* occ, Gen& g) {
+    const int nel = s.nel;
+    g.nexcit = 2; g.perm = false; g.to1 = 0; g.to2 = 0;
+    const int ind = (int)(rng.next() * nel * (nel - 1) / 2) + 1;
+    const int j_ind = (int)(1.50 + sqrt(2 * ind - 1.750));
+    const int i_ind = ind - ((j_ind - 1) * (j_ind - 2)) / 2;
+    const int i = occ[i_ind - 1], j = occ[j_ind - 1];
+    g.from1 = i; g.from2 = j;
+    const int ij_spin = s.bf_ms[i] + s.bf_ms[j];
+    const K4 ki = s.ueg_k[i], kj = s.ueg_k[j];
+    const int kx = ki.x + kj.x, ky = ki.y + kj.y, kz = ki.z + kj.z;
+    const uint64_t* __restrict__ t =
+        s.ueg_tern + (size_t)(W + 1) * ((kx + s.ueg_tK) + (size_t)s.ueg_tD * ((ky + s.ueg_tK) + (size_t)s.ueg_tD * (kz + s.ueg_tK)));
+    uint64_t poss[W];
+    int max_na = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        const uint64_t tc = (ij_spin == -2) ? (t[1 + w] << 1) : t[1 + w];
+        poss[w] = ~f[w] & tc;
+        max_na += popc64(poss[w]);
+    }
+    g.allowed = false;
+    if (max_na > 0) {
+        int a = (int)(max_na * rng.next()) + 1;
+        int n = 0;
+        bool found = false;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            const int c = popc64(poss[w]);
+            if (!found) {
+                if (n + c >= a) {
+                    uint64_t x = poss[w];
+                    for (int q = 1; q < a - n; ++q) x &= x - 1;
+                    a = w * 64 + ctz64(x) + 1;
+                    found = true;
+                } else {
+                    n += c;
+                }
+            }
+        }
+        const K4 ka = s.ueg_k[a];
+        int b = ueg_basis_index(s, kx - ka.x, ky - ka.y, kz - ka.z, ij_spin == 2 ? 1 : -1);
+        g.allowed = !det_test(f, b);
+        if (a > b) { const int tmp = a; a = b; b = tmp; }
+        g.to1 = a; g.to2 = b;
+    }
+    if (g.allowed) {
+        g.pgen = 2.0 / (nel * (nel - 1) * max_na);
+        if (ij_spin != 0) g.pgen = g.pgen * 2;
+        g.perm = excit_perm2<W>(f, i, j, g.to1, g.to2);
+        g.hmatel = slater_condon2_ueg_excit(s, i, g.to1, g.to2, g.perm);
+    } else {
+        g.hmatel = 0.0; g.pgen = 1.0;
+    }
+}
+
 template <int W, class R>
 HB_HD void gen_excit(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ, const uint8_t* su,
                      Gen& g) {
-    if (p.excit_gen == EXCIT_GEN_RENORM) gen_excit_renorm<W>(rng, s, p, f, occ, su, g);
+    if (s.kind == SYS_UEG) gen_excit_ueg_no_renorm<W>(rng, s, f, occ, g);
+    else if (p.excit_gen == EXCIT_GEN_RENORM) gen_excit_renorm<W>(rng, s, p, f, occ, su, g);
     else if (p.excit_gen == EXCIT_GEN_NO_RENORM) gen_excit_no_renorm<W>(rng, s, p, f, occ, g);
     else gen_excit_heat_bath<W>(rng, s, p, f, occ, g);
 }
@@ -1059,6 +1176,12 @@ HB_HDN double proj_energy_hmatel(const Sys& s, const Params& p, const uint64_t* 
         }
     }
     bool pm = (((perm % 2) + 2) % 2) == 1;
+    if (s.kind == SYS_UEG) {
+        // update_proj_energy_ueg (src/energy_evaluation.F90:1072-1127): slater_condon2_ueg, doubles only
+        if (nexcit != 2) return 0.0;
+        const double h = ueg_two_e_int(s, from[0], from[1], to[0], to[1]);
+        return pm ? -h : h;
+    }
     if (nexcit == 1) {
         if (s.bf_ms[from[0]] == s.bf_ms[to[0]] && s.bf_sym[from[0]] == s.bf_sym[to[0]])
             return slater_condon1_excit(s, occ, from[0], to[0], pm);

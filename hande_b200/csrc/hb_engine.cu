@@ -424,7 +424,8 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
             }
             hb_phase_f<W>(s, f, st, hmk, psum, g);
         } else if (active) {
-            if (p.excit_gen == EXCIT_GEN_RENORM) gen_excit_renorm<W>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, g);
+            if (s.kind == SYS_UEG) gen_excit_ueg_no_renorm<W>(rng, s, f, socc + lo * nel, g);
+            else if (p.excit_gen == EXCIT_GEN_RENORM) gen_excit_renorm<W>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, g);
             else gen_excit_no_renorm<W>(rng, s, p, f, socc + lo * nel, g);
         }
         int64_t nspawn = 0;
@@ -778,7 +779,7 @@ k_sc0(Sys s, double H00, const uint64_t* __restrict__ dets, long long stride_wor
     for (int w = 0; w < W; ++w) f[w] = dets[k * stride_words + w];
     uint8_t occ[HB_MAXNEL];
     decode_det<W>(f, occ);
-    out[k] = slater_condon0(s, occ) - H00;
+    out[k] = ((s.kind == SYS_UEG) ? slater_condon0_ueg(s, occ) : slater_condon0(s, occ)) - H00;
 }
 
 // remove_unoccupied_dets, first half (src/annihilation.f90:537-598): stochastic rounding of main-list
@@ -1027,7 +1028,7 @@ __global__ void k_gen_excit_batch(Sys s, Params p, const uint64_t* __restrict__ 
     for (int k = 0; k < W; ++k) f[k] = states[t * W + k];
     uint8_t occ[HB_MAXNEL], su[64];
     decode_det<W>(f, occ);
-    build_symunocc(s, occ, su);
+    if (s.kind != SYS_UEG) build_symunocc(s, occ, su);
     PhiloxStream rng;
     rng.begin(p.seed, p.cycle, RNG_SPAWN, det_hash64<W>(f), attempt[t]);
     Gen g;
@@ -1248,6 +1249,7 @@ int hb200_set_system_read_in(hb200_engine* e, const hb200_system_read_in* in) {
     CK(cudaSetDevice(e->cfg.device));
     if (in->nbasis != e->cfg.nbasis || in->nel != e->cfg.nel) FAIL("set_system: nbasis/nel differ from hb200_create");
     Sys& s = e->sys;
+    s.kind = SYS_READ_IN;
     s.nbasis = in->nbasis; s.nel = in->nel; s.W = e->W;
     s.nsym_tot = in->nsym_tot; s.sym0 = in->sym0; s.sym_max = in->sym_max; s.pg_mask = in->pg_mask;
     s.Lz_mask = in->Lz_mask; s.Lz_offset = in->Lz_offset; s.gamma_sym = in->gamma_sym; s.uhf = in->uhf;
@@ -1283,6 +1285,41 @@ int hb200_set_system_read_in(hb200_engine* e, const hb200_system_read_in* in) {
         CK(cudaStreamSynchronize(e->stream));
         s.sc1CX = CX; s.NT = NT;
     }
+    e->have_sys = true;
+    return 0;
+}
+
+int hb200_set_system_ueg(hb200_engine* e, const hb200_system_ueg* in) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (in->nbasis != e->cfg.nbasis || in->nel != e->cfg.nel) FAIL("set_system_ueg: nbasis/nel differ from hb200_create");
+    if (e->cfg.excit_gen == HB200_EXCIT_GEN_HEAT_BATH) FAIL("set_system_ueg: heat_bath is a molecular generator");
+    Sys& s = e->sys;
+    s.kind = SYS_UEG;
+    s.nbasis = in->nbasis; s.nel = in->nel; s.W = e->W;
+    s.nsym_tot = 1; s.sym0 = 0; s.sym_max = 0; s.pg_mask = 0; s.Lz_mask = 0; s.Lz_offset = 0; s.gamma_sym = 0; s.uhf = 0;
+    const int nb = s.nbasis;
+    std::vector<uint8_t> sym(nb + 1, 0);
+    std::vector<int8_t> ms(nb + 1, 0);
+    std::vector<uint16_t> sp(nb + 1, 0);
+    std::vector<K4> kv(nb + 1);
+    for (int i = 1; i <= nb; ++i) {
+        ms[i] = (int8_t)((i & 1) ? 1 : -1);
+        sp[i] = (uint16_t)((i + 1) / 2);
+        kv[i].x = in->kvec[3 * i]; kv[i].y = in->kvec[3 * i + 1]; kv[i].z = in->kvec[3 * i + 2]; kv[i].w = 0;
+    }
+    kv[0].x = kv[0].y = kv[0].z = kv[0].w = 0;
+    if (dupload(e, &s.bf_sym, sym.data(), sym.size())) return 1;
+    if (dupload(e, &s.bf_ms, ms.data(), ms.size())) return 1;
+    if (dupload(e, &s.bf_spatial, sp.data(), sp.size())) return 1;
+    if (dupload(e, &s.ueg_k, kv.data(), kv.size())) return 1;
+    if (dupload(e, &s.sp_eigv, in->sp_eigv, (size_t)nb + 1)) return 1;
+    if (dupload(e, &s.ueg_lookup, in->lookup, (size_t)in->n_lookup + 1)) return 1;
+    const size_t tD = 2 * (size_t)in->tern_kmax + 1;
+    if (dupload(e, &s.ueg_tern, in->ternary_conserve, (size_t)(e->W + 1) * tD * tD * tD)) return 1;
+    s.ueg_piL = 3.1415926535897931 * in->box_length;   // pi*cell_param, as evaluated first in coulomb_int_ueg_3d
+    s.ueg_kmax = in->kmax; s.ueg_offset = in->offset;
+    for (int d = 0; d < 3; ++d) s.ueg_oi[d] = in->offset_inds[d];
+    s.ueg_tK = in->tern_kmax; s.ueg_tD = (int)tD;
     e->have_sys = true;
     return 0;
 }

@@ -40,6 +40,16 @@ class SystemReadIn(C.Structure):
     ]
 
 
+class SystemUeg(C.Structure):
+    _fields_ = [
+        ("nbasis", C.c_int32), ("nel", C.c_int32), ("box_length", C.c_double),
+        ("kvec", C.c_void_p), ("sp_eigv", C.c_void_p),
+        ("kmax", C.c_int32), ("offset", C.c_int32), ("offset_inds", C.c_int32 * 3),
+        ("lookup", C.c_void_p), ("n_lookup", C.c_int64),
+        ("tern_kmax", C.c_int32), ("ternary_conserve", C.c_void_p),
+    ]
+
+
 class IterIn(C.Structure):
     _fields_ = [("tau", C.c_double), ("shift", C.c_double), ("proj_energy_old", C.c_double),
                 ("first_cycle", C.c_uint32)]
@@ -94,6 +104,7 @@ def load_library():
     L.hb200_create.argtypes = [C.POINTER(Config)]
     L.hb200_destroy.argtypes = [C.c_void_p]
     L.hb200_set_system_read_in.argtypes = [C.c_void_p, C.POINTER(SystemReadIn)]
+    L.hb200_set_system_ueg.argtypes = [C.c_void_p, C.POINTER(SystemUeg)]
     L.hb200_build_heat_bath.argtypes = [C.c_void_p]
     L.hb200_download_heat_bath.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]
     L.hb200_set_reference.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
@@ -120,7 +131,8 @@ def load_library():
 
 
 ABI_SYMBOLS = [
-    "hb200_last_error", "hb200_create", "hb200_destroy", "hb200_set_system_read_in", "hb200_build_heat_bath",
+    "hb200_last_error", "hb200_create", "hb200_destroy", "hb200_set_system_read_in", "hb200_set_system_ueg",
+    "hb200_build_heat_bath",
     "hb200_download_heat_bath", "hb200_set_reference", "hb200_set_proc_map", "hb200_upload_psips",
     "hb200_download_psips", "hb200_nstates", "hb200_iterate", "hb200_spawn_death", "hb200_comm_spawn",
     "hb200_annihilate_spawn", "hb200_annihilate_main", "hb200_download_spawn", "hb200_upload_spawn",
@@ -179,6 +191,15 @@ class Engine:
 
     def _set_system(self, s):
         i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)  # noqa: E731
+        if getattr(s, "kind", "read_in") == "ueg":
+            keep = [i32(s.kvec), np.ascontiguousarray(s.sp_eigv, dtype=np.float64), i32(s.lookup),
+                    np.ascontiguousarray(s.ternary_conserve, dtype=np.uint64)]
+            su = SystemUeg(nbasis=s.nbasis, nel=s.nel, box_length=s.L, kvec=keep[0].ctypes.data,
+                           sp_eigv=keep[1].ctypes.data, kmax=s.kmax, offset=s.offset,
+                           offset_inds=(C.c_int32 * 3)(*[int(x) for x in s.offset_inds]), lookup=keep[2].ctypes.data,
+                           n_lookup=len(keep[2]) - 1, tern_kmax=s.tern_kmax, ternary_conserve=keep[3].ctypes.data)
+            self._chk(self.L.hb200_set_system_ueg(self.h, C.byref(su)))
+            return
         keep = [i32(s.sym), i32(s.ms), i32(s.spatial), i32(s.nbasis_sym_spin), i32(s.sym_spin_basis_fns),
                 np.ascontiguousarray(s.h1, dtype=np.float64)]
         v2 = [np.ascontiguousarray(v, dtype=np.float64) for v in s.v2]

@@ -46,6 +46,7 @@ class QmcIn:
     spawned_state_size: int = -1
     ex_level: int = -1              # reference = {ex_level = ...}: truncation level, -1 = none
     nslots: int = 1
+    reference_det: list = None      # reference = {det = {...}}: explicit reference determinant (1-based orbitals)
 
 
 def murmurhash2(data: bytes, seed: int) -> int:
@@ -162,17 +163,24 @@ def do_fciqmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, 
     nprocs, iproc = comm.size, comm.rank
     out = io if io is not None else None
     # init_reference (src/qmc.F90:1162-1226)
-    occ0 = _ri.set_reference_det(sys)
+    is_ueg = getattr(sys, "kind", "read_in") == "ueg"
+    if qmc.reference_det:
+        occ0 = sorted(int(x) for x in qmc.reference_det)
+    else:
+        occ0 = sys.aufbau_reference() if is_ueg else _ri.set_reference_det(sys)
     f0 = sys.encode(occ0)
     H00 = sys.slater_condon0(occ0)
     # init_excit_gen (src/qmc.F90:910-1010)
-    if qmc.pattempt_single < 0 or qmc.pattempt_double < 0:
+    if is_ueg:
+        ps, pd = 0.0, 1.0               # find_single_double_prob, src/qmc_common.F90:178-182: doubles only
+    elif qmc.pattempt_single < 0 or qmc.pattempt_double < 0:
         ps, pd = _ri.find_single_double_prob(sys, occ0)
     else:
         ps = qmc.pattempt_single / (qmc.pattempt_single + qmc.pattempt_double)
         pd = 1.0 - qmc.pattempt_single
     wl, sl = list_sizes(qmc, sys.W, nprocs)
-    eng = engine_cls(sys, excit_gen=qmc.excit_gen, pattempt_single=ps, pattempt_double=pd,
+    # UEG: "renormalised excitation generators not implemented" -> gen_excit_ueg_no_renorm (src/qmc.F90:466-476)
+    eng = engine_cls(sys, excit_gen=("no_renorm" if is_ueg else qmc.excit_gen), pattempt_single=ps, pattempt_double=pd,
                      real_amplitudes=qmc.real_amplitudes, spawn_cutoff=qmc.spawn_cutoff,
                      initiator_approx=qmc.initiator, initiator_pop=qmc.initiator_population,
                      trunc_level=qmc.ex_level, walker_length=wl, spawned_walker_length=sl, seed=qmc.rng_seed,

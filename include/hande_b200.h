@@ -65,6 +65,22 @@ typedef struct hb200_system_read_in {
     int64_t nintgrls;              /* length of each two-body channel */
 } hb200_system_read_in;
 
+/* sys_t for the 3D uniform electron gas (sys = ueg{...}): plane-wave basis ordered by kinetic energy
+ * (init_model_basis_fns, src/basis.f90:258-501), ueg_basis_t lookup (src/ueg.f90:43-85, src/ueg_types.f90) and
+ * excit_gen_data_t%ueg_ternary_conserve (src/ueg.f90:87-140).  Basis arrays have nbasis+1 entries (entry 0
+ * unused); odd index = alpha.  Integrals are analytic (coulomb_int_ueg_3d, src/ueg.f90:250-280). */
+typedef struct hb200_system_ueg {
+    int32_t nbasis, nel;
+    double box_length;             /* sys%lattice%box_length(1) = r_s (4 pi N / 3)^(1/3) */
+    const int32_t* kvec;           /* basis_fns(:)%l, (3, nbasis+1) */
+    const double* sp_eigv;         /* basis_fns(:)%sp_eigv (kinetic energies) */
+    int32_t kmax, offset, offset_inds[3];  /* ueg_basis_t */
+    const int32_t* lookup;         /* ueg_basis_t%lookup, 1-based: n_lookup + 1 entries (entry 0 unused) */
+    int64_t n_lookup;
+    int32_t tern_kmax;             /* ternary_conserve(0:W, -tern_kmax:tern_kmax, ... x3), tern_kmax = 2 kmax */
+    const uint64_t* ternary_conserve;
+} hb200_system_ueg;
+
 /* Per-call propagation inputs (qmc_state_t scalars read by the hot loop). */
 typedef struct hb200_iter_in {
     double tau;                    /* qs%tau */
@@ -97,6 +113,9 @@ void hb200_destroy(hb200_engine* e);
 
 /* Copies the system tables to the device (read_in systems); builds the J/K diagonal tables. */
 int hb200_set_system_read_in(hb200_engine* e, const hb200_system_read_in* sys);
+/* Copies the UEG tables to the device: the decoder / gen_excit_ueg_no_renorm / slater_condon0_ueg /
+ * update_proj_energy_ueg bindings of init_proc_pointers (src/qmc.F90:466-476) are selected by this call. */
+int hb200_set_system_ueg(hb200_engine* e, const hb200_system_ueg* sys);
 /* init_excit_mol_heat_bath (src/excit_gen_heat_bath_mol.F90:14-256) evaluated on the device. */
 int hb200_build_heat_bath(hb200_engine* e);
 /* Test/inspection: copy heat-bath table `which` to the host (0 i_w,1 ij_w,2 ija_w,3 ija_U,4 ija_tot,

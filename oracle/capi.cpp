@@ -134,6 +134,15 @@ double orc_sc0(void* h, const uint64_t* f) {
     const System& s = ((Oracle*)h)->sys;
     return diag_hmatel(s, mkdet(s, f));
 }
+// update_proj_energy_ptr for unit population: returns <D|H|D0> as accumulated into proj_energy (0 for the reference)
+double orc_proj_hmatel(void* h, const uint64_t* f) {
+    Oracle* o = (Oracle*)h;
+    DetInfo d;
+    decode_det_occ(o->sys, mkdet(o->sys, f), d);
+    double d0 = 0.0, pe = 0.0;
+    o->update_proj_energy(d, 1.0, d0, pe);
+    return pe;
+}
 // Slater-Condon single: matrix element <D|H|D_i^a> incl. permutation sign
 double orc_sc1(void* h, const uint64_t* f, int i, int a) {
     const System& s = ((Oracle*)h)->sys;

@@ -53,7 +53,7 @@ def lib():
         L.orc_destroy.argtypes = [C.c_void_p]
         L.orc_ecore.restype = C.c_double
         L.orc_ecore.argtypes = [C.c_void_p]
-        for name in ("orc_sc0",):
+        for name in ("orc_sc0", "orc_proj_hmatel"):
             getattr(L, name).restype = C.c_double
             getattr(L, name).argtypes = [C.c_void_p, C.c_void_p]
         for name in ("orc_sc1", "orc_sc1_checked"):
@@ -227,6 +227,10 @@ class Oracle:
     def sc0(self, f):
         f = np.ascontiguousarray(f, dtype=np.uint64)
         return self.L.orc_sc0(self.h, _p(f))
+
+    def proj_hmatel(self, f):
+        f = np.ascontiguousarray(f, dtype=np.uint64)
+        return self.L.orc_proj_hmatel(self.h, _p(f))
 
     def sc1(self, f, i, a, checked=False):
         f = np.ascontiguousarray(f, dtype=np.uint64)

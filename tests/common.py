@@ -19,6 +19,9 @@ SYSTEMS = {
     "s10": dict(synthetic=(10, 8), kw={}),
     "s12": dict(synthetic=(12, 8), kw={}),
     "s40": dict(synthetic=(40, 10), kw={}),    # W = 2
+    # uniform electron gas: (electrons, ms, rs, cutoff)
+    "ueg6": dict(ueg=(6, 0, 2.0, 2.0)),        # the reference's np2/np4 fixture system, 66 spin-orbitals (W = 2)
+    "ueg14": dict(ueg=(14, 0, 1.0, 4.0)),      # 186 spin-orbitals (W = 3)
 }
 
 
@@ -40,10 +43,16 @@ def system_path(name):
 def make_pair(name, *, excit_gen="renorm", tau=0.01, seed=11, real=False, initiator=False, ex_level=-1,
               walker_length=1 << 17, spawned_walker_length=1 << 16, engine=True, device=0):
     """Host system + oracle (Philox stream, symmetric initiator event rule) + GPU engine with identical options."""
-    path, kw = system_path(name)
-    s = R.read_in(path, **kw)
     o = Oracle()
-    o.read_fcidump(path, **kw)
+    if "ueg" in SYSTEMS[name]:
+        from hande_b200.ueg import UegSystem
+        s = UegSystem(*SYSTEMS[name]["ueg"])
+        o.init_ueg(*SYSTEMS[name]["ueg"])
+        excit_gen = "no_renorm"
+    else:
+        path, kw = system_path(name)
+        s = R.read_in(path, **kw)
+        o.read_fcidump(path, **kw)
     o.set_qmc(tau=tau, seed=seed, excit_gen=excit_gen, rng_kind=1, real_amplitudes=int(real), spawn_cutoff=0.01,
               initiator_approx=int(initiator), ex_level=ex_level, literal_event_int32=0, walker_length=walker_length,
               spawned_walker_length=spawned_walker_length)

@@ -30,6 +30,16 @@ class HdCheck:
         self.sys = sys
         self.keep = []
         ia = lambda a: np.ascontiguousarray(a, dtype=np.int32)  # noqa: E731
+        if getattr(sys, "kind", "read_in") == "ueg":
+            arrs = [ia(sys.kvec), np.ascontiguousarray(sys.sp_eigv, dtype=np.float64), ia(sys.offset_inds),
+                    ia(sys.lookup), np.ascontiguousarray(sys.ternary_conserve, dtype=np.uint64)]
+            self.keep.append(arrs)
+            L.hd_set_sys_ueg.argtypes = [C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+            L.hd_set_sys_ueg(sys.nbasis, sys.nel, sys.L, _p(arrs[0]), _p(arrs[1]), sys.kmax, sys.offset, _p(arrs[2]),
+                             _p(arrs[3]), sys.tern_kmax, _p(arrs[4]))
+            self._finish(excit_gen, ps, pd, tau, shift, pe_old, real_factor, spawn_cutoff, seed, f0, H00)
+            return
         sym, ms, sp = ia(sys.sym), ia(sys.ms), ia(sys.spatial)
         nbss, ssbf = ia(sys.nbasis_sym_spin), ia(sys.sym_spin_basis_fns)
         h1 = np.ascontiguousarray(sys.h1, dtype=np.float64)
@@ -46,6 +56,10 @@ class HdCheck:
                                                           "ija_tot", "ijab_w", "ijab_U", "ijab_K", "ijab_tot")]
             self.keep.append(arrs)
             L.hd_set_heat_bath(*[_p(a) for a in arrs])
+        self._finish(excit_gen, ps, pd, tau, shift, pe_old, real_factor, spawn_cutoff, seed, f0, H00)
+
+    def _finish(self, excit_gen, ps, pd, tau, shift, pe_old, real_factor, spawn_cutoff, seed, f0, H00):
+        L = self.L
         f0 = np.ascontiguousarray(f0, dtype=np.uint64)
         L.hd_set_params.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64,
                                     C.c_int64, C.c_uint32, C.c_void_p, C.c_double]

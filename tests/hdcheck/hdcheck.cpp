@@ -20,7 +20,7 @@ template <int W, class R>
 static void gen_one(R& rng, const uint64_t* f, int64_t parent_pop, int* iout, double* dout, int64_t* nspawn) {
     uint8_t occ[HB_MAXNEL], su[64];
     decode_det<W>(f, occ);
-    build_symunocc(g_sys, occ, su);
+    if (g_sys.kind != SYS_UEG) build_symunocc(g_sys, occ, su);
     Gen g;
     gen_excit<W>(rng, g_sys, g_par, f, occ, su, g);
     *nspawn = attempt_to_spawn(rng, g_par, g.hmatel, g.pgen, parent_pop);
@@ -64,6 +64,26 @@ void hd_set_sys(int nbasis, int nel, int nsym_tot, int sym0, int sym_max, int pg
             }
     s.sc1CX = g_CX.data();
 }
+// uniform electron gas (hb200_set_system_ueg on the host side of the engine)
+static std::vector<K4> g_kv;
+void hd_set_sys_ueg(int nbasis, int nel, double box_length, const int* kvec, const double* sp_eigv, int kmax, int offset,
+                    const int* offset_inds, const int* lookup, int tern_kmax, const uint64_t* tern) {
+    Sys& s = g_sys;
+    memset(&s, 0, sizeof(s));
+    s.kind = SYS_UEG;
+    s.nbasis = nbasis; s.nel = nel; s.W = (nbasis + 63) / 64; s.nsym_tot = 1;
+    g_sym.assign(nbasis + 1, 0); g_ms.assign(nbasis + 1, 0); g_spatial.assign(nbasis + 1, 0); g_kv.assign(nbasis + 1, K4{0, 0, 0, 0});
+    for (int i = 1; i <= nbasis; ++i) {
+        g_ms[i] = (i & 1) ? 1 : -1; g_spatial[i] = (uint16_t)((i + 1) / 2);
+        g_kv[i] = K4{kvec[3 * i], kvec[3 * i + 1], kvec[3 * i + 2], 0};
+    }
+    s.bf_sym = g_sym.data(); s.bf_ms = g_ms.data(); s.bf_spatial = g_spatial.data();
+    s.ueg_k = g_kv.data(); s.sp_eigv = sp_eigv; s.ueg_lookup = lookup; s.ueg_tern = tern;
+    s.ueg_piL = 3.1415926535897931 * box_length;
+    s.ueg_kmax = kmax; s.ueg_offset = offset;
+    for (int d = 0; d < 3; ++d) s.ueg_oi[d] = offset_inds[d];
+    s.ueg_tK = tern_kmax; s.ueg_tD = 2 * tern_kmax + 1;
+}
 void hd_set_heat_bath(const double* i_w, const double* ij_w, const double* ija_w, const double* ija_U, const int* ija_K,
                       const double* ija_tot, const double* ijab_w, const double* ijab_U, const int* ijab_K,
                       const double* ijab_tot) {
@@ -106,7 +126,7 @@ double hd_sc0(const uint64_t* f) {
     uint8_t occ[HB_MAXNEL];
     switch (g_sys.W) { case 1: decode_det<1>(f, occ); break; case 2: decode_det<2>(f, occ); break;
                        case 3: decode_det<3>(f, occ); break; default: decode_det<4>(f, occ); }
-    return slater_condon0(g_sys, occ);
+    return g_sys.kind == SYS_UEG ? slater_condon0_ueg(g_sys, occ) : slater_condon0(g_sys, occ);
 }
 double hd_sc1(const uint64_t* f, int i, int a) {
     uint8_t occ[HB_MAXNEL];

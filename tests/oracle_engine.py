@@ -12,7 +12,7 @@ from oracle.pyoracle import Oracle
 _PATH = {}
 
 
-def make_engine_cls(fcidump_path, sys_kw, rng_kind=0):
+def make_engine_cls(fcidump_path, sys_kw, rng_kind=0, ueg=None, ref_det=None):
     class OracleRankEngine:
         def __init__(self, sys, *, excit_gen, pattempt_single, pattempt_double, real_amplitudes, spawn_cutoff,
                      initiator_approx, initiator_pop, trunc_level, walker_length, spawned_walker_length, seed, nprocs,
@@ -21,7 +21,12 @@ def make_engine_cls(fcidump_path, sys_kw, rng_kind=0):
             self.dist = dist
             self.rank, self.world = iproc, nprocs
             o = self.o = Oracle()
-            o.read_fcidump(fcidump_path, **sys_kw)
+            if ueg is not None:
+                o.init_ueg(*ueg)
+                if ref_det is not None:
+                    o.set_ref_det(ref_det)
+            else:
+                o.read_fcidump(fcidump_path, **sys_kw)
             o.set_qmc(seed=seed, excit_gen=excit_gen, rng_kind=rng_kind, real_amplitudes=int(real_amplitudes),
                       spawn_cutoff=spawn_cutoff, initiator_approx=int(initiator_approx), initiator_pop=initiator_pop,
                       ex_level=trunc_level, walker_length=walker_length, spawned_walker_length=spawned_walker_length,

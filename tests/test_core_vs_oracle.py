@@ -79,6 +79,50 @@ def test_heat_bath_generator_synthetic(s10):
     assert n > 1500
 
 
+@pytest.mark.parametrize("nel,ms,rs,cutoff", [(6, 0, 2.0, 2.0), (14, 0, 1.0, 3.0), (5, 1, 0.5, 1.0)])
+def test_ueg_generator_and_slater_condon(nel, ms, rs, cutoff):
+    """host tables (hande_b200/ueg.py) == oracle tables; gen_excit_ueg_no_renorm, slater_condon0_ueg,
+    update_proj_energy_ueg of the engine core bit-exact against the oracle under the same Philox stream."""
+    from hande_b200.ueg import UegSystem
+    s = UegSystem(nel, ms, rs, cutoff)
+    o = Oracle()
+    o.init_ueg(nel, ms, rs, cutoff)
+    t = o.ueg_tables()
+    assert s.nbasis == o.nbasis and (s.kvec[1:] == t["kvec"]).all() and (s.lookup == t["lookup"]).all()
+    assert (s.ternary_conserve == t["ternary"]).all() and (s.sp_eigv[1:] == o.basis()["sp_eigv"]).all()
+    tau = 0.01
+    o.set_qmc(tau=tau, seed=11, rng_kind=1, excit_gen="no_renorm")
+    o.init()
+    ref = o.reference()
+    assert s.slater_condon0(list(ref["occ"])) == ref["H00"]
+    h = HdCheck(s, EXCIT_GEN["no_renorm"], 0.0, 1.0, tau, 0.0, 0.0, 1, 0, 11, ref["f0"], ref["H00"])
+    dets = synthetic.random_dets(80, s.nbasis, s.nalpha, s.nbeta, seed=3)
+    pops = np.where(np.arange(len(dets)) % 2 == 0, 3, -2)
+    n = _compare_attempts(s, o, h, dets, pops, tau, ncycle=2, nattempt=6)
+    assert n > 900
+    for f in dets[:40]:
+        assert h.sc0(f) == o.sc0(f)
+        assert h.murmur(f) == o.murmur_bit_string(f)
+    # projected-energy matrix elements: double excitations of the reference conserve momentum only sometimes
+    nz = 0
+    occ0 = list(ref["occ"])
+    rng = np.random.default_rng(1)
+    for _ in range(300):
+        i, j = sorted(int(x) for x in rng.choice(occ0, 2, replace=False))
+        virt = [v for v in range(1, s.nbasis + 1) if v not in occ0]
+        a, b = sorted(int(x) for x in rng.choice(virt, 2, replace=False))
+        f = ref["f0"].copy()
+        for orb, on in ((i, 0), (j, 0), (a, 1), (b, 1)):
+            w, bit = (orb - 1) // 64, np.uint64((orb - 1) % 64)
+            f[w] = (f[w] | (np.uint64(1) << bit)) if on else (f[w] & ~(np.uint64(1) << bit))
+        hm, isref = h.proj_hmatel(f)
+        assert not isref
+        assert hm == o.proj_hmatel(f)
+        nz += hm != 0.0
+    hm, isref = h.proj_hmatel(ref["f0"])
+    assert isref and hm == 0.0
+
+
 def test_slater_condon_two_word_bitstrings(tmp_path):
     # 40 spatial orbitals -> 80 spin orbitals -> W = 2 words
     p = tmp_path / "s40.fcidump"

@@ -22,6 +22,23 @@ def _worker(rank, world, port, fcidump, q):
     from hande_b200 import read_in as R
     from hande_b200.fciqmc import QmcIn, TorchDist, do_fciqmc
     from tests.oracle_engine import make_engine_cls
+    if fcidump == "ueg_np2":
+        from hande_b200.ueg import UegSystem
+        g = load_golden("ueg_np2")
+        u = g["ueg"]
+        ueg = (u["nel"], u["ms"], u["rs"], u["cutoff"])
+        s = UegSystem(*ueg)
+        gq = g["qmc"]
+        qmc = QmcIn(tau=gq["tau"], rng_seed=gq["seed"], init_pop=gq["D0_population"], mc_cycles=gq["ncycles"],
+                    nreports=NROWS, target_population=gq["target_particles"], state_size=gq["walker_length"],
+                    spawned_state_size=gq["spawned_walker_length"], reference_det=g["ref_det"])
+        res = do_fciqmc(s, qmc, comm=TorchDist(),
+                        engine_cls=make_engine_cls(None, None, rng_kind=0, ueg=ueg, ref_det=g["ref_det"]))
+        if rank == 0:
+            q.put(res.rows)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     g = load_golden("ne_ci6_np2")
     kw = dict(nel=g["sys"]["nel"], ms=g["sys"]["ms"], sym=g["sys"]["sym"], cas=tuple(g["sys"]["cas"]))
     s = R.read_in(fcidump, **kw)
@@ -36,22 +53,24 @@ def _worker(rank, world, port, fcidump, q):
     dist.destroy_process_group()
 
 
-def test_np2_driver_reproduces_golden(fcidump_path):
+@pytest.mark.parametrize("case", ["ne_ci6_np2", "ueg_np2"])
+def test_np2_driver_reproduces_golden(fcidump_path, case):
     from oracle import pyoracle
     if not pyoracle.have_ref_lib():
         pytest.skip("oracle/_ref not built")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    path = fcidump_path("ne")
-    procs = [ctx.Process(target=_worker, args=(r, 2, 29577, path, q)) for r in range(2)]
+    path = fcidump_path("ne") if case == "ne_ci6_np2" else case
+    port = 29577 if case == "ne_ci6_np2" else 29579
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, path, q)) for r in range(2)]
     for p in procs:
         p.start()
     rows = q.get(timeout=600)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    gold = np.array(load_golden("ne_ci6_np2")["rows"])
+    gold = np.array(load_golden(case)["rows"])
 
     def pr(x):
         return float("%.10E" % x)

@@ -58,3 +58,38 @@ def test_reblocked_energies_agree_with_reference_stream():
     assert abs(mg - mo) < 2.0 * np.hypot(esg, eso), (mg, esg, mo, eso)
     # and both sit at the correlation energy of this active space (FCI ~ -0.1 Eh scale): sanity, not parity
     assert -0.5 < eg < 0.0
+
+
+def test_ueg_trajectory_and_fci_energy():
+    """UEG (the reference's ueg_n10_rs2_e4 fixture system: 6 electrons, 66 plane-wave spin-orbitals, rs = 2).
+    (i) trajectory parity of the host driver + GPU engine with the oracle under the same Philox stream;
+    (ii) the reblocked projected energy agrees with the exact correlation energy quoted in the reference's input
+    file (test_suite/fciqmc/np2/ueg_n10_rs2_e4_fciqmc/ueg.fciqmc.in: "-0.176123766865", HANDE FCI)."""
+    from hande_b200.ueg import UegSystem
+    ueg = (6, 0, 2.0, 2.0)
+    ref_det = [1, 2, 3, 10, 11, 14]
+    s = UegSystem(*ueg)
+    qmc = QmcIn(tau=0.005, rng_seed=122, init_pop=10, mc_cycles=10, nreports=60, target_population=90000,
+                state_size=50000, spawned_state_size=5000, reference_det=ref_det)
+    res = do_fciqmc(s, qmc)
+    o = Oracle()
+    o.init_ueg(*ueg)
+    o.set_ref_det(ref_det)
+    o.set_qmc(rng_kind=1, literal_event_int32=0, tau=0.005, seed=122, D0_population=10, ncycles=10, nreport=60,
+              target_particles=90000, walker_length=50000, spawned_walker_length=5000)
+    o.init()
+    rows = o.run()
+    assert res.H00 == o.reference()["H00"]
+    assert len(res.rows) == len(rows) == 61
+    for g, r in zip(res.rows, rows):
+        assert g[0] == r[0] and g[4] == r[4] and g[5] == r[5] and g[6] == r[6] and g[3] == r[3], (g, r)
+        assert abs(g[2] - r[2]) <= 1e-10 * max(1.0, abs(r[2]))
+    # (ii) production-like run in the variable-shift regime, real amplitudes
+    qmc = QmcIn(tau=0.02, rng_seed=5, init_pop=200, mc_cycles=10, nreports=1000, target_population=20000,
+                state_size=400000, spawned_state_size=200000, real_amplitudes=True, reference_det=ref_det)
+    g = np.array(do_fciqmc(s, qmc).rows)[1:]
+    k = 400
+    e, se = ratio_with_error(g[k:, 2], g[k:, 3])
+    assert abs(e - (-0.176123766865)) < 4.0 * se + 2e-4, (e, se)
+    m, sm = optimal_error(g[k:, 1])
+    assert abs(m - (-0.176123766865)) < 4.0 * sm + 2e-3, (m, sm)

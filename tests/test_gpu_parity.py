@@ -51,6 +51,12 @@ def test_gen_excit_heat_bath():
     _check_gen("s10", "heat_bath", True, 0.01, n=150, nattempt=6)
 
 
+def test_gen_excit_ueg():
+    # gen_excit_ueg_no_renorm + slater_condon0_ueg on the device, W = 2 and W = 3
+    _check_gen("ueg6", "no_renorm", False, 0.005, n=150, nattempt=5)
+    _check_gen("ueg14", "no_renorm", True, 0.002, n=150, nattempt=5)
+
+
 def test_heat_bath_tables_match_oracle():
     s, o, eng, ref = make_pair("s10", excit_gen="heat_bath")
     hb = o.heat_bath_tables()
@@ -94,6 +100,8 @@ CASES = [
     ("ne", "renorm", True, True, 0.005, 5000, -1),
     ("s40", "renorm", False, True, 0.02, 3000, -1),
     ("s12", "heat_bath", True, True, 0.01, 2500, -1),
+    ("ueg6", "no_renorm", False, False, 0.01, 3000, -1),
+    ("ueg14", "no_renorm", True, True, 0.004, 4000, -1),
 ]
 
 
@@ -134,7 +142,9 @@ def test_stage_and_cycle_parity(name, gen, real, init, tau, n, exl):
 
 @pytest.mark.parametrize("name,gen,real,init,tau", [("h2o", "renorm", False, False, 0.003),
                                                      ("ne", "renorm", True, True, 0.005),
-                                                     ("s12", "heat_bath", True, True, 0.002)])
+                                                     ("s12", "heat_bath", True, True, 0.002),
+                                                     ("ueg6", "no_renorm", False, False, 0.005),
+                                                     ("ueg14", "no_renorm", True, True, 0.002)])
 def test_iterate_from_single_determinant(name, gen, real, init, tau):
     """Population growth from the reference determinant: 60 cycles in blocks of 10 through hb200_iterate."""
     s, o, eng, ref = make_pair(name, excit_gen=gen, tau=tau, real=real, initiator=init)

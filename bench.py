@@ -88,13 +88,13 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def oracle_cpu_run(path, n_sample, ncycles, tau, nthreads, seed=1):
+def oracle_cpu_run(path, n_sample, ncycles, tau, nthreads, seed=1, excit_gen="heat_bath"):
     """Time the oracle (CPU restatement of the reference path) on a bounded sample of the workload."""
     from hande_b200 import synthetic
     from oracle.pyoracle import Oracle
     o = Oracle()
     o.read_fcidump(path)
-    o.set_qmc(tau=tau, seed=7, excit_gen="heat_bath", rng_kind=1, real_amplitudes=1, initiator_approx=1,
+    o.set_qmc(tau=tau, seed=7, excit_gen=excit_gen, rng_kind=1, real_amplitudes=1, initiator_approx=1,
               literal_event_int32=0, walker_length=4 * n_sample, spawned_walker_length=2 * n_sample)
     t0 = time.time()
     o.init()
@@ -149,6 +149,8 @@ def main():
     ap.add_argument("--impl", default="engine")
     ap.add_argument("--walkers", type=float, default=1e8, help="walkers (= occupied determinants) per GPU")
     ap.add_argument("--tau", type=float, default=0.0, help="0 => calibrate for R_spawn ~ 0.05")
+    ap.add_argument("--excit-gen", default="heat_bath", choices=["heat_bath", "heat_bath_uniform", "renorm", "no_renorm"],
+                    help="excitation generator (headline = heat_bath, BASELINE.json configs[1]; others are side measurements)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -193,7 +195,7 @@ def main():
     ps, pd = R.find_single_double_prob(s, occ0)
     wl = int(n * 1.25) + 4096
     sl = max(int(n * 0.30), 1 << 16) * 1
-    eng = Engine(s, excit_gen="heat_bath", pattempt_single=ps, pattempt_double=pd, real_amplitudes=True,
+    eng = Engine(s, excit_gen=args.excit_gen, pattempt_single=ps, pattempt_double=pd, real_amplitudes=True,
                  spawn_cutoff=0.01, initiator_approx=True, walker_length=wl, spawned_walker_length=sl * world, seed=7,
                  nprocs=world, iproc=rank, device=local_rank)
     eng.set_reference(f0, H00)
@@ -275,7 +277,8 @@ def main():
     P = out["nspawn_events"]
     # ---- roofline of the dominant kernel (k_spawn_death): algorithmic bytes per launch / its launch duration
     Em, Es = 8 * (s.W + 2), 8 * (s.W + 2)
-    alg_bytes = S * Em + S * 8 + A * T_HB + P * Es
+    t_hb = {"heat_bath": T_HB, "heat_bath_uniform": 12.0 + 2 * 16.0}.get(args.excit_gen, 0.0)
+    alg_bytes = S * Em + S * 8 + A * t_hb + P * Es
     k_ms = tm["spawn_kernel_ms"] / args.steps
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
@@ -285,7 +288,7 @@ def main():
                 "stage_ms_per_step": {k: tm[k] / args.steps for k in ("spawn_ms", "comm_ms", "sort_ms", "annihilate_ms")}}
     # whole-cycle algorithmic traffic (SURVEY.md 8d B_alg) for context
     U = P
-    b_alg = S * (2 * Em + 8) + S * Em + A * T_HB + P * 6 * Es + U * 2 * Es
+    b_alg = S * (2 * Em + 8) + S * Em + A * t_hb + P * 6 * Es + U * 2 * Es
     roofline["cycle_alg_bytes"] = b_alg
     roofline["cycle_frac"] = b_alg / (dev_s / args.steps) / 1e9 / peak
 
@@ -313,9 +316,9 @@ def main():
     if rank == 0 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         ns_cpu = 20000
-        r, t_init = oracle_cpu_run(path, ns_cpu, 2, tau, cores)
+        r, t_init = oracle_cpu_run(path, ns_cpu, 2, tau, cores, excit_gen=args.excit_gen)
         cpu = {"value": r["walker_iters"] / r["seconds"], "unit": "walker-iterations/s", "cores": cores, "kind": "port",
-               "sample": f"{cores} replicas x {ns_cpu} walkers x 2 cycles of the same S50 heat-bath workload "
+               "sample": f"{cores} replicas x {ns_cpu} walkers x 2 cycles of the same S50 {args.excit_gen} workload "
                          f"(oracle restatement; {r['seconds']:.1f}s timed, table init {t_init:.1f}s untimed)"}
 
     if rank == 0:
@@ -323,8 +326,8 @@ def main():
             "metric": "walker-iterations/s (FCIQMC MC cycles x walkers)", "value": value, "unit": "walker-iterations/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tmax / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64+f64", "data": "synthetic",
-            "config": {"workload": "S50 synthetic FCIDUMP (50 orb / 20 el, C1, 8-fold), real-valued iFCIQMC, heat_bath, "
-                                   f"{n:.3g} unit walkers per GPU (distribution A)",
+            "config": {"workload": "S50 synthetic FCIDUMP (50 orb / 20 el, C1, 8-fold), real-valued iFCIQMC, "
+                                   f"{args.excit_gen}, {n:.3g} unit walkers per GPU (distribution A)",
                        "tau": tau, "R_spawn": float(P) / max(A, 1.0), "walkers_per_gpu": n, "nstates": int(S),
                        "l2": "inputs (3.2 GB walker list) larger than L2; no flush needed",
                        "sharding": "hash-owner (MurmurHash2) + NCCL all-to-all" if world > 1 else "single rank"},

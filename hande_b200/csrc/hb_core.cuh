@@ -51,6 +51,7 @@ struct Sys {
     // symmetry tables (src/point_group_symmetry.f90:82-229)
     const int* nbss;            // nbasis_sym_spin[(ims-1) + 2*sym]
     const int* ssbf;            // sym_spin_basis_fns[(ind-1) + max_nbss*((ims-1)+2*sym)]
+    const uint64_t* su_mask;    // [2*nsym_tot][W] bit strings of the basis functions of each (spin, sym) class
     // integrals (src/molecular_integrals.F90): dense one-body <i|h|j> (0 where symmetry forbids),
     // two-body store v[indx-1] per spin channel exactly as two_body_t%integrals(chan)%v
     const double* h1;           // [(i-1)*nbasis + (j-1)]
@@ -103,7 +104,7 @@ struct Params {
     double H00;
 };
 
-enum { EXCIT_GEN_NO_RENORM = 0, EXCIT_GEN_RENORM = 1, EXCIT_GEN_HEAT_BATH = 4 };
+enum { EXCIT_GEN_NO_RENORM = 0, EXCIT_GEN_RENORM = 1, EXCIT_GEN_HEAT_BATH = 4, EXCIT_GEN_HEAT_BATH_UNIFORM = 5 };
 enum { RNG_NATTEMPTS = 0, RNG_SPAWN = 1, RNG_DEATH = 2, RNG_ROUND_MAIN = 3, RNG_ROUND_SPAWN = 4 };
 
 // ------------------------------------------------------------------------------------------------
@@ -148,14 +149,31 @@ HB_HD uint64_t det_hash64(const uint64_t* f) {
 struct PhiloxStream {
     uint32_t k0, k1, c1, c2, c3, purpose, draw;
     uint32_t buf[4];
+    uint32_t pre[8];     // blocks 0 and 1 (draws 0..3) when prefetched
+    bool have_pre;
     HB_HD void begin(uint32_t seed, uint32_t cycle, uint32_t purpose_, uint64_t dethash, uint32_t attempt) {
         k0 = seed; k1 = cycle; purpose = purpose_; c1 = attempt;
-        c2 = (uint32_t)dethash; c3 = (uint32_t)(dethash >> 32); draw = 0;
+        c2 = (uint32_t)dethash; c3 = (uint32_t)(dethash >> 32); draw = 0; have_pre = false;
+    }
+    // Evaluate the first two blocks (draws 0..3) now - called where the warp is converged, so that the draws made
+    // inside divergent generator code (rejection loops, single/double branches) cost a register read instead of a
+    // serialised 10-round Philox evaluation per divergent path.  The stream itself is unchanged.
+    HB_HD void prefetch() {
+        philox4x32_10((purpose << 24) | 0u, c1, c2, c3, k0, k1, pre);
+        philox4x32_10((purpose << 24) | 1u, c1, c2, c3, k0, k1, pre + 4);
+        have_pre = true;
     }
     HB_HD double next() {
-        if ((draw & 1u) == 0) philox4x32_10((purpose << 24) | (draw >> 1), c1, c2, c3, k0, k1, buf);
-        uint32_t lo = (draw & 1u) ? buf[2] : buf[0];
-        uint32_t hi = (draw & 1u) ? buf[3] : buf[1];
+        uint32_t lo, hi;
+        if (have_pre && draw < 4u) {
+            const uint32_t* q = pre;
+            lo = (draw == 0) ? q[0] : (draw == 1) ? q[2] : (draw == 2) ? q[4] : q[6];
+            hi = (draw == 0) ? q[1] : (draw == 1) ? q[3] : (draw == 2) ? q[5] : q[7];
+        } else {
+            if ((draw & 1u) == 0) philox4x32_10((purpose << 24) | (draw >> 1), c1, c2, c3, k0, k1, buf);
+            lo = (draw & 1u) ? buf[2] : buf[0];
+            hi = (draw & 1u) ? buf[3] : buf[1];
+        }
         draw++;
         uint64_t u = ((uint64_t)hi << 32) | lo;
         return (double)(u >> 11) * (1.0 / 9007199254740992.0);
@@ -210,6 +228,11 @@ HB_HD int ctz64(uint64_t x) {
     return __builtin_ctzll(x);
 #endif
 }
+// basis_fns(:)%ms and the ims index (ms+3)/2: spin-orbitals are stored alpha (odd index, ms=+1), beta (even, ms=-1)
+// for every system the reference builds (src/read_in.F90:862-920, src/basis.f90:465-486); spatial_index = (i+1)/2.
+HB_HD int ms_of(int o) { return (o & 1) ? 1 : -1; }
+HB_HD int ims_of(int o) { return (o & 1) ? 2 : 1; }
+HB_HD int spatial_of(int o) { return (o + 1) >> 1; }
 HB_HD bool det_test(const uint64_t* f, int orb) { return (f[(orb - 1) >> 6] >> ((orb - 1) & 63)) & 1ull; }
 
 // decode_det (src/determinants.f90:243-297): occupied orbitals ascending.
@@ -217,11 +240,15 @@ template <int W>
 HB_HD int decode_det(const uint64_t* f, uint8_t* occ) {
     int n = 0;
 #pragma unroll
-    for (int iw = 0; iw < W; ++iw) {
-        uint64_t x = f[iw];
+    for (int iw = 0; iw < 2 * W; ++iw) {
+        uint32_t x = (uint32_t)(f[iw >> 1] >> ((iw & 1) * 32));
         while (x) {
-            int b = ctz64(x);
-            occ[n++] = (uint8_t)(iw * 64 + b + 1);
+#if defined(__CUDA_ARCH__)
+            const int b = __ffs((int)x) - 1;
+#else
+            const int b = __builtin_ctz(x);
+#endif
+            occ[n++] = (uint8_t)(iw * 32 + b + 1);
             x &= x - 1;
         }
     }
@@ -316,18 +343,20 @@ HB_HD int ssbf(const Sys& s, int ind, int ims, int sym) {
 // ------------------------------------------------------------------------------------------------
 HB_HD int64_t tri_ind(int64_t i, int64_t j) { return (i * (i - 1)) / 2 + j; }
 
+HB_HD int tri_ind32(int i, int j) { return (i * (i - 1)) / 2 + j; }
 HB_HD double two_body(const Sys& s, int i, int j, int a, int b) {
+    // 32-bit index arithmetic: nbasis <= 255 (engine limit) => < 2^14 pairs => index < 2^27
     int ii, jj, aa, bb;
     if (i < a) { ii = a; aa = i; } else { ii = i; aa = a; }
     if (j < b) { jj = b; bb = j; } else { jj = j; bb = b; }
-    int64_t ia = tri_ind(s.bf_spatial[ii], s.bf_spatial[aa]);
-    int64_t jb = tri_ind(s.bf_spatial[jj], s.bf_spatial[bb]);
-    int64_t indx = (ia < jb) ? tri_ind(jb, ia) : tri_ind(ia, jb);
+    const int ia = tri_ind32(spatial_of(ii), spatial_of(aa));
+    const int jb = tri_ind32(spatial_of(jj), spatial_of(bb));
+    const int indx = (ia < jb) ? tri_ind32(jb, ia) : tri_ind32(ia, jb);
     int chan = 0;
     if (s.uhf) {
         if (ia < jb || (ia == jb && ii < jj)) { int t = ii; ii = jj; jj = t; }
-        if (s.bf_ms[ii] == -1) chan = (s.bf_ms[jj] == -1) ? 0 : 2;
-        else chan = (s.bf_ms[jj] == 1) ? 1 : 3;
+        if (ms_of(ii) == -1) chan = (ms_of(jj) == -1) ? 0 : 2;
+        else chan = (ms_of(jj) == 1) ? 1 : 3;
     }
     return s.v2[chan][indx - 1];
 }
@@ -343,7 +372,7 @@ HB_HDN double slater_condon0(const Sys& s, const uint8_t* occ) {
         for (int jel = iel + 1; jel < s.nel; ++jel) {
             int j = occ[jel];
             h = h + s.Jd[(i - 1) * nb + (j - 1)];
-            if (s.bf_ms[i] == s.bf_ms[j]) h = h - s.Kd[(i - 1) * nb + (j - 1)];
+            if (ms_of(i) == ms_of(j)) h = h - s.Kd[(i - 1) * nb + (j - 1)];
         }
     }
     return h;
@@ -368,7 +397,7 @@ HB_HDN double slater_condon1_excit(const Sys& s, const uint8_t* occ, int i, int 
             const int j = jj[k];
             if (j != i) {
                 h = h + v[k].x;
-                const bool same = s.uhf ? (s.bf_ms[j] == s.bf_ms[i]) : (((j ^ i) & 1) == 0);
+                const bool same = s.uhf ? (ms_of(j) == ms_of(i)) : (((j ^ i) & 1) == 0);
                 if (same) h = h - v[k].y;
             }
         }
@@ -378,8 +407,8 @@ HB_HDN double slater_condon1_excit(const Sys& s, const uint8_t* occ, int i, int 
 // slater_condon2_mol_excit (src/hamiltonian_molecular.f90:300-346)
 HB_HD double slater_condon2_excit(const Sys& s, int i, int j, int a, int b, bool perm) {
     double h = 0.0;
-    if (s.bf_ms[i] == s.bf_ms[a]) h = two_body(s, i, j, a, b);
-    if (s.bf_ms[i] == s.bf_ms[b]) h = h - two_body(s, i, j, b, a);
+    if (ms_of(i) == ms_of(a)) h = two_body(s, i, j, a, b);
+    if (ms_of(i) == ms_of(b)) h = h - two_body(s, i, j, b, a);
     return perm ? -h : h;
 }
 
@@ -398,7 +427,18 @@ HB_HD void build_symunocc(const Sys& s, const uint8_t* occ, uint8_t* su) {
     for (int k = 0; k < 2 * s.nsym_tot; ++k) su[k] = (uint8_t)s.nbss[k];
     for (int i = 0; i < s.nel; ++i) {
         int o = occ[i];
-        su[((s.bf_ms[o] + 3) / 2 - 1) + 2 * s.bf_sym[o]]--;
+        su[(ims_of(o) - 1) + 2 * s.bf_sym[o]]--;
+    }
+}
+// the same through per-class occupation masks: symunocc(c) = nbasis_sym_spin(c) - popcount(f & mask(c)),
+// su_mask[c*W + w] = bit string of the basis functions of class c = (ims-1) + 2*sym
+template <int W>
+HB_HD void build_symunocc_masks(const Sys& s, const uint64_t* f, uint8_t* su) {
+    for (int c = 0; c < 2 * s.nsym_tot; ++c) {
+        int n = 0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) n += popc64(f[w] & s.su_mask[c * W + w]);
+        su[c] = (uint8_t)(s.nbss[c] - n);
     }
 }
 #define HB_SU(ims, sym) ((int)su[((ims) - 1) + 2 * (sym)])
@@ -413,24 +453,22 @@ HB_HD void choose_ij(R& rng, const Sys& s, const uint8_t* occ, int& i, int& j, i
     i = occ[i_ind - 1];
     j = occ[j_ind - 1];
     ij_sym = sym_conj(s, cross_product(s, s.bf_sym[i], s.bf_sym[j]));
-    ij_spin = s.bf_ms[i] + s.bf_ms[j];
+    ij_spin = ms_of(i) + ms_of(j);
 }
 
-// gen_excit_mol: renormalised uniform generator (src/excit_gen_mol.f90:16-101,384-448,521-616,
-// 802-946,1140-1327)
+// gen_single_excit_mol (src/excit_gen_mol.f90:384-448): choose_ia_mol (:802-870) + calc_pgen_single_mol (:1140-1190)
 template <int W, class R>
-HB_HDN void gen_excit_renorm(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ,
-                             const uint8_t* su, Gen& g) {
+HB_HDN void gen_single_renorm(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ,
+                              const uint8_t* su, Gen& g) {
     const int nel = s.nel;
     g.from2 = 0; g.to2 = 0; g.perm = false;
-    if (rng.next() < p.pattempt_single) {
         // choose_ia_mol
         g.nexcit = 1;
         bool allowed = false;
         int ni = nel;
         for (int k = 0; k < nel; ++k) {
             int o = occ[k];
-            int imsa = (s.bf_ms[o] + 3) / 2;
+            int imsa = ims_of(o);
             int isyma = cross_product(s, s.bf_sym[o], s.gamma_sym);
             if (HB_SU(imsa, isyma) != 0) allowed = true; else ni--;
         }
@@ -439,7 +477,7 @@ HB_HDN void gen_excit_renorm(R& rng, const Sys& s, const Params& p, const uint64
             int i, a;
             for (;;) {
                 i = occ[(int)(rng.next() * nel)];
-                int imsa = (s.bf_ms[i] + 3) / 2;
+                int imsa = ims_of(i);
                 int isyma = cross_product(s, s.bf_sym[i], s.gamma_sym);
                 if (HB_SU(imsa, isyma) != 0) {
                     int n = nbss(s, imsa, isyma);
@@ -453,12 +491,23 @@ HB_HDN void gen_excit_renorm(R& rng, const Sys& s, const Params& p, const uint64
             }
             g.from1 = i; g.to1 = a;
             // calc_pgen_single_mol
-            g.pgen = p.pattempt_single * (1.0 / (ni * HB_SU((s.bf_ms[a] + 3) / 2, s.bf_sym[a])));
+            g.pgen = p.pattempt_single * (1.0 / (ni * HB_SU(ims_of(a), s.bf_sym[a])));
             g.perm = excit_perm1<W>(f, i, a);
             g.hmatel = slater_condon1_excit(s, occ, i, a, g.perm);
         } else {
             g.hmatel = 0.0; g.pgen = 1.0; g.from1 = 0; g.to1 = 0;
         }
+}
+
+// gen_excit_mol: renormalised uniform generator (src/excit_gen_mol.f90:16-101,384-448,521-616,
+// 802-946,1140-1327)
+template <int W, class R>
+HB_HDN void gen_excit_renorm(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ,
+                             const uint8_t* su, Gen& g) {
+    const int nel = s.nel;
+    g.from2 = 0; g.to2 = 0; g.perm = false;
+    if (rng.next() < p.pattempt_single) {
+        gen_single_renorm<W>(rng, s, p, f, occ, su, g);
     } else {
         g.nexcit = 2;
         int i, j, ij_sym, spin;
@@ -491,7 +540,7 @@ HB_HDN void gen_excit_renorm(R& rng, const Sys& s, const Params& p, const uint64
                 a = (int)(rng.next() * na) + 1;
                 a = fac * a - shift;
                 if (!det_test(f, a)) {
-                    int imsb = (spin - s.bf_ms[a] + 3) / 2;
+                    int imsb = (spin - ms_of(a) + 3) / 2;
                     int isymb = sym_conj(s, cross_product(s, ij_sym, s.bf_sym[a]));
                     int nu = HB_SU(imsb, isymb);
                     if (nu > 1 || (nu == 1 && (isymb != s.bf_sym[a] || spin == 0))) {
@@ -508,7 +557,7 @@ HB_HDN void gen_excit_renorm(R& rng, const Sys& s, const Params& p, const uint64
             if (a > b) { int t = a; a = b; b = t; }
             g.to1 = a; g.to2 = b;
             // calc_pgen_double_mol
-            int imsa = (s.bf_ms[a] + 3) / 2, imsb = (s.bf_ms[b] + 3) / 2;
+            int imsa = ims_of(a), imsb = ims_of(b);
             int n_aij;
             double p_aijb, p_bija;
             if (spin != 0) {
@@ -555,7 +604,7 @@ HB_HDN void gen_excit_no_renorm(R& rng, const Sys& s, const Params& p, const uin
     if (rng.next() < p.pattempt_single) {
         g.nexcit = 1;
         int i = occ[(int)(rng.next() * nel)];
-        int imsa = (s.bf_ms[i] + 3) / 2;
+        int imsa = ims_of(i);
         int isyma = cross_product(s, s.bf_sym[i], s.gamma_sym);
         int n = nbss(s, imsa, isyma);
         int ind = (int)(n * rng.next()) + 1;
@@ -569,7 +618,7 @@ HB_HDN void gen_excit_no_renorm(R& rng, const Sys& s, const Params& p, const uin
         }
         if (g.allowed) {
             g.to1 = a;
-            g.pgen = p.pattempt_single * (1.0 / (nel * nbss(s, (s.bf_ms[a] + 3) / 2, s.bf_sym[a])));
+            g.pgen = p.pattempt_single * (1.0 / (nel * nbss(s, ims_of(a), s.bf_sym[a])));
             g.perm = excit_perm1<W>(f, i, a);
             g.hmatel = slater_condon1_excit(s, occ, i, a, g.perm);
         } else {
@@ -589,7 +638,7 @@ HB_HDN void gen_excit_no_renorm(R& rng, const Sys& s, const Params& p, const uin
             a = fac * a - shift;
             if (!det_test(f, a)) break;
         }
-        int imsb = (spin - s.bf_ms[a] + 3) / 2;
+        int imsb = (spin - ms_of(a) + 3) / 2;
         int isymb = sym_conj(s, cross_product(s, ij_sym, s.bf_sym[a]));
         int n = nbss(s, imsb, isymb);
         if (n == 0) {
@@ -608,8 +657,8 @@ HB_HDN void gen_excit_no_renorm(R& rng, const Sys& s, const Params& p, const uin
         if (g.allowed) {
             g.to1 = a; g.to2 = b;
             int n_aij = (spin == -2) ? s.nvirt_beta : (spin == 0 ? s.nvirt : s.nvirt_alpha);
-            int imsa = (s.bf_ms[a] + 3) / 2, isyma = s.bf_sym[a];
-            int imsb2 = (s.bf_ms[b] + 3) / 2, isymb2 = s.bf_sym[b];
+            int imsa = ims_of(a), isyma = s.bf_sym[a];
+            int imsb2 = ims_of(b), isymb2 = s.bf_sym[b];
             double p_aijb, p_bija;
             if (isyma == isymb2 && imsa == imsb2) {
                 p_aijb = 1.0 / (nbss(s, imsa, isyma) - 1);
@@ -807,7 +856,7 @@ HB_HD void hb_ordering(const HbState& st, int k, int& fr, int& to, int& ot) {
 }
 HB_HD bool hb_single_allowed(const Sys& s, int fr, int to) {
     const int isyma = cross_product(s, s.bf_sym[fr], s.gamma_sym);
-    return s.bf_sym[to] == isyma && s.bf_ms[to] == s.bf_ms[fr];
+    return s.bf_sym[to] == isyma && ms_of(to) == ms_of(fr);
 }
 
 // Phase A: select i, j (on-the-fly alias tables) and a (precomputed alias table); 2-3 random numbers.
@@ -965,6 +1014,64 @@ HB_HDN void gen_excit_heat_bath(R& rng, const Sys& s, const Params& p, const uin
     hb_phase_f<W>(s, f, st, hm, psum, g);
 }
 
+// gen_excit_mol_heat_bath_uniform (src/excit_gen_heat_bath_mol.F90:550-718), excit_gen = heat_bath_uniform: single
+// excitations from the renormalised uniform generator with probability pattempt_single, double excitations from the
+// heat-bath tables (i, j, a, b in turn); the generation probability of a double needs no matrix elements.
+template <int W, class R>
+HB_HDN void gen_excit_heat_bath_uniform(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ,
+                                        const uint8_t* su, const double* __restrict__ iw, double* scr, int stride, Gen& g) {
+    const int nel = s.nel;
+    const int64_t nb = s.nbasis;
+    g.from1 = 0; g.from2 = 0; g.to1 = 0; g.to2 = 0; g.perm = false;
+    if (rng.next() < p.pattempt_single) {
+        gen_single_renorm<W>(rng, s, p, f, occ, su, g);
+        return;
+    }
+    g.nexcit = 2;
+    const double i_tot = stage_occ(iw, occ, nel, scr, stride);
+    const int iq = select_alias_staged(rng, nel, scr, stride, i_tot);
+    int i = occ[iq - 1];
+    const double wi = scr[(iq - 1) * stride];
+    const double ij_tot = stage_occ(s.hb_ij_w + nb * (i - 1), occ, nel, scr, stride);
+    bool allowed = false;
+    int j = 0;
+    double pgen = 0.0;
+    if (ij_tot > 0.0) {
+        const int jq = select_alias_staged(rng, nel, scr, stride, ij_tot);
+        j = occ[jq - 1];
+        const double wij = scr[(jq - 1) * stride];
+        const double ji_tot = sum_occ(s.hb_ij_w + nb * (j - 1), occ, nel);
+        allowed = fabs(s.hb_ija_tot[HB_I2(j, i)]) > 0.0;
+        if (allowed)
+            pgen = ((wi / i_tot) * (wij / ij_tot)) + ((iw[j - 1] / i_tot) * (s.hb_ij_w[HB_I2(i, j)] / ji_tot));
+    }
+    if (j < i) { const int t = i; i = j; j = t; }
+    int a = 0, b = 0;
+    if (allowed) {
+        a = select_precalc(rng, (int)nb, s.hb_ija_U + HB_I3(1, j, i), s.hb_ija_K + HB_I3(1, j, i));
+        if (fabs(s.hb_ijab_tot[HB_I3(a, j, i)]) > 0.0 && !det_test(f, a)) {
+            b = select_precalc(rng, (int)nb, s.hb_ijab_U + HB_I4(1, a, j, i), s.hb_ijab_K + HB_I4(1, a, j, i));
+            allowed = !det_test(f, b);
+        } else {
+            allowed = false;
+        }
+    }
+    g.allowed = allowed;
+    if (allowed) {
+        g.from1 = i; g.from2 = j;
+        g.to1 = (a < b) ? a : b; g.to2 = (a < b) ? b : a;
+        g.perm = excit_perm2<W>(f, i, j, g.to1, g.to2);
+        g.hmatel = slater_condon2_excit(s, i, j, g.to1, g.to2, g.perm);
+        g.pgen = (1.0 - p.pattempt_single) * pgen *
+                 (((s.hb_ija_w[HB_I3(a, j, i)] / s.hb_ija_tot[HB_I2(j, i)]) *
+                   (s.hb_ijab_w[HB_I4(b, a, j, i)] / s.hb_ijab_tot[HB_I3(a, j, i)])) +
+                  ((s.hb_ija_w[HB_I3(b, j, i)] / s.hb_ija_tot[HB_I2(j, i)]) *
+                   (s.hb_ijab_w[HB_I4(a, b, j, i)] / s.hb_ijab_tot[HB_I3(b, j, i)])));
+    } else {
+        g.hmatel = 0.0; g.pgen = 1.0;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Uniform electron gas (3D): analytic integrals, Slater-Condon rules and the no_renorm generator
 // ------------------------------------------------------------------------------------------------
@@ -979,8 +1086,8 @@ HB_HD double ueg_two_e_int(const Sys& s, int i, int j, int a, int b) {
     const K4 ki = s.ueg_k[i], kj = s.ueg_k[j], ka = s.ueg_k[a], kb = s.ueg_k[b];
     double v = 0.0;
     if (ki.x + kj.x - ka.x - kb.x == 0 && ki.y + kj.y - ka.y - kb.y == 0 && ki.z + kj.z - ka.z - kb.z == 0) {
-        if (s.bf_ms[i] == s.bf_ms[a] && s.bf_ms[j] == s.bf_ms[b]) v = v + ueg_coulomb(s, i, a);
-        if (s.bf_ms[i] == s.bf_ms[b] && s.bf_ms[j] == s.bf_ms[a]) v = v - ueg_coulomb(s, i, b);
+        if (ms_of(i) == ms_of(a) && ms_of(j) == ms_of(b)) v = v + ueg_coulomb(s, i, a);
+        if (ms_of(i) == ms_of(b) && ms_of(j) == ms_of(a)) v = v - ueg_coulomb(s, i, b);
     }
     return v;
 }
@@ -997,8 +1104,8 @@ HB_HDN double slater_condon0_ueg(const Sys& s, const uint8_t* occ) {
 // slater_condon2_ueg_excit (src/hamiltonian_ueg.f90:186-223)
 HB_HD double slater_condon2_ueg_excit(const Sys& s, int i, int a, int b, bool perm) {
     double h = 0.0;
-    if (s.bf_ms[i] == s.bf_ms[a]) h = ueg_coulomb(s, i, a);
-    if (s.bf_ms[i] == s.bf_ms[b]) h = h - ueg_coulomb(s, i, b);
+    if (ms_of(i) == ms_of(a)) h = ueg_coulomb(s, i, a);
+    if (ms_of(i) == ms_of(b)) h = h - ueg_coulomb(s, i, b);
     return perm ? -h : h;
 }
 // ueg_basis_index (src/ueg.f90:142-172)
@@ -1021,7 +1128,7 @@ HB_HDN void gen_excit_ueg_no_renorm(R& rng, const Sys& s, const uint64_t* f, con
     const int i_ind = ind - ((j_ind - 1) * (j_ind - 2)) / 2;
     const int i = occ[i_ind - 1], j = occ[j_ind - 1];
     g.from1 = i; g.from2 = j;
-    const int ij_spin = s.bf_ms[i] + s.bf_ms[j];
+    const int ij_spin = ms_of(i) + ms_of(j);
     const K4 ki = s.ueg_k[i], kj = s.ueg_k[j];
     const int kx = ki.x + kj.x, ky = ki.y + kj.y, kz = ki.z + kj.z;
     const uint64_t* __restrict__ t =
@@ -1075,6 +1182,10 @@ HB_HD void gen_excit(R& rng, const Sys& s, const Params& p, const uint64_t* f, c
     if (s.kind == SYS_UEG) gen_excit_ueg_no_renorm<W>(rng, s, f, occ, g);
     else if (p.excit_gen == EXCIT_GEN_RENORM) gen_excit_renorm<W>(rng, s, p, f, occ, su, g);
     else if (p.excit_gen == EXCIT_GEN_NO_RENORM) gen_excit_no_renorm<W>(rng, s, p, f, occ, g);
+    else if (p.excit_gen == EXCIT_GEN_HEAT_BATH_UNIFORM) {
+        double scr[HB_MAXNEL];
+        gen_excit_heat_bath_uniform<W>(rng, s, p, f, occ, su, s.hb_i_w, scr, 1, g);
+    }
     else gen_excit_heat_bath<W>(rng, s, p, f, occ, g);
 }
 
@@ -1183,11 +1294,11 @@ HB_HDN double proj_energy_hmatel(const Sys& s, const Params& p, const uint64_t* 
         return pm ? -h : h;
     }
     if (nexcit == 1) {
-        if (s.bf_ms[from[0]] == s.bf_ms[to[0]] && s.bf_sym[from[0]] == s.bf_sym[to[0]])
+        if (ms_of(from[0]) == ms_of(to[0]) && s.bf_sym[from[0]] == s.bf_sym[to[0]])
             return slater_condon1_excit(s, occ, from[0], to[0], pm);
         return 0.0;
     }
-    if (s.bf_ms[from[0]] + s.bf_ms[from[1]] == s.bf_ms[to[0]] + s.bf_ms[to[1]]) {
+    if (ms_of(from[0]) + ms_of(from[1]) == ms_of(to[0]) + ms_of(to[1])) {
         int ij = cross_product(s, s.bf_sym[from[0]], s.bf_sym[from[1]]);
         int ab = cross_product(s, s.bf_sym[to[0]], s.bf_sym[to[1]]);
         if (ij == ab) return slater_condon2_excit(s, from[0], from[1], to[0], to[1], pm);

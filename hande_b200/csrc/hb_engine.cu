@@ -175,13 +175,15 @@ constexpr int SINGLES_CHUNK = 64;  // single excitations whose pgen terms are st
 struct SpawnSmem {
     size_t sf, shash, spop, sscan, swarp, sred, siw, sw, sh1, shm, ssp, spsum, sterm, sok, sq, scnt, sflag, slo, sperm, ssq,
         ssi, socc, ssu, total;
-    __host__ __device__ SpawnSmem(int W, int nel, int nsu, int nb, bool heat_bath) {
+    // heat_bath: the original heat-bath generator (phase buffers); hb_stage: any generator that selects i, j from the
+    // heat-bath weights (needs the hb_i_w copy and the per-thread staging area of nel doubles)
+    __host__ __device__ SpawnSmem(int W, int nel, int nsu, int nb, bool heat_bath, bool hb_stage) {
         size_t o = 0;
         sf = o;     o += (size_t)TILE * W * 8;
         shash = o;  o += (size_t)TILE * 8;
         spop = o;   o += (size_t)TILE * 8;
         sred = o;   o += 40 * 8;
-        siw = o;    o += heat_bath ? (size_t)nb * 8 : 0;          // copy of hb_i_w
+        siw = o;    o += hb_stage ? (size_t)nb * 8 : 0;           // copy of hb_i_w
         // ---- union: phase A staging | phase B..F buffers
         const size_t u0 = o;
         sw = o;
@@ -192,7 +194,7 @@ struct SpawnSmem {
         spsum = v;  v += heat_bath ? (size_t)TILE * 8 : 0;        // singles: sum of pgen terms
         sterm = v;  v += heat_bath ? (size_t)SINGLES_CHUNK * nel * 8 : 0;  // singles: pgen terms of one chunk
         sok = v;    v += heat_bath ? (size_t)SINGLES_CHUNK * nel : 0;
-        const size_t stage = heat_bath ? (size_t)TILE * nel * 8 : 0;
+        const size_t stage = hb_stage ? (size_t)TILE * nel * 8 : 0;
         o = u0 + (stage > (v - u0) ? stage : (v - u0));
         o = (o + 7) & ~(size_t)7;
         // ---- end of union
@@ -224,17 +226,21 @@ __device__ __forceinline__ void make_child(const uint64_t* f, const Gen& g, uint
     }
 }
 
-template <int W>
-__global__ void __launch_bounds__(TILE, 3)
+// GEN: compile-time generator of this instantiation (one kernel per generator keeps the code - and the instruction
+// cache footprint - to what the run actually executes): EXCIT_GEN_* for read_in systems, GEN_UEG for the UEG.
+enum { GEN_UEG = 100 };
+template <int W, int GEN>
+__global__ void __launch_bounds__(TILE, (GEN == EXCIT_GEN_HEAT_BATH || GEN == EXCIT_GEN_HEAT_BATH_UNIFORM) ? 3 : 4)
 k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __restrict__ pops,
               const double* __restrict__ dat, long long nstates, int64_t* __restrict__ spawn,
               unsigned long long* __restrict__ head, long long block_size, const int* __restrict__ proc_map,
               SpawnPartials* __restrict__ partials, int* __restrict__ err) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nel = s.nel;
-    const bool heat_bath = (p.excit_gen == EXCIT_GEN_HEAT_BATH);
-    const int nsu = (p.excit_gen == EXCIT_GEN_RENORM) ? 2 * s.nsym_tot : 0;
-    const SpawnSmem L(W, nel, nsu, s.nbasis, heat_bath);
+    constexpr bool heat_bath = (GEN == EXCIT_GEN_HEAT_BATH);
+    constexpr bool hb_stage = heat_bath || (GEN == EXCIT_GEN_HEAT_BATH_UNIFORM);
+    const int nsu = (GEN == EXCIT_GEN_RENORM || GEN == EXCIT_GEN_HEAT_BATH_UNIFORM) ? 2 * s.nsym_tot : 0;
+    const SpawnSmem L(W, nel, nsu, s.nbasis, heat_bath, hb_stage);
     uint64_t* sf = reinterpret_cast<uint64_t*>(smem_raw + L.sf);
     uint64_t* shash = reinterpret_cast<uint64_t*>(smem_raw + L.shash);
     int64_t* spop = reinterpret_cast<int64_t*>(smem_raw + L.spop);
@@ -268,7 +274,7 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
     double pe = 0.0, d0 = 0.0;
     long long ndeath = 0, npart = 0;
     int natt = 0;
-    if (heat_bath)
+    if (hb_stage)
         for (int k = tid; k < s.nbasis; k += TILE) siw[k] = s.hb_i_w[k];
     if (idx < nstates) {
         uint64_t f[W];
@@ -280,7 +286,7 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
         spop[tid] = pop;
         uint8_t* occ = socc + tid * nel;
         decode_det<W>(f, occ);
-        if (nsu) build_symunocc(s, occ, ssu + tid * nsu);
+        if (nsu) build_symunocc_masks<W>(s, f, ssu + tid * nsu);
         const uint64_t h = det_hash64<W>(f);
         shash[tid] = h;
         const double real_pop = (double)pop / (double)p.real_factor;
@@ -323,6 +329,7 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
         for (int k = 0; k < W; ++k) f[k] = sf[lo * W + k];
         PhiloxStream rng;
         rng.begin(p.seed, p.cycle, RNG_SPAWN, shash[lo], (uint32_t)att);
+        if (!hb_stage) rng.prefetch();   // uniform generators draw inside divergent rejection loops
         Gen g;
         if (heat_bath) {
             // ---- phase A: i, j, a for every attempt of the round
@@ -424,8 +431,10 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
             }
             hb_phase_f<W>(s, f, st, hmk, psum, g);
         } else if (active) {
-            if (s.kind == SYS_UEG) gen_excit_ueg_no_renorm<W>(rng, s, f, socc + lo * nel, g);
-            else if (p.excit_gen == EXCIT_GEN_RENORM) gen_excit_renorm<W>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, g);
+            if (GEN == GEN_UEG) gen_excit_ueg_no_renorm<W>(rng, s, f, socc + lo * nel, g);
+            else if (GEN == EXCIT_GEN_HEAT_BATH_UNIFORM)
+                gen_excit_heat_bath_uniform<W>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, siw, sw + tid, TILE, g);
+            else if (GEN == EXCIT_GEN_RENORM) gen_excit_renorm<W>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, g);
             else gen_excit_no_renorm<W>(rng, s, p, f, socc + lo * nel, g);
         }
         int64_t nspawn = 0;
@@ -1139,9 +1148,15 @@ static cudaError_t copy_sync(hb200_engine* e, void* dst, const void* src, size_t
     return cudaStreamSynchronize(e->stream);
 }
 
+static bool uses_heat_bath_tables(const hb200_engine* e) {
+    return e->cfg.excit_gen == HB200_EXCIT_GEN_HEAT_BATH || e->cfg.excit_gen == HB200_EXCIT_GEN_HEAT_BATH_UNIFORM;
+}
 static size_t spawn_smem_bytes(const hb200_engine* e) {
-    const int nsu = (e->cfg.excit_gen == HB200_EXCIT_GEN_RENORM) ? 2 * e->sys.nsym_tot : 0;
-    return SpawnSmem(e->W, e->sys.nel, nsu, e->sys.nbasis, e->cfg.excit_gen == HB200_EXCIT_GEN_HEAT_BATH).total;
+    const int eg = e->cfg.excit_gen;
+    const int nsu = (e->sys.kind == SYS_READ_IN && (eg == HB200_EXCIT_GEN_RENORM || eg == HB200_EXCIT_GEN_HEAT_BATH_UNIFORM))
+                        ? 2 * e->sys.nsym_tot : 0;
+    const bool hb = eg == HB200_EXCIT_GEN_HEAT_BATH;
+    return SpawnSmem(e->W, e->sys.nel, nsu, e->sys.nbasis, hb, hb || eg == HB200_EXCIT_GEN_HEAT_BATH_UNIFORM).total;
 }
 
 extern "C" {
@@ -1266,6 +1281,14 @@ int hb200_set_system_read_in(hb200_engine* e, const hb200_system_read_in* in) {
     if (dupload(e, &s.bf_spatial, sp.data(), sp.size())) return 1;
     if (dupload(e, &s.nbss, in->nbasis_sym_spin, (size_t)2 * s.nsym_tot)) return 1;
     if (dupload(e, &s.ssbf, in->sym_spin_basis_fns, (size_t)s.max_nbss * 2 * s.nsym_tot)) return 1;
+    {
+        std::vector<uint64_t> mask((size_t)2 * s.nsym_tot * e->W, 0);
+        for (int i = 1; i <= nb; ++i) {
+            const int c = (in->bf_ms[i] > 0 ? 1 : 0) + 2 * in->bf_sym[i];
+            mask[(size_t)c * e->W + ((i - 1) >> 6)] |= 1ull << ((i - 1) & 63);
+        }
+        if (dupload(e, &s.su_mask, mask.data(), mask.size())) return 1;
+    }
     if (dupload(e, &s.h1, in->one_body, (size_t)nb * nb)) return 1;
     for (int c = 0; c < (s.uhf ? 4 : 1); ++c)
         if (dupload(e, &s.v2[c], in->two_body[c], (size_t)in->nintgrls)) return 1;
@@ -1292,7 +1315,7 @@ int hb200_set_system_read_in(hb200_engine* e, const hb200_system_read_in* in) {
 int hb200_set_system_ueg(hb200_engine* e, const hb200_system_ueg* in) {
     CK(cudaSetDevice(e->cfg.device));
     if (in->nbasis != e->cfg.nbasis || in->nel != e->cfg.nel) FAIL("set_system_ueg: nbasis/nel differ from hb200_create");
-    if (e->cfg.excit_gen == HB200_EXCIT_GEN_HEAT_BATH) FAIL("set_system_ueg: heat_bath is a molecular generator");
+    if (uses_heat_bath_tables(e)) FAIL("set_system_ueg: heat_bath is a molecular generator");
     Sys& s = e->sys;
     s.kind = SYS_UEG;
     s.nbasis = in->nbasis; s.nel = in->nel; s.W = e->W;
@@ -1450,16 +1473,26 @@ static int stage_spawn_death(hb200_engine* e, const hb200_iter_in* in, uint32_t 
         const size_t smem = spawn_smem_bytes(e);
         const int c = e->cur;
         CK(cudaEventRecord(e->evk[0], st));
-        DISPATCH_W(e, {
-            static bool attr_set[5] = {false, false, false, false, false};
-            if (!attr_set[WW]) {
-                CK(cudaFuncSetAttribute(k_spawn_death<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-                attr_set[WW] = true;
-            }
-            k_spawn_death<WW><<<ntiles, TILE, smem, st>>>(e->sys, p, e->d_states[c], e->d_pops[c], e->d_dat[c], n,
-                                                           e->d_spawn[0], e->d_head, e->block_size, e->d_proc_map,
-                                                           e->d_partials, e->d_err);
-        });
+#define LAUNCH_SPAWN(GG)                                                                                          \
+    DISPATCH_W(e, {                                                                                               \
+        static bool attr_set = false;                                                                             \
+        if (!attr_set) {                                                                                          \
+            CK(cudaFuncSetAttribute(k_spawn_death<WW, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); \
+            attr_set = true;                                                                                      \
+        }                                                                                                         \
+        k_spawn_death<WW, GG><<<ntiles, TILE, smem, st>>>(e->sys, p, e->d_states[c], e->d_pops[c], e->d_dat[c], n, \
+                                                          e->d_spawn[0], e->d_head, e->block_size, e->d_proc_map, \
+                                                          e->d_partials, e->d_err);                               \
+    })
+        if (e->sys.kind == SYS_UEG) { LAUNCH_SPAWN(GEN_UEG); }
+        else switch (e->cfg.excit_gen) {
+            case HB200_EXCIT_GEN_NO_RENORM: LAUNCH_SPAWN(EXCIT_GEN_NO_RENORM); break;
+            case HB200_EXCIT_GEN_RENORM: LAUNCH_SPAWN(EXCIT_GEN_RENORM); break;
+            case HB200_EXCIT_GEN_HEAT_BATH: LAUNCH_SPAWN(EXCIT_GEN_HEAT_BATH); break;
+            case HB200_EXCIT_GEN_HEAT_BATH_UNIFORM: LAUNCH_SPAWN(EXCIT_GEN_HEAT_BATH_UNIFORM); break;
+            default: FAIL("spawn_death: excitation generator not implemented");
+        }
+#undef LAUNCH_SPAWN
         CK(cudaGetLastError());
         CK(cudaEventRecord(e->evk[1], st));
         e->launches++; e->spawn_launches++;
@@ -1657,7 +1690,7 @@ extern "C" {
 int hb200_spawn_death(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, hb200_iter_out* out) {
     CK(cudaSetDevice(e->cfg.device));
     if (!e->have_sys) FAIL("spawn_death: system not set");
-    if (e->cfg.excit_gen == HB200_EXCIT_GEN_HEAT_BATH && !e->have_hb) FAIL("spawn_death: heat-bath tables not built");
+    if (uses_heat_bath_tables(e) && !e->have_hb) FAIL("spawn_death: heat-bath tables not built");
     CycleStats st;
     memset(&st, 0, sizeof(st));
     const long long nattempts = llround(2.0 * ((double)e->nparticles_enc / (double)e->par.real_factor));
@@ -1733,7 +1766,7 @@ int hb200_upload_spawn(hb200_engine* e, const int64_t* sdata, int64_t n) {
 int hb200_iterate(hb200_engine* e, int32_t ncycles, const hb200_iter_in* in, hb200_iter_out* out) {
     CK(cudaSetDevice(e->cfg.device));
     if (!e->have_sys) FAIL("iterate: system not set");
-    if (e->cfg.excit_gen == HB200_EXCIT_GEN_HEAT_BATH && !e->have_hb) FAIL("iterate: heat-bath tables not built");
+    if (uses_heat_bath_tables(e) && !e->have_hb) FAIL("iterate: heat-bath tables not built");
     memset(out, 0, sizeof(*out));
     cudaStream_t st = e->stream;
     float acc[4] = {0, 0, 0, 0};

@@ -11,7 +11,7 @@ import numpy as np
 
 from . import build as _build
 
-EXCIT_GEN = {"no_renorm": 0, "renorm": 1, "heat_bath": 4}
+EXCIT_GEN = {"no_renorm": 0, "renorm": 1, "heat_bath": 4, "heat_bath_uniform": 5}
 
 
 class Config(C.Structure):
@@ -171,7 +171,7 @@ class Engine:
             raise EngineError(self.L.hb200_last_error().decode())
         self.h = C.c_void_p(h)
         self._set_system(sys)
-        if eg == EXCIT_GEN["heat_bath"]:
+        if eg in (EXCIT_GEN["heat_bath"], EXCIT_GEN["heat_bath_uniform"]):
             self._chk(self.L.hb200_build_heat_bath(self.h))
 
     def close(self):

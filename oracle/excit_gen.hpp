@@ -31,6 +31,11 @@ struct DetInfo {
     bool double_precalc = false;
     double i_d_weights[MAXNEL];
     double i_d_weights_tot = 0.0;
+    // heat_bath_single per-determinant cache (det_info_t%i_s_occ, ia_s_weights_occ, unocc_list)
+    bool single_precalc = false;
+    std::vector<int> unocc;
+    std::vector<double> i_s_weights, ia_s_weights;   // ia_s_weights[(a_ind-1) + nvirt*(i_ind-1)]
+    double i_s_weights_tot = 0.0;
     inline int su(int ims, int sym) const { return symunocc[(ims - 1) + 2 * sym]; }
 };
 
@@ -39,6 +44,7 @@ inline void decode_det_occ(const System& sys, const Det& f, DetInfo& d) {
     d.f = f;
     sys.decode(f, d.occ);
     d.double_precalc = false;
+    d.single_precalc = false;
 }
 inline void decode_det_occ_symunocc(const System& sys, const Det& f, DetInfo& d) {
     decode_det_occ(sys, f, d);
@@ -612,16 +618,138 @@ inline GenResult gen_excit_mol_heat_bath(Rng& rng, const System& sys, const Exci
     return r;
 }
 
+// gen_excit_mol_heat_bath_uniform (src/excit_gen_heat_bath_mol.F90:550-718): heat_bath_uniform (singles from the
+// renormalised uniform generator) and heat_bath_single (singles with exact weights,
+// gen_single_excit_heat_bath_exact :720-805 + find_ia_single_weights src/excit_gen_utils.f90:162-218).
+inline GenResult gen_excit_mol_heat_bath_uniform(Rng& rng, const System& sys, const ExcitGenData& eg, DetInfo& d) {
+    GenResult r;
+    const HeatBath& hb = eg.hb;
+    const int nel = sys.nel, nb = sys.nbasis;
+    if (rng.next() < eg.pattempt_single) {
+        r.conn.nexcit = 1;
+        if (eg.excit_gen == EXCIT_GEN_HEAT_BATH_UNIFORM) {
+            // gen_single_excit_mol (src/excit_gen_mol.f90:384-448)
+            choose_ia_mol(rng, sys, sys.gamma_sym, d, r.conn.from_orb[0], r.conn.to_orb[0], r.allowed);
+            if (r.allowed) {
+                r.pgen = eg.pattempt_single * calc_pgen_single_mol(sys, sys.gamma_sym, d, r.conn.to_orb[0]);
+                sys.find_excitation_permutation1(d.f, r.conn);
+                r.hmatel = sys.slater_condon1_excit(d.occ, r.conn.from_orb[0], r.conn.to_orb[0], r.conn.perm);
+            } else { r.hmatel = 0.0; r.pgen = 1.0; }
+        } else {
+            if (!d.single_precalc) {
+                // decode_det_occ_unocc: unocc_list ascending; find_ia_single_weights
+                d.unocc.clear();
+                for (int o = 1; o <= nb; ++o) if (!det_test(d.f, o)) d.unocc.push_back(o);
+                const int nvirt = (int)d.unocc.size();
+                d.ia_s_weights.assign((size_t)nvirt * nel, 0.0);
+                d.i_s_weights.assign(nel, 0.0);
+                d.i_s_weights_tot = 0.0;
+                for (int ii = 0; ii < nel; ++ii) {
+                    d.i_s_weights[ii] = 0.0;
+                    for (int aa = 0; aa < nvirt; ++aa) {
+                        double h = sys.slater_condon1(d.occ, d.occ[ii], d.unocc[aa], false);
+                        d.ia_s_weights[(size_t)aa + (size_t)nvirt * ii] = std::fabs(h);
+                        d.i_s_weights[ii] = d.i_s_weights[ii] + std::fabs(h);
+                    }
+                    d.i_s_weights_tot = d.i_s_weights_tot + d.i_s_weights[ii];
+                }
+                d.single_precalc = true;
+            }
+            const int nvirt = (int)d.unocc.size();
+            r.allowed = true;
+            if (d.i_s_weights_tot < depsilon) {
+                r.allowed = false; r.hmatel = 0.0; r.pgen = 1.0;
+            } else {
+                int i_ind = select_weighted_value(rng, nel, d.i_s_weights.data(), d.i_s_weights_tot);
+                int i = d.occ[i_ind - 1];
+                const double* col = &d.ia_s_weights[(size_t)nvirt * (i_ind - 1)];
+                int a_ind = select_weighted_value(rng, nvirt, col, d.i_s_weights[i_ind - 1]);
+                int a = d.unocc[a_ind - 1];
+                r.conn.from_orb[0] = i; r.conn.to_orb[0] = a;
+                r.pgen = eg.pattempt_single * (d.i_s_weights[i_ind - 1] / d.i_s_weights_tot) *
+                         (col[a_ind - 1] / d.i_s_weights[i_ind - 1]);
+                sys.find_excitation_permutation1(d.f, r.conn);
+                r.hmatel = sys.slater_condon1_excit(d.occ, i, a, r.conn.perm);
+            }
+        }
+        return r;
+    }
+    double ij_w[MAXNEL], ji_w[MAXNEL];
+    double ij_tot = 0.0, ji_tot = 0.0;
+    if (!d.double_precalc) {
+        d.i_d_weights_tot = 0.0;
+        for (int p = 0; p < nel; ++p) {
+            d.i_d_weights[p] = hb.i_weights[d.occ[p] - 1];
+            d.i_d_weights_tot = d.i_d_weights_tot + d.i_d_weights[p];
+        }
+        d.double_precalc = true;
+    }
+    // select_ij_heat_bath (src/excit_gen_utils.f90:9-66)
+    int i_ind = select_weighted_value(rng, nel, d.i_d_weights, d.i_d_weights_tot);
+    int i = d.occ[i_ind - 1];
+    int j_ind = 0, j = 0;
+    for (int p = 0; p < nel; ++p) {
+        ij_w[p] = hb.ij_weights[hb.i2(d.occ[p], i)];
+        ij_tot = ij_tot + ij_w[p];
+    }
+    bool allowed = false;
+    if (ij_tot > 0.0) {
+        j_ind = select_weighted_value(rng, nel, ij_w, ij_tot);
+        j = d.occ[j_ind - 1];
+        for (int p = 0; p < nel; ++p) {
+            ji_w[p] = hb.ij_weights[hb.i2(d.occ[p], j)];
+            ji_tot = ji_tot + ji_w[p];
+        }
+        allowed = std::fabs(hb.ija_tot[hb.i2(j, i)]) > 0.0;
+    }
+    double pgen = 0.0;
+    if (allowed)
+        pgen = ((d.i_d_weights[i_ind - 1] / d.i_d_weights_tot) * (ij_w[j_ind - 1] / ij_tot)) +
+               ((d.i_d_weights[j_ind - 1] / d.i_d_weights_tot) * (ji_w[i_ind - 1] / ji_tot));
+    if (j < i) std::swap(i, j);
+    int a = 0, b = 0;
+    if (allowed) {
+        size_t o3 = hb.i3(1, j, i);
+        a = select_weighted_value_precalc(rng, nb, &hb.ija_U[o3], &hb.ija_K[o3]);
+        if (std::fabs(hb.ijab_tot[hb.i3(a, j, i)]) > 0.0 && !det_test(d.f, a)) {
+            size_t o4 = hb.i4(1, a, j, i);
+            b = select_weighted_value_precalc(rng, nb, &hb.ijab_U[o4], &hb.ijab_K[o4]);
+            allowed = !det_test(d.f, b);
+        } else {
+            allowed = false;
+        }
+    }
+    r.allowed = allowed;
+    if (allowed) {
+        r.conn.from_orb[0] = i; r.conn.from_orb[1] = j;
+        r.conn.to_orb[0] = std::min(a, b); r.conn.to_orb[1] = std::max(a, b);
+        r.conn.nexcit = 2;
+        sys.find_excitation_permutation2(d.f, r.conn);
+        r.hmatel = sys.slater_condon2_excit(i, j, r.conn.to_orb[0], r.conn.to_orb[1], r.conn.perm);
+        r.pgen = (1.0 - eg.pattempt_single) * pgen *
+                 (((hb.ija_w[hb.i3(a, j, i)] / hb.ija_tot[hb.i2(j, i)]) *
+                   (hb.ijab_w[hb.i4(b, a, j, i)] / hb.ijab_tot[hb.i3(a, j, i)])) +
+                  ((hb.ija_w[hb.i3(b, j, i)] / hb.ija_tot[hb.i2(j, i)]) *
+                   (hb.ijab_w[hb.i4(a, b, j, i)] / hb.ijab_tot[hb.i3(b, j, i)])));
+    } else {
+        r.conn.nexcit = 2;
+        r.hmatel = 0.0; r.pgen = 1.0;
+    }
+    return r;
+}
+
 inline GenResult gen_excit(Rng& rng, const System& sys, const ExcitGenData& eg, DetInfo& d) {
     switch (eg.excit_gen) {
         case EXCIT_GEN_RENORM: return gen_excit_mol(rng, sys, eg, d);
         case EXCIT_GEN_NO_RENORM: return gen_excit_mol_no_renorm(rng, sys, eg, d);
         case EXCIT_GEN_HEAT_BATH: return gen_excit_mol_heat_bath(rng, sys, eg, d);
+        case EXCIT_GEN_HEAT_BATH_UNIFORM:
+        case EXCIT_GEN_HEAT_BATH_SINGLE: return gen_excit_mol_heat_bath_uniform(rng, sys, eg, d);
         default: throw std::runtime_error("oracle: excitation generator not implemented");
     }
 }
 inline void decode_for(const System& sys, const ExcitGenData& eg, const Det& f, DetInfo& d) {
-    if (eg.excit_gen == EXCIT_GEN_RENORM) decode_det_occ_symunocc(sys, f, d);
+    if (eg.excit_gen == EXCIT_GEN_RENORM || eg.excit_gen == EXCIT_GEN_HEAT_BATH_UNIFORM) decode_det_occ_symunocc(sys, f, d);
     else decode_det_occ(sys, f, d);
 }
 

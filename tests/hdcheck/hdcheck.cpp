@@ -20,7 +20,12 @@ template <int W, class R>
 static void gen_one(R& rng, const uint64_t* f, int64_t parent_pop, int* iout, double* dout, int64_t* nspawn) {
     uint8_t occ[HB_MAXNEL], su[64];
     decode_det<W>(f, occ);
-    if (g_sys.kind != SYS_UEG) build_symunocc(g_sys, occ, su);
+    if (g_sys.kind != SYS_UEG) {
+        uint8_t su2[64];
+        build_symunocc(g_sys, occ, su);
+        build_symunocc_masks<W>(g_sys, f, su2);
+        for (int c = 0; c < 2 * g_sys.nsym_tot; ++c) if (su[c] != su2[c]) { iout[6] = -99; return; }   // mask-based == loop-based
+    }
     Gen g;
     gen_excit<W>(rng, g_sys, g_par, f, occ, su, g);
     *nspawn = attempt_to_spawn(rng, g_par, g.hmatel, g.pgen, parent_pop);
@@ -53,6 +58,13 @@ void hd_set_sys(int nbasis, int nel, int nsym_tot, int sym0, int sym_max, int pg
             g_K[(size_t)(i - 1) * nbasis + (j - 1)] = two_body(s, i, j, j, i);
         }
     s.Jd = g_J.data(); s.Kd = g_K.data();
+    static std::vector<uint64_t> g_sumask;
+    g_sumask.assign((size_t)2 * nsym_tot * s.W, 0);
+    for (int i = 1; i <= nbasis; ++i) {
+        const int c = (ms[i] > 0 ? 1 : 0) + 2 * sym[i];
+        g_sumask[(size_t)c * s.W + ((i - 1) >> 6)] |= 1ull << ((i - 1) & 63);
+    }
+    s.su_mask = g_sumask.data();
     const int NT = uhf ? nbasis : nbasis / 2;
     s.NT = NT;
     g_CX.assign((size_t)NT * NT * NT, D2{0.0, 0.0});

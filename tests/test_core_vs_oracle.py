@@ -17,7 +17,7 @@ def _setup(path, kw, excit_gen, tau=0.01, real=False, seed=11):
     o.set_qmc(tau=tau, seed=seed, excit_gen=excit_gen, rng_kind=1, real_amplitudes=int(real), spawn_cutoff=0.01)
     o.init()
     ref = o.reference()
-    hb = o.heat_bath_tables() if excit_gen == "heat_bath" else None
+    hb = o.heat_bath_tables() if excit_gen.startswith("heat_bath") else None
     rf = 2**31 if real else 1
     cutoff = int(np.ceil(0.01 * rf)) if real else 0
     h = HdCheck(s, EXCIT_GEN[excit_gen], ref["pattempt_single"], ref["pattempt_double"], tau, 0.0, 0.0, rf, cutoff,
@@ -123,6 +123,14 @@ def test_ueg_generator_and_slater_condon(nel, ms, rs, cutoff):
     assert isref and hm == 0.0
 
 
+def test_heat_bath_uniform_generator_synthetic(s10):
+    s, o, h = _setup(s10, {}, "heat_bath_uniform", tau=0.01, real=True)
+    dets = synthetic.random_dets(120, s.nbasis, s.nalpha, s.nbeta, seed=9)
+    pops = np.where(np.arange(len(dets)) % 3 == 0, -(2**31), 2**32 + 17)
+    n = _compare_attempts(s, o, h, dets, pops, 0.01, ncycle=2, nattempt=8)
+    assert n > 1500
+
+
 def test_slater_condon_two_word_bitstrings(tmp_path):
     # 40 spatial orbitals -> 80 spin orbitals -> W = 2 words
     p = tmp_path / "s40.fcidump"
@@ -163,11 +171,16 @@ def test_philox_stream_matches_oracle():
         assert ((out >= 0) & (out < 1)).all()
 
 
-def test_heat_bath_pgen_normalisation(s10):
+@pytest.mark.parametrize("gen", ["heat_bath", "heat_bath_uniform", "heat_bath_single"])
+def test_heat_bath_pgen_normalisation(s10, gen):
     """SURVEY 8c gap-filler: heat-bath has no single-rank golden trajectory, so pin it statistically.  The
     generator reports pgen for the excitation it produced; over many samples each excitation must appear with
     that frequency, and the reported pgen of all distinct excitations plus the null fraction must sum to one."""
-    s, o, h = _setup(s10, {}, "heat_bath", tau=0.01)
+    s = R.read_in(s10)
+    o = Oracle()
+    o.read_fcidump(s10)
+    o.set_qmc(tau=0.01, seed=11, excit_gen=gen, rng_kind=1)
+    o.init()
     dets = synthetic.random_dets(3, s.nbasis, s.nalpha, s.nbeta, seed=4)
     rng = np.random.default_rng(5)
     n = 150000
@@ -175,7 +188,7 @@ def test_heat_bath_pgen_normalisation(s10):
         counts, pg = {}, {}
         nnull = 0
         for _ in range(n):
-            io, do, k = o.gen_excit_list(f, rng.random(12))
+            io, do, k = o.gen_excit_list(f, rng.random(96))
             if not io[6]:
                 nnull += 1
                 continue

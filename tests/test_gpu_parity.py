@@ -51,6 +51,10 @@ def test_gen_excit_heat_bath():
     _check_gen("s10", "heat_bath", True, 0.01, n=150, nattempt=6)
 
 
+def test_gen_excit_heat_bath_uniform():
+    _check_gen("s10", "heat_bath_uniform", True, 0.01, n=150, nattempt=6)
+
+
 def test_gen_excit_ueg():
     # gen_excit_ueg_no_renorm + slater_condon0_ueg on the device, W = 2 and W = 3
     _check_gen("ueg6", "no_renorm", False, 0.005, n=150, nattempt=5)
@@ -100,6 +104,7 @@ CASES = [
     ("ne", "renorm", True, True, 0.005, 5000, -1),
     ("s40", "renorm", False, True, 0.02, 3000, -1),
     ("s12", "heat_bath", True, True, 0.01, 2500, -1),
+    ("s12", "heat_bath_uniform", True, True, 0.01, 2500, -1),
     ("ueg6", "no_renorm", False, False, 0.01, 3000, -1),
     ("ueg14", "no_renorm", True, True, 0.004, 4000, -1),
 ]
@@ -143,6 +148,7 @@ def test_stage_and_cycle_parity(name, gen, real, init, tau, n, exl):
 @pytest.mark.parametrize("name,gen,real,init,tau", [("h2o", "renorm", False, False, 0.003),
                                                      ("ne", "renorm", True, True, 0.005),
                                                      ("s12", "heat_bath", True, True, 0.002),
+                                                     ("s12", "heat_bath_uniform", True, False, 0.0004),
                                                      ("ueg6", "no_renorm", False, False, 0.005),
                                                      ("ueg14", "no_renorm", True, True, 0.002)])
 def test_iterate_from_single_determinant(name, gen, real, init, tau):

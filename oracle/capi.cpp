@@ -8,6 +8,7 @@
 #include "rng.hpp"
 #include "excit_gen.hpp"
 #include "fciqmc.hpp"
+#include "ccmc.hpp"
 
 using namespace oracle;
 
@@ -52,8 +53,8 @@ int orc_set_ref_lib(const char* path) {
     ORC_CATCH(-1)
 }
 
-void* orc_create() { return new Oracle(); }
-void orc_destroy(void* h) { delete (Oracle*)h; }
+void* orc_create() { return (Oracle*)new OracleCcmc(); }
+void orc_destroy(void* h) { delete (OracleCcmc*)(Oracle*)h; }
 
 int orc_read_fcidump(void* h, const char* path, int nel, int ms, int sym, int cas_nel, int cas_norb) {
     ORC_TRY
@@ -239,6 +240,17 @@ int orc_run(void* h) {
     ((Oracle*)h)->run();
     return 0;
     ORC_CATCH(-1)
+}
+// ccmc{...}: stochastic-selection CCMC on the current system (single rank)
+int orc_run_ccmc(void* h) {
+    ORC_TRY
+    ((OracleCcmc*)(Oracle*)h)->run_ccmc();
+    return 0;
+    ORC_CATCH(-1)
+}
+void orc_get_nattempts_rows(void* h, int64_t* out) {
+    OracleCcmc* o = (OracleCcmc*)(Oracle*)h;
+    for (size_t i = 0; i < o->nattempts_rows.size(); ++i) out[i] = o->nattempts_rows[i];
 }
 int orc_nrows(void* h) { return (int)((Oracle*)h)->rows.size(); }
 // rows[nrows][8]: iter, shift, proj_energy, D0, nparticles, nstates, nspawn_events, rspawn

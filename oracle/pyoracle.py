@@ -34,7 +34,7 @@ def build(force=False):
     """Compile the oracle (and oracle/_ref when the reference tree is present)."""
     if force or not os.path.exists(LIB) or any(
             os.path.getmtime(os.path.join(HERE, f)) > os.path.getmtime(LIB)
-            for f in ("capi.cpp", "system.hpp", "rng.hpp", "excit_gen.hpp", "ueg.hpp", "fciqmc.hpp")):
+            for f in ("capi.cpp", "system.hpp", "rng.hpp", "excit_gen.hpp", "ueg.hpp", "fciqmc.hpp", "ccmc.hpp")):
         subprocess.check_call(["make", "-C", HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     if not os.path.exists(REF_LIB) and os.path.isdir("/root/reference/lib/dSFMT-src-2.2.3"):
         subprocess.check_call(["make", "-C", HERE, "ref"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
@@ -92,6 +92,8 @@ def lib():
         L.orc_set_qmc.argtypes = [C.c_void_p, C.POINTER(QmcIn)]
         L.orc_init.argtypes = [C.c_void_p]
         L.orc_run.argtypes = [C.c_void_p]
+        L.orc_run_ccmc.argtypes = [C.c_void_p]
+        L.orc_get_nattempts_rows.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_nrows.argtypes = [C.c_void_p]
         L.orc_get_rows.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_reference.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -274,6 +276,14 @@ class Oracle:
     def run(self):
         self._chk(self.L.orc_run(self.h))
         return self.rows()
+
+    def run_ccmc(self):
+        """ccmc{...}: returns (rows, nattempts column)."""
+        self._chk(self.L.orc_run_ccmc(self.h))
+        rows = self.rows()
+        na = np.zeros(len(rows), dtype=np.int64)
+        self.L.orc_get_nattempts_rows(self.h, _p(na))
+        return rows, na
 
     def rows(self):
         n = self.L.orc_nrows(self.h)

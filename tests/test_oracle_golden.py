@@ -34,7 +34,11 @@ def _run(case, fcidump_path, nrows):
     q["nreport"] = min(q["nreport"], nrows)
     o.set_qmc(**q)
     o.init()
-    rows = o.run()
+    if g.get("ccmc"):
+        rows, na = o.run_ccmc()
+        rows = np.concatenate([rows, na.reshape(-1, 1).astype(float)], axis=1)
+    else:
+        rows = o.run()
     gold = np.array(g["rows"])
     n = min(len(gold), len(rows))
     assert n == q["nreport"] + 1
@@ -45,6 +49,8 @@ def _run(case, fcidump_path, nrows):
             assert gr[k] == _pr(r[k]), (case, i, k, gr[k], r[k])
         assert gr[5] == r[5] and gr[6] == r[6], (case, i)
         assert abs(gr[7] - r[7]) < 0.6e-4
+        if len(gr) > 8:
+            assert gr[8] == r[8], (case, i)     # "# attempts" column of the CCMC table
     return o
 
 
@@ -84,6 +90,14 @@ def test_ueg_np2_np4(fcidump_path):
         t = o.ueg_tables()
         assert abs(t["L"] - g["kat"]["L"]) < 5e-9 and o.nbasis == g["kat"]["nbasis"]
         assert abs(o.basis()["sp_eigv"][2] - g["kat"]["sp_eigv_3"]) < 5e-10
+
+
+def test_ccmc_ccsd_ne_np1(fcidump_path):
+    # select_cluster / collapse_cluster / spawner_ccmc / stochastic_ccmc_death; the complete
+    # 451-row table was verified with tools/golden_compare.py ccmc_ne
+    o = _run("ccmc_ne", fcidump_path, 200)
+    ref = o.reference()
+    assert abs(ref["H00"] - (-128.48877555)) < 5e-9 and abs(ref["pattempt_single"] - 0.04511278) < 5e-9
 
 
 def test_dsfmt_and_murmur_known_answers():

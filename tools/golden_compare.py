@@ -51,18 +51,31 @@ CASES = {
                     ueg=dict(nel=6, ms=0, rs=2.0, cutoff=2.0), ref_det=[1, 2, 3, 10, 11, 14],
                     qmc=dict(tau=0.005, seed=122, D0_population=10, ncycles=10, nreport=1000, target_particles=90000,
                              walker_length=50000, spawned_walker_length=5000, nprocs=4)),
+    # CCMC: CCSD on Ne cc-pVDZ, stochastic cluster selection, integer walkers
+    "ccmc_ne": dict(dir="ccmc/np1/Ne-RHF-cc-pVDZ_ccmc", bench="benchmark.out.9712b5a3.inp=ne.ccsdmc.in",
+                    int_file="INTDUMP", sys=dict(nel=10, ms=0, sym=0), ccmc=True,
+                    qmc=dict(tau=0.01, seed=5691, D0_population=10, ncycles=10, nreport=450, target_particles=20000,
+                             walker_length=3571428, spawned_walker_length=1562500, ex_level=2)),
 }
 
+ROW_CCMC = re.compile(r"^\s*#?\s+(\d+)\s+(-?\d\.\d+E[+-]\d+)\s+(-?\d\.\d+E[+-]\d+)\s+(-?\d\.\d+E[+-]\d+)\s+"
+                      r"(-?\d\.\d+E[+-]\d+)\s+(\d+)\s+(\d+)\s+(\d+)\s+(\d\.\d+)\s+(\d+\.\d+)\s*$")
 ROW = re.compile(r"^\s*#?\s+(\d+)\s+(-?\d\.\d+E[+-]\d+)\s+(-?\d\.\d+E[+-]\d+)\s+(-?\d\.\d+E[+-]\d+)\s+"
                  r"(-?\d\.\d+E[+-]\d+)\s+(\d+)\s+(\d+)\s+(\d\.\d+)\s+(\d+\.\d+)\s*$")
 
 
 def parse_table(path):
+    """rows: iterations, shift, proj_energy, D0, nparticles, nstates, nspawn_events, rspawn[, nattempts (CCMC tables)]"""
     rows = []
     for line in open(path):
         m = ROW.match(line)
         if m:
             rows.append([float(x) for x in m.groups()[:8]])
+            continue
+        m = ROW_CCMC.match(line)
+        if m:
+            g = [float(x) for x in m.groups()]
+            rows.append(g[:7] + [g[8], g[7]])
     return np.array(rows)
 
 
@@ -70,8 +83,11 @@ def row_matches(g, r):
     """testcode tolerance is (1e-10 abs, 1e-10 rel) on printed values; the table prints es17.10."""
     def pr(x):
         return float("%.10E" % x)
-    return (g[0] == r[0] and g[1] == pr(r[1]) and g[2] == pr(r[2]) and g[3] == pr(r[3]) and g[4] == pr(r[4])
-            and g[5] == r[5] and g[6] == r[6] and abs(g[7] - r[7]) < 0.6e-4)
+    ok = (g[0] == r[0] and g[1] == pr(r[1]) and g[2] == pr(r[2]) and g[3] == pr(r[3]) and g[4] == pr(r[4])
+          and g[5] == r[5] and g[6] == r[6] and abs(g[7] - r[7]) < 0.6e-4)
+    if len(g) > 8:
+        ok = ok and g[8] == r[8]
+    return ok
 
 
 def run_case(name, max_rows=None, quiet=False):
@@ -92,7 +108,11 @@ def run_case(name, max_rows=None, quiet=False):
     o.set_qmc(**q)
     o.init()
     t = time.time()
-    rows = o.run()
+    if c.get("ccmc"):
+        rows, na = o.run_ccmc()
+        rows = np.concatenate([rows, na.reshape(-1, 1).astype(float)], axis=1)
+    else:
+        rows = o.run()
     dt = time.time() - t
     n = min(len(gold), len(rows))
     bad = [i for i in range(n) if not row_matches(gold[i], rows[i])]

@@ -17,7 +17,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tools.golden_compare import CASES, TS, parse_table  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
-FCIDUMP_NAME = {"h2o": "h2o", "ne_init": "ne", "ne_ci6_np2": "ne", "ne_ci6_np4": "ne", "ne_ci6_real64_np2": "ne"}
+FCIDUMP_NAME = {"h2o": "h2o", "ne_init": "ne", "ne_ci6_np2": "ne", "ne_ci6_np4": "ne", "ne_ci6_real64_np2": "ne",
+                "ccmc_ne": "ne_vdz"}
 
 os.makedirs(os.path.join(OUT, "fcidump"), exist_ok=True)
 for name, c in CASES.items():
@@ -39,9 +40,9 @@ for name, c in CASES.items():
         with open(d + c["int_file"], "rb") as fi, gzip.GzipFile(dst, "wb", compresslevel=9, mtime=0) as fo:
             shutil.copyfileobj(fi, fo)
     rows = parse_table(d + c["bench"]).tolist()
+    cols = ["iterations", "shift", "proj_energy", "D0_population", "nparticles", "nstates", "nspawn_events", "rspawn"]
     json.dump({"source": "test_suite/" + c["dir"] + "/" + c["bench"], "fcidump": FCIDUMP_NAME[name], "sys": c["sys"],
-               "qmc": c["qmc"],
-               "columns": ["iterations", "shift", "proj_energy", "D0_population", "nparticles", "nstates",
-                           "nspawn_events", "rspawn"],
+               "qmc": c["qmc"], "ccmc": bool(c.get("ccmc")),
+               "columns": cols + (["nattempts"] if c.get("ccmc") else []),
                "rows": rows}, open(os.path.join(OUT, name + ".json"), "w"))
     print(name, len(rows), "rows")

@@ -1315,4 +1315,212 @@ HB_HD int excit_level(const uint64_t* f, const uint64_t* f0) {
     return nx / 2;
 }
 
+// ------------------------------------------------------------------------------------------------
+// CCMC: stochastic cluster selection and cluster algebra (src/ccmc_selection.f90, src/ccmc_utils.F90)
+// ------------------------------------------------------------------------------------------------
+struct CcmcArgs {
+    long long nstates;          // psip_list%nstates
+    long long nattempts;        // selection_data%nstochastic_clusters (= estimators%nattempts)
+    long long D0_pos;           // 1-based position of the reference in the main list
+    double D0_normalisation;    // population on the reference / real_factor
+    double tot_abs_real_pop;    // cumulative population of all excitors but the reference
+    int ex_level;               // qs%ref%ex_level (CC truncation level)
+    int max_cluster_size;       // min(nel, ex_level+2, nstates-1)
+    int nprocs;
+};
+struct Cluster {
+    int nexcitors, excitation_level, sign;   // excitation_level < 0: cluster not allowed (huge(0) in the reference)
+    double pselect, amplitude;
+    long long first_pos;                     // 1-based position of the first excitor (cdet%data)
+};
+
+// cumulative_excip_pop(pos): cumulative |population| / real_factor of excitors 1..pos with the reference skipped
+// (cumulative_population, src/ccmc_utils.F90:427-563).  The engine keeps the exact integer prefix sums of the
+// encoded populations; the quotient equals the reference's running double sum while the total stays below 2^53
+// encoded units (2^22 walkers with real amplitudes) - see DESIGN.md.
+HB_HD double ccmc_cum(const long long* __restrict__ cum_enc, long long pos, double real_factor) {
+    return (double)cum_enc[pos - 1] / real_factor;
+}
+// binary_search_real_p (src/search.f90:378-481) followed by the step back over zero-population entries
+// (src/ccmc_selection.f90:253-262)
+HB_HDN long long ccmc_find_excitor(const long long* __restrict__ cum_enc, double item, long long istart, long long iend,
+                                   double real_factor) {
+    long long pos = istart;
+    if (istart <= iend) {
+        long long lo = istart, hi = iend;
+        bool hit = false;
+        while (hi != lo) {
+            pos = (hi + lo) / 2;
+            const double compare = item - ccmc_cum(cum_enc, pos, real_factor);
+            if (fabs(compare) < 1.e-12) { hit = true; break; }
+            else if (compare > 0.0) lo = pos + 1;
+            else hi = pos;
+        }
+        if (!hit) {
+            const double compare = item - ccmc_cum(cum_enc, hi, real_factor);
+            if (fabs(compare) < 1.e-12) pos = hi;
+            else if (compare > 0.0) pos = hi + 1;
+            else pos = hi;
+        }
+    }
+    for (;;) {
+        if (pos == 1) break;
+        if (fabs(ccmc_cum(cum_enc, pos, real_factor) - ccmc_cum(cum_enc, pos - 1, real_factor)) > 1.e-12) break;
+        pos = pos - 1;
+    }
+    return pos;
+}
+template <int W>
+HB_HD void excit_mask_of(int orb, uint64_t* m) {
+    const int iw = (orb - 1) >> 6, ib = (orb - 1) & 63;
+#pragma unroll
+    for (int k = 0; k < W; ++k) m[k] = (k < iw) ? 0ull : ((k > iw) ? ~0ull : ((ib == 63) ? 0ull : (~0ull << (ib + 1))));
+}
+// collapse_cluster + collapse_excitor_onto_cluster (src/ccmc_utils.F90:132-295)
+template <int W>
+HB_HDN bool ccmc_collapse(const uint64_t* f0, const uint64_t* excitor, double excitor_population, uint64_t* cluster_excitor,
+                          double& cluster_population) {
+    uint64_t ee[W], ca[W], cc[W];
+    bool clash = false;
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+        ee[k] = f0[k] ^ excitor[k];
+        const uint64_t ce = f0[k] ^ cluster_excitor[k];
+        const uint64_t ea = ee[k] & f0[k], ec = ee[k] & excitor[k];
+        ca[k] = ce & f0[k];
+        cc[k] = ce & cluster_excitor[k];
+        if ((ec & cc[k]) != 0 || (ea & ca[k]) != 0) clash = true;
+    }
+    cluster_population = cluster_population * excitor_population;
+    if (clash) return false;
+#pragma unroll
+    for (int ib = 0; ib < W; ++ib) {
+        uint64_t x = ee[ib];
+        while (x) {
+            const int bit = ctz64(x);
+            x &= x - 1;
+            const int orb = ib * 64 + bit + 1;
+            uint64_t mask[W];
+            excit_mask_of<W>(orb, mask);
+            int n = 0;
+            if ((f0[ib] >> bit) & 1ull) {
+                cluster_excitor[ib] &= ~(1ull << bit);
+#pragma unroll
+                for (int k = 0; k < W; ++k) n += popc64((mask[k] & ca[k]) | cc[k]);
+            } else {
+                cluster_excitor[ib] |= (1ull << bit);
+#pragma unroll
+                for (int k = 0; k < W; ++k) {
+                    uint64_t pm = (~mask[k]) & cc[k];
+                    if (k == ib) pm &= ~(1ull << bit);
+                    n += popc64(pm);
+                }
+            }
+            if (n & 1) cluster_population = -cluster_population;
+        }
+    }
+    return true;
+}
+// convert_excitor_to_determinant (src/ccmc_utils.F90:296-412): sign of the excitor applied to the reference
+template <int W>
+HB_HDN int ccmc_excitor_sign(const uint64_t* f0, const uint64_t* excitor, int excitor_level) {
+    int nann = excitor_level, ncre = excitor_level, sign = 1;
+#pragma unroll
+    for (int ib = 0; ib < W; ++ib) {
+        const uint64_t ex = f0[ib] ^ excitor[ib];
+        uint64_t x = f0[ib] | ex;        // only these bit positions change state in the reference's loop
+        while (x) {
+            const int bit = ctz64(x);
+            x &= x - 1;
+            if ((f0[ib] >> bit) & 1ull) {
+                if ((ex >> bit) & 1ull) nann--;
+                else if ((nann + ncre) & 1) sign = -sign;
+            } else {
+                ncre--;
+            }
+        }
+    }
+    return sign;
+}
+// select_cluster (src/ccmc_selection.f90:93-392; linked = false, no discard threshold) with create_null_cluster
+// (:394-460).  cf receives the collapsed excitor (cdet%f).
+template <int W, class R>
+HB_HDN void ccmc_select_cluster(R& rng, const Params& p, const CcmcArgs& a, const uint64_t* __restrict__ states,
+                                const int64_t* __restrict__ pops, const long long* __restrict__ cum_enc, uint64_t* cf,
+                                Cluster& cl) {
+    const int min_size = 0, max_size = a.max_cluster_size;
+    const double rf = (double)p.real_factor;
+    cl.pselect = (double)(a.nattempts * a.nprocs);
+    const double rand = rng.next();
+    double psize = 0.0;
+    cl.nexcitors = -1;
+    for (int i = 0; i <= max_size - min_size - 1; ++i) {
+        psize = psize + 1.0 / (double)(1ll << (i + 1));
+        if (rand < psize) {
+            cl.nexcitors = i + min_size;
+            cl.pselect = cl.pselect / (double)(1ll << (i + 1));
+            break;
+        }
+    }
+    if (cl.nexcitors == -1) {
+        cl.nexcitors = max_size;
+        cl.pselect = cl.pselect * (1.0 - psize);
+    }
+    cl.first_pos = 0;
+    if (cl.nexcitors == 0) {
+#pragma unroll
+        for (int k = 0; k < W; ++k) cf[k] = p.f0[k];
+        cl.excitation_level = 0;
+        cl.amplitude = a.D0_normalisation;
+        cl.sign = 1;
+        return;
+    }
+    double pop[8];
+    for (int i = 0; i < cl.nexcitors; ++i) pop[i] = rng.next() * a.tot_abs_real_pop;
+    for (int i = 1; i < cl.nexcitors; ++i) {      // insert_sort_real_p (src/sort.f90:827-852)
+        int j = i - 1;
+        const double tmp = pop[i];
+        while (j >= 0 && !(pop[j] <= tmp)) { pop[j + 1] = pop[j]; j--; }
+        pop[j + 1] = tmp;
+    }
+    long long prev_pos = 1;
+    double cluster_population = 0.0;
+    bool allowed = true;
+    for (int i = 1; i <= cl.nexcitors; ++i) {
+        const long long pos = ccmc_find_excitor(cum_enc, pop[i - 1], prev_pos, a.nstates, rf);
+        const double excitor_pop = (double)pops[pos - 1] / rf;
+        uint64_t ex[W];
+#pragma unroll
+        for (int k = 0; k < W; ++k) ex[k] = states[(pos - 1) * W + k];
+        if (i == 1) {
+#pragma unroll
+            for (int k = 0; k < W; ++k) cf[k] = ex[k];
+            cl.first_pos = pos;
+            cluster_population = excitor_pop;
+            cl.pselect = cl.pselect / a.nprocs;
+        } else {
+            allowed = ccmc_collapse<W>(p.f0, ex, excitor_pop, cf, cluster_population);
+            if (!allowed) break;
+            if (pos != prev_pos) cl.pselect = cl.pselect / a.nprocs;
+        }
+        cl.pselect = (cl.pselect * fabs(excitor_pop)) / a.tot_abs_real_pop;
+        prev_pos = pos;
+    }
+    if (allowed) {
+        cl.excitation_level = excit_level<W>(p.f0, cf);
+        allowed = cl.excitation_level <= a.ex_level + 2;
+    }
+    if (allowed) {
+        double fact = 1.0;
+        for (int k = 2; k <= cl.nexcitors; ++k) fact = fact * k;
+        cl.pselect = cl.pselect * fact;
+        cl.sign = ccmc_excitor_sign<W>(p.f0, cf, cl.excitation_level);
+        double norm_pow = 1.0;
+        for (int k = 0; k < cl.nexcitors - 1; ++k) norm_pow = norm_pow * a.D0_normalisation;
+        cl.amplitude = cluster_population / norm_pow;
+    } else {
+        cl.excitation_level = -1;
+    }
+}
+
 }  // namespace hb

@@ -505,6 +505,227 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// CCMC (src/ccmc.f90:603-896): one thread per cluster-selection attempt - select_cluster, do_ccmc_accumulation,
+// spawner_ccmc and stochastic_ccmc_death; spawned and killed excips are appended to the spawn list and then go through
+// the same sort / annihilation / merge kernels as FCIQMC (direct_annihilation).
+// ------------------------------------------------------------------------------------------------
+// add_spawned_particle (src/spawning.F90:907-1018): warp-aggregated pointer bump; every lane of the warp must call it
+template <int W>
+__device__ __forceinline__ void append_spawn_warp(const uint64_t* f, int64_t nspawn, int dest, int nprocs,
+                                                  int64_t* __restrict__ spawn, unsigned long long* __restrict__ head,
+                                                  long long block_size, int* __restrict__ err) {
+    constexpr int E = W + 2;
+    const int lane = threadIdx.x & 31;
+    const unsigned has = __ballot_sync(0xffffffffu, nspawn != 0);
+    if (nspawn != 0) {
+        const unsigned peers = (nprocs > 1) ? __match_any_sync(has, dest) : has;
+        const int leader = __ffs(peers) - 1;
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        unsigned long long slot0 = 0;
+        if (lane == leader) slot0 = atomicAdd(&head[dest], (unsigned long long)__popc(peers));
+        slot0 = __shfl_sync(peers, slot0, leader);
+        const long long slot = (long long)slot0 + rank;
+        if (slot < block_size) {
+            int64_t* dst = spawn + ((long long)dest * block_size + slot) * E;
+#pragma unroll
+            for (int k = 0; k < W; ++k) dst[k] = (int64_t)f[k];
+            dst[W] = nspawn;
+            dst[W + 1] = 0;
+        } else {
+            atomicOr(err, 1);
+        }
+    }
+}
+
+struct CcmcPartials { double pe, d0; long long ndeath, nattempts_spawn; };
+
+template <int W>
+__global__ void __launch_bounds__(256)
+k_ccmc_cluster(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states, const int64_t* __restrict__ pops,
+               const double* __restrict__ dat, const long long* __restrict__ cum_enc, int64_t* __restrict__ spawn,
+               unsigned long long* __restrict__ head, long long block_size, const int* __restrict__ proc_map,
+               CcmcPartials* __restrict__ partials, int* __restrict__ err) {
+    __shared__ double sd[2][8];
+    __shared__ long long sl[2][8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long idx = (long long)blockIdx.x * blockDim.x + tid;
+    double pe = 0.0, d0 = 0.0;
+    long long ndeath = 0, nas = 0;
+    int64_t nspawn = 0, nkill = 0;
+    uint64_t cf[W], child[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) { cf[k] = 0; child[k] = 0; }
+    int dest_s = 0, dest_k = 0;
+    if (idx < a.nattempts) {
+        PhiloxStream rng;
+        rng.begin(p.seed, p.cycle, RNG_SPAWN, det_hash64<W>(p.f0), (uint32_t)(idx + 1));
+        Cluster cl;
+        ccmc_select_cluster<W>(rng, p, a, states, pops, cum_enc, cf, cl);
+        if (cl.excitation_level >= 0 && cl.excitation_level <= a.ex_level + 2) {
+            uint8_t occ[HB_MAXNEL], su[64];
+            decode_det<W>(cf, occ);
+            if (s.kind == SYS_READ_IN && (p.excit_gen == EXCIT_GEN_RENORM || p.excit_gen == EXCIT_GEN_HEAT_BATH_UNIFORM))
+                build_symunocc_masks<W>(s, cf, su);
+            // do_ccmc_accumulation (src/ccmc.f90:1007-1101)
+            bool is_ref;
+            const double hm0 = proj_energy_hmatel<W>(s, p, cf, occ, is_ref);
+            const double wpop = cl.amplitude * cl.sign / cl.pselect;
+            if (is_ref) d0 = wpop; else pe = hm0 * wpop;
+            nas = 1;
+            // spawner_ccmc (src/ccmc_death_spawning.f90:11-211)
+            Gen g;
+            gen_excit<W>(rng, s, p, cf, occ, su, g);
+            const double hmatel = g.hmatel * cl.amplitude * 1.0 * cl.sign;
+            const double pgen = g.pgen * cl.pselect * 1;
+            nspawn = attempt_to_spawn(rng, p, hmatel, pgen, (int64_t)1);
+            if (nspawn != 0) {
+                make_child<W>(cf, g, child);
+                const int lvl = excit_level<W>(child, p.f0);
+                if (ccmc_excitor_sign<W>(p.f0, child, lvl) < 0) nspawn = -nspawn;
+                if (p.trunc_level >= 0 && lvl > p.trunc_level) nspawn = 0;   // create_spawned_particle_truncated
+                else dest_s = (p.nprocs > 1) ? proc_map[owner_slot(child, s.nbasis, p.hash_seed, p.nprocs, p.nslots)] : 0;
+            }
+            // stochastic_ccmc_death + stochastic_death_attempt (src/ccmc_death_spawning.f90:213-441)
+            if (cl.excitation_level <= a.ex_level) {
+                const double pe_old = p.proj_energy_old;
+                double KiiAi;
+                if (cl.nexcitors == 0) KiiAi = ((-pe_old) * 1.0 + (pe_old - p.shift) * 1.0) * cl.amplitude;
+                else if (cl.nexcitors == 1) KiiAi = ((dat[cl.first_pos - 1] - pe_old) * 1.0 + (pe_old - p.shift) * 1.0) * cl.amplitude;
+                else {
+                    const double hii = (s.kind == SYS_UEG) ? slater_condon0_ueg(s, occ) : slater_condon0(s, occ);
+                    KiiAi = ((hii - p.H00) - pe_old) * 1.0 * cl.amplitude;
+                }
+                KiiAi = 1.0 * (double)p.real_factor * KiiAi;
+                KiiAi = KiiAi * p.tau / cl.pselect;
+                double pdeath = fabs(KiiAi);
+                if (pdeath < (double)p.spawn_cutoff) {
+                    nkill = (pdeath > rng.next() * (double)p.spawn_cutoff) ? p.spawn_cutoff : 0;
+                } else {
+                    nkill = (int64_t)pdeath;
+                    pdeath = pdeath - (double)nkill;
+                    if (pdeath > rng.next()) nkill++;
+                }
+                ndeath = nkill;
+                if (nkill != 0) {
+                    if (KiiAi > 0) nkill = -nkill;
+                    dest_k = (p.nprocs > 1) ? proc_map[owner_slot(cf, s.nbasis, p.hash_seed, p.nprocs, p.nslots)] : 0;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    append_spawn_warp<W>(child, nspawn, dest_s, p.nprocs, spawn, head, block_size, err);
+    append_spawn_warp<W>(cf, nkill, dest_k, p.nprocs, spawn, head, block_size, err);
+    const double r0 = warp_sum_d(pe), r1 = warp_sum_d(d0);
+    const long long r2 = warp_sum_ll(ndeath), r3 = warp_sum_ll(nas);
+    if (lane == 0) { sd[0][warp] = r0; sd[1][warp] = r1; sl[0][warp] = r2; sl[1][warp] = r3; }
+    __syncthreads();
+    if (tid == 0) {
+        CcmcPartials out;
+        out.pe = 0.0; out.d0 = 0.0; out.ndeath = 0; out.nattempts_spawn = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { out.pe += sd[0][w]; out.d0 += sd[1][w]; out.ndeath += sl[0][w]; out.nattempts_spawn += sl[1][w]; }
+        partials[blockIdx.x] = out;
+    }
+}
+__global__ void k_ccmc_reduce(const CcmcPartials* __restrict__ partials, int n, CcmcPartials* out) {
+    __shared__ double sd[2][32];
+    __shared__ long long sl[2][32];
+    double pe = 0.0, d0 = 0.0;
+    long long nd = 0, na = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { pe += partials[i].pe; d0 += partials[i].d0; nd += partials[i].ndeath; na += partials[i].nattempts_spawn; }
+    pe = warp_sum_d(pe); d0 = warp_sum_d(d0); nd = warp_sum_ll(nd); na = warp_sum_ll(na);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { sd[0][warp] = pe; sd[1][warp] = d0; sl[0][warp] = nd; sl[1][warp] = na; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        CcmcPartials o; o.pe = 0; o.d0 = 0; o.ndeath = 0; o.nattempts_spawn = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { o.pe += sd[0][w]; o.d0 += sd[1][w]; o.ndeath += sl[0][w]; o.nattempts_spawn += sl[1][w]; }
+        *out = o;
+    }
+}
+// find_D0 (src/ccmc_utils.F90:21-67): position (1-based, 0 = absent) and population of f0 in the sorted main list
+template <int W>
+__global__ void k_find_det(Params p, const uint64_t* __restrict__ states, const int64_t* __restrict__ pops, long long n,
+                           long long* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const long long pos = lower_bound_det<W>(states, n, p.f0);
+    bool hit = false;
+    if (pos < n) {
+        uint64_t f[W];
+        load_det<W>(states + pos * W, f);
+        hit = det_eq<W>(f, p.f0);
+    }
+    out[0] = hit ? pos + 1 : 0;
+    out[1] = hit ? pops[pos] : 0;
+}
+// inclusive prefix sums of |pop| (encoded) with the reference skipped (cumulative_population): exact integer scan
+constexpr int SCAN64_ITEMS = 8;
+__global__ void __launch_bounds__(256) k_cum_block(const int64_t* __restrict__ pops, long long n, long long skip,
+                                                  long long* __restrict__ out, long long* __restrict__ block_sums) {
+    __shared__ long long sw[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long base = ((long long)blockIdx.x * 256 + tid) * SCAN64_ITEMS;
+    long long v[SCAN64_ITEMS], sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN64_ITEMS; ++k) {
+        const long long i = base + k;
+        long long x = (i < n && i != skip) ? pops[i] : 0;
+        x = x < 0 ? -x : x;
+        sum += x;
+        v[k] = sum;
+    }
+    long long incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) sw[warp] = incl;
+    __syncthreads();
+    long long off = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { if (w < warp) off += sw[w]; tot += sw[w]; }
+    const long long excl = off + incl - sum;
+#pragma unroll
+    for (int k = 0; k < SCAN64_ITEMS; ++k)
+        if (base + k < n) out[base + k] = excl + v[k];
+    if (tid == 0) block_sums[blockIdx.x] = tot;
+}
+__global__ void k_cum_sums(long long* data, int m) {   // in-place exclusive scan of the block sums, single block
+    __shared__ long long swarp[32];
+    __shared__ long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int base = 0; base < m; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const long long v = (i < m) ? data[i] : 0;
+        long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) swarp[warp] = incl;
+        __syncthreads();
+        long long off = 0, tot = 0;
+        for (int w = 0; w < nw; ++w) { const long long sv = swarp[w]; if (w < warp) off += sv; tot += sv; }
+        const long long c = carry;
+        if (i < m) data[i] = c + off + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry = c + tot;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256) k_cum_add(long long* __restrict__ out, long long n, const long long* __restrict__ offs) {
+    const long long base = ((long long)blockIdx.x * 256 + threadIdx.x) * SCAN64_ITEMS;
+    const long long off = offs[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN64_ITEMS; ++k)
+        if (base + k < n) out[base + k] += off;
+}
+
 struct CycleStats {
     double pe, d0;              // this cycle
     long long ndeath, npart_after_death, nattempts_spawn;
@@ -1109,6 +1330,11 @@ struct hb200_engine {
     int* d_total = nullptr;   // [4] small ints
     long long* d_part_ll = nullptr;
     long long* d_ll = nullptr;  // [4]
+    // CCMC scratch
+    long long* d_cum = nullptr;        // [walker_length] inclusive prefix sums of |pop| (reference skipped)
+    long long* d_cum_blk = nullptr;
+    CcmcPartials* d_cc_part = nullptr;
+    CcmcPartials* d_cc_tot = nullptr;
     // NCCL
     ncclComm_t comm = nullptr;
     long long* d_counts = nullptr;  // [nprocs*nprocs]
@@ -1705,6 +1931,118 @@ int hb200_spawn_death(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, 
         out->nattempts_spawn = st.nattempts_spawn;
         fill_out(e, out, st, nattempts);
     }
+    return 0;
+}
+
+// One CCMC cycle up to (not including) annihilation: get_D0_info, init_mc_cycle, cumulative_population,
+// set_cluster_selections and the iattempt loop of do_ccmc (src/ccmc.f90:625-857).
+int hb200_ccmc_spawn(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, int32_t ex_level, hb200_ccmc_out* out) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (!e->have_sys) FAIL("ccmc_spawn: system not set");
+    if (uses_heat_bath_tables(e) && !e->have_hb) FAIL("ccmc_spawn: heat-bath tables not built");
+    if (e->par.nprocs != 1) FAIL("ccmc_spawn: single rank only (redistribute_particles is not implemented)");
+    if (e->cfg.initiator_approx) FAIL("ccmc_spawn: the initiator approximation is not implemented for CCMC");
+    Params& p = e->par;
+    p.tau = in->tau; p.shift = in->shift; p.proj_energy_old = in->proj_energy_old; p.cycle = cycle;
+    cudaStream_t st = e->stream;
+    const long long n = e->nstates;
+    const int c = e->cur;
+    memset(out, 0, sizeof(*out));
+    if (!e->d_cum) {
+        const long long cap = e->cfg.walker_length;
+        if (dalloc(e, &e->d_cum, (size_t)cap)) return 1;
+        if (dalloc(e, &e->d_cum_blk, (size_t)(cap / (256 * SCAN64_ITEMS) + 2))) return 1;
+        if (dalloc(e, &e->d_cc_part, (size_t)(e->cfg.spawned_walker_length / 256 + cap / 256 + 4))) return 1;
+        if (dalloc(e, &e->d_cc_tot, 1)) return 1;
+    }
+    CK(cudaMemsetAsync(e->d_head, 0, sizeof(unsigned long long) * p.nprocs, st));
+    // get_D0_info (src/ccmc_utils.F90:69-130)
+    long long d0info[2] = {0, 0};
+    if (n > 0) {
+        DISPATCH_W(e, k_find_det<WW><<<1, 32, 0, st>>>(p, e->d_states[c], e->d_pops[c], n, e->d_ll));
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(d0info, e->d_ll, 2 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        e->launches++;
+    }
+    if (d0info[0] == 0) FAIL("ccmc_spawn: find_D0: cannot find the reference in the excip list");
+    CcmcArgs a;
+    a.nstates = n; a.D0_pos = d0info[0];
+    a.D0_normalisation = (double)d0info[1] / (double)p.real_factor;
+    a.ex_level = ex_level; a.nprocs = p.nprocs;
+    a.max_cluster_size = (int)std::min<long long>(std::min(e->sys.nel, ex_level + 2), n - 1);
+    // init_mc_cycle (src/qmc_common.F90:950-1017, ccmc branch) with min_attempts = nint(|D0_normalisation|)
+    long long nattempts = (long long)((double)e->nparticles_enc / (double)p.real_factor);
+    nattempts = std::max<long long>(nattempts, llround(fabs(a.D0_normalisation)));
+    a.nattempts = nattempts;
+    // cumulative_population (src/ccmc_utils.F90:427-563)
+    const int nb = (int)((n + 256 * SCAN64_ITEMS - 1) / (256 * SCAN64_ITEMS));
+    k_cum_block<<<nb, 256, 0, st>>>(e->d_pops[c], n, a.D0_pos - 1, e->d_cum, e->d_cum_blk);
+    k_cum_sums<<<1, 1024, 0, st>>>(e->d_cum_blk, nb);
+    k_cum_add<<<nb, 256, 0, st>>>(e->d_cum, n, e->d_cum_blk);
+    CK(cudaGetLastError());
+    long long tot_enc = 0;
+    CK(cudaMemcpyAsync(&tot_enc, e->d_cum + (n - 1), sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    e->launches += 3;
+    a.tot_abs_real_pop = (double)tot_enc / (double)p.real_factor;
+    CcmcPartials tot;
+    memset(&tot, 0, sizeof(tot));
+    if (nattempts > 0) {
+        const long long nblk = (nattempts + 255) / 256;
+        if ((size_t)nblk > (size_t)(e->cfg.spawned_walker_length / 256 + e->cfg.walker_length / 256 + 4))
+            FAIL("ccmc_spawn: more cluster selections than the partial-sum scratch holds");
+        DISPATCH_W(e, k_ccmc_cluster<WW><<<(unsigned)nblk, 256, 0, st>>>(e->sys, p, a, e->d_states[c], e->d_pops[c], e->d_dat[c],
+                                                                          e->d_cum, e->d_spawn[0], e->d_head, e->block_size,
+                                                                          e->d_proc_map, e->d_cc_part, e->d_err));
+        CK(cudaGetLastError());
+        k_ccmc_reduce<<<1, 1024, 0, st>>>(e->d_cc_part, (int)nblk, e->d_cc_tot);
+        CK(cudaGetLastError());
+        e->launches += 2;
+        CK(cudaMemcpyAsync(&tot, e->d_cc_tot, sizeof(tot), cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaMemcpyAsync(e->h_head.data(), e->d_head, sizeof(unsigned long long) * p.nprocs, cudaMemcpyDeviceToHost, st));
+    int herr[2] = {0, 0};
+    CK(cudaMemcpyAsync(herr, e->d_err, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int d = 0; d < p.nprocs; ++d)
+        if ((long long)e->h_head[d] > e->block_size) e->h_head[d] = (unsigned long long)e->block_size;
+    e->sp_cur = 0;
+    e->sp_blocked = false;
+    e->sp_n = (long long)e->h_head[0];
+    out->proj_energy = tot.pe; out->D0_population = tot.d0; out->D0_normalisation = a.D0_normalisation;
+    out->nattempts = nattempts; out->nattempts_spawn = tot.nattempts_spawn; out->ndeath = tot.ndeath;
+    out->nspawn_events = e->sp_n; out->tot_abs_real_pop = a.tot_abs_real_pop;
+    out->spawn_error = herr[0]; out->psip_error = herr[1];
+    return 0;
+}
+
+// ncycles full CCMC cycles (the icycle loop of do_ccmc, src/ccmc.f90:603-896): cluster selection / spawning / death,
+// then direct_annihilation and end_mc_cycle.
+int hb200_ccmc_iterate(hb200_engine* e, int32_t ncycles, const hb200_iter_in* in, int32_t ex_level, hb200_iter_out* out) {
+    CK(cudaSetDevice(e->cfg.device));
+    memset(out, 0, sizeof(*out));
+    CycleStats cs;
+    memset(&cs, 0, sizeof(cs));
+    hb200_ccmc_out co;
+    long long nattempts = 0;
+    for (int c = 0; c < ncycles; ++c) {
+        const uint32_t cycle = in->first_cycle + (uint32_t)c;
+        out->walker_iterations += (double)e->nparticles_enc / (double)e->par.real_factor;
+        if (hb200_ccmc_spawn(e, in, cycle, ex_level, &co)) return 1;
+        nattempts = co.nattempts;
+        out->proj_energy += co.proj_energy;
+        out->D0_population += co.D0_population;
+        out->nattempts_spawn += co.nattempts_spawn;
+        out->nspawn_events = co.nspawn_events;
+        out->ndeath = co.ndeath;
+        if (stage_sort(e)) return 1;
+        if (stage_annihilate_main(e, cycle, &cs)) return 1;
+        // end_mc_cycle(nspawn_events, ndeath_nc = 0, real_factor, nattempts_spawn, rspawn)
+        if (co.nattempts_spawn > 0) out->rspawn += (double)co.nspawn_events / (double)co.nattempts_spawn;
+    }
+    fill_out(e, out, cs, nattempts);
+    out->ndeath = co.ndeath;
     return 0;
 }
 

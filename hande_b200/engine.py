@@ -67,6 +67,17 @@ class IterOut(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class CcmcOut(C.Structure):
+    _fields_ = [
+        ("proj_energy", C.c_double), ("D0_population", C.c_double), ("D0_normalisation", C.c_double),
+        ("tot_abs_real_pop", C.c_double), ("nattempts", C.c_int64), ("nattempts_spawn", C.c_int64),
+        ("nspawn_events", C.c_int64), ("ndeath", C.c_int64), ("spawn_error", C.c_int32), ("psip_error", C.c_int32),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 _LIB = None
 
 
@@ -115,6 +126,8 @@ def load_library():
     L.hb200_nstates.argtypes = [C.c_void_p]
     L.hb200_iterate.argtypes = [C.c_void_p, C.c_int32, C.POINTER(IterIn), C.POINTER(IterOut)]
     L.hb200_spawn_death.argtypes = [C.c_void_p, C.POINTER(IterIn), C.c_uint32, C.POINTER(IterOut)]
+    L.hb200_ccmc_spawn.argtypes = [C.c_void_p, C.POINTER(IterIn), C.c_uint32, C.c_int32, C.POINTER(CcmcOut)]
+    L.hb200_ccmc_iterate.argtypes = [C.c_void_p, C.c_int32, C.POINTER(IterIn), C.c_int32, C.POINTER(IterOut)]
     L.hb200_comm_spawn.argtypes = [C.c_void_p]
     L.hb200_annihilate_spawn.argtypes = [C.c_void_p]
     L.hb200_annihilate_main.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(IterOut)]
@@ -135,7 +148,7 @@ ABI_SYMBOLS = [
     "hb200_build_heat_bath",
     "hb200_download_heat_bath", "hb200_set_reference", "hb200_set_proc_map", "hb200_upload_psips",
     "hb200_download_psips", "hb200_nstates", "hb200_iterate", "hb200_spawn_death", "hb200_comm_spawn",
-    "hb200_annihilate_spawn", "hb200_annihilate_main", "hb200_download_spawn", "hb200_upload_spawn",
+    "hb200_ccmc_spawn", "hb200_ccmc_iterate", "hb200_annihilate_spawn", "hb200_annihilate_main", "hb200_download_spawn", "hb200_upload_spawn",
     "hb200_sc0_batch", "hb200_gen_excit_batch", "hb200_get_unique_id", "hb200_comm_init", "hb200_last_timing",
 ]
 
@@ -263,6 +276,19 @@ class Engine:
         i = IterIn(tau=tau, shift=shift, proj_energy_old=proj_energy_old, first_cycle=cycle)
         o = IterOut()
         self._chk(self.L.hb200_spawn_death(self.h, C.byref(i), cycle, C.byref(o)))
+        return o.as_dict()
+
+    # ---- CCMC
+    def ccmc_spawn(self, tau, shift, proj_energy_old, cycle, ex_level):
+        i = IterIn(tau=tau, shift=shift, proj_energy_old=proj_energy_old, first_cycle=cycle)
+        o = CcmcOut()
+        self._chk(self.L.hb200_ccmc_spawn(self.h, C.byref(i), cycle, ex_level, C.byref(o)))
+        return o.as_dict()
+
+    def ccmc_iterate(self, ncycles, tau, shift, proj_energy_old, first_cycle, ex_level):
+        i = IterIn(tau=tau, shift=shift, proj_energy_old=proj_energy_old, first_cycle=first_cycle)
+        o = IterOut()
+        self._chk(self.L.hb200_ccmc_iterate(self.h, ncycles, C.byref(i), ex_level, C.byref(o)))
         return o.as_dict()
 
     def comm_spawn(self):

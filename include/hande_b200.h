@@ -106,6 +106,19 @@ typedef struct hb200_iter_out {
     double walker_iterations;      /* sum over cycles of nparticles at the start of the cycle (throughput metric) */
 } hb200_iter_out;
 
+/* Per-cycle outputs of the CCMC cluster stage (what do_ccmc accumulates per cycle, src/ccmc.f90:625-880). */
+typedef struct hb200_ccmc_out {
+    double proj_energy;            /* proj_energy_cycle: sum of <D0|H|D_cluster> amplitude sign / pselect */
+    double D0_population;          /* D0_population_cycle */
+    double D0_normalisation;       /* population on the reference (get_D0_info) */
+    double tot_abs_real_pop;       /* cumulative excip population without the reference */
+    int64_t nattempts;             /* qs%estimators%nattempts = number of cluster selections */
+    int64_t nattempts_spawn;       /* spawning attempts made (accepted clusters) */
+    int64_t nspawn_events;         /* entries added to the spawn list (spawns and deaths) */
+    int64_t ndeath;                /* sum |nkill| */
+    int32_t spawn_error, psip_error;
+} hb200_ccmc_out;
+
 const char* hb200_last_error(void);
 
 /* init_qmc sizing (src/qmc.F90:10-215): allocates all device state. NULL on failure. */
@@ -137,6 +150,14 @@ int64_t hb200_nstates(hb200_engine* e);
 /* ncycles full MC cycles: the body of do_fciqmc's icycle loop (src/fciqmc.f90:293-398):
  * init_mc_cycle, the idet loop (spawn + death + projected energy), direct_annihilation, end_mc_cycle. */
 int hb200_iterate(hb200_engine* e, int32_t ncycles, const hb200_iter_in* in, hb200_iter_out* out);
+
+/* CCMC (ccmc{...}; src/ccmc.f90:603-896), stochastic cluster selection: one thread per selection attempt runs
+ * select_cluster (src/ccmc_selection.f90:93-392), do_ccmc_accumulation, spawner_ccmc and stochastic_ccmc_death
+ * (src/ccmc_death_spawning.f90:11-441); spawned and killed excips enter the spawn list and are annihilated by the same
+ * stages as FCIQMC.  ex_level = reference%ex_level (2 = CCSD, 3 = CCSDT); the engine must have been created with
+ * trunc_level = ex_level.  Single rank only in this version. */
+int hb200_ccmc_spawn(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, int32_t ex_level, hb200_ccmc_out* out);
+int hb200_ccmc_iterate(hb200_engine* e, int32_t ncycles, const hb200_iter_in* in, int32_t ex_level, hb200_iter_out* out);
 
 /* Stage-level entry points (same state machine as hb200_iterate, one stage per call). */
 /* do idet loop: decoder_ptr, set_parent_flag, update_proj_energy_ptr, decide_nattempts,

@@ -347,6 +347,22 @@ int orc_stage_spawn(void* h, uint32_t cycle_id, double tau, double shift, double
     return 0;
     ORC_CATCH(-1)
 }
+// CCMC stage probe: cluster selection + spawning + death of one cycle on rank 0 (no annihilation); the spawn list is
+// read with orc_get_spawn and the cycle finished with orc_stage_annihilate.
+// out: proj_energy_cycle, D0_population_cycle, D0_normalisation, nattempts, nattempts_spawn, nspawn_events, ndeath
+int orc_ccmc_stage_spawn(void* h, uint32_t cycle_id, double tau, double shift, double proj_energy_old, double* out) {
+    ORC_TRY
+    OracleCcmc* o = (OracleCcmc*)(Oracle*)h;
+    o->tau = tau; o->shift = shift; o->est.proj_energy_old = proj_energy_old;
+    RankState& r = o->ranks[0];
+    r.proj_energy = 0.0; r.D0_population = 0.0;
+    o->ccmc_cycle_rank(r, cycle_id);
+    out[0] = o->last.proj_energy; out[1] = o->last.D0_population; out[2] = o->last.D0_normalisation;
+    out[3] = (double)o->last.nattempts; out[4] = (double)o->last.nattempts_spawn; out[5] = (double)o->last.nspawn_events;
+    out[6] = (double)o->last.ndeath;
+    return 0;
+    ORC_CATCH(-1)
+}
 int64_t orc_spawn_count(void* h, int rank) {
     int64_t n = 0;
     for (auto& b : ((Oracle*)h)->ranks[rank].send) n += (int64_t)b.size();

@@ -106,6 +106,7 @@ def lib():
         L.orc_set_reference_det.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_iterate.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_void_p]
         L.orc_stage_spawn.argtypes = [C.c_void_p, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_void_p]
+        L.orc_ccmc_stage_spawn.argtypes = [C.c_void_p, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_void_p]
         L.orc_spawn_count.restype = C.c_int64
         L.orc_spawn_count.argtypes = [C.c_void_p, C.c_int]
         L.orc_get_spawn.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -331,6 +332,17 @@ class Oracle:
         sd = np.zeros((n, self.W + 2), dtype=np.int64)
         self.L.orc_get_spawn(self.h, rank, _p(sd))
         return dict(zip(["proj_energy", "D0_population", "nspawn_events", "ndeath"], out)), sd
+
+    def ccmc_stage_spawn(self, cycle, tau, shift, proj_energy_old):
+        """CCMC cluster selection / spawning / death of one cycle (rank 0); returns (stats, sdata[n][W+2])."""
+        out = np.zeros(8)
+        self._chk(self.L.orc_ccmc_stage_spawn(self.h, cycle, tau, shift, proj_energy_old, _p(out)))
+        n = self.L.orc_spawn_count(self.h, 0)
+        sd = np.zeros((n, self.W + 2), dtype=np.int64)
+        self.L.orc_get_spawn(self.h, 0, _p(sd))
+        keys = ["proj_energy", "D0_population", "D0_normalisation", "nattempts", "nattempts_spawn", "nspawn_events",
+                "ndeath"]
+        return dict(zip(keys, out)), sd
 
     def stage_annihilate(self):
         self._chk(self.L.orc_stage_annihilate(self.h))

@@ -17,8 +17,9 @@ def make_engine_cls(fcidump_path, sys_kw, rng_kind=0, ueg=None, ref_det=None):
         def __init__(self, sys, *, excit_gen, pattempt_single, pattempt_double, real_amplitudes, spawn_cutoff,
                      initiator_approx, initiator_pop, trunc_level, walker_length, spawned_walker_length, seed, nprocs,
                      iproc, nslots, device):
-            import torch.distributed as dist
-            self.dist = dist
+            if nprocs > 1:
+                import torch.distributed as dist
+                self.dist = dist
             self.rank, self.world = iproc, nprocs
             o = self.o = Oracle()
             if ueg is not None:
@@ -89,6 +90,25 @@ def make_engine_cls(fcidump_path, sys_kw, rng_kind=0, ueg=None, ref_det=None):
                     out["rspawn"] += (st[2] + st[3] / self.real_factor) / st[4]
                 out["nparticles"], out["nstates"] = res[0], int(res[1])
                 out["spawn_error"] = int(res[2])
+            return out
+
+        def ccmc_iterate(self, ncycles, tau, shift, proj_energy_old, first_cycle, ex_level):
+            """CCMC cycles on the oracle (single rank): same outputs as Engine.ccmc_iterate."""
+            o = self.o
+            out = dict(proj_energy=0.0, D0_population=0.0, rspawn=0.0, nspawn_events=0, ndeath=0, nattempts=0,
+                       spawn_error=0, psip_error=0, nattempts_spawn=0, walker_iterations=0.0)
+            for c in range(ncycles):
+                st, _ = o.ccmc_stage_spawn(first_cycle + c, tau, shift, proj_energy_old)
+                o.stage_annihilate()
+                out["proj_energy"] += st["proj_energy"]
+                out["D0_population"] += st["D0_population"]
+                out["nspawn_events"], out["ndeath"] = int(st["nspawn_events"]), int(st["ndeath"])
+                out["nattempts"] = int(st["nattempts"])
+                out["nattempts_spawn"] += int(st["nattempts_spawn"])
+                if st["nattempts_spawn"] > 0:
+                    out["rspawn"] += st["nspawn_events"] / st["nattempts_spawn"]
+            out["nparticles"] = float(o.L.orc_nparticles(o.h, self.rank))
+            out["nstates"] = self.nstates
             return out
 
         def last_timing(self):

@@ -93,3 +93,44 @@ def test_ueg_trajectory_and_fci_energy():
     assert abs(e - (-0.176123766865)) < 4.0 * se + 2e-4, (e, se)
     m, sm = optimal_error(g[k:, 1])
     assert abs(m - (-0.176123766865)) < 4.0 * sm + 2e-3, (m, sm)
+
+
+def test_ccmc_driver_trajectory_and_energy():
+    """CCMC host driver on the GPU engine (the reference's CCSD fixture system, Ne cc-pVDZ):
+    (i) report-loop trajectory identical to the oracle's under the same Philox stream;
+    (ii) reblocked projected energy agrees within combined 2 sigma with the oracle run on the REFERENCE stream (dSFMT),
+    which itself reproduces the reference's golden table."""
+    from hande_b200.ccmc import do_ccmc
+    path, kw = system_path("ne_vdz")
+    s = R.read_in(path, **kw)
+    qmc = QmcIn(tau=0.01, rng_seed=5691, init_pop=10, mc_cycles=10, nreports=60, target_population=20000,
+                state_size=200000, spawned_state_size=100000, ex_level=2)
+    res = do_ccmc(s, qmc)
+    o = Oracle()
+    o.read_fcidump(path, **kw)
+    o.set_qmc(rng_kind=1, tau=0.01, seed=5691, D0_population=10, ncycles=10, nreport=60, target_particles=20000,
+              walker_length=200000, spawned_walker_length=100000, ex_level=2)
+    o.init()
+    rows, na = o.run_ccmc()
+    assert len(res.rows) == len(rows) == 61
+    for g, r, a in zip(res.rows, rows, na):
+        assert g[0] == r[0] and g[4] == r[4] and g[5] == r[5] and g[6] == r[6] and g[8] == a, (g, r, a)
+        assert abs(g[2] - r[2]) <= 1e-10 * max(1.0, abs(r[2])) and abs(g[3] - r[3]) <= 1e-10 * max(1.0, abs(r[3]))
+    # (ii) variable-shift regime, real amplitudes
+    common = dict(tau=0.01, ncycles=10, target=3000.0, nrep=700, skip=300)
+    qmc = QmcIn(tau=common["tau"], rng_seed=3, init_pop=100, mc_cycles=common["ncycles"], nreports=common["nrep"],
+                target_population=common["target"], state_size=200000, spawned_state_size=100000, ex_level=2,
+                real_amplitudes=True)
+    g = np.array(do_ccmc(s, qmc).rows)[1:]
+    o = Oracle()
+    o.read_fcidump(path, **kw)
+    o.set_qmc(rng_kind=0, tau=common["tau"], seed=11, D0_population=100, ncycles=common["ncycles"], nreport=common["nrep"],
+              target_particles=common["target"], walker_length=200000, spawned_walker_length=100000, ex_level=2,
+              real_amplitudes=1)
+    o.init()
+    orow = o.run_ccmc()[0][1:]
+    k = common["skip"]
+    eg, sg = ratio_with_error(g[k:, 2], g[k:, 3])
+    eo, so = ratio_with_error(orow[k:, 2], orow[k:, 3])
+    assert abs(eg - eo) < 2.0 * np.hypot(sg, so) + 1e-4, (eg, sg, eo, so)
+    assert -0.25 < eg < -0.15      # CCSD correlation energy of Ne/cc-pVDZ is about -0.19 Eh

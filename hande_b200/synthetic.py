@@ -171,3 +171,67 @@ def random_walkers_torch(n, nbasis, nalpha, nbeta, real_factor, device, seed=1, 
     pops = sign * int(real_factor)
     states = w[:, :W].contiguous().cpu().numpy().view(np.uint64)
     return states, pops.cpu().numpy()
+
+
+def random_excitors(n, occ0, nbasis, max_level, seed=1):
+    """n distinct random excitors of the reference `occ0` (1-based spin-orbitals) with excitation level 1..max_level
+    (spin-conserving replacements), sorted in the reference's list order; the reference itself is not included.
+    Synthetic CCMC excip lists for throughput measurements (BASELINE config 5)."""
+    rng = np.random.Generator(np.random.Philox(key=seed + 31))
+    W = (nbasis + 63) // 64
+    occ0 = np.asarray(sorted(occ0))
+    occ_s = [occ0[occ0 % 2 == 1], occ0[occ0 % 2 == 0]]                       # alpha (odd), beta (even)
+    allo = np.arange(1, nbasis + 1)
+    virt = np.setdiff1d(allo, occ0)
+    virt_s = [virt[virt % 2 == 1], virt[virt % 2 == 0]]
+    f0 = np.zeros(W, dtype=np.uint64)
+    for o in occ0:
+        f0[(o - 1) // 64] |= np.uint64(1) << np.uint64((o - 1) % 64)
+    out = None
+    need = n
+    while True:
+        m = int(need * 1.3) + 64
+        f = np.tile(f0, (m, 1))
+        level = rng.integers(1, max_level + 1, size=m)
+        for k in range(max_level):
+            act = level > k
+            spin = rng.integers(0, 2, size=m)
+            for sp in (0, 1):
+                sel = act & (spin == sp)
+                cnt = int(sel.sum())
+                if cnt == 0:
+                    continue
+                i = occ_s[sp][rng.integers(0, len(occ_s[sp]), size=cnt)]
+                a = virt_s[sp][rng.integers(0, len(virt_s[sp]), size=cnt)]
+                rows = np.nonzero(sel)[0]
+                for orb, setbit in ((i, False), (a, True)):
+                    w = (orb - 1) // 64
+                    bit = np.uint64(1) << ((orb - 1) % 64).astype(np.uint64)
+                    for iw in range(W):
+                        msk = w == iw
+                        if setbit:
+                            f[rows[msk], iw] |= bit[msk]
+                        else:
+                            f[rows[msk], iw] &= ~bit[msk]
+        # keep rows with the right electron count (an orbital hit twice changes it) and drop the reference
+        nel = np.zeros(m, dtype=np.int64)
+        for iw in range(W):
+            nel += np.array([bin(int(x)).count("1") for x in f[:, iw]]) if m < 4096 else _popcount64(f[:, iw])
+        keep = (nel == len(occ0)) & ~(f == f0).all(axis=1)
+        f = f[keep]
+        out = f if out is None else np.concatenate([out, f])
+        out = sort_dets(out)
+        out = out[np.concatenate([[True], (out[1:] != out[:-1]).any(axis=1)])]
+        if len(out) >= n:
+            break
+        need = n - len(out)
+    out = out[np.sort(rng.permutation(len(out))[:n])]
+    return np.ascontiguousarray(out)
+
+
+def _popcount64(x):
+    x = x.astype(np.uint64)
+    x = x - ((x >> np.uint64(1)) & np.uint64(0x5555555555555555))
+    x = (x & np.uint64(0x3333333333333333)) + ((x >> np.uint64(2)) & np.uint64(0x3333333333333333))
+    x = (x + (x >> np.uint64(4))) & np.uint64(0x0F0F0F0F0F0F0F0F)
+    return ((x * np.uint64(0x0101010101010101)) >> np.uint64(56)).astype(np.int64)

@@ -175,4 +175,52 @@ double hd_proj_hmatel(const uint64_t* f, int* is_ref) {
     *is_ref = r;
     return h;
 }
+// Brute-force check of the guarded prefix-sum alias selection against the reference's table construction
+// (generate_alias_tables + select_weighted_value_precalc).  Returns the number of mismatches; out[0] = calls,
+// out[1] = fallbacks to the exact walk.
+long long hd_alias_selftest_mode(long long ntrials, unsigned long long seed, long long* out, int only_mode);
+long long hd_alias_selftest(long long ntrials, unsigned long long seed, long long* out) { return hd_alias_selftest_mode(ntrials, seed, out, -1); }
+long long hd_alias_selftest_mode(long long ntrials, unsigned long long seed, long long* out, int only_mode) {
+    unsigned long long st = seed * 0x9E3779B97F4A7C15ull + 12345;
+    auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (double)(st >> 11) * (1.0 / 9007199254740992.0); };
+    long long bad = 0;
+    for (long long t = 0; t < ntrials; ++t) {
+        const int N = 2 + (int)(rnd() * 39);
+        double w[HB_MAXNEL], U[HB_MAXNEL];
+        int K[HB_MAXNEL], un[HB_MAXNEL], ov[HB_MAXNEL];
+        const bool aimed = only_mode < 100;
+        const int mode = only_mode >= 100 ? only_mode - 100 : (only_mode >= 0 ? only_mode : (int)(rnd() * 7));
+        double tot = 0.0;
+        for (int q = 0; q < N; ++q) {
+            double v;
+            switch (mode) {
+                case 0: v = rnd(); break;                                   // uniform
+                case 1: v = -log(1.0 - rnd()); break;                        // exponential
+                case 2: v = (rnd() < 0.3) ? 0.0 : rnd(); break;              // many zeros
+                case 3: v = 1.0 + 1e-10 * (rnd() - 0.5); break;              // nearly equal
+                case 4: v = 1.0 + 4e-16 * (double)((int)(rnd() * 5) - 2); break;  // equal up to a few ulps
+                case 5: v = (q == 0) ? 50.0 * rnd() : rnd() * rnd() * rnd(); break;  // one dominant entry
+                default: v = (double)(1 + (int)(rnd() * 4)); break;         // small integers (exact ties)
+            }
+            w[q] = v; 
+        }
+        for (int q = 0; q < N; ++q) tot = tot + w[q];
+        if (!(tot > 0.0)) continue;
+        generate_alias_tables(N, w, tot, U, K, un, ov);
+        for (int rep = 0; rep < 8; ++rep) {
+            double r = rnd();
+            if (rep == 7 && aimed) {   // aim at a table boundary to exercise the guard on x
+                const int kk = (int)(rnd() * N);
+                r = ((double)kk + fmin(fmax(U[kk], 0.0), 0.999999) * (1.0 + 1e-12 * (rnd() - 0.5))) / N;
+                if (!(r >= 0.0 && r < 1.0)) r = rnd();
+            }
+            ListStream a{&r, 1, 0}, b{&r, 1, 0};
+            const int ref = select_precalc(a, N, U, K);
+            const int got = select_alias_staged(b, N, w, 1, tot);
+            if (ref != got) bad++;
+        }
+    }
+    out[0] = 8 * ntrials; out[1] = 0;
+    return bad;
+}
 }  // extern "C"

@@ -203,3 +203,19 @@ def test_heat_bath_pgen_normalisation(s10, gen):
             e = n * pg[key]
             if e > 50:
                 assert abs(c - e) < 5.5 * np.sqrt(e), (key, c, e)
+
+
+def test_alias_prefix_sum_selection_equals_table_walk():
+    """The engine's table-free alias selection (hb_core.cuh select_alias_staged: only the drawn slot's aliasU/aliasK are
+    tracked through the stack walk) must return the index of the reference's generate_alias_tables +
+    select_weighted_value_precalc (lib/local/alias.f90:68-184) for every weight vector and draw, including exact and
+    near ties (7 weight families, draws aimed at table boundaries)."""
+    import ctypes as C
+    from tests.hdcheck import harness
+    harness.build()
+    L = C.CDLL(harness.LIB)
+    L.hd_alias_selftest.restype = C.c_longlong
+    L.hd_alias_selftest.argtypes = [C.c_longlong, C.c_ulonglong, C.c_void_p]
+    out = np.zeros(2, dtype=np.int64)
+    bad = L.hd_alias_selftest(400000, 7, out.ctypes.data)
+    assert bad == 0

@@ -5,7 +5,8 @@ averages, shift update, one output row in HANDE's CCMC table format (with the "#
 src/qmc_io.f90:412-508).
 
 Scope of this version: stochastic cluster selection (the default; not full_nc, linked,
-even_selection or multi-reference), real orbitals, one rank.  Option names follow the Lua `ccmc{ qmc = {...},
+even_selection or multi-reference), real orbitals; any number of ranks (the engine re-hashes and redistributes the
+excips every cycle as the reference does, src/qmc_common.F90:505-595).  Option names follow the Lua `ccmc{ qmc = {...},
 reference = { ex_level = ... } }` table.
 """
 from __future__ import annotations
@@ -17,7 +18,7 @@ import numpy as np
 
 from . import read_in as _ri
 from .engine import Engine
-from .fciqmc import FciqmcResult, QmcIn, _SingleProcess, list_sizes
+from .fciqmc import FciqmcResult, QmcIn, _SingleProcess, list_sizes, owner_of
 
 HEADER = (" #     iterations   Shift                 \\sum H_0j N_j         N_0                   # H psips"
           "                  # states  # spawn_events            # attempts   R_spawn    time    ")
@@ -33,8 +34,7 @@ def do_ccmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, ke
     """ccmc{sys=sys, qmc={...}, reference={ex_level=qmc.ex_level}} on the GPU engine.  rows: iterations, shift,
     proj_energy, D0_population, nparticles, nstates, nspawn_events, rspawn, nattempts."""
     comm = comm or _SingleProcess()
-    if comm.size != 1:
-        raise NotImplementedError("CCMC runs on one rank in this version (redistribute_particles is not implemented)")
+    nprocs, iproc = comm.size, comm.rank
     if qmc.ex_level < 0:
         raise ValueError("ccmc: reference ex_level (the CC truncation level) must be given")
     is_ueg = getattr(sys, "kind", "read_in") == "ueg"
@@ -51,21 +51,28 @@ def do_ccmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, ke
     else:
         ps = qmc.pattempt_single / (qmc.pattempt_single + qmc.pattempt_double)
         pd = 1.0 - qmc.pattempt_single
-    wl, sl = list_sizes(qmc, sys.W, 1)
+    wl, sl = list_sizes(qmc, sys.W, nprocs)
     eng = engine_cls(sys, excit_gen=("no_renorm" if is_ueg else qmc.excit_gen), pattempt_single=ps, pattempt_double=pd,
                      real_amplitudes=qmc.real_amplitudes, spawn_cutoff=qmc.spawn_cutoff, initiator_approx=False,
                      initiator_pop=qmc.initiator_population, trunc_level=qmc.ex_level, walker_length=wl,
-                     spawned_walker_length=sl, seed=qmc.rng_seed, nprocs=1, iproc=0, nslots=qmc.nslots, device=device)
+                     spawned_walker_length=sl, seed=qmc.rng_seed, nprocs=nprocs, iproc=iproc, nslots=qmc.nslots,
+                     device=device)
     eng.set_reference(f0, H00)
+    if nprocs > 1:
+        uid = eng.get_unique_id() if iproc == 0 else np.zeros(128, dtype=np.uint8)
+        eng.comm_init(comm.broadcast_bytes(uid, src=0))
     real_factor = (1 << 31) if qmc.real_amplitudes else 1
     # initial_distribution + initial_cc_projected_energy (src/qmc_common.F90:799-925): all excips on the reference
     n0 = int(round(qmc.init_pop))
-    eng.upload_psips(f0.reshape(1, -1), np.array([n0 * real_factor], dtype=np.int64), np.zeros(1))
+    if owner_of(f0, sys.nbasis, nprocs, qmc.nslots) == iproc:       # hash_shift = 0 at the start: plain owner rule
+        eng.upload_psips(f0.reshape(1, -1), np.array([n0 * real_factor], dtype=np.int64), np.zeros(1))
+    else:
+        eng.upload_psips(np.zeros((0, sys.W), dtype=np.uint64), np.zeros(0, dtype=np.int64), np.zeros(0))
     proj_energy, D0, ntot_old, tot_nstates = 0.0, float(n0), float(n0), 1
     shift, vary_shift = qmc.initial_shift, False
     res = FciqmcResult(H00=H00, occ0=occ0)
     res.rows.append([0, shift, proj_energy, D0, ntot_old, tot_nstates, 0, 0.0, n0])
-    if io is not None:
+    if io is not None and iproc == 0:
         io.write(HEADER + "\n")
         io.write(format_row(0, shift, proj_energy, D0, ntot_old, tot_nstates, 0, n0, 0.0, 0.0, comment=True) + "\n")
     for ireport in range(1, qmc.nreports + 1):
@@ -73,12 +80,17 @@ def do_ccmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, ke
         pe_old = 0.0 if abs(D0) < np.finfo(np.float64).tiny else proj_energy / D0
         first_cycle = (ireport - 1) * qmc.mc_cycles + 1
         o = eng.ccmc_iterate(qmc.mc_cycles, qmc.tau, shift, pe_old, first_cycle, qmc.ex_level)
-        proj_energy = o["proj_energy"] / qmc.mc_cycles
-        D0 = o["D0_population"] / qmc.mc_cycles
-        rspawn = o["rspawn"] / qmc.mc_cycles
-        ntot = o["nparticles"]
-        tot_nstates, tot_nev = int(o["nstates"]), int(o["nspawn_events"])
-        error = bool(o["spawn_error"] or o["psip_error"])
+        # local_energy_estimators + MPI_Allreduce + communicated_energy_estimators (src/energy_evaluation.F90:126-655)
+        tot = comm.allreduce_sum(np.array([o["proj_energy"], o["D0_population"], o["rspawn"], o["nparticles"],
+                                           float(o["nstates"]), float(o["nspawn_events"]), float(o["nattempts"]),
+                                           float(bool(o["spawn_error"] or o["psip_error"]))]))
+        proj_energy = float(tot[0]) / qmc.mc_cycles
+        D0 = float(tot[1]) / qmc.mc_cycles
+        rspawn = float(tot[2]) / (qmc.mc_cycles * nprocs)
+        ntot = float(tot[3])
+        tot_nstates, tot_nev = int(round(tot[4])), int(round(tot[5]))
+        o = dict(o, nattempts=int(round(tot[6])))
+        error = tot[7] > 0
         if vary_shift:   # update_shift (src/energy_evaluation.F90:659-711)
             shift = shift - math.log(ntot / ntot_old) * qmc.shift_damping / (1.0 * qmc.tau * qmc.mc_cycles) \
                 - math.log(ntot / qmc.target_population) * 0.0 / (1.0 * qmc.tau * qmc.mc_cycles)
@@ -88,7 +100,7 @@ def do_ccmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, ke
             shift = proj_energy / D0 if qmc.vary_shift_from_proje else qmc.vary_shift_from
         it = ireport * qmc.mc_cycles
         res.rows.append([it, shift, proj_energy, D0, ntot, tot_nstates, tot_nev, rspawn, int(o["nattempts"])])
-        if io is not None:
+        if io is not None and iproc == 0:
             io.write(format_row(it, shift, proj_energy, D0, ntot, tot_nstates, tot_nev, int(o["nattempts"]), rspawn,
                                 (time.time() - t0) / qmc.mc_cycles) + "\n")
         if error:

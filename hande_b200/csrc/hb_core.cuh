@@ -102,6 +102,7 @@ struct Params {
     uint32_t seed, cycle;
     uint32_t hash_seed;         // 7 (src/qmc.F90:1497)
     int nprocs, iproc, nslots;
+    int ccmc_shift, ccmc_freq;  // spawn%hash_shift / spawn%move_freq (CCMC only)
     uint64_t f0[HB_MAXW];
     double H00;
 };
@@ -211,6 +212,19 @@ HB_HD int owner_slot(const uint64_t* f, int nbits, uint32_t seed, int nprocs, in
     int64_t r = (int64_t)hash % p;
     if (r < 0) r += p;  // Fortran modulo
     return (int)r;
+}
+
+// assign_particle_processor with a time-varying shift (CCMC; src/spawning.F90:812-836): the hash of the label is
+// re-hashed after xor-ing ishft(hash + shift, -freq) (logical shift of a default integer) into its first word
+template <int W>
+HB_HD int owner_slot_shift(const uint64_t* f, int nbits, uint32_t seed, int shift, int freq, int nprocs, int nslots) {
+    if (shift == 0) return owner_slot(f, nbits, seed, nprocs, nslots);
+    const uint32_t hs = murmur2_words(f, nbits, seed) + (uint32_t)shift;   // 32-bit wrap-around as in the reference build
+    uint64_t g[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) g[k] = f[k];
+    g[0] ^= (uint64_t)(hs >> freq);
+    return owner_slot(g, nbits, seed, nprocs, nslots);
 }
 
 // ------------------------------------------------------------------------------------------------

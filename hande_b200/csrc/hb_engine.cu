@@ -49,6 +49,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -62,7 +63,7 @@ struct NcclApi {
         if (!h) { err = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
 #define HB_SYM(field, name) field = (decltype(field))dlsym(h, name); if (!field) { err = std::string("NCCL symbol missing: ") + name; return false; }
         HB_SYM(GetUniqueId, "ncclGetUniqueId") HB_SYM(CommInitRank, "ncclCommInitRank") HB_SYM(CommDestroy, "ncclCommDestroy")
-        HB_SYM(AllGather, "ncclAllGather") HB_SYM(Send, "ncclSend") HB_SYM(Recv, "ncclRecv")
+        HB_SYM(AllGather, "ncclAllGather") HB_SYM(Broadcast, "ncclBroadcast") HB_SYM(Send, "ncclSend") HB_SYM(Recv, "ncclRecv")
         HB_SYM(GroupStart, "ncclGroupStart") HB_SYM(GroupEnd, "ncclGroupEnd") HB_SYM(GetErrorString, "ncclGetErrorString")
 #undef HB_SYM
         return true;
@@ -559,7 +560,8 @@ k_ccmc_cluster(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states,
     int dest_s = 0, dest_k = 0;
     if (idx < a.nattempts) {
         PhiloxStream rng;
-        rng.begin(p.seed, p.cycle, RNG_SPAWN, det_hash64<W>(p.f0), (uint32_t)(idx + 1));
+        rng.begin(p.seed, p.cycle, RNG_SPAWN, det_hash64<W>(p.f0) + (uint64_t)p.iproc * 0x9E3779B97F4A7C15ull,
+                  (uint32_t)(idx + 1));
         Cluster cl;
         ccmc_select_cluster<W>(rng, p, a, states, pops, cum_enc, cf, cl);
         if (cl.excitation_level >= 0 && cl.excitation_level <= a.ex_level + 2) {
@@ -584,7 +586,8 @@ k_ccmc_cluster(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states,
                 const int lvl = excit_level<W>(child, p.f0);
                 if (ccmc_excitor_sign<W>(p.f0, child, lvl) < 0) nspawn = -nspawn;
                 if (p.trunc_level >= 0 && lvl > p.trunc_level) nspawn = 0;   // create_spawned_particle_truncated
-                else dest_s = (p.nprocs > 1) ? proc_map[owner_slot(child, s.nbasis, p.hash_seed, p.nprocs, p.nslots)] : 0;
+                else dest_s = (p.nprocs > 1) ? proc_map[owner_slot_shift<W>(child, s.nbasis, p.hash_seed, p.ccmc_shift, p.ccmc_freq,
+                                                                            p.nprocs, p.nslots)] : 0;
             }
             // stochastic_ccmc_death + stochastic_death_attempt (src/ccmc_death_spawning.f90:213-441)
             if (cl.excitation_level <= a.ex_level) {
@@ -609,7 +612,8 @@ k_ccmc_cluster(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states,
                 ndeath = nkill;
                 if (nkill != 0) {
                     if (KiiAi > 0) nkill = -nkill;
-                    dest_k = (p.nprocs > 1) ? proc_map[owner_slot(cf, s.nbasis, p.hash_seed, p.nprocs, p.nslots)] : 0;
+                    dest_k = (p.nprocs > 1) ? proc_map[owner_slot_shift<W>(cf, s.nbasis, p.hash_seed, p.ccmc_shift, p.ccmc_freq,
+                                                                            p.nprocs, p.nslots)] : 0;
                 }
             }
         }
@@ -643,6 +647,29 @@ __global__ void k_ccmc_reduce(const CcmcPartials* __restrict__ partials, int n, 
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { o.pe += sd[0][w]; o.d0 += sd[1][w]; o.ndeath += sl[0][w]; o.nattempts_spawn += sl[1][w]; }
         *out = o;
     }
+}
+// redistribute_particles (src/qmc_common.F90:505-595): excips whose owner under the current hash shift is another
+// rank are moved to that rank's block of the spawn list and zeroed in the main list
+template <int W>
+__global__ void __launch_bounds__(256)
+k_ccmc_redistribute(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __restrict__ pops, long long n,
+                    int64_t* __restrict__ spawn, unsigned long long* __restrict__ head, long long block_size,
+                    const int* __restrict__ proc_map, int* __restrict__ err) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t f[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) f[k] = 0;
+    int64_t pop = 0;
+    int dest = 0;
+    if (i < n) {
+        load_det<W>(states + i * W, f);
+        dest = proc_map[owner_slot_shift<W>(f, s.nbasis, p.hash_seed, p.ccmc_shift, p.ccmc_freq, p.nprocs, p.nslots)];
+        if (dest != p.iproc) {
+            pop = pops[i];
+            pops[i] = 0;
+        }
+    }
+    append_spawn_warp<W>(f, pop, dest, p.nprocs, spawn, head, block_size, err);
 }
 // find_D0 (src/ccmc_utils.F90:21-67): position (1-based, 0 = absent) and population of f0 in the sorted main list
 template <int W>
@@ -1330,6 +1357,7 @@ struct hb200_engine {
     int* d_total = nullptr;   // [4] small ints
     long long* d_part_ll = nullptr;
     long long* d_ll = nullptr;  // [4]
+    int ccmc_hash_shift = 0, ccmc_move_freq = 5;   // spawn%hash_shift (+1 per cycle), spawn%move_freq
     // CCMC scratch
     long long* d_cum = nullptr;        // [walker_length] inclusive prefix sums of |pop| (reference skipped)
     long long* d_cum_blk = nullptr;
@@ -1940,7 +1968,7 @@ int hb200_ccmc_spawn(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, i
     CK(cudaSetDevice(e->cfg.device));
     if (!e->have_sys) FAIL("ccmc_spawn: system not set");
     if (uses_heat_bath_tables(e) && !e->have_hb) FAIL("ccmc_spawn: heat-bath tables not built");
-    if (e->par.nprocs != 1) FAIL("ccmc_spawn: single rank only (redistribute_particles is not implemented)");
+    if (e->par.nprocs > 1 && !e->comm) FAIL("ccmc_spawn: nprocs > 1 but hb200_comm_init was not called");
     if (e->cfg.initiator_approx) FAIL("ccmc_spawn: the initiator approximation is not implemented for CCMC");
     Params& p = e->par;
     p.tau = in->tau; p.shift = in->shift; p.proj_energy_old = in->proj_energy_old; p.cycle = cycle;
@@ -1956,35 +1984,56 @@ int hb200_ccmc_spawn(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, i
         if (dalloc(e, &e->d_cc_tot, 1)) return 1;
     }
     CK(cudaMemsetAsync(e->d_head, 0, sizeof(unsigned long long) * p.nprocs, st));
-    // get_D0_info (src/ccmc_utils.F90:69-130)
-    long long d0info[2] = {0, 0};
-    if (n > 0) {
-        DISPATCH_W(e, k_find_det<WW><<<1, 32, 0, st>>>(p, e->d_states[c], e->d_pops[c], n, e->d_ll));
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(d0info, e->d_ll, 2 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    // get_D0_info (src/ccmc_utils.F90:69-130): owner of the reference under the current hash shift, its position and
+    // population there, broadcast to every rank (MPI_Bcast -> ncclBroadcast)
+    p.ccmc_shift = e->ccmc_hash_shift; p.ccmc_freq = e->ccmc_move_freq;
+    int D0_proc = 0;
+    if (p.nprocs > 1) {
+        std::vector<int> map((size_t)p.nprocs * p.nslots);
+        CK(cudaMemcpyAsync(map.data(), e->d_proc_map, map.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        e->launches++;
+        int slot = 0;
+        DISPATCH_W(e, slot = owner_slot_shift<WW>(p.f0, e->sys.nbasis, p.hash_seed, p.ccmc_shift, p.ccmc_freq, p.nprocs, p.nslots));
+        D0_proc = map[slot];
     }
+    long long d0info[2] = {0, 0};
+    const bool have_D0 = (p.iproc == D0_proc);
+    if (have_D0) {
+        if (n > 0) {
+            DISPATCH_W(e, k_find_det<WW><<<1, 32, 0, st>>>(p, e->d_states[c], e->d_pops[c], n, e->d_ll));
+            CK(cudaGetLastError());
+            e->launches++;
+        } else {
+            CK(cudaMemsetAsync(e->d_ll, 0, 2 * sizeof(long long), st));
+        }
+    }
+    if (p.nprocs > 1) NCK(g_nccl.Broadcast(e->d_ll, e->d_ll, 2, ncclInt64, D0_proc, e->comm, st));
+    CK(cudaMemcpyAsync(d0info, e->d_ll, 2 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     if (d0info[0] == 0) FAIL("ccmc_spawn: find_D0: cannot find the reference in the excip list");
+    e->ccmc_hash_shift += 1;                    // src/ccmc.f90:625
+    p.ccmc_shift = e->ccmc_hash_shift;
     CcmcArgs a;
-    a.nstates = n; a.D0_pos = d0info[0];
+    a.nstates = n; a.D0_pos = have_D0 ? d0info[0] : -1;
     a.D0_normalisation = (double)d0info[1] / (double)p.real_factor;
     a.ex_level = ex_level; a.nprocs = p.nprocs;
-    a.max_cluster_size = (int)std::min<long long>(std::min(e->sys.nel, ex_level + 2), n - 1);
+    a.max_cluster_size = (int)std::min<long long>(std::min(e->sys.nel, ex_level + 2), n - (have_D0 ? 1 : 0));
     // init_mc_cycle (src/qmc_common.F90:950-1017, ccmc branch) with min_attempts = nint(|D0_normalisation|)
     long long nattempts = (long long)((double)e->nparticles_enc / (double)p.real_factor);
     nattempts = std::max<long long>(nattempts, llround(fabs(a.D0_normalisation)));
     a.nattempts = nattempts;
     // cumulative_population (src/ccmc_utils.F90:427-563)
-    const int nb = (int)((n + 256 * SCAN64_ITEMS - 1) / (256 * SCAN64_ITEMS));
-    k_cum_block<<<nb, 256, 0, st>>>(e->d_pops[c], n, a.D0_pos - 1, e->d_cum, e->d_cum_blk);
-    k_cum_sums<<<1, 1024, 0, st>>>(e->d_cum_blk, nb);
-    k_cum_add<<<nb, 256, 0, st>>>(e->d_cum, n, e->d_cum_blk);
-    CK(cudaGetLastError());
     long long tot_enc = 0;
-    CK(cudaMemcpyAsync(&tot_enc, e->d_cum + (n - 1), sizeof(long long), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    e->launches += 3;
+    if (n > 0) {
+        const int nb = (int)((n + 256 * SCAN64_ITEMS - 1) / (256 * SCAN64_ITEMS));
+        k_cum_block<<<nb, 256, 0, st>>>(e->d_pops[c], n, have_D0 ? a.D0_pos - 1 : -1, e->d_cum, e->d_cum_blk);
+        k_cum_sums<<<1, 1024, 0, st>>>(e->d_cum_blk, nb);
+        k_cum_add<<<nb, 256, 0, st>>>(e->d_cum, n, e->d_cum_blk);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&tot_enc, e->d_cum + (n - 1), sizeof(long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        e->launches += 3;
+    }
     a.tot_abs_real_pop = (double)tot_enc / (double)p.real_factor;
     CcmcPartials tot;
     memset(&tot, 0, sizeof(tot));
@@ -2005,15 +2054,36 @@ int hb200_ccmc_spawn(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, i
     int herr[2] = {0, 0};
     CK(cudaMemcpyAsync(herr, e->d_err, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    for (int d = 0; d < p.nprocs; ++d)
+    long long nspawn_events = 0;                 // calc_events_spawn_t: counted before redistribute_particles
+    for (int d = 0; d < p.nprocs; ++d) {
         if ((long long)e->h_head[d] > e->block_size) e->h_head[d] = (unsigned long long)e->block_size;
+        nspawn_events += (long long)e->h_head[d];
+    }
+    if (p.nprocs > 1 && n > 0) {
+        DISPATCH_W(e, k_ccmc_redistribute<WW><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e->sys, p, e->d_states[c], e->d_pops[c], n,
+                                                                                          e->d_spawn[0], e->d_head, e->block_size,
+                                                                                          e->d_proc_map, e->d_err));
+        CK(cudaGetLastError());
+        e->launches++;
+        CK(cudaMemcpyAsync(e->h_head.data(), e->d_head, sizeof(unsigned long long) * p.nprocs, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(herr, e->d_err, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (int d = 0; d < p.nprocs; ++d)
+            if ((long long)e->h_head[d] > e->block_size) e->h_head[d] = (unsigned long long)e->block_size;
+    }
     e->sp_cur = 0;
-    e->sp_blocked = false;
-    e->sp_n = (long long)e->h_head[0];
+    e->sp_blocked = p.nprocs > 1;
+    e->sp_n = (p.nprocs == 1) ? (long long)e->h_head[0] : 0;
     out->proj_energy = tot.pe; out->D0_population = tot.d0; out->D0_normalisation = a.D0_normalisation;
     out->nattempts = nattempts; out->nattempts_spawn = tot.nattempts_spawn; out->ndeath = tot.ndeath;
-    out->nspawn_events = e->sp_n; out->tot_abs_real_pop = a.tot_abs_real_pop;
+    out->nspawn_events = nspawn_events; out->tot_abs_real_pop = a.tot_abs_real_pop;
     out->spawn_error = herr[0]; out->psip_error = herr[1];
+    return 0;
+}
+
+int hb200_ccmc_set_hash_shift(hb200_engine* e, int32_t hash_shift, int32_t move_freq) {
+    e->ccmc_hash_shift = hash_shift;
+    e->ccmc_move_freq = move_freq;
     return 0;
 }
 
@@ -2036,6 +2106,7 @@ int hb200_ccmc_iterate(hb200_engine* e, int32_t ncycles, const hb200_iter_in* in
         out->nattempts_spawn += co.nattempts_spawn;
         out->nspawn_events = co.nspawn_events;
         out->ndeath = co.ndeath;
+        if (stage_comm(e)) return 1;
         if (stage_sort(e)) return 1;
         if (stage_annihilate_main(e, cycle, &cs)) return 1;
         // end_mc_cycle(nspawn_events, ndeath_nc = 0, real_factor, nattempts_spawn, rspawn)

@@ -155,9 +155,14 @@ int hb200_iterate(hb200_engine* e, int32_t ncycles, const hb200_iter_in* in, hb2
  * select_cluster (src/ccmc_selection.f90:93-392), do_ccmc_accumulation, spawner_ccmc and stochastic_ccmc_death
  * (src/ccmc_death_spawning.f90:11-441); spawned and killed excips enter the spawn list and are annihilated by the same
  * stages as FCIQMC.  ex_level = reference%ex_level (2 = CCSD, 3 = CCSDT); the engine must have been created with
- * trunc_level = ex_level.  Single rank only in this version. */
+ * trunc_level = ex_level. */
 int hb200_ccmc_spawn(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, int32_t ex_level, hb200_ccmc_out* out);
 int hb200_ccmc_iterate(hb200_engine* e, int32_t ncycles, const hb200_iter_in* in, int32_t ex_level, hb200_iter_out* out);
+/* spawn%hash_shift (number of CCMC cycles done: the engine adds one per cycle, src/ccmc.f90:540,625) and
+ * spawn%move_freq (ccmc_in%move_freq, default 5) of the time-varying owner rule (src/spawning.F90:812-836); call after
+ * a restart.  With nprocs > 1 every cycle ends with redistribute_particles (src/qmc_common.F90:505-595) through the
+ * same NCCL exchange as the spawned excips, and the reference population is broadcast from its owner (get_D0_info). */
+int hb200_ccmc_set_hash_shift(hb200_engine* e, int32_t hash_shift, int32_t move_freq);
 
 /* Stage-level entry points (same state machine as hb200_iterate, one stage per call). */
 /* do idet loop: decoder_ptr, set_parent_flag, update_proj_energy_ptr, decide_nattempts,

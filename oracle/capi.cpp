@@ -355,13 +355,18 @@ int orc_ccmc_stage_spawn(void* h, uint32_t cycle_id, double tau, double shift, d
     OracleCcmc* o = (OracleCcmc*)(Oracle*)h;
     o->tau = tau; o->shift = shift; o->est.proj_energy_old = proj_energy_old;
     RankState& r = o->ranks[0];
-    r.proj_energy = 0.0; r.D0_population = 0.0;
-    o->ccmc_cycle_rank(r, cycle_id);
+    for (auto& rr : o->ranks) { rr.proj_energy = 0.0; rr.D0_population = 0.0; }
+    o->ccmc_spawn_stage(cycle_id);
     out[0] = o->last.proj_energy; out[1] = o->last.D0_population; out[2] = o->last.D0_normalisation;
     out[3] = (double)o->last.nattempts; out[4] = (double)o->last.nattempts_spawn; out[5] = (double)o->last.nspawn_events;
     out[6] = (double)o->last.ndeath;
     return 0;
     ORC_CATCH(-1)
+}
+int orc_ccmc_get_hash_shift(void* h) { return ((OracleCcmc*)(Oracle*)h)->hash_shift; }
+void orc_ccmc_set_hash_shift(void* h, int shift, int move_freq) {
+    OracleCcmc* o = (OracleCcmc*)(Oracle*)h;
+    o->hash_shift = shift; o->move_freq = move_freq;
 }
 int64_t orc_spawn_count(void* h, int rank) {
     int64_t n = 0;

@@ -36,6 +36,7 @@ struct CcmcStats {   // what the device engine is compared against, per cycle
 
 struct OracleCcmc : Oracle {
     int move_freq = 5;                 // ccmc_in%move_freq (default)
+    int hash_shift = 0;                // spawn%hash_shift: +1 per cycle (src/ccmc.f90:540,625)
     int64_t nattempts_last = 0;
     std::vector<double> cumulative_abs_real_pops;
     CcmcStats last;
@@ -234,12 +235,33 @@ struct OracleCcmc : Oracle {
         return c[n - 1];
     }
 
+    // assign_particle_processor with spawn%hash_shift / spawn%move_freq (src/spawning.F90:770-838)
+    int owner_ccmc(const Det& f) const {
+        return assign_particle_processor(f, sys.nbasis, hash_seed, hash_shift, move_freq, in.nprocs, proc_map.data(), in.nslots);
+    }
+    // redistribute_particles (src/qmc_common.F90:505-595)
+    void redistribute_particles(RankState& r) {
+        const int64_t block_size = in.spawned_walker_length / in.nprocs;
+        double nsent = 0.0;
+        for (int64_t i = 0; i < r.nstates; ++i) {
+            const int pproc = owner_ccmc(r.states[i]);
+            if (pproc != r.iproc) {
+                if ((int64_t)r.send[pproc].size() + 1 > block_size) { r.spawn_error = true; }
+                else { SpawnElem e; e.f = r.states[i]; e.pop = r.pops[i]; e.flag = 0; r.send[pproc].push_back(e); }
+                nsent = nsent + std::fabs((double)r.pops[i]);
+                r.pops[i] = 0;
+            }
+        }
+        nsent = nsent / (double)pop_real_factor;
+        r.nparticles = r.nparticles - nsent;
+    }
+
     // add a particle to the spawn list of rank r through create_spawned_particle_truncated / create_spawned_particle
     // (src/spawning.F90:1074-1319) - same rule as the FCIQMC path of this oracle
     void add_spawn(RankState& r, const Det& fnew, int64_t nspawned) {
         if (in.ex_level >= 0 && sys.excitation_level(f0, fnew) > ref_ex_level) return;
         const int64_t block_size = in.spawned_walker_length / in.nprocs;
-        int dest = owner(fnew);
+        int dest = owner_ccmc(fnew);
         if ((int64_t)r.send[dest].size() + 1 > block_size) { r.spawn_error = true; return; }
         SpawnElem e;
         e.f = fnew; e.pop = nspawned; e.flag = 0;
@@ -247,22 +269,22 @@ struct OracleCcmc : Oracle {
     }
 
     // one MC cycle on one rank up to (not including) annihilation: src/ccmc.f90:625-857
-    void ccmc_cycle_rank(RankState& r, uint32_t cycle_id) {
+    // get_D0_info (src/ccmc_utils.F90:69-130) with the current hash_shift; the population is broadcast from D0_proc
+    void get_D0_info(int& D0_proc, int& D0_pos, double& D0_normalisation) const {
+        D0_proc = owner_ccmc(f0);
+        const RankState& r = ranks[D0_proc];
+        bool hit;
+        int pos;
+        binary_search(r.states, f0, 1, (int)r.nstates, sys.W, hit, pos);
+        if (!hit) throw std::runtime_error("find_D0: Cannot find reference!");
+        D0_pos = pos;
+        D0_normalisation = (double)r.pops[D0_pos - 1] / (double)pop_real_factor;
+    }
+    void ccmc_cycle_rank(RankState& r, uint32_t cycle_id, int D0_proc, int D0_pos_in, double D0_normalisation) {
         Rng& rng = *r.rng;
         rng.set_cycle(cycle_id);
-        // get_D0_info (src/ccmc_utils.F90:69-130)
-        const int D0_proc = owner(f0);
-        int D0_pos = -1, nD0_proc = 0;
-        double D0_normalisation = 0.0;
-        if (r.iproc == D0_proc) {
-            bool hit;
-            int pos;
-            binary_search(r.states, f0, 1, (int)r.nstates, sys.W, hit, pos);
-            if (!hit) throw std::runtime_error("find_D0: Cannot find reference!");
-            D0_pos = pos;
-            D0_normalisation = (double)r.pops[D0_pos - 1] / (double)pop_real_factor;
-            nD0_proc = 1;
-        }
+        const int nD0_proc = (r.iproc == D0_proc) ? 1 : 0;
+        const int D0_pos = nD0_proc ? D0_pos_in : -1;
         const int max_cluster_size = (int)std::min<int64_t>(std::min(sys.nel, ref_ex_level + 2), r.nstates - nD0_proc);
         // init_mc_cycle (src/qmc_common.F90:950-1017), ccmc branch
         for (auto& b : r.send) b.clear();
@@ -280,6 +302,7 @@ struct OracleCcmc : Oracle {
         Cluster cl;
         for (int64_t iattempt = 1; iattempt <= nstochastic_clusters; ++iattempt) {
             rng.begin(RNG_SPAWN, f0, sys.W, (uint32_t)iattempt);
+            rng.mix((uint64_t)r.iproc * 0x9E3779B97F4A7C15ull);
             select_cluster(rng, r, ref_ex_level, nstochastic_clusters, D0_normalisation, tot_abs_real_pop, min_cluster_size,
                            max_cluster_size, cdet, cl);
             if (!(cl.excitation_level <= ref_ex_level + 2)) continue;
@@ -341,7 +364,6 @@ struct OracleCcmc : Oracle {
         int ev = 0;
         for (auto& b : r.send) ev += (int)b.size();
         r.nspawn_events = ev;
-        nattempts_last = nattempts;
         last.nattempts = nattempts; last.nattempts_spawn = nattempts_spawn; last.nspawn_events = ev; last.ndeath = r.ndeath;
         last.proj_energy = proj_energy_cycle; last.D0_population = D0_population_cycle; last.D0_normalisation = D0_normalisation;
         // end_mc_cycle(nspawn_events, ndeath_nc = 0, real_factor, nattempts_spawn, rspawn)
@@ -349,9 +371,20 @@ struct OracleCcmc : Oracle {
     }
     static double invdiag() { return 1.0; }
 
+    // spawn/death stage of one cycle on every rank (src/ccmc.f90:625-857) incl. redistribute_particles (:868-869)
+    void ccmc_spawn_stage(uint32_t cycle_id) {
+        int D0_proc, D0_pos;
+        double D0_normalisation;
+        get_D0_info(D0_proc, D0_pos, D0_normalisation);
+        hash_shift = hash_shift + 1;
+        int64_t na = 0;
+        for (auto& r : ranks) { ccmc_cycle_rank(r, cycle_id, D0_proc, D0_pos, D0_normalisation); na += r.nattempts; }
+        nattempts_last = na;
+        if (in.nprocs > 1)
+            for (auto& r : ranks) redistribute_particles(r);
+    }
     void ccmc_cycle(uint32_t cycle_id) {
-        if (in.nprocs != 1) throw std::runtime_error("oracle ccmc: single rank only (redistribute_particles not restated)");
-        for (auto& r : ranks) ccmc_cycle_rank(r, cycle_id);
+        ccmc_spawn_stage(cycle_id);
         comm_spawn();
         for (auto& r : ranks) annihilate_rank(r);
     }

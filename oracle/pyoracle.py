@@ -344,6 +344,9 @@ class Oracle:
                 "ndeath"]
         return dict(zip(keys, out)), sd
 
+    def ccmc_hash_shift(self):
+        return int(self.L.orc_ccmc_get_hash_shift(self.h))
+
     def stage_annihilate(self):
         self._chk(self.L.orc_stage_annihilate(self.h))
 

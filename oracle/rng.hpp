@@ -37,6 +37,9 @@ struct Rng {
     virtual void begin(uint32_t purpose, const Det& f, int W, uint32_t attempt) = 0;
     virtual void set_cycle(uint32_t cycle) = 0;
     virtual double next() = 0;  // uniform in [0,1)
+    // Add a salt to the stream selector chosen by begin() (counter-based generators only): CCMC streams are keyed by
+    // (attempt, rank) instead of a determinant.
+    virtual void mix(uint64_t salt) { (void)salt; }
     uint64_t ndraws = 0;
 };
 
@@ -146,6 +149,12 @@ struct PhiloxRng : Rng {
         ctr[2] = (uint32_t)h;
         ctr[3] = (uint32_t)(h >> 32);
         draw = 0;
+    }
+    void mix(uint64_t salt) override {
+        uint64_t h = ((uint64_t)ctr[3] << 32) | ctr[2];
+        h += salt;
+        ctr[2] = (uint32_t)h;
+        ctr[3] = (uint32_t)(h >> 32);
     }
     double next() override {
         if ((draw & 1u) == 0) {

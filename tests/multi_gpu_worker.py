@@ -10,6 +10,67 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def main_ccmc():
+    """argv: ccmc <system> <generator> <real> <ex_level> <tau>: multi-rank CCMC (time-varying hash owner,
+    redistribute_particles, D0 broadcast) against the oracle's emulated ranks."""
+    import torch
+    import torch.distributed as dist
+    from hande_b200 import read_in as R
+    from hande_b200.engine import Engine
+    from hande_b200.fciqmc import TorchDist
+    from oracle.pyoracle import Oracle
+    from tests.common import system_path
+
+    name, gen, real, exl, tau = sys.argv[2], sys.argv[3], bool(int(sys.argv[4])), int(sys.argv[5]), float(sys.argv[6])
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    comm = TorchDist(device=dev)
+    if rank == 0:
+        system_path(name)
+    dist.barrier()
+    path, kw = system_path(name)
+    s = R.read_in(path, **kw)
+    o = Oracle()
+    o.read_fcidump(path, **kw)
+    o.set_qmc(tau=tau, seed=11, excit_gen=gen, rng_kind=1, real_amplitudes=int(real), spawn_cutoff=0.01, ex_level=exl,
+              D0_population=300, walker_length=1 << 17, spawned_walker_length=1 << 16, nprocs=world)
+    o.init()
+    ref = o.reference()
+    eng = Engine(s, excit_gen=gen, pattempt_single=ref["pattempt_single"], pattempt_double=ref["pattempt_double"],
+                 real_amplitudes=real, spawn_cutoff=0.01, trunc_level=exl, walker_length=1 << 17,
+                 spawned_walker_length=1 << 16, seed=11, nprocs=world, iproc=rank, device=local)
+    eng.set_reference(ref["f0"], ref["H00"])
+    uid = eng.get_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)
+    eng.comm_init(comm.broadcast_bytes(uid, src=0))
+    # warm-up on the oracle (all ranks emulated) to get a spread-out excip list, then hand each GPU its rank's share
+    pe_old = 0.0
+    warm = 40
+    for c in range(1, warm + 1):
+        st, _ = o.ccmc_stage_spawn(c, tau, 0.0, pe_old)
+        o.stage_annihilate()
+    f, pops, dat = o.get_psips(rank)
+    eng.upload_psips(f, pops, dat)
+    eng.ccmc_set_hash_shift(o.ccmc_hash_shift(), 5)
+    ntot = 0
+    for c in range(warm + 1, warm + 9):
+        o.ccmc_stage_spawn(c, tau, -0.01, -0.1)
+        o.stage_annihilate()
+        rg = eng.ccmc_iterate(1, tau, -0.01, -0.1, c, exl)
+        assert rg["spawn_error"] == 0 and rg["psip_error"] == 0
+        fo, po, do_ = o.get_psips(rank)
+        fg, pg, dg = eng.download_psips()
+        assert len(fg) == len(fo), (rank, c, len(fg), len(fo))
+        assert (fg == fo).all() and (pg == po).all() and (dg == do_).all(), (rank, c)
+        ntot = comm.allreduce_sum(np.array([float(len(fg))]))[0]
+    assert ntot > 50
+    print(f"rank {rank}: OK {len(fg)} states of {int(ntot)}", flush=True)
+    eng.close()
+    dist.destroy_process_group()
+
+
 def main():
     import torch
     import torch.distributed as dist
@@ -71,4 +132,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if sys.argv[1] == "ccmc":
+        main_ccmc()
+    else:
+        main()

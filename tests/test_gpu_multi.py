@@ -29,3 +29,19 @@ def test_two_rank_parity(name, gen, real, init, tau):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert res.stdout.count("OK") == nproc
+
+
+@pytest.mark.parametrize("name,gen,real,exl,tau", [("ne_vdz", "renorm", 0, 2, 0.01), ("s12", "renorm", 1, 3, 0.001)])
+def test_multi_rank_ccmc_parity(name, gen, real, exl, tau):
+    """CCMC on 2 (or 4) GPUs: time-varying hash owner, redistribute_particles and the reference broadcast against the
+    oracle's emulated ranks (which reproduce the reference's np2 CCMC golden table)."""
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    nproc = 4 if n >= 4 else 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", "29535", os.path.join(ROOT, "tests", "multi_gpu_worker.py"),
+           "ccmc", name, gen, str(real), str(exl), str(tau)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.stdout.count("OK") == nproc

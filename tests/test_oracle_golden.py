@@ -100,6 +100,12 @@ def test_ccmc_ccsd_ne_np1(fcidump_path):
     assert abs(ref["H00"] - (-128.48877555)) < 5e-9 and abs(ref["pattempt_single"] - 0.04511278) < 5e-9
 
 
+def test_ccmc_ccsd_h2o_np2(fcidump_path):
+    # two ranks: time-varying hash owner (hash_shift / move_freq), redistribute_particles, per-rank dSFMT streams;
+    # the complete 176-row table was verified with tools/golden_compare.py ccmc_h2o_np2
+    _run("ccmc_h2o_np2", fcidump_path, 45)
+
+
 def test_dsfmt_and_murmur_known_answers():
     # seed 7 -> first close-open double 0.73384649635214716; MurmurHash2(0xFF, 4 bytes, seed 7) = -1594541972
     pyoracle.use_ref_lib()

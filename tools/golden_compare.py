@@ -56,6 +56,11 @@ CASES = {
                     int_file="INTDUMP", sys=dict(nel=10, ms=0, sym=0), ccmc=True,
                     qmc=dict(tau=0.01, seed=5691, D0_population=10, ncycles=10, nreport=450, target_particles=20000,
                              walker_length=3571428, spawned_walker_length=1562500, ex_level=2)),
+    "ccmc_h2o_np2": dict(dir="ccmc/np2/H2O-cc-pVDZ_ccsdmc", bench="benchmark.out.9712b5a3.inp=ccmc.in",
+                         int_file="INTDUMP", sys=dict(nel=10, ms=0, sym=0), ccmc=True,
+                         qmc=dict(tau=0.01, seed=1660032958, D0_population=500, ncycles=10, nreport=175,
+                                  target_particles=50000, walker_length=3571428 // 1, spawned_walker_length=1562500,
+                                  ex_level=2, nprocs=2)),
 }
 
 ROW_CCMC = re.compile(r"^\s*#?\s+(\d+)\s+(-?\d\.\d+E[+-]\d+)\s+(-?\d\.\d+E[+-]\d+)\s+(-?\d\.\d+E[+-]\d+)\s+"

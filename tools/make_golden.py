@@ -18,7 +18,7 @@ from tools.golden_compare import CASES, TS, parse_table  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 FCIDUMP_NAME = {"h2o": "h2o", "ne_init": "ne", "ne_ci6_np2": "ne", "ne_ci6_np4": "ne", "ne_ci6_real64_np2": "ne",
-                "ccmc_ne": "ne_vdz"}
+                "ccmc_ne": "ne_vdz", "ccmc_h2o_np2": "h2o_vdz"}
 
 os.makedirs(os.path.join(OUT, "fcidump"), exist_ok=True)
 for name, c in CASES.items():

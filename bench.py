@@ -88,12 +88,19 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+UEG = dict(electrons=14, ms=0, rs=1.0, cutoff=2.5)   # --system ueg: 14 electrons, 57 plane waves (114 spin-orbitals)
+
+
 def oracle_cpu_run(path, n_sample, ncycles, tau, nthreads, seed=1, excit_gen="heat_bath"):
     """Time the oracle (CPU restatement of the reference path) on a bounded sample of the workload."""
     from hande_b200 import synthetic
     from oracle.pyoracle import Oracle
     o = Oracle()
-    o.read_fcidump(path)
+    if path is None:
+        o.init_ueg(UEG["electrons"], UEG["ms"], UEG["rs"], UEG["cutoff"])
+        excit_gen = "no_renorm"
+    else:
+        o.read_fcidump(path)
     o.set_qmc(tau=tau, seed=7, excit_gen=excit_gen, rng_kind=1, real_amplitudes=1, initiator_approx=1,
               literal_event_int32=0, walker_length=4 * n_sample, spawned_walker_length=2 * n_sample)
     t0 = time.time()
@@ -151,6 +158,9 @@ def main():
     ap.add_argument("--tau", type=float, default=0.0, help="0 => calibrate for R_spawn ~ 0.05")
     ap.add_argument("--excit-gen", default="heat_bath", choices=["heat_bath", "heat_bath_uniform", "renorm", "no_renorm"],
                     help="excitation generator (headline = heat_bath, BASELINE.json configs[1]; others are side measurements)")
+    ap.add_argument("--system", default="s50", choices=["s50", "ueg"],
+                    help="s50 = BASELINE configs[1] (headline); ueg = side measurement on the 3D UEG (14 electrons, "
+                         "114 plane-wave spin-orbitals: the largest basis of BASELINE configs[3] this version's W <= 4 holds)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -182,17 +192,24 @@ def main():
         comm = _SingleProcess()
 
     t_setup = time.time()
-    if rank == 0:
-        s, path = s50_system()
-    if world > 1:
-        torch.distributed.barrier()
-    if rank != 0:
-        s, path = s50_system()
+    if args.system == "ueg":
+        from hande_b200.ueg import UegSystem
+        s, path = UegSystem(**UEG), None
+        args.excit_gen = "no_renorm"
+        occ0 = s.aufbau_reference()
+        ps, pd = 0.0, 1.0
+    else:
+        if rank == 0:
+            s, path = s50_system()
+        if world > 1:
+            torch.distributed.barrier()
+        if rank != 0:
+            s, path = s50_system()
+        occ0 = R.set_reference_det(s)
+        ps, pd = R.find_single_double_prob(s, occ0)
     n = int(args.walkers)
-    occ0 = R.set_reference_det(s)
     f0 = s.encode(occ0)
     H00 = s.slater_condon0(occ0)
-    ps, pd = R.find_single_double_prob(s, occ0)
     wl = int(n * 1.25) + 4096
     sl = max(int(n * 0.30), 1 << 16) * 1
     eng = Engine(s, excit_gen=args.excit_gen, pattempt_single=ps, pattempt_double=pd, real_amplitudes=True,
@@ -296,13 +313,18 @@ def main():
     e2e = None
     if not args.no_e2e:
         nst = max(3, min(args.steps, 5))
+        ptrs = (h_states.data_ptr(), h_pops.data_ptr(), h_dat.data_ptr(), n)
         upload(); eng.iterate(1, tau, shift, pe_old, cyc); cyc += 1
+        upload()
         barrier()
         t0 = time.perf_counter()
         wi = 0.0
         for _ in range(nst):
-            upload()
+            # the host's copy of the NEXT list streams to the device (second stream, third buffer) while the current
+            # one propagates; every timed step contains one full list upload, one hb200_iterate and the result structs
+            eng.upload_psips_begin_ptr(*ptrs)
             o2 = eng.iterate(1, tau, shift, pe_old, cyc); cyc += 1
+            eng.upload_psips_commit()
             wi += o2["walker_iterations"]
         barrier()
         dt = time.perf_counter() - t0
@@ -310,7 +332,8 @@ def main():
         dt_max = float(np.max(comm.allreduce_sum(np.eye(world)[rank] * dt))) if world > 1 else dt
         e2e = {"value": wi_all / dt_max, "unit": "walker-iterations/s", "h2d_bytes_per_step": int(n * Em + 32),
                "d2h_bytes_per_step": 96 + 8 * 12, "steps": nst,
-               "note": "hb200_upload_psips from pinned host memory + hb200_iterate(1) + result structs, per step"}
+               "note": "per step: hb200_upload_psips_begin (full walker list from pinned host memory, overlapped with the "
+                       "propagation of the resident list) + hb200_iterate(1) + hb200_upload_psips_commit + result structs"}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -318,7 +341,7 @@ def main():
         ns_cpu = 20000
         r, t_init = oracle_cpu_run(path, ns_cpu, 2, tau, cores, excit_gen=args.excit_gen)
         cpu = {"value": r["walker_iters"] / r["seconds"], "unit": "walker-iterations/s", "cores": cores, "kind": "port",
-               "sample": f"{cores} replicas x {ns_cpu} walkers x 2 cycles of the same S50 {args.excit_gen} workload "
+               "sample": f"{cores} replicas x {ns_cpu} walkers x 2 cycles of the same {args.system} {args.excit_gen} workload "
                          f"(oracle restatement; {r['seconds']:.1f}s timed, table init {t_init:.1f}s untimed)"}
 
     if rank == 0:
@@ -326,8 +349,9 @@ def main():
             "metric": "walker-iterations/s (FCIQMC MC cycles x walkers)", "value": value, "unit": "walker-iterations/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tmax / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64+f64", "data": "synthetic",
-            "config": {"workload": "S50 synthetic FCIDUMP (50 orb / 20 el, C1, 8-fold), real-valued iFCIQMC, "
-                                   f"{args.excit_gen}, {n:.3g} unit walkers per GPU (distribution A)",
+            "config": {"workload": ("S50 synthetic FCIDUMP (50 orb / 20 el, C1, 8-fold)" if args.system == "s50" else
+                                    "3D UEG (14 electrons, rs = 1, 114 plane-wave spin-orbitals)") +
+                                   f", real-valued iFCIQMC, {args.excit_gen}, {n:.3g} unit walkers per GPU (distribution A)",
                        "tau": tau, "R_spawn": float(P) / max(A, 1.0), "walkers_per_gpu": n, "nstates": int(S),
                        "l2": "inputs (3.2 GB walker list) larger than L2; no flush needed",
                        "sharding": "hash-owner (MurmurHash2) + NCCL all-to-all" if world > 1 else "single rank"},

@@ -1325,10 +1325,15 @@ struct hb200_engine {
     std::vector<void*> owned;
     int* d_proc_map = nullptr;
     // main list (double buffered)
-    uint64_t* d_states[2] = {nullptr, nullptr};
-    int64_t* d_pops[2] = {nullptr, nullptr};
-    double* d_dat[2] = {nullptr, nullptr};
-    int cur = 0;
+    // buffers 0/1: current list and the merge output (swapped every cycle); buffer 2 (allocated on first use): staging
+    // area of the asynchronous upload, rotated in by hb200_upload_psips_commit
+    uint64_t* d_states[3] = {nullptr, nullptr, nullptr};
+    int64_t* d_pops[3] = {nullptr, nullptr, nullptr};
+    double* d_dat[3] = {nullptr, nullptr, nullptr};
+    int cur = 0, alt = 1, stg = 2;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_done = nullptr;
+    long long stg_n = -1;
     long long nstates = 0;
     long long nparticles_enc = 0;  // sum |pop| (encoded) of the current list
     // spawn store
@@ -1510,6 +1515,8 @@ void hb200_destroy(hb200_engine* e) {
     cudaSetDevice(e->cfg.device);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     for (void* q : e->owned) cudaFree(q);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->copy_done) cudaEventDestroy(e->copy_done);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -1679,6 +1686,52 @@ int hb200_upload_psips(hb200_engine* e, const uint64_t* states, const int64_t* p
         CK(cudaMemcpyAsync(&s, e->d_ll, sizeof(long long), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
     }
+    e->nstates = n;
+    e->nparticles_enc = s;
+    return 0;
+}
+
+// Asynchronous variant for hosts that keep particle_t on the CPU: the copy of the NEXT list runs on a second stream
+// into a third buffer while hb200_iterate works on the current one; hb200_upload_psips_commit makes it current.
+int hb200_upload_psips_begin(hb200_engine* e, const uint64_t* states, const int64_t* pops, const double* dat, int64_t n) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (n > e->cfg.walker_length) FAIL("upload_psips_begin: more states than walker_length");
+    if (!e->copy_stream) {
+        const size_t cap = (size_t)e->cfg.walker_length;
+        if (dalloc(e, &e->d_states[2], cap * e->W)) return 1;
+        if (dalloc(e, &e->d_pops[2], cap)) return 1;
+        if (dalloc(e, &e->d_dat[2], cap)) return 1;
+        CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&e->copy_done, cudaEventDisableTiming));
+    }
+    const int g = e->stg;
+    if (n) {
+        CK(cudaMemcpyAsync(e->d_states[g], states, (size_t)n * e->W * 8, cudaMemcpyHostToDevice, e->copy_stream));
+        CK(cudaMemcpyAsync(e->d_pops[g], pops, (size_t)n * 8, cudaMemcpyHostToDevice, e->copy_stream));
+        CK(cudaMemcpyAsync(e->d_dat[g], dat, (size_t)n * 8, cudaMemcpyHostToDevice, e->copy_stream));
+    }
+    CK(cudaEventRecord(e->copy_done, e->copy_stream));
+    e->stg_n = n;
+    return 0;
+}
+int hb200_upload_psips_commit(hb200_engine* e) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (e->stg_n < 0) FAIL("upload_psips_commit: no upload in flight");
+    cudaStream_t st = e->stream;
+    CK(cudaStreamWaitEvent(st, e->copy_done, 0));
+    const long long n = e->stg_n;
+    const int g = e->stg;
+    e->stg = e->cur; e->cur = g; e->stg_n = -1;
+    long long s = 0;
+    CK(cudaMemsetAsync(e->d_err, 0, 4 * sizeof(int), st));
+    if (n) {
+        const int nb = (int)std::min<long long>(1184, (n + TILE - 1) / TILE);
+        k_abs_sum<<<nb, TILE, 0, st>>>(e->d_pops[g], n, e->d_part_ll);
+        k_reduce_ll<<<1, 1024, 0, st>>>(e->d_part_ll, nb, e->d_ll);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&s, e->d_ll, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
     e->nstates = n;
     e->nparticles_enc = s;
     return 0;
@@ -1871,7 +1924,7 @@ static int stage_annihilate_main(hb200_engine* e, uint32_t cycle, CycleStats* hs
     p.cycle = cycle;
     cudaStream_t st = e->stream;
     const long long n = e->sp_n, ns = e->nstates;
-    const int c = e->cur, o = c ^ 1;
+    const int c = e->cur, o = e->alt;
     int64_t* sp = e->d_spawn[e->sp_cur];
     int64_t* ins = e->d_spawn[e->sp_cur ^ 1];
     int h_tot[2] = {0, 0};
@@ -1920,6 +1973,7 @@ static int stage_annihilate_main(hb200_engine* e, uint32_t cycle, CycleStats* hs
     CK(cudaMemcpyAsync(&npart, e->d_ll, sizeof(long long), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     e->cur = o;
+    e->alt = c;
     e->nstates = nkept + nins;
     e->nparticles_enc = npart;
     hst->nkept = nkept;

@@ -121,6 +121,8 @@ def load_library():
     L.hb200_set_reference.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
     L.hb200_set_proc_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
     L.hb200_upload_psips.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    L.hb200_upload_psips_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    L.hb200_upload_psips_commit.argtypes = [C.c_void_p]
     L.hb200_download_psips.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     L.hb200_nstates.restype = C.c_int64
     L.hb200_nstates.argtypes = [C.c_void_p]
@@ -148,6 +150,7 @@ ABI_SYMBOLS = [
     "hb200_last_error", "hb200_create", "hb200_destroy", "hb200_set_system_read_in", "hb200_set_system_ueg",
     "hb200_build_heat_bath",
     "hb200_download_heat_bath", "hb200_set_reference", "hb200_set_proc_map", "hb200_upload_psips",
+    "hb200_upload_psips_begin", "hb200_upload_psips_commit",
     "hb200_download_psips", "hb200_nstates", "hb200_iterate", "hb200_spawn_death", "hb200_comm_spawn",
     "hb200_ccmc_spawn", "hb200_ccmc_iterate", "hb200_ccmc_set_hash_shift", "hb200_annihilate_spawn", "hb200_annihilate_main", "hb200_download_spawn", "hb200_upload_spawn",
     "hb200_sc0_batch", "hb200_gen_excit_batch", "hb200_get_unique_id", "hb200_comm_init", "hb200_last_timing",
@@ -246,6 +249,14 @@ class Engine:
     def upload_psips_ptr(self, states_ptr, pops_ptr, dat_ptr, n):
         """hb200_upload_psips from caller-owned (e.g. pinned) host buffers given as integer addresses."""
         self._chk(self.L.hb200_upload_psips(self.h, C.c_void_p(states_ptr), C.c_void_p(pops_ptr), C.c_void_p(dat_ptr), n))
+
+    def upload_psips_begin_ptr(self, states_ptr, pops_ptr, dat_ptr, n):
+        """Start the asynchronous upload of the next list (pinned host buffers) while the current one propagates."""
+        self._chk(self.L.hb200_upload_psips_begin(self.h, C.c_void_p(states_ptr), C.c_void_p(pops_ptr),
+                                                  C.c_void_p(dat_ptr), n))
+
+    def upload_psips_commit(self):
+        self._chk(self.L.hb200_upload_psips_commit(self.h))
 
     def download_psips_ptr(self, states_ptr, pops_ptr, dat_ptr, capacity):
         nn = C.c_int64(0)

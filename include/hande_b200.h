@@ -144,6 +144,11 @@ int hb200_set_proc_map(hb200_engine* e, const int32_t* map, int32_t n);
 /* particle_t upload/download: states(W,N), pops(1,N), dat(1,N), sorted ascending
  * (src/qmc_data.f90:615-682); used at init, restart read/write (src/restart_hdf5.F90:307,539). */
 int hb200_upload_psips(hb200_engine* e, const uint64_t* states, const int64_t* pops, const double* dat, int64_t nstates);
+/* The same upload split in two so that it overlaps the propagation of the list that is already resident (for hosts
+ * that keep particle_t on the CPU and push a list every report loop): _begin starts the host-to-device copy on a
+ * second stream into a staging buffer and returns; _commit waits for it and makes that list the current one. */
+int hb200_upload_psips_begin(hb200_engine* e, const uint64_t* states, const int64_t* pops, const double* dat, int64_t nstates);
+int hb200_upload_psips_commit(hb200_engine* e);
 int hb200_download_psips(hb200_engine* e, uint64_t* states, int64_t* pops, double* dat, int64_t capacity, int64_t* nstates);
 int64_t hb200_nstates(hb200_engine* e);
 

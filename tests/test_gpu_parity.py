@@ -188,3 +188,26 @@ def test_edge_cases_empty_and_overflow():
     assert out["spawn_error"] == 1
     assert out["nstates"] <= 64
     eng.close()
+
+
+def test_async_upload_begin_commit():
+    """hb200_upload_psips_begin/_commit: a list uploaded on the copy stream while another one propagates becomes the
+    current list at commit and then evolves exactly like a synchronously uploaded one."""
+    s, o, eng, ref = make_pair("h2o", tau=0.003)
+    fa, pa, da = random_population(s, o, 2000, False, seed=5)
+    fb, pb, db = random_population(s, o, 1500, False, seed=8)
+    eng.upload_psips(fa, pa, da)
+    keep = [np.ascontiguousarray(fb), np.ascontiguousarray(pb), np.ascontiguousarray(db)]
+    eng.upload_psips_begin_ptr(keep[0].ctypes.data, keep[1].ctypes.data, keep[2].ctypes.data, len(pb))
+    eng.iterate(2, 0.003, 0.0, 0.0, 1)          # list A propagates while B is in flight
+    eng.upload_psips_commit()
+    f1, p1, d1 = eng.download_psips()
+    assert (f1 == fb).all() and (p1 == pb).all() and (d1 == db).all()
+    out_async = eng.iterate(3, 0.003, 0.0, -0.1, 11)
+    g1 = eng.download_psips()
+    eng.upload_psips(fb, pb, db)
+    out_sync = eng.iterate(3, 0.003, 0.0, -0.1, 11)
+    g2 = eng.download_psips()
+    assert all((x == y).all() for x, y in zip(g1, g2))
+    assert out_async["nparticles"] == out_sync["nparticles"] and out_async["proj_energy"] == out_sync["proj_energy"]
+    eng.close()

@@ -174,16 +174,16 @@ constexpr int SINGLES_CHUNK = 64;  // single excitations whose pgen terms are st
 // phase-A staging area (column i of hb_ij_w at the occupied orbitals, [q][thread]) shares its storage with the buffers
 // that are only live in the later phases.
 struct SpawnSmem {
-    size_t sf, shash, spop, sscan, swarp, sred, siw, sw, sh1, shm, ssp, spsum, sterm, sok, sq, scnt, sflag, slo, sperm, ssq,
+    size_t sf, shash, ssign, sscan, swarp, sred, siw, sw, sh1, shm, ssp, spsum, sterm, sok, sq, scnt, sflag, slo, sperm, ssq,
         ssi, socc, ssu, total;
     // heat_bath: the original heat-bath generator (phase buffers); hb_stage: any generator that selects i, j from the
     // heat-bath weights (needs the hb_i_w copy and the per-thread staging area of nel doubles)
     __host__ __device__ SpawnSmem(int W, int nel, int nsu, int nb, bool heat_bath, bool hb_stage) {
         size_t o = 0;
         sf = o;     o += (size_t)TILE * W * 8;
-        shash = o;  o += (size_t)TILE * 8;
-        spop = o;   o += (size_t)TILE * 8;
         sred = o;   o += 40 * 8;
+        shash = o;  o += hb_stage ? 0 : (size_t)TILE * 8;         // stream selector per state (recomputed per attempt when
+                                                                   // shared memory is scarce: it also buys L1 capacity)
         siw = o;    o += hb_stage ? (size_t)nb * 8 : 0;           // copy of hb_i_w
         // ---- union: phase A staging | phase B..F buffers
         const size_t u0 = o;
@@ -195,15 +195,17 @@ struct SpawnSmem {
         spsum = v;  v += heat_bath ? (size_t)TILE * 8 : 0;        // singles: sum of pgen terms
         sterm = v;  v += heat_bath ? (size_t)SINGLES_CHUNK * nel * 8 : 0;  // singles: pgen terms of one chunk
         sok = v;    v += heat_bath ? (size_t)SINGLES_CHUNK * nel : 0;
+        v = (v + 3) & ~(size_t)3;
+        sq = v;     v += heat_bath ? (size_t)4 * TILE * 4 : 0;    // request queues: [TILE] phase B, [3*TILE] phase D
         const size_t stage = hb_stage ? (size_t)TILE * nel * 8 : 0;
         o = u0 + (stage > (v - u0) ? stage : (v - u0));
         o = (o + 7) & ~(size_t)7;
         // ---- end of union
         sscan = o;  o += (size_t)(TILE + 1) * 4;
         swarp = o;  o += 8 * 4;
-        sq = o;     o += heat_bath ? (size_t)4 * TILE * 4 : 0;    // request queues: [TILE] phase B, [3*TILE] phase D
         scnt = o;   o += 4 * 4;                                    // queue counters
         sflag = o;  o += TILE;
+        ssign = o;  o += TILE;                                     // sign of the parent population (attempt_to_spawn)
         slo = o;    o += heat_bath ? TILE : 0;                     // tile-state index of each attempt slot
         sperm = o;  o += heat_bath ? TILE : 0;
         ssq = o;    o += heat_bath ? TILE : 0;                     // queue of single-excitation slots
@@ -243,8 +245,8 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
     const int nsu = (GEN == EXCIT_GEN_RENORM || GEN == EXCIT_GEN_HEAT_BATH_UNIFORM) ? 2 * s.nsym_tot : 0;
     const SpawnSmem L(W, nel, nsu, s.nbasis, heat_bath, hb_stage);
     uint64_t* sf = reinterpret_cast<uint64_t*>(smem_raw + L.sf);
+    uint8_t* ssign = smem_raw + L.ssign;
     uint64_t* shash = reinterpret_cast<uint64_t*>(smem_raw + L.shash);
-    int64_t* spop = reinterpret_cast<int64_t*>(smem_raw + L.spop);
     double* sred = reinterpret_cast<double*>(smem_raw + L.sred);
     double* sh1 = reinterpret_cast<double*>(smem_raw + L.sh1);
     double* shm = reinterpret_cast<double*>(smem_raw + L.shm);
@@ -284,12 +286,12 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
         const double Kii = dat[idx];
 #pragma unroll
         for (int k = 0; k < W; ++k) sf[tid * W + k] = f[k];
-        spop[tid] = pop;
+        ssign[tid] = pop < 0;
         uint8_t* occ = socc + tid * nel;
         decode_det<W>(f, occ);
         if (nsu) build_symunocc_masks<W>(s, f, ssu + tid * nsu);
         const uint64_t h = det_hash64<W>(f);
-        shash[tid] = h;
+        if (!hb_stage) shash[tid] = h;
         const double real_pop = (double)pop / (double)p.real_factor;
         // set_parent_flag (src/ifciqmc.f90:13-57)
         sflag[tid] = (fabs(real_pop) > p.initiator_pop) ? 0 : 1;
@@ -329,7 +331,7 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
 #pragma unroll
         for (int k = 0; k < W; ++k) f[k] = sf[lo * W + k];
         PhiloxStream rng;
-        rng.begin(p.seed, p.cycle, RNG_SPAWN, shash[lo], (uint32_t)att);
+        rng.begin(p.seed, p.cycle, RNG_SPAWN, hb_stage ? det_hash64<W>(f) : shash[lo], (uint32_t)att);
         if (!hb_stage) rng.prefetch();   // uniform generators draw inside divergent rejection loops
         Gen g;
         if (heat_bath) {
@@ -338,8 +340,9 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
             __syncthreads();
             HbState st;
             st.allowed = false; st.need_ia = false; st.dbl = true; st.need_k = 0;
+            if (active) hb_phase_a<W>(rng, s, f, socc + lo * nel, st, siw, sw + tid, TILE);
+            __syncthreads();   // the request queues share their storage with the phase-A staging area
             if (active) {
-                hb_phase_a<W>(rng, s, f, socc + lo * nel, st, siw, sw + tid, TILE);
                 slo[tid] = (uint8_t)lo;
                 if (st.allowed && st.need_ia) {
                     const int q = atomicAdd(&scnt[0], 1);
@@ -442,7 +445,7 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
         uint64_t child[W];
         int dest = 0, pflag = 0;
         if (active) {
-            nspawn = attempt_to_spawn(rng, p, g.hmatel, g.pgen, spop[lo]);
+            nspawn = attempt_to_spawn(rng, p, g.hmatel, g.pgen, ssign[lo] ? (int64_t)-1 : (int64_t)1);
             if (nspawn != 0) {
                 make_child<W>(f, g, child);
                 // create_spawned_particle[_initiator]_truncated (src/spawning.F90:1186-1319)

@@ -30,6 +30,14 @@
 #endif
 #define HB_MAXNEL 64
 
+// Streaming (evict-first) loads for data with no reuse on the SM - the 2 GB heat-bath row tables and the walker list -
+// so that they do not displace the small reused tables (hb_ij_w, single-excitation rows) from L1.
+#if defined(__CUDA_ARCH__)
+#define HB_LDCS(p) __ldcs(p)
+#else
+#define HB_LDCS(p) (*(p))
+#endif
+
 namespace hb {
 
 struct alignas(16) D2 { double x, y; };
@@ -722,8 +730,8 @@ HB_HD int select_precalc(R& rng, int N, const double* aliasU, const int* aliasK)
     double x = rng.next() * N;
     int K = (int)floor(x);
     x = x - K;
-    if (x < aliasU[K]) return K + 1;
-    return aliasK[K];
+    if (x < HB_LDCS(aliasU + K)) return K + 1;
+    return HB_LDCS(aliasK + K);
 }
 template <class R>
 HB_HDN int select_weighted_value(R& rng, int N, const double* weights, double totweight) {
@@ -986,13 +994,13 @@ HB_HDN void hb_phase_f(const Sys& s, const uint64_t* f, const HbState& st, const
             }
         }
         double pgen_ija = ((pi_) * (pij)) * (s.hb_ija_w[HB_I3(a, j, i)] / s.hb_ija_tot[HB_I2(j, i)]) *
-                          (1.0 - st.psingle) * (s.hb_ijab_w[HB_I4(b, a, j, i)] / s.hb_ijab_tot[HB_I3(a, j, i)]);
+                          (1.0 - st.psingle) * (HB_LDCS(s.hb_ijab_w + HB_I4(b, a, j, i)) / s.hb_ijab_tot[HB_I3(a, j, i)]);
         double pgen_ijb = ((pi_) * (pij)) * (s.hb_ija_w[HB_I3(b, j, i)] / s.hb_ija_tot[HB_I2(j, i)]) *
-                          (1.0 - ps[0]) * (s.hb_ijab_w[HB_I4(a, b, j, i)] / s.hb_ijab_tot[HB_I3(b, j, i)]);
+                          (1.0 - ps[0]) * (HB_LDCS(s.hb_ijab_w + HB_I4(a, b, j, i)) / s.hb_ijab_tot[HB_I3(b, j, i)]);
         double pgen_jia = ((pj_) * (pji)) * (s.hb_ija_w[HB_I3(a, i, j)] / s.hb_ija_tot[HB_I2(i, j)]) *
-                          (1.0 - ps[1]) * (s.hb_ijab_w[HB_I4(b, a, i, j)] / s.hb_ijab_tot[HB_I3(a, i, j)]);
+                          (1.0 - ps[1]) * (HB_LDCS(s.hb_ijab_w + HB_I4(b, a, i, j)) / s.hb_ijab_tot[HB_I3(a, i, j)]);
         double pgen_jib = ((pj_) * (pji)) * (s.hb_ija_w[HB_I3(b, i, j)] / s.hb_ija_tot[HB_I2(i, j)]) *
-                          (1.0 - ps[2]) * (s.hb_ijab_w[HB_I4(a, b, i, j)] / s.hb_ijab_tot[HB_I3(b, i, j)]);
+                          (1.0 - ps[2]) * (HB_LDCS(s.hb_ijab_w + HB_I4(a, b, i, j)) / s.hb_ijab_tot[HB_I3(b, i, j)]);
         g.pgen = pgen_ija + pgen_ijb + pgen_jia + pgen_jib;
         g.from1 = (i < j) ? i : j; g.from2 = (i < j) ? j : i;
         g.to1 = (a < b) ? a : b; g.to2 = (a < b) ? b : a;
@@ -1087,9 +1095,9 @@ HB_HDN void gen_excit_heat_bath_uniform(R& rng, const Sys& s, const Params& p, c
         g.hmatel = slater_condon2_excit(s, i, j, g.to1, g.to2, g.perm);
         g.pgen = (1.0 - p.pattempt_single) * pgen *
                  (((s.hb_ija_w[HB_I3(a, j, i)] / s.hb_ija_tot[HB_I2(j, i)]) *
-                   (s.hb_ijab_w[HB_I4(b, a, j, i)] / s.hb_ijab_tot[HB_I3(a, j, i)])) +
+                   (HB_LDCS(s.hb_ijab_w + HB_I4(b, a, j, i)) / s.hb_ijab_tot[HB_I3(a, j, i)])) +
                   ((s.hb_ija_w[HB_I3(b, j, i)] / s.hb_ija_tot[HB_I2(j, i)]) *
-                   (s.hb_ijab_w[HB_I4(a, b, j, i)] / s.hb_ijab_tot[HB_I3(b, j, i)])));
+                   (HB_LDCS(s.hb_ijab_w + HB_I4(a, b, j, i)) / s.hb_ijab_tot[HB_I3(b, j, i)])));
     } else {
         g.hmatel = 0.0; g.pgen = 1.0;
     }

@@ -130,7 +130,7 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
 template <int W>
 __device__ __forceinline__ void load_det(const uint64_t* p, uint64_t* f) {
     if (W == 2) {
-        ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p);
+        ulonglong2 v = __ldcs(reinterpret_cast<const ulonglong2*>(p));   // streamed once per cycle
         f[0] = v.x; f[1] = v.y;
     } else {
 #pragma unroll
@@ -282,8 +282,8 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
     if (idx < nstates) {
         uint64_t f[W];
         load_det<W>(states + idx * W, f);
-        const int64_t pop = pops[idx];
-        const double Kii = dat[idx];
+        const int64_t pop = __ldcs(pops + idx);
+        const double Kii = __ldcs(dat + idx);
 #pragma unroll
         for (int k = 0; k < W; ++k) sf[tid * W + k] = f[k];
         ssign[tid] = pop < 0;

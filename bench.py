@@ -299,8 +299,16 @@ def main():
     k_ms = tm["spawn_kernel_ms"] / args.steps
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    traffic = None   # DRAM bytes of one k_spawn_death launch from the committed ncu --set full capture of this workload
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp) and args.excit_gen == "heat_bath" and args.system == "s50":
+        tj = json.load(open(tp))
+        if int(tj.get("walkers_per_gpu", 0)) == int(args.walkers):
+            for k, v in tj.get("dram_bytes_per_launch", {}).items():
+                if k.startswith("k_spawn_death"):
+                    traffic = v
     roofline = {"bound": "hbm", "kernel": "k_spawn_death", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": alg_bytes, "kernel_ms": k_ms,
                 "stage_ms_per_step": {k: tm[k] / args.steps for k in ("spawn_ms", "comm_ms", "sort_ms", "annihilate_ms")}}
     # whole-cycle algorithmic traffic (SURVEY.md 8d B_alg) for context

@@ -725,13 +725,15 @@ HB_HDN void generate_alias_tables(int N, const double* weights, double totweight
         }
     }
 }
-template <class R>
+// STREAM: evict-first loads for tables with no reuse (the 2 GB hb_ijab rows); the 30 MB hb_ija rows stay L2-resident
+template <bool STREAM = false, class R>
 HB_HD int select_precalc(R& rng, int N, const double* aliasU, const int* aliasK) {
     double x = rng.next() * N;
     int K = (int)floor(x);
     x = x - K;
-    const double u = HB_LDCS(aliasU + K);   // both loads are issued together: one memory round trip instead of two
-    const int alias = HB_LDCS(aliasK + K);
+    // both loads are issued together: one memory round trip instead of two
+    const double u = STREAM ? HB_LDCS(aliasU + K) : aliasU[K];
+    const int alias = STREAM ? HB_LDCS(aliasK + K) : aliasK[K];
     return (x < u) ? K + 1 : alias;
 }
 template <class R>
@@ -940,7 +942,7 @@ HB_HDN void hb_phase_c(R& rng, const Sys& s, const uint64_t* f, HbState& st) {
         st.dbl = true; st.psingle = 0.0;
     }
     if (st.dbl) {
-        st.b = select_precalc(rng, (int)nb, s.hb_ijab_U + HB_I4(1, st.a, st.j, st.i), s.hb_ijab_K + HB_I4(1, st.a, st.j, st.i));
+        st.b = select_precalc<true>(rng, (int)nb, s.hb_ijab_U + HB_I4(1, st.a, st.j, st.i), s.hb_ijab_K + HB_I4(1, st.a, st.j, st.i));
         if (det_test(f, st.b)) { st.allowed = false; return; }
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -1082,7 +1084,7 @@ HB_HDN void gen_excit_heat_bath_uniform(R& rng, const Sys& s, const Params& p, c
     if (allowed) {
         a = select_precalc(rng, (int)nb, s.hb_ija_U + HB_I3(1, j, i), s.hb_ija_K + HB_I3(1, j, i));
         if (fabs(s.hb_ijab_tot[HB_I3(a, j, i)]) > 0.0 && !det_test(f, a)) {
-            b = select_precalc(rng, (int)nb, s.hb_ijab_U + HB_I4(1, a, j, i), s.hb_ijab_K + HB_I4(1, a, j, i));
+            b = select_precalc<true>(rng, (int)nb, s.hb_ijab_U + HB_I4(1, a, j, i), s.hb_ijab_K + HB_I4(1, a, j, i));
             allowed = !det_test(f, b);
         } else {
             allowed = false;

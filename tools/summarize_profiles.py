@@ -120,7 +120,7 @@ if os.path.exists(rep):
                              capture_output=True, text=True).stdout
         tmp = os.path.join(G, f"{tag}_src_spawn.csv")
         open(tmp, "w").write(src)
-        bl = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_by_line.py"), tmp, lib, "k_spawn_deathILi2", "25"],
+        bl = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_by_line.py"), tmp, lib, "k_spawn_deathILi2ELi4E", "25"],
                             capture_output=True, text=True).stdout
         out.append("## k_spawn_death: instruction / stall-sample share by source line (tools/ncu_by_line.py)\n\n```\n" + bl + "```\n")
 

@@ -98,7 +98,7 @@ struct Sys {
 
 // Per-calculation parameters (qmc_in_t / qmc_state_t scalars the kernels need).
 struct Params {
-    int excit_gen;              // src/qmc_data.f90:31-69 values: 0 no_renorm, 1 renorm, 4 heat_bath
+    int excit_gen;              // EXCIT_GEN_* (the reference's enumerator values)
     double pattempt_single, pattempt_double;
     double tau, shift, proj_energy_old;
     int64_t real_factor;        // pop_real_factor (1 or 2^31)
@@ -115,7 +115,11 @@ struct Params {
     double H00;
 };
 
-enum { EXCIT_GEN_NO_RENORM = 0, EXCIT_GEN_RENORM = 1, EXCIT_GEN_HEAT_BATH = 4, EXCIT_GEN_HEAT_BATH_UNIFORM = 5 };
+// the reference's enumerator values (src/qmc_data.f90:31-69: renorm, renorm_spin, no_renorm, no_renorm_spin, power_pitzer,
+// power_pitzer_occ, power_pitzer_occ_ij, power_pitzer_orderN, cauchy_schwarz_occ, cauchy_schwarz_occ_ij, heat_bath,
+// heat_bath_uniform, heat_bath_single)
+enum { EXCIT_GEN_RENORM = 0, EXCIT_GEN_NO_RENORM = 2, EXCIT_GEN_POWER_PITZER_OCC = 5, EXCIT_GEN_CAUCHY_SCHWARZ_OCC = 8,
+       EXCIT_GEN_HEAT_BATH = 10, EXCIT_GEN_HEAT_BATH_UNIFORM = 11 };
 enum { RNG_NATTEMPTS = 0, RNG_SPAWN = 1, RNG_DEATH = 2, RNG_ROUND_MAIN = 3, RNG_ROUND_SPAWN = 4 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1107,6 +1111,157 @@ HB_HDN void gen_excit_heat_bath_uniform(R& rng, const Sys& s, const Params& p, c
 }
 
 // ------------------------------------------------------------------------------------------------
+// Power-Pitzer / Cauchy-Schwarz "occ" generators with uniformly selected ij
+// (gen_excit_mol_power_pitzer_occ, src/excit_gen_power_pitzer_mol.F90:1260-1549; weights
+// create_weighted_excitation_list_mol, src/hamiltonian_molecular.f90:348-390): O(M) weights sqrt|<ia|ai>| (or
+// sqrt|<ia|ia>|) are formed on the fly over the unoccupied orbitals of i's spin and over the (spin, symmetry) class of b,
+// each followed by an on-the-fly alias selection.  Lists of up to HB_MAXLIST entries live in thread-local memory.
+// ------------------------------------------------------------------------------------------------
+#define HB_MAXLIST 128
+template <class R>
+HB_HDN int select_weighted_value_list(R& rng, int N, const double* weights, double totweight) {
+    double aliasU[HB_MAXLIST];
+    int aliasK[HB_MAXLIST], under[HB_MAXLIST], over[HB_MAXLIST];
+    generate_alias_tables(N, weights, totweight, aliasU, aliasK, under, over);
+    return select_precalc(rng, N, aliasU, aliasK);
+}
+HB_HD double pp_weight(const Sys& s, bool cauchy_schwarz, int i, int a) {
+    return sqrt(fabs(cauchy_schwarz ? two_body(s, i, a, i, a) : two_body(s, i, a, a, i)));
+}
+// k-th (1-based) unoccupied orbital of the given spin parity (1 = alpha/odd orbitals, 0 = beta/even), ascending
+template <int W>
+HB_HD int nth_unocc_of_spin(const uint64_t* f, int nbasis, int alpha, int k) {
+    const uint64_t par = alpha ? 0x5555555555555555ull : 0xAAAAAAAAAAAAAAAAull;   // orbital o <-> bit o-1
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        uint64_t x = ~f[w] & par;
+        const int top = nbasis - 64 * w;
+        if (top < 64) x &= (top <= 0) ? 0ull : ((1ull << top) - 1ull);
+        const int c = popc64(x);
+        if (k <= c) {
+            for (int q = 1; q < k; ++q) x &= x - 1;
+            return w * 64 + ctz64(x) + 1;
+        }
+        k -= c;
+    }
+    return 0;
+}
+// position (1-based) of unoccupied orbital b within the ascending list of unoccupied orbitals of its spin
+template <int W>
+HB_HD int unocc_rank_of(const uint64_t* f, int b) {
+    const uint64_t par = (b & 1) ? 0x5555555555555555ull : 0xAAAAAAAAAAAAAAAAull;
+    const int bw = (b - 1) >> 6, bb = (b - 1) & 63;
+    int n = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        uint64_t x = ~f[w] & par;
+        if (w > bw) x = 0;
+        else if (w == bw) x &= (bb == 0) ? 0ull : ((1ull << bb) - 1ull);
+        n += popc64(x);
+    }
+    return n + 1;
+}
+template <int W, class R>
+HB_HDN void gen_excit_power_pitzer_occ(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ,
+                                       const uint8_t* su, Gen& g) {
+    const bool cs = p.excit_gen == EXCIT_GEN_CAUCHY_SCHWARZ_OCC;
+    g.from1 = 0; g.from2 = 0; g.to1 = 0; g.to2 = 0; g.perm = false;
+    if (rng.next() < p.pattempt_single) {
+        gen_single_renorm<W>(rng, s, p, f, occ, su, g);
+        return;
+    }
+    g.nexcit = 2;
+    int i, j, ij_sym, ij_spin;
+    choose_ij(rng, s, occ, i, j, ij_sym, ij_spin);
+    const double pgen_ij = 2.0 / (s.nel * (s.nel - 1));
+    const int ialpha = i & 1;
+    // number of unoccupied orbitals of i's spin
+    int ni = 0;
+    {
+        const uint64_t par = ialpha ? 0x5555555555555555ull : 0xAAAAAAAAAAAAAAAAull;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            uint64_t x = ~f[w] & par;
+            const int top = s.nbasis - 64 * w;
+            if (top < 64) x &= (top <= 0) ? 0ull : ((1ull << top) - 1ull);
+            ni += popc64(x);
+        }
+    }
+    double ia_w[HB_MAXLIST], jb_w[HB_MAXLIST];
+    double ia_tot = 0.0, jb_tot = 0.0;
+    bool a_found = false;
+    int a = 0, b = 0, a_ind = 0, b_ind = 0;
+    if (ni > 0) {
+        // walk the unoccupied orbitals of i's spin in ascending order
+        int k = 0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            uint64_t x = ~f[w] & (ialpha ? 0x5555555555555555ull : 0xAAAAAAAAAAAAAAAAull);
+            const int top = s.nbasis - 64 * w;
+            if (top < 64) x &= (top <= 0) ? 0ull : ((1ull << top) - 1ull);
+            while (x) {
+                const int orb = w * 64 + ctz64(x) + 1;
+                x &= x - 1;
+                ia_w[k] = pp_weight(s, cs, i, orb);
+                ia_tot = ia_tot + ia_w[k];
+                ++k;
+            }
+        }
+        if (ia_tot > 0.0) {
+            a_ind = select_weighted_value_list(rng, ni, ia_w, ia_tot);
+            a = nth_unocc_of_spin<W>(f, s.nbasis, ialpha, a_ind);
+            a_found = true;
+        }
+    }
+    int isymb = 0, imsb = 0, nb_list = 0;
+    if (a_found) {
+        isymb = sym_conj(s, cross_product(s, ij_sym, s.bf_sym[a]));
+        imsb = (ij_spin - ms_of(a) + 3) / 2;
+        nb_list = nbss(s, imsb, isymb);
+        if (nb_list > 0) {
+            for (int k = 0; k < nb_list; ++k) {
+                const int orb = ssbf(s, k + 1, imsb, isymb);
+                if (orb != a) { jb_w[k] = pp_weight(s, cs, j, orb); jb_tot = jb_tot + jb_w[k]; }
+                else jb_w[k] = 0.0;
+            }
+        }
+    }
+    g.allowed = false;
+    if (a_found && jb_tot > 0.0) {
+        b_ind = select_weighted_value_list(rng, nb_list, jb_w, jb_tot);
+        b = ssbf(s, b_ind, imsb, isymb);
+        if (!det_test(f, b)) {
+            double pgen;
+            if (ij_spin == 0) {
+                pgen = ia_w[a_ind - 1] / ia_tot * jb_w[b_ind - 1] / jb_tot;
+            } else {
+                const int b_ind_rev = unocc_rank_of<W>(f, b);
+                const int isyma = sym_conj(s, cross_product(s, ij_sym, isymb));
+                const int na_list = nbss(s, imsb, isyma);
+                double ja_tot = 0.0, ja_a = 0.0;
+                for (int k = 0; k < na_list; ++k) {
+                    const int orb = ssbf(s, k + 1, imsb, isyma);
+                    double wk = 0.0;
+                    if (orb != b) { wk = pp_weight(s, cs, j, orb); ja_tot = ja_tot + wk; }
+                    if (orb == a) ja_a = wk;
+                }
+                pgen = (ia_w[a_ind - 1] * jb_w[b_ind - 1]) / (ia_tot * jb_tot) + (ia_w[b_ind_rev - 1] * ja_a) / (ia_tot * ja_tot);
+            }
+            g.pgen = p.pattempt_double * pgen * pgen_ij;
+            g.from1 = (i < j) ? i : j; g.from2 = (i < j) ? j : i;
+            g.to1 = (a < b) ? a : b; g.to2 = (a < b) ? b : a;
+            g.allowed = true;
+        }
+    }
+    if (g.allowed) {
+        g.perm = excit_perm2<W>(f, g.from1, g.from2, g.to1, g.to2);
+        g.hmatel = slater_condon2_excit(s, g.from1, g.from2, g.to1, g.to2, g.perm);
+    } else {
+        g.hmatel = 0.0; g.pgen = 1.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Uniform electron gas (3D): analytic integrals, Slater-Condon rules and the no_renorm generator
 // ------------------------------------------------------------------------------------------------
 // coulomb_int_ueg_3d (src/ueg.f90:250-280): 1 / (pi L |k_i - k_a|^2)
@@ -1216,6 +1371,8 @@ HB_HD void gen_excit(R& rng, const Sys& s, const Params& p, const uint64_t* f, c
     if (s.kind == SYS_UEG) gen_excit_ueg_no_renorm<W>(rng, s, f, occ, g);
     else if (p.excit_gen == EXCIT_GEN_RENORM) gen_excit_renorm<W>(rng, s, p, f, occ, su, g);
     else if (p.excit_gen == EXCIT_GEN_NO_RENORM) gen_excit_no_renorm<W>(rng, s, p, f, occ, g);
+    else if (p.excit_gen == EXCIT_GEN_POWER_PITZER_OCC || p.excit_gen == EXCIT_GEN_CAUCHY_SCHWARZ_OCC)
+        gen_excit_power_pitzer_occ<W>(rng, s, p, f, occ, su, g);
     else if (p.excit_gen == EXCIT_GEN_HEAT_BATH_UNIFORM) {
         double scr[HB_MAXNEL];
         gen_excit_heat_bath_uniform<W>(rng, s, p, f, occ, su, s.hb_i_w, scr, 1, g);

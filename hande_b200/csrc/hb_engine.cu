@@ -242,7 +242,7 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
     const int nel = s.nel;
     constexpr bool heat_bath = (GEN == EXCIT_GEN_HEAT_BATH);
     constexpr bool hb_stage = heat_bath || (GEN == EXCIT_GEN_HEAT_BATH_UNIFORM);
-    const int nsu = (GEN == EXCIT_GEN_RENORM || GEN == EXCIT_GEN_HEAT_BATH_UNIFORM) ? 2 * s.nsym_tot : 0;
+    const int nsu = (GEN == EXCIT_GEN_RENORM || GEN == EXCIT_GEN_HEAT_BATH_UNIFORM || GEN == EXCIT_GEN_POWER_PITZER_OCC) ? 2 * s.nsym_tot : 0;
     const SpawnSmem L(W, nel, nsu, s.nbasis, heat_bath, hb_stage);
     uint64_t* sf = reinterpret_cast<uint64_t*>(smem_raw + L.sf);
     uint8_t* ssign = smem_raw + L.ssign;
@@ -438,6 +438,8 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
             if (GEN == GEN_UEG) gen_excit_ueg_no_renorm<W>(rng, s, f, socc + lo * nel, g);
             else if (GEN == EXCIT_GEN_HEAT_BATH_UNIFORM)
                 gen_excit_heat_bath_uniform<W>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, siw, sw + tid, TILE, g);
+            else if (GEN == EXCIT_GEN_POWER_PITZER_OCC)     // also cauchy_schwarz_occ (p.excit_gen picks the integral)
+                gen_excit_power_pitzer_occ<W>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, g);
             else if (GEN == EXCIT_GEN_RENORM) gen_excit_renorm<W>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, g);
             else gen_excit_no_renorm<W>(rng, s, p, f, socc + lo * nel, g);
         }
@@ -570,7 +572,7 @@ k_ccmc_cluster(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states,
         if (cl.excitation_level >= 0 && cl.excitation_level <= a.ex_level + 2) {
             uint8_t occ[HB_MAXNEL], su[64];
             decode_det<W>(cf, occ);
-            if (s.kind == SYS_READ_IN && (p.excit_gen == EXCIT_GEN_RENORM || p.excit_gen == EXCIT_GEN_HEAT_BATH_UNIFORM))
+            if (s.kind == SYS_READ_IN && p.excit_gen != EXCIT_GEN_NO_RENORM && p.excit_gen != EXCIT_GEN_HEAT_BATH)
                 build_symunocc_masks<W>(s, cf, su);
             // do_ccmc_accumulation (src/ccmc.f90:1007-1101)
             bool is_ref;
@@ -1415,7 +1417,8 @@ static bool uses_heat_bath_tables(const hb200_engine* e) {
 }
 static size_t spawn_smem_bytes(const hb200_engine* e) {
     const int eg = e->cfg.excit_gen;
-    const int nsu = (e->sys.kind == SYS_READ_IN && (eg == HB200_EXCIT_GEN_RENORM || eg == HB200_EXCIT_GEN_HEAT_BATH_UNIFORM))
+    const int nsu = (e->sys.kind == SYS_READ_IN && (eg == HB200_EXCIT_GEN_RENORM || eg == HB200_EXCIT_GEN_HEAT_BATH_UNIFORM ||
+                                                    eg == HB200_EXCIT_GEN_POWER_PITZER_OCC || eg == HB200_EXCIT_GEN_CAUCHY_SCHWARZ_OCC))
                         ? 2 * e->sys.nsym_tot : 0;
     const bool hb = eg == HB200_EXCIT_GEN_HEAT_BATH;
     return SpawnSmem(e->W, e->sys.nel, nsu, e->sys.nbasis, hb, hb || eg == HB200_EXCIT_GEN_HEAT_BATH_UNIFORM).total;
@@ -1800,6 +1803,8 @@ static int stage_spawn_death(hb200_engine* e, const hb200_iter_in* in, uint32_t 
             case HB200_EXCIT_GEN_RENORM: LAUNCH_SPAWN(EXCIT_GEN_RENORM); break;
             case HB200_EXCIT_GEN_HEAT_BATH: LAUNCH_SPAWN(EXCIT_GEN_HEAT_BATH); break;
             case HB200_EXCIT_GEN_HEAT_BATH_UNIFORM: LAUNCH_SPAWN(EXCIT_GEN_HEAT_BATH_UNIFORM); break;
+            case HB200_EXCIT_GEN_POWER_PITZER_OCC:
+            case HB200_EXCIT_GEN_CAUCHY_SCHWARZ_OCC: LAUNCH_SPAWN(EXCIT_GEN_POWER_PITZER_OCC); break;
             default: FAIL("spawn_death: excitation generator not implemented");
         }
 #undef LAUNCH_SPAWN

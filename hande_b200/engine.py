@@ -11,7 +11,9 @@ import numpy as np
 
 from . import build as _build
 
-EXCIT_GEN = {"no_renorm": 0, "renorm": 1, "heat_bath": 4, "heat_bath_uniform": 5}
+# values of the reference's excit_gen enumerators (src/qmc_data.f90:31-69)
+EXCIT_GEN = {"renorm": 0, "no_renorm": 2, "power_pitzer_occ": 5, "cauchy_schwarz_occ": 8, "heat_bath": 10,
+             "heat_bath_uniform": 11}
 
 
 class Config(C.Structure):

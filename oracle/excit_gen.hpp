@@ -15,11 +15,13 @@ namespace oracle {
 constexpr int MAXNEL = 64;
 
 enum ExcitGenKind {  // values of src/qmc_data.f90:31-69
-    EXCIT_GEN_NO_RENORM = 0,
-    EXCIT_GEN_RENORM = 1,
-    EXCIT_GEN_HEAT_BATH = 4,
-    EXCIT_GEN_HEAT_BATH_UNIFORM = 5,
-    EXCIT_GEN_HEAT_BATH_SINGLE = 6,
+    EXCIT_GEN_RENORM = 0,
+    EXCIT_GEN_NO_RENORM = 2,
+    EXCIT_GEN_POWER_PITZER_OCC = 5,
+    EXCIT_GEN_CAUCHY_SCHWARZ_OCC = 8,
+    EXCIT_GEN_HEAT_BATH = 10,
+    EXCIT_GEN_HEAT_BATH_UNIFORM = 11,
+    EXCIT_GEN_HEAT_BATH_SINGLE = 12,
 };
 
 struct DetInfo {
@@ -31,6 +33,8 @@ struct DetInfo {
     bool double_precalc = false;
     double i_d_weights[MAXNEL];
     double i_d_weights_tot = 0.0;
+    // decode_det_spinocc_spinsymunocc (src/determinant_decoders.f90:371-495): unoccupied orbitals per spin, ascending
+    std::vector<int> unocc_alpha, unocc_beta;
     // heat_bath_single per-determinant cache (det_info_t%i_s_occ, ia_s_weights_occ, unocc_list)
     bool single_precalc = false;
     std::vector<int> unocc;
@@ -738,18 +742,130 @@ inline GenResult gen_excit_mol_heat_bath_uniform(Rng& rng, const System& sys, co
     return r;
 }
 
+// decode_det_spinocc_spinsymunocc (src/determinant_decoders.f90:371-495)
+inline void decode_det_spinocc_spinsymunocc(const System& sys, const Det& f, DetInfo& d) {
+    decode_det_occ_symunocc(sys, f, d);
+    d.unocc_alpha.clear(); d.unocc_beta.clear();
+    for (int o = 1; o <= sys.nbasis; ++o)
+        if (!det_test(f, o)) ((o % 2 == 1) ? d.unocc_alpha : d.unocc_beta).push_back(o);
+}
+// create_weighted_excitation_list_mol (src/hamiltonian_molecular.f90:348-390): weights sqrt|<ia|ai>| (Power-Pitzer) or
+// sqrt|<ia|ia>| (Cauchy-Schwarz; get_two_body_int_cou_mol_real, src/qmc.F90:437-441) over a_list, zero for a == b
+inline double create_weighted_excitation_list_mol(const System& sys, bool cauchy_schwarz, int i, int b, const int* a_list,
+                                                  int n, double* weights) {
+    double tot = 0.0;
+    for (int k = 0; k < n; ++k) {
+        if (a_list[k] != b) {
+            const int a = a_list[k];
+            const double w = cauchy_schwarz ? sys.get_two_body_real(i, a, i, a) : sys.get_two_body_real(i, a, a, i);
+            weights[k] = std::sqrt(std::fabs(w));
+            tot = tot + weights[k];
+        } else {
+            weights[k] = 0.0;
+        }
+    }
+    return tot;
+}
+// gen_excit_mol_power_pitzer_occ (src/excit_gen_power_pitzer_mol.F90:1260-1549), ij selected uniformly
+// (excit_gen_power_pitzer_occ, excit_gen_cauchy_schwarz_occ)
+inline GenResult gen_excit_mol_power_pitzer_occ(Rng& rng, const System& sys, const ExcitGenData& eg, const DetInfo& d) {
+    GenResult r;
+    const bool cs = eg.excit_gen == EXCIT_GEN_CAUCHY_SCHWARZ_OCC;
+    if (rng.next() < eg.pattempt_single) {
+        choose_ia_mol(rng, sys, sys.gamma_sym, d, r.conn.from_orb[0], r.conn.to_orb[0], r.allowed);
+        r.conn.nexcit = 1;
+        if (r.allowed) {
+            r.pgen = eg.pattempt_single * calc_pgen_single_mol(sys, sys.gamma_sym, d, r.conn.to_orb[0]);
+            sys.find_excitation_permutation1(d.f, r.conn);
+            r.hmatel = sys.slater_condon1_excit(d.occ, r.conn.from_orb[0], r.conn.to_orb[0], r.conn.perm);
+        } else { r.hmatel = 0.0; r.pgen = 1.0; }
+        return r;
+    }
+    int i, j, ij_sym, ij_spin;
+    double pgen_ij;
+    choose_ij_mol(rng, sys, d.occ, i, j, ij_sym, ij_spin, pgen_ij);
+    bool allowed = true, a_found = false;
+    const std::vector<int>& ilist = (sys.bf[i].ms < 0) ? d.unocc_beta : d.unocc_alpha;
+    const int ni = (int)ilist.size();
+    std::vector<double> ia_w(std::max(ni, 1)), jb_w, ja_w;
+    double ia_tot = 0.0, jb_tot = 0.0, ja_tot = 0.0;
+    int a = 0, b = 0, a_ind = 0, b_ind = 0;
+    if (ni > 0) {
+        ia_tot = create_weighted_excitation_list_mol(sys, cs, i, 0, ilist.data(), ni, ia_w.data());
+        if (ia_tot > 0.0) {
+            a_ind = select_weighted_value(rng, ni, ia_w.data(), ia_tot);
+            a = ilist[a_ind - 1];
+            a_found = true;
+        }
+    }
+    int isymb = 0, imsb = 0, nb_list = 0;
+    const int* blist = nullptr;
+    if (a_found && allowed) {
+        isymb = sys.sym_conj(sys.cross_product(ij_sym, sys.bf[a].sym));
+        imsb = (ij_spin - sys.bf[a].ms + 3) / 2;
+        nb_list = sys.nbss(imsb, isymb);
+        if (nb_list > 0) {
+            blist = &sys.sym_spin_basis_fns[(size_t)sys.max_nbss * ((imsb - 1) + 2 * isymb)];
+            jb_w.resize(nb_list);
+            jb_tot = create_weighted_excitation_list_mol(sys, cs, j, a, blist, nb_list, jb_w.data());
+        } else {
+            jb_tot = 0.0;
+        }
+    }
+    r.allowed = false;
+    if (a_found && jb_tot > 0.0 && allowed) {
+        b_ind = select_weighted_value(rng, nb_list, jb_w.data(), jb_tot);
+        b = blist[b_ind - 1];
+        if (!det_test(d.f, b)) {
+            double pgen;
+            if (ij_spin == 0) {
+                pgen = ia_w[a_ind - 1] / ia_tot * jb_w[b_ind - 1] / jb_tot;
+            } else {
+                const std::vector<int>& ul = (imsb == 1) ? d.unocc_beta : d.unocc_alpha;
+                const int b_ind_rev = (int)(std::lower_bound(ul.begin(), ul.end(), b) - ul.begin()) + 1;
+                const int isyma = sys.sym_conj(sys.cross_product(ij_sym, isymb));
+                const int na_list = sys.nbss(imsb, isyma);
+                const int* alist = &sys.sym_spin_basis_fns[(size_t)sys.max_nbss * ((imsb - 1) + 2 * isyma)];
+                ja_w.resize(na_list);
+                ja_tot = create_weighted_excitation_list_mol(sys, cs, j, b, alist, na_list, ja_w.data());
+                const int a_ind_rev = (int)(std::lower_bound(alist, alist + na_list, a) - alist) + 1;
+                pgen = (ia_w[a_ind - 1] * jb_w[b_ind - 1]) / (ia_tot * jb_tot) +
+                       (ia_w[b_ind_rev - 1] * ja_w[a_ind_rev - 1]) / (ia_tot * ja_tot);
+            }
+            r.pgen = eg.pattempt_double * pgen * pgen_ij;
+            r.conn.nexcit = 2;
+            r.conn.from_orb[0] = std::min(i, j); r.conn.from_orb[1] = std::max(i, j);
+            r.conn.to_orb[0] = std::min(a, b); r.conn.to_orb[1] = std::max(a, b);
+            r.allowed = true;
+        }
+    }
+    if (r.allowed) {
+        sys.find_excitation_permutation2(d.f, r.conn);
+        r.hmatel = sys.slater_condon2_excit(r.conn.from_orb[0], r.conn.from_orb[1], r.conn.to_orb[0], r.conn.to_orb[1],
+                                            r.conn.perm);
+    } else {
+        r.conn.nexcit = 2;
+        r.hmatel = 0.0; r.pgen = 1.0;
+    }
+    return r;
+}
+
 inline GenResult gen_excit(Rng& rng, const System& sys, const ExcitGenData& eg, DetInfo& d) {
     switch (eg.excit_gen) {
         case EXCIT_GEN_RENORM: return gen_excit_mol(rng, sys, eg, d);
         case EXCIT_GEN_NO_RENORM: return gen_excit_mol_no_renorm(rng, sys, eg, d);
         case EXCIT_GEN_HEAT_BATH: return gen_excit_mol_heat_bath(rng, sys, eg, d);
+        case EXCIT_GEN_POWER_PITZER_OCC:
+        case EXCIT_GEN_CAUCHY_SCHWARZ_OCC: return gen_excit_mol_power_pitzer_occ(rng, sys, eg, d);
         case EXCIT_GEN_HEAT_BATH_UNIFORM:
         case EXCIT_GEN_HEAT_BATH_SINGLE: return gen_excit_mol_heat_bath_uniform(rng, sys, eg, d);
         default: throw std::runtime_error("oracle: excitation generator not implemented");
     }
 }
 inline void decode_for(const System& sys, const ExcitGenData& eg, const Det& f, DetInfo& d) {
-    if (eg.excit_gen == EXCIT_GEN_RENORM || eg.excit_gen == EXCIT_GEN_HEAT_BATH_UNIFORM) decode_det_occ_symunocc(sys, f, d);
+    if (eg.excit_gen == EXCIT_GEN_POWER_PITZER_OCC || eg.excit_gen == EXCIT_GEN_CAUCHY_SCHWARZ_OCC)
+        decode_det_spinocc_spinsymunocc(sys, f, d);
+    else if (eg.excit_gen == EXCIT_GEN_RENORM || eg.excit_gen == EXCIT_GEN_HEAT_BATH_UNIFORM) decode_det_occ_symunocc(sys, f, d);
     else decode_det_occ(sys, f, d);
 }
 

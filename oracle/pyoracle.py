@@ -12,7 +12,8 @@ LIB = os.path.join(HERE, "liboracle.so")
 REF_LIB = os.path.join(HERE, "_ref", "libhande_ref_c.so")
 HUGE = 2**31 - 1
 
-EXCIT_GEN = {"no_renorm": 0, "renorm": 1, "heat_bath": 4, "heat_bath_uniform": 5, "heat_bath_single": 6}
+EXCIT_GEN = {"renorm": 0, "no_renorm": 2, "power_pitzer_occ": 5, "cauchy_schwarz_occ": 8, "heat_bath": 10,
+             "heat_bath_uniform": 11, "heat_bath_single": 12}
 
 
 class QmcIn(C.Structure):
@@ -256,7 +257,7 @@ class Oracle:
     def set_qmc(self, **kw):
         q = QmcIn(tau=0.001, seed=7, D0_population=10.0, ncycles=20, nreport=10, target_particles=1e7,
                   initial_shift=0.0, shift_damping=0.05, vary_shift_from=0.0, vary_shift_from_proje=0,
-                  initiator_approx=0, initiator_pop=3.0, real_amplitudes=0, spawn_cutoff=0.01, excit_gen=1,
+                  initiator_approx=0, initiator_pop=3.0, real_amplitudes=0, spawn_cutoff=0.01, excit_gen=EXCIT_GEN["renorm"],
                   pattempt_single=-1.0, pattempt_double=-1.0, walker_length=1 << 20,
                   spawned_walker_length=1 << 18, ex_level=-1, nprocs=1, nslots=1, rng_kind=0,
                   literal_event_int32=1)

@@ -56,6 +56,21 @@ def test_uniform_generators_h2o(fcidump_path, gen):
         assert isref == int((f == o.reference()["f0"]).all())
 
 
+@pytest.mark.parametrize("gen", ["power_pitzer_occ", "cauchy_schwarz_occ"])
+def test_power_pitzer_occ_generators(fcidump_path, s10, gen):
+    """SURVEY 8a row a10 (O(M) variants with uniform ij): bit-exact against the oracle on a D2h molecule (symmetry
+    classes of different sizes) and on the C1 synthetic system."""
+    kw = dict(nel=10, ms=0, sym=0, cas=(8, 13))
+    s, o, h = _setup(fcidump_path("h2o"), kw, gen, tau=0.003)
+    dets = synthetic.random_dets(100, s.nbasis, s.nalpha, s.nbeta, seed=3)
+    pops = np.where(np.arange(len(dets)) % 2 == 0, 3, -2)
+    assert _compare_attempts(s, o, h, dets, pops, 0.003) > 1000
+    s, o, h = _setup(s10, {}, gen, tau=0.01, real=True)
+    dets = synthetic.random_dets(80, s.nbasis, s.nalpha, s.nbeta, seed=9)
+    pops = np.where(np.arange(len(dets)) % 3 == 0, -(2**31), 2**32 + 17)
+    assert _compare_attempts(s, o, h, dets, pops, 0.01, ncycle=2, nattempt=6) > 900
+
+
 def test_ne_large_basis_two_sym(fcidump_path):
     kw = dict(nel=10, ms=0, sym=0)
     s, o, h = _setup(fcidump_path("ne"), kw, "renorm", tau=0.005, real=True)
@@ -171,7 +186,8 @@ def test_philox_stream_matches_oracle():
         assert ((out >= 0) & (out < 1)).all()
 
 
-@pytest.mark.parametrize("gen", ["heat_bath", "heat_bath_uniform", "heat_bath_single"])
+@pytest.mark.parametrize("gen", ["heat_bath", "heat_bath_uniform", "heat_bath_single", "power_pitzer_occ",
+                                 "cauchy_schwarz_occ"])
 def test_heat_bath_pgen_normalisation(s10, gen):
     """SURVEY 8c gap-filler: heat-bath has no single-rank golden trajectory, so pin it statistically.  The
     generator reports pgen for the excitation it produced; over many samples each excitation must appear with

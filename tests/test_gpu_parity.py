@@ -55,6 +55,12 @@ def test_gen_excit_heat_bath_uniform():
     _check_gen("s10", "heat_bath_uniform", True, 0.01, n=150, nattempt=6)
 
 
+def test_gen_excit_power_pitzer_and_cauchy_schwarz_occ():
+    # the O(M) on-the-fly variants with uniformly chosen ij
+    _check_gen("h2o", "power_pitzer_occ", False, 0.003, n=120)
+    _check_gen("s10", "cauchy_schwarz_occ", True, 0.01, n=120, nattempt=6)
+
+
 def test_gen_excit_ueg():
     # gen_excit_ueg_no_renorm + slater_condon0_ueg on the device, W = 2 and W = 3
     _check_gen("ueg6", "no_renorm", False, 0.005, n=150, nattempt=5)
@@ -105,6 +111,8 @@ CASES = [
     ("s40", "renorm", False, True, 0.02, 3000, -1),
     ("s12", "heat_bath", True, True, 0.01, 2500, -1),
     ("s12", "heat_bath_uniform", True, True, 0.01, 2500, -1),
+    ("h2o", "power_pitzer_occ", False, True, 0.003, 2500, -1),
+    ("s12", "cauchy_schwarz_occ", True, False, 0.004, 2500, -1),
     ("ueg6", "no_renorm", False, False, 0.01, 3000, -1),
     ("ueg14", "no_renorm", True, True, 0.004, 4000, -1),
 ]

@@ -1120,6 +1120,7 @@ HB_HDN void gen_excit_heat_bath_uniform(R& rng, const Sys& s, const Params& p, c
 #define HB_MAXLIST 128
 template <class R>
 HB_HDN int select_weighted_value_list(R& rng, int N, const double* weights, double totweight) {
+    if (N <= 64) return select_alias_staged(rng, N, weights, 1, totweight);   // table-free walk (same index)
     double aliasU[HB_MAXLIST];
     int aliasK[HB_MAXLIST], under[HB_MAXLIST], over[HB_MAXLIST];
     generate_alias_tables(N, weights, totweight, aliasU, aliasK, under, over);

@@ -157,7 +157,7 @@ def main():
     ap.add_argument("--walkers", type=float, default=1e8, help="walkers (= occupied determinants) per GPU")
     ap.add_argument("--tau", type=float, default=0.0, help="0 => calibrate for R_spawn ~ 0.05")
     ap.add_argument("--excit-gen", default="heat_bath", choices=["heat_bath", "heat_bath_uniform", "renorm", "no_renorm", "power_pitzer_occ",
-                                                              "cauchy_schwarz_occ"],
+                                                              "cauchy_schwarz_occ", "power_pitzer_occ_ij", "cauchy_schwarz_occ_ij"],
                     help="excitation generator (headline = heat_bath, BASELINE.json configs[1]; others are side measurements)")
     ap.add_argument("--system", default="s50", choices=["s50", "ueg"],
                     help="s50 = BASELINE configs[1] (headline); ueg = side measurement on the 3D UEG (14 electrons, "
@@ -295,7 +295,7 @@ def main():
     P = out["nspawn_events"]
     # ---- roofline of the dominant kernel (k_spawn_death): algorithmic bytes per launch / its launch duration
     Em, Es = 8 * (s.W + 2), 8 * (s.W + 2)
-    t_hb = {"heat_bath": T_HB, "heat_bath_uniform": 12.0 + 2 * 16.0}.get(args.excit_gen, 0.0)
+    t_hb = {"heat_bath": T_HB, "heat_bath_uniform": 12.0 + 2 * 16.0}.get(args.excit_gen, 0.0)   # others: L2-resident tables
     alg_bytes = S * Em + S * 8 + A * t_hb + P * Es
     k_ms = tm["spawn_kernel_ms"] / args.steps
     peak, peak_src = measured_peak()

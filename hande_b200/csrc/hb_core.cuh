@@ -118,7 +118,8 @@ struct Params {
 // the reference's enumerator values (src/qmc_data.f90:31-69: renorm, renorm_spin, no_renorm, no_renorm_spin, power_pitzer,
 // power_pitzer_occ, power_pitzer_occ_ij, power_pitzer_orderN, cauchy_schwarz_occ, cauchy_schwarz_occ_ij, heat_bath,
 // heat_bath_uniform, heat_bath_single)
-enum { EXCIT_GEN_RENORM = 0, EXCIT_GEN_NO_RENORM = 2, EXCIT_GEN_POWER_PITZER_OCC = 5, EXCIT_GEN_CAUCHY_SCHWARZ_OCC = 8,
+enum { EXCIT_GEN_RENORM = 0, EXCIT_GEN_NO_RENORM = 2, EXCIT_GEN_POWER_PITZER_OCC = 5, EXCIT_GEN_POWER_PITZER_OCC_IJ = 6,
+       EXCIT_GEN_CAUCHY_SCHWARZ_OCC = 8, EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ = 9,
        EXCIT_GEN_HEAT_BATH = 10, EXCIT_GEN_HEAT_BATH_UNIFORM = 11 };
 enum { RNG_NATTEMPTS = 0, RNG_SPAWN = 1, RNG_DEATH = 2, RNG_ROUND_MAIN = 3, RNG_ROUND_SPAWN = 4 };
 
@@ -1162,10 +1163,14 @@ HB_HD int unocc_rank_of(const uint64_t* f, int b) {
     }
     return n + 1;
 }
+// iw/scr/stride: hb_i_w (or its shared-memory copy) and the staging area of nel doubles for the _occ_ij variants, whose
+// (i, j) are drawn from ppm_i_d_weights / ppm_ij_d_weights (init_excit_mol_power_pitzer_orderM_ij, :585-647) - the same
+// sums as hb_i_w / hb_ij_w of the heat-bath tables, which are used for them.
 template <int W, class R>
 HB_HDN void gen_excit_power_pitzer_occ(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ,
-                                       const uint8_t* su, Gen& g) {
-    const bool cs = p.excit_gen == EXCIT_GEN_CAUCHY_SCHWARZ_OCC;
+                                       const uint8_t* su, const double* __restrict__ iw, double* scr, int stride, Gen& g) {
+    const bool cs = p.excit_gen == EXCIT_GEN_CAUCHY_SCHWARZ_OCC || p.excit_gen == EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ;
+    const bool weighted_ij = p.excit_gen == EXCIT_GEN_POWER_PITZER_OCC_IJ || p.excit_gen == EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ;
     g.from1 = 0; g.from2 = 0; g.to1 = 0; g.to2 = 0; g.perm = false;
     if (rng.next() < p.pattempt_single) {
         gen_single_renorm<W>(rng, s, p, f, occ, su, g);
@@ -1173,8 +1178,32 @@ HB_HDN void gen_excit_power_pitzer_occ(R& rng, const Sys& s, const Params& p, co
     }
     g.nexcit = 2;
     int i, j, ij_sym, ij_spin;
-    choose_ij(rng, s, occ, i, j, ij_sym, ij_spin);
-    const double pgen_ij = 2.0 / (s.nel * (s.nel - 1));
+    double pgen_ij;
+    if (weighted_ij) {
+        // select_ij_heat_bath (src/excit_gen_utils.f90:9-66)
+        const int nel = s.nel;
+        const int64_t nb = s.nbasis;
+        const double i_tot = stage_occ(iw, occ, nel, scr, stride);
+        const int iq = select_alias_staged(rng, nel, scr, stride, i_tot);
+        i = occ[iq - 1];
+        const double wi = scr[(iq - 1) * stride];
+        const double ij_tot = stage_occ(s.hb_ij_w + nb * (i - 1), occ, nel, scr, stride);
+        if (!(ij_tot > 0.0)) {
+            g.allowed = false; g.hmatel = 0.0; g.pgen = 1.0;
+            return;
+        }
+        const int jq = select_alias_staged(rng, nel, scr, stride, ij_tot);
+        j = occ[jq - 1];
+        const double wij = scr[(jq - 1) * stride];
+        const double ji_tot = sum_occ(s.hb_ij_w + nb * (j - 1), occ, nel);
+        ij_spin = ms_of(i) + ms_of(j);
+        ij_sym = sym_conj(s, cross_product(s, s.bf_sym[i], s.bf_sym[j]));
+        pgen_ij = ((wi / i_tot) * (wij / ij_tot)) + ((iw[j - 1] / i_tot) * (s.hb_ij_w[HB_I2(i, j)] / ji_tot));
+        if (j < i) { const int t = i; i = j; j = t; }
+    } else {
+        choose_ij(rng, s, occ, i, j, ij_sym, ij_spin);
+        pgen_ij = 2.0 / (s.nel * (s.nel - 1));
+    }
     const int ialpha = i & 1;
     // number of unoccupied orbitals of i's spin
     int ni = 0;
@@ -1372,8 +1401,11 @@ HB_HD void gen_excit(R& rng, const Sys& s, const Params& p, const uint64_t* f, c
     if (s.kind == SYS_UEG) gen_excit_ueg_no_renorm<W>(rng, s, f, occ, g);
     else if (p.excit_gen == EXCIT_GEN_RENORM) gen_excit_renorm<W>(rng, s, p, f, occ, su, g);
     else if (p.excit_gen == EXCIT_GEN_NO_RENORM) gen_excit_no_renorm<W>(rng, s, p, f, occ, g);
-    else if (p.excit_gen == EXCIT_GEN_POWER_PITZER_OCC || p.excit_gen == EXCIT_GEN_CAUCHY_SCHWARZ_OCC)
-        gen_excit_power_pitzer_occ<W>(rng, s, p, f, occ, su, g);
+    else if (p.excit_gen == EXCIT_GEN_POWER_PITZER_OCC || p.excit_gen == EXCIT_GEN_CAUCHY_SCHWARZ_OCC ||
+             p.excit_gen == EXCIT_GEN_POWER_PITZER_OCC_IJ || p.excit_gen == EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ) {
+        double scr[HB_MAXNEL];
+        gen_excit_power_pitzer_occ<W>(rng, s, p, f, occ, su, s.hb_i_w, scr, 1, g);
+    }
     else if (p.excit_gen == EXCIT_GEN_HEAT_BATH_UNIFORM) {
         double scr[HB_MAXNEL];
         gen_excit_heat_bath_uniform<W>(rng, s, p, f, occ, su, s.hb_i_w, scr, 1, g);

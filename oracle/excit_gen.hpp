@@ -18,7 +18,9 @@ enum ExcitGenKind {  // values of src/qmc_data.f90:31-69
     EXCIT_GEN_RENORM = 0,
     EXCIT_GEN_NO_RENORM = 2,
     EXCIT_GEN_POWER_PITZER_OCC = 5,
+    EXCIT_GEN_POWER_PITZER_OCC_IJ = 6,
     EXCIT_GEN_CAUCHY_SCHWARZ_OCC = 8,
+    EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ = 9,
     EXCIT_GEN_HEAT_BATH = 10,
     EXCIT_GEN_HEAT_BATH_UNIFORM = 11,
     EXCIT_GEN_HEAT_BATH_SINGLE = 12,
@@ -766,11 +768,15 @@ inline double create_weighted_excitation_list_mol(const System& sys, bool cauchy
     }
     return tot;
 }
-// gen_excit_mol_power_pitzer_occ (src/excit_gen_power_pitzer_mol.F90:1260-1549), ij selected uniformly
-// (excit_gen_power_pitzer_occ, excit_gen_cauchy_schwarz_occ)
-inline GenResult gen_excit_mol_power_pitzer_occ(Rng& rng, const System& sys, const ExcitGenData& eg, const DetInfo& d) {
+// gen_excit_mol_power_pitzer_occ (src/excit_gen_power_pitzer_mol.F90:1260-1549): ij selected uniformly
+// (excit_gen_power_pitzer_occ, excit_gen_cauchy_schwarz_occ) or with the heat-bath-like weights ppm_i_d_weights /
+// ppm_ij_d_weights (the _occ_ij variants).  init_excit_mol_power_pitzer_orderM_ij (:585-647) builds those tables with
+// init_double_weights_ab (src/excit_gen_utils.f90:68-140): the same sums, in the same order, as i_weights / ij_weights
+// of init_excit_mol_heat_bath, so the heat-bath tables are used for them.
+inline GenResult gen_excit_mol_power_pitzer_occ(Rng& rng, const System& sys, const ExcitGenData& eg, DetInfo& d) {
     GenResult r;
-    const bool cs = eg.excit_gen == EXCIT_GEN_CAUCHY_SCHWARZ_OCC;
+    const bool cs = eg.excit_gen == EXCIT_GEN_CAUCHY_SCHWARZ_OCC || eg.excit_gen == EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ;
+    const bool weighted_ij = eg.excit_gen == EXCIT_GEN_POWER_PITZER_OCC_IJ || eg.excit_gen == EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ;
     if (rng.next() < eg.pattempt_single) {
         choose_ia_mol(rng, sys, sys.gamma_sym, d, r.conn.from_orb[0], r.conn.to_orb[0], r.allowed);
         r.conn.nexcit = 1;
@@ -783,14 +789,50 @@ inline GenResult gen_excit_mol_power_pitzer_occ(Rng& rng, const System& sys, con
     }
     int i, j, ij_sym, ij_spin;
     double pgen_ij;
-    choose_ij_mol(rng, sys, d.occ, i, j, ij_sym, ij_spin, pgen_ij);
     bool allowed = true, a_found = false;
+    if (weighted_ij) {
+        const HeatBath& hb = eg.hb;
+        const int nel = sys.nel;
+        double ij_w[MAXNEL], ji_w[MAXNEL], ij_tot = 0.0, ji_tot = 0.0;
+        if (!d.double_precalc) {
+            d.i_d_weights_tot = 0.0;
+            for (int p = 0; p < nel; ++p) {
+                d.i_d_weights[p] = hb.i_weights[d.occ[p] - 1];
+                d.i_d_weights_tot = d.i_d_weights_tot + d.i_d_weights[p];
+            }
+            d.double_precalc = true;
+        }
+        int i_ind = select_weighted_value(rng, nel, d.i_d_weights, d.i_d_weights_tot);
+        i = d.occ[i_ind - 1];
+        int j_ind = 1;
+        j = i;
+        for (int p = 0; p < nel; ++p) { ij_w[p] = hb.ij_weights[hb.i2(d.occ[p], i)]; ij_tot = ij_tot + ij_w[p]; }
+        if (ij_tot > 0.0) {
+            j_ind = select_weighted_value(rng, nel, ij_w, ij_tot);
+            j = d.occ[j_ind - 1];
+            for (int p = 0; p < nel; ++p) { ji_w[p] = hb.ij_weights[hb.i2(d.occ[p], j)]; ji_tot = ji_tot + ji_w[p]; }
+            allowed = true;
+        } else {
+            allowed = false;
+        }
+        pgen_ij = 0.0;
+        ij_spin = 0; ij_sym = 0;
+        if (allowed) {
+            ij_spin = sys.bf[i].ms + sys.bf[j].ms;
+            ij_sym = sys.sym_conj(sys.cross_product_basis(i, j));
+            pgen_ij = ((d.i_d_weights[i_ind - 1] / d.i_d_weights_tot) * (ij_w[j_ind - 1] / ij_tot)) +
+                      ((d.i_d_weights[j_ind - 1] / d.i_d_weights_tot) * (ji_w[i_ind - 1] / ji_tot));
+            if (j < i) std::swap(i, j);
+        }
+    } else {
+        choose_ij_mol(rng, sys, d.occ, i, j, ij_sym, ij_spin, pgen_ij);
+    }
     const std::vector<int>& ilist = (sys.bf[i].ms < 0) ? d.unocc_beta : d.unocc_alpha;
     const int ni = (int)ilist.size();
     std::vector<double> ia_w(std::max(ni, 1)), jb_w, ja_w;
     double ia_tot = 0.0, jb_tot = 0.0, ja_tot = 0.0;
     int a = 0, b = 0, a_ind = 0, b_ind = 0;
-    if (ni > 0) {
+    if (ni > 0 && allowed) {
         ia_tot = create_weighted_excitation_list_mol(sys, cs, i, 0, ilist.data(), ni, ia_w.data());
         if (ia_tot > 0.0) {
             a_ind = select_weighted_value(rng, ni, ia_w.data(), ia_tot);
@@ -856,14 +898,17 @@ inline GenResult gen_excit(Rng& rng, const System& sys, const ExcitGenData& eg, 
         case EXCIT_GEN_NO_RENORM: return gen_excit_mol_no_renorm(rng, sys, eg, d);
         case EXCIT_GEN_HEAT_BATH: return gen_excit_mol_heat_bath(rng, sys, eg, d);
         case EXCIT_GEN_POWER_PITZER_OCC:
-        case EXCIT_GEN_CAUCHY_SCHWARZ_OCC: return gen_excit_mol_power_pitzer_occ(rng, sys, eg, d);
+        case EXCIT_GEN_POWER_PITZER_OCC_IJ:
+        case EXCIT_GEN_CAUCHY_SCHWARZ_OCC:
+        case EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ: return gen_excit_mol_power_pitzer_occ(rng, sys, eg, d);
         case EXCIT_GEN_HEAT_BATH_UNIFORM:
         case EXCIT_GEN_HEAT_BATH_SINGLE: return gen_excit_mol_heat_bath_uniform(rng, sys, eg, d);
         default: throw std::runtime_error("oracle: excitation generator not implemented");
     }
 }
 inline void decode_for(const System& sys, const ExcitGenData& eg, const Det& f, DetInfo& d) {
-    if (eg.excit_gen == EXCIT_GEN_POWER_PITZER_OCC || eg.excit_gen == EXCIT_GEN_CAUCHY_SCHWARZ_OCC)
+    if (eg.excit_gen == EXCIT_GEN_POWER_PITZER_OCC || eg.excit_gen == EXCIT_GEN_CAUCHY_SCHWARZ_OCC ||
+        eg.excit_gen == EXCIT_GEN_POWER_PITZER_OCC_IJ || eg.excit_gen == EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ)
         decode_det_spinocc_spinsymunocc(sys, f, d);
     else if (eg.excit_gen == EXCIT_GEN_RENORM || eg.excit_gen == EXCIT_GEN_HEAT_BATH_UNIFORM) decode_det_occ_symunocc(sys, f, d);
     else decode_det_occ(sys, f, d);

@@ -224,7 +224,8 @@ struct Oracle {
             eg.pattempt_single = in.pattempt_single / (in.pattempt_single + in.pattempt_double);
             eg.pattempt_double = 1.0 - in.pattempt_single;
         }
-        if (in.excit_gen == EXCIT_GEN_HEAT_BATH_UNIFORM || in.excit_gen == EXCIT_GEN_HEAT_BATH_SINGLE)
+        if (in.excit_gen == EXCIT_GEN_HEAT_BATH_UNIFORM || in.excit_gen == EXCIT_GEN_HEAT_BATH_SINGLE ||
+            in.excit_gen == EXCIT_GEN_POWER_PITZER_OCC_IJ || in.excit_gen == EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ)
             init_excit_mol_heat_bath(sys, eg.hb, false);
         if (in.excit_gen == EXCIT_GEN_HEAT_BATH) {
             if (!init_excit_mol_heat_bath(sys, eg.hb, true))

@@ -12,7 +12,8 @@ LIB = os.path.join(HERE, "liboracle.so")
 REF_LIB = os.path.join(HERE, "_ref", "libhande_ref_c.so")
 HUGE = 2**31 - 1
 
-EXCIT_GEN = {"renorm": 0, "no_renorm": 2, "power_pitzer_occ": 5, "cauchy_schwarz_occ": 8, "heat_bath": 10,
+EXCIT_GEN = {"renorm": 0, "no_renorm": 2, "power_pitzer_occ": 5, "power_pitzer_occ_ij": 6, "cauchy_schwarz_occ": 8,
+             "cauchy_schwarz_occ_ij": 9, "heat_bath": 10,
              "heat_bath_uniform": 11, "heat_bath_single": 12}
 
 

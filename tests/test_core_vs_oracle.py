@@ -17,7 +17,7 @@ def _setup(path, kw, excit_gen, tau=0.01, real=False, seed=11):
     o.set_qmc(tau=tau, seed=seed, excit_gen=excit_gen, rng_kind=1, real_amplitudes=int(real), spawn_cutoff=0.01)
     o.init()
     ref = o.reference()
-    hb = o.heat_bath_tables() if excit_gen.startswith("heat_bath") else None
+    hb = o.heat_bath_tables() if (excit_gen.startswith("heat_bath") or excit_gen.endswith("_ij")) else None
     rf = 2**31 if real else 1
     cutoff = int(np.ceil(0.01 * rf)) if real else 0
     h = HdCheck(s, EXCIT_GEN[excit_gen], ref["pattempt_single"], ref["pattempt_double"], tau, 0.0, 0.0, rf, cutoff,
@@ -56,7 +56,7 @@ def test_uniform_generators_h2o(fcidump_path, gen):
         assert isref == int((f == o.reference()["f0"]).all())
 
 
-@pytest.mark.parametrize("gen", ["power_pitzer_occ", "cauchy_schwarz_occ"])
+@pytest.mark.parametrize("gen", ["power_pitzer_occ", "cauchy_schwarz_occ", "power_pitzer_occ_ij", "cauchy_schwarz_occ_ij"])
 def test_power_pitzer_occ_generators(fcidump_path, s10, gen):
     """SURVEY 8a row a10 (O(M) variants with uniform ij): bit-exact against the oracle on a D2h molecule (symmetry
     classes of different sizes) and on the C1 synthetic system."""
@@ -187,7 +187,7 @@ def test_philox_stream_matches_oracle():
 
 
 @pytest.mark.parametrize("gen", ["heat_bath", "heat_bath_uniform", "heat_bath_single", "power_pitzer_occ",
-                                 "cauchy_schwarz_occ"])
+                                 "cauchy_schwarz_occ", "power_pitzer_occ_ij", "cauchy_schwarz_occ_ij"])
 def test_heat_bath_pgen_normalisation(s10, gen):
     """SURVEY 8c gap-filler: heat-bath has no single-rank golden trajectory, so pin it statistically.  The
     generator reports pgen for the excitation it produced; over many samples each excitation must appear with

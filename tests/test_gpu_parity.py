@@ -59,6 +59,8 @@ def test_gen_excit_power_pitzer_and_cauchy_schwarz_occ():
     # the O(M) on-the-fly variants with uniformly chosen ij
     _check_gen("h2o", "power_pitzer_occ", False, 0.003, n=120)
     _check_gen("s10", "cauchy_schwarz_occ", True, 0.01, n=120, nattempt=6)
+    _check_gen("s10", "power_pitzer_occ_ij", True, 0.01, n=120, nattempt=6)
+    _check_gen("s12", "cauchy_schwarz_occ_ij", False, 0.01, n=100, nattempt=4)
 
 
 def test_gen_excit_ueg():
@@ -113,6 +115,7 @@ CASES = [
     ("s12", "heat_bath_uniform", True, True, 0.01, 2500, -1),
     ("h2o", "power_pitzer_occ", False, True, 0.003, 2500, -1),
     ("s12", "cauchy_schwarz_occ", True, False, 0.004, 2500, -1),
+    ("s12", "power_pitzer_occ_ij", True, True, 0.004, 2500, -1),
     ("ueg6", "no_renorm", False, False, 0.01, 3000, -1),
     ("ueg14", "no_renorm", True, True, 0.004, 4000, -1),
 ]

@@ -359,10 +359,11 @@ int orc_ccmc_stage_spawn(void* h, uint32_t cycle_id, double tau, double shift, d
     o->ccmc_spawn_stage(cycle_id);
     out[0] = o->last.proj_energy; out[1] = o->last.D0_population; out[2] = o->last.D0_normalisation;
     out[3] = (double)o->last.nattempts; out[4] = (double)o->last.nattempts_spawn; out[5] = (double)o->last.nspawn_events;
-    out[6] = (double)o->last.ndeath;
+    out[6] = (double)o->last.ndeath; out[7] = (double)o->last.ndeath_nc;
     return 0;
     ORC_CATCH(-1)
 }
+void orc_ccmc_set_full_nc(void* h, int full_nc) { ((OracleCcmc*)(Oracle*)h)->full_nc = full_nc != 0; }
 int orc_ccmc_get_hash_shift(void* h) { return ((OracleCcmc*)(Oracle*)h)->hash_shift; }
 void orc_ccmc_set_hash_shift(void* h, int shift, int move_freq) {
     OracleCcmc* o = (OracleCcmc*)(Oracle*)h;

@@ -30,12 +30,13 @@ struct Cluster {
 };
 
 struct CcmcStats {   // what the device engine is compared against, per cycle
-    int64_t nattempts = 0, nattempts_spawn = 0, nspawn_events = 0, ndeath = 0;
+    int64_t nattempts = 0, nattempts_spawn = 0, nspawn_events = 0, ndeath = 0, ndeath_nc = 0;
     double proj_energy = 0.0, D0_population = 0.0, D0_normalisation = 0.0;
 };
 
 struct OracleCcmc : Oracle {
     int move_freq = 5;                 // ccmc_in%move_freq (default)
+    bool full_nc = false;              // ccmc_in%full_nc (full_non_composite)
     int hash_shift = 0;                // spawn%hash_shift: +1 per cycle (src/ccmc.f90:540,625)
     int64_t nattempts_last = 0;
     std::vector<double> cumulative_abs_real_pops;
@@ -293,47 +294,81 @@ struct OracleCcmc : Oracle {
         nattempts = std::max<int64_t>(nattempts, (int64_t)std::llround(std::fabs(D0_normalisation)));
         r.nattempts = nattempts;
         const double tot_abs_real_pop = cumulative_population(r, D0_proc, D0_pos);
-        // set_cluster_selections (src/ccmc_selection.f90:874-948): all clusters selected stochastically
-        const int min_cluster_size = 0;
-        const int64_t nstochastic_clusters = nattempts;
+        // set_cluster_selections (src/ccmc_selection.f90:874-948)
+        int min_cluster_size = 0;
+        int64_t nD0_select = 0, nstochastic_clusters = nattempts, nsingle_excitors = 0;
+        if (full_nc) {
+            min_cluster_size = 2;
+            nD0_select = (int64_t)std::llround(std::fabs(D0_normalisation));
+            nstochastic_clusters = (int64_t)std::ceil(tot_abs_real_pop);
+            nsingle_excitors = r.nstates;
+            nattempts = (int64_t)std::llround(tot_abs_real_pop) + nD0_select + nstochastic_clusters;
+            r.nattempts = nattempts;
+        }
         int64_t nattempts_spawn = 0;
+        int64_t ndeath_nc = 0;
         double proj_energy_cycle = 0.0, D0_population_cycle = 0.0;
         DetInfo cdet;
         Cluster cl;
+        // do_ccmc_accumulation (src/ccmc.f90:1007-1101)
+        auto accumulate = [&]() {
+            double d0 = 0.0, pe = 0.0;
+            update_proj_energy(cdet, cl.amplitude * cl.cluster_to_det_sign / cl.pselect, d0, pe);
+            D0_population_cycle = D0_population_cycle + d0;
+            proj_energy_cycle = proj_energy_cycle + pe;
+        };
+        // perform_ccmc_spawning_attempt -> spawner_ccmc (src/ccmc_death_spawning.f90:11-211)
+        auto spawn_attempt = [&](int nspawnings_total) {
+            GenResult g = gen_excit_sys(rng, sys, EG(), cdet);
+            double hmatel = g.hmatel;
+            const double invdiagel = 1.0;
+            hmatel = hmatel * cl.amplitude * invdiagel * cl.cluster_to_det_sign;
+            const double pgen = g.pgen * cl.pselect * nspawnings_total;
+            int64_t nspawn = attempt_to_spawn(rng, hmatel, pgen, 1);
+            if (nspawn != 0) {
+                Det fexcit = sys.create_excited_det(cdet.f, g.conn);
+                const int excitor_level = sys.excitation_level(f0, fexcit);
+                const int excitor_sign = convert_excitor_to_determinant(fexcit, excitor_level);
+                if (excitor_sign < 0) nspawn = -nspawn;
+                add_spawn(r, fexcit, nspawn);   // create_spawned_particle_ccmc
+            }
+        };
+        // non-composite clusters, one per excitor (full_nc): select_nc_cluster (src/ccmc_selection.f90:462-561) +
+        // do_nc_ccmc_propagation (src/ccmc.f90:1275-1360)
+        for (int64_t iexcitor = 1; iexcitor <= nsingle_excitors; ++iexcitor) {
+            if (iexcitor == D0_pos) continue;
+            const Det& fx = r.states[iexcitor - 1];
+            cl.pselect = 1.0;
+            cl.nexcitors = 1;
+            cl.first_pos = iexcitor;
+            const double excitor_pop = (double)r.pops[iexcitor - 1] / (double)pop_real_factor;
+            cl.excitation_level = sys.excitation_level(f0, fx);
+            cl.amplitude = excitor_pop;
+            cl.cluster_to_det_sign = convert_excitor_to_determinant(fx, cl.excitation_level);
+            decode_for(sys, EG(), fx, cdet);
+            accumulate();
+            rng.begin(RNG_NATTEMPTS, fx, sys.W, 0);
+            const int nspawnings_cluster = decide_nattempts(rng, std::fabs(cl.amplitude) / cl.pselect);
+            nattempts_spawn += nspawnings_cluster;
+            cl.amplitude = cl.amplitude / std::fabs(cl.amplitude);
+            for (int ip = 0; ip < nspawnings_cluster; ++ip) {
+                rng.begin(RNG_SPAWN, fx, sys.W, (uint32_t)ip);
+                spawn_attempt(1);
+            }
+        }
         for (int64_t iattempt = 1; iattempt <= nstochastic_clusters; ++iattempt) {
             rng.begin(RNG_SPAWN, f0, sys.W, (uint32_t)iattempt);
             rng.mix((uint64_t)r.iproc * 0x9E3779B97F4A7C15ull);
             select_cluster(rng, r, ref_ex_level, nstochastic_clusters, D0_normalisation, tot_abs_real_pop, min_cluster_size,
                            max_cluster_size, cdet, cl);
             if (!(cl.excitation_level <= ref_ex_level + 2)) continue;
-            // do_ccmc_accumulation (src/ccmc.f90:1007-1101)
-            {
-                double d0 = 0.0, pe = 0.0;
-                update_proj_energy(cdet, cl.amplitude * cl.cluster_to_det_sign / cl.pselect, d0, pe);
-                D0_population_cycle = D0_population_cycle + d0;
-                proj_energy_cycle = proj_energy_cycle + pe;
-            }
+            accumulate();
             // do_stochastic_ccmc_propagation (src/ccmc.f90:1103-1191), cluster_multispawn_threshold = huge => 1 attempt
             const int nspawnings_cluster = 1;
             nattempts_spawn += nspawnings_cluster;
             const bool attempt_death = cl.excitation_level <= ref_ex_level;
-            // perform_ccmc_spawning_attempt -> spawner_ccmc (src/ccmc_death_spawning.f90:11-211)
-            {
-                GenResult g = gen_excit_sys(rng, sys, EG(), cdet);
-                double hmatel = g.hmatel;
-                const double invdiagel = 1.0;
-                hmatel = hmatel * cl.amplitude * invdiagel * cl.cluster_to_det_sign;
-                const double pgen = g.pgen * cl.pselect * nspawnings_cluster;
-                int64_t nspawn = attempt_to_spawn(rng, hmatel, pgen, 1);
-                if (nspawn != 0) {
-                    Det fexcit = sys.create_excited_det(cdet.f, g.conn);
-                    const int excitor_level = sys.excitation_level(f0, fexcit);
-                    const int excitor_sign = convert_excitor_to_determinant(fexcit, excitor_level);
-                    if (excitor_sign < 0) nspawn = -nspawn;
-                    add_spawn(r, fexcit, nspawn);   // create_spawned_particle_ccmc
-                }
-            }
-            if (attempt_death) {
+            spawn_attempt(nspawnings_cluster);
+            if (attempt_death && (cl.nexcitors >= 2 || !full_nc)) {
                 // stochastic_ccmc_death (src/ccmc_death_spawning.f90:213-361), not linked
                 const double pe_old = est.proj_energy_old;
                 double KiiAi;
@@ -359,6 +394,43 @@ struct OracleCcmc : Oracle {
                 r.ndeath += (nkill < 0 ? -nkill : nkill);
             }
         }
+        // deterministic selections of the reference (full_nc; src/ccmc.f90:803-821)
+        for (int64_t k = 1; k <= nD0_select; ++k) {
+            if (k == 1) create_null_cluster((double)in.nprocs * (double)nD0_select, D0_normalisation, cdet, cl);
+            accumulate();
+            nattempts_spawn += 1;
+            rng.begin(RNG_SPAWN, f0, sys.W, (uint32_t)(nstochastic_clusters + k));
+            rng.mix((uint64_t)r.iproc * 0x9E3779B97F4A7C15ull);
+            spawn_attempt(1);
+        }
+        // stochastic_ccmc_death_nc in place on every excip incl. the reference (full_nc; src/ccmc.f90:823-841,
+        // src/ccmc_death_spawning.f90:443-547)
+        if (full_nc) {
+            double nparticles_change = 0.0;
+            for (int64_t i = 1; i <= r.nstates; ++i) {
+                const bool isD0 = (i == D0_pos);
+                const double pe_old = est.proj_energy_old;
+                int64_t& population = r.pops[i - 1];
+                double KiiAi;
+                if (isD0) KiiAi = ((-pe_old) * 1.0 + (pe_old - shift) * 1.0) * (double)population;
+                else KiiAi = ((r.dat[i - 1] - pe_old) * 1.0 + (pe_old - shift) * 1.0) * (double)population;
+                const int64_t old_pop = population;
+                KiiAi = KiiAi * 1.0;
+                double pdeath = tau * std::fabs(KiiAi);
+                int64_t nkill = (int64_t)pdeath;
+                pdeath = pdeath - (double)nkill;
+                rng.begin(RNG_DEATH, r.states[i - 1], sys.W, 0);
+                if (pdeath > rng.next()) nkill = nkill + 1;
+                if (nkill != 0) {
+                    if (KiiAi > 0) nkill = -nkill;
+                    population = population + nkill;
+                    nparticles_change = nparticles_change +
+                        (double)((population < 0 ? -population : population) - (old_pop < 0 ? -old_pop : old_pop)) / (double)pop_real_factor;
+                    ndeath_nc += (nkill < 0 ? -nkill : nkill);
+                }
+            }
+            r.nparticles = r.nparticles + nparticles_change;
+        }
         r.D0_population = r.D0_population + D0_population_cycle;
         r.proj_energy = r.proj_energy + proj_energy_cycle;
         int ev = 0;
@@ -366,8 +438,10 @@ struct OracleCcmc : Oracle {
         r.nspawn_events = ev;
         last.nattempts = nattempts; last.nattempts_spawn = nattempts_spawn; last.nspawn_events = ev; last.ndeath = r.ndeath;
         last.proj_energy = proj_energy_cycle; last.D0_population = D0_population_cycle; last.D0_normalisation = D0_normalisation;
-        // end_mc_cycle(nspawn_events, ndeath_nc = 0, real_factor, nattempts_spawn, rspawn)
-        r.rspawn = r.rspawn + ((nattempts_spawn > 0) ? (double)ev / (double)nattempts_spawn : 0.0);
+        // end_mc_cycle(nspawn_events, ndeath_nc, real_factor, nattempts_spawn, rspawn): spawning_rate
+        r.rspawn = r.rspawn + ((nattempts_spawn > 0)
+                                   ? ((double)ev + (double)ndeath_nc / (double)pop_real_factor) / (double)nattempts_spawn : 0.0);
+        last.ndeath_nc = ndeath_nc;
     }
     static double invdiag() { return 1.0; }
 

@@ -108,6 +108,7 @@ def lib():
         L.orc_set_reference_det.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_iterate.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_void_p]
         L.orc_stage_spawn.argtypes = [C.c_void_p, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_void_p]
+        L.orc_ccmc_set_full_nc.argtypes = [C.c_void_p, C.c_int]
         L.orc_ccmc_stage_spawn.argtypes = [C.c_void_p, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_void_p]
         L.orc_spawn_count.restype = C.c_int64
         L.orc_spawn_count.argtypes = [C.c_void_p, C.c_int]
@@ -343,8 +344,12 @@ class Oracle:
         sd = np.zeros((n, self.W + 2), dtype=np.int64)
         self.L.orc_get_spawn(self.h, 0, _p(sd))
         keys = ["proj_energy", "D0_population", "D0_normalisation", "nattempts", "nattempts_spawn", "nspawn_events",
-                "ndeath"]
+                "ndeath", "ndeath_nc"]
         return dict(zip(keys, out)), sd
+
+    def ccmc_set_full_nc(self, full_nc=True):
+        """ccmc = { full_non_composite = true }"""
+        self.L.orc_ccmc_set_full_nc(self.h, int(full_nc))
 
     def ccmc_hash_shift(self):
         return int(self.L.orc_ccmc_get_hash_shift(self.h))

@@ -35,6 +35,7 @@ def _run(case, fcidump_path, nrows):
     o.set_qmc(**q)
     o.init()
     if g.get("ccmc"):
+        o.ccmc_set_full_nc(bool(g.get("full_nc")))
         rows, na = o.run_ccmc()
         rows = np.concatenate([rows, na.reshape(-1, 1).astype(float)], axis=1)
     else:
@@ -104,6 +105,12 @@ def test_ccmc_ccsd_h2o_np2(fcidump_path):
     # two ranks: time-varying hash owner (hash_shift / move_freq), redistribute_particles, per-rank dSFMT streams;
     # the complete 176-row table was verified with tools/golden_compare.py ccmc_h2o_np2
     _run("ccmc_h2o_np2", fcidump_path, 45)
+
+
+def test_ccmc_ccsdt_full_non_composite_np2(fcidump_path):
+    # ccmc = { full_non_composite = true }, CCSDT in a CAS, two ranks: select_nc_cluster, do_nc_ccmc_propagation,
+    # stochastic_ccmc_death_nc, deterministic reference selections (all 91 rows verified with tools/golden_compare.py)
+    _run("ccmc_h2o_ccsdt_fullnc_np2", fcidump_path, 40)
 
 
 def test_dsfmt_and_murmur_known_answers():

@@ -61,6 +61,12 @@ CASES = {
                          qmc=dict(tau=0.01, seed=1660032958, D0_population=500, ncycles=10, nreport=175,
                                   target_particles=50000, walker_length=3571428 // 1, spawned_walker_length=1562500,
                                   ex_level=2, nprocs=2)),
+    # CCSDT, full_non_composite = true (select_nc_cluster, stochastic_ccmc_death_nc, deterministic reference attempts)
+    "ccmc_h2o_ccsdt_fullnc_np2": dict(dir="ccmc/np2/H2O-cc-pVDZ_ccsdt", bench="benchmark.out.9712b5a3.inp=ccsdt.in",
+                                      int_file="INTDUMP", sys=dict(nel=10, ms=0, sym=0, cas=(8, 22)), ccmc=True, full_nc=True,
+                                      qmc=dict(tau=0.002, seed=1660032958, D0_population=2000, ncycles=10, nreport=90,
+                                               target_particles=62327.28366800, walker_length=3571428,
+                                               spawned_walker_length=1562500, ex_level=3, nprocs=2)),
 }
 
 ROW_CCMC = re.compile(r"^\s*#?\s+(\d+)\s+(-?\d\.\d+E[+-]\d+)\s+(-?\d\.\d+E[+-]\d+)\s+(-?\d\.\d+E[+-]\d+)\s+"
@@ -114,6 +120,7 @@ def run_case(name, max_rows=None, quiet=False):
     o.init()
     t = time.time()
     if c.get("ccmc"):
+        o.ccmc_set_full_nc(bool(c.get("full_nc")))
         rows, na = o.run_ccmc()
         rows = np.concatenate([rows, na.reshape(-1, 1).astype(float)], axis=1)
     else:

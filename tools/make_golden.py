@@ -18,7 +18,8 @@ from tools.golden_compare import CASES, TS, parse_table  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 FCIDUMP_NAME = {"h2o": "h2o", "ne_init": "ne", "ne_ci6_np2": "ne", "ne_ci6_np4": "ne", "ne_ci6_real64_np2": "ne",
-                "ccmc_ne": "ne_vdz", "ccmc_h2o_np2": "h2o_vdz"}
+                "ccmc_ne": "ne_vdz", "ccmc_h2o_np2": "h2o_vdz",
+                "ccmc_h2o_ccsdt_fullnc_np2": "h2o_vdz"}
 
 os.makedirs(os.path.join(OUT, "fcidump"), exist_ok=True)
 for name, c in CASES.items():
@@ -42,7 +43,7 @@ for name, c in CASES.items():
     rows = parse_table(d + c["bench"]).tolist()
     cols = ["iterations", "shift", "proj_energy", "D0_population", "nparticles", "nstates", "nspawn_events", "rspawn"]
     json.dump({"source": "test_suite/" + c["dir"] + "/" + c["bench"], "fcidump": FCIDUMP_NAME[name], "sys": c["sys"],
-               "qmc": c["qmc"], "ccmc": bool(c.get("ccmc")),
+               "qmc": c["qmc"], "ccmc": bool(c.get("ccmc")), "full_nc": bool(c.get("full_nc")),
                "columns": cols + (["nattempts"] if c.get("ccmc") else []),
                "rows": rows}, open(os.path.join(OUT, name + ".json"), "w"))
     print(name, len(rows), "rows")

@@ -4,8 +4,8 @@ death and annihilation on the GPU) and then does `end_report_loop` exactly as th
 averages, shift update, one output row in HANDE's CCMC table format (with the "# attempts" column,
 src/qmc_io.f90:412-508).
 
-Scope of this version: stochastic cluster selection (the default; not full_nc, linked,
-even_selection or multi-reference), real orbitals; any number of ranks (the engine re-hashes and redistributes the
+Scope of this version: stochastic cluster selection (the default) and
+`full_non_composite` (not linked, even_selection or multi-reference), real orbitals; any number of ranks (the engine re-hashes and redistributes the
 excips every cycle as the reference does, src/qmc_common.F90:505-595).  Option names follow the Lua `ccmc{ qmc = {...},
 reference = { ex_level = ... } }` table.
 """
@@ -58,6 +58,8 @@ def do_ccmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, ke
                      spawned_walker_length=sl, seed=qmc.rng_seed, nprocs=nprocs, iproc=iproc, nslots=qmc.nslots,
                      device=device)
     eng.set_reference(f0, H00)
+    if qmc.full_non_composite:
+        eng.ccmc_set_full_nc(True)
     if nprocs > 1:
         uid = eng.get_unique_id() if iproc == 0 else np.zeros(128, dtype=np.uint8)
         eng.comm_init(comm.broadcast_bytes(uid, src=0))

@@ -1544,13 +1544,19 @@ HB_HD int excit_level(const uint64_t* f, const uint64_t* f0) {
 // ------------------------------------------------------------------------------------------------
 struct CcmcArgs {
     long long nstates;          // psip_list%nstates
-    long long nattempts;        // selection_data%nstochastic_clusters (= estimators%nattempts)
+    long long nattempts;        // cluster-kernel attempts: nstochastic + nD0_select
+    long long nstochastic;      // selection_data%nstochastic_clusters (enters pselect)
     long long D0_pos;           // 1-based position of the reference in the main list
     double D0_normalisation;    // population on the reference / real_factor
     double tot_abs_real_pop;    // cumulative population of all excitors but the reference
     int ex_level;               // qs%ref%ex_level (CC truncation level)
     int max_cluster_size;       // min(nel, ex_level+2, nstates-1)
     int nprocs;
+    // set_cluster_selections (src/ccmc_selection.f90:874-948): full_nc = 0: all nattempts clusters are stochastic with
+    // sizes from 0; full_nc = 1: composite clusters (size >= 2) are stochastic, every excitor is a non-composite cluster
+    // of its own and the reference is selected nD0_select times
+    int full_nc, min_cluster_size;
+    long long nD0_select;
 };
 struct Cluster {
     int nexcitors, excitation_level, sign;   // excitation_level < 0: cluster not allowed (huge(0) in the reference)
@@ -1672,9 +1678,9 @@ template <int W, class R>
 HB_HDN void ccmc_select_cluster(R& rng, const Params& p, const CcmcArgs& a, const uint64_t* __restrict__ states,
                                 const int64_t* __restrict__ pops, const long long* __restrict__ cum_enc, uint64_t* cf,
                                 Cluster& cl) {
-    const int min_size = 0, max_size = a.max_cluster_size;
+    const int min_size = a.min_cluster_size, max_size = a.max_cluster_size;
     const double rf = (double)p.real_factor;
-    cl.pselect = (double)(a.nattempts * a.nprocs);
+    cl.pselect = (double)(a.nstochastic * a.nprocs);
     const double rand = rng.next();
     double psize = 0.0;
     cl.nexcitors = -1;
@@ -1709,7 +1715,7 @@ HB_HDN void ccmc_select_cluster(R& rng, const Params& p, const CcmcArgs& a, cons
     }
     long long prev_pos = 1;
     double cluster_population = 0.0;
-    bool allowed = true;
+    bool allowed = min_size <= max_size;
     for (int i = 1; i <= cl.nexcitors; ++i) {
         const long long pos = ccmc_find_excitor(cum_enc, pop[i - 1], prev_pos, a.nstates, rf);
         const double excitor_pop = (double)pops[pos - 1] / rf;
@@ -1723,8 +1729,8 @@ HB_HDN void ccmc_select_cluster(R& rng, const Params& p, const CcmcArgs& a, cons
             cluster_population = excitor_pop;
             cl.pselect = cl.pselect / a.nprocs;
         } else {
-            allowed = ccmc_collapse<W>(p.f0, ex, excitor_pop, cf, cluster_population);
-            if (!allowed) break;
+            const bool ok = ccmc_collapse<W>(p.f0, ex, excitor_pop, cf, cluster_population);
+            if (!ok) { allowed = false; break; }
             if (pos != prev_pos) cl.pselect = cl.pselect / a.nprocs;
         }
         cl.pselect = (cl.pselect * fabs(excitor_pop)) / a.tot_abs_real_pop;

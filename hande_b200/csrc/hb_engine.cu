@@ -571,7 +571,17 @@ k_ccmc_cluster(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states,
         rng.begin(p.seed, p.cycle, RNG_SPAWN, det_hash64<W>(p.f0) + (uint64_t)p.iproc * 0x9E3779B97F4A7C15ull,
                   (uint32_t)(idx + 1));
         Cluster cl;
-        ccmc_select_cluster<W>(rng, p, a, states, pops, cum_enc, cf, cl);
+        const bool det_D0 = idx >= a.nattempts - a.nD0_select;    // deterministic selections of the reference (full_nc)
+        if (det_D0) {
+            // create_null_cluster(prob = nprocs * nD0_select) (src/ccmc.f90:803-812)
+#pragma unroll
+            for (int k = 0; k < W; ++k) cf[k] = p.f0[k];
+            cl.nexcitors = 0; cl.excitation_level = 0; cl.sign = 1; cl.first_pos = 0;
+            cl.amplitude = a.D0_normalisation;
+            cl.pselect = (double)a.nprocs * (double)a.nD0_select;
+        } else {
+            ccmc_select_cluster<W>(rng, p, a, states, pops, cum_enc, cf, cl);
+        }
         if (cl.excitation_level >= 0 && cl.excitation_level <= a.ex_level + 2) {
             uint8_t occ[HB_MAXNEL], su[64];
             decode_det<W>(cf, occ);
@@ -598,7 +608,7 @@ k_ccmc_cluster(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states,
                                                                             p.nprocs, p.nslots)] : 0;
             }
             // stochastic_ccmc_death + stochastic_death_attempt (src/ccmc_death_spawning.f90:213-441)
-            if (cl.excitation_level <= a.ex_level) {
+            if (!det_D0 && cl.excitation_level <= a.ex_level && (cl.nexcitors >= 2 || !a.full_nc)) {
                 const double pe_old = p.proj_energy_old;
                 double KiiAi;
                 if (cl.nexcitors == 0) KiiAi = ((-pe_old) * 1.0 + (pe_old - p.shift) * 1.0) * cl.amplitude;
@@ -639,6 +649,105 @@ k_ccmc_cluster(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states,
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { out.pe += sd[0][w]; out.d0 += sd[1][w]; out.ndeath += sl[0][w]; out.nattempts_spawn += sl[1][w]; }
         partials[blockIdx.x] = out;
     }
+}
+// full_nc: every excitor is a non-composite cluster of its own - select_nc_cluster (src/ccmc_selection.f90:462-561),
+// do_nc_ccmc_propagation (src/ccmc.f90:1275-1360) - and every excip (the reference included) dies in place through
+// stochastic_ccmc_death_nc (src/ccmc_death_spawning.f90:443-547).  Thread per excitor; launched after k_ccmc_cluster,
+// which reads the populations this kernel changes.
+template <int W>
+__global__ void __launch_bounds__(256)
+k_ccmc_nc(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states, int64_t* __restrict__ pops,
+          const double* __restrict__ dat, int64_t* __restrict__ spawn, unsigned long long* __restrict__ head,
+          long long block_size, const int* __restrict__ proc_map, CcmcPartials* __restrict__ partials,
+          long long* __restrict__ ndeath_nc_out, int* __restrict__ err) {
+    __shared__ double sd[2][8];
+    __shared__ long long sl[2][8];
+    constexpr int E = W + 2;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long i = (long long)blockIdx.x * blockDim.x + tid;
+    double pe = 0.0, d0 = 0.0;
+    long long ndeath_nc = 0, nas = 0;
+    if (i < a.nstates) {
+        uint64_t f[W];
+        load_det<W>(states + i * W, f);
+        const int64_t pop = pops[i];
+        const uint64_t h = det_hash64<W>(f);
+        const bool isD0 = (i + 1 == a.D0_pos);
+        PhiloxStream rng;
+        if (!isD0) {
+            const double amp = (double)pop / (double)p.real_factor;
+            const int level = excit_level<W>(f, p.f0);
+            const int sign = ccmc_excitor_sign<W>(p.f0, f, level);
+            uint8_t occ[HB_MAXNEL], su[64];
+            decode_det<W>(f, occ);
+            if (s.kind == SYS_READ_IN && p.excit_gen != EXCIT_GEN_NO_RENORM && p.excit_gen != EXCIT_GEN_HEAT_BATH)
+                build_symunocc_masks<W>(s, f, su);
+            bool is_ref;
+            const double hm0 = proj_energy_hmatel<W>(s, p, f, occ, is_ref);
+            pe = hm0 * (amp * sign / 1.0);
+            rng.begin(p.seed, p.cycle, RNG_NATTEMPTS, h, 0);
+            const int nsp = decide_nattempts(rng, fabs(amp) / 1.0);
+            nas = nsp;
+            const double unit = amp / fabs(amp);
+            for (int ip = 0; ip < nsp; ++ip) {
+                rng.begin(p.seed, p.cycle, RNG_SPAWN, h, (uint32_t)ip);
+                Gen g;
+                gen_excit<W>(rng, s, p, f, occ, su, g);
+                const double hmatel = g.hmatel * unit * 1.0 * sign;
+                const double pgen = g.pgen * 1.0 * 1;
+                int64_t nspawn = attempt_to_spawn(rng, p, hmatel, pgen, (int64_t)1);
+                if (nspawn != 0) {
+                    uint64_t child[W];
+                    make_child<W>(f, g, child);
+                    const int lvl = excit_level<W>(child, p.f0);
+                    if (ccmc_excitor_sign<W>(p.f0, child, lvl) < 0) nspawn = -nspawn;
+                    if (!(p.trunc_level >= 0 && lvl > p.trunc_level)) {
+                        const int dest = (p.nprocs > 1) ? proc_map[owner_slot_shift<W>(child, s.nbasis, p.hash_seed, p.ccmc_shift,
+                                                                                         p.ccmc_freq, p.nprocs, p.nslots)] : 0;
+                        const long long slot = (long long)atomicAdd(&head[dest], 1ull);
+                        if (slot < block_size) {
+                            int64_t* dst = spawn + ((long long)dest * block_size + slot) * E;
+#pragma unroll
+                            for (int k = 0; k < W; ++k) dst[k] = (int64_t)child[k];
+                            dst[W] = nspawn;
+                            dst[W + 1] = 0;
+                        } else {
+                            atomicOr(err, 1);
+                        }
+                    }
+                }
+            }
+        }
+        // stochastic_ccmc_death_nc
+        {
+            const double pe_old = p.proj_energy_old;
+            double KiiAi;
+            if (isD0) KiiAi = ((-pe_old) * 1.0 + (pe_old - p.shift) * 1.0) * (double)pop;
+            else KiiAi = ((dat[i] - pe_old) * 1.0 + (pe_old - p.shift) * 1.0) * (double)pop;
+            KiiAi = KiiAi * 1.0;
+            double pdeath = p.tau * fabs(KiiAi);
+            int64_t nkill = (int64_t)pdeath;
+            pdeath = pdeath - (double)nkill;
+            rng.begin(p.seed, p.cycle, RNG_DEATH, h, 0);
+            if (pdeath > rng.next()) nkill = nkill + 1;
+            if (nkill != 0) {
+                if (KiiAi > 0) nkill = -nkill;
+                pops[i] = pop + nkill;
+                ndeath_nc = nkill < 0 ? -nkill : nkill;
+            }
+        }
+    }
+    const double r0 = warp_sum_d(pe), r1 = warp_sum_d(d0);
+    const long long r2 = warp_sum_ll(ndeath_nc), r3 = warp_sum_ll(nas);
+    if (lane == 0) { sd[0][warp] = r0; sd[1][warp] = r1; sl[0][warp] = r2; sl[1][warp] = r3; }
+    __syncthreads();
+    if (tid == 0) {
+        CcmcPartials out;
+        out.pe = 0.0; out.d0 = 0.0; out.ndeath = 0; out.nattempts_spawn = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { out.pe += sd[0][w]; out.d0 += sd[1][w]; out.ndeath += sl[0][w]; out.nattempts_spawn += sl[1][w]; }
+        partials[blockIdx.x] = out;
+    }
+    (void)ndeath_nc_out;
 }
 __global__ void k_ccmc_reduce(const CcmcPartials* __restrict__ partials, int n, CcmcPartials* out) {
     __shared__ double sd[2][32];
@@ -1370,6 +1479,7 @@ struct hb200_engine {
     int* d_total = nullptr;   // [4] small ints
     long long* d_part_ll = nullptr;
     long long* d_ll = nullptr;  // [4]
+    bool ccmc_full_nc = false;                     // ccmc_in%full_nc
     int ccmc_hash_shift = 0, ccmc_move_freq = 5;   // spawn%hash_shift (+1 per cycle), spawn%move_freq
     // CCMC scratch
     long long* d_cum = nullptr;        // [walker_length] inclusive prefix sums of |pop| (reference skipped)
@@ -2048,8 +2158,8 @@ int hb200_ccmc_spawn(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, i
         const long long cap = e->cfg.walker_length;
         if (dalloc(e, &e->d_cum, (size_t)cap)) return 1;
         if (dalloc(e, &e->d_cum_blk, (size_t)(cap / (256 * SCAN64_ITEMS) + 2))) return 1;
-        if (dalloc(e, &e->d_cc_part, (size_t)(e->cfg.spawned_walker_length / 256 + cap / 256 + 4))) return 1;
-        if (dalloc(e, &e->d_cc_tot, 1)) return 1;
+        if (dalloc(e, &e->d_cc_part, 2 * (size_t)(e->cfg.spawned_walker_length / 256 + cap / 256 + 4))) return 1;
+        if (dalloc(e, &e->d_cc_tot, 2)) return 1;
     }
     CK(cudaMemsetAsync(e->d_head, 0, sizeof(unsigned long long) * p.nprocs, st));
     // get_D0_info (src/ccmc_utils.F90:69-130): owner of the reference under the current hash shift, its position and
@@ -2089,7 +2199,6 @@ int hb200_ccmc_spawn(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, i
     // init_mc_cycle (src/qmc_common.F90:950-1017, ccmc branch) with min_attempts = nint(|D0_normalisation|)
     long long nattempts = (long long)((double)e->nparticles_enc / (double)p.real_factor);
     nattempts = std::max<long long>(nattempts, llround(fabs(a.D0_normalisation)));
-    a.nattempts = nattempts;
     // cumulative_population (src/ccmc_utils.F90:427-563)
     long long tot_enc = 0;
     if (n > 0) {
@@ -2103,11 +2212,26 @@ int hb200_ccmc_spawn(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, i
         e->launches += 3;
     }
     a.tot_abs_real_pop = (double)tot_enc / (double)p.real_factor;
-    CcmcPartials tot;
+    // set_cluster_selections (src/ccmc_selection.f90:874-948)
+    a.full_nc = e->ccmc_full_nc ? 1 : 0;
+    if (e->ccmc_full_nc) {
+        a.min_cluster_size = 2;
+        a.nD0_select = llround(fabs(a.D0_normalisation));
+        a.nstochastic = (long long)ceil(a.tot_abs_real_pop);
+        nattempts = llround(a.tot_abs_real_pop) + a.nD0_select + a.nstochastic;   // estimators%nattempts
+    } else {
+        a.min_cluster_size = 0;
+        a.nD0_select = 0;
+        a.nstochastic = nattempts;
+    }
+    a.nattempts = a.nstochastic + a.nD0_select;
+    CcmcPartials tot, tot_nc;
     memset(&tot, 0, sizeof(tot));
-    if (nattempts > 0) {
-        const long long nblk = (nattempts + 255) / 256;
-        if ((size_t)nblk > (size_t)(e->cfg.spawned_walker_length / 256 + e->cfg.walker_length / 256 + 4))
+    memset(&tot_nc, 0, sizeof(tot_nc));
+    const size_t part_cap = (size_t)(e->cfg.spawned_walker_length / 256 + e->cfg.walker_length / 256 + 4);
+    if (a.nattempts > 0) {
+        const long long nblk = (a.nattempts + 255) / 256;
+        if ((size_t)nblk > part_cap)
             FAIL("ccmc_spawn: more cluster selections than the partial-sum scratch holds");
         DISPATCH_W(e, k_ccmc_cluster<WW><<<(unsigned)nblk, 256, 0, st>>>(e->sys, p, a, e->d_states[c], e->d_pops[c], e->d_dat[c],
                                                                           e->d_cum, e->d_spawn[0], e->d_head, e->block_size,
@@ -2117,6 +2241,18 @@ int hb200_ccmc_spawn(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, i
         CK(cudaGetLastError());
         e->launches += 2;
         CK(cudaMemcpyAsync(&tot, e->d_cc_tot, sizeof(tot), cudaMemcpyDeviceToHost, st));
+    }
+    if (e->ccmc_full_nc && n > 0) {
+        // non-composite clusters + in-place death; after k_ccmc_cluster, which reads the populations changed here
+        const long long nblk = (n + 255) / 256;
+        DISPATCH_W(e, k_ccmc_nc<WW><<<(unsigned)nblk, 256, 0, st>>>(e->sys, p, a, e->d_states[c], e->d_pops[c], e->d_dat[c],
+                                                                     e->d_spawn[0], e->d_head, e->block_size, e->d_proc_map,
+                                                                     e->d_cc_part + part_cap, nullptr, e->d_err));
+        CK(cudaGetLastError());
+        k_ccmc_reduce<<<1, 1024, 0, st>>>(e->d_cc_part + part_cap, (int)nblk, e->d_cc_tot + 1);
+        CK(cudaGetLastError());
+        e->launches += 2;
+        CK(cudaMemcpyAsync(&tot_nc, e->d_cc_tot + 1, sizeof(tot_nc), cudaMemcpyDeviceToHost, st));
     }
     CK(cudaMemcpyAsync(e->h_head.data(), e->d_head, sizeof(unsigned long long) * p.nprocs, cudaMemcpyDeviceToHost, st));
     int herr[2] = {0, 0};
@@ -2142,13 +2278,19 @@ int hb200_ccmc_spawn(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, i
     e->sp_cur = 0;
     e->sp_blocked = p.nprocs > 1;
     e->sp_n = (p.nprocs == 1) ? (long long)e->h_head[0] : 0;
-    out->proj_energy = tot.pe; out->D0_population = tot.d0; out->D0_normalisation = a.D0_normalisation;
-    out->nattempts = nattempts; out->nattempts_spawn = tot.nattempts_spawn; out->ndeath = tot.ndeath;
+    out->proj_energy = tot.pe + tot_nc.pe; out->D0_population = tot.d0 + tot_nc.d0;
+    out->D0_normalisation = a.D0_normalisation;
+    out->nattempts = nattempts; out->nattempts_spawn = tot.nattempts_spawn + tot_nc.nattempts_spawn;
+    out->ndeath = tot.ndeath; out->ndeath_nc = tot_nc.ndeath;
     out->nspawn_events = nspawn_events; out->tot_abs_real_pop = a.tot_abs_real_pop;
     out->spawn_error = herr[0]; out->psip_error = herr[1];
     return 0;
 }
 
+int hb200_ccmc_set_full_nc(hb200_engine* e, int32_t full_nc) {
+    e->ccmc_full_nc = full_nc != 0;
+    return 0;
+}
 int hb200_ccmc_set_hash_shift(hb200_engine* e, int32_t hash_shift, int32_t move_freq) {
     e->ccmc_hash_shift = hash_shift;
     e->ccmc_move_freq = move_freq;
@@ -2177,8 +2319,9 @@ int hb200_ccmc_iterate(hb200_engine* e, int32_t ncycles, const hb200_iter_in* in
         if (stage_comm(e)) return 1;
         if (stage_sort(e)) return 1;
         if (stage_annihilate_main(e, cycle, &cs)) return 1;
-        // end_mc_cycle(nspawn_events, ndeath_nc = 0, real_factor, nattempts_spawn, rspawn)
-        if (co.nattempts_spawn > 0) out->rspawn += (double)co.nspawn_events / (double)co.nattempts_spawn;
+        // end_mc_cycle(nspawn_events, ndeath_nc, real_factor, nattempts_spawn, rspawn)
+        if (co.nattempts_spawn > 0)
+            out->rspawn += ((double)co.nspawn_events + (double)co.ndeath_nc / (double)e->par.real_factor) / (double)co.nattempts_spawn;
     }
     fill_out(e, out, cs, nattempts);
     out->ndeath = co.ndeath;

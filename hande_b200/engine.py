@@ -73,7 +73,8 @@ class CcmcOut(C.Structure):
     _fields_ = [
         ("proj_energy", C.c_double), ("D0_population", C.c_double), ("D0_normalisation", C.c_double),
         ("tot_abs_real_pop", C.c_double), ("nattempts", C.c_int64), ("nattempts_spawn", C.c_int64),
-        ("nspawn_events", C.c_int64), ("ndeath", C.c_int64), ("spawn_error", C.c_int32), ("psip_error", C.c_int32),
+        ("nspawn_events", C.c_int64), ("ndeath", C.c_int64), ("ndeath_nc", C.c_int64), ("spawn_error", C.c_int32),
+        ("psip_error", C.c_int32),
     ]
 
     def as_dict(self):
@@ -133,6 +134,7 @@ def load_library():
     L.hb200_ccmc_spawn.argtypes = [C.c_void_p, C.POINTER(IterIn), C.c_uint32, C.c_int32, C.POINTER(CcmcOut)]
     L.hb200_ccmc_iterate.argtypes = [C.c_void_p, C.c_int32, C.POINTER(IterIn), C.c_int32, C.POINTER(IterOut)]
     L.hb200_ccmc_set_hash_shift.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+    L.hb200_ccmc_set_full_nc.argtypes = [C.c_void_p, C.c_int32]
     L.hb200_comm_spawn.argtypes = [C.c_void_p]
     L.hb200_annihilate_spawn.argtypes = [C.c_void_p]
     L.hb200_annihilate_main.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(IterOut)]
@@ -154,7 +156,7 @@ ABI_SYMBOLS = [
     "hb200_download_heat_bath", "hb200_set_reference", "hb200_set_proc_map", "hb200_upload_psips",
     "hb200_upload_psips_begin", "hb200_upload_psips_commit",
     "hb200_download_psips", "hb200_nstates", "hb200_iterate", "hb200_spawn_death", "hb200_comm_spawn",
-    "hb200_ccmc_spawn", "hb200_ccmc_iterate", "hb200_ccmc_set_hash_shift", "hb200_annihilate_spawn", "hb200_annihilate_main", "hb200_download_spawn", "hb200_upload_spawn",
+    "hb200_ccmc_spawn", "hb200_ccmc_iterate", "hb200_ccmc_set_hash_shift", "hb200_ccmc_set_full_nc", "hb200_annihilate_spawn", "hb200_annihilate_main", "hb200_download_spawn", "hb200_upload_spawn",
     "hb200_sc0_batch", "hb200_gen_excit_batch", "hb200_get_unique_id", "hb200_comm_init", "hb200_last_timing",
 ]
 
@@ -305,6 +307,9 @@ class Engine:
         o = IterOut()
         self._chk(self.L.hb200_ccmc_iterate(self.h, ncycles, C.byref(i), ex_level, C.byref(o)))
         return o.as_dict()
+
+    def ccmc_set_full_nc(self, full_nc=True):
+        self._chk(self.L.hb200_ccmc_set_full_nc(self.h, int(bool(full_nc))))
 
     def ccmc_set_hash_shift(self, hash_shift, move_freq=5):
         self._chk(self.L.hb200_ccmc_set_hash_shift(self.h, int(hash_shift), int(move_freq)))

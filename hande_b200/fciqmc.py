@@ -46,6 +46,7 @@ class QmcIn:
     spawned_state_size: int = -1
     ex_level: int = -1              # reference = {ex_level = ...}: truncation level, -1 = none
     nslots: int = 1
+    full_non_composite: bool = False  # ccmc = {full_non_composite = true} (CCMC only)
     reference_det: list = None      # reference = {det = {...}}: explicit reference determinant (1-based orbitals)
 
 

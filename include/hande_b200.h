@@ -115,7 +115,8 @@ typedef struct hb200_ccmc_out {
     int64_t nattempts;             /* qs%estimators%nattempts = number of cluster selections */
     int64_t nattempts_spawn;       /* spawning attempts made (accepted clusters) */
     int64_t nspawn_events;         /* entries added to the spawn list (spawns and deaths) */
-    int64_t ndeath;                /* sum |nkill| */
+    int64_t ndeath;                /* sum |nkill| of stochastic_ccmc_death (spawned as anti-excips) */
+    int64_t ndeath_nc;             /* sum |nkill| of stochastic_ccmc_death_nc (full_nc: in place) */
     int32_t spawn_error, psip_error;
 } hb200_ccmc_out;
 
@@ -168,6 +169,10 @@ int hb200_ccmc_iterate(hb200_engine* e, int32_t ncycles, const hb200_iter_in* in
  * a restart.  With nprocs > 1 every cycle ends with redistribute_particles (src/qmc_common.F90:505-595) through the
  * same NCCL exchange as the spawned excips, and the reference population is broadcast from its owner (get_D0_info). */
 int hb200_ccmc_set_hash_shift(hb200_engine* e, int32_t hash_shift, int32_t move_freq);
+/* ccmc = { full_non_composite = true } (ccmc_in%full_nc): every excitor is propagated as a non-composite cluster of its
+ * own (select_nc_cluster, do_nc_ccmc_propagation) and dies in place (stochastic_ccmc_death_nc), composite clusters of
+ * size >= 2 are selected stochastically and the reference is selected nint(|N_0|) times. */
+int hb200_ccmc_set_full_nc(hb200_engine* e, int32_t full_nc);
 
 /* Stage-level entry points (same state machine as hb200_iterate, one stage per call). */
 /* do idet loop: decoder_ptr, set_parent_flag, update_proj_energy_ptr, decide_nattempts,

@@ -23,20 +23,24 @@ def _grow(o, tau, ncycles, pop0, rf):
 
 
 CASES = [
-    # system, generator, real amplitudes, ex_level, tau, warm-up cycles
-    ("ne_vdz", "renorm", False, 2, 0.01, 120),     # the reference's CCSD fixture
-    ("ne_vdz", "no_renorm", True, 3, 0.005, 120),  # CCSDT, real amplitudes
-    ("s12", "renorm", True, 3, 0.001, 40),
-    ("s12", "heat_bath_uniform", True, 2, 0.001, 40),
-    ("s40", "renorm", False, 3, 0.0003, 30),         # two-word bit strings
-    ("ueg6", "no_renorm", True, 2, 0.01, 80),      # CCMC on the UEG (doubles only)
+    # system, generator, real amplitudes, ex_level, tau, warm-up cycles, full_non_composite
+    ("ne_vdz", "renorm", False, 2, 0.01, 120, False),     # the reference's CCSD fixture
+    ("ne_vdz", "no_renorm", True, 3, 0.005, 120, False),  # CCSDT, real amplitudes
+    ("s12", "renorm", True, 3, 0.001, 40, False),
+    ("s12", "heat_bath_uniform", True, 2, 0.001, 40, False),
+    ("s40", "renorm", False, 3, 0.0003, 30, False),         # two-word bit strings
+    ("ueg6", "no_renorm", True, 2, 0.01, 80, False),      # CCMC on the UEG (doubles only)
+    ("ne_vdz", "renorm", False, 3, 0.005, 100, True),     # full_nc: non-composite clusters + in-place death
+    ("s12", "renorm", True, 2, 0.001, 40, True),
 ]
 
 
-@pytest.mark.parametrize("name,gen,real,exl,tau,warm", CASES)
-def test_ccmc_stage_and_cycle_parity(name, gen, real, exl, tau, warm):
+@pytest.mark.parametrize("name,gen,real,exl,tau,warm,full_nc", CASES)
+def test_ccmc_stage_and_cycle_parity(name, gen, real, exl, tau, warm, full_nc):
     s, o, eng, ref = make_pair(name, excit_gen=gen, tau=tau, real=real, ex_level=exl, walker_length=1 << 18,
                                spawned_walker_length=1 << 17)
+    o.ccmc_set_full_nc(full_nc)
+    eng.ccmc_set_full_nc(full_nc)
     rf = 2**31 if real else 1
     pe_old = _grow(o, tau, warm, 200, rf)
     f, pops, dat = o.get_psips()
@@ -51,7 +55,7 @@ def test_ccmc_stage_and_cycle_parity(name, gen, real, exl, tau, warm):
         assert st_g["D0_normalisation"] == st_o["D0_normalisation"]
         assert st_g["nspawn_events"] == st_o["nspawn_events"] == len(sd_o)
         assert (sort_rows(sd_g) == sort_rows(sd_o)).all()
-        assert st_g["ndeath"] == st_o["ndeath"]
+        assert st_g["ndeath"] == st_o["ndeath"] and st_g["ndeath_nc"] == st_o["ndeath_nc"]
         for key in ("proj_energy", "D0_population"):
             assert abs(st_g[key] - st_o[key]) <= 1e-11 * max(1.0, abs(st_o[key])), key
         eng.annihilate_spawn()

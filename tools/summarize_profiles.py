@@ -70,8 +70,12 @@ if os.path.exists(lp):
 
 # ---- full captures
 rep = os.path.join(G, f"{tag}_prof_1e8.ncu-rep")
-if os.path.exists(rep):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rawcsv = os.path.join(G, f"{tag}_raw_1e8.csv")
+if os.path.exists(rep) or os.path.exists(rawcsv):
+    if os.path.exists(rawcsv):
+        raw = open(rawcsv).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     kn = hdr.index("Kernel Name")
@@ -115,14 +119,41 @@ if os.path.exists(rep):
                "dram_bytes_per_launch": {k: v for k, v in traffic.items() if v == v}},
               open(os.path.join(P, "traffic.json"), "w"), indent=1)
     lib = os.path.join(G, f"lib_{tag}.so")
+    if not os.path.exists(lib):
+        lib = os.path.join(ROOT, "hande_b200", "libhande_b200.so")   # the build that was sent to the GPU box
     if os.path.exists(lib):
-        src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:k_spawn_death"],
-                             capture_output=True, text=True).stdout
         tmp = os.path.join(G, f"{tag}_src_spawn.csv")
-        open(tmp, "w").write(src)
-        bl = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_by_line.py"), tmp, lib, "k_spawn_deathILi2ELi4E", "25"],
+        if not os.path.exists(tmp) or os.path.exists(rep):
+            src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:k_spawn_death"],
+                                 capture_output=True, text=True).stdout
+            open(tmp, "w").write(src)
+        bl = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_by_line.py"), tmp, lib, "k_spawn_deathILi2ELi10E", "25"],
                             capture_output=True, text=True).stdout
         out.append("## k_spawn_death: instruction / stall-sample share by source line (tools/ncu_by_line.py)\n\n```\n" + bl + "```\n")
+
+# ---- side measurements committed next to the headline line
+side = sorted(f for f in os.listdir(P) if f.startswith(f"{tag}_bench_") and f.endswith(".json") and "reference" not in f)
+if side:
+    out.append("## other measured lines (`profiles/%s_bench_*.json`)\n" % tag)
+    out.append("| file | GPUs | workload | value | ms per step |\n|---|---|---|---|---|")
+    for f in side:
+        try:
+            d = json.loads(open(os.path.join(P, f)).read().strip().splitlines()[-1])
+        except Exception:
+            continue
+        out.append(f"| {f} | {d.get('n_gpus')} | {d['config']['workload']} | {d['value']:.4g} {d['unit']} | {d['ms_per_step']:.2f} |")
+    out.append("")
+gens = sorted(f for f in os.listdir(G) if f.startswith("gen_") and f.endswith(".json"))
+if gens:
+    out.append("## spawn kernel per generator (bench.py --excit-gen G, 1e8 walkers, one B200; `gpurun_out/gen_*.json` of the final build)\n")
+    out.append("| generator | k_spawn_death ms | cycle ms | walker-iterations/s |\n|---|---|---|---|")
+    for f in gens:
+        try:
+            d = json.loads(open(os.path.join(G, f)).read().strip().splitlines()[-1])
+        except Exception:
+            continue
+        out.append(f"| {f[4:-5]} | {d['roofline']['kernel_ms']:.2f} | {d['ms_per_step']:.2f} | {d['value']:.4g} |")
+    out.append("")
 
 open(os.path.join(P, f"{tag}_summary.md"), "w").write("\n".join(out) + "\n")
 print("\n".join(out))

@@ -29,6 +29,7 @@
 #define HB_MAXW 4
 #endif
 #define HB_MAXNEL 64
+#define HB_MAXLIST 128      // longest per-spin / per-symmetry-class orbital list (nbasis <= 254)
 
 // Streaming (evict-first) loads for data with no reuse on the SM - the 2 GB heat-bath row tables and the walker list -
 // so that they do not displace the small reused tables (hb_ij_w, single-excitation rows) from L1.
@@ -120,7 +121,7 @@ struct Params {
 // heat_bath_uniform, heat_bath_single)
 enum { EXCIT_GEN_RENORM = 0, EXCIT_GEN_NO_RENORM = 2, EXCIT_GEN_POWER_PITZER_OCC = 5, EXCIT_GEN_POWER_PITZER_OCC_IJ = 6,
        EXCIT_GEN_CAUCHY_SCHWARZ_OCC = 8, EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ = 9,
-       EXCIT_GEN_HEAT_BATH = 10, EXCIT_GEN_HEAT_BATH_UNIFORM = 11 };
+       EXCIT_GEN_HEAT_BATH = 10, EXCIT_GEN_HEAT_BATH_UNIFORM = 11, EXCIT_GEN_HEAT_BATH_SINGLE = 12 };
 enum { RNG_NATTEMPTS = 0, RNG_SPAWN = 1, RNG_DEATH = 2, RNG_ROUND_MAIN = 3, RNG_ROUND_SPAWN = 4 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1053,17 +1054,89 @@ HB_HDN void gen_excit_heat_bath(R& rng, const Sys& s, const Params& p, const uin
     hb_phase_f<W>(s, f, st, hm, psum, g);
 }
 
+// k-th (1-based) unoccupied orbital, ascending (decode_det_occ_unocc, src/determinant_decoders.f90)
+template <int W>
+HB_HD int nth_unocc(const uint64_t* f, int k) {
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        uint64_t x = ~f[w];
+        const int c = popc64(x);
+        if (k <= c) {
+            for (int q = 1; q < k; ++q) x &= x - 1;
+            return w * 64 + ctz64(x) + 1;
+        }
+        k -= c;
+    }
+    return 0;
+}
+// select_weighted_value for lists of up to 2*HB_MAXLIST entries (explicit tables as in lib/local/alias.f90)
+template <class R>
+HB_HDN int select_weighted_value_big(R& rng, int N, const double* weights, double totweight) {
+    double aliasU[2 * HB_MAXLIST];
+    int aliasK[2 * HB_MAXLIST], under[2 * HB_MAXLIST], over[2 * HB_MAXLIST];
+    generate_alias_tables(N, weights, totweight, aliasU, aliasK, under, over);
+    return select_precalc(rng, N, aliasU, aliasK);
+}
+// gen_single_excit_heat_bath_exact (src/excit_gen_heat_bath_mol.F90:720-805) with find_ia_single_weights
+// (src/excit_gen_utils.f90:162-218): weights |<D|H|D_i^a>| over all (occupied i, unoccupied a); i then a are drawn with
+// on-the-fly alias tables.  O(N M) slater_condon1 evaluations per call - correctness-first (the reference caches the
+// weights per determinant; here they are recomputed per single-excitation attempt).
+template <int W, class R>
+HB_HDN void gen_single_heat_bath_exact(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ, Gen& g) {
+    const int nel = s.nel, nvirt = s.nbasis - s.nel;
+    g.nexcit = 1; g.from1 = 0; g.from2 = 0; g.to1 = 0; g.to2 = 0; g.perm = false;
+    double wi[HB_MAXNEL];
+    double tot = 0.0;
+    // slater_condon1_mol (src/hamiltonian_molecular.f90:141-197) is zero unless i and a share spin and symmetry; for the
+    // allowed pairs it is the unchecked sum (subtracting the 0.0 of a forbidden exchange integral changes nothing)
+    for (int q = 0; q < nel; ++q) {
+        const int i = occ[q];
+        double wsum = 0.0;
+        for (int k = 1; k <= nvirt; ++k) {
+            const int a = nth_unocc<W>(f, k);
+            double w = 0.0;
+            if (((a ^ i) & 1) == 0 && s.bf_sym[a] == s.bf_sym[i]) w = fabs(slater_condon1_excit(s, occ, i, a, false));
+            wsum = wsum + w;
+        }
+        wi[q] = wsum;
+        tot = tot + wsum;
+    }
+    if (tot < 1.e-12) {
+        g.allowed = false; g.hmatel = 0.0; g.pgen = 1.0;
+        return;
+    }
+    const int i_ind = select_weighted_value_list(rng, nel, wi, tot);
+    const int i = occ[i_ind - 1];
+    double wa[HB_MAXLIST * 2];
+    for (int k = 1; k <= nvirt; ++k) {
+        const int a = nth_unocc<W>(f, k);
+        double w = 0.0;
+        if (((a ^ i) & 1) == 0 && s.bf_sym[a] == s.bf_sym[i]) w = fabs(slater_condon1_excit(s, occ, i, a, false));
+        wa[k - 1] = w;
+    }
+    const int a_ind = select_weighted_value_big(rng, nvirt, wa, wi[i_ind - 1]);
+    const int a = nth_unocc<W>(f, a_ind);
+    g.from1 = i; g.to1 = a;
+    g.pgen = p.pattempt_single * (wi[i_ind - 1] / tot) * (wa[a_ind - 1] / wi[i_ind - 1]);
+    g.perm = excit_perm1<W>(f, i, a);
+    g.hmatel = slater_condon1_excit(s, occ, i, a, g.perm);
+    g.allowed = true;
+}
+
 // gen_excit_mol_heat_bath_uniform (src/excit_gen_heat_bath_mol.F90:550-718), excit_gen = heat_bath_uniform: single
 // excitations from the renormalised uniform generator with probability pattempt_single, double excitations from the
 // heat-bath tables (i, j, a, b in turn); the generation probability of a double needs no matrix elements.
-template <int W, class R>
+// EXACT_SINGLE: excit_gen = heat_bath_single (src/excit_gen_heat_bath_mol.F90:720-805) - the same doubles, singles
+// from gen_single_heat_bath_exact.
+template <int W, bool EXACT_SINGLE = false, class R>
 HB_HDN void gen_excit_heat_bath_uniform(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ,
                                         const uint8_t* su, const double* __restrict__ iw, double* scr, int stride, Gen& g) {
     const int nel = s.nel;
     const int64_t nb = s.nbasis;
     g.from1 = 0; g.from2 = 0; g.to1 = 0; g.to2 = 0; g.perm = false;
     if (rng.next() < p.pattempt_single) {
-        gen_single_renorm<W>(rng, s, p, f, occ, su, g);
+        if (EXACT_SINGLE) gen_single_heat_bath_exact<W>(rng, s, p, f, occ, g);
+        else gen_single_renorm<W>(rng, s, p, f, occ, su, g);
         return;
     }
     g.nexcit = 2;
@@ -1118,7 +1191,6 @@ HB_HDN void gen_excit_heat_bath_uniform(R& rng, const Sys& s, const Params& p, c
 // sqrt|<ia|ia>|) are formed on the fly over the unoccupied orbitals of i's spin and over the (spin, symmetry) class of b,
 // each followed by an on-the-fly alias selection.  Lists of up to HB_MAXLIST entries live in thread-local memory.
 // ------------------------------------------------------------------------------------------------
-#define HB_MAXLIST 128
 template <class R>
 HB_HDN int select_weighted_value_list(R& rng, int N, const double* weights, double totweight) {
     if (N <= 64) return select_alias_staged(rng, N, weights, 1, totweight);   // table-free walk (same index)
@@ -1406,7 +1478,10 @@ HB_HD void gen_excit(R& rng, const Sys& s, const Params& p, const uint64_t* f, c
         double scr[HB_MAXNEL];
         gen_excit_power_pitzer_occ<W>(rng, s, p, f, occ, su, s.hb_i_w, scr, 1, g);
     }
-    else if (p.excit_gen == EXCIT_GEN_HEAT_BATH_UNIFORM) {
+    else if (p.excit_gen == EXCIT_GEN_HEAT_BATH_SINGLE) {
+        double scr[HB_MAXNEL];
+        gen_excit_heat_bath_uniform<W, true>(rng, s, p, f, occ, su, s.hb_i_w, scr, 1, g);
+    } else if (p.excit_gen == EXCIT_GEN_HEAT_BATH_UNIFORM) {
         double scr[HB_MAXNEL];
         gen_excit_heat_bath_uniform<W>(rng, s, p, f, occ, su, s.hb_i_w, scr, 1, g);
     }

@@ -241,7 +241,8 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nel = s.nel;
     constexpr bool heat_bath = (GEN == EXCIT_GEN_HEAT_BATH);
-    constexpr bool hb_stage = heat_bath || (GEN == EXCIT_GEN_HEAT_BATH_UNIFORM) || (GEN == EXCIT_GEN_POWER_PITZER_OCC_IJ);
+    constexpr bool hb_stage = heat_bath || (GEN == EXCIT_GEN_HEAT_BATH_UNIFORM) || (GEN == EXCIT_GEN_HEAT_BATH_SINGLE) ||
+                              (GEN == EXCIT_GEN_POWER_PITZER_OCC_IJ);
     const int nsu = (GEN == EXCIT_GEN_RENORM || GEN == EXCIT_GEN_HEAT_BATH_UNIFORM || GEN == EXCIT_GEN_POWER_PITZER_OCC ||
                      GEN == EXCIT_GEN_POWER_PITZER_OCC_IJ) ? 2 * s.nsym_tot : 0;
     const SpawnSmem L(W, nel, nsu, s.nbasis, heat_bath, hb_stage);
@@ -439,6 +440,8 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
             if (GEN == GEN_UEG) gen_excit_ueg_no_renorm<W>(rng, s, f, socc + lo * nel, g);
             else if (GEN == EXCIT_GEN_HEAT_BATH_UNIFORM)
                 gen_excit_heat_bath_uniform<W>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, siw, sw + tid, TILE, g);
+            else if (GEN == EXCIT_GEN_HEAT_BATH_SINGLE)
+                gen_excit_heat_bath_uniform<W, true>(rng, s, p, f, socc + lo * nel, nullptr, siw, sw + tid, TILE, g);
             else if (GEN == EXCIT_GEN_POWER_PITZER_OCC)     // also cauchy_schwarz_occ (p.excit_gen picks the integral)
                 gen_excit_power_pitzer_occ<W>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, nullptr, nullptr, 0, g);
             else if (GEN == EXCIT_GEN_POWER_PITZER_OCC_IJ)  // also cauchy_schwarz_occ_ij
@@ -1527,12 +1530,13 @@ static cudaError_t copy_sync(hb200_engine* e, void* dst, const void* src, size_t
 
 static bool uses_heat_bath_tables(const hb200_engine* e) {
     const int eg = e->cfg.excit_gen;
-    return eg == HB200_EXCIT_GEN_HEAT_BATH || eg == HB200_EXCIT_GEN_HEAT_BATH_UNIFORM ||
+    return eg == HB200_EXCIT_GEN_HEAT_BATH || eg == HB200_EXCIT_GEN_HEAT_BATH_UNIFORM || eg == HB200_EXCIT_GEN_HEAT_BATH_SINGLE ||
            eg == HB200_EXCIT_GEN_POWER_PITZER_OCC_IJ || eg == HB200_EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ;
 }
 static size_t spawn_smem_bytes(const hb200_engine* e) {
     const int eg = e->cfg.excit_gen;
-    const int nsu = (e->sys.kind == SYS_READ_IN && eg != HB200_EXCIT_GEN_NO_RENORM && eg != HB200_EXCIT_GEN_HEAT_BATH)
+    const int nsu = (e->sys.kind == SYS_READ_IN && eg != HB200_EXCIT_GEN_NO_RENORM && eg != HB200_EXCIT_GEN_HEAT_BATH &&
+                     eg != HB200_EXCIT_GEN_HEAT_BATH_SINGLE)
                         ? 2 * e->sys.nsym_tot : 0;
     const bool hb = eg == HB200_EXCIT_GEN_HEAT_BATH;
     return SpawnSmem(e->W, e->sys.nel, nsu, e->sys.nbasis, hb, uses_heat_bath_tables(e)).total;
@@ -1917,6 +1921,7 @@ static int stage_spawn_death(hb200_engine* e, const hb200_iter_in* in, uint32_t 
             case HB200_EXCIT_GEN_RENORM: LAUNCH_SPAWN(EXCIT_GEN_RENORM); break;
             case HB200_EXCIT_GEN_HEAT_BATH: LAUNCH_SPAWN(EXCIT_GEN_HEAT_BATH); break;
             case HB200_EXCIT_GEN_HEAT_BATH_UNIFORM: LAUNCH_SPAWN(EXCIT_GEN_HEAT_BATH_UNIFORM); break;
+            case HB200_EXCIT_GEN_HEAT_BATH_SINGLE: LAUNCH_SPAWN(EXCIT_GEN_HEAT_BATH_SINGLE); break;
             case HB200_EXCIT_GEN_POWER_PITZER_OCC:
             case HB200_EXCIT_GEN_CAUCHY_SCHWARZ_OCC: LAUNCH_SPAWN(EXCIT_GEN_POWER_PITZER_OCC); break;
             case HB200_EXCIT_GEN_POWER_PITZER_OCC_IJ:

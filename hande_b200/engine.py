@@ -13,7 +13,7 @@ from . import build as _build
 
 # values of the reference's excit_gen enumerators (src/qmc_data.f90:31-69)
 EXCIT_GEN = {"renorm": 0, "no_renorm": 2, "power_pitzer_occ": 5, "power_pitzer_occ_ij": 6, "cauchy_schwarz_occ": 8,
-             "cauchy_schwarz_occ_ij": 9, "heat_bath": 10, "heat_bath_uniform": 11}
+             "cauchy_schwarz_occ_ij": 9, "heat_bath": 10, "heat_bath_uniform": 11, "heat_bath_single": 12}
 
 
 class Config(C.Structure):
@@ -192,7 +192,8 @@ class Engine:
             raise EngineError(self.L.hb200_last_error().decode())
         self.h = C.c_void_p(h)
         self._set_system(sys)
-        if eg in (EXCIT_GEN["heat_bath"], EXCIT_GEN["heat_bath_uniform"], EXCIT_GEN["power_pitzer_occ_ij"],
+        if eg in (EXCIT_GEN["heat_bath"], EXCIT_GEN["heat_bath_uniform"], EXCIT_GEN["heat_bath_single"],
+                  EXCIT_GEN["power_pitzer_occ_ij"],
                   EXCIT_GEN["cauchy_schwarz_occ_ij"]):   # the _occ_ij weights are the heat-bath i/ij tables
             self._chk(self.L.hb200_build_heat_bath(self.h))
 

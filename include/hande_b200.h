@@ -27,7 +27,8 @@ typedef struct hb200_engine hb200_engine;
 
 /* Values of qmc_in%excit_gen (src/qmc_data.f90:31-69) that the engine implements. */
 enum { HB200_EXCIT_GEN_RENORM = 0, HB200_EXCIT_GEN_NO_RENORM = 2, HB200_EXCIT_GEN_POWER_PITZER_OCC = 5,
-       HB200_EXCIT_GEN_POWER_PITZER_OCC_IJ = 6, HB200_EXCIT_GEN_CAUCHY_SCHWARZ_OCC = 8, HB200_EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ = 9, HB200_EXCIT_GEN_HEAT_BATH = 10, HB200_EXCIT_GEN_HEAT_BATH_UNIFORM = 11 };
+       HB200_EXCIT_GEN_POWER_PITZER_OCC_IJ = 6, HB200_EXCIT_GEN_CAUCHY_SCHWARZ_OCC = 8, HB200_EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ = 9, HB200_EXCIT_GEN_HEAT_BATH = 10, HB200_EXCIT_GEN_HEAT_BATH_UNIFORM = 11,
+       HB200_EXCIT_GEN_HEAT_BATH_SINGLE = 12 };
 
 /* qmc_in_t / fciqmc options that size and configure the device state
  * (src/qmc_data.f90:121-512; lua keys src/lua_hande_calc.f90:1244-1503). */

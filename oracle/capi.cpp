@@ -364,6 +364,14 @@ int orc_ccmc_stage_spawn(void* h, uint32_t cycle_id, double tau, double shift, d
     ORC_CATCH(-1)
 }
 void orc_ccmc_set_full_nc(void* h, int full_nc) { ((OracleCcmc*)(Oracle*)h)->full_nc = full_nc != 0; }
+// qmc = { pattempt_update = true }; orc_ccmc_get_pattempt_log copies up to n values of pattempt_single after each change
+void orc_ccmc_set_pattempt_update(void* h, int on) { ((OracleCcmc*)(Oracle*)h)->vary_psingles = on != 0; }
+int orc_ccmc_get_pattempt_log(void* h, double* out, int n) {
+    OracleCcmc* o = (OracleCcmc*)(Oracle*)h;
+    const int m = (int)o->pattempt_log.size();
+    for (int i = 0; i < m && i < n; ++i) out[i] = o->pattempt_log[i];
+    return m;
+}
 int orc_ccmc_get_hash_shift(void* h) { return ((OracleCcmc*)(Oracle*)h)->hash_shift; }
 void orc_ccmc_set_hash_shift(void* h, int shift, int move_freq) {
     OracleCcmc* o = (OracleCcmc*)(Oracle*)h;

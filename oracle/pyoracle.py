@@ -351,6 +351,15 @@ class Oracle:
         """ccmc = { full_non_composite = true }"""
         self.L.orc_ccmc_set_full_nc(self.h, int(full_nc))
 
+    def ccmc_set_pattempt_update(self, on=True):
+        """qmc = { pattempt_update = true } (CCMC runs): pattempt_single follows the spawn statistics until the shift varies"""
+        self.L.orc_ccmc_set_pattempt_update(self.h, int(on))
+
+    def ccmc_pattempt_log(self):
+        out = np.zeros(4096)
+        n = int(self.L.orc_ccmc_get_pattempt_log(self.h, out.ctypes.data_as(C.c_void_p), len(out)))
+        return out[:min(n, len(out))]
+
     def ccmc_hash_shift(self):
         return int(self.L.orc_ccmc_get_hash_shift(self.h))
 

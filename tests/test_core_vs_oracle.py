@@ -146,6 +146,18 @@ def test_heat_bath_uniform_generator_synthetic(s10):
     assert n > 1500
 
 
+def test_heat_bath_single_generator(fcidump_path, s10):
+    # exact single excitations (weights |<D|H|D_i^a>|), doubles as heat_bath_uniform; h2o has symmetry-forbidden pairs
+    s, o, h = _setup(fcidump_path("h2o"), dict(nel=10, ms=0, sym=0, cas=(8, 13)), "heat_bath_single", tau=0.003)
+    dets = synthetic.random_dets(60, s.nbasis, s.nalpha, s.nbeta, seed=3)
+    assert _compare_attempts(s, o, h, dets, np.where(np.arange(len(dets)) % 2 == 0, 3, -2), 0.003, nattempt=8) > 800
+    s, o, h = _setup(s10, {}, "heat_bath_single", tau=0.01, real=True)
+    dets = synthetic.random_dets(120, s.nbasis, s.nalpha, s.nbeta, seed=9)
+    pops = np.where(np.arange(len(dets)) % 3 == 0, -(2**31), 2**32 + 17)
+    n = _compare_attempts(s, o, h, dets, pops, 0.01, ncycle=2, nattempt=8)
+    assert n > 1500
+
+
 def test_slater_condon_two_word_bitstrings(tmp_path):
     # 40 spatial orbitals -> 80 spin orbitals -> W = 2 words
     p = tmp_path / "s40.fcidump"

@@ -55,6 +55,11 @@ def test_gen_excit_heat_bath_uniform():
     _check_gen("s10", "heat_bath_uniform", True, 0.01, n=150, nattempt=6)
 
 
+def test_gen_excit_heat_bath_single():
+    _check_gen("s10", "heat_bath_single", True, 0.01, n=150, nattempt=6)
+    _check_gen("h2o", "heat_bath_single", False, 0.003, n=100)
+
+
 def test_gen_excit_power_pitzer_and_cauchy_schwarz_occ():
     # the O(M) on-the-fly variants with uniformly chosen ij
     _check_gen("h2o", "power_pitzer_occ", False, 0.003, n=120)
@@ -113,6 +118,7 @@ CASES = [
     ("s40", "renorm", False, True, 0.02, 3000, -1),
     ("s12", "heat_bath", True, True, 0.01, 2500, -1),
     ("s12", "heat_bath_uniform", True, True, 0.01, 2500, -1),
+    ("s12", "heat_bath_single", True, True, 0.01, 2500, -1),
     ("h2o", "power_pitzer_occ", False, True, 0.003, 2500, -1),
     ("s12", "cauchy_schwarz_occ", True, False, 0.004, 2500, -1),
     ("s12", "power_pitzer_occ_ij", True, True, 0.004, 2500, -1),

@@ -36,6 +36,7 @@ def _run(case, fcidump_path, nrows):
     o.init()
     if g.get("ccmc"):
         o.ccmc_set_full_nc(bool(g.get("full_nc")))
+        o.ccmc_set_pattempt_update(bool(g.get("pattempt_update")))
         rows, na = o.run_ccmc()
         rows = np.concatenate([rows, na.reshape(-1, 1).astype(float)], axis=1)
     else:
@@ -111,6 +112,31 @@ def test_ccmc_ccsdt_full_non_composite_np2(fcidump_path):
     # ccmc = { full_non_composite = true }, CCSDT in a CAS, two ranks: select_nc_cluster, do_nc_ccmc_propagation,
     # stochastic_ccmc_death_nc, deterministic reference selections (all 91 rows verified with tools/golden_compare.py)
     _run("ccmc_h2o_ccsdt_fullnc_np2", fcidump_path, 40)
+
+
+@pytest.mark.parametrize("gen,nrows", [("hb", 150), ("hb_uni", 150), ("hb_single", 100), ("ppM", 120), ("ppMij", 120),
+                                       ("csM", 120), ("csMij", 120), ("renorm", 250), ("no_renorm", 250)])
+def test_ccmc_ccsdt_nh3_np4_excitation_generators(fcidump_path, gen, nrows):
+    """test_suite/ccmc_real_64/np4/NH3-6-31g_ccsdt_excit_gens: the reference's one golden trajectory per excitation
+    generator (CCSDT, four ranks, real amplitudes) - the pin for heat_bath, heat_bath_uniform, heat_bath_single and the
+    Power-Pitzer / Cauchy-Schwarz generators, and for qmc_in%pattempt_update (pattempt_single follows the spawn
+    statistics; the printed '# pattempt_single changed to be:' values are compared too).  Comparable until the shift
+    varies (blocking-on-the-fly with auto_shift_damping then changes the damping); tools/golden_compare.py verified
+    every such row: hb 327, hb_uni 460, hb_single 179, ppM 691, ppMij 818, csM 701, csMij 817, renorm 1508,
+    no_renorm 1424."""
+    case = "ccmc_nh3_" + gen
+    g = load_golden(case)
+    assert all(r[1] == 0.0 for r in g["rows"][:nrows + 1])
+    o = _run(case, fcidump_path, nrows)
+    last_it = g["rows"][nrows][0]
+    got = o.ccmc_pattempt_log()
+    # a change printed after row `it` happens at the end of the following report loop
+    want = [v for it, v in g["pattempt_changes"] if it + g["qmc"]["ncycles"] <= last_it]
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert float("%.10E" % a) == b
+    if g["pattempt_update"] and nrows >= 60:
+        assert len(want) >= 1
 
 
 def test_dsfmt_and_murmur_known_answers():

@@ -20,6 +20,20 @@ OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 
 FCIDUMP_NAME = {"h2o": "h2o", "ne_init": "ne", "ne_ci6_np2": "ne", "ne_ci6_np4": "ne", "ne_ci6_real64_np2": "ne",
                 "ccmc_ne": "ne_vdz", "ccmc_h2o_np2": "h2o_vdz",
                 "ccmc_h2o_ccsdt_fullnc_np2": "h2o_vdz"}
+FCIDUMP_NAME.update({k: "nh3_631g" for k in CASES if k.startswith("ccmc_nh3_")})
+
+
+def pattempt_changes(path):
+    """(iteration of the preceding table row, value) of every '# pattempt_single changed to be:' line"""
+    out, last = [], 0
+    for line in open(path):
+        if "pattempt_single changed to be:" in line:
+            out.append([last, float(line.split(":")[1])])
+        else:
+            t = line.split()
+            if len(t) > 8 and t[0].isdigit():
+                last = int(t[0])
+    return out
 
 os.makedirs(os.path.join(OUT, "fcidump"), exist_ok=True)
 for name, c in CASES.items():
@@ -41,9 +55,16 @@ for name, c in CASES.items():
         with open(d + c["int_file"], "rb") as fi, gzip.GzipFile(dst, "wb", compresslevel=9, mtime=0) as fo:
             shutil.copyfileobj(fi, fo)
     rows = parse_table(d + c["bench"]).tolist()
+    extra = {}
+    if c.get("until_shift"):
+        # keep the rows before the shift varies (the comparable part, see golden_compare.py) and a few after
+        nz = [i for i, r in enumerate(rows) if r[1] != 0.0]
+        rows = rows[:min(len(rows), (nz[0] if nz else len(rows)) + 3)]
+        extra = {"until_shift": True, "pattempt_update": bool(c.get("pattempt_update")),
+                 "pattempt_changes": [pc for pc in pattempt_changes(d + c["bench"]) if pc[0] <= rows[-1][0]]}
     cols = ["iterations", "shift", "proj_energy", "D0_population", "nparticles", "nstates", "nspawn_events", "rspawn"]
     json.dump({"source": "test_suite/" + c["dir"] + "/" + c["bench"], "fcidump": FCIDUMP_NAME[name], "sys": c["sys"],
                "qmc": c["qmc"], "ccmc": bool(c.get("ccmc")), "full_nc": bool(c.get("full_nc")),
                "columns": cols + (["nattempts"] if c.get("ccmc") else []),
-               "rows": rows}, open(os.path.join(OUT, name + ".json"), "w"))
+               "rows": rows, **extra}, open(os.path.join(OUT, name + ".json"), "w"))
     print(name, len(rows), "rows")

@@ -18,7 +18,7 @@ import numpy as np
 
 from . import read_in as _ri
 from .engine import Engine
-from .fciqmc import FciqmcResult, QmcIn, _SingleProcess, list_sizes, owner_of
+from .fciqmc import FciqmcResult, PattemptUpdate, QmcIn, _SingleProcess, list_sizes, owner_of
 
 HEADER = (" #     iterations   Shift                 \\sum H_0j N_j         N_0                   # H psips"
           "                  # states  # spawn_events            # attempts   R_spawn    time    ")
@@ -73,6 +73,7 @@ def do_ccmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, ke
     proj_energy, D0, ntot_old, tot_nstates = 0.0, float(n0), float(n0), 1
     shift, vary_shift = qmc.initial_shift, False
     res = FciqmcResult(H00=H00, occ0=occ0)
+    pupd = PattemptUpdate(eng, comm, ps, pd, io=io) if qmc.pattempt_update else None
     res.rows.append([0, shift, proj_energy, D0, ntot_old, tot_nstates, 0, 0.0, n0])
     if io is not None and iproc == 0:
         io.write(HEADER + "\n")
@@ -100,6 +101,8 @@ def do_ccmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, ke
         if not vary_shift and ntot > qmc.target_population:
             vary_shift = True
             shift = proj_energy / D0 if qmc.vary_shift_from_proje else qmc.vary_shift_from
+        if pupd is not None:
+            pupd.end_report_loop(vary_shift)
         it = ireport * qmc.mc_cycles
         res.rows.append([it, shift, proj_energy, D0, ntot, tot_nstates, tot_nev, rspawn, int(o["nattempts"])])
         if io is not None and iproc == 0:
@@ -109,6 +112,7 @@ def do_ccmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, ke
             res.error = True
             break
     res.shift, res.vary_shift = shift, vary_shift
+    res.pattempt_log = pupd.log if pupd is not None else []
     if keep_engine:
         res.engine = eng
     else:

@@ -114,7 +114,11 @@ struct Params {
     int ccmc_shift, ccmc_freq;  // spawn%hash_shift / spawn%move_freq (CCMC only)
     uint64_t f0[HB_MAXW];
     double H00;
+    struct PsPartials* ps_part; // per-block sums for qmc_in%pattempt_update (null: not accumulating)
 };
+// p_single_double_coll_t (src/excit_gens.f90:13-27): sums of |H_ij| pattempt_{single,double} / pgen over the allowed
+// single / double excitations generated, and how many there were
+struct PsPartials { double h_pgen_singles_sum, h_pgen_doubles_sum; long long excit_gen_singles, excit_gen_doubles; };
 
 // the reference's enumerator values (src/qmc_data.f90:31-69: renorm, renorm_spin, no_renorm, no_renorm_spin, power_pitzer,
 // power_pitzer_occ, power_pitzer_occ_ij, power_pitzer_orderN, cauchy_schwarz_occ, cauchy_schwarz_occ_ij, heat_bath,

@@ -175,10 +175,11 @@ constexpr int SINGLES_CHUNK = 64;  // single excitations whose pgen terms are st
 // that are only live in the later phases.
 struct SpawnSmem {
     size_t sf, shash, ssign, sscan, swarp, sred, siw, sw, sh1, shm, ssp, spsum, sterm, sok, sq, scnt, sflag, slo, sperm, ssq,
-        ssi, socc, ssu, total;
+        ssi, socc, ssu, sps, total;
     // heat_bath: the original heat-bath generator (phase buffers); hb_stage: any generator that selects i, j from the
     // heat-bath weights (needs the hb_i_w copy and the per-thread staging area of nel doubles)
-    __host__ __device__ SpawnSmem(int W, int nel, int nsu, int nb, bool heat_bath, bool hb_stage) {
+    // ps: pattempt_update statistics are accumulated (per thread: two doubles and two counters)
+    __host__ __device__ SpawnSmem(int W, int nel, int nsu, int nb, bool heat_bath, bool hb_stage, bool ps) {
         size_t o = 0;
         sf = o;     o += (size_t)TILE * W * 8;
         sred = o;   o += 40 * 8;
@@ -212,6 +213,8 @@ struct SpawnSmem {
         ssi = o;    o += heat_bath ? 2 * TILE : 0;                 // singles: i, a
         socc = o;   o += (size_t)TILE * nel;
         ssu = o;    o += (size_t)TILE * nsu;
+        o = (o + 7) & ~(size_t)7;
+        sps = o;    o += ps ? (size_t)TILE * 24 : 0;
         total = (o + 15) & ~(size_t)15;
     }
 };
@@ -245,7 +248,14 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
                               (GEN == EXCIT_GEN_POWER_PITZER_OCC_IJ);
     const int nsu = (GEN == EXCIT_GEN_RENORM || GEN == EXCIT_GEN_HEAT_BATH_UNIFORM || GEN == EXCIT_GEN_POWER_PITZER_OCC ||
                      GEN == EXCIT_GEN_POWER_PITZER_OCC_IJ) ? 2 * s.nsym_tot : 0;
-    const SpawnSmem L(W, nel, nsu, s.nbasis, heat_bath, hb_stage);
+    const bool ps_on = !heat_bath && p.ps_part != nullptr;
+    const SpawnSmem L(W, nel, nsu, s.nbasis, heat_bath, hb_stage, ps_on);
+    double* sps_h = reinterpret_cast<double*>(smem_raw + L.sps);                  // [2][TILE]: singles, doubles
+    unsigned* sps_n = reinterpret_cast<unsigned*>(smem_raw + L.sps + 16 * TILE);  // [2][TILE]
+    if (ps_on) {
+        sps_h[threadIdx.x] = 0.0; sps_h[TILE + threadIdx.x] = 0.0;
+        sps_n[threadIdx.x] = 0u; sps_n[TILE + threadIdx.x] = 0u;
+    }
     uint64_t* sf = reinterpret_cast<uint64_t*>(smem_raw + L.sf);
     uint8_t* ssign = smem_raw + L.ssign;
     uint64_t* shash = reinterpret_cast<uint64_t*>(smem_raw + L.shash);
@@ -453,6 +463,11 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
         uint64_t child[W];
         int dest = 0, pflag = 0;
         if (active) {
+            if (ps_on && g.allowed) {   // update_p_single_double_data (src/spawning.F90:104-109,2139-2215)
+                const int k = (g.nexcit == 2) ? TILE : 0;
+                sps_h[k + tid] = sps_h[k + tid] + (fabs(g.hmatel) * (g.nexcit == 2 ? p.pattempt_double : p.pattempt_single)) / g.pgen;
+                sps_n[k + tid] += 1u;
+            }
             nspawn = attempt_to_spawn(rng, p, g.hmatel, g.pgen, ssign[lo] ? (int64_t)-1 : (int64_t)1);
             if (nspawn != 0) {
                 make_child<W>(f, g, child);
@@ -494,6 +509,26 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
         }
     }
 
+    if (ps_on) {
+        const double a = warp_sum_d(sps_h[tid]), b = warp_sum_d(sps_h[TILE + tid]);
+        const long long c = warp_sum_ll((long long)sps_n[tid]), d = warp_sum_ll((long long)sps_n[TILE + tid]);
+        __syncthreads();
+        if (lane == 0) {
+            sred[warp] = a; sred[8 + warp] = b;
+            reinterpret_cast<long long*>(sred)[16 + warp] = c;
+            reinterpret_cast<long long*>(sred)[24 + warp] = d;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            PsPartials out = {0.0, 0.0, 0, 0};
+            for (int w = 0; w < TILE / 32; ++w) {
+                out.h_pgen_singles_sum += sred[w]; out.h_pgen_doubles_sum += sred[8 + w];
+                out.excit_gen_singles += reinterpret_cast<long long*>(sred)[16 + w];
+                out.excit_gen_doubles += reinterpret_cast<long long*>(sred)[24 + w];
+            }
+            p.ps_part[blockIdx.x] = out;
+        }
+    }
     // deterministic block reduction of the estimators
     double r0 = warp_sum_d(pe), r1 = warp_sum_d(d0);
     long long r2 = warp_sum_ll(ndeath), r3 = warp_sum_ll(npart);
@@ -552,6 +587,42 @@ __device__ __forceinline__ void append_spawn_warp(const uint64_t* f, int64_t nsp
 
 struct CcmcPartials { double pe, d0; long long ndeath, nattempts_spawn; };
 
+// block sums of the pattempt_update statistics of a 256-thread CCMC block (all threads call it)
+__device__ __forceinline__ void ps_block_reduce(PsPartials* out, double hs, double hd, int ns, int nd) {
+    __shared__ double sh[2][8];
+    __shared__ long long sn[2][8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double a = warp_sum_d(hs), b = warp_sum_d(hd);
+    const long long c = warp_sum_ll((long long)ns), d = warp_sum_ll((long long)nd);
+    if (lane == 0) { sh[0][warp] = a; sh[1][warp] = b; sn[0][warp] = c; sn[1][warp] = d; }
+    __syncthreads();
+    if (tid == 0) {
+        PsPartials o = {0.0, 0.0, 0, 0};
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+            o.h_pgen_singles_sum += sh[0][w]; o.h_pgen_doubles_sum += sh[1][w];
+            o.excit_gen_singles += sn[0][w]; o.excit_gen_doubles += sn[1][w];
+        }
+        out[blockIdx.x] = o;
+    }
+}
+// running totals of the report loop: acc[0..3] += block sums in fixed order
+__global__ void k_reduce_ps(const PsPartials* __restrict__ part, int n, double* __restrict__ acc) {
+    __shared__ double sh[4][32];
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        v[0] += part[i].h_pgen_singles_sum; v[1] += (double)part[i].excit_gen_singles;
+        v[2] += part[i].h_pgen_doubles_sum; v[3] += (double)part[i].excit_gen_doubles;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = 0; k < 4; ++k) { v[k] = warp_sum_d(v[k]); if (lane == 0) sh[k][warp] = v[k]; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[threadIdx.x][w];
+        acc[threadIdx.x] = acc[threadIdx.x] + t;
+    }
+}
+
 template <int W>
 __global__ void __launch_bounds__(256)
 k_ccmc_cluster(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states, const int64_t* __restrict__ pops,
@@ -565,6 +636,8 @@ k_ccmc_cluster(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states,
     double pe = 0.0, d0 = 0.0;
     long long ndeath = 0, nas = 0;
     int64_t nspawn = 0, nkill = 0;
+    double ps_hs = 0.0, ps_hd = 0.0;
+    int ps_ns = 0, ps_nd = 0;
     uint64_t cf[W], child[W];
 #pragma unroll
     for (int k = 0; k < W; ++k) { cf[k] = 0; child[k] = 0; }
@@ -601,6 +674,10 @@ k_ccmc_cluster(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states,
             gen_excit<W>(rng, s, p, cf, occ, su, g);
             const double hmatel = g.hmatel * cl.amplitude * 1.0 * cl.sign;
             const double pgen = g.pgen * cl.pselect * 1;
+            if (p.ps_part && g.allowed) {   // src/ccmc_death_spawning.f90:150-157
+                if (g.nexcit == 2) { ps_hd = (fabs(hmatel) * p.pattempt_double) / pgen; ps_nd = 1; }
+                else { ps_hs = (fabs(hmatel) * p.pattempt_single) / pgen; ps_ns = 1; }
+            }
             nspawn = attempt_to_spawn(rng, p, hmatel, pgen, (int64_t)1);
             if (nspawn != 0) {
                 make_child<W>(cf, g, child);
@@ -642,6 +719,7 @@ k_ccmc_cluster(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states,
     __syncwarp();
     append_spawn_warp<W>(child, nspawn, dest_s, p.nprocs, spawn, head, block_size, err);
     append_spawn_warp<W>(cf, nkill, dest_k, p.nprocs, spawn, head, block_size, err);
+    if (p.ps_part) ps_block_reduce(p.ps_part, ps_hs, ps_hd, ps_ns, ps_nd);
     const double r0 = warp_sum_d(pe), r1 = warp_sum_d(d0);
     const long long r2 = warp_sum_ll(ndeath), r3 = warp_sum_ll(nas);
     if (lane == 0) { sd[0][warp] = r0; sd[1][warp] = r1; sl[0][warp] = r2; sl[1][warp] = r3; }
@@ -670,6 +748,8 @@ k_ccmc_nc(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states, int6
     const long long i = (long long)blockIdx.x * blockDim.x + tid;
     double pe = 0.0, d0 = 0.0;
     long long ndeath_nc = 0, nas = 0;
+    double ps_hs = 0.0, ps_hd = 0.0;
+    int ps_ns = 0, ps_nd = 0;
     if (i < a.nstates) {
         uint64_t f[W];
         load_det<W>(states + i * W, f);
@@ -698,6 +778,10 @@ k_ccmc_nc(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states, int6
                 gen_excit<W>(rng, s, p, f, occ, su, g);
                 const double hmatel = g.hmatel * unit * 1.0 * sign;
                 const double pgen = g.pgen * 1.0 * 1;
+                if (p.ps_part && g.allowed) {
+                    if (g.nexcit == 2) { ps_hd = ps_hd + (fabs(hmatel) * p.pattempt_double) / pgen; ps_nd += 1; }
+                    else { ps_hs = ps_hs + (fabs(hmatel) * p.pattempt_single) / pgen; ps_ns += 1; }
+                }
                 int64_t nspawn = attempt_to_spawn(rng, p, hmatel, pgen, (int64_t)1);
                 if (nspawn != 0) {
                     uint64_t child[W];
@@ -740,6 +824,7 @@ k_ccmc_nc(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states, int6
             }
         }
     }
+    if (p.ps_part) ps_block_reduce(p.ps_part, ps_hs, ps_hd, ps_ns, ps_nd);
     const double r0 = warp_sum_d(pe), r1 = warp_sum_d(d0);
     const long long r2 = warp_sum_ll(ndeath_nc), r3 = warp_sum_ll(nas);
     if (lane == 0) { sd[0][warp] = r0; sd[1][warp] = r1; sl[0][warp] = r2; sl[1][warp] = r3; }
@@ -1488,6 +1573,9 @@ struct hb200_engine {
     long long* d_cum = nullptr;        // [walker_length] inclusive prefix sums of |pop| (reference skipped)
     long long* d_cum_blk = nullptr;
     CcmcPartials* d_cc_part = nullptr;
+    PsPartials* d_ps_part = nullptr;   // pattempt_update: per-block sums of one launch
+    double* d_ps_acc = nullptr;        // [4] running totals since the last hb200_get_ps_stats(reset)
+    size_t ps_part_cap = 0;
     CcmcPartials* d_cc_tot = nullptr;
     // NCCL
     ncclComm_t comm = nullptr;
@@ -1539,7 +1627,7 @@ static size_t spawn_smem_bytes(const hb200_engine* e) {
                      eg != HB200_EXCIT_GEN_HEAT_BATH_SINGLE)
                         ? 2 * e->sys.nsym_tot : 0;
     const bool hb = eg == HB200_EXCIT_GEN_HEAT_BATH;
-    return SpawnSmem(e->W, e->sys.nel, nsu, e->sys.nbasis, hb, uses_heat_bath_tables(e)).total;
+    return SpawnSmem(e->W, e->sys.nel, nsu, e->sys.nbasis, hb, uses_heat_bath_tables(e), !hb && e->par.ps_part != nullptr).total;
 }
 
 extern "C" {
@@ -1936,6 +2024,11 @@ static int stage_spawn_death(hb200_engine* e, const hb200_iter_in* in, uint32_t 
     k_reduce_partials<<<1, 1024, 0, st>>>(e->d_partials, ntiles, e->d_stats);
     CK(cudaGetLastError());
     e->launches++;
+    if (p.ps_part && ntiles > 0) {
+        k_reduce_ps<<<1, 1024, 0, st>>>(e->d_ps_part, ntiles, e->d_ps_acc);
+        CK(cudaGetLastError());
+        e->launches++;
+    }
     CK(cudaMemcpyAsync(e->h_head.data(), e->d_head, sizeof(unsigned long long) * p.nprocs, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(hst, e->d_stats, sizeof(CycleStats), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -2245,18 +2338,30 @@ int hb200_ccmc_spawn(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, i
         k_ccmc_reduce<<<1, 1024, 0, st>>>(e->d_cc_part, (int)nblk, e->d_cc_tot);
         CK(cudaGetLastError());
         e->launches += 2;
+        if (p.ps_part) {
+            k_reduce_ps<<<1, 1024, 0, st>>>(e->d_ps_part, (int)nblk, e->d_ps_acc);
+            CK(cudaGetLastError());
+            e->launches++;
+        }
         CK(cudaMemcpyAsync(&tot, e->d_cc_tot, sizeof(tot), cudaMemcpyDeviceToHost, st));
     }
     if (e->ccmc_full_nc && n > 0) {
         // non-composite clusters + in-place death; after k_ccmc_cluster, which reads the populations changed here
         const long long nblk = (n + 255) / 256;
-        DISPATCH_W(e, k_ccmc_nc<WW><<<(unsigned)nblk, 256, 0, st>>>(e->sys, p, a, e->d_states[c], e->d_pops[c], e->d_dat[c],
+        Params pn = p;
+        if (pn.ps_part) pn.ps_part += part_cap;
+        DISPATCH_W(e, k_ccmc_nc<WW><<<(unsigned)nblk, 256, 0, st>>>(e->sys, pn, a, e->d_states[c], e->d_pops[c], e->d_dat[c],
                                                                      e->d_spawn[0], e->d_head, e->block_size, e->d_proc_map,
                                                                      e->d_cc_part + part_cap, nullptr, e->d_err));
         CK(cudaGetLastError());
         k_ccmc_reduce<<<1, 1024, 0, st>>>(e->d_cc_part + part_cap, (int)nblk, e->d_cc_tot + 1);
         CK(cudaGetLastError());
         e->launches += 2;
+        if (pn.ps_part) {
+            k_reduce_ps<<<1, 1024, 0, st>>>(pn.ps_part, (int)nblk, e->d_ps_acc);
+            CK(cudaGetLastError());
+            e->launches++;
+        }
         CK(cudaMemcpyAsync(&tot_nc, e->d_cc_tot + 1, sizeof(tot_nc), cudaMemcpyDeviceToHost, st));
     }
     CK(cudaMemcpyAsync(e->h_head.data(), e->d_head, sizeof(unsigned long long) * p.nprocs, cudaMemcpyDeviceToHost, st));
@@ -2289,6 +2394,40 @@ int hb200_ccmc_spawn(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, i
     out->ndeath = tot.ndeath; out->ndeath_nc = tot_nc.ndeath;
     out->nspawn_events = nspawn_events; out->tot_abs_real_pop = a.tot_abs_real_pop;
     out->spawn_error = herr[0]; out->psip_error = herr[1];
+    return 0;
+}
+
+// qmc_in%pattempt_update (src/qmc.F90:1049-1060, src/spawning.F90:2139-2372): the engine holds pattempt_single /
+// pattempt_double and, while `accumulate` is set, sums |H_ij| pattempt / pgen and the counts of the allowed single and
+// double excitations it generates; the host reads the sums once per report loop, allreduces them and sets the new
+// probabilities (update_pattempt_single).
+int hb200_set_pattempt(hb200_engine* e, double pattempt_single, double pattempt_double, int32_t accumulate) {
+    if (accumulate) {
+        // src/check_input.F90:192-197
+        if (e->sys.kind != SYS_READ_IN) FAIL("pattempt_update only used in read_in systems.");
+        if (e->cfg.excit_gen == HB200_EXCIT_GEN_HEAT_BATH) FAIL("pattempt_update is not used with heat bath excitation generator.");
+        if (!e->d_ps_part) {
+            const size_t cc = 2 * (size_t)(e->cfg.spawned_walker_length / 256 + e->cfg.walker_length / 256 + 4);
+            e->ps_part_cap = std::max<size_t>((size_t)e->max_tiles, cc);
+            if (dalloc(e, &e->d_ps_part, e->ps_part_cap)) return 1;
+            if (dalloc(e, &e->d_ps_acc, 4)) return 1;
+            CK(cudaMemsetAsync(e->d_ps_acc, 0, 4 * sizeof(double), e->stream));
+        }
+    }
+    e->par.pattempt_single = pattempt_single;
+    e->par.pattempt_double = pattempt_double;
+    e->cfg.pattempt_single = pattempt_single;
+    e->cfg.pattempt_double = pattempt_double;
+    e->par.ps_part = accumulate ? e->d_ps_part : nullptr;
+    return 0;
+}
+// out[0..3] = h_pgen_singles_sum, excit_gen_singles, h_pgen_doubles_sum, excit_gen_doubles accumulated on this rank since
+// the last reset (p_single_double_coll_t rep_accum, src/excit_gens.f90:13-27)
+int hb200_get_ps_stats(hb200_engine* e, double* out, int32_t reset) {
+    if (!e->d_ps_acc) { for (int k = 0; k < 4; ++k) out[k] = 0.0; return 0; }
+    CK(cudaMemcpyAsync(out, e->d_ps_acc, 4 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    if (reset) CK(cudaMemsetAsync(e->d_ps_acc, 0, 4 * sizeof(double), e->stream));
+    CK(cudaStreamSynchronize(e->stream));
     return 0;
 }
 

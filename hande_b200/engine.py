@@ -135,6 +135,8 @@ def load_library():
     L.hb200_ccmc_iterate.argtypes = [C.c_void_p, C.c_int32, C.POINTER(IterIn), C.c_int32, C.POINTER(IterOut)]
     L.hb200_ccmc_set_hash_shift.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
     L.hb200_ccmc_set_full_nc.argtypes = [C.c_void_p, C.c_int32]
+    L.hb200_set_pattempt.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int32]
+    L.hb200_get_ps_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
     L.hb200_comm_spawn.argtypes = [C.c_void_p]
     L.hb200_annihilate_spawn.argtypes = [C.c_void_p]
     L.hb200_annihilate_main.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(IterOut)]
@@ -156,7 +158,7 @@ ABI_SYMBOLS = [
     "hb200_download_heat_bath", "hb200_set_reference", "hb200_set_proc_map", "hb200_upload_psips",
     "hb200_upload_psips_begin", "hb200_upload_psips_commit",
     "hb200_download_psips", "hb200_nstates", "hb200_iterate", "hb200_spawn_death", "hb200_comm_spawn",
-    "hb200_ccmc_spawn", "hb200_ccmc_iterate", "hb200_ccmc_set_hash_shift", "hb200_ccmc_set_full_nc", "hb200_annihilate_spawn", "hb200_annihilate_main", "hb200_download_spawn", "hb200_upload_spawn",
+    "hb200_ccmc_spawn", "hb200_ccmc_iterate", "hb200_ccmc_set_hash_shift", "hb200_ccmc_set_full_nc", "hb200_set_pattempt", "hb200_get_ps_stats", "hb200_annihilate_spawn", "hb200_annihilate_main", "hb200_download_spawn", "hb200_upload_spawn",
     "hb200_sc0_batch", "hb200_gen_excit_batch", "hb200_get_unique_id", "hb200_comm_init", "hb200_last_timing",
 ]
 
@@ -311,6 +313,16 @@ class Engine:
 
     def ccmc_set_full_nc(self, full_nc=True):
         self._chk(self.L.hb200_ccmc_set_full_nc(self.h, int(bool(full_nc))))
+
+    def set_pattempt(self, pattempt_single, pattempt_double, accumulate=False):
+        """excit_gen_data%pattempt_single/double; accumulate: collect the pattempt_update statistics on the device"""
+        self._chk(self.L.hb200_set_pattempt(self.h, float(pattempt_single), float(pattempt_double), int(bool(accumulate))))
+
+    def get_ps_stats(self, reset=True):
+        """this rank's (h_pgen_singles_sum, excit_gen_singles, h_pgen_doubles_sum, excit_gen_doubles) since the last reset"""
+        out = np.zeros(4)
+        self._chk(self.L.hb200_get_ps_stats(self.h, _p(out), int(bool(reset))))
+        return out
 
     def ccmc_set_hash_shift(self, hash_shift, move_freq=5):
         self._chk(self.L.hb200_ccmc_set_hash_shift(self.h, int(hash_shift), int(move_freq)))

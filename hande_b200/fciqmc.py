@@ -42,12 +42,57 @@ class QmcIn:
     excit_gen: str = "renorm"
     pattempt_single: float = -1.0
     pattempt_double: float = -1.0
+    pattempt_update: bool = False   # qmc_in%pattempt_update: pattempt_single follows the spawn statistics until the shift varies
     state_size: int = -5            # <0: MB (src/particle_t_utils.f90), >0: elements
     spawned_state_size: int = -1
     ex_level: int = -1              # reference = {ex_level = ...}: truncation level, -1 = none
     nslots: int = 1
     full_non_composite: bool = False  # ccmc = {full_non_composite = true} (CCMC only)
     reference_det: list = None      # reference = {det = {...}}: explicit reference determinant (1-based orbitals)
+
+
+class PattemptUpdate:
+    """Host half of qmc_in%pattempt_update (src/qmc.F90:1049-1060): the engine accumulates this rank's
+    p_single_double_coll_t sums (hb200_set_pattempt / hb200_get_ps_stats); once per report loop this does
+    end_report_loop's vary_psingles branch (src/qmc_common.F90:1206-1231): communicate_pattempt_single_data,
+    add_rep_accum_to_total and update_pattempt_single (src/spawning.F90:2217-2372)."""
+    every_attempts = 10000.0       # src/excit_gens.f90:36-37
+    every_min_attempts = 10.0
+
+    def __init__(self, eng, comm, ps, pd, io=None):
+        self.eng, self.comm, self.ps, self.pd, self.io = eng, comm, ps, pd, io
+        self.total = np.zeros(4)   # h_pgen_singles_sum, excit_gen_singles, h_pgen_doubles_sum, excit_gen_doubles
+        self.counter = 1.0
+        self.vary_psingles = True
+        self.log = []
+        eng.set_pattempt(ps, pd, True)
+
+    def end_report_loop(self, vary_shift):
+        if not self.vary_psingles:
+            return
+        if vary_shift:
+            self.vary_psingles = False
+            self.eng.set_pattempt(self.ps, self.pd, False)
+            if self.io is not None and self.comm.rank == 0:
+                self.io.write(" # pattempt_single chosen to be: %17.10E\n" % self.ps)
+            return
+        self.total = self.total + self.comm.allreduce_sum(self.eng.get_ps_stats(reset=True))
+        hs, ns, hd, nd = (float(x) for x in self.total)
+        if (ns + nd) > self.counter * self.every_attempts and ns > self.counter * self.every_min_attempts \
+                and nd > self.counter * self.every_min_attempts:
+            self.counter += 1.0
+            ps = (hs / ns) / ((hd / nd) + (hs / ns))
+            if ps < 1.0 / self.every_attempts:
+                ps = 1.0 / self.every_attempts
+            pd = 1.0 - ps
+            if pd < 1.0 / self.every_attempts:
+                pd = 1.0 / self.every_attempts
+                ps = 1.0 - pd
+            self.ps, self.pd = ps, pd
+            self.log.append(ps)
+            self.eng.set_pattempt(ps, pd, True)
+            if self.io is not None and self.comm.rank == 0:
+                self.io.write(" # pattempt_single changed to be: %17.10E\n" % ps)
 
 
 def murmurhash2(data: bytes, seed: int) -> int:
@@ -155,6 +200,7 @@ class FciqmcResult:
     engine: object = None
     error: bool = False
     timings: list = field(default_factory=list)
+    pattempt_log: list = field(default_factory=list)   # pattempt_single after each pattempt_update change
 
 
 def do_fciqmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, keep_engine=False, psips=None):
@@ -213,6 +259,7 @@ def do_fciqmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, 
     proj_energy, D0, ntot_old, tot_nstates = float(buf[0]), float(buf[1]), float(buf[2]), int(round(buf[3]))
     shift, vary_shift = qmc.initial_shift, False
     res = FciqmcResult(H00=H00, occ0=occ0)
+    pupd = PattemptUpdate(eng, comm, ps, pd, io=out) if qmc.pattempt_update else None
     res.rows.append([0, shift, proj_energy, D0, ntot_old, tot_nstates, 0, 0.0])
     if out is not None and iproc == 0:
         out.write(HEADER + "\n")
@@ -246,6 +293,8 @@ def do_fciqmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, 
         if not vary_shift and ntot > qmc.target_population:
             vary_shift = True
             shift = proj_energy / D0 if qmc.vary_shift_from_proje else qmc.vary_shift_from
+        if pupd is not None:
+            pupd.end_report_loop(vary_shift)
         it = mc_cycles_done + ireport * qmc.mc_cycles
         res.rows.append([it, shift, proj_energy, D0, ntot, tot_nstates, tot_nev, rspawn])
         if out is not None and iproc == 0:
@@ -255,6 +304,7 @@ def do_fciqmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, 
             res.error = True
             break
     res.shift, res.vary_shift = shift, vary_shift
+    res.pattempt_log = pupd.log if pupd is not None else []
     if keep_engine:
         res.engine = eng
     else:

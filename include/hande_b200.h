@@ -175,6 +175,17 @@ int hb200_ccmc_set_hash_shift(hb200_engine* e, int32_t hash_shift, int32_t move_
  * size >= 2 are selected stochastically and the reference is selected nint(|N_0|) times. */
 int hb200_ccmc_set_full_nc(hb200_engine* e, int32_t full_nc);
 
+/* qmc = { pattempt_update = true } (qmc_in%pattempt_update, src/qmc.F90:1049-1060).  hb200_set_pattempt replaces
+ * excit_gen_data%pattempt_single / pattempt_double; while accumulate != 0 every allowed excitation generated by
+ * hb200_iterate / hb200_ccmc_iterate adds |H_ij| pattempt_{single,double} / pgen and 1 to the p_single_double_coll_t sums
+ * (update_p_single_double_data, src/spawning.F90:2139-2215; call sites src/spawning.F90:104-109 and
+ * src/ccmc_death_spawning.f90:150-157).  hb200_get_ps_stats returns this rank's rep_accum
+ * {h_pgen_singles_sum, excit_gen_singles, h_pgen_doubles_sum, excit_gen_doubles} and optionally zeroes it; the host does
+ * communicate_pattempt_single_data + update_pattempt_single (src/spawning.F90:2217-2372) once per report loop.  As in
+ * src/check_input.F90:192-197 accumulation is refused for the UEG and for excit_gen = heat_bath. */
+int hb200_set_pattempt(hb200_engine* e, double pattempt_single, double pattempt_double, int32_t accumulate);
+int hb200_get_ps_stats(hb200_engine* e, double* out4, int32_t reset);
+
 /* Stage-level entry points (same state machine as hb200_iterate, one stage per call). */
 /* do idet loop: decoder_ptr, set_parent_flag, update_proj_energy_ptr, decide_nattempts,
  * do_fciqmc_spawning_attempt, stochastic_death (src/fciqmc.f90:315-371). */

@@ -365,9 +365,20 @@ int orc_ccmc_stage_spawn(void* h, uint32_t cycle_id, double tau, double shift, d
 }
 void orc_ccmc_set_full_nc(void* h, int full_nc) { ((OracleCcmc*)(Oracle*)h)->full_nc = full_nc != 0; }
 // qmc = { pattempt_update = true }; orc_ccmc_get_pattempt_log copies up to n values of pattempt_single after each change
-void orc_ccmc_set_pattempt_update(void* h, int on) { ((OracleCcmc*)(Oracle*)h)->vary_psingles = on != 0; }
-int orc_ccmc_get_pattempt_log(void* h, double* out, int n) {
-    OracleCcmc* o = (OracleCcmc*)(Oracle*)h;
+void orc_set_pattempt_update(void* h, int on) { ((Oracle*)h)->vary_psingles = on != 0; }
+// rep_accum of one rank: h_pgen_singles_sum, excit_gen_singles, h_pgen_doubles_sum, excit_gen_doubles
+void orc_get_ps_stats(void* h, int rank, double* out, int reset) {
+    Oracle* o = (Oracle*)h;
+    for (int k = 0; k < 4; ++k) out[k] = 0.0;
+    if (rank < (int)o->ps_rep_accum.size()) {
+        auto& a = o->ps_rep_accum[rank];
+        out[0] = a.h_pgen_singles_sum; out[1] = a.excit_gen_singles; out[2] = a.h_pgen_doubles_sum; out[3] = a.excit_gen_doubles;
+        if (reset) a = Oracle::PsColl();
+    }
+}
+void orc_set_pattempt(void* h, double ps, double pd) { ((Oracle*)h)->eg.pattempt_single = ps; ((Oracle*)h)->eg.pattempt_double = pd; }
+int orc_get_pattempt_log(void* h, double* out, int n) {
+    Oracle* o = (Oracle*)h;
     const int m = (int)o->pattempt_log.size();
     for (int i = 0; i < m && i < n; ++i) out[i] = o->pattempt_log[i];
     return m;

@@ -37,13 +37,6 @@ struct CcmcStats {   // what the device engine is compared against, per cycle
 struct OracleCcmc : Oracle {
     int move_freq = 5;                 // ccmc_in%move_freq (default)
     bool full_nc = false;              // ccmc_in%full_nc (full_non_composite)
-    // qmc_in%pattempt_update (src/qmc.F90:1049-1060): p_single_double_t of src/excit_gens.f90:13-41
-    struct PsColl { double h_pgen_singles_sum = 0.0, excit_gen_singles = 0.0, h_pgen_doubles_sum = 0.0, excit_gen_doubles = 0.0; };
-    bool vary_psingles = false;
-    std::vector<PsColl> ps_rep_accum;  // per rank, zeroed after each update
-    PsColl ps_total;
-    double ps_counter = 1.0;
-    std::vector<double> pattempt_log;  // pattempt_single after each change ("# pattempt_single changed to be:")
     int hash_shift = 0;                // spawn%hash_shift: +1 per cycle (src/ccmc.f90:540,625)
     int64_t nattempts_last = 0;
     std::vector<double> cumulative_abs_real_pops;
@@ -518,10 +511,7 @@ struct OracleCcmc : Oracle {
             else shift = in.vary_shift_from;
         }
         error = err;
-        if (vary_psingles) {   // end_report_loop (src/qmc_common.F90:1206-1231)
-            if (vary_shift) vary_psingles = false;
-            else update_pattempt();
-        }
+        end_report_loop_pattempt();
         ReportRow row;
         row.iter = mc_cycles_done + ireport * in.ncycles;
         row.shift = shift; row.proj_energy = est.proj_energy; row.D0_population = est.D0_population;
@@ -532,34 +522,6 @@ struct OracleCcmc : Oracle {
     }
     std::vector<int64_t> nattempts_rows;
 
-    // update_pattempt + communicate_pattempt_single_data + add_rep_accum_to_total + update_pattempt_single
-    // (src/spawning.F90:2217-2372); every_attempts = 10000, every_min_attempts = 10 (src/excit_gens.f90:36-37)
-    void update_pattempt() {
-        PsColl sum;
-        for (auto& a : ps_rep_accum) {
-            sum.excit_gen_singles += a.excit_gen_singles; sum.excit_gen_doubles += a.excit_gen_doubles;
-            sum.h_pgen_singles_sum += a.h_pgen_singles_sum; sum.h_pgen_doubles_sum += a.h_pgen_doubles_sum;
-        }
-        ps_total.excit_gen_singles = ps_total.excit_gen_singles + sum.excit_gen_singles;
-        ps_total.excit_gen_doubles = ps_total.excit_gen_doubles + sum.excit_gen_doubles;
-        ps_total.h_pgen_singles_sum = ps_total.h_pgen_singles_sum + sum.h_pgen_singles_sum;
-        ps_total.h_pgen_doubles_sum = ps_total.h_pgen_doubles_sum + sum.h_pgen_doubles_sum;
-        const double every_attempts = 10000.0, every_min_attempts = 10.0;
-        if ((ps_total.excit_gen_singles + ps_total.excit_gen_doubles) > (ps_counter * every_attempts) &&
-            ps_total.excit_gen_singles > (ps_counter * every_min_attempts) &&
-            ps_total.excit_gen_doubles > (ps_counter * every_min_attempts)) {
-            ps_counter = ps_counter + 1.0;
-            double ps = (ps_total.h_pgen_singles_sum / ps_total.excit_gen_singles) /
-                        ((ps_total.h_pgen_doubles_sum / ps_total.excit_gen_doubles) +
-                         (ps_total.h_pgen_singles_sum / ps_total.excit_gen_singles));
-            if (ps < (1.0 / every_attempts)) ps = 1.0 / every_attempts;
-            double pd = 1.0 - ps;
-            if (pd < (1.0 / every_attempts)) { pd = 1.0 / every_attempts; ps = 1.0 - pd; }
-            eg.pattempt_single = ps; eg.pattempt_double = pd;
-            pattempt_log.push_back(ps);
-        }
-        for (auto& a : ps_rep_accum) a = PsColl();
-    }
 
     void run_ccmc() {
         // initial_cc_projected_energy (src/qmc_common.F90:799-925) for a population on the reference only:

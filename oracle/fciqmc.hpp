@@ -177,6 +177,47 @@ struct Oracle {
     ExcitGenData eg;
     const ExcitGenData* eg_shared = nullptr;  // replicas of orc_cpu_baseline share the (2 GB) heat-bath tables
     const ExcitGenData& EG() const { return eg_shared ? *eg_shared : eg; }
+    // qmc_in%pattempt_update (src/qmc.F90:1049-1060): p_single_double_t of src/excit_gens.f90:13-41
+    struct PsColl { double h_pgen_singles_sum = 0.0, excit_gen_singles = 0.0, h_pgen_doubles_sum = 0.0, excit_gen_doubles = 0.0; };
+    bool vary_psingles = false;
+    std::vector<PsColl> ps_rep_accum;  // per rank, zeroed after each update
+    PsColl ps_total;
+    double ps_counter = 1.0;
+    std::vector<double> pattempt_log;  // pattempt_single after each change ("# pattempt_single changed to be:")
+    // end_report_loop (src/qmc_common.F90:1206-1231)
+    void end_report_loop_pattempt() {
+        if (!vary_psingles) return;
+        if (vary_shift) vary_psingles = false;
+        else update_pattempt();
+    }
+    // update_pattempt + communicate_pattempt_single_data + add_rep_accum_to_total + update_pattempt_single
+    // (src/spawning.F90:2217-2372); every_attempts = 10000, every_min_attempts = 10 (src/excit_gens.f90:36-37)
+    void update_pattempt() {
+        PsColl sum;
+        for (auto& a : ps_rep_accum) {
+            sum.excit_gen_singles += a.excit_gen_singles; sum.excit_gen_doubles += a.excit_gen_doubles;
+            sum.h_pgen_singles_sum += a.h_pgen_singles_sum; sum.h_pgen_doubles_sum += a.h_pgen_doubles_sum;
+        }
+        ps_total.excit_gen_singles = ps_total.excit_gen_singles + sum.excit_gen_singles;
+        ps_total.excit_gen_doubles = ps_total.excit_gen_doubles + sum.excit_gen_doubles;
+        ps_total.h_pgen_singles_sum = ps_total.h_pgen_singles_sum + sum.h_pgen_singles_sum;
+        ps_total.h_pgen_doubles_sum = ps_total.h_pgen_doubles_sum + sum.h_pgen_doubles_sum;
+        const double every_attempts = 10000.0, every_min_attempts = 10.0;
+        if ((ps_total.excit_gen_singles + ps_total.excit_gen_doubles) > (ps_counter * every_attempts) &&
+            ps_total.excit_gen_singles > (ps_counter * every_min_attempts) &&
+            ps_total.excit_gen_doubles > (ps_counter * every_min_attempts)) {
+            ps_counter = ps_counter + 1.0;
+            double ps = (ps_total.h_pgen_singles_sum / ps_total.excit_gen_singles) /
+                        ((ps_total.h_pgen_doubles_sum / ps_total.excit_gen_doubles) +
+                         (ps_total.h_pgen_singles_sum / ps_total.excit_gen_singles));
+            if (ps < (1.0 / every_attempts)) ps = 1.0 / every_attempts;
+            double pd = 1.0 - ps;
+            if (pd < (1.0 / every_attempts)) { pd = 1.0 / every_attempts; ps = 1.0 - pd; }
+            eg.pattempt_single = ps; eg.pattempt_double = pd;
+            pattempt_log.push_back(ps);
+        }
+        for (auto& a : ps_rep_accum) a = PsColl();
+    }
     // reference_t
     std::vector<int> occ_list0;
     Det f0;
@@ -378,6 +419,17 @@ struct Oracle {
             for (int ip = 0; ip < nattempts_det; ++ip) {
                 rng.begin(RNG_SPAWN, d.f, sys.W, (uint32_t)ip);
                 GenResult g = gen_excit_sys(rng, sys, EG(), d);
+                if (g.allowed && vary_psingles) {   // spawn_standard (src/spawning.F90:101-109): straight into rep_accum
+                    if ((int)ps_rep_accum.size() != in.nprocs) ps_rep_accum.assign(in.nprocs, PsColl());
+                    PsColl& a = ps_rep_accum[r.iproc];
+                    if (g.conn.nexcit == 1) {
+                        a.h_pgen_singles_sum = a.h_pgen_singles_sum + ((std::fabs(g.hmatel) * eg.pattempt_single) / g.pgen);
+                        a.excit_gen_singles = a.excit_gen_singles + 1.0;
+                    } else if (g.conn.nexcit == 2) {
+                        a.h_pgen_doubles_sum = a.h_pgen_doubles_sum + ((std::fabs(g.hmatel) * eg.pattempt_double) / g.pgen);
+                        a.excit_gen_doubles = a.excit_gen_doubles + 1.0;
+                    }
+                }
                 int64_t nspawned = attempt_to_spawn(rng, g.hmatel, g.pgen, pop);
                 if (nspawned != 0) {
                     Det fnew = sys.create_excited_det(d.f, g.conn);
@@ -704,6 +756,7 @@ struct Oracle {
             else shift = in.vary_shift_from;
         }
         error = err;
+        end_report_loop_pattempt();
         ReportRow row;
         row.iter = mc_cycles_done + ireport * in.ncycles;
         row.shift = shift; row.proj_energy = est.proj_energy; row.D0_population = est.D0_population;

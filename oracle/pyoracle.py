@@ -351,14 +351,28 @@ class Oracle:
         """ccmc = { full_non_composite = true }"""
         self.L.orc_ccmc_set_full_nc(self.h, int(full_nc))
 
-    def ccmc_set_pattempt_update(self, on=True):
-        """qmc = { pattempt_update = true } (CCMC runs): pattempt_single follows the spawn statistics until the shift varies"""
-        self.L.orc_ccmc_set_pattempt_update(self.h, int(on))
+    def set_pattempt_update(self, on=True):
+        """qmc = { pattempt_update = true }: pattempt_single follows the spawn statistics until the shift varies"""
+        self.L.orc_set_pattempt_update(self.h, int(on))
 
-    def ccmc_pattempt_log(self):
+    ccmc_set_pattempt_update = set_pattempt_update
+
+    def pattempt_log(self):
         out = np.zeros(4096)
-        n = int(self.L.orc_ccmc_get_pattempt_log(self.h, out.ctypes.data_as(C.c_void_p), len(out)))
+        n = int(self.L.orc_get_pattempt_log(self.h, out.ctypes.data_as(C.c_void_p), len(out)))
         return out[:min(n, len(out))]
+
+    ccmc_pattempt_log = pattempt_log
+
+    def ps_stats(self, rank=0, reset=False):
+        """rep_accum of one rank: h_pgen_singles_sum, excit_gen_singles, h_pgen_doubles_sum, excit_gen_doubles"""
+        out = np.zeros(4)
+        self.L.orc_get_ps_stats(self.h, int(rank), out.ctypes.data_as(C.c_void_p), int(reset))
+        return out
+
+    def set_pattempt(self, ps, pd):
+        self.L.orc_set_pattempt.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        self.L.orc_set_pattempt(self.h, float(ps), float(pd))
 
     def ccmc_hash_shift(self):
         return int(self.L.orc_ccmc_get_hash_shift(self.h))

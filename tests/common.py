@@ -16,6 +16,7 @@ SYSTEMS = {
     "h2o": dict(fcidump="h2o", kw=dict(nel=10, ms=0, sym=0, cas=(8, 13))),
     "ne": dict(fcidump="ne", kw=dict(nel=10, ms=0, sym=0)),
     "ne_vdz": dict(fcidump="ne_vdz", kw=dict(nel=10, ms=0, sym=0)),   # the reference's CCMC fixture (28 spin-orbitals, D2h)
+    "nh3": dict(fcidump="nh3_631g", kw=dict(nel=10, ms=0, sym=0)),    # the reference's per-generator CCSDT fixture (C3v in Cs)
     "ne_cas": dict(fcidump="ne", kw=dict(nel=10, ms=0, sym=0, cas=(8, 22))),
     "s10": dict(synthetic=(10, 8), kw={}),
     "s12": dict(synthetic=(12, 8), kw={}),

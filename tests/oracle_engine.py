@@ -111,6 +111,13 @@ def make_engine_cls(fcidump_path, sys_kw, rng_kind=0, ueg=None, ref_det=None):
             out["nstates"] = self.nstates
             return out
 
+        def set_pattempt(self, pattempt_single, pattempt_double, accumulate=False):
+            self.o.set_pattempt(pattempt_single, pattempt_double)
+            self.o.set_pattempt_update(accumulate)
+
+        def get_ps_stats(self, reset=True):
+            return self.o.ps_stats(self.rank, reset=reset)
+
         def last_timing(self):
             return {}
 

@@ -38,3 +38,35 @@ def test_ccmc_driver_reproduces_golden(fcidump_path):
             assert gr[k] == pr(r[k]), (i, k, gr[k], r[k])
         assert gr[5] == r[5] and gr[6] == r[6] and gr[8] == r[8], (i, gr, r)
         assert abs(gr[7] - r[7]) < 0.6e-4
+
+
+def test_ccmc_driver_pattempt_update(fcidump_path):
+    """qmc = { pattempt_update = true }: the host half (hande_b200.fciqmc.PattemptUpdate: rep_accum -> total,
+    update_pattempt_single, stop when the shift varies) against the oracle's own report loop, whose np4 runs reproduce
+    the reference's NH3 golden tables with pattempt_update (tests/test_oracle_golden.py)."""
+    if not pyoracle.have_ref_lib():
+        pytest.skip("oracle/_ref not built")
+    g = load_golden("ccmc_nh3_renorm")
+    kw = dict(nel=g["sys"]["nel"], ms=g["sys"]["ms"], sym=g["sys"]["sym"])
+    path = fcidump_path(g["fcidump"])
+    s = R.read_in(path, **kw)
+    gq = g["qmc"]
+    nrows = 160
+    o = pyoracle.Oracle()
+    o.read_fcidump(path, **kw)
+    q = dict(gq, nprocs=1, nreport=nrows, target_particles=2500.0)
+    o.set_qmc(**q)
+    o.init()
+    o.set_pattempt_update(True)
+    rows, na = o.run_ccmc()
+    log = o.pattempt_log()
+    assert len(log) >= 3 and rows[-1][1] != 0.0       # several updates, then the shift varies and the updates stop
+    qmc = QmcIn(tau=gq["tau"], rng_seed=gq["seed"], init_pop=gq["D0_population"], mc_cycles=gq["ncycles"],
+                nreports=nrows, target_population=2500.0, state_size=gq["walker_length"],
+                spawned_state_size=gq["spawned_walker_length"], ex_level=gq["ex_level"], real_amplitudes=True,
+                excit_gen="renorm", pattempt_update=True)
+    res = do_ccmc(s, qmc, engine_cls=make_engine_cls(path, kw, rng_kind=0))
+    assert list(res.pattempt_log) == list(log)
+    assert len(res.rows) == len(rows)
+    for r, ro, n in zip(res.rows, rows, na):
+        assert list(r[:8]) == list(ro[:8]) and r[8] == n

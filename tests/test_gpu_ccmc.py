@@ -47,6 +47,11 @@ def test_ccmc_stage_and_cycle_parity(name, gen, real, exl, tau, warm, full_nc):
     assert len(f) > 30
     eng.upload_psips(f, pops, dat)
     shift = -0.02
+    ps_on = name != "ueg6"
+    if ps_on:      # qmc_in%pattempt_update statistics of the spawning attempts (cluster and non-composite kernels)
+        o.set_pattempt_update(True)
+        eng.set_pattempt(ref["pattempt_single"], ref["pattempt_double"], True)
+        o.ps_stats(0, reset=True)
     for cycle in range(warm + 1, warm + 5):
         st_o, sd_o = o.ccmc_stage_spawn(cycle, tau, shift, pe_old)
         st_g = eng.ccmc_spawn(tau, shift, pe_old, cycle, exl)
@@ -67,6 +72,10 @@ def test_ccmc_stage_and_cycle_parity(name, gen, real, exl, tau, warm, full_nc):
         assert (fg == fo).all() and (pg == po).all() and (dg == do_).all()
         if st_o["D0_population"] != 0:
             pe_old = st_o["proj_energy"] / st_o["D0_population"]
+    if ps_on:
+        a, b = eng.get_ps_stats(reset=True), o.ps_stats(0)
+        assert a[1] == b[1] and a[3] == b[3] and a[1] + a[3] > 100
+        assert abs(a[0] - b[0]) <= 1e-12 * abs(b[0]) and abs(a[2] - b[2]) <= 1e-12 * abs(b[2])
     eng.close()
 
 

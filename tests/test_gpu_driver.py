@@ -134,3 +134,35 @@ def test_ccmc_driver_trajectory_and_energy():
     eo, so = ratio_with_error(orow[k:, 2], orow[k:, 3])
     assert abs(eg - eo) < 2.0 * np.hypot(sg, so) + 1e-4, (eg, sg, eo, so)
     assert -0.25 < eg < -0.15      # CCSD correlation energy of Ne/cc-pVDZ is about -0.19 Eh
+
+
+@pytest.mark.parametrize("gen,tau", [("renorm", 0.0007), ("heat_bath_single", 0.003), ("power_pitzer_occ_ij", 0.0015)])
+def test_ccmc_driver_pattempt_update(gen, tau):
+    """qmc = { pattempt_update = true } through do_ccmc on the GPU engine, NH3 CCSDT (the system of the reference's
+    per-generator golden tables): device-accumulated p_single_double sums -> host update_pattempt_single.  Same Philox
+    stream as the oracle: identical trajectory, pattempt_single after each change to summation-order accuracy."""
+    from hande_b200.ccmc import do_ccmc
+    path, kw = system_path("nh3")
+    s = R.read_in(path, **kw)
+    nrep = 60
+    qmc = QmcIn(tau=tau, rng_seed=30513, init_pop=200, mc_cycles=10, nreports=nrep, target_population=1200,
+                state_size=200000, spawned_state_size=100000, ex_level=3, real_amplitudes=True, excit_gen=gen,
+                pattempt_update=True)
+    res = do_ccmc(s, qmc)
+    o = Oracle()
+    o.read_fcidump(path, **kw)
+    o.set_qmc(rng_kind=1, tau=tau, seed=30513, D0_population=200, ncycles=10, nreport=nrep, target_particles=1200,
+              walker_length=200000, spawned_walker_length=100000, ex_level=3, real_amplitudes=1, spawn_cutoff=0.01,
+              excit_gen=gen)
+    o.init()
+    o.set_pattempt_update(True)
+    rows, na = o.run_ccmc()
+    log = o.pattempt_log()
+    assert len(log) >= 2 and len(res.pattempt_log) == len(log)
+    for a, b in zip(res.pattempt_log, log):
+        assert abs(a - b) <= 1e-12 * b
+    assert res.vary_shift and len(res.rows) == len(rows) == nrep + 1
+    for g, r, a in zip(res.rows, rows, na):
+        assert g[0] == r[0] and g[5] == r[5] and g[6] == r[6] and g[8] == a, (g, r, a)
+        assert abs(g[1] - r[1]) <= 1e-9 * max(1.0, abs(r[1])) and abs(g[4] - r[4]) <= 1e-10 * max(1.0, abs(r[4]))
+        assert abs(g[2] - r[2]) <= 1e-10 * max(1.0, abs(r[2])) and abs(g[3] - r[3]) <= 1e-10 * max(1.0, abs(r[3]))

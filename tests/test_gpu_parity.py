@@ -4,6 +4,7 @@ main list (states, pops) and dat (same summation order, no FMA).  1e-12 relative
 import numpy as np
 import pytest
 
+from hande_b200.engine import EngineError
 from tests.common import make_pair, random_population, sort_rows
 
 pytestmark = pytest.mark.gpu
@@ -135,7 +136,18 @@ def test_stage_and_cycle_parity(name, gen, real, init, tau, n, exl):
     eng.upload_psips(f, pops, dat)
     shift, pe_old = -0.05, -0.11
     rf = 2**31 if real else 1
+    # qmc_in%pattempt_update statistics (refused for heat_bath and the UEG as in src/check_input.F90:192-197)
+    ps_on = gen != "heat_bath" and not name.startswith("ueg")
+    if ps_on:
+        o.set_pattempt_update(True)
+        eng.set_pattempt(ref["pattempt_single"], ref["pattempt_double"], True)
+    else:
+        with pytest.raises(EngineError):
+            eng.set_pattempt(ref["pattempt_single"], ref["pattempt_double"], True)
     for cycle in (1, 2, 3):
+        if ps_on and cycle == 3:      # a changed pattempt_single takes effect in the generators and in the sums
+            o.set_pattempt(0.21, 0.79)
+            eng.set_pattempt(0.21, 0.79, True)
         st_o, sd_o = o.stage_spawn(cycle, tau, shift, pe_old)
         st_g = eng.spawn_death(tau, shift, pe_old, cycle)
         sd_g = eng.download_spawn()
@@ -159,7 +171,17 @@ def test_stage_and_cycle_parity(name, gen, real, init, tau, n, exl):
         assert (pg == po).all()
         assert (dg == do_).all()
         assert out["nparticles"] == pytest.approx(np.abs(po).sum() / rf, rel=1e-14)
+    if ps_on:
+        _check_ps_stats(eng, o)
     eng.close()
+
+
+def _check_ps_stats(eng, o):
+    """p_single_double_coll_t sums of the report loop: counts exact, sums to summation-order accuracy"""
+    a, b = eng.get_ps_stats(reset=True), o.ps_stats(0)
+    assert a[1] == b[1] and a[3] == b[3] and a[1] + a[3] > 100
+    assert abs(a[0] - b[0]) <= 1e-12 * abs(b[0]) and abs(a[2] - b[2]) <= 1e-12 * abs(b[2])
+    assert (eng.get_ps_stats() == 0).all()
 
 
 @pytest.mark.parametrize("name,gen,real,init,tau", [("h2o", "renorm", False, False, 0.003),

@@ -56,7 +56,7 @@ def do_ccmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, ke
                      real_amplitudes=qmc.real_amplitudes, spawn_cutoff=qmc.spawn_cutoff, initiator_approx=False,
                      initiator_pop=qmc.initiator_population, trunc_level=qmc.ex_level, walker_length=wl,
                      spawned_walker_length=sl, seed=qmc.rng_seed, nprocs=nprocs, iproc=iproc, nslots=qmc.nslots,
-                     device=device)
+                     device=device, pattempt_parallel=qmc.pattempt_parallel)
     eng.set_reference(f0, H00)
     if qmc.full_non_composite:
         eng.ccmc_set_full_nc(True)

@@ -101,6 +101,7 @@ struct Sys {
 struct Params {
     int excit_gen;              // EXCIT_GEN_* (the reference's enumerator values)
     double pattempt_single, pattempt_double;
+    double pattempt_parallel;   // renorm_spin / no_renorm_spin: probability that i and j have parallel spins
     double tau, shift, proj_energy_old;
     int64_t real_factor;        // pop_real_factor (1 or 2^31)
     int64_t spawn_cutoff;       // encoded (src/spawn_data.F90:215)
@@ -123,7 +124,7 @@ struct PsPartials { double h_pgen_singles_sum, h_pgen_doubles_sum; long long exc
 // the reference's enumerator values (src/qmc_data.f90:31-69: renorm, renorm_spin, no_renorm, no_renorm_spin, power_pitzer,
 // power_pitzer_occ, power_pitzer_occ_ij, power_pitzer_orderN, cauchy_schwarz_occ, cauchy_schwarz_occ_ij, heat_bath,
 // heat_bath_uniform, heat_bath_single)
-enum { EXCIT_GEN_RENORM = 0, EXCIT_GEN_NO_RENORM = 2, EXCIT_GEN_POWER_PITZER_OCC = 5, EXCIT_GEN_POWER_PITZER_OCC_IJ = 6,
+enum { EXCIT_GEN_RENORM = 0, EXCIT_GEN_RENORM_SPIN = 1, EXCIT_GEN_NO_RENORM = 2, EXCIT_GEN_NO_RENORM_SPIN = 3, EXCIT_GEN_POWER_PITZER_OCC = 5, EXCIT_GEN_POWER_PITZER_OCC_IJ = 6,
        EXCIT_GEN_CAUCHY_SCHWARZ_OCC = 8, EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ = 9,
        EXCIT_GEN_HEAT_BATH = 10, EXCIT_GEN_HEAT_BATH_UNIFORM = 11, EXCIT_GEN_HEAT_BATH_SINGLE = 12 };
 enum { RNG_NATTEMPTS = 0, RNG_SPAWN = 1, RNG_DEATH = 2, RNG_ROUND_MAIN = 3, RNG_ROUND_SPAWN = 4 };
@@ -490,6 +491,51 @@ HB_HD void choose_ij(R& rng, const Sys& s, const uint8_t* occ, int& i, int& j, i
     ij_spin = ms_of(i) + ms_of(j);
 }
 
+// choose_ij_spin_mol (src/excit_gen_mol.f90:684-800): parallel or anti-parallel pair first (pattempt_parallel), then the
+// pair from occ_list_alpha / occ_list_beta (decode_det_spinocc_symunocc: alpha = ms +1)
+HB_HD int nth_occ_of_spin(const uint8_t* occ, int nel, int ms, int k) {
+    for (int q = 0; q < nel; ++q)
+        if (ms_of(occ[q]) == ms && --k == 0) return occ[q];
+    return 0;
+}
+template <class R>
+HB_HD void choose_ij_spin(R& rng, const Sys& s, const Params& p, const uint8_t* occ, int& i, int& j, int& ij_sym,
+                          int& ij_spin, double& pgen_ij, bool& allowed) {
+    const int nalpha = s.nbasis / 2 - s.nvirt_alpha, nbeta = s.nbasis / 2 - s.nvirt_beta;
+    allowed = true;
+    if (rng.next() < p.pattempt_parallel) {
+        const bool alpha = rng.next() < ((double)nalpha / (double)(nalpha + nbeta));
+        const int n = alpha ? nalpha : nbeta;
+        if (n < 2) {
+            allowed = false;
+        } else {
+            const int ind = (int)(rng.next() * (double)(n * (n - 1)) / 2.0) + 1;
+            const int j_ind = (int)(1.50 + sqrt(2 * ind - 1.750));
+            const int i_ind = ind - ((j_ind - 1) * (j_ind - 2)) / 2;
+            i = nth_occ_of_spin(occ, s.nel, alpha ? 1 : -1, i_ind);
+            j = nth_occ_of_spin(occ, s.nel, alpha ? 1 : -1, j_ind);
+            pgen_ij = (p.pattempt_parallel * ((double)n / (double)(nalpha + nbeta)) * 2.0 * (1.0 / n) * (1.0 / (n - 1)));
+        }
+    } else {
+        if (nbeta < 1 || nalpha < 1) {
+            allowed = false;
+        } else {
+            const int i_ind = (int)(rng.next() * nalpha) + 1;
+            const int j_ind = (int)(rng.next() * nbeta) + 1;
+            i = nth_occ_of_spin(occ, s.nel, 1, i_ind);
+            j = nth_occ_of_spin(occ, s.nel, -1, j_ind);
+            if (j < i) { const int t = i; i = j; j = t; }
+            pgen_ij = (1.0 - p.pattempt_parallel) * (1.0 / (nalpha * nbeta));
+        }
+    }
+    if (allowed) {
+        ij_sym = sym_conj(s, cross_product(s, s.bf_sym[i], s.bf_sym[j]));
+        ij_spin = ms_of(i) + ms_of(j);
+    } else {
+        pgen_ij = 1.0; i = 0; j = 0; ij_sym = 0; ij_spin = 0;
+    }
+}
+
 // gen_single_excit_mol (src/excit_gen_mol.f90:384-448): choose_ia_mol (:802-870) + calc_pgen_single_mol (:1140-1190)
 template <int W, class R>
 HB_HDN void gen_single_renorm(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ,
@@ -535,7 +581,8 @@ HB_HDN void gen_single_renorm(R& rng, const Sys& s, const Params& p, const uint6
 
 // gen_excit_mol: renormalised uniform generator (src/excit_gen_mol.f90:16-101,384-448,521-616,
 // 802-946,1140-1327)
-template <int W, class R>
+// SPIN: gen_excit_mol_spin (src/excit_gen_mol.f90:103-193), excit_gen = renorm_spin - ij from choose_ij_spin_mol
+template <int W, bool SPIN = false, class R>
 HB_HDN void gen_excit_renorm(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ,
                              const uint8_t* su, Gen& g) {
     const int nel = s.nel;
@@ -545,12 +592,16 @@ HB_HDN void gen_excit_renorm(R& rng, const Sys& s, const Params& p, const uint64
     } else {
         g.nexcit = 2;
         int i, j, ij_sym, spin;
-        choose_ij(rng, s, occ, i, j, ij_sym, spin);
+        double pgen_ij = 2.0 / (nel * (nel - 1));
+        bool ij_ok = true;
+        if (SPIN) choose_ij_spin(rng, s, p, occ, i, j, ij_sym, spin, pgen_ij, ij_ok);
+        else choose_ij(rng, s, occ, i, j, ij_sym, spin);
         g.from1 = i; g.from2 = j;
         // choose_ab_mol
         bool allowed = false;
         int fac = 1, shift = 0, na = s.nbasis;
-        if (spin == 0) {
+        if (!ij_ok) {
+        } else if (spin == 0) {
             for (int isyma = s.sym0; isyma <= s.sym_max; ++isyma) {
                 int isymb = sym_conj(s, cross_product(s, isyma, ij_sym));
                 if ((HB_SU(1, isyma) > 0 && HB_SU(2, isymb) > 0) || (HB_SU(2, isyma) > 0 && HB_SU(1, isymb) > 0)) {
@@ -619,7 +670,6 @@ HB_HDN void gen_excit_renorm(R& rng, const Sys& s, const Params& p, const uint64
                 p_aijb = 1.0 / HB_SU(imsa, s.bf_sym[a]);
                 p_bija = 1.0 / HB_SU(imsb, s.bf_sym[b]);
             }
-            double pgen_ij = 2.0 / (nel * (nel - 1));
             g.pgen = p.pattempt_double * pgen_ij * ((1.0 / n_aij) * (p_bija + p_aijb));
             g.perm = excit_perm2<W>(f, i, j, a, b);
             g.hmatel = slater_condon2_excit(s, i, j, a, b, g.perm);
@@ -630,7 +680,8 @@ HB_HDN void gen_excit_renorm(R& rng, const Sys& s, const Params& p, const uint64
 }
 
 // gen_excit_mol_no_renorm (src/excit_gen_mol.f90:195-284,450-517,950-1136,1329-1445)
-template <int W, class R>
+// SPIN: gen_excit_mol_no_renorm_spin (src/excit_gen_mol.f90:286-380), excit_gen = no_renorm_spin
+template <int W, bool SPIN = false, class R>
 HB_HDN void gen_excit_no_renorm(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ,
                                 Gen& g) {
     const int nel = s.nel;
@@ -661,20 +712,26 @@ HB_HDN void gen_excit_no_renorm(R& rng, const Sys& s, const Params& p, const uin
     } else {
         g.nexcit = 2;
         int i, j, ij_sym, spin;
-        choose_ij(rng, s, occ, i, j, ij_sym, spin);
+        double pgen_ij = 2.0 / (nel * (nel - 1));
+        bool ij_ok = true;
+        if (SPIN) choose_ij_spin(rng, s, p, occ, i, j, ij_sym, spin, pgen_ij, ij_ok);
+        else choose_ij(rng, s, occ, i, j, ij_sym, spin);
         g.from1 = i; g.from2 = j;
         int fac = 1, shift = 0, na = s.nbasis;
         if (spin == -2) { fac = 2; shift = 0; na = s.nbasis / 2; }
         else if (spin == 2) { fac = 2; shift = 1; na = s.nbasis / 2; }
-        int a, b = 0;
-        for (;;) {
-            a = (int)(rng.next() * na) + 1;
-            a = fac * a - shift;
-            if (!det_test(f, a)) break;
+        int a = 0, b = 0;
+        int imsb = 1, isymb = 0, n = 0;
+        if (ij_ok) {
+            for (;;) {
+                a = (int)(rng.next() * na) + 1;
+                a = fac * a - shift;
+                if (!det_test(f, a)) break;
+            }
+            imsb = (spin - ms_of(a) + 3) / 2;
+            isymb = sym_conj(s, cross_product(s, ij_sym, s.bf_sym[a]));
+            n = nbss(s, imsb, isymb);
         }
-        int imsb = (spin - ms_of(a) + 3) / 2;
-        int isymb = sym_conj(s, cross_product(s, ij_sym, s.bf_sym[a]));
-        int n = nbss(s, imsb, isymb);
         if (n == 0) {
             g.allowed = false;
         } else if (spin != 0 && isymb == s.bf_sym[a] && n == 1) {
@@ -701,7 +758,6 @@ HB_HDN void gen_excit_no_renorm(R& rng, const Sys& s, const Params& p, const uin
                 p_aijb = 1.0 / nbss(s, imsa, isyma);
                 p_bija = 1.0 / nbss(s, imsb2, isymb2);
             }
-            double pgen_ij = 2.0 / (nel * (nel - 1));
             g.pgen = p.pattempt_double * pgen_ij * ((1.0 / n_aij) * (p_bija + p_aijb));
             g.perm = excit_perm2<W>(f, i, j, a, b);
             g.hmatel = slater_condon2_excit(s, i, j, a, b, g.perm);
@@ -1477,6 +1533,8 @@ HB_HD void gen_excit(R& rng, const Sys& s, const Params& p, const uint64_t* f, c
     if (s.kind == SYS_UEG) gen_excit_ueg_no_renorm<W>(rng, s, f, occ, g);
     else if (p.excit_gen == EXCIT_GEN_RENORM) gen_excit_renorm<W>(rng, s, p, f, occ, su, g);
     else if (p.excit_gen == EXCIT_GEN_NO_RENORM) gen_excit_no_renorm<W>(rng, s, p, f, occ, g);
+    else if (p.excit_gen == EXCIT_GEN_RENORM_SPIN) gen_excit_renorm<W, true>(rng, s, p, f, occ, su, g);
+    else if (p.excit_gen == EXCIT_GEN_NO_RENORM_SPIN) gen_excit_no_renorm<W, true>(rng, s, p, f, occ, g);
     else if (p.excit_gen == EXCIT_GEN_POWER_PITZER_OCC || p.excit_gen == EXCIT_GEN_CAUCHY_SCHWARZ_OCC ||
              p.excit_gen == EXCIT_GEN_POWER_PITZER_OCC_IJ || p.excit_gen == EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ) {
         double scr[HB_MAXNEL];

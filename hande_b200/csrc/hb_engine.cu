@@ -246,7 +246,7 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
     constexpr bool heat_bath = (GEN == EXCIT_GEN_HEAT_BATH);
     constexpr bool hb_stage = heat_bath || (GEN == EXCIT_GEN_HEAT_BATH_UNIFORM) || (GEN == EXCIT_GEN_HEAT_BATH_SINGLE) ||
                               (GEN == EXCIT_GEN_POWER_PITZER_OCC_IJ);
-    const int nsu = (GEN == EXCIT_GEN_RENORM || GEN == EXCIT_GEN_HEAT_BATH_UNIFORM || GEN == EXCIT_GEN_POWER_PITZER_OCC ||
+    const int nsu = (GEN == EXCIT_GEN_RENORM || GEN == EXCIT_GEN_RENORM_SPIN || GEN == EXCIT_GEN_HEAT_BATH_UNIFORM || GEN == EXCIT_GEN_POWER_PITZER_OCC ||
                      GEN == EXCIT_GEN_POWER_PITZER_OCC_IJ) ? 2 * s.nsym_tot : 0;
     const bool ps_on = !heat_bath && p.ps_part != nullptr;
     const SpawnSmem L(W, nel, nsu, s.nbasis, heat_bath, hb_stage, ps_on);
@@ -457,6 +457,8 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
             else if (GEN == EXCIT_GEN_POWER_PITZER_OCC_IJ)  // also cauchy_schwarz_occ_ij
                 gen_excit_power_pitzer_occ<W>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, siw, sw + tid, TILE, g);
             else if (GEN == EXCIT_GEN_RENORM) gen_excit_renorm<W>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, g);
+            else if (GEN == EXCIT_GEN_RENORM_SPIN) gen_excit_renorm<W, true>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, g);
+            else if (GEN == EXCIT_GEN_NO_RENORM_SPIN) gen_excit_no_renorm<W, true>(rng, s, p, f, socc + lo * nel, g);
             else gen_excit_no_renorm<W>(rng, s, p, f, socc + lo * nel, g);
         }
         int64_t nspawn = 0;
@@ -661,7 +663,8 @@ k_ccmc_cluster(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states,
         if (cl.excitation_level >= 0 && cl.excitation_level <= a.ex_level + 2) {
             uint8_t occ[HB_MAXNEL], su[64];
             decode_det<W>(cf, occ);
-            if (s.kind == SYS_READ_IN && p.excit_gen != EXCIT_GEN_NO_RENORM && p.excit_gen != EXCIT_GEN_HEAT_BATH)
+            if (s.kind == SYS_READ_IN && p.excit_gen != EXCIT_GEN_NO_RENORM && p.excit_gen != EXCIT_GEN_NO_RENORM_SPIN &&
+                p.excit_gen != EXCIT_GEN_HEAT_BATH)
                 build_symunocc_masks<W>(s, cf, su);
             // do_ccmc_accumulation (src/ccmc.f90:1007-1101)
             bool is_ref;
@@ -763,7 +766,8 @@ k_ccmc_nc(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states, int6
             const int sign = ccmc_excitor_sign<W>(p.f0, f, level);
             uint8_t occ[HB_MAXNEL], su[64];
             decode_det<W>(f, occ);
-            if (s.kind == SYS_READ_IN && p.excit_gen != EXCIT_GEN_NO_RENORM && p.excit_gen != EXCIT_GEN_HEAT_BATH)
+            if (s.kind == SYS_READ_IN && p.excit_gen != EXCIT_GEN_NO_RENORM && p.excit_gen != EXCIT_GEN_NO_RENORM_SPIN &&
+                p.excit_gen != EXCIT_GEN_HEAT_BATH)
                 build_symunocc_masks<W>(s, f, su);
             bool is_ref;
             const double hm0 = proj_energy_hmatel<W>(s, p, f, occ, is_ref);
@@ -1623,7 +1627,8 @@ static bool uses_heat_bath_tables(const hb200_engine* e) {
 }
 static size_t spawn_smem_bytes(const hb200_engine* e) {
     const int eg = e->cfg.excit_gen;
-    const int nsu = (e->sys.kind == SYS_READ_IN && eg != HB200_EXCIT_GEN_NO_RENORM && eg != HB200_EXCIT_GEN_HEAT_BATH &&
+    const int nsu = (e->sys.kind == SYS_READ_IN && eg != HB200_EXCIT_GEN_NO_RENORM && eg != HB200_EXCIT_GEN_NO_RENORM_SPIN &&
+                     eg != HB200_EXCIT_GEN_HEAT_BATH &&
                      eg != HB200_EXCIT_GEN_HEAT_BATH_SINGLE)
                         ? 2 * e->sys.nsym_tot : 0;
     const bool hb = eg == HB200_EXCIT_GEN_HEAT_BATH;
@@ -2007,6 +2012,8 @@ static int stage_spawn_death(hb200_engine* e, const hb200_iter_in* in, uint32_t 
         else switch (e->cfg.excit_gen) {
             case HB200_EXCIT_GEN_NO_RENORM: LAUNCH_SPAWN(EXCIT_GEN_NO_RENORM); break;
             case HB200_EXCIT_GEN_RENORM: LAUNCH_SPAWN(EXCIT_GEN_RENORM); break;
+            case HB200_EXCIT_GEN_RENORM_SPIN: LAUNCH_SPAWN(EXCIT_GEN_RENORM_SPIN); break;
+            case HB200_EXCIT_GEN_NO_RENORM_SPIN: LAUNCH_SPAWN(EXCIT_GEN_NO_RENORM_SPIN); break;
             case HB200_EXCIT_GEN_HEAT_BATH: LAUNCH_SPAWN(EXCIT_GEN_HEAT_BATH); break;
             case HB200_EXCIT_GEN_HEAT_BATH_UNIFORM: LAUNCH_SPAWN(EXCIT_GEN_HEAT_BATH_UNIFORM); break;
             case HB200_EXCIT_GEN_HEAT_BATH_SINGLE: LAUNCH_SPAWN(EXCIT_GEN_HEAT_BATH_SINGLE); break;
@@ -2396,6 +2403,58 @@ int hb200_ccmc_spawn(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, i
     out->spawn_error = herr[0]; out->psip_error = herr[1];
     return 0;
 }
+
+// find_parallel_spin_prob_mol (src/qmc_common.F90:262-377): sum |<ij|H|ab>| over all orbital quadruples, split by
+// parallel / anti-parallel ij.  One block per i; fixed-order reductions.
+__global__ void __launch_bounds__(256) k_parallel_spin_prob(Sys s, double* __restrict__ part) {
+    __shared__ double sh[2][8];
+    const int nb = s.nbasis;
+    const int i = blockIdx.x + 1;
+    double par = 0.0, ortho = 0.0;
+    for (int t = threadIdx.x; t < nb * nb; t += blockDim.x) {
+        const int j = t / nb + 1, a = t % nb + 1;
+        if (i == j || a == i || a == j) continue;
+        const int it = min(i, j), jt = max(i, j);
+        const int ij_sym = sym_conj(s, cross_product(s, s.bf_sym[it], s.bf_sym[jt]));
+        const int isymb = sym_conj(s, cross_product(s, ij_sym, s.bf_sym[a]));
+        for (int b = 1; b <= nb; ++b) {
+            const bool spin_ok = (ms_of(it) == ms_of(a) && ms_of(jt) == ms_of(b)) || (ms_of(it) == ms_of(b) && ms_of(jt) == ms_of(a));
+            if (!(spin_ok && s.bf_sym[b] == isymb && b != a && b != i && b != j)) continue;
+            const double h = fabs(slater_condon2_excit(s, it, jt, min(a, b), max(a, b), false));
+            if (ms_of(it) == ms_of(jt)) par = par + h; else ortho = ortho + h;
+        }
+    }
+    par = warp_sum_d(par); ortho = warp_sum_d(ortho);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { sh[0][warp] = par; sh[1][warp] = ortho; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < 8; ++w) { a += sh[0][w]; b += sh[1][w]; }
+        part[2 * blockIdx.x] = a; part[2 * blockIdx.x + 1] = b;
+    }
+}
+// qmc_in%pattempt_parallel (src/qmc.F90:974-988) for excit_gen = renorm_spin / no_renorm_spin: a negative value asks
+// for find_parallel_spin_prob_mol.
+int hb200_set_pattempt_parallel(hb200_engine* e, double pattempt_parallel) {
+    if (pattempt_parallel < 0.0) {
+        if (e->sys.kind != SYS_READ_IN || e->sys.nbasis <= 0) FAIL("set_pattempt_parallel: needs a read_in system");
+        const int nb = e->sys.nbasis;
+        double* d_part = nullptr;
+        CK(cudaMalloc(&d_part, sizeof(double) * 2 * nb));
+        k_parallel_spin_prob<<<nb, 256, 0, e->stream>>>(e->sys, d_part);
+        std::vector<double> h(2 * (size_t)nb);
+        CK(cudaMemcpyAsync(h.data(), d_part, sizeof(double) * 2 * nb, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        CK(cudaFree(d_part));
+        double par = 0.0, ortho = 0.0;
+        for (int i = 0; i < nb; ++i) { par += h[2 * i]; ortho += h[2 * i + 1]; }
+        pattempt_parallel = par / (par + ortho);
+    }
+    e->par.pattempt_parallel = pattempt_parallel;
+    return 0;
+}
+double hb200_get_pattempt_parallel(hb200_engine* e) { return e->par.pattempt_parallel; }
 
 // qmc_in%pattempt_update (src/qmc.F90:1049-1060, src/spawning.F90:2139-2372): the engine holds pattempt_single /
 // pattempt_double and, while `accumulate` is set, sums |H_ij| pattempt / pgen and the counts of the allowed single and

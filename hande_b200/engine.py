@@ -12,7 +12,7 @@ import numpy as np
 from . import build as _build
 
 # values of the reference's excit_gen enumerators (src/qmc_data.f90:31-69)
-EXCIT_GEN = {"renorm": 0, "no_renorm": 2, "power_pitzer_occ": 5, "power_pitzer_occ_ij": 6, "cauchy_schwarz_occ": 8,
+EXCIT_GEN = {"renorm": 0, "renorm_spin": 1, "no_renorm": 2, "no_renorm_spin": 3, "power_pitzer_occ": 5, "power_pitzer_occ_ij": 6, "cauchy_schwarz_occ": 8,
              "cauchy_schwarz_occ_ij": 9, "heat_bath": 10, "heat_bath_uniform": 11, "heat_bath_single": 12}
 
 
@@ -137,6 +137,9 @@ def load_library():
     L.hb200_ccmc_set_full_nc.argtypes = [C.c_void_p, C.c_int32]
     L.hb200_set_pattempt.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int32]
     L.hb200_get_ps_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    L.hb200_set_pattempt_parallel.argtypes = [C.c_void_p, C.c_double]
+    L.hb200_get_pattempt_parallel.argtypes = [C.c_void_p]
+    L.hb200_get_pattempt_parallel.restype = C.c_double
     L.hb200_comm_spawn.argtypes = [C.c_void_p]
     L.hb200_annihilate_spawn.argtypes = [C.c_void_p]
     L.hb200_annihilate_main.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(IterOut)]
@@ -158,7 +161,7 @@ ABI_SYMBOLS = [
     "hb200_download_heat_bath", "hb200_set_reference", "hb200_set_proc_map", "hb200_upload_psips",
     "hb200_upload_psips_begin", "hb200_upload_psips_commit",
     "hb200_download_psips", "hb200_nstates", "hb200_iterate", "hb200_spawn_death", "hb200_comm_spawn",
-    "hb200_ccmc_spawn", "hb200_ccmc_iterate", "hb200_ccmc_set_hash_shift", "hb200_ccmc_set_full_nc", "hb200_set_pattempt", "hb200_get_ps_stats", "hb200_annihilate_spawn", "hb200_annihilate_main", "hb200_download_spawn", "hb200_upload_spawn",
+    "hb200_ccmc_spawn", "hb200_ccmc_iterate", "hb200_ccmc_set_hash_shift", "hb200_ccmc_set_full_nc", "hb200_set_pattempt", "hb200_get_ps_stats", "hb200_set_pattempt_parallel", "hb200_get_pattempt_parallel", "hb200_annihilate_spawn", "hb200_annihilate_main", "hb200_download_spawn", "hb200_upload_spawn",
     "hb200_sc0_batch", "hb200_gen_excit_batch", "hb200_get_unique_id", "hb200_comm_init", "hb200_last_timing",
 ]
 
@@ -176,7 +179,8 @@ class Engine:
 
     def __init__(self, sys, *, excit_gen="renorm", pattempt_single, pattempt_double, real_amplitudes=False,
                  spawn_cutoff=0.01, initiator_approx=False, initiator_pop=3.0, trunc_level=-1, walker_length=1 << 20,
-                 spawned_walker_length=1 << 18, seed=7, nprocs=1, iproc=0, nslots=1, device=0, hash_seed=7):
+                 spawned_walker_length=1 << 18, seed=7, nprocs=1, iproc=0, nslots=1, device=0, hash_seed=7,
+                 pattempt_parallel=-1.0):
         self.L = load_library()
         self.sys = sys
         self.W = sys.W
@@ -198,6 +202,8 @@ class Engine:
                   EXCIT_GEN["power_pitzer_occ_ij"],
                   EXCIT_GEN["cauchy_schwarz_occ_ij"]):   # the _occ_ij weights are the heat-bath i/ij tables
             self._chk(self.L.hb200_build_heat_bath(self.h))
+        if eg in (EXCIT_GEN["renorm_spin"], EXCIT_GEN["no_renorm_spin"]):
+            self.pattempt_parallel = self.set_pattempt_parallel(pattempt_parallel)
 
     def close(self):
         if getattr(self, "h", None):
@@ -317,6 +323,11 @@ class Engine:
     def set_pattempt(self, pattempt_single, pattempt_double, accumulate=False):
         """excit_gen_data%pattempt_single/double; accumulate: collect the pattempt_update statistics on the device"""
         self._chk(self.L.hb200_set_pattempt(self.h, float(pattempt_single), float(pattempt_double), int(bool(accumulate))))
+
+    def set_pattempt_parallel(self, pattempt_parallel=-1.0):
+        """qmc_in%pattempt_parallel (renorm_spin / no_renorm_spin); negative: find_parallel_spin_prob_mol on the device"""
+        self._chk(self.L.hb200_set_pattempt_parallel(self.h, float(pattempt_parallel)))
+        return float(self.L.hb200_get_pattempt_parallel(self.h))
 
     def get_ps_stats(self, reset=True):
         """this rank's (h_pgen_singles_sum, excit_gen_singles, h_pgen_doubles_sum, excit_gen_doubles) since the last reset"""

@@ -42,6 +42,7 @@ class QmcIn:
     excit_gen: str = "renorm"
     pattempt_single: float = -1.0
     pattempt_double: float = -1.0
+    pattempt_parallel: float = -1.0   # renorm_spin / no_renorm_spin; < 0: find_parallel_spin_prob_mol
     pattempt_update: bool = False   # qmc_in%pattempt_update: pattempt_single follows the spawn statistics until the shift varies
     state_size: int = -5            # <0: MB (src/particle_t_utils.f90), >0: elements
     spawned_state_size: int = -1
@@ -231,7 +232,8 @@ def do_fciqmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, 
                      real_amplitudes=qmc.real_amplitudes, spawn_cutoff=qmc.spawn_cutoff,
                      initiator_approx=qmc.initiator, initiator_pop=qmc.initiator_population,
                      trunc_level=qmc.ex_level, walker_length=wl, spawned_walker_length=sl, seed=qmc.rng_seed,
-                     nprocs=nprocs, iproc=iproc, nslots=qmc.nslots, device=device)
+                     nprocs=nprocs, iproc=iproc, nslots=qmc.nslots, device=device,
+                     pattempt_parallel=qmc.pattempt_parallel)
     eng.set_reference(f0, H00)
     if nprocs > 1:
         uid = eng.get_unique_id() if iproc == 0 else np.zeros(128, dtype=np.uint8)

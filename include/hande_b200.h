@@ -26,7 +26,7 @@ extern "C" {
 typedef struct hb200_engine hb200_engine;
 
 /* Values of qmc_in%excit_gen (src/qmc_data.f90:31-69) that the engine implements. */
-enum { HB200_EXCIT_GEN_RENORM = 0, HB200_EXCIT_GEN_NO_RENORM = 2, HB200_EXCIT_GEN_POWER_PITZER_OCC = 5,
+enum { HB200_EXCIT_GEN_RENORM = 0, HB200_EXCIT_GEN_RENORM_SPIN = 1, HB200_EXCIT_GEN_NO_RENORM_SPIN = 3, HB200_EXCIT_GEN_NO_RENORM = 2, HB200_EXCIT_GEN_POWER_PITZER_OCC = 5,
        HB200_EXCIT_GEN_POWER_PITZER_OCC_IJ = 6, HB200_EXCIT_GEN_CAUCHY_SCHWARZ_OCC = 8, HB200_EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ = 9, HB200_EXCIT_GEN_HEAT_BATH = 10, HB200_EXCIT_GEN_HEAT_BATH_UNIFORM = 11,
        HB200_EXCIT_GEN_HEAT_BATH_SINGLE = 12 };
 
@@ -184,6 +184,12 @@ int hb200_ccmc_set_full_nc(hb200_engine* e, int32_t full_nc);
  * communicate_pattempt_single_data + update_pattempt_single (src/spawning.F90:2217-2372) once per report loop.  As in
  * src/check_input.F90:192-197 accumulation is refused for the UEG and for excit_gen = heat_bath. */
 int hb200_set_pattempt(hb200_engine* e, double pattempt_single, double pattempt_double, int32_t accumulate);
+/* excit_gen = renorm_spin / no_renorm_spin (gen_excit_mol_spin, gen_excit_mol_no_renorm_spin, src/excit_gen_mol.f90:103-193,
+ * 286-380; choose_ij_spin_mol :684-800): qmc_in%pattempt_parallel, the probability that i and j have parallel spins.  A
+ * negative value computes it as find_parallel_spin_prob_mol does (src/qmc_common.F90:262-377, src/qmc.F90:974-988); call
+ * after hb200_set_system_read_in and before the first iteration. */
+int hb200_set_pattempt_parallel(hb200_engine* e, double pattempt_parallel);
+double hb200_get_pattempt_parallel(hb200_engine* e);
 int hb200_get_ps_stats(hb200_engine* e, double* out4, int32_t reset);
 
 /* Stage-level entry points (same state machine as hb200_iterate, one stage per call). */

@@ -376,6 +376,8 @@ void orc_get_ps_stats(void* h, int rank, double* out, int reset) {
         if (reset) a = Oracle::PsColl();
     }
 }
+void orc_set_pattempt_parallel(void* h, double pp) { ((Oracle*)h)->in.pattempt_parallel = pp; ((Oracle*)h)->eg.pattempt_parallel = pp; }
+double orc_get_pattempt_parallel(void* h) { return ((Oracle*)h)->eg.pattempt_parallel; }
 void orc_set_pattempt(void* h, double ps, double pd) { ((Oracle*)h)->eg.pattempt_single = ps; ((Oracle*)h)->eg.pattempt_double = pd; }
 int orc_get_pattempt_log(void* h, double* out, int n) {
     Oracle* o = (Oracle*)h;

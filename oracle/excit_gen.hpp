@@ -16,7 +16,9 @@ constexpr int MAXNEL = 64;
 
 enum ExcitGenKind {  // values of src/qmc_data.f90:31-69
     EXCIT_GEN_RENORM = 0,
+    EXCIT_GEN_RENORM_SPIN = 1,
     EXCIT_GEN_NO_RENORM = 2,
+    EXCIT_GEN_NO_RENORM_SPIN = 3,
     EXCIT_GEN_POWER_PITZER_OCC = 5,
     EXCIT_GEN_POWER_PITZER_OCC_IJ = 6,
     EXCIT_GEN_CAUCHY_SCHWARZ_OCC = 8,
@@ -204,6 +206,7 @@ inline bool init_excit_mol_heat_bath(const System& sys, HeatBath& hb, bool origi
 struct ExcitGenData {
     int excit_gen = EXCIT_GEN_RENORM;
     double pattempt_single = 0.0, pattempt_double = 1.0;
+    double pattempt_parallel = 0.0;   // renorm_spin / no_renorm_spin: probability that i and j have parallel spins
     HeatBath hb;
 };
 
@@ -479,6 +482,127 @@ inline GenResult gen_excit_mol_no_renorm(Rng& rng, const System& sys, const Exci
         if (r.allowed) {
             r.pgen = eg.pattempt_double * pgen_ij *
                      calc_pgen_double_mol_no_renorm(sys, r.conn.to_orb[0], r.conn.to_orb[1], ij_spin);
+            sys.find_excitation_permutation2(d.f, r.conn);
+            r.hmatel = sys.slater_condon2_excit(r.conn.from_orb[0], r.conn.from_orb[1], r.conn.to_orb[0],
+                                                r.conn.to_orb[1], r.conn.perm);
+        } else { r.hmatel = 0.0; r.pgen = 1.0; }
+    }
+    return r;
+}
+
+// ------------------------------------------------------------------------ renorm_spin / no_renorm_spin
+// find_parallel_spin_prob_mol (src/qmc_common.F90:262-377): ratio of sum |H_ij->ab| over parallel-spin ij to the sum over
+// all ij; the i loop is split over the MPI ranks (get_proc_loop_range, lib/local/parallel.F90:227-269) and the partial
+// sums are reduced, which fixes the summation order reproduced here.
+inline double find_parallel_spin_prob_mol(const System& sys, int nprocs) {
+    const int nb = sys.nbasis;
+    double par_tot = 0.0, ortho_tot = 0.0;
+    int i_end = 0;
+    for (int ip = 0; ip < nprocs; ++ip) {
+        const int i_start = i_end + 1;
+        i_end = i_start + nb / nprocs - 1;
+        if (ip < nb % nprocs) i_end = i_end + 1;
+        double par = 0.0, ortho = 0.0;
+        for (int i = i_start; i <= i_end; ++i)
+            for (int j = 1; j <= nb; ++j) {
+                if (i == j) continue;
+                const int it = std::min(i, j), jt = std::max(i, j);
+                const int ij_sym = sys.sym_conj(sys.cross_product_basis(it, jt));
+                for (int a = 1; a <= nb; ++a) {
+                    if (a == i || a == j) continue;
+                    const int isymb = sys.sym_conj(sys.cross_product(ij_sym, sys.bf[a].sym));
+                    for (int b = 1; b <= nb; ++b) {
+                        const bool spin_ok = (sys.bf[it].ms == sys.bf[a].ms && sys.bf[jt].ms == sys.bf[b].ms) ||
+                                             (sys.bf[it].ms == sys.bf[b].ms && sys.bf[jt].ms == sys.bf[a].ms);
+                        if (!(spin_ok && sys.bf[b].sym == isymb && b != a && b != i && b != j)) continue;
+                        const int at = std::min(a, b), bt = std::max(a, b);
+                        const double h = std::fabs(sys.slater_condon2_excit(it, jt, at, bt, false));
+                        if (sys.bf[it].ms == sys.bf[jt].ms) par = par + h;
+                        else ortho = ortho + h;
+                    }
+                }
+            }
+        par_tot += par; ortho_tot += ortho;
+    }
+    return par_tot / (par_tot + ortho_tot);
+}
+
+// choose_ij_spin_mol (src/excit_gen_mol.f90:684-800): decide parallel / anti-parallel first, then pick the pair
+inline void choose_ij_spin_mol(Rng& rng, const System& sys, const DetInfo& d, double pattempt_parallel, int& i, int& j,
+                               int& ij_sym, int& ij_spin, double& pgen_ij, bool& allowed) {
+    // decode_det_spinocc_symunocc (src/determinant_decoders.f90:208-262): alpha = ms +1
+    int occ_a[MAXNEL], occ_b[MAXNEL], na = 0, nb = 0;
+    for (int q = 0; q < sys.nel; ++q) {
+        if (sys.bf[d.occ[q]].ms > 0) occ_a[na++] = d.occ[q];
+        else occ_b[nb++] = d.occ[q];
+    }
+    const int nalpha = sys.nalpha, nbeta = sys.nbeta;
+    allowed = true;
+    if (rng.next() < pattempt_parallel) {
+        if (rng.next() < ((double)nalpha / (double)(nalpha + nbeta))) {
+            if (nalpha < 2) allowed = false;
+            else {
+                const int ind = (int)(rng.next() * (double)(nalpha * (nalpha - 1)) / 2.0) + 1;
+                const int j_ind = (int)(1.50 + std::sqrt(2 * ind - 1.750));
+                const int i_ind = ind - ((j_ind - 1) * (j_ind - 2)) / 2;
+                i = occ_a[i_ind - 1]; j = occ_a[j_ind - 1];
+                pgen_ij = (pattempt_parallel * ((double)nalpha / (double)(nalpha + nbeta)) * 2.0 * (1.0 / nalpha) *
+                           (1.0 / (nalpha - 1)));
+            }
+        } else {
+            if (nbeta < 2) allowed = false;
+            else {
+                const int ind = (int)(rng.next() * (double)(nbeta * (nbeta - 1)) / 2.0) + 1;
+                const int j_ind = (int)(1.50 + std::sqrt(2 * ind - 1.750));
+                const int i_ind = ind - ((j_ind - 1) * (j_ind - 2)) / 2;
+                i = occ_b[i_ind - 1]; j = occ_b[j_ind - 1];
+                pgen_ij = (pattempt_parallel * ((double)nbeta / (double)(nalpha + nbeta)) * 2.0 * (1.0 / nbeta) *
+                           (1.0 / (nbeta - 1)));
+            }
+        }
+    } else {
+        if (nbeta < 1 || nalpha < 1) allowed = false;
+        else {
+            const int i_ind = (int)(rng.next() * nalpha) + 1;
+            const int j_ind = (int)(rng.next() * nbeta) + 1;
+            i = occ_a[i_ind - 1]; j = occ_b[j_ind - 1];
+            if (j < i) std::swap(i, j);
+            pgen_ij = (1.0 - pattempt_parallel) * (1.0 / (nalpha * nbeta));
+        }
+    }
+    if (allowed) {
+        ij_sym = sys.sym_conj(sys.cross_product_basis(i, j));
+        ij_spin = sys.bf[i].ms + sys.bf[j].ms;
+    } else { pgen_ij = 1.0; i = -1; j = -1; ij_sym = -1; ij_spin = -1; }
+}
+
+// gen_excit_mol_spin / gen_excit_mol_no_renorm_spin (src/excit_gen_mol.f90:103-193,286-380)
+inline GenResult gen_excit_mol_spin(Rng& rng, const System& sys, const ExcitGenData& eg, const DetInfo& d, bool renorm) {
+    GenResult r;
+    if (rng.next() < eg.pattempt_single) {
+        if (renorm) choose_ia_mol(rng, sys, sys.gamma_sym, d, r.conn.from_orb[0], r.conn.to_orb[0], r.allowed);
+        else find_ia_mol(rng, sys, sys.gamma_sym, d, r.conn.from_orb[0], r.conn.to_orb[0], r.allowed);
+        r.conn.nexcit = 1;
+        if (r.allowed) {
+            r.pgen = eg.pattempt_single * (renorm ? calc_pgen_single_mol(sys, sys.gamma_sym, d, r.conn.to_orb[0])
+                                                  : calc_pgen_single_mol_no_renorm(sys, r.conn.to_orb[0]));
+            sys.find_excitation_permutation1(d.f, r.conn);
+            r.hmatel = sys.slater_condon1_excit(d.occ, r.conn.from_orb[0], r.conn.to_orb[0], r.conn.perm);
+        } else { r.hmatel = 0.0; r.pgen = 1.0; }
+    } else {
+        int ij_sym, ij_spin;
+        double pgen_ij;
+        choose_ij_spin_mol(rng, sys, d, eg.pattempt_parallel, r.conn.from_orb[0], r.conn.from_orb[1], ij_sym, ij_spin,
+                           pgen_ij, r.allowed);
+        if (r.allowed) {
+            if (renorm) choose_ab_mol(rng, sys, d, ij_sym, ij_spin, r.conn.to_orb[0], r.conn.to_orb[1], r.allowed);
+            else find_ab_mol(rng, sys, d, ij_sym, ij_spin, r.conn.to_orb[0], r.conn.to_orb[1], r.allowed);
+            r.conn.nexcit = 2;
+        }
+        if (r.allowed) {
+            r.pgen = eg.pattempt_double * pgen_ij *
+                     (renorm ? calc_pgen_double_mol(sys, ij_sym, r.conn.to_orb[0], r.conn.to_orb[1], ij_spin, d)
+                             : calc_pgen_double_mol_no_renorm(sys, r.conn.to_orb[0], r.conn.to_orb[1], ij_spin));
             sys.find_excitation_permutation2(d.f, r.conn);
             r.hmatel = sys.slater_condon2_excit(r.conn.from_orb[0], r.conn.from_orb[1], r.conn.to_orb[0],
                                                 r.conn.to_orb[1], r.conn.perm);
@@ -896,6 +1020,8 @@ inline GenResult gen_excit(Rng& rng, const System& sys, const ExcitGenData& eg, 
     switch (eg.excit_gen) {
         case EXCIT_GEN_RENORM: return gen_excit_mol(rng, sys, eg, d);
         case EXCIT_GEN_NO_RENORM: return gen_excit_mol_no_renorm(rng, sys, eg, d);
+        case EXCIT_GEN_RENORM_SPIN: return gen_excit_mol_spin(rng, sys, eg, d, true);
+        case EXCIT_GEN_NO_RENORM_SPIN: return gen_excit_mol_spin(rng, sys, eg, d, false);
         case EXCIT_GEN_HEAT_BATH: return gen_excit_mol_heat_bath(rng, sys, eg, d);
         case EXCIT_GEN_POWER_PITZER_OCC:
         case EXCIT_GEN_POWER_PITZER_OCC_IJ:
@@ -910,7 +1036,8 @@ inline void decode_for(const System& sys, const ExcitGenData& eg, const Det& f, 
     if (eg.excit_gen == EXCIT_GEN_POWER_PITZER_OCC || eg.excit_gen == EXCIT_GEN_CAUCHY_SCHWARZ_OCC ||
         eg.excit_gen == EXCIT_GEN_POWER_PITZER_OCC_IJ || eg.excit_gen == EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ)
         decode_det_spinocc_spinsymunocc(sys, f, d);
-    else if (eg.excit_gen == EXCIT_GEN_RENORM || eg.excit_gen == EXCIT_GEN_HEAT_BATH_UNIFORM) decode_det_occ_symunocc(sys, f, d);
+    else if (eg.excit_gen == EXCIT_GEN_RENORM || eg.excit_gen == EXCIT_GEN_RENORM_SPIN ||
+             eg.excit_gen == EXCIT_GEN_HEAT_BATH_UNIFORM) decode_det_occ_symunocc(sys, f, d);
     else decode_det_occ(sys, f, d);
 }
 

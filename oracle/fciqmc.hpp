@@ -43,6 +43,7 @@ struct QmcIn {
     double spawn_cutoff = 0.01;
     int excit_gen = EXCIT_GEN_RENORM;
     double pattempt_single = -1.0, pattempt_double = -1.0;
+    double pattempt_parallel = -1.0;
     int64_t walker_length = 1 << 20;          // elements per rank
     int64_t spawned_walker_length = 1 << 18;  // elements per rank
     int ex_level = -1;                        // truncation level (reference%ex_level); -1 => none
@@ -265,6 +266,8 @@ struct Oracle {
             eg.pattempt_single = in.pattempt_single / (in.pattempt_single + in.pattempt_double);
             eg.pattempt_double = 1.0 - in.pattempt_single;
         }
+        if (in.excit_gen == EXCIT_GEN_RENORM_SPIN || in.excit_gen == EXCIT_GEN_NO_RENORM_SPIN)   // src/qmc.F90:974-988
+            eg.pattempt_parallel = (in.pattempt_parallel < 0.0) ? find_parallel_spin_prob_mol(sys, in.nprocs) : in.pattempt_parallel;
         if (in.excit_gen == EXCIT_GEN_HEAT_BATH_UNIFORM || in.excit_gen == EXCIT_GEN_HEAT_BATH_SINGLE ||
             in.excit_gen == EXCIT_GEN_POWER_PITZER_OCC_IJ || in.excit_gen == EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ)
             init_excit_mol_heat_bath(sys, eg.hb, false);

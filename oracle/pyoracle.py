@@ -12,7 +12,7 @@ LIB = os.path.join(HERE, "liboracle.so")
 REF_LIB = os.path.join(HERE, "_ref", "libhande_ref_c.so")
 HUGE = 2**31 - 1
 
-EXCIT_GEN = {"renorm": 0, "no_renorm": 2, "power_pitzer_occ": 5, "power_pitzer_occ_ij": 6, "cauchy_schwarz_occ": 8,
+EXCIT_GEN = {"renorm": 0, "renorm_spin": 1, "no_renorm": 2, "no_renorm_spin": 3, "power_pitzer_occ": 5, "power_pitzer_occ_ij": 6, "cauchy_schwarz_occ": 8,
              "cauchy_schwarz_occ_ij": 9, "heat_bath": 10,
              "heat_bath_uniform": 11, "heat_bath_single": 12}
 
@@ -369,6 +369,15 @@ class Oracle:
         out = np.zeros(4)
         self.L.orc_get_ps_stats(self.h, int(rank), out.ctypes.data_as(C.c_void_p), int(reset))
         return out
+
+    def pattempt_parallel(self):
+        self.L.orc_get_pattempt_parallel.restype = C.c_double
+        self.L.orc_get_pattempt_parallel.argtypes = [C.c_void_p]
+        return float(self.L.orc_get_pattempt_parallel(self.h))
+
+    def set_pattempt_parallel(self, pp):
+        self.L.orc_set_pattempt_parallel.argtypes = [C.c_void_p, C.c_double]
+        self.L.orc_set_pattempt_parallel(self.h, float(pp))
 
     def set_pattempt(self, ps, pd):
         self.L.orc_set_pattempt.argtypes = [C.c_void_p, C.c_double, C.c_double]

@@ -66,7 +66,8 @@ def make_pair(name, *, excit_gen="renorm", tau=0.01, seed=11, real=False, initia
         eng = Engine(s, excit_gen=excit_gen, pattempt_single=ref["pattempt_single"],
                      pattempt_double=ref["pattempt_double"], real_amplitudes=real, spawn_cutoff=0.01,
                      initiator_approx=initiator, trunc_level=ex_level, walker_length=walker_length,
-                     spawned_walker_length=spawned_walker_length, seed=seed, device=device)
+                     spawned_walker_length=spawned_walker_length, seed=seed, device=device,
+                     pattempt_parallel=(o.pattempt_parallel() if excit_gen.endswith("_spin") else -1.0))
         eng.set_reference(ref["f0"], ref["H00"])
     return s, o, eng, ref
 

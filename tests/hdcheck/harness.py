@@ -81,6 +81,10 @@ class HdCheck:
         L.hd_proj_hmatel.restype = C.c_double
         L.hd_proj_hmatel.argtypes = [C.c_void_p, C.c_void_p]
 
+    def set_pattempt_parallel(self, pp):
+        self.L.hd_set_pattempt_parallel.argtypes = [C.c_double]
+        self.L.hd_set_pattempt_parallel(float(pp))
+
     def gen_excit_philox(self, f, cycle, attempt, parent_pop):
         f = np.ascontiguousarray(f, dtype=np.uint64)
         io = np.zeros(8, dtype=np.int32)

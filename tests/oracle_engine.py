@@ -16,7 +16,7 @@ def make_engine_cls(fcidump_path, sys_kw, rng_kind=0, ueg=None, ref_det=None):
     class OracleRankEngine:
         def __init__(self, sys, *, excit_gen, pattempt_single, pattempt_double, real_amplitudes, spawn_cutoff,
                      initiator_approx, initiator_pop, trunc_level, walker_length, spawned_walker_length, seed, nprocs,
-                     iproc, nslots, device):
+                     iproc, nslots, device, pattempt_parallel=-1.0):
             if nprocs > 1:
                 import torch.distributed as dist
                 self.dist = dist
@@ -32,6 +32,8 @@ def make_engine_cls(fcidump_path, sys_kw, rng_kind=0, ueg=None, ref_det=None):
                       spawn_cutoff=spawn_cutoff, initiator_approx=int(initiator_approx), initiator_pop=initiator_pop,
                       ex_level=trunc_level, walker_length=walker_length, spawned_walker_length=spawned_walker_length,
                       nprocs=nprocs, nslots=nslots)
+            if pattempt_parallel >= 0:
+                o.set_pattempt_parallel(pattempt_parallel)
             o.init()
             L = o.L
             L.orc_rank_spawn.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_void_p]

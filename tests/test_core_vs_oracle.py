@@ -22,6 +22,8 @@ def _setup(path, kw, excit_gen, tau=0.01, real=False, seed=11):
     cutoff = int(np.ceil(0.01 * rf)) if real else 0
     h = HdCheck(s, EXCIT_GEN[excit_gen], ref["pattempt_single"], ref["pattempt_double"], tau, 0.0, 0.0, rf, cutoff,
                 seed, ref["f0"], ref["H00"], hb=hb)
+    if excit_gen.endswith("_spin"):
+        h.set_pattempt_parallel(o.pattempt_parallel())
     return s, o, h
 
 
@@ -41,7 +43,7 @@ def _compare_attempts(s, o, h, dets, pops, tau, ncycle=2, nattempt=6):
     return nchecked
 
 
-@pytest.mark.parametrize("gen", ["renorm", "no_renorm"])
+@pytest.mark.parametrize("gen", ["renorm", "no_renorm", "renorm_spin", "no_renorm_spin"])
 def test_uniform_generators_h2o(fcidump_path, gen):
     kw = dict(nel=10, ms=0, sym=0, cas=(8, 13))
     s, o, h = _setup(fcidump_path("h2o"), kw, gen, tau=0.003)

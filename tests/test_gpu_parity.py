@@ -56,6 +56,25 @@ def test_gen_excit_heat_bath_uniform():
     _check_gen("s10", "heat_bath_uniform", True, 0.01, n=150, nattempt=6)
 
 
+def test_gen_excit_renorm_spin_and_no_renorm_spin():
+    # choose_ij_spin_mol variants of the uniform generators
+    _check_gen("h2o", "renorm_spin", False, 0.003, n=120)
+    _check_gen("nh3", "no_renorm_spin", True, 0.002, n=120)
+    _check_gen("s40", "renorm_spin", True, 0.01, n=80)
+
+
+def test_pattempt_parallel_on_device():
+    """find_parallel_spin_prob_mol on the device against the oracle (whose value reproduces the 0.22360108 printed in
+    the reference's NH3 renorm_spin golden output)."""
+    for name in ("nh3", "h2o"):
+        s, o, eng, ref = make_pair(name, excit_gen="renorm_spin", tau=0.003)
+        pp = eng.set_pattempt_parallel(-1.0)
+        assert abs(pp - o.pattempt_parallel()) <= 1e-13
+        if name == "nh3":
+            assert abs(pp - 0.22360108) < 5e-9
+        eng.close()
+
+
 def test_gen_excit_heat_bath_single():
     _check_gen("s10", "heat_bath_single", True, 0.01, n=150, nattempt=6)
     _check_gen("h2o", "heat_bath_single", False, 0.003, n=100)
@@ -120,6 +139,8 @@ CASES = [
     ("s12", "heat_bath", True, True, 0.01, 2500, -1),
     ("s12", "heat_bath_uniform", True, True, 0.01, 2500, -1),
     ("s12", "heat_bath_single", True, True, 0.01, 2500, -1),
+    ("nh3", "renorm_spin", True, True, 0.003, 2500, -1),
+    ("h2o", "no_renorm_spin", False, False, 0.003, 2500, -1),
     ("h2o", "power_pitzer_occ", False, True, 0.003, 2500, -1),
     ("s12", "cauchy_schwarz_occ", True, False, 0.004, 2500, -1),
     ("s12", "power_pitzer_occ_ij", True, True, 0.004, 2500, -1),

@@ -75,7 +75,8 @@ _NH3 = dict(hb=("heat_bath", 0.002, 10000), hb_uni=("heat_bath_uniform", 0.002, 
             hb_single=("heat_bath_single", 0.003, 12000), ppM=("power_pitzer_occ", 0.0015, 14000),
             ppMij=("power_pitzer_occ_ij", 0.0015, 14000), csM=("cauchy_schwarz_occ", 0.0015, 14000),
             csMij=("cauchy_schwarz_occ_ij", 0.0015, 14000), no_renorm=("no_renorm", 0.0007, 12000),
-            renorm=("renorm", 0.0007, 12000))
+            renorm=("renorm", 0.0007, 12000), renorm_spin=("renorm_spin", 0.0007, 11000),
+            no_renorm_spin=("no_renorm_spin", 0.0007, 9000))
 for _k, (_g, _tau, _tp) in _NH3.items():
     CASES["ccmc_nh3_" + _k] = dict(dir="ccmc_real_64/np4/NH3-6-31g_ccsdt_excit_gens",
                                    bench=f"benchmark.out.9712b5a3.inp=nh3.ccsdt.{_k}.in", int_file="INTDUMP",
@@ -84,6 +85,7 @@ for _k, (_g, _tau, _tp) in _NH3.items():
                                    qmc=dict(tau=_tau, seed=30513, D0_population=200, ncycles=10, nreport=400,
                                             target_particles=_tp, walker_length=1000000, spawned_walker_length=400000,
                                             ex_level=3, nprocs=4, real_amplitudes=1, spawn_cutoff=0.01, excit_gen=_g))
+CASES["ccmc_nh3_no_renorm_spin"]["pattempt_parallel"] = 0.22     # set in the input; renorm_spin computes it (0.22360108)
 
 ROW_CCMC = re.compile(r"^\s*#?\s+(\d+)\s+(-?\d\.\d+E[+-]\d+)\s+(-?\d\.\d+E[+-]\d+)\s+(-?\d\.\d+E[+-]\d+)\s+"
                       r"(-?\d\.\d+E[+-]\d+)\s+(\d+)\s+(\d+)\s+(\d+)\s+(\d\.\d+)\s+(\d+\.\d+)\s*$")
@@ -135,6 +137,8 @@ def run_case(name, max_rows=None, quiet=False):
     if max_rows is not None:
         q["nreport"] = min(q["nreport"], max_rows)
     o.set_qmc(**q)
+    if "pattempt_parallel" in c:
+        o.set_pattempt_parallel(c["pattempt_parallel"])
     o.init()
     t = time.time()
     if c.get("ccmc"):

@@ -61,6 +61,7 @@ for name, c in CASES.items():
         nz = [i for i, r in enumerate(rows) if r[1] != 0.0]
         rows = rows[:min(len(rows), (nz[0] if nz else len(rows)) + 3)]
         extra = {"until_shift": True, "pattempt_update": bool(c.get("pattempt_update")),
+                 "pattempt_parallel": c.get("pattempt_parallel", -1.0),
                  "pattempt_changes": [pc for pc in pattempt_changes(d + c["bench"]) if pc[0] <= rows[-1][0]]}
     cols = ["iterations", "shift", "proj_energy", "D0_population", "nparticles", "nstates", "nspawn_events", "rspawn"]
     json.dump({"source": "test_suite/" + c["dir"] + "/" + c["bench"], "fcidump": FCIDUMP_NAME[name], "sys": c["sys"],

@@ -87,6 +87,11 @@ struct Sys {
     const double* hb_ijab_U;
     const int* hb_ijab_K;
     const double* hb_ijab_tot;  // (a,j,i)
+    // power_pitzer_orderN tables (excit_gen_power_pitzer_t ppn_*, src/excit_gens.f90:102-141), column-major:
+    // PPN_IS (nel), PPN_IAS (max_nbss, i), PPN_ID (nel), PPN_IJD (nel, i), PPN_IAD (nbasis/2, i), PPN_JBD (max_nbss, sym, i)
+    // with i = 0..nbasis (column 0 unused)
+    struct AliasTab { const double* w; const double* U; const int* K; const double* tot; } ppn[6];
+    const int* ppn_occ;         // the reference's occupied orbitals, ascending
     // uniform electron gas (src/ueg.f90, src/ueg_types.f90): plane-wave basis, analytic integrals
     const K4* ueg_k;            // [nbasis+1] wavevectors in units of 2 pi / L
     const double* sp_eigv;      // [nbasis+1] kinetic energies
@@ -125,8 +130,10 @@ struct PsPartials { double h_pgen_singles_sum, h_pgen_doubles_sum; long long exc
 // power_pitzer_occ, power_pitzer_occ_ij, power_pitzer_orderN, cauchy_schwarz_occ, cauchy_schwarz_occ_ij, heat_bath,
 // heat_bath_uniform, heat_bath_single)
 enum { EXCIT_GEN_RENORM = 0, EXCIT_GEN_RENORM_SPIN = 1, EXCIT_GEN_NO_RENORM = 2, EXCIT_GEN_NO_RENORM_SPIN = 3, EXCIT_GEN_POWER_PITZER_OCC = 5, EXCIT_GEN_POWER_PITZER_OCC_IJ = 6,
+       EXCIT_GEN_POWER_PITZER_ORDERN = 7,
        EXCIT_GEN_CAUCHY_SCHWARZ_OCC = 8, EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ = 9,
        EXCIT_GEN_HEAT_BATH = 10, EXCIT_GEN_HEAT_BATH_UNIFORM = 11, EXCIT_GEN_HEAT_BATH_SINGLE = 12 };
+enum { PPN_IS = 0, PPN_IAS = 1, PPN_ID = 2, PPN_IJD = 3, PPN_IAD = 4, PPN_JBD = 5 };
 enum { RNG_NATTEMPTS = 0, RNG_SPAWN = 1, RNG_DEATH = 2, RNG_ROUND_MAIN = 3, RNG_ROUND_SPAWN = 4 };
 
 // ------------------------------------------------------------------------------------------------
@@ -394,6 +401,12 @@ HB_HD double two_body(const Sys& s, int i, int j, int a, int b) {
         else chan = (ms_of(jj) == 1) ? 1 : 3;
     }
     return s.v2[chan][indx - 1];
+}
+// get_two_body_int_mol_real (src/molecular_integrals.F90:1177-1215): zero unless spin and symmetry allow <ij|ab>
+HB_HD double two_body_real(const Sys& s, int i, int j, int a, int b) {
+    const int sij = cross_product(s, s.bf_sym[i], s.bf_sym[j]), sab = cross_product(s, s.bf_sym[a], s.bf_sym[b]);
+    if (sij == cross_product(s, sab, s.gamma_sym) && ms_of(i) == ms_of(a) && ms_of(j) == ms_of(b)) return two_body(s, i, j, a, b);
+    return 0.0;
 }
 HB_HD double one_body(const Sys& s, int i, int j) { return s.h1[(i - 1) * s.nbasis + (j - 1)]; }
 
@@ -1424,6 +1437,144 @@ HB_HDN void gen_excit_power_pitzer_occ(R& rng, const Sys& s, const Params& p, co
 }
 
 // ------------------------------------------------------------------------------------------------
+// power_pitzer_orderN ('heat_bath_power_pitzer_ref'): every choice is one look-up in a precomputed alias table indexed
+// through the mapping reference orbital -> orbital of this determinant.
+// ------------------------------------------------------------------------------------------------
+// get_excitation_locations (src/excitations.F90) + find_diff_ref_cdet (src/excit_gen_utils.f90:220-269)
+HB_HDN void find_diff_ref_cdet(const Sys& s, const uint8_t* occ, uint8_t* ref_cdet) {
+    const int nel = s.nel;
+    const int* ref_list = s.ppn_occ;
+    uint8_t ref_store[HB_MAXNEL], det_store[HB_MAXNEL];
+    int j = 1, det_sind = 0, ref_sind = 0;
+    bool done = false;
+    for (int i = 1; i <= nel && !done; ++i) {
+        while ((int)occ[j - 1] < ref_list[i - 1]) {
+            det_store[det_sind++] = (uint8_t)j;
+            j++;
+            if (j > nel) { done = true; break; }
+        }
+        if (done) break;
+        if ((int)occ[j - 1] > ref_list[i - 1]) ref_store[ref_sind++] = (uint8_t)i;
+        else j++;
+        if (j > nel) break;
+    }
+    while (j <= nel) { det_store[det_sind++] = (uint8_t)j; j++; }
+    int i_back = nel, i_back_pos = det_sind;
+    while (ref_sind < det_sind) {
+        ref_store[i_back_pos - 1] = (uint8_t)i_back;
+        i_back--; i_back_pos--; ref_sind++;
+    }
+    const int nex = ref_sind;
+    for (int k = 0; k < nel; ++k) ref_cdet[k] = (uint8_t)ref_list[k];
+    for (int ii = 0; ii < nex; ++ii) {
+        if (ms_of(ref_list[ref_store[ii] - 1]) != ms_of(occ[det_store[ii] - 1])) {
+            int jj = ii + 1;
+            while (ms_of(ref_list[ref_store[ii] - 1]) != ms_of(occ[det_store[jj] - 1])) jj++;
+            const uint8_t t = det_store[ii]; det_store[ii] = det_store[jj]; det_store[jj] = t;
+        }
+        ref_cdet[ref_store[ii] - 1] = occ[det_store[ii] - 1];
+    }
+}
+// gen_excit_mol_power_pitzer_orderN (src/excit_gen_power_pitzer_mol.F90:941-1258)
+template <int W, class R>
+HB_HDN void gen_excit_power_pitzer_orderN(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ,
+                                          const uint8_t* ref_cdet, Gen& g) {
+    const int nel = s.nel, mv = s.max_nbss, nsym = s.nsym_tot, nall = s.nbasis / 2;
+    g.from1 = 0; g.from2 = 0; g.to1 = 0; g.to2 = 0; g.perm = false;
+    if (rng.next() < p.pattempt_single) {
+        g.nexcit = 1;
+        const int i_ind = select_precalc(rng, nel, s.ppn[PPN_IS].U, s.ppn[PPN_IS].K);
+        const int i = ref_cdet[i_ind - 1];
+        const int imsa = ims_of(i);
+        const int isyma = cross_product(s, s.bf_sym[i], s.gamma_sym);
+        const int n = nbss(s, imsa, isyma);
+        int a_ind = 0, a = 0;
+        if (n > 0) {
+            a_ind = select_precalc(rng, n, s.ppn[PPN_IAS].U + (size_t)mv * i, s.ppn[PPN_IAS].K + (size_t)mv * i);
+            a = ssbf(s, a_ind, imsa, isyma);
+            g.allowed = !det_test(f, a);
+        } else {
+            g.allowed = false;
+        }
+        if (g.allowed) {
+            g.pgen = (s.ppn[PPN_IS].w[i_ind - 1] / s.ppn[PPN_IS].tot[0]) *
+                     (s.ppn[PPN_IAS].w[(size_t)mv * i + a_ind - 1] / s.ppn[PPN_IAS].tot[i]);
+            g.pgen = p.pattempt_single * g.pgen;
+            g.from1 = i; g.to1 = a;
+            g.perm = excit_perm1<W>(f, i, a);
+            g.hmatel = slater_condon1_excit(s, occ, i, a, g.perm);
+        } else {
+            g.hmatel = 0.0; g.pgen = 1.0;
+        }
+        return;
+    }
+    g.nexcit = 2;
+    const int i_ind = select_precalc(rng, nel, s.ppn[PPN_ID].U, s.ppn[PPN_ID].K);
+    int i = ref_cdet[i_ind - 1];
+    const int j_ind = select_precalc(rng, nel, s.ppn[PPN_IJD].U + (size_t)nel * i, s.ppn[PPN_IJD].K + (size_t)nel * i);
+    int j = ref_cdet[j_ind - 1];
+    double pgen = 1.0;
+    int ij_spin = 0;
+    if (j != i) {
+        g.allowed = true;
+        pgen = (s.ppn[PPN_ID].w[i_ind - 1] / s.ppn[PPN_ID].tot[0]) *
+               (s.ppn[PPN_IJD].w[(size_t)nel * i + j_ind - 1] / s.ppn[PPN_IJD].tot[i]);
+        ij_spin = ms_of(i) + ms_of(j);
+        pgen = pgen + ((s.ppn[PPN_ID].w[j_ind - 1] / s.ppn[PPN_ID].tot[0]) *
+                       (s.ppn[PPN_IJD].w[(size_t)nel * j + i_ind - 1] / s.ppn[PPN_IJD].tot[j]));
+        if (j < i) { const int t = i; i = j; j = t; }
+    } else {
+        g.allowed = false;
+    }
+    int a_ind = 0, a = 0, b_ind = 0, b = 0, ij_sym = 0, isymb = 0, imsb = 1;
+    if (g.allowed) {
+        a_ind = select_precalc(rng, nall, s.ppn[PPN_IAD].U + (size_t)nall * i, s.ppn[PPN_IAD].K + (size_t)nall * i);
+        a = (ms_of(i) < 0) ? 2 * a_ind : 2 * a_ind - 1;      // all_list_beta / all_list_alpha
+        if (det_test(f, a)) g.allowed = false;
+    }
+    if (g.allowed) {
+        ij_sym = sym_conj(s, cross_product(s, s.bf_sym[i], s.bf_sym[j]));
+        isymb = sym_conj(s, cross_product(s, ij_sym, s.bf_sym[a]));
+        imsb = ims_of(j);
+        if (nbss(s, imsb, isymb) == 0) g.allowed = false;
+    }
+    if (g.allowed) {
+        const size_t colb = (size_t)isymb + (size_t)nsym * j;
+        b_ind = select_precalc(rng, nbss(s, imsb, isymb), s.ppn[PPN_JBD].U + (size_t)mv * colb, s.ppn[PPN_JBD].K + (size_t)mv * colb);
+        b = ssbf(s, b_ind, imsb, isymb);
+        if (a != b && !det_test(f, b)) {
+            const double pa = s.ppn[PPN_IAD].w[(size_t)nall * i + a_ind - 1] / s.ppn[PPN_IAD].tot[i];
+            if (ij_spin == 0) {
+                pgen = pgen * (pa * s.ppn[PPN_JBD].w[(size_t)mv * colb + b_ind - 1] / s.ppn[PPN_JBD].tot[colb]);
+            } else {
+                const int b_rev = (b + 1) >> 1;               // position of b in all_list_{alpha,beta}
+                const int isyma = sym_conj(s, cross_product(s, ij_sym, isymb));
+                int a_rev = 0;
+                const int na = nbss(s, imsb, isyma);
+                for (int k = 1; k <= na; ++k)
+                    if (ssbf(s, k, imsb, isyma) == a) { a_rev = k; break; }
+                const size_t cola = (size_t)isyma + (size_t)nsym * j;
+                pgen = pgen * (pa * s.ppn[PPN_JBD].w[(size_t)mv * colb + b_ind - 1] / s.ppn[PPN_JBD].tot[colb] +
+                               s.ppn[PPN_IAD].w[(size_t)nall * i + b_rev - 1] / s.ppn[PPN_IAD].tot[i] *
+                                   s.ppn[PPN_JBD].w[(size_t)mv * cola + a_rev - 1] / s.ppn[PPN_JBD].tot[cola]);
+            }
+            pgen = p.pattempt_double * pgen;
+        } else {
+            g.allowed = false;
+        }
+    }
+    if (g.allowed) {
+        g.pgen = pgen;
+        g.from1 = i; g.from2 = j;
+        g.to1 = (a < b) ? a : b; g.to2 = (a < b) ? b : a;
+        g.perm = excit_perm2<W>(f, g.from1, g.from2, g.to1, g.to2);
+        g.hmatel = slater_condon2_excit(s, g.from1, g.from2, g.to1, g.to2, g.perm);
+    } else {
+        g.hmatel = 0.0; g.pgen = 1.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Uniform electron gas (3D): analytic integrals, Slater-Condon rules and the no_renorm generator
 // ------------------------------------------------------------------------------------------------
 // coulomb_int_ueg_3d (src/ueg.f90:250-280): 1 / (pi L |k_i - k_a|^2)
@@ -1533,6 +1684,11 @@ HB_HD void gen_excit(R& rng, const Sys& s, const Params& p, const uint64_t* f, c
     if (s.kind == SYS_UEG) gen_excit_ueg_no_renorm<W>(rng, s, f, occ, g);
     else if (p.excit_gen == EXCIT_GEN_RENORM) gen_excit_renorm<W>(rng, s, p, f, occ, su, g);
     else if (p.excit_gen == EXCIT_GEN_NO_RENORM) gen_excit_no_renorm<W>(rng, s, p, f, occ, g);
+    else if (p.excit_gen == EXCIT_GEN_POWER_PITZER_ORDERN) {
+        uint8_t ref_cdet[HB_MAXNEL];
+        find_diff_ref_cdet(s, occ, ref_cdet);
+        gen_excit_power_pitzer_orderN<W>(rng, s, p, f, occ, ref_cdet, g);
+    }
     else if (p.excit_gen == EXCIT_GEN_RENORM_SPIN) gen_excit_renorm<W, true>(rng, s, p, f, occ, su, g);
     else if (p.excit_gen == EXCIT_GEN_NO_RENORM_SPIN) gen_excit_no_renorm<W, true>(rng, s, p, f, occ, g);
     else if (p.excit_gen == EXCIT_GEN_POWER_PITZER_OCC || p.excit_gen == EXCIT_GEN_CAUCHY_SCHWARZ_OCC ||

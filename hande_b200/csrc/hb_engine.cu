@@ -246,7 +246,7 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
     constexpr bool heat_bath = (GEN == EXCIT_GEN_HEAT_BATH);
     constexpr bool hb_stage = heat_bath || (GEN == EXCIT_GEN_HEAT_BATH_UNIFORM) || (GEN == EXCIT_GEN_HEAT_BATH_SINGLE) ||
                               (GEN == EXCIT_GEN_POWER_PITZER_OCC_IJ);
-    const int nsu = (GEN == EXCIT_GEN_RENORM || GEN == EXCIT_GEN_RENORM_SPIN || GEN == EXCIT_GEN_HEAT_BATH_UNIFORM || GEN == EXCIT_GEN_POWER_PITZER_OCC ||
+    const int nsu = (GEN == EXCIT_GEN_POWER_PITZER_ORDERN) ? nel : (GEN == EXCIT_GEN_RENORM || GEN == EXCIT_GEN_RENORM_SPIN || GEN == EXCIT_GEN_HEAT_BATH_UNIFORM || GEN == EXCIT_GEN_POWER_PITZER_OCC ||
                      GEN == EXCIT_GEN_POWER_PITZER_OCC_IJ) ? 2 * s.nsym_tot : 0;
     const bool ps_on = !heat_bath && p.ps_part != nullptr;
     const SpawnSmem L(W, nel, nsu, s.nbasis, heat_bath, hb_stage, ps_on);
@@ -301,7 +301,8 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
         ssign[tid] = pop < 0;
         uint8_t* occ = socc + tid * nel;
         decode_det<W>(f, occ);
-        if (nsu) build_symunocc_masks<W>(s, f, ssu + tid * nsu);
+        if (GEN == EXCIT_GEN_POWER_PITZER_ORDERN) find_diff_ref_cdet(s, occ, ssu + tid * nsu);
+        else if (nsu) build_symunocc_masks<W>(s, f, ssu + tid * nsu);
         const uint64_t h = det_hash64<W>(f);
         if (!hb_stage) shash[tid] = h;
         const double real_pop = (double)pop / (double)p.real_factor;
@@ -458,6 +459,8 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
                 gen_excit_power_pitzer_occ<W>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, siw, sw + tid, TILE, g);
             else if (GEN == EXCIT_GEN_RENORM) gen_excit_renorm<W>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, g);
             else if (GEN == EXCIT_GEN_RENORM_SPIN) gen_excit_renorm<W, true>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, g);
+            else if (GEN == EXCIT_GEN_POWER_PITZER_ORDERN)     // ssu holds ref_cdet_occ_list of each state (nsu = nel)
+                gen_excit_power_pitzer_orderN<W>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, g);
             else if (GEN == EXCIT_GEN_NO_RENORM_SPIN) gen_excit_no_renorm<W, true>(rng, s, p, f, socc + lo * nel, g);
             else gen_excit_no_renorm<W>(rng, s, p, f, socc + lo * nel, g);
         }
@@ -1529,7 +1532,7 @@ struct hb200_engine {
     cudaStream_t stream = nullptr;
     Sys sys;
     Params par;
-    bool have_sys = false, have_hb = false;
+    bool have_sys = false, have_hb = false, have_ref = false, have_ppn = false;
     // owned device buffers for system tables
     std::vector<void*> owned;
     int* d_proc_map = nullptr;
@@ -1627,7 +1630,8 @@ static bool uses_heat_bath_tables(const hb200_engine* e) {
 }
 static size_t spawn_smem_bytes(const hb200_engine* e) {
     const int eg = e->cfg.excit_gen;
-    const int nsu = (e->sys.kind == SYS_READ_IN && eg != HB200_EXCIT_GEN_NO_RENORM && eg != HB200_EXCIT_GEN_NO_RENORM_SPIN &&
+    const int nsu = (eg == HB200_EXCIT_GEN_POWER_PITZER_ORDERN) ? e->sys.nel :
+                    (e->sys.kind == SYS_READ_IN && eg != HB200_EXCIT_GEN_NO_RENORM && eg != HB200_EXCIT_GEN_NO_RENORM_SPIN &&
                      eg != HB200_EXCIT_GEN_HEAT_BATH &&
                      eg != HB200_EXCIT_GEN_HEAT_BATH_SINGLE)
                         ? 2 * e->sys.nsym_tot : 0;
@@ -1860,6 +1864,207 @@ int hb200_build_heat_bath(hb200_engine* e) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// power_pitzer_orderN tables (init_excit_mol_power_pitzer_orderN, src/excit_gen_power_pitzer_mol.F90:215-572), built on
+// the device: every weight is one thread's sequential sum in the reference's order (bit-identical to the CPU tables),
+// then one thread per column applies check_min_weight_ratio (:140-213) and generate_alias_tables.
+// ------------------------------------------------------------------------------------------------
+struct PpnBuild { double* w[6]; double* U[6]; int* K[6]; double* tot[6]; const int* occ; double min_weight; };
+
+// single_excitation_weight_mol (src/hamiltonian_molecular.f90:444-523); occ0 ascending
+__device__ double ppn_single_excitation_weight(const Sys& s, const int* occ0, int i, int a) {
+    const int nel = s.nel, nb = s.nbasis;
+    int n_jb = 0;
+    double weight = 0.0;
+    for (int j = 0; j < nel; ++j) {
+        const int oj = occ0[j];
+        const double t1 = two_body_real(s, i, oj, oj, a) - two_body_real(s, i, oj, a, oj);
+        int op = 0;
+        for (int pos = 1; pos <= nb; ++pos) {            // the virtual orbitals of the reference, ascending
+            if (op < nel && occ0[op] == pos) { op++; continue; }
+            n_jb++;
+            weight = weight + fabs(t1 + two_body_real(s, i, pos, a, pos) - two_body_real(s, i, pos, pos, a));
+        }
+    }
+    return weight / (double)n_jb;
+}
+// init_double_weights_ab (src/excit_gen_utils.f90:68-140): accumulates onto weight
+__device__ void ppn_double_weights_ab(const Sys& s, int i, int j, double& weight) {
+    const int it = min(i, j), jt = max(i, j);
+    const int ij_sym = sym_conj(s, cross_product(s, s.bf_sym[it], s.bf_sym[jt]));
+    for (int a = 1; a <= s.nbasis; ++a) {
+        if (a == it || a == jt) continue;
+        const int isymb = sym_conj(s, cross_product(s, ij_sym, s.bf_sym[a]));
+        for (int b = 1; b <= s.nbasis; ++b) {
+            const bool spin_ok = (ms_of(it) == ms_of(a) && ms_of(jt) == ms_of(b)) || (ms_of(it) == ms_of(b) && ms_of(jt) == ms_of(a));
+            if (spin_ok && s.bf_sym[b] == isymb && a != b && b != it && b != jt)
+                weight = weight + fabs(slater_condon2_excit(s, it, jt, min(a, b), max(a, b), false));
+        }
+    }
+}
+__global__ void k_ppn_weights(Sys s, PpnBuild t) {
+    const int nel = s.nel, nb = s.nbasis, mv = s.max_nbss, nsym = s.nsym_tot, nall = nb / 2;
+    const long long nA = nel, nB = nel, nC = (long long)nb * mv, nD = (long long)nb * nel, nE = (long long)nb * nall,
+                    nF = (long long)nb * nsym * mv;
+    long long job = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int* occ = t.occ;
+    const double depsilon = 1.e-12;
+    if (job < nA) {                       // i in a single excitation
+        const int oi = occ[job];
+        const int isyma = cross_product(s, s.bf_sym[oi], s.gamma_sym);
+        double w = 0.0;
+        for (int a = 1; a <= nb; ++a)
+            if (a != oi && s.bf_sym[a] == isyma && ms_of(a) == ms_of(oi)) w = w + ppn_single_excitation_weight(s, occ, oi, a);
+        if (w < depsilon) w = 10.0 * depsilon;
+        t.w[PPN_IS][job] = w;
+        return;
+    }
+    job -= nA;
+    if (job < nB) {                       // i in a double excitation: one running sum over all j, a, b
+        double w = 0.0;
+        for (int j = 0; j < nel; ++j)
+            if (j != job) ppn_double_weights_ab(s, occ[job], occ[j], w);
+        if (w < depsilon) w = 10.0 * depsilon;
+        t.w[PPN_ID][job] = w;
+        return;
+    }
+    job -= nB;
+    if (job < nC) {                       // a given i, single excitation
+        const int i = (int)(job / mv) + 1, a = (int)(job % mv) + 1;
+        const int imsa = ims_of(i), isyma = cross_product(s, s.bf_sym[i], s.gamma_sym);
+        double w = 0.0;
+        if (a <= nbss(s, imsa, isyma)) {
+            const int oa = ssbf(s, a, imsa, isyma);
+            if (oa != i) {
+                w = ppn_single_excitation_weight(s, occ, i, oa);
+                if (w < depsilon) w = 10.0 * depsilon;
+            }
+        }
+        t.w[PPN_IAS][(size_t)mv * i + a - 1] = w;
+        return;
+    }
+    job -= nC;
+    if (job < nD) {                       // j given i, double excitation
+        const int i = (int)(job / nel) + 1, j = (int)(job % nel);
+        double w = 0.0;
+        if (occ[j] != i) ppn_double_weights_ab(s, i, occ[j], w);
+        if (w < depsilon) w = 10.0 * depsilon;
+        t.w[PPN_IJD][(size_t)nel * i + j] = w;
+        return;
+    }
+    job -= nD;
+    if (job < nE) {                       // a given i: sqrt|<ia|ai>| over the orbitals of the spin of i
+        const int i = (int)(job / nall) + 1, k = (int)(job % nall) + 1;
+        const int a = (ms_of(i) < 0) ? 2 * k : 2 * k - 1;
+        t.w[PPN_IAD][(size_t)nall * i + k - 1] = (a != i) ? pp_weight(s, false, i, a) : 0.0;
+        return;
+    }
+    job -= nE;
+    if (job < nF) {                       // b given j, per symmetry class
+        const int i = (int)(job / ((long long)nsym * mv)) + 1;
+        const int bsym = (int)((job / mv) % nsym), k = (int)(job % mv) + 1;
+        const int ims = ims_of(i);
+        double w = 0.0;
+        if (k <= nbss(s, ims, bsym)) {
+            const int a = ssbf(s, k, ims, bsym);
+            if (a != i) w = pp_weight(s, false, i, a);
+        }
+        t.w[PPN_JBD][(size_t)mv * (bsym + (size_t)nsym * i) + k - 1] = w;
+    }
+}
+__device__ void ppn_check_min_weight_ratio(double* weights, double& weights_tot, int n, double min_ratio) {
+    double min_weight_tmp = 0.0;
+    int nonzero = 0;
+    if (!(weights_tot > 0.0 && min_ratio > 0.0)) return;
+    for (int i = 0; i < n; ++i) if (weights[i] > 0.0) nonzero++;
+    double min_weight = (min_ratio / (float)nonzero) * weights_tot;
+    while (fabs(min_weight_tmp - min_weight) > 1.e-12) {
+        min_weight_tmp = min_weight;
+        double keep = 0.0;
+        int cnt = 0;
+        for (int k = 0; k < n; ++k) {
+            if (weights[k] > 0.0 && weights[k] < min_weight) cnt++;
+            else keep = keep + weights[k];
+        }
+        if (cnt == nonzero) break;
+        min_weight = (min_ratio / (float)nonzero) * (keep / (1 - (min_ratio * (float)cnt / (float)nonzero)));
+    }
+    weights_tot = 0.0;
+    for (int j = 0; j < n; ++j) {
+        if (weights[j] > 0.0 && weights[j] < min_weight) weights[j] = min_weight;
+        weights_tot = weights_tot + weights[j];
+    }
+}
+__global__ void k_ppn_alias(Sys s, PpnBuild t) {
+    const int nel = s.nel, nb = s.nbasis, mv = s.max_nbss, nsym = s.nsym_tot, nall = nb / 2;
+    long long job = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int which, n;
+    size_t col, stride;
+    bool min_ratio = true;
+    if (job == 0) { which = PPN_IS; col = 0; stride = nel; n = nel; }
+    else if (job == 1) { which = PPN_ID; col = 0; stride = nel; n = nel; }
+    else if ((job -= 2) < nb) {
+        const int i = (int)job + 1;
+        which = PPN_IAS; col = i; stride = mv; n = nbss(s, ims_of(i), cross_product(s, s.bf_sym[i], s.gamma_sym));
+    } else if ((job -= nb) < nb) { which = PPN_IJD; col = (size_t)job + 1; stride = nel; n = nel; }
+    else if ((job -= nb) < nb) { which = PPN_IAD; col = (size_t)job + 1; stride = nall; n = nall; min_ratio = false; }
+    else if ((job -= nb) < (long long)nb * nsym) {
+        const int i = (int)(job / nsym) + 1, bsym = (int)(job % nsym);
+        which = PPN_JBD; col = (size_t)bsym + (size_t)nsym * i; stride = mv; n = nbss(s, ims_of(i), bsym); min_ratio = false;
+    } else return;
+    double* w = t.w[which] + stride * col;
+    double tot = 0.0;
+    for (int k = 0; k < n; ++k) tot = tot + w[k];
+    if (min_ratio) ppn_check_min_weight_ratio(w, tot, n, t.min_weight);
+    t.tot[which][col] = tot;
+    if (n > 0) {
+        int under[HB_MAXLIST], over[HB_MAXLIST];
+        generate_alias_tables(n, w, tot, t.U[which] + stride * col, t.K[which] + stride * col, under, over);
+    }
+}
+
+int hb200_build_power_pitzer_orderN(hb200_engine* e, double min_weight) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (!e->have_sys || e->sys.kind != SYS_READ_IN) FAIL("build_power_pitzer_orderN: needs a read_in system");
+    if (!e->have_ref) FAIL("build_power_pitzer_orderN: reference not set (call hb200_set_reference first)");
+    Sys& s = e->sys;
+    const int nel = s.nel, nb = s.nbasis, mv = s.max_nbss, nsym = s.nsym_tot, nall = nb / 2;
+    if (nall > HB_MAXLIST || mv > HB_MAXLIST || nel > HB_MAXLIST) FAIL("build_power_pitzer_orderN: basis too large");
+    const size_t len[6] = {(size_t)nel, (size_t)mv * (nb + 1), (size_t)nel, (size_t)nel * (nb + 1), (size_t)nall * (nb + 1),
+                           (size_t)mv * nsym * (nb + 1)};
+    const size_t ncol[6] = {1, (size_t)nb + 1, 1, (size_t)nb + 1, (size_t)nb + 1, (size_t)nsym * (nb + 1)};
+    PpnBuild t;
+    cudaStream_t st = e->stream;
+    for (int k = 0; k < 6; ++k) {
+        if (dalloc(e, &t.w[k], len[k]) || dalloc(e, &t.U[k], len[k]) || dalloc(e, &t.K[k], len[k]) || dalloc(e, &t.tot[k], ncol[k]))
+            return 1;
+        CK(cudaMemsetAsync(t.w[k], 0, len[k] * sizeof(double), st));
+        CK(cudaMemsetAsync(t.U[k], 0, len[k] * sizeof(double), st));
+        CK(cudaMemsetAsync(t.K[k], 0, len[k] * sizeof(int), st));
+        CK(cudaMemsetAsync(t.tot[k], 0, ncol[k] * sizeof(double), st));
+    }
+    // the reference's occupied orbitals, ascending (pp%occ_list)
+    std::vector<int> occ0;
+    for (int o = 1; o <= nb; ++o)
+        if ((e->par.f0[(o - 1) >> 6] >> ((o - 1) & 63)) & 1ull) occ0.push_back(o);
+    if ((int)occ0.size() != nel) FAIL("build_power_pitzer_orderN: reference does not have nel electrons");
+    int* d_occ = nullptr;
+    if (dalloc(e, &d_occ, (size_t)nel)) return 1;
+    CK(cudaMemcpyAsync(d_occ, occ0.data(), sizeof(int) * nel, cudaMemcpyHostToDevice, st));
+    t.occ = d_occ;
+    t.min_weight = min_weight;
+    const long long njobs = 2LL * nel + (long long)nb * mv + (long long)nb * nel + (long long)nb * nall + (long long)nb * nsym * mv;
+    k_ppn_weights<<<(unsigned)((njobs + 63) / 64), 64, 0, st>>>(s, t);
+    const long long ncols = 2 + 3LL * nb + (long long)nb * nsym;
+    k_ppn_alias<<<(unsigned)((ncols + 63) / 64), 64, 0, st>>>(s, t);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    for (int k = 0; k < 6; ++k) { s.ppn[k].w = t.w[k]; s.ppn[k].U = t.U[k]; s.ppn[k].K = t.K[k]; s.ppn[k].tot = t.tot[k]; }
+    s.ppn_occ = d_occ;
+    e->have_ppn = true;
+    return 0;
+}
+
 int hb200_download_heat_bath(hb200_engine* e, int which, void* out, int64_t n) {
     CK(cudaSetDevice(e->cfg.device));
     if (!e->have_hb) FAIL("heat-bath tables not built");
@@ -1875,6 +2080,7 @@ int hb200_download_heat_bath(hb200_engine* e, int which, void* out, int64_t n) {
 int hb200_set_reference(hb200_engine* e, const uint64_t* f0, double H00) {
     for (int k = 0; k < HB_MAXW; ++k) e->par.f0[k] = (k < e->W) ? f0[k] : 0;
     e->par.H00 = H00;
+    e->have_ref = true;
     return 0;
 }
 
@@ -2013,6 +2219,7 @@ static int stage_spawn_death(hb200_engine* e, const hb200_iter_in* in, uint32_t 
             case HB200_EXCIT_GEN_NO_RENORM: LAUNCH_SPAWN(EXCIT_GEN_NO_RENORM); break;
             case HB200_EXCIT_GEN_RENORM: LAUNCH_SPAWN(EXCIT_GEN_RENORM); break;
             case HB200_EXCIT_GEN_RENORM_SPIN: LAUNCH_SPAWN(EXCIT_GEN_RENORM_SPIN); break;
+            case HB200_EXCIT_GEN_POWER_PITZER_ORDERN: LAUNCH_SPAWN(EXCIT_GEN_POWER_PITZER_ORDERN); break;
             case HB200_EXCIT_GEN_NO_RENORM_SPIN: LAUNCH_SPAWN(EXCIT_GEN_NO_RENORM_SPIN); break;
             case HB200_EXCIT_GEN_HEAT_BATH: LAUNCH_SPAWN(EXCIT_GEN_HEAT_BATH); break;
             case HB200_EXCIT_GEN_HEAT_BATH_UNIFORM: LAUNCH_SPAWN(EXCIT_GEN_HEAT_BATH_UNIFORM); break;
@@ -2228,6 +2435,7 @@ int hb200_spawn_death(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, 
     CK(cudaSetDevice(e->cfg.device));
     if (!e->have_sys) FAIL("spawn_death: system not set");
     if (uses_heat_bath_tables(e) && !e->have_hb) FAIL("spawn_death: heat-bath tables not built");
+    if (e->cfg.excit_gen == HB200_EXCIT_GEN_POWER_PITZER_ORDERN && !e->have_ppn) FAIL("spawn_death: power_pitzer_orderN tables not built");
     CycleStats st;
     memset(&st, 0, sizeof(st));
     const long long nattempts = llround(2.0 * ((double)e->nparticles_enc / (double)e->par.real_factor));
@@ -2251,6 +2459,7 @@ int hb200_ccmc_spawn(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, i
     CK(cudaSetDevice(e->cfg.device));
     if (!e->have_sys) FAIL("ccmc_spawn: system not set");
     if (uses_heat_bath_tables(e) && !e->have_hb) FAIL("ccmc_spawn: heat-bath tables not built");
+    if (e->cfg.excit_gen == HB200_EXCIT_GEN_POWER_PITZER_ORDERN && !e->have_ppn) FAIL("ccmc_spawn: power_pitzer_orderN tables not built");
     if (e->par.nprocs > 1 && !e->comm) FAIL("ccmc_spawn: nprocs > 1 but hb200_comm_init was not called");
     if (e->cfg.initiator_approx) FAIL("ccmc_spawn: the initiator approximation is not implemented for CCMC");
     Params& p = e->par;
@@ -2590,6 +2799,7 @@ int hb200_iterate(hb200_engine* e, int32_t ncycles, const hb200_iter_in* in, hb2
     CK(cudaSetDevice(e->cfg.device));
     if (!e->have_sys) FAIL("iterate: system not set");
     if (uses_heat_bath_tables(e) && !e->have_hb) FAIL("iterate: heat-bath tables not built");
+    if (e->cfg.excit_gen == HB200_EXCIT_GEN_POWER_PITZER_ORDERN && !e->have_ppn) FAIL("iterate: power_pitzer_orderN tables not built");
     memset(out, 0, sizeof(*out));
     cudaStream_t st = e->stream;
     float acc[4] = {0, 0, 0, 0};
@@ -2658,6 +2868,7 @@ int hb200_gen_excit_batch(hb200_engine* e, const uint64_t* states, const int64_t
                           int64_t n, uint32_t cycle, double tau, int32_t* iout, double* dout, int64_t* nspawn) {
     CK(cudaSetDevice(e->cfg.device));
     if (!e->have_sys) FAIL("gen_excit_batch: system not set");
+    if (e->cfg.excit_gen == HB200_EXCIT_GEN_POWER_PITZER_ORDERN && !e->have_ppn) FAIL("gen_excit_batch: power_pitzer_orderN tables not built");
     if (n == 0) return 0;
     Params p = e->par;
     p.cycle = cycle; p.tau = tau;

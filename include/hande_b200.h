@@ -27,7 +27,7 @@ typedef struct hb200_engine hb200_engine;
 
 /* Values of qmc_in%excit_gen (src/qmc_data.f90:31-69) that the engine implements. */
 enum { HB200_EXCIT_GEN_RENORM = 0, HB200_EXCIT_GEN_RENORM_SPIN = 1, HB200_EXCIT_GEN_NO_RENORM_SPIN = 3, HB200_EXCIT_GEN_NO_RENORM = 2, HB200_EXCIT_GEN_POWER_PITZER_OCC = 5,
-       HB200_EXCIT_GEN_POWER_PITZER_OCC_IJ = 6, HB200_EXCIT_GEN_CAUCHY_SCHWARZ_OCC = 8, HB200_EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ = 9, HB200_EXCIT_GEN_HEAT_BATH = 10, HB200_EXCIT_GEN_HEAT_BATH_UNIFORM = 11,
+       HB200_EXCIT_GEN_POWER_PITZER_OCC_IJ = 6, HB200_EXCIT_GEN_POWER_PITZER_ORDERN = 7, HB200_EXCIT_GEN_CAUCHY_SCHWARZ_OCC = 8, HB200_EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ = 9, HB200_EXCIT_GEN_HEAT_BATH = 10, HB200_EXCIT_GEN_HEAT_BATH_UNIFORM = 11,
        HB200_EXCIT_GEN_HEAT_BATH_SINGLE = 12 };
 
 /* qmc_in_t / fciqmc options that size and configure the device state
@@ -189,6 +189,12 @@ int hb200_set_pattempt(hb200_engine* e, double pattempt_single, double pattempt_
  * negative value computes it as find_parallel_spin_prob_mol does (src/qmc_common.F90:262-377, src/qmc.F90:974-988); call
  * after hb200_set_system_read_in and before the first iteration. */
 int hb200_set_pattempt_parallel(hb200_engine* e, double pattempt_parallel);
+/* excit_gen = power_pitzer_orderN ('heat_bath_power_pitzer_ref'; gen_excit_mol_power_pitzer_orderN,
+ * src/excit_gen_power_pitzer_mol.F90:941-1258): builds the reference-mapped alias tables ppn_i_s, ppn_ia_s, ppn_i_d,
+ * ppn_ij_d, ppn_ia_d, ppn_jb_d on the device as init_excit_mol_power_pitzer_orderN does (:215-572, with
+ * check_min_weight_ratio :140-213; min_weight = qmc_in%power_pitzer_min_weight, default 0.01).  Call after
+ * hb200_set_reference (the tables depend on the reference determinant). */
+int hb200_build_power_pitzer_orderN(hb200_engine* e, double min_weight);
 double hb200_get_pattempt_parallel(hb200_engine* e);
 int hb200_get_ps_stats(hb200_engine* e, double* out4, int32_t reset);
 

@@ -376,6 +376,21 @@ void orc_get_ps_stats(void* h, int rank, double* out, int reset) {
         if (reset) a = Oracle::PsColl();
     }
 }
+// power_pitzer_orderN tables: which = 0..5 (i_s, ia_s, i_d, ij_d, ia_d, jb_d); part = 0 w, 1 U, 2 tot (doubles), K via _i
+const double* orc_ppn_ptr_d(void* h, int which, int part, int64_t* n) {
+    Oracle* o = (Oracle*)h;
+    AliasCols* t[6] = {&o->eg.ppn.i_s, &o->eg.ppn.ia_s, &o->eg.ppn.i_d, &o->eg.ppn.ij_d, &o->eg.ppn.ia_d, &o->eg.ppn.jb_d};
+    std::vector<double>& v = part == 0 ? t[which]->w : (part == 1 ? t[which]->U : t[which]->tot);
+    *n = (int64_t)v.size();
+    return v.data();
+}
+const int* orc_ppn_ptr_i(void* h, int which, int64_t* n) {
+    Oracle* o = (Oracle*)h;
+    AliasCols* t[6] = {&o->eg.ppn.i_s, &o->eg.ppn.ia_s, &o->eg.ppn.i_d, &o->eg.ppn.ij_d, &o->eg.ppn.ia_d, &o->eg.ppn.jb_d};
+    *n = (int64_t)t[which]->K.size();
+    return t[which]->K.data();
+}
+const int* orc_ppn_occ(void* h) { return ((Oracle*)h)->eg.ppn.occ_list.data(); }
 void orc_set_pattempt_parallel(void* h, double pp) { ((Oracle*)h)->in.pattempt_parallel = pp; ((Oracle*)h)->eg.pattempt_parallel = pp; }
 double orc_get_pattempt_parallel(void* h) { return ((Oracle*)h)->eg.pattempt_parallel; }
 void orc_set_pattempt(void* h, double ps, double pd) { ((Oracle*)h)->eg.pattempt_single = ps; ((Oracle*)h)->eg.pattempt_double = pd; }

@@ -21,6 +21,7 @@ enum ExcitGenKind {  // values of src/qmc_data.f90:31-69
     EXCIT_GEN_NO_RENORM_SPIN = 3,
     EXCIT_GEN_POWER_PITZER_OCC = 5,
     EXCIT_GEN_POWER_PITZER_OCC_IJ = 6,
+    EXCIT_GEN_POWER_PITZER_ORDERN = 7,
     EXCIT_GEN_CAUCHY_SCHWARZ_OCC = 8,
     EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ = 9,
     EXCIT_GEN_HEAT_BATH = 10,
@@ -44,6 +45,8 @@ struct DetInfo {
     std::vector<int> unocc;
     std::vector<double> i_s_weights, ia_s_weights;   // ia_s_weights[(a_ind-1) + nvirt*(i_ind-1)]
     double i_s_weights_tot = 0.0;
+    // power_pitzer_orderN: det_info_t%ref_cdet_occ_list (find_diff_ref_cdet, src/excit_gen_utils.f90:220-269)
+    int ref_cdet_occ[MAXNEL];
     inline int su(int ims, int sym) const { return symunocc[(ims - 1) + 2 * sym]; }
 };
 
@@ -203,8 +206,28 @@ inline bool init_excit_mol_heat_bath(const System& sys, HeatBath& hb, bool origi
     return ok;
 }
 
+// alias_table_data_*_t (src/excit_gens.f90:43-100): columns of `stride` entries
+struct AliasCols {
+    int stride = 0;
+    std::vector<double> w, U, tot;
+    std::vector<int> K;
+    void alloc(int stride_, size_t ncols) {
+        stride = stride_;
+        w.assign((size_t)stride * ncols, 0.0); U.assign((size_t)stride * ncols, 0.0); K.assign((size_t)stride * ncols, 0);
+        tot.assign(ncols, 0.0);
+    }
+};
+// excit_gen_power_pitzer_t, the ppn_* members (src/excit_gens.f90:102-141): reference-mapped O(N) Power-Pitzer tables
+struct PowerPitzerN {
+    std::vector<int> occ_list, all_list_alpha, all_list_beta;
+    int n_all_alpha = 0, n_all_beta = 0;
+    double min_weight = 0.01;        // qmc_in%power_pitzer_min_weight (src/qmc_data.f90:224)
+    AliasCols i_s, ia_s, i_d, ij_d, ia_d, jb_d;   // columns: [1], [nbasis], [1], [nbasis], [nbasis], [nsym_tot * nbasis]
+};
+
 struct ExcitGenData {
     int excit_gen = EXCIT_GEN_RENORM;
+    PowerPitzerN ppn;
     double pattempt_single = 0.0, pattempt_double = 1.0;
     double pattempt_parallel = 0.0;   // renorm_spin / no_renorm_spin: probability that i and j have parallel spins
     HeatBath hb;
@@ -1016,6 +1039,308 @@ inline GenResult gen_excit_mol_power_pitzer_occ(Rng& rng, const System& sys, con
     return r;
 }
 
+// ------------------------------------------------------------------------ power_pitzer_orderN
+// check_min_weight_ratio (src/excit_gen_power_pitzer_mol.F90:140-213): raise the non-zero weights below
+// min_ratio/(number of non-zero weights) of the total to that floor
+inline void check_min_weight_ratio(double* weights, double& weights_tot, int n, double min_ratio) {
+    double min_weight_tmp = 0.0;
+    int nonzero = 0;
+    if (!(weights_tot > 0.0 && min_ratio > 0.0)) return;
+    for (int i = 0; i < n; ++i) if (weights[i] > 0.0) nonzero++;
+    double min_weight = (min_ratio / (float)nonzero) * weights_tot;
+    while (std::fabs(min_weight_tmp - min_weight) > depsilon) {
+        min_weight_tmp = min_weight;
+        double keep = 0.0;
+        int cnt = 0;
+        for (int k = 0; k < n; ++k) {
+            if (weights[k] > 0.0 && weights[k] < min_weight) cnt++;
+            else keep = keep + weights[k];
+        }
+        if (cnt == nonzero) break;
+        min_weight = (min_ratio / (float)nonzero) * (keep / (1 - (min_ratio * (float)cnt / (float)nonzero)));
+    }
+    weights_tot = 0.0;
+    for (int j = 0; j < n; ++j) {
+        if (weights[j] > 0.0 && weights[j] < min_weight) weights[j] = min_weight;
+        weights_tot = weights_tot + weights[j];
+    }
+}
+// single_excitation_weight_mol (src/hamiltonian_molecular.f90:444-523)
+inline double single_excitation_weight_mol(const System& sys, const int* occ0, int i, int a) {
+    const int nel = sys.nel, nvirt = sys.nbasis - sys.nel;
+    std::vector<int> virt(nvirt);
+    int vp = 0, op = 0;
+    for (int pos = 1; pos <= sys.nbasis; ++pos) {
+        if (op >= nel) virt[vp++] = pos;
+        else if (occ0[op] == pos) op++;
+        else virt[vp++] = pos;
+    }
+    int n_jb = 0;
+    double weight = 0.0;
+    for (int j = 0; j < nel; ++j)
+        for (int b = 0; b < nvirt; ++b) {
+            n_jb++;
+            weight = weight + std::fabs(sys.get_two_body_real(i, occ0[j], occ0[j], a) - sys.get_two_body_real(i, occ0[j], a, occ0[j]) +
+                                        sys.get_two_body_real(i, virt[b], a, virt[b]) - sys.get_two_body_real(i, virt[b], virt[b], a));
+        }
+    return weight / (double)n_jb;
+}
+// init_double_weights_ab (src/excit_gen_utils.f90:68-140)
+inline void init_double_weights_ab(const System& sys, int i, int j, double& weight) {
+    const int it = std::min(i, j), jt = std::max(i, j);
+    const int ij_sym = sys.sym_conj(sys.cross_product_basis(it, jt));
+    for (int a = 1; a <= sys.nbasis; ++a) {
+        if (a == it || a == jt) continue;
+        const int isymb = sys.sym_conj(sys.cross_product(ij_sym, sys.bf[a].sym));
+        for (int b = 1; b <= sys.nbasis; ++b) {
+            const bool spin_ok = (sys.bf[it].ms == sys.bf[a].ms && sys.bf[jt].ms == sys.bf[b].ms) ||
+                                 (sys.bf[it].ms == sys.bf[b].ms && sys.bf[jt].ms == sys.bf[a].ms);
+            if (spin_ok && sys.bf[b].sym == isymb && a != b && b != it && b != jt)
+                weight = weight + std::fabs(sys.slater_condon2_excit(it, jt, std::min(a, b), std::max(a, b), false));
+        }
+    }
+}
+// init_excit_mol_power_pitzer_orderN (src/excit_gen_power_pitzer_mol.F90:215-572).  Every table entry is computed by one
+// rank and gathered, so the result does not depend on the number of ranks.
+inline void init_excit_mol_power_pitzer_orderN(const System& sys, const int* occ0, PowerPitzerN& pp) {
+    const int nel = sys.nel, nb = sys.nbasis, mv = sys.max_nbss, nsym = sys.nsym_tot;
+    pp.occ_list.assign(occ0, occ0 + nel);
+    std::sort(pp.occ_list.begin(), pp.occ_list.end());
+    pp.all_list_alpha.clear(); pp.all_list_beta.clear();
+    for (int i = 1; i <= nb; ++i) (sys.bf[i].ms == -1 ? pp.all_list_beta : pp.all_list_alpha).push_back(i);
+    pp.n_all_alpha = (int)pp.all_list_alpha.size(); pp.n_all_beta = (int)pp.all_list_beta.size();
+    const int nall_max = std::max(pp.n_all_alpha, pp.n_all_beta);
+    pp.i_s.alloc(nel, 1); pp.i_d.alloc(nel, 1);
+    pp.ia_s.alloc(mv, nb + 1); pp.ij_d.alloc(nel, nb + 1); pp.ia_d.alloc(nall_max, nb + 1);
+    pp.jb_d.alloc(mv, (size_t)nsym * (nb + 1));
+    const int* occ = pp.occ_list.data();
+    // i in a single excitation
+    for (int i = 0; i < nel; ++i) {
+        double i_weight = 0.0;
+        const int ims = sys.bf[occ[i]].ms;
+        const int isyma = sys.cross_product(sys.bf[occ[i]].sym, sys.gamma_sym);
+        for (int a = 1; a <= nb; ++a)
+            if (a != occ[i] && sys.bf[a].sym == isyma && sys.bf[a].ms == ims)
+                i_weight = i_weight + single_excitation_weight_mol(sys, occ0, occ[i], a);
+        if (i_weight < depsilon) i_weight = 10.0 * depsilon;
+        pp.i_s.w[i] = i_weight;
+    }
+    pp.i_s.tot[0] = 0.0;
+    for (int i = 0; i < nel; ++i) pp.i_s.tot[0] += pp.i_s.w[i];
+    check_min_weight_ratio(pp.i_s.w.data(), pp.i_s.tot[0], nel, pp.min_weight);
+    generate_alias_tables(nel, pp.i_s.w.data(), pp.i_s.tot[0], pp.i_s.U.data(), pp.i_s.K.data());
+    // a given i in a single excitation (i: any basis function)
+    for (int i = 1; i <= nb; ++i) {
+        double tot = 0.0;
+        const int imsa = (3 + sys.bf[i].ms) / 2;
+        const int isyma = sys.cross_product(sys.bf[i].sym, sys.gamma_sym);
+        double* w = &pp.ia_s.w[(size_t)mv * i];
+        const int n = sys.nbss(imsa, isyma);
+        for (int a = 1; a <= n; ++a) {
+            w[a - 1] = 0.0;
+            if (sys.ssbf(a, imsa, isyma) != i) {
+                w[a - 1] = single_excitation_weight_mol(sys, occ0, i, sys.ssbf(a, imsa, isyma));
+                if (w[a - 1] < depsilon) w[a - 1] = 10.0 * depsilon;
+            }
+            tot = tot + w[a - 1];
+        }
+        pp.ia_s.tot[i] = tot;
+        check_min_weight_ratio(w, pp.ia_s.tot[i], n, pp.min_weight);
+        generate_alias_tables(n, w, pp.ia_s.tot[i], &pp.ia_s.U[(size_t)mv * i], &pp.ia_s.K[(size_t)mv * i]);
+    }
+    // i in a double excitation
+    for (int i = 0; i < nel; ++i) {
+        double i_weight = 0.0;
+        for (int j = 0; j < nel; ++j)
+            if (i != j) init_double_weights_ab(sys, occ[i], occ[j], i_weight);
+        if (i_weight < depsilon) i_weight = 10.0 * depsilon;
+        pp.i_d.w[i] = i_weight;
+    }
+    pp.i_d.tot[0] = 0.0;
+    for (int i = 0; i < nel; ++i) pp.i_d.tot[0] += pp.i_d.w[i];
+    check_min_weight_ratio(pp.i_d.w.data(), pp.i_d.tot[0], nel, pp.min_weight);
+    generate_alias_tables(nel, pp.i_d.w.data(), pp.i_d.tot[0], pp.i_d.U.data(), pp.i_d.K.data());
+    // j given i (i: any basis function, j: position in the reference)
+    for (int i = 1; i <= nb; ++i) {
+        double tot = 0.0;
+        double* w = &pp.ij_d.w[(size_t)nel * i];
+        for (int j = 0; j < nel; ++j) {
+            double ij_weight = 0.0;
+            if (occ[j] != i) init_double_weights_ab(sys, i, occ[j], ij_weight);
+            if (ij_weight < depsilon) ij_weight = 10.0 * depsilon;
+            w[j] = ij_weight;
+            tot = tot + ij_weight;
+        }
+        pp.ij_d.tot[i] = tot;
+        check_min_weight_ratio(w, pp.ij_d.tot[i], nel, pp.min_weight);
+        generate_alias_tables(nel, w, pp.ij_d.tot[i], &pp.ij_d.U[(size_t)nel * i], &pp.ij_d.K[(size_t)nel * i]);
+    }
+    // a given i and b given j: sqrt|<ia|ai>| over all orbitals of the spin of i / over each symmetry class
+    for (int i = 1; i <= nb; ++i) {
+        const bool beta = sys.bf[i].ms == -1;
+        const std::vector<int>& all = beta ? pp.all_list_beta : pp.all_list_alpha;
+        const int nall = (int)all.size();
+        if (nall > 0) {
+            double* w = &pp.ia_d.w[(size_t)nall_max * i];
+            pp.ia_d.tot[i] = create_weighted_excitation_list_mol(sys, false, i, i, all.data(), nall, w);
+            generate_alias_tables(nall, w, pp.ia_d.tot[i], &pp.ia_d.U[(size_t)nall_max * i], &pp.ia_d.K[(size_t)nall_max * i]);
+        }
+        const int ims = beta ? 1 : 2;
+        for (int bsym = 0; bsym <= sys.sym_max_tot; ++bsym) {
+            const int n = sys.nbss(ims, bsym);
+            if (n <= 0) continue;
+            std::vector<int> list(n);
+            for (int k = 1; k <= n; ++k) list[k - 1] = sys.ssbf(k, ims, bsym);
+            const size_t col = (size_t)bsym + (size_t)nsym * i;
+            double* w = &pp.jb_d.w[(size_t)mv * col];
+            pp.jb_d.tot[col] = create_weighted_excitation_list_mol(sys, false, i, i, list.data(), n, w);
+            generate_alias_tables(n, w, pp.jb_d.tot[col], &pp.jb_d.U[(size_t)mv * col], &pp.jb_d.K[(size_t)mv * col]);
+        }
+    }
+}
+// get_excitation_locations (src/excitations.F90) + find_diff_ref_cdet (src/excit_gen_utils.f90:220-269): the occupied
+// orbitals of cdet in the order of the reference's (same-spin replacements for the orbitals that differ)
+inline void find_diff_ref_cdet(const System& sys, const PowerPitzerN& pp, DetInfo& d) {
+    const int nel = sys.nel;
+    const int* ref_list = pp.occ_list.data();
+    const int* det_list = d.occ;
+    int ref_store[MAXNEL], det_store[MAXNEL];
+    int j = 1, det_sind = 0, ref_sind = 0;
+    bool done = false;
+    for (int i = 1; i <= nel && !done; ++i) {
+        while (det_list[j - 1] < ref_list[i - 1]) {
+            det_store[det_sind++] = j;
+            j++;
+            if (j > nel) { done = true; break; }
+        }
+        if (done) break;
+        if (det_list[j - 1] > ref_list[i - 1]) ref_store[ref_sind++] = i;
+        else j++;
+        if (j > nel) break;
+    }
+    while (j <= nel) { det_store[det_sind++] = j; j++; }
+    int i_back = nel, i_back_pos = det_sind;
+    while (ref_sind < det_sind) {
+        ref_store[i_back_pos - 1] = i_back;
+        i_back--; i_back_pos--; ref_sind++;
+    }
+    const int nex = ref_sind;
+    for (int k = 0; k < nel; ++k) d.ref_cdet_occ[k] = ref_list[k];
+    for (int ii = 0; ii < nex; ++ii) {
+        if (sys.bf[ref_list[ref_store[ii] - 1]].ms != sys.bf[det_list[det_store[ii] - 1]].ms) {
+            int jj = ii + 1;
+            while (sys.bf[ref_list[ref_store[ii] - 1]].ms != sys.bf[det_list[det_store[jj] - 1]].ms) jj++;
+            std::swap(det_store[ii], det_store[jj]);
+        }
+        d.ref_cdet_occ[ref_store[ii] - 1] = det_list[det_store[ii] - 1];
+    }
+}
+inline int binary_search_int(const int* list, int n, int item) {   // 1-based position, list ascending
+    int lo = 1, hi = n;
+    while (lo <= hi) {
+        const int mid = (lo + hi) / 2;
+        if (list[mid - 1] == item) return mid;
+        if (list[mid - 1] < item) lo = mid + 1; else hi = mid - 1;
+    }
+    return 0;
+}
+// gen_excit_mol_power_pitzer_orderN (src/excit_gen_power_pitzer_mol.F90:941-1258)
+inline GenResult gen_excit_mol_power_pitzer_orderN(Rng& rng, const System& sys, const ExcitGenData& eg, DetInfo& d) {
+    GenResult r;
+    const PowerPitzerN& pp = eg.ppn;
+    const int nel = sys.nel, mv = sys.max_nbss, nsym = sys.nsym_tot;
+    const int nall_max = std::max(pp.n_all_alpha, pp.n_all_beta);
+    if (!d.single_precalc) {
+        find_diff_ref_cdet(sys, pp, d);
+        d.single_precalc = true; d.double_precalc = true;
+    }
+    if (rng.next() < eg.pattempt_single) {
+        const int i_ind_ref = select_weighted_value_precalc(rng, nel, pp.i_s.U.data(), pp.i_s.K.data());
+        const int i_cdet = d.ref_cdet_occ[i_ind_ref - 1];
+        const int imsa = (3 + sys.bf[i_cdet].ms) / 2;
+        const int isyma = sys.cross_product(sys.bf[i_cdet].sym, sys.gamma_sym);
+        int a_ind = 0, a_cdet = 0;
+        r.conn.nexcit = 1;
+        if (sys.nbss(imsa, isyma) > 0) {
+            a_ind = select_weighted_value_precalc(rng, sys.nbss(imsa, isyma), &pp.ia_s.U[(size_t)mv * i_cdet],
+                                                  &pp.ia_s.K[(size_t)mv * i_cdet]);
+            a_cdet = sys.ssbf(a_ind, imsa, isyma);
+            r.allowed = !det_test(d.f, a_cdet);
+        } else r.allowed = false;
+        if (r.allowed) {
+            r.pgen = (pp.i_s.w[i_ind_ref - 1] / pp.i_s.tot[0]) *
+                     (pp.ia_s.w[(size_t)mv * i_cdet + a_ind - 1] / pp.ia_s.tot[i_cdet]);
+            r.pgen = eg.pattempt_single * r.pgen;
+            r.conn.from_orb[0] = i_cdet; r.conn.to_orb[0] = a_cdet;
+            sys.find_excitation_permutation1(d.f, r.conn);
+            r.hmatel = sys.slater_condon1_excit(d.occ, i_cdet, a_cdet, r.conn.perm);
+        } else { r.hmatel = 0.0; r.pgen = 1.0; }
+        return r;
+    }
+    r.conn.nexcit = 2;
+    const int i_ind_ref = select_weighted_value_precalc(rng, nel, pp.i_d.U.data(), pp.i_d.K.data());
+    int i_cdet = d.ref_cdet_occ[i_ind_ref - 1];
+    const int j_ind_ref = select_weighted_value_precalc(rng, nel, &pp.ij_d.U[(size_t)nel * i_cdet], &pp.ij_d.K[(size_t)nel * i_cdet]);
+    int j_cdet = d.ref_cdet_occ[j_ind_ref - 1];
+    double pgen = 1.0;
+    int ij_spin = 0;
+    if (j_cdet != i_cdet) {
+        r.allowed = true;
+        pgen = (pp.i_d.w[i_ind_ref - 1] / pp.i_d.tot[0]) * (pp.ij_d.w[(size_t)nel * i_cdet + j_ind_ref - 1] / pp.ij_d.tot[i_cdet]);
+        ij_spin = sys.bf[i_cdet].ms + sys.bf[j_cdet].ms;
+        pgen = pgen + ((pp.i_d.w[j_ind_ref - 1] / pp.i_d.tot[0]) * (pp.ij_d.w[(size_t)nel * j_cdet + i_ind_ref - 1] / pp.ij_d.tot[j_cdet]));
+        if (j_cdet < i_cdet) std::swap(i_cdet, j_cdet);
+    } else r.allowed = false;
+    int a_ind = 0, a_cdet = 0, b_ind = 0, b_cdet = 0, ij_sym = 0, isymb = 0, imsb = 1;
+    if (r.allowed) {
+        if (sys.bf[i_cdet].ms < 0) {
+            a_ind = select_weighted_value_precalc(rng, pp.n_all_beta, &pp.ia_d.U[(size_t)nall_max * i_cdet], &pp.ia_d.K[(size_t)nall_max * i_cdet]);
+            a_cdet = pp.all_list_beta[a_ind - 1];
+        } else {
+            a_ind = select_weighted_value_precalc(rng, pp.n_all_alpha, &pp.ia_d.U[(size_t)nall_max * i_cdet], &pp.ia_d.K[(size_t)nall_max * i_cdet]);
+            a_cdet = pp.all_list_alpha[a_ind - 1];
+        }
+        if (det_test(d.f, a_cdet)) r.allowed = false;
+    }
+    if (r.allowed) {
+        ij_sym = sys.sym_conj(sys.cross_product_basis(i_cdet, j_cdet));
+        isymb = sys.sym_conj(sys.cross_product(ij_sym, sys.bf[a_cdet].sym));
+        imsb = (sys.bf[j_cdet].ms + 3) / 2;
+        if (sys.nbss(imsb, isymb) == 0) r.allowed = false;
+    }
+    if (r.allowed) {
+        const size_t colb = (size_t)isymb + (size_t)nsym * j_cdet;
+        b_ind = select_weighted_value_precalc(rng, sys.nbss(imsb, isymb), &pp.jb_d.U[(size_t)mv * colb], &pp.jb_d.K[(size_t)mv * colb]);
+        b_cdet = sys.ssbf(b_ind, imsb, isymb);
+        if (a_cdet != b_cdet && !det_test(d.f, b_cdet)) {
+            const double pa = pp.ia_d.w[(size_t)nall_max * i_cdet + a_ind - 1] / pp.ia_d.tot[i_cdet];
+            if (ij_spin == 0) {
+                pgen = pgen * (pa * pp.jb_d.w[(size_t)mv * colb + b_ind - 1] / pp.jb_d.tot[colb]);
+            } else {
+                const int b_rev = (imsb == 1) ? binary_search_int(pp.all_list_beta.data(), pp.n_all_beta, b_cdet)
+                                              : binary_search_int(pp.all_list_alpha.data(), pp.n_all_alpha, b_cdet);
+                const int isyma = sys.sym_conj(sys.cross_product(ij_sym, isymb));
+                int a_rev = 0;
+                for (int k = 1; k <= sys.nbss(imsb, isyma); ++k)
+                    if (sys.ssbf(k, imsb, isyma) == a_cdet) { a_rev = k; break; }
+                const size_t cola = (size_t)isyma + (size_t)nsym * j_cdet;
+                pgen = pgen * (pa * pp.jb_d.w[(size_t)mv * colb + b_ind - 1] / pp.jb_d.tot[colb] +
+                               pp.ia_d.w[(size_t)nall_max * i_cdet + b_rev - 1] / pp.ia_d.tot[i_cdet] *
+                                   pp.jb_d.w[(size_t)mv * cola + a_rev - 1] / pp.jb_d.tot[cola]);
+            }
+            pgen = eg.pattempt_double * pgen;
+        } else r.allowed = false;
+    }
+    if (r.allowed) {
+        r.pgen = pgen;
+        r.conn.from_orb[0] = i_cdet; r.conn.from_orb[1] = j_cdet;
+        r.conn.to_orb[0] = std::min(a_cdet, b_cdet); r.conn.to_orb[1] = std::max(a_cdet, b_cdet);
+        sys.find_excitation_permutation2(d.f, r.conn);
+        r.hmatel = sys.slater_condon2_excit(r.conn.from_orb[0], r.conn.from_orb[1], r.conn.to_orb[0], r.conn.to_orb[1], r.conn.perm);
+    } else { r.hmatel = 0.0; r.pgen = 1.0; }
+    return r;
+}
+
 inline GenResult gen_excit(Rng& rng, const System& sys, const ExcitGenData& eg, DetInfo& d) {
     switch (eg.excit_gen) {
         case EXCIT_GEN_RENORM: return gen_excit_mol(rng, sys, eg, d);
@@ -1029,6 +1354,7 @@ inline GenResult gen_excit(Rng& rng, const System& sys, const ExcitGenData& eg, 
         case EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ: return gen_excit_mol_power_pitzer_occ(rng, sys, eg, d);
         case EXCIT_GEN_HEAT_BATH_UNIFORM:
         case EXCIT_GEN_HEAT_BATH_SINGLE: return gen_excit_mol_heat_bath_uniform(rng, sys, eg, d);
+        case EXCIT_GEN_POWER_PITZER_ORDERN: return gen_excit_mol_power_pitzer_orderN(rng, sys, eg, d);
         default: throw std::runtime_error("oracle: excitation generator not implemented");
     }
 }

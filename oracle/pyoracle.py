@@ -12,7 +12,7 @@ LIB = os.path.join(HERE, "liboracle.so")
 REF_LIB = os.path.join(HERE, "_ref", "libhande_ref_c.so")
 HUGE = 2**31 - 1
 
-EXCIT_GEN = {"renorm": 0, "renorm_spin": 1, "no_renorm": 2, "no_renorm_spin": 3, "power_pitzer_occ": 5, "power_pitzer_occ_ij": 6, "cauchy_schwarz_occ": 8,
+EXCIT_GEN = {"renorm": 0, "renorm_spin": 1, "no_renorm": 2, "no_renorm_spin": 3, "power_pitzer_occ": 5, "power_pitzer_occ_ij": 6, "power_pitzer_orderN": 7, "cauchy_schwarz_occ": 8,
              "cauchy_schwarz_occ_ij": 9, "heat_bath": 10,
              "heat_bath_uniform": 11, "heat_bath_single": 12}
 
@@ -418,6 +418,29 @@ class Oracle:
         out["ijab_K"] = np.ctypeslib.as_array(self.L.orc_hb_ptr_i(self.h, 1), shape=(nb ** 4,))
         out["nb"] = nb
         return out
+
+    def power_pitzer_orderN_tables(self):
+        """ppn_* alias tables of excit_gen = power_pitzer_orderN: list of 6 dicts (i_s, ia_s, i_d, ij_d, ia_d, jb_d)"""
+        L = self.L
+        L.orc_ppn_ptr_d.restype = C.POINTER(C.c_double)
+        L.orc_ppn_ptr_d.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.orc_ppn_ptr_i.restype = C.POINTER(C.c_int)
+        L.orc_ppn_ptr_i.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_ppn_occ.restype = C.POINTER(C.c_int)
+        L.orc_ppn_occ.argtypes = [C.c_void_p]
+        out = []
+        n = C.c_int64(0)
+        for which in range(6):
+            t = {}
+            for part, nm in enumerate(("w", "U", "tot")):
+                ptr = L.orc_ppn_ptr_d(self.h, which, part, C.byref(n))
+                t[nm] = np.ctypeslib.as_array(ptr, shape=(n.value,)).copy()
+            ptr = L.orc_ppn_ptr_i(self.h, which, C.byref(n))
+            t["K"] = np.ctypeslib.as_array(ptr, shape=(n.value,)).astype(np.int32)
+            out.append(t)
+        nel = len(out[0]["w"])
+        occ = np.ctypeslib.as_array(L.orc_ppn_occ(self.h), shape=(nel,)).astype(np.int32)
+        return out, occ
 
     def cpu_baseline(self, nthreads, ncycles, tau, shift, proj_energy_old):
         out = np.zeros(4)

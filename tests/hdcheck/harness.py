@@ -81,6 +81,14 @@ class HdCheck:
         L.hd_proj_hmatel.restype = C.c_double
         L.hd_proj_hmatel.argtypes = [C.c_void_p, C.c_void_p]
 
+    def set_power_pitzer_orderN(self, tables, occ):
+        self.L.hd_set_ppn.argtypes = [C.c_int] + [C.c_void_p] * 4
+        self.L.hd_set_ppn_occ.argtypes = [C.c_void_p]
+        self.keep.append((tables, occ))
+        for which, t in enumerate(tables):
+            self.L.hd_set_ppn(which, _p(t["w"]), _p(t["U"]), _p(t["K"]), _p(t["tot"]))
+        self.L.hd_set_ppn_occ(_p(occ))
+
     def set_pattempt_parallel(self, pp):
         self.L.hd_set_pattempt_parallel.argtypes = [C.c_double]
         self.L.hd_set_pattempt_parallel(float(pp))

@@ -113,6 +113,10 @@ void hd_set_params(int excit_gen, double ps, double pd, double tau, double shift
     for (int k = 0; k < g_sys.W; ++k) p.f0[k] = f0[k];
 }
 
+void hd_set_ppn(int which, const double* w, const double* U, const int* K, const double* tot) {
+    g_sys.ppn[which].w = w; g_sys.ppn[which].U = U; g_sys.ppn[which].K = K; g_sys.ppn[which].tot = tot;
+}
+void hd_set_ppn_occ(const int* occ) { g_sys.ppn_occ = occ; }
 void hd_set_pattempt_parallel(double pp) { g_par.pattempt_parallel = pp; }
 
 void hd_gen_excit_philox(const uint64_t* f, uint32_t cycle, uint32_t attempt, int64_t parent_pop, int* iout,

@@ -30,6 +30,7 @@ CASES = [
     ("s12", "heat_bath_uniform", True, 2, 0.001, 40, False),
     ("nh3", "renorm_spin", True, 3, 0.002, 60, False),    # the reference's per-generator CCSDT fixture system
     ("nh3", "heat_bath_single", True, 3, 0.003, 40, False),
+    ("nh3", "power_pitzer_orderN", True, 3, 0.001, 80, False),
     ("s40", "renorm", False, 3, 0.0003, 30, False),         # two-word bit strings
     ("ueg6", "no_renorm", True, 2, 0.01, 80, False),      # CCMC on the UEG (doubles only)
     ("ne_vdz", "renorm", False, 3, 0.005, 100, True),     # full_nc: non-composite clusters + in-place death

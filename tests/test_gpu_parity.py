@@ -63,6 +63,15 @@ def test_gen_excit_renorm_spin_and_no_renorm_spin():
     _check_gen("s40", "renorm_spin", True, 0.01, n=80)
 
 
+def test_gen_excit_power_pitzer_orderN():
+    # 'heat_bath_power_pitzer_ref': tables built on the device (hb200_build_power_pitzer_orderN) - any differing bit in
+    # a weight, a total or an alias entry would show up in pgen or in the excitation chosen
+    _check_gen("nh3", "power_pitzer_orderN", True, 0.002, n=150, nattempt=6)
+    _check_gen("h2o", "power_pitzer_orderN", False, 0.003, n=120)
+    _check_gen("s12", "power_pitzer_orderN", True, 0.01, n=120)
+    _check_gen("s40", "power_pitzer_orderN", False, 0.01, n=60)
+
+
 def test_pattempt_parallel_on_device():
     """find_parallel_spin_prob_mol on the device against the oracle (whose value reproduces the 0.22360108 printed in
     the reference's NH3 renorm_spin golden output)."""
@@ -140,6 +149,8 @@ CASES = [
     ("s12", "heat_bath_uniform", True, True, 0.01, 2500, -1),
     ("s12", "heat_bath_single", True, True, 0.01, 2500, -1),
     ("nh3", "renorm_spin", True, True, 0.003, 2500, -1),
+    ("nh3", "power_pitzer_orderN", True, True, 0.002, 2500, -1),
+    ("s12", "power_pitzer_orderN", False, False, 0.004, 2500, 4),
     ("h2o", "no_renorm_spin", False, False, 0.003, 2500, -1),
     ("h2o", "power_pitzer_occ", False, True, 0.003, 2500, -1),
     ("s12", "cauchy_schwarz_occ", True, False, 0.004, 2500, -1),

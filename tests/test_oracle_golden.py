@@ -118,7 +118,7 @@ def test_ccmc_ccsdt_full_non_composite_np2(fcidump_path):
 
 @pytest.mark.parametrize("gen,nrows", [("hb", 150), ("hb_uni", 150), ("hb_single", 100), ("ppM", 120), ("ppMij", 120),
                                        ("csM", 120), ("csMij", 120), ("renorm", 250), ("no_renorm", 250),
-                                       ("renorm_spin", 250), ("no_renorm_spin", 200)])
+                                       ("renorm_spin", 250), ("no_renorm_spin", 200), ("ppN", 150)])
 def test_ccmc_ccsdt_nh3_np4_excitation_generators(fcidump_path, gen, nrows):
     """test_suite/ccmc_real_64/np4/NH3-6-31g_ccsdt_excit_gens: the reference's one golden trajectory per excitation
     generator (CCSDT, four ranks, real amplitudes) - the pin for heat_bath, heat_bath_uniform, heat_bath_single and the
@@ -127,7 +127,8 @@ def test_ccmc_ccsdt_nh3_np4_excitation_generators(fcidump_path, gen, nrows):
     varies (blocking-on-the-fly with auto_shift_damping then changes the damping); tools/golden_compare.py verified
     every such row: hb 327, hb_uni 460, hb_single 179, ppM 691, ppMij 818, csM 701, csMij 817, renorm 1508,
     no_renorm 1424, renorm_spin 1476 (pattempt_parallel from find_parallel_spin_prob_mol: 0.22360108 in the golden
-    JSON block), no_renorm_spin 373 (pattempt_parallel = 0.22 from the input)."""
+    JSON block), no_renorm_spin 373 (pattempt_parallel = 0.22 from the input), ppN ('heat_bath_power_pitzer_ref' =
+    power_pitzer_orderN) 653."""
     case = "ccmc_nh3_" + gen
     g = load_golden(case)
     assert all(r[1] == 0.0 for r in g["rows"][:nrows + 1])

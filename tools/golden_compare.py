@@ -76,7 +76,7 @@ _NH3 = dict(hb=("heat_bath", 0.002, 10000), hb_uni=("heat_bath_uniform", 0.002, 
             ppMij=("power_pitzer_occ_ij", 0.0015, 14000), csM=("cauchy_schwarz_occ", 0.0015, 14000),
             csMij=("cauchy_schwarz_occ_ij", 0.0015, 14000), no_renorm=("no_renorm", 0.0007, 12000),
             renorm=("renorm", 0.0007, 12000), renorm_spin=("renorm_spin", 0.0007, 11000),
-            no_renorm_spin=("no_renorm_spin", 0.0007, 9000))
+            no_renorm_spin=("no_renorm_spin", 0.0007, 9000), ppN=("power_pitzer_orderN", 0.001, 10000))
 for _k, (_g, _tau, _tp) in _NH3.items():
     CASES["ccmc_nh3_" + _k] = dict(dir="ccmc_real_64/np4/NH3-6-31g_ccsdt_excit_gens",
                                    bench=f"benchmark.out.9712b5a3.inp=nh3.ccsdt.{_k}.in", int_file="INTDUMP",

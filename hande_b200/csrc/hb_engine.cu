@@ -629,15 +629,58 @@ __global__ void k_reduce_ps(const PsPartials* __restrict__ part, int n, double* 
 }
 
 template <int W>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_ccmc_cluster(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states, const int64_t* __restrict__ pops,
                const double* __restrict__ dat, const long long* __restrict__ cum_enc, int64_t* __restrict__ spawn,
                unsigned long long* __restrict__ head, long long block_size, const int* __restrict__ proc_map,
                CcmcPartials* __restrict__ partials, int* __restrict__ err) {
     __shared__ double sd[2][8];
     __shared__ long long sl[2][8];
+    __shared__ unsigned short sperm[256];
+    __shared__ unsigned char swc[8][8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long idx = (long long)blockIdx.x * blockDim.x + tid;
+    // The attempts of a block are dealt to its threads grouped by cluster size (a stable counting sort on the size each
+    // attempt's stream will draw first), so that the lanes of a warp walk select_cluster / collapse_cluster in step:
+    // half of all attempts are the empty cluster, a quarter single excitors, ...  Which thread runs an attempt changes
+    // neither its random stream nor its result.
+    long long idx;
+    {
+        const long long idx0 = (long long)blockIdx.x * blockDim.x + tid;
+        int cls = 7;
+        if (idx0 < a.nattempts) {
+            if (idx0 >= a.nattempts - a.nD0_select) {
+                cls = 0;
+            } else {
+                PhiloxStream r0;
+                r0.begin(p.seed, p.cycle, RNG_SPAWN, det_hash64<W>(p.f0) + (uint64_t)p.iproc * 0x9E3779B97F4A7C15ull,
+                         (uint32_t)(idx0 + 1));
+                const double rand = r0.next();
+                double psize = 0.0;
+                int n = -1;
+                for (int i = 0; i <= a.max_cluster_size - a.min_cluster_size - 1; ++i) {
+                    psize = psize + 1.0 / (double)(1ll << (i + 1));
+                    if (rand < psize) { n = i + a.min_cluster_size; break; }
+                }
+                if (n == -1) n = a.max_cluster_size;
+                cls = min(max(n, 0), 6);
+            }
+        }
+        int rnk = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const unsigned m = __ballot_sync(0xffffffffu, cls == k);
+            if (cls == k) rnk = __popc(m & ((1u << lane) - 1u));
+            if (lane == 0) swc[warp][k] = (unsigned char)__popc(m);
+        }
+        __syncthreads();
+        int base = 0;
+        for (int k = 0; k < cls; ++k)
+            for (int w = 0; w < 8; ++w) base += swc[w][k];
+        for (int w = 0; w < warp; ++w) base += swc[w][cls];
+        sperm[base + rnk] = (unsigned short)tid;
+        __syncthreads();
+        idx = (long long)blockIdx.x * blockDim.x + sperm[tid];
+    }
     double pe = 0.0, d0 = 0.0;
     long long ndeath = 0, nas = 0;
     int64_t nspawn = 0, nkill = 0;

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared():
     hdr = open(os.path.join(ROOT, "include", "hande_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    return sorted(set(re.findall(r"\b(hb200_[a-z0-9_]+)\s*\(", hdr)))
+    return sorted(set(re.findall(r"\b(hb200_[A-Za-z0-9_]+)\s*\(", hdr)))
 
 
 def test_library_exports_every_declared_symbol():

@@ -629,7 +629,7 @@ __global__ void k_reduce_ps(const PsPartials* __restrict__ part, int n, double* 
 }
 
 template <int W>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256)      // 80 registers, 3 blocks/SM: 64 (4 blocks) and 99 (2 blocks) are both ~18 % slower
 k_ccmc_cluster(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states, const int64_t* __restrict__ pops,
                const double* __restrict__ dat, const long long* __restrict__ cum_enc, int64_t* __restrict__ spawn,
                unsigned long long* __restrict__ head, long long block_size, const int* __restrict__ proc_map,

@@ -22,6 +22,7 @@ def main_ccmc():
     from tests.common import system_path
 
     name, gen, real, exl, tau = sys.argv[2], sys.argv[3], bool(int(sys.argv[4])), int(sys.argv[5]), float(sys.argv[6])
+    full_nc = len(sys.argv) > 7 and bool(int(sys.argv[7]))
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
@@ -43,6 +44,8 @@ def main_ccmc():
                  real_amplitudes=real, spawn_cutoff=0.01, trunc_level=exl, walker_length=1 << 17,
                  spawned_walker_length=1 << 16, seed=11, nprocs=world, iproc=rank, device=local)
     eng.set_reference(ref["f0"], ref["H00"])
+    o.ccmc_set_full_nc(full_nc)
+    eng.ccmc_set_full_nc(full_nc)
     uid = eng.get_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)
     eng.comm_init(comm.broadcast_bytes(uid, src=0))
     # warm-up on the oracle (all ranks emulated) to get a spread-out excip list, then hand each GPU its rank's share
@@ -54,6 +57,8 @@ def main_ccmc():
     f, pops, dat = o.get_psips(rank)
     eng.upload_psips(f, pops, dat)
     eng.ccmc_set_hash_shift(o.ccmc_hash_shift(), 5)
+    o.set_pattempt_update(True)           # pattempt_update statistics, per rank
+    eng.set_pattempt(ref["pattempt_single"], ref["pattempt_double"], True)
     ntot = 0
     for c in range(warm + 1, warm + 9):
         o.ccmc_stage_spawn(c, tau, -0.01, -0.1)
@@ -66,6 +71,8 @@ def main_ccmc():
         assert (fg == fo).all() and (pg == po).all() and (dg == do_).all(), (rank, c)
         ntot = comm.allreduce_sum(np.array([float(len(fg))]))[0]
     assert ntot > 50
+    a, b = eng.get_ps_stats(), o.ps_stats(rank)
+    assert a[1] == b[1] and a[3] == b[3] and abs(a[0] - b[0]) <= 1e-12 * abs(b[0]) and abs(a[2] - b[2]) <= 1e-12 * abs(b[2])
     print(f"rank {rank}: OK {len(fg)} states of {int(ntot)}", flush=True)
     eng.close()
     dist.destroy_process_group()
@@ -100,10 +107,15 @@ def main():
     ref = o.reference()
     eng = Engine(s, excit_gen=gen, pattempt_single=ref["pattempt_single"], pattempt_double=ref["pattempt_double"],
                  real_amplitudes=real, spawn_cutoff=0.01, initiator_approx=init, walker_length=1 << 17,
-                 spawned_walker_length=1 << 16, seed=11, nprocs=world, iproc=rank, device=local)
+                 spawned_walker_length=1 << 16, seed=11, nprocs=world, iproc=rank, device=local,
+                 pattempt_parallel=(o.pattempt_parallel() if gen.endswith("_spin") else -1.0))
     eng.set_reference(ref["f0"], ref["H00"])
     uid = eng.get_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)
     eng.comm_init(comm.broadcast_bytes(uid, src=0))
+    ps_on = gen != "heat_bath"
+    if ps_on:
+        o.set_pattempt_update(True)
+        eng.set_pattempt(ref["pattempt_single"], ref["pattempt_double"], True)
     f, pops, dat = random_population(s, o, 4000, real, seed=5)
     own = np.array([owner_of(x, s.nbasis, world, 1) for x in f])
     for r in range(world):
@@ -126,6 +138,9 @@ def main():
         assert abs(tot[0] - ro["proj_energy"]) <= 1e-12 * max(1.0, abs(ro["proj_energy"]))
         assert abs(tot[1] - ro["D0_population"]) <= 1e-12 * max(1.0, abs(ro["D0_population"]))
         assert tot[2] == ro["nspawn_events"] and tot[3] == ro["ndeath"] and tot[4] == ro["nstates"]
+    if ps_on:
+        a, b = eng.get_ps_stats(), o.ps_stats(rank)
+        assert a[1] == b[1] and a[3] == b[3] and abs(a[0] - b[0]) <= 1e-12 * abs(b[0]) and abs(a[2] - b[2]) <= 1e-12 * abs(b[2])
     print(f"rank {rank}: OK {len(fg)} states", flush=True)
     eng.close()
     dist.destroy_process_group()

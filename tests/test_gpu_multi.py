@@ -17,7 +17,9 @@ def _ngpu():
         return 0
 
 
-@pytest.mark.parametrize("name,gen,real,init,tau", [("h2o", "renorm", 0, 0, 0.003), ("s12", "heat_bath", 1, 1, 0.004)])
+@pytest.mark.parametrize("name,gen,real,init,tau", [("h2o", "renorm", 0, 0, 0.003), ("s12", "heat_bath", 1, 1, 0.004),
+                                                     ("nh3", "power_pitzer_orderN", 1, 1, 0.002),
+                                                     ("nh3", "renorm_spin", 1, 0, 0.002)])
 def test_two_rank_parity(name, gen, real, init, tau):
     n = _ngpu()
     if n < 2:
@@ -31,8 +33,9 @@ def test_two_rank_parity(name, gen, real, init, tau):
     assert res.stdout.count("OK") == nproc
 
 
-@pytest.mark.parametrize("name,gen,real,exl,tau", [("ne_vdz", "renorm", 0, 2, 0.01), ("s12", "renorm", 1, 3, 0.001)])
-def test_multi_rank_ccmc_parity(name, gen, real, exl, tau):
+@pytest.mark.parametrize("name,gen,real,exl,tau,full_nc", [("ne_vdz", "renorm", 0, 2, 0.01, 0), ("s12", "renorm", 1, 3, 0.001, 0),
+                                                           ("nh3", "heat_bath_uniform", 1, 3, 0.002, 1)])
+def test_multi_rank_ccmc_parity(name, gen, real, exl, tau, full_nc):
     """CCMC on 2 (or 4) GPUs: time-varying hash owner, redistribute_particles and the reference broadcast against the
     oracle's emulated ranks (which reproduce the reference's np2 CCMC golden table)."""
     n = _ngpu()
@@ -41,7 +44,7 @@ def test_multi_rank_ccmc_parity(name, gen, real, exl, tau):
     nproc = 4 if n >= 4 else 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", "29535", os.path.join(ROOT, "tests", "multi_gpu_worker.py"),
-           "ccmc", name, gen, str(real), str(exl), str(tau)]
+           "ccmc", name, gen, str(real), str(exl), str(tau), str(full_nc)]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert res.stdout.count("OK") == nproc

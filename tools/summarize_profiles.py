@@ -131,6 +131,43 @@ if os.path.exists(rep) or os.path.exists(rawcsv):
                             capture_output=True, text=True).stdout
         out.append("## k_spawn_death: instruction / stall-sample share by source line (tools/ncu_by_line.py)\n\n```\n" + bl + "```\n")
 
+# ---- CCMC cluster kernel (tools/gpu_prof_ccmc.sh): before / after grouping a block's attempts by cluster size
+ccmc_rows = []
+for lab, fn in (("one thread per attempt in index order", "raw_ccmc_a.csv"),
+                ("attempts of a block grouped by cluster size (final)", "raw_ccmc_b.csv")):
+    pth = os.path.join(G, fn)
+    if not os.path.exists(pth):
+        pth = os.path.join(P, f"{tag}_ncu_" + fn.replace("raw_", ""))
+    if not os.path.exists(pth):
+        continue
+    rows = list(csv.reader(open(pth).read().splitlines()))
+    hdr = rows[0]
+    rr = rows[2]
+    want = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "smsp__inst_executed.sum",
+            "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__warps_active.avg.pct_of_peak_sustained_active",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "dram__bytes_read.sum",
+            "lts__t_sector_hit_rate.pct"]
+    keep = [hdr.index(w) for w in want if w in hdr]
+    with open(os.path.join(P, f"{tag}_ncu_" + fn.replace("raw_", "")), "w", newline="") as f:
+        wtr = csv.writer(f)
+        for r3 in rows[:3]:
+            wtr.writerow([r3[i] for i in keep])
+
+    def g(name):
+        try:
+            return float(rr[hdr.index(name)])
+        except Exception:
+            return float("nan")
+    natt = g("launch__grid_size") * 256
+    ccmc_rows.append(f"| {lab} | {natt:.3g} | {g('gpu__time_duration.sum'):.2f} | {g('smsp__inst_executed.sum') / natt:.0f} | "
+                     f"{g('smsp__thread_inst_executed_per_inst_executed.ratio'):.1f} | "
+                     f"{g('sm__warps_active.avg.pct_of_peak_sustained_active'):.0f} | {g('launch__registers_per_thread'):.0f} |")
+if ccmc_rows:
+    out.append("## k_ccmc_cluster (CCSDT, S40; ncu --set full of one launch, `%s_ncu_ccmc_*.csv`)\n" % tag)
+    out.append("| version | attempts in the launch | ms (under ncu) | warp-inst per attempt | lanes/inst | warps active % | regs |\n|---|---|---|---|---|---|---|")
+    out += ccmc_rows
+    out.append("")
+
 # ---- side measurements committed next to the headline line
 side = sorted(f for f in os.listdir(P) if f.startswith(f"{tag}_bench_") and f.endswith(".json") and "reference" not in f)
 if side:

@@ -156,7 +156,7 @@ def main():
     ap.add_argument("--impl", default="engine")
     ap.add_argument("--walkers", type=float, default=1e8, help="walkers (= occupied determinants) per GPU")
     ap.add_argument("--tau", type=float, default=0.0, help="0 => calibrate for R_spawn ~ 0.05")
-    ap.add_argument("--excit-gen", default="heat_bath", choices=["heat_bath", "heat_bath_uniform", "heat_bath_single", "power_pitzer_orderN", "renorm", "renorm_spin", "no_renorm_spin", "no_renorm", "power_pitzer_occ",
+    ap.add_argument("--excit-gen", default="heat_bath", choices=["heat_bath", "heat_bath_uniform", "heat_bath_single", "power_pitzer_orderN", "power_pitzer", "renorm", "renorm_spin", "no_renorm_spin", "no_renorm", "power_pitzer_occ",
                                                               "cauchy_schwarz_occ", "power_pitzer_occ_ij", "cauchy_schwarz_occ_ij"],
                     help="excitation generator (headline = heat_bath, BASELINE.json configs[1]; others are side measurements)")
     ap.add_argument("--system", default="s50", choices=["s50", "ueg"],

@@ -92,6 +92,11 @@ struct Sys {
     // with i = 0..nbasis (column 0 unused)
     struct AliasTab { const double* w; const double* U; const int* K; const double* tot; } ppn[6];
     const int* ppn_occ;         // the reference's occupied orbitals, ascending
+    // power_pitzer tables (pp_ia_d (max nvirt per spin, nel), pp_jb_d (max_nbss, sym, nel)) and the reference's virtual
+    // orbitals per spin ([0] beta, [1] alpha), ascending
+    AliasTab pp_ia, pp_jb;
+    const int* pp_virt[2];
+    int pp_nvirt[2], pp_sia;
     // uniform electron gas (src/ueg.f90, src/ueg_types.f90): plane-wave basis, analytic integrals
     const K4* ueg_k;            // [nbasis+1] wavevectors in units of 2 pi / L
     const double* sp_eigv;      // [nbasis+1] kinetic energies
@@ -129,7 +134,7 @@ struct PsPartials { double h_pgen_singles_sum, h_pgen_doubles_sum; long long exc
 // the reference's enumerator values (src/qmc_data.f90:31-69: renorm, renorm_spin, no_renorm, no_renorm_spin, power_pitzer,
 // power_pitzer_occ, power_pitzer_occ_ij, power_pitzer_orderN, cauchy_schwarz_occ, cauchy_schwarz_occ_ij, heat_bath,
 // heat_bath_uniform, heat_bath_single)
-enum { EXCIT_GEN_RENORM = 0, EXCIT_GEN_RENORM_SPIN = 1, EXCIT_GEN_NO_RENORM = 2, EXCIT_GEN_NO_RENORM_SPIN = 3, EXCIT_GEN_POWER_PITZER_OCC = 5, EXCIT_GEN_POWER_PITZER_OCC_IJ = 6,
+enum { EXCIT_GEN_RENORM = 0, EXCIT_GEN_RENORM_SPIN = 1, EXCIT_GEN_NO_RENORM = 2, EXCIT_GEN_NO_RENORM_SPIN = 3, EXCIT_GEN_POWER_PITZER = 4, EXCIT_GEN_POWER_PITZER_OCC = 5, EXCIT_GEN_POWER_PITZER_OCC_IJ = 6,
        EXCIT_GEN_POWER_PITZER_ORDERN = 7,
        EXCIT_GEN_CAUCHY_SCHWARZ_OCC = 8, EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ = 9,
        EXCIT_GEN_HEAT_BATH = 10, EXCIT_GEN_HEAT_BATH_UNIFORM = 11, EXCIT_GEN_HEAT_BATH_SINGLE = 12 };
@@ -1441,10 +1446,9 @@ HB_HDN void gen_excit_power_pitzer_occ(R& rng, const Sys& s, const Params& p, co
 // through the mapping reference orbital -> orbital of this determinant.
 // ------------------------------------------------------------------------------------------------
 // get_excitation_locations (src/excitations.F90) + find_diff_ref_cdet (src/excit_gen_utils.f90:220-269)
-HB_HDN void find_diff_ref_cdet(const Sys& s, const uint8_t* occ, uint8_t* ref_cdet) {
+HB_HDN int ref_cdet_locations(const Sys& s, const uint8_t* occ, uint8_t* ref_store, uint8_t* det_store) {
     const int nel = s.nel;
     const int* ref_list = s.ppn_occ;
-    uint8_t ref_store[HB_MAXNEL], det_store[HB_MAXNEL];
     int j = 1, det_sind = 0, ref_sind = 0;
     bool done = false;
     for (int i = 1; i <= nel && !done; ++i) {
@@ -1465,14 +1469,119 @@ HB_HDN void find_diff_ref_cdet(const Sys& s, const uint8_t* occ, uint8_t* ref_cd
         i_back--; i_back_pos--; ref_sind++;
     }
     const int nex = ref_sind;
-    for (int k = 0; k < nel; ++k) ref_cdet[k] = (uint8_t)ref_list[k];
-    for (int ii = 0; ii < nex; ++ii) {
+    for (int ii = 0; ii < nex; ++ii) {     // pair every differing reference orbital with a determinant orbital of its spin
         if (ms_of(ref_list[ref_store[ii] - 1]) != ms_of(occ[det_store[ii] - 1])) {
             int jj = ii + 1;
             while (ms_of(ref_list[ref_store[ii] - 1]) != ms_of(occ[det_store[jj] - 1])) jj++;
             const uint8_t t = det_store[ii]; det_store[ii] = det_store[jj]; det_store[jj] = t;
         }
-        ref_cdet[ref_store[ii] - 1] = occ[det_store[ii] - 1];
+    }
+    return nex;
+}
+HB_HDN void find_diff_ref_cdet(const Sys& s, const uint8_t* occ, uint8_t* ref_cdet) {
+    uint8_t ref_store[HB_MAXNEL], det_store[HB_MAXNEL];
+    const int nex = ref_cdet_locations(s, occ, ref_store, det_store);
+    for (int k = 0; k < s.nel; ++k) ref_cdet[k] = (uint8_t)s.ppn_occ[k];
+    for (int ii = 0; ii < nex; ++ii) ref_cdet[ref_store[ii] - 1] = occ[det_store[ii] - 1];
+}
+// gen_excit_mol_power_pitzer_occ_ref (src/excit_gen_power_pitzer_mol.F90:650-939), excit_gen = power_pitzer: ij uniform
+// among the reference's occupied orbitals, a and b from the reference's alias tables, mapped onto this determinant
+template <int W, class R>
+HB_HDN void gen_excit_power_pitzer_ref(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ, Gen& g) {
+    const int nel = s.nel, mv = s.max_nbss, nsym = s.nsym_tot;
+    g.from1 = 0; g.from2 = 0; g.to1 = 0; g.to2 = 0; g.perm = false;
+    if (rng.next() < p.pattempt_single) {     // gen_single_excit_mol_no_renorm (src/excit_gen_mol.f90:450-517)
+        g.nexcit = 1;
+        const int i = occ[(int)(rng.next() * nel)];
+        const int imsa = ims_of(i);
+        const int isyma = cross_product(s, s.bf_sym[i], s.gamma_sym);
+        const int n = nbss(s, imsa, isyma);
+        const int ind = (int)(n * rng.next()) + 1;
+        g.from1 = i;
+        int a = 0;
+        if (n == 0) g.allowed = false;
+        else { a = ssbf(s, ind, imsa, isyma); g.allowed = !det_test(f, a); }
+        if (g.allowed) {
+            g.to1 = a;
+            g.pgen = p.pattempt_single * (1.0 / (nel * nbss(s, ims_of(a), s.bf_sym[a])));
+            g.perm = excit_perm1<W>(f, i, a);
+            g.hmatel = slater_condon1_excit(s, occ, i, a, g.perm);
+        } else { g.hmatel = 0.0; g.pgen = 1.0; }
+        return;
+    }
+    g.nexcit = 2;
+    const int ind = (int)(rng.next() * nel * (nel - 1) / 2) + 1;
+    const int j_ind = (int)(1.50 + sqrt(2 * ind - 1.750));
+    const int i_ind = ind - ((j_ind - 1) * (j_ind - 2)) / 2;
+    const double pgen_ij = 2.0 / (nel * (nel - 1));
+    const int i_ref = s.ppn_occ[i_ind - 1], j_ref = s.ppn_occ[j_ind - 1];
+    const int ij_spin = ms_of(i_ref) + ms_of(j_ref);
+    const int sp = (ms_of(i_ref) < 0) ? 0 : 1;
+    const int nv = s.pp_nvirt[sp];
+    const int* virt = s.pp_virt[sp];
+    const size_t sia = (size_t)s.pp_sia;
+    bool a_found = false;
+    int a_ind = 0, a_ref = 0;
+    if (nv > 0) {
+        a_ind = select_precalc(rng, nv, s.pp_ia.U + sia * (i_ind - 1), s.pp_ia.K + sia * (i_ind - 1));
+        a_ref = virt[a_ind - 1];
+        a_found = true;
+    }
+    uint8_t ref_store[HB_MAXNEL], det_store[HB_MAXNEL];
+    int nex = 0, i = i_ref, j = j_ref, a = a_ref, ij_sym = 0, isymb = 0, imsb = 1;
+    if (a_found) {
+        nex = ref_cdet_locations(s, occ, ref_store, det_store);
+        for (int ii = 0; ii < nex; ++ii) {
+            if (ref_store[ii] == i_ind) i = occ[det_store[ii] - 1];
+            else if (ref_store[ii] == j_ind) j = occ[det_store[ii] - 1];
+            if ((int)occ[det_store[ii] - 1] == a_ref) a = s.ppn_occ[ref_store[ii] - 1];
+        }
+        ij_sym = sym_conj(s, cross_product(s, s.bf_sym[i], s.bf_sym[j]));
+        isymb = sym_conj(s, cross_product(s, ij_sym, s.bf_sym[a]));
+        imsb = ims_of(j_ref);
+    }
+    g.allowed = false;
+    int b = 0;
+    if (a_found && nbss(s, imsb, isymb) > 0) {
+        const size_t colb = (size_t)isymb + (size_t)nsym * (j_ind - 1);
+        const int b_ind = select_precalc(rng, nbss(s, imsb, isymb), s.pp_jb.U + (size_t)mv * colb, s.pp_jb.K + (size_t)mv * colb);
+        b = ssbf(s, b_ind, imsb, isymb);
+        if (a != b && !det_test(f, b)) {
+            double pgen;
+            const double pa = s.pp_ia.w[sia * (i_ind - 1) + a_ind - 1] / s.pp_ia.tot[i_ind - 1];
+            if (ij_spin == 0) {
+                pgen = pa * s.pp_jb.w[(size_t)mv * colb + b_ind - 1] / s.pp_jb.tot[colb];
+            } else {
+                int b_ref = b;
+                for (int ii = 0; ii < nex; ++ii)
+                    if (s.ppn_occ[ref_store[ii] - 1] == b) { b_ref = occ[det_store[ii] - 1]; break; }
+                int b_rev = 0;
+                for (int lo = 1, hi = nv; lo <= hi;) {      // binary_search in virt_list_{alpha,beta}
+                    const int mid = (lo + hi) / 2;
+                    if (virt[mid - 1] == b_ref) { b_rev = mid; break; }
+                    if (virt[mid - 1] < b_ref) lo = mid + 1; else hi = mid - 1;
+                }
+                const int isyma = sym_conj(s, cross_product(s, ij_sym, isymb));
+                int a_rev = 0;
+                const int na = nbss(s, imsb, isyma);
+                for (int k = 1; k <= na; ++k)
+                    if (ssbf(s, k, imsb, isyma) == a) { a_rev = k; break; }
+                const size_t cola = (size_t)isyma + (size_t)nsym * (j_ind - 1);
+                pgen = pa * s.pp_jb.w[(size_t)mv * colb + b_ind - 1] / s.pp_jb.tot[colb] +
+                       s.pp_ia.w[sia * (i_ind - 1) + b_rev - 1] / s.pp_ia.tot[i_ind - 1] *
+                           s.pp_jb.w[(size_t)mv * cola + a_rev - 1] / s.pp_jb.tot[cola];
+            }
+            g.pgen = p.pattempt_double * pgen * pgen_ij;
+            g.allowed = true;
+        }
+    }
+    if (g.allowed) {
+        g.from1 = (i < j) ? i : j; g.from2 = (i < j) ? j : i;
+        g.to1 = (a < b) ? a : b; g.to2 = (a < b) ? b : a;
+        g.perm = excit_perm2<W>(f, g.from1, g.from2, g.to1, g.to2);
+        g.hmatel = slater_condon2_excit(s, g.from1, g.from2, g.to1, g.to2, g.perm);
+    } else {
+        g.hmatel = 0.0; g.pgen = 1.0;
     }
 }
 // gen_excit_mol_power_pitzer_orderN (src/excit_gen_power_pitzer_mol.F90:941-1258)
@@ -1684,6 +1793,7 @@ HB_HD void gen_excit(R& rng, const Sys& s, const Params& p, const uint64_t* f, c
     if (s.kind == SYS_UEG) gen_excit_ueg_no_renorm<W>(rng, s, f, occ, g);
     else if (p.excit_gen == EXCIT_GEN_RENORM) gen_excit_renorm<W>(rng, s, p, f, occ, su, g);
     else if (p.excit_gen == EXCIT_GEN_NO_RENORM) gen_excit_no_renorm<W>(rng, s, p, f, occ, g);
+    else if (p.excit_gen == EXCIT_GEN_POWER_PITZER) gen_excit_power_pitzer_ref<W>(rng, s, p, f, occ, g);
     else if (p.excit_gen == EXCIT_GEN_POWER_PITZER_ORDERN) {
         uint8_t ref_cdet[HB_MAXNEL];
         find_diff_ref_cdet(s, occ, ref_cdet);

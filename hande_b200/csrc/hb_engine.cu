@@ -459,6 +459,7 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
                 gen_excit_power_pitzer_occ<W>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, siw, sw + tid, TILE, g);
             else if (GEN == EXCIT_GEN_RENORM) gen_excit_renorm<W>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, g);
             else if (GEN == EXCIT_GEN_RENORM_SPIN) gen_excit_renorm<W, true>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, g);
+            else if (GEN == EXCIT_GEN_POWER_PITZER) gen_excit_power_pitzer_ref<W>(rng, s, p, f, socc + lo * nel, g);
             else if (GEN == EXCIT_GEN_POWER_PITZER_ORDERN)     // ssu holds ref_cdet_occ_list of each state (nsu = nel)
                 gen_excit_power_pitzer_orderN<W>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, g);
             else if (GEN == EXCIT_GEN_NO_RENORM_SPIN) gen_excit_no_renorm<W, true>(rng, s, p, f, socc + lo * nel, g);
@@ -1575,7 +1576,7 @@ struct hb200_engine {
     cudaStream_t stream = nullptr;
     Sys sys;
     Params par;
-    bool have_sys = false, have_hb = false, have_ref = false, have_ppn = false;
+    bool have_sys = false, have_hb = false, have_ref = false, have_ppn = false, have_pp = false;
     // owned device buffers for system tables
     std::vector<void*> owned;
     int* d_proc_map = nullptr;
@@ -1674,7 +1675,7 @@ static bool uses_heat_bath_tables(const hb200_engine* e) {
 static size_t spawn_smem_bytes(const hb200_engine* e) {
     const int eg = e->cfg.excit_gen;
     const int nsu = (eg == HB200_EXCIT_GEN_POWER_PITZER_ORDERN) ? e->sys.nel :
-                    (e->sys.kind == SYS_READ_IN && eg != HB200_EXCIT_GEN_NO_RENORM && eg != HB200_EXCIT_GEN_NO_RENORM_SPIN &&
+                    (e->sys.kind == SYS_READ_IN && eg != HB200_EXCIT_GEN_POWER_PITZER && eg != HB200_EXCIT_GEN_NO_RENORM && eg != HB200_EXCIT_GEN_NO_RENORM_SPIN &&
                      eg != HB200_EXCIT_GEN_HEAT_BATH &&
                      eg != HB200_EXCIT_GEN_HEAT_BATH_SINGLE)
                         ? 2 * e->sys.nsym_tot : 0;
@@ -2108,6 +2109,93 @@ int hb200_build_power_pitzer_orderN(hb200_engine* e, double min_weight) {
     return 0;
 }
 
+// power_pitzer tables (init_excit_mol_power_pitzer_occ_ref, src/excit_gen_power_pitzer_mol.F90:19-138): weights over the
+// reference's virtual orbitals (pp_ia_d) and over each symmetry class (pp_jb_d) for every reference electron
+struct PpBuild { double* w[2]; double* U[2]; int* K[2]; double* tot[2]; const int* occ; const int* virt[2]; int nvirt[2];
+                 int sia; double min_weight; };
+__global__ void k_pp_weights(Sys s, PpBuild t) {
+    const int nel = s.nel, mv = s.max_nbss, nsym = s.nsym_tot;
+    long long job = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nA = (long long)nel * t.sia, nB = (long long)nel * nsym * mv;
+    if (job < nA) {
+        const int i = (int)(job / t.sia), k = (int)(job % t.sia);
+        const int oj = t.occ[i], sp = (ms_of(oj) < 0) ? 0 : 1;
+        t.w[0][job] = (k < t.nvirt[sp]) ? pp_weight(s, false, oj, t.virt[sp][k]) : 0.0;
+        return;
+    }
+    job -= nA;
+    if (job < nB) {
+        const int i = (int)(job / ((long long)nsym * mv)), bsym = (int)((job / mv) % nsym), k = (int)(job % mv) + 1;
+        const int oj = t.occ[i], ims = ims_of(oj);
+        t.w[1][job] = (k <= nbss(s, ims, bsym)) ? pp_weight(s, false, oj, ssbf(s, k, ims, bsym)) : 0.0;
+    }
+}
+__global__ void k_pp_alias(Sys s, PpBuild t) {
+    const int nel = s.nel, mv = s.max_nbss, nsym = s.nsym_tot;
+    long long job = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int which, n;
+    size_t col, stride;
+    if (job < nel) {
+        which = 0; col = (size_t)job; stride = t.sia; n = t.nvirt[(ms_of(t.occ[job]) < 0) ? 0 : 1];
+    } else if ((job -= nel) < (long long)nel * nsym) {
+        const int i = (int)(job / nsym), bsym = (int)(job % nsym);
+        which = 1; col = (size_t)job; stride = mv; n = nbss(s, ims_of(t.occ[i]), bsym);
+    } else return;
+    if (n <= 0) return;
+    double* w = t.w[which] + stride * col;
+    double tot = 0.0;
+    for (int k = 0; k < n; ++k) tot = tot + w[k];
+    ppn_check_min_weight_ratio(w, tot, n, t.min_weight);
+    t.tot[which][col] = tot;
+    int under[HB_MAXLIST], over[HB_MAXLIST];
+    generate_alias_tables(n, w, tot, t.U[which] + stride * col, t.K[which] + stride * col, under, over);
+}
+int hb200_build_power_pitzer(hb200_engine* e, double min_weight) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (!e->have_sys || e->sys.kind != SYS_READ_IN) FAIL("build_power_pitzer: needs a read_in system");
+    if (!e->have_ref) FAIL("build_power_pitzer: reference not set (call hb200_set_reference first)");
+    Sys& s = e->sys;
+    const int nel = s.nel, nb = s.nbasis, mv = s.max_nbss, nsym = s.nsym_tot;
+    std::vector<int> occ0, virt[2];
+    for (int o = 1; o <= nb; ++o) {
+        if ((e->par.f0[(o - 1) >> 6] >> ((o - 1) & 63)) & 1ull) occ0.push_back(o);
+        else virt[(o & 1) ? 1 : 0].push_back(o);          // odd orbitals are alpha (ms = +1)
+    }
+    if ((int)occ0.size() != nel) FAIL("build_power_pitzer: reference does not have nel electrons");
+    const int sia = std::max<int>(1, (int)std::max(virt[0].size(), virt[1].size()));
+    if (sia > HB_MAXLIST || mv > HB_MAXLIST) FAIL("build_power_pitzer: basis too large");
+    PpBuild t;
+    cudaStream_t st = e->stream;
+    const size_t len[2] = {(size_t)nel * sia, (size_t)nel * nsym * mv}, ncol[2] = {(size_t)nel, (size_t)nel * nsym};
+    for (int k = 0; k < 2; ++k) {
+        if (dalloc(e, &t.w[k], len[k]) || dalloc(e, &t.U[k], len[k]) || dalloc(e, &t.K[k], len[k]) || dalloc(e, &t.tot[k], ncol[k]))
+            return 1;
+        CK(cudaMemsetAsync(t.U[k], 0, len[k] * sizeof(double), st));
+        CK(cudaMemsetAsync(t.K[k], 0, len[k] * sizeof(int), st));
+        CK(cudaMemsetAsync(t.tot[k], 0, ncol[k] * sizeof(double), st));
+    }
+    int *d_occ = nullptr, *d_virt[2] = {nullptr, nullptr};
+    if (dalloc(e, &d_occ, (size_t)nel) || dalloc(e, &d_virt[0], virt[0].size()) || dalloc(e, &d_virt[1], virt[1].size())) return 1;
+    CK(cudaMemcpyAsync(d_occ, occ0.data(), sizeof(int) * nel, cudaMemcpyHostToDevice, st));
+    for (int k = 0; k < 2; ++k)
+        if (!virt[k].empty()) CK(cudaMemcpyAsync(d_virt[k], virt[k].data(), sizeof(int) * virt[k].size(), cudaMemcpyHostToDevice, st));
+    t.occ = d_occ; t.virt[0] = d_virt[0]; t.virt[1] = d_virt[1];
+    t.nvirt[0] = (int)virt[0].size(); t.nvirt[1] = (int)virt[1].size();
+    t.sia = sia; t.min_weight = min_weight;
+    const long long njobs = (long long)(len[0] + len[1]);
+    k_pp_weights<<<(unsigned)((njobs + 127) / 128), 128, 0, st>>>(s, t);
+    const long long ncols = (long long)(ncol[0] + ncol[1]);
+    k_pp_alias<<<(unsigned)((ncols + 63) / 64), 64, 0, st>>>(s, t);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    s.pp_ia.w = t.w[0]; s.pp_ia.U = t.U[0]; s.pp_ia.K = t.K[0]; s.pp_ia.tot = t.tot[0];
+    s.pp_jb.w = t.w[1]; s.pp_jb.U = t.U[1]; s.pp_jb.K = t.K[1]; s.pp_jb.tot = t.tot[1];
+    s.pp_virt[0] = d_virt[0]; s.pp_virt[1] = d_virt[1]; s.pp_nvirt[0] = t.nvirt[0]; s.pp_nvirt[1] = t.nvirt[1]; s.pp_sia = sia;
+    s.ppn_occ = d_occ;
+    e->have_pp = true;
+    return 0;
+}
+
 int hb200_download_heat_bath(hb200_engine* e, int which, void* out, int64_t n) {
     CK(cudaSetDevice(e->cfg.device));
     if (!e->have_hb) FAIL("heat-bath tables not built");
@@ -2263,6 +2351,7 @@ static int stage_spawn_death(hb200_engine* e, const hb200_iter_in* in, uint32_t 
             case HB200_EXCIT_GEN_RENORM: LAUNCH_SPAWN(EXCIT_GEN_RENORM); break;
             case HB200_EXCIT_GEN_RENORM_SPIN: LAUNCH_SPAWN(EXCIT_GEN_RENORM_SPIN); break;
             case HB200_EXCIT_GEN_POWER_PITZER_ORDERN: LAUNCH_SPAWN(EXCIT_GEN_POWER_PITZER_ORDERN); break;
+            case HB200_EXCIT_GEN_POWER_PITZER: LAUNCH_SPAWN(EXCIT_GEN_POWER_PITZER); break;
             case HB200_EXCIT_GEN_NO_RENORM_SPIN: LAUNCH_SPAWN(EXCIT_GEN_NO_RENORM_SPIN); break;
             case HB200_EXCIT_GEN_HEAT_BATH: LAUNCH_SPAWN(EXCIT_GEN_HEAT_BATH); break;
             case HB200_EXCIT_GEN_HEAT_BATH_UNIFORM: LAUNCH_SPAWN(EXCIT_GEN_HEAT_BATH_UNIFORM); break;
@@ -2479,6 +2568,7 @@ int hb200_spawn_death(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, 
     if (!e->have_sys) FAIL("spawn_death: system not set");
     if (uses_heat_bath_tables(e) && !e->have_hb) FAIL("spawn_death: heat-bath tables not built");
     if (e->cfg.excit_gen == HB200_EXCIT_GEN_POWER_PITZER_ORDERN && !e->have_ppn) FAIL("spawn_death: power_pitzer_orderN tables not built");
+    if (e->cfg.excit_gen == HB200_EXCIT_GEN_POWER_PITZER && !e->have_pp) FAIL("spawn_death: power_pitzer tables not built");
     CycleStats st;
     memset(&st, 0, sizeof(st));
     const long long nattempts = llround(2.0 * ((double)e->nparticles_enc / (double)e->par.real_factor));
@@ -2503,6 +2593,7 @@ int hb200_ccmc_spawn(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, i
     if (!e->have_sys) FAIL("ccmc_spawn: system not set");
     if (uses_heat_bath_tables(e) && !e->have_hb) FAIL("ccmc_spawn: heat-bath tables not built");
     if (e->cfg.excit_gen == HB200_EXCIT_GEN_POWER_PITZER_ORDERN && !e->have_ppn) FAIL("ccmc_spawn: power_pitzer_orderN tables not built");
+    if (e->cfg.excit_gen == HB200_EXCIT_GEN_POWER_PITZER && !e->have_pp) FAIL("ccmc_spawn: power_pitzer tables not built");
     if (e->par.nprocs > 1 && !e->comm) FAIL("ccmc_spawn: nprocs > 1 but hb200_comm_init was not called");
     if (e->cfg.initiator_approx) FAIL("ccmc_spawn: the initiator approximation is not implemented for CCMC");
     Params& p = e->par;
@@ -2843,6 +2934,7 @@ int hb200_iterate(hb200_engine* e, int32_t ncycles, const hb200_iter_in* in, hb2
     if (!e->have_sys) FAIL("iterate: system not set");
     if (uses_heat_bath_tables(e) && !e->have_hb) FAIL("iterate: heat-bath tables not built");
     if (e->cfg.excit_gen == HB200_EXCIT_GEN_POWER_PITZER_ORDERN && !e->have_ppn) FAIL("iterate: power_pitzer_orderN tables not built");
+    if (e->cfg.excit_gen == HB200_EXCIT_GEN_POWER_PITZER && !e->have_pp) FAIL("iterate: power_pitzer tables not built");
     memset(out, 0, sizeof(*out));
     cudaStream_t st = e->stream;
     float acc[4] = {0, 0, 0, 0};
@@ -2912,6 +3004,7 @@ int hb200_gen_excit_batch(hb200_engine* e, const uint64_t* states, const int64_t
     CK(cudaSetDevice(e->cfg.device));
     if (!e->have_sys) FAIL("gen_excit_batch: system not set");
     if (e->cfg.excit_gen == HB200_EXCIT_GEN_POWER_PITZER_ORDERN && !e->have_ppn) FAIL("gen_excit_batch: power_pitzer_orderN tables not built");
+    if (e->cfg.excit_gen == HB200_EXCIT_GEN_POWER_PITZER && !e->have_pp) FAIL("gen_excit_batch: power_pitzer tables not built");
     if (n == 0) return 0;
     Params p = e->par;
     p.cycle = cycle; p.tau = tau;

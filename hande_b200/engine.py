@@ -12,7 +12,7 @@ import numpy as np
 from . import build as _build
 
 # values of the reference's excit_gen enumerators (src/qmc_data.f90:31-69)
-EXCIT_GEN = {"renorm": 0, "renorm_spin": 1, "no_renorm": 2, "no_renorm_spin": 3, "power_pitzer_occ": 5, "power_pitzer_occ_ij": 6, "power_pitzer_orderN": 7, "cauchy_schwarz_occ": 8,
+EXCIT_GEN = {"renorm": 0, "renorm_spin": 1, "no_renorm": 2, "no_renorm_spin": 3, "power_pitzer": 4, "power_pitzer_occ": 5, "power_pitzer_occ_ij": 6, "power_pitzer_orderN": 7, "cauchy_schwarz_occ": 8,
              "cauchy_schwarz_occ_ij": 9, "heat_bath": 10, "heat_bath_uniform": 11, "heat_bath_single": 12}
 
 
@@ -138,6 +138,7 @@ def load_library():
     L.hb200_set_pattempt.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int32]
     L.hb200_get_ps_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
     L.hb200_build_power_pitzer_orderN.argtypes = [C.c_void_p, C.c_double]
+    L.hb200_build_power_pitzer.argtypes = [C.c_void_p, C.c_double]
     L.hb200_set_pattempt_parallel.argtypes = [C.c_void_p, C.c_double]
     L.hb200_get_pattempt_parallel.argtypes = [C.c_void_p]
     L.hb200_get_pattempt_parallel.restype = C.c_double
@@ -162,7 +163,7 @@ ABI_SYMBOLS = [
     "hb200_download_heat_bath", "hb200_set_reference", "hb200_set_proc_map", "hb200_upload_psips",
     "hb200_upload_psips_begin", "hb200_upload_psips_commit",
     "hb200_download_psips", "hb200_nstates", "hb200_iterate", "hb200_spawn_death", "hb200_comm_spawn",
-    "hb200_ccmc_spawn", "hb200_ccmc_iterate", "hb200_ccmc_set_hash_shift", "hb200_ccmc_set_full_nc", "hb200_set_pattempt", "hb200_get_ps_stats", "hb200_set_pattempt_parallel", "hb200_get_pattempt_parallel", "hb200_build_power_pitzer_orderN", "hb200_annihilate_spawn", "hb200_annihilate_main", "hb200_download_spawn", "hb200_upload_spawn",
+    "hb200_ccmc_spawn", "hb200_ccmc_iterate", "hb200_ccmc_set_hash_shift", "hb200_ccmc_set_full_nc", "hb200_set_pattempt", "hb200_get_ps_stats", "hb200_set_pattempt_parallel", "hb200_get_pattempt_parallel", "hb200_build_power_pitzer_orderN", "hb200_build_power_pitzer", "hb200_annihilate_spawn", "hb200_annihilate_main", "hb200_download_spawn", "hb200_upload_spawn",
     "hb200_sc0_batch", "hb200_gen_excit_batch", "hb200_get_unique_id", "hb200_comm_init", "hb200_last_timing",
 ]
 
@@ -252,6 +253,8 @@ class Engine:
         self._chk(self.L.hb200_set_reference(self.h, _p(f0), float(H00)))
         if self.cfg.excit_gen == EXCIT_GEN["power_pitzer_orderN"]:   # reference-mapped tables (src/qmc.F90:1009-1018)
             self._chk(self.L.hb200_build_power_pitzer_orderN(self.h, float(self.power_pitzer_min_weight)))
+        if self.cfg.excit_gen == EXCIT_GEN["power_pitzer"]:          # src/qmc.F90:994-1007
+            self._chk(self.L.hb200_build_power_pitzer(self.h, float(self.power_pitzer_min_weight)))
 
     def set_proc_map(self, pmap):
         pmap = np.ascontiguousarray(pmap, dtype=np.int32)

@@ -26,7 +26,7 @@ extern "C" {
 typedef struct hb200_engine hb200_engine;
 
 /* Values of qmc_in%excit_gen (src/qmc_data.f90:31-69) that the engine implements. */
-enum { HB200_EXCIT_GEN_RENORM = 0, HB200_EXCIT_GEN_RENORM_SPIN = 1, HB200_EXCIT_GEN_NO_RENORM_SPIN = 3, HB200_EXCIT_GEN_NO_RENORM = 2, HB200_EXCIT_GEN_POWER_PITZER_OCC = 5,
+enum { HB200_EXCIT_GEN_RENORM = 0, HB200_EXCIT_GEN_RENORM_SPIN = 1, HB200_EXCIT_GEN_NO_RENORM_SPIN = 3, HB200_EXCIT_GEN_NO_RENORM = 2, HB200_EXCIT_GEN_POWER_PITZER = 4, HB200_EXCIT_GEN_POWER_PITZER_OCC = 5,
        HB200_EXCIT_GEN_POWER_PITZER_OCC_IJ = 6, HB200_EXCIT_GEN_POWER_PITZER_ORDERN = 7, HB200_EXCIT_GEN_CAUCHY_SCHWARZ_OCC = 8, HB200_EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ = 9, HB200_EXCIT_GEN_HEAT_BATH = 10, HB200_EXCIT_GEN_HEAT_BATH_UNIFORM = 11,
        HB200_EXCIT_GEN_HEAT_BATH_SINGLE = 12 };
 
@@ -195,6 +195,9 @@ int hb200_set_pattempt_parallel(hb200_engine* e, double pattempt_parallel);
  * check_min_weight_ratio :140-213; min_weight = qmc_in%power_pitzer_min_weight, default 0.01).  Call after
  * hb200_set_reference (the tables depend on the reference determinant). */
 int hb200_build_power_pitzer_orderN(hb200_engine* e, double min_weight);
+/* excit_gen = power_pitzer (gen_excit_mol_power_pitzer_occ_ref, src/excit_gen_power_pitzer_mol.F90:650-939): the
+ * reference's pp_ia_d / pp_jb_d alias tables (init_excit_mol_power_pitzer_occ_ref, :19-138); after hb200_set_reference. */
+int hb200_build_power_pitzer(hb200_engine* e, double min_weight);
 double hb200_get_pattempt_parallel(hb200_engine* e);
 int hb200_get_ps_stats(hb200_engine* e, double* out4, int32_t reset);
 

@@ -390,6 +390,27 @@ const int* orc_ppn_ptr_i(void* h, int which, int64_t* n) {
     *n = (int64_t)t[which]->K.size();
     return t[which]->K.data();
 }
+// power_pitzer (occ_ref) tables: which = 0 pp_ia_d, 1 pp_jb_d; virt lists: spin 0 beta, 1 alpha
+const double* orc_pp_ptr_d(void* h, int which, int part, int64_t* n) {
+    Oracle* o = (Oracle*)h;
+    AliasCols& t = which == 0 ? o->eg.ppn.pp_ia_d : o->eg.ppn.pp_jb_d;
+    std::vector<double>& v = part == 0 ? t.w : (part == 1 ? t.U : t.tot);
+    *n = (int64_t)v.size();
+    return v.data();
+}
+const int* orc_pp_ptr_i(void* h, int which, int64_t* n) {
+    Oracle* o = (Oracle*)h;
+    AliasCols& t = which == 0 ? o->eg.ppn.pp_ia_d : o->eg.ppn.pp_jb_d;
+    *n = (int64_t)t.K.size();
+    return t.K.data();
+}
+const int* orc_pp_virt(void* h, int spin, int* n) {
+    Oracle* o = (Oracle*)h;
+    std::vector<int>& v = spin ? o->eg.ppn.virt_list_alpha : o->eg.ppn.virt_list_beta;
+    *n = (int)v.size();
+    return v.data();
+}
+int orc_pp_stride(void* h) { return ((Oracle*)h)->eg.ppn.pp_ia_d.stride; }
 const int* orc_ppn_occ(void* h) { return ((Oracle*)h)->eg.ppn.occ_list.data(); }
 void orc_set_pattempt_parallel(void* h, double pp) { ((Oracle*)h)->in.pattempt_parallel = pp; ((Oracle*)h)->eg.pattempt_parallel = pp; }
 double orc_get_pattempt_parallel(void* h) { return ((Oracle*)h)->eg.pattempt_parallel; }

@@ -19,6 +19,7 @@ enum ExcitGenKind {  // values of src/qmc_data.f90:31-69
     EXCIT_GEN_RENORM_SPIN = 1,
     EXCIT_GEN_NO_RENORM = 2,
     EXCIT_GEN_NO_RENORM_SPIN = 3,
+    EXCIT_GEN_POWER_PITZER = 4,
     EXCIT_GEN_POWER_PITZER_OCC = 5,
     EXCIT_GEN_POWER_PITZER_OCC_IJ = 6,
     EXCIT_GEN_POWER_PITZER_ORDERN = 7,
@@ -223,6 +224,9 @@ struct PowerPitzerN {
     int n_all_alpha = 0, n_all_beta = 0;
     double min_weight = 0.01;        // qmc_in%power_pitzer_min_weight (src/qmc_data.f90:224)
     AliasCols i_s, ia_s, i_d, ij_d, ia_d, jb_d;   // columns: [1], [nbasis], [1], [nbasis], [nbasis], [nsym_tot * nbasis]
+    // excit_gen = power_pitzer (pp_ia_d, pp_jb_d of init_excit_mol_power_pitzer_occ_ref): columns [nel], [nsym_tot * nel]
+    std::vector<int> virt_list_alpha, virt_list_beta;
+    AliasCols pp_ia_d, pp_jb_d;
 };
 
 struct ExcitGenData {
@@ -1200,11 +1204,10 @@ inline void init_excit_mol_power_pitzer_orderN(const System& sys, const int* occ
 }
 // get_excitation_locations (src/excitations.F90) + find_diff_ref_cdet (src/excit_gen_utils.f90:220-269): the occupied
 // orbitals of cdet in the order of the reference's (same-spin replacements for the orbitals that differ)
-inline void find_diff_ref_cdet(const System& sys, const PowerPitzerN& pp, DetInfo& d) {
+inline int ref_cdet_locations(const System& sys, const PowerPitzerN& pp, const DetInfo& d, int* ref_store, int* det_store) {
     const int nel = sys.nel;
     const int* ref_list = pp.occ_list.data();
     const int* det_list = d.occ;
-    int ref_store[MAXNEL], det_store[MAXNEL];
     int j = 1, det_sind = 0, ref_sind = 0;
     bool done = false;
     for (int i = 1; i <= nel && !done; ++i) {
@@ -1225,15 +1228,21 @@ inline void find_diff_ref_cdet(const System& sys, const PowerPitzerN& pp, DetInf
         i_back--; i_back_pos--; ref_sind++;
     }
     const int nex = ref_sind;
-    for (int k = 0; k < nel; ++k) d.ref_cdet_occ[k] = ref_list[k];
+    // pair every differing reference orbital with a determinant orbital of the same spin
     for (int ii = 0; ii < nex; ++ii) {
         if (sys.bf[ref_list[ref_store[ii] - 1]].ms != sys.bf[det_list[det_store[ii] - 1]].ms) {
             int jj = ii + 1;
             while (sys.bf[ref_list[ref_store[ii] - 1]].ms != sys.bf[det_list[det_store[jj] - 1]].ms) jj++;
             std::swap(det_store[ii], det_store[jj]);
         }
-        d.ref_cdet_occ[ref_store[ii] - 1] = det_list[det_store[ii] - 1];
     }
+    return nex;
+}
+inline void find_diff_ref_cdet(const System& sys, const PowerPitzerN& pp, DetInfo& d) {
+    int ref_store[MAXNEL], det_store[MAXNEL];
+    const int nex = ref_cdet_locations(sys, pp, d, ref_store, det_store);
+    for (int k = 0; k < sys.nel; ++k) d.ref_cdet_occ[k] = pp.occ_list[k];
+    for (int ii = 0; ii < nex; ++ii) d.ref_cdet_occ[ref_store[ii] - 1] = d.occ[det_store[ii] - 1];
 }
 inline int binary_search_int(const int* list, int n, int item) {   // 1-based position, list ascending
     int lo = 1, hi = n;
@@ -1341,6 +1350,132 @@ inline GenResult gen_excit_mol_power_pitzer_orderN(Rng& rng, const System& sys, 
     return r;
 }
 
+// ------------------------------------------------------------------------ power_pitzer (reference-mapped, O(N))
+// init_excit_mol_power_pitzer_occ_ref (src/excit_gen_power_pitzer_mol.F90:19-138)
+inline void init_excit_mol_power_pitzer_occ_ref(const System& sys, const int* occ0, PowerPitzerN& pp) {
+    const int nel = sys.nel, nb = sys.nbasis, mv = sys.max_nbss, nsym = sys.nsym_tot;
+    const int maxv = std::max(sys.nvirt_alpha, sys.nvirt_beta);
+    pp.occ_list.assign(occ0, occ0 + nel);
+    std::sort(pp.occ_list.begin(), pp.occ_list.end());
+    pp.virt_list_alpha.clear(); pp.virt_list_beta.clear();
+    int j = 0;
+    for (int i = 1; i <= nb; ++i) {
+        if (i == pp.occ_list[j]) { if (j < nel - 1) j++; }
+        else (sys.bf[i].ms == -1 ? pp.virt_list_beta : pp.virt_list_alpha).push_back(i);
+    }
+    pp.pp_ia_d.alloc(std::max(maxv, 1), nel);
+    pp.pp_jb_d.alloc(mv, (size_t)nsym * nel);
+    for (int i = 0; i < nel; ++i) {
+        const int oj = pp.occ_list[i];
+        const bool beta = sys.bf[oj].ms == -1;
+        const std::vector<int>& virt = beta ? pp.virt_list_beta : pp.virt_list_alpha;
+        const int nv = (int)virt.size();
+        if (nv > 0) {
+            double* w = &pp.pp_ia_d.w[(size_t)pp.pp_ia_d.stride * i];
+            pp.pp_ia_d.tot[i] = create_weighted_excitation_list_mol(sys, false, oj, 0, virt.data(), nv, w);
+            check_min_weight_ratio(w, pp.pp_ia_d.tot[i], nv, pp.min_weight);
+            generate_alias_tables(nv, w, pp.pp_ia_d.tot[i], &pp.pp_ia_d.U[(size_t)pp.pp_ia_d.stride * i],
+                                  &pp.pp_ia_d.K[(size_t)pp.pp_ia_d.stride * i]);
+        }
+        const int ims = beta ? 1 : 2;
+        for (int bsym = 0; bsym <= sys.sym_max_tot; ++bsym) {
+            const int n = sys.nbss(ims, bsym);
+            if (n <= 0) continue;
+            std::vector<int> list(n);
+            for (int k = 1; k <= n; ++k) list[k - 1] = sys.ssbf(k, ims, bsym);
+            const size_t col = (size_t)bsym + (size_t)nsym * i;
+            double* w = &pp.pp_jb_d.w[(size_t)mv * col];
+            pp.pp_jb_d.tot[col] = create_weighted_excitation_list_mol(sys, false, oj, 0, list.data(), n, w);
+            check_min_weight_ratio(w, pp.pp_jb_d.tot[col], n, pp.min_weight);
+            generate_alias_tables(n, w, pp.pp_jb_d.tot[col], &pp.pp_jb_d.U[(size_t)mv * col], &pp.pp_jb_d.K[(size_t)mv * col]);
+        }
+    }
+}
+// gen_excit_mol_power_pitzer_occ_ref (src/excit_gen_power_pitzer_mol.F90:650-939): ij uniform among the REFERENCE's
+// occupied orbitals, a and b from the reference's alias tables, all three mapped onto the determinant
+inline GenResult gen_excit_mol_power_pitzer_occ_ref(Rng& rng, const System& sys, const ExcitGenData& eg, DetInfo& d) {
+    GenResult r;
+    const PowerPitzerN& pp = eg.ppn;
+    const int nel = sys.nel, mv = sys.max_nbss, nsym = sys.nsym_tot;
+    if (rng.next() < eg.pattempt_single) {   // gen_single_excit_mol_no_renorm
+        find_ia_mol(rng, sys, sys.gamma_sym, d, r.conn.from_orb[0], r.conn.to_orb[0], r.allowed);
+        r.conn.nexcit = 1;
+        if (r.allowed) {
+            r.pgen = eg.pattempt_single * calc_pgen_single_mol_no_renorm(sys, r.conn.to_orb[0]);
+            sys.find_excitation_permutation1(d.f, r.conn);
+            r.hmatel = sys.slater_condon1_excit(d.occ, r.conn.from_orb[0], r.conn.to_orb[0], r.conn.perm);
+        } else { r.hmatel = 0.0; r.pgen = 1.0; }
+        return r;
+    }
+    r.conn.nexcit = 2;
+    // choose_ij_mol on the reference's list
+    const int ind = (int)(rng.next() * nel * (nel - 1) / 2) + 1;
+    const int j_ind_ref = (int)(1.50 + std::sqrt(2 * ind - 1.750));
+    const int i_ind_ref = ind - ((j_ind_ref - 1) * (j_ind_ref - 2)) / 2;
+    const double pgen_ij = 2.0 / (nel * (nel - 1));
+    const int i_ref = pp.occ_list[i_ind_ref - 1], j_ref = pp.occ_list[j_ind_ref - 1];
+    const int ij_spin = sys.bf[i_ref].ms + sys.bf[j_ref].ms;
+    const std::vector<int>& virt = (sys.bf[i_ref].ms < 0) ? pp.virt_list_beta : pp.virt_list_alpha;
+    const int nv = (int)virt.size();
+    bool a_found = false;
+    int a_ind_ref = 0, a_ref = 0;
+    const size_t sia = (size_t)pp.pp_ia_d.stride;
+    if (nv > 0) {
+        a_ind_ref = select_weighted_value_precalc(rng, nv, &pp.pp_ia_d.U[sia * (i_ind_ref - 1)], &pp.pp_ia_d.K[sia * (i_ind_ref - 1)]);
+        a_ref = virt[a_ind_ref - 1];
+        a_found = true;
+    }
+    int ref_store[MAXNEL], det_store[MAXNEL], nex = 0;
+    int i_cdet = i_ref, j_cdet = j_ref, a_cdet = a_ref, ij_sym = 0, isymb = 0, imsb = 1;
+    if (a_found) {
+        nex = ref_cdet_locations(sys, pp, d, ref_store, det_store);
+        for (int ii = 0; ii < nex; ++ii) {
+            if (ref_store[ii] == i_ind_ref) i_cdet = d.occ[det_store[ii] - 1];
+            else if (ref_store[ii] == j_ind_ref) j_cdet = d.occ[det_store[ii] - 1];
+            if (d.occ[det_store[ii] - 1] == a_ref) a_cdet = pp.occ_list[ref_store[ii] - 1];
+        }
+        ij_sym = sys.sym_conj(sys.cross_product_basis(i_cdet, j_cdet));
+        isymb = sys.sym_conj(sys.cross_product(ij_sym, sys.bf[a_cdet].sym));
+        imsb = (sys.bf[j_ref].ms + 3) / 2;
+    }
+    r.allowed = false;
+    int b_cdet = 0;
+    if (a_found && sys.nbss(imsb, isymb) > 0) {
+        const size_t colb = (size_t)isymb + (size_t)nsym * (j_ind_ref - 1);
+        const int b_ind = select_weighted_value_precalc(rng, sys.nbss(imsb, isymb), &pp.pp_jb_d.U[(size_t)mv * colb], &pp.pp_jb_d.K[(size_t)mv * colb]);
+        b_cdet = sys.ssbf(b_ind, imsb, isymb);
+        if (a_cdet != b_cdet && !det_test(d.f, b_cdet)) {
+            double pgen;
+            const double pa = pp.pp_ia_d.w[sia * (i_ind_ref - 1) + a_ind_ref - 1] / pp.pp_ia_d.tot[i_ind_ref - 1];
+            if (ij_spin == 0) {
+                pgen = pa * pp.pp_jb_d.w[(size_t)mv * colb + b_ind - 1] / pp.pp_jb_d.tot[colb];
+            } else {
+                int b_ref = b_cdet;
+                for (int ii = 0; ii < nex; ++ii)
+                    if (pp.occ_list[ref_store[ii] - 1] == b_cdet) { b_ref = d.occ[det_store[ii] - 1]; break; }
+                const int b_rev = binary_search_int(virt.data(), nv, b_ref);
+                const int isyma = sys.sym_conj(sys.cross_product(ij_sym, isymb));
+                int a_rev = 0;
+                for (int k = 1; k <= sys.nbss(imsb, isyma); ++k)
+                    if (sys.ssbf(k, imsb, isyma) == a_cdet) { a_rev = k; break; }
+                const size_t cola = (size_t)isyma + (size_t)nsym * (j_ind_ref - 1);
+                pgen = pa * pp.pp_jb_d.w[(size_t)mv * colb + b_ind - 1] / pp.pp_jb_d.tot[colb] +
+                       pp.pp_ia_d.w[sia * (i_ind_ref - 1) + b_rev - 1] / pp.pp_ia_d.tot[i_ind_ref - 1] *
+                           pp.pp_jb_d.w[(size_t)mv * cola + a_rev - 1] / pp.pp_jb_d.tot[cola];
+            }
+            r.pgen = eg.pattempt_double * pgen * pgen_ij;
+            r.allowed = true;
+        }
+    }
+    if (r.allowed) {
+        r.conn.from_orb[0] = std::min(i_cdet, j_cdet); r.conn.from_orb[1] = std::max(i_cdet, j_cdet);
+        r.conn.to_orb[0] = std::min(a_cdet, b_cdet); r.conn.to_orb[1] = std::max(a_cdet, b_cdet);
+        sys.find_excitation_permutation2(d.f, r.conn);
+        r.hmatel = sys.slater_condon2_excit(r.conn.from_orb[0], r.conn.from_orb[1], r.conn.to_orb[0], r.conn.to_orb[1], r.conn.perm);
+    } else { r.hmatel = 0.0; r.pgen = 1.0; }
+    return r;
+}
+
 inline GenResult gen_excit(Rng& rng, const System& sys, const ExcitGenData& eg, DetInfo& d) {
     switch (eg.excit_gen) {
         case EXCIT_GEN_RENORM: return gen_excit_mol(rng, sys, eg, d);
@@ -1355,6 +1490,7 @@ inline GenResult gen_excit(Rng& rng, const System& sys, const ExcitGenData& eg, 
         case EXCIT_GEN_HEAT_BATH_UNIFORM:
         case EXCIT_GEN_HEAT_BATH_SINGLE: return gen_excit_mol_heat_bath_uniform(rng, sys, eg, d);
         case EXCIT_GEN_POWER_PITZER_ORDERN: return gen_excit_mol_power_pitzer_orderN(rng, sys, eg, d);
+        case EXCIT_GEN_POWER_PITZER: return gen_excit_mol_power_pitzer_occ_ref(rng, sys, eg, d);
         default: throw std::runtime_error("oracle: excitation generator not implemented");
     }
 }

@@ -12,7 +12,7 @@ LIB = os.path.join(HERE, "liboracle.so")
 REF_LIB = os.path.join(HERE, "_ref", "libhande_ref_c.so")
 HUGE = 2**31 - 1
 
-EXCIT_GEN = {"renorm": 0, "renorm_spin": 1, "no_renorm": 2, "no_renorm_spin": 3, "power_pitzer_occ": 5, "power_pitzer_occ_ij": 6, "power_pitzer_orderN": 7, "cauchy_schwarz_occ": 8,
+EXCIT_GEN = {"renorm": 0, "renorm_spin": 1, "no_renorm": 2, "no_renorm_spin": 3, "power_pitzer": 4, "power_pitzer_occ": 5, "power_pitzer_occ_ij": 6, "power_pitzer_orderN": 7, "cauchy_schwarz_occ": 8,
              "cauchy_schwarz_occ_ij": 9, "heat_bath": 10,
              "heat_bath_uniform": 11, "heat_bath_single": 12}
 
@@ -441,6 +441,36 @@ class Oracle:
         nel = len(out[0]["w"])
         occ = np.ctypeslib.as_array(L.orc_ppn_occ(self.h), shape=(nel,)).astype(np.int32)
         return out, occ
+
+    def power_pitzer_tables(self):
+        """pp_ia_d / pp_jb_d alias tables and virtual lists of excit_gen = power_pitzer (reference-mapped)"""
+        L = self.L
+        L.orc_pp_ptr_d.restype = C.POINTER(C.c_double)
+        L.orc_pp_ptr_d.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.orc_pp_ptr_i.restype = C.POINTER(C.c_int)
+        L.orc_pp_ptr_i.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_pp_virt.restype = C.POINTER(C.c_int)
+        L.orc_pp_virt.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_ppn_occ.restype = C.POINTER(C.c_int)
+        L.orc_ppn_occ.argtypes = [C.c_void_p]
+        out = []
+        n = C.c_int64(0)
+        for which in range(2):
+            t = {}
+            for part, nm in enumerate(("w", "U", "tot")):
+                ptr = L.orc_pp_ptr_d(self.h, which, part, C.byref(n))
+                t[nm] = np.ctypeslib.as_array(ptr, shape=(n.value,)).copy()
+            ptr = L.orc_pp_ptr_i(self.h, which, C.byref(n))
+            t["K"] = np.ctypeslib.as_array(ptr, shape=(n.value,)).astype(np.int32)
+            out.append(t)
+        virt = []
+        m = C.c_int(0)
+        for spin in range(2):
+            ptr = L.orc_pp_virt(self.h, spin, C.byref(m))
+            virt.append(np.ctypeslib.as_array(ptr, shape=(max(m.value, 1),))[:m.value].astype(np.int32).copy())
+        nel = len(out[0]["tot"])
+        occ = np.ctypeslib.as_array(L.orc_ppn_occ(self.h), shape=(nel,)).astype(np.int32)
+        return out, virt, occ, int(L.orc_pp_stride(self.h))
 
     def cpu_baseline(self, nthreads, ncycles, tau, shift, proj_energy_old):
         out = np.zeros(4)

@@ -89,6 +89,16 @@ class HdCheck:
             self.L.hd_set_ppn(which, _p(t["w"]), _p(t["U"]), _p(t["K"]), _p(t["tot"]))
         self.L.hd_set_ppn_occ(_p(occ))
 
+    def set_power_pitzer(self, tables, virt, occ, stride):
+        self.L.hd_set_pp.argtypes = [C.c_int] + [C.c_void_p] * 4
+        self.L.hd_set_pp_virt.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        self.L.hd_set_ppn_occ.argtypes = [C.c_void_p]
+        self.keep.append((tables, virt, occ))
+        for which, t in enumerate(tables):
+            self.L.hd_set_pp(which, _p(t["w"]), _p(t["U"]), _p(t["K"]), _p(t["tot"]))
+        self.L.hd_set_pp_virt(_p(virt[0]), len(virt[0]), _p(virt[1]), len(virt[1]), stride)
+        self.L.hd_set_ppn_occ(_p(occ))
+
     def set_pattempt_parallel(self, pp):
         self.L.hd_set_pattempt_parallel.argtypes = [C.c_double]
         self.L.hd_set_pattempt_parallel(float(pp))

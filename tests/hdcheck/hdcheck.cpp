@@ -117,6 +117,13 @@ void hd_set_ppn(int which, const double* w, const double* U, const int* K, const
     g_sys.ppn[which].w = w; g_sys.ppn[which].U = U; g_sys.ppn[which].K = K; g_sys.ppn[which].tot = tot;
 }
 void hd_set_ppn_occ(const int* occ) { g_sys.ppn_occ = occ; }
+void hd_set_pp(int which, const double* w, const double* U, const int* K, const double* tot) {
+    Sys::AliasTab& t = which == 0 ? g_sys.pp_ia : g_sys.pp_jb;
+    t.w = w; t.U = U; t.K = K; t.tot = tot;
+}
+void hd_set_pp_virt(const int* vb, int nb, const int* va, int na, int stride) {
+    g_sys.pp_virt[0] = vb; g_sys.pp_virt[1] = va; g_sys.pp_nvirt[0] = nb; g_sys.pp_nvirt[1] = na; g_sys.pp_sia = stride;
+}
 void hd_set_pattempt_parallel(double pp) { g_par.pattempt_parallel = pp; }
 
 void hd_gen_excit_philox(const uint64_t* f, uint32_t cycle, uint32_t attempt, int64_t parent_pop, int* iout,

@@ -24,6 +24,8 @@ def _setup(path, kw, excit_gen, tau=0.01, real=False, seed=11):
                 seed, ref["f0"], ref["H00"], hb=hb)
     if excit_gen.endswith("_spin"):
         h.set_pattempt_parallel(o.pattempt_parallel())
+    if excit_gen == "power_pitzer":
+        h.set_power_pitzer(*o.power_pitzer_tables())
     if excit_gen == "power_pitzer_orderN":
         h.set_power_pitzer_orderN(*o.power_pitzer_orderN_tables())
     return s, o, h
@@ -75,12 +77,13 @@ def test_power_pitzer_occ_generators(fcidump_path, s10, gen):
     assert _compare_attempts(s, o, h, dets, pops, 0.01, ncycle=2, nattempt=6) > 900
 
 
-def test_power_pitzer_orderN_generator(fcidump_path, s10):
+@pytest.mark.parametrize("gen", ["power_pitzer_orderN", "power_pitzer"])
+def test_power_pitzer_orderN_generator(fcidump_path, s10, gen):
     """SURVEY 8a row a10, the reference-mapped O(N) variant ('heat_bath_power_pitzer_ref'): alias-table look-ups through
     find_diff_ref_cdet; tables from the oracle (pinned on the NH3 ppN golden table)."""
     for path, kw, tau, real in ((fcidump_path("h2o"), dict(nel=10, ms=0, sym=0, cas=(8, 13)), 0.003, False),
                                 (fcidump_path("nh3_631g"), dict(nel=10, ms=0, sym=0), 0.002, True), (s10, {}, 0.01, True)):
-        s, o, h = _setup(path, kw, "power_pitzer_orderN", tau=tau, real=real)
+        s, o, h = _setup(path, kw, gen, tau=tau, real=real)
         dets = synthetic.random_dets(100, s.nbasis, s.nalpha, s.nbeta, seed=3)
         dets[0] = o.reference()["f0"]
         pops = np.where(np.arange(len(dets)) % 2 == 0, 3, -2) * (2**31 if real else 1)
@@ -214,7 +217,7 @@ def test_philox_stream_matches_oracle():
         assert ((out >= 0) & (out < 1)).all()
 
 
-@pytest.mark.parametrize("gen", ["power_pitzer_orderN", "heat_bath", "heat_bath_uniform", "heat_bath_single", "power_pitzer_occ",
+@pytest.mark.parametrize("gen", ["power_pitzer", "power_pitzer_orderN", "heat_bath", "heat_bath_uniform", "heat_bath_single", "power_pitzer_occ",
                                  "cauchy_schwarz_occ", "power_pitzer_occ_ij", "cauchy_schwarz_occ_ij"])
 def test_heat_bath_pgen_normalisation(s10, gen):
     """SURVEY 8c gap-filler: heat-bath has no single-rank golden trajectory, so pin it statistically.  The

@@ -72,6 +72,27 @@ def test_gen_excit_power_pitzer_orderN():
     _check_gen("s40", "power_pitzer_orderN", False, 0.01, n=60)
 
 
+def test_gen_excit_power_pitzer_reference_mapped():
+    # excit_gen = power_pitzer (gen_excit_mol_power_pitzer_occ_ref): pp_ia_d / pp_jb_d built on the device
+    _check_gen("nh3", "power_pitzer", True, 0.002, n=150, nattempt=6)
+    _check_gen("h2o", "power_pitzer", False, 0.003, n=120)
+    _check_gen("s40", "power_pitzer", False, 0.01, n=60)
+
+
+def test_tables_need_the_reference():
+    from hande_b200 import read_in as R
+    from hande_b200.engine import Engine
+    from tests.common import system_path
+    path, kw = system_path("nh3")
+    s = R.read_in(path, **kw)
+    for gen in ("power_pitzer", "power_pitzer_orderN"):
+        eng = Engine(s, excit_gen=gen, pattempt_single=0.1, pattempt_double=0.9, walker_length=1024, spawned_walker_length=512)
+        eng.upload_psips(np.zeros((0, 1), dtype=np.uint64), [], [])
+        with pytest.raises(EngineError):
+            eng.iterate(1, 0.001, 0.0, 0.0, 1)         # tables are built by set_reference
+        eng.close()
+
+
 def test_pattempt_parallel_on_device():
     """find_parallel_spin_prob_mol on the device against the oracle (whose value reproduces the 0.22360108 printed in
     the reference's NH3 renorm_spin golden output)."""
@@ -150,6 +171,7 @@ CASES = [
     ("s12", "heat_bath_single", True, True, 0.01, 2500, -1),
     ("nh3", "renorm_spin", True, True, 0.003, 2500, -1),
     ("nh3", "power_pitzer_orderN", True, True, 0.002, 2500, -1),
+    ("nh3", "power_pitzer", True, False, 0.002, 2500, -1),
     ("s12", "power_pitzer_orderN", False, False, 0.004, 2500, 4),
     ("h2o", "no_renorm_spin", False, False, 0.003, 2500, -1),
     ("h2o", "power_pitzer_occ", False, True, 0.003, 2500, -1),

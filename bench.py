@@ -196,7 +196,7 @@ def main():
     if args.system == "ueg":
         from hande_b200.ueg import UegSystem
         s, path = UegSystem(**UEG), None
-        args.excit_gen = "no_renorm"
+        args.excit_gen = "power_pitzer" if args.excit_gen == "power_pitzer" else "no_renorm"
         occ0 = s.aufbau_reference()
         ps, pd = 0.0, 1.0
     else:

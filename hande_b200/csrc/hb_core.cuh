@@ -1787,10 +1787,53 @@ HB_HDN void gen_excit_ueg_no_renorm(R& rng, const Sys& s, const uint64_t* f, con
     }
 }
 
+// gen_excit_ueg_power_pitzer (src/excit_gen_ueg.f90:410-566), excit_gen = power_pitzer on the UEG: ij uniform, a from
+// the alias table of i over the orbitals of its spin (weights |<ia|ai>|, s.pp_ia), b from momentum conservation
+template <int W, class R>
+HB_HDN void gen_excit_ueg_power_pitzer(R& rng, const Sys& s, const uint64_t* f, const uint8_t* occ, Gen& g) {
+    const int nel = s.nel, maxv = s.nbasis / 2;
+    g.nexcit = 2; g.perm = false; g.to1 = 0; g.to2 = 0;
+    const int ind = (int)(rng.next() * nel * (nel - 1) / 2) + 1;
+    const int j_ind = (int)(1.50 + sqrt(2 * ind - 1.750));
+    const int i_ind = ind - ((j_ind - 1) * (j_ind - 2)) / 2;
+    const int i = occ[i_ind - 1], j = occ[j_ind - 1];
+    g.from1 = i; g.from2 = j;
+    const int ij_spin = ms_of(i) + ms_of(j);
+    const K4 ki = s.ueg_k[i], kj = s.ueg_k[j];
+    const int kx = ki.x + kj.x, ky = ki.y + kj.y, kz = ki.z + kj.z;
+    const int a_ind = select_precalc(rng, maxv, s.pp_ia.U + (size_t)maxv * i, s.pp_ia.K + (size_t)maxv * i);
+    const int a = 2 * a_ind - (i & 1);
+    int b = 0, b_ind = 0;
+    g.allowed = !det_test(f, a);
+    if (g.allowed) {
+        const K4 ka = s.ueg_k[a];
+        const int spin_b = (ij_spin == 2) ? 1 : ((ij_spin == 0) ? -ms_of(a) : -1);
+        b = ueg_basis_index(s, kx - ka.x, ky - ka.y, kz - ka.z, spin_b);
+        if (b <= 0) g.allowed = false;
+        else { b_ind = (b + 1) >> 1; g.allowed = !det_test(f, b); }
+    }
+    if (g.allowed) {
+        const double* w = s.pp_ia.w + (size_t)maxv * i;
+        if (ij_spin == 0) g.pgen = w[a_ind - 1] / s.pp_ia.tot[i];
+        else g.pgen = (w[a_ind - 1] + w[b_ind - 1]) / s.pp_ia.tot[i];
+        g.pgen = g.pgen * 2.0 / (nel * (nel - 1));
+        g.allowed = (a != b);
+    }
+    if (g.allowed) {
+        g.to1 = (a < b) ? a : b; g.to2 = (a < b) ? b : a;
+        g.perm = excit_perm2<W>(f, i, j, g.to1, g.to2);
+        g.hmatel = slater_condon2_ueg_excit(s, i, g.to1, g.to2, g.perm);
+    } else {
+        g.hmatel = 0.0; g.pgen = 1.0;
+    }
+}
 template <int W, class R>
 HB_HD void gen_excit(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ, const uint8_t* su,
                      Gen& g) {
-    if (s.kind == SYS_UEG) gen_excit_ueg_no_renorm<W>(rng, s, f, occ, g);
+    if (s.kind == SYS_UEG) {
+        if (p.excit_gen == EXCIT_GEN_POWER_PITZER) gen_excit_ueg_power_pitzer<W>(rng, s, f, occ, g);
+        else gen_excit_ueg_no_renorm<W>(rng, s, f, occ, g);
+    }
     else if (p.excit_gen == EXCIT_GEN_RENORM) gen_excit_renorm<W>(rng, s, p, f, occ, su, g);
     else if (p.excit_gen == EXCIT_GEN_NO_RENORM) gen_excit_no_renorm<W>(rng, s, p, f, occ, g);
     else if (p.excit_gen == EXCIT_GEN_POWER_PITZER) gen_excit_power_pitzer_ref<W>(rng, s, p, f, occ, g);

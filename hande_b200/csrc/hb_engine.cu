@@ -234,7 +234,7 @@ __device__ __forceinline__ void make_child(const uint64_t* f, const Gen& g, uint
 
 // GEN: compile-time generator of this instantiation (one kernel per generator keeps the code - and the instruction
 // cache footprint - to what the run actually executes): EXCIT_GEN_* for read_in systems, GEN_UEG for the UEG.
-enum { GEN_UEG = 100 };
+enum { GEN_UEG = 100, GEN_UEG_PP = 101 };
 template <int W, int GEN>
 __global__ void __launch_bounds__(TILE, (GEN == EXCIT_GEN_HEAT_BATH || GEN == EXCIT_GEN_HEAT_BATH_UNIFORM) ? 3 : 4)
 k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __restrict__ pops,
@@ -449,6 +449,7 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
             hb_phase_f<W>(s, f, st, hmk, psum, g);
         } else if (active) {
             if (GEN == GEN_UEG) gen_excit_ueg_no_renorm<W>(rng, s, f, socc + lo * nel, g);
+            else if (GEN == GEN_UEG_PP) gen_excit_ueg_power_pitzer<W>(rng, s, f, socc + lo * nel, g);
             else if (GEN == EXCIT_GEN_HEAT_BATH_UNIFORM)
                 gen_excit_heat_bath_uniform<W>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, siw, sw + tid, TILE, g);
             else if (GEN == EXCIT_GEN_HEAT_BATH_SINGLE)
@@ -2150,9 +2151,45 @@ __global__ void k_pp_alias(Sys s, PpBuild t) {
     int under[HB_MAXLIST], over[HB_MAXLIST];
     generate_alias_tables(n, w, tot, t.U[which] + stride * col, t.K[which] + stride * col, under, over);
 }
+// init_excit_ueg_power_pitzer (src/excit_gen_ueg.f90:362-408): one thread per orbital i builds its column
+__global__ void k_ueg_pp_build(Sys s, double* w, double* U, int* K, double* tot) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (i > s.nbasis) return;
+    const int maxv = s.nbasis / 2;
+    double* wc = w + (size_t)maxv * i;
+    double t = 0.0;
+    for (int j = 1; j <= maxv; ++j) {
+        const int a = j * 2 - (i & 1);
+        const double weight = (a != i) ? fabs(ueg_coulomb(s, i, a)) : 0.0;
+        wc[j - 1] = weight;
+        t = t + weight;
+    }
+    tot[i] = t;
+    int under[HB_MAXLIST], over[HB_MAXLIST];
+    generate_alias_tables(maxv, wc, t, U + (size_t)maxv * i, K + (size_t)maxv * i, under, over);
+}
 int hb200_build_power_pitzer(hb200_engine* e, double min_weight) {
     CK(cudaSetDevice(e->cfg.device));
-    if (!e->have_sys || e->sys.kind != SYS_READ_IN) FAIL("build_power_pitzer: needs a read_in system");
+    if (!e->have_sys) FAIL("build_power_pitzer: system not set");
+    if (e->sys.kind == SYS_UEG) {
+        Sys& s = e->sys;
+        const int nb = s.nbasis, maxv = nb / 2;
+        if (maxv > HB_MAXLIST) FAIL("build_power_pitzer: basis too large");
+        double *w, *U, *tot;
+        int* K;
+        const size_t len = (size_t)maxv * (nb + 1);
+        if (dalloc(e, &w, len) || dalloc(e, &U, len) || dalloc(e, &K, len) || dalloc(e, &tot, (size_t)nb + 1)) return 1;
+        CK(cudaMemsetAsync(w, 0, len * sizeof(double), e->stream));
+        CK(cudaMemsetAsync(U, 0, len * sizeof(double), e->stream));
+        CK(cudaMemsetAsync(K, 0, len * sizeof(int), e->stream));
+        CK(cudaMemsetAsync(tot, 0, ((size_t)nb + 1) * sizeof(double), e->stream));
+        k_ueg_pp_build<<<(nb + 63) / 64, 64, 0, e->stream>>>(s, w, U, K, tot);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(e->stream));
+        s.pp_ia.w = w; s.pp_ia.U = U; s.pp_ia.K = K; s.pp_ia.tot = tot;
+        e->have_pp = true;
+        return 0;
+    }
     if (!e->have_ref) FAIL("build_power_pitzer: reference not set (call hb200_set_reference first)");
     Sys& s = e->sys;
     const int nel = s.nel, nb = s.nbasis, mv = s.max_nbss, nsym = s.nsym_tot;
@@ -2345,7 +2382,10 @@ static int stage_spawn_death(hb200_engine* e, const hb200_iter_in* in, uint32_t 
                                                           e->d_spawn[0], e->d_head, e->block_size, e->d_proc_map, \
                                                           e->d_partials, e->d_err);                               \
     })
-        if (e->sys.kind == SYS_UEG) { LAUNCH_SPAWN(GEN_UEG); }
+        if (e->sys.kind == SYS_UEG) {
+            if (e->cfg.excit_gen == HB200_EXCIT_GEN_POWER_PITZER) { LAUNCH_SPAWN(GEN_UEG_PP); }
+            else { LAUNCH_SPAWN(GEN_UEG); }
+        }
         else switch (e->cfg.excit_gen) {
             case HB200_EXCIT_GEN_NO_RENORM: LAUNCH_SPAWN(EXCIT_GEN_NO_RENORM); break;
             case HB200_EXCIT_GEN_RENORM: LAUNCH_SPAWN(EXCIT_GEN_RENORM); break;

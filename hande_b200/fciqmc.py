@@ -228,7 +228,7 @@ def do_fciqmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, 
         pd = 1.0 - qmc.pattempt_single
     wl, sl = list_sizes(qmc, sys.W, nprocs)
     # UEG: "renormalised excitation generators not implemented" -> gen_excit_ueg_no_renorm (src/qmc.F90:466-476)
-    eng = engine_cls(sys, excit_gen=("no_renorm" if is_ueg else qmc.excit_gen), pattempt_single=ps, pattempt_double=pd,
+    eng = engine_cls(sys, excit_gen=(("power_pitzer" if qmc.excit_gen == "power_pitzer" else "no_renorm") if is_ueg else qmc.excit_gen), pattempt_single=ps, pattempt_double=pd,
                      real_amplitudes=qmc.real_amplitudes, spawn_cutoff=qmc.spawn_cutoff,
                      initiator_approx=qmc.initiator, initiator_pop=qmc.initiator_population,
                      trunc_level=qmc.ex_level, walker_length=wl, spawned_walker_length=sl, seed=qmc.rng_seed,

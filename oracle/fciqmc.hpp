@@ -268,8 +268,10 @@ struct Oracle {
         }
         if (in.excit_gen == EXCIT_GEN_RENORM_SPIN || in.excit_gen == EXCIT_GEN_NO_RENORM_SPIN)   // src/qmc.F90:974-988
             eg.pattempt_parallel = (in.pattempt_parallel < 0.0) ? find_parallel_spin_prob_mol(sys, in.nprocs) : in.pattempt_parallel;
-        if (in.excit_gen == EXCIT_GEN_POWER_PITZER)          // src/qmc.F90:994-1007
-            init_excit_mol_power_pitzer_occ_ref(sys, occ_list0.data(), eg.ppn);
+        if (in.excit_gen == EXCIT_GEN_POWER_PITZER) {        // src/qmc.F90:994-1007
+            if (sys.kind == SYS_UEG) init_excit_ueg_power_pitzer(sys, eg.ppn);
+            else init_excit_mol_power_pitzer_occ_ref(sys, occ_list0.data(), eg.ppn);
+        }
         if (in.excit_gen == EXCIT_GEN_POWER_PITZER_ORDERN)   // src/qmc.F90:1009-1018
             init_excit_mol_power_pitzer_orderN(sys, occ_list0.data(), eg.ppn);
         if (in.excit_gen == EXCIT_GEN_HEAT_BATH_UNIFORM || in.excit_gen == EXCIT_GEN_HEAT_BATH_SINGLE ||

@@ -443,7 +443,8 @@ class Oracle:
         return out, occ
 
     def power_pitzer_tables(self):
-        """pp_ia_d / pp_jb_d alias tables and virtual lists of excit_gen = power_pitzer (reference-mapped)"""
+        """pp_ia_d / pp_jb_d alias tables and virtual lists of excit_gen = power_pitzer (reference-mapped; on the UEG
+        only pp_ia_d exists, one column per orbital)"""
         L = self.L
         L.orc_pp_ptr_d.restype = C.POINTER(C.c_double)
         L.orc_pp_ptr_d.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -453,23 +454,26 @@ class Oracle:
         L.orc_pp_virt.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.orc_ppn_occ.restype = C.POINTER(C.c_int)
         L.orc_ppn_occ.argtypes = [C.c_void_p]
+
+        def arr(ptr, n, dtype):
+            return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype).copy() if n > 0 else np.zeros(0, dtype=dtype)
         out = []
         n = C.c_int64(0)
         for which in range(2):
             t = {}
             for part, nm in enumerate(("w", "U", "tot")):
                 ptr = L.orc_pp_ptr_d(self.h, which, part, C.byref(n))
-                t[nm] = np.ctypeslib.as_array(ptr, shape=(n.value,)).copy()
+                t[nm] = arr(ptr, n.value, np.float64)
             ptr = L.orc_pp_ptr_i(self.h, which, C.byref(n))
-            t["K"] = np.ctypeslib.as_array(ptr, shape=(n.value,)).astype(np.int32)
+            t["K"] = arr(ptr, n.value, np.int32)
             out.append(t)
         virt = []
         m = C.c_int(0)
         for spin in range(2):
             ptr = L.orc_pp_virt(self.h, spin, C.byref(m))
-            virt.append(np.ctypeslib.as_array(ptr, shape=(max(m.value, 1),))[:m.value].astype(np.int32).copy())
-        nel = len(out[0]["tot"])
-        occ = np.ctypeslib.as_array(L.orc_ppn_occ(self.h), shape=(nel,)).astype(np.int32)
+            virt.append(arr(ptr, m.value, np.int32))
+        nocc = len(out[1]["tot"]) and len(out[0]["tot"])
+        occ = arr(L.orc_ppn_occ(self.h), nocc, np.int32)
         return out, virt, occ, int(L.orc_pp_stride(self.h))
 
     def cpu_baseline(self, nthreads, ncycles, tau, shift, proj_energy_old):

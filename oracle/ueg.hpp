@@ -226,6 +226,70 @@ inline GenResult gen_excit_ueg_no_renorm(Rng& rng, const System& sys, const DetI
     return g;
 }
 
+// init_excit_ueg_power_pitzer (src/excit_gen_ueg.f90:362-408) with create_weighted_excitation_list_ueg
+// (src/hamiltonian_ueg.f90): for every orbital i an alias table over all orbitals a of its spin, weights |<ia|ai>|
+inline void init_excit_ueg_power_pitzer(const System& sys, PowerPitzerN& pp) {
+    const int nbas = sys.nbasis, maxv = nbas / 2;
+    pp.pp_ia_d.alloc(maxv, nbas + 1);
+    for (int i = 1; i <= nbas; ++i) {
+        double* w = &pp.pp_ia_d.w[(size_t)maxv * i];
+        double tot = 0.0;
+        for (int j = 1; j <= maxv; ++j) {
+            const int a = j * 2 - (i % 2);
+            const double weight = (a != i) ? std::fabs(coulomb_int_ueg_3d(sys, i, a)) : 0.0;
+            w[j - 1] = weight;
+            tot = tot + weight;
+        }
+        pp.pp_ia_d.tot[i] = tot;
+        generate_alias_tables(maxv, w, tot, &pp.pp_ia_d.U[(size_t)maxv * i], &pp.pp_ia_d.K[(size_t)maxv * i]);
+    }
+}
+// gen_excit_ueg_power_pitzer (src/excit_gen_ueg.f90:410-566)
+inline GenResult gen_excit_ueg_power_pitzer(Rng& rng, const System& sys, const ExcitGenData& eg, const DetInfo& d) {
+    const UegData& u = sys.ueg;
+    const PowerPitzerN& pp = eg.ppn;
+    GenResult g;
+    g.conn.nexcit = 2;
+    const int nel = sys.nel, maxv = sys.nbasis / 2;
+    double r = rng.next();
+    int ind = (int)(r * nel * (nel - 1) / 2) + 1;
+    int jj = (int)(1.50 + std::sqrt(2 * ind - 1.750));
+    int ii = ind - ((jj - 1) * (jj - 2)) / 2;
+    const int i = d.occ[ii - 1], j = d.occ[jj - 1];
+    const int ij_spin = sys.bf[i].ms + sys.bf[j].ms;
+    int ij_k[3];
+    for (int dd = 0; dd < 3; ++dd) ij_k[dd] = u.l[3 * i + dd] + u.l[3 * j + dd];
+    const int a_ind = select_weighted_value_precalc(rng, maxv, &pp.pp_ia_d.U[(size_t)maxv * i], &pp.pp_ia_d.K[(size_t)maxv * i]);
+    const int a = 2 * a_ind - (i % 2);
+    int b = 0, b_ind = 0;
+    g.allowed = !det_test(d.f, a);
+    if (g.allowed) {
+        int kb[3];
+        for (int dd = 0; dd < 3; ++dd) kb[dd] = ij_k[dd] - u.l[3 * a + dd];
+        if (ij_spin == 2) b = ueg_basis_index(sys, kb, 1);
+        else if (ij_spin == 0) b = ueg_basis_index(sys, kb, -sys.bf[a].ms);
+        else b = ueg_basis_index(sys, kb, -1);
+        if (b <= 0) g.allowed = false;
+        else { b_ind = (b + 1) / 2; g.allowed = !det_test(d.f, b); }
+    }
+    if (g.allowed) {
+        const double* w = &pp.pp_ia_d.w[(size_t)maxv * i];
+        if (ij_spin == 0) g.pgen = w[a_ind - 1] / pp.pp_ia_d.tot[i];
+        else g.pgen = (w[a_ind - 1] + w[b_ind - 1]) / pp.pp_ia_d.tot[i];
+        g.pgen = g.pgen * 2.0 / (nel * (nel - 1));
+        g.allowed = (a != b);
+    }
+    if (g.allowed) {
+        g.conn.from_orb[0] = i; g.conn.from_orb[1] = j;
+        g.conn.to_orb[0] = std::min(a, b); g.conn.to_orb[1] = std::max(a, b);
+        sys.find_excitation_permutation2(d.f, g.conn);
+        g.hmatel = slater_condon2_ueg_excit(sys, g.conn.from_orb[0], g.conn.to_orb[0], g.conn.to_orb[1], g.conn.perm);
+    } else {
+        g.hmatel = 0.0; g.pgen = 1.0;
+    }
+    return g;
+}
+
 // sc0_ptr / gen_excit_ptr%full dispatch over the system kind (init_proc_pointers, src/qmc.F90:217-703)
 inline double diag_hmatel(const System& sys, const Det& f) {
     if (sys.kind == SYS_UEG) {
@@ -236,7 +300,8 @@ inline double diag_hmatel(const System& sys, const Det& f) {
     return sys.slater_condon0(f);
 }
 inline GenResult gen_excit_sys(Rng& rng, const System& sys, const ExcitGenData& eg, DetInfo& d) {
-    if (sys.kind == SYS_UEG) return gen_excit_ueg_no_renorm(rng, sys, d);
+    if (sys.kind == SYS_UEG)
+        return eg.excit_gen == EXCIT_GEN_POWER_PITZER ? gen_excit_ueg_power_pitzer(rng, sys, eg, d) : gen_excit_ueg_no_renorm(rng, sys, d);
     return gen_excit(rng, sys, eg, d);
 }
 

@@ -50,7 +50,7 @@ def make_pair(name, *, excit_gen="renorm", tau=0.01, seed=11, real=False, initia
         from hande_b200.ueg import UegSystem
         s = UegSystem(*SYSTEMS[name]["ueg"])
         o.init_ueg(*SYSTEMS[name]["ueg"])
-        excit_gen = "no_renorm"
+        excit_gen = "power_pitzer" if excit_gen == "power_pitzer" else "no_renorm"
     else:
         path, kw = system_path(name)
         s = R.read_in(path, **kw)

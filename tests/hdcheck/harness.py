@@ -89,6 +89,11 @@ class HdCheck:
             self.L.hd_set_ppn(which, _p(t["w"]), _p(t["U"]), _p(t["K"]), _p(t["tot"]))
         self.L.hd_set_ppn_occ(_p(occ))
 
+    def set_ueg_power_pitzer(self, table):
+        self.L.hd_set_pp.argtypes = [C.c_int] + [C.c_void_p] * 4
+        self.keep.append(table)
+        self.L.hd_set_pp(0, _p(table["w"]), _p(table["U"]), _p(table["K"]), _p(table["tot"]))
+
     def set_power_pitzer(self, tables, virt, occ, stride):
         self.L.hd_set_pp.argtypes = [C.c_int] + [C.c_void_p] * 4
         self.L.hd_set_pp_virt.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]

@@ -157,6 +157,46 @@ def test_ueg_generator_and_slater_condon(nel, ms, rs, cutoff):
     assert isref and hm == 0.0
 
 
+@pytest.mark.parametrize("nel,ms,rs,cutoff", [(6, 0, 2.0, 2.0), (7, 1, 1.0, 3.0)])
+def test_ueg_power_pitzer_generator(nel, ms, rs, cutoff):
+    """gen_excit_ueg_power_pitzer (src/excit_gen_ueg.f90:362-566): (i) the oracle's pgen is the true
+    sampling probability - each excitation appears with the frequency it reports and sum pgen + P(null) = 1 - (the
+    reference's only fixtures for it use even_selection CCMC); (ii) the engine core is bit-exact against the oracle."""
+    from hande_b200.ueg import UegSystem
+    s = UegSystem(nel, ms, rs, cutoff)
+    o = Oracle()
+    o.init_ueg(nel, ms, rs, cutoff)
+    tau = 0.01
+    o.set_qmc(tau=tau, seed=11, rng_kind=1, excit_gen="power_pitzer")
+    o.init()
+    ref = o.reference()
+    tables, _, _, _ = o.power_pitzer_tables()
+    h = HdCheck(s, EXCIT_GEN["power_pitzer"], 0.0, 1.0, tau, 0.0, 0.0, 1, 0, 11, ref["f0"], ref["H00"])
+    h.set_ueg_power_pitzer(tables[0])
+    dets = synthetic.random_dets(80, s.nbasis, s.nalpha, s.nbeta, seed=3)
+    dets[0] = ref["f0"]
+    pops = np.where(np.arange(len(dets)) % 2 == 0, 3, -2)
+    assert _compare_attempts(s, o, h, dets, pops, tau, ncycle=2, nattempt=6) > 300
+    rng = np.random.default_rng(5)
+    n = 120000
+    for f in [ref["f0"], dets[1]]:
+        counts, pg = {}, {}
+        nnull = 0
+        for _ in range(n):
+            io, do, k = o.gen_excit_list(f, rng.random(16))
+            if not io[6]:
+                nnull += 1
+                continue
+            key = tuple(io[:5])
+            counts[key] = counts.get(key, 0) + 1
+            pg[key] = do[0]
+        total = sum(pg.values()) + nnull / n
+        assert abs(total - 1.0) < 0.02, total
+        for key, c in counts.items():
+            if pg[key] * n > 400:
+                assert abs(c / n - pg[key]) < 5.0 * np.sqrt(pg[key] / n), (key, c / n, pg[key])
+
+
 def test_heat_bath_uniform_generator_synthetic(s10):
     s, o, h = _setup(s10, {}, "heat_bath_uniform", tau=0.01, real=True)
     dets = synthetic.random_dets(120, s.nbasis, s.nalpha, s.nbeta, seed=9)

@@ -122,6 +122,9 @@ def test_gen_excit_ueg():
     # gen_excit_ueg_no_renorm + slater_condon0_ueg on the device, W = 2 and W = 3
     _check_gen("ueg6", "no_renorm", False, 0.005, n=150, nattempt=5)
     _check_gen("ueg14", "no_renorm", True, 0.002, n=150, nattempt=5)
+    # gen_excit_ueg_power_pitzer, table built on the device (init_excit_ueg_power_pitzer)
+    _check_gen("ueg6", "power_pitzer", False, 0.005, n=150, nattempt=5)
+    _check_gen("ueg14", "power_pitzer", True, 0.002, n=150, nattempt=5)
 
 
 def test_heat_bath_tables_match_oracle():
@@ -179,6 +182,7 @@ CASES = [
     ("s12", "power_pitzer_occ_ij", True, True, 0.004, 2500, -1),
     ("ueg6", "no_renorm", False, False, 0.01, 3000, -1),
     ("ueg14", "no_renorm", True, True, 0.004, 4000, -1),
+    ("ueg14", "power_pitzer", True, True, 0.004, 4000, -1),
 ]
 
 
@@ -243,7 +247,8 @@ def _check_ps_stats(eng, o):
                                                      ("s12", "heat_bath", True, True, 0.002),
                                                      ("s12", "heat_bath_uniform", True, False, 0.0004),
                                                      ("ueg6", "no_renorm", False, False, 0.005),
-                                                     ("ueg14", "no_renorm", True, True, 0.002)])
+                                                     ("ueg14", "no_renorm", True, True, 0.002),
+                                                     ("ueg6", "power_pitzer", True, False, 0.005)])
 def test_iterate_from_single_determinant(name, gen, real, init, tau):
     """Population growth from the reference determinant: 60 cycles in blocks of 10 through hb200_iterate."""
     s, o, eng, ref = make_pair(name, excit_gen=gen, tau=tau, real=real, initiator=init)

@@ -37,6 +37,8 @@ def do_ccmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, ke
     nprocs, iproc = comm.size, comm.rank
     if qmc.ex_level < 0:
         raise ValueError("ccmc: reference ex_level (the CC truncation level) must be given")
+    if qmc.quasi_newton:
+        raise NotImplementedError("ccmc: the quasi-Newton propagator is only implemented for FCIQMC")
     is_ueg = getattr(sys, "kind", "read_in") == "ueg"
     if qmc.reference_det:
         occ0 = sorted(int(x) for x in qmc.reference_det)

@@ -126,6 +126,10 @@ struct Params {
     uint64_t f0[HB_MAXW];
     double H00;
     struct PsPartials* ps_part; // per-block sums for qmc_in%pattempt_update (null: not accumulating)
+    // quasi-Newton propagator (propagator_t, src/qmc_data.f90:866-884); sp_fock is 1-based
+    int qn;
+    double qn_threshold, qn_value, qn_pop_control, ref_fock_sum;
+    const double* sp_fock;
 };
 // p_single_double_coll_t (src/excit_gens.f90:13-27): sums of |H_ij| pattempt_{single,double} / pgen over the allowed
 // single / double excitations generated, and how many there were
@@ -1862,6 +1866,23 @@ HB_HD void gen_excit(R& rng, const Sys& s, const Params& p, const uint64_t* f, c
 // ------------------------------------------------------------------------------------------------
 // Spawning / death arithmetic
 // ------------------------------------------------------------------------------------------------
+// quasi-Newton weights: cdet%fock_sum (src/fciqmc.f90:321-322), calc_qn_spawned_weighting and calc_qn_weighting
+// (src/spawning.F90:2063-2137)
+HB_HD double qn_fock_sum(const Sys& s, const Params& p, const uint8_t* occ) {
+    double fs = 0.0;
+    for (int k = 0; k < s.nel; ++k) fs = fs + p.sp_fock[occ[k]];
+    return fs - p.ref_fock_sum;
+}
+HB_HD double qn_spawned_weighting(const Params& p, double spawner_dfock, const Gen& g) {
+    double diagel = spawner_dfock;
+    diagel = diagel + p.sp_fock[g.to1] - p.sp_fock[g.from1];
+    if (g.nexcit == 2) diagel = diagel + p.sp_fock[g.to2] - p.sp_fock[g.from2];
+    if (diagel < p.qn_threshold) diagel = p.qn_value;
+    return 1.0 / diagel;
+}
+HB_HD double qn_weighting(const Params& p, double dfock) {
+    return (dfock < p.qn_threshold) ? 1.0 / p.qn_value : 1.0 / dfock;
+}
 // attempt_to_spawn + stochastic_round_spawned_particle (src/spawning.F90:711-766,
 // src/stoch_utils.f90:87-136).  Always draws exactly one random number.
 template <class R>
@@ -1896,8 +1917,9 @@ HB_HD int decide_nattempts(R& rng, double population) {
 // stochastic_death (src/death.f90:11-130), no quasi-Newton / Chebyshev weights.  Returns the new
 // population; kill_abs receives |kill| (ndeath contribution).
 template <class R>
-HB_HD int64_t stochastic_death(R& rng, const Params& p, double Kii, int64_t population, int64_t& kill_abs) {
-    double pd = p.tau * ((Kii - p.proj_energy_old) * 1.0 + (p.proj_energy_old - p.shift) * 1.0) * 1.0;
+HB_HD int64_t stochastic_death(R& rng, const Params& p, double Kii, int64_t population, int64_t& kill_abs, double weight = 1.0) {
+    const double pop_control = p.qn ? p.qn_pop_control : 1.0;
+    double pd = p.tau * ((Kii - p.proj_energy_old) * weight + (p.proj_energy_old - p.shift) * pop_control) * 1.0;
     pd = pd * 1.0;
     int64_t apop = population < 0 ? -population : population;
     pd = pd * (double)apop;

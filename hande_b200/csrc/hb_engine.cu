@@ -175,11 +175,12 @@ constexpr int SINGLES_CHUNK = 64;  // single excitations whose pgen terms are st
 // that are only live in the later phases.
 struct SpawnSmem {
     size_t sf, shash, ssign, sscan, swarp, sred, siw, sw, sh1, shm, ssp, spsum, sterm, sok, sq, scnt, sflag, slo, sperm, ssq,
-        ssi, socc, ssu, sps, total;
+        ssi, socc, ssu, sps, sdf, total;
     // heat_bath: the original heat-bath generator (phase buffers); hb_stage: any generator that selects i, j from the
     // heat-bath weights (needs the hb_i_w copy and the per-thread staging area of nel doubles)
     // ps: pattempt_update statistics are accumulated (per thread: two doubles and two counters)
-    __host__ __device__ SpawnSmem(int W, int nel, int nsu, int nb, bool heat_bath, bool hb_stage, bool ps) {
+    // qn: quasi-Newton propagator (fock_sum of each state of the tile)
+    __host__ __device__ SpawnSmem(int W, int nel, int nsu, int nb, bool heat_bath, bool hb_stage, bool ps, bool qn) {
         size_t o = 0;
         sf = o;     o += (size_t)TILE * W * 8;
         sred = o;   o += 40 * 8;
@@ -215,6 +216,7 @@ struct SpawnSmem {
         ssu = o;    o += (size_t)TILE * nsu;
         o = (o + 7) & ~(size_t)7;
         sps = o;    o += ps ? (size_t)TILE * 24 : 0;
+        sdf = o;    o += qn ? (size_t)TILE * 8 : 0;
         total = (o + 15) & ~(size_t)15;
     }
 };
@@ -249,7 +251,8 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
     const int nsu = (GEN == EXCIT_GEN_POWER_PITZER_ORDERN) ? nel : (GEN == EXCIT_GEN_RENORM || GEN == EXCIT_GEN_RENORM_SPIN || GEN == EXCIT_GEN_HEAT_BATH_UNIFORM || GEN == EXCIT_GEN_POWER_PITZER_OCC ||
                      GEN == EXCIT_GEN_POWER_PITZER_OCC_IJ) ? 2 * s.nsym_tot : 0;
     const bool ps_on = !heat_bath && p.ps_part != nullptr;
-    const SpawnSmem L(W, nel, nsu, s.nbasis, heat_bath, hb_stage, ps_on);
+    const SpawnSmem L(W, nel, nsu, s.nbasis, heat_bath, hb_stage, ps_on, p.qn != 0);
+    double* sdf = reinterpret_cast<double*>(smem_raw + L.sdf);
     double* sps_h = reinterpret_cast<double*>(smem_raw + L.sps);                  // [2][TILE]: singles, doubles
     unsigned* sps_n = reinterpret_cast<unsigned*>(smem_raw + L.sps + 16 * TILE);  // [2][TILE]
     if (ps_on) {
@@ -317,7 +320,13 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
         natt = decide_nattempts(rng, real_pop);
         rng.begin(p.seed, p.cycle, RNG_DEATH, h, 0);
         int64_t kill_abs;
-        const int64_t newpop = stochastic_death(rng, p, Kii, pop, kill_abs);
+        double death_weight = 1.0;
+        if (p.qn) {
+            const double dfock = qn_fock_sum(s, p, occ);
+            sdf[tid] = dfock;
+            death_weight = qn_weighting(p, dfock);
+        }
+        const int64_t newpop = stochastic_death(rng, p, Kii, pop, kill_abs, death_weight);
         pops[idx] = newpop;
         ndeath = kill_abs;
         npart = newpop < 0 ? -newpop : newpop;
@@ -470,12 +479,14 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
         uint64_t child[W];
         int dest = 0, pflag = 0;
         if (active) {
+            double hmq = g.hmatel;
+            if (p.qn && g.allowed) hmq = hmq * qn_spawned_weighting(p, sdf[lo], g);   // spawn_standard (src/spawning.F90:101-103)
             if (ps_on && g.allowed) {   // update_p_single_double_data (src/spawning.F90:104-109,2139-2215)
                 const int k = (g.nexcit == 2) ? TILE : 0;
-                sps_h[k + tid] = sps_h[k + tid] + (fabs(g.hmatel) * (g.nexcit == 2 ? p.pattempt_double : p.pattempt_single)) / g.pgen;
+                sps_h[k + tid] = sps_h[k + tid] + (fabs(hmq) * (g.nexcit == 2 ? p.pattempt_double : p.pattempt_single)) / g.pgen;
                 sps_n[k + tid] += 1u;
             }
-            nspawn = attempt_to_spawn(rng, p, g.hmatel, g.pgen, ssign[lo] ? (int64_t)-1 : (int64_t)1);
+            nspawn = attempt_to_spawn(rng, p, hmq, g.pgen, ssign[lo] ? (int64_t)-1 : (int64_t)1);
             if (nspawn != 0) {
                 make_child<W>(f, g, child);
                 // create_spawned_particle[_initiator]_truncated (src/spawning.F90:1186-1319)
@@ -1681,7 +1692,8 @@ static size_t spawn_smem_bytes(const hb200_engine* e) {
                      eg != HB200_EXCIT_GEN_HEAT_BATH_SINGLE)
                         ? 2 * e->sys.nsym_tot : 0;
     const bool hb = eg == HB200_EXCIT_GEN_HEAT_BATH;
-    return SpawnSmem(e->W, e->sys.nel, nsu, e->sys.nbasis, hb, uses_heat_bath_tables(e), !hb && e->par.ps_part != nullptr).total;
+    return SpawnSmem(e->W, e->sys.nel, nsu, e->sys.nbasis, hb, uses_heat_bath_tables(e), !hb && e->par.ps_part != nullptr,
+                     e->par.qn != 0).total;
 }
 
 extern "C" {
@@ -2632,6 +2644,7 @@ int hb200_ccmc_spawn(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, i
     CK(cudaSetDevice(e->cfg.device));
     if (!e->have_sys) FAIL("ccmc_spawn: system not set");
     if (uses_heat_bath_tables(e) && !e->have_hb) FAIL("ccmc_spawn: heat-bath tables not built");
+    if (e->par.qn) FAIL("ccmc_spawn: the quasi-Newton propagator is only implemented for FCIQMC");
     if (e->cfg.excit_gen == HB200_EXCIT_GEN_POWER_PITZER_ORDERN && !e->have_ppn) FAIL("ccmc_spawn: power_pitzer_orderN tables not built");
     if (e->cfg.excit_gen == HB200_EXCIT_GEN_POWER_PITZER && !e->have_pp) FAIL("ccmc_spawn: power_pitzer tables not built");
     if (e->par.nprocs > 1 && !e->comm) FAIL("ccmc_spawn: nprocs > 1 but hb200_comm_init was not called");
@@ -2838,6 +2851,23 @@ int hb200_set_pattempt_parallel(hb200_engine* e, double pattempt_parallel) {
     return 0;
 }
 double hb200_get_pattempt_parallel(hb200_engine* e) { return e->par.pattempt_parallel; }
+
+// qmc = { quasi_newton = true } (propagator_t, src/qmc_data.f90:866-884; init_sp_fock / init_quasi_newton,
+// src/qmc.F90:1064-1160): sp_fock[0..nbasis] (entry 0 unused; null switches the propagator off), the reference's
+// fock_sum and the threshold / value / population-control scalars.  FCIQMC only.
+int hb200_set_quasi_newton(hb200_engine* e, const double* sp_fock, double ref_fock_sum, double threshold, double value,
+                           double pop_control) {
+    CK(cudaSetDevice(e->cfg.device));
+    Params& p = e->par;
+    if (!sp_fock) { p.qn = 0; p.sp_fock = nullptr; return 0; }
+    if (!e->have_sys) FAIL("set_quasi_newton: system not set");
+    double* d = nullptr;
+    if (dalloc(e, &d, (size_t)e->sys.nbasis + 1)) return 1;
+    CK(copy_sync(e, d, sp_fock, ((size_t)e->sys.nbasis + 1) * sizeof(double), cudaMemcpyHostToDevice));
+    p.sp_fock = d; p.ref_fock_sum = ref_fock_sum; p.qn_threshold = threshold; p.qn_value = value; p.qn_pop_control = pop_control;
+    p.qn = 1;
+    return 0;
+}
 
 // qmc_in%pattempt_update (src/qmc.F90:1049-1060, src/spawning.F90:2139-2372): the engine holds pattempt_single /
 // pattempt_double and, while `accumulate` is set, sums |H_ij| pattempt / pgen and the counts of the allowed single and

@@ -139,6 +139,7 @@ def load_library():
     L.hb200_get_ps_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
     L.hb200_build_power_pitzer_orderN.argtypes = [C.c_void_p, C.c_double]
     L.hb200_build_power_pitzer.argtypes = [C.c_void_p, C.c_double]
+    L.hb200_set_quasi_newton.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]
     L.hb200_set_pattempt_parallel.argtypes = [C.c_void_p, C.c_double]
     L.hb200_get_pattempt_parallel.argtypes = [C.c_void_p]
     L.hb200_get_pattempt_parallel.restype = C.c_double
@@ -163,7 +164,7 @@ ABI_SYMBOLS = [
     "hb200_download_heat_bath", "hb200_set_reference", "hb200_set_proc_map", "hb200_upload_psips",
     "hb200_upload_psips_begin", "hb200_upload_psips_commit",
     "hb200_download_psips", "hb200_nstates", "hb200_iterate", "hb200_spawn_death", "hb200_comm_spawn",
-    "hb200_ccmc_spawn", "hb200_ccmc_iterate", "hb200_ccmc_set_hash_shift", "hb200_ccmc_set_full_nc", "hb200_set_pattempt", "hb200_get_ps_stats", "hb200_set_pattempt_parallel", "hb200_get_pattempt_parallel", "hb200_build_power_pitzer_orderN", "hb200_build_power_pitzer", "hb200_annihilate_spawn", "hb200_annihilate_main", "hb200_download_spawn", "hb200_upload_spawn",
+    "hb200_ccmc_spawn", "hb200_ccmc_iterate", "hb200_ccmc_set_hash_shift", "hb200_ccmc_set_full_nc", "hb200_set_pattempt", "hb200_get_ps_stats", "hb200_set_pattempt_parallel", "hb200_get_pattempt_parallel", "hb200_build_power_pitzer_orderN", "hb200_build_power_pitzer", "hb200_set_quasi_newton", "hb200_annihilate_spawn", "hb200_annihilate_main", "hb200_download_spawn", "hb200_upload_spawn",
     "hb200_sc0_batch", "hb200_gen_excit_batch", "hb200_get_unique_id", "hb200_comm_init", "hb200_last_timing",
 ]
 
@@ -330,6 +331,13 @@ class Engine:
     def set_pattempt(self, pattempt_single, pattempt_double, accumulate=False):
         """excit_gen_data%pattempt_single/double; accumulate: collect the pattempt_update statistics on the device"""
         self._chk(self.L.hb200_set_pattempt(self.h, float(pattempt_single), float(pattempt_double), int(bool(accumulate))))
+
+    def set_quasi_newton(self, sp_fock, ref_fock_sum, threshold, value, pop_control):
+        """qmc = { quasi_newton = true }: propagator%sp_fock (1-based, entry 0 unused) and the resolved scalars"""
+        sp = np.ascontiguousarray(sp_fock, dtype=np.float64)
+        assert len(sp) == self.sys.nbasis + 1
+        self._chk(self.L.hb200_set_quasi_newton(self.h, _p(sp), float(ref_fock_sum), float(threshold), float(value),
+                                                float(pop_control)))
 
     def set_pattempt_parallel(self, pattempt_parallel=-1.0):
         """qmc_in%pattempt_parallel (renorm_spin / no_renorm_spin); negative: find_parallel_spin_prob_mol on the device"""

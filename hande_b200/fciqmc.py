@@ -43,6 +43,10 @@ class QmcIn:
     pattempt_single: float = -1.0
     pattempt_double: float = -1.0
     pattempt_parallel: float = -1.0   # renorm_spin / no_renorm_spin; < 0: find_parallel_spin_prob_mol
+    quasi_newton: bool = False            # qmc = { quasi_newton = true, ... } (FCIQMC); negative scalars: defaults
+    quasi_newton_threshold: float = -1.0
+    quasi_newton_value: float = -1.0
+    quasi_newton_pop_control: float = -1.0
     pattempt_update: bool = False   # qmc_in%pattempt_update: pattempt_single follows the spawn statistics until the shift varies
     state_size: int = -5            # <0: MB (src/particle_t_utils.f90), >0: elements
     spawned_state_size: int = -1
@@ -50,6 +54,35 @@ class QmcIn:
     nslots: int = 1
     full_non_composite: bool = False  # ccmc = {full_non_composite = true} (CCMC only)
     reference_det: list = None      # reference = {det = {...}}: explicit reference determinant (1-based orbitals)
+
+
+def init_propagator(sys, occ0, qmc):
+    """init_sp_fock + init_quasi_newton (src/qmc.F90:1064-1160) with calc_fock_values_3d_ueg
+    (src/hamiltonian_ueg.f90:299-395).  Returns (sp_fock[0..nbasis], ref_fock_sum, threshold, value, pop_control)."""
+    nb, nel = sys.nbasis, sys.nel
+    sp = np.zeros(nb + 1)
+    sp[1:] = np.asarray(sys.sp_eigv, dtype=np.float64)[1:nb + 1]
+    if getattr(sys, "kind", "read_in") == "ueg":
+        mad_c = float(np.float32(-2.837297))       # a default-kind (single precision) literal in the reference
+        for i in range(1, nb + 1):
+            ex = 0.0
+            for o in occ0:
+                if (o % 2) == (i % 2) and o != i:
+                    ex = ex - sys.coulomb_int(o, i)
+            mad = mad_c * (0.75 / (math.pi * (sys.rs ** 3) * float(nel))) ** (1.0 / 3.0) if i in occ0 else 0.0
+            sp[i] = sp[i] + ex + 0.5 * mad
+    ref_fock_sum = 0.0
+    for o in occ0:
+        ref_fock_sum = ref_fock_sum + sp[o]
+    if qmc.quasi_newton_threshold < 0.0:
+        thr = sp[nel + 1] - sp[nel]
+        if getattr(sys, "kind", "read_in") == "ueg":
+            thr = 2.0 * thr
+    else:
+        thr = qmc.quasi_newton_threshold
+    val = thr if qmc.quasi_newton_value < 0.0 else qmc.quasi_newton_value
+    pc = 1.0 / thr if qmc.quasi_newton_pop_control < 0.0 else qmc.quasi_newton_pop_control
+    return sp, float(ref_fock_sum), float(thr), float(val), float(pc)
 
 
 class PattemptUpdate:
@@ -235,6 +268,8 @@ def do_fciqmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, 
                      nprocs=nprocs, iproc=iproc, nslots=qmc.nslots, device=device,
                      pattempt_parallel=qmc.pattempt_parallel)
     eng.set_reference(f0, H00)
+    if qmc.quasi_newton:
+        eng.set_quasi_newton(*init_propagator(sys, occ0, qmc))
     if nprocs > 1:
         uid = eng.get_unique_id() if iproc == 0 else np.zeros(128, dtype=np.uint8)
         uid = comm.broadcast_bytes(uid, src=0)

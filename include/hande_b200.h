@@ -175,6 +175,14 @@ int hb200_ccmc_set_hash_shift(hb200_engine* e, int32_t hash_shift, int32_t move_
  * size >= 2 are selected stochastically and the reference is selected nint(|N_0|) times. */
 int hb200_ccmc_set_full_nc(hb200_engine* e, int32_t full_nc);
 
+/* qmc = { quasi_newton = true } (src/qmc_data.f90:227-241,866-884): spawning amplitudes are scaled by
+ * calc_qn_spawned_weighting and the death probability by calc_qn_weighting / quasi_newton_pop_control
+ * (src/spawning.F90:2063-2137, src/death.f90:87).  sp_fock[0..nbasis] (entry 0 unused) is propagator%sp_fock as
+ * init_sp_fock makes it (src/qmc.F90:1064-1090: sp_eigv, plus exchange and Madelung terms for the 3D UEG), ref_fock_sum
+ * its sum over the reference; threshold / value / pop_control as init_quasi_newton resolves them (:1092-1160).
+ * sp_fock = NULL switches the propagator off.  FCIQMC only in this version. */
+int hb200_set_quasi_newton(hb200_engine* e, const double* sp_fock, double ref_fock_sum, double threshold, double value,
+                           double pop_control);
 /* qmc = { pattempt_update = true } (qmc_in%pattempt_update, src/qmc.F90:1049-1060).  hb200_set_pattempt replaces
  * excit_gen_data%pattempt_single / pattempt_double; while accumulate != 0 every allowed excitation generated by
  * hb200_iterate / hb200_ccmc_iterate adds |H_ij| pattempt_{single,double} / pgen and 1 to the p_single_double_coll_t sums

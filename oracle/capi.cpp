@@ -412,6 +412,18 @@ const int* orc_pp_virt(void* h, int spin, int* n) {
 }
 int orc_pp_stride(void* h) { return ((Oracle*)h)->eg.ppn.pp_ia_d.stride; }
 const int* orc_ppn_occ(void* h) { return ((Oracle*)h)->eg.ppn.occ_list.data(); }
+// qmc = { quasi_newton = true, quasi_newton_threshold/value/pop_control (negative: defaults) }; call before orc_init
+void orc_set_quasi_newton(void* h, int on, double threshold, double value, double pop_control) {
+    Oracle* o = (Oracle*)h;
+    o->in.quasi_newton = on != 0; o->in.quasi_newton_threshold = threshold; o->in.quasi_newton_value = value;
+    o->in.quasi_newton_pop_control = pop_control;
+}
+// out: ref_fock_sum, threshold, value, pop_control; sp_fock[nbasis+1]
+void orc_get_quasi_newton(void* h, double* out, double* sp_fock) {
+    Oracle* o = (Oracle*)h;
+    out[0] = o->ref_fock_sum; out[1] = o->qn_threshold; out[2] = o->qn_value; out[3] = o->qn_pop_control;
+    for (size_t i = 0; i < o->sp_fock.size(); ++i) sp_fock[i] = o->sp_fock[i];
+}
 void orc_set_pattempt_parallel(void* h, double pp) { ((Oracle*)h)->in.pattempt_parallel = pp; ((Oracle*)h)->eg.pattempt_parallel = pp; }
 double orc_get_pattempt_parallel(void* h) { return ((Oracle*)h)->eg.pattempt_parallel; }
 void orc_set_pattempt(void* h, double ps, double pd) { ((Oracle*)h)->eg.pattempt_single = ps; ((Oracle*)h)->eg.pattempt_double = pd; }

@@ -44,6 +44,9 @@ struct QmcIn {
     int excit_gen = EXCIT_GEN_RENORM;
     double pattempt_single = -1.0, pattempt_double = -1.0;
     double pattempt_parallel = -1.0;
+    // quasi-Newton propagator (src/qmc_data.f90:227-241)
+    bool quasi_newton = false;
+    double quasi_newton_threshold = -1.0, quasi_newton_value = -1.0, quasi_newton_pop_control = -1.0;
     int64_t walker_length = 1 << 20;          // elements per rank
     int64_t spawned_walker_length = 1 << 18;  // elements per rank
     int ex_level = -1;                        // truncation level (reference%ex_level); -1 => none
@@ -185,6 +188,59 @@ struct Oracle {
     PsColl ps_total;
     double ps_counter = 1.0;
     std::vector<double> pattempt_log;  // pattempt_single after each change ("# pattempt_single changed to be:")
+    // propagator_t (src/qmc_data.f90:866-884): quasi-Newton weights
+    bool qn = false;
+    std::vector<double> sp_fock;      // 1-based
+    double ref_fock_sum = 0.0, qn_threshold = 0.0, qn_value = 0.0, qn_pop_control = 1.0;
+    // init_sp_fock + init_quasi_newton (src/qmc.F90:1064-1160), calc_fock_values_3d_ueg (src/hamiltonian_ueg.f90:299-395)
+    void init_propagator() {
+        sp_fock.assign(sys.nbasis + 1, 0.0);
+        for (int i = 1; i <= sys.nbasis; ++i) sp_fock[i] = sys.bf[i].sp_eigv;
+        if (sys.kind == SYS_UEG) {
+            const double pi = 3.1415926535897931;
+            for (int i = 1; i <= sys.nbasis; ++i) {
+                double ex = 0.0;
+                bool in_ref = false;
+                for (int k = 0; k < sys.nel; ++k) {
+                    const int o = occ_list0[k];
+                    if ((o % 2) == (i % 2) && o != i) ex = ex - coulomb_int_ueg_3d(sys, o, i);
+                    if (o == i) in_ref = true;
+                }
+                // the reference writes the Madelung constant as a default-kind (single precision) literal
+                const double mad = in_ref ? (double)(-2.837297f) * std::pow(0.75 / (pi * (sys.ueg.rs * sys.ueg.rs * sys.ueg.rs) * (double)sys.nel), 1.0 / 3.0) : 0.0;
+                sp_fock[i] = sp_fock[i] + ex + 0.5 * mad;
+            }
+        }
+        ref_fock_sum = 0.0;
+        for (int k = 0; k < sys.nel; ++k) ref_fock_sum = ref_fock_sum + sp_fock[occ_list0[k]];
+        qn = in.quasi_newton;
+        if (qn) {
+            if (in.quasi_newton_threshold < 0.0) {
+                qn_threshold = sp_fock[sys.nel + 1] - sp_fock[sys.nel];
+                if (sys.kind == SYS_UEG) qn_threshold = 2.0 * qn_threshold;
+            } else qn_threshold = in.quasi_newton_threshold;
+        }
+        qn_value = (in.quasi_newton_value < 0.0) ? qn_threshold : in.quasi_newton_value;
+        if (qn) qn_pop_control = (in.quasi_newton_pop_control < 0.0) ? 1.0 / qn_threshold : in.quasi_newton_pop_control;
+        else qn_pop_control = 1.0;
+    }
+    double fock_sum_of(const int* occ) const {   // sum_fock_values_occ_list - ref%fock_sum (src/fciqmc.f90:321-322)
+        double fs = 0.0;
+        for (int k = 0; k < sys.nel; ++k) fs = fs + sp_fock[occ[k]];
+        return fs - ref_fock_sum;
+    }
+    // calc_qn_spawned_weighting / calc_qn_weighting (src/spawning.F90:2063-2137)
+    double qn_spawned_weighting(double spawner_dfock, const Excit& c) const {
+        if (!qn) return 1.0;
+        double diagel = spawner_dfock;
+        for (int k = 0; k < c.nexcit; ++k) diagel = diagel + sp_fock[c.to_orb[k]] - sp_fock[c.from_orb[k]];
+        if (diagel < qn_threshold) diagel = qn_value;
+        return 1.0 / diagel;
+    }
+    double qn_weighting(double dfock) const {
+        if (!qn) return 1.0;
+        return (dfock < qn_threshold) ? 1.0 / qn_value : 1.0 / dfock;
+    }
     // end_report_loop (src/qmc_common.F90:1206-1231)
     void end_report_loop_pattempt() {
         if (!vary_psingles) return;
@@ -257,6 +313,7 @@ struct Oracle {
         tau = in.tau;
         shift = in.initial_shift;
         vary_shift = false;
+        init_propagator();
         // init_excit_gen (src/qmc.F90:910-1010)
         eg.excit_gen = in.excit_gen;
         if (in.pattempt_single < 0 || in.pattempt_double < 0) {
@@ -422,6 +479,7 @@ struct Oracle {
             // set_parent_flag (src/ifciqmc.f90:13-57), nspaces=1, no deterministic space (determ_flag=1)
             d.initiator_flag = (std::fabs(real_population) > in.initiator_pop) ? 0 : 1;
             update_proj_energy(d, real_population, r.D0_population, r.proj_energy);
+            const double dfock = qn ? fock_sum_of(d.occ) : 0.0;
             rng.begin(RNG_NATTEMPTS, d.f, sys.W, 0);
             int nattempts_det = decide_nattempts(rng, real_population);
             int64_t pop = r.pops[idet];
@@ -439,7 +497,8 @@ struct Oracle {
                         a.excit_gen_doubles = a.excit_gen_doubles + 1.0;
                     }
                 }
-                int64_t nspawned = attempt_to_spawn(rng, g.hmatel, g.pgen, pop);
+                const double qn_weight = g.allowed ? qn_spawned_weighting(dfock, g.conn) : 1.0;   // spawn_standard
+                int64_t nspawned = attempt_to_spawn(rng, g.hmatel * qn_weight, g.pgen, pop);
                 if (nspawned != 0) {
                     Det fnew = sys.create_excited_det(d.f, g.conn);
                     // create_spawned_particle[_initiator][_truncated] (src/spawning.F90:1074-1319)
@@ -460,8 +519,8 @@ struct Oracle {
             {
                 rng.begin(RNG_DEATH, d.f, sys.W, 0);
                 double Kii = r.dat[idet];
-                double weight = 1.0;
-                double pd = tau * ((Kii - est.proj_energy_old) * weight + (est.proj_energy_old - shift) * 1.0) * 1.0;
+                double weight = qn_weighting(dfock);
+                double pd = tau * ((Kii - est.proj_energy_old) * weight + (est.proj_energy_old - shift) * qn_pop_control) * 1.0;
                 pd = pd * 1.0;
                 int64_t& population = r.pops[idet];
                 int64_t apop = population < 0 ? -population : population;

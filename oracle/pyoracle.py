@@ -370,6 +370,17 @@ class Oracle:
         self.L.orc_get_ps_stats(self.h, int(rank), out.ctypes.data_as(C.c_void_p), int(reset))
         return out
 
+    def set_quasi_newton(self, on=True, threshold=-1.0, value=-1.0, pop_control=-1.0):
+        """qmc = { quasi_newton = true, ... } (before init)"""
+        self.L.orc_set_quasi_newton.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double]
+        self.L.orc_set_quasi_newton(self.h, int(on), float(threshold), float(value), float(pop_control))
+
+    def quasi_newton(self):
+        out, sp = np.zeros(4), np.zeros(self.nbasis + 1)
+        self.L.orc_get_quasi_newton.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        self.L.orc_get_quasi_newton(self.h, out.ctypes.data_as(C.c_void_p), sp.ctypes.data_as(C.c_void_p))
+        return dict(ref_fock_sum=out[0], threshold=out[1], value=out[2], pop_control=out[3], sp_fock=sp)
+
     def pattempt_parallel(self):
         self.L.orc_get_pattempt_parallel.restype = C.c_double
         self.L.orc_get_pattempt_parallel.argtypes = [C.c_void_p]

@@ -43,7 +43,7 @@ def system_path(name):
 
 
 def make_pair(name, *, excit_gen="renorm", tau=0.01, seed=11, real=False, initiator=False, ex_level=-1,
-              walker_length=1 << 17, spawned_walker_length=1 << 16, engine=True, device=0):
+              walker_length=1 << 17, spawned_walker_length=1 << 16, engine=True, device=0, quasi_newton=None):
     """Host system + oracle (Philox stream, symmetric initiator event rule) + GPU engine with identical options."""
     o = Oracle()
     if "ueg" in SYSTEMS[name]:
@@ -58,6 +58,8 @@ def make_pair(name, *, excit_gen="renorm", tau=0.01, seed=11, real=False, initia
     o.set_qmc(tau=tau, seed=seed, excit_gen=excit_gen, rng_kind=1, real_amplitudes=int(real), spawn_cutoff=0.01,
               initiator_approx=int(initiator), ex_level=ex_level, literal_event_int32=0, walker_length=walker_length,
               spawned_walker_length=spawned_walker_length)
+    if quasi_newton is not None:
+        o.set_quasi_newton(True, **quasi_newton)
     o.init()
     ref = o.reference()
     eng = None
@@ -69,6 +71,9 @@ def make_pair(name, *, excit_gen="renorm", tau=0.01, seed=11, real=False, initia
                      spawned_walker_length=spawned_walker_length, seed=seed, device=device,
                      pattempt_parallel=(o.pattempt_parallel() if excit_gen.endswith("_spin") else -1.0))
         eng.set_reference(ref["f0"], ref["H00"])
+        if quasi_newton is not None:
+            q = o.quasi_newton()
+            eng.set_quasi_newton(q["sp_fock"], q["ref_fock_sum"], q["threshold"], q["value"], q["pop_control"])
     return s, o, eng, ref
 
 

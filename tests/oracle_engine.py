@@ -12,7 +12,7 @@ from oracle.pyoracle import Oracle
 _PATH = {}
 
 
-def make_engine_cls(fcidump_path, sys_kw, rng_kind=0, ueg=None, ref_det=None):
+def make_engine_cls(fcidump_path, sys_kw, rng_kind=0, ueg=None, ref_det=None, quasi_newton=None):
     class OracleRankEngine:
         def __init__(self, sys, *, excit_gen, pattempt_single, pattempt_double, real_amplitudes, spawn_cutoff,
                      initiator_approx, initiator_pop, trunc_level, walker_length, spawned_walker_length, seed, nprocs,
@@ -34,6 +34,8 @@ def make_engine_cls(fcidump_path, sys_kw, rng_kind=0, ueg=None, ref_det=None):
                       nprocs=nprocs, nslots=nslots)
             if pattempt_parallel >= 0:
                 o.set_pattempt_parallel(pattempt_parallel)
+            if quasi_newton is not None:
+                o.set_quasi_newton(True, **quasi_newton)
             o.init()
             L = o.L
             L.orc_rank_spawn.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_void_p]
@@ -112,6 +114,12 @@ def make_engine_cls(fcidump_path, sys_kw, rng_kind=0, ueg=None, ref_det=None):
             out["nparticles"] = float(o.L.orc_nparticles(o.h, self.rank))
             out["nstates"] = self.nstates
             return out
+
+        def set_quasi_newton(self, sp_fock, ref_fock_sum, threshold, value, pop_control):
+            # the stand-in was created with the same options: the host's propagator must equal the oracle's
+            q = self.o.quasi_newton()
+            assert (np.asarray(sp_fock) == q["sp_fock"]).all() and ref_fock_sum == q["ref_fock_sum"]
+            assert (threshold, value, pop_control) == (q["threshold"], q["value"], q["pop_control"])
 
         def set_pattempt(self, pattempt_single, pattempt_double, accumulate=False):
             self.o.set_pattempt(pattempt_single, pattempt_double)

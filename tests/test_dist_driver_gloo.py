@@ -22,18 +22,22 @@ def _worker(rank, world, port, fcidump, q):
     from hande_b200 import read_in as R
     from hande_b200.fciqmc import QmcIn, TorchDist, do_fciqmc
     from tests.oracle_engine import make_engine_cls
-    if fcidump == "ueg_np2":
+    if fcidump in ("ueg_np2", "ueg_qn_real64_np2"):
         from hande_b200.ueg import UegSystem
-        g = load_golden("ueg_np2")
+        g = load_golden(fcidump)
         u = g["ueg"]
         ueg = (u["nel"], u["ms"], u["rs"], u["cutoff"])
         s = UegSystem(*ueg)
         gq = g["qmc"]
         qmc = QmcIn(tau=gq["tau"], rng_seed=gq["seed"], init_pop=gq["D0_population"], mc_cycles=gq["ncycles"],
                     nreports=NROWS, target_population=gq["target_particles"], state_size=gq["walker_length"],
-                    spawned_state_size=gq["spawned_walker_length"], reference_det=g["ref_det"])
+                    spawned_state_size=gq["spawned_walker_length"], reference_det=g["ref_det"],
+                    real_amplitudes=bool(gq.get("real_amplitudes", 0)), spawn_cutoff=gq.get("spawn_cutoff", 0.01))
+        qn = g.get("quasi_newton")
+        if qn is not None:     # the host's init_propagator is checked against the oracle's inside the stand-in engine
+            qmc.quasi_newton, qmc.quasi_newton_threshold = True, qn["threshold"]
         res = do_fciqmc(s, qmc, comm=TorchDist(),
-                        engine_cls=make_engine_cls(None, None, rng_kind=0, ueg=ueg, ref_det=g["ref_det"]))
+                        engine_cls=make_engine_cls(None, None, rng_kind=0, ueg=ueg, ref_det=g["ref_det"], quasi_newton=qn))
         if rank == 0:
             q.put(res.rows)
         dist.barrier()
@@ -53,7 +57,7 @@ def _worker(rank, world, port, fcidump, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case", ["ne_ci6_np2", "ueg_np2"])
+@pytest.mark.parametrize("case", ["ne_ci6_np2", "ueg_np2", "ueg_qn_real64_np2"])
 def test_np2_driver_reproduces_golden(fcidump_path, case):
     from oracle import pyoracle
     if not pyoracle.have_ref_lib():
@@ -62,7 +66,7 @@ def test_np2_driver_reproduces_golden(fcidump_path, case):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     path = fcidump_path("ne") if case == "ne_ci6_np2" else case
-    port = 29577 if case == "ne_ci6_np2" else 29579
+    port = {"ne_ci6_np2": 29577, "ueg_np2": 29579}.get(case, 29581)
     procs = [ctx.Process(target=_worker, args=(r, 2, port, path, q)) for r in range(2)]
     for p in procs:
         p.start()

@@ -274,6 +274,32 @@ def test_iterate_from_single_determinant(name, gen, real, init, tau):
     eng.close()
 
 
+@pytest.mark.parametrize("name,gen,real,init,tau,qn", [("ueg6", "no_renorm", True, False, 0.005, dict(threshold=1.0)),
+                                                        ("h2o", "renorm", False, True, 0.003, dict()),
+                                                        ("s12", "heat_bath", True, True, 0.002, dict(threshold=0.3, value=0.5))])
+def test_quasi_newton_propagator(name, gen, real, init, tau, qn):
+    """qmc = { quasi_newton = true }: spawn amplitudes scaled by calc_qn_spawned_weighting, death by
+    calc_qn_weighting and quasi_newton_pop_control; 40 cycles from the reference determinant against the oracle, whose
+    quasi-Newton runs reproduce the reference's UEG golden table."""
+    s, o, eng, ref = make_pair(name, excit_gen=gen, tau=tau, real=real, initiator=init, quasi_newton=qn)
+    rf = 2**31 if real else 1
+    f0 = ref["f0"].reshape(1, -1)
+    o.set_psips(f0, [50 * rf], [0.0])
+    eng.upload_psips(f0, [50 * rf], [0.0])
+    cyc = 1
+    for block in range(4):
+        ro = o.iterate(10, cyc, tau, 0.01, -0.02 * block)
+        rg = eng.iterate(10, tau, 0.01, -0.02 * block, cyc)
+        cyc += 10
+        fo, po, do_ = o.get_psips()
+        fg, pg, dg = eng.download_psips()
+        assert len(fg) == len(fo)
+        assert (fg == fo).all() and (pg == po).all() and (dg == do_).all()
+        assert rg["nspawn_events"] == ro["nspawn_events"] and rg["ndeath"] == ro["ndeath"]
+    assert len(fg) > 10
+    eng.close()
+
+
 def test_edge_cases_empty_and_overflow():
     s, o, eng, ref = make_pair("h2o", tau=0.003, walker_length=64, spawned_walker_length=32)
     # empty main list

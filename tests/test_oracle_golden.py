@@ -35,6 +35,8 @@ def _run(case, fcidump_path, nrows):
     o.set_qmc(**q)
     if g.get("pattempt_parallel", -1.0) >= 0:
         o.set_pattempt_parallel(g["pattempt_parallel"])
+    if "quasi_newton" in g:
+        o.set_quasi_newton(True, **g["quasi_newton"])
     o.init()
     if g.get("ccmc"):
         o.ccmc_set_full_nc(bool(g.get("full_nc")))
@@ -94,6 +96,15 @@ def test_ueg_np2_np4(fcidump_path):
         t = o.ueg_tables()
         assert abs(t["L"] - g["kat"]["L"]) < 5e-9 and o.nbasis == g["kat"]["nbasis"]
         assert abs(o.basis()["sp_eigv"][2] - g["kat"]["sp_eigv_3"]) < 5e-10
+
+
+def test_ueg_quasi_newton_np2(fcidump_path):
+    # quasi-Newton propagator (calc_qn_spawned_weighting, calc_qn_weighting, quasi_newton_pop_control,
+    # sp_fock of the 3D UEG with exchange and Madelung terms); the complete 1001-row table was verified with
+    # tools/golden_compare.py ueg_qn_real64_np2
+    o = _run("ueg_qn_real64_np2", fcidump_path, 150)
+    q = o.quasi_newton()
+    assert q["threshold"] == 1.0 and q["value"] == 1.0 and q["pop_control"] == 1.0
 
 
 def test_ccmc_ccsd_ne_np1(fcidump_path):

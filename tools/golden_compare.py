@@ -51,6 +51,12 @@ CASES = {
                     ueg=dict(nel=6, ms=0, rs=2.0, cutoff=2.0), ref_det=[1, 2, 3, 10, 11, 14],
                     qmc=dict(tau=0.005, seed=122, D0_population=10, ncycles=10, nreport=1000, target_particles=90000,
                              walker_length=50000, spawned_walker_length=5000, nprocs=4)),
+    # quasi-Newton propagator on the same UEG, real amplitudes
+    "ueg_qn_real64_np2": dict(dir="fciqmc_real_64/np2/ueg_qn_n10_rs2_e4_fciqmc_real_64", bench="benchmark.out.9712b5a3.inp=ueg.fciqmc.in",
+                              ueg=dict(nel=6, ms=0, rs=2.0, cutoff=2.0), ref_det=[1, 2, 3, 10, 11, 14], quasi_newton=dict(threshold=1.0),
+                              qmc=dict(tau=0.005, seed=122, D0_population=10, ncycles=10, nreport=1000, target_particles=90000,
+                                       walker_length=50000, spawned_walker_length=50000, nprocs=2, real_amplitudes=1,
+                                       spawn_cutoff=0.01)),
     # CCMC: CCSD on Ne cc-pVDZ, stochastic cluster selection, integer walkers
     "ccmc_ne": dict(dir="ccmc/np1/Ne-RHF-cc-pVDZ_ccmc", bench="benchmark.out.9712b5a3.inp=ne.ccsdmc.in",
                     int_file="INTDUMP", sys=dict(nel=10, ms=0, sym=0), ccmc=True,
@@ -139,6 +145,8 @@ def run_case(name, max_rows=None, quiet=False):
     o.set_qmc(**q)
     if "pattempt_parallel" in c:
         o.set_pattempt_parallel(c["pattempt_parallel"])
+    if "quasi_newton" in c:
+        o.set_quasi_newton(True, **c["quasi_newton"])
     o.init()
     t = time.time()
     if c.get("ccmc"):

@@ -41,7 +41,7 @@ for name, c in CASES.items():
     if "ueg" in c:
         rows = parse_table(d + c["bench"]).tolist()
         json.dump({"source": "test_suite/" + c["dir"] + "/" + c["bench"], "ueg": c["ueg"], "ref_det": c["ref_det"],
-                   "qmc": c["qmc"],
+                   "qmc": c["qmc"], **({"quasi_newton": c["quasi_newton"]} if "quasi_newton" in c else {}),
                    "columns": ["iterations", "shift", "proj_energy", "D0_population", "nparticles", "nstates",
                                "nspawn_events", "rspawn"],
                    "kat": {"H00": 2.02890441, "L": 5.85836755, "nbasis": 66, "sp_eigv_3": 5.75143889E-01},

@@ -270,7 +270,7 @@ def test_heat_bath_pgen_normalisation(s10, gen):
     o.init()
     dets = synthetic.random_dets(3, s.nbasis, s.nalpha, s.nbeta, seed=4)
     rng = np.random.default_rng(5)
-    n = 150000
+    n = 90000
     for f in [o.reference()["f0"], dets[1]]:
         counts, pg = {}, {}
         nnull = 0

@@ -61,7 +61,7 @@ def _run(case, fcidump_path, nrows):
 
 
 def test_h2o_renorm_integer_np1(fcidump_path):
-    o = _run("h2o", fcidump_path, 120)
+    o = _run("h2o", fcidump_path, 90)
     ref = o.reference()
     assert abs(ref["H00"] - (-76.02403856)) < 5e-9           # JSON block of the golden output
     assert abs(ref["pattempt_single"] - 0.04938272) < 5e-9
@@ -75,15 +75,15 @@ def test_ne_initiator_np1(fcidump_path):
 
 
 def test_ne_ci6_np2_hash_sharding(fcidump_path):
-    _run("ne_ci6_np2", fcidump_path, 250)
+    _run("ne_ci6_np2", fcidump_path, 160)
 
 
 def test_ne_ci6_np4_hash_sharding(fcidump_path):
-    _run("ne_ci6_np4", fcidump_path, 250)
+    _run("ne_ci6_np4", fcidump_path, 160)
 
 
 def test_ne_ci6_real_amplitudes_np2(fcidump_path):
-    _run("ne_ci6_real64_np2", fcidump_path, 200)
+    _run("ne_ci6_real64_np2", fcidump_path, 130)
 
 
 def test_ueg_np2_np4(fcidump_path):
@@ -127,7 +127,7 @@ def test_ccmc_ccsdt_full_non_composite_np2(fcidump_path):
     _run("ccmc_h2o_ccsdt_fullnc_np2", fcidump_path, 40)
 
 
-@pytest.mark.parametrize("gen,nrows", [("hb", 150), ("hb_uni", 150), ("hb_single", 100), ("ppM", 120), ("ppMij", 120),
+@pytest.mark.parametrize("gen,nrows", [("hb", 150), ("hb_uni", 150), ("hb_single", 70), ("ppM", 120), ("ppMij", 120),
                                        ("csM", 120), ("csMij", 120), ("renorm", 250), ("no_renorm", 250),
                                        ("renorm_spin", 250), ("no_renorm_spin", 200), ("ppN", 150)])
 def test_ccmc_ccsdt_nh3_np4_excitation_generators(fcidump_path, gen, nrows):

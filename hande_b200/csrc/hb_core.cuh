@@ -1449,44 +1449,49 @@ HB_HDN void gen_excit_power_pitzer_occ(R& rng, const Sys& s, const Params& p, co
 // power_pitzer_orderN ('heat_bath_power_pitzer_ref'): every choice is one look-up in a precomputed alias table indexed
 // through the mapping reference orbital -> orbital of this determinant.
 // ------------------------------------------------------------------------------------------------
-// get_excitation_locations (src/excitations.F90) + find_diff_ref_cdet (src/excit_gen_utils.f90:220-269)
-HB_HDN int ref_cdet_locations(const Sys& s, const uint8_t* occ, uint8_t* ref_store, uint8_t* det_store) {
-    const int nel = s.nel;
-    const int* ref_list = s.ppn_occ;
-    int j = 1, det_sind = 0, ref_sind = 0;
-    bool done = false;
-    for (int i = 1; i <= nel && !done; ++i) {
-        while ((int)occ[j - 1] < ref_list[i - 1]) {
-            det_store[det_sind++] = (uint8_t)j;
-            j++;
-            if (j > nel) { done = true; break; }
+// get_excitation_locations (src/excitations.F90) + the spin pairing of find_diff_ref_cdet (src/excit_gen_utils.f90:220-269)
+// from the bit strings: the reference's orbitals missing in the determinant ("holes": position in the reference's
+// list and orbital, ascending) and the determinant's orbitals missing in the reference ("particles", ascending), then
+// the reference's forward swaps so that every hole is paired with a particle of its spin.  Same pairs as the
+// reference's merge walk over the two occupied lists (tests/test_core_vs_oracle.py compares them with the oracle's
+// literal restatement).
+template <int W>
+HB_HDN int ref_det_diff(const uint64_t* f0, const uint64_t* f, uint8_t* hole_idx, uint8_t* hole_orb, uint8_t* part_orb) {
+    int nh = 0, np = 0, base = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        uint64_t h = f0[w] & ~f[w];
+        while (h) {
+            const int bit = ctz64(h);
+            h &= h - 1;
+            hole_orb[nh] = (uint8_t)(w * 64 + bit + 1);
+            hole_idx[nh] = (uint8_t)(base + popc64(f0[w] & ((1ull << bit) - 1ull)) + 1);
+            nh++;
         }
-        if (done) break;
-        if ((int)occ[j - 1] > ref_list[i - 1]) ref_store[ref_sind++] = (uint8_t)i;
-        else j++;
-        if (j > nel) break;
+        uint64_t q = f[w] & ~f0[w];
+        while (q) {
+            const int bit = ctz64(q);
+            q &= q - 1;
+            part_orb[np++] = (uint8_t)(w * 64 + bit + 1);
+        }
+        base += popc64(f0[w]);
     }
-    while (j <= nel) { det_store[det_sind++] = (uint8_t)j; j++; }
-    int i_back = nel, i_back_pos = det_sind;
-    while (ref_sind < det_sind) {
-        ref_store[i_back_pos - 1] = (uint8_t)i_back;
-        i_back--; i_back_pos--; ref_sind++;
-    }
-    const int nex = ref_sind;
-    for (int ii = 0; ii < nex; ++ii) {     // pair every differing reference orbital with a determinant orbital of its spin
-        if (ms_of(ref_list[ref_store[ii] - 1]) != ms_of(occ[det_store[ii] - 1])) {
+    for (int ii = 0; ii < nh; ++ii) {
+        if (ms_of(hole_orb[ii]) != ms_of(part_orb[ii])) {
             int jj = ii + 1;
-            while (ms_of(ref_list[ref_store[ii] - 1]) != ms_of(occ[det_store[jj] - 1])) jj++;
-            const uint8_t t = det_store[ii]; det_store[ii] = det_store[jj]; det_store[jj] = t;
+            while (ms_of(hole_orb[ii]) != ms_of(part_orb[jj])) jj++;
+            const uint8_t t = part_orb[ii]; part_orb[ii] = part_orb[jj]; part_orb[jj] = t;
         }
     }
-    return nex;
+    return nh;
 }
-HB_HDN void find_diff_ref_cdet(const Sys& s, const uint8_t* occ, uint8_t* ref_cdet) {
-    uint8_t ref_store[HB_MAXNEL], det_store[HB_MAXNEL];
-    const int nex = ref_cdet_locations(s, occ, ref_store, det_store);
+// det_info_t%ref_cdet_occ_list: the determinant's occupied orbitals in the order of the reference's
+template <int W>
+HB_HDN void find_diff_ref_cdet(const Sys& s, const uint64_t* f0, const uint64_t* f, uint8_t* ref_cdet) {
+    uint8_t hole_idx[HB_MAXNEL], hole_orb[HB_MAXNEL], part_orb[HB_MAXNEL];
+    const int nex = ref_det_diff<W>(f0, f, hole_idx, hole_orb, part_orb);
     for (int k = 0; k < s.nel; ++k) ref_cdet[k] = (uint8_t)s.ppn_occ[k];
-    for (int ii = 0; ii < nex; ++ii) ref_cdet[ref_store[ii] - 1] = occ[det_store[ii] - 1];
+    for (int ii = 0; ii < nex; ++ii) ref_cdet[hole_idx[ii] - 1] = part_orb[ii];
 }
 // gen_excit_mol_power_pitzer_occ_ref (src/excit_gen_power_pitzer_mol.F90:650-939), excit_gen = power_pitzer: ij uniform
 // among the reference's occupied orbitals, a and b from the reference's alias tables, mapped onto this determinant
@@ -1531,14 +1536,14 @@ HB_HDN void gen_excit_power_pitzer_ref(R& rng, const Sys& s, const Params& p, co
         a_ref = virt[a_ind - 1];
         a_found = true;
     }
-    uint8_t ref_store[HB_MAXNEL], det_store[HB_MAXNEL];
+    uint8_t hole_idx[HB_MAXNEL], hole_orb[HB_MAXNEL], part_orb[HB_MAXNEL];
     int nex = 0, i = i_ref, j = j_ref, a = a_ref, ij_sym = 0, isymb = 0, imsb = 1;
     if (a_found) {
-        nex = ref_cdet_locations(s, occ, ref_store, det_store);
+        nex = ref_det_diff<W>(p.f0, f, hole_idx, hole_orb, part_orb);
         for (int ii = 0; ii < nex; ++ii) {
-            if (ref_store[ii] == i_ind) i = occ[det_store[ii] - 1];
-            else if (ref_store[ii] == j_ind) j = occ[det_store[ii] - 1];
-            if ((int)occ[det_store[ii] - 1] == a_ref) a = s.ppn_occ[ref_store[ii] - 1];
+            if (hole_idx[ii] == i_ind) i = part_orb[ii];
+            else if (hole_idx[ii] == j_ind) j = part_orb[ii];
+            if ((int)part_orb[ii] == a_ref) a = hole_orb[ii];
         }
         ij_sym = sym_conj(s, cross_product(s, s.bf_sym[i], s.bf_sym[j]));
         isymb = sym_conj(s, cross_product(s, ij_sym, s.bf_sym[a]));
@@ -1558,7 +1563,7 @@ HB_HDN void gen_excit_power_pitzer_ref(R& rng, const Sys& s, const Params& p, co
             } else {
                 int b_ref = b;
                 for (int ii = 0; ii < nex; ++ii)
-                    if (s.ppn_occ[ref_store[ii] - 1] == b) { b_ref = occ[det_store[ii] - 1]; break; }
+                    if ((int)hole_orb[ii] == b) { b_ref = part_orb[ii]; break; }
                 int b_rev = 0;
                 for (int lo = 1, hi = nv; lo <= hi;) {      // binary_search in virt_list_{alpha,beta}
                     const int mid = (lo + hi) / 2;
@@ -1843,7 +1848,7 @@ HB_HD void gen_excit(R& rng, const Sys& s, const Params& p, const uint64_t* f, c
     else if (p.excit_gen == EXCIT_GEN_POWER_PITZER) gen_excit_power_pitzer_ref<W>(rng, s, p, f, occ, g);
     else if (p.excit_gen == EXCIT_GEN_POWER_PITZER_ORDERN) {
         uint8_t ref_cdet[HB_MAXNEL];
-        find_diff_ref_cdet(s, occ, ref_cdet);
+        find_diff_ref_cdet<W>(s, p.f0, f, ref_cdet);
         gen_excit_power_pitzer_orderN<W>(rng, s, p, f, occ, ref_cdet, g);
     }
     else if (p.excit_gen == EXCIT_GEN_RENORM_SPIN) gen_excit_renorm<W, true>(rng, s, p, f, occ, su, g);

@@ -304,7 +304,7 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
         ssign[tid] = pop < 0;
         uint8_t* occ = socc + tid * nel;
         decode_det<W>(f, occ);
-        if (GEN == EXCIT_GEN_POWER_PITZER_ORDERN) find_diff_ref_cdet(s, occ, ssu + tid * nsu);
+        if (GEN == EXCIT_GEN_POWER_PITZER_ORDERN) find_diff_ref_cdet<W>(s, p.f0, f, ssu + tid * nsu);
         else if (nsu) build_symunocc_masks<W>(s, f, ssu + tid * nsu);
         const uint64_t h = det_hash64<W>(f);
         if (!hb_stage) shash[tid] = h;

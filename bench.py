@@ -123,7 +123,7 @@ def run_reference(args, rank, world):
         return
     s, path = s50_system()
     cores = os.cpu_count() or 1
-    n_sample = 20000
+    n_sample = 200000     # ~2 s timed on 16 cores (tens of core-seconds of CPU work)
     tau = args.tau
     for _ in range(max(0, min(args.warmup, 1))):
         oracle_cpu_run(path, 2000, 1, tau, cores)
@@ -171,7 +171,7 @@ def main():
 
     if args.impl == "reference":
         if args.tau == 0.0:
-            args.tau = 2.0e-4
+            args.tau = 5.3e-7     # what the GPU arm's calibration (R_spawn ~ 0.05) gives for this workload
         run_reference(args, rank, world)
         return
 
@@ -347,10 +347,10 @@ def main():
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        ns_cpu = 20000
-        r, t_init = oracle_cpu_run(path, ns_cpu, 2, tau, cores, excit_gen=args.excit_gen)
+        ns_cpu = 200000
+        r, t_init = oracle_cpu_run(path, ns_cpu, 5, tau, cores, excit_gen=args.excit_gen)
         cpu = {"value": r["walker_iters"] / r["seconds"], "unit": "walker-iterations/s", "cores": cores, "kind": "port",
-               "sample": f"{cores} replicas x {ns_cpu} walkers x 2 cycles of the same {args.system} {args.excit_gen} workload "
+               "sample": f"{cores} replicas x {ns_cpu} walkers x 5 cycles of the same {args.system} {args.excit_gen} workload "
                          f"(oracle restatement; {r['seconds']:.1f}s timed, table init {t_init:.1f}s untimed)"}
 
     if rank == 0:

@@ -17,8 +17,8 @@
 
 #if defined(__CUDACC__)
 #define HB_HD __host__ __device__ __forceinline__
-#define HB_HDN __host__ __device__
-#define HB_HDNI __host__ __device__ __noinline__
+#define HB_HDN inline __host__ __device__
+#define HB_HDNI inline __host__ __device__ __noinline__
 #else
 #define HB_HD inline
 #define HB_HDN inline

@@ -9,37 +9,18 @@
 //       except the nb^4 heat-bath tables.
 //
 // Kernels (all HBM/L2-bound integer + fp64 scalar work; no tensor cores - nothing is a dense contraction):
-//   k_spawn_death     fused: decode, initiator flag, projected energy, decide_nattempts, spawning attempts
-//                     (load-balanced over a 256-state tile), stochastic death; warp-aggregated append
-//   k_radix_*         LSD radix sort of the spawn list on the bit-string key (8-bit digits)
+//   k_spawn_death     (hb_spawn.cuh) fused: decode, initiator flag, projected energy, decide_nattempts, spawning
+//                     attempts (load-balanced over a 256-state tile), stochastic death; warp-aggregated append
+//   k_ccmc_*          (hb_ccmc.cuh) CCMC cluster selection / spawning / death
+//   k_radix_*         LSD radix sort of the spawn list on the bit-string key
 //   k_annihilate      segmented sum of equal keys + initiator flag algebra + binary search into the main list
 //   k_round_count     stochastic rounding of main-list populations + per-tile survivor counts
 //   k_merge           single pass merge of survivors and new determinants into the other main-list buffer
 //   k_sc0             <D|H|D> - H00 for new determinants
-#include <cuda_runtime.h>
-#include <nccl.h>   // types only: the library is bound at run time (see NcclApi below)
 #include <dlfcn.h>
-#include <stdio.h>
-#include <stdlib.h>
-#include <string.h>
-#include <string>
-#include <vector>
-#include <algorithm>
+#include "hb_common.cuh"
 
-#include "../../include/hande_b200.h"
-#include "hb_core.cuh"
-
-using namespace hb;
-
-static thread_local std::string g_err;
-#define CK(call)                                                                                   \
-    do {                                                                                           \
-        cudaError_t _e = (call);                                                                   \
-        if (_e != cudaSuccess) {                                                                   \
-            g_err = std::string(#call) + ": " + cudaGetErrorString(_e) + " @" + std::to_string(__LINE__); \
-            return 1;                                                                              \
-        }                                                                                          \
-    } while (0)
+thread_local std::string g_err;
 // NCCL is resolved lazily with dlopen/dlsym instead of a link-time dependency: a host process that also uses
 // torch (bench.py, the multi-GPU tests) must end up with ONE libnccl.so.2, and torch's bundled copy (2.28) is newer
 // than the system one (2.27).  Order: a copy already loaded in the process, $HB200_NCCL_LIB, the system library.
@@ -79,550 +60,7 @@ static NcclApi g_nccl;
             return 1;                                                                              \
         }                                                                                          \
     } while (0)
-#define FAIL(msg)        \
-    do {                 \
-        g_err = (msg);   \
-        return 1;        \
-    } while (0)
 
-constexpr int TILE = 256;  // states per block in the fused spawn kernel and in the merge passes
-
-// ------------------------------------------------------------------------------------------------
-// small device helpers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int warp_incl_scan(int v) {
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= o) v += t;
-    }
-    return v;
-}
-// exclusive scan over a block of TILE threads; returns exclusive prefix, total in *total.  warp_sums: >= 8 ints smem
-__device__ __forceinline__ int block_excl_scan(int v, int* warp_sums, int* total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int incl = warp_incl_scan(v);
-    if (lane == 31) warp_sums[warp] = incl;
-    __syncthreads();
-    int off = 0, tot = 0;
-#pragma unroll
-    for (int w = 0; w < TILE / 32; ++w) {
-        int s = warp_sums[w];
-        if (w < warp) off += s;
-        tot += s;
-    }
-    __syncthreads();
-    *total = tot;
-    return off + incl - v;
-}
-__device__ __forceinline__ double warp_sum_d(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ long long warp_sum_ll(long long v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    return v;
-}
-
-template <int W>
-__device__ __forceinline__ void load_det(const uint64_t* p, uint64_t* f) {
-    if (W == 2) {
-        ulonglong2 v = __ldcs(reinterpret_cast<const ulonglong2*>(p));   // streamed once per cycle
-        f[0] = v.x; f[1] = v.y;
-    } else {
-#pragma unroll
-        for (int k = 0; k < W; ++k) f[k] = p[k];
-    }
-}
-template <int W>
-__device__ __forceinline__ void store_det(uint64_t* p, const uint64_t* f) {
-    if (W == 2) {
-        *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2(f[0], f[1]);
-    } else {
-#pragma unroll
-        for (int k = 0; k < W; ++k) p[k] = f[k];
-    }
-}
-
-// lower_bound in the sorted main list: first index with states[idx] >= key
-template <int W>
-__device__ __forceinline__ long long lower_bound_det(const uint64_t* states, long long n, const uint64_t* key) {
-    long long lo = 0, hi = n;
-    while (lo < hi) {
-        long long mid = (lo + hi) >> 1;
-        uint64_t f[W];
-        load_det<W>(states + mid * W, f);
-        if (det_less<W>(f, key)) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Kernel: fused spawn + death + estimators  (src/fciqmc.f90:315-371, 635-769)
-// ------------------------------------------------------------------------------------------------
-struct SpawnPartials {  // one per block; reduced in fixed order by k_reduce_partials
-    double pe, d0;
-    long long ndeath, npart, nattempts;
-};
-
-constexpr int SINGLES_CHUNK = 64;  // single excitations whose pgen terms are staged in shared memory at a time
-
-// Shared-memory carve-up of k_spawn_death (same arithmetic on host and device).  For the heat-bath generator the
-// phase-A staging area (column i of hb_ij_w at the occupied orbitals, [q][thread]) shares its storage with the buffers
-// that are only live in the later phases.
-struct SpawnSmem {
-    size_t sf, shash, ssign, sscan, swarp, sred, siw, sw, sh1, shm, ssp, spsum, sterm, sok, sq, scnt, sflag, slo, sperm, ssq,
-        ssi, socc, ssu, sps, sdf, total;
-    // heat_bath: the original heat-bath generator (phase buffers); hb_stage: any generator that selects i, j from the
-    // heat-bath weights (needs the hb_i_w copy and the per-thread staging area of nel doubles)
-    // ps: pattempt_update statistics are accumulated (per thread: two doubles and two counters)
-    // qn: quasi-Newton propagator (fock_sum of each state of the tile)
-    __host__ __device__ SpawnSmem(int W, int nel, int nsu, int nb, bool heat_bath, bool hb_stage, bool ps, bool qn) {
-        size_t o = 0;
-        sf = o;     o += (size_t)TILE * W * 8;
-        sred = o;   o += 40 * 8;
-        shash = o;  o += hb_stage ? 0 : (size_t)TILE * 8;         // stream selector per state (recomputed per attempt when
-                                                                   // shared memory is scarce: it also buys L1 capacity)
-        siw = o;    o += hb_stage ? (size_t)nb * 8 : 0;           // copy of hb_i_w
-        // ---- union: phase A staging | phase B..F buffers
-        const size_t u0 = o;
-        sw = o;
-        size_t v = u0;
-        sh1 = v;    v += heat_bath ? (size_t)TILE * 8 : 0;        // signed slater_condon1(i,a) per attempt slot
-        shm = v;    v += heat_bath ? (size_t)3 * TILE * 8 : 0;    // |slater_condon1| of the three other orderings
-        ssp = v;    v += heat_bath ? (size_t)2 * TILE * 8 : 0;    // singles: hmod_ia, ij_tot
-        spsum = v;  v += heat_bath ? (size_t)TILE * 8 : 0;        // singles: sum of pgen terms
-        sterm = v;  v += heat_bath ? (size_t)SINGLES_CHUNK * nel * 8 : 0;  // singles: pgen terms of one chunk
-        sok = v;    v += heat_bath ? (size_t)SINGLES_CHUNK * nel : 0;
-        v = (v + 3) & ~(size_t)3;
-        sq = v;     v += heat_bath ? (size_t)4 * TILE * 4 : 0;    // request queues: [TILE] phase B, [3*TILE] phase D
-        const size_t stage = hb_stage ? (size_t)TILE * nel * 8 : 0;
-        o = u0 + (stage > (v - u0) ? stage : (v - u0));
-        o = (o + 7) & ~(size_t)7;
-        // ---- end of union
-        sscan = o;  o += (size_t)(TILE + 1) * 4;
-        swarp = o;  o += 8 * 4;
-        scnt = o;   o += 4 * 4;                                    // queue counters
-        sflag = o;  o += TILE;
-        ssign = o;  o += TILE;                                     // sign of the parent population (attempt_to_spawn)
-        slo = o;    o += heat_bath ? TILE : 0;                     // tile-state index of each attempt slot
-        sperm = o;  o += heat_bath ? TILE : 0;
-        ssq = o;    o += heat_bath ? TILE : 0;                     // queue of single-excitation slots
-        ssi = o;    o += heat_bath ? 2 * TILE : 0;                 // singles: i, a
-        socc = o;   o += (size_t)TILE * nel;
-        ssu = o;    o += (size_t)TILE * nsu;
-        o = (o + 7) & ~(size_t)7;
-        sps = o;    o += ps ? (size_t)TILE * 24 : 0;
-        sdf = o;    o += qn ? (size_t)TILE * 8 : 0;
-        total = (o + 15) & ~(size_t)15;
-    }
-};
-
-// create_excited_det (src/excitations.F90:365-406)
-template <int W>
-__device__ __forceinline__ void make_child(const uint64_t* f, const Gen& g, uint64_t* child) {
-#pragma unroll
-    for (int k = 0; k < W; ++k) child[k] = f[k];
-    child[(g.from1 - 1) >> 6] &= ~(1ull << ((g.from1 - 1) & 63));
-    child[(g.to1 - 1) >> 6] |= (1ull << ((g.to1 - 1) & 63));
-    if (g.nexcit == 2) {
-        child[(g.from2 - 1) >> 6] &= ~(1ull << ((g.from2 - 1) & 63));
-        child[(g.to2 - 1) >> 6] |= (1ull << ((g.to2 - 1) & 63));
-    }
-}
-
-// GEN: compile-time generator of this instantiation (one kernel per generator keeps the code - and the instruction
-// cache footprint - to what the run actually executes): EXCIT_GEN_* for read_in systems, GEN_UEG for the UEG.
-enum { GEN_UEG = 100, GEN_UEG_PP = 101 };
-template <int W, int GEN>
-__global__ void __launch_bounds__(TILE, (GEN == EXCIT_GEN_HEAT_BATH || GEN == EXCIT_GEN_HEAT_BATH_UNIFORM) ? 3 : 4)
-k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __restrict__ pops,
-              const double* __restrict__ dat, long long nstates, int64_t* __restrict__ spawn,
-              unsigned long long* __restrict__ head, long long block_size, const int* __restrict__ proc_map,
-              SpawnPartials* __restrict__ partials, int* __restrict__ err) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int nel = s.nel;
-    constexpr bool heat_bath = (GEN == EXCIT_GEN_HEAT_BATH);
-    constexpr bool hb_stage = heat_bath || (GEN == EXCIT_GEN_HEAT_BATH_UNIFORM) || (GEN == EXCIT_GEN_HEAT_BATH_SINGLE) ||
-                              (GEN == EXCIT_GEN_POWER_PITZER_OCC_IJ);
-    const int nsu = (GEN == EXCIT_GEN_POWER_PITZER_ORDERN) ? nel : (GEN == EXCIT_GEN_RENORM || GEN == EXCIT_GEN_RENORM_SPIN || GEN == EXCIT_GEN_HEAT_BATH_UNIFORM || GEN == EXCIT_GEN_POWER_PITZER_OCC ||
-                     GEN == EXCIT_GEN_POWER_PITZER_OCC_IJ) ? 2 * s.nsym_tot : 0;
-    const bool ps_on = !heat_bath && p.ps_part != nullptr;
-    const SpawnSmem L(W, nel, nsu, s.nbasis, heat_bath, hb_stage, ps_on, p.qn != 0);
-    double* sdf = reinterpret_cast<double*>(smem_raw + L.sdf);
-    double* sps_h = reinterpret_cast<double*>(smem_raw + L.sps);                  // [2][TILE]: singles, doubles
-    unsigned* sps_n = reinterpret_cast<unsigned*>(smem_raw + L.sps + 16 * TILE);  // [2][TILE]
-    if (ps_on) {
-        sps_h[threadIdx.x] = 0.0; sps_h[TILE + threadIdx.x] = 0.0;
-        sps_n[threadIdx.x] = 0u; sps_n[TILE + threadIdx.x] = 0u;
-    }
-    uint64_t* sf = reinterpret_cast<uint64_t*>(smem_raw + L.sf);
-    uint8_t* ssign = smem_raw + L.ssign;
-    uint64_t* shash = reinterpret_cast<uint64_t*>(smem_raw + L.shash);
-    double* sred = reinterpret_cast<double*>(smem_raw + L.sred);
-    double* sh1 = reinterpret_cast<double*>(smem_raw + L.sh1);
-    double* shm = reinterpret_cast<double*>(smem_raw + L.shm);
-    double* ssp = reinterpret_cast<double*>(smem_raw + L.ssp);
-    double* spsum = reinterpret_cast<double*>(smem_raw + L.spsum);
-    double* siw = reinterpret_cast<double*>(smem_raw + L.siw);
-    double* sw = reinterpret_cast<double*>(smem_raw + L.sw);
-    double* sterm = reinterpret_cast<double*>(smem_raw + L.sterm);
-    uint8_t* sok = smem_raw + L.sok;
-    int* sscan = reinterpret_cast<int*>(smem_raw + L.sscan);
-    int* swarp = reinterpret_cast<int*>(smem_raw + L.swarp);
-    uint32_t* sq1 = reinterpret_cast<uint32_t*>(smem_raw + L.sq);
-    uint32_t* sq2 = sq1 + TILE;
-    int* scnt = reinterpret_cast<int*>(smem_raw + L.scnt);
-    uint8_t* sflag = smem_raw + L.sflag;
-    uint8_t* slo = smem_raw + L.slo;
-    uint8_t* sperm = smem_raw + L.sperm;
-    uint8_t* ssq = smem_raw + L.ssq;
-    uint8_t* ssi = smem_raw + L.ssi;
-    uint8_t* socc = smem_raw + L.socc;
-    uint8_t* ssu = smem_raw + L.ssu;
-
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    const long long idx = (long long)blockIdx.x * TILE + tid;
-    const int E = W + 2;
-
-    double pe = 0.0, d0 = 0.0;
-    long long ndeath = 0, npart = 0;
-    int natt = 0;
-    if (hb_stage)
-        for (int k = tid; k < s.nbasis; k += TILE) siw[k] = s.hb_i_w[k];
-    if (idx < nstates) {
-        uint64_t f[W];
-        load_det<W>(states + idx * W, f);
-        const int64_t pop = __ldcs(pops + idx);
-        const double Kii = __ldcs(dat + idx);
-#pragma unroll
-        for (int k = 0; k < W; ++k) sf[tid * W + k] = f[k];
-        ssign[tid] = pop < 0;
-        uint8_t* occ = socc + tid * nel;
-        decode_det<W>(f, occ);
-        if (GEN == EXCIT_GEN_POWER_PITZER_ORDERN) find_diff_ref_cdet<W>(s, p.f0, f, ssu + tid * nsu);
-        else if (nsu) build_symunocc_masks<W>(s, f, ssu + tid * nsu);
-        const uint64_t h = det_hash64<W>(f);
-        if (!hb_stage) shash[tid] = h;
-        const double real_pop = (double)pop / (double)p.real_factor;
-        // set_parent_flag (src/ifciqmc.f90:13-57)
-        sflag[tid] = (fabs(real_pop) > p.initiator_pop) ? 0 : 1;
-        // update_proj_energy_mol (src/energy_evaluation.F90:906-986)
-        bool is_ref;
-        double hm = proj_energy_hmatel<W>(s, p, f, occ, is_ref);
-        if (is_ref) d0 = real_pop; else pe = hm * real_pop;
-        PhiloxStream rng;
-        rng.begin(p.seed, p.cycle, RNG_NATTEMPTS, h, 0);
-        natt = decide_nattempts(rng, real_pop);
-        rng.begin(p.seed, p.cycle, RNG_DEATH, h, 0);
-        int64_t kill_abs;
-        double death_weight = 1.0;
-        if (p.qn) {
-            const double dfock = qn_fock_sum(s, p, occ);
-            sdf[tid] = dfock;
-            death_weight = qn_weighting(p, dfock);
-        }
-        const int64_t newpop = stochastic_death(rng, p, Kii, pop, kill_abs, death_weight);
-        pops[idx] = newpop;
-        ndeath = kill_abs;
-        npart = newpop < 0 ? -newpop : newpop;
-    }
-    int T;
-    const int excl = block_excl_scan(natt, swarp, &T);
-    sscan[tid] = excl;
-    if (tid == 0) sscan[TILE] = T;
-    __syncthreads();
-
-    for (int base = 0; base < T; base += TILE) {
-        const int a = base + tid;
-        const bool active = a < T;
-        int lo = 0, att = 0;
-        if (active) {
-            int hi = TILE;
-            while (hi - lo > 1) {
-                int mid = (lo + hi) >> 1;
-                if (sscan[mid] <= a) lo = mid; else hi = mid;
-            }
-            att = a - sscan[lo];
-        }
-        uint64_t f[W];
-#pragma unroll
-        for (int k = 0; k < W; ++k) f[k] = sf[lo * W + k];
-        PhiloxStream rng;
-        rng.begin(p.seed, p.cycle, RNG_SPAWN, hb_stage ? det_hash64<W>(f) : shash[lo], (uint32_t)att);
-        if (!hb_stage) rng.prefetch();   // uniform generators draw inside divergent rejection loops
-        Gen g;
-        if (heat_bath) {
-            // ---- phase A: i, j, a for every attempt of the round
-            if (tid < 4) scnt[tid] = 0;
-            __syncthreads();
-            HbState st;
-            st.allowed = false; st.need_ia = false; st.dbl = true; st.need_k = 0;
-            if (active) hb_phase_a<W>(rng, s, f, socc + lo * nel, st, siw, sw + tid, TILE);
-            __syncthreads();   // the request queues share their storage with the phase-A staging area
-            if (active) {
-                slo[tid] = (uint8_t)lo;
-                if (st.allowed && st.need_ia) {
-                    const int q = atomicAdd(&scnt[0], 1);
-                    sq1[q] = (uint32_t)tid | ((uint32_t)st.i << 8) | ((uint32_t)st.a << 16);
-                }
-            }
-            __syncthreads();
-            // ---- phase B: the queued slater_condon1(i,a), one request per thread
-            for (int r = tid; r < scnt[0]; r += TILE) {
-                const uint32_t rq = sq1[r];
-                const int slot = rq & 255, fr = (rq >> 8) & 255, to = (rq >> 16) & 255, l = slo[slot];
-                uint64_t ff[W];
-#pragma unroll
-                for (int k = 0; k < W; ++k) ff[k] = sf[l * W + k];
-                bool pm;
-                sh1[slot] = hb_sc1<W>(s, ff, socc + l * nel, fr, to, pm);
-                sperm[slot] = pm;
-            }
-            __syncthreads();
-            // ---- phase C: single/double coin, b; queue the remaining slater_condon1 and the singles
-            if (active) {
-                if (st.allowed && st.need_ia) { st.h_ia = sh1[tid]; st.perm_ia = sperm[tid] != 0; }
-                hb_phase_c<W>(rng, s, f, st);
-                if (st.allowed) {
-                    if (st.dbl) {
-#pragma unroll
-                        for (int k = 0; k < 3; ++k)
-                            if (st.need_k & (1u << k)) {
-                                int fr, to, ot;
-                                hb_ordering(st, k, fr, to, ot);
-                                const int q = atomicAdd(&scnt[1], 1);
-                                sq2[q] = (uint32_t)tid | ((uint32_t)fr << 8) | ((uint32_t)to << 16) | ((uint32_t)k << 24);
-                            }
-                    } else {
-                        const int q = atomicAdd(&scnt[2], 1);
-                        ssq[q] = (uint8_t)tid;
-                        ssi[tid] = (uint8_t)st.i; ssi[TILE + tid] = (uint8_t)st.a;
-                        ssp[tid] = st.hmod_ia; ssp[TILE + tid] = st.ij_tot;
-                    }
-                }
-            }
-            __syncthreads();
-            // ---- phase D: queued slater_condon1 of the other orderings (dense)
-            for (int r = tid; r < scnt[1]; r += TILE) {
-                const uint32_t rq = sq2[r];
-                const int slot = rq & 255, fr = (rq >> 8) & 255, to = (rq >> 16) & 255, k = rq >> 24, l = slo[slot];
-                uint64_t ff[W];
-#pragma unroll
-                for (int kk = 0; kk < W; ++kk) ff[kk] = sf[l * W + kk];
-                bool pm;
-                shm[k * TILE + slot] = fabs(hb_sc1<W>(s, ff, socc + l * nel, fr, to, pm));
-            }
-            // ---- phase E: singles.  The (division-heavy) pgen terms are evaluated one per thread over all
-            //      (single, occupied orbital) pairs of a chunk, then summed in occ_list order, one single per thread.
-            {
-                const int ns = scnt[2];
-                for (int c0 = 0; c0 < ns; c0 += SINGLES_CHUNK) {
-                    const int nc = min(SINGLES_CHUNK, ns - c0);
-                    for (int w = tid; w < nc * nel; w += TILE) {
-                        const int r = w / nel, q = w - r * nel;
-                        const int slot = ssq[c0 + r], l = slo[slot];
-                        double term = 0.0;
-                        const bool ok = hb_single_term(s, ssi[slot], ssi[TILE + slot], ssp[slot], ssp[TILE + slot],
-                                                       socc[l * nel + q], term);
-                        sterm[w] = term;
-                        sok[w] = ok;
-                    }
-                    __syncthreads();
-                    for (int r = tid; r < nc; r += TILE) {
-                        double psum = 0.0;
-                        for (int q = 0; q < nel; ++q)
-                            if (sok[r * nel + q]) psum = psum + sterm[r * nel + q];
-                        spsum[ssq[c0 + r]] = psum;
-                    }
-                    __syncthreads();
-                }
-            }
-            __syncthreads();
-            // ---- phase F: pgen, H_ij
-            double hmk[3] = {0.0, 0.0, 0.0};
-            double psum = 0.0;
-            if (active && st.allowed) {
-                if (st.dbl) {
-#pragma unroll
-                    for (int k = 0; k < 3; ++k)
-                        if (st.need_k & (1u << k)) hmk[k] = shm[k * TILE + tid];
-                } else {
-                    psum = spsum[tid];
-                }
-            }
-            hb_phase_f<W>(s, f, st, hmk, psum, g);
-        } else if (active) {
-            if (GEN == GEN_UEG) gen_excit_ueg_no_renorm<W>(rng, s, f, socc + lo * nel, g);
-            else if (GEN == GEN_UEG_PP) gen_excit_ueg_power_pitzer<W>(rng, s, f, socc + lo * nel, g);
-            else if (GEN == EXCIT_GEN_HEAT_BATH_UNIFORM)
-                gen_excit_heat_bath_uniform<W>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, siw, sw + tid, TILE, g);
-            else if (GEN == EXCIT_GEN_HEAT_BATH_SINGLE)
-                gen_excit_heat_bath_uniform<W, true>(rng, s, p, f, socc + lo * nel, nullptr, siw, sw + tid, TILE, g);
-            else if (GEN == EXCIT_GEN_POWER_PITZER_OCC)     // also cauchy_schwarz_occ (p.excit_gen picks the integral)
-                gen_excit_power_pitzer_occ<W>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, nullptr, nullptr, 0, g);
-            else if (GEN == EXCIT_GEN_POWER_PITZER_OCC_IJ)  // also cauchy_schwarz_occ_ij
-                gen_excit_power_pitzer_occ<W>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, siw, sw + tid, TILE, g);
-            else if (GEN == EXCIT_GEN_RENORM) gen_excit_renorm<W>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, g);
-            else if (GEN == EXCIT_GEN_RENORM_SPIN) gen_excit_renorm<W, true>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, g);
-            else if (GEN == EXCIT_GEN_POWER_PITZER) gen_excit_power_pitzer_ref<W>(rng, s, p, f, socc + lo * nel, g);
-            else if (GEN == EXCIT_GEN_POWER_PITZER_ORDERN)     // ssu holds ref_cdet_occ_list of each state (nsu = nel)
-                gen_excit_power_pitzer_orderN<W>(rng, s, p, f, socc + lo * nel, ssu + lo * nsu, g);
-            else if (GEN == EXCIT_GEN_NO_RENORM_SPIN) gen_excit_no_renorm<W, true>(rng, s, p, f, socc + lo * nel, g);
-            else gen_excit_no_renorm<W>(rng, s, p, f, socc + lo * nel, g);
-        }
-        int64_t nspawn = 0;
-        uint64_t child[W];
-        int dest = 0, pflag = 0;
-        if (active) {
-            double hmq = g.hmatel;
-            if (p.qn && g.allowed) hmq = hmq * qn_spawned_weighting(p, sdf[lo], g);   // spawn_standard (src/spawning.F90:101-103)
-            if (ps_on && g.allowed) {   // update_p_single_double_data (src/spawning.F90:104-109,2139-2215)
-                const int k = (g.nexcit == 2) ? TILE : 0;
-                sps_h[k + tid] = sps_h[k + tid] + (fabs(hmq) * (g.nexcit == 2 ? p.pattempt_double : p.pattempt_single)) / g.pgen;
-                sps_n[k + tid] += 1u;
-            }
-            nspawn = attempt_to_spawn(rng, p, hmq, g.pgen, ssign[lo] ? (int64_t)-1 : (int64_t)1);
-            if (nspawn != 0) {
-                make_child<W>(f, g, child);
-                // create_spawned_particle[_initiator]_truncated (src/spawning.F90:1186-1319)
-                if (p.trunc_level >= 0 && excit_level<W>(child, p.f0) > p.trunc_level) {
-                    nspawn = 0;
-                } else {
-                    // assign_particle_processor (src/spawning.F90:770-838)
-                    dest = (p.nprocs > 1) ? proc_map[owner_slot(child, s.nbasis, p.hash_seed, p.nprocs, p.nslots)] : 0;
-                    pflag = p.initiator ? sflag[lo] : 0;
-                }
-            }
-        }
-        __syncwarp();
-        const unsigned has = __ballot_sync(0xffffffffu, nspawn != 0);
-        if (nspawn != 0) {
-            // add_[flagged_]spawned_particle (src/spawning.F90:907-1018): warp-aggregated pointer bump per destination
-            const unsigned peers = (p.nprocs > 1) ? __match_any_sync(has, dest) : has;
-            const int leader = __ffs(peers) - 1;
-            const int rank = __popc(peers & ((1u << lane) - 1u));
-            unsigned long long slot0 = 0;
-            if (lane == leader) slot0 = atomicAdd(&head[dest], (unsigned long long)__popc(peers));
-            slot0 = __shfl_sync(peers, slot0, leader);
-            const long long slot = (long long)slot0 + rank;
-            if (slot < block_size) {
-                int64_t* dst = spawn + ((long long)dest * block_size + slot) * E;
-                if (W == 2) {
-                    reinterpret_cast<ulonglong2*>(dst)[0] = make_ulonglong2(child[0], child[1]);
-                    reinterpret_cast<longlong2*>(dst)[1] = make_longlong2((long long)nspawn, (long long)pflag);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < W; ++k) dst[k] = (int64_t)child[k];
-                    dst[W] = nspawn;
-                    dst[W + 1] = pflag;
-                }
-            } else {
-                atomicOr(err, 1);  // spawn%error: no space left in the spawning array
-            }
-        }
-    }
-
-    if (ps_on) {
-        const double a = warp_sum_d(sps_h[tid]), b = warp_sum_d(sps_h[TILE + tid]);
-        const long long c = warp_sum_ll((long long)sps_n[tid]), d = warp_sum_ll((long long)sps_n[TILE + tid]);
-        __syncthreads();
-        if (lane == 0) {
-            sred[warp] = a; sred[8 + warp] = b;
-            reinterpret_cast<long long*>(sred)[16 + warp] = c;
-            reinterpret_cast<long long*>(sred)[24 + warp] = d;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            PsPartials out = {0.0, 0.0, 0, 0};
-            for (int w = 0; w < TILE / 32; ++w) {
-                out.h_pgen_singles_sum += sred[w]; out.h_pgen_doubles_sum += sred[8 + w];
-                out.excit_gen_singles += reinterpret_cast<long long*>(sred)[16 + w];
-                out.excit_gen_doubles += reinterpret_cast<long long*>(sred)[24 + w];
-            }
-            p.ps_part[blockIdx.x] = out;
-        }
-    }
-    // deterministic block reduction of the estimators
-    double r0 = warp_sum_d(pe), r1 = warp_sum_d(d0);
-    long long r2 = warp_sum_ll(ndeath), r3 = warp_sum_ll(npart);
-    __syncthreads();
-    if (lane == 0) {
-        sred[warp] = r0; sred[8 + warp] = r1;
-        reinterpret_cast<long long*>(sred)[16 + warp] = r2;
-        reinterpret_cast<long long*>(sred)[24 + warp] = r3;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        SpawnPartials out;
-        out.pe = 0.0; out.d0 = 0.0; out.ndeath = 0; out.npart = 0;
-        for (int w = 0; w < TILE / 32; ++w) {
-            out.pe += sred[w]; out.d0 += sred[8 + w];
-            out.ndeath += reinterpret_cast<long long*>(sred)[16 + w];
-            out.npart += reinterpret_cast<long long*>(sred)[24 + w];
-        }
-        out.nattempts = T;
-        partials[blockIdx.x] = out;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// CCMC (src/ccmc.f90:603-896): one thread per cluster-selection attempt - select_cluster, do_ccmc_accumulation,
-// spawner_ccmc and stochastic_ccmc_death; spawned and killed excips are appended to the spawn list and then go through
-// the same sort / annihilation / merge kernels as FCIQMC (direct_annihilation).
-// ------------------------------------------------------------------------------------------------
-// add_spawned_particle (src/spawning.F90:907-1018): warp-aggregated pointer bump; every lane of the warp must call it
-template <int W>
-__device__ __forceinline__ void append_spawn_warp(const uint64_t* f, int64_t nspawn, int dest, int nprocs,
-                                                  int64_t* __restrict__ spawn, unsigned long long* __restrict__ head,
-                                                  long long block_size, int* __restrict__ err) {
-    constexpr int E = W + 2;
-    const int lane = threadIdx.x & 31;
-    const unsigned has = __ballot_sync(0xffffffffu, nspawn != 0);
-    if (nspawn != 0) {
-        const unsigned peers = (nprocs > 1) ? __match_any_sync(has, dest) : has;
-        const int leader = __ffs(peers) - 1;
-        const int rank = __popc(peers & ((1u << lane) - 1u));
-        unsigned long long slot0 = 0;
-        if (lane == leader) slot0 = atomicAdd(&head[dest], (unsigned long long)__popc(peers));
-        slot0 = __shfl_sync(peers, slot0, leader);
-        const long long slot = (long long)slot0 + rank;
-        if (slot < block_size) {
-            int64_t* dst = spawn + ((long long)dest * block_size + slot) * E;
-#pragma unroll
-            for (int k = 0; k < W; ++k) dst[k] = (int64_t)f[k];
-            dst[W] = nspawn;
-            dst[W + 1] = 0;
-        } else {
-            atomicOr(err, 1);
-        }
-    }
-}
-
-struct CcmcPartials { double pe, d0; long long ndeath, nattempts_spawn; };
-
-// block sums of the pattempt_update statistics of a 256-thread CCMC block (all threads call it)
-__device__ __forceinline__ void ps_block_reduce(PsPartials* out, double hs, double hd, int ns, int nd) {
-    __shared__ double sh[2][8];
-    __shared__ long long sn[2][8];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const double a = warp_sum_d(hs), b = warp_sum_d(hd);
-    const long long c = warp_sum_ll((long long)ns), d = warp_sum_ll((long long)nd);
-    if (lane == 0) { sh[0][warp] = a; sh[1][warp] = b; sn[0][warp] = c; sn[1][warp] = d; }
-    __syncthreads();
-    if (tid == 0) {
-        PsPartials o = {0.0, 0.0, 0, 0};
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
-            o.h_pgen_singles_sum += sh[0][w]; o.h_pgen_doubles_sum += sh[1][w];
-            o.excit_gen_singles += sn[0][w]; o.excit_gen_doubles += sn[1][w];
-        }
-        out[blockIdx.x] = o;
-    }
-}
 // running totals of the report loop: acc[0..3] += block sums in fixed order
 __global__ void k_reduce_ps(const PsPartials* __restrict__ part, int n, double* __restrict__ acc) {
     __shared__ double sh[4][32];
@@ -640,266 +78,6 @@ __global__ void k_reduce_ps(const PsPartials* __restrict__ part, int n, double* 
         acc[threadIdx.x] = acc[threadIdx.x] + t;
     }
 }
-
-template <int W>
-__global__ void __launch_bounds__(256)      // 80 registers, 3 blocks/SM: 64 (4 blocks) and 99 (2 blocks) are both ~18 % slower
-k_ccmc_cluster(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states, const int64_t* __restrict__ pops,
-               const double* __restrict__ dat, const long long* __restrict__ cum_enc, int64_t* __restrict__ spawn,
-               unsigned long long* __restrict__ head, long long block_size, const int* __restrict__ proc_map,
-               CcmcPartials* __restrict__ partials, int* __restrict__ err) {
-    __shared__ double sd[2][8];
-    __shared__ long long sl[2][8];
-    __shared__ unsigned short sperm[256];
-    __shared__ unsigned char swc[8][8];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // The attempts of a block are dealt to its threads grouped by cluster size (a stable counting sort on the size each
-    // attempt's stream will draw first), so that the lanes of a warp walk select_cluster / collapse_cluster in step:
-    // half of all attempts are the empty cluster, a quarter single excitors, ...  Which thread runs an attempt changes
-    // neither its random stream nor its result.
-    long long idx;
-    {
-        const long long idx0 = (long long)blockIdx.x * blockDim.x + tid;
-        int cls = 7;
-        if (idx0 < a.nattempts) {
-            if (idx0 >= a.nattempts - a.nD0_select) {
-                cls = 0;
-            } else {
-                PhiloxStream r0;
-                r0.begin(p.seed, p.cycle, RNG_SPAWN, det_hash64<W>(p.f0) + (uint64_t)p.iproc * 0x9E3779B97F4A7C15ull,
-                         (uint32_t)(idx0 + 1));
-                const double rand = r0.next();
-                double psize = 0.0;
-                int n = -1;
-                for (int i = 0; i <= a.max_cluster_size - a.min_cluster_size - 1; ++i) {
-                    psize = psize + 1.0 / (double)(1ll << (i + 1));
-                    if (rand < psize) { n = i + a.min_cluster_size; break; }
-                }
-                if (n == -1) n = a.max_cluster_size;
-                cls = min(max(n, 0), 6);
-            }
-        }
-        int rnk = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const unsigned m = __ballot_sync(0xffffffffu, cls == k);
-            if (cls == k) rnk = __popc(m & ((1u << lane) - 1u));
-            if (lane == 0) swc[warp][k] = (unsigned char)__popc(m);
-        }
-        __syncthreads();
-        int base = 0;
-        for (int k = 0; k < cls; ++k)
-            for (int w = 0; w < 8; ++w) base += swc[w][k];
-        for (int w = 0; w < warp; ++w) base += swc[w][cls];
-        sperm[base + rnk] = (unsigned short)tid;
-        __syncthreads();
-        idx = (long long)blockIdx.x * blockDim.x + sperm[tid];
-    }
-    double pe = 0.0, d0 = 0.0;
-    long long ndeath = 0, nas = 0;
-    int64_t nspawn = 0, nkill = 0;
-    double ps_hs = 0.0, ps_hd = 0.0;
-    int ps_ns = 0, ps_nd = 0;
-    uint64_t cf[W], child[W];
-#pragma unroll
-    for (int k = 0; k < W; ++k) { cf[k] = 0; child[k] = 0; }
-    int dest_s = 0, dest_k = 0;
-    if (idx < a.nattempts) {
-        PhiloxStream rng;
-        rng.begin(p.seed, p.cycle, RNG_SPAWN, det_hash64<W>(p.f0) + (uint64_t)p.iproc * 0x9E3779B97F4A7C15ull,
-                  (uint32_t)(idx + 1));
-        Cluster cl;
-        const bool det_D0 = idx >= a.nattempts - a.nD0_select;    // deterministic selections of the reference (full_nc)
-        if (det_D0) {
-            // create_null_cluster(prob = nprocs * nD0_select) (src/ccmc.f90:803-812)
-#pragma unroll
-            for (int k = 0; k < W; ++k) cf[k] = p.f0[k];
-            cl.nexcitors = 0; cl.excitation_level = 0; cl.sign = 1; cl.first_pos = 0;
-            cl.amplitude = a.D0_normalisation;
-            cl.pselect = (double)a.nprocs * (double)a.nD0_select;
-        } else {
-            ccmc_select_cluster<W>(rng, p, a, states, pops, cum_enc, cf, cl);
-        }
-        if (cl.excitation_level >= 0 && cl.excitation_level <= a.ex_level + 2) {
-            uint8_t occ[HB_MAXNEL], su[64];
-            decode_det<W>(cf, occ);
-            if (s.kind == SYS_READ_IN && p.excit_gen != EXCIT_GEN_NO_RENORM && p.excit_gen != EXCIT_GEN_NO_RENORM_SPIN &&
-                p.excit_gen != EXCIT_GEN_HEAT_BATH)
-                build_symunocc_masks<W>(s, cf, su);
-            // do_ccmc_accumulation (src/ccmc.f90:1007-1101)
-            bool is_ref;
-            const double hm0 = proj_energy_hmatel<W>(s, p, cf, occ, is_ref);
-            const double wpop = cl.amplitude * cl.sign / cl.pselect;
-            if (is_ref) d0 = wpop; else pe = hm0 * wpop;
-            nas = 1;
-            // spawner_ccmc (src/ccmc_death_spawning.f90:11-211)
-            Gen g;
-            gen_excit<W>(rng, s, p, cf, occ, su, g);
-            const double hmatel = g.hmatel * cl.amplitude * 1.0 * cl.sign;
-            const double pgen = g.pgen * cl.pselect * 1;
-            if (p.ps_part && g.allowed) {   // src/ccmc_death_spawning.f90:150-157
-                if (g.nexcit == 2) { ps_hd = (fabs(hmatel) * p.pattempt_double) / pgen; ps_nd = 1; }
-                else { ps_hs = (fabs(hmatel) * p.pattempt_single) / pgen; ps_ns = 1; }
-            }
-            nspawn = attempt_to_spawn(rng, p, hmatel, pgen, (int64_t)1);
-            if (nspawn != 0) {
-                make_child<W>(cf, g, child);
-                const int lvl = excit_level<W>(child, p.f0);
-                if (ccmc_excitor_sign<W>(p.f0, child, lvl) < 0) nspawn = -nspawn;
-                if (p.trunc_level >= 0 && lvl > p.trunc_level) nspawn = 0;   // create_spawned_particle_truncated
-                else dest_s = (p.nprocs > 1) ? proc_map[owner_slot_shift<W>(child, s.nbasis, p.hash_seed, p.ccmc_shift, p.ccmc_freq,
-                                                                            p.nprocs, p.nslots)] : 0;
-            }
-            // stochastic_ccmc_death + stochastic_death_attempt (src/ccmc_death_spawning.f90:213-441)
-            if (!det_D0 && cl.excitation_level <= a.ex_level && (cl.nexcitors >= 2 || !a.full_nc)) {
-                const double pe_old = p.proj_energy_old;
-                double KiiAi;
-                if (cl.nexcitors == 0) KiiAi = ((-pe_old) * 1.0 + (pe_old - p.shift) * 1.0) * cl.amplitude;
-                else if (cl.nexcitors == 1) KiiAi = ((dat[cl.first_pos - 1] - pe_old) * 1.0 + (pe_old - p.shift) * 1.0) * cl.amplitude;
-                else {
-                    const double hii = (s.kind == SYS_UEG) ? slater_condon0_ueg(s, occ) : slater_condon0(s, occ);
-                    KiiAi = ((hii - p.H00) - pe_old) * 1.0 * cl.amplitude;
-                }
-                KiiAi = 1.0 * (double)p.real_factor * KiiAi;
-                KiiAi = KiiAi * p.tau / cl.pselect;
-                double pdeath = fabs(KiiAi);
-                if (pdeath < (double)p.spawn_cutoff) {
-                    nkill = (pdeath > rng.next() * (double)p.spawn_cutoff) ? p.spawn_cutoff : 0;
-                } else {
-                    nkill = (int64_t)pdeath;
-                    pdeath = pdeath - (double)nkill;
-                    if (pdeath > rng.next()) nkill++;
-                }
-                ndeath = nkill;
-                if (nkill != 0) {
-                    if (KiiAi > 0) nkill = -nkill;
-                    dest_k = (p.nprocs > 1) ? proc_map[owner_slot_shift<W>(cf, s.nbasis, p.hash_seed, p.ccmc_shift, p.ccmc_freq,
-                                                                            p.nprocs, p.nslots)] : 0;
-                }
-            }
-        }
-    }
-    __syncwarp();
-    append_spawn_warp<W>(child, nspawn, dest_s, p.nprocs, spawn, head, block_size, err);
-    append_spawn_warp<W>(cf, nkill, dest_k, p.nprocs, spawn, head, block_size, err);
-    if (p.ps_part) ps_block_reduce(p.ps_part, ps_hs, ps_hd, ps_ns, ps_nd);
-    const double r0 = warp_sum_d(pe), r1 = warp_sum_d(d0);
-    const long long r2 = warp_sum_ll(ndeath), r3 = warp_sum_ll(nas);
-    if (lane == 0) { sd[0][warp] = r0; sd[1][warp] = r1; sl[0][warp] = r2; sl[1][warp] = r3; }
-    __syncthreads();
-    if (tid == 0) {
-        CcmcPartials out;
-        out.pe = 0.0; out.d0 = 0.0; out.ndeath = 0; out.nattempts_spawn = 0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { out.pe += sd[0][w]; out.d0 += sd[1][w]; out.ndeath += sl[0][w]; out.nattempts_spawn += sl[1][w]; }
-        partials[blockIdx.x] = out;
-    }
-}
-// full_nc: every excitor is a non-composite cluster of its own - select_nc_cluster (src/ccmc_selection.f90:462-561),
-// do_nc_ccmc_propagation (src/ccmc.f90:1275-1360) - and every excip (the reference included) dies in place through
-// stochastic_ccmc_death_nc (src/ccmc_death_spawning.f90:443-547).  Thread per excitor; launched after k_ccmc_cluster,
-// which reads the populations this kernel changes.
-template <int W>
-__global__ void __launch_bounds__(256)
-k_ccmc_nc(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states, int64_t* __restrict__ pops,
-          const double* __restrict__ dat, int64_t* __restrict__ spawn, unsigned long long* __restrict__ head,
-          long long block_size, const int* __restrict__ proc_map, CcmcPartials* __restrict__ partials,
-          long long* __restrict__ ndeath_nc_out, int* __restrict__ err) {
-    __shared__ double sd[2][8];
-    __shared__ long long sl[2][8];
-    constexpr int E = W + 2;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long i = (long long)blockIdx.x * blockDim.x + tid;
-    double pe = 0.0, d0 = 0.0;
-    long long ndeath_nc = 0, nas = 0;
-    double ps_hs = 0.0, ps_hd = 0.0;
-    int ps_ns = 0, ps_nd = 0;
-    if (i < a.nstates) {
-        uint64_t f[W];
-        load_det<W>(states + i * W, f);
-        const int64_t pop = pops[i];
-        const uint64_t h = det_hash64<W>(f);
-        const bool isD0 = (i + 1 == a.D0_pos);
-        PhiloxStream rng;
-        if (!isD0) {
-            const double amp = (double)pop / (double)p.real_factor;
-            const int level = excit_level<W>(f, p.f0);
-            const int sign = ccmc_excitor_sign<W>(p.f0, f, level);
-            uint8_t occ[HB_MAXNEL], su[64];
-            decode_det<W>(f, occ);
-            if (s.kind == SYS_READ_IN && p.excit_gen != EXCIT_GEN_NO_RENORM && p.excit_gen != EXCIT_GEN_NO_RENORM_SPIN &&
-                p.excit_gen != EXCIT_GEN_HEAT_BATH)
-                build_symunocc_masks<W>(s, f, su);
-            bool is_ref;
-            const double hm0 = proj_energy_hmatel<W>(s, p, f, occ, is_ref);
-            pe = hm0 * (amp * sign / 1.0);
-            rng.begin(p.seed, p.cycle, RNG_NATTEMPTS, h, 0);
-            const int nsp = decide_nattempts(rng, fabs(amp) / 1.0);
-            nas = nsp;
-            const double unit = amp / fabs(amp);
-            for (int ip = 0; ip < nsp; ++ip) {
-                rng.begin(p.seed, p.cycle, RNG_SPAWN, h, (uint32_t)ip);
-                Gen g;
-                gen_excit<W>(rng, s, p, f, occ, su, g);
-                const double hmatel = g.hmatel * unit * 1.0 * sign;
-                const double pgen = g.pgen * 1.0 * 1;
-                if (p.ps_part && g.allowed) {
-                    if (g.nexcit == 2) { ps_hd = ps_hd + (fabs(hmatel) * p.pattempt_double) / pgen; ps_nd += 1; }
-                    else { ps_hs = ps_hs + (fabs(hmatel) * p.pattempt_single) / pgen; ps_ns += 1; }
-                }
-                int64_t nspawn = attempt_to_spawn(rng, p, hmatel, pgen, (int64_t)1);
-                if (nspawn != 0) {
-                    uint64_t child[W];
-                    make_child<W>(f, g, child);
-                    const int lvl = excit_level<W>(child, p.f0);
-                    if (ccmc_excitor_sign<W>(p.f0, child, lvl) < 0) nspawn = -nspawn;
-                    if (!(p.trunc_level >= 0 && lvl > p.trunc_level)) {
-                        const int dest = (p.nprocs > 1) ? proc_map[owner_slot_shift<W>(child, s.nbasis, p.hash_seed, p.ccmc_shift,
-                                                                                         p.ccmc_freq, p.nprocs, p.nslots)] : 0;
-                        const long long slot = (long long)atomicAdd(&head[dest], 1ull);
-                        if (slot < block_size) {
-                            int64_t* dst = spawn + ((long long)dest * block_size + slot) * E;
-#pragma unroll
-                            for (int k = 0; k < W; ++k) dst[k] = (int64_t)child[k];
-                            dst[W] = nspawn;
-                            dst[W + 1] = 0;
-                        } else {
-                            atomicOr(err, 1);
-                        }
-                    }
-                }
-            }
-        }
-        // stochastic_ccmc_death_nc
-        {
-            const double pe_old = p.proj_energy_old;
-            double KiiAi;
-            if (isD0) KiiAi = ((-pe_old) * 1.0 + (pe_old - p.shift) * 1.0) * (double)pop;
-            else KiiAi = ((dat[i] - pe_old) * 1.0 + (pe_old - p.shift) * 1.0) * (double)pop;
-            KiiAi = KiiAi * 1.0;
-            double pdeath = p.tau * fabs(KiiAi);
-            int64_t nkill = (int64_t)pdeath;
-            pdeath = pdeath - (double)nkill;
-            rng.begin(p.seed, p.cycle, RNG_DEATH, h, 0);
-            if (pdeath > rng.next()) nkill = nkill + 1;
-            if (nkill != 0) {
-                if (KiiAi > 0) nkill = -nkill;
-                pops[i] = pop + nkill;
-                ndeath_nc = nkill < 0 ? -nkill : nkill;
-            }
-        }
-    }
-    if (p.ps_part) ps_block_reduce(p.ps_part, ps_hs, ps_hd, ps_ns, ps_nd);
-    const double r0 = warp_sum_d(pe), r1 = warp_sum_d(d0);
-    const long long r2 = warp_sum_ll(ndeath_nc), r3 = warp_sum_ll(nas);
-    if (lane == 0) { sd[0][warp] = r0; sd[1][warp] = r1; sl[0][warp] = r2; sl[1][warp] = r3; }
-    __syncthreads();
-    if (tid == 0) {
-        CcmcPartials out;
-        out.pe = 0.0; out.d0 = 0.0; out.ndeath = 0; out.nattempts_spawn = 0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { out.pe += sd[0][w]; out.d0 += sd[1][w]; out.ndeath += sl[0][w]; out.nattempts_spawn += sl[1][w]; }
-        partials[blockIdx.x] = out;
-    }
-    (void)ndeath_nc_out;
-}
 __global__ void k_ccmc_reduce(const CcmcPartials* __restrict__ partials, int n, CcmcPartials* out) {
     __shared__ double sd[2][32];
     __shared__ long long sl[2][32];
@@ -915,44 +93,6 @@ __global__ void k_ccmc_reduce(const CcmcPartials* __restrict__ partials, int n, 
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { o.pe += sd[0][w]; o.d0 += sd[1][w]; o.ndeath += sl[0][w]; o.nattempts_spawn += sl[1][w]; }
         *out = o;
     }
-}
-// redistribute_particles (src/qmc_common.F90:505-595): excips whose owner under the current hash shift is another
-// rank are moved to that rank's block of the spawn list and zeroed in the main list
-template <int W>
-__global__ void __launch_bounds__(256)
-k_ccmc_redistribute(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __restrict__ pops, long long n,
-                    int64_t* __restrict__ spawn, unsigned long long* __restrict__ head, long long block_size,
-                    const int* __restrict__ proc_map, int* __restrict__ err) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    uint64_t f[W];
-#pragma unroll
-    for (int k = 0; k < W; ++k) f[k] = 0;
-    int64_t pop = 0;
-    int dest = 0;
-    if (i < n) {
-        load_det<W>(states + i * W, f);
-        dest = proc_map[owner_slot_shift<W>(f, s.nbasis, p.hash_seed, p.ccmc_shift, p.ccmc_freq, p.nprocs, p.nslots)];
-        if (dest != p.iproc) {
-            pop = pops[i];
-            pops[i] = 0;
-        }
-    }
-    append_spawn_warp<W>(f, pop, dest, p.nprocs, spawn, head, block_size, err);
-}
-// find_D0 (src/ccmc_utils.F90:21-67): position (1-based, 0 = absent) and population of f0 in the sorted main list
-template <int W>
-__global__ void k_find_det(Params p, const uint64_t* __restrict__ states, const int64_t* __restrict__ pops, long long n,
-                           long long* __restrict__ out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const long long pos = lower_bound_det<W>(states, n, p.f0);
-    bool hit = false;
-    if (pos < n) {
-        uint64_t f[W];
-        load_det<W>(states + pos * W, f);
-        hit = det_eq<W>(f, p.f0);
-    }
-    out[0] = hit ? pos + 1 : 0;
-    out[1] = hit ? pops[pos] : 0;
 }
 // inclusive prefix sums of |pop| (encoded) with the reference skipped (cumulative_population): exact integer scan
 constexpr int SCAN64_ITEMS = 8;
@@ -1021,11 +161,6 @@ __global__ void __launch_bounds__(256) k_cum_add(long long* __restrict__ out, lo
         if (base + k < n) out[base + k] += off;
 }
 
-struct CycleStats {
-    double pe, d0;              // this cycle
-    long long ndeath, npart_after_death, nattempts_spawn;
-    long long nkept, npart_new; // after merge
-};
 
 __global__ void k_reduce_partials(const SpawnPartials* __restrict__ partials, int n, CycleStats* st) {
     __shared__ double sd[2][32];
@@ -1539,118 +674,6 @@ __global__ void k_hb_alias(int nb, long long nrows, const double* __restrict__ w
     generate_alias_tables(nb, w + r * nb, tot[r], U + r * nb, K + r * nb, scratch + 2 * r * nb, scratch + 2 * r * nb + nb);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Probe kernels (parity tests through the C ABI)
-// ------------------------------------------------------------------------------------------------
-template <int W>
-__global__ void k_gen_excit_batch(Sys s, Params p, const uint64_t* __restrict__ states, const int64_t* __restrict__ pops,
-                                  const uint32_t* __restrict__ attempt, long long n, const int* __restrict__ proc_map,
-                                  int* __restrict__ iout, double* __restrict__ dout, int64_t* __restrict__ nspawn) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    uint64_t f[W];
-#pragma unroll
-    for (int k = 0; k < W; ++k) f[k] = states[t * W + k];
-    uint8_t occ[HB_MAXNEL], su[64];
-    decode_det<W>(f, occ);
-    if (s.kind != SYS_UEG) build_symunocc(s, occ, su);
-    PhiloxStream rng;
-    rng.begin(p.seed, p.cycle, RNG_SPAWN, det_hash64<W>(f), attempt[t]);
-    Gen g;
-    gen_excit<W>(rng, s, p, f, occ, su, g);
-    const int64_t ns = attempt_to_spawn(rng, p, g.hmatel, g.pgen, pops[t]);
-    int own = -1;
-    if (g.allowed) {
-        uint64_t child[W];
-#pragma unroll
-        for (int k = 0; k < W; ++k) child[k] = f[k];
-        child[(g.from1 - 1) >> 6] &= ~(1ull << ((g.from1 - 1) & 63));
-        child[(g.to1 - 1) >> 6] |= (1ull << ((g.to1 - 1) & 63));
-        if (g.nexcit == 2) {
-            child[(g.from2 - 1) >> 6] &= ~(1ull << ((g.from2 - 1) & 63));
-            child[(g.to2 - 1) >> 6] |= (1ull << ((g.to2 - 1) & 63));
-        }
-        own = proc_map[owner_slot(child, s.nbasis, p.hash_seed, p.nprocs, p.nslots)];
-    }
-    int* io = iout + t * 8;
-    io[0] = g.nexcit; io[1] = g.from1; io[2] = g.from2; io[3] = g.to1; io[4] = g.to2; io[5] = g.perm; io[6] = g.allowed;
-    io[7] = own;
-    dout[t * 2] = g.pgen; dout[t * 2 + 1] = g.hmatel;
-    nspawn[t] = ns;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Engine
-// ------------------------------------------------------------------------------------------------
-struct hb200_engine {
-    hb200_config cfg;
-    int W = 1, E = 3;
-    cudaStream_t stream = nullptr;
-    Sys sys;
-    Params par;
-    bool have_sys = false, have_hb = false, have_ref = false, have_ppn = false, have_pp = false;
-    // owned device buffers for system tables
-    std::vector<void*> owned;
-    int* d_proc_map = nullptr;
-    // main list (double buffered)
-    // buffers 0/1: current list and the merge output (swapped every cycle); buffer 2 (allocated on first use): staging
-    // area of the asynchronous upload, rotated in by hb200_upload_psips_commit
-    uint64_t* d_states[3] = {nullptr, nullptr, nullptr};
-    int64_t* d_pops[3] = {nullptr, nullptr, nullptr};
-    double* d_dat[3] = {nullptr, nullptr, nullptr};
-    int cur = 0, alt = 1, stg = 2;
-    cudaStream_t copy_stream = nullptr;
-    cudaEvent_t copy_done = nullptr;
-    long long stg_n = -1;
-    long long nstates = 0;
-    long long nparticles_enc = 0;  // sum |pop| (encoded) of the current list
-    // spawn store
-    int64_t* d_spawn[2] = {nullptr, nullptr};
-    int sp_cur = 0;      // buffer holding the current stage's list
-    long long sp_n = 0;  // number of elements in it (contiguous from 0) after comm
-    bool sp_blocked = true;  // true: still partitioned in per-destination blocks (before comm)
-    long long block_size = 0;
-    unsigned long long* d_head = nullptr;
-    std::vector<unsigned long long> h_head;
-    int* d_err = nullptr;
-    // scratch
-    SpawnPartials* d_partials = nullptr;
-    long long max_tiles = 0;
-    CycleStats* d_stats = nullptr;
-    unsigned* d_hist = nullptr;
-    long long hist_cap = 0;
-    int* d_ins_flag = nullptr;
-    int* d_ins_idx = nullptr;
-    long long* d_ins_pos = nullptr;
-    double* d_ins_dat = nullptr;
-    int* d_tile_keep = nullptr;
-    int* d_tile_off = nullptr;
-    int* d_scan_l1 = nullptr;
-    int* d_scan_l1o = nullptr;
-    int* d_total = nullptr;   // [4] small ints
-    long long* d_part_ll = nullptr;
-    long long* d_ll = nullptr;  // [4]
-    bool ccmc_full_nc = false;                     // ccmc_in%full_nc
-    int ccmc_hash_shift = 0, ccmc_move_freq = 5;   // spawn%hash_shift (+1 per cycle), spawn%move_freq
-    // CCMC scratch
-    long long* d_cum = nullptr;        // [walker_length] inclusive prefix sums of |pop| (reference skipped)
-    long long* d_cum_blk = nullptr;
-    CcmcPartials* d_cc_part = nullptr;
-    PsPartials* d_ps_part = nullptr;   // pattempt_update: per-block sums of one launch
-    double* d_ps_acc = nullptr;        // [4] running totals since the last hb200_get_ps_stats(reset)
-    size_t ps_part_cap = 0;
-    CcmcPartials* d_cc_tot = nullptr;
-    // NCCL
-    ncclComm_t comm = nullptr;
-    long long* d_counts = nullptr;  // [nprocs*nprocs]
-    // timing / counters
-    cudaEvent_t ev[6];
-    cudaEvent_t evk[2];           // brackets the k_spawn_death launch alone (roofline timing)
-    float spawn_kernel_ms = 0.f;  // accumulated over the cycles of the last hb200_iterate
-    double ms[8] = {0};
-    long long launches = 0, spawn_launches = 0;
-};
-
 
 // All host<->device copies are issued on the engine's own (non-blocking) stream and then synchronised: a plain
 // cudaMemcpy runs on the legacy stream, which is NOT ordered with kernels on a cudaStreamNonBlocking stream, and a
@@ -1684,17 +707,7 @@ static bool uses_heat_bath_tables(const hb200_engine* e) {
     return eg == HB200_EXCIT_GEN_HEAT_BATH || eg == HB200_EXCIT_GEN_HEAT_BATH_UNIFORM || eg == HB200_EXCIT_GEN_HEAT_BATH_SINGLE ||
            eg == HB200_EXCIT_GEN_POWER_PITZER_OCC_IJ || eg == HB200_EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ;
 }
-static size_t spawn_smem_bytes(const hb200_engine* e) {
-    const int eg = e->cfg.excit_gen;
-    const int nsu = (eg == HB200_EXCIT_GEN_POWER_PITZER_ORDERN) ? e->sys.nel :
-                    (e->sys.kind == SYS_READ_IN && eg != HB200_EXCIT_GEN_POWER_PITZER && eg != HB200_EXCIT_GEN_NO_RENORM && eg != HB200_EXCIT_GEN_NO_RENORM_SPIN &&
-                     eg != HB200_EXCIT_GEN_HEAT_BATH &&
-                     eg != HB200_EXCIT_GEN_HEAT_BATH_SINGLE)
-                        ? 2 * e->sys.nsym_tot : 0;
-    const bool hb = eg == HB200_EXCIT_GEN_HEAT_BATH;
-    return SpawnSmem(e->W, e->sys.nel, nsu, e->sys.nbasis, hb, uses_heat_bath_tables(e), !hb && e->par.ps_part != nullptr,
-                     e->par.qn != 0).total;
-}
+bool hb_uses_heat_bath_tables(const hb200_engine* e) { return uses_heat_bath_tables(e); }
 
 extern "C" {
 
@@ -2372,6 +1385,15 @@ int64_t hb200_nstates(hb200_engine* e) { return e->nstates; }
         default: { constexpr int WW = 4; __VA_ARGS__; } break; \
     }
 
+// launchers of hb_ccmc_tu.cu (one object file per W)
+#define DISPATCH_CCMC(e, rc, fn, ...)               \
+    switch ((e)->W) {                               \
+        case 1: rc = fn##1(__VA_ARGS__); break;     \
+        case 2: rc = fn##2(__VA_ARGS__); break;     \
+        case 3: rc = fn##3(__VA_ARGS__); break;     \
+        default: rc = fn##4(__VA_ARGS__); break;    \
+    }
+
 static int stage_spawn_death(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, CycleStats* hst) {
     Params& p = e->par;
     p.tau = in->tau; p.shift = in->shift; p.proj_energy_old = in->proj_energy_old; p.cycle = cycle;
@@ -2380,41 +1402,32 @@ static int stage_spawn_death(hb200_engine* e, const hb200_iter_in* in, uint32_t 
     const long long n = e->nstates;
     const int ntiles = (int)((n + TILE - 1) / TILE);
     if (ntiles > 0) {
-        const size_t smem = spawn_smem_bytes(e);
-        const int c = e->cur;
         CK(cudaEventRecord(e->evk[0], st));
-#define LAUNCH_SPAWN(GG)                                                                                          \
-    DISPATCH_W(e, {                                                                                               \
-        static bool attr_set = false;                                                                             \
-        if (!attr_set) {                                                                                          \
-            CK(cudaFuncSetAttribute(k_spawn_death<WW, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); \
-            attr_set = true;                                                                                      \
-        }                                                                                                         \
-        k_spawn_death<WW, GG><<<ntiles, TILE, smem, st>>>(e->sys, p, e->d_states[c], e->d_pops[c], e->d_dat[c], n, \
-                                                          e->d_spawn[0], e->d_head, e->block_size, e->d_proc_map, \
-                                                          e->d_partials, e->d_err);                               \
-    })
+        // (generator group, GEN) of this calculation -> the object file holding its k_spawn_death instantiation
+        int group, gen;
         if (e->sys.kind == SYS_UEG) {
-            if (e->cfg.excit_gen == HB200_EXCIT_GEN_POWER_PITZER) { LAUNCH_SPAWN(GEN_UEG_PP); }
-            else { LAUNCH_SPAWN(GEN_UEG); }
-        }
-        else switch (e->cfg.excit_gen) {
-            case HB200_EXCIT_GEN_NO_RENORM: LAUNCH_SPAWN(EXCIT_GEN_NO_RENORM); break;
-            case HB200_EXCIT_GEN_RENORM: LAUNCH_SPAWN(EXCIT_GEN_RENORM); break;
-            case HB200_EXCIT_GEN_RENORM_SPIN: LAUNCH_SPAWN(EXCIT_GEN_RENORM_SPIN); break;
-            case HB200_EXCIT_GEN_POWER_PITZER_ORDERN: LAUNCH_SPAWN(EXCIT_GEN_POWER_PITZER_ORDERN); break;
-            case HB200_EXCIT_GEN_POWER_PITZER: LAUNCH_SPAWN(EXCIT_GEN_POWER_PITZER); break;
-            case HB200_EXCIT_GEN_NO_RENORM_SPIN: LAUNCH_SPAWN(EXCIT_GEN_NO_RENORM_SPIN); break;
-            case HB200_EXCIT_GEN_HEAT_BATH: LAUNCH_SPAWN(EXCIT_GEN_HEAT_BATH); break;
-            case HB200_EXCIT_GEN_HEAT_BATH_UNIFORM: LAUNCH_SPAWN(EXCIT_GEN_HEAT_BATH_UNIFORM); break;
-            case HB200_EXCIT_GEN_HEAT_BATH_SINGLE: LAUNCH_SPAWN(EXCIT_GEN_HEAT_BATH_SINGLE); break;
+            group = SPAWN_GROUP_TABLES;
+            gen = (e->cfg.excit_gen == HB200_EXCIT_GEN_POWER_PITZER) ? (int)GEN_UEG_PP : (int)GEN_UEG;
+        } else switch (e->cfg.excit_gen) {
+            case HB200_EXCIT_GEN_NO_RENORM: case HB200_EXCIT_GEN_RENORM: case HB200_EXCIT_GEN_RENORM_SPIN:
+            case HB200_EXCIT_GEN_NO_RENORM_SPIN: group = SPAWN_GROUP_UNIFORM; gen = e->cfg.excit_gen; break;
+            case HB200_EXCIT_GEN_POWER_PITZER_ORDERN: case HB200_EXCIT_GEN_POWER_PITZER:
+                group = SPAWN_GROUP_TABLES; gen = e->cfg.excit_gen; break;
+            case HB200_EXCIT_GEN_HEAT_BATH: group = SPAWN_GROUP_HEAT_BATH; gen = EXCIT_GEN_HEAT_BATH; break;
+            case HB200_EXCIT_GEN_HEAT_BATH_UNIFORM: case HB200_EXCIT_GEN_HEAT_BATH_SINGLE:
+                group = SPAWN_GROUP_HB_UNIFORM; gen = e->cfg.excit_gen; break;
             case HB200_EXCIT_GEN_POWER_PITZER_OCC:
-            case HB200_EXCIT_GEN_CAUCHY_SCHWARZ_OCC: LAUNCH_SPAWN(EXCIT_GEN_POWER_PITZER_OCC); break;
+            case HB200_EXCIT_GEN_CAUCHY_SCHWARZ_OCC: group = SPAWN_GROUP_PP_OCC; gen = EXCIT_GEN_POWER_PITZER_OCC; break;
             case HB200_EXCIT_GEN_POWER_PITZER_OCC_IJ:
-            case HB200_EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ: LAUNCH_SPAWN(EXCIT_GEN_POWER_PITZER_OCC_IJ); break;
+            case HB200_EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ: group = SPAWN_GROUP_PP_OCC; gen = EXCIT_GEN_POWER_PITZER_OCC_IJ; break;
             default: FAIL("spawn_death: excitation generator not implemented");
         }
-#undef LAUNCH_SPAWN
+#define HB_ROW(W) {hb_spawn_w##W##_g0, hb_spawn_w##W##_g1, hb_spawn_w##W##_g2, hb_spawn_w##W##_g3, hb_spawn_w##W##_g4}
+        static const hb_spawn_fn table[4][SPAWN_NGROUPS] = {HB_ROW(1), HB_ROW(2), HB_ROW(3), HB_ROW(4)};
+#undef HB_ROW
+        SpawnLaunch L;
+        L.gen = gen; L.ntiles = ntiles; L.smem = 0; L.n = n;
+        if (table[e->W - 1][group](e, p, L)) return 1;
         CK(cudaGetLastError());
         CK(cudaEventRecord(e->evk[1], st));
         e->launches++; e->spawn_launches++;
@@ -2679,8 +1692,7 @@ int hb200_ccmc_spawn(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, i
     const bool have_D0 = (p.iproc == D0_proc);
     if (have_D0) {
         if (n > 0) {
-            DISPATCH_W(e, k_find_det<WW><<<1, 32, 0, st>>>(p, e->d_states[c], e->d_pops[c], n, e->d_ll));
-            CK(cudaGetLastError());
+            { int rc = 0; DISPATCH_CCMC(e, rc, hb_ccmc_find_det_w, e, p); if (rc) return 1; }
             e->launches++;
         } else {
             CK(cudaMemsetAsync(e->d_ll, 0, 2 * sizeof(long long), st));
@@ -2734,10 +1746,10 @@ int hb200_ccmc_spawn(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, i
         const long long nblk = (a.nattempts + 255) / 256;
         if ((size_t)nblk > part_cap)
             FAIL("ccmc_spawn: more cluster selections than the partial-sum scratch holds");
-        DISPATCH_W(e, k_ccmc_cluster<WW><<<(unsigned)nblk, 256, 0, st>>>(e->sys, p, a, e->d_states[c], e->d_pops[c], e->d_dat[c],
-                                                                          e->d_cum, e->d_spawn[0], e->d_head, e->block_size,
-                                                                          e->d_proc_map, e->d_cc_part, e->d_err));
-        CK(cudaGetLastError());
+        {
+            CcmcLaunch L; L.a = a; L.nblk = nblk; L.partials = e->d_cc_part; L.cum = e->d_cum;
+            int rc = 0; DISPATCH_CCMC(e, rc, hb_ccmc_cluster_w, e, p, L); if (rc) return 1;
+        }
         k_ccmc_reduce<<<1, 1024, 0, st>>>(e->d_cc_part, (int)nblk, e->d_cc_tot);
         CK(cudaGetLastError());
         e->launches += 2;
@@ -2753,10 +1765,10 @@ int hb200_ccmc_spawn(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, i
         const long long nblk = (n + 255) / 256;
         Params pn = p;
         if (pn.ps_part) pn.ps_part += part_cap;
-        DISPATCH_W(e, k_ccmc_nc<WW><<<(unsigned)nblk, 256, 0, st>>>(e->sys, pn, a, e->d_states[c], e->d_pops[c], e->d_dat[c],
-                                                                     e->d_spawn[0], e->d_head, e->block_size, e->d_proc_map,
-                                                                     e->d_cc_part + part_cap, nullptr, e->d_err));
-        CK(cudaGetLastError());
+        {
+            CcmcLaunch L; L.a = a; L.nblk = nblk; L.partials = e->d_cc_part + part_cap; L.cum = e->d_cum;
+            int rc = 0; DISPATCH_CCMC(e, rc, hb_ccmc_nc_w, e, pn, L); if (rc) return 1;
+        }
         k_ccmc_reduce<<<1, 1024, 0, st>>>(e->d_cc_part + part_cap, (int)nblk, e->d_cc_tot + 1);
         CK(cudaGetLastError());
         e->launches += 2;
@@ -2777,10 +1789,7 @@ int hb200_ccmc_spawn(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, i
         nspawn_events += (long long)e->h_head[d];
     }
     if (p.nprocs > 1 && n > 0) {
-        DISPATCH_W(e, k_ccmc_redistribute<WW><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e->sys, p, e->d_states[c], e->d_pops[c], n,
-                                                                                          e->d_spawn[0], e->d_head, e->block_size,
-                                                                                          e->d_proc_map, e->d_err));
-        CK(cudaGetLastError());
+        { int rc = 0; DISPATCH_CCMC(e, rc, hb_ccmc_redistribute_w, e, p); if (rc) return 1; }
         e->launches++;
         CK(cudaMemcpyAsync(e->h_head.data(), e->d_head, sizeof(unsigned long long) * p.nprocs, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(herr, e->d_err, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -3088,9 +2097,7 @@ int hb200_gen_excit_batch(hb200_engine* e, const uint64_t* states, const int64_t
     CK(copy_sync(e, d_f, states, (size_t)n * e->W * 8, cudaMemcpyHostToDevice));
     CK(copy_sync(e, d_p, pops, (size_t)n * 8, cudaMemcpyHostToDevice));
     CK(copy_sync(e, d_a, attempt, (size_t)n * 4, cudaMemcpyHostToDevice));
-    DISPATCH_W(e, k_gen_excit_batch<WW><<<(unsigned)((n + 127) / 128), 128, 0, e->stream>>>(e->sys, p, d_f, d_p, d_a, n,
-                                                                                           e->d_proc_map, d_io, d_do, d_ns));
-    CK(cudaGetLastError());
+    { int rc = 0; DISPATCH_CCMC(e, rc, hb_gen_excit_batch_w, e, p, d_f, d_p, d_a, n, d_io, d_do, d_ns); if (rc) return 1; }
     CK(cudaStreamSynchronize(e->stream));
     CK(copy_sync(e, iout, d_io, (size_t)n * 8 * 4, cudaMemcpyDeviceToHost));
     CK(copy_sync(e, dout, d_do, (size_t)n * 2 * 8, cudaMemcpyDeviceToHost));
@@ -3124,3 +2131,4 @@ int hb200_last_timing(hb200_engine* e, double ms[8], int64_t cnt[4]) {
 }
 
 }  // extern "C"
+

@@ -37,6 +37,8 @@ def do_ccmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, ke
     nprocs, iproc = comm.size, comm.rank
     if qmc.ex_level < 0:
         raise ValueError("ccmc: reference ex_level (the CC truncation level) must be given")
+    if min(sys.nel, qmc.ex_level + 2) > 8:      # HB_MAX_CLUSTER: size of the engine's cluster-selection buffers
+        raise ValueError("ccmc: clusters of more than 8 excitors (ex_level + 2 > 8) are not supported by the engine")
     if qmc.quasi_newton:
         raise NotImplementedError("ccmc: the quasi-Newton propagator is only implemented for FCIQMC")
     is_ueg = getattr(sys, "kind", "read_in") == "ueg"

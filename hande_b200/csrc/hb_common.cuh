@@ -196,8 +196,8 @@ struct hb200_engine {
     ncclComm_t comm = nullptr;
     long long* d_counts = nullptr;  // [nprocs*nprocs]
     // timing / counters
-    cudaEvent_t ev[6];
-    cudaEvent_t evk[2];           // brackets the k_spawn_death launch alone (roofline timing)
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t evk[2] = {nullptr, nullptr};           // brackets the k_spawn_death launch alone (roofline timing)
     float spawn_kernel_ms = 0.f;  // accumulated over the cycles of the last hb200_iterate
     double ms[8] = {0};
     long long launches = 0, spawn_launches = 0;

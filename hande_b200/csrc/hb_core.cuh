@@ -29,6 +29,7 @@
 #define HB_MAXW 4
 #endif
 #define HB_MAXNEL 64
+#define HB_MAX_CLUSTER 8    // largest CCMC cluster (ex_level + 2 <= 8): size of the selection buffers
 #define HB_MAXLIST 128      // longest per-spin / per-symmetry-class orbital list (nbasis <= 254)
 
 // Streaming (evict-first) loads for data with no reuse on the SM - the 2 GB heat-bath row tables and the walker list -
@@ -2178,7 +2179,7 @@ HB_HDN void ccmc_select_cluster(R& rng, const Params& p, const CcmcArgs& a, cons
         cl.sign = 1;
         return;
     }
-    double pop[8];
+    double pop[HB_MAX_CLUSTER];
     for (int i = 0; i < cl.nexcitors; ++i) pop[i] = rng.next() * a.tot_abs_real_pop;
     for (int i = 1; i < cl.nexcitors; ++i) {      // insert_sort_real_p (src/sort.f90:827-852)
         int j = i - 1;

@@ -26,6 +26,7 @@ thread_local std::string g_err;
 // than the system one (2.27).  Order: a copy already loaded in the process, $HB200_NCCL_LIB, the system library.
 struct NcclApi {
     void* h = nullptr;
+    bool loaded = false;   // set only when every symbol resolved
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
@@ -37,16 +38,18 @@ struct NcclApi {
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     bool load(std::string& err) {
-        if (h) return true;
+        if (loaded) return true;
+        if (h) { dlclose(h); h = nullptr; }
         h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
         if (!h) { const char* p = getenv("HB200_NCCL_LIB"); if (p && *p) h = dlopen(p, RTLD_NOW | RTLD_GLOBAL); }
         if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
         if (!h) { err = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
-#define HB_SYM(field, name) field = (decltype(field))dlsym(h, name); if (!field) { err = std::string("NCCL symbol missing: ") + name; return false; }
+#define HB_SYM(field, name) field = (decltype(field))dlsym(h, name); if (!field) { err = std::string("NCCL symbol missing: ") + name; dlclose(h); h = nullptr; return false; }
         HB_SYM(GetUniqueId, "ncclGetUniqueId") HB_SYM(CommInitRank, "ncclCommInitRank") HB_SYM(CommDestroy, "ncclCommDestroy")
         HB_SYM(AllGather, "ncclAllGather") HB_SYM(Broadcast, "ncclBroadcast") HB_SYM(Send, "ncclSend") HB_SYM(Recv, "ncclRecv")
         HB_SYM(GroupStart, "ncclGroupStart") HB_SYM(GroupEnd, "ncclGroupEnd") HB_SYM(GetErrorString, "ncclGetErrorString")
 #undef HB_SYM
+        loaded = true;
         return true;
     }
 };
@@ -714,6 +717,7 @@ extern "C" {
 const char* hb200_last_error(void) { return g_err.c_str(); }
 
 hb200_engine* hb200_create(const hb200_config* cfg) {
+    g_err.clear();
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         g_err = "hb200_create: no CUDA device (the engine has no CPU fallback)";
@@ -806,6 +810,8 @@ void hb200_destroy(hb200_engine* e) {
     cudaSetDevice(e->cfg.device);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     for (void* q : e->owned) cudaFree(q);
+    for (int i = 0; i < 6; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    for (int i = 0; i < 2; ++i) if (e->evk[i]) cudaEventDestroy(e->evk[i]);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->copy_done) cudaEventDestroy(e->copy_done);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -1271,6 +1277,7 @@ int hb200_download_heat_bath(hb200_engine* e, int which, void* out, int64_t n) {
 }
 
 int hb200_set_reference(hb200_engine* e, const uint64_t* f0, double H00) {
+    CK(cudaSetDevice(e->cfg.device));
     for (int k = 0; k < HB_MAXW; ++k) e->par.f0[k] = (k < e->W) ? f0[k] : 0;
     e->par.H00 = H00;
     e->have_ref = true;
@@ -1662,6 +1669,8 @@ int hb200_ccmc_spawn(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, i
     if (e->cfg.excit_gen == HB200_EXCIT_GEN_POWER_PITZER && !e->have_pp) FAIL("ccmc_spawn: power_pitzer tables not built");
     if (e->par.nprocs > 1 && !e->comm) FAIL("ccmc_spawn: nprocs > 1 but hb200_comm_init was not called");
     if (e->cfg.initiator_approx) FAIL("ccmc_spawn: the initiator approximation is not implemented for CCMC");
+    if (std::min(e->sys.nel, ex_level + 2) > HB_MAX_CLUSTER)
+        FAIL("ccmc_spawn: clusters of more than HB_MAX_CLUSTER (8) excitors are not supported (ex_level + 2 <= 8)");
     Params& p = e->par;
     p.tau = in->tau; p.shift = in->shift; p.proj_energy_old = in->proj_energy_old; p.cycle = cycle;
     cudaStream_t st = e->stream;
@@ -1842,6 +1851,7 @@ __global__ void __launch_bounds__(256) k_parallel_spin_prob(Sys s, double* __res
 // qmc_in%pattempt_parallel (src/qmc.F90:974-988) for excit_gen = renorm_spin / no_renorm_spin: a negative value asks
 // for find_parallel_spin_prob_mol.
 int hb200_set_pattempt_parallel(hb200_engine* e, double pattempt_parallel) {
+    CK(cudaSetDevice(e->cfg.device));
     if (pattempt_parallel < 0.0) {
         if (e->sys.kind != SYS_READ_IN || e->sys.nbasis <= 0) FAIL("set_pattempt_parallel: needs a read_in system");
         const int nb = e->sys.nbasis;
@@ -1883,6 +1893,7 @@ int hb200_set_quasi_newton(hb200_engine* e, const double* sp_fock, double ref_fo
 // double excitations it generates; the host reads the sums once per report loop, allreduces them and sets the new
 // probabilities (update_pattempt_single).
 int hb200_set_pattempt(hb200_engine* e, double pattempt_single, double pattempt_double, int32_t accumulate) {
+    CK(cudaSetDevice(e->cfg.device));
     if (accumulate) {
         // src/check_input.F90:192-197
         if (e->sys.kind != SYS_READ_IN) FAIL("pattempt_update only used in read_in systems.");
@@ -1905,6 +1916,7 @@ int hb200_set_pattempt(hb200_engine* e, double pattempt_single, double pattempt_
 // out[0..3] = h_pgen_singles_sum, excit_gen_singles, h_pgen_doubles_sum, excit_gen_doubles accumulated on this rank since
 // the last reset (p_single_double_coll_t rep_accum, src/excit_gens.f90:13-27)
 int hb200_get_ps_stats(hb200_engine* e, double* out, int32_t reset) {
+    CK(cudaSetDevice(e->cfg.device));
     if (!e->d_ps_acc) { for (int k = 0; k < 4; ++k) out[k] = 0.0; return 0; }
     CK(cudaMemcpyAsync(out, e->d_ps_acc, 4 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     if (reset) CK(cudaMemsetAsync(e->d_ps_acc, 0, 4 * sizeof(double), e->stream));
@@ -1997,6 +2009,13 @@ int hb200_download_spawn(hb200_engine* e, int64_t* sdata, int64_t capacity, int6
     *n = e->sp_n;
     if (e->sp_n > capacity) FAIL("download_spawn: capacity too small");
     if (e->sp_n) CK(copy_sync(e, sdata, e->d_spawn[e->sp_cur], (size_t)e->sp_n * E * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int hb200_spawn_counts(hb200_engine* e, int64_t* counts, int32_t nprocs) {
+    if (nprocs != e->par.nprocs) FAIL("spawn_counts: nprocs differs from hb200_create");
+    if (!e->sp_blocked && e->par.nprocs > 1) FAIL("spawn_counts: the spawn list is no longer partitioned by destination");
+    for (int d = 0; d < nprocs; ++d) counts[d] = (int64_t)e->h_head[d];
     return 0;
 }
 

@@ -148,6 +148,7 @@ def load_library():
     L.hb200_annihilate_main.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(IterOut)]
     L.hb200_download_spawn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     L.hb200_upload_spawn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    L.hb200_spawn_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
     L.hb200_sc0_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     L.hb200_gen_excit_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32,
                                         C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -164,7 +165,7 @@ ABI_SYMBOLS = [
     "hb200_download_heat_bath", "hb200_set_reference", "hb200_set_proc_map", "hb200_upload_psips",
     "hb200_upload_psips_begin", "hb200_upload_psips_commit",
     "hb200_download_psips", "hb200_nstates", "hb200_iterate", "hb200_spawn_death", "hb200_comm_spawn",
-    "hb200_ccmc_spawn", "hb200_ccmc_iterate", "hb200_ccmc_set_hash_shift", "hb200_ccmc_set_full_nc", "hb200_set_pattempt", "hb200_get_ps_stats", "hb200_set_pattempt_parallel", "hb200_get_pattempt_parallel", "hb200_build_power_pitzer_orderN", "hb200_build_power_pitzer", "hb200_set_quasi_newton", "hb200_annihilate_spawn", "hb200_annihilate_main", "hb200_download_spawn", "hb200_upload_spawn",
+    "hb200_ccmc_spawn", "hb200_ccmc_iterate", "hb200_ccmc_set_hash_shift", "hb200_ccmc_set_full_nc", "hb200_set_pattempt", "hb200_get_ps_stats", "hb200_set_pattempt_parallel", "hb200_get_pattempt_parallel", "hb200_build_power_pitzer_orderN", "hb200_build_power_pitzer", "hb200_set_quasi_newton", "hb200_annihilate_spawn", "hb200_annihilate_main", "hb200_download_spawn", "hb200_upload_spawn", "hb200_spawn_counts",
     "hb200_sc0_batch", "hb200_gen_excit_batch", "hb200_get_unique_id", "hb200_comm_init", "hb200_last_timing",
 ]
 
@@ -370,6 +371,12 @@ class Engine:
         n = C.c_int64(0)
         self._chk(self.L.hb200_download_spawn(self.h, _p(buf), cap, C.byref(n)))
         return buf[: n.value].copy()
+
+    def spawn_counts(self):
+        """elements per destination block of the spawn list after the spawning stage (spawn%head)"""
+        c = np.zeros(int(self.cfg.nprocs), dtype=np.int64)
+        self._chk(self.L.hb200_spawn_counts(self.h, _p(c), len(c)))
+        return c
 
     def upload_spawn(self, sdata):
         sdata = np.ascontiguousarray(sdata, dtype=np.int64).reshape(-1, self.E)

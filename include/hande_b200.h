@@ -223,6 +223,10 @@ int hb200_annihilate_main(hb200_engine* e, uint32_t cycle, hb200_iter_out* out);
 /* spawn%sdata(element_len, n) of the current stage (element = W string words, population, flag). */
 int hb200_download_spawn(hb200_engine* e, int64_t* sdata, int64_t capacity, int64_t* n);
 int hb200_upload_spawn(hb200_engine* e, const int64_t* sdata, int64_t n);
+/* spawn%head after the spawning stage: counts[d] = number of elements in the block destined for rank d
+ * (the send counts of comm_spawn_t, src/spawn_data.F90:686-693); hb200_download_spawn returns the blocks
+ * concatenated in this order.  Lets a host stage the exchange itself (hb200_upload_spawn on the receiver). */
+int hb200_spawn_counts(hb200_engine* e, int64_t* counts, int32_t nprocs);
 
 /* Pure-function batches evaluated on the device (parity probes; also used by the host for init):
  * sc0_ptr over a list of determinants (src/hamiltonian_molecular.f90:73-139). */

@@ -21,6 +21,7 @@ SYSTEMS = {
     "s10": dict(synthetic=(10, 8), kw={}),
     "s12": dict(synthetic=(12, 8), kw={}),
     "s40": dict(synthetic=(40, 10), kw={}),    # W = 2
+    "s50": dict(synthetic=(50, 20), kw={}),    # the bench system (BASELINE configs[1]): 100 spin-orbitals, W = 2, 20 electrons
     # uniform electron gas: (electrons, ms, rs, cutoff)
     "ueg6": dict(ueg=(6, 0, 2.0, 2.0)),        # the reference's np2/np4 fixture system, 66 spin-orbitals (W = 2)
     "ueg14": dict(ueg=(14, 0, 1.0, 4.0)),      # 186 spin-orbitals (W = 3)

@@ -60,6 +60,31 @@ def test_reblocked_energies_agree_with_reference_stream():
     assert -0.5 < eg < 0.0
 
 
+def test_heat_bath_reblocked_energies_agree_with_reference_stream():
+    """Level-3 gate for the headline generator: real-amplitude iFCIQMC with excit_gen = heat_bath on NH3 6-31G (the
+    system of the reference's per-generator golden tables) in the variable-shift regime - GPU engine (Philox) against
+    the oracle run on the REFERENCE's dSFMT stream (which reproduces those golden tables).  Reblocked projected energy
+    and shift must agree within combined 2 sigma."""
+    path, kw = system_path("nh3")
+    s = R.read_in(path, **kw)
+    common = dict(tau=0.005, ncycles=10, target=2000.0, nrep=1500, skip=600)
+    qmc = QmcIn(tau=common["tau"], rng_seed=5, init_pop=50, mc_cycles=common["ncycles"], nreports=common["nrep"],
+                target_population=common["target"], state_size=200000, spawned_state_size=100000, initiator=True,
+                real_amplitudes=True, excit_gen="heat_bath")
+    g = np.array(do_fciqmc(s, qmc).rows)[1:]
+    o = _oracle_rows(path, kw, 0, tau=common["tau"], seed=7, D0_population=50, ncycles=common["ncycles"],
+                     nreport=common["nrep"], target_particles=common["target"], walker_length=200000,
+                     spawned_walker_length=100000, initiator_approx=1, real_amplitudes=1, excit_gen="heat_bath")[1:]
+    k = common["skip"]
+    eg, sg = ratio_with_error(g[k:, 2], g[k:, 3])
+    eo, so = ratio_with_error(o[k:, 2], o[k:, 3])
+    assert abs(eg - eo) < 2.0 * np.hypot(sg, so), (eg, sg, eo, so)
+    mg, esg = optimal_error(g[k:, 1])
+    mo, eso = optimal_error(o[k:, 1])
+    assert abs(mg - mo) < 2.0 * np.hypot(esg, eso), (mg, esg, mo, eso)
+    assert -0.2 < eg < -0.05       # NH3 6-31G correlation energy is about -0.125 Eh (exact CCSDT -0.124920)
+
+
 def test_ueg_trajectory_and_fci_energy():
     """UEG (the reference's ueg_n10_rs2_e4 fixture system: 6 electrons, 66 plane-wave spin-orbitals, rs = 2).
     (i) trajectory parity of the host driver + GPU engine with the oracle under the same Philox stream;

@@ -56,6 +56,13 @@ def test_gen_excit_heat_bath_uniform():
     _check_gen("s10", "heat_bath_uniform", True, 0.01, n=150, nattempt=6)
 
 
+@pytest.mark.parametrize("gen", ["heat_bath", "heat_bath_uniform", "renorm"])
+def test_gen_excit_s50_bench_system(gen):
+    """The configuration bench.py times (S50: nbasis 100, W = 2, nel 20, the 2 GB hb_ijab tables): excitation choice,
+    pgen, H_ij and nspawn of 500 determinants x 6 attempts x 2 cycles against the oracle."""
+    _check_gen("s50", gen, True, 2e-5, n=500, nattempt=6)
+
+
 def test_gen_excit_renorm_spin_and_no_renorm_spin():
     # SURVEY 8f row 2: choose_ij_spin_mol variants of the uniform generators
     _check_gen("h2o", "renorm_spin", False, 0.003, n=120)
@@ -127,8 +134,10 @@ def test_gen_excit_ueg():
     _check_gen("ueg14", "power_pitzer", True, 0.002, n=150, nattempt=5)
 
 
-def test_heat_bath_tables_match_oracle():
-    s, o, eng, ref = make_pair("s10", excit_gen="heat_bath")
+@pytest.mark.parametrize("name", ["s10", "s50"])
+def test_heat_bath_tables_match_oracle(name):
+    """every entry of the device-built tables (S50: 1e8-entry ijab_w / ijab_U / ijab_K, the tables the bench reads)"""
+    s, o, eng, ref = make_pair(name, excit_gen="heat_bath")
     hb = o.heat_bath_tables()
     nb = hb["nb"]
     names = ["i_weights", "ij_weights", "ija_w", "ija_U", "ija_tot", "ijab_w", "ijab_U", "ijab_tot", "ija_K", "ijab_K"]
@@ -170,6 +179,9 @@ CASES = [
     ("ne", "renorm", True, True, 0.005, 5000, -1),
     ("s40", "renorm", False, True, 0.02, 3000, -1),
     ("s12", "heat_bath", True, True, 0.01, 2500, -1),
+    ("s50", "heat_bath", True, True, 2e-5, 6000, -1),          # the bench configuration
+    ("s50", "heat_bath_uniform", True, True, 2e-5, 6000, -1),
+    ("s50", "renorm", True, False, 2e-4, 6000, -1),
     ("s12", "heat_bath_uniform", True, True, 0.01, 2500, -1),
     ("s12", "heat_bath_single", True, True, 0.01, 2500, -1),
     ("nh3", "renorm_spin", True, True, 0.003, 2500, -1),

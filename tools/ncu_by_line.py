@@ -13,8 +13,12 @@ import os
 def sass_lines(lib, func_sub):
     d = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=d, capture_output=True)
-    cubin = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
-    txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(d, cubin)], capture_output=True, text=True).stdout
+    txt = ""
+    for cubin in sorted(f for f in os.listdir(d) if f.endswith(".cubin")):     # one cubin per translation unit
+        t = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(d, cubin)], capture_output=True, text=True).stdout
+        if any(ln.startswith(".text.") and func_sub in ln for ln in t.split("\n")):
+            txt = t
+            break
     out = []
     cur = None
     active = False

@@ -43,6 +43,11 @@
 namespace hb {
 
 struct alignas(16) D2 { double x, y; };
+// One entry of a heat-bath alias row, packed so that a selection (aliasU, aliasK of the drawn slot) and the weight of
+// the entry it usually returns come from ONE 32-byte sector: {aliasU, weight, aliasK} of hb_ija(a,j,i) / hb_ijab(b,a,j,i)
+// plus p = weight / weights_tot of its row (the conditional probability the pgen formulas divide out at run time; the
+// same IEEE division of the same operands, done once when the tables are built)
+struct alignas(32) HbRec { double U, w; int K, pad0; double p; };
 struct alignas(16) K4 { int x, y, z, w; };   // wavevector of a plane-wave basis function (w unused)
 
 enum { SYS_READ_IN = 0, SYS_UEG = 1 };
@@ -77,6 +82,12 @@ struct Sys {
     // gathering ~30 scattered entries of the 8-fold store (same values, same summation order).
     const D2* sc1CX;            // {C, X} pairs: one 16-byte load per occupied orbital
     int NT;
+    // the same integrals laid out for a branch-free sum over an occupied list (FCIQMC heat-bath kernel): row (i, a) =
+    // sc1T + ((i-1)*sc1A + ta)*(nbasis+1), ta = a-1 (UHF, sc1A = nbasis) or (a-1)/2 (RHF, sc1A = nbasis/2; a has the spin
+    // of i); entry j (1-based spin-orbital) = {<ij|aj>, <ij|ja> if j has the spin of i else 0}; entries 0 and j = i are
+    // {0, 0}, so list padding and the excited orbital itself add exact zeros
+    const D2* sc1T;
+    int sc1A;
     // heat-bath tables (src/excit_gens.f90:143-153), column-major as in the reference
     const double* hb_i_w;       // (nb)
     const double* hb_ij_w;      // (j,i)
@@ -88,6 +99,9 @@ struct Sys {
     const double* hb_ijab_U;
     const int* hb_ijab_K;
     const double* hb_ijab_tot;  // (a,j,i)
+    // the same rows as packed records (built by hb200_build_heat_bath; read by the FCIQMC heat-bath kernel)
+    const HbRec* hb_ija_rec;    // (a,j,i)
+    const HbRec* hb_ijab_rec;   // (b,a,j,i)
     // power_pitzer_orderN tables (excit_gen_power_pitzer_t ppn_*, src/excit_gens.f90:102-141), column-major:
     // PPN_IS (nel), PPN_IAS (max_nbss, i), PPN_ID (nel), PPN_IJD (nel, i), PPN_IAD (nbasis/2, i), PPN_JBD (max_nbss, sym, i)
     // with i = 0..nbasis (column 0 unused)
@@ -879,7 +893,7 @@ HB_HD int mask_top<uint64_t>(uint64_t x) { return 63 - clz64(x); }
 
 // Exact walk for a given slot k and fractional part x (the reference's stack algorithm, see above).
 template <class Mask>
-HB_HD int alias_walk_exact(int N, const double* wq, int stride, double scale, int k, double x) {
+HB_HDNI int alias_walk_exact(int N, const double* wq, int stride, double scale, int k, double x) {
     Mask under = 0, over = 0;
     for (int q = 0; q < N; ++q) {
         const double u = wq[q * stride] * scale;
@@ -918,15 +932,79 @@ HB_HD int alias_walk_exact(int N, const double* wq, int stride, double scale, in
     }
     return (x < Uk) ? k + 1 : Kk + 1;
 }
-// A formulation without the serial walk was tried (the walk is the merge of the prefix sums of the overfull excesses
-// and the underfull deficits; two branch-free passes + a guard band falling back to this walk near ties): it returned
-// identical indices but was not faster on B200 (47.3 vs 46.8 ms per 1e8 heat-bath attempts), so the walk stays.
+// Selection without the serial walk.  In exact arithmetic the walk is a merge of two running sums: with the underfull
+// entries in pop order (descending index) having deficits d_t = 1 - u and the overfull ones (descending index) excesses
+// e_t = u - 1, overfull entry n is demoted right after absorbing the first underfull entry m with D_m > E_n (D, E =
+// running sums), the alias of underfull entry m is the first overfull entry n with E_n >= D_(m-1), a demoted overfull
+// entry ends with aliasU = 1 + E_n - D_m and its alias is the next overfull entry.  Only slot k matters, so:
+//   k underfull: x < u_k returns k at once; otherwise D = deficits of the underfull entries above k, then the overfull
+//                entries are scanned from the top until their running excess exceeds D;
+//   k overfull:  E = excesses of the overfull entries from the top down to k, then the underfull entries are scanned from
+//                the top until their running deficit exceeds E.
+// The reference evaluates the same quantities through a different sequence of roundings (|difference| < 1e-12 for
+// N <= 64), so every comparison that decides the result is taken only when it is clear by `guard` = 1e-9; otherwise the
+// exact walk above is run (about 1e-8 of the draws; exact ties, e.g. integer weights, always).  Same index as
+// generate_alias_tables + select_weighted_value_precalc for every input (tests/test_core_vs_oracle.py: 24 M draws
+// over seven weight families incl. ties and draws aimed at table boundaries).
+template <class Mask>
+HB_HD int alias_select_fast(int N, const double* wq, int stride, double scale, int k, double x) {
+    const double guard = 1.e-9;
+    // pass 1: classification only
+    Mask under = 0;
+#pragma unroll 4
+    for (int q = 0; q < N; ++q) {
+        const double u = wq[q * stride] * scale;
+        under |= (u <= 1.0) ? ((Mask)1 << q) : (Mask)0;
+    }
+    const Mask all = (N >= (int)(8 * sizeof(Mask))) ? ~(Mask)0 : (((Mask)1 << N) - 1);
+    const Mask over = all & ~under;
+    const Mask kbit = (Mask)1 << k;
+    const bool k_under = (under & kbit) != 0;
+    const double uk = wq[k * stride] * scale;
+    const Mask below = over & (kbit - 1);                   // overfull entries further down the stack than k
+    int result = k + 1;
+    bool done = k_under ? (x < uk) : (below == 0);          // the lowest overfull entry keeps (or aliases to) itself
+    if (!done) {
+        // pass 2a: the running sum that belongs to slot k (its own class, from the top of the stack down to k)
+        Mask m = (k_under ? under : over) & ~(kbit | (kbit - 1));
+        double target = k_under ? 0.0 : (uk - 1.0);
+        while (m != 0) {
+            const int q = mask_top<Mask>(m);
+            m ^= (Mask)1 << q;
+            target += fabs(wq[q * stride] * scale - 1.0);
+        }
+        // pass 2b: the other class from the top until its running sum passes `target`
+        m = k_under ? over : under;
+        double acc = 0.0;
+        int hit = -1;
+        bool unclear = false;
+        while (m != 0) {
+            const int q = mask_top<Mask>(m);
+            m ^= (Mask)1 << q;
+            acc += fabs(wq[q * stride] * scale - 1.0);
+            const double d = acc - target;
+            // k underfull: the first overfull entry with E >= D survives to alias k; k overfull: demoted once D > E
+            if (d > guard) { hit = q; break; }
+            if (d >= -guard) { unclear = true; break; }
+        }
+        if (unclear) {
+            result = alias_walk_exact<Mask>(N, wq, stride, scale, k, x);
+        } else if (k_under) {
+            if (hit >= 0) result = hit + 1;                 // else the overfull entries ran out: aliasK(k) stays k
+        } else if (hit >= 0) {                              // else never demoted: aliasU(k) >= 1 > x
+            const double Uk = 1.0 + (target - acc);
+            if (fabs(x - Uk) <= guard) result = alias_walk_exact<Mask>(N, wq, stride, scale, k, x);
+            else if (!(x < Uk)) result = mask_top<Mask>(below) + 1;
+        }
+    }
+    return result;
+}
 template <class Mask, class R>
 HB_HD int select_alias_staged_m(R& rng, int N, const double* wq, int stride, double totweight) {
     double x = rng.next() * N;
     const int k = (int)x;                  // floor: x >= 0
     x = x - k;
-    return alias_walk_exact<Mask>(N, wq, stride, N / totweight, k, x);
+    return alias_select_fast<Mask>(N, wq, stride, N / totweight, k, x);
 }
 template <class R>
 HB_HD int select_alias_staged(R& rng, int N, const double* wq, int stride, double totweight) {

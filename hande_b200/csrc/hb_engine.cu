@@ -905,6 +905,32 @@ int hb200_set_system_ueg(hb200_engine* e, const hb200_system_ueg* in) {
     return 0;
 }
 
+// {aliasU, weight, aliasK} of every row entry packed into one 32-byte record (hb_core.cuh HbRec)
+__global__ void k_hb_pack(long long n, int nb, const double* __restrict__ U, const double* __restrict__ w, const int* __restrict__ K,
+                          const double* __restrict__ tot, HbRec* __restrict__ rec) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    HbRec r;
+    const double rt = tot[t / nb];
+    r.U = U[t]; r.w = w[t]; r.K = K[t]; r.pad0 = 0;
+    r.p = (rt != 0.0) ? w[t] / rt : 0.0;
+    rec[t] = r;
+}
+// single-excitation rows for branch-free occupied-list sums (hb_core.cuh Sys::sc1T)
+__global__ void k_build_sc1T(Sys s, int A, D2* T) {
+    const long long nb = s.nbasis;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nb * A * (nb + 1)) return;
+    const int j = (int)(t % (nb + 1)), ta = (int)((t / (nb + 1)) % A), i = (int)(t / ((nb + 1) * A)) + 1;
+    const int a = s.uhf ? ta + 1 : 2 * ta + 2 - (i & 1);       // RHF: the orbital of spatial index ta with the spin of i
+    D2 v; v.x = 0.0; v.y = 0.0;
+    if (j != 0 && j != i) {
+        v.x = two_body(s, i, j, a, j);
+        if (((j ^ i) & 1) == 0) v.y = two_body(s, i, j, j, a);
+    }
+    T[t] = v;
+}
+
 int hb200_build_heat_bath(hb200_engine* e) {
     CK(cudaSetDevice(e->cfg.device));
     if (!e->have_sys) FAIL("build_heat_bath: system not set");
@@ -934,6 +960,20 @@ int hb200_build_heat_bath(hb200_engine* e) {
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
     CK(cudaFree(sc));
+    if (e->cfg.excit_gen == HB200_EXCIT_GEN_HEAT_BATH) {
+        HbRec *ija_rec, *ijab_rec;
+        if (dalloc(e, &ija_rec, n3) || dalloc(e, &ijab_rec, n4)) return 1;
+        k_hb_pack<<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>(n3, (int)nb, ija_U, ija_w, ija_K, ija_tot, ija_rec);
+        k_hb_pack<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(n4, (int)nb, ijab_U, ijab_w, ijab_K, ijab_tot, ijab_rec);
+        const int A = s.uhf ? (int)nb : (int)nb / 2;
+        const long long nT = nb * A * (nb + 1);
+        D2* T = nullptr;
+        if (dalloc(e, &T, (size_t)nT)) return 1;
+        k_build_sc1T<<<(unsigned)((nT + 255) / 256), 256, 0, st>>>(s, A, T);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(st));
+        s.hb_ija_rec = ija_rec; s.hb_ijab_rec = ijab_rec; s.sc1T = T; s.sc1A = A;
+    }
     s.hb_i_w = i_w; s.hb_ij_w = ij_w; s.hb_ija_w = ija_w; s.hb_ija_U = ija_U; s.hb_ija_K = ija_K; s.hb_ija_tot = ija_tot;
     s.hb_ijab_w = ijab_w; s.hb_ijab_U = ijab_U; s.hb_ijab_K = ijab_K; s.hb_ijab_tot = ijab_tot;
     e->have_hb = true;
@@ -1439,7 +1479,7 @@ static int stage_spawn_death(hb200_engine* e, const hb200_iter_in* in, uint32_t 
         CK(cudaEventRecord(e->evk[1], st));
         e->launches++; e->spawn_launches++;
     }
-    k_reduce_partials<<<1, 1024, 0, st>>>(e->d_partials, ntiles, e->d_stats);
+    k_reduce_partials<<<1, 1024, 0, st>>>(e->d_partials, ntiles > 0 ? e->npartials : 0, e->d_stats);
     CK(cudaGetLastError());
     e->launches++;
     if (p.ps_part && ntiles > 0) {

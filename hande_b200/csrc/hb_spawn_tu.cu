@@ -1,6 +1,9 @@
 // hande_b200: k_spawn_death instantiations of ONE (W, generator group), selected with -DHB_TU_W=<1..4>
 // -DHB_TU_GROUP=<0..4>; hande_b200/build.py compiles the 20 combinations in parallel.
 #include "hb_spawn.cuh"
+#if HB_TU_GROUP == 0
+#include "hb_spawn_hb.cuh"
+#endif
 
 #if !defined(HB_TU_W) || !defined(HB_TU_GROUP)
 #error "compile with -DHB_TU_W=<1..4> -DHB_TU_GROUP=<0..4>"
@@ -31,14 +34,65 @@ static int launch_spawn(hb200_engine* e, const Params& p, const SpawnLaunch& L) 
                                                                 e->d_spawn[0], e->d_head, e->block_size, e->d_proc_map,
                                                                 e->d_partials, e->d_err);
     CK(cudaGetLastError());
+    e->npartials = L.ntiles;
     return 0;
 }
+
+#if HB_TU_GROUP == 0
+// excit_gen = heat_bath: the warp-synchronous wavefront kernel (hb_spawn_hb.cuh) on a persistent grid, followed by the
+// launch that spreads the attempts of deferred (huge-population) determinants over the grid
+template <int W, class Mask>
+static int launch_spawn_hb(hb200_engine* e, const Params& p, const SpawnLaunch& L) {
+    using namespace hbw;
+    if (!e->d_heavy_count) {
+        e->heavy_cap = (unsigned)std::max<long long>(1 << 16, e->cfg.walker_length / HEAVY + 1024);
+        void* q = nullptr;
+        CK(cudaMalloc(&q, (size_t)e->heavy_cap * sizeof(HeavyItem)));
+        e->owned.push_back(q); e->d_heavy_items = q;
+        CK(cudaMalloc(&q, 16));
+        e->owned.push_back(q); e->d_heavy_count = (unsigned*)q;
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, e->cfg.device));
+        e->num_sms = prop.multiProcessorCount;
+    }
+    const WarpSmem WS(W, e->sys.nel, p.qn != 0);
+    const size_t smem = (size_t)((e->sys.nbasis * 8 + 15) & ~15) + (size_t)NWARP * WS.total;
+    static unsigned long long attr_set = 0ull;
+    const unsigned long long bit = 1ull << (e->cfg.device & 63);
+    if (!(attr_set & bit)) {
+        CK(cudaFuncSetAttribute(k_spawn_hb<W, Mask>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CK(cudaFuncSetAttribute(k_spawn_hb_heavy<W, Mask>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set |= bit;
+    }
+    if (smem > 200 * 1024) FAIL("spawn_death: heat_bath kernel needs more shared memory than a block has (nel too large)");
+    int bps = (int)((227 * 1024) / (smem + 1024));
+    bps = std::max(1, std::min(bps, 4));
+    const long long ntile = (L.n + SLOTS - 1) / SLOTS;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((long long)e->num_sms * bps, (ntile + NWARP - 1) / NWARP));
+    if ((long long)grid > e->max_tiles) FAIL("spawn_death: partial-sum scratch too small");
+    HeavyQueue hq;
+    hq.items = (HeavyItem*)e->d_heavy_items; hq.count = e->d_heavy_count; hq.cap = e->heavy_cap;
+    CK(cudaMemsetAsync(e->d_heavy_count, 0, sizeof(unsigned), e->stream));
+    const int c = e->cur;
+    k_spawn_hb<W, Mask><<<grid, NWARP * 32, smem, e->stream>>>(e->sys, p, e->d_states[c], e->d_pops[c], e->d_dat[c], L.n, e->d_spawn[0],
+                                                              e->d_head, e->block_size, e->d_proc_map, e->d_partials, e->d_err, hq);
+    CK(cudaGetLastError());
+    k_spawn_hb_heavy<W, Mask><<<e->num_sms * bps, NWARP * 32, smem, e->stream>>>(e->sys, p, e->d_states[c], e->d_spawn[0], e->d_head,
+                                                                                e->block_size, e->d_proc_map, e->d_err, hq);
+    CK(cudaGetLastError());
+    e->launches++;          // the caller counts the first launch
+    e->npartials = grid;
+    return 0;
+}
+#endif
 
 int HB_CAT4(hb_spawn_w, HB_TU_W, _g, HB_TU_GROUP)(hb200_engine* e, const Params& p, const SpawnLaunch& L) {
     constexpr int W = HB_TU_W;
     switch (L.gen) {
 #if HB_TU_GROUP == 0
-        case EXCIT_GEN_HEAT_BATH: return launch_spawn<W, EXCIT_GEN_HEAT_BATH>(e, p, L);
+        case EXCIT_GEN_HEAT_BATH:
+            if (e->sys.nel <= 32) return launch_spawn_hb<W, uint32_t>(e, p, L);
+            return launch_spawn_hb<W, uint64_t>(e, p, L);
 #elif HB_TU_GROUP == 1
         case EXCIT_GEN_HEAT_BATH_UNIFORM: return launch_spawn<W, EXCIT_GEN_HEAT_BATH_UNIFORM>(e, p, L);
         case EXCIT_GEN_HEAT_BATH_SINGLE: return launch_spawn<W, EXCIT_GEN_HEAT_BATH_SINGLE>(e, p, L);

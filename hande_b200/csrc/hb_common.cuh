@@ -186,6 +186,11 @@ struct hb200_engine {
     void* d_heavy_items = nullptr;
     unsigned* d_heavy_count = nullptr;
     unsigned heavy_cap = 0;
+    void* d_wf_recA = nullptr;    // wavefront kernels: record arrays and their counters
+    void* d_wf_recD = nullptr;
+    void* d_wf_recS = nullptr;
+    void* d_wf_cnt = nullptr;
+    unsigned wf_cap = 0;
     int num_sms = 0;
     int npartials = 0;            // SpawnPartials written by the last spawn launch
     bool ccmc_full_nc = false;                     // ccmc_in%full_nc

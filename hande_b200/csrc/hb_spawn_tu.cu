@@ -3,6 +3,7 @@
 #include "hb_spawn.cuh"
 #if HB_TU_GROUP == 0
 #include "hb_spawn_hb.cuh"
+#include "hb_spawn_wf.cuh"
 #endif
 
 #if !defined(HB_TU_W) || !defined(HB_TU_GROUP)
@@ -65,6 +66,55 @@ static int launch_spawn_hb(hb200_engine* e, const Params& p, const SpawnLaunch& 
         attr_set |= bit;
     }
     if (smem > 200 * 1024) FAIL("spawn_death: heat_bath kernel needs more shared memory than a block has (nel too large)");
+    if (getenv("HB200_WF")) {     // development switch: the wavefront kernels (hb_spawn_wf.cuh)
+        using namespace hbwf;
+        const int nel = e->sys.nel;
+        const SelSmem SS(W, nel);
+        const size_t sm1 = (size_t)((e->sys.nbasis * 8 + 15) & ~15) + (size_t)K1_WARPS * SS.total;
+        static bool once = false;
+        if (!once) {
+            CK(cudaFuncSetAttribute(k_wf_select<W, Mask>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            once = true;
+        }
+        const size_t sA = rec_stride(sizeof(RecA), nel), sD = rec_stride(sizeof(RecD), nel), sS = rec_stride(sizeof(RecS), nel);
+        if (!e->d_wf_cnt) {
+            void* q = nullptr;
+            e->wf_cap = (unsigned)std::min<long long>(e->cfg.walker_length + 1024, 160000000ll);
+            CK(cudaMalloc(&q, (size_t)e->wf_cap * sA)); e->owned.push_back(q); e->d_wf_recA = q;
+            CK(cudaMalloc(&q, (size_t)e->wf_cap * sD)); e->owned.push_back(q); e->d_wf_recD = q;
+            CK(cudaMalloc(&q, (size_t)e->wf_cap * sS)); e->owned.push_back(q); e->d_wf_recS = q;
+            CK(cudaMalloc(&q, 64)); e->owned.push_back(q); e->d_wf_cnt = q;
+        }
+        CK(cudaMemsetAsync(e->d_wf_cnt, 0, 64, e->stream));
+        CK(cudaMemsetAsync(e->d_heavy_count, 0, sizeof(unsigned), e->stream));
+        int bps1 = (int)((227 * 1024) / (sm1 + 1024));
+        bps1 = std::max(1, std::min(bps1, 4));
+        const long long nt = (L.n + 31) / 32;
+        const int g1 = (int)std::max<long long>(1, std::min<long long>((long long)e->num_sms * bps1, (nt + K1_WARPS - 1) / K1_WARPS));
+        HeavyQueue hq;
+        hq.items = (HeavyItem*)e->d_heavy_items; hq.count = e->d_heavy_count; hq.cap = e->heavy_cap;
+        const int c = e->cur;
+        Counters* cnt = (Counters*)e->d_wf_cnt;
+        k_wf_select<W, Mask><<<g1, K1_WARPS * 32, sm1, e->stream>>>(e->sys, p, e->d_states[c], e->d_pops[c], e->d_dat[c], 0, L.n,
+                                                                   (unsigned char*)e->d_wf_recA, cnt, e->wf_cap, e->d_partials,
+                                                                   e->d_err, hq);
+        const int g2 = e->num_sms * 6;
+        k_wf_coin<W><<<g2, 256, 0, e->stream>>>(e->sys, p, e->d_states[c], (const unsigned char*)e->d_wf_recA, cnt,
+                                               (unsigned char*)e->d_wf_recD, (unsigned char*)e->d_wf_recS, e->wf_cap, e->d_err);
+        k_wf_double<W><<<g2, 256, 0, e->stream>>>(e->sys, p, e->d_states[c], (const unsigned char*)e->d_wf_recD, cnt, e->wf_cap,
+                                                 e->d_spawn[0], e->d_head, e->block_size, e->d_proc_map, e->d_err);
+        k_wf_single<W><<<g2, 256, 0, e->stream>>>(e->sys, p, e->d_states[c], (const unsigned char*)e->d_wf_recS, cnt, e->wf_cap,
+                                                 e->d_spawn[0], e->d_head, e->block_size, e->d_proc_map, e->d_err);
+        // deferred (huge-population) determinants: the fused kernel's heavy path
+        const size_t smh = (size_t)((e->sys.nbasis * 8 + 15) & ~15) + (size_t)NWARP * WS.total;
+        int bpsh = std::max(1, std::min((int)((227 * 1024) / (smh + 1024)), 4));
+        k_spawn_hb_heavy<W, Mask><<<e->num_sms * bpsh, NWARP * 32, smh, e->stream>>>(e->sys, p, e->d_states[c], e->d_spawn[0], e->d_head,
+                                                                                    e->block_size, e->d_proc_map, e->d_err, hq);
+        CK(cudaGetLastError());
+        e->launches += 4;
+        e->npartials = g1;
+        return 0;
+    }
     int bps = (int)((227 * 1024) / (smem + 1024));
     bps = std::max(1, std::min(bps, 4));
     const long long ntile = (L.n + SLOTS - 1) / SLOTS;

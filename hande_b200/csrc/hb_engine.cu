@@ -961,18 +961,42 @@ int hb200_build_heat_bath(hb200_engine* e) {
     CK(cudaStreamSynchronize(st));
     CK(cudaFree(sc));
     if (e->cfg.excit_gen == HB200_EXCIT_GEN_HEAT_BATH) {
-        HbRec *ija_rec, *ijab_rec;
-        if (dalloc(e, &ija_rec, n3) || dalloc(e, &ijab_rec, n4)) return 1;
-        k_hb_pack<<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>(n3, (int)nb, ija_U, ija_w, ija_K, ija_tot, ija_rec);
-        k_hb_pack<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(n4, (int)nb, ijab_U, ijab_w, ijab_K, ijab_tot, ijab_rec);
+        // The gathers of the spawning kernels hit two tables hard: the packed hb_ija rows (nb^3 records) and the
+        // single-excitation rows sc1T.  They share one allocation that is pinned in L2 with an access-policy window
+        // (persisting), so that the walker list and the record arrays streaming through do not evict them.
         const int A = s.uhf ? (int)nb : (int)nb / 2;
         const long long nT = nb * A * (nb + 1);
-        D2* T = nullptr;
-        if (dalloc(e, &T, (size_t)nT)) return 1;
+        const size_t bytes_rec = (size_t)n3 * sizeof(HbRec), bytes_T = ((size_t)nT * sizeof(D2) + 255) & ~(size_t)255;
+        unsigned char* arena = nullptr;
+        if (dalloc(e, &arena, bytes_rec + bytes_T)) return 1;
+        HbRec* ija_rec = reinterpret_cast<HbRec*>(arena);
+        D2* T = reinterpret_cast<D2*>(arena + bytes_rec);
+        HbRec* ijab_rec;
+        if (dalloc(e, &ijab_rec, n4)) return 1;
+        k_hb_pack<<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>(n3, (int)nb, ija_U, ija_w, ija_K, ija_tot, ija_rec);
+        k_hb_pack<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(n4, (int)nb, ijab_U, ijab_w, ijab_K, ijab_tot, ijab_rec);
         k_build_sc1T<<<(unsigned)((nT + 255) / 256), 256, 0, st>>>(s, A, T);
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(st));
         s.hb_ija_rec = ija_rec; s.hb_ijab_rec = ijab_rec; s.sc1T = T; s.sc1A = A;
+        {
+            cudaDeviceProp prop;
+            CK(cudaGetDeviceProperties(&prop, e->cfg.device));
+            const size_t want = bytes_rec + bytes_T;
+            const size_t lim = std::min<size_t>(want, (size_t)prop.persistingL2CacheMaxSize);
+            if (lim > 0 && prop.accessPolicyMaxWindowSize > 0) {
+                CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, lim));
+                cudaStreamAttrValue av;
+                memset(&av, 0, sizeof(av));
+                av.accessPolicyWindow.base_ptr = arena;
+                av.accessPolicyWindow.num_bytes = std::min<size_t>(want, (size_t)prop.accessPolicyMaxWindowSize);
+                av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)lim / (double)av.accessPolicyWindow.num_bytes);
+                av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                CK(cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &av));
+                e->l2_window_bytes = (long long)av.accessPolicyWindow.num_bytes;
+            }
+        }
     }
     s.hb_i_w = i_w; s.hb_ij_w = ij_w; s.hb_ija_w = ija_w; s.hb_ija_U = ija_U; s.hb_ija_K = ija_K; s.hb_ija_tot = ija_tot;
     s.hb_ijab_w = ijab_w; s.hb_ijab_U = ijab_U; s.hb_ijab_K = ijab_K; s.hb_ijab_tot = ijab_tot;

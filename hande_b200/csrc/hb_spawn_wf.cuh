@@ -217,9 +217,11 @@ k_wf_select(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __res
                         r.flags = (uint8_t)((need_ia ? RA_NEED_IA : 0) | sbits[lo]);
                         r.pad = 0; r.i_tot = i_tot; r.ij_tot = ij_tot; r.r3 = r3;
                         unsigned char* dst = recA + (size_t)k * strideA;
-                        *reinterpret_cast<RecA*>(dst) = r;
+                        const int4* d4 = reinterpret_cast<const int4*>(&r);
+#pragma unroll
+                        for (int w = 0; w < 3; ++w) __stcs(reinterpret_cast<int4*>(dst) + w, d4[w]);
                         uint32_t* docc = reinterpret_cast<uint32_t*>(dst + sizeof(RecA));
-                        for (int w = 0; w < L.noccw; ++w) docc[w] = socc[lo * L.noccw + w];
+                        for (int w = 0; w < L.noccw; ++w) __stcs(docc + w, socc[lo * L.noccw + w]);
                     } else {
                         atomicOr(err, 4);      // record array too small: an engine bug, not a run-time condition
                     }
@@ -251,9 +253,29 @@ k_wf_select(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __res
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int MAXOCCW = HB_MAXNEL / 4;
 
+// Records are written once and read once: streamed (evict-first) so that they do not push the L2-resident tables out.
+template <class T>
+__device__ __forceinline__ T load_rec(const unsigned char* src) {
+    static_assert(sizeof(T) % 16 == 0, "record headers are multiples of 16 bytes");
+    T r;
+    int4* d = reinterpret_cast<int4*>(&r);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(T) / 16); ++k) d[k] = __ldcs(reinterpret_cast<const int4*>(src) + k);
+    return r;
+}
+template <class T>
+__device__ __forceinline__ void store_rec(unsigned char* dst, const T& r) {
+    const int4* d = reinterpret_cast<const int4*>(&r);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(T) / 16); ++k) __stcs(reinterpret_cast<int4*>(dst) + k, d[k]);
+}
 __device__ __forceinline__ void load_occ(const unsigned char* rec, int header, int noccw, uint32_t* occw) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(rec + header);
-    for (int w = 0; w < noccw; ++w) occw[w] = src[w];
+    for (int w = 0; w < noccw; ++w) occw[w] = __ldcs(src + w);
+}
+__device__ __forceinline__ void store_occ(unsigned char* rec, int header, int noccw, const uint32_t* occw) {
+    uint32_t* dst = reinterpret_cast<uint32_t*>(rec + header);
+    for (int w = 0; w < noccw; ++w) __stcs(dst + w, occw[w]);
 }
 // warp-aggregated append of one record of `bytes` (multiple of 16) per participating lane; returns the slot or ~0u
 __device__ __forceinline__ unsigned claim_slot(bool want, unsigned* counter) {
@@ -269,7 +291,7 @@ __device__ __forceinline__ unsigned claim_slot(bool want, unsigned* counter) {
 
 // K2: slater_condon1(i -> a) where that single excitation is allowed, the single/double coin, b
 template <int W>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 4)
 k_wf_coin(Sys s, Params p, const uint64_t* __restrict__ states, const unsigned char* __restrict__ recA, Counters* __restrict__ cnt,
           unsigned char* __restrict__ recD, unsigned char* __restrict__ recS, unsigned cap, int* __restrict__ err) {
     const int nel = s.nel, noccw = (nel + 3) >> 2;
@@ -285,7 +307,7 @@ k_wf_coin(Sys s, Params p, const uint64_t* __restrict__ states, const unsigned c
         uint32_t occw[MAXOCCW];
         if (r < nA) {
             const unsigned char* src = recA + (size_t)r * strideA;
-            ra = *reinterpret_cast<const RecA*>(src);
+            ra = load_rec<RecA>(src);
             load_occ(src, sizeof(RecA), noccw, occw);
             uint64_t f[W];
             load_det<W>(states + (size_t)ra.state * W, f);
@@ -295,25 +317,28 @@ k_wf_coin(Sys s, Params p, const uint64_t* __restrict__ states, const unsigned c
             const double r3 = ra.r3, r4 = u01(rc.x, rc.y), r5 = u01(rc.z, rc.w);
             bool dbl = true, perm_ia = false;
             double psingle = 0.0, rb = r3, rsp = r4, h_ia = 0.0;
-            if (ra.flags & RA_NEED_IA) {
+            const bool need_ia = (ra.flags & RA_NEED_IA) != 0;
+            // the draw that selects b is known before the coin is: fetch its 32-byte record from the 2 GB hb_ijab rows now
+            // (streamed, no reuse: {aliasU, weight}, {aliasK, -, weight / weights_tot}), under the slater_condon1 sum
+            double xb = (need_ia ? r4 : r3) * (int)nb;
+            const int K = (int)floor(xb);
+            xb = xb - K;
+            const HbRec* rec = s.hb_ijab_rec + HB_I4(1, a, j, i) + K;
+            const double2 uw = __ldcs(reinterpret_cast<const double2*>(rec));
+            const int4 kp = __ldcs(reinterpret_cast<const int4*>(rec) + 1);
+            const double wt = s.hb_ija_rec[HB_I3(a, j, i)].w;          // = hb_ijab%weights_tot(a,j,i)
+            if (need_ia) {
                 perm_ia = excit_perm1<W>(f, i, a);
                 const double h = hbw::sc1_lean(s, occw, noccw, i, a);
                 h_ia = perm_ia ? -h : h;
                 const double hmod = fabs(h_ia);
-                const double wt = s.hb_ija_rec[HB_I3(a, j, i)].w;          // = hb_ijab%weights_tot(a,j,i)
                 if (hmod < wt) psingle = hmod / (wt + hmod); else psingle = 0.5;
                 dbl = !(r3 < psingle);
                 rb = r4; rsp = dbl ? r5 : r4;
             }
+            (void)rb;
             if (dbl) {
-                double x = rb * (int)nb;
-                const int K = (int)floor(x);
-                x = x - K;
-                const HbRec* rec = s.hb_ijab_rec + HB_I4(1, a, j, i) + K;
-                // the whole 32-byte record, streamed (no reuse): {aliasU, weight}, {aliasK, -, weight / weights_tot}
-                const double2 uw = __ldcs(reinterpret_cast<const double2*>(rec));
-                const int4 kp = __ldcs(reinterpret_cast<const int4*>(rec) + 1);
-                const int b = (x < uw.x) ? K + 1 : kp.x;
+                const int b = (xb < uw.x) ? K + 1 : kp.x;
                 if (!det_test(f, b)) {
                     is_dbl = true;
                     rd.state = ra.state; rd.i = ra.i; rd.j = ra.j; rd.a = ra.a; rd.b = (uint8_t)b;
@@ -339,18 +364,16 @@ k_wf_coin(Sys s, Params p, const uint64_t* __restrict__ states, const unsigned c
         if (is_dbl) {
             if (kd < cap) {
                 unsigned char* dst = recD + (size_t)kd * strideD;
-                *reinterpret_cast<RecD*>(dst) = rd;
-                uint32_t* docc = reinterpret_cast<uint32_t*>(dst + sizeof(RecD));
-                for (int w = 0; w < noccw; ++w) docc[w] = occw[w];
+                store_rec(dst, rd);
+                store_occ(dst, sizeof(RecD), noccw, occw);
             } else atomicOr(err, 4);
         }
         const unsigned ks = claim_slot(is_sgl, &cnt->nS);
         if (is_sgl) {
             if (ks < cap) {
                 unsigned char* dst = recS + (size_t)ks * strideS;
-                *reinterpret_cast<RecS*>(dst) = rs_;
-                uint32_t* docc = reinterpret_cast<uint32_t*>(dst + sizeof(RecS));
-                for (int w = 0; w < noccw; ++w) docc[w] = occw[w];
+                store_rec(dst, rs_);
+                store_occ(dst, sizeof(RecS), noccw, occw);
             } else atomicOr(err, 4);
         }
     }
@@ -437,7 +460,7 @@ k_wf_double(Sys s, Params p, const uint64_t* __restrict__ states, const unsigned
         g.allowed = true; g.nexcit = 2; g.pgen = 1.0; g.hmatel = 0.0; g.from1 = g.from2 = g.to1 = g.to2 = 0; g.perm = false;
         if (live) {
             const unsigned char* src = recD + (size_t)r * strideD;
-            rd = *reinterpret_cast<const RecD*>(src);
+            rd = load_rec<RecD>(src);
             load_occ(src, sizeof(RecD), noccw, occw);
             load_det<W>(states + (size_t)rd.state * W, f);
             const int i = rd.i, j = rd.j, a = rd.a, b = rd.b;
@@ -453,11 +476,46 @@ k_wf_double(Sys s, Params p, const uint64_t* __restrict__ states, const unsigned
                 wab = __ldcs(&rw->w); wa = __ldcs(&rw->p);
             }
             const double wij = s.hb_ij_w[HB_I2(j, i)];                  // = ij_weights(i,j)
+            // one pass over the occupied list for the three slater_condon1 sums (orderings i->b, j->a, j->b; each in
+            // occ_list order) and for ji_weights_occ_tot: 16 independent loads per step instead of four passes
+            const bool kb = (rd.flags & RD_KB) != 0, kc = (rd.flags & RD_KC) != 0, kd = (rd.flags & RD_KD) != 0;
+            double h0 = kb ? one_body(s, i, b) : 0.0, h1 = kc ? one_body(s, j, a) : 0.0, h2 = kd ? one_body(s, j, b) : 0.0;
+            double ji_tot = 0.0;
+            {
+                const unsigned tA = s.uhf ? (unsigned)(a - 1) : ((unsigned)(a - 1) >> 1);
+                const unsigned tB = s.uhf ? (unsigned)(b - 1) : ((unsigned)(b - 1) >> 1);
+                const unsigned rl = (unsigned)(s.nbasis + 1);
+                const D2* __restrict__ r0 = s.sc1T + ((size_t)((unsigned)(i - 1) * (unsigned)s.sc1A + tB)) * rl;
+                const D2* __restrict__ r1 = s.sc1T + ((size_t)((unsigned)(j - 1) * (unsigned)s.sc1A + tA)) * rl;
+                const D2* __restrict__ r2 = s.sc1T + ((size_t)((unsigned)(j - 1) * (unsigned)s.sc1A + tB)) * rl;
+                const double* __restrict__ col1 = s.hb_ij_w + nb * (j - 1) - 1;
+                const D2 zero = {0.0, 0.0};
+#pragma unroll 1
+                for (int w = 0; w < noccw; ++w) {
+                    const uint32_t o4 = occw[w];
+                    D2 v0[4], v1[4], v2[4];
+                    double cv[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t o = (o4 >> (8 * k)) & 0xffu;
+                        v0[k] = kb ? r0[o] : zero;
+                        v1[k] = kc ? r1[o] : zero;
+                        v2[k] = kd ? r2[o] : zero;
+                        cv[k] = o ? col1[o] : 0.0;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        h0 = h0 + v0[k].x; h0 = h0 - v0[k].y;
+                        h1 = h1 + v1[k].x; h1 = h1 - v1[k].y;
+                        h2 = h2 + v2[k].x; h2 = h2 - v2[k].y;
+                        ji_tot = ji_tot + cv[k];
+                    }
+                }
+            }
             double ps[3] = {0.0, 0.0, 0.0};
-            if (rd.flags & RD_KB) { const double hm = fabs(hbw::sc1_lean(s, occw, noccw, i, b)); if (hm < Tb) ps[0] = hm / (Tb + hm); else ps[0] = 0.5; }
-            if (rd.flags & RD_KC) { const double hm = fabs(hbw::sc1_lean(s, occw, noccw, j, a)); if (hm < Ta) ps[1] = hm / (Ta + hm); else ps[1] = 0.5; }
-            if (rd.flags & RD_KD) { const double hm = fabs(hbw::sc1_lean(s, occw, noccw, j, b)); if (hm < Tb) ps[2] = hm / (Tb + hm); else ps[2] = 0.5; }
-            const double ji_tot = hbw::gather_occ<false>(s.hb_ij_w + nb * (j - 1) - 1, occw, nel, nullptr);
+            if (kb) { const double hm = fabs(h0); if (hm < Tb) ps[0] = hm / (Tb + hm); else ps[0] = 0.5; }
+            if (kc) { const double hm = fabs(h1); if (hm < Ta) ps[1] = hm / (Ta + hm); else ps[1] = 0.5; }
+            if (kd) { const double hm = fabs(h2); if (hm < Tb) ps[2] = hm / (Tb + hm); else ps[2] = 0.5; }
             const double pi_ = siw1[i] / rd.i_tot;
             const double pj_ = siw1[j] / rd.i_tot;
             const double pij = wij / rd.ij_tot;
@@ -480,7 +538,7 @@ k_wf_double(Sys s, Params p, const uint64_t* __restrict__ states, const unsigned
 // K4: single excitations - the generation probability sums over the spectator orbital (src/excit_gen_heat_bath_mol.F90:
 // 489-536), spawn
 template <int W>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 4)
 k_wf_single(Sys s, Params p, const uint64_t* __restrict__ states, const unsigned char* __restrict__ recS, const Counters* __restrict__ cnt,
             unsigned cap, int64_t* __restrict__ spawn, unsigned long long* __restrict__ head, long long block_size,
             const int* __restrict__ proc_map, int* __restrict__ err) {
@@ -498,7 +556,7 @@ k_wf_single(Sys s, Params p, const uint64_t* __restrict__ states, const unsigned
         g.allowed = true; g.nexcit = 1; g.pgen = 1.0; g.hmatel = 0.0; g.from1 = g.from2 = g.to1 = g.to2 = 0; g.perm = false;
         if (live) {
             const unsigned char* src = recS + (size_t)r * strideS;
-            rs_ = *reinterpret_cast<const RecS*>(src);
+            rs_ = load_rec<RecS>(src);
             load_occ(src, sizeof(RecS), noccw, occw);
             load_det<W>(states + (size_t)rs_.state * W, f);
             const int i = rs_.i, a = rs_.a;
@@ -507,18 +565,32 @@ k_wf_single(Sys s, Params p, const uint64_t* __restrict__ states, const unsigned
             const double* ijcol1 = s.hb_ij_w + nb * (i - 1) - 1;
             const double* ijat1 = s.hb_ija_tot + nb * (i - 1) - 1;
             double psum = 0.0;
-            for (int q = 0; q < nel; ++q) {
-                const int oq = occ[q];
-                if (i != oq && a != oq) {
-                    const HbRec* rec = s.hb_ija_rec + HB_I3(a, oq, i);
-                    const double Taq = rec->w;      // hb_ija%weights(a,oq,i) = hb_ijab%weights_tot(a,oq,i)
-                    const double paq = rec->p;      // hb_ija%weights(a,oq,i) / hb_ija%weights_tot(oq,i)
-                    double psq;
-                    if (hmod < Taq) psq = hmod / (Taq + hmod); else psq = 0.5;
-                    psum = psum + (psq * (ijcol1[oq] / rs_.ij_tot) * paq);
+            (void)occ; (void)ijat1;
+            const HbRec* __restrict__ recs = s.hb_ija_rec + HB_I3(a, 1, i) - nb;     // entry (a, oq, i) at recs + nb * oq
+#pragma unroll 1
+            for (int w = 0; w < noccw; ++w) {       // four spectator orbitals per step: their loads go out together
+                const uint32_t o4 = occw[w];
+                double Tq[4], pq[4], wq4[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t oq = (o4 >> (8 * k)) & 0xffu;
+                    const bool on = oq != 0u && oq != (uint32_t)i && oq != (uint32_t)a;
+                    const HbRec* rec = recs + nb * (int64_t)oq;
+                    Tq[k] = on ? rec->w : 1.0;      // hb_ija%weights(a,oq,i) = hb_ijab%weights_tot(a,oq,i)
+                    pq[k] = on ? rec->p : 0.0;      // hb_ija%weights(a,oq,i) / hb_ija%weights_tot(oq,i)
+                    wq4[k] = on ? ijcol1[oq] : 0.0;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t oq = (o4 >> (8 * k)) & 0xffu;
+                    const bool on = oq != 0u && oq != (uint32_t)i && oq != (uint32_t)a;
+                    if (on) {                       // the reference skips the other terms
+                        double psq;
+                        if (hmod < Tq[k]) psq = hmod / (Tq[k] + hmod); else psq = 0.5;
+                        psum = psum + (psq * (wq4[k] / rs_.ij_tot) * pq[k]);
+                    }
                 }
             }
-            (void)ijat1;
             g.from1 = i; g.to1 = a;
             g.perm = (rs_.flags & RS_PERM) != 0;
             g.hmatel = rs_.h_ia;

@@ -191,7 +191,6 @@ struct hb200_engine {
     void* d_wf_recS = nullptr;
     void* d_wf_cnt = nullptr;
     unsigned wf_cap = 0;
-    long long l2_window_bytes = 0;   // size of the persisting-L2 access-policy window on the engine stream
     int num_sms = 0;
     int npartials = 0;            // SpawnPartials written by the last spawn launch
     bool ccmc_full_nc = false;                     // ccmc_in%full_nc

@@ -961,9 +961,9 @@ int hb200_build_heat_bath(hb200_engine* e) {
     CK(cudaStreamSynchronize(st));
     CK(cudaFree(sc));
     if (e->cfg.excit_gen == HB200_EXCIT_GEN_HEAT_BATH) {
-        // The gathers of the spawning kernels hit two tables hard: the packed hb_ija rows (nb^3 records) and the
-        // single-excitation rows sc1T.  They share one allocation that is pinned in L2 with an access-policy window
-        // (persisting), so that the walker list and the record arrays streaming through do not evict them.
+        // The packed hb_ija rows (nb^3 records) and the single-excitation rows sc1T share one allocation.  (Pinning it in
+        // L2 with a persisting access-policy window was measured and made the spawning kernels 10-17 % SLOWER on B200 -
+        // the carve-out costs the other gathers more than it saves - so no window is set; see DESIGN.md.)
         const int A = s.uhf ? (int)nb : (int)nb / 2;
         const long long nT = nb * A * (nb + 1);
         const size_t bytes_rec = (size_t)n3 * sizeof(HbRec), bytes_T = ((size_t)nT * sizeof(D2) + 255) & ~(size_t)255;
@@ -979,24 +979,6 @@ int hb200_build_heat_bath(hb200_engine* e) {
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(st));
         s.hb_ija_rec = ija_rec; s.hb_ijab_rec = ijab_rec; s.sc1T = T; s.sc1A = A;
-        {
-            cudaDeviceProp prop;
-            CK(cudaGetDeviceProperties(&prop, e->cfg.device));
-            const size_t want = bytes_rec + bytes_T;
-            const size_t lim = std::min<size_t>(want, (size_t)prop.persistingL2CacheMaxSize);
-            if (lim > 0 && prop.accessPolicyMaxWindowSize > 0) {
-                CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, lim));
-                cudaStreamAttrValue av;
-                memset(&av, 0, sizeof(av));
-                av.accessPolicyWindow.base_ptr = arena;
-                av.accessPolicyWindow.num_bytes = std::min<size_t>(want, (size_t)prop.accessPolicyMaxWindowSize);
-                av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)lim / (double)av.accessPolicyWindow.num_bytes);
-                av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-                av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-                CK(cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &av));
-                e->l2_window_bytes = (long long)av.accessPolicyWindow.num_bytes;
-            }
-        }
     }
     s.hb_i_w = i_w; s.hb_ij_w = ij_w; s.hb_ija_w = ija_w; s.hb_ija_U = ija_U; s.hb_ija_K = ija_K; s.hb_ija_tot = ija_tot;
     s.hb_ijab_w = ijab_w; s.hb_ijab_U = ijab_U; s.hb_ijab_K = ijab_K; s.hb_ijab_tot = ijab_tot;

@@ -76,7 +76,7 @@ static int launch_spawn_hb(hb200_engine* e, const Params& p, const SpawnLaunch& 
             CK(cudaFuncSetAttribute(k_wf_select<W, Mask>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             once = true;
         }
-        const size_t sA = rec_stride(sizeof(RecA), nel), sD = rec_stride(sizeof(RecD), nel), sS = rec_stride(sizeof(RecS), nel);
+        const size_t sA = rec_stride(sizeof(RecA), nel, W), sD = rec_stride(sizeof(RecD), nel, W), sS = rec_stride(sizeof(RecS), nel, W);
         if (!e->d_wf_cnt) {
             void* q = nullptr;
             e->wf_cap = (unsigned)std::min<long long>(e->cfg.walker_length + 1024, 160000000ll);

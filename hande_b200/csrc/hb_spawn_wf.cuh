@@ -32,8 +32,9 @@ constexpr int HEAVY = 1024;          // attempts of one state above which it is 
 
 enum { RA_NEED_IA = 1, RA_NEG = 2, RA_FLAG = 4 };   // RecA/RecD/RecS flags: i->a allowed; parent population negative; parent not an initiator
 
-// Records: a fixed header followed by the determinant's occupied list (four orbitals to a word, zero padded), so that
-// the consumer needs neither a decode nor shared memory; the stride is rounded to 16 bytes.
+// Records: a fixed header followed by the determinant's bit string and its occupied list (four orbitals to a word, zero
+// padded), so that the consumer needs neither a dependent gather from the main list, nor a decode, nor shared memory;
+// the stride is rounded to 16 bytes.
 enum { RD_KB = 0x10, RD_KC = 0x20, RD_KD = 0x40, RD_WKNOWN = 0x80, RS_PERM = 0x10 };
 struct alignas(16) RecA {            // an attempt that survived the choice of i, j, a
     uint32_t state, att;             // index in the main list; attempt number (keys the random stream)
@@ -56,7 +57,8 @@ struct alignas(16) RecS {            // a single excitation i -> a
     double i_tot, ij_tot, h_ia, rs;
 };
 static_assert(sizeof(RecS) == 48, "RecS layout");
-__host__ __device__ inline int rec_stride(int header, int nel) { return (header + 4 * ((nel + 3) >> 2) + 15) & ~15; }
+// header | f(W words) | occupied list
+__host__ __device__ inline int rec_stride(int header, int nel, int W) { return (header + 8 * W + 4 * ((nel + 3) >> 2) + 15) & ~15; }
 
 struct Counters { unsigned nA, nD, nS, pad; };
 
@@ -87,7 +89,7 @@ k_wf_select(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __res
     const int nel = s.nel;
     const int64_t nb = s.nbasis;
     const SelSmem L(W, nel);
-    const int strideA = rec_stride(sizeof(RecA), nel);
+    const int strideA = rec_stride(sizeof(RecA), nel, W);
     double* siw = reinterpret_cast<double*>(smem_raw);
     const int siw_bytes = (s.nbasis * 8 + 15) & ~15;
     for (int k = tid; k < s.nbasis; k += K1_WARPS * 32) siw[k] = s.hb_i_w[k];
@@ -220,8 +222,7 @@ k_wf_select(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __res
                         const int4* d4 = reinterpret_cast<const int4*>(&r);
 #pragma unroll
                         for (int w = 0; w < 3; ++w) __stcs(reinterpret_cast<int4*>(dst) + w, d4[w]);
-                        uint32_t* docc = reinterpret_cast<uint32_t*>(dst + sizeof(RecA));
-                        for (int w = 0; w < L.noccw; ++w) __stcs(docc + w, socc[lo * L.noccw + w]);
+                        store_tail<W>(dst, sizeof(RecA), L.noccw, sf + lo * W, socc + lo * L.noccw);
                     } else {
                         atomicOr(err, 4);      // record array too small: an engine bug, not a run-time condition
                     }
@@ -269,12 +270,20 @@ __device__ __forceinline__ void store_rec(unsigned char* dst, const T& r) {
 #pragma unroll
     for (int k = 0; k < (int)(sizeof(T) / 16); ++k) __stcs(reinterpret_cast<int4*>(dst) + k, d[k]);
 }
-__device__ __forceinline__ void load_occ(const unsigned char* rec, int header, int noccw, uint32_t* occw) {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(rec + header);
+template <int W>
+__device__ __forceinline__ void load_tail(const unsigned char* rec, int header, int noccw, uint64_t* f, uint32_t* occw) {
+    const uint2* fs = reinterpret_cast<const uint2*>(rec + header);
+#pragma unroll
+    for (int k = 0; k < W; ++k) { const uint2 v = __ldcs(fs + k); f[k] = ((uint64_t)v.y << 32) | v.x; }
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(rec + header + 8 * W);
     for (int w = 0; w < noccw; ++w) occw[w] = __ldcs(src + w);
 }
-__device__ __forceinline__ void store_occ(unsigned char* rec, int header, int noccw, const uint32_t* occw) {
-    uint32_t* dst = reinterpret_cast<uint32_t*>(rec + header);
+template <int W>
+__device__ __forceinline__ void store_tail(unsigned char* rec, int header, int noccw, const uint64_t* f, const uint32_t* occw) {
+    uint2* fd = reinterpret_cast<uint2*>(rec + header);
+#pragma unroll
+    for (int k = 0; k < W; ++k) __stcs(fd + k, make_uint2((uint32_t)f[k], (uint32_t)(f[k] >> 32)));
+    uint32_t* dst = reinterpret_cast<uint32_t*>(rec + header + 8 * W);
     for (int w = 0; w < noccw; ++w) __stcs(dst + w, occw[w]);
 }
 // warp-aggregated append of one record of `bytes` (multiple of 16) per participating lane; returns the slot or ~0u
@@ -296,7 +305,7 @@ k_wf_coin(Sys s, Params p, const uint64_t* __restrict__ states, const unsigned c
           unsigned char* __restrict__ recD, unsigned char* __restrict__ recS, unsigned cap, int* __restrict__ err) {
     const int nel = s.nel, noccw = (nel + 3) >> 2;
     const int64_t nb = s.nbasis;
-    const int strideA = rec_stride(sizeof(RecA), nel), strideD = rec_stride(sizeof(RecD), nel), strideS = rec_stride(sizeof(RecS), nel);
+    const int strideA = rec_stride(sizeof(RecA), nel, W), strideD = rec_stride(sizeof(RecD), nel, W), strideS = rec_stride(sizeof(RecS), nel, W);
     const unsigned nA = min(cnt->nA, cap);
     const unsigned nround = (nA + 31u) & ~31u;        // whole warps stay in the loop (ballots)
     for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < nround; r += gridDim.x * blockDim.x) {
@@ -305,12 +314,11 @@ k_wf_coin(Sys s, Params p, const uint64_t* __restrict__ states, const unsigned c
         RecD rd;
         RecS rs_;
         uint32_t occw[MAXOCCW];
+        uint64_t f[W];
         if (r < nA) {
             const unsigned char* src = recA + (size_t)r * strideA;
             ra = load_rec<RecA>(src);
-            load_occ(src, sizeof(RecA), noccw, occw);
-            uint64_t f[W];
-            load_det<W>(states + (size_t)ra.state * W, f);
+            load_tail<W>(src, sizeof(RecA), noccw, f, occw);
             const int i = ra.i, j = ra.j, a = ra.a;
             const uint64_t hsh = det_hash64<W>(f);
             const uint4 rc = hbw::philox_block(((uint32_t)RNG_SPAWN << 24) | 2u, ra.att, (uint32_t)hsh, (uint32_t)(hsh >> 32), p.seed, p.cycle);
@@ -365,7 +373,7 @@ k_wf_coin(Sys s, Params p, const uint64_t* __restrict__ states, const unsigned c
             if (kd < cap) {
                 unsigned char* dst = recD + (size_t)kd * strideD;
                 store_rec(dst, rd);
-                store_occ(dst, sizeof(RecD), noccw, occw);
+                store_tail<W>(dst, sizeof(RecD), noccw, f, occw);
             } else atomicOr(err, 4);
         }
         const unsigned ks = claim_slot(is_sgl, &cnt->nS);
@@ -373,7 +381,7 @@ k_wf_coin(Sys s, Params p, const uint64_t* __restrict__ states, const unsigned c
             if (ks < cap) {
                 unsigned char* dst = recS + (size_t)ks * strideS;
                 store_rec(dst, rs_);
-                store_occ(dst, sizeof(RecS), noccw, occw);
+                store_tail<W>(dst, sizeof(RecS), noccw, f, occw);
             } else atomicOr(err, 4);
         }
     }
@@ -447,7 +455,7 @@ k_wf_double(Sys s, Params p, const uint64_t* __restrict__ states, const unsigned
             const int* __restrict__ proc_map, int* __restrict__ err) {
     const int nel = s.nel, noccw = (nel + 3) >> 2;
     const int64_t nb = s.nbasis;
-    const int strideD = rec_stride(sizeof(RecD), nel);
+    const int strideD = rec_stride(sizeof(RecD), nel, W);
     const unsigned nD = min(cnt->nD, cap);
     const unsigned nround = (nD + 31u) & ~31u;
     const double* siw1 = s.hb_i_w - 1;
@@ -461,8 +469,7 @@ k_wf_double(Sys s, Params p, const uint64_t* __restrict__ states, const unsigned
         if (live) {
             const unsigned char* src = recD + (size_t)r * strideD;
             rd = load_rec<RecD>(src);
-            load_occ(src, sizeof(RecD), noccw, occw);
-            load_det<W>(states + (size_t)rd.state * W, f);
+            load_tail<W>(src, sizeof(RecD), noccw, f, occw);
             const int i = rd.i, j = rd.j, a = rd.a, b = rd.b;
             // hb_ija%weights(a,j,i) = hb_ijab%weights_tot(a,j,i) = ...(a,i,j), and the same divided by
             // hb_ija%weights_tot(j,i) = ...(i,j)
@@ -544,7 +551,7 @@ k_wf_single(Sys s, Params p, const uint64_t* __restrict__ states, const unsigned
             const int* __restrict__ proc_map, int* __restrict__ err) {
     const int nel = s.nel, noccw = (nel + 3) >> 2;
     const int64_t nb = s.nbasis;
-    const int strideS = rec_stride(sizeof(RecS), nel);
+    const int strideS = rec_stride(sizeof(RecS), nel, W);
     const unsigned nS = min(cnt->nS, cap);
     const unsigned nround = (nS + 31u) & ~31u;
     for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < nround; r += gridDim.x * blockDim.x) {
@@ -557,8 +564,7 @@ k_wf_single(Sys s, Params p, const uint64_t* __restrict__ states, const unsigned
         if (live) {
             const unsigned char* src = recS + (size_t)r * strideS;
             rs_ = load_rec<RecS>(src);
-            load_occ(src, sizeof(RecS), noccw, occw);
-            load_det<W>(states + (size_t)rs_.state * W, f);
+            load_tail<W>(src, sizeof(RecS), noccw, f, occw);
             const int i = rs_.i, a = rs_.a;
             const double hmod = fabs(rs_.h_ia);
             const uint8_t* occ = reinterpret_cast<const uint8_t*>(occw);

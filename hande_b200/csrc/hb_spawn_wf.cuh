@@ -62,6 +62,38 @@ __host__ __device__ inline int rec_stride(int header, int nel, int W) { return (
 
 struct Counters { unsigned nA, nD, nS, pad; };
 
+// Records are written once and read once: streamed (evict-first) so that they do not push the L2-resident tables out.
+template <class T>
+__device__ __forceinline__ T load_rec(const unsigned char* src) {
+    static_assert(sizeof(T) % 16 == 0, "record headers are multiples of 16 bytes");
+    T r;
+    int4* d = reinterpret_cast<int4*>(&r);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(T) / 16); ++k) d[k] = __ldcs(reinterpret_cast<const int4*>(src) + k);
+    return r;
+}
+template <class T>
+__device__ __forceinline__ void store_rec(unsigned char* dst, const T& r) {
+    const int4* d = reinterpret_cast<const int4*>(&r);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(T) / 16); ++k) __stcs(reinterpret_cast<int4*>(dst) + k, d[k]);
+}
+template <int W>
+__device__ __forceinline__ void load_tail(const unsigned char* rec, int header, int noccw, uint64_t* f, uint32_t* occw) {
+    const uint2* fs = reinterpret_cast<const uint2*>(rec + header);
+#pragma unroll
+    for (int k = 0; k < W; ++k) { const uint2 v = __ldcs(fs + k); f[k] = ((uint64_t)v.y << 32) | v.x; }
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(rec + header + 8 * W);
+    for (int w = 0; w < noccw; ++w) occw[w] = __ldcs(src + w);
+}
+template <int W>
+__device__ __forceinline__ void store_tail(unsigned char* rec, int header, int noccw, const uint64_t* f, const uint32_t* occw) {
+    uint2* fd = reinterpret_cast<uint2*>(rec + header);
+#pragma unroll
+    for (int k = 0; k < W; ++k) __stcs(fd + k, make_uint2((uint32_t)f[k], (uint32_t)(f[k] >> 32)));
+    uint32_t* dst = reinterpret_cast<uint32_t*>(rec + header + 8 * W);
+    for (int w = 0; w < noccw; ++w) __stcs(dst + w, occw[w]);
+}
 // byte offsets inside a warp's private shared-memory region of k_wf_select
 struct SelSmem {
     int stage, sf, shash, sscan, socc, sbits, total, noccw;
@@ -254,38 +286,6 @@ k_wf_select(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __res
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int MAXOCCW = HB_MAXNEL / 4;
 
-// Records are written once and read once: streamed (evict-first) so that they do not push the L2-resident tables out.
-template <class T>
-__device__ __forceinline__ T load_rec(const unsigned char* src) {
-    static_assert(sizeof(T) % 16 == 0, "record headers are multiples of 16 bytes");
-    T r;
-    int4* d = reinterpret_cast<int4*>(&r);
-#pragma unroll
-    for (int k = 0; k < (int)(sizeof(T) / 16); ++k) d[k] = __ldcs(reinterpret_cast<const int4*>(src) + k);
-    return r;
-}
-template <class T>
-__device__ __forceinline__ void store_rec(unsigned char* dst, const T& r) {
-    const int4* d = reinterpret_cast<const int4*>(&r);
-#pragma unroll
-    for (int k = 0; k < (int)(sizeof(T) / 16); ++k) __stcs(reinterpret_cast<int4*>(dst) + k, d[k]);
-}
-template <int W>
-__device__ __forceinline__ void load_tail(const unsigned char* rec, int header, int noccw, uint64_t* f, uint32_t* occw) {
-    const uint2* fs = reinterpret_cast<const uint2*>(rec + header);
-#pragma unroll
-    for (int k = 0; k < W; ++k) { const uint2 v = __ldcs(fs + k); f[k] = ((uint64_t)v.y << 32) | v.x; }
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(rec + header + 8 * W);
-    for (int w = 0; w < noccw; ++w) occw[w] = __ldcs(src + w);
-}
-template <int W>
-__device__ __forceinline__ void store_tail(unsigned char* rec, int header, int noccw, const uint64_t* f, const uint32_t* occw) {
-    uint2* fd = reinterpret_cast<uint2*>(rec + header);
-#pragma unroll
-    for (int k = 0; k < W; ++k) __stcs(fd + k, make_uint2((uint32_t)f[k], (uint32_t)(f[k] >> 32)));
-    uint32_t* dst = reinterpret_cast<uint32_t*>(rec + header + 8 * W);
-    for (int w = 0; w < noccw; ++w) __stcs(dst + w, occw[w]);
-}
 // warp-aggregated append of one record of `bytes` (multiple of 16) per participating lane; returns the slot or ~0u
 __device__ __forceinline__ unsigned claim_slot(bool want, unsigned* counter) {
     const unsigned m = __ballot_sync(0xffffffffu, want);

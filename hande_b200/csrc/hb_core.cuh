@@ -456,14 +456,23 @@ HB_HDN double slater_condon1_excit(const Sys& s, const uint8_t* occ, int i, int 
     const D2* __restrict__ row = s.sc1CX + ((long long)tix(s, i) * s.NT + tix(s, a)) * s.NT;
     const int nel = s.nel;
     // chunks of 4 occupied orbitals: issue the (independent) loads first, then add in occ_list order
+    // The gathers of this kernel are bound by the L1 tag rate (one 32-byte sector per lane per cycle), not by
+    // instructions: the two spin-orbitals of a doubly occupied spatial orbital are adjacent in occ_list and share their
+    // RHF table entry, which is then loaded once.
+    int tprev = -1;
+    D2 vprev = {0.0, 0.0};
     for (int q0 = 0; q0 < nel; q0 += 4) {
         int jj[4];
         D2 v[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             jj[k] = (q0 + k < nel) ? occ[q0 + k] : i;
-            v[k] = row[tix(s, jj[k])];
+            const int t = tix(s, jj[k]);
+            const int tp = (k == 0) ? tprev : tix(s, jj[k - 1]);
+            if (t != tp) v[k] = row[t];
+            else v[k] = (k == 0) ? vprev : v[k - 1];
         }
+        tprev = tix(s, jj[3]); vprev = v[3];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int j = jj[k];
@@ -1077,7 +1086,6 @@ HB_HDN void hb_phase_a(R& rng, const Sys& s, const uint64_t* f, const uint8_t* o
     st.ij_tot = stage_occ(s.hb_ij_w + nb * (st.i - 1), occ, nel, scr, stride);
     if (st.ij_tot > 0.0) {
         st.j = occ[select_alias_staged(rng, nel, scr, stride, st.ij_tot) - 1];
-        st.ji_tot = sum_occ(s.hb_ij_w + nb * (st.j - 1), occ, nel);
         st.allowed = fabs(s.hb_ija_tot[HB_I2(st.j, st.i)]) > 0.0;
     }
     if (st.allowed) {
@@ -1109,7 +1117,17 @@ HB_HDN void hb_phase_c(R& rng, const Sys& s, const uint64_t* f, HbState& st) {
         st.dbl = true; st.psingle = 0.0;
     }
     if (st.dbl) {
-        st.b = select_precalc<true>(rng, (int)nb, s.hb_ijab_U + HB_I4(1, st.a, st.j, st.i), s.hb_ijab_K + HB_I4(1, st.a, st.j, st.i));
+        if (s.hb_ijab_rec) {      // {aliasU, aliasK} of the drawn slot from one 32-byte record instead of two arrays
+            double x = rng.next() * (int)nb;
+            const int K = (int)floor(x);
+            x = x - K;
+            const HbRec* rec = s.hb_ijab_rec + HB_I4(1, st.a, st.j, st.i) + K;
+            const double U = HB_LDCS(&rec->U);
+            const int alias = HB_LDCS(&rec->K);
+            st.b = (x < U) ? K + 1 : alias;
+        } else {
+            st.b = select_precalc<true>(rng, (int)nb, s.hb_ijab_U + HB_I4(1, st.a, st.j, st.i), s.hb_ijab_K + HB_I4(1, st.a, st.j, st.i));
+        }
         if (det_test(f, st.b)) { st.allowed = false; return; }
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -1125,18 +1143,24 @@ HB_HDN void hb_phase_c(R& rng, const Sys& s, const uint64_t* f, HbState& st) {
 HB_HD bool hb_single_term(const Sys& s, int i, int a, double hmod_ia, double ij_tot, int oq, double& term) {
     if (i == oq || a == oq) return false;
     const int64_t nb = s.nbasis;
-    const double wt = s.hb_ijab_tot[HB_I3(a, oq, i)];
+    // hb_ijab%weights_tot(a,oq,i) and hb_ija%weights(a,oq,i) are the same number (the same sum): one load
+    const double wt = s.hb_ija_w[HB_I3(a, oq, i)];
     double psq;
     if (hmod_ia < wt) psq = hmod_ia / (wt + hmod_ia); else psq = 0.5;
-    term = (psq * (s.hb_ij_w[HB_I2(oq, i)] / ij_tot) * (s.hb_ija_w[HB_I3(a, oq, i)] / s.hb_ija_tot[HB_I2(oq, i)]));
+    term = (psq * (s.hb_ij_w[HB_I2(oq, i)] / ij_tot) * (wt / s.hb_ija_tot[HB_I2(oq, i)]));
     return true;
 }
 
 // Phase F: generation probability, matrix element and excitation.  hm[k] = |slater_condon1| of ordering k (only
 // read where need_k has the bit); pgen_single_sum = sum of hb_single_term over the occupied orbitals (singles).
+// The tables are exactly symmetric - ij_weights(j,i) = ij_weights(i,j), hb_ija%weights_tot(j,i) = ...(i,j),
+// hb_ija%weights(a,j,i) = hb_ijab%weights_tot(a,j,i) = ...(a,i,j), hb_ijab%weights invariant under i<->j and a<->b: the
+// same sums of the same numbers (checked bitwise in tests/test_core_vs_oracle.py) - so the four-ordering formula below
+// reads 7 numbers where it names 20, with every operation of the reference kept in its order.  ji_weights_occ_tot is
+// only needed here and is summed for the double excitations that got this far.
 template <int W>
-HB_HDN void hb_phase_f(const Sys& s, const uint64_t* f, const HbState& st, const double* hm, double pgen_single_sum,
-                       Gen& g) {
+HB_HDN void hb_phase_f(const Sys& s, const uint64_t* f, const uint8_t* occ, const HbState& st, const double* hm,
+                       double pgen_single_sum, const double* __restrict__ iw, Gen& g) {
     const int64_t nb = s.nbasis;
     g.from1 = 0; g.from2 = 0; g.to1 = 0; g.to2 = 0; g.perm = false; g.nexcit = 2;
     if (!st.allowed) {
@@ -1145,32 +1169,30 @@ HB_HDN void hb_phase_f(const Sys& s, const uint64_t* f, const HbState& st, const
     }
     const int i = st.i, j = st.j, a = st.a, b = st.b;
     if (st.dbl) {
-        const double* __restrict__ ijcol = s.hb_ij_w + nb * (i - 1);
-        const double* __restrict__ jicol = s.hb_ij_w + nb * (j - 1);
-        const double pi_ = s.hb_i_w[i - 1] / st.i_tot;
-        const double pj_ = s.hb_i_w[j - 1] / st.i_tot;
-        const double pij = ijcol[j - 1] / st.ij_tot;   // ij_weights_occ(j_ind)/ij_weights_occ_tot
-        const double pji = jicol[i - 1] / st.ji_tot;   // ji_weights_occ(i_ind)/ji_weights_occ_tot
+        const double ji_tot = sum_occ(s.hb_ij_w + nb * (j - 1), occ, s.nel);
+        const double wij = s.hb_ij_w[HB_I2(j, i)];
+        const double Tij = s.hb_ija_tot[HB_I2(j, i)];
+        const double Ta = s.hb_ija_w[HB_I3(a, j, i)], Tb = s.hb_ija_w[HB_I3(b, j, i)];
+        const double wab = HB_LDCS(s.hb_ijab_w + HB_I4(b, a, j, i));
+        const double pi_ = iw[i - 1] / st.i_tot;
+        const double pj_ = iw[j - 1] / st.i_tot;
+        const double pij = wij / st.ij_tot;      // ij_weights_occ(j_ind)/ij_weights_occ_tot
+        const double pji = wij / ji_tot;         // ji_weights_occ(i_ind)/ji_weights_occ_tot
         double ps[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             if (st.need_k & (1u << k)) {
-                int fr, to, ot;
-                hb_ordering(st, k, fr, to, ot);
-                const double wt = s.hb_ijab_tot[HB_I3(to, ot, fr)];
+                const double wt = (k == 1) ? Ta : Tb;    // weights_tot(to, other, from) of ordering k
                 if (hm[k] < wt) ps[k] = hm[k] / (wt + hm[k]); else ps[k] = 0.5;
             } else {
                 ps[k] = 0.0;
             }
         }
-        double pgen_ija = ((pi_) * (pij)) * (s.hb_ija_w[HB_I3(a, j, i)] / s.hb_ija_tot[HB_I2(j, i)]) *
-                          (1.0 - st.psingle) * (HB_LDCS(s.hb_ijab_w + HB_I4(b, a, j, i)) / s.hb_ijab_tot[HB_I3(a, j, i)]);
-        double pgen_ijb = ((pi_) * (pij)) * (s.hb_ija_w[HB_I3(b, j, i)] / s.hb_ija_tot[HB_I2(j, i)]) *
-                          (1.0 - ps[0]) * (HB_LDCS(s.hb_ijab_w + HB_I4(a, b, j, i)) / s.hb_ijab_tot[HB_I3(b, j, i)]);
-        double pgen_jia = ((pj_) * (pji)) * (s.hb_ija_w[HB_I3(a, i, j)] / s.hb_ija_tot[HB_I2(i, j)]) *
-                          (1.0 - ps[1]) * (HB_LDCS(s.hb_ijab_w + HB_I4(b, a, i, j)) / s.hb_ijab_tot[HB_I3(a, i, j)]);
-        double pgen_jib = ((pj_) * (pji)) * (s.hb_ija_w[HB_I3(b, i, j)] / s.hb_ija_tot[HB_I2(i, j)]) *
-                          (1.0 - ps[2]) * (HB_LDCS(s.hb_ijab_w + HB_I4(a, b, i, j)) / s.hb_ijab_tot[HB_I3(b, i, j)]);
+        const double ra = Ta / Tij, rb = Tb / Tij, wa = wab / Ta, wb = wab / Tb;
+        double pgen_ija = ((pi_) * (pij)) * ra * (1.0 - st.psingle) * wa;
+        double pgen_ijb = ((pi_) * (pij)) * rb * (1.0 - ps[0]) * wb;
+        double pgen_jia = ((pj_) * (pji)) * ra * (1.0 - ps[1]) * wa;
+        double pgen_jib = ((pj_) * (pji)) * rb * (1.0 - ps[2]) * wb;
         g.pgen = pgen_ija + pgen_ijb + pgen_jia + pgen_jib;
         g.from1 = (i < j) ? i : j; g.from2 = (i < j) ? j : i;
         g.to1 = (a < b) ? a : b; g.to2 = (a < b) ? b : a;
@@ -1181,7 +1203,7 @@ HB_HDN void hb_phase_f(const Sys& s, const uint64_t* f, const HbState& st, const
     } else {
         g.nexcit = 1; g.from1 = i; g.to1 = a; g.perm = st.perm_ia;
         g.hmatel = st.h_ia;
-        g.pgen = pgen_single_sum * (s.hb_i_w[i - 1] / st.i_tot);
+        g.pgen = pgen_single_sum * (iw[i - 1] / st.i_tot);
         g.allowed = true;
     }
 }
@@ -1212,7 +1234,7 @@ HB_HDN void gen_excit_heat_bath(R& rng, const Sys& s, const Params& p, const uin
             }
         }
     }
-    hb_phase_f<W>(s, f, st, hm, psum, g);
+    hb_phase_f<W>(s, f, occ, st, hm, psum, s.hb_i_w, g);
 }
 
 // k-th (1-based) unoccupied orbital, ascending (decode_det_occ_unocc, src/determinant_decoders.f90)

@@ -279,7 +279,7 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
                     psum = spsum[tid];
                 }
             }
-            hb_phase_f<W>(s, f, st, hmk, psum, g);
+            hb_phase_f<W>(s, f, socc + lo * nel, st, hmk, psum, siw, g);
         } else if (active) {
             if (GEN == GEN_UEG) gen_excit_ueg_no_renorm<W>(rng, s, f, socc + lo * nel, g);
             else if (GEN == GEN_UEG_PP) gen_excit_ueg_power_pitzer<W>(rng, s, f, socc + lo * nel, g);

@@ -141,8 +141,11 @@ int HB_CAT4(hb_spawn_w, HB_TU_W, _g, HB_TU_GROUP)(hb200_engine* e, const Params&
     switch (L.gen) {
 #if HB_TU_GROUP == 0
         case EXCIT_GEN_HEAT_BATH:
-            if (e->sys.nel <= 32) return launch_spawn_hb<W, uint32_t>(e, p, L);
-            return launch_spawn_hb<W, uint64_t>(e, p, L);
+            if (getenv("HB200_WF") || getenv("HB200_MEGA")) {      // development switches: the other two designs measured
+                if (e->sys.nel <= 32) return launch_spawn_hb<W, uint32_t>(e, p, L);
+                return launch_spawn_hb<W, uint64_t>(e, p, L);
+            }
+            return launch_spawn<W, EXCIT_GEN_HEAT_BATH>(e, p, L);
 #elif HB_TU_GROUP == 1
         case EXCIT_GEN_HEAT_BATH_UNIFORM: return launch_spawn<W, EXCIT_GEN_HEAT_BATH_UNIFORM>(e, p, L);
         case EXCIT_GEN_HEAT_BATH_SINGLE: return launch_spawn<W, EXCIT_GEN_HEAT_BATH_SINGLE>(e, p, L);

@@ -136,7 +136,7 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": "walker-iterations/s (FCIQMC MC cycles x walkers)", "value": v,
         "unit": "walker-iterations/s", "n_gpus": args.gpus, "steps": nsteps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * tot_t / nsteps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * tot_t / nsteps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "int64+f64", "data": "synthetic",
         "config": {"workload": "S50 (50 orb / 20 el) real-valued iFCIQMC, heat_bath, unit walkers", "tau": tau},
         "cpu_baseline": {"value": v, "unit": "walker-iterations/s", "cores": cores, "kind": "port",
@@ -154,7 +154,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine")
-    ap.add_argument("--walkers", type=float, default=1e8, help="walkers (= occupied determinants) per GPU")
+    ap.add_argument("--walkers", type=float, default=0.0,
+                    help="walkers (= occupied determinants) per GPU; 0 = from --scaling")
+    ap.add_argument("--scaling", default="auto", choices=["auto", "weak", "strong"],
+                    help="auto: 1 GPU = BASELINE configs[1] (1e8 walkers); N > 1 GPUs = configs[2], strong scaling: "
+                         "--total-walkers sharded by hash owner over the N ranks.  weak: 1e8 walkers per GPU")
+    ap.add_argument("--total-walkers", type=float, default=1e9, help="strong scaling: walkers over all GPUs")
     ap.add_argument("--tau", type=float, default=0.0, help="0 => calibrate for R_spawn ~ 0.05")
     ap.add_argument("--excit-gen", default="heat_bath", choices=["heat_bath", "heat_bath_uniform", "heat_bath_single", "power_pitzer_orderN", "power_pitzer", "renorm", "renorm_spin", "no_renorm_spin", "no_renorm", "power_pitzer_occ",
                                                               "cauchy_schwarz_occ", "power_pitzer_occ_ij", "cauchy_schwarz_occ_ij"],
@@ -169,6 +174,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+    if args.scaling == "auto":
+        args.scaling = "strong" if (world > 1 and args.walkers == 0.0) else "weak"
+    if args.walkers == 0.0:
+        args.walkers = args.total_walkers / world if args.scaling == "strong" else 1e8
     if args.impl == "reference":
         if args.tau == 0.0:
             args.tau = 5.3e-7     # what the GPU arm's calibration (R_spawn ~ 0.05) gives for this workload
@@ -212,14 +221,13 @@ def main():
     f0 = s.encode(occ0)
     H00 = s.slater_condon0(occ0)
     wl = int(n * 1.25) + 4096
-    sl = max(int(n * 0.30), 1 << 16) * 1
+    sl = max(int(n * 0.15), 1 << 16) * 1      # per-destination block: 3x the ~5 % of attempts that spawn
     eng = Engine(s, excit_gen=args.excit_gen, pattempt_single=ps, pattempt_double=pd, real_amplitudes=True,
                  spawn_cutoff=0.01, initiator_approx=True, walker_length=wl, spawned_walker_length=sl * world, seed=7,
                  nprocs=world, iproc=rank, device=local_rank)
     eng.set_reference(f0, H00)
     if world > 1:
-        uid = eng.get_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)
-        eng.comm_init(comm.broadcast_bytes(uid, src=0))
+        eng.comm_setup(comm)
     rf = 1 << 31
     states, pops = synthetic.random_walkers_torch(n, s.nbasis, s.nalpha, s.nbeta, rf, dev, seed=1, nprocs=world,
                                                   iproc=rank)
@@ -285,7 +293,7 @@ def main():
     tm = eng.last_timing()
     clocks = sampler.stop() if rank == 0 else None
     dev_s = tm["total_ms"] / 1e3           # CUDA events on the engine stream around the K cycles
-    agg = comm.allreduce_sum(np.array([out["walker_iterations"], float(out["nattempts_spawn"])]))
+    agg = comm.allreduce_sum(np.array([out["walker_iterations"], float(out["nattempts_spawn"]), float(n)]))
     tmax = float(np.max(comm.allreduce_sum(np.eye(world)[rank] * dev_s))) if world > 1 else dev_s
     value = agg[0] / tmax
     attempts_per_s = agg[1] / tmax
@@ -309,7 +317,10 @@ def main():
                 if k.startswith("k_spawn_death"):
                     traffic = v
     roofline = {"bound": "hbm", "kernel": "k_spawn_death", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": "profiles/traffic.json (ncu --set full capture of this workload, committed; not measured "
+                                  "in this run)" if traffic else None,
+                "peak_source": peak_src,
                 "alg_bytes_per_launch": alg_bytes, "kernel_ms": k_ms,
                 "stage_ms_per_step": {k: tm[k] / args.steps for k in ("spawn_ms", "comm_ms", "sort_ms", "annihilate_ms")}}
     # whole-cycle algorithmic traffic (SURVEY.md 8d B_alg) for context
@@ -318,31 +329,83 @@ def main():
     roofline["cycle_alg_bytes"] = b_alg
     roofline["cycle_frac"] = b_alg / (dev_s / args.steps) / 1e9 / peak
 
-    # ---- end-to-end: walker list in pinned host memory, uploaded every step through the C ABI
-    e2e = None
+    # ---- end-to-end through the C ABI with HOST buffers, three integrations:
+    #   e2e            the walker list lives in pinned host memory and a full copy of it is uploaded every step; the
+    #                  estimators (result structs) come back; the propagated list stays on the device
+    #   e2e_roundtrip  as above and the propagated list is downloaded to pinned host memory every step as well
+    #   e2e_resident   the intended integration: list uploaded once, one hb200_iterate(ncycles) per
+    #                  report loop, hb200_iter_in in / hb200_iter_out back
+    e2e = e2e_rt = e2e_res = None
     if not args.no_e2e:
         nst = max(3, min(args.steps, 5))
         ptrs = (h_states.data_ptr(), h_pops.data_ptr(), h_dat.data_ptr(), n)
-        upload(); eng.iterate(1, tau, shift, pe_old, cyc); cyc += 1
-        upload()
-        barrier()
-        t0 = time.perf_counter()
-        wi = 0.0
-        for _ in range(nst):
+
+        def timed(body, nsteps):
+            barrier()
+            t0 = time.perf_counter()
+            wi = 0.0
+            for _ in range(nsteps):
+                wi += body()
+            barrier()
+            dt = time.perf_counter() - t0
+            wi_all = comm.allreduce_sum(np.array([wi]))[0]
+            dt_max = float(np.max(comm.allreduce_sum(np.eye(world)[rank] * dt))) if world > 1 else dt
+            return wi_all / dt_max
+
+        def step_upload():
             # the host's copy of the NEXT list streams to the device (second stream, third buffer) while the current
             # one propagates; every timed step contains one full list upload, one hb200_iterate and the result structs
+            nonlocal cyc
             eng.upload_psips_begin_ptr(*ptrs)
             o2 = eng.iterate(1, tau, shift, pe_old, cyc); cyc += 1
             eng.upload_psips_commit()
-            wi += o2["walker_iterations"]
-        barrier()
-        dt = time.perf_counter() - t0
-        wi_all = comm.allreduce_sum(np.array([wi]))[0]
-        dt_max = float(np.max(comm.allreduce_sum(np.eye(world)[rank] * dt))) if world > 1 else dt
-        e2e = {"value": wi_all / dt_max, "unit": "walker-iterations/s", "h2d_bytes_per_step": int(n * Em + 32),
+            return o2["walker_iterations"]
+
+        upload(); eng.iterate(1, tau, shift, pe_old, cyc); cyc += 1
+        upload()
+        v = timed(step_upload, nst)
+        e2e = {"value": v, "unit": "walker-iterations/s", "h2d_bytes_per_step": int(n * Em + 32),
                "d2h_bytes_per_step": 96 + 8 * 12, "steps": nst,
-               "note": "per step: hb200_upload_psips_begin (full walker list from pinned host memory, overlapped with the "
-                       "propagation of the resident list) + hb200_iterate(1) + hb200_upload_psips_commit + result structs"}
+               "note": "upload-only: per step hb200_upload_psips_begin (full walker list from pinned host memory, overlapped "
+                       "with the propagation of the resident list) + hb200_iterate(1) + hb200_upload_psips_commit + result "
+                       "structs; the propagated list stays on the device (see e2e_roundtrip, e2e_resident)"}
+        # round trip: the propagated list also returns to pinned host memory (separate buffers: the input is re-used)
+        cap = int(n * 1.1) + 4096
+        r_states = torch.empty((cap, s.W), dtype=torch.int64).pin_memory()
+        r_pops = torch.empty(cap, dtype=torch.int64).pin_memory()
+        r_dat = torch.empty(cap, dtype=torch.float64).pin_memory()
+        nback = [0]
+
+        def step_roundtrip():
+            nonlocal cyc
+            eng.upload_psips_begin_ptr(*ptrs)
+            o2 = eng.iterate(1, tau, shift, pe_old, cyc); cyc += 1
+            nback[0] = eng.download_psips_ptr(r_states.data_ptr(), r_pops.data_ptr(), r_dat.data_ptr(), cap)
+            eng.upload_psips_commit()
+            return o2["walker_iterations"]
+
+        upload()
+        v = timed(step_roundtrip, nst)
+        e2e_rt = {"value": v, "unit": "walker-iterations/s", "h2d_bytes_per_step": int(n * Em + 32),
+                  "d2h_bytes_per_step": int(nback[0] * Em + 192), "steps": nst,
+                  "note": "per step: full list upload (overlapped) + hb200_iterate(1) + hb200_download_psips of the "
+                          "propagated list + result structs"}
+        del r_states, r_pops, r_dat
+        # resident: one upload, then report loops of ncycles cycles per hb200_iterate call
+        ncyc = 5
+
+        def step_resident():
+            nonlocal cyc
+            o2 = eng.iterate(ncyc, tau, shift, pe_old, cyc); cyc += ncyc
+            return o2["walker_iterations"]
+
+        upload()
+        v = timed(step_resident, 2)
+        e2e_res = {"value": v, "unit": "walker-iterations/s", "h2d_bytes_per_step": 32, "d2h_bytes_per_step": 96,
+                   "steps": 2, "cycles_per_call": ncyc,
+                   "note": "list resident on the device across report loops: per step one hb200_iterate(ncycles=5) call, "
+                           "hb200_iter_in in, hb200_iter_out back (wall clock around the calls); the one-off upload is "
+                           "outside the timed region"}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -357,15 +420,20 @@ def main():
         line = {
             "metric": "walker-iterations/s (FCIQMC MC cycles x walkers)", "value": value, "unit": "walker-iterations/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tmax / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64+f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "int64+f64", "data": "synthetic",
             "config": {"workload": ("S50 synthetic FCIDUMP (50 orb / 20 el, C1, 8-fold)" if args.system == "s50" else
                                     "3D UEG (14 electrons, rs = 1, 114 plane-wave spin-orbitals)") +
                                    f", real-valued iFCIQMC, {args.excit_gen}, {n:.3g} unit walkers per GPU (distribution A)",
-                       "tau": tau, "R_spawn": float(P) / max(A, 1.0), "walkers_per_gpu": n, "nstates": int(S),
-                       "l2": "inputs (3.2 GB walker list) larger than L2; no flush needed",
-                       "sharding": "hash-owner (MurmurHash2) + NCCL all-to-all" if world > 1 else "single rank"},
+                       "tau": tau, "R_spawn": float(P) / max(A, 1.0), "walkers_per_gpu": n, "walkers_total": int(agg[2]),
+                       "nstates": int(S),
+                       "l2": f"inputs ({n * Em / 1e9:.2g} GB walker list per GPU) " +
+                             ("larger than L2; no flush needed" if n * Em > 2.5e8 else "NOT larger than L2 (side measurement)"),
+                       "sharding": ("hash-owner (MurmurHash2); spawn blocks pushed peer-to-peer over NVLink while the spawning "
+                                    "step runs" + ("" if getattr(eng, "p2p", False) else " [disabled: NCCL send/recv]"))
+                                   if world > 1 else "single rank"},
             "spawn_attempts_per_s": attempts_per_s,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_roundtrip": e2e_rt, "e2e_resident": e2e_res,
+            "gpu_launches": int(launches), "host_syncs_per_step": 1,
             "clocks": clocks, "wall_s_timed": wall, "setup_s": setup_s,
             "errors": {"spawn_error": out["spawn_error"], "psip_error": out["psip_error"]},
         }

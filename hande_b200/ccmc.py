@@ -65,8 +65,7 @@ def do_ccmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, ke
     if qmc.full_non_composite:
         eng.ccmc_set_full_nc(True)
     if nprocs > 1:
-        uid = eng.get_unique_id() if iproc == 0 else np.zeros(128, dtype=np.uint8)
-        eng.comm_init(comm.broadcast_bytes(uid, src=0))
+        eng.comm_setup(comm, p2p=False)     # CCMC cycles are host-stepped: NCCL send/recv exchange
     real_factor = (1 << 31) if qmc.real_amplitudes else 1
     # initial_distribution + initial_cc_projected_energy (src/qmc_common.F90:799-925): all excips on the reference
     n0 = int(round(qmc.init_pop))

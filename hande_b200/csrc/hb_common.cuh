@@ -131,6 +131,17 @@ struct CycleStats {
     long long nkept, npart_new; // after merge
 };
 
+// layout of the pinned host block the results of a cycle are copied to
+struct HostOut {
+    CycleStats st;
+    long long npart_new;
+    int tot[4];            // [0] new determinants, [1] surviving states
+    int err[4];
+    unsigned long long spn;
+    unsigned long long head[1];   // [nprocs]
+};
+
+
 // ------------------------------------------------------------------------------------------------
 // Engine
 // ------------------------------------------------------------------------------------------------
@@ -158,8 +169,35 @@ struct hb200_engine {
     long long nparticles_enc = 0;  // sum |pop| (encoded) of the current list
     // spawn store
     int64_t* d_spawn[2] = {nullptr, nullptr};
-    int sp_cur = 0;      // buffer holding the current stage's list
-    long long sp_n = 0;  // number of elements in it (contiguous from 0) after comm
+    int64_t* sp_ptr[2] = {nullptr, nullptr};   // the two buffers the sort ping-pongs between (d_spawn, or a receive
+                                               // buffer of the peer-to-peer exchange and d_spawn[0])
+    int sp_cur = 0;      // buffer (index into sp_ptr) holding the current stage's list
+    long long sp_n = 0;  // number of elements in it (contiguous from 0) after comm - staged calls only; hb200_iterate
+                         // keeps the count on the device:
+    unsigned long long* d_spn = nullptr;       // [1] element count written by the host for the staged calls
+    const unsigned long long* sp_pn = nullptr; // where the sort / annihilation kernels read the element count
+    long long sp_cap = 0;                      // ... and the bound they clamp it to
+    long long* d_long_q = nullptr;             // k_annihilate: heads of the long runs of equal keys
+    unsigned* d_long_n = nullptr;
+    // pinned host block the cycle's results are copied into (one synchronisation per cycle)
+    unsigned char* h_out = nullptr;
+    // peer-to-peer exchange of the spawn blocks (hb200_p2p_export / hb200_p2p_import): receive buffers of this rank,
+    // double buffered by cycle parity, exported through CUDA IPC; peer pointers of every rank
+    unsigned char* d_p2p_block = nullptr;      // [heads (256 B) | recv 0 | recv 1], one allocation = one IPC handle
+    int64_t* d_recv[2] = {nullptr, nullptr};
+    unsigned long long* d_recv_head = nullptr; // [2]
+    std::vector<void*> peer_base;              // mapped base of every rank's block (own: d_p2p_block)
+    int64_t** d_peer_recv = nullptr;           // device array [2][nprocs]
+    unsigned long long** d_peer_head = nullptr;// device array [nprocs] (head of parity k at +k)
+    unsigned long long* d_snap = nullptr;      // [(chunks + 1)][nprocs] d_head after each spawn chunk
+    long long* d_push = nullptr;               // [3][nprocs] lo, count, remote offset of the chunk being pushed
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_comm = nullptr;
+    bool p2p = false;
+    hb200_barrier_fn host_barrier = nullptr;   // ends an exchange instead of the NCCL collective (hb200_set_host_barrier)
+    void* host_barrier_arg = nullptr;
+    int xparity = 0;                           // receive buffer of the next exchange
     bool sp_blocked = true;  // true: still partitioned in per-destination blocks (before comm)
     long long block_size = 0;
     unsigned long long* d_head = nullptr;
@@ -222,9 +260,10 @@ enum { SPAWN_GROUP_HEAT_BATH = 0, SPAWN_GROUP_HB_UNIFORM = 1, SPAWN_GROUP_PP_OCC
 // launchers defined in hb_spawn_tu.cu (one per W and group) and hb_ccmc_tu.cu (one per W)
 struct SpawnLaunch {
     int gen;            // GEN of the instantiation
-    int ntiles;
+    int ntiles;         // tiles of this launch
     size_t smem;
-    long long n;
+    long long n;        // states of the whole list
+    int tile0;          // first tile of this launch (the spawning step of a multi-rank cycle is launched in chunks)
 };
 typedef int (*hb_spawn_fn)(hb200_engine* e, const Params& p, const SpawnLaunch& L);
 #define HB_DECL_SPAWN(W, G) int hb_spawn_w##W##_g##G(hb200_engine* e, const Params& p, const SpawnLaunch& L);

@@ -192,13 +192,26 @@ __global__ void k_reduce_partials(const SpawnPartials* __restrict__ partials, in
 // ------------------------------------------------------------------------------------------------
 constexpr int SORT_THREADS = 256;
 
+// The element count of the spawn list is read on the device (*pn, clamped to cap): hb200_iterate never brings it to the
+// host, so grids are sized from a host-side upper bound and the chunk of a block follows from the real count.
+__device__ __forceinline__ long long dev_count(const unsigned long long* __restrict__ pn, long long cap) {
+    const unsigned long long v = *pn;
+    return v > (unsigned long long)cap ? cap : (long long)v;
+}
+__device__ __forceinline__ long long sort_chunk(long long n, int nblk) {
+    const long long c = (n + nblk - 1) / nblk;
+    return (c + SORT_THREADS - 1) / SORT_THREADS * SORT_THREADS;
+}
+
 template <int E>
 __global__ void __launch_bounds__(SORT_THREADS)
-k_radix_hist(const int64_t* __restrict__ in, long long n, int word, int shift, unsigned* __restrict__ hist, int nblk,
-             long long chunk) {
+k_radix_hist(const int64_t* __restrict__ in, const unsigned long long* __restrict__ pn, long long cap, int word, int shift,
+             unsigned* __restrict__ hist, int nblk) {
     __shared__ unsigned sh[256];
     sh[threadIdx.x] = 0;
     __syncthreads();
+    const long long n = dev_count(pn, cap);
+    const long long chunk = sort_chunk(n, nblk);
     const long long start = (long long)blockIdx.x * chunk;
     const long long end = min(n, start + chunk);
     for (long long i = start + threadIdx.x; i < end; i += SORT_THREADS) {
@@ -239,12 +252,14 @@ __global__ void k_scan_u32_single(unsigned* data, long long m) {
 
 template <int E>
 __global__ void __launch_bounds__(SORT_THREADS)
-k_radix_scatter(const int64_t* __restrict__ in, int64_t* __restrict__ out, long long n, int word, int shift,
-                const unsigned* __restrict__ hist, int nblk, long long chunk) {
+k_radix_scatter(const int64_t* __restrict__ in, int64_t* __restrict__ out, const unsigned long long* __restrict__ pn,
+                long long cap, int word, int shift, const unsigned* __restrict__ hist, int nblk) {
     __shared__ unsigned sbase[256];
     __shared__ unsigned swc[SORT_THREADS / 32][256];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     sbase[tid] = hist[(size_t)tid * nblk + blockIdx.x];
+    const long long n = dev_count(pn, cap);
+    const long long chunk = sort_chunk(n, nblk);
     const long long start = (long long)blockIdx.x * chunk;
     const long long end = min(n, start + chunk);
     for (long long t0 = start; t0 < end; t0 += SORT_THREADS) {
@@ -296,9 +311,11 @@ k_radix_scatter(const int64_t* __restrict__ in, int64_t* __restrict__ out, long 
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_BLOCK = TILE * SCAN_ITEMS;
 
+// pn != nullptr: the element count is min(*pn, n) (read on the device), n the bound the grid was sized from
 __global__ void __launch_bounds__(TILE) k_scan_block(const int* __restrict__ in, int* __restrict__ out, long long n,
-                                                     int* __restrict__ block_sums) {
+                                                     int* __restrict__ block_sums, const unsigned long long* __restrict__ pn) {
     __shared__ int swarp[8];
+    if (pn) n = dev_count(pn, n);
     const long long base = (long long)blockIdx.x * SCAN_BLOCK + (long long)threadIdx.x * SCAN_ITEMS;
     int v[SCAN_ITEMS];
     int sum = 0;
@@ -316,7 +333,9 @@ __global__ void __launch_bounds__(TILE) k_scan_block(const int* __restrict__ in,
     }
     if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
 }
-__global__ void __launch_bounds__(TILE) k_scan_add(int* __restrict__ out, long long n, const int* __restrict__ block_offs) {
+__global__ void __launch_bounds__(TILE) k_scan_add(int* __restrict__ out, long long n, const int* __restrict__ block_offs,
+                                                   const unsigned long long* __restrict__ pn) {
+    if (pn) n = dev_count(pn, n);
     const long long base = (long long)blockIdx.x * SCAN_BLOCK + (long long)threadIdx.x * SCAN_ITEMS;
     const int off = block_offs[blockIdx.x];
 #pragma unroll
@@ -324,9 +343,11 @@ __global__ void __launch_bounds__(TILE) k_scan_add(int* __restrict__ out, long l
         if (base + k < n) out[base + k] += off;
 }
 // single-block scan for small arrays; also writes the total to *total
-__global__ void k_scan_small(const int* __restrict__ in, int* __restrict__ out, long long n, int* total) {
+__global__ void k_scan_small(const int* __restrict__ in, int* __restrict__ out, long long n, int* total,
+                             const unsigned long long* __restrict__ pn) {
     __shared__ int swarp[32];
     __shared__ int carry;
+    if (pn) n = dev_count(pn, n);
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -351,38 +372,16 @@ __global__ void k_scan_small(const int* __restrict__ in, int* __restrict__ out, 
 // Kernel: annihilate_spawn_t[_initiator] + annihilate_main_list[_initiator] + round_low_population_spawns
 // (src/spawn_data.F90:859-1101, src/annihilation.f90:294-486, 600-675) on the sorted spawn list.
 // ------------------------------------------------------------------------------------------------
+constexpr int ANN_SHORT = 32;   // runs of equal keys up to this length are summed by the thread of their first element
+
+// What happens to one distinct spawned determinant once its events are summed: annihilation against the main list or
+// a new entry of it.  pop / initiator_pop / events: totals over the run that starts at element i.
 template <int W>
-__global__ void __launch_bounds__(256)
-k_annihilate(Params p, int64_t* __restrict__ sp, long long n, const uint64_t* __restrict__ states,
-             int64_t* __restrict__ pops, long long nstates, int* __restrict__ ins_flag, long long* __restrict__ ins_pos) {
+__device__ __forceinline__ void annihilate_apply(const Params& p, int64_t* __restrict__ sp, long long i, const uint64_t* key,
+                                                 long long pop, long long initiator_pop, long long events,
+                                                 const uint64_t* __restrict__ states, int64_t* __restrict__ pops,
+                                                 long long nstates, int* __restrict__ ins_flag, long long* __restrict__ ins_pos) {
     constexpr int E = W + 2;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    ins_flag[i] = 0;
-    uint64_t key[W];
-#pragma unroll
-    for (int k = 0; k < W; ++k) key[k] = (uint64_t)sp[i * E + k];
-    if (i > 0) {
-        bool same = true;
-#pragma unroll
-        for (int k = 0; k < W; ++k) same = same && ((uint64_t)sp[(i - 1) * E + k] == key[k]);
-        if (same) return;  // not the head of its segment
-    }
-    long long pop = 0, initiator_pop = 0, events = 0;
-    for (long long j = i; j < n; ++j) {
-        if (j > i) {
-            bool same = true;
-#pragma unroll
-            for (int k = 0; k < W; ++k) same = same && ((uint64_t)sp[j * E + k] == key[k]);
-            if (!same) break;
-        }
-        const long long pj = sp[j * E + W];
-        pop += pj;
-        if (p.initiator) {
-            if (!(sp[j * E + W + 1] & 1)) initiator_pop += pj;
-            else events += (pj < 0) ? -1 : ((pj > 0) ? 1 : 0);
-        }
-    }
     int flag = 0;
     if (p.initiator) {
         const bool sgn_tot = pop >= 0, sgn_ini = initiator_pop >= 0;  // Fortran sign(1,0) = +1
@@ -416,12 +415,113 @@ k_annihilate(Params p, int64_t* __restrict__ sp, long long n, const uint64_t* __
     ins_pos[i] = pos;
 }
 
+template <int W>
+__global__ void __launch_bounds__(256)
+k_annihilate(Params p, int64_t* __restrict__ sp, const unsigned long long* __restrict__ pn, long long cap,
+             const uint64_t* __restrict__ states, int64_t* __restrict__ pops, long long nstates, int* __restrict__ ins_flag,
+             long long* __restrict__ ins_pos, long long* __restrict__ long_q, unsigned* __restrict__ long_n) {
+    constexpr int E = W + 2;
+    const long long n = dev_count(pn, cap);
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ins_flag[i] = 0;
+    uint64_t key[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) key[k] = (uint64_t)sp[i * E + k];
+    if (i > 0) {
+        bool same = true;
+#pragma unroll
+        for (int k = 0; k < W; ++k) same = same && ((uint64_t)sp[(i - 1) * E + k] == key[k]);
+        if (same) return;  // not the head of its segment
+    }
+    long long pop = 0, initiator_pop = 0, events = 0;
+    long long j = i;
+    for (; j < n && j < i + ANN_SHORT; ++j) {
+        if (j > i) {
+            bool same = true;
+#pragma unroll
+            for (int k = 0; k < W; ++k) same = same && ((uint64_t)sp[j * E + k] == key[k]);
+            if (!same) break;
+        }
+        const long long pj = sp[j * E + W];
+        pop += pj;
+        if (p.initiator) {
+            if (!(sp[j * E + W + 1] & 1)) initiator_pop += pj;
+            else events += (pj < 0) ? -1 : ((pj > 0) ? 1 : 0);
+        }
+    }
+    if (j == i + ANN_SHORT && j < n) {
+        bool same = true;
+#pragma unroll
+        for (int k = 0; k < W; ++k) same = same && ((uint64_t)sp[j * E + k] == key[k]);
+        if (same) {     // a long run (e.g. the reference determinant near convergence): one warp sums it, k_annihilate_long
+            long_q[atomicAdd(long_n, 1u)] = i;
+            return;
+        }
+    }
+    annihilate_apply<W>(p, sp, i, key, pop, initiator_pop, events, states, pops, nstates, ins_flag, ins_pos);
+}
+
+// The long runs queued by k_annihilate: one warp per run (grid-stride over the queue); the end of the run is found by a
+// galloping + binary search on the sorted keys, the sums are integer (order-independent).
+template <int W>
+__global__ void __launch_bounds__(256)
+k_annihilate_long(Params p, int64_t* __restrict__ sp, const unsigned long long* __restrict__ pn, long long cap,
+                  const uint64_t* __restrict__ states, int64_t* __restrict__ pops, long long nstates,
+                  int* __restrict__ ins_flag, long long* __restrict__ ins_pos, const long long* __restrict__ long_q,
+                  const unsigned* __restrict__ long_n) {
+    constexpr int E = W + 2;
+    const long long n = dev_count(pn, cap);
+    const unsigned nq = *long_n;
+    const int lane = threadIdx.x & 31;
+    const unsigned gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned q = gw; q < nq; q += nw) {
+        const long long i = long_q[q];
+        uint64_t key[W];
+#pragma unroll
+        for (int k = 0; k < W; ++k) key[k] = (uint64_t)sp[i * E + k];
+        auto same_at = [&](long long j) {
+            bool same = true;
+#pragma unroll
+            for (int k = 0; k < W; ++k) same = same && ((uint64_t)sp[j * E + k] == key[k]);
+            return same;
+        };
+        long long lo = i + ANN_SHORT, step = ANN_SHORT;      // element lo belongs to the run
+        long long hi = lo + step;
+        while (hi < n && same_at(hi)) { lo = hi; step <<= 1; hi = lo + step; }
+        if (hi > n) hi = n;                                   // first element not in the run lies in (lo, hi]
+        while (hi - lo > 1) {
+            const long long mid = (lo + hi) >> 1;
+            if (same_at(mid)) lo = mid; else hi = mid;
+        }
+        long long pop = 0, initiator_pop = 0, events = 0;
+        for (long long j = i + lane; j < hi; j += 32) {
+            const long long pj = sp[j * E + W];
+            pop += pj;
+            if (p.initiator) {
+                if (!(sp[j * E + W + 1] & 1)) initiator_pop += pj;
+                else events += (pj < 0) ? -1 : ((pj > 0) ? 1 : 0);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            pop += __shfl_xor_sync(0xffffffffu, pop, o);
+            initiator_pop += __shfl_xor_sync(0xffffffffu, initiator_pop, o);
+            events += __shfl_xor_sync(0xffffffffu, events, o);
+        }
+        if (lane == 0) annihilate_apply<W>(p, sp, i, key, pop, initiator_pop, events, states, pops, nstates, ins_flag, ins_pos);
+        __syncwarp();
+    }
+}
+
 // compaction of the surviving new determinants: ins[k] = [f, pop, pos]
 template <int W>
 __global__ void __launch_bounds__(256)
-k_compact_inserts(const int64_t* __restrict__ sp, long long n, const int* __restrict__ ins_flag,
-                  const int* __restrict__ ins_idx, const long long* __restrict__ ins_pos, int64_t* __restrict__ ins) {
+k_compact_inserts(const int64_t* __restrict__ sp, const unsigned long long* __restrict__ pn, long long cap,
+                  const int* __restrict__ ins_flag, const int* __restrict__ ins_idx, const long long* __restrict__ ins_pos,
+                  int64_t* __restrict__ ins) {
     constexpr int E = W + 2;
+    const long long n = dev_count(pn, cap);
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || !ins_flag[i]) return;
     const long long k = ins_idx[i];
@@ -434,7 +534,9 @@ k_compact_inserts(const int64_t* __restrict__ sp, long long n, const int* __rest
 // insert_new_walker: dat(1) = sc0_ptr(f) - H00 (src/annihilation.f90:820-901)
 template <int W>
 __global__ void __launch_bounds__(256)
-k_sc0(Sys s, double H00, const uint64_t* __restrict__ dets, long long stride_words, long long n, double* __restrict__ out) {
+k_sc0(Sys s, double H00, const uint64_t* __restrict__ dets, long long stride_words, long long n, double* __restrict__ out,
+      const int* __restrict__ pn) {
+    if (pn) n = min(n, (long long)*pn);
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     uint64_t f[W];
@@ -480,9 +582,10 @@ template <int W>
 __global__ void __launch_bounds__(TILE)
 k_merge(const uint64_t* __restrict__ states, const int64_t* __restrict__ pops, const double* __restrict__ dat,
         long long nstates, const int* __restrict__ tile_off, const int64_t* __restrict__ ins,
-        const double* __restrict__ ins_dat, long long nins, uint64_t* __restrict__ ostates, int64_t* __restrict__ opops,
-        double* __restrict__ odat, long long* __restrict__ part_npart, int ntiles) {
+        const double* __restrict__ ins_dat, const int* __restrict__ pnins, uint64_t* __restrict__ ostates,
+        int64_t* __restrict__ opops, double* __restrict__ odat, long long* __restrict__ part_npart, int ntiles) {
     constexpr int E = W + 2;
+    const long long nins = *pnins;
     __shared__ int swarp[8];
     __shared__ int skept[TILE + 1];
     __shared__ long long sk[2];
@@ -793,6 +896,12 @@ hb200_engine* hb200_create(const hb200_config* cfg) {
     if (dalloc(e, &e->d_part_ll, (size_t)e->max_tiles)) return fail("alloc");
     if (dalloc(e, &e->d_ll, 4)) return fail("alloc");
     if (dalloc(e, &e->d_counts, (size_t)p.nprocs * p.nprocs)) return fail("alloc");
+    if (dalloc(e, &e->d_spn, 2)) return fail("alloc");
+    if (dalloc(e, &e->d_long_q, (size_t)(scap / ANN_SHORT + 2))) return fail("alloc");
+    if (dalloc(e, &e->d_long_n, 2)) return fail("alloc");
+    if (cudaMallocHost((void**)&e->h_out, sizeof(HostOut) + sizeof(unsigned long long) * p.nprocs) != cudaSuccess) return fail("alloc pinned");
+    e->sp_ptr[0] = e->d_spawn[0]; e->sp_ptr[1] = e->d_spawn[1];
+    e->sp_pn = e->d_spn;
     {
         std::vector<int> map((size_t)p.nprocs * p.nslots);
         for (size_t i = 0; i < map.size(); ++i) map[i] = (int)(i % p.nprocs);  // src/load_balancing.F90:170
@@ -808,7 +917,15 @@ hb200_engine* hb200_create(const hb200_config* cfg) {
 void hb200_destroy(hb200_engine* e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->comm_stream) cudaStreamSynchronize(e->comm_stream);
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+    for (size_t r = 0; r < e->peer_base.size(); ++r)
+        if (e->peer_base[r] && e->peer_base[r] != (void*)e->d_p2p_block) cudaIpcCloseMemHandle(e->peer_base[r]);
+    if (e->h_out) cudaFreeHost(e->h_out);
+    for (int i = 0; i < 8; ++i) if (e->ev_chunk[i]) cudaEventDestroy(e->ev_chunk[i]);
+    if (e->ev_comm) cudaEventDestroy(e->ev_comm);
+    if (e->comm_stream) cudaStreamDestroy(e->comm_stream);
     for (void* q : e->owned) cudaFree(q);
     for (int i = 0; i < 6; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     for (int i = 0; i < 2; ++i) if (e->evk[i]) cudaEventDestroy(e->evk[i]);
@@ -1447,44 +1564,143 @@ int64_t hb200_nstates(hb200_engine* e) { return e->nstates; }
         default: rc = fn##4(__VA_ARGS__); break;    \
     }
 
-static int stage_spawn_death(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, CycleStats* hst) {
+// ---- peer-to-peer exchange kernels (hb200_iterate with nprocs > 1 after hb200_p2p_import) ---------------------------
+// Reserve room for this chunk's elements in every destination rank's receive buffer: one system-scope atomic per
+// destination on the REMOTE head counter (NVLink atomics), replacing the count exchange of MPI_Alltoall
+// (src/spawn_data.F90:693).  snap_lo / snap_hi: d_head before / after the spawn chunk.
+__global__ void k_push_reserve(const unsigned long long* __restrict__ snap_lo, const unsigned long long* __restrict__ snap_hi,
+                               unsigned long long* const* __restrict__ peer_head, int parity, int np, long long block_size,
+                               long long cap, long long* __restrict__ push, int* __restrict__ err) {
+    const int d = threadIdx.x;
+    if (d >= np) return;
+    const long long lo = min((long long)snap_lo[d], block_size), hi = min((long long)snap_hi[d], block_size);
+    long long cnt = hi - lo, off = 0;
+    if (cnt > 0) {
+        off = (long long)atomicAdd_system(peer_head[d] + parity, (unsigned long long)cnt);
+        if (off + cnt > cap) {          // the destination's receive buffer is full: spawn%error
+            atomicOr(err, 1);
+            cnt = max(0ll, cap - off);
+        }
+    }
+    push[d] = lo; push[np + d] = cnt; push[2 * np + d] = off;
+}
+// Copy the chunk's elements of every per-destination block straight into the destination rank's receive buffer
+// (peer stores over NVLink; blockIdx.y = destination).  Replaces MPI_Alltoallv (src/spawn_data.F90:721).
+__global__ void __launch_bounds__(256) k_push_copy(const int64_t* __restrict__ blocks, long long block_size, int E, int np,
+                                                   const long long* __restrict__ push, int64_t* const* __restrict__ peer_recv,
+                                                   int parity) {
+    const int d = blockIdx.y;
+    const long long lo = push[d], cnt = push[np + d], off = push[2 * np + d];
+    if (cnt <= 0) return;
+    const int64_t* src = blocks + ((long long)d * block_size + lo) * E;
+    int64_t* dst = peer_recv[parity * np + d] + off * E;
+    const long long nw = cnt * E;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    if ((E & 1) == 0) {       // 16-byte elements of an even-E list are 16-byte aligned on both sides
+        const longlong2* s2 = reinterpret_cast<const longlong2*>(src);
+        longlong2* d2 = reinterpret_cast<longlong2*>(dst);
+        for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nw / 2; k += stride) d2[k] = s2[k];
+    } else {
+        for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nw; k += stride) dst[k] = src[k];
+    }
+    __threadfence_system();
+}
+// insert_new_walkers capacity check (src/annihilation.f90:750-771) on the device: tot[0] = new determinants,
+// tot[1] = surviving states
+__global__ void k_cap_check(int* __restrict__ tot, long long walker_length, int* __restrict__ err) {
+    if ((long long)tot[0] + (long long)tot[1] > walker_length) { err[1] = 1; tot[0] = 0; }
+}
+
+static int set_count_host(hb200_engine* e, long long n) {     // staged calls: the host knows the element count
+    e->sp_n = n;
+    unsigned long long v = (unsigned long long)n;
+    CK(cudaMemcpyAsync(e->d_spn, &v, sizeof(v), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));       // v is a stack variable
+    e->sp_pn = e->d_spn;
+    e->sp_cap = std::max<long long>(n, 0);
+    return 0;
+}
+
+static int spawn_dispatch(hb200_engine* e, int tile0, int ntiles, long long n) {
+    Params& p = e->par;
+    // (generator group, GEN) of this calculation -> the object file holding its k_spawn_death instantiation
+    int group, gen;
+    if (e->sys.kind == SYS_UEG) {
+        group = SPAWN_GROUP_TABLES;
+        gen = (e->cfg.excit_gen == HB200_EXCIT_GEN_POWER_PITZER) ? (int)GEN_UEG_PP : (int)GEN_UEG;
+    } else switch (e->cfg.excit_gen) {
+        case HB200_EXCIT_GEN_NO_RENORM: case HB200_EXCIT_GEN_RENORM: case HB200_EXCIT_GEN_RENORM_SPIN:
+        case HB200_EXCIT_GEN_NO_RENORM_SPIN: group = SPAWN_GROUP_UNIFORM; gen = e->cfg.excit_gen; break;
+        case HB200_EXCIT_GEN_POWER_PITZER_ORDERN: case HB200_EXCIT_GEN_POWER_PITZER:
+            group = SPAWN_GROUP_TABLES; gen = e->cfg.excit_gen; break;
+        case HB200_EXCIT_GEN_HEAT_BATH: group = SPAWN_GROUP_HEAT_BATH; gen = EXCIT_GEN_HEAT_BATH; break;
+        case HB200_EXCIT_GEN_HEAT_BATH_UNIFORM: case HB200_EXCIT_GEN_HEAT_BATH_SINGLE:
+            group = SPAWN_GROUP_HB_UNIFORM; gen = e->cfg.excit_gen; break;
+        case HB200_EXCIT_GEN_POWER_PITZER_OCC:
+        case HB200_EXCIT_GEN_CAUCHY_SCHWARZ_OCC: group = SPAWN_GROUP_PP_OCC; gen = EXCIT_GEN_POWER_PITZER_OCC; break;
+        case HB200_EXCIT_GEN_POWER_PITZER_OCC_IJ:
+        case HB200_EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ: group = SPAWN_GROUP_PP_OCC; gen = EXCIT_GEN_POWER_PITZER_OCC_IJ; break;
+        default: FAIL("spawn_death: excitation generator not implemented");
+    }
+#define HB_ROW(W) {hb_spawn_w##W##_g0, hb_spawn_w##W##_g1, hb_spawn_w##W##_g2, hb_spawn_w##W##_g3, hb_spawn_w##W##_g4}
+    static const hb_spawn_fn table[4][SPAWN_NGROUPS] = {HB_ROW(1), HB_ROW(2), HB_ROW(3), HB_ROW(4)};
+#undef HB_ROW
+    SpawnLaunch L;
+    L.gen = gen; L.ntiles = ntiles; L.smem = 0; L.n = n; L.tile0 = tile0;
+    if (table[e->W - 1][group](e, p, L)) return 1;
+    CK(cudaGetLastError());
+    e->launches++; e->spawn_launches++;
+    return 0;
+}
+
+// The spawning step.  overlap = false: one launch (staged calls, single rank).  overlap = true (peer-to-peer exchange
+// set up): the tile range is launched in chunks; as soon as a chunk has finished, its part of every per-destination
+// block is pushed into the destination rank's receive buffer on the communication stream while the next chunk spawns.
+static int stage_spawn_launch(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, bool overlap) {
     Params& p = e->par;
     p.tau = in->tau; p.shift = in->shift; p.proj_energy_old = in->proj_energy_old; p.cycle = cycle;
     cudaStream_t st = e->stream;
-    CK(cudaMemsetAsync(e->d_head, 0, sizeof(unsigned long long) * p.nprocs, st));
+    const int np = p.nprocs;
+    CK(cudaMemsetAsync(e->d_head, 0, sizeof(unsigned long long) * np, st));
     const long long n = e->nstates;
     const int ntiles = (int)((n + TILE - 1) / TILE);
-    if (ntiles > 0) {
-        CK(cudaEventRecord(e->evk[0], st));
-        // (generator group, GEN) of this calculation -> the object file holding its k_spawn_death instantiation
-        int group, gen;
-        if (e->sys.kind == SYS_UEG) {
-            group = SPAWN_GROUP_TABLES;
-            gen = (e->cfg.excit_gen == HB200_EXCIT_GEN_POWER_PITZER) ? (int)GEN_UEG_PP : (int)GEN_UEG;
-        } else switch (e->cfg.excit_gen) {
-            case HB200_EXCIT_GEN_NO_RENORM: case HB200_EXCIT_GEN_RENORM: case HB200_EXCIT_GEN_RENORM_SPIN:
-            case HB200_EXCIT_GEN_NO_RENORM_SPIN: group = SPAWN_GROUP_UNIFORM; gen = e->cfg.excit_gen; break;
-            case HB200_EXCIT_GEN_POWER_PITZER_ORDERN: case HB200_EXCIT_GEN_POWER_PITZER:
-                group = SPAWN_GROUP_TABLES; gen = e->cfg.excit_gen; break;
-            case HB200_EXCIT_GEN_HEAT_BATH: group = SPAWN_GROUP_HEAT_BATH; gen = EXCIT_GEN_HEAT_BATH; break;
-            case HB200_EXCIT_GEN_HEAT_BATH_UNIFORM: case HB200_EXCIT_GEN_HEAT_BATH_SINGLE:
-                group = SPAWN_GROUP_HB_UNIFORM; gen = e->cfg.excit_gen; break;
-            case HB200_EXCIT_GEN_POWER_PITZER_OCC:
-            case HB200_EXCIT_GEN_CAUCHY_SCHWARZ_OCC: group = SPAWN_GROUP_PP_OCC; gen = EXCIT_GEN_POWER_PITZER_OCC; break;
-            case HB200_EXCIT_GEN_POWER_PITZER_OCC_IJ:
-            case HB200_EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ: group = SPAWN_GROUP_PP_OCC; gen = EXCIT_GEN_POWER_PITZER_OCC_IJ; break;
-            default: FAIL("spawn_death: excitation generator not implemented");
+    CK(cudaEventRecord(e->evk[0], st));
+    if (!overlap) {
+        if (ntiles > 0 && spawn_dispatch(e, 0, ntiles, n)) return 1;
+    } else {
+        const int par = e->xparity;
+        static const int min_tiles = getenv("HB200_P2P_MIN_TILES") ? atoi(getenv("HB200_P2P_MIN_TILES")) : 4096;
+        const int nchunk = (ntiles >= min_tiles && !getenv("HB200_WF") && !getenv("HB200_MEGA")) ? 4 : 1;
+        CK(cudaMemsetAsync(e->d_snap, 0, sizeof(unsigned long long) * np, st));
+        for (int c = 0; c < nchunk; ++c) {
+            const int t0 = (int)((long long)ntiles * c / nchunk), t1 = (int)((long long)ntiles * (c + 1) / nchunk);
+            if (t1 > t0 && spawn_dispatch(e, t0, t1 - t0, n)) return 1;
+            CK(cudaMemcpyAsync(e->d_snap + (size_t)(c + 1) * np, e->d_head, sizeof(unsigned long long) * np,
+                               cudaMemcpyDeviceToDevice, st));
+            CK(cudaEventRecord(e->ev_chunk[c], st));
+            CK(cudaStreamWaitEvent(e->comm_stream, e->ev_chunk[c], 0));
+            k_push_reserve<<<1, std::max(32, np), 0, e->comm_stream>>>(e->d_snap + (size_t)c * np, e->d_snap + (size_t)(c + 1) * np,
+                                                                        e->d_peer_head, par, np, e->block_size,
+                                                                        e->cfg.spawned_walker_length, e->d_push, e->d_err);
+            k_push_copy<<<dim3(32, np), 256, 0, e->comm_stream>>>(e->d_spawn[0], e->block_size, e->E, np, e->d_push,
+                                                                   e->d_peer_recv, par);
+            CK(cudaGetLastError());
+            e->launches += 2;
         }
-#define HB_ROW(W) {hb_spawn_w##W##_g0, hb_spawn_w##W##_g1, hb_spawn_w##W##_g2, hb_spawn_w##W##_g3, hb_spawn_w##W##_g4}
-        static const hb_spawn_fn table[4][SPAWN_NGROUPS] = {HB_ROW(1), HB_ROW(2), HB_ROW(3), HB_ROW(4)};
-#undef HB_ROW
-        SpawnLaunch L;
-        L.gen = gen; L.ntiles = ntiles; L.smem = 0; L.n = n;
-        if (table[e->W - 1][group](e, p, L)) return 1;
-        CK(cudaGetLastError());
-        CK(cudaEventRecord(e->evk[1], st));
-        e->launches++; e->spawn_launches++;
+        if (e->host_barrier) {
+            // the host's own barrier (MPI_Barrier in a Fortran host without NCCL): this rank's pushes have landed when
+            // its communication stream has drained, everybody's after the barrier
+            CK(cudaStreamSynchronize(e->comm_stream));
+            e->host_barrier(e->host_barrier_arg);
+        } else {
+            // every rank's pushes have landed once this collective completes (it also hands every rank the count matrix)
+            CK(cudaMemcpyAsync(e->d_counts + (size_t)p.iproc * np, e->d_head, sizeof(long long) * np, cudaMemcpyDeviceToDevice,
+                               e->comm_stream));
+            NCK(g_nccl.AllGather(e->d_counts + (size_t)p.iproc * np, e->d_counts, np, ncclInt64, e->comm, e->comm_stream));
+        }
+        CK(cudaEventRecord(e->ev_comm, e->comm_stream));
     }
+    CK(cudaEventRecord(e->evk[1], st));
     k_reduce_partials<<<1, 1024, 0, st>>>(e->d_partials, ntiles > 0 ? e->npartials : 0, e->d_stats);
     CK(cudaGetLastError());
     e->launches++;
@@ -1493,26 +1709,42 @@ static int stage_spawn_death(hb200_engine* e, const hb200_iter_in* in, uint32_t 
         CK(cudaGetLastError());
         e->launches++;
     }
+    return 0;
+}
+
+// staged call: spawning step + the host reads the counts
+static int stage_spawn_death(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, CycleStats* hst) {
+    Params& p = e->par;
+    cudaStream_t st = e->stream;
+    if (stage_spawn_launch(e, in, cycle, false)) return 1;
     CK(cudaMemcpyAsync(e->h_head.data(), e->d_head, sizeof(unsigned long long) * p.nprocs, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(hst, e->d_stats, sizeof(CycleStats), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (ntiles > 0) {
+    {
         float t = 0.f;
         cudaEventElapsedTime(&t, e->evk[0], e->evk[1]);
         e->spawn_kernel_ms += t;
     }
     for (int d = 0; d < p.nprocs; ++d)
         if ((long long)e->h_head[d] > e->block_size) e->h_head[d] = (unsigned long long)e->block_size;  // overflow: dropped
+    e->sp_ptr[0] = e->d_spawn[0]; e->sp_ptr[1] = e->d_spawn[1];
     e->sp_cur = 0;
     e->sp_blocked = true;
-    e->sp_n = (p.nprocs == 1) ? (long long)e->h_head[0] : 0;
-    if (p.nprocs == 1) e->sp_blocked = false;
+    e->sp_n = 0;
+    if (p.nprocs == 1) {
+        e->sp_blocked = false;
+        if (set_count_host(e, (long long)e->h_head[0])) return 1;
+    }
     return 0;
 }
 
 static int stage_comm(hb200_engine* e) {
     Params& p = e->par;
-    if (p.nprocs == 1) { e->sp_blocked = false; e->sp_n = (long long)e->h_head[0]; e->sp_cur = 0; return 0; }
+    if (p.nprocs == 1) {
+        e->sp_blocked = false; e->sp_cur = 0;
+        e->sp_ptr[0] = e->d_spawn[0]; e->sp_ptr[1] = e->d_spawn[1];
+        return set_count_host(e, (long long)e->h_head[0]);
+    }
     if (!e->comm) FAIL("comm_spawn: nprocs > 1 but hb200_comm_init was not called");
     cudaStream_t st = e->stream;
     const int np = p.nprocs, me = p.iproc, E = e->E;
@@ -1524,61 +1756,74 @@ static int stage_comm(hb200_engine* e) {
     std::vector<long long> counts((size_t)np * np);
     CK(cudaMemcpyAsync(counts.data(), e->d_counts, sizeof(long long) * np * np, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    // MPI_Alltoallv (src/spawn_data.F90:721): receive blocks ordered by source rank
+    // MPI_Alltoallv (src/spawn_data.F90:721): receive blocks ordered by source rank.  Every rank evaluates the same
+    // capacity checks on the same count matrix BEFORE any send/recv is posted, so a failure is collective.
     long long off = 0;
+    for (int r = 0; r < np; ++r) off += counts[(size_t)r * np + me];
+    bool too_many = false;
+    for (int d = 0; d < np; ++d) {
+        long long t = 0;
+        for (int r = 0; r < np; ++r) t += counts[(size_t)r * np + d];
+        if (t > e->cfg.spawned_walker_length) too_many = true;
+    }
+    if (too_many) FAIL("comm_spawn: a rank would receive more than spawned_walker_length");
+    off = 0;
+    int rc = 0;
     NCK(g_nccl.GroupStart());
-    for (int r = 0; r < np; ++r) {
+    for (int r = 0; r < np && !rc; ++r) {
         const long long nsend = counts[(size_t)me * np + r], nrecv = counts[(size_t)r * np + me];
         if (r == me) {
-            if (nsend) CK(cudaMemcpyAsync(e->d_spawn[1] + off * E, e->d_spawn[0] + (long long)r * e->block_size * E,
-                                          (size_t)nsend * E * 8, cudaMemcpyDeviceToDevice, st));
+            if (nsend && cudaMemcpyAsync(e->d_spawn[1] + off * E, e->d_spawn[0] + (long long)r * e->block_size * E,
+                                         (size_t)nsend * E * 8, cudaMemcpyDeviceToDevice, st) != cudaSuccess) rc = 1;
         } else {
-            if (nsend) NCK(g_nccl.Send(e->d_spawn[0] + (long long)r * e->block_size * E, (size_t)nsend * E, ncclInt64, r, e->comm, st));
-            if (nrecv) NCK(g_nccl.Recv(e->d_spawn[1] + off * E, (size_t)nrecv * E, ncclInt64, r, e->comm, st));
+            if (nsend && g_nccl.Send(e->d_spawn[0] + (long long)r * e->block_size * E, (size_t)nsend * E, ncclInt64, r, e->comm, st) != ncclSuccess) rc = 1;
+            if (nrecv && g_nccl.Recv(e->d_spawn[1] + off * E, (size_t)nrecv * E, ncclInt64, r, e->comm, st) != ncclSuccess) rc = 1;
         }
         off += nrecv;
     }
-    NCK(g_nccl.GroupEnd());
-    if (off > e->cfg.spawned_walker_length) FAIL("comm_spawn: received more than spawned_walker_length");
+    NCK(g_nccl.GroupEnd());       // always reached: the group is never left open
+    if (rc) FAIL("comm_spawn: posting the send/recv of the spawn blocks failed");
+    e->sp_ptr[0] = e->d_spawn[0]; e->sp_ptr[1] = e->d_spawn[1];
     e->sp_cur = 1;
-    e->sp_n = off;
     e->sp_blocked = false;
-    return 0;
+    return set_count_host(e, off);
 }
 
-static int device_scan(hb200_engine* e, const int* d_in, int* d_out, long long n, int slot);
+static int device_scan(hb200_engine* e, const int* d_in, int* d_out, long long n, int slot, const unsigned long long* pn);
 
-static int stage_sort(hb200_engine* e) {
-    const long long n = e->sp_n;
-    if (n <= 1) return 0;
+// LSD radix sort of the current spawn list.  bound: host-side upper bound of the element count (the grids are sized from
+// it); the count itself is read by the kernels from e->sp_pn.
+static int stage_sort(hb200_engine* e, long long bound) {
+    if (bound <= 1) return 0;
     cudaStream_t st = e->stream;
     const int E = e->E;
-    const long long chunk = std::max<long long>(2048, ((n + 1183) / 1184 + SORT_THREADS - 1) / SORT_THREADS * SORT_THREADS);
-    const int nblk = (int)((n + chunk - 1) / chunk);
+    const int nblk = (int)std::max<long long>(1, std::min<long long>(1184, (bound + 2047) / 2048));
     if (256ll * nblk > e->hist_cap) FAIL("sort: histogram scratch too small");
+    const unsigned long long* pn = e->sp_pn;
+    const long long cap = e->sp_cap;
     const int npass = (e->cfg.nbasis + 7) / 8;
     for (int ps = 0; ps < npass; ++ps) {
         const int word = (8 * ps) / 64, shift = (8 * ps) % 64;
-        const int64_t* src = e->d_spawn[e->sp_cur];
-        int64_t* dst = e->d_spawn[e->sp_cur ^ 1];
+        const int64_t* src = e->sp_ptr[e->sp_cur];
+        int64_t* dst = e->sp_ptr[e->sp_cur ^ 1];
         switch (E) {
-            case 3: k_radix_hist<3><<<nblk, SORT_THREADS, 0, st>>>(src, n, word, shift, e->d_hist, nblk, chunk); break;
-            case 4: k_radix_hist<4><<<nblk, SORT_THREADS, 0, st>>>(src, n, word, shift, e->d_hist, nblk, chunk); break;
-            case 5: k_radix_hist<5><<<nblk, SORT_THREADS, 0, st>>>(src, n, word, shift, e->d_hist, nblk, chunk); break;
-            default: k_radix_hist<6><<<nblk, SORT_THREADS, 0, st>>>(src, n, word, shift, e->d_hist, nblk, chunk); break;
+            case 3: k_radix_hist<3><<<nblk, SORT_THREADS, 0, st>>>(src, pn, cap, word, shift, e->d_hist, nblk); break;
+            case 4: k_radix_hist<4><<<nblk, SORT_THREADS, 0, st>>>(src, pn, cap, word, shift, e->d_hist, nblk); break;
+            case 5: k_radix_hist<5><<<nblk, SORT_THREADS, 0, st>>>(src, pn, cap, word, shift, e->d_hist, nblk); break;
+            default: k_radix_hist<6><<<nblk, SORT_THREADS, 0, st>>>(src, pn, cap, word, shift, e->d_hist, nblk); break;
         }
         if (256ll * nblk <= 8192) {
             k_scan_u32_single<<<1, 1024, 0, st>>>(e->d_hist, 256ll * nblk);
         } else {
             // multi-block exclusive scan (counts < 2^31, so the int scan is bit-identical); in place
-            if (device_scan(e, (const int*)e->d_hist, (int*)e->d_hist, 256ll * nblk, 2)) return 1;
+            if (device_scan(e, (const int*)e->d_hist, (int*)e->d_hist, 256ll * nblk, 2, nullptr)) return 1;
             e->launches += 2;
         }
         switch (E) {
-            case 3: k_radix_scatter<3><<<nblk, SORT_THREADS, 0, st>>>(src, dst, n, word, shift, e->d_hist, nblk, chunk); break;
-            case 4: k_radix_scatter<4><<<nblk, SORT_THREADS, 0, st>>>(src, dst, n, word, shift, e->d_hist, nblk, chunk); break;
-            case 5: k_radix_scatter<5><<<nblk, SORT_THREADS, 0, st>>>(src, dst, n, word, shift, e->d_hist, nblk, chunk); break;
-            default: k_radix_scatter<6><<<nblk, SORT_THREADS, 0, st>>>(src, dst, n, word, shift, e->d_hist, nblk, chunk); break;
+            case 3: k_radix_scatter<3><<<nblk, SORT_THREADS, 0, st>>>(src, dst, pn, cap, word, shift, e->d_hist, nblk); break;
+            case 4: k_radix_scatter<4><<<nblk, SORT_THREADS, 0, st>>>(src, dst, pn, cap, word, shift, e->d_hist, nblk); break;
+            case 5: k_radix_scatter<5><<<nblk, SORT_THREADS, 0, st>>>(src, dst, pn, cap, word, shift, e->d_hist, nblk); break;
+            default: k_radix_scatter<6><<<nblk, SORT_THREADS, 0, st>>>(src, dst, pn, cap, word, shift, e->d_hist, nblk); break;
         }
         CK(cudaGetLastError());
         e->launches += 3;
@@ -1587,41 +1832,48 @@ static int stage_sort(hb200_engine* e) {
     return 0;
 }
 
-// exclusive scan of n ints (d_in -> d_out), total to d_total[slot]
-static int device_scan(hb200_engine* e, const int* d_in, int* d_out, long long n, int slot) {
+// exclusive scan of n ints (d_in -> d_out), total to d_total[slot]; pn != nullptr: the count is min(*pn, n) on the device
+static int device_scan(hb200_engine* e, const int* d_in, int* d_out, long long n, int slot, const unsigned long long* pn) {
     cudaStream_t st = e->stream;
     if (n <= 0) { CK(cudaMemsetAsync(e->d_total + slot, 0, sizeof(int), st)); return 0; }
     if (n <= 4 * SCAN_BLOCK) {
-        k_scan_small<<<1, 1024, 0, st>>>(d_in, d_out, n, e->d_total + slot);
+        k_scan_small<<<1, 1024, 0, st>>>(d_in, d_out, n, e->d_total + slot, pn);
         e->launches++;
     } else {
         const long long nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
-        k_scan_block<<<(unsigned)nb, TILE, 0, st>>>(d_in, d_out, n, e->d_scan_l1);
-        k_scan_small<<<1, 1024, 0, st>>>(e->d_scan_l1, e->d_scan_l1o, nb, e->d_total + slot);
-        k_scan_add<<<(unsigned)nb, TILE, 0, st>>>(d_out, n, e->d_scan_l1o);
+        k_scan_block<<<(unsigned)nb, TILE, 0, st>>>(d_in, d_out, n, e->d_scan_l1, pn);
+        k_scan_small<<<1, 1024, 0, st>>>(e->d_scan_l1, e->d_scan_l1o, nb, e->d_total + slot, nullptr);
+        k_scan_add<<<(unsigned)nb, TILE, 0, st>>>(d_out, n, e->d_scan_l1o, pn);
         e->launches += 3;
     }
     CK(cudaGetLastError());
     return 0;
 }
 
-static int stage_annihilate_main(hb200_engine* e, uint32_t cycle, CycleStats* hst) {
+// annihilate_main_list + remove_unoccupied_dets + insert_new_walkers, all counts kept on the device: nothing is read
+// back here.  bound: host-side upper bound of the spawn-list length.
+static int stage_annihilate_launch(hb200_engine* e, uint32_t cycle, long long bound) {
     Params& p = e->par;
     p.cycle = cycle;
     cudaStream_t st = e->stream;
-    const long long n = e->sp_n, ns = e->nstates;
+    const long long ns = e->nstates;
     const int c = e->cur, o = e->alt;
-    int64_t* sp = e->d_spawn[e->sp_cur];
-    int64_t* ins = e->d_spawn[e->sp_cur ^ 1];
-    int h_tot[2] = {0, 0};
-    if (n > 0) {
-        DISPATCH_W(e, k_annihilate<WW><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, sp, n, e->d_states[c], e->d_pops[c], ns,
-                                                                                   e->d_ins_flag, e->d_ins_pos));
+    int64_t* sp = e->sp_ptr[e->sp_cur];
+    int64_t* ins = e->sp_ptr[e->sp_cur ^ 1];
+    const unsigned long long* pn = e->sp_pn;
+    const long long cap = e->sp_cap;
+    if (bound > 0) {
+        CK(cudaMemsetAsync(e->d_long_n, 0, sizeof(unsigned), st));
+        const unsigned nb = (unsigned)((bound + 255) / 256);
+        DISPATCH_W(e, k_annihilate<WW><<<nb, 256, 0, st>>>(p, sp, pn, cap, e->d_states[c], e->d_pops[c], ns, e->d_ins_flag,
+                                                          e->d_ins_pos, e->d_long_q, e->d_long_n));
+        DISPATCH_W(e, k_annihilate_long<WW><<<std::min(nb, 592u), 256, 0, st>>>(p, sp, pn, cap, e->d_states[c], e->d_pops[c], ns,
+                                                                                e->d_ins_flag, e->d_ins_pos, e->d_long_q,
+                                                                                e->d_long_n));
         CK(cudaGetLastError());
-        e->launches++;
-        if (device_scan(e, e->d_ins_flag, e->d_ins_idx, n, 0)) return 1;
-        DISPATCH_W(e, k_compact_inserts<WW><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sp, n, e->d_ins_flag, e->d_ins_idx,
-                                                                                        e->d_ins_pos, ins));
+        e->launches += 2;
+        if (device_scan(e, e->d_ins_flag, e->d_ins_idx, bound, 0, pn)) return 1;
+        DISPATCH_W(e, k_compact_inserts<WW><<<nb, 256, 0, st>>>(sp, pn, cap, e->d_ins_flag, e->d_ins_idx, e->d_ins_pos, ins));
         CK(cudaGetLastError());
         e->launches++;
     } else {
@@ -1631,33 +1883,26 @@ static int stage_annihilate_main(hb200_engine* e, uint32_t cycle, CycleStats* hs
     DISPATCH_W(e, k_round_count<WW><<<ntiles, TILE, 0, st>>>(p, e->d_states[c], e->d_pops[c], ns, e->d_tile_keep));
     CK(cudaGetLastError());
     e->launches++;
-    if (device_scan(e, e->d_tile_keep, e->d_tile_off, ntiles, 1)) return 1;
-    CK(cudaMemcpyAsync(h_tot, e->d_total, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    long long nins = h_tot[0];
-    const long long nkept = h_tot[1];
-    // insert_new_walkers capacity check (src/annihilation.f90:750-771)
-    if (nkept + nins > e->cfg.walker_length) {
-        int one = 1;
-        CK(cudaMemcpyAsync(e->d_err + 1, &one, sizeof(int), cudaMemcpyHostToDevice, st));
-        nins = 0;
-    }
-    if (nins > 0) {
-        DISPATCH_W(e, k_sc0<WW><<<(unsigned)((nins + 255) / 256), 256, 0, st>>>(e->sys, p.H00, (const uint64_t*)ins, e->E, nins,
-                                                                               e->d_ins_dat));
-        CK(cudaGetLastError());
+    if (device_scan(e, e->d_tile_keep, e->d_tile_off, ntiles, 1, nullptr)) return 1;
+    k_cap_check<<<1, 1, 0, st>>>(e->d_total, e->cfg.walker_length, e->d_err);
+    if (bound > 0) {
+        DISPATCH_W(e, k_sc0<WW><<<(unsigned)((bound + 255) / 256), 256, 0, st>>>(e->sys, p.H00, (const uint64_t*)ins, e->E, bound,
+                                                                                e->d_ins_dat, e->d_total));
         e->launches++;
     }
     DISPATCH_W(e, k_merge<WW><<<ntiles, TILE, 0, st>>>(e->d_states[c], e->d_pops[c], e->d_dat[c], ns, e->d_tile_off, ins,
-                                                        e->d_ins_dat, nins, e->d_states[o], e->d_pops[o], e->d_dat[o],
+                                                        e->d_ins_dat, e->d_total, e->d_states[o], e->d_pops[o], e->d_dat[o],
                                                         e->d_part_ll, ntiles));
     CK(cudaGetLastError());
     k_reduce_ll<<<1, 1024, 0, st>>>(e->d_part_ll, ntiles, e->d_ll);
     CK(cudaGetLastError());
-    e->launches += 2;
-    long long npart = 0;
-    CK(cudaMemcpyAsync(&npart, e->d_ll, sizeof(long long), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    e->launches += 3;
+    return 0;
+}
+
+// host bookkeeping once the counts of the merge are known
+static void finish_merge(hb200_engine* e, CycleStats* hst, long long nins, long long nkept, long long npart) {
+    const int c = e->cur, o = e->alt;
     e->cur = o;
     e->alt = c;
     e->nstates = nkept + nins;
@@ -1665,6 +1910,18 @@ static int stage_annihilate_main(hb200_engine* e, uint32_t cycle, CycleStats* hs
     hst->nkept = nkept;
     hst->npart_new = npart;
     e->sp_n = 0;
+}
+
+// staged call: annihilation + merge, then the host reads the counts
+static int stage_annihilate_main(hb200_engine* e, uint32_t cycle, CycleStats* hst) {
+    cudaStream_t st = e->stream;
+    if (stage_annihilate_launch(e, cycle, e->sp_n)) return 1;
+    int h_tot[2] = {0, 0};
+    long long npart = 0;
+    CK(cudaMemcpyAsync(h_tot, e->d_total, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&npart, e->d_ll, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    finish_merge(e, hst, h_tot[0], h_tot[1], npart);
     return 0;
 }
 
@@ -1852,9 +2109,10 @@ int hb200_ccmc_spawn(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, i
         for (int d = 0; d < p.nprocs; ++d)
             if ((long long)e->h_head[d] > e->block_size) e->h_head[d] = (unsigned long long)e->block_size;
     }
+    e->sp_ptr[0] = e->d_spawn[0]; e->sp_ptr[1] = e->d_spawn[1];
     e->sp_cur = 0;
     e->sp_blocked = p.nprocs > 1;
-    e->sp_n = (p.nprocs == 1) ? (long long)e->h_head[0] : 0;
+    if (set_count_host(e, (p.nprocs == 1) ? (long long)e->h_head[0] : 0)) return 1;
     out->proj_energy = tot.pe + tot_nc.pe; out->D0_population = tot.d0 + tot_nc.d0;
     out->D0_normalisation = a.D0_normalisation;
     out->nattempts = nattempts; out->nattempts_spawn = tot.nattempts_spawn + tot_nc.nattempts_spawn;
@@ -2000,7 +2258,7 @@ int hb200_ccmc_iterate(hb200_engine* e, int32_t ncycles, const hb200_iter_in* in
         out->nspawn_events = co.nspawn_events;
         out->ndeath = co.ndeath;
         if (stage_comm(e)) return 1;
-        if (stage_sort(e)) return 1;
+        if (stage_sort(e, e->sp_n)) return 1;
         if (stage_annihilate_main(e, cycle, &cs)) return 1;
         // end_mc_cycle(nspawn_events, ndeath_nc, real_factor, nattempts_spawn, rspawn)
         if (co.nattempts_spawn > 0)
@@ -2019,7 +2277,7 @@ int hb200_comm_spawn(hb200_engine* e) {
 int hb200_annihilate_spawn(hb200_engine* e) {
     CK(cudaSetDevice(e->cfg.device));
     if (e->sp_blocked) FAIL("annihilate_spawn: call hb200_comm_spawn first");
-    if (stage_sort(e)) return 1;
+    if (stage_sort(e, e->sp_n)) return 1;
     CK(cudaStreamSynchronize(e->stream));
     return 0;
 }
@@ -2054,7 +2312,7 @@ int hb200_download_spawn(hb200_engine* e, int64_t* sdata, int64_t capacity, int6
     }
     *n = e->sp_n;
     if (e->sp_n > capacity) FAIL("download_spawn: capacity too small");
-    if (e->sp_n) CK(copy_sync(e, sdata, e->d_spawn[e->sp_cur], (size_t)e->sp_n * E * 8, cudaMemcpyDeviceToHost));
+    if (e->sp_n) CK(copy_sync(e, sdata, e->sp_ptr[e->sp_cur], (size_t)e->sp_n * E * 8, cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -2069,16 +2327,25 @@ int hb200_upload_spawn(hb200_engine* e, const int64_t* sdata, int64_t n) {
     CK(cudaSetDevice(e->cfg.device));
     if (n > e->cfg.spawned_walker_length) FAIL("upload_spawn: too many elements");
     if (n) CK(copy_sync(e, e->d_spawn[0], sdata, (size_t)n * e->E * 8, cudaMemcpyHostToDevice));
-    e->sp_cur = 0; e->sp_n = n; e->sp_blocked = false;
-    return 0;
+    e->sp_ptr[0] = e->d_spawn[0]; e->sp_ptr[1] = e->d_spawn[1];
+    e->sp_cur = 0; e->sp_blocked = false;
+    return set_count_host(e, n);
 }
 
+// ncycles MC cycles with ONE host synchronisation per cycle: every count a later stage needs (spawn-list length, new
+// determinants, surviving states) stays on the device, grids are sized from host-side upper bounds, and the results
+// of the cycle (estimators, counts, error flags) arrive in one pinned block after the merge.  With the peer-to-peer
+// exchange set up (hb200_p2p_import) the spawn blocks travel to their owner ranks while the spawning step is still
+// running (stage_spawn_launch); otherwise comm_spawn_t's NCCL send/recv path (stage_comm) is used.
 int hb200_iterate(hb200_engine* e, int32_t ncycles, const hb200_iter_in* in, hb200_iter_out* out) {
     CK(cudaSetDevice(e->cfg.device));
     if (!e->have_sys) FAIL("iterate: system not set");
     if (uses_heat_bath_tables(e) && !e->have_hb) FAIL("iterate: heat-bath tables not built");
     if (e->cfg.excit_gen == HB200_EXCIT_GEN_POWER_PITZER_ORDERN && !e->have_ppn) FAIL("iterate: power_pitzer_orderN tables not built");
     if (e->cfg.excit_gen == HB200_EXCIT_GEN_POWER_PITZER && !e->have_pp) FAIL("iterate: power_pitzer tables not built");
+    const int np = e->par.nprocs;
+    const bool overlap = np > 1 && e->p2p && (e->comm || e->host_barrier);
+    if (np > 1 && !e->comm && !overlap) FAIL("iterate: nprocs > 1 but hb200_comm_init was not called");
     memset(out, 0, sizeof(*out));
     cudaStream_t st = e->stream;
     float acc[4] = {0, 0, 0, 0};
@@ -2086,33 +2353,79 @@ int hb200_iterate(hb200_engine* e, int32_t ncycles, const hb200_iter_in* in, hb2
     CycleStats cs;
     memset(&cs, 0, sizeof(cs));
     long long nattempts = 0;
+    HostOut* ho = reinterpret_cast<HostOut*>(e->h_out);
     CK(cudaEventRecord(e->ev[5], st));
     for (int c = 0; c < ncycles; ++c) {
         const uint32_t cycle = in->first_cycle + (uint32_t)c;
         // init_mc_cycle (src/qmc_common.F90:950-1017)
-        nattempts = llround(2.0 * ((double)e->nparticles_enc / (double)e->par.real_factor));
-        out->walker_iterations += (double)e->nparticles_enc / (double)e->par.real_factor;
+        const double npart_real = (double)e->nparticles_enc / (double)e->par.real_factor;
+        nattempts = llround(2.0 * npart_real);
+        out->walker_iterations += npart_real;
         CK(cudaEventRecord(e->ev[0], st));
-        if (stage_spawn_death(e, in, cycle, &cs)) return 1;
+        if (stage_spawn_launch(e, in, cycle, overlap)) return 1;
         CK(cudaEventRecord(e->ev[1], st));
-        out->proj_energy += cs.pe;
-        out->D0_population += cs.d0;
-        out->nattempts_spawn += cs.nattempts_spawn;
-        long long ev = 0;
-        for (int d = 0; d < e->par.nprocs; ++d) ev += (long long)e->h_head[d];
-        out->nspawn_events = ev;
-        if (stage_comm(e)) return 1;
+        long long bound;
+        if (np == 1) {
+            // one spawn-list element per successful attempt; attempts per state <= |population| + 1
+            bound = std::min<long long>(e->block_size, (long long)ceil(npart_real) + e->nstates + 1);
+            e->sp_ptr[0] = e->d_spawn[0]; e->sp_ptr[1] = e->d_spawn[1];
+            e->sp_cur = 0; e->sp_blocked = false;
+            e->sp_pn = e->d_head; e->sp_cap = e->block_size;
+        } else if (overlap) {
+            const int par = e->xparity;
+            CK(cudaStreamWaitEvent(st, e->ev_comm, 0));
+            bound = e->cfg.spawned_walker_length;
+            e->sp_ptr[0] = e->d_recv[par]; e->sp_ptr[1] = e->d_spawn[0];
+            e->sp_cur = 0; e->sp_blocked = false;
+            e->sp_pn = e->d_recv_head + par; e->sp_cap = e->cfg.spawned_walker_length;
+        } else {
+            CK(cudaMemcpyAsync(e->h_head.data(), e->d_head, sizeof(unsigned long long) * np, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            for (int d = 0; d < np; ++d)
+                if ((long long)e->h_head[d] > e->block_size) e->h_head[d] = (unsigned long long)e->block_size;
+            if (stage_comm(e)) return 1;
+            bound = e->sp_n;
+        }
         CK(cudaEventRecord(e->ev[2], st));
-        if (stage_sort(e)) return 1;
+        if (stage_sort(e, bound)) return 1;
         CK(cudaEventRecord(e->ev[3], st));
-        if (stage_annihilate_main(e, cycle, &cs)) return 1;
+        if (stage_annihilate_launch(e, cycle, bound)) return 1;
         CK(cudaEventRecord(e->ev[4], st));
-        CK(cudaEventSynchronize(e->ev[4]));
+        // the cycle's results: one pinned block, one synchronisation
+        CK(cudaMemcpyAsync(&ho->st, e->d_stats, sizeof(CycleStats), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&ho->npart_new, e->d_ll, sizeof(long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ho->tot, e->d_total, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ho->err, e->d_err, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ho->head, e->d_head, sizeof(unsigned long long) * np, cudaMemcpyDeviceToHost, st));
+        if (overlap) {
+            // this receive buffer is next written two exchanges from now; peers cannot get there before this rank has
+            // joined the next exchange's collective, which is stream-ordered after this reset
+            CK(cudaMemsetAsync(e->d_recv_head + e->xparity, 0, sizeof(unsigned long long), st));
+            e->xparity ^= 1;
+        }
+        CK(cudaStreamSynchronize(st));
         for (int k = 0; k < 4; ++k) {
             float t = 0;
             cudaEventElapsedTime(&t, e->ev[k], e->ev[k + 1]);
             acc[k] += t;
         }
+        {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, e->evk[0], e->evk[1]);
+            e->spawn_kernel_ms += t;
+        }
+        cs = ho->st;
+        long long ev = 0;
+        for (int d = 0; d < np; ++d) {
+            e->h_head[d] = std::min<unsigned long long>(ho->head[d], (unsigned long long)e->block_size);
+            ev += (long long)e->h_head[d];
+        }
+        out->proj_energy += cs.pe;
+        out->D0_population += cs.d0;
+        out->nattempts_spawn += cs.nattempts_spawn;
+        out->nspawn_events = ev;
+        finish_merge(e, &cs, ho->tot[0], ho->tot[1], ho->npart_new);
+        e->sp_pn = e->d_spn; e->sp_cap = 0;
         // end_mc_cycle / spawning_rate (src/qmc_common.F90:1240-1304)
         const double ndeath_real = (double)cs.ndeath / (double)e->par.real_factor;
         if (nattempts > 0) out->rspawn += ((double)ev + ndeath_real) / (double)nattempts;
@@ -2122,7 +2435,83 @@ int hb200_iterate(hb200_engine* e, int32_t ncycles, const hb200_iter_in* in, hb2
     for (int k = 0; k < 4; ++k) e->ms[k] = acc[k];
     e->ms[4] = tot;
     e->ms[5] = e->spawn_kernel_ms;
-    fill_out(e, out, cs, nattempts);
+    out->nparticles = (double)e->nparticles_enc / (double)e->par.real_factor;
+    out->nstates = e->nstates;
+    out->ndeath = cs.ndeath;
+    out->nattempts = nattempts;
+    out->spawn_error = ho->err[0];
+    out->psip_error = ho->err[1];
+    return 0;
+}
+
+// ---- peer-to-peer exchange set-up -------------------------------------------------------------------------------
+// hb200_p2p_export: allocate this rank's receive block and return its CUDA IPC handle (64 bytes); the host gathers the
+// handles of all ranks (MPI_Allgather / torch.distributed) and passes them to hb200_p2p_import, which maps every
+// peer's block.  One process per GPU, all on one node (NVLink / NVSwitch or PCIe peer access).
+int hb200_p2p_export(hb200_engine* e, uint8_t handle[64]) {
+    CK(cudaSetDevice(e->cfg.device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+    const size_t bufb = (size_t)e->cfg.spawned_walker_length * e->E * 8;
+    const size_t bufa = (bufb + 255) & ~(size_t)255;
+    if (!e->d_p2p_block) {
+        void* q = nullptr;
+        CK(cudaMalloc(&q, 256 + 2 * bufa));
+        e->owned.push_back(q);
+        e->d_p2p_block = (unsigned char*)q;
+        CK(cudaMemset(q, 0, 256));
+        e->d_recv_head = (unsigned long long*)q;
+        e->d_recv[0] = (int64_t*)(e->d_p2p_block + 256);
+        e->d_recv[1] = (int64_t*)(e->d_p2p_block + 256 + bufa);
+    }
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, e->d_p2p_block));
+    memcpy(handle, &h, 64);
+    return 0;
+}
+
+int hb200_set_host_barrier(hb200_engine* e, hb200_barrier_fn fn, void* arg) {
+    e->host_barrier = fn;
+    e->host_barrier_arg = arg;
+    return 0;
+}
+
+int hb200_p2p_import(hb200_engine* e, const uint8_t* handles, int32_t nprocs) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (nprocs != e->par.nprocs) FAIL("p2p_import: nprocs differs from hb200_create");
+    if (!e->d_p2p_block) FAIL("p2p_import: call hb200_p2p_export first");
+    const int np = nprocs, me = e->par.iproc;
+    const size_t bufb = (size_t)e->cfg.spawned_walker_length * e->E * 8;
+    const size_t bufa = (bufb + 255) & ~(size_t)255;
+    e->peer_base.assign(np, nullptr);
+    for (int r = 0; r < np; ++r) {
+        if (r == me) { e->peer_base[r] = e->d_p2p_block; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * 64, 64);
+        void* q = nullptr;
+        CK(cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess));
+        e->peer_base[r] = q;
+    }
+    std::vector<int64_t*> pr((size_t)2 * np);
+    std::vector<unsigned long long*> ph(np);
+    for (int r = 0; r < np; ++r) {
+        unsigned char* b = (unsigned char*)e->peer_base[r];
+        ph[r] = (unsigned long long*)b;
+        pr[r] = (int64_t*)(b + 256);
+        pr[np + r] = (int64_t*)(b + 256 + bufa);
+    }
+    if (dalloc(e, &e->d_peer_recv, (size_t)2 * np)) return 1;
+    if (dalloc(e, &e->d_peer_head, (size_t)np)) return 1;
+    if (dalloc(e, &e->d_snap, (size_t)9 * np)) return 1;
+    if (dalloc(e, &e->d_push, (size_t)3 * np)) return 1;
+    CK(copy_sync(e, e->d_peer_recv, pr.data(), sizeof(int64_t*) * 2 * np, cudaMemcpyHostToDevice));
+    CK(copy_sync(e, e->d_peer_head, ph.data(), sizeof(unsigned long long*) * np, cudaMemcpyHostToDevice));
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&e->comm_stream, cudaStreamNonBlocking, hi));
+    for (int i = 0; i < 8; ++i) CK(cudaEventCreateWithFlags(&e->ev_chunk[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->ev_comm, cudaEventDisableTiming));
+    e->xparity = 0;
+    e->p2p = true;
     return 0;
 }
 
@@ -2135,7 +2524,7 @@ int hb200_sc0_batch(hb200_engine* e, const uint64_t* states, int64_t n, double* 
     CK(cudaMalloc((void**)&d_f, (size_t)n * e->W * 8));
     CK(cudaMalloc((void**)&d_o, (size_t)n * 8));
     CK(copy_sync(e, d_f, states, (size_t)n * e->W * 8, cudaMemcpyHostToDevice));
-    DISPATCH_W(e, k_sc0<WW><<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->sys, 0.0, d_f, e->W, n, d_o));
+    DISPATCH_W(e, k_sc0<WW><<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->sys, 0.0, d_f, e->W, n, d_o, nullptr));
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e->stream));
     CK(copy_sync(e, out, d_o, (size_t)n * 8, cudaMemcpyDeviceToHost));

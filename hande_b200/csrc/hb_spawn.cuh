@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(TILE, (GEN == EXCIT_GEN_HEAT_BATH || GEN == EX
 k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __restrict__ pops,
               const double* __restrict__ dat, long long nstates, int64_t* __restrict__ spawn,
               unsigned long long* __restrict__ head, long long block_size, const int* __restrict__ proc_map,
-              SpawnPartials* __restrict__ partials, int* __restrict__ err) {
+              SpawnPartials* __restrict__ partials, int* __restrict__ err, int tile0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nel = s.nel;
     constexpr bool heat_bath = (GEN == EXCIT_GEN_HEAT_BATH);
@@ -110,7 +110,7 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const long long idx = (long long)blockIdx.x * TILE + tid;
+    const long long idx = ((long long)blockIdx.x + tile0) * TILE + tid;
     const int E = W + 2;
 
     double pe = 0.0, d0 = 0.0;
@@ -368,7 +368,7 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
                 out.excit_gen_singles += reinterpret_cast<long long*>(sred)[16 + w];
                 out.excit_gen_doubles += reinterpret_cast<long long*>(sred)[24 + w];
             }
-            p.ps_part[blockIdx.x] = out;
+            p.ps_part[tile0 + blockIdx.x] = out;
         }
     }
     // deterministic block reduction of the estimators
@@ -390,6 +390,6 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
             out.npart += reinterpret_cast<long long*>(sred)[24 + w];
         }
         out.nattempts = T;
-        partials[blockIdx.x] = out;
+        partials[tile0 + blockIdx.x] = out;
     }
 }

@@ -33,9 +33,9 @@ static int launch_spawn(hb200_engine* e, const Params& p, const SpawnLaunch& L) 
     const int c = e->cur;
     k_spawn_death<W, GEN><<<L.ntiles, TILE, smem, e->stream>>>(e->sys, p, e->d_states[c], e->d_pops[c], e->d_dat[c], L.n,
                                                                 e->d_spawn[0], e->d_head, e->block_size, e->d_proc_map,
-                                                                e->d_partials, e->d_err);
+                                                                e->d_partials, e->d_err, L.tile0);
     CK(cudaGetLastError());
-    e->npartials = L.ntiles;
+    e->npartials = L.tile0 + L.ntiles;
     return 0;
 }
 

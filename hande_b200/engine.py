@@ -154,6 +154,9 @@ def load_library():
                                         C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
     L.hb200_get_unique_id.argtypes = [C.c_void_p]
     L.hb200_comm_init.argtypes = [C.c_void_p, C.c_void_p]
+    L.hb200_p2p_export.argtypes = [C.c_void_p, C.c_void_p]
+    L.hb200_p2p_import.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    L.hb200_set_host_barrier.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.hb200_last_timing.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     _LIB = L
     return L
@@ -167,6 +170,7 @@ ABI_SYMBOLS = [
     "hb200_download_psips", "hb200_nstates", "hb200_iterate", "hb200_spawn_death", "hb200_comm_spawn",
     "hb200_ccmc_spawn", "hb200_ccmc_iterate", "hb200_ccmc_set_hash_shift", "hb200_ccmc_set_full_nc", "hb200_set_pattempt", "hb200_get_ps_stats", "hb200_set_pattempt_parallel", "hb200_get_pattempt_parallel", "hb200_build_power_pitzer_orderN", "hb200_build_power_pitzer", "hb200_set_quasi_newton", "hb200_annihilate_spawn", "hb200_annihilate_main", "hb200_download_spawn", "hb200_upload_spawn", "hb200_spawn_counts",
     "hb200_sc0_batch", "hb200_gen_excit_batch", "hb200_get_unique_id", "hb200_comm_init", "hb200_last_timing",
+    "hb200_p2p_export", "hb200_p2p_import", "hb200_set_host_barrier",
 ]
 
 
@@ -418,6 +422,29 @@ class Engine:
     def comm_init(self, uid):
         uid = np.ascontiguousarray(uid, dtype=np.uint8)
         self._chk(self.L.hb200_comm_init(self.h, _p(uid)))
+
+    def comm_setup(self, comm, p2p=None, nccl=True):
+        """Everything a multi-rank engine needs before hb200_iterate: the NCCL communicator (unique id broadcast from
+        rank 0) and, unless disabled (p2p=False or HB200_NO_P2P=1), the peer-to-peer receive buffers (CUDA IPC
+        handles all-gathered through `comm`).  `comm` offers broadcast_bytes / allgather_bytes (TorchDist).
+        nccl=False: no NCCL communicator; exchanges end with the host's barrier (`comm.barrier`) - the way a plain-MPI
+        host, or several ranks sharing one GPU, run the peer-to-peer exchange."""
+        if nccl:
+            uid = self.get_unique_id() if comm.rank == 0 else np.zeros(128, dtype=np.uint8)
+            self.comm_init(comm.broadcast_bytes(uid, src=0))
+        else:
+            self._barrier_cb = C.CFUNCTYPE(None, C.c_void_p)(lambda _arg: comm.barrier())   # kept alive with the engine
+            self._chk(self.L.hb200_set_host_barrier(self.h, C.cast(self._barrier_cb, C.c_void_p), None))
+            p2p = True
+        if p2p is None:
+            p2p = os.environ.get("HB200_NO_P2P", "0") in ("", "0")
+        self.p2p = False
+        if p2p:
+            h = np.zeros(64, dtype=np.uint8)
+            self._chk(self.L.hb200_p2p_export(self.h, _p(h)))
+            allh = np.ascontiguousarray(comm.allgather_bytes(h), dtype=np.uint8)
+            self._chk(self.L.hb200_p2p_import(self.h, _p(allh), comm.size))
+            self.p2p = True
 
     def last_timing(self):
         ms = np.zeros(8)

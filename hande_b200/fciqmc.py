@@ -192,6 +192,12 @@ class _SingleProcess:
     def broadcast_bytes(self, arr, src=0):
         return arr
 
+    def allgather_bytes(self, arr):
+        return np.asarray(arr, dtype=np.uint8).reshape(1, -1)
+
+    def barrier(self):
+        pass
+
 
 class TorchDist:
     """Collective layer over torch.distributed (gloo on CPU tests, nccl on GPUs) - replaces MPI_Allreduce of rep_loop."""
@@ -211,6 +217,16 @@ class TorchDist:
         t = self.torch.tensor(np.asarray(arr, dtype=np.uint8), device=self.device)
         self.dist.broadcast(t, src=src)
         return t.cpu().numpy()
+
+    def barrier(self):
+        self.dist.barrier()
+
+    def allgather_bytes(self, arr):
+        """MPI_Allgather of a fixed-size byte record -> [size][len(arr)]"""
+        t = self.torch.tensor(np.asarray(arr, dtype=np.uint8), device=self.device)
+        out = [self.torch.empty_like(t) for _ in range(self.size)]
+        self.dist.all_gather(out, t)
+        return np.stack([x.cpu().numpy() for x in out])
 
 
 HEADER = (" #     iterations   Shift                 \\sum H_0j N_j         N_0                   # H psips"
@@ -271,9 +287,7 @@ def do_fciqmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, 
     if qmc.quasi_newton:
         eng.set_quasi_newton(*init_propagator(sys, occ0, qmc))
     if nprocs > 1:
-        uid = eng.get_unique_id() if iproc == 0 else np.zeros(128, dtype=np.uint8)
-        uid = comm.broadcast_bytes(uid, src=0)
-        eng.comm_init(uid)
+        eng.comm_setup(comm)
     real_factor = (1 << 31) if qmc.real_amplitudes else 1
     # initial_distribution (src/qmc.F90:1507-1646)
     if psips is None:

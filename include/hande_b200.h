@@ -243,6 +243,23 @@ int hb200_gen_excit_batch(hb200_engine* e, const uint64_t* states, const int64_t
 int hb200_get_unique_id(uint8_t id[128]);
 int hb200_comm_init(hb200_engine* e, const uint8_t id[128]);
 
+/* Peer-to-peer exchange of the spawn blocks inside hb200_iterate (all ranks on one node, one process per GPU).
+ * Replaces comm_spawn_t's MPI_Alltoall + MPI_Alltoallv (src/spawn_data.F90:624-739) by stores into the owner rank's
+ * receive buffer over NVLink that overlap the spawning step (the north-star's "exchange overlaps the next spawning
+ * chunk"): the spawning kernel runs in chunks of tiles, and while chunk c+1 spawns, chunk c's part of every
+ * per-destination block is pushed - one system-scope atomic on the destination's head counter reserves the room, a
+ * copy kernel writes the elements through the peer mapping.  hb200_p2p_export allocates this rank's receive block and
+ * returns its 64-byte CUDA IPC handle; the host all-gathers the handles (MPI_Allgather in the Fortran host) and every
+ * rank calls hb200_p2p_import(handles[nprocs][64]).  Call after hb200_comm_init (the NCCL communicator is still used
+ * for the collective that ends an exchange).  Without these calls hb200_iterate uses the NCCL send/recv path. */
+int hb200_p2p_export(hb200_engine* e, uint8_t handle[64]);
+int hb200_p2p_import(hb200_engine* e, const uint8_t* handles, int32_t nprocs);
+/* A host without NCCL (plain MPI; or several ranks sharing one GPU, which NCCL refuses) ends an exchange with its own
+ * barrier instead: fn(arg) must return once every rank has called it (MPI_Barrier).  With a host barrier set,
+ * hb200_comm_init is not needed for hb200_iterate. */
+typedef void (*hb200_barrier_fn)(void* arg);
+int hb200_set_host_barrier(hb200_engine* e, hb200_barrier_fn fn, void* arg);
+
 /* Timing of the stages of the last hb200_iterate call, milliseconds (CUDA events on the engine stream):
  * ms[0] spawn+death kernel, ms[1] exchange, ms[2] sort+annihilate_spawn, ms[3] main-list annihilation+merge,
  * ms[4] total, ms[5] the k_spawn_death kernel alone.  Counters: cnt[0] = spawn kernel launches, cnt[1] = all kernel launches. */

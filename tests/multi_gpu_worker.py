@@ -46,8 +46,7 @@ def main_ccmc():
     eng.set_reference(ref["f0"], ref["H00"])
     o.ccmc_set_full_nc(full_nc)
     eng.ccmc_set_full_nc(full_nc)
-    uid = eng.get_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)
-    eng.comm_init(comm.broadcast_bytes(uid, src=0))
+    eng.comm_setup(comm, p2p=False)
     # warm-up on the oracle (all ranks emulated) to get a spread-out excip list, then hand each GPU its rank's share
     pe_old = 0.0
     warm = 40
@@ -90,10 +89,20 @@ def main():
     name, gen, real, init, tau = sys.argv[1], sys.argv[2], bool(int(sys.argv[3])), bool(int(sys.argv[4])), float(sys.argv[5])
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
+    # HB200_TEST_ONE_DEVICE=1: every rank on cuda:0 (NCCL refuses that): gloo for the host collectives, the spawn
+    # exchange goes peer-to-peer through CUDA IPC and ends with the host's barrier
+    one_device = os.environ.get("HB200_TEST_ONE_DEVICE", "0") == "1"
+    if one_device:
+        local = 0
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
-    comm = TorchDist(device=dev)
+    if one_device:
+        dist.init_process_group("gloo")
+        comm = TorchDist(device=None)
+    else:
+        dist.init_process_group("nccl", device_id=dev)
+        comm = TorchDist(device=dev)
+    nwalkers = int(os.environ.get("HB200_TEST_WALKERS", "4000"))
     path, kw = system_path(name) if rank == 0 else (None, None)
     dist.barrier()
     path, kw = system_path(name)
@@ -110,13 +119,13 @@ def main():
                  spawned_walker_length=1 << 16, seed=11, nprocs=world, iproc=rank, device=local,
                  pattempt_parallel=(o.pattempt_parallel() if gen.endswith("_spin") else -1.0))
     eng.set_reference(ref["f0"], ref["H00"])
-    uid = eng.get_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)
-    eng.comm_init(comm.broadcast_bytes(uid, src=0))
+    eng.comm_setup(comm, nccl=not one_device)
+    assert eng.p2p or os.environ.get("HB200_NO_P2P", "0") == "1"
     ps_on = gen != "heat_bath"
     if ps_on:
         o.set_pattempt_update(True)
         eng.set_pattempt(ref["pattempt_single"], ref["pattempt_double"], True)
-    f, pops, dat = random_population(s, o, 4000, real, seed=5)
+    f, pops, dat = random_population(s, o, nwalkers, real, seed=5)
     own = np.array([owner_of(x, s.nbasis, world, 1) for x in f])
     for r in range(world):
         m = own == r

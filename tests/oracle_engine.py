@@ -58,6 +58,12 @@ def make_engine_cls(fcidump_path, sys_kw, rng_kind=0, ueg=None, ref_det=None, qu
         def comm_init(self, uid):
             assert (np.asarray(uid) == np.arange(128)).all()           # broadcast reached every rank
 
+        def comm_setup(self, comm, p2p=None):
+            uid = self.get_unique_id() if comm.rank == 0 else np.zeros(128, dtype=np.uint8)
+            self.comm_init(comm.broadcast_bytes(uid, src=0))
+            h = comm.allgather_bytes(np.full(64, comm.rank, dtype=np.uint8))     # the IPC-handle all-gather
+            assert h.shape == (comm.size, 64) and all((h[r] == r).all() for r in range(comm.size))
+
         def upload_psips(self, states, pops, dat):
             self.o.set_psips(np.asarray(states).reshape(-1, self.o.W), pops, dat, rank=self.rank)
             self._nparticles = float(np.abs(np.asarray(pops, dtype=np.int64)).sum()) / self.real_factor

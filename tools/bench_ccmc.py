@@ -75,8 +75,7 @@ def main():
                  nprocs=world, iproc=rank, device=local_rank)
     eng.set_reference(f0, H00)
     if world > 1:
-        uid = eng.get_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)
-        eng.comm_init(comm.broadcast_bytes(uid, src=0))
+        eng.comm_setup(comm, p2p=False)
     dat = np.zeros(len(f))
     CH = 5_000_000
     for a in range(0, len(f), CH):

@@ -177,6 +177,7 @@ struct hb200_engine {
     unsigned long long* d_spn = nullptr;       // [1] element count written by the host for the staged calls
     const unsigned long long* sp_pn = nullptr; // where the sort / annihilation kernels read the element count
     long long sp_cap = 0;                      // ... and the bound they clamp it to
+    long long last_spn = 1 << 20;              // spawn-list length of the previous cycle (sizes the sort's grid)
     long long* d_long_q = nullptr;             // k_annihilate: heads of the long runs of equal keys
     unsigned* d_long_n = nullptr;
     // pinned host block the cycle's results are copied into (one synchronisation per cycle)

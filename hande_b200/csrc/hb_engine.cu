@@ -657,6 +657,20 @@ k_merge(const uint64_t* __restrict__ states, const int64_t* __restrict__ pops, c
     }
 }
 
+// initialise_slot_pop (src/load_balancing.F90:624-654): encoded |population| per load-balancing slot
+// (slot = modulo(hash(f), nprocs * nslots)); integer atomics, so the sums are exact and order-independent
+template <int W>
+__global__ void __launch_bounds__(256)
+k_slot_pop(const uint64_t* __restrict__ states, const int64_t* __restrict__ pops, long long n, int nbasis, uint32_t seed,
+           int nprocs, int nslots, unsigned long long* __restrict__ slot_pop) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t f[W];
+    load_det<W>(states + i * W, f);
+    const long long pp = pops[i];
+    if (pp != 0) atomicAdd(&slot_pop[owner_slot(f, nbasis, seed, nprocs, nslots)], (unsigned long long)(pp < 0 ? -pp : pp));
+}
+
 // sum |pop| over a list: per-block partials (fixed order) -> k_reduce_ll
 __global__ void __launch_bounds__(TILE) k_abs_sum(const int64_t* __restrict__ pops, long long n, long long* __restrict__ part) {
     __shared__ long long sl[TILE / 32];
@@ -2274,6 +2288,66 @@ int hb200_comm_spawn(hb200_engine* e) {
     return stage_comm(e);
 }
 
+// initialise_slot_pop (src/load_balancing.F90:624-654): this rank's population in each of the nprocs * nslots
+// load-balancing slots; the host sums the ranks (MPI_AllReduce) and runs the policy (do_load_balancing).
+int hb200_slot_populations(hb200_engine* e, double* slot_pop, int32_t n) {
+    CK(cudaSetDevice(e->cfg.device));
+    const int ns = e->par.nprocs * e->par.nslots;
+    if (n != ns) FAIL("slot_populations: wrong length");
+    unsigned long long* d = nullptr;
+    CK(cudaMalloc((void**)&d, sizeof(unsigned long long) * ns));
+    CK(cudaMemsetAsync(d, 0, sizeof(unsigned long long) * ns, e->stream));
+    const long long m = e->nstates;
+    if (m > 0) {
+        DISPATCH_W(e, k_slot_pop<WW><<<(unsigned)((m + 255) / 256), 256, 0, e->stream>>>(e->d_states[e->cur], e->d_pops[e->cur], m,
+                                                                                       e->sys.nbasis, e->par.hash_seed,
+                                                                                       e->par.nprocs, e->par.nslots, d));
+        CK(cudaGetLastError());
+    }
+    std::vector<unsigned long long> h(ns);
+    CK(copy_sync(e, h.data(), d, sizeof(unsigned long long) * ns, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    for (int k = 0; k < ns; ++k) slot_pop[k] = (double)h[k] / (double)e->par.real_factor;
+    return 0;
+}
+
+// redistribute_particles (src/qmc_common.F90:505-595) after the host changed proc_map (hb200_set_proc_map): every
+// determinant whose owner is now another rank goes, with its whole population and flag 0, into that rank's block of
+// the spawn list and is zeroed here.  Leaves the engine where hb200_spawn_death leaves it: the host continues with
+// hb200_comm_spawn / hb200_annihilate_spawn / hb200_annihilate_main (direct_annihilation in
+// redistribute_load_balancing_dets, src/qmc_common.F90:1332-1390).  nsent: population that left (real units).
+int hb200_redistribute_particles(hb200_engine* e, double* nsent) {
+    CK(cudaSetDevice(e->cfg.device));
+    Params p = e->par;
+    p.ccmc_shift = 0; p.ccmc_freq = 0;
+    cudaStream_t st = e->stream;
+    CK(cudaMemsetAsync(e->d_head, 0, sizeof(unsigned long long) * p.nprocs, st));
+    const long long before = e->nparticles_enc;
+    long long after = before;
+    if (e->nstates > 0 && p.nprocs > 1) {
+        { int rc = 0; DISPATCH_CCMC(e, rc, hb_ccmc_redistribute_w, e, p); if (rc) return 1; }
+        const int c = e->cur;
+        const int nb = (int)std::min<long long>(1184, (e->nstates + TILE - 1) / TILE);
+        k_abs_sum<<<nb, TILE, 0, st>>>(e->d_pops[c], e->nstates, e->d_part_ll);
+        k_reduce_ll<<<1, 1024, 0, st>>>(e->d_part_ll, nb, e->d_ll);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&after, e->d_ll, sizeof(long long), cudaMemcpyDeviceToHost, st));
+        e->launches += 3;
+    }
+    CK(cudaMemcpyAsync(e->h_head.data(), e->d_head, sizeof(unsigned long long) * p.nprocs, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int d = 0; d < p.nprocs; ++d)
+        if ((long long)e->h_head[d] > e->block_size) e->h_head[d] = (unsigned long long)e->block_size;
+    e->nparticles_enc = after;
+    if (nsent) *nsent = (double)(before - after) / (double)p.real_factor;
+    e->sp_ptr[0] = e->d_spawn[0]; e->sp_ptr[1] = e->d_spawn[1];
+    e->sp_cur = 0;
+    e->sp_blocked = p.nprocs > 1;
+    e->sp_n = 0;
+    if (p.nprocs == 1 && set_count_host(e, 0)) return 1;
+    return 0;
+}
+
 int hb200_annihilate_spawn(hb200_engine* e) {
     CK(cudaSetDevice(e->cfg.device));
     if (e->sp_blocked) FAIL("annihilate_spawn: call hb200_comm_spawn first");
@@ -2387,7 +2461,9 @@ int hb200_iterate(hb200_engine* e, int32_t ncycles, const hb200_iter_in* in, hb2
             bound = e->sp_n;
         }
         CK(cudaEventRecord(e->ev[2], st));
-        if (stage_sort(e, bound)) return 1;
+        // the sort kernels split the list by its real length whatever their grid is, so the grid follows the length of
+        // the previous cycle's list (a hint) rather than the loose upper bound
+        if (stage_sort(e, std::min(bound, std::max<long long>(4096, 2 * e->last_spn + 1024)))) return 1;
         CK(cudaEventRecord(e->ev[3], st));
         if (stage_annihilate_launch(e, cycle, bound)) return 1;
         CK(cudaEventRecord(e->ev[4], st));
@@ -2397,6 +2473,7 @@ int hb200_iterate(hb200_engine* e, int32_t ncycles, const hb200_iter_in* in, hb2
         CK(cudaMemcpyAsync(ho->tot, e->d_total, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(ho->err, e->d_err, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(ho->head, e->d_head, sizeof(unsigned long long) * np, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&ho->spn, e->sp_pn, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         if (overlap) {
             // this receive buffer is next written two exchanges from now; peers cannot get there before this rank has
             // joined the next exchange's collective, which is stream-ordered after this reset
@@ -2425,6 +2502,7 @@ int hb200_iterate(hb200_engine* e, int32_t ncycles, const hb200_iter_in* in, hb2
         out->nattempts_spawn += cs.nattempts_spawn;
         out->nspawn_events = ev;
         finish_merge(e, &cs, ho->tot[0], ho->tot[1], ho->npart_new);
+        e->last_spn = (long long)std::min<unsigned long long>(ho->spn, (unsigned long long)e->sp_cap);
         e->sp_pn = e->d_spn; e->sp_cap = 0;
         // end_mc_cycle / spawning_rate (src/qmc_common.F90:1240-1304)
         const double ndeath_real = (double)cs.ndeath / (double)e->par.real_factor;

@@ -155,6 +155,8 @@ def load_library():
     L.hb200_get_unique_id.argtypes = [C.c_void_p]
     L.hb200_comm_init.argtypes = [C.c_void_p, C.c_void_p]
     L.hb200_p2p_export.argtypes = [C.c_void_p, C.c_void_p]
+    L.hb200_slot_populations.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    L.hb200_redistribute_particles.argtypes = [C.c_void_p, C.c_void_p]
     L.hb200_p2p_import.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
     L.hb200_set_host_barrier.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.hb200_last_timing.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -170,7 +172,8 @@ ABI_SYMBOLS = [
     "hb200_download_psips", "hb200_nstates", "hb200_iterate", "hb200_spawn_death", "hb200_comm_spawn",
     "hb200_ccmc_spawn", "hb200_ccmc_iterate", "hb200_ccmc_set_hash_shift", "hb200_ccmc_set_full_nc", "hb200_set_pattempt", "hb200_get_ps_stats", "hb200_set_pattempt_parallel", "hb200_get_pattempt_parallel", "hb200_build_power_pitzer_orderN", "hb200_build_power_pitzer", "hb200_set_quasi_newton", "hb200_annihilate_spawn", "hb200_annihilate_main", "hb200_download_spawn", "hb200_upload_spawn", "hb200_spawn_counts",
     "hb200_sc0_batch", "hb200_gen_excit_batch", "hb200_get_unique_id", "hb200_comm_init", "hb200_last_timing",
-    "hb200_p2p_export", "hb200_p2p_import", "hb200_set_host_barrier",
+    "hb200_p2p_export", "hb200_p2p_import", "hb200_set_host_barrier", "hb200_slot_populations",
+    "hb200_redistribute_particles",
 ]
 
 
@@ -195,6 +198,7 @@ class Engine:
         self.W = sys.W
         self.E = sys.W + 2
         self.real_factor = (1 << 31) if real_amplitudes else 1
+        self.nprocs, self.iproc, self.nslots = nprocs, iproc, nslots
         eg = EXCIT_GEN[excit_gen] if isinstance(excit_gen, str) else int(excit_gen)
         self.cfg = Config(device=device, nbasis=sys.nbasis, nel=sys.nel, excit_gen=eg,
                           pattempt_single=pattempt_single, pattempt_double=pattempt_double,
@@ -357,6 +361,25 @@ class Engine:
 
     def ccmc_set_hash_shift(self, hash_shift, move_freq=5):
         self._chk(self.L.hb200_ccmc_set_hash_shift(self.h, int(hash_shift), int(move_freq)))
+
+    def slot_populations(self):
+        out = np.zeros(self.nprocs * self.nslots)
+        self._chk(self.L.hb200_slot_populations(self.h, _p(out), len(out)))
+        return out
+
+    def redistribute_particles(self):
+        """redistribute_particles after set_proc_map; continue with comm_spawn / annihilate_spawn / annihilate_main
+        (or redistribute() for all four).  Returns the population that left this rank."""
+        ns = C.c_double(0.0)
+        self._chk(self.L.hb200_redistribute_particles(self.h, C.byref(ns)))
+        return ns.value
+
+    def redistribute(self, cycle):
+        """redistribute_load_balancing_dets (src/qmc_common.F90:1332-1390) through the NCCL exchange."""
+        self.redistribute_particles()
+        self.comm_spawn()
+        self.annihilate_spawn()
+        return self.annihilate_main(cycle)
 
     def comm_spawn(self):
         self._chk(self.L.hb200_comm_spawn(self.h))

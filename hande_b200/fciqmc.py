@@ -18,6 +18,7 @@ import numpy as np
 
 from . import read_in as _ri
 from .engine import Engine
+from . import load_balancing as _lb
 
 HUGE = _ri.HUGE
 
@@ -52,6 +53,11 @@ class QmcIn:
     spawned_state_size: int = -1
     ex_level: int = -1              # reference = {ex_level = ...}: truncation level, -1 = none
     nslots: int = 1
+    # load_bal_in_t (src/qmc_data.f90:491-512) and fciqmc_in%doing_load_balancing; nslots above = load_balancing_slots
+    load_balancing: bool = False
+    load_balancing_pop: float = 1000.0
+    percent_imbal: float = 0.05
+    max_load_attempts: int = 2
     full_non_composite: bool = False  # ccmc = {full_non_composite = true} (CCMC only)
     reference_det: list = None      # reference = {det = {...}}: explicit reference determinant (1-based orbitals)
 
@@ -157,13 +163,16 @@ def murmurhash2(data: bytes, seed: int) -> int:
     return h
 
 
-def owner_of(f, nbasis, nprocs, nslots, proc_map=None, seed=7):
-    """assign_particle_processor (src/spawning.F90:770-838), shift == 0."""
+def owner_of(f, nbasis, nprocs, nslots, proc_map=None, seed=7, slot=False):
+    """assign_particle_processor (src/spawning.F90:770-838), shift == 0.  slot=True: the load-balancing slot instead."""
     nbytes = ((nbasis + 31) // 32) * 4
     h = murmurhash2(np.ascontiguousarray(f, dtype=np.uint64).tobytes()[:nbytes], seed)
     if h >= 2**31:
         h -= 2**32
-    slot = h % (nprocs * nslots)          # Python % == Fortran modulo for positive divisor
+    islot = h % (nprocs * nslots)         # Python % == Fortran modulo for positive divisor
+    if slot:
+        return islot
+    slot = islot
     return (slot % nprocs) if proc_map is None else int(proc_map[slot])
 
 
@@ -251,6 +260,7 @@ class FciqmcResult:
     error: bool = False
     timings: list = field(default_factory=list)
     pattempt_log: list = field(default_factory=list)   # pattempt_single after each pattempt_update change
+    load_balancing_log: list = field(default_factory=list)   # (first cycle, proc_map) of every load-balancing step
 
 
 def do_fciqmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, keep_engine=False, psips=None):
@@ -316,11 +326,26 @@ def do_fciqmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, 
         out.write(HEADER + "\n")
         out.write(format_row(0, shift, proj_energy, D0, ntot_old, tot_nstates, 0, 0.0, 0.0, comment=True) + "\n")
     mc_cycles_done = 0
+    lb_needed, lb_attempts = False, 0
+    proc_map = [i % nprocs for i in range(nprocs * qmc.nslots)]      # src/load_balancing.F90:170
     for ireport in range(1, qmc.nreports + 1):
         t0 = time.time()
         # get_sanitized_projected_energy (src/energy_evaluation.F90:1433-1456)
         pe_old = 0.0 if abs(D0) < np.finfo(np.float64).tiny else proj_energy / D0
         first_cycle = mc_cycles_done + (ireport - 1) * qmc.mc_cycles + 1
+        if lb_needed:
+            # load_balancing_wrapper at the first cycle after the report loop that found the imbalance
+            # (src/qmc_common.F90:1019-1078): do_load_balancing on the all-reduced slot populations, then
+            # redistribute_load_balancing_dets
+            slot_list = comm.allreduce_sum(eng.slot_populations())
+            needed, new_map, _ = _lb.do_load_balancing(slot_list, proc_map, nprocs, qmc.percent_imbal)
+            if needed:
+                proc_map = new_map
+                lb_attempts += 1
+                eng.set_proc_map(proc_map)
+                eng.redistribute(0x80000000 | first_cycle)
+                res.load_balancing_log.append((first_cycle, list(proc_map)))
+            lb_needed = False
         o = eng.iterate(qmc.mc_cycles, qmc.tau, shift, pe_old, first_cycle)
         res.timings.append(eng.last_timing())
         # local_energy_estimators + MPI_Allreduce + communicated_energy_estimators
@@ -334,6 +359,10 @@ def do_fciqmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, 
         ntot = float(tot[3])
         tot_nstates, tot_nev = int(round(tot[4])), int(round(tot[5]))
         error = tot[6] > 0
+        if qmc.load_balancing and nprocs > 1 and ntot > qmc.load_balancing_pop and lb_attempts < qmc.max_load_attempts:
+            # communicated_energy_estimators (src/energy_evaluation.F90:555-563): check_imbalance on the per-rank populations
+            per_rank = comm.allreduce_sum(np.eye(nprocs)[iproc] * o["nparticles"])
+            lb_needed = _lb.check_imbalance(per_rank, float(per_rank.sum()) / nprocs, qmc.percent_imbal)
         if vary_shift:
             # update_shift (src/energy_evaluation.F90:659-711)
             shift = shift - math.log(ntot / ntot_old) * qmc.shift_damping / (1.0 * qmc.tau * qmc.mc_cycles) \

@@ -55,6 +55,33 @@ def synthetic_fcidump(norb, nelec, ms2=0, seed=SEED, path=None):
     return text
 
 
+def synthetic_fcidump_uhf(norb, nelec, ms2=0, seed=SEED, path=None):
+    """UHF variant (UHF=.TRUE.: NORB = 2*norb spin-orbitals, odd = alpha, even = beta; src/read_in.F90:300-420): the
+    spatial integrals of `synthetic_integrals` scaled differently per spin channel - (aa|aa) x 1, (bb|bb) x 0.9,
+    (aa|bb) = (bb|aa) x 0.95; h_beta = 0.97 h_alpha off the diagonal, eps_beta = eps_alpha + 0.013 - so that the four
+    two-body channels and the spin-dependent one-body terms of the UHF code paths all differ."""
+    eps, h, (P, Q, R, S, val) = synthetic_integrals(norb, seed)
+    out = io.StringIO()
+    out.write(f" &FCI NORB={2 * norb},NELEC={nelec},MS2={ms2},\n  ORBSYM=" + ",".join(["1"] * (2 * norb)) +
+              ",\n  ISYM=1 UHF=.TRUE.\n &END\n")
+    so = lambda p, spin: 2 * p - 1 + spin          # spatial p (1-based), spin 0 = alpha / 1 = beta
+    for s1, s2, c in ((0, 0, 1.0), (1, 1, 0.9), (0, 1, 0.95), (1, 0, 0.95)):
+        np.savetxt(out, np.column_stack([c * val, so(P, s1), so(Q, s1), so(R, s2), so(S, s2)]), fmt="%23.16e %3d %3d %3d %3d")
+    pp, qq = np.tril_indices(norb)
+    for spin, c, de in ((0, 1.0, 0.0), (1, 0.97, 0.013)):
+        hv = np.where(pp == qq, h[pp, qq] + de, c * h[pp, qq])
+        np.savetxt(out, np.column_stack([hv, so(pp + 1, spin), so(qq + 1, spin), 0 * pp, 0 * pp]), fmt="%23.16e %3d %3d %3d %3d")
+    for spin, de in ((0, 0.0), (1, 0.013)):
+        np.savetxt(out, np.column_stack([eps + de, so(np.arange(1, norb + 1), spin), 0 * eps, 0 * eps, 0 * eps]),
+                   fmt="%23.16e %3d %3d %3d %3d")
+    out.write("%23.16e %3d %3d %3d %3d\n" % (0.0, 0, 0, 0, 0))
+    text = out.getvalue()
+    if path is not None:
+        with open(path, "w") as f:
+            f.write(text)
+    return text
+
+
 def random_dets(n, nbasis, nalpha, nbeta, seed=1):
     """n distinct random determinants (alpha = odd orbitals, beta = even), sorted ascending in the reference order
     (unsigned compare, last word most significant).  Returns uint64 array (n, W)."""

@@ -142,6 +142,15 @@ int hb200_download_heat_bath(hb200_engine* e, int which, void* out, int64_t n);
 int hb200_set_reference(hb200_engine* e, const uint64_t* f0, double H00);
 /* proc_map%map(0:nprocs*nslots-1) (src/spawn_data.F90:13-24, src/load_balancing.F90:141-172). */
 int hb200_set_proc_map(hb200_engine* e, const int32_t* map, int32_t n);
+/* Load balancing (src/load_balancing.F90:209-323, src/qmc_common.F90:1019-1078, 1332-1390).  The policy stays on the
+ * host; the engine supplies what it needs from the resident list and moves the determinants:
+ *   hb200_slot_populations      initialise_slot_pop: this rank's population in each of the nprocs*nslots slots
+ *   (host)                      MPI_AllReduce of the slots, check_imbalance / find_processors / redistribute_slots
+ *   hb200_set_proc_map          the modified proc_map%map
+ *   hb200_redistribute_particles  redistribute_particles: determinants now owned elsewhere -> spawn blocks
+ *   hb200_comm_spawn + hb200_annihilate_spawn + hb200_annihilate_main   direct_annihilation of the moved list */
+int hb200_slot_populations(hb200_engine* e, double* slot_pop, int32_t n);
+int hb200_redistribute_particles(hb200_engine* e, double* nsent);
 
 /* particle_t upload/download: states(W,N), pops(1,N), dat(1,N), sorted ascending
  * (src/qmc_data.f90:615-682); used at init, restart read/write (src/restart_hdf5.F90:307,539). */

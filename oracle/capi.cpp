@@ -456,6 +456,37 @@ void orc_get_spawn(void* h, int rank, int64_t* sdata) {
             ++k;
         }
 }
+// load balancing: slot populations of one rank, the policy on the summed slots, the proc_map, the redistribution
+int orc_slot_pop(void* h, int rank, double* out) {
+    ORC_TRY
+    Oracle* o = (Oracle*)h;
+    std::vector<double> sp = o->slot_pop(o->ranks[rank]);
+    for (size_t k = 0; k < sp.size(); ++k) out[k] = sp[k];
+    return (int)sp.size();
+    ORC_CATCH(-1)
+}
+int orc_do_load_balancing(void* h, double percent) {
+    ORC_TRY
+    return ((Oracle*)h)->do_load_balancing(percent) ? 1 : 0;
+    ORC_CATCH(-1)
+}
+int orc_get_proc_map(void* h, int* out) {
+    Oracle* o = (Oracle*)h;
+    for (size_t k = 0; k < o->proc_map.size(); ++k) out[k] = o->proc_map[k];
+    return (int)o->proc_map.size();
+}
+int orc_set_proc_map(void* h, const int* map, int n) {
+    Oracle* o = (Oracle*)h;
+    if ((size_t)n != o->proc_map.size()) return -1;
+    for (int k = 0; k < n; ++k) o->proc_map[k] = map[k];
+    return 0;
+}
+int orc_redistribute(void* h, uint32_t cycle_id) {
+    ORC_TRY
+    ((Oracle*)h)->redistribute_fciqmc(cycle_id);
+    return 0;
+    ORC_CATCH(-1)
+}
 // finish the cycle started by orc_stage_spawn: comm + annihilation on every rank
 int orc_stage_annihilate(void* h) {
     ORC_TRY

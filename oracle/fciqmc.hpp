@@ -750,6 +750,108 @@ struct Oracle {
         }
     }
 
+    // ---------------------------------------------------------------- load balancing
+    // initialise_slot_pop (src/load_balancing.F90:624-654): population of rank r in every slot
+    std::vector<double> slot_pop(const RankState& r) const {
+        std::vector<double> sp(proc_map.size(), 0.0);
+        for (int64_t i = 0; i < r.nstates; ++i) {
+            int det_pos = 0;
+            assign_particle_processor(r.states[i], sys.nbasis, hash_seed, 0, 0, in.nprocs, proc_map.data(), in.nslots, &det_pos);
+            sp[(size_t)det_pos] = sp[(size_t)det_pos] + std::fabs((double)r.pops[i]);
+        }
+        for (auto& x : sp) x = x / (double)pop_real_factor;
+        return sp;
+    }
+    // insertion_rank (lib/local/ranking.f90:81-117), 0-based
+    static std::vector<int> insertion_rank(const std::vector<double>& arr, double tol) {
+        std::vector<int> rank(arr.size());
+        for (size_t i = 0; i < arr.size(); ++i) rank[i] = (int)i;
+        for (int i = 1; i < (int)arr.size(); ++i) {
+            int j = i - 1;
+            const int tmp = rank[i];
+            while (j >= 0) {
+                if (arr[rank[j]] - arr[tmp] < tol) break;
+                rank[j + 1] = rank[j];
+                --j;
+            }
+            rank[j + 1] = tmp;
+        }
+        return rank;
+    }
+    // do_load_balancing (src/load_balancing.F90:209-323) on the slot list summed over the ranks (MPI_AllReduce):
+    // check_imbalance (:353-381), find_processors (:520-601), reduce_slots (:478-518), redistribute_slots (:419-476).
+    // Modifies proc_map; returns load%needed.
+    bool do_load_balancing(double percent) {
+        std::vector<double> slot_list(proc_map.size(), 0.0);
+        for (auto& r : ranks) {
+            std::vector<double> sp = slot_pop(r);
+            for (size_t k = 0; k < sp.size(); ++k) slot_list[k] = slot_list[k] + sp[k];
+        }
+        const int np = in.nprocs;
+        std::vector<double> procs_pop(np, 0.0);
+        for (int pr = 0; pr < np; ++pr)
+            for (size_t k = 0; k < proc_map.size(); ++k)
+                if (proc_map[k] == pr) procs_pop[pr] = procs_pop[pr] + slot_list[k];
+        double tot = 0.0;
+        for (double x : procs_pop) tot = tot + x;
+        const double pop_av = tot / np;
+        bool needed = false;
+        for (double x : procs_pop) if (x > pop_av + pop_av * percent) needed = true;
+        if (!needed) return false;
+        const double up_thresh = pop_av + (double)(int)(pop_av * percent), low_thresh = pop_av - (double)(int)(pop_av * percent);
+        std::vector<int> donors;
+        int nrecv = 0;
+        for (int i = 0; i < np; ++i) {
+            if (procs_pop[i] < low_thresh) nrecv++;
+            else if (procs_pop[i] > up_thresh) donors.push_back(i);
+        }
+        std::vector<int> prank = insertion_rank(procs_pop, 1.0e-8);
+        std::vector<int> receivers(prank.begin(), prank.begin() + nrecv);
+        std::vector<int> d_index;
+        std::vector<double> d_pop;
+        for (int d : donors)
+            for (size_t j = 0; j < slot_list.size(); ++j)
+                if (proc_map[j] == d) { d_pop.push_back(slot_list[j]); d_index.push_back((int)j); }
+        std::vector<int> d_rank = insertion_rank(d_pop, 1.0e-8);
+        for (int pos : d_rank)
+            for (int rcv : receivers) {
+                const double new_pop = d_pop[pos] + procs_pop[rcv];
+                const double donor_pop = procs_pop[proc_map[d_index[pos]]] - d_pop[pos];
+                if (donor_pop >= low_thresh && new_pop <= up_thresh) {
+                    procs_pop[proc_map[d_index[pos]]] = donor_pop;
+                    procs_pop[rcv] = new_pop;
+                    proc_map[d_index[pos]] = rcv;
+                    break;
+                }
+            }
+        return true;
+    }
+    // redistribute_load_balancing_dets (src/qmc_common.F90:1332-1390): redistribute_particles (:505-595) on every rank,
+    // then direct_annihilation of the moved determinants.  The rounding streams of this extra annihilation are keyed
+    // by cycle_id (the engine and the tests pass the cycle with the top bit set).
+    void redistribute_fciqmc(uint32_t cycle_id) {
+        const int64_t block_size = in.spawned_walker_length / in.nprocs;
+        for (auto& r : ranks) {
+            for (auto& b : r.send) b.clear();
+            double nsent = 0.0;
+            for (int64_t i = 0; i < r.nstates; ++i) {
+                const int pproc = owner(r.states[i]);
+                if (pproc != r.iproc) {
+                    if ((int64_t)r.send[pproc].size() + 1 > block_size) r.spawn_error = true;
+                    else { SpawnElem e; e.f = r.states[i]; e.pop = r.pops[i]; e.flag = 0; r.send[pproc].push_back(e); }
+                    nsent = nsent + std::fabs((double)r.pops[i]);
+                    r.pops[i] = 0;
+                }
+            }
+            r.nparticles = r.nparticles - nsent / (double)pop_real_factor;
+        }
+        comm_spawn();
+        for (auto& r : ranks) {
+            r.rng->set_cycle(cycle_id);
+            annihilate_rank(r);
+        }
+    }
+
     void mc_cycle(uint32_t cycle_id) {
         for (auto& r : ranks) spawn_death_rank(r, cycle_id);
         comm_spawn();

@@ -400,6 +400,30 @@ class Oracle:
     def stage_annihilate(self):
         self._chk(self.L.orc_stage_annihilate(self.h))
 
+    # ---- load balancing (src/load_balancing.F90, src/qmc_common.F90:505-595, 1332-1390)
+    def proc_map(self):
+        out = np.zeros(4096, dtype=np.int32)
+        n = self.L.orc_get_proc_map(self.h, _p(out))
+        return out[:n].copy()
+
+    def set_proc_map(self, pmap):
+        pmap = np.ascontiguousarray(pmap, dtype=np.int32)
+        self._chk(self.L.orc_set_proc_map(self.h, _p(pmap), len(pmap)))
+
+    def slot_pop(self, rank=0):
+        out = np.zeros(4096)
+        n = self.L.orc_slot_pop(self.h, rank, _p(out))
+        return out[:n].copy()
+
+    def do_load_balancing(self, percent=0.05):
+        r = self.L.orc_do_load_balancing(self.h, C.c_double(percent))
+        self._chk(min(r, 0))
+        return bool(r)
+
+    def redistribute(self, cycle):
+        self.L.orc_redistribute.argtypes = [C.c_void_p, C.c_uint32]
+        self._chk(self.L.orc_redistribute(self.h, cycle))
+
     def gen_excit_philox(self, f, cycle, attempt, parent_pop, tau):
         f = np.ascontiguousarray(f, dtype=np.uint64)
         io = np.zeros(8, dtype=np.int32)

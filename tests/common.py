@@ -20,6 +20,7 @@ SYSTEMS = {
     "ne_cas": dict(fcidump="ne", kw=dict(nel=10, ms=0, sym=0, cas=(8, 22))),
     "s10": dict(synthetic=(10, 8), kw={}),
     "s12": dict(synthetic=(12, 8), kw={}),
+    "s10u": dict(synthetic_uhf=(10, 8), kw={}),   # UHF: four two-body channels, spin-dependent one-body terms
     "s40": dict(synthetic=(40, 10), kw={}),    # W = 2
     "s50": dict(synthetic=(50, 20), kw={}),    # the bench system (BASELINE configs[1]): 100 spin-orbitals, W = 2, 20 electrons
     # uniform electron gas: (electrons, ms, rs, cutoff)
@@ -38,6 +39,8 @@ def system_path(name):
                 txt = fi.read()
             with open(path, "w") as fo:
                 fo.write(txt)
+        elif "synthetic_uhf" in spec:
+            synthetic.synthetic_fcidump_uhf(*spec["synthetic_uhf"], path=path)
         else:
             synthetic.synthetic_fcidump(*spec["synthetic"], path=path)
     return path, spec["kw"]

@@ -155,8 +155,49 @@ def main():
     dist.destroy_process_group()
 
 
+def main_lb():
+    """argv: lb <system>: do_fciqmc with load balancing on every rank (NCCL exchange): the imbalance check fires, the
+    policy moves slots, redistribute_particles sends the determinants; afterwards every determinant sits on the rank
+    the new proc_map names and the total population matches the report row."""
+    import torch
+    import torch.distributed as dist
+    from hande_b200 import read_in as R
+    from hande_b200.fciqmc import QmcIn, TorchDist, do_fciqmc, owner_of
+    from tests.common import system_path
+
+    name = sys.argv[2]
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    comm = TorchDist(device=dev)
+    if rank == 0:
+        system_path(name)
+    dist.barrier()
+    path, kw = system_path(name)
+    s = R.read_in(path, **kw)
+    qmc = QmcIn(tau=0.003, init_pop=200, mc_cycles=5, nreports=12, target_population=1e9, real_amplitudes=True,
+                excit_gen="renorm", nslots=20, load_balancing=True, load_balancing_pop=500, percent_imbal=0.001,
+                max_load_attempts=2, state_size=1 << 17, spawned_state_size=1 << 16, initial_shift=0.3)
+    res = do_fciqmc(s, qmc, comm=comm, device=local, keep_engine=True)
+    assert not res.error
+    assert 1 <= len(res.load_balancing_log) <= 2, res.load_balancing_log
+    pmap = res.load_balancing_log[-1][1]
+    assert pmap != [i % world for i in range(world * 20)]
+    f, pops, _ = res.engine.download_psips()
+    assert all(owner_of(x, s.nbasis, world, 20, proc_map=pmap) == rank for x in f)
+    tot = comm.allreduce_sum(np.array([float(np.abs(pops).sum()) / 2**31, float(len(f))]))
+    assert abs(tot[0] - res.rows[-1][4]) < 1e-9 * tot[0] and int(tot[1]) == res.rows[-1][5]
+    print(f"rank {rank}: OK {len(f)} states after {len(res.load_balancing_log)} load-balancing steps", flush=True)
+    res.engine.close()
+    dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "ccmc":
         main_ccmc()
+    elif sys.argv[1] == "lb":
+        main_lb()
     else:
         main()

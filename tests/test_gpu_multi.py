@@ -28,6 +28,22 @@ def test_two_rank_parity(name, gen, real, init, tau):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "multi_gpu_worker.py"),
            name, gen, str(real), str(init), str(tau)]
+    # HB200_P2P_MIN_TILES=1: the spawning step is launched in chunks (as on bench-sized lists), each chunk pushed
+    # peer-to-peer while the next one spawns
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, HB200_P2P_MIN_TILES="1"))
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.stdout.count("OK") == nproc
+
+
+def test_driver_load_balancing():
+    """do_fciqmc with load balancing over NCCL: imbalance check, policy, redistribute_particles, direct_annihilation."""
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    nproc = 4 if n >= 4 else 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", "29537", os.path.join(ROOT, "tests", "multi_gpu_worker.py"),
+           "lb", "h2o"]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert res.stdout.count("OK") == nproc

@@ -63,6 +63,12 @@ def test_gen_excit_s50_bench_system(gen):
     _check_gen("s50", gen, True, 2e-5, n=500, nattempt=6)
 
 
+@pytest.mark.parametrize("gen", ["renorm", "heat_bath", "heat_bath_uniform", "power_pitzer_orderN", "renorm_spin"])
+def test_gen_excit_uhf(gen):
+    """UHF integral channels on the device (four two-body channels, spin-resolved one-body and sc1 tables)"""
+    _check_gen("s10u", gen, True, 0.01, n=150, nattempt=6)
+
+
 def test_gen_excit_renorm_spin_and_no_renorm_spin():
     # SURVEY 8f row 2: choose_ij_spin_mol variants of the uniform generators
     _check_gen("h2o", "renorm_spin", False, 0.003, n=120)
@@ -179,6 +185,8 @@ CASES = [
     ("ne", "renorm", True, True, 0.005, 5000, -1),
     ("s40", "renorm", False, True, 0.02, 3000, -1),
     ("s12", "heat_bath", True, True, 0.01, 2500, -1),
+    ("s10u", "heat_bath", True, True, 0.01, 2500, -1),          # UHF channels
+    ("s10u", "renorm", False, False, 0.01, 2500, -1),
     ("s50", "heat_bath", True, True, 2e-5, 6000, -1),          # the bench configuration
     ("s50", "heat_bath_uniform", True, True, 2e-5, 6000, -1),
     ("s50", "renorm", True, False, 2e-4, 6000, -1),

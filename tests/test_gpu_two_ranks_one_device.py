@@ -17,26 +17,29 @@ from tests.common import random_population, system_path
 pytestmark = pytest.mark.gpu
 
 
-def _setup(name, gen, real, init, tau, world, nwalkers):
+def _setup(name, gen, real, init, tau, world, nwalkers, nslots=1, skew=None):
     path, kw = system_path(name)
     s = R.read_in(path, **kw)
     o = Oracle()
     o.read_fcidump(path, **kw)
     o.set_qmc(tau=tau, seed=11, excit_gen=gen, rng_kind=1, real_amplitudes=int(real), spawn_cutoff=0.01,
               initiator_approx=int(init), literal_event_int32=0, walker_length=1 << 17, spawned_walker_length=1 << 16,
-              nprocs=world)
+              nprocs=world, nslots=nslots)
     o.init()
     ref = o.reference()
     engs = []
     for r in range(world):
         e = Engine(s, excit_gen=gen, pattempt_single=ref["pattempt_single"], pattempt_double=ref["pattempt_double"],
                    real_amplitudes=real, spawn_cutoff=0.01, initiator_approx=init, walker_length=1 << 17,
-                   spawned_walker_length=1 << 16, seed=11, nprocs=world, iproc=r, device=0,
+                   spawned_walker_length=1 << 16, seed=11, nprocs=world, iproc=r, nslots=nslots, device=0,
                    pattempt_parallel=(o.pattempt_parallel() if gen.endswith("_spin") else -1.0))
         e.set_reference(ref["f0"], ref["H00"])
         engs.append(e)
     f, pops, dat = random_population(s, o, nwalkers, real, seed=5)
-    own = np.array([owner_of(x, s.nbasis, world, 1) for x in f])
+    own = np.array([owner_of(x, s.nbasis, world, nslots) for x in f])
+    if skew is not None:       # a population imbalance between the slots, for the load-balancing test
+        slot = np.array([owner_of(x, s.nbasis, world, nslots, slot=True) for x in f])
+        pops = np.where(np.isin(slot, skew), pops * 6, pops)
     for r in range(world):
         m = own == r
         assert m.sum() > nwalkers // (3 * world)
@@ -82,5 +85,81 @@ def test_ranks_on_one_device_match_oracle_ranks(name, gen, real, init, tau, worl
         assert abs(tot[1] - ro["D0_population"]) <= 1e-12 * max(1.0, abs(ro["D0_population"]))
         assert tot[2] == ro["nspawn_events"] and tot[3] == ro["ndeath"] and tot[4] == ro["nstates"]
     assert sum(e.nstates for e in engs) > n // 2
+    for e in engs:
+        e.close()
+
+
+def _exchange_and_annihilate(s, o, engs, cycle):
+    """comm_spawn_t staged through the C ABI (see the module docstring), then annihilation + merge on every rank."""
+    world, E = len(engs), s.W + 2
+    blocks = []
+    for e in engs:
+        cnt = e.spawn_counts()
+        sd = e.download_spawn()
+        assert cnt.sum() == len(sd)
+        off = np.concatenate([[0], np.cumsum(cnt)])
+        blocks.append([sd[off[d]:off[d + 1]] for d in range(world)])
+    outs = []
+    for d, e in enumerate(engs):
+        recv = np.concatenate([blocks[src][d] for src in range(world)]).reshape(-1, E)
+        e.upload_spawn(recv)
+        e.annihilate_spawn()
+        outs.append(e.annihilate_main(cycle))
+    return outs
+
+
+@pytest.mark.parametrize("name,gen,real,init,tau,world", [("h2o", "renorm", True, False, 0.003, 3),
+                                                          ("s12", "heat_bath", True, True, 0.004, 2)])
+def test_load_balancing_redistribution_matches_oracle(name, gen, real, init, tau, world):
+    """do_load_balancing + redistribute_load_balancing_dets (src/load_balancing.F90:209-323, src/qmc_common.F90:505-595,
+    1332-1390): slot populations from the device, the policy on the host, the moved determinants through the spawn
+    list - against the oracle's emulated ranks, before and after more MC cycles with the new proc_map."""
+    from hande_b200 import load_balancing as LB
+    nslots = 20
+    rng = np.random.default_rng(1)
+    skew = rng.choice(world * nslots, size=world * nslots // 4, replace=False)
+    s, o, engs = _setup(name, gen, real, init, tau, world, 4000, nslots=nslots, skew=skew)
+    shift, pe_old = -0.05, -0.1
+
+    def cycle_all(cycle):
+        o.iterate(1, cycle, tau, shift, pe_old)
+        for e in engs:
+            e.spawn_death(tau, shift, pe_old, cycle)
+        _exchange_and_annihilate(s, o, engs, cycle)
+
+    def compare(tag):
+        for d, e in enumerate(engs):
+            fo, po, do_ = o.get_psips(d)
+            fg, pg, dg = e.download_psips()
+            assert len(fg) == len(fo), (tag, d, len(fg), len(fo))
+            assert (fg == fo).all() and (pg == po).all() and (dg == do_).all(), (tag, d)
+
+    for cycle in (1, 2):
+        cycle_all(cycle)
+    compare("before")
+    # initialise_slot_pop on the device == oracle; MPI_AllReduce = the sum over the engines
+    slot_list = np.zeros(world * nslots)
+    for d, e in enumerate(engs):
+        sp = e.slot_populations()
+        assert (sp == o.slot_pop(d)).all()
+        slot_list += sp
+    needed, pmap, _ = LB.do_load_balancing(slot_list, o.proc_map(), world, 0.05)
+    assert needed and o.do_load_balancing(0.05)
+    assert (np.asarray(pmap) == o.proc_map()).all() and (np.asarray(pmap) != np.arange(world * nslots) % world).any()
+    lb_cycle = 0x80000000 | 3
+    o.redistribute(lb_cycle)
+    nsent = 0.0
+    for e in engs:
+        e.set_proc_map(pmap)
+        nsent += e.redistribute_particles()
+    assert nsent > 0
+    _exchange_and_annihilate(s, o, engs, lb_cycle)
+    compare("redistributed")
+    for d, e in enumerate(engs):
+        fg = e.download_psips()[0]
+        assert all(owner_of(x, s.nbasis, world, nslots, proc_map=pmap) == d for x in fg[:200])
+    for cycle in (3, 4, 5):
+        cycle_all(cycle)
+    compare("after")
     for e in engs:
         e.close()

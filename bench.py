@@ -89,15 +89,18 @@ def measured_peak():
 
 
 UEG = dict(electrons=14, ms=0, rs=1.0, cutoff=2.5)   # --system ueg: 14 electrons, 57 plane waves (114 spin-orbitals)
+UEG1000 = dict(electrons=14, ms=0, rs=1.0, cutoff=19.0)   # --system ueg1000: BASELINE configs[3], 1021 plane waves (2042
+                                                           # spin-orbitals, 32-word bit strings: the wide list layout)
 
 
-def oracle_cpu_run(path, n_sample, ncycles, tau, nthreads, seed=1, excit_gen="heat_bath"):
+def oracle_cpu_run(path, n_sample, ncycles, tau, nthreads, seed=1, excit_gen="heat_bath", ueg=None):
     """Time the oracle (CPU restatement of the reference path) on a bounded sample of the workload."""
     from hande_b200 import synthetic
     from oracle.pyoracle import Oracle
-    o = Oracle()
+    ueg = ueg or UEG
+    o = Oracle(wide=(path is None and ueg["cutoff"] > 5.0))
     if path is None:
-        o.init_ueg(UEG["electrons"], UEG["ms"], UEG["rs"], UEG["cutoff"])
+        o.init_ueg(ueg["electrons"], ueg["ms"], ueg["rs"], ueg["cutoff"])
         excit_gen = "no_renorm"
     else:
         o.read_fcidump(path)
@@ -164,7 +167,7 @@ def main():
     ap.add_argument("--excit-gen", default="heat_bath", choices=["heat_bath", "heat_bath_uniform", "heat_bath_single", "power_pitzer_orderN", "power_pitzer", "renorm", "renorm_spin", "no_renorm_spin", "no_renorm", "power_pitzer_occ",
                                                               "cauchy_schwarz_occ", "power_pitzer_occ_ij", "cauchy_schwarz_occ_ij"],
                     help="excitation generator (headline = heat_bath, BASELINE.json configs[1]; others are side measurements)")
-    ap.add_argument("--system", default="s50", choices=["s50", "ueg"],
+    ap.add_argument("--system", default="s50", choices=["s50", "ueg", "ueg1000"],
                     help="s50 = BASELINE configs[1] (headline); ueg = side measurement on the 3D UEG (14 electrons, "
                          "114 plane-wave spin-orbitals: the largest basis of BASELINE configs[3] this version's W <= 4 holds)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -202,9 +205,9 @@ def main():
         comm = _SingleProcess()
 
     t_setup = time.time()
-    if args.system == "ueg":
+    if args.system in ("ueg", "ueg1000"):
         from hande_b200.ueg import UegSystem
-        s, path = UegSystem(**UEG), None
+        s, path = UegSystem(**(UEG if args.system == "ueg" else UEG1000)), None
         args.excit_gen = "power_pitzer" if args.excit_gen == "power_pitzer" else "no_renorm"
         occ0 = s.aufbau_reference()
         ps, pd = 0.0, 1.0
@@ -411,7 +414,8 @@ def main():
     if rank == 0 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         ns_cpu = 200000
-        r, t_init = oracle_cpu_run(path, ns_cpu, 5, tau, cores, excit_gen=args.excit_gen)
+        r, t_init = oracle_cpu_run(path, ns_cpu, 5, tau, cores, excit_gen=args.excit_gen,
+                                   ueg=UEG1000 if args.system == "ueg1000" else UEG)
         cpu = {"value": r["walker_iters"] / r["seconds"], "unit": "walker-iterations/s", "cores": cores, "kind": "port",
                "sample": f"{cores} replicas x {ns_cpu} walkers x 5 cycles of the same {args.system} {args.excit_gen} workload "
                          f"(oracle restatement; {r['seconds']:.1f}s timed, table init {t_init:.1f}s untimed)"}
@@ -422,7 +426,7 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tmax / args.steps,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "int64+f64", "data": "synthetic",
             "config": {"workload": ("S50 synthetic FCIDUMP (50 orb / 20 el, C1, 8-fold)" if args.system == "s50" else
-                                    "3D UEG (14 electrons, rs = 1, 114 plane-wave spin-orbitals)") +
+                                    f"3D UEG (14 electrons, rs = 1, {s.nbasis} plane-wave spin-orbitals)") +
                                    f", real-valued iFCIQMC, {args.excit_gen}, {n:.3g} unit walkers per GPU (distribution A)",
                        "tau": tau, "R_spawn": float(P) / max(A, 1.0), "walkers_per_gpu": n, "walkers_total": int(agg[2]),
                        "nstates": int(S),

@@ -80,7 +80,7 @@ k_ccmc_cluster(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states,
                 cls = 0;
             } else {
                 PhiloxStream r0;
-                r0.begin(p.seed, p.cycle, RNG_SPAWN, det_hash64<W>(p.f0) + (uint64_t)p.iproc * 0x9E3779B97F4A7C15ull,
+                r0.begin(p.seed, p.cycle, RNG_SPAWN, det_hash64<W>(p.f0, HB_NW(p)) + (uint64_t)p.iproc * 0x9E3779B97F4A7C15ull,
                          (uint32_t)(idx0 + 1));
                 const double rand = r0.next();
                 double psize = 0.0;
@@ -120,7 +120,7 @@ k_ccmc_cluster(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states,
     int dest_s = 0, dest_k = 0;
     if (idx < a.nattempts) {
         PhiloxStream rng;
-        rng.begin(p.seed, p.cycle, RNG_SPAWN, det_hash64<W>(p.f0) + (uint64_t)p.iproc * 0x9E3779B97F4A7C15ull,
+        rng.begin(p.seed, p.cycle, RNG_SPAWN, det_hash64<W>(p.f0, HB_NW(p)) + (uint64_t)p.iproc * 0x9E3779B97F4A7C15ull,
                   (uint32_t)(idx + 1));
         Cluster cl;
         const bool det_D0 = idx >= a.nattempts - a.nD0_select;    // deterministic selections of the reference (full_nc)
@@ -135,7 +135,7 @@ k_ccmc_cluster(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states,
             ccmc_select_cluster<W>(rng, p, a, states, pops, cum_enc, cf, cl);
         }
         if (cl.excitation_level >= 0 && cl.excitation_level <= a.ex_level + 2) {
-            uint8_t occ[HB_MAXNEL], su[64];
+            occ_t occ[HB_MAXNEL]; uint8_t su[64];
             decode_det<W>(cf, occ);
             if (s.kind == SYS_READ_IN && p.excit_gen != EXCIT_GEN_NO_RENORM && p.excit_gen != EXCIT_GEN_NO_RENORM_SPIN &&
                 p.excit_gen != EXCIT_GEN_HEAT_BATH)
@@ -231,14 +231,14 @@ k_ccmc_nc(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states, int6
         uint64_t f[W];
         load_det<W>(states + i * W, f);
         const int64_t pop = pops[i];
-        const uint64_t h = det_hash64<W>(f);
+        const uint64_t h = det_hash64<W>(f, HB_NW(p));
         const bool isD0 = (i + 1 == a.D0_pos);
         PhiloxStream rng;
         if (!isD0) {
             const double amp = (double)pop / (double)p.real_factor;
             const int level = excit_level<W>(f, p.f0);
             const int sign = ccmc_excitor_sign<W>(p.f0, f, level);
-            uint8_t occ[HB_MAXNEL], su[64];
+            occ_t occ[HB_MAXNEL]; uint8_t su[64];
             decode_det<W>(f, occ);
             if (s.kind == SYS_READ_IN && p.excit_gen != EXCIT_GEN_NO_RENORM && p.excit_gen != EXCIT_GEN_NO_RENORM_SPIN &&
                 p.excit_gen != EXCIT_GEN_HEAT_BATH)
@@ -365,11 +365,11 @@ __global__ void k_gen_excit_batch(Sys s, Params p, const uint64_t* __restrict__ 
     uint64_t f[W];
 #pragma unroll
     for (int k = 0; k < W; ++k) f[k] = states[t * W + k];
-    uint8_t occ[HB_MAXNEL], su[64];
+    occ_t occ[HB_MAXNEL]; uint8_t su[64];
     decode_det<W>(f, occ);
     if (s.kind != SYS_UEG) build_symunocc(s, occ, su);
     PhiloxStream rng;
-    rng.begin(p.seed, p.cycle, RNG_SPAWN, det_hash64<W>(f), attempt[t]);
+    rng.begin(p.seed, p.cycle, RNG_SPAWN, det_hash64<W>(f, HB_NW(p)), attempt[t]);
     Gen g;
     gen_excit<W>(rng, s, p, f, occ, su, g);
     const int64_t ns = attempt_to_spawn(rng, p, g.hmatel, g.pgen, pops[t]);

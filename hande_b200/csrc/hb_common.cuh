@@ -33,6 +33,7 @@ extern thread_local std::string g_err;
         return 1;        \
     } while (0)
 
+constexpr int ANN_SHORT = 32;   // k_annihilate: runs of equal keys up to this length are summed by the thread of their first element
 constexpr int TILE = 256;  // states per block in the fused spawn kernel and in the merge passes
 // ------------------------------------------------------------------------------------------------
 // small device helpers
@@ -72,6 +73,13 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     return v;
+}
+
+// The element count of the spawn list is read on the device (*pn, clamped to cap): hb200_iterate never brings it to the
+// host, so grids are sized from a host-side upper bound and the chunk of a block follows from the real count.
+__device__ __forceinline__ long long dev_count(const unsigned long long* __restrict__ pn, long long cap) {
+    const unsigned long long v = *pn;
+    return v > (unsigned long long)cap ? cap : (long long)v;
 }
 
 template <int W>
@@ -147,7 +155,11 @@ struct HostOut {
 // ------------------------------------------------------------------------------------------------
 struct hb200_engine {
     hb200_config cfg;
-    int W = 1, E = 3;
+    int W = 1, E = 3;            // words per determinant / per spawn element on the DEVICE (1..4, or 32 = wide layout)
+    int We = 1;                  // words per determinant in the host's layout, ceil(nbasis/64)
+    const struct ListOps* ops = nullptr;
+    int64_t* d_items[2] = {nullptr, nullptr};   // wide layout: compressed sort keys
+    int key_bits = 0, key_words = 0;
     cudaStream_t stream = nullptr;
     Sys sys;
     Params par;
@@ -269,9 +281,27 @@ struct SpawnLaunch {
 typedef int (*hb_spawn_fn)(hb200_engine* e, const Params& p, const SpawnLaunch& L);
 #define HB_DECL_SPAWN(W, G) int hb_spawn_w##W##_g##G(hb200_engine* e, const Params& p, const SpawnLaunch& L);
 #define HB_DECL_SPAWN_W(W) HB_DECL_SPAWN(W, 0) HB_DECL_SPAWN(W, 1) HB_DECL_SPAWN(W, 2) HB_DECL_SPAWN(W, 3) HB_DECL_SPAWN(W, 4)
-HB_DECL_SPAWN_W(1) HB_DECL_SPAWN_W(2) HB_DECL_SPAWN_W(3) HB_DECL_SPAWN_W(4)
+HB_DECL_SPAWN_W(1) HB_DECL_SPAWN_W(2) HB_DECL_SPAWN_W(3) HB_DECL_SPAWN_W(4) HB_DECL_SPAWN(32, 4)
 size_t hb_spawn_smem_bytes(const hb200_engine* e);
 bool hb_uses_heat_bath_tables(const hb200_engine* e);
+
+// list kernels of one bit-string width (hb_list.cuh / hb_list_tu.cu)
+struct ListOps {
+    int (*annihilate)(hb200_engine* e, const Params& p, int64_t* sp, long long bound);
+    int (*compact)(hb200_engine* e, const int64_t* sp, long long bound, int64_t* ins);
+    int (*round_count)(hb200_engine* e, const Params& p, int ntiles);
+    int (*sc0)(hb200_engine* e, double H00, const uint64_t* dets, long long stride_words, long long n, double* out, const int* pn);
+    int (*merge)(hb200_engine* e, const int64_t* ins, int ntiles);
+    int (*slot_pop)(hb200_engine* e, unsigned long long* d);
+    int (*compress)(hb200_engine* e, const int64_t* sp, long long bound, int bits, int kw, int64_t* items);
+    int (*gather)(hb200_engine* e, const int64_t* sp, int kw, const int64_t* items, int64_t* out);
+    int (*owner_slot_shift)(const hb200_engine* e, const Params& p);
+};
+const ListOps* hb_list_ops_w1();
+const ListOps* hb_list_ops_w2();
+const ListOps* hb_list_ops_w3();
+const ListOps* hb_list_ops_w4();
+const ListOps* hb_list_ops_w32();
 
 struct CcmcLaunch {
     CcmcArgs a;
@@ -286,4 +316,4 @@ struct CcmcLaunch {
     int hb_ccmc_find_det_w##W(hb200_engine* e, const Params& p);                                                     \
     int hb_gen_excit_batch_w##W(hb200_engine* e, const Params& p, const uint64_t* d_f, const int64_t* d_p,           \
                                 const uint32_t* d_a, long long n, int* d_io, double* d_do, int64_t* d_ns);
-HB_DECL_CCMC(1) HB_DECL_CCMC(2) HB_DECL_CCMC(3) HB_DECL_CCMC(4)
+HB_DECL_CCMC(1) HB_DECL_CCMC(2) HB_DECL_CCMC(3) HB_DECL_CCMC(4) HB_DECL_CCMC(32)

@@ -26,7 +26,14 @@
 #endif
 
 #ifndef HB_MAXW
-#define HB_MAXW 4
+#define HB_MAXW 32          // widest bit string (words): wide lists are stored with 32 words per determinant
+#endif
+// Occupied-orbital lists hold 1-based spin-orbital indices: bytes while nbasis <= 254 (W <= 4); the translation units
+// of the wide layout (W = 32, up to 2048 spin-orbitals: the plane-wave bases of the UEG) are compiled with -DHB_OCC16.
+#ifdef HB_OCC16
+typedef uint16_t occ_t;
+#else
+typedef uint8_t occ_t;
 #endif
 #define HB_MAXNEL 64
 #define HB_MAX_CLUSTER 8    // largest CCMC cluster (ex_level + 2 <= 8): size of the selection buffers
@@ -139,6 +146,7 @@ struct Params {
     int nprocs, iproc, nslots;
     int ccmc_shift, ccmc_freq;  // spawn%hash_shift / spawn%move_freq (CCMC only)
     uint64_t f0[HB_MAXW];
+    int we;                     // words of a bit string in the host's layout (ceil(nbasis/64)); the wide layout pads to 32
     double H00;
     struct PsPartials* ps_part; // per-block sums for qmc_in%pattempt_update (null: not accumulating)
     // quasi-Newton propagator (propagator_t, src/qmc_data.f90:866-884); sp_fock is 1-based
@@ -158,6 +166,7 @@ enum { EXCIT_GEN_RENORM = 0, EXCIT_GEN_RENORM_SPIN = 1, EXCIT_GEN_NO_RENORM = 2,
        EXCIT_GEN_CAUCHY_SCHWARZ_OCC = 8, EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ = 9,
        EXCIT_GEN_HEAT_BATH = 10, EXCIT_GEN_HEAT_BATH_UNIFORM = 11, EXCIT_GEN_HEAT_BATH_SINGLE = 12 };
 enum { PPN_IS = 0, PPN_IAS = 1, PPN_ID = 2, PPN_IJD = 3, PPN_IAD = 4, PPN_JBD = 5 };
+#define HB_NW(p) ((W > 4) ? (p).we : W)
 enum { RNG_NATTEMPTS = 0, RNG_SPAWN = 1, RNG_DEATH = 2, RNG_ROUND_MAIN = 3, RNG_ROUND_SPAWN = 4 };
 
 // ------------------------------------------------------------------------------------------------
@@ -185,11 +194,13 @@ HB_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uin
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+// nw: words hashed (the host's width; the wide layout pads a determinant with zero words that must not enter the key)
 template <int W>
-HB_HD uint64_t det_hash64(const uint64_t* f) {
+HB_HD uint64_t det_hash64(const uint64_t* f, int nw = W) {
     uint64_t h = 0x9E3779B97F4A7C15ull;
 #pragma unroll
     for (int i = 0; i < W; ++i) {
+        if (W > 4 && i >= nw) break;
         uint64_t z = f[i] + h;
         z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
         z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
@@ -303,7 +314,7 @@ HB_HD bool det_test(const uint64_t* f, int orb) { return (f[(orb - 1) >> 6] >> (
 
 // decode_det (src/determinants.f90:243-297): occupied orbitals ascending.
 template <int W>
-HB_HD int decode_det(const uint64_t* f, uint8_t* occ) {
+HB_HD int decode_det(const uint64_t* f, occ_t* occ) {
     int n = 0;
 #pragma unroll
     for (int iw = 0; iw < 2 * W; ++iw) {
@@ -314,7 +325,7 @@ HB_HD int decode_det(const uint64_t* f, uint8_t* occ) {
 #else
             const int b = __builtin_ctz(x);
 #endif
-            occ[n++] = (uint8_t)(iw * 32 + b + 1);
+            occ[n++] = (occ_t)(iw * 32 + b + 1);
             x &= x - 1;
         }
     }
@@ -435,7 +446,7 @@ HB_HD double two_body_real(const Sys& s, int i, int j, int a, int b) {
 HB_HD double one_body(const Sys& s, int i, int j) { return s.h1[(i - 1) * s.nbasis + (j - 1)]; }
 
 // slater_condon0_mol_orb_list (src/hamiltonian_molecular.f90:99-139) through the J/K tables.
-HB_HDN double slater_condon0(const Sys& s, const uint8_t* occ) {
+HB_HDN double slater_condon0(const Sys& s, const occ_t* occ) {
     double h = s.Ecore;
     const int nb = s.nbasis;
     for (int iel = 0; iel < s.nel; ++iel) {
@@ -451,7 +462,7 @@ HB_HDN double slater_condon0(const Sys& s, const uint8_t* occ) {
 }
 // slater_condon1_mol_excit (src/hamiltonian_molecular.f90:199-259); integrals through the C/X row tables
 HB_HD int tix(const Sys& s, int i) { return s.uhf ? (i - 1) : ((i - 1) >> 1); }
-HB_HDN double slater_condon1_excit(const Sys& s, const uint8_t* occ, int i, int a, bool perm) {
+HB_HDN double slater_condon1_excit(const Sys& s, const occ_t* occ, int i, int a, bool perm) {
     double h = one_body(s, i, a);
     const D2* __restrict__ row = s.sc1CX + ((long long)tix(s, i) * s.NT + tix(s, a)) * s.NT;
     const int nel = s.nel;
@@ -504,7 +515,7 @@ struct Gen {
 
 // symunocc(ims, sym) = nbasis_sym_spin - occupied (decode_det_occ_symunocc,
 // src/determinant_decoders.f90:166-206); stored as uint8 [(ims-1)+2*sym]
-HB_HD void build_symunocc(const Sys& s, const uint8_t* occ, uint8_t* su) {
+HB_HD void build_symunocc(const Sys& s, const occ_t* occ, uint8_t* su) {
     for (int k = 0; k < 2 * s.nsym_tot; ++k) su[k] = (uint8_t)s.nbss[k];
     for (int i = 0; i < s.nel; ++i) {
         int o = occ[i];
@@ -526,7 +537,7 @@ HB_HD void build_symunocc_masks(const Sys& s, const uint64_t* f, uint8_t* su) {
 
 // choose_ij_mol (src/excit_gen_mol.f90:620-682)
 template <class R>
-HB_HD void choose_ij(R& rng, const Sys& s, const uint8_t* occ, int& i, int& j, int& ij_sym, int& ij_spin) {
+HB_HD void choose_ij(R& rng, const Sys& s, const occ_t* occ, int& i, int& j, int& ij_sym, int& ij_spin) {
     int nel = s.nel;
     int ind = (int)(rng.next() * nel * (nel - 1) / 2) + 1;
     int j_ind = (int)(1.50 + sqrt(2 * ind - 1.750));
@@ -539,13 +550,13 @@ HB_HD void choose_ij(R& rng, const Sys& s, const uint8_t* occ, int& i, int& j, i
 
 // choose_ij_spin_mol (src/excit_gen_mol.f90:684-800): parallel or anti-parallel pair first (pattempt_parallel), then the
 // pair from occ_list_alpha / occ_list_beta (decode_det_spinocc_symunocc: alpha = ms +1)
-HB_HD int nth_occ_of_spin(const uint8_t* occ, int nel, int ms, int k) {
+HB_HD int nth_occ_of_spin(const occ_t* occ, int nel, int ms, int k) {
     for (int q = 0; q < nel; ++q)
         if (ms_of(occ[q]) == ms && --k == 0) return occ[q];
     return 0;
 }
 template <class R>
-HB_HD void choose_ij_spin(R& rng, const Sys& s, const Params& p, const uint8_t* occ, int& i, int& j, int& ij_sym,
+HB_HD void choose_ij_spin(R& rng, const Sys& s, const Params& p, const occ_t* occ, int& i, int& j, int& ij_sym,
                           int& ij_spin, double& pgen_ij, bool& allowed) {
     const int nalpha = s.nbasis / 2 - s.nvirt_alpha, nbeta = s.nbasis / 2 - s.nvirt_beta;
     allowed = true;
@@ -584,7 +595,7 @@ HB_HD void choose_ij_spin(R& rng, const Sys& s, const Params& p, const uint8_t* 
 
 // gen_single_excit_mol (src/excit_gen_mol.f90:384-448): choose_ia_mol (:802-870) + calc_pgen_single_mol (:1140-1190)
 template <int W, class R>
-HB_HDN void gen_single_renorm(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ,
+HB_HDN void gen_single_renorm(R& rng, const Sys& s, const Params& p, const uint64_t* f, const occ_t* occ,
                               const uint8_t* su, Gen& g) {
     const int nel = s.nel;
     g.from2 = 0; g.to2 = 0; g.perm = false;
@@ -629,7 +640,7 @@ HB_HDN void gen_single_renorm(R& rng, const Sys& s, const Params& p, const uint6
 // 802-946,1140-1327)
 // SPIN: gen_excit_mol_spin (src/excit_gen_mol.f90:103-193), excit_gen = renorm_spin - ij from choose_ij_spin_mol
 template <int W, bool SPIN = false, class R>
-HB_HDN void gen_excit_renorm(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ,
+HB_HDN void gen_excit_renorm(R& rng, const Sys& s, const Params& p, const uint64_t* f, const occ_t* occ,
                              const uint8_t* su, Gen& g) {
     const int nel = s.nel;
     g.from2 = 0; g.to2 = 0; g.perm = false;
@@ -728,7 +739,7 @@ HB_HDN void gen_excit_renorm(R& rng, const Sys& s, const Params& p, const uint64
 // gen_excit_mol_no_renorm (src/excit_gen_mol.f90:195-284,450-517,950-1136,1329-1445)
 // SPIN: gen_excit_mol_no_renorm_spin (src/excit_gen_mol.f90:286-380), excit_gen = no_renorm_spin
 template <int W, bool SPIN = false, class R>
-HB_HDN void gen_excit_no_renorm(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ,
+HB_HDN void gen_excit_no_renorm(R& rng, const Sys& s, const Params& p, const uint64_t* f, const occ_t* occ,
                                 Gen& g) {
     const int nel = s.nel;
     g.from2 = 0; g.to2 = 0; g.perm = false; g.to1 = 0;
@@ -868,7 +879,7 @@ HB_HD int clz64(uint64_t x) {
 #endif
 }
 // sum_q tab[occ[q]-1] in occ_list order; loads issued four at a time (adding the 0.0 padding is exact)
-HB_HD double sum_occ(const double* __restrict__ tab, const uint8_t* occ, int nel) {
+HB_HD double sum_occ(const double* __restrict__ tab, const occ_t* occ, int nel) {
     double tot = 0.0;
     for (int q0 = 0; q0 < nel; q0 += 4) {
         double v[4];
@@ -1021,7 +1032,7 @@ HB_HD int select_alias_staged(R& rng, int N, const double* wq, int stride, doubl
     return select_alias_staged_m<uint64_t>(rng, N, wq, stride, totweight);
 }
 // gather tab[occ[q]-1] into wq[q*stride] and return their sum in list order; loads issued four at a time
-HB_HD double stage_occ(const double* __restrict__ tab, const uint8_t* occ, int nel, double* wq, int stride) {
+HB_HD double stage_occ(const double* __restrict__ tab, const occ_t* occ, int nel, double* wq, int stride) {
     double tot = 0.0;
     for (int q0 = 0; q0 < nel; q0 += 4) {
         double v[4];
@@ -1073,7 +1084,7 @@ HB_HD bool hb_single_allowed(const Sys& s, int fr, int to) {
 // iw = hb_i_w (or a shared-memory copy); scr/stride = staging area of nel doubles for the weight list being selected
 // from (first S_i at the occupied orbitals, then column i of hb_ij_w at the occupied orbitals).
 template <int W, class R>
-HB_HDN void hb_phase_a(R& rng, const Sys& s, const uint64_t* f, const uint8_t* occ, HbState& st,
+HB_HDN void hb_phase_a(R& rng, const Sys& s, const uint64_t* f, const occ_t* occ, HbState& st,
                        const double* __restrict__ iw, double* scr, int stride) {
     const int nel = s.nel;
     const int64_t nb = s.nbasis;
@@ -1097,7 +1108,7 @@ HB_HDN void hb_phase_a(R& rng, const Sys& s, const uint64_t* f, const uint8_t* o
 
 // slater_condon1 request of the tile queues: |<D|H|D_fr^to>| with its sign
 template <int W>
-HB_HD double hb_sc1(const Sys& s, const uint64_t* f, const uint8_t* occ, int fr, int to, bool& perm) {
+HB_HD double hb_sc1(const Sys& s, const uint64_t* f, const occ_t* occ, int fr, int to, bool& perm) {
     perm = excit_perm1<W>(f, fr, to);
     return slater_condon1_excit(s, occ, fr, to, perm);
 }
@@ -1159,7 +1170,7 @@ HB_HD bool hb_single_term(const Sys& s, int i, int a, double hmod_ia, double ij_
 // reads 7 numbers where it names 20, with every operation of the reference kept in its order.  ji_weights_occ_tot is
 // only needed here and is summed for the double excitations that got this far.
 template <int W>
-HB_HDN void hb_phase_f(const Sys& s, const uint64_t* f, const uint8_t* occ, const HbState& st, const double* hm,
+HB_HDN void hb_phase_f(const Sys& s, const uint64_t* f, const occ_t* occ, const HbState& st, const double* hm,
                        double pgen_single_sum, const double* __restrict__ iw, Gen& g) {
     const int64_t nb = s.nbasis;
     g.from1 = 0; g.from2 = 0; g.to1 = 0; g.to2 = 0; g.perm = false; g.nexcit = 2;
@@ -1209,7 +1220,7 @@ HB_HDN void hb_phase_f(const Sys& s, const uint64_t* f, const uint8_t* occ, cons
 }
 
 template <int W, class R>
-HB_HDN void gen_excit_heat_bath(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ,
+HB_HDN void gen_excit_heat_bath(R& rng, const Sys& s, const Params& p, const uint64_t* f, const occ_t* occ,
                                 Gen& g) {
     HbState st;
     double scr[HB_MAXNEL];
@@ -1265,7 +1276,7 @@ HB_HDN int select_weighted_value_big(R& rng, int N, const double* weights, doubl
 // on-the-fly alias tables.  O(N M) slater_condon1 evaluations per call - correctness-first (the reference caches the
 // weights per determinant; here they are recomputed per single-excitation attempt).
 template <int W, class R>
-HB_HDN void gen_single_heat_bath_exact(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ, Gen& g) {
+HB_HDN void gen_single_heat_bath_exact(R& rng, const Sys& s, const Params& p, const uint64_t* f, const occ_t* occ, Gen& g) {
     const int nel = s.nel, nvirt = s.nbasis - s.nel;
     g.nexcit = 1; g.from1 = 0; g.from2 = 0; g.to1 = 0; g.to2 = 0; g.perm = false;
     double wi[HB_MAXNEL];
@@ -1312,7 +1323,7 @@ HB_HDN void gen_single_heat_bath_exact(R& rng, const Sys& s, const Params& p, co
 // EXACT_SINGLE: excit_gen = heat_bath_single (src/excit_gen_heat_bath_mol.F90:720-805) - the same doubles, singles
 // from gen_single_heat_bath_exact.
 template <int W, bool EXACT_SINGLE = false, class R>
-HB_HDN void gen_excit_heat_bath_uniform(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ,
+HB_HDN void gen_excit_heat_bath_uniform(R& rng, const Sys& s, const Params& p, const uint64_t* f, const occ_t* occ,
                                         const uint8_t* su, const double* __restrict__ iw, double* scr, int stride, Gen& g) {
     const int nel = s.nel;
     const int64_t nb = s.nbasis;
@@ -1422,7 +1433,7 @@ HB_HD int unocc_rank_of(const uint64_t* f, int b) {
 // (i, j) are drawn from ppm_i_d_weights / ppm_ij_d_weights (init_excit_mol_power_pitzer_orderM_ij, :585-647) - the same
 // sums as hb_i_w / hb_ij_w of the heat-bath tables, which are used for them.
 template <int W, class R>
-HB_HDN void gen_excit_power_pitzer_occ(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ,
+HB_HDN void gen_excit_power_pitzer_occ(R& rng, const Sys& s, const Params& p, const uint64_t* f, const occ_t* occ,
                                        const uint8_t* su, const double* __restrict__ iw, double* scr, int stride, Gen& g) {
     const bool cs = p.excit_gen == EXCIT_GEN_CAUCHY_SCHWARZ_OCC || p.excit_gen == EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ;
     const bool weighted_ij = p.excit_gen == EXCIT_GEN_POWER_PITZER_OCC_IJ || p.excit_gen == EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ;
@@ -1597,7 +1608,7 @@ HB_HDN void find_diff_ref_cdet(const Sys& s, const uint64_t* f0, const uint64_t*
 // gen_excit_mol_power_pitzer_occ_ref (src/excit_gen_power_pitzer_mol.F90:650-939), excit_gen = power_pitzer: ij uniform
 // among the reference's occupied orbitals, a and b from the reference's alias tables, mapped onto this determinant
 template <int W, class R>
-HB_HDN void gen_excit_power_pitzer_ref(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ, Gen& g) {
+HB_HDN void gen_excit_power_pitzer_ref(R& rng, const Sys& s, const Params& p, const uint64_t* f, const occ_t* occ, Gen& g) {
     const int nel = s.nel, mv = s.max_nbss, nsym = s.nsym_tot;
     g.from1 = 0; g.from2 = 0; g.to1 = 0; g.to2 = 0; g.perm = false;
     if (rng.next() < p.pattempt_single) {     // gen_single_excit_mol_no_renorm (src/excit_gen_mol.f90:450-517)
@@ -1696,7 +1707,7 @@ HB_HDN void gen_excit_power_pitzer_ref(R& rng, const Sys& s, const Params& p, co
 }
 // gen_excit_mol_power_pitzer_orderN (src/excit_gen_power_pitzer_mol.F90:941-1258)
 template <int W, class R>
-HB_HDN void gen_excit_power_pitzer_orderN(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ,
+HB_HDN void gen_excit_power_pitzer_orderN(R& rng, const Sys& s, const Params& p, const uint64_t* f, const occ_t* occ,
                                           const uint8_t* ref_cdet, Gen& g) {
     const int nel = s.nel, mv = s.max_nbss, nsym = s.nsym_tot, nall = s.nbasis / 2;
     g.from1 = 0; g.from2 = 0; g.to1 = 0; g.to2 = 0; g.perm = false;
@@ -1813,7 +1824,7 @@ HB_HD double ueg_two_e_int(const Sys& s, int i, int j, int a, int b) {
     return v;
 }
 // slater_condon0_ueg (src/hamiltonian_ueg.f90:71-99,127-156; src/determinants.f90:403-425)
-HB_HDN double slater_condon0_ueg(const Sys& s, const uint8_t* occ) {
+HB_HDN double slater_condon0_ueg(const Sys& s, const occ_t* occ) {
     double spe = 0.0;
     for (int i = 0; i < s.nel; ++i) spe = spe + s.sp_eigv[occ[i]];
     double ex = 0.0;
@@ -1841,7 +1852,7 @@ HB_HD int ueg_basis_index(const Sys& s, int kx, int ky, int kz, int spin) {
 // gen_excit_ueg_no_renorm (src/excit_gen_ueg.f90:27-101): choose_ij_k (:105-190), find_ab_ueg (:194-306),
 // calc_pgen_ueg_no_renorm (:310-360).  Two random numbers (the second only if an a exists).
 template <int W, class R>
-HB_HDN void gen_excit_ueg_no_renorm(R& rng, const Sys& s, const uint64_t* f, const uint8_t* occ, Gen& g) {
+HB_HDN void gen_excit_ueg_no_renorm(R& rng, const Sys& s, const uint64_t* f, const occ_t* occ, Gen& g) {
     const int nel = s.nel;
     g.nexcit = 2; g.perm = false; g.to1 = 0; g.to2 = 0;
     const int ind = (int)(rng.next() * nel * (nel - 1) / 2) + 1;
@@ -1900,7 +1911,7 @@ HB_HDN void gen_excit_ueg_no_renorm(R& rng, const Sys& s, const uint64_t* f, con
 // gen_excit_ueg_power_pitzer (src/excit_gen_ueg.f90:410-566), excit_gen = power_pitzer on the UEG: ij uniform, a from
 // the alias table of i over the orbitals of its spin (weights |<ia|ai>|, s.pp_ia), b from momentum conservation
 template <int W, class R>
-HB_HDN void gen_excit_ueg_power_pitzer(R& rng, const Sys& s, const uint64_t* f, const uint8_t* occ, Gen& g) {
+HB_HDN void gen_excit_ueg_power_pitzer(R& rng, const Sys& s, const uint64_t* f, const occ_t* occ, Gen& g) {
     const int nel = s.nel, maxv = s.nbasis / 2;
     g.nexcit = 2; g.perm = false; g.to1 = 0; g.to2 = 0;
     const int ind = (int)(rng.next() * nel * (nel - 1) / 2) + 1;
@@ -1938,7 +1949,7 @@ HB_HDN void gen_excit_ueg_power_pitzer(R& rng, const Sys& s, const uint64_t* f, 
     }
 }
 template <int W, class R>
-HB_HD void gen_excit(R& rng, const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ, const uint8_t* su,
+HB_HD void gen_excit(R& rng, const Sys& s, const Params& p, const uint64_t* f, const occ_t* occ, const uint8_t* su,
                      Gen& g) {
     if (s.kind == SYS_UEG) {
         if (p.excit_gen == EXCIT_GEN_POWER_PITZER) gen_excit_ueg_power_pitzer<W>(rng, s, f, occ, g);
@@ -1974,7 +1985,7 @@ HB_HD void gen_excit(R& rng, const Sys& s, const Params& p, const uint64_t* f, c
 // ------------------------------------------------------------------------------------------------
 // quasi-Newton weights: cdet%fock_sum (src/fciqmc.f90:321-322), calc_qn_spawned_weighting and calc_qn_weighting
 // (src/spawning.F90:2063-2137)
-HB_HD double qn_fock_sum(const Sys& s, const Params& p, const uint8_t* occ) {
+HB_HD double qn_fock_sum(const Sys& s, const Params& p, const occ_t* occ) {
     double fs = 0.0;
     for (int k = 0; k < s.nel; ++k) fs = fs + p.sp_fock[occ[k]];
     return fs - p.ref_fock_sum;
@@ -2054,7 +2065,7 @@ HB_HD int64_t stochastic_round(R& rng, int64_t pop, int64_t cutoff) {
 // update_proj_energy_mol src/energy_evaluation.F90:906-986).  Returns H_0j (incl. sign) or 0; sets
 // is_ref when f == f0.
 template <int W>
-HB_HDN double proj_energy_hmatel(const Sys& s, const Params& p, const uint64_t* f, const uint8_t* occ, bool& is_ref) {
+HB_HDN double proj_energy_hmatel(const Sys& s, const Params& p, const uint64_t* f, const occ_t* occ, bool& is_ref) {
     int nx = 0;
 #pragma unroll
     for (int k = 0; k < W; ++k) nx += popc64(f[k] ^ p.f0[k]);

@@ -192,12 +192,6 @@ __global__ void k_reduce_partials(const SpawnPartials* __restrict__ partials, in
 // ------------------------------------------------------------------------------------------------
 constexpr int SORT_THREADS = 256;
 
-// The element count of the spawn list is read on the device (*pn, clamped to cap): hb200_iterate never brings it to the
-// host, so grids are sized from a host-side upper bound and the chunk of a block follows from the real count.
-__device__ __forceinline__ long long dev_count(const unsigned long long* __restrict__ pn, long long cap) {
-    const unsigned long long v = *pn;
-    return v > (unsigned long long)cap ? cap : (long long)v;
-}
 __device__ __forceinline__ long long sort_chunk(long long n, int nblk) {
     const long long c = (n + nblk - 1) / nblk;
     return (c + SORT_THREADS - 1) / SORT_THREADS * SORT_THREADS;
@@ -368,309 +362,6 @@ __global__ void k_scan_small(const int* __restrict__ in, int* __restrict__ out, 
     if (threadIdx.x == 0 && total) *total = carry;
 }
 
-// ------------------------------------------------------------------------------------------------
-// Kernel: annihilate_spawn_t[_initiator] + annihilate_main_list[_initiator] + round_low_population_spawns
-// (src/spawn_data.F90:859-1101, src/annihilation.f90:294-486, 600-675) on the sorted spawn list.
-// ------------------------------------------------------------------------------------------------
-constexpr int ANN_SHORT = 32;   // runs of equal keys up to this length are summed by the thread of their first element
-
-// What happens to one distinct spawned determinant once its events are summed: annihilation against the main list or
-// a new entry of it.  pop / initiator_pop / events: totals over the run that starts at element i.
-template <int W>
-__device__ __forceinline__ void annihilate_apply(const Params& p, int64_t* __restrict__ sp, long long i, const uint64_t* key,
-                                                 long long pop, long long initiator_pop, long long events,
-                                                 const uint64_t* __restrict__ states, int64_t* __restrict__ pops,
-                                                 long long nstates, int* __restrict__ ins_flag, long long* __restrict__ ins_pos) {
-    constexpr int E = W + 2;
-    int flag = 0;
-    if (p.initiator) {
-        const bool sgn_tot = pop >= 0, sgn_ini = initiator_pop >= 0;  // Fortran sign(1,0) = +1
-        const bool keep = (initiator_pop != 0 && sgn_tot == sgn_ini) || ((events < 0 ? -events : events) > 1);
-        flag = keep ? 0 : 1;
-    }
-    if (pop == 0) return;
-    const long long pos = lower_bound_det<W>(states, nstates, key);
-    bool hit = false;
-    if (pos < nstates) {
-        uint64_t f[W];
-        load_det<W>(states + pos * W, f);
-        hit = det_eq<W>(f, key);
-    }
-    if (hit) {
-        const long long cur = pops[pos];
-        if (!p.initiator) pops[pos] = cur + pop;
-        else if (cur != 0) pops[pos] = cur + pop;
-        else if (!flag) pops[pos] = pop;
-        return;
-    }
-    if (p.initiator && flag) return;  // spawned by non-initiators onto an unoccupied determinant
-    if (p.real_amplitudes) {
-        PhiloxStream rng;
-        rng.begin(p.seed, p.cycle, RNG_ROUND_SPAWN, det_hash64<W>(key), 0);
-        pop = stochastic_round(rng, (int64_t)pop, p.real_factor);
-        if (pop == 0) return;
-    }
-    sp[i * E + W] = pop;
-    ins_flag[i] = 1;
-    ins_pos[i] = pos;
-}
-
-template <int W>
-__global__ void __launch_bounds__(256)
-k_annihilate(Params p, int64_t* __restrict__ sp, const unsigned long long* __restrict__ pn, long long cap,
-             const uint64_t* __restrict__ states, int64_t* __restrict__ pops, long long nstates, int* __restrict__ ins_flag,
-             long long* __restrict__ ins_pos, long long* __restrict__ long_q, unsigned* __restrict__ long_n) {
-    constexpr int E = W + 2;
-    const long long n = dev_count(pn, cap);
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    ins_flag[i] = 0;
-    uint64_t key[W];
-#pragma unroll
-    for (int k = 0; k < W; ++k) key[k] = (uint64_t)sp[i * E + k];
-    if (i > 0) {
-        bool same = true;
-#pragma unroll
-        for (int k = 0; k < W; ++k) same = same && ((uint64_t)sp[(i - 1) * E + k] == key[k]);
-        if (same) return;  // not the head of its segment
-    }
-    long long pop = 0, initiator_pop = 0, events = 0;
-    long long j = i;
-    for (; j < n && j < i + ANN_SHORT; ++j) {
-        if (j > i) {
-            bool same = true;
-#pragma unroll
-            for (int k = 0; k < W; ++k) same = same && ((uint64_t)sp[j * E + k] == key[k]);
-            if (!same) break;
-        }
-        const long long pj = sp[j * E + W];
-        pop += pj;
-        if (p.initiator) {
-            if (!(sp[j * E + W + 1] & 1)) initiator_pop += pj;
-            else events += (pj < 0) ? -1 : ((pj > 0) ? 1 : 0);
-        }
-    }
-    if (j == i + ANN_SHORT && j < n) {
-        bool same = true;
-#pragma unroll
-        for (int k = 0; k < W; ++k) same = same && ((uint64_t)sp[j * E + k] == key[k]);
-        if (same) {     // a long run (e.g. the reference determinant near convergence): one warp sums it, k_annihilate_long
-            long_q[atomicAdd(long_n, 1u)] = i;
-            return;
-        }
-    }
-    annihilate_apply<W>(p, sp, i, key, pop, initiator_pop, events, states, pops, nstates, ins_flag, ins_pos);
-}
-
-// The long runs queued by k_annihilate: one warp per run (grid-stride over the queue); the end of the run is found by a
-// galloping + binary search on the sorted keys, the sums are integer (order-independent).
-template <int W>
-__global__ void __launch_bounds__(256)
-k_annihilate_long(Params p, int64_t* __restrict__ sp, const unsigned long long* __restrict__ pn, long long cap,
-                  const uint64_t* __restrict__ states, int64_t* __restrict__ pops, long long nstates,
-                  int* __restrict__ ins_flag, long long* __restrict__ ins_pos, const long long* __restrict__ long_q,
-                  const unsigned* __restrict__ long_n) {
-    constexpr int E = W + 2;
-    const long long n = dev_count(pn, cap);
-    const unsigned nq = *long_n;
-    const int lane = threadIdx.x & 31;
-    const unsigned gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    for (unsigned q = gw; q < nq; q += nw) {
-        const long long i = long_q[q];
-        uint64_t key[W];
-#pragma unroll
-        for (int k = 0; k < W; ++k) key[k] = (uint64_t)sp[i * E + k];
-        auto same_at = [&](long long j) {
-            bool same = true;
-#pragma unroll
-            for (int k = 0; k < W; ++k) same = same && ((uint64_t)sp[j * E + k] == key[k]);
-            return same;
-        };
-        long long lo = i + ANN_SHORT, step = ANN_SHORT;      // element lo belongs to the run
-        long long hi = lo + step;
-        while (hi < n && same_at(hi)) { lo = hi; step <<= 1; hi = lo + step; }
-        if (hi > n) hi = n;                                   // first element not in the run lies in (lo, hi]
-        while (hi - lo > 1) {
-            const long long mid = (lo + hi) >> 1;
-            if (same_at(mid)) lo = mid; else hi = mid;
-        }
-        long long pop = 0, initiator_pop = 0, events = 0;
-        for (long long j = i + lane; j < hi; j += 32) {
-            const long long pj = sp[j * E + W];
-            pop += pj;
-            if (p.initiator) {
-                if (!(sp[j * E + W + 1] & 1)) initiator_pop += pj;
-                else events += (pj < 0) ? -1 : ((pj > 0) ? 1 : 0);
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            pop += __shfl_xor_sync(0xffffffffu, pop, o);
-            initiator_pop += __shfl_xor_sync(0xffffffffu, initiator_pop, o);
-            events += __shfl_xor_sync(0xffffffffu, events, o);
-        }
-        if (lane == 0) annihilate_apply<W>(p, sp, i, key, pop, initiator_pop, events, states, pops, nstates, ins_flag, ins_pos);
-        __syncwarp();
-    }
-}
-
-// compaction of the surviving new determinants: ins[k] = [f, pop, pos]
-template <int W>
-__global__ void __launch_bounds__(256)
-k_compact_inserts(const int64_t* __restrict__ sp, const unsigned long long* __restrict__ pn, long long cap,
-                  const int* __restrict__ ins_flag, const int* __restrict__ ins_idx, const long long* __restrict__ ins_pos,
-                  int64_t* __restrict__ ins) {
-    constexpr int E = W + 2;
-    const long long n = dev_count(pn, cap);
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || !ins_flag[i]) return;
-    const long long k = ins_idx[i];
-#pragma unroll
-    for (int w = 0; w < W; ++w) ins[k * E + w] = sp[i * E + w];
-    ins[k * E + W] = sp[i * E + W];
-    ins[k * E + W + 1] = ins_pos[i];
-}
-
-// insert_new_walker: dat(1) = sc0_ptr(f) - H00 (src/annihilation.f90:820-901)
-template <int W>
-__global__ void __launch_bounds__(256)
-k_sc0(Sys s, double H00, const uint64_t* __restrict__ dets, long long stride_words, long long n, double* __restrict__ out,
-      const int* __restrict__ pn) {
-    if (pn) n = min(n, (long long)*pn);
-    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    uint64_t f[W];
-#pragma unroll
-    for (int w = 0; w < W; ++w) f[w] = dets[k * stride_words + w];
-    uint8_t occ[HB_MAXNEL];
-    decode_det<W>(f, occ);
-    out[k] = ((s.kind == SYS_UEG) ? slater_condon0_ueg(s, occ) : slater_condon0(s, occ)) - H00;
-}
-
-// remove_unoccupied_dets, first half (src/annihilation.f90:537-598): stochastic rounding of main-list
-// populations (real amplitudes) and per-tile survivor counts.
-template <int W>
-__global__ void __launch_bounds__(TILE)
-k_round_count(Params p, const uint64_t* __restrict__ states, int64_t* __restrict__ pops, long long nstates,
-              int* __restrict__ tile_keep) {
-    __shared__ int swarp[8];
-    const long long i = (long long)blockIdx.x * TILE + threadIdx.x;
-    int keep = 0;
-    if (i < nstates) {
-        int64_t pop = pops[i];
-        if (p.real_amplitudes) {
-            const int64_t ap = pop < 0 ? -pop : pop;
-            if (pop != 0 && ap < p.real_factor) {
-                uint64_t f[W];
-                load_det<W>(states + i * W, f);
-                PhiloxStream rng;
-                rng.begin(p.seed, p.cycle, RNG_ROUND_MAIN, det_hash64<W>(f), 0);
-                pop = stochastic_round(rng, pop, p.real_factor);
-                pops[i] = pop;
-            }
-        }
-        keep = pop != 0;
-    }
-    int tot;
-    block_excl_scan(keep, swarp, &tot);
-    if (threadIdx.x == 0) tile_keep[blockIdx.x] = tot;
-}
-
-// remove_unoccupied_dets (compaction) + insert_new_walkers (src/annihilation.f90:537-598, 677-818) as ONE
-// out-of-place merge: tile of TILE old states + the new determinants whose insertion point falls in the tile.
-template <int W>
-__global__ void __launch_bounds__(TILE)
-k_merge(const uint64_t* __restrict__ states, const int64_t* __restrict__ pops, const double* __restrict__ dat,
-        long long nstates, const int* __restrict__ tile_off, const int64_t* __restrict__ ins,
-        const double* __restrict__ ins_dat, const int* __restrict__ pnins, uint64_t* __restrict__ ostates,
-        int64_t* __restrict__ opops, double* __restrict__ odat, long long* __restrict__ part_npart, int ntiles) {
-    constexpr int E = W + 2;
-    const long long nins = *pnins;
-    __shared__ int swarp[8];
-    __shared__ int skept[TILE + 1];
-    __shared__ long long sk[2];
-    __shared__ long long sred[8];
-    const int tid = threadIdx.x;
-    const long long t0 = (long long)blockIdx.x * TILE;
-    const long long t1 = min(nstates, t0 + TILE);
-    const bool last = (blockIdx.x == ntiles - 1);
-    if (tid < 2) {
-        // inserts with pos in [t0, t1) (last tile: also pos == nstates) are a contiguous range [k_lo, k_hi)
-        const long long target = (tid == 0) ? t0 : t1;
-        long long lo = 0, hi = nins;
-        if (tid == 1 && last) lo = nins;
-        while (lo < hi) {
-            long long mid = (lo + hi) >> 1;
-            if (ins[mid * E + W + 1] < target) lo = mid + 1; else hi = mid;
-        }
-        sk[tid] = lo;
-    }
-    const long long m = t0 + tid;
-    int keep = 0;
-    int64_t pop = 0;
-    if (m < t1) { pop = pops[m]; keep = pop != 0; }
-    int tot;
-    const int kb = block_excl_scan(keep, swarp, &tot);
-    skept[tid] = kb;
-    if (tid == 0) skept[TILE] = tot;
-    __syncthreads();
-    const long long k_lo = sk[0], k_hi = sk[1];
-    const long long ns = k_hi - k_lo;
-    const long long out_base = (long long)tile_off[blockIdx.x] + k_lo;
-    long long npart = 0;
-    if (keep) {
-        // number of new determinants in this tile inserted at or before old state m
-        long long lo = 0, hi = ns;
-        while (lo < hi) {
-            long long mid = (lo + hi) >> 1;
-            if (ins[(k_lo + mid) * E + W + 1] <= m) lo = mid + 1; else hi = mid;
-        }
-        const long long o = out_base + kb + lo;
-        uint64_t f[W];
-        load_det<W>(states + m * W, f);
-        store_det<W>(ostates + o * W, f);
-        opops[o] = pop;
-        odat[o] = dat[m];
-        npart += pop < 0 ? -pop : pop;
-    }
-    for (long long j = tid; j < ns; j += TILE) {
-        const long long k = k_lo + j;
-        const long long pos = ins[k * E + W + 1];
-        const int loc = (int)(pos - t0);  // 0..TILE (TILE only for pos == nstates in the last tile)
-        const long long o = out_base + skept[loc] + j;
-        uint64_t f[W];
-#pragma unroll
-        for (int w = 0; w < W; ++w) f[w] = (uint64_t)ins[k * E + w];
-        store_det<W>(ostates + o * W, f);
-        const int64_t ip = ins[k * E + W];
-        opops[o] = ip;
-        odat[o] = ins_dat[k];
-        npart += ip < 0 ? -ip : ip;
-    }
-    npart = warp_sum_ll(npart);
-    if ((tid & 31) == 0) sred[tid >> 5] = npart;
-    __syncthreads();
-    if (tid == 0) {
-        long long t = 0;
-        for (int w = 0; w < TILE / 32; ++w) t += sred[w];
-        part_npart[blockIdx.x] = t;
-    }
-}
-
-// initialise_slot_pop (src/load_balancing.F90:624-654): encoded |population| per load-balancing slot
-// (slot = modulo(hash(f), nprocs * nslots)); integer atomics, so the sums are exact and order-independent
-template <int W>
-__global__ void __launch_bounds__(256)
-k_slot_pop(const uint64_t* __restrict__ states, const int64_t* __restrict__ pops, long long n, int nbasis, uint32_t seed,
-           int nprocs, int nslots, unsigned long long* __restrict__ slot_pop) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint64_t f[W];
-    load_det<W>(states + i * W, f);
-    const long long pp = pops[i];
-    if (pp != 0) atomicAdd(&slot_pop[owner_slot(f, nbasis, seed, nprocs, nslots)], (unsigned long long)(pp < 0 ? -pp : pp));
-}
-
 // sum |pop| over a list: per-block partials (fixed order) -> k_reduce_ll
 __global__ void __launch_bounds__(TILE) k_abs_sum(const int64_t* __restrict__ pops, long long n, long long* __restrict__ part) {
     __shared__ long long sl[TILE / 32];
@@ -816,6 +507,39 @@ static int dupload(hb200_engine* e, const T** dst, const T* src, size_t n) {
     return 0;
 }
 
+// determinants host <-> device: the wide layout pads every determinant to 32 words
+static cudaError_t copy_states_h2d(hb200_engine* e, uint64_t* dst, const uint64_t* src, long long n, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    if (e->W == e->We) return cudaMemcpyAsync(dst, src, (size_t)n * e->W * 8, cudaMemcpyHostToDevice, st);
+    cudaError_t r = cudaMemsetAsync(dst, 0, (size_t)n * e->W * 8, st);
+    if (r != cudaSuccess) return r;
+    return cudaMemcpy2DAsync(dst, (size_t)e->W * 8, src, (size_t)e->We * 8, (size_t)e->We * 8, (size_t)n, cudaMemcpyHostToDevice, st);
+}
+static cudaError_t copy_states_d2h(hb200_engine* e, uint64_t* dst, const uint64_t* src, long long n, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    if (e->W == e->We) return cudaMemcpyAsync(dst, src, (size_t)n * e->W * 8, cudaMemcpyDeviceToHost, st);
+    return cudaMemcpy2DAsync(dst, (size_t)e->We * 8, src, (size_t)e->W * 8, (size_t)e->We * 8, (size_t)n, cudaMemcpyDeviceToHost, st);
+}
+
+// spawn elements [f(1:W), population, flag] host <-> device (wide layout: f padded to 32 words)
+static cudaError_t copy_spawn(hb200_engine* e, int64_t* dst, const int64_t* src, long long n, bool to_device, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    if (e->W == e->We) return cudaMemcpyAsync(dst, src, (size_t)n * e->E * 8, kind, st);
+    const size_t hs = (size_t)(e->We + 2) * 8, ds = (size_t)e->E * 8;
+    cudaError_t r;
+    if (to_device) {
+        r = cudaMemsetAsync(dst, 0, (size_t)n * ds, st);
+        if (r != cudaSuccess) return r;
+        r = cudaMemcpy2DAsync(dst, ds, src, hs, (size_t)e->We * 8, (size_t)n, kind, st);
+        if (r != cudaSuccess) return r;
+        return cudaMemcpy2DAsync(dst + e->W, ds, src + e->We, hs, 16, (size_t)n, kind, st);
+    }
+    r = cudaMemcpy2DAsync(dst, hs, src, ds, (size_t)e->We * 8, (size_t)n, kind, st);
+    if (r != cudaSuccess) return r;
+    return cudaMemcpy2DAsync(dst + e->We, hs, src + e->W, ds, 16, (size_t)n, kind, st);
+}
+
 static cudaError_t copy_sync(hb200_engine* e, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
     cudaError_t r = cudaMemcpyAsync(dst, src, bytes, kind, e->stream);
     if (r != cudaSuccess) return r;
@@ -840,14 +564,36 @@ hb200_engine* hb200_create(const hb200_config* cfg) {
         g_err = "hb200_create: no CUDA device (the engine has no CPU fallback)";
         return nullptr;
     }
-    if (cfg->nel > HB_MAXNEL || cfg->nbasis > 64 * HB_MAXW || cfg->nbasis > 255) {
+    if (cfg->nel > HB_MAXNEL || cfg->nbasis > 64 * HB_MAXW) {
         g_err = "hb200_create: nel/nbasis beyond compiled limits (HB_MAXNEL, HB_MAXW)";
         return nullptr;
     }
     hb200_engine* e = new hb200_engine();
     e->cfg = *cfg;
-    e->W = (cfg->nbasis + 63) / 64;
+    // host layout: We = ceil(nbasis/64) words per determinant (particle_t%states).  Device layout: the same for
+    // We <= 4 (nbasis <= 254: byte occupied lists); wider bit strings - the plane-wave bases of the UEG - use the wide
+    // layout, 32 words per determinant (zero padded) with 16-bit occupied lists and a compressed-key sort.
+    e->We = (cfg->nbasis + 63) / 64;
+    e->W = (e->We <= 4 && cfg->nbasis <= 254) ? e->We : 32;
     e->E = e->W + 2;
+    switch (e->W) {
+        case 1: e->ops = hb_list_ops_w1(); break;
+        case 2: e->ops = hb_list_ops_w2(); break;
+        case 3: e->ops = hb_list_ops_w3(); break;
+        case 4: e->ops = hb_list_ops_w4(); break;
+        default: e->ops = hb_list_ops_w32(); break;
+    }
+    if (e->W > 4) {
+        int b = 1;
+        while ((1 << b) < cfg->nbasis + 1) ++b;
+        e->key_bits = b;
+        e->key_words = (cfg->nel * b + 63) / 64;
+        if (e->key_words > 5) {
+            g_err = "hb200_create: wide layout: nel * bits(nbasis) exceeds the 320-bit compressed sort key";
+            delete e;
+            return nullptr;
+        }
+    }
     auto fail = [&](const char* what) -> hb200_engine* {
         if (g_err.empty()) g_err = what;
         hb200_destroy(e);
@@ -877,6 +623,7 @@ hb200_engine* hb200_create(const hb200_config* cfg) {
     p.nprocs = std::max(1, cfg->nprocs);
     p.iproc = cfg->iproc;
     p.nslots = std::max(1, cfg->nslots);
+    p.we = e->We;
     const long long cap = cfg->walker_length;
     long long scap = cfg->spawned_walker_length;
     if (scap % p.nprocs != 0) scap = ((scap + p.nprocs - 1) / p.nprocs) * p.nprocs;  // src/qmc.F90:1461-1468
@@ -911,6 +658,9 @@ hb200_engine* hb200_create(const hb200_config* cfg) {
     if (dalloc(e, &e->d_ll, 4)) return fail("alloc");
     if (dalloc(e, &e->d_counts, (size_t)p.nprocs * p.nprocs)) return fail("alloc");
     if (dalloc(e, &e->d_spn, 2)) return fail("alloc");
+    if (e->W > 4)
+        for (int b = 0; b < 2; ++b)
+            if (dalloc(e, &e->d_items[b], (size_t)scap * (e->key_words + 1))) return fail("alloc sort keys");
     if (dalloc(e, &e->d_long_q, (size_t)(scap / ANN_SHORT + 2))) return fail("alloc");
     if (dalloc(e, &e->d_long_n, 2)) return fail("alloc");
     if (cudaMallocHost((void**)&e->h_out, sizeof(HostOut) + sizeof(unsigned long long) * p.nprocs) != cudaSuccess) return fail("alloc pinned");
@@ -1027,7 +777,14 @@ int hb200_set_system_ueg(hb200_engine* e, const hb200_system_ueg* in) {
     if (dupload(e, &s.sp_eigv, in->sp_eigv, (size_t)nb + 1)) return 1;
     if (dupload(e, &s.ueg_lookup, in->lookup, (size_t)in->n_lookup + 1)) return 1;
     const size_t tD = 2 * (size_t)in->tern_kmax + 1;
-    if (dupload(e, &s.ueg_tern, in->ternary_conserve, (size_t)(e->W + 1) * tD * tD * tD)) return 1;
+    if (e->W == e->We) {
+        if (dupload(e, &s.ueg_tern, in->ternary_conserve, (size_t)(e->W + 1) * tD * tD * tD)) return 1;
+    } else {     // wide layout: (0:We) words per entry -> (0:32), zero padded
+        std::vector<uint64_t> t((size_t)(e->W + 1) * tD * tD * tD, 0ull);
+        for (size_t k = 0; k < tD * tD * tD; ++k)
+            for (int w = 0; w <= e->We; ++w) t[k * (e->W + 1) + w] = in->ternary_conserve[k * (e->We + 1) + w];
+        if (dupload(e, &s.ueg_tern, t.data(), t.size())) return 1;
+    }
     s.ueg_piL = 3.1415926535897931 * in->box_length;   // pi*cell_param, as evaluated first in coulomb_int_ueg_3d
     s.ueg_kmax = in->kmax; s.ueg_offset = in->offset;
     for (int d = 0; d < 3; ++d) s.ueg_oi[d] = in->offset_inds[d];
@@ -1455,7 +1212,7 @@ int hb200_download_heat_bath(hb200_engine* e, int which, void* out, int64_t n) {
 
 int hb200_set_reference(hb200_engine* e, const uint64_t* f0, double H00) {
     CK(cudaSetDevice(e->cfg.device));
-    for (int k = 0; k < HB_MAXW; ++k) e->par.f0[k] = (k < e->W) ? f0[k] : 0;
+    for (int k = 0; k < HB_MAXW; ++k) e->par.f0[k] = (k < e->We) ? f0[k] : 0;
     e->par.H00 = H00;
     e->have_ref = true;
     return 0;
@@ -1476,7 +1233,7 @@ int hb200_upload_psips(hb200_engine* e, const uint64_t* states, const int64_t* p
     CK(cudaMemsetAsync(e->d_err, 0, 4 * sizeof(int), e->stream));  // a new list starts a new calculation
     if (n) {
         cudaStream_t st = e->stream;
-        CK(cudaMemcpyAsync(e->d_states[c], states, (size_t)n * e->W * 8, cudaMemcpyHostToDevice, st));
+        CK(copy_states_h2d(e, e->d_states[c], states, n, st));
         CK(cudaMemcpyAsync(e->d_pops[c], pops, (size_t)n * 8, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(e->d_dat[c], dat, (size_t)n * 8, cudaMemcpyHostToDevice, st));
         const int nb = (int)std::min<long long>(1184, (n + TILE - 1) / TILE);
@@ -1506,7 +1263,7 @@ int hb200_upload_psips_begin(hb200_engine* e, const uint64_t* states, const int6
     }
     const int g = e->stg;
     if (n) {
-        CK(cudaMemcpyAsync(e->d_states[g], states, (size_t)n * e->W * 8, cudaMemcpyHostToDevice, e->copy_stream));
+        CK(copy_states_h2d(e, e->d_states[g], states, n, e->copy_stream));
         CK(cudaMemcpyAsync(e->d_pops[g], pops, (size_t)n * 8, cudaMemcpyHostToDevice, e->copy_stream));
         CK(cudaMemcpyAsync(e->d_dat[g], dat, (size_t)n * 8, cudaMemcpyHostToDevice, e->copy_stream));
     }
@@ -1546,7 +1303,7 @@ int hb200_download_psips(hb200_engine* e, uint64_t* states, int64_t* pops, doubl
     const int c = e->cur;
     if (n) {
         cudaStream_t st = e->stream;
-        CK(cudaMemcpyAsync(states, e->d_states[c], (size_t)n * e->W * 8, cudaMemcpyDeviceToHost, st));
+        CK(copy_states_d2h(e, states, e->d_states[c], n, st));
         CK(cudaMemcpyAsync(pops, e->d_pops[c], (size_t)n * 8, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(dat, e->d_dat[c], (size_t)n * 8, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -1561,21 +1318,14 @@ int64_t hb200_nstates(hb200_engine* e) { return e->nstates; }
 // ------------------------------------------------------------------------------------------------
 // stage drivers
 // ------------------------------------------------------------------------------------------------
-#define DISPATCH_W(e, ...)                                    \
-    switch ((e)->W) {                                         \
-        case 1: { constexpr int WW = 1; __VA_ARGS__; } break; \
-        case 2: { constexpr int WW = 2; __VA_ARGS__; } break; \
-        case 3: { constexpr int WW = 3; __VA_ARGS__; } break; \
-        default: { constexpr int WW = 4; __VA_ARGS__; } break; \
-    }
-
 // launchers of hb_ccmc_tu.cu (one object file per W)
 #define DISPATCH_CCMC(e, rc, fn, ...)               \
     switch ((e)->W) {                               \
         case 1: rc = fn##1(__VA_ARGS__); break;     \
         case 2: rc = fn##2(__VA_ARGS__); break;     \
         case 3: rc = fn##3(__VA_ARGS__); break;     \
-        default: rc = fn##4(__VA_ARGS__); break;    \
+        case 4: rc = fn##4(__VA_ARGS__); break;     \
+        default: rc = fn##32(__VA_ARGS__); break;   \
     }
 
 // ---- peer-to-peer exchange kernels (hb200_iterate with nprocs > 1 after hb200_p2p_import) ---------------------------
@@ -1657,11 +1407,15 @@ static int spawn_dispatch(hb200_engine* e, int tile0, int ntiles, long long n) {
         default: FAIL("spawn_death: excitation generator not implemented");
     }
 #define HB_ROW(W) {hb_spawn_w##W##_g0, hb_spawn_w##W##_g1, hb_spawn_w##W##_g2, hb_spawn_w##W##_g3, hb_spawn_w##W##_g4}
-    static const hb_spawn_fn table[4][SPAWN_NGROUPS] = {HB_ROW(1), HB_ROW(2), HB_ROW(3), HB_ROW(4)};
+    // wide layout (W = 32): only the generators that need no nbasis^3 / nbasis^4 tables are built (the UEG's)
+    static const hb_spawn_fn table[5][SPAWN_NGROUPS] = {HB_ROW(1), HB_ROW(2), HB_ROW(3), HB_ROW(4),
+                                                        {nullptr, nullptr, nullptr, nullptr, hb_spawn_w32_g4}};
 #undef HB_ROW
     SpawnLaunch L;
     L.gen = gen; L.ntiles = ntiles; L.smem = 0; L.n = n; L.tile0 = tile0;
-    if (table[e->W - 1][group](e, p, L)) return 1;
+    const hb_spawn_fn fn = table[e->W <= 4 ? e->W - 1 : 4][group];
+    if (!fn) FAIL("spawn_death: this excitation generator is not built for the wide layout (nbasis > 254)");
+    if (fn(e, p, L)) return 1;
     CK(cudaGetLastError());
     e->launches++; e->spawn_launches++;
     return 0;
@@ -1810,16 +1564,24 @@ static int device_scan(hb200_engine* e, const int* d_in, int* d_out, long long n
 static int stage_sort(hb200_engine* e, long long bound) {
     if (bound <= 1) return 0;
     cudaStream_t st = e->stream;
-    const int E = e->E;
     const int nblk = (int)std::max<long long>(1, std::min<long long>(1184, (bound + 2047) / 2048));
     if (256ll * nblk > e->hist_cap) FAIL("sort: histogram scratch too small");
     const unsigned long long* pn = e->sp_pn;
     const long long cap = e->sp_cap;
-    const int npass = (e->cfg.nbasis + 7) / 8;
+    const bool wide = e->W > 4;
+    // wide layout: sort compressed keys (hb_list.cuh: the occupied orbitals packed key_bits apiece, nel * key_bits bits
+    // instead of nbasis) with the element index as payload, then move the elements once
+    const int E = wide ? e->key_words + 1 : e->E;
+    const int npass = wide ? (e->cfg.nel * e->key_bits + 7) / 8 : (e->cfg.nbasis + 7) / 8;
+    int icur = 0;
+    if (wide) {
+        if (e->ops->compress(e, e->sp_ptr[e->sp_cur], bound, e->key_bits, e->key_words, e->d_items[0])) return 1;
+        e->launches++;
+    }
     for (int ps = 0; ps < npass; ++ps) {
         const int word = (8 * ps) / 64, shift = (8 * ps) % 64;
-        const int64_t* src = e->sp_ptr[e->sp_cur];
-        int64_t* dst = e->sp_ptr[e->sp_cur ^ 1];
+        const int64_t* src = wide ? e->d_items[icur] : e->sp_ptr[e->sp_cur];
+        int64_t* dst = wide ? e->d_items[icur ^ 1] : e->sp_ptr[e->sp_cur ^ 1];
         switch (E) {
             case 3: k_radix_hist<3><<<nblk, SORT_THREADS, 0, st>>>(src, pn, cap, word, shift, e->d_hist, nblk); break;
             case 4: k_radix_hist<4><<<nblk, SORT_THREADS, 0, st>>>(src, pn, cap, word, shift, e->d_hist, nblk); break;
@@ -1841,6 +1603,11 @@ static int stage_sort(hb200_engine* e, long long bound) {
         }
         CK(cudaGetLastError());
         e->launches += 3;
+        if (wide) icur ^= 1; else e->sp_cur ^= 1;
+    }
+    if (wide) {
+        if (e->ops->gather(e, e->sp_ptr[e->sp_cur], e->key_words, e->d_items[icur], e->sp_ptr[e->sp_cur ^ 1])) return 1;
+        e->launches++;
         e->sp_cur ^= 1;
     }
     return 0;
@@ -1871,43 +1638,29 @@ static int stage_annihilate_launch(hb200_engine* e, uint32_t cycle, long long bo
     p.cycle = cycle;
     cudaStream_t st = e->stream;
     const long long ns = e->nstates;
-    const int c = e->cur, o = e->alt;
     int64_t* sp = e->sp_ptr[e->sp_cur];
     int64_t* ins = e->sp_ptr[e->sp_cur ^ 1];
     const unsigned long long* pn = e->sp_pn;
-    const long long cap = e->sp_cap;
     if (bound > 0) {
         CK(cudaMemsetAsync(e->d_long_n, 0, sizeof(unsigned), st));
-        const unsigned nb = (unsigned)((bound + 255) / 256);
-        DISPATCH_W(e, k_annihilate<WW><<<nb, 256, 0, st>>>(p, sp, pn, cap, e->d_states[c], e->d_pops[c], ns, e->d_ins_flag,
-                                                          e->d_ins_pos, e->d_long_q, e->d_long_n));
-        DISPATCH_W(e, k_annihilate_long<WW><<<std::min(nb, 592u), 256, 0, st>>>(p, sp, pn, cap, e->d_states[c], e->d_pops[c], ns,
-                                                                                e->d_ins_flag, e->d_ins_pos, e->d_long_q,
-                                                                                e->d_long_n));
-        CK(cudaGetLastError());
+        if (e->ops->annihilate(e, p, sp, bound)) return 1;
         e->launches += 2;
         if (device_scan(e, e->d_ins_flag, e->d_ins_idx, bound, 0, pn)) return 1;
-        DISPATCH_W(e, k_compact_inserts<WW><<<nb, 256, 0, st>>>(sp, pn, cap, e->d_ins_flag, e->d_ins_idx, e->d_ins_pos, ins));
-        CK(cudaGetLastError());
+        if (e->ops->compact(e, sp, bound, ins)) return 1;
         e->launches++;
     } else {
         CK(cudaMemsetAsync(e->d_total, 0, sizeof(int), st));
     }
     const int ntiles = std::max<int>(1, (int)((ns + TILE - 1) / TILE));
-    DISPATCH_W(e, k_round_count<WW><<<ntiles, TILE, 0, st>>>(p, e->d_states[c], e->d_pops[c], ns, e->d_tile_keep));
-    CK(cudaGetLastError());
+    if (e->ops->round_count(e, p, ntiles)) return 1;
     e->launches++;
     if (device_scan(e, e->d_tile_keep, e->d_tile_off, ntiles, 1, nullptr)) return 1;
     k_cap_check<<<1, 1, 0, st>>>(e->d_total, e->cfg.walker_length, e->d_err);
     if (bound > 0) {
-        DISPATCH_W(e, k_sc0<WW><<<(unsigned)((bound + 255) / 256), 256, 0, st>>>(e->sys, p.H00, (const uint64_t*)ins, e->E, bound,
-                                                                                e->d_ins_dat, e->d_total));
+        if (e->ops->sc0(e, p.H00, (const uint64_t*)ins, e->E, bound, e->d_ins_dat, e->d_total)) return 1;
         e->launches++;
     }
-    DISPATCH_W(e, k_merge<WW><<<ntiles, TILE, 0, st>>>(e->d_states[c], e->d_pops[c], e->d_dat[c], ns, e->d_tile_off, ins,
-                                                        e->d_ins_dat, e->d_total, e->d_states[o], e->d_pops[o], e->d_dat[o],
-                                                        e->d_part_ll, ntiles));
-    CK(cudaGetLastError());
+    if (e->ops->merge(e, ins, ntiles)) return 1;
     k_reduce_ll<<<1, 1024, 0, st>>>(e->d_part_ll, ntiles, e->d_ll);
     CK(cudaGetLastError());
     e->launches += 3;
@@ -2011,7 +1764,7 @@ int hb200_ccmc_spawn(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, i
         CK(cudaMemcpyAsync(map.data(), e->d_proc_map, map.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         int slot = 0;
-        DISPATCH_W(e, slot = owner_slot_shift<WW>(p.f0, e->sys.nbasis, p.hash_seed, p.ccmc_shift, p.ccmc_freq, p.nprocs, p.nslots));
+        slot = e->ops->owner_slot_shift(e, p);
         D0_proc = map[slot];
     }
     long long d0info[2] = {0, 0};
@@ -2299,10 +2052,7 @@ int hb200_slot_populations(hb200_engine* e, double* slot_pop, int32_t n) {
     CK(cudaMemsetAsync(d, 0, sizeof(unsigned long long) * ns, e->stream));
     const long long m = e->nstates;
     if (m > 0) {
-        DISPATCH_W(e, k_slot_pop<WW><<<(unsigned)((m + 255) / 256), 256, 0, e->stream>>>(e->d_states[e->cur], e->d_pops[e->cur], m,
-                                                                                       e->sys.nbasis, e->par.hash_seed,
-                                                                                       e->par.nprocs, e->par.nslots, d));
-        CK(cudaGetLastError());
+        if (e->ops->slot_pop(e, d)) return 1;
     }
     std::vector<unsigned long long> h(ns);
     CK(copy_sync(e, h.data(), d, sizeof(unsigned long long) * ns, cudaMemcpyDeviceToHost));
@@ -2368,7 +2118,7 @@ int hb200_annihilate_main(hb200_engine* e, uint32_t cycle, hb200_iter_out* out) 
 int hb200_download_spawn(hb200_engine* e, int64_t* sdata, int64_t capacity, int64_t* n) {
     CK(cudaSetDevice(e->cfg.device));
     CK(cudaStreamSynchronize(e->stream));
-    const int E = e->E;
+    const int E = e->E, Eh = e->We + 2;      // element length on the device / in the host's layout
     if (e->sp_blocked) {
         // still partitioned by destination: concatenate the blocks
         long long tot = 0;
@@ -2378,15 +2128,16 @@ int hb200_download_spawn(hb200_engine* e, int64_t* sdata, int64_t capacity, int6
         long long off = 0;
         for (int d = 0; d < e->par.nprocs; ++d) {
             const long long c = (long long)e->h_head[d];
-            if (c) CK(copy_sync(e, sdata + off * E, e->d_spawn[0] + (long long)d * e->block_size * E, (size_t)c * E * 8,
-                                 cudaMemcpyDeviceToHost));
+            if (c) CK(copy_spawn(e, sdata + off * Eh, e->d_spawn[0] + (long long)d * e->block_size * E, c, false, e->stream));
             off += c;
         }
+        CK(cudaStreamSynchronize(e->stream));
         return 0;
     }
     *n = e->sp_n;
     if (e->sp_n > capacity) FAIL("download_spawn: capacity too small");
-    if (e->sp_n) CK(copy_sync(e, sdata, e->sp_ptr[e->sp_cur], (size_t)e->sp_n * E * 8, cudaMemcpyDeviceToHost));
+    if (e->sp_n) CK(copy_spawn(e, sdata, e->sp_ptr[e->sp_cur], e->sp_n, false, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
     return 0;
 }
 
@@ -2400,7 +2151,8 @@ int hb200_spawn_counts(hb200_engine* e, int64_t* counts, int32_t nprocs) {
 int hb200_upload_spawn(hb200_engine* e, const int64_t* sdata, int64_t n) {
     CK(cudaSetDevice(e->cfg.device));
     if (n > e->cfg.spawned_walker_length) FAIL("upload_spawn: too many elements");
-    if (n) CK(copy_sync(e, e->d_spawn[0], sdata, (size_t)n * e->E * 8, cudaMemcpyHostToDevice));
+    if (n) CK(copy_spawn(e, e->d_spawn[0], sdata, n, true, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
     e->sp_ptr[0] = e->d_spawn[0]; e->sp_ptr[1] = e->d_spawn[1];
     e->sp_cur = 0; e->sp_blocked = false;
     return set_count_host(e, n);
@@ -2601,9 +2353,8 @@ int hb200_sc0_batch(hb200_engine* e, const uint64_t* states, int64_t n, double* 
     double* d_o = nullptr;
     CK(cudaMalloc((void**)&d_f, (size_t)n * e->W * 8));
     CK(cudaMalloc((void**)&d_o, (size_t)n * 8));
-    CK(copy_sync(e, d_f, states, (size_t)n * e->W * 8, cudaMemcpyHostToDevice));
-    DISPATCH_W(e, k_sc0<WW><<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->sys, 0.0, d_f, e->W, n, d_o, nullptr));
-    CK(cudaGetLastError());
+    CK(copy_states_h2d(e, d_f, states, n, e->stream));
+    if (e->ops->sc0(e, 0.0, d_f, e->W, n, d_o, nullptr)) return 1;
     CK(cudaStreamSynchronize(e->stream));
     CK(copy_sync(e, out, d_o, (size_t)n * 8, cudaMemcpyDeviceToHost));
     cudaFree(d_f); cudaFree(d_o);
@@ -2626,7 +2377,7 @@ int hb200_gen_excit_batch(hb200_engine* e, const uint64_t* states, const int64_t
     CK(cudaMalloc((void**)&d_io, (size_t)n * 8 * 4));
     CK(cudaMalloc((void**)&d_do, (size_t)n * 2 * 8));
     CK(cudaMalloc((void**)&d_ns, (size_t)n * 8));
-    CK(copy_sync(e, d_f, states, (size_t)n * e->W * 8, cudaMemcpyHostToDevice));
+    CK(copy_states_h2d(e, d_f, states, n, e->stream));
     CK(copy_sync(e, d_p, pops, (size_t)n * 8, cudaMemcpyHostToDevice));
     CK(copy_sync(e, d_a, attempt, (size_t)n * 4, cudaMemcpyHostToDevice));
     { int rc = 0; DISPATCH_CCMC(e, rc, hb_gen_excit_batch_w, e, p, d_f, d_p, d_a, n, d_io, d_do, d_ns); if (rc) return 1; }

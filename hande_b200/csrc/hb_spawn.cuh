@@ -50,7 +50,8 @@ struct SpawnSmem {
         sperm = o;  o += heat_bath ? TILE : 0;
         ssq = o;    o += heat_bath ? TILE : 0;                     // queue of single-excitation slots
         ssi = o;    o += heat_bath ? 2 * TILE : 0;                 // singles: i, a
-        socc = o;   o += (size_t)TILE * nel;
+        o = (o + 1) & ~(size_t)1;
+        socc = o;   o += (size_t)TILE * nel * sizeof(occ_t);
         ssu = o;    o += (size_t)TILE * nsu;
         o = (o + 7) & ~(size_t)7;
         sps = o;    o += ps ? (size_t)TILE * 24 : 0;
@@ -105,7 +106,7 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
     uint8_t* sperm = smem_raw + L.sperm;
     uint8_t* ssq = smem_raw + L.ssq;
     uint8_t* ssi = smem_raw + L.ssi;
-    uint8_t* socc = smem_raw + L.socc;
+    occ_t* socc = reinterpret_cast<occ_t*>(smem_raw + L.socc);
     uint8_t* ssu = smem_raw + L.ssu;
 
     const int tid = threadIdx.x;
@@ -126,11 +127,11 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
 #pragma unroll
         for (int k = 0; k < W; ++k) sf[tid * W + k] = f[k];
         ssign[tid] = pop < 0;
-        uint8_t* occ = socc + tid * nel;
+        occ_t* occ = socc + tid * nel;
         decode_det<W>(f, occ);
         if (GEN == EXCIT_GEN_POWER_PITZER_ORDERN) find_diff_ref_cdet<W>(s, p.f0, f, ssu + tid * nsu);
         else if (nsu) build_symunocc_masks<W>(s, f, ssu + tid * nsu);
-        const uint64_t h = det_hash64<W>(f);
+        const uint64_t h = det_hash64<W>(f, HB_NW(p));
         if (!hb_stage) shash[tid] = h;
         const double real_pop = (double)pop / (double)p.real_factor;
         // set_parent_flag (src/ifciqmc.f90:13-57)
@@ -177,7 +178,7 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
 #pragma unroll
         for (int k = 0; k < W; ++k) f[k] = sf[lo * W + k];
         PhiloxStream rng;
-        rng.begin(p.seed, p.cycle, RNG_SPAWN, hb_stage ? det_hash64<W>(f) : shash[lo], (uint32_t)att);
+        rng.begin(p.seed, p.cycle, RNG_SPAWN, hb_stage ? det_hash64<W>(f, HB_NW(p)) : shash[lo], (uint32_t)att);
         if (!hb_stage) rng.prefetch();   // uniform generators draw inside divergent rejection loops
         Gen g;
         if (heat_bath) {

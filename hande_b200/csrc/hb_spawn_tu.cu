@@ -158,8 +158,10 @@ int HB_CAT4(hb_spawn_w, HB_TU_W, _g, HB_TU_GROUP)(hb200_engine* e, const Params&
         case EXCIT_GEN_NO_RENORM: return launch_spawn<W, EXCIT_GEN_NO_RENORM>(e, p, L);
         case EXCIT_GEN_NO_RENORM_SPIN: return launch_spawn<W, EXCIT_GEN_NO_RENORM_SPIN>(e, p, L);
 #else
+#if HB_TU_W <= 4      // molecular generators: reference-mapped tables hold byte orbital lists (nbasis <= 254)
         case EXCIT_GEN_POWER_PITZER: return launch_spawn<W, EXCIT_GEN_POWER_PITZER>(e, p, L);
         case EXCIT_GEN_POWER_PITZER_ORDERN: return launch_spawn<W, EXCIT_GEN_POWER_PITZER_ORDERN>(e, p, L);
+#endif
         case GEN_UEG: return launch_spawn<W, GEN_UEG>(e, p, L);
         case GEN_UEG_PP: return launch_spawn<W, GEN_UEG_PP>(e, p, L);
 #endif

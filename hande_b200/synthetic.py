@@ -162,23 +162,21 @@ def random_walkers_torch(n, nbasis, nalpha, nbeta, real_factor, device, seed=1, 
     (distribution A of SURVEY.md 8d), generated on the GPU with torch (data plumbing only).
     Returns numpy (states[n, W] uint64, pops[n] int64)."""
     import torch
-    assert nbasis <= 126, "two signed 64-bit words"
     norb = nbasis // 2
     W = (nbasis + 63) // 64
     g = torch.Generator(device=device)
     g.manual_seed(seed * 1000003 + iproc)
     parts = []
     have = 0
+    if norb > 128:
+        chunk = min(chunk, max(1 << 16, (1 << 29) // norb))     # the (chunk, norb) random matrix stays below 2 GB
     while have < n:
         m = chunk
-        w = torch.zeros((m, 2), dtype=torch.int64, device=device)
+        w = torch.zeros((m, max(W, 2)), dtype=torch.int64, device=device)
         for nocc, off in ((nalpha, 0), (nbeta, 1)):
             sel = torch.rand((m, norb), device=device, generator=g).topk(nocc, dim=1).indices  # nocc of norb
             bit = 2 * sel + off
-            for wi in range(W):
-                inw = (bit // 64) == wi
-                contrib = torch.where(inw, torch.ones_like(bit) << (bit % 64), torch.zeros_like(bit)).sum(dim=1)
-                w[:, wi] |= contrib
+            w.scatter_add_(1, bit // 64, torch.ones_like(bit) << (bit % 64))    # distinct bits: add == or
         if nprocs > 1:
             w = w[murmur_owner_torch(w, nbasis, nprocs) == iproc]
         parts.append(w)

@@ -9,6 +9,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "liboracle.so")
+LIB_WIDE = os.path.join(HERE, "liboracle_wide.so")     # MAXW = 32 (bit strings of up to 2048 spin-orbitals)
 REF_LIB = os.path.join(HERE, "_ref", "libhande_ref_c.so")
 HUGE = 2**31 - 1
 
@@ -34,22 +35,22 @@ class QmcIn(C.Structure):
 
 def build(force=False):
     """Compile the oracle (and oracle/_ref when the reference tree is present)."""
-    if force or not os.path.exists(LIB) or any(
-            os.path.getmtime(os.path.join(HERE, f)) > os.path.getmtime(LIB)
-            for f in ("capi.cpp", "system.hpp", "rng.hpp", "excit_gen.hpp", "ueg.hpp", "fciqmc.hpp", "ccmc.hpp")):
-        subprocess.check_call(["make", "-C", HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    for target in (LIB, LIB_WIDE):
+        if force or not os.path.exists(target) or any(
+                os.path.getmtime(os.path.join(HERE, f)) > os.path.getmtime(target)
+                for f in ("capi.cpp", "system.hpp", "rng.hpp", "excit_gen.hpp", "ueg.hpp", "fciqmc.hpp", "ccmc.hpp")):
+            subprocess.check_call(["make", "-C", HERE, os.path.basename(target)], stdout=subprocess.DEVNULL)
     if not os.path.exists(REF_LIB) and os.path.isdir("/root/reference/lib/dSFMT-src-2.2.3"):
         subprocess.check_call(["make", "-C", HERE, "ref"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 
 
-_lib = None
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
+def lib(wide=False):
+    if wide not in _libs:
         build()
-        L = C.CDLL(LIB)
+        L = C.CDLL(LIB_WIDE if wide else LIB)
         L.orc_last_error.restype = C.c_char_p
         L.orc_create.restype = C.c_void_p
         L.orc_destroy.argtypes = [C.c_void_p]
@@ -124,8 +125,8 @@ def lib():
         L.orc_hb_ptr_i.restype = C.POINTER(C.c_int)
         L.orc_hb_ptr_i.argtypes = [C.c_void_p, C.c_int]
         L.orc_cpu_baseline.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p]
-        _lib = L
-    return _lib
+        _libs[wide] = L
+    return _libs[wide]
 
 
 def have_ref_lib():
@@ -144,8 +145,9 @@ def _p(a):
 class Oracle:
     """One restated HANDE calculation (system + FCIQMC state)."""
 
-    def __init__(self):
-        self.L = lib()
+    def __init__(self, wide=False):
+        """wide=True: the 32-word build (bit strings of more than 256 spin-orbitals)"""
+        self.L = lib(wide)
         self.h = C.c_void_p(self.L.orc_create())
 
     def __del__(self):

@@ -29,7 +29,10 @@
 namespace oracle {
 
 constexpr double depsilon = 1.e-12;  // lib/local/const.F90:91
-constexpr int MAXW = 4;              // max 64-bit words per determinant handled by the oracle
+#ifndef ORACLE_MAXW
+#define ORACLE_MAXW 4
+#endif
+constexpr int MAXW = ORACLE_MAXW;    // max 64-bit words per determinant: 4 in liboracle.so, 32 in liboracle_wide.so
 
 struct BasisFn {
     int sym = 0;            // point-group irrep (0-based, incl. Lz field if used)

@@ -26,6 +26,9 @@ SYSTEMS = {
     # uniform electron gas: (electrons, ms, rs, cutoff)
     "ueg6": dict(ueg=(6, 0, 2.0, 2.0)),        # the reference's np2/np4 fixture system, 66 spin-orbitals (W = 2)
     "ueg14": dict(ueg=(14, 0, 1.0, 4.0)),      # 186 spin-orbitals (W = 3)
+    # wide layout (more than 254 spin-orbitals: 32-word device lists, 16-bit occupied lists, compressed-key sort)
+    "ueg358": dict(ueg=(14, 0, 1.0, 6.0), wide=True),     # 358 spin-orbitals (host W = 6)
+    "ueg2042": dict(ueg=(14, 0, 1.0, 19.0), wide=True),   # BASELINE configs[3]: 14 electrons, 1021 plane waves (W = 32)
 }
 
 
@@ -49,7 +52,7 @@ def system_path(name):
 def make_pair(name, *, excit_gen="renorm", tau=0.01, seed=11, real=False, initiator=False, ex_level=-1,
               walker_length=1 << 17, spawned_walker_length=1 << 16, engine=True, device=0, quasi_newton=None):
     """Host system + oracle (Philox stream, symmetric initiator event rule) + GPU engine with identical options."""
-    o = Oracle()
+    o = Oracle(wide=SYSTEMS[name].get("wide", False))
     if "ueg" in SYSTEMS[name]:
         from hande_b200.ueg import UegSystem
         s = UegSystem(*SYSTEMS[name]["ueg"])

@@ -140,6 +140,13 @@ def test_gen_excit_ueg():
     _check_gen("ueg14", "power_pitzer", True, 0.002, n=150, nattempt=5)
 
 
+@pytest.mark.parametrize("name,gen", [("ueg358", "no_renorm"), ("ueg2042", "no_renorm")])
+def test_gen_excit_ueg_wide(name, gen):
+    """Bit strings wider than 4 words (BASELINE configs[3], ~1000 plane waves): find_ab_ueg over 32-word strings,
+    ternary_conserve rows re-strided to the device width, 16-bit occupied lists, slater_condon0_ueg"""
+    _check_gen(name, gen, True, 0.002, n=150, nattempt=5)
+
+
 @pytest.mark.parametrize("name", ["s10", "s50"])
 def test_heat_bath_tables_match_oracle(name):
     """every entry of the device-built tables (S50: 1e8-entry ijab_w / ijab_U / ijab_K, the tables the bench reads)"""
@@ -203,6 +210,9 @@ CASES = [
     ("ueg6", "no_renorm", False, False, 0.01, 3000, -1),
     ("ueg14", "no_renorm", True, True, 0.004, 4000, -1),
     ("ueg14", "power_pitzer", True, True, 0.004, 4000, -1),
+    ("ueg358", "no_renorm", True, True, 0.004, 4000, -1),       # wide layout
+    ("ueg2042", "no_renorm", True, False, 0.004, 4000, -1),     # BASELINE configs[3] size
+    ("ueg2042", "no_renorm", False, True, 0.004, 3000, -1),
 ]
 
 
@@ -268,7 +278,9 @@ def _check_ps_stats(eng, o):
                                                      ("s12", "heat_bath_uniform", True, False, 0.0004),
                                                      ("ueg6", "no_renorm", False, False, 0.005),
                                                      ("ueg14", "no_renorm", True, True, 0.002),
-                                                     ("ueg6", "power_pitzer", True, False, 0.005)])
+                                                     ("ueg6", "power_pitzer", True, False, 0.005),
+                                                     ("ueg358", "no_renorm", True, True, 0.002),
+                                                     ("ueg2042", "no_renorm", True, False, 0.0003)])
 def test_iterate_from_single_determinant(name, gen, real, init, tau):
     """Population growth from the reference determinant: 60 cycles in blocks of 10 through hb200_iterate."""
     s, o, eng, ref = make_pair(name, excit_gen=gen, tau=tau, real=real, initiator=init)

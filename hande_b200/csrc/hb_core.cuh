@@ -879,8 +879,26 @@ HB_HD int clz64(uint64_t x) {
 #endif
 }
 // sum_q tab[occ[q]-1] in occ_list order; loads issued four at a time (adding the 0.0 padding is exact)
+// byte lists whose length is a multiple of four and that start on a word boundary (the spawn kernel's staged lists) are
+// read four orbitals to a 32-bit word
+HB_HD bool occ_words_ok(const occ_t* occ, int nel) {
+    return sizeof(occ_t) == 1 && (nel & 3) == 0 && (((size_t)occ) & 3) == 0;
+}
 HB_HD double sum_occ(const double* __restrict__ tab, const occ_t* occ, int nel) {
     double tot = 0.0;
+    if (occ_words_ok(occ, nel)) {
+        const uint32_t* ow = reinterpret_cast<const uint32_t*>(occ);
+        const double* __restrict__ tab1 = tab - 1;
+        for (int q0 = 0; q0 < nel; q0 += 4) {
+            const uint32_t o4 = ow[q0 >> 2];
+            double v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = tab1[(o4 >> (8 * k)) & 0xffu];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tot = tot + v[k];
+        }
+        return tot;
+    }
     for (int q0 = 0; q0 < nel; q0 += 4) {
         double v[4];
 #pragma unroll
@@ -1034,6 +1052,22 @@ HB_HD int select_alias_staged(R& rng, int N, const double* wq, int stride, doubl
 // gather tab[occ[q]-1] into wq[q*stride] and return their sum in list order; loads issued four at a time
 HB_HD double stage_occ(const double* __restrict__ tab, const occ_t* occ, int nel, double* wq, int stride) {
     double tot = 0.0;
+    if (occ_words_ok(occ, nel)) {
+        const uint32_t* ow = reinterpret_cast<const uint32_t*>(occ);
+        const double* __restrict__ tab1 = tab - 1;
+        for (int q0 = 0; q0 < nel; q0 += 4) {
+            const uint32_t o4 = ow[q0 >> 2];
+            double v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = tab1[(o4 >> (8 * k)) & 0xffu];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                wq[(q0 + k) * stride] = v[k];
+                tot = tot + v[k];
+            }
+        }
+        return tot;
+    }
     for (int q0 = 0; q0 < nel; q0 += 4) {
         double v[4];
 #pragma unroll
@@ -1110,6 +1144,35 @@ HB_HDN void hb_phase_a(R& rng, const Sys& s, const uint64_t* f, const occ_t* occ
 template <int W>
 HB_HD double hb_sc1(const Sys& s, const uint64_t* f, const occ_t* occ, int fr, int to, bool& perm) {
     perm = excit_perm1<W>(f, fr, to);
+    if (s.sc1T) {
+        // slater_condon1_mol_excit through the branch-free rows (Sys::sc1T): entry j = {<ij|aj>, <ij|ja> or 0}; the entry
+        // of the excited orbital itself and entry 0 (list padding) are {0, 0}, so every partial sum equals the
+        // reference's, in occ_list order.  Loads issued four at a time.
+        const unsigned ta = s.uhf ? (unsigned)(to - 1) : ((unsigned)(to - 1) >> 1);
+        const D2* __restrict__ row = s.sc1T + ((size_t)((unsigned)(fr - 1) * (unsigned)s.sc1A + ta)) * (unsigned)(s.nbasis + 1);
+        double h = one_body(s, fr, to);
+        const int nel = s.nel;
+        if (occ_words_ok(occ, nel)) {
+            const uint32_t* ow = reinterpret_cast<const uint32_t*>(occ);
+            for (int q0 = 0; q0 < nel; q0 += 4) {
+                const uint32_t o4 = ow[q0 >> 2];
+                D2 v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = row[(o4 >> (8 * k)) & 0xffu];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { h = h + v[k].x; h = h - v[k].y; }
+            }
+            return perm ? -h : h;
+        }
+        for (int q0 = 0; q0 < nel; q0 += 4) {
+            D2 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = row[(q0 + k < nel) ? occ[q0 + k] : 0];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { h = h + v[k].x; h = h - v[k].y; }
+        }
+        return perm ? -h : h;
+    }
     return slater_condon1_excit(s, occ, fr, to, perm);
 }
 
@@ -1155,6 +1218,16 @@ HB_HD bool hb_single_term(const Sys& s, int i, int a, double hmod_ia, double ij_
     if (i == oq || a == oq) return false;
     const int64_t nb = s.nbasis;
     // hb_ijab%weights_tot(a,oq,i) and hb_ija%weights(a,oq,i) are the same number (the same sum): one load
+    if (s.hb_ija_rec) {
+        // packed record: {w = hb_ija%weights(a,oq,i), p = w / hb_ija%weights_tot(oq,i)} - the same division, done once
+        // when the tables were built
+        const HbRec* rec = s.hb_ija_rec + HB_I3(a, oq, i);
+        const double wt = rec->w, pa = rec->p;
+        double psq;
+        if (hmod_ia < wt) psq = hmod_ia / (wt + hmod_ia); else psq = 0.5;
+        term = (psq * (s.hb_ij_w[HB_I2(oq, i)] / ij_tot) * pa);
+        return true;
+    }
     const double wt = s.hb_ija_w[HB_I3(a, oq, i)];
     double psq;
     if (hmod_ia < wt) psq = hmod_ia / (wt + hmod_ia); else psq = 0.5;

@@ -50,7 +50,7 @@ struct SpawnSmem {
         sperm = o;  o += heat_bath ? TILE : 0;
         ssq = o;    o += heat_bath ? TILE : 0;                     // queue of single-excitation slots
         ssi = o;    o += heat_bath ? 2 * TILE : 0;                 // singles: i, a
-        o = (o + 1) & ~(size_t)1;
+        o = (o + 3) & ~(size_t)3;
         socc = o;   o += (size_t)TILE * nel * sizeof(occ_t);
         ssu = o;    o += (size_t)TILE * nsu;
         o = (o + 7) & ~(size_t)7;

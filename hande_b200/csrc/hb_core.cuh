@@ -1390,11 +1390,44 @@ HB_HDN void gen_single_heat_bath_exact(R& rng, const Sys& s, const Params& p, co
     g.allowed = true;
 }
 
+// One weight of find_ia_single_weights: |<D|H|D_i^a>| for an allowed (same spin, same symmetry) pair, else 0
+HB_HD double hb_single_weight(const Sys& s, const occ_t* occ, int i, int a) {
+    if (((a ^ i) & 1) == 0 && s.bf_sym[a] == s.bf_sym[i]) return fabs(slater_condon1_excit(s, occ, i, a, false));
+    return 0.0;
+}
+// gen_single_excit_heat_bath_exact once the weights are known: wi[q] = sum over a of w(q, a) (a ascending), wall =
+// the nel x nvirt weights, unocc = the unoccupied orbitals ascending.  Draws i then a (two random numbers).
+template <int W, class R, class U>
+HB_HDN void gen_single_heat_bath_select(R& rng, const Sys& s, const Params& p, const uint64_t* f, const occ_t* occ,
+                                        const double* wi, const double* wall, const U* unocc, Gen& g) {
+    const int nel = s.nel, nvirt = s.nbasis - s.nel;
+    g.nexcit = 1; g.from1 = 0; g.from2 = 0; g.to1 = 0; g.to2 = 0; g.perm = false;
+    double tot = 0.0;
+    for (int q = 0; q < nel; ++q) tot = tot + wi[q];
+    if (tot < 1.e-12) {
+        g.allowed = false; g.hmatel = 0.0; g.pgen = 1.0;
+        return;
+    }
+    const int i_ind = select_weighted_value_list(rng, nel, wi, tot);
+    const int i = occ[i_ind - 1];
+    const double* wa = wall + (size_t)(i_ind - 1) * nvirt;
+    const int a_ind = select_weighted_value_big(rng, nvirt, wa, wi[i_ind - 1]);
+    const int a = unocc[a_ind - 1];
+    g.from1 = i; g.to1 = a;
+    g.pgen = p.pattempt_single * (wi[i_ind - 1] / tot) * (wa[a_ind - 1] / wi[i_ind - 1]);
+    g.perm = excit_perm1<W>(f, i, a);
+    g.hmatel = slater_condon1_excit(s, occ, i, a, g.perm);
+    g.allowed = true;
+}
+
 // gen_excit_mol_heat_bath_uniform (src/excit_gen_heat_bath_mol.F90:550-718), excit_gen = heat_bath_uniform: single
 // excitations from the renormalised uniform generator with probability pattempt_single, double excitations from the
 // heat-bath tables (i, j, a, b in turn); the generation probability of a double needs no matrix elements.
 // EXACT_SINGLE: excit_gen = heat_bath_single (src/excit_gen_heat_bath_mol.F90:720-805) - the same doubles, singles
 // from gen_single_heat_bath_exact.
+template <int W, class R>
+HB_HDN void gen_double_heat_bath_uniform(R& rng, const Sys& s, const Params& p, const uint64_t* f, const occ_t* occ,
+                                         const double* __restrict__ iw, double* scr, int stride, Gen& g);
 template <int W, bool EXACT_SINGLE = false, class R>
 HB_HDN void gen_excit_heat_bath_uniform(R& rng, const Sys& s, const Params& p, const uint64_t* f, const occ_t* occ,
                                         const uint8_t* su, const double* __restrict__ iw, double* scr, int stride, Gen& g) {
@@ -1406,6 +1439,15 @@ HB_HDN void gen_excit_heat_bath_uniform(R& rng, const Sys& s, const Params& p, c
         else gen_single_renorm<W>(rng, s, p, f, occ, su, g);
         return;
     }
+    gen_double_heat_bath_uniform<W>(rng, s, p, f, occ, iw, scr, stride, g);
+}
+// the double excitation of heat_bath_uniform / heat_bath_single (after the single/double coin)
+template <int W, class R>
+HB_HDN void gen_double_heat_bath_uniform(R& rng, const Sys& s, const Params& p, const uint64_t* f, const occ_t* occ,
+                                         const double* __restrict__ iw, double* scr, int stride, Gen& g) {
+    const int nel = s.nel;
+    const int64_t nb = s.nbasis;
+    g.from1 = 0; g.from2 = 0; g.to1 = 0; g.to2 = 0; g.perm = false;
     g.nexcit = 2;
     const double i_tot = stage_occ(iw, occ, nel, scr, stride);
     const int iq = select_alias_staged(rng, nel, scr, stride, i_tot);
@@ -2028,6 +2070,9 @@ HB_HD void gen_excit(R& rng, const Sys& s, const Params& p, const uint64_t* f, c
         if (p.excit_gen == EXCIT_GEN_POWER_PITZER) gen_excit_ueg_power_pitzer<W>(rng, s, f, occ, g);
         else gen_excit_ueg_no_renorm<W>(rng, s, f, occ, g);
     }
+    // the wide layout (W > 4, more than 254 spin-orbitals) is built for the UEG generators only: the molecular ones keep
+    // byte orbital lists and nbasis^3 / nbasis^4 tables
+    else if (W > 4) { g.allowed = false; g.hmatel = 0.0; g.pgen = 1.0; g.nexcit = 0; }
     else if (p.excit_gen == EXCIT_GEN_RENORM) gen_excit_renorm<W>(rng, s, p, f, occ, su, g);
     else if (p.excit_gen == EXCIT_GEN_NO_RENORM) gen_excit_no_renorm<W>(rng, s, p, f, occ, g);
     else if (p.excit_gen == EXCIT_GEN_POWER_PITZER) gen_excit_power_pitzer_ref<W>(rng, s, p, f, occ, g);

@@ -702,6 +702,7 @@ void hb200_destroy(hb200_engine* e) {
 int hb200_set_system_read_in(hb200_engine* e, const hb200_system_read_in* in) {
     CK(cudaSetDevice(e->cfg.device));
     if (in->nbasis != e->cfg.nbasis || in->nel != e->cfg.nel) FAIL("set_system: nbasis/nel differ from hb200_create");
+    if (e->W > 4) FAIL("set_system: read_in systems are limited to 254 spin-orbitals (the wide layout is built for the UEG generators)");
     Sys& s = e->sys;
     s.kind = SYS_READ_IN;
     s.nbasis = in->nbasis; s.nel = in->nel; s.W = e->W;

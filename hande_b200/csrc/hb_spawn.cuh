@@ -13,12 +13,14 @@ constexpr int SINGLES_CHUNK = 64;  // single excitations whose pgen terms are st
 // that are only live in the later phases.
 struct SpawnSmem {
     size_t sf, shash, ssign, sscan, swarp, sred, siw, sw, sh1, shm, ssp, spsum, sterm, sok, sq, scnt, sflag, slo, sperm, ssq,
-        ssi, socc, ssu, sps, sdf, total;
+        ssi, socc, ssu, sps, sdf, hs_wi, hs_un, hs_q, hs_lo, total;
     // heat_bath: the original heat-bath generator (phase buffers); hb_stage: any generator that selects i, j from the
     // heat-bath weights (needs the hb_i_w copy and the per-thread staging area of nel doubles)
     // ps: pattempt_update statistics are accumulated (per thread: two doubles and two counters)
     // qn: quasi-Newton propagator (fock_sum of each state of the tile)
-    __host__ __device__ SpawnSmem(int W, int nel, int nsu, int nb, bool heat_bath, bool hb_stage, bool ps, bool qn) {
+    // hbs: heat_bath_single (block-cooperative exact single-excitation weights: per batch slot the row sums, the
+    // unoccupied list, the queue of single-excitation attempts and their tile states)
+    __host__ __device__ SpawnSmem(int W, int nel, int nsu, int nb, bool heat_bath, bool hb_stage, bool ps, bool qn, bool hbs = false) {
         size_t o = 0;
         sf = o;     o += (size_t)TILE * W * 8;
         sred = o;   o += 40 * 8;
@@ -56,6 +58,10 @@ struct SpawnSmem {
         o = (o + 7) & ~(size_t)7;
         sps = o;    o += ps ? (size_t)TILE * 24 : 0;
         sdf = o;    o += qn ? (size_t)TILE * 8 : 0;
+        hs_wi = o;  o += hbs ? (size_t)8 * 64 * 8 : 0;
+        hs_un = o;  o += hbs ? (size_t)8 * 256 : 0;
+        hs_q = o;   o += hbs ? TILE : 0;
+        hs_lo = o;  o += hbs ? TILE : 0;
         total = (o + 15) & ~(size_t)15;
     }
 };
@@ -76,7 +82,12 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
     const int nsu = (GEN == EXCIT_GEN_POWER_PITZER_ORDERN) ? nel : (GEN == EXCIT_GEN_RENORM || GEN == EXCIT_GEN_RENORM_SPIN || GEN == EXCIT_GEN_HEAT_BATH_UNIFORM || GEN == EXCIT_GEN_POWER_PITZER_OCC ||
                      GEN == EXCIT_GEN_POWER_PITZER_OCC_IJ) ? 2 * s.nsym_tot : 0;
     const bool ps_on = !heat_bath && p.ps_part != nullptr;
-    const SpawnSmem L(W, nel, nsu, s.nbasis, heat_bath, hb_stage, ps_on, p.qn != 0);
+    constexpr bool hbs = (GEN == EXCIT_GEN_HEAT_BATH_SINGLE);
+    const SpawnSmem L(W, nel, nsu, s.nbasis, heat_bath, hb_stage, ps_on, p.qn != 0, hbs);
+    double* hs_wi = reinterpret_cast<double*>(smem_raw + L.hs_wi);
+    uint8_t* hs_un = smem_raw + L.hs_un;
+    uint8_t* hs_q = smem_raw + L.hs_q;
+    uint8_t* hs_lo = smem_raw + L.hs_lo;
     double* sdf = reinterpret_cast<double*>(smem_raw + L.sdf);
     double* sps_h = reinterpret_cast<double*>(smem_raw + L.sps);                  // [2][TILE]: singles, doubles
     unsigned* sps_n = reinterpret_cast<unsigned*>(smem_raw + L.sps + 16 * TILE);  // [2][TILE]
@@ -281,6 +292,59 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
                 }
             }
             hb_phase_f<W>(s, f, socc + lo * nel, st, hmk, psum, siw, g);
+        } else if (hbs) {
+            // ---- heat_bath_single: the double excitations are generated per thread; the single excitations (probability
+            // pattempt_single) need |<D|H|D_i^a>| for ALL nel x nvirt (i, a) pairs of their determinant
+            // (find_ia_single_weights, src/excit_gen_utils.f90:162-218; the reference caches them per determinant).
+            // They are queued and the whole block evaluates the weights of a batch of them, one weight per thread, into
+            // the staging area; row sums and the two alias selections follow in the reference's order.
+            if (tid == 0) scnt[0] = 0;
+            __syncthreads();
+            bool single = false;
+            if (active) {
+                single = rng.next() < p.pattempt_single;
+                if (single) {
+                    const int q = atomicAdd(&scnt[0], 1);
+                    hs_q[q] = (uint8_t)tid;
+                    hs_lo[tid] = (uint8_t)lo;
+                } else {
+                    gen_double_heat_bath_uniform<W>(rng, s, p, f, socc + lo * nel, siw, sw + tid, TILE, g);
+                }
+            }
+            __syncthreads();       // the staging area is free again; the queue is complete
+            const int nq = scnt[0];
+            const int nvirt = s.nbasis - nel, npair = nel * nvirt;
+            const int B = max(1, min(8, (TILE * nel) / npair));
+            for (int q0 = 0; q0 < nq; q0 += B) {
+                const int nbat = min(B, nq - q0);
+                for (int t = tid; t < nbat * nvirt; t += TILE) {
+                    const int b = t / nvirt, k = t - b * nvirt, l = hs_lo[hs_q[q0 + b]];
+                    uint64_t ff[W];
+#pragma unroll
+                    for (int w = 0; w < W; ++w) ff[w] = sf[l * W + w];
+                    hs_un[b * 256 + k] = (uint8_t)nth_unocc<W>(ff, k + 1);
+                }
+                __syncthreads();
+                for (int t = tid; t < nbat * npair; t += TILE) {
+                    const int b = t / npair, r = t - b * npair, q = r / nvirt, k = r - q * nvirt, l = hs_lo[hs_q[q0 + b]];
+                    sw[t] = hb_single_weight(s, socc + l * nel, socc[l * nel + q], hs_un[b * 256 + k]);
+                }
+                __syncthreads();
+                for (int t = tid; t < nbat * nel; t += TILE) {
+                    const int b = t / nel, q = t - b * nel;
+                    const double* row = sw + b * npair + q * nvirt;
+                    double wsum = 0.0;
+                    for (int k = 0; k < nvirt; ++k) wsum = wsum + row[k];
+                    hs_wi[b * 64 + q] = wsum;
+                }
+                __syncthreads();
+                if (active && single)
+                    for (int b = 0; b < nbat; ++b)
+                        if (hs_q[q0 + b] == tid)
+                            gen_single_heat_bath_select<W>(rng, s, p, f, socc + lo * nel, hs_wi + b * 64, sw + b * npair,
+                                                           hs_un + b * 256, g);
+                __syncthreads();
+            }
         } else if (active) {
             if (GEN == GEN_UEG) gen_excit_ueg_no_renorm<W>(rng, s, f, socc + lo * nel, g);
             else if (GEN == GEN_UEG_PP) gen_excit_ueg_power_pitzer<W>(rng, s, f, socc + lo * nel, g);

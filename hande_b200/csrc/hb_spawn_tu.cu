@@ -22,7 +22,7 @@ static int launch_spawn(hb200_engine* e, const Params& p, const SpawnLaunch& L) 
                         ? 2 * e->sys.nsym_tot : 0;
     const bool hb = eg == HB200_EXCIT_GEN_HEAT_BATH;
     const size_t smem = SpawnSmem(e->W, e->sys.nel, nsu, e->sys.nbasis, hb, hb_uses_heat_bath_tables(e), !hb && p.ps_part != nullptr,
-                                  p.qn != 0).total;
+                                  p.qn != 0, GEN == EXCIT_GEN_HEAT_BATH_SINGLE).total;
     // the attribute is per device: one bit per device ordinal and instantiation
     static unsigned long long attr_set = 0ull;
     const unsigned long long bit = 1ull << (e->cfg.device & 63);

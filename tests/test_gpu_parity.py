@@ -367,3 +367,40 @@ def test_async_upload_begin_commit():
     assert all((x == y).all() for x, y in zip(g1, g2))
     assert out_async["nparticles"] == out_sync["nparticles"] and out_async["proj_energy"] == out_sync["proj_energy"]
     eng.close()
+
+
+@pytest.mark.parametrize("initiator", [False, True])
+def test_annihilation_of_long_runs(initiator):
+    """Runs of thousands of spawn events on one determinant (the reference near convergence): k_annihilate hands runs
+    longer than 32 elements to the warp-per-run kernel (galloping search for the end of the run, integer sums,
+    initiator flag algebra) - annihilate_spawn_t[_initiator] + annihilate_main_list + insert_new_walkers against the
+    oracle on the same list."""
+    import ctypes as C
+    from hande_b200 import synthetic
+    s, o, eng, ref = make_pair("s40", real=False, initiator=initiator, spawned_walker_length=1 << 17)
+    f, pops, dat = random_population(s, o, 300, False, seed=7)
+    o.set_psips(f, pops, dat)
+    eng.upload_psips(f, pops, dat)
+    rng = np.random.default_rng(5)
+    have = {tuple(x) for x in f}
+    new = np.array([x for x in synthetic.random_dets(400, s.nbasis, s.nalpha, s.nbeta, seed=99) if tuple(x) not in have])
+    runs = [(f[10], 5000), (f[150], 40), (f[151], 33), (f[299], 32), (new[0], 700), (new[1], 32), (new[2], 33), (new[3], 1)]
+    runs += [(f[k], 1) for k in rng.integers(0, len(f), 200)] + [(new[k], int(rng.integers(1, 4))) for k in range(4, 200)]
+    rows = []
+    for det, n in runs:
+        for _ in range(n):
+            pop = int(rng.integers(1, 4)) * (1 if rng.random() < 0.5 else -1)
+            rows.append(list(det.view(np.int64)) + [pop, int(rng.random() < 0.5) if initiator else 0])
+    sd = np.array(rows, dtype=np.int64)[rng.permutation(len(rows))]
+    eng.upload_spawn(sd)
+    eng.annihilate_spawn()
+    out = eng.annihilate_main(1)
+    res = np.zeros(4)
+    o.L.orc_rank_annihilate.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
+    assert o.L.orc_rank_annihilate(o.h, 0, np.ascontiguousarray(sd).ctypes.data_as(C.c_void_p), len(sd),
+                                   res.ctypes.data_as(C.c_void_p)) == 0
+    fo, po, do_ = o.get_psips()
+    fg, pg, dg = eng.download_psips()
+    assert len(fg) == len(fo) == out["nstates"] and len(fg) > 300
+    assert (fg == fo).all() and (pg == po).all() and (dg == do_).all()
+    eng.close()

@@ -12,7 +12,7 @@ python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
     python bench.py --walkers 1e7 --steps 2 --warmup 1 --tau 5.3e-7 --no-cpu-baseline --no-e2e > gpurun_out/${tag}_launches.log 2>&1
 ncu --set full --import-source on --clock-control none -k regex:'k_spawn_death|k_merge|k_round_count|k_radix_scatter|k_annihilate' \
-    -s 17 -c 17 -f -o gpurun_out/${tag}_prof_1e8 \
+    -s 18 -c 18 -f -o gpurun_out/${tag}_prof_1e8 \
     python bench.py --walkers 1e8 --steps 1 --warmup 1 --tau 5.3e-7 --no-cpu-baseline --no-e2e > gpurun_out/${tag}_prof_1e8.log 2>&1
 # export what the summary needs and drop the (large) report: gpurun brings back at most 64 MiB
 ncu -i gpurun_out/${tag}_prof_1e8.ncu-rep --page raw --csv > gpurun_out/${tag}_raw_1e8.csv

@@ -153,6 +153,9 @@ struct Params {
     int qn;
     double qn_threshold, qn_value, qn_pop_control, ref_fock_sum;
     const double* sp_fock;
+    // wall-Chebyshev propagator (src/propagators.f90): weight 1/(S_i - E_0) of the current sub-cycle on the spawning
+    // amplitude (src/spawning.F90:117-118) and the death probability (src/death.f90:89); 1 for the linear projector
+    double cheby_weight;
 };
 // p_single_double_coll_t (src/excit_gens.f90:13-27): sums of |H_ij| pattempt_{single,double} / pgen over the allowed
 // single / double excitations generated, and how many there were
@@ -2155,7 +2158,7 @@ template <class R>
 HB_HD int64_t stochastic_death(R& rng, const Params& p, double Kii, int64_t population, int64_t& kill_abs, double weight = 1.0) {
     const double pop_control = p.qn ? p.qn_pop_control : 1.0;
     double pd = p.tau * ((Kii - p.proj_energy_old) * weight + (p.proj_energy_old - p.shift) * pop_control) * 1.0;
-    pd = pd * 1.0;
+    pd = pd * p.cheby_weight;
     int64_t apop = population < 0 ? -population : population;
     pd = pd * (double)apop;
     int64_t kill = (int64_t)pd;

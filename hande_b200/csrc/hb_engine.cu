@@ -624,6 +624,7 @@ hb200_engine* hb200_create(const hb200_config* cfg) {
     p.iproc = cfg->iproc;
     p.nslots = std::max(1, cfg->nslots);
     p.we = e->We;
+    p.cheby_weight = 1.0;
     const long long cap = cfg->walker_length;
     long long scap = cfg->spawned_walker_length;
     if (scap % p.nprocs != 0) scap = ((scap + p.nprocs - 1) / p.nprocs) * p.nprocs;  // src/qmc.F90:1461-1468
@@ -1736,6 +1737,7 @@ int hb200_ccmc_spawn(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, i
     if (!e->have_sys) FAIL("ccmc_spawn: system not set");
     if (uses_heat_bath_tables(e) && !e->have_hb) FAIL("ccmc_spawn: heat-bath tables not built");
     if (e->par.qn) FAIL("ccmc_spawn: the quasi-Newton propagator is only implemented for FCIQMC");
+    if (e->par.cheby_weight != 1.0) FAIL("ccmc_spawn: the wall-Chebyshev propagator is only implemented for FCIQMC");
     if (e->cfg.excit_gen == HB200_EXCIT_GEN_POWER_PITZER_ORDERN && !e->have_ppn) FAIL("ccmc_spawn: power_pitzer_orderN tables not built");
     if (e->cfg.excit_gen == HB200_EXCIT_GEN_POWER_PITZER && !e->have_pp) FAIL("ccmc_spawn: power_pitzer tables not built");
     if (e->par.nprocs > 1 && !e->comm) FAIL("ccmc_spawn: nprocs > 1 but hb200_comm_init was not called");
@@ -1957,6 +1959,15 @@ int hb200_set_quasi_newton(hb200_engine* e, const double* sp_fock, double ref_fo
     CK(copy_sync(e, d, sp_fock, ((size_t)e->sys.nbasis + 1) * sizeof(double), cudaMemcpyHostToDevice));
     p.sp_fock = d; p.ref_fock_sum = ref_fock_sum; p.qn_threshold = threshold; p.qn_value = value; p.qn_pop_control = pop_control;
     p.qn = 1;
+    return 0;
+}
+
+// Wall-Chebyshev propagator (src/propagators.f90:11-208): the host owns the spectral range, the zeroes and the weights
+// (init_chebyshev / update_chebyshev) and loops over the `order` sub-cycles of an MC cycle (src/fciqmc.f90:298-299); the
+// engine applies the weight of the current sub-cycle in attempt_to_spawn and stochastic_death.  1.0 = linear projector.
+int hb200_set_propagator_weight(hb200_engine* e, double weight) {
+    if (e->cfg.excit_gen < 0) FAIL("set_propagator_weight: engine not configured");
+    e->par.cheby_weight = weight;
     return 0;
 }
 

@@ -370,6 +370,7 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
         if (active) {
             double hmq = g.hmatel;
             if (p.qn && g.allowed) hmq = hmq * qn_spawned_weighting(p, sdf[lo], g);   // spawn_standard (src/spawning.F90:101-103)
+            hmq = hmq * p.cheby_weight;                                              // (src/spawning.F90:117-118)
             if (ps_on && g.allowed) {   // update_p_single_double_data (src/spawning.F90:104-109,2139-2215)
                 const int k = (g.nexcit == 2) ? TILE : 0;
                 sps_h[k + tid] = sps_h[k + tid] + (fabs(hmq) * (g.nexcit == 2 ? p.pattempt_double : p.pattempt_single)) / g.pgen;

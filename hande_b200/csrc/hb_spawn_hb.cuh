@@ -460,6 +460,7 @@ __device__ void warp_spawn_rounds(const Sys& s, const Params& p, WarpCtx<W>& c, 
                 }
                 double hmq = g.hmatel;
                 if (p.qn) hmq = hmq * qn_spawned_weighting(p, c.sdf[lo], g);   // spawn_standard (src/spawning.F90:101-103)
+                hmq = hmq * p.cheby_weight;
                 OneDraw rng{c.sr3[slot]};
                 const uint8_t bits = c.sbits[lo];
                 nspawn = attempt_to_spawn(rng, p, hmq, g.pgen, (bits & 1) ? (int64_t)-1 : (int64_t)1);

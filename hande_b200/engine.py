@@ -155,6 +155,7 @@ def load_library():
     L.hb200_get_unique_id.argtypes = [C.c_void_p]
     L.hb200_comm_init.argtypes = [C.c_void_p, C.c_void_p]
     L.hb200_p2p_export.argtypes = [C.c_void_p, C.c_void_p]
+    L.hb200_set_propagator_weight.argtypes = [C.c_void_p, C.c_double]
     L.hb200_slot_populations.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
     L.hb200_redistribute_particles.argtypes = [C.c_void_p, C.c_void_p]
     L.hb200_p2p_import.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
@@ -172,7 +173,7 @@ ABI_SYMBOLS = [
     "hb200_download_psips", "hb200_nstates", "hb200_iterate", "hb200_spawn_death", "hb200_comm_spawn",
     "hb200_ccmc_spawn", "hb200_ccmc_iterate", "hb200_ccmc_set_hash_shift", "hb200_ccmc_set_full_nc", "hb200_set_pattempt", "hb200_get_ps_stats", "hb200_set_pattempt_parallel", "hb200_get_pattempt_parallel", "hb200_build_power_pitzer_orderN", "hb200_build_power_pitzer", "hb200_set_quasi_newton", "hb200_annihilate_spawn", "hb200_annihilate_main", "hb200_download_spawn", "hb200_upload_spawn", "hb200_spawn_counts",
     "hb200_sc0_batch", "hb200_gen_excit_batch", "hb200_get_unique_id", "hb200_comm_init", "hb200_last_timing",
-    "hb200_p2p_export", "hb200_p2p_import", "hb200_set_host_barrier", "hb200_slot_populations",
+    "hb200_p2p_export", "hb200_p2p_import", "hb200_set_host_barrier", "hb200_slot_populations", "hb200_set_propagator_weight",
     "hb200_redistribute_particles",
 ]
 
@@ -347,6 +348,10 @@ class Engine:
         assert len(sp) == self.sys.nbasis + 1
         self._chk(self.L.hb200_set_quasi_newton(self.h, _p(sp), float(ref_fock_sum), float(threshold), float(value),
                                                 float(pop_control)))
+
+    def set_propagator_weight(self, weight):
+        """wall-Chebyshev: weight 1/(S_i - E_0) of the sub-cycle the next iterate()/spawn_death() calls run"""
+        self._chk(self.L.hb200_set_propagator_weight(self.h, float(weight)))
 
     def set_pattempt_parallel(self, pattempt_parallel=-1.0):
         """qmc_in%pattempt_parallel (renorm_spin / no_renorm_spin); negative: find_parallel_spin_prob_mol on the device"""

@@ -19,6 +19,7 @@ import numpy as np
 from . import read_in as _ri
 from .engine import Engine
 from . import load_balancing as _lb
+from . import propagators as _prop
 
 HUGE = _ri.HUGE
 
@@ -53,6 +54,16 @@ class QmcIn:
     spawned_state_size: int = -1
     ex_level: int = -1              # reference = {ex_level = ...}: truncation level, -1 = none
     nslots: int = 1
+    # wall-Chebyshev propagator (qmc_in%chebyshev*, src/qmc_data.f90:244-251) and the harmonic forcing of the shift
+    # (src/qmc_data.f90:182-186, src/qmc.F90:195-212)
+    chebyshev: bool = False
+    chebyshev_order: int = 5
+    chebyshev_shift: float = 0.0
+    chebyshev_scale: float = 1.1
+    chebyshev_skip_gershgorin: bool = False
+    shift_harmonic_forcing: float = 0.0
+    shift_harmonic_crit_damp: bool = False
+    shift_harmonic_forcing_two_stage: bool = False
     # load_bal_in_t (src/qmc_data.f90:491-512) and fciqmc_in%doing_load_balancing; nslots above = load_balancing_slots
     load_balancing: bool = False
     load_balancing_pop: float = 1000.0
@@ -261,6 +272,7 @@ class FciqmcResult:
     timings: list = field(default_factory=list)
     pattempt_log: list = field(default_factory=list)   # pattempt_single after each pattempt_update change
     load_balancing_log: list = field(default_factory=list)   # (first cycle, proc_map) of every load-balancing step
+    chebyshev: object = None                                  # propagators.Chebyshev of the run (None: linear projector)
 
 
 def do_fciqmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, keep_engine=False, psips=None):
@@ -319,7 +331,20 @@ def do_fciqmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, 
     buf = comm.allreduce_sum(np.array([pe_loc, d0_loc, nparticles_loc, float(eng.nstates)]))
     proj_energy, D0, ntot_old, tot_nstates = float(buf[0]), float(buf[1]), float(buf[2]), int(round(buf[3]))
     shift, vary_shift = qmc.initial_shift, False
+    # init_qmc (src/qmc.F90:195-212): harmonic forcing of the shift
+    harmonic = (qmc.shift_damping ** 2) / 4.0 if qmc.shift_harmonic_crit_damp else qmc.shift_harmonic_forcing
+    if harmonic != 0.0 and not qmc.shift_harmonic_forcing_two_stage:
+        vary_shift = True
+    tau = qmc.tau
+    cheb = None
+    if qmc.chebyshev:
+        # init_chebyshev (src/propagators.f90:11-165); the wall-Chebyshev projector is independent of tau: tau = 1
+        cheb = _prop.Chebyshev(sys, H00, qmc.chebyshev_order, qmc.chebyshev_shift, qmc.chebyshev_scale,
+                               qmc.chebyshev_skip_gershgorin)
+        tau = 1.0
+    order = cheb.order if cheb else 1
     res = FciqmcResult(H00=H00, occ0=occ0)
+    res.chebyshev = cheb
     pupd = PattemptUpdate(eng, comm, ps, pd, io=out) if qmc.pattempt_update else None
     res.rows.append([0, shift, proj_energy, D0, ntot_old, tot_nstates, 0, 0.0])
     if out is not None and iproc == 0:
@@ -346,16 +371,34 @@ def do_fciqmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, 
                 eng.redistribute(0x80000000 | first_cycle)
                 res.load_balancing_log.append((first_cycle, list(proc_map)))
             lb_needed = False
-        o = eng.iterate(qmc.mc_cycles, qmc.tau, shift, pe_old, first_cycle)
+        if cheb is None:
+            o = eng.iterate(qmc.mc_cycles, tau, shift, pe_old, first_cycle)
+        else:
+            # `order` linear projectors per MC cycle (src/fciqmc.f90:298-299), each a full spawn / annihilation cycle
+            # with its own weight; the engine's random stream is keyed by the sub-cycle index
+            o = None
+            for icycle in range(qmc.mc_cycles):
+                for icheb in range(1, order + 1):
+                    eng.set_propagator_weight(cheb.weights[icheb - 1])
+                    oc = eng.iterate(1, tau, shift, pe_old, (first_cycle + icycle - 1) * order + icheb)
+                    if o is None:
+                        o = dict(oc)
+                    else:
+                        for key in ("proj_energy", "D0_population", "rspawn", "nattempts_spawn", "walker_iterations"):
+                            o[key] = o[key] + oc[key]
+                        for key in ("nparticles", "nstates", "nspawn_events", "ndeath", "nattempts"):
+                            o[key] = oc[key]
+                        o["spawn_error"] = o["spawn_error"] or oc["spawn_error"]
+                        o["psip_error"] = o["psip_error"] or oc["psip_error"]
         res.timings.append(eng.last_timing())
         # local_energy_estimators + MPI_Allreduce + communicated_energy_estimators
         # (src/energy_evaluation.F90:126-201, 320-655)
         loc = np.array([o["proj_energy"], o["D0_population"], o["rspawn"], o["nparticles"], float(o["nstates"]),
                         float(o["nspawn_events"]), float(bool(o["spawn_error"] or o["psip_error"]))])
         tot = comm.allreduce_sum(loc)
-        proj_energy = float(tot[0]) / qmc.mc_cycles
-        D0 = float(tot[1]) / qmc.mc_cycles
-        rspawn = float(tot[2]) / (qmc.mc_cycles * nprocs)
+        proj_energy = float(tot[0]) / (qmc.mc_cycles * order)
+        D0 = float(tot[1]) / (qmc.mc_cycles * order)
+        rspawn = float(tot[2]) / (qmc.mc_cycles * order * nprocs)
         ntot = float(tot[3])
         tot_nstates, tot_nev = int(round(tot[4])), int(round(tot[5]))
         error = tot[6] > 0
@@ -365,16 +408,18 @@ def do_fciqmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, 
             lb_needed = _lb.check_imbalance(per_rank, float(per_rank.sum()) / nprocs, qmc.percent_imbal)
         if vary_shift:
             # update_shift (src/energy_evaluation.F90:659-711)
-            shift = shift - math.log(ntot / ntot_old) * qmc.shift_damping / (1.0 * qmc.tau * qmc.mc_cycles) \
-                - math.log(ntot / qmc.target_population) * 0.0 / (1.0 * qmc.tau * qmc.mc_cycles) \
+            shift = shift - math.log(ntot / ntot_old) * qmc.shift_damping / (1.0 * tau * qmc.mc_cycles) \
+                - math.log(ntot / qmc.target_population) * harmonic / (1.0 * tau * qmc.mc_cycles) \
                 if qmc.target_population > 0 else \
-                shift - math.log(ntot / ntot_old) * qmc.shift_damping / (1.0 * qmc.tau * qmc.mc_cycles)
+                shift - math.log(ntot / ntot_old) * qmc.shift_damping / (1.0 * tau * qmc.mc_cycles)
         ntot_old = ntot
         if not vary_shift and ntot > qmc.target_population:
             vary_shift = True
             shift = proj_energy / D0 if qmc.vary_shift_from_proje else qmc.vary_shift_from
         if pupd is not None:
             pupd.end_report_loop(vary_shift)
+        if cheb is not None:
+            cheb.update(shift)          # src/fciqmc.f90:427
         it = mc_cycles_done + ireport * qmc.mc_cycles
         res.rows.append([it, shift, proj_energy, D0, ntot, tot_nstates, tot_nev, rspawn])
         if out is not None and iproc == 0:

@@ -246,6 +246,12 @@ int hb200_sc0_batch(hb200_engine* e, const uint64_t* states, int64_t n, double* 
 int hb200_gen_excit_batch(hb200_engine* e, const uint64_t* states, const int64_t* pops, const uint32_t* attempt,
                           int64_t n, uint32_t cycle, double tau, int32_t* iout, double* dout, int64_t* nspawn);
 
+/* Wall-Chebyshev propagator (qmc = { chebyshev = {...} }; src/propagators.f90:11-208, src/fciqmc.f90:298-299,427): the
+ * host keeps the spectral range and the weights 1/(S_i - E_0) (init_chebyshev, update_chebyshev) and runs the `order`
+ * sub-cycles of an MC cycle as separate hb200_iterate(1) calls; this sets the weight applied to the spawning amplitude
+ * (src/spawning.F90:117-118) and to the death probability (src/death.f90:89) until the next call.  Default 1. */
+int hb200_set_propagator_weight(hb200_engine* e, double weight);
+
 /* NCCL bootstrap for nprocs > 1: rank 0 calls hb200_get_unique_id, the host broadcasts the 128 bytes
  * (MPI_Bcast in the Fortran host, torch.distributed in this repo's harness), every rank calls
  * hb200_comm_init.  Replaces MPI_COMM_WORLD use in comm_spawn_t. */

@@ -456,6 +456,33 @@ void orc_get_spawn(void* h, int rank, int64_t* sdata) {
             ++k;
         }
 }
+// wall-Chebyshev propagator: init_chebyshev (call after orc_init), optional harmonic forcing of the shift
+int orc_init_chebyshev(void* h, int order, double cshift, double cscale, int skip_gershgorin, double harmonic_forcing,
+                       double* out) {
+    ORC_TRY
+    Oracle* o = (Oracle*)h;
+    o->init_chebyshev(order, cshift, cscale, skip_gershgorin != 0);
+    o->shift_harmonic_forcing = harmonic_forcing;
+    out[0] = o->cheb.range_hi;
+    for (int i = 0; i < order; ++i) { out[1 + i] = o->cheb.zeroes[i]; out[1 + order + i] = o->cheb.weights[i]; }
+    return 0;
+    ORC_CATCH(-1)
+}
+// staged use (the host owns the Chebyshev state and passes the weight of the sub-cycle, as hb200_set_propagator_weight)
+int orc_set_propagator_weight(void* h, double w) {
+    Oracle* o = (Oracle*)h;
+    o->cheb.weights.assign(1, w);
+    o->cheb.icheb = 1;
+    return 0;
+}
+int orc_set_chebyshev_step(void* h, int icheb, double shift_for_update, int do_update) {
+    ORC_TRY
+    Oracle* o = (Oracle*)h;
+    if (do_update) o->update_chebyshev(shift_for_update);
+    o->cheb.icheb = icheb;
+    return 0;
+    ORC_CATCH(-1)
+}
 // load balancing: slot populations of one rank, the policy on the summed slots, the proc_map, the redistribution
 int orc_slot_pop(void* h, int rank, double* out) {
     ORC_TRY

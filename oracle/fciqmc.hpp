@@ -278,6 +278,85 @@ struct Oracle {
     // reference_t
     std::vector<int> occ_list0;
     Det f0;
+    // wall-Chebyshev propagator (cheb_t, src/qmc_data.f90:886-907; src/propagators.f90): order sub-cycles per MC cycle,
+    // each with its own weight 1/(S_i - E_0) on the spawning amplitude and the death probability
+    struct Cheby {
+        bool on = false;
+        int order = 1, icheb = 1;
+        double range_lo = 0.0, range_hi = 0.0;
+        std::vector<double> zeroes, weights = std::vector<double>(1, 1.0);
+    } cheb;
+    double shift_harmonic_forcing = 0.0;      // qmc_state%shift_harmonic_forcing (src/qmc.F90:195-212)
+    double cheb_weight() const { return cheb.weights[cheb.icheb - 1]; }
+    // update_chebyshev (src/propagators.f90:188-208)
+    void update_chebyshev(double sh) {
+        const double pi = 3.1415926535897931;
+        cheb.range_lo = sh;
+        for (int i = 1; i <= cheb.order; ++i) {
+            cheb.zeroes[i - 1] = sh + (cheb.range_hi - cheb.range_lo) / 2 * (1 - std::cos(pi * i / (cheb.order + 0.5)));
+            cheb.weights[i - 1] = 1 / (cheb.zeroes[i - 1] - sh);
+        }
+    }
+    // <f1|H|f2> for two different determinants (get_hmatel, src/hamiltonian_molecular.f90:10-103: symmetry- and
+    // spin-checked slater_condon1_mol / slater_condon2_mol)
+    double offdiag_hmatel(const Det& f1, const Det& f2) const {
+        DetInfo d;
+        decode_det_occ(sys, f1, d);
+        Excit ex = sys.get_excitation(f1, f2);
+        if (ex.nexcit == 1) {
+            if (sys.bf[ex.from_orb[0]].ms == sys.bf[ex.to_orb[0]].ms && sys.bf[ex.from_orb[0]].sym == sys.bf[ex.to_orb[0]].sym)
+                return sys.slater_condon1_excit(d.occ, ex.from_orb[0], ex.to_orb[0], ex.perm);
+        } else if (ex.nexcit == 2) {
+            if (sys.bf[ex.from_orb[0]].ms + sys.bf[ex.from_orb[1]].ms == sys.bf[ex.to_orb[0]].ms + sys.bf[ex.to_orb[1]].ms &&
+                sys.cross_product_basis(ex.from_orb[0], ex.from_orb[1]) == sys.cross_product_basis(ex.to_orb[0], ex.to_orb[1]))
+                return sys.slater_condon2_excit(ex.from_orb[0], ex.from_orb[1], ex.to_orb[0], ex.to_orb[1], ex.perm);
+        }
+        return 0.0;
+    }
+    // init_chebyshev (src/propagators.f90:11-165): upper spectral bound from the Gershgorin circle of the highest
+    // determinant (highest_det, :167-186) over its single and double excitations, or from its diagonal element only
+    void init_chebyshev(int order, double cshift, double cscale, bool skip_gershgorin) {
+        cheb.on = true; cheb.order = order; cheb.icheb = 1;
+        cheb.zeroes.assign(order, 0.0); cheb.weights.assign(order, 1.0);
+        std::vector<int> occ_max;
+        for (int ia = 1; ia <= sys.nalpha; ++ia) occ_max.push_back(sys.nbasis - (ia * 2 - 1));
+        for (int ib = 1; ib <= sys.nbeta; ++ib) occ_max.push_back(sys.nbasis - (ib - 1) * 2);
+        Det f_max;
+        for (int o : occ_max) det_set(f_max, o);
+        const double hmm = diag_hmatel(sys, f_max);
+        double e_max;
+        if (!skip_gershgorin) {
+            // enumerate_determinants(..., ex_level = 2, ref_sym = sys%symmetry, occ_list_max): every determinant of the
+            // calculation's symmetry within two excitations of f_max, f_max included when it has that symmetry
+            e_max = 0.0;
+            std::vector<int> occ, virt;
+            for (int o = 1; o <= sys.nbasis; ++o) (det_test(f_max, o) ? occ : virt).push_back(o);
+            std::vector<int> so(occ_max);
+            std::sort(so.begin(), so.end());
+            const bool in_list = sys.symmetry_orb_list(so.data(), sys.nel) == sys.symmetry;
+            if (in_list) {
+                for (size_t i = 0; i < occ.size(); ++i)
+                    for (int a : virt) {
+                        Det g = f_max; det_clr(g, occ[i]); det_set(g, a);
+                        e_max = e_max + std::fabs(offdiag_hmatel(f_max, g));
+                        for (size_t j = i + 1; j < occ.size(); ++j)
+                            for (int b : virt) {
+                                if (b <= a) continue;
+                                Det g2 = g; det_clr(g2, occ[j]); det_set(g2, b);
+                                e_max = e_max + std::fabs(offdiag_hmatel(f_max, g2));
+                            }
+                    }
+                e_max = e_max + std::fabs(hmm);
+            }
+            e_max = e_max - std::fabs(hmm) + hmm - H00;
+        } else {
+            e_max = hmm - H00;
+        }
+        e_max = (e_max + cshift) * cscale;
+        cheb.range_lo = 0.0; cheb.range_hi = e_max;
+        update_chebyshev(0.0);
+    }
+
     double H00 = 0.0;
     int ref_ex_level = 0;
     // qmc_state_t
@@ -498,7 +577,7 @@ struct Oracle {
                     }
                 }
                 const double qn_weight = g.allowed ? qn_spawned_weighting(dfock, g.conn) : 1.0;   // spawn_standard
-                int64_t nspawned = attempt_to_spawn(rng, g.hmatel * qn_weight, g.pgen, pop);
+                int64_t nspawned = attempt_to_spawn(rng, g.hmatel * qn_weight * cheb_weight(), g.pgen, pop);
                 if (nspawned != 0) {
                     Det fnew = sys.create_excited_det(d.f, g.conn);
                     // create_spawned_particle[_initiator][_truncated] (src/spawning.F90:1074-1319)
@@ -521,7 +600,7 @@ struct Oracle {
                 double Kii = r.dat[idet];
                 double weight = qn_weighting(dfock);
                 double pd = tau * ((Kii - est.proj_energy_old) * weight + (est.proj_energy_old - shift) * qn_pop_control) * 1.0;
-                pd = pd * 1.0;
+                pd = pd * cheb_weight();
                 int64_t& population = r.pops[idet];
                 int64_t apop = population < 0 ? -population : population;
                 pd = pd * (double)apop;
@@ -888,7 +967,7 @@ struct Oracle {
             shift = shift - std::log(nparticles / nparticles_old) * in.shift_damping / (1.0 * tau * nupdate_steps);
         } else {
             shift = shift - std::log(nparticles / nparticles_old) * in.shift_damping / (1.0 * tau * nupdate_steps) -
-                    std::log(nparticles / in.target_particles) * (0.0) / (1.0 * tau * nupdate_steps);
+                    std::log(nparticles / in.target_particles) * (shift_harmonic_forcing) / (1.0 * tau * nupdate_steps);
         }
     }
 
@@ -902,7 +981,12 @@ struct Oracle {
         for (auto& r : ranks) { r.rspawn = 0.0; r.proj_energy = 0.0; r.D0_population = 0.0; }
         for (int icycle = 1; icycle <= in.ncycles; ++icycle) {
             int iter = mc_cycles_done + (ireport - 1) * in.ncycles + icycle;
-            mc_cycle((uint32_t)iter);
+            // the wall-Chebyshev propagator applies `order` linear projectors per cycle (src/fciqmc.f90:298-299); the
+            // counter-based stream is keyed by the sub-cycle index
+            for (int icheb = 1; icheb <= cheb.order; ++icheb) {
+                cheb.icheb = icheb;
+                mc_cycle((uint32_t)(cheb.on ? (iter - 1) * cheb.order + icheb : iter));
+            }
         }
         // update_energy_estimators (src/energy_evaluation.F90:126-201, 320-655)
         double pe = 0.0, d0 = 0.0, rsp = 0.0, ntot = 0.0;
@@ -913,9 +997,9 @@ struct Oracle {
             nst += r.nstates; nev += r.nspawn_events;
             err = err || r.spawn_error || r.psip_error;
         }
-        est.proj_energy = pe / (in.ncycles * 1);
-        est.D0_population = d0 / (in.ncycles * 1);
-        rspawn_report = rsp / (in.ncycles * 1 * in.nprocs);
+        est.proj_energy = pe / (in.ncycles * cheb.order);
+        est.D0_population = d0 / (in.ncycles * cheb.order);
+        rspawn_report = rsp / (in.ncycles * cheb.order * in.nprocs);
         est.tot_nstates = nst; est.tot_nspawn_events = nev;
         if (vary_shift) update_shift(ntot_particles_old, ntot, in.ncycles);
         est.D0_population_old = est.D0_population;
@@ -926,6 +1010,7 @@ struct Oracle {
             else shift = in.vary_shift_from;
         }
         error = err;
+        if (cheb.on) update_chebyshev(shift);       // src/fciqmc.f90:427
         end_report_loop_pattempt();
         ReportRow row;
         row.iter = mc_cycles_done + ireport * in.ncycles;

@@ -402,6 +402,24 @@ class Oracle:
     def stage_annihilate(self):
         self._chk(self.L.orc_stage_annihilate(self.h))
 
+    # ---- wall-Chebyshev propagator (src/propagators.f90)
+    def init_chebyshev(self, order=5, shift=0.0, scale=1.1, skip_gershgorin=False, harmonic_forcing=0.0):
+        """after init(); returns (upper spectral bound, zeroes, weights).  The oracle sets tau itself? no: as in the
+        reference the caller passes tau = 1 (lua_hande_calc.f90:1410)."""
+        out = np.zeros(1 + 2 * order)
+        self.L.orc_init_chebyshev.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_void_p]
+        self._chk(self.L.orc_init_chebyshev(self.h, order, shift, scale, int(skip_gershgorin), harmonic_forcing, _p(out)))
+        return out[0], out[1:1 + order].copy(), out[1 + order:].copy()
+
+    def set_propagator_weight(self, w):
+        self.L.orc_set_propagator_weight.argtypes = [C.c_void_p, C.c_double]
+        self.L.orc_set_propagator_weight(self.h, float(w))
+
+    def set_chebyshev_step(self, icheb, shift=None):
+        """select the sub-cycle whose weight the next staged cycle uses; shift != None: update_chebyshev(shift) first"""
+        self.L.orc_set_chebyshev_step.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int]
+        self._chk(self.L.orc_set_chebyshev_step(self.h, icheb, 0.0 if shift is None else shift, int(shift is not None)))
+
     # ---- load balancing (src/load_balancing.F90, src/qmc_common.F90:505-595, 1332-1390)
     def proc_map(self):
         out = np.zeros(4096, dtype=np.int32)

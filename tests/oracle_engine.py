@@ -64,6 +64,9 @@ def make_engine_cls(fcidump_path, sys_kw, rng_kind=0, ueg=None, ref_det=None, qu
             h = comm.allgather_bytes(np.full(64, comm.rank, dtype=np.uint8))     # the IPC-handle all-gather
             assert h.shape == (comm.size, 64) and all((h[r] == r).all() for r in range(comm.size))
 
+        def set_propagator_weight(self, weight):
+            self.o.set_propagator_weight(weight)
+
         def upload_psips(self, states, pops, dat):
             self.o.set_psips(np.asarray(states).reshape(-1, self.o.W), pops, dat, rank=self.rank)
             self._nparticles = float(np.abs(np.asarray(pops, dtype=np.int64)).sum()) / self.real_factor
@@ -87,7 +90,10 @@ def make_engine_cls(fcidump_path, sys_kw, rng_kind=0, ueg=None, ref_det=None, qu
                     L.orc_rank_get_send(o.h, self.rank, d, buf.ctypes.data_as(C.c_void_p))
                     blocks.append(buf)
                 gathered = [None] * self.world
-                self.dist.all_gather_object(gathered, blocks)            # comm_spawn_t: personalised all-to-all
+                if self.world > 1:
+                    self.dist.all_gather_object(gathered, blocks)        # comm_spawn_t: personalised all-to-all
+                else:
+                    gathered = [blocks]
                 recv = np.concatenate([gathered[src][self.rank] for src in range(self.world)]).reshape(-1, self.E)
                 recv = np.ascontiguousarray(recv)
                 res = np.zeros(4)

@@ -191,3 +191,34 @@ def test_ccmc_driver_pattempt_update(gen, tau):
         assert g[0] == r[0] and g[5] == r[5] and g[6] == r[6] and g[8] == a, (g, r, a)
         assert abs(g[1] - r[1]) <= 1e-9 * max(1.0, abs(r[1])) and abs(g[4] - r[4]) <= 1e-10 * max(1.0, abs(r[4]))
         assert abs(g[2] - r[2]) <= 1e-10 * max(1.0, abs(r[2])) and abs(g[3] - r[3]) <= 1e-10 * max(1.0, abs(r[3]))
+
+
+def test_wall_chebyshev_trajectory_matches_oracle_philox():
+    """qmc = { chebyshev = { chebyshev_order = 5 } } through do_fciqmc on the GPU engine (weights set per sub-cycle with
+    hb200_set_propagator_weight) against the oracle's own Chebyshev run under the same Philox stream: every report row."""
+    from tests.conftest import load_golden
+    import gzip, os, tempfile
+    g = load_golden("h4_cheby")
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fcidump", g["fcidump"] + ".INTDUMP.gz")
+    path = os.path.join(tempfile.gettempdir(), "hande_b200_h4.fcidump")
+    with gzip.open(src, "rt") as fi, open(path, "w") as fo:
+        fo.write(fi.read())
+    s = R.read_in(path, sym=0)
+    qmc = QmcIn(tau=0.001, rng_seed=11, init_pop=200, mc_cycles=2, nreports=25, target_population=2e4, state_size=1 << 16,
+                spawned_state_size=1 << 16, real_amplitudes=True, vary_shift_from_proje=True, shift_damping=0.05,
+                chebyshev=True, chebyshev_order=5, shift_harmonic_crit_damp=True, shift_harmonic_forcing_two_stage=True)
+    res = do_fciqmc(s, qmc)
+    o = Oracle()
+    o.read_fcidump(path, sym=0)
+    o.set_qmc(rng_kind=1, literal_event_int32=0, tau=1.0, seed=11, D0_population=200, ncycles=2, nreport=25,
+              target_particles=2e4, real_amplitudes=1, spawn_cutoff=0.01, vary_shift_from_proje=1, shift_damping=0.05,
+              walker_length=1 << 16, spawned_walker_length=1 << 16)
+    o.init()
+    o.init_chebyshev(order=5, harmonic_forcing=0.05 ** 2 / 4.0)
+    rows = o.run()
+    assert len(res.rows) == len(rows) == 26 and not res.error
+    assert res.vary_shift and rows[-1][1] != 0.0          # the shift varied: update_chebyshev was exercised
+    for a, b in zip(res.rows, rows):
+        assert a[0] == b[0] and a[5] == b[5] and a[6] == b[6], (a, b)
+        for k in (1, 2, 3, 4):
+            assert abs(a[k] - b[k]) <= 1e-10 * max(1.0, abs(b[k])), (k, a, b)

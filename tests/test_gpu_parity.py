@@ -404,3 +404,24 @@ def test_annihilation_of_long_runs(initiator):
     assert len(fg) == len(fo) == out["nstates"] and len(fg) > 300
     assert (fg == fo).all() and (pg == po).all() and (dg == do_).all()
     eng.close()
+
+
+def test_propagator_weight_in_spawn_and_death():
+    """hb200_set_propagator_weight (wall-Chebyshev sub-cycle weights) in attempt_to_spawn and stochastic_death"""
+    s, o, eng, ref = make_pair("s12", excit_gen="heat_bath", tau=0.002, real=True, initiator=True)
+    f, pops, dat = random_population(s, o, 2500, True, seed=4)
+    o.set_psips(f, pops, dat)
+    eng.upload_psips(f, pops, dat)
+    cyc = 1
+    for w in (2.5, 0.9, 0.4, 1.0):
+        o.set_propagator_weight(w)
+        eng.set_propagator_weight(w)
+        ro = o.iterate(2, cyc, 0.002, -0.05, -0.1)
+        rg = eng.iterate(2, 0.002, -0.05, -0.1, cyc)
+        cyc += 2
+        assert rg["spawn_error"] == 0 and rg["psip_error"] == 0 and ro["error"] == 0
+        fo, po, do_ = o.get_psips()
+        fg, pg, dg = eng.download_psips()
+        assert len(fg) == len(fo) and (fg == fo).all() and (pg == po).all() and (dg == do_).all(), w
+        assert rg["nspawn_events"] == ro["nspawn_events"] and rg["ndeath"] == ro["ndeath"]
+    eng.close()

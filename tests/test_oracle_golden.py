@@ -38,6 +38,11 @@ def _run(case, fcidump_path, nrows):
     if "quasi_newton" in g:
         o.set_quasi_newton(True, **g["quasi_newton"])
     o.init()
+    if "chebyshev" in g:
+        hi, z, w = o.init_chebyshev(order=g["chebyshev"]["order"], harmonic_forcing=g["chebyshev"]["harmonic_forcing"])
+        k = g["kat"]        # the spectral range, zeroes and weights the reference prints (9 significant digits)
+        assert float("%.8E" % hi) == k["spectral_range"]
+        assert [float("%.8E" % x) for x in z] == k["zeroes"] and [float("%.8E" % x) for x in w] == k["weights"]
     if g.get("ccmc"):
         o.ccmc_set_full_nc(bool(g.get("full_nc")))
         o.ccmc_set_pattempt_update(bool(g.get("pattempt_update")))
@@ -84,6 +89,13 @@ def test_ne_ci6_np4_hash_sharding(fcidump_path):
 
 def test_ne_ci6_real_amplitudes_np2(fcidump_path):
     _run("ne_ci6_real64_np2", fcidump_path, 130)
+
+
+def test_h4_wall_chebyshev_np1(fcidump_path):
+    """the wall-Chebyshev propagator (order 5: init_chebyshev with the Gershgorin bound, five weighted
+    sub-cycles per cycle, update_chebyshev) with harmonic forcing of the shift, real amplitudes - every row of the
+    reference's table"""
+    _run("h4_cheby", fcidump_path, 30)
 
 
 def test_ueg_np2_np4(fcidump_path):

@@ -42,6 +42,12 @@ CASES = {
                        qmc=dict(tau=0.002, seed=18, D0_population=10, ncycles=10, nreport=1200,
                                 target_particles=50000, walker_length=50000, spawned_walker_length=5000,
                                 ex_level=5, nprocs=4)),
+    # wall-Chebyshev propagator, order 5, harmonic forcing of the shift (critical damping, two-stage)
+    "h4_cheby": dict(dir="fciqmc_real_64/np1/H4-STO-3g_cheby", bench="benchmark.out.9712b5a3.inp=H4.in", int_file="INTDUMP",
+                     sys=dict(sym=0), chebyshev=dict(order=5, harmonic_forcing=0.05 ** 2 / 4.0),
+                     qmc=dict(tau=1.0, seed=2004313765, D0_population=200, ncycles=1, nreport=30, target_particles=1e5,
+                              real_amplitudes=1, spawn_cutoff=0.01, vary_shift_from_proje=1, shift_damping=0.05,
+                              walker_length=71428571 // 64, spawned_walker_length=62500000 // 64)),
     # uniform electron gas: sys = ueg{electrons=6, ms=0, dim=3, cutoff=2, rs=2}, explicit reference
     "ueg_np2": dict(dir="fciqmc/np2/ueg_n10_rs2_e4_fciqmc", bench="benchmark.out.9712b5a3.inp=ueg.fciqmc.in",
                     ueg=dict(nel=6, ms=0, rs=2.0, cutoff=2.0), ref_det=[1, 2, 3, 10, 11, 14],

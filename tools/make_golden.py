@@ -21,6 +21,7 @@ FCIDUMP_NAME = {"h2o": "h2o", "ne_init": "ne", "ne_ci6_np2": "ne", "ne_ci6_np4":
                 "ccmc_ne": "ne_vdz", "ccmc_h2o_np2": "h2o_vdz",
                 "ccmc_h2o_ccsdt_fullnc_np2": "h2o_vdz"}
 FCIDUMP_NAME.update({k: "nh3_631g" for k in CASES if k.startswith("ccmc_nh3_")})
+FCIDUMP_NAME["h4_cheby"] = "h4_sto3g"
 
 
 def pattempt_changes(path):
@@ -66,6 +67,11 @@ for name, c in CASES.items():
     cols = ["iterations", "shift", "proj_energy", "D0_population", "nparticles", "nstates", "nspawn_events", "rspawn"]
     json.dump({"source": "test_suite/" + c["dir"] + "/" + c["bench"], "fcidump": FCIDUMP_NAME[name], "sys": c["sys"],
                "qmc": c["qmc"], "ccmc": bool(c.get("ccmc")), "full_nc": bool(c.get("full_nc")),
+               **({"chebyshev": c["chebyshev"],
+                   "kat": {"spectral_range": 2.92929139E+00,     # the "Initial estimate of spectral range" and the
+                           "zeroes": [2.32507329E-01, 8.56209883E-01, 1.67308651E+00, 2.42378465E+00, 2.86996294E+00],
+                           "weights": [4.30093969E+00, 1.16793793E+00, 5.97697725E-01, 4.12577909E-01, 3.48436555E-01]}}
+                  if "chebyshev" in c else {}),
                "columns": cols + (["nattempts"] if c.get("ccmc") else []),
                "rows": rows, **extra}, open(os.path.join(OUT, name + ".json"), "w"))
     print(name, len(rows), "rows")

@@ -170,6 +170,10 @@ def main():
     ap.add_argument("--system", default="s50", choices=["s50", "ueg", "ueg1000"],
                     help="s50 = BASELINE configs[1] (headline); ueg = side measurement on the 3D UEG (14 electrons, "
                          "114 plane-wave spin-orbitals: the largest basis of BASELINE configs[3] this version's W <= 4 holds)")
+    ap.add_argument("--calc", default="fciqmc", choices=["fciqmc", "ccmc"],
+                    help="ccmc: side line for BASELINE configs[4] (CCSDT-truncated CCMC on the synthetic 40-orbital FCIDUMP): "
+                         "cluster-selection attempts/s, see tools/bench_ccmc.py")
+    ap.add_argument("--excips", type=float, default=4e6, help="--calc ccmc: excips per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -177,6 +181,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+    if args.calc == "ccmc":
+        from tools import bench_ccmc
+        sys.argv = [sys.argv[0], "--excips", str(args.excips), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        bench_ccmc.main()
+        return
     if args.scaling == "auto":
         args.scaling = "strong" if (world > 1 and args.walkers == 0.0) else "weak"
     if args.walkers == 0.0:

@@ -120,14 +120,16 @@ if os.path.exists(rep) or os.path.exists(rawcsv):
               open(os.path.join(P, "traffic.json"), "w"), indent=1)
     lib = os.path.join(G, f"lib_{tag}.so")
     if not os.path.exists(lib):
-        lib = os.path.join(ROOT, "hande_b200", "libhande_b200.so")   # the build that was sent to the GPU box
+        # the object file of the profiled build (the library holds one cubin per translation unit; the spawn kernel of
+        # the bench lives in the W = 2 / heat-bath unit)
+        lib = os.path.join(ROOT, "hande_b200", "build", "hb_spawn_w2_g0.o")
     if os.path.exists(lib):
         tmp = os.path.join(G, f"{tag}_src_spawn.csv")
         if not os.path.exists(tmp) or os.path.exists(rep):
             src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:k_spawn_death"],
                                  capture_output=True, text=True).stdout
             open(tmp, "w").write(src)
-        bl = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_by_line.py"), tmp, lib, "k_spawn_deathILi2ELi10E", "25"],
+        bl = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_by_line.py"), tmp, lib, "k_spawn_death", "40"],
                             capture_output=True, text=True).stdout
         out.append("## k_spawn_death: instruction / stall-sample share by source line (tools/ncu_by_line.py)\n\n```\n" + bl + "```\n")
 

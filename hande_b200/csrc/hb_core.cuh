@@ -95,6 +95,9 @@ struct Sys {
     // {0, 0}, so list padding and the excited orbital itself add exact zeros
     const D2* sc1T;
     int sc1A;
+    // Power-Pitzer / Cauchy-Schwarz weights sqrt|<ia|ai>| and sqrt|<ia|ia>| for every orbital pair: [2][nbasis][nbasis]
+    // (null: computed on the fly)
+    const double* ppw;
     // heat-bath tables (src/excit_gens.f90:143-153), column-major as in the reference
     const double* hb_i_w;       // (nb)
     const double* hb_ij_w;      // (j,i)
@@ -1512,6 +1515,9 @@ HB_HDN int select_weighted_value_list(R& rng, int N, const double* weights, doub
     return select_precalc(rng, N, aliasU, aliasK);
 }
 HB_HD double pp_weight(const Sys& s, bool cauchy_schwarz, int i, int a) {
+    // the weights depend on (i, a) only: once the engine has tabulated them (k_build_ppw: the same expression, evaluated
+    // once per orbital pair) a weight is one load from an nbasis^2 table instead of an integral look-up and a square root
+    if (s.ppw) return s.ppw[(cauchy_schwarz ? (size_t)s.nbasis * s.nbasis : 0) + (size_t)(i - 1) * s.nbasis + (a - 1)];
     return sqrt(fabs(cauchy_schwarz ? two_body(s, i, a, i, a) : two_body(s, i, a, a, i)));
 }
 // k-th (1-based) unoccupied orbital of the given spin parity (1 = alpha/odd orbitals, 0 = beta/even), ascending

@@ -408,6 +408,14 @@ __global__ void k_build_JK(Sys s, double* J, double* K) {
 }
 
 // single-excitation row tables C(i,a,j) = <ij|aj>, X(i,a,j) = <ij|ja> (see hb_core.cuh Sys::sc1C)
+// create_weighted_excitation_list_mol's weights (src/hamiltonian_molecular.f90:348-390) for every orbital pair
+__global__ void k_build_ppw(Sys s, double* w) {
+    const int nb = s.nbasis;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * nb * nb) return;
+    const int cs = t / (nb * nb), r = t % (nb * nb), i = r / nb + 1, a = r % nb + 1;
+    w[t] = sqrt(fabs(cs ? two_body(s, i, a, i, a) : two_body(s, i, a, a, i)));
+}
 __global__ void k_build_sc1_tables(Sys s, int NT, D2* CX) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)NT * NT * NT) return;
@@ -748,6 +756,18 @@ int hb200_set_system_read_in(hb200_engine* e, const hb200_system_read_in* in) {
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(e->stream));
         s.sc1CX = CX; s.NT = NT;
+    }
+    {
+        const int eg = e->cfg.excit_gen;
+        if (eg == HB200_EXCIT_GEN_POWER_PITZER_OCC || eg == HB200_EXCIT_GEN_POWER_PITZER_OCC_IJ ||
+            eg == HB200_EXCIT_GEN_CAUCHY_SCHWARZ_OCC || eg == HB200_EXCIT_GEN_CAUCHY_SCHWARZ_OCC_IJ) {
+            double* w = nullptr;
+            if (dalloc(e, &w, (size_t)2 * nb * nb)) return 1;
+            k_build_ppw<<<(2 * nb * nb + 255) / 256, 256, 0, e->stream>>>(s, w);
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(e->stream));
+            s.ppw = w;
+        }
     }
     e->have_sys = true;
     return 0;

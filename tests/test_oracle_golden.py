@@ -20,9 +20,9 @@ def _pr(x):
     return float("%.10E" % x)
 
 
-def _run(case, fcidump_path, nrows):
+def _run(case, fcidump_path, nrows, wide=False):
     g = load_golden(case)
-    o = Oracle()
+    o = Oracle(wide=wide)
     if "ueg" in g:
         o.init_ueg(**g["ueg"])
         o.set_ref_det(g["ref_det"])
@@ -108,6 +108,13 @@ def test_ueg_np2_np4(fcidump_path):
         t = o.ueg_tables()
         assert abs(t["L"] - g["kat"]["L"]) < 5e-9 and o.nbasis == g["kat"]["nbasis"]
         assert abs(o.basis()["sp_eigv"][2] - g["kat"]["sp_eigv_3"]) < 5e-10
+
+
+def test_wide_oracle_build_reproduces_golden_tables(fcidump_path):
+    """liboracle_wide.so (the same source with 32-word determinants, the checker of the wide device layout) on fixtures
+    the 4-word build reproduces too: UEG np2 and the real-amplitude Ne CI6 np2 run"""
+    _run("ueg_np2", fcidump_path, 150, wide=True)
+    _run("ne_ci6_real64_np2", fcidump_path, 60, wide=True)
 
 
 def test_ueg_quasi_newton_np2(fcidump_path):

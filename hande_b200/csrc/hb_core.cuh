@@ -1043,6 +1043,57 @@ HB_HD int alias_select_fast(int N, const double* wq, int stride, double scale, i
     }
     return result;
 }
+// The same selection with fixed trip counts (no per-lane loops over mask bits, whose length is the warp maximum): ONE
+// top-down pass classifies every entry, forms slot k's own running sum (`target`, the entries of its class above it)
+// and overwrites wq[q] with the running sum of the OTHER class down to q - non-decreasing along the pass, so the first
+// entry whose running sum reaches `target` is found by a binary search instead of a second pass.  Sums are formed in
+// the order of alias_select_fast (descending index within a class), hence the same values and the same decisions.
+// CLOBBERS the staged weights; returns 0 where alias_select_fast would fall back to the exact walk (the caller stages the
+// weights again and calls alias_walk_exact).
+template <class Mask>
+HB_HD int alias_select_scan(int N, double* wq, int stride, double scale, int k, double x) {
+    const double guard = 1.e-9;
+    const double uk = wq[k * stride] * scale;
+    const bool k_under = uk <= 1.0;
+    Mask under = 0;
+    double target = k_under ? 0.0 : (uk - 1.0);
+    double acc = 0.0;
+#pragma unroll 4
+    for (int q = N - 1; q >= 0; --q) {
+        const double u = wq[q * stride] * scale;
+        const bool un = u <= 1.0;
+        under |= un ? ((Mask)1 << q) : (Mask)0;
+        const double d = fabs(u - 1.0);
+        const bool own = (un == k_under);
+        if (own && q > k) target += d;
+        if (!own) acc += d;
+        wq[q * stride] = acc;
+    }
+    const Mask all = (N >= (int)(8 * sizeof(Mask))) ? ~(Mask)0 : (((Mask)1 << N) - 1);
+    const Mask over = all & ~under;
+    const Mask kbit = (Mask)1 << k;
+    const Mask below = over & (kbit - 1);
+    if (k_under ? (x < uk) : (below == 0)) return k + 1;
+    const Mask other = k_under ? over : under;
+    if (other == 0) return k + 1;
+    // largest q with (running sum - target) >= -guard; the running sum at q = 0 is the class total
+    if (!(wq[0] - target >= -guard)) return k + 1;          // the other class runs out first
+    int lo = 0, hi = N - 1;                                  // invariant: predicate true at lo
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (wq[mid * stride] - target >= -guard) lo = mid; else hi = mid - 1;
+    }
+    // the first entry of the other class at or below lo (the running sum is constant across entries of k's own class)
+    const Mask cand = other & ((lo >= (int)(8 * sizeof(Mask)) - 1) ? ~(Mask)0 : ((((Mask)1 << lo) << 1) - 1));
+    const int hit = mask_top<Mask>(cand);
+    const double acc_hit = wq[hit * stride];
+    const double d = acc_hit - target;
+    if (!(d > guard)) return 0;                              // within the guard band: exact walk
+    if (k_under) return hit + 1;
+    const double Uk = 1.0 + (target - acc_hit);
+    if (fabs(x - Uk) <= guard) return 0;
+    return (x < Uk) ? k + 1 : mask_top<Mask>(below) + 1;
+}
 template <class Mask, class R>
 HB_HD int select_alias_staged_m(R& rng, int N, const double* wq, int stride, double totweight) {
     double x = rng.next() * N;
@@ -1094,6 +1145,22 @@ HB_HD double stage_occ(const double* __restrict__ tab, const occ_t* occ, int nel
 // CPU parity harness and the probe kernel run; k_spawn_death calls the same phase functions with block-level
 // queues in between.  The per-determinant weight lists (i_d_occ%weights, ij_weights_occ, ji_weights_occ) are columns
 // of hb_i_w / hb_ij_w gathered at the occupied orbitals and are re-read where needed.
+// select_weighted_value over the staged weights wq[q] = tab[occ[q]-1] with the fixed-trip-count scan; the staged weights
+// are consumed (clobbered), and staged again for the exact walk in the rare guard-band case
+template <class R>
+HB_HD int select_alias_restage(R& rng, int N, const double* __restrict__ tab, const occ_t* occ, double* wq, int stride,
+                               double totweight) {
+    double x = rng.next() * N;
+    const int k = (int)x;                  // floor: x >= 0
+    x = x - k;
+    const double scale = N / totweight;
+    int r = (N <= 32) ? alias_select_scan<uint32_t>(N, wq, stride, scale, k, x) : alias_select_scan<uint64_t>(N, wq, stride, scale, k, x);
+    if (r == 0) {
+        stage_occ(tab, occ, N, wq, stride);
+        r = (N <= 32) ? alias_walk_exact<uint32_t>(N, wq, stride, scale, k, x) : alias_walk_exact<uint64_t>(N, wq, stride, scale, k, x);
+    }
+    return r;
+}
 #define HB_I2(j, i) ((int64_t)((j) - 1) + nb * ((i) - 1))
 #define HB_I3(a, j, i) ((int64_t)((a) - 1) + nb * (((j) - 1) + nb * ((i) - 1)))
 #define HB_I4(b, a, j, i) ((int64_t)((b) - 1) + nb * (((a) - 1) + nb * (((j) - 1) + nb * ((i) - 1))))
@@ -1133,10 +1200,10 @@ HB_HDN void hb_phase_a(R& rng, const Sys& s, const uint64_t* f, const occ_t* occ
     st.psingle = 0.0; st.hmod_ia = 0.0; st.h_ia = 0.0; st.perm_ia = false;
     st.dbl = true; st.need_ia = false; st.need_k = 0; st.allowed = false;
     st.i_tot = stage_occ(iw, occ, nel, scr, stride);
-    st.i = occ[select_alias_staged(rng, nel, scr, stride, st.i_tot) - 1];
+    st.i = occ[select_alias_restage(rng, nel, iw, occ, scr, stride, st.i_tot) - 1];
     st.ij_tot = stage_occ(s.hb_ij_w + nb * (st.i - 1), occ, nel, scr, stride);
     if (st.ij_tot > 0.0) {
-        st.j = occ[select_alias_staged(rng, nel, scr, stride, st.ij_tot) - 1];
+        st.j = occ[select_alias_restage(rng, nel, s.hb_ij_w + nb * (st.i - 1), occ, scr, stride, st.ij_tot) - 1];
         st.allowed = fabs(s.hb_ija_tot[HB_I2(st.j, st.i)]) > 0.0;
     }
     if (st.allowed) {

@@ -196,7 +196,7 @@ long long hd_alias_selftest(long long ntrials, unsigned long long seed, long lon
 long long hd_alias_selftest_mode(long long ntrials, unsigned long long seed, long long* out, int only_mode) {
     unsigned long long st = seed * 0x9E3779B97F4A7C15ull + 12345;
     auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (double)(st >> 11) * (1.0 / 9007199254740992.0); };
-    long long bad = 0;
+    long long bad = 0, nfallback = 0;
     for (long long t = 0; t < ntrials; ++t) {
         const int N = 2 + (int)(rnd() * 39);
         double w[HB_MAXNEL], U[HB_MAXNEL];
@@ -231,9 +231,20 @@ long long hd_alias_selftest_mode(long long ntrials, unsigned long long seed, lon
             const int ref = select_precalc(a, N, U, K);
             const int got = select_alias_staged(b, N, w, 1, tot);
             if (ref != got) bad++;
+            // the fixed-trip-count scan (clobbers its copy of the weights; 0 = "run the exact walk")
+            {
+                double wc[HB_MAXNEL];
+                for (int q = 0; q < N; ++q) wc[q] = w[q];
+                double xx = r * N;
+                const int kk = (int)xx;
+                xx = xx - kk;
+                int got2 = (N <= 32) ? alias_select_scan<uint32_t>(N, wc, 1, N / tot, kk, xx) : alias_select_scan<uint64_t>(N, wc, 1, N / tot, kk, xx);
+                if (got2 == 0) { nfallback++; got2 = (N <= 32) ? alias_walk_exact<uint32_t>(N, w, 1, N / tot, kk, xx) : alias_walk_exact<uint64_t>(N, w, 1, N / tot, kk, xx); }
+                if (ref != got2) bad++;
+            }
         }
     }
-    out[0] = 8 * ntrials; out[1] = 0;
+    out[0] = 8 * ntrials; out[1] = nfallback;
     return bad;
 }
 }  // extern "C"

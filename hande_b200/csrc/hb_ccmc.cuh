@@ -357,11 +357,34 @@ __global__ void k_find_det(Params p, const uint64_t* __restrict__ states, const 
 // Probe kernels (parity tests through the C ABI)
 // ------------------------------------------------------------------------------------------------
 template <int W>
+// rn != nullptr: INJECTED random numbers - attempt t draws rn[t*nrn], rn[t*nrn+1], ... in order (the excitation generator
+// first, attempt_to_spawn after it) instead of the Philox stream, and nused[t] receives how many it drew: the level-1
+// parity hook (a host feeds the numbers its own generator consumed and compares choice, pgen, H_ij and nspawn).
 __global__ void k_gen_excit_batch(Sys s, Params p, const uint64_t* __restrict__ states, const int64_t* __restrict__ pops,
                                   const uint32_t* __restrict__ attempt, long long n, const int* __restrict__ proc_map,
-                                  int* __restrict__ iout, double* __restrict__ dout, int64_t* __restrict__ nspawn) {
+                                  int* __restrict__ iout, double* __restrict__ dout, int64_t* __restrict__ nspawn,
+                                  const double* __restrict__ rn, int nrn, int* __restrict__ nused) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
+    if (rn) {
+        uint64_t f[W];
+#pragma unroll
+        for (int k = 0; k < W; ++k) f[k] = states[t * W + k];
+        occ_t occ[HB_MAXNEL]; uint8_t su[64];
+        decode_det<W>(f, occ);
+        if (s.kind != SYS_UEG) build_symunocc(s, occ, su);
+        ListStream rng{rn + t * nrn, nrn, 0};
+        Gen g;
+        gen_excit<W>(rng, s, p, f, occ, su, g);
+        const int64_t ns = attempt_to_spawn(rng, p, g.hmatel, g.pgen, pops[t]);
+        int* io = iout + t * 8;
+        io[0] = g.nexcit; io[1] = g.from1; io[2] = g.from2; io[3] = g.to1; io[4] = g.to2; io[5] = g.perm; io[6] = g.allowed;
+        io[7] = -1;
+        dout[t * 2] = g.pgen; dout[t * 2 + 1] = g.hmatel;
+        nspawn[t] = ns;
+        nused[t] = rng.k;
+        return;
+    }
     uint64_t f[W];
 #pragma unroll
     for (int k = 0; k < W; ++k) f[k] = states[t * W + k];

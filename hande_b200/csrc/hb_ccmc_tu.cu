@@ -43,10 +43,10 @@ int HB_FN(hb_ccmc_find_det_w)(hb200_engine* e, const Params& p) {
     return 0;
 }
 int HB_FN(hb_gen_excit_batch_w)(hb200_engine* e, const Params& p, const uint64_t* d_f, const int64_t* d_p, const uint32_t* d_a,
-                                long long n, int* d_io, double* d_do, int64_t* d_ns) {
+                                long long n, int* d_io, double* d_do, int64_t* d_ns, const double* d_rn, int nrn, int* d_nused) {
     constexpr int W = HB_TU_W;
     k_gen_excit_batch<W><<<(unsigned)((n + 127) / 128), 128, 0, e->stream>>>(e->sys, p, d_f, d_p, d_a, n, e->d_proc_map, d_io, d_do,
-                                                                             d_ns);
+                                                                             d_ns, d_rn, nrn, d_nused);
     CK(cudaGetLastError());
     return 0;
 }

@@ -315,5 +315,6 @@ struct CcmcLaunch {
     int hb_ccmc_redistribute_w##W(hb200_engine* e, const Params& p);                                                 \
     int hb_ccmc_find_det_w##W(hb200_engine* e, const Params& p);                                                     \
     int hb_gen_excit_batch_w##W(hb200_engine* e, const Params& p, const uint64_t* d_f, const int64_t* d_p,           \
-                                const uint32_t* d_a, long long n, int* d_io, double* d_do, int64_t* d_ns);
+                                const uint32_t* d_a, long long n, int* d_io, double* d_do, int64_t* d_ns,             \
+                                const double* d_rn, int nrn, int* d_nused);
 HB_DECL_CCMC(1) HB_DECL_CCMC(2) HB_DECL_CCMC(3) HB_DECL_CCMC(4) HB_DECL_CCMC(32)

@@ -251,9 +251,15 @@ struct PhiloxStream {
 };
 
 // Test stream: a caller-provided list of uniforms (hdcheck only).
+// injected list of uniform numbers; past its end the stream continues with an equidistributed sequence (so that a
+// rejection loop always terminates) and k > n tells the caller the list was too short
 struct ListStream {
     const double* v; int n; int k;
-    HB_HD double next() { return (k < n) ? v[k++] : 0.0; }
+    HB_HD double next() {
+        if (k < n) return v[k++];
+        const double x = 0.5 + 0.6180339887498949 * (double)(++k);
+        return x - floor(x);
+    }
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -841,35 +841,22 @@ __global__ void k_build_sc1T(Sys s, int A, D2* T) {
     T[t] = v;
 }
 
-int hb200_build_heat_bath(hb200_engine* e) {
-    CK(cudaSetDevice(e->cfg.device));
-    if (!e->have_sys) FAIL("build_heat_bath: system not set");
-    Sys& s = e->sys;
-    const long long nb = s.nbasis;
-    const long long n2 = nb * nb, n3 = n2 * nb, n4 = n3 * nb;
-    double *i_w, *ij_w, *ija_w, *ija_U, *ija_tot, *ijab_w, *ijab_U, *ijab_tot;
-    int *ija_K, *ijab_K, *scratch;
-    if (dalloc(e, &i_w, nb) || dalloc(e, &ij_w, n2) || dalloc(e, &ija_w, n3) || dalloc(e, &ija_U, n3) ||
-        dalloc(e, &ija_K, n3) || dalloc(e, &ija_tot, n2) || dalloc(e, &ijab_w, n4) || dalloc(e, &ijab_U, n4) ||
-        dalloc(e, &ijab_K, n4) || dalloc(e, &ijab_tot, n3))
+struct HbArrays { double *i_w, *ij_w, *ija_w, *ija_U, *ija_tot, *ijab_w, *ijab_U, *ijab_tot; int *ija_K, *ijab_K; };
+
+static int hb_alloc_arrays(hb200_engine* e, HbArrays& t) {
+    const long long nb = e->sys.nbasis, n2 = nb * nb, n3 = n2 * nb, n4 = n3 * nb;
+    if (dalloc(e, &t.i_w, nb) || dalloc(e, &t.ij_w, n2) || dalloc(e, &t.ija_w, n3) || dalloc(e, &t.ija_U, n3) ||
+        dalloc(e, &t.ija_K, n3) || dalloc(e, &t.ija_tot, n2) || dalloc(e, &t.ijab_w, n4) || dalloc(e, &t.ijab_U, n4) ||
+        dalloc(e, &t.ijab_K, n4) || dalloc(e, &t.ijab_tot, n3))
         return 1;
-    void* sc = nullptr;
-    CK(cudaMalloc(&sc, (size_t)2 * n4 * sizeof(int)));
-    scratch = (int*)sc;
+    return 0;
+}
+// the derived layouts of excit_gen = heat_bath (packed records, branch-free single-excitation rows) and the hand-over
+// of the tables to the kernels
+static int hb_finish_tables(hb200_engine* e, const HbArrays& t) {
+    Sys& s = e->sys;
     cudaStream_t st = e->stream;
-    CK(cudaMemsetAsync(ija_U, 0, n3 * sizeof(double), st));
-    CK(cudaMemsetAsync(ija_K, 0, n3 * sizeof(int), st));
-    CK(cudaMemsetAsync(ijab_U, 0, n4 * sizeof(double), st));
-    CK(cudaMemsetAsync(ijab_K, 0, n4 * sizeof(int), st));
-    k_hb_ijab_w<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(s, ijab_w);
-    k_hb_ijab_tot<<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>((int)nb, ijab_w, ijab_tot, ija_w);
-    k_hb_ij<<<(unsigned)((n2 + 127) / 128), 128, 0, st>>>((int)nb, ijab_w, ija_w, ija_tot, ij_w);
-    k_hb_i<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>((int)nb, ij_w, i_w);
-    k_hb_alias<<<(unsigned)((n2 + 127) / 128), 128, 0, st>>>((int)nb, n2, ija_w, ija_tot, ija_U, ija_K, scratch);
-    k_hb_alias<<<(unsigned)((n3 + 127) / 128), 128, 0, st>>>((int)nb, n3, ijab_w, ijab_tot, ijab_U, ijab_K, scratch);
-    CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(st));
-    CK(cudaFree(sc));
+    const long long nb = s.nbasis, n2 = nb * nb, n3 = n2 * nb, n4 = n3 * nb;
     if (e->cfg.excit_gen == HB200_EXCIT_GEN_HEAT_BATH) {
         // The packed hb_ija rows (nb^3 records) and the single-excitation rows sc1T share one allocation.  (Pinning it in
         // L2 with a persisting access-policy window was measured and made the spawning kernels 10-17 % SLOWER on B200 -
@@ -883,17 +870,69 @@ int hb200_build_heat_bath(hb200_engine* e) {
         D2* T = reinterpret_cast<D2*>(arena + bytes_rec);
         HbRec* ijab_rec;
         if (dalloc(e, &ijab_rec, n4)) return 1;
-        k_hb_pack<<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>(n3, (int)nb, ija_U, ija_w, ija_K, ija_tot, ija_rec);
-        k_hb_pack<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(n4, (int)nb, ijab_U, ijab_w, ijab_K, ijab_tot, ijab_rec);
+        k_hb_pack<<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>(n3, (int)nb, t.ija_U, t.ija_w, t.ija_K, t.ija_tot, ija_rec);
+        k_hb_pack<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(n4, (int)nb, t.ijab_U, t.ijab_w, t.ijab_K, t.ijab_tot, ijab_rec);
         k_build_sc1T<<<(unsigned)((nT + 255) / 256), 256, 0, st>>>(s, A, T);
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(st));
         s.hb_ija_rec = ija_rec; s.hb_ijab_rec = ijab_rec; s.sc1T = T; s.sc1A = A;
     }
-    s.hb_i_w = i_w; s.hb_ij_w = ij_w; s.hb_ija_w = ija_w; s.hb_ija_U = ija_U; s.hb_ija_K = ija_K; s.hb_ija_tot = ija_tot;
-    s.hb_ijab_w = ijab_w; s.hb_ijab_U = ijab_U; s.hb_ijab_K = ijab_K; s.hb_ijab_tot = ijab_tot;
+    s.hb_i_w = t.i_w; s.hb_ij_w = t.ij_w; s.hb_ija_w = t.ija_w; s.hb_ija_U = t.ija_U; s.hb_ija_K = t.ija_K; s.hb_ija_tot = t.ija_tot;
+    s.hb_ijab_w = t.ijab_w; s.hb_ijab_U = t.ijab_U; s.hb_ijab_K = t.ijab_K; s.hb_ijab_tot = t.ijab_tot;
     e->have_hb = true;
     return 0;
+}
+
+int hb200_build_heat_bath(hb200_engine* e) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (!e->have_sys) FAIL("build_heat_bath: system not set");
+    Sys& s = e->sys;
+    const long long nb = s.nbasis;
+    const long long n2 = nb * nb, n3 = n2 * nb, n4 = n3 * nb;
+    HbArrays t;
+    if (hb_alloc_arrays(e, t)) return 1;
+    void* sc = nullptr;
+    CK(cudaMalloc(&sc, (size_t)2 * n4 * sizeof(int)));
+    int* scratch = (int*)sc;
+    cudaStream_t st = e->stream;
+    CK(cudaMemsetAsync(t.ija_U, 0, n3 * sizeof(double), st));
+    CK(cudaMemsetAsync(t.ija_K, 0, n3 * sizeof(int), st));
+    CK(cudaMemsetAsync(t.ijab_U, 0, n4 * sizeof(double), st));
+    CK(cudaMemsetAsync(t.ijab_K, 0, n4 * sizeof(int), st));
+    k_hb_ijab_w<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(s, t.ijab_w);
+    k_hb_ijab_tot<<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>((int)nb, t.ijab_w, t.ijab_tot, t.ija_w);
+    k_hb_ij<<<(unsigned)((n2 + 127) / 128), 128, 0, st>>>((int)nb, t.ijab_w, t.ija_w, t.ija_tot, t.ij_w);
+    k_hb_i<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>((int)nb, t.ij_w, t.i_w);
+    k_hb_alias<<<(unsigned)((n2 + 127) / 128), 128, 0, st>>>((int)nb, n2, t.ija_w, t.ija_tot, t.ija_U, t.ija_K, scratch);
+    k_hb_alias<<<(unsigned)((n3 + 127) / 128), 128, 0, st>>>((int)nb, n3, t.ijab_w, t.ijab_tot, t.ijab_U, t.ijab_K, scratch);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    CK(cudaFree(sc));
+    return hb_finish_tables(e, t);
+}
+
+// excit_gen_heat_bath_t as the HOST built it (init_excit_mol_heat_bath, src/excit_gen_heat_bath_mol.F90:14-256): the
+// tables are uploaded as they are, nothing is recomputed.  Arrays in the reference's (column-major) order:
+// i_weights(nb), ij_weights(nb,nb), hb_ija%{weights, aliasU, aliasK}(nb,nb,nb), hb_ija%weights_tot(nb,nb),
+// hb_ijab%{weights, aliasU, aliasK}(nb,nb,nb,nb), hb_ijab%weights_tot(nb,nb,nb); aliasK 1-based as in the reference.
+int hb200_set_excit_tables(hb200_engine* e, const hb200_heat_bath_tables* in) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (!e->have_sys) FAIL("set_excit_tables: system not set");
+    if (!uses_heat_bath_tables(e)) FAIL("set_excit_tables: the configured excitation generator does not use the heat-bath tables");
+    const long long nb = e->sys.nbasis, n2 = nb * nb, n3 = n2 * nb, n4 = n3 * nb;
+    HbArrays t;
+    if (hb_alloc_arrays(e, t)) return 1;
+    CK(copy_sync(e, t.i_w, in->i_weights, (size_t)nb * 8, cudaMemcpyHostToDevice));
+    CK(copy_sync(e, t.ij_w, in->ij_weights, (size_t)n2 * 8, cudaMemcpyHostToDevice));
+    CK(copy_sync(e, t.ija_w, in->ija_weights, (size_t)n3 * 8, cudaMemcpyHostToDevice));
+    CK(copy_sync(e, t.ija_U, in->ija_aliasU, (size_t)n3 * 8, cudaMemcpyHostToDevice));
+    CK(copy_sync(e, t.ija_K, in->ija_aliasK, (size_t)n3 * 4, cudaMemcpyHostToDevice));
+    CK(copy_sync(e, t.ija_tot, in->ija_weights_tot, (size_t)n2 * 8, cudaMemcpyHostToDevice));
+    CK(copy_sync(e, t.ijab_w, in->ijab_weights, (size_t)n4 * 8, cudaMemcpyHostToDevice));
+    CK(copy_sync(e, t.ijab_U, in->ijab_aliasU, (size_t)n4 * 8, cudaMemcpyHostToDevice));
+    CK(copy_sync(e, t.ijab_K, in->ijab_aliasK, (size_t)n4 * 4, cudaMemcpyHostToDevice));
+    CK(copy_sync(e, t.ijab_tot, in->ijab_weights_tot, (size_t)n3 * 8, cudaMemcpyHostToDevice));
+    return hb_finish_tables(e, t);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2412,12 +2451,46 @@ int hb200_gen_excit_batch(hb200_engine* e, const uint64_t* states, const int64_t
     CK(copy_states_h2d(e, d_f, states, n, e->stream));
     CK(copy_sync(e, d_p, pops, (size_t)n * 8, cudaMemcpyHostToDevice));
     CK(copy_sync(e, d_a, attempt, (size_t)n * 4, cudaMemcpyHostToDevice));
-    { int rc = 0; DISPATCH_CCMC(e, rc, hb_gen_excit_batch_w, e, p, d_f, d_p, d_a, n, d_io, d_do, d_ns); if (rc) return 1; }
+    { int rc = 0; DISPATCH_CCMC(e, rc, hb_gen_excit_batch_w, e, p, d_f, d_p, d_a, n, d_io, d_do, d_ns, nullptr, 0, nullptr); if (rc) return 1; }
     CK(cudaStreamSynchronize(e->stream));
     CK(copy_sync(e, iout, d_io, (size_t)n * 8 * 4, cudaMemcpyDeviceToHost));
     CK(copy_sync(e, dout, d_do, (size_t)n * 2 * 8, cudaMemcpyDeviceToHost));
     CK(copy_sync(e, nspawn, d_ns, (size_t)n * 8, cudaMemcpyDeviceToHost));
     cudaFree(d_f); cudaFree(d_p); cudaFree(d_a); cudaFree(d_io); cudaFree(d_do); cudaFree(d_ns);
+    return 0;
+}
+
+// Level-1 parity hook (SURVEY 8b "inject_rng"): the same as hb200_gen_excit_batch with INJECTED uniform random numbers -
+// attempt k consumes rn[k][0], rn[k][1], ... in order (excitation generator, then attempt_to_spawn) instead of the Philox
+// stream; nused[k] = how many it drew.  A host compares its own generator fed the same numbers.
+int hb200_gen_excit_batch_rn(hb200_engine* e, const uint64_t* states, const int64_t* pops, const double* rn, int32_t nrn,
+                             int64_t n, double tau, int32_t* iout, double* dout, int64_t* nspawn, int32_t* nused) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (!e->have_sys) FAIL("gen_excit_batch_rn: system not set");
+    if (uses_heat_bath_tables(e) && !e->have_hb) FAIL("gen_excit_batch_rn: heat-bath tables not built");
+    if (e->cfg.excit_gen == HB200_EXCIT_GEN_POWER_PITZER_ORDERN && !e->have_ppn) FAIL("gen_excit_batch_rn: power_pitzer_orderN tables not built");
+    if (e->cfg.excit_gen == HB200_EXCIT_GEN_POWER_PITZER && !e->have_pp) FAIL("gen_excit_batch_rn: power_pitzer tables not built");
+    if (n == 0) return 0;
+    Params p = e->par;
+    p.tau = tau;
+    uint64_t* d_f; int64_t* d_p; double* d_rn; int* d_io; double* d_do; int64_t* d_ns; int* d_nu;
+    CK(cudaMalloc((void**)&d_f, (size_t)n * e->W * 8));
+    CK(cudaMalloc((void**)&d_p, (size_t)n * 8));
+    CK(cudaMalloc((void**)&d_rn, (size_t)n * nrn * 8));
+    CK(cudaMalloc((void**)&d_io, (size_t)n * 8 * 4));
+    CK(cudaMalloc((void**)&d_do, (size_t)n * 2 * 8));
+    CK(cudaMalloc((void**)&d_ns, (size_t)n * 8));
+    CK(cudaMalloc((void**)&d_nu, (size_t)n * 4));
+    CK(copy_states_h2d(e, d_f, states, n, e->stream));
+    CK(copy_sync(e, d_p, pops, (size_t)n * 8, cudaMemcpyHostToDevice));
+    CK(copy_sync(e, d_rn, rn, (size_t)n * nrn * 8, cudaMemcpyHostToDevice));
+    { int rc = 0; DISPATCH_CCMC(e, rc, hb_gen_excit_batch_w, e, p, d_f, d_p, nullptr, n, d_io, d_do, d_ns, d_rn, nrn, d_nu); if (rc) return 1; }
+    CK(cudaStreamSynchronize(e->stream));
+    CK(copy_sync(e, iout, d_io, (size_t)n * 8 * 4, cudaMemcpyDeviceToHost));
+    CK(copy_sync(e, dout, d_do, (size_t)n * 2 * 8, cudaMemcpyDeviceToHost));
+    CK(copy_sync(e, nspawn, d_ns, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    CK(copy_sync(e, nused, d_nu, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    cudaFree(d_f); cudaFree(d_p); cudaFree(d_rn); cudaFree(d_io); cudaFree(d_do); cudaFree(d_ns); cudaFree(d_nu);
     return 0;
 }
 

@@ -120,6 +120,7 @@ def load_library():
     L.hb200_set_system_read_in.argtypes = [C.c_void_p, C.POINTER(SystemReadIn)]
     L.hb200_set_system_ueg.argtypes = [C.c_void_p, C.POINTER(SystemUeg)]
     L.hb200_build_heat_bath.argtypes = [C.c_void_p]
+    L.hb200_set_excit_tables.argtypes = [C.c_void_p, C.c_void_p]
     L.hb200_download_heat_bath.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]
     L.hb200_set_reference.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
     L.hb200_set_proc_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
@@ -152,6 +153,8 @@ def load_library():
     L.hb200_sc0_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     L.hb200_gen_excit_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32,
                                         C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hb200_gen_excit_batch_rn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_double,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.hb200_get_unique_id.argtypes = [C.c_void_p]
     L.hb200_comm_init.argtypes = [C.c_void_p, C.c_void_p]
     L.hb200_p2p_export.argtypes = [C.c_void_p, C.c_void_p]
@@ -167,7 +170,7 @@ def load_library():
 
 ABI_SYMBOLS = [
     "hb200_last_error", "hb200_create", "hb200_destroy", "hb200_set_system_read_in", "hb200_set_system_ueg",
-    "hb200_build_heat_bath",
+    "hb200_build_heat_bath", "hb200_set_excit_tables", "hb200_gen_excit_batch_rn",
     "hb200_download_heat_bath", "hb200_set_reference", "hb200_set_proc_map", "hb200_upload_psips",
     "hb200_upload_psips_begin", "hb200_upload_psips_commit",
     "hb200_download_psips", "hb200_nstates", "hb200_iterate", "hb200_spawn_death", "hb200_comm_spawn",
@@ -186,13 +189,21 @@ class EngineError(RuntimeError):
     pass
 
 
+# field order of hb200_heat_bath_tables (include/hande_b200.h)
+HEAT_BATH_TABLE_KEYS = ("i_weights", "ij_weights", "ija_weights", "ija_aliasU", "ija_aliasK", "ija_weights_tot",
+                        "ijab_weights", "ijab_aliasU", "ijab_aliasK", "ijab_weights_tot")
+
+
 class Engine:
     """One GPU's share of the walker population (one MPI rank of the reference)."""
 
     def __init__(self, sys, *, excit_gen="renorm", pattempt_single, pattempt_double, real_amplitudes=False,
                  spawn_cutoff=0.01, initiator_approx=False, initiator_pop=3.0, trunc_level=-1, walker_length=1 << 20,
                  spawned_walker_length=1 << 18, seed=7, nprocs=1, iproc=0, nslots=1, device=0, hash_seed=7,
-                 pattempt_parallel=-1.0, power_pitzer_min_weight=0.01):
+                 pattempt_parallel=-1.0, power_pitzer_min_weight=0.01, heat_bath_tables=None):
+        """heat_bath_tables: the ten arrays of excit_gen_heat_bath_t as a host built them (dict with the keys of
+        HEAT_BATH_TABLE_KEYS, the reference's column-major order) - handed over with hb200_set_excit_tables instead of
+        being built on the device"""
         self.L = load_library()
         self.power_pitzer_min_weight = power_pitzer_min_weight
         self.sys = sys
@@ -215,7 +226,13 @@ class Engine:
         if eg in (EXCIT_GEN["heat_bath"], EXCIT_GEN["heat_bath_uniform"], EXCIT_GEN["heat_bath_single"],
                   EXCIT_GEN["power_pitzer_occ_ij"],
                   EXCIT_GEN["cauchy_schwarz_occ_ij"]):   # the _occ_ij weights are the heat-bath i/ij tables
-            self._chk(self.L.hb200_build_heat_bath(self.h))
+            if heat_bath_tables is None:
+                self._chk(self.L.hb200_build_heat_bath(self.h))
+            else:
+                keep = [np.ascontiguousarray(heat_bath_tables[k], dtype=(np.int32 if k.endswith("aliasK") else np.float64))
+                        for k in HEAT_BATH_TABLE_KEYS]
+                ptrs = (C.c_void_p * len(keep))(*[a.ctypes.data for a in keep])
+                self._chk(self.L.hb200_set_excit_tables(self.h, C.cast(ptrs, C.c_void_p)))
         if eg in (EXCIT_GEN["renorm_spin"], EXCIT_GEN["no_renorm_spin"]):
             self.pattempt_parallel = self.set_pattempt_parallel(pattempt_parallel)
 
@@ -432,6 +449,20 @@ class Engine:
         self._chk(self.L.hb200_gen_excit_batch(self.h, _p(states), _p(pops), _p(attempts), n, cycle, tau, _p(io), _p(do),
                                                _p(ns)))
         return io, do, ns
+
+    def gen_excit_batch_rn(self, states, pops, rn, tau):
+        """gen_excit + attempt_to_spawn on injected random numbers rn[n][nrn]; returns (iout, dout, nspawn, nused)"""
+        states = np.ascontiguousarray(states, dtype=np.uint64).reshape(-1, self.W)
+        pops = np.ascontiguousarray(pops, dtype=np.int64)
+        rn = np.ascontiguousarray(rn, dtype=np.float64)
+        n = len(pops)
+        io = np.zeros((n, 8), dtype=np.int32)
+        do = np.zeros((n, 2))
+        ns = np.zeros(n, dtype=np.int64)
+        nu = np.zeros(n, dtype=np.int32)
+        self._chk(self.L.hb200_gen_excit_batch_rn(self.h, _p(states), _p(pops), _p(rn), rn.shape[1], n, tau, _p(io), _p(do),
+                                                  _p(ns), _p(nu)))
+        return io, do, ns, nu
 
     def heat_bath_table(self, which, n):
         out = np.zeros(n, dtype=np.int32 if which >= 8 else np.float64)

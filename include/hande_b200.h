@@ -134,6 +134,22 @@ int hb200_set_system_read_in(hb200_engine* e, const hb200_system_read_in* sys);
 int hb200_set_system_ueg(hb200_engine* e, const hb200_system_ueg* sys);
 /* init_excit_mol_heat_bath (src/excit_gen_heat_bath_mol.F90:14-256) evaluated on the device. */
 int hb200_build_heat_bath(hb200_engine* e);
+/* The same tables handed over by a host that has already built them (excit_gen_heat_bath_t after
+ * init_excit_mol_heat_bath, src/excit_gens.f90:143-153, src/excit_gen_heat_bath_mol.F90:14-256) instead of
+ * hb200_build_heat_bath: uploaded as they are.  Arrays in the reference's column-major order, aliasK 1-based. */
+typedef struct hb200_heat_bath_tables {
+    const double* i_weights;          /* (nbasis) */
+    const double* ij_weights;         /* (nbasis, nbasis) */
+    const double* ija_weights;        /* hb_ija%weights(nbasis, nbasis, nbasis) */
+    const double* ija_aliasU;
+    const int32_t* ija_aliasK;
+    const double* ija_weights_tot;    /* (nbasis, nbasis) */
+    const double* ijab_weights;       /* hb_ijab%weights(nbasis, nbasis, nbasis, nbasis) */
+    const double* ijab_aliasU;
+    const int32_t* ijab_aliasK;
+    const double* ijab_weights_tot;   /* (nbasis, nbasis, nbasis) */
+} hb200_heat_bath_tables;
+int hb200_set_excit_tables(hb200_engine* e, const hb200_heat_bath_tables* tables);
 /* Test/inspection: copy heat-bath table `which` to the host (0 i_w,1 ij_w,2 ija_w,3 ija_U,4 ija_tot,
  * 5 ijab_w,6 ijab_U,7 ijab_tot as double; 8 ija_K, 9 ijab_K as int32). n = element count expected. */
 int hb200_download_heat_bath(hb200_engine* e, int which, void* out, int64_t n);
@@ -245,6 +261,13 @@ int hb200_sc0_batch(hb200_engine* e, const uint64_t* states, int64_t n, double* 
  * to1, to2, perm, allowed, owner; dout[n][2] = pgen, hmatel; nspawn[n]. */
 int hb200_gen_excit_batch(hb200_engine* e, const uint64_t* states, const int64_t* pops, const uint32_t* attempt,
                           int64_t n, uint32_t cycle, double tau, int32_t* iout, double* dout, int64_t* nspawn);
+
+/* The same with INJECTED random numbers (level 1 of the correctness contract: "kernels fed identical injected random
+ * numbers"): attempt k draws rn[k][0], rn[k][1], ... (nrn per attempt, uniform on [0,1)) in the order the reference's
+ * gen_excit_ptr%full and then attempt_to_spawn draw from dSFMT, instead of the engine's Philox stream; nused[k] = how
+ * many were drawn.  A Fortran host feeds the numbers its own generator consumed and compares choice, pgen, H_ij, nspawn. */
+int hb200_gen_excit_batch_rn(hb200_engine* e, const uint64_t* states, const int64_t* pops, const double* rn, int32_t nrn,
+                             int64_t n, double tau, int32_t* iout, double* dout, int64_t* nspawn, int32_t* nused);
 
 /* Wall-Chebyshev propagator (qmc = { chebyshev = {...} }; src/propagators.f90:11-208, src/fciqmc.f90:298-299,427): the
  * host keeps the spectral range and the weights 1/(S_i - E_0) (init_chebyshev, update_chebyshev) and runs the `order`

@@ -555,7 +555,14 @@ struct ListRng : Rng {
     ListRng(const double* v_, int n_) : v(v_), n(n_) {}
     void begin(uint32_t, const Det&, int, uint32_t) override {}
     void set_cycle(uint32_t) override {}
-    double next() override { if (k >= n) throw std::runtime_error("ListRng exhausted"); ndraws++; return v[k++]; }
+    bool continue_past_end = false;      // like the engine's ListStream: an equidistributed continuation, k > n flags it
+    double next() override {
+        ndraws++;
+        if (k < n) return v[k++];
+        if (!continue_past_end) throw std::runtime_error("ListRng exhausted");
+        const double x = 0.5 + 0.6180339887498949 * (double)(++k);
+        return x - std::floor(x);
+    }
 };
 int orc_gen_excit_list(void* h, const uint64_t* f, const double* rn, int nrn, int* iout, double* dout) {
     ORC_TRY
@@ -568,6 +575,28 @@ int orc_gen_excit_list(void* h, const uint64_t* f, const double* rn, int nrn, in
     iout[0] = g.conn.nexcit; iout[1] = g.conn.from_orb[0]; iout[2] = g.conn.from_orb[1];
     iout[3] = g.conn.to_orb[0]; iout[4] = g.conn.to_orb[1]; iout[5] = g.conn.perm; iout[6] = g.allowed;
     dout[0] = g.pgen; dout[1] = g.hmatel;
+    return rng.k;
+    ORC_CATCH(-1)
+}
+
+// the same followed by attempt_to_spawn on the next number of the list (tau from orc_set_qmc / the last staged cycle)
+int orc_gen_excit_spawn_list(void* h, const uint64_t* f, int64_t parent_pop, double tau, const double* rn, int nrn, int* iout,
+                             double* dout, int64_t* nspawn) {
+    ORC_TRY
+    Oracle* o = (Oracle*)h;
+    ListRng rng(rn, nrn);
+    rng.continue_past_end = true;
+    DetInfo d;
+    Det fd = mkdet(o->sys, f);
+    decode_for(o->sys, o->eg, fd, d);
+    GenResult g = gen_excit_sys(rng, o->sys, o->eg, d);
+    iout[0] = g.conn.nexcit; iout[1] = g.conn.from_orb[0]; iout[2] = g.conn.from_orb[1];
+    iout[3] = g.conn.to_orb[0]; iout[4] = g.conn.to_orb[1]; iout[5] = g.conn.perm; iout[6] = g.allowed;
+    dout[0] = g.pgen; dout[1] = g.hmatel;
+    const double tau_keep = o->tau;
+    o->tau = tau;
+    *nspawn = o->attempt_to_spawn(rng, g.hmatel, g.pgen, parent_pop);
+    o->tau = tau_keep;
     return rng.k;
     ORC_CATCH(-1)
 }

@@ -460,6 +460,18 @@ class Oracle:
         k = self._chk(self.L.orc_gen_excit_list(self.h, _p(f), _p(rn), len(rn), _p(io), _p(do)))
         return io, do, k
 
+    def gen_excit_spawn_list(self, f, parent_pop, tau, rn):
+        """gen_excit + attempt_to_spawn on an injected list of uniform numbers; returns (io, do, nspawn, numbers used)"""
+        f = np.ascontiguousarray(f, dtype=np.uint64)
+        rn = np.ascontiguousarray(rn, dtype=np.float64)
+        io = np.zeros(8, dtype=np.int32)
+        do = np.zeros(2)
+        ns = np.zeros(1, dtype=np.int64)
+        self.L.orc_gen_excit_spawn_list.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_int,
+                                                    C.c_void_p, C.c_void_p, C.c_void_p]
+        k = self._chk(self.L.orc_gen_excit_spawn_list(self.h, _p(f), int(parent_pop), tau, _p(rn), len(rn), _p(io), _p(do), _p(ns)))
+        return io, do, int(ns[0]), k
+
     def heat_bath_tables(self):
         nb = self.L.orc_hb_nb(self.h)
         shp = {0: (nb,), 1: (nb, nb), 2: (nb,) * 3, 3: (nb,) * 3, 4: (nb, nb), 5: (nb,) * 4, 6: (nb,) * 4,

@@ -14,6 +14,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    # a kernel that never returns must not hold the GPU box until the harness's own limit: every GPU test gets a time
+    # limit (pytest-timeout, thread method: the process is ended, later tests are reported as not run)
+    for item in items:
+        if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+            item.add_marker(pytest.mark.timeout(420, method="thread"))
+
+
 @pytest.fixture(scope="session")
 def fcidump_path(tmp_path_factory):
     """Decompress a committed FCIDUMP fixture (tests/golden/fcidump/<name>.INTDUMP.gz) to a temp file."""

@@ -425,3 +425,57 @@ def test_propagator_weight_in_spawn_and_death():
         assert len(fg) == len(fo) and (fg == fo).all() and (pg == po).all() and (dg == do_).all(), w
         assert rg["nspawn_events"] == ro["nspawn_events"] and rg["ndeath"] == ro["ndeath"]
     eng.close()
+
+
+def test_host_built_heat_bath_tables_are_accepted():
+    """hb200_set_excit_tables: a host that has already run init_excit_mol_heat_bath hands its excit_gen_heat_bath_t over
+    (here: the oracle's tables); the generator must behave exactly as with the tables built on the device."""
+    from hande_b200 import read_in as R
+    from hande_b200.engine import Engine
+    from tests.common import system_path
+    s, o, eng, ref = make_pair("s12", excit_gen="heat_bath", tau=0.01, real=True)
+    hb = o.heat_bath_tables()
+    tabs = dict(i_weights=hb["i_weights"], ij_weights=hb["ij_weights"], ija_weights=hb["ija_w"], ija_aliasU=hb["ija_U"],
+                ija_aliasK=hb["ija_K"], ija_weights_tot=hb["ija_tot"], ijab_weights=hb["ijab_w"], ijab_aliasU=hb["ijab_U"],
+                ijab_aliasK=hb["ijab_K"], ijab_weights_tot=hb["ijab_tot"])
+    e2 = Engine(s, excit_gen="heat_bath", pattempt_single=ref["pattempt_single"], pattempt_double=ref["pattempt_double"],
+                real_amplitudes=True, spawn_cutoff=0.01, walker_length=1 << 17, spawned_walker_length=1 << 16, seed=11,
+                heat_bath_tables=tabs)
+    e2.set_reference(ref["f0"], ref["H00"])
+    f, pops, dat = random_population(s, o, 150, True, seed=3)
+    att = np.tile(np.arange(6, dtype=np.uint32), len(f))
+    ff, pp = np.repeat(f, 6, axis=0), np.repeat(pops, 6)
+    a = eng.gen_excit_batch(ff, pp, att, 3, 0.01)
+    b = e2.gen_excit_batch(ff, pp, att, 3, 0.01)
+    for x, y in zip(a, b):
+        assert (x == y).all()
+    for k in range(0, len(pp), 7):
+        io_o, do_o, ns_o = o.gen_excit_philox(ff[k], 3, int(att[k]), int(pp[k]), 0.01)
+        assert io_o[6] == b[0][k, 6] and do_o[0] == b[1][k, 0] and do_o[1] == b[1][k, 1] and ns_o == b[2][k]
+    eng.close(); e2.close()
+
+
+@pytest.mark.parametrize("name,gen,real", [("h2o", "renorm", False), ("s12", "heat_bath", True), ("nh3", "power_pitzer_orderN", True),
+                                           ("s10u", "heat_bath_uniform", True), ("ueg14", "no_renorm", True)])
+def test_injected_random_numbers(name, gen, real):
+    """Level 1 of the correctness contract: the generator and attempt_to_spawn fed an injected list of uniform numbers
+    (hb200_gen_excit_batch_rn) against the oracle fed the same list (its list-driven generator is what reproduces the
+    reference's golden tables through dSFMT): choice and nspawn exact, pgen and H_ij bit-identical, and the same number
+    of random numbers consumed."""
+    tau = 0.01
+    s, o, eng, ref = make_pair(name, excit_gen=gen, tau=tau, real=real)
+    f, pops, dat = random_population(s, o, 300, real, seed=9)
+    nrn = 48      # rejection loops of the uniform generators can draw many; a list that is too short continues identically on both sides
+    rn = np.random.default_rng(17).random((len(f), nrn))
+    io, do, ns, nu = eng.gen_excit_batch_rn(f, pops, rn, tau)
+    nallowed = 0
+    for k in range(len(f)):
+        io_o, do_o, ns_o, k_o = o.gen_excit_spawn_list(f[k], int(pops[k]), tau, rn[k])
+        assert io_o[6] == io[k, 6], (k, io_o, io[k])
+        if io_o[6]:
+            assert list(io_o[:6]) == list(io[k, :6]), (k, io_o, io[k])
+            nallowed += 1
+        assert do_o[0] == do[k, 0] and do_o[1] == do[k, 1], (k, do_o, do[k])
+        assert ns_o == ns[k] and k_o == nu[k], (k, ns_o, ns[k], k_o, nu[k])
+    assert nallowed > 100
+    eng.close()

@@ -1471,7 +1471,23 @@ HB_HDN void gen_single_heat_bath_exact(R& rng, const Sys& s, const Params& p, co
 
 // One weight of find_ia_single_weights: |<D|H|D_i^a>| for an allowed (same spin, same symmetry) pair, else 0
 HB_HD double hb_single_weight(const Sys& s, const occ_t* occ, int i, int a) {
-    if (((a ^ i) & 1) == 0 && s.bf_sym[a] == s.bf_sym[i]) return fabs(slater_condon1_excit(s, occ, i, a, false));
+    if (((a ^ i) & 1) == 0 && s.bf_sym[a] == s.bf_sym[i]) {
+        if (s.sc1T) {     // the branch-free rows (see hb_sc1): the same partial sums in occ_list order
+            const unsigned ta = s.uhf ? (unsigned)(a - 1) : ((unsigned)(a - 1) >> 1);
+            const D2* __restrict__ row = s.sc1T + ((size_t)((unsigned)(i - 1) * (unsigned)s.sc1A + ta)) * (unsigned)(s.nbasis + 1);
+            double h = one_body(s, i, a);
+            const int nel = s.nel;
+            for (int q0 = 0; q0 < nel; q0 += 4) {
+                D2 v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = row[(q0 + k < nel) ? occ[q0 + k] : 0];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { h = h + v[k].x; h = h - v[k].y; }
+            }
+            return fabs(h);
+        }
+        return fabs(slater_condon1_excit(s, occ, i, a, false));
+    }
     return 0.0;
 }
 // gen_single_excit_heat_bath_exact once the weights are known: wi[q] = sum over a of w(q, a) (a ascending), wall =

@@ -857,6 +857,17 @@ static int hb_finish_tables(hb200_engine* e, const HbArrays& t) {
     Sys& s = e->sys;
     cudaStream_t st = e->stream;
     const long long nb = s.nbasis, n2 = nb * nb, n3 = n2 * nb, n4 = n3 * nb;
+    if (e->cfg.excit_gen == HB200_EXCIT_GEN_HEAT_BATH_SINGLE) {
+        // heat_bath_single evaluates nel x nvirt single-excitation matrix elements per single attempt: the branch-free rows
+        const int A = s.uhf ? (int)nb : (int)nb / 2;
+        const long long nT = nb * A * (nb + 1);
+        D2* T = nullptr;
+        if (dalloc(e, &T, (size_t)nT)) return 1;
+        k_build_sc1T<<<(unsigned)((nT + 255) / 256), 256, 0, st>>>(s, A, T);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(st));
+        s.sc1T = T; s.sc1A = A;
+    }
     if (e->cfg.excit_gen == HB200_EXCIT_GEN_HEAT_BATH) {
         // The packed hb_ija rows (nb^3 records) and the single-excitation rows sc1T share one allocation.  (Pinning it in
         // L2 with a persisting access-policy window was measured and made the spawning kernels 10-17 % SLOWER on B200 -

@@ -69,7 +69,8 @@ struct SpawnSmem {
 // GEN: compile-time generator of this instantiation (one kernel per generator keeps the code - and the instruction
 // cache footprint - to what the run actually executes): EXCIT_GEN_* for read_in systems, GEN_UEG for the UEG.
 template <int W, int GEN>
-__global__ void __launch_bounds__(TILE, ((GEN == EXCIT_GEN_HEAT_BATH || GEN == EXCIT_GEN_HEAT_BATH_UNIFORM) ? 3 : 4) * (256 / TILE))
+// wide layout (W = 32): the 64 KB of staged determinants per block allow two blocks per SM anyway - take the registers
+__global__ void __launch_bounds__(TILE, (W > 4) ? 2 : ((GEN == EXCIT_GEN_HEAT_BATH || GEN == EXCIT_GEN_HEAT_BATH_UNIFORM) ? 3 : 4) * (256 / TILE))
 k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __restrict__ pops,
               const double* __restrict__ dat, long long nstates, int64_t* __restrict__ spawn,
               unsigned long long* __restrict__ head, long long block_size, const int* __restrict__ proc_map,

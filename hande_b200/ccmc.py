@@ -18,7 +18,7 @@ import numpy as np
 
 from . import read_in as _ri
 from .engine import Engine
-from .fciqmc import FciqmcResult, PattemptUpdate, QmcIn, _SingleProcess, list_sizes, owner_of
+from .fciqmc import init_propagator, FciqmcResult, PattemptUpdate, QmcIn, _SingleProcess, list_sizes, owner_of
 
 HEADER = (" #     iterations   Shift                 \\sum H_0j N_j         N_0                   # H psips"
           "                  # states  # spawn_events            # attempts   R_spawn    time    ")
@@ -39,8 +39,6 @@ def do_ccmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, ke
         raise ValueError("ccmc: reference ex_level (the CC truncation level) must be given")
     if min(sys.nel, qmc.ex_level + 2) > 8:      # HB_MAX_CLUSTER: size of the engine's cluster-selection buffers
         raise ValueError("ccmc: clusters of more than 8 excitors (ex_level + 2 > 8) are not supported by the engine")
-    if qmc.quasi_newton:
-        raise NotImplementedError("ccmc: the quasi-Newton propagator is only implemented for FCIQMC")
     is_ueg = getattr(sys, "kind", "read_in") == "ueg"
     if qmc.reference_det:
         occ0 = sorted(int(x) for x in qmc.reference_det)
@@ -62,6 +60,8 @@ def do_ccmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, ke
                      spawned_walker_length=sl, seed=qmc.rng_seed, nprocs=nprocs, iproc=iproc, nslots=qmc.nslots,
                      device=device, pattempt_parallel=qmc.pattempt_parallel)
     eng.set_reference(f0, H00)
+    if qmc.quasi_newton:      # init_sp_fock / init_quasi_newton (src/qmc.F90:1064-1160), as in do_fciqmc
+        eng.set_quasi_newton(*init_propagator(sys, occ0, qmc))
     if qmc.full_non_composite:
         eng.ccmc_set_full_nc(True)
     if nprocs > 1:

@@ -149,7 +149,10 @@ k_ccmc_cluster(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states,
             // spawner_ccmc (src/ccmc_death_spawning.f90:11-211)
             Gen g;
             gen_excit<W>(rng, s, p, cf, occ, su, g);
-            const double hmatel = g.hmatel * cl.amplitude * 1.0 * cl.sign;
+            // quasi-Newton (src/ccmc_death_spawning.f90:141-144,295): cdet%fock_sum = sum_fock_values_occ_list - ref%fock_sum
+            const double dfock = p.qn ? qn_fock_sum(s, p, occ) : 0.0;
+            const double invd_s = (p.qn && g.allowed) ? qn_spawned_weighting(p, dfock, g) : 1.0;
+            const double hmatel = g.hmatel * cl.amplitude * invd_s * cl.sign;
             const double pgen = g.pgen * cl.pselect * 1;
             if (p.ps_part && g.allowed) {   // src/ccmc_death_spawning.f90:150-157
                 if (g.nexcit == 2) { ps_hd = (fabs(hmatel) * p.pattempt_double) / pgen; ps_nd = 1; }
@@ -167,12 +170,13 @@ k_ccmc_cluster(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states,
             // stochastic_ccmc_death + stochastic_death_attempt (src/ccmc_death_spawning.f90:213-441)
             if (!det_D0 && cl.excitation_level <= a.ex_level && (cl.nexcitors >= 2 || !a.full_nc)) {
                 const double pe_old = p.proj_energy_old;
+                const double invd = p.qn ? qn_weighting(p, dfock) : 1.0, pc = p.qn ? p.qn_pop_control : 1.0;
                 double KiiAi;
-                if (cl.nexcitors == 0) KiiAi = ((-pe_old) * 1.0 + (pe_old - p.shift) * 1.0) * cl.amplitude;
-                else if (cl.nexcitors == 1) KiiAi = ((dat[cl.first_pos - 1] - pe_old) * 1.0 + (pe_old - p.shift) * 1.0) * cl.amplitude;
+                if (cl.nexcitors == 0) KiiAi = ((-pe_old) * invd + (pe_old - p.shift) * pc) * cl.amplitude;
+                else if (cl.nexcitors == 1) KiiAi = ((dat[cl.first_pos - 1] - pe_old) * invd + (pe_old - p.shift) * pc) * cl.amplitude;
                 else {
                     const double hii = (s.kind == SYS_UEG) ? slater_condon0_ueg(s, occ) : slater_condon0(s, occ);
-                    KiiAi = ((hii - p.H00) - pe_old) * 1.0 * cl.amplitude;
+                    KiiAi = ((hii - p.H00) - pe_old) * invd * cl.amplitude;
                 }
                 KiiAi = 1.0 * (double)p.real_factor * KiiAi;
                 KiiAi = KiiAi * p.tau / cl.pselect;
@@ -234,6 +238,7 @@ k_ccmc_nc(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states, int6
         const uint64_t h = det_hash64<W>(f, HB_NW(p));
         const bool isD0 = (i + 1 == a.D0_pos);
         PhiloxStream rng;
+        double dfock = 0.0;       // quasi-Newton: sum_fock_values_bit_string(f) - ref%fock_sum (0 for the reference)
         if (!isD0) {
             const double amp = (double)pop / (double)p.real_factor;
             const int level = excit_level<W>(f, p.f0);
@@ -245,6 +250,7 @@ k_ccmc_nc(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states, int6
                 build_symunocc_masks<W>(s, f, su);
             bool is_ref;
             const double hm0 = proj_energy_hmatel<W>(s, p, f, occ, is_ref);
+            if (p.qn) dfock = qn_fock_sum(s, p, occ);
             pe = hm0 * (amp * sign / 1.0);
             rng.begin(p.seed, p.cycle, RNG_NATTEMPTS, h, 0);
             const int nsp = decide_nattempts(rng, fabs(amp) / 1.0);
@@ -254,7 +260,8 @@ k_ccmc_nc(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states, int6
                 rng.begin(p.seed, p.cycle, RNG_SPAWN, h, (uint32_t)ip);
                 Gen g;
                 gen_excit<W>(rng, s, p, f, occ, su, g);
-                const double hmatel = g.hmatel * unit * 1.0 * sign;
+                const double invd_s = (p.qn && g.allowed) ? qn_spawned_weighting(p, dfock, g) : 1.0;
+                const double hmatel = g.hmatel * unit * invd_s * sign;
                 const double pgen = g.pgen * 1.0 * 1;
                 if (p.ps_part && g.allowed) {
                     if (g.nexcit == 2) { ps_hd = ps_hd + (fabs(hmatel) * p.pattempt_double) / pgen; ps_nd += 1; }
@@ -286,9 +293,10 @@ k_ccmc_nc(Sys s, Params p, CcmcArgs a, const uint64_t* __restrict__ states, int6
         // stochastic_ccmc_death_nc
         {
             const double pe_old = p.proj_energy_old;
+            const double invd = p.qn ? qn_weighting(p, dfock) : 1.0, pc = p.qn ? p.qn_pop_control : 1.0;
             double KiiAi;
-            if (isD0) KiiAi = ((-pe_old) * 1.0 + (pe_old - p.shift) * 1.0) * (double)pop;
-            else KiiAi = ((dat[i] - pe_old) * 1.0 + (pe_old - p.shift) * 1.0) * (double)pop;
+            if (isD0) KiiAi = ((-pe_old) * invd + (pe_old - p.shift) * pc) * (double)pop;
+            else KiiAi = ((dat[i] - pe_old) * invd + (pe_old - p.shift) * pc) * (double)pop;
             KiiAi = KiiAi * 1.0;
             double pdeath = p.tau * fabs(KiiAi);
             int64_t nkill = (int64_t)pdeath;

@@ -1806,7 +1806,6 @@ int hb200_ccmc_spawn(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, i
     CK(cudaSetDevice(e->cfg.device));
     if (!e->have_sys) FAIL("ccmc_spawn: system not set");
     if (uses_heat_bath_tables(e) && !e->have_hb) FAIL("ccmc_spawn: heat-bath tables not built");
-    if (e->par.qn) FAIL("ccmc_spawn: the quasi-Newton propagator is only implemented for FCIQMC");
     if (e->par.cheby_weight != 1.0) FAIL("ccmc_spawn: the wall-Chebyshev propagator is only implemented for FCIQMC");
     if (e->cfg.excit_gen == HB200_EXCIT_GEN_POWER_PITZER_ORDERN && !e->have_ppn) FAIL("ccmc_spawn: power_pitzer_orderN tables not built");
     if (e->cfg.excit_gen == HB200_EXCIT_GEN_POWER_PITZER && !e->have_pp) FAIL("ccmc_spawn: power_pitzer tables not built");

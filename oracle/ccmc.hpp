@@ -322,7 +322,9 @@ struct OracleCcmc : Oracle {
         auto spawn_attempt = [&](int nspawnings_total) {
             GenResult g = gen_excit_sys(rng, sys, EG(), cdet);
             double hmatel = g.hmatel;
-            const double invdiagel = 1.0;
+            // calc_qn_spawned_weighting(propagator, cdet%fock_sum, connection) for an allowed excitation, else 1
+            // (src/ccmc_death_spawning.f90:141-144); cdet%fock_sum = sum_fock_values_occ_list - ref%fock_sum (src/ccmc.f90:747-749)
+            const double invdiagel = g.allowed ? qn_spawned_weighting(qn ? fock_sum_of(cdet.occ) : 0.0, g.conn) : 1.0;
             hmatel = hmatel * cl.amplitude * invdiagel * cl.cluster_to_det_sign;
             const double pgen = g.pgen * cl.pselect * nspawnings_total;
             if (g.allowed && vary_psingles) {   // update_p_single_double_data (src/spawning.F90:2139-2215)
@@ -382,9 +384,11 @@ struct OracleCcmc : Oracle {
                 // stochastic_ccmc_death (src/ccmc_death_spawning.f90:213-361), not linked
                 const double pe_old = est.proj_energy_old;
                 double KiiAi;
-                if (cl.nexcitors == 0) KiiAi = ((-pe_old) * invdiag() + (pe_old - shift) * 1.0) * cl.amplitude;
-                else if (cl.nexcitors == 1) KiiAi = ((r.dat[cl.first_pos - 1] - pe_old) * invdiag() + (pe_old - shift) * 1.0) * cl.amplitude;
-                else KiiAi = ((diag_hmatel(sys, cdet.f) - H00) - pe_old) * invdiag() * cl.amplitude;
+                // invdiagel = calc_qn_weighting(propagator, cdet%fock_sum) (src/ccmc_death_spawning.f90:295)
+                const double invd = qn ? qn_weighting(fock_sum_of(cdet.occ)) : 1.0;
+                if (cl.nexcitors == 0) KiiAi = ((-pe_old) * invd + (pe_old - shift) * qn_pop_control) * cl.amplitude;
+                else if (cl.nexcitors == 1) KiiAi = ((r.dat[cl.first_pos - 1] - pe_old) * invd + (pe_old - shift) * qn_pop_control) * cl.amplitude;
+                else KiiAi = ((diag_hmatel(sys, cdet.f) - H00) - pe_old) * invd * cl.amplitude;
                 KiiAi = 1.0 * (double)pop_real_factor * KiiAi;
                 KiiAi = KiiAi * tau / cl.pselect;
                 // stochastic_death_attempt (:363-441)
@@ -422,8 +426,16 @@ struct OracleCcmc : Oracle {
                 const double pe_old = est.proj_energy_old;
                 int64_t& population = r.pops[i - 1];
                 double KiiAi;
-                if (isD0) KiiAi = ((-pe_old) * 1.0 + (pe_old - shift) * 1.0) * (double)population;
-                else KiiAi = ((r.dat[i - 1] - pe_old) * 1.0 + (pe_old - shift) * 1.0) * (double)population;
+                // dfock = sum_fock_values_bit_string(states(:,i)) - ref%fock_sum (src/ccmc.f90:839-842);
+                // invdiagel = calc_qn_weighting(propagator, dfock) (src/ccmc_death_spawning.f90:504)
+                double invd = 1.0;
+                if (qn) {
+                    DetInfo dd;
+                    decode_det_occ(sys, r.states[i - 1], dd);
+                    invd = qn_weighting(fock_sum_of(dd.occ));
+                }
+                if (isD0) KiiAi = ((-pe_old) * invd + (pe_old - shift) * qn_pop_control) * (double)population;
+                else KiiAi = ((r.dat[i - 1] - pe_old) * invd + (pe_old - shift) * qn_pop_control) * (double)population;
                 const int64_t old_pop = population;
                 KiiAi = KiiAi * 1.0;
                 double pdeath = tau * std::fabs(KiiAi);

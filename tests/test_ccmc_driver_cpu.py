@@ -70,3 +70,33 @@ def test_ccmc_driver_pattempt_update(fcidump_path):
     assert len(res.rows) == len(rows)
     for r, ro, n in zip(res.rows, rows, na):
         assert list(r[:8]) == list(ro[:8]) and r[8] == n
+
+
+def test_ccmc_driver_quasi_newton_reproduces_golden(fcidump_path):
+    """do_ccmc with qmc = { quasi_newton = true, ... } (host init_propagator -> hb200_set_quasi_newton) on the oracle
+    stand-in: the reference's CCSDT quasi-Newton table test_suite/ccmc/np1/H2O-cc-pVDZ_ccsdtmc_qn, first 60 rows."""
+    if not pyoracle.have_ref_lib():
+        pytest.skip("oracle/_ref not built")
+    g = load_golden("ccmc_h2o_ccsdt_qn")
+    kw = dict(nel=g["sys"]["nel"], ms=g["sys"]["ms"], sym=g["sys"]["sym"])
+    path = fcidump_path(g["fcidump"])
+    s = R.read_in(path, **kw)
+    gq, qn = g["qmc"], g["quasi_newton"]
+    nrows = 60
+    qmc = QmcIn(tau=gq["tau"], rng_seed=gq["seed"], init_pop=gq["D0_population"], mc_cycles=gq["ncycles"],
+                nreports=nrows, target_population=gq["target_particles"], state_size=gq["walker_length"],
+                spawned_state_size=gq["spawned_walker_length"], ex_level=gq["ex_level"], quasi_newton=True,
+                quasi_newton_threshold=qn["threshold"], quasi_newton_value=qn["value"],
+                quasi_newton_pop_control=qn["pop_control"])
+    res = do_ccmc(s, qmc, engine_cls=make_engine_cls(path, kw, rng_kind=0, quasi_newton=qn))
+    gold = np.array(g["rows"])
+
+    def pr(x):
+        return float("%.10E" % x)
+    assert len(res.rows) == nrows + 1
+    for i, r in enumerate(res.rows):
+        gr = gold[i]
+        assert gr[0] == r[0]
+        for k in (1, 2, 3, 4):
+            assert gr[k] == pr(r[k]), (i, k, gr[k], r[k])
+        assert gr[5] == r[5] and gr[6] == r[6] and gr[8] == r[8], (i, gr, r)

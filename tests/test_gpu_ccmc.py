@@ -23,7 +23,9 @@ def _grow(o, tau, ncycles, pop0, rf):
 
 
 CASES = [
-    # system, generator, real amplitudes, ex_level, tau, warm-up cycles, full_non_composite
+    # system, generator, real amplitudes, ex_level, tau, warm-up cycles, full_non_composite[, quasi-Newton options]
+    ("ne_vdz", "renorm", False, 3, 0.008, 100, False, dict(threshold=1e-5, value=1.0, pop_control=1.0)),   # quasi-Newton CCMC
+    ("s12", "renorm", True, 3, 0.0005, 40, True, dict(threshold=0.3, value=1.0)),                          # ... full_nc
     ("ne_vdz", "renorm", False, 2, 0.01, 120, False),     # the reference's CCSD fixture
     ("ne_vdz", "no_renorm", True, 3, 0.005, 120, False),  # CCSDT, real amplitudes
     ("s12", "renorm", True, 3, 0.001, 40, False),
@@ -38,10 +40,12 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("name,gen,real,exl,tau,warm,full_nc", CASES)
-def test_ccmc_stage_and_cycle_parity(name, gen, real, exl, tau, warm, full_nc):
+@pytest.mark.parametrize("case", CASES)
+def test_ccmc_stage_and_cycle_parity(case):
+    name, gen, real, exl, tau, warm, full_nc = case[:7]
+    qn = case[7] if len(case) > 7 else None
     s, o, eng, ref = make_pair(name, excit_gen=gen, tau=tau, real=real, ex_level=exl, walker_length=1 << 18,
-                               spawned_walker_length=1 << 17)
+                               spawned_walker_length=1 << 17, quasi_newton=qn)
     o.ccmc_set_full_nc(full_nc)
     eng.ccmc_set_full_nc(full_nc)
     rf = 2**31 if real else 1

@@ -140,6 +140,13 @@ def test_ccmc_ccsd_h2o_np2(fcidump_path):
     _run("ccmc_h2o_np2", fcidump_path, 45)
 
 
+@pytest.mark.parametrize("case,nrows", [("ccmc_h2o_ccsdt_qn", 150), ("ccmc_h2o_ccsdt_qn_fullnc", 120)])
+def test_ccmc_quasi_newton_np1(fcidump_path, case, nrows):
+    """CCSDT with the quasi-Newton propagator (calc_qn_spawned_weighting in spawner_ccmc, calc_qn_weighting and
+    quasi_newton_pop_control in stochastic_ccmc_death[_nc]), stochastic and full_non_composite selection"""
+    _run(case, fcidump_path, nrows)
+
+
 def test_ccmc_ccsdt_full_non_composite_np2(fcidump_path):
     # ccmc = { full_non_composite = true }, CCSDT in a CAS, two ranks: select_nc_cluster, do_nc_ccmc_propagation,
     # stochastic_ccmc_death_nc, deterministic reference selections (all 91 rows verified with tools/golden_compare.py)

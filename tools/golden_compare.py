@@ -73,6 +73,19 @@ CASES = {
                          qmc=dict(tau=0.01, seed=1660032958, D0_population=500, ncycles=10, nreport=175,
                                   target_particles=50000, walker_length=3571428 // 1, spawned_walker_length=1562500,
                                   ex_level=2, nprocs=2)),
+    # CCSDT with the quasi-Newton propagator, default and full_non_composite selection (np1, integer walkers)
+    "ccmc_h2o_ccsdt_qn": dict(dir="ccmc/np1/H2O-cc-pVDZ_ccsdtmc_qn", bench="benchmark.out.9712b5a3.inp=ccmc.in",
+                              int_file="INTDUMP", sys=dict(nel=10, ms=0, sym=0), ccmc=True,
+                              quasi_newton=dict(threshold=1e-5, value=1.0, pop_control=1.0),
+                              qmc=dict(tau=0.008, seed=1660032958, D0_population=500, ncycles=5, nreport=150,
+                                       target_particles=70000, walker_length=100 * 10**6 // 28,
+                                       spawned_walker_length=50 * 10**6 // 32, ex_level=3)),
+    "ccmc_h2o_ccsdt_qn_fullnc": dict(dir="ccmc/np1/H2O-cc-pVDZ_ccsdtmc_qn", bench="benchmark.out.9712b5a3.inp=ccmc_nc.in",
+                                     int_file="INTDUMP", sys=dict(nel=10, ms=0, sym=0), ccmc=True, full_nc=True,
+                                     quasi_newton=dict(threshold=1e-5, value=1.0, pop_control=1.0),
+                                     qmc=dict(tau=0.015, seed=1660032958, D0_population=500, ncycles=5, nreport=200,
+                                              target_particles=70000, walker_length=100 * 10**6 // 28,
+                                              spawned_walker_length=50 * 10**6 // 32, ex_level=3)),
     # CCSDT, full_non_composite = true (select_nc_cluster, stochastic_ccmc_death_nc, deterministic reference attempts)
     "ccmc_h2o_ccsdt_fullnc_np2": dict(dir="ccmc/np2/H2O-cc-pVDZ_ccsdt", bench="benchmark.out.9712b5a3.inp=ccsdt.in",
                                       int_file="INTDUMP", sys=dict(nel=10, ms=0, sym=0, cas=(8, 22)), ccmc=True, full_nc=True,

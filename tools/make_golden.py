@@ -22,6 +22,8 @@ FCIDUMP_NAME = {"h2o": "h2o", "ne_init": "ne", "ne_ci6_np2": "ne", "ne_ci6_np4":
                 "ccmc_h2o_ccsdt_fullnc_np2": "h2o_vdz"}
 FCIDUMP_NAME.update({k: "nh3_631g" for k in CASES if k.startswith("ccmc_nh3_")})
 FCIDUMP_NAME["h4_cheby"] = "h4_sto3g"
+FCIDUMP_NAME["ccmc_h2o_ccsdt_qn"] = "h2o_vdz"
+FCIDUMP_NAME["ccmc_h2o_ccsdt_qn_fullnc"] = "h2o_vdz"
 
 
 def pattempt_changes(path):
@@ -67,6 +69,7 @@ for name, c in CASES.items():
     cols = ["iterations", "shift", "proj_energy", "D0_population", "nparticles", "nstates", "nspawn_events", "rspawn"]
     json.dump({"source": "test_suite/" + c["dir"] + "/" + c["bench"], "fcidump": FCIDUMP_NAME[name], "sys": c["sys"],
                "qmc": c["qmc"], "ccmc": bool(c.get("ccmc")), "full_nc": bool(c.get("full_nc")),
+               **({"quasi_newton": c["quasi_newton"]} if "quasi_newton" in c else {}),
                **({"chebyshev": c["chebyshev"],
                    "kat": {"spectral_range": 2.92929139E+00,     # the "Initial estimate of spectral range" and the
                            "zeroes": [2.32507329E-01, 8.56209883E-01, 1.67308651E+00, 2.42378465E+00, 2.86996294E+00],

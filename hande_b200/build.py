@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libhande_b200.so")
-HEADERS = ["hb_core.cuh", "hb_common.cuh", "hb_spawn.cuh", "hb_spawn_hb.cuh", "hb_spawn_wf.cuh", "hb_ccmc.cuh", "hb_list.cuh", os.path.join("..", "..", "include", "hande_b200.h")]
+HEADERS = ["hb_core.cuh", "hb_common.cuh", "hb_spawn.cuh", "hb_ccmc.cuh", "hb_list.cuh", os.path.join("..", "..", "include", "hande_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     # no FMA contraction: sums must follow the reference's operation order (bit-exact excitation choice / nspawn)
@@ -29,7 +29,7 @@ def units():
     for w in range(1, MAXW + 1):
         for g in range(NGROUPS):
             u.append((f"hb_spawn_w{w}_g{g}.o", "hb_spawn_tu.cu", [f"-DHB_TU_W={w}", f"-DHB_TU_GROUP={g}"],
-                      ["hb_core.cuh", "hb_common.cuh", "hb_spawn.cuh", HEADERS[-1]] + (["hb_spawn_hb.cuh", "hb_spawn_wf.cuh"] if g == 0 else [])))
+                      ["hb_core.cuh", "hb_common.cuh", "hb_spawn.cuh", HEADERS[-1]]))
         u.append((f"hb_ccmc_w{w}.o", "hb_ccmc_tu.cu", [f"-DHB_TU_W={w}"],
                   ["hb_core.cuh", "hb_common.cuh", "hb_ccmc.cuh", HEADERS[-1]]))
         u.append((f"hb_list_w{w}.o", "hb_list_tu.cu", [f"-DHB_TU_W={w}"],

@@ -233,16 +233,6 @@ struct hb200_engine {
     int* d_total = nullptr;   // [4] small ints
     long long* d_part_ll = nullptr;
     long long* d_ll = nullptr;  // [4]
-    // heat-bath wavefront kernel: determinants whose attempts are spread over the grid by a second launch
-    void* d_heavy_items = nullptr;
-    unsigned* d_heavy_count = nullptr;
-    unsigned heavy_cap = 0;
-    void* d_wf_recA = nullptr;    // wavefront kernels: record arrays and their counters
-    void* d_wf_recD = nullptr;
-    void* d_wf_recS = nullptr;
-    void* d_wf_cnt = nullptr;
-    unsigned wf_cap = 0;
-    int num_sms = 0;
     int npartials = 0;            // SpawnPartials written by the last spawn launch
     bool ccmc_full_nc = false;                     // ccmc_in%full_nc
     int ccmc_hash_shift = 0, ccmc_move_freq = 5;   // spawn%hash_shift (+1 per cycle), spawn%move_freq

@@ -1510,7 +1510,7 @@ static int stage_spawn_launch(hb200_engine* e, const hb200_iter_in* in, uint32_t
     } else {
         const int par = e->xparity;
         static const int min_tiles = getenv("HB200_P2P_MIN_TILES") ? atoi(getenv("HB200_P2P_MIN_TILES")) : 4096;
-        const int nchunk = (ntiles >= min_tiles && !getenv("HB200_WF") && !getenv("HB200_MEGA")) ? 4 : 1;
+        const int nchunk = (ntiles >= min_tiles) ? 4 : 1;
         CK(cudaMemsetAsync(e->d_snap, 0, sizeof(unsigned long long) * np, st));
         for (int c = 0; c < nchunk; ++c) {
             const int t0 = (int)((long long)ntiles * c / nchunk), t1 = (int)((long long)ntiles * (c + 1) / nchunk);

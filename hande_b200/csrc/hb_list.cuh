@@ -253,6 +253,7 @@ k_merge(const uint64_t* __restrict__ states, const int64_t* __restrict__ pops, c
     const long long ns = k_hi - k_lo;
     const long long out_base = (long long)tile_off[blockIdx.x] + k_lo;
     long long npart = 0;
+    long long o_out = 0;
     if (keep) {
         // number of new determinants in this tile inserted at or before old state m
         long long lo = 0, hi = ns;
@@ -261,12 +262,27 @@ k_merge(const uint64_t* __restrict__ states, const int64_t* __restrict__ pops, c
             if (ins[(k_lo + mid) * E + W + 1] <= m) lo = mid + 1; else hi = mid;
         }
         const long long o = out_base + kb + lo;
-        uint64_t f[W];
-        load_det<W>(states + m * W, f);
-        store_det<W>(ostates + o * W, f);
+        o_out = o;
+        if (W <= 4) {
+            uint64_t f[W];
+            load_det<W>(states + m * W, f);
+            store_det<W>(ostates + o * W, f);
+        }
         opops[o] = pop;
         odat[o] = dat[m];
         npart += pop < 0 ? -pop : pop;
+    }
+    if (W > 4) {
+        // wide layout: the warp moves the kept determinants one after the other, lane k word k (coalesced 256-byte rows
+        // instead of 32 strided 8-byte accesses per lane)
+        const int lane = tid & 31;
+        unsigned mm = __ballot_sync(0xffffffffu, keep != 0);
+        while (mm) {
+            const int src = __ffs(mm) - 1;
+            mm &= mm - 1;
+            const long long ms = __shfl_sync(0xffffffffu, m, src), os = __shfl_sync(0xffffffffu, o_out, src);
+            for (int k = lane; k < W; k += 32) ostates[os * W + k] = __ldcs(states + ms * W + k);
+        }
     }
     for (long long j = tid; j < ns; j += TILE) {
         const long long k = k_lo + j;

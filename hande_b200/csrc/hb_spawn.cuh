@@ -22,7 +22,7 @@ struct SpawnSmem {
     // unoccupied list, the queue of single-excitation attempts and their tile states)
     __host__ __device__ SpawnSmem(int W, int nel, int nsu, int nb, bool heat_bath, bool hb_stage, bool ps, bool qn, bool hbs = false) {
         size_t o = 0;
-        sf = o;     o += (size_t)TILE * W * 8;
+        sf = o;     o += (size_t)TILE * (W > 4 ? W + 1 : W) * 8;   // wide rows are padded by one word (bank conflicts)
         sred = o;   o += 40 * 8;
         shash = o;  o += hb_stage ? 0 : (size_t)TILE * 8;         // stream selector per state (recomputed per attempt when
                                                                    // shared memory is scarce: it also buys L1 capacity)
@@ -77,6 +77,7 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
               SpawnPartials* __restrict__ partials, int* __restrict__ err, int tile0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nel = s.nel;
+    constexpr int SW = (W > 4) ? W + 1 : W;     // words between the staged determinants of a tile
     constexpr bool heat_bath = (GEN == EXCIT_GEN_HEAT_BATH);
     constexpr bool hb_stage = heat_bath || (GEN == EXCIT_GEN_HEAT_BATH_UNIFORM) || (GEN == EXCIT_GEN_HEAT_BATH_SINGLE) ||
                               (GEN == EXCIT_GEN_POWER_PITZER_OCC_IJ);
@@ -131,13 +132,28 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
     int natt = 0;
     if (hb_stage)
         for (int k = tid; k < s.nbasis; k += TILE) siw[k] = s.hb_i_w[k];
+    if (W > 4) {
+        // wide layout: a thread's 256-byte determinant is 8 sectors - the tile is staged with coalesced loads instead
+        const long long base = ((long long)blockIdx.x + tile0) * TILE;
+        const int nst_tile = (int)min((long long)TILE, nstates - base);
+        for (int t = tid; t < nst_tile * W; t += TILE) {
+            const int l = t / W, k = t - l * W;
+            sf[l * SW + k] = __ldcs(states + base * W + t);
+        }
+        __syncthreads();
+    }
     if (idx < nstates) {
         uint64_t f[W];
-        load_det<W>(states + idx * W, f);
+        if (W > 4) {
+#pragma unroll
+            for (int k = 0; k < W; ++k) f[k] = sf[tid * SW + k];
+        } else {
+            load_det<W>(states + idx * W, f);
+        }
         const int64_t pop = __ldcs(pops + idx);
         const double Kii = __ldcs(dat + idx);
 #pragma unroll
-        for (int k = 0; k < W; ++k) sf[tid * W + k] = f[k];
+        for (int k = 0; k < W; ++k) sf[tid * SW + k] = f[k];
         ssign[tid] = pop < 0;
         occ_t* occ = socc + tid * nel;
         decode_det<W>(f, occ);
@@ -188,7 +204,7 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
         }
         uint64_t f[W];
 #pragma unroll
-        for (int k = 0; k < W; ++k) f[k] = sf[lo * W + k];
+        for (int k = 0; k < W; ++k) f[k] = sf[lo * SW + k];
         PhiloxStream rng;
         rng.begin(p.seed, p.cycle, RNG_SPAWN, hb_stage ? det_hash64<W>(f, HB_NW(p)) : shash[lo], (uint32_t)att);
         if (!hb_stage) rng.prefetch();   // uniform generators draw inside divergent rejection loops
@@ -215,7 +231,7 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
                 const int slot = rq & 255, fr = (rq >> 8) & 255, to = (rq >> 16) & 255, l = slo[slot];
                 uint64_t ff[W];
 #pragma unroll
-                for (int k = 0; k < W; ++k) ff[k] = sf[l * W + k];
+                for (int k = 0; k < W; ++k) ff[k] = sf[l * SW + k];
                 bool pm;
                 sh1[slot] = hb_sc1<W>(s, ff, socc + l * nel, fr, to, pm);
                 sperm[slot] = pm;
@@ -250,7 +266,7 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
                 const int slot = rq & 255, fr = (rq >> 8) & 255, to = (rq >> 16) & 255, k = rq >> 24, l = slo[slot];
                 uint64_t ff[W];
 #pragma unroll
-                for (int kk = 0; kk < W; ++kk) ff[kk] = sf[l * W + kk];
+                for (int kk = 0; kk < W; ++kk) ff[kk] = sf[l * SW + kk];
                 bool pm;
                 shm[k * TILE + slot] = fabs(hb_sc1<W>(s, ff, socc + l * nel, fr, to, pm));
             }
@@ -322,7 +338,7 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
                     const int b = t / nvirt, k = t - b * nvirt, l = hs_lo[hs_q[q0 + b]];
                     uint64_t ff[W];
 #pragma unroll
-                    for (int w = 0; w < W; ++w) ff[w] = sf[l * W + w];
+                    for (int w = 0; w < W; ++w) ff[w] = sf[l * SW + w];
                     hs_un[b * 256 + k] = (uint8_t)nth_unocc<W>(ff, k + 1);
                 }
                 __syncthreads();

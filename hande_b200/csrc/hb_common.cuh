@@ -190,6 +190,8 @@ struct hb200_engine {
     const unsigned long long* sp_pn = nullptr; // where the sort / annihilation kernels read the element count
     long long sp_cap = 0;                      // ... and the bound they clamp it to
     long long last_spn = 1 << 20;              // spawn-list length of the previous cycle (sizes the sort's grid)
+    unsigned long long* d_tile_state = nullptr; // fused merge: per-tile {flag, survivor count} words of the look-back
+    unsigned* d_ticket = nullptr;
     long long* d_long_q = nullptr;             // k_annihilate: heads of the long runs of equal keys
     unsigned* d_long_n = nullptr;
     // pinned host block the cycle's results are copied into (one synchronisation per cycle)
@@ -281,7 +283,7 @@ struct ListOps {
     int (*compact)(hb200_engine* e, const int64_t* sp, long long bound, int64_t* ins);
     int (*round_count)(hb200_engine* e, const Params& p, int ntiles);
     int (*sc0)(hb200_engine* e, double H00, const uint64_t* dets, long long stride_words, long long n, double* out, const int* pn);
-    int (*merge)(hb200_engine* e, const int64_t* ins, int ntiles);
+    int (*merge)(hb200_engine* e, const Params& p, const int64_t* ins, int ntiles, bool fused);
     int (*slot_pop)(hb200_engine* e, unsigned long long* d);
     int (*compress)(hb200_engine* e, const int64_t* sp, long long bound, int bits, int kw, int64_t* items);
     int (*gather)(hb200_engine* e, const int64_t* sp, int kw, const int64_t* items, int64_t* out);

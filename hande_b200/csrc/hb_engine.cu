@@ -672,6 +672,8 @@ hb200_engine* hb200_create(const hb200_config* cfg) {
             if (dalloc(e, &e->d_items[b], (size_t)scap * (e->key_words + 1))) return fail("alloc sort keys");
     if (dalloc(e, &e->d_long_q, (size_t)(scap / ANN_SHORT + 2))) return fail("alloc");
     if (dalloc(e, &e->d_long_n, 2)) return fail("alloc");
+    if (dalloc(e, &e->d_tile_state, (size_t)e->max_tiles)) return fail("alloc");
+    if (dalloc(e, &e->d_ticket, 2)) return fail("alloc");
     if (cudaMallocHost((void**)&e->h_out, sizeof(HostOut) + sizeof(unsigned long long) * p.nprocs) != cudaSuccess) return fail("alloc pinned");
     e->sp_ptr[0] = e->d_spawn[0]; e->sp_ptr[1] = e->d_spawn[1];
     e->sp_pn = e->d_spn;
@@ -1724,15 +1726,23 @@ static int stage_annihilate_launch(hb200_engine* e, uint32_t cycle, long long bo
         CK(cudaMemsetAsync(e->d_total, 0, sizeof(int), st));
     }
     const int ntiles = std::max<int>(1, (int)((ns + TILE - 1) / TILE));
-    if (e->ops->round_count(e, p, ntiles)) return 1;
-    e->launches++;
-    if (device_scan(e, e->d_tile_keep, e->d_tile_off, ntiles, 1, nullptr)) return 1;
-    k_cap_check<<<1, 1, 0, st>>>(e->d_total, e->cfg.walker_length, e->d_err);
+    // Wide layout, when the list cannot overflow (survivors <= states, new determinants <= spawn-list bound): the
+    // rounding, the survivor counts and the merge are ONE pass over the 272-byte states (k_merge<W, true>, decoupled
+    // look-back over the tiles).  With 32-byte states the look-back chain over 4e5 tiles costs more than the second pass
+    // it saves (measured at 1e8 walkers: 6.8 ms against 2.9 ms), so the counts come first there - as they must whenever
+    // insert_new_walkers' capacity check (src/annihilation.f90:750-771) may have to drop the new determinants.
+    const bool fused = (e->W > 4 || getenv("HB200_FUSED_MERGE")) && ns + std::min<long long>(bound, e->sp_cap) <= e->cfg.walker_length;
+    if (!fused) {
+        if (e->ops->round_count(e, p, ntiles)) return 1;
+        e->launches++;
+        if (device_scan(e, e->d_tile_keep, e->d_tile_off, ntiles, 1, nullptr)) return 1;
+        k_cap_check<<<1, 1, 0, st>>>(e->d_total, e->cfg.walker_length, e->d_err);
+    }
     if (bound > 0) {
         if (e->ops->sc0(e, p.H00, (const uint64_t*)ins, e->E, bound, e->d_ins_dat, e->d_total)) return 1;
         e->launches++;
     }
-    if (e->ops->merge(e, ins, ntiles)) return 1;
+    if (e->ops->merge(e, p, ins, ntiles, fused)) return 1;
     k_reduce_ll<<<1, 1024, 0, st>>>(e->d_part_ll, ntiles, e->d_ll);
     CK(cudaGetLastError());
     e->launches += 3;

@@ -213,22 +213,38 @@ k_round_count(Params p, const uint64_t* __restrict__ states, int64_t* __restrict
 
 // remove_unoccupied_dets (compaction) + insert_new_walkers (src/annihilation.f90:537-598, 677-818) as ONE
 // out-of-place merge: tile of TILE old states + the new determinants whose insertion point falls in the tile.
-template <int W>
+// FUSED: the stochastic rounding of remove_unoccupied_dets and the survivor counts (k_round_count + the scan of the
+// tile counts) happen here as well - one pass over the old list instead of two.  Tiles take a ticket (so that every
+// predecessor has started), publish their survivor count in a packed {flag, value} word and look back over their
+// predecessors for the exclusive prefix (decoupled look-back, as in single-pass scans); the last tile writes the
+// total.  The spin is bounded: a protocol failure sets the error flag instead of hanging the device.
+constexpr unsigned long long LB_AGG = 1ull << 62, LB_PREFIX = 2ull << 62, LB_MASK = (1ull << 62) - 1ull;
+template <int W, bool FUSED>
 __global__ void __launch_bounds__(TILE)
-k_merge(const uint64_t* __restrict__ states, const int64_t* __restrict__ pops, const double* __restrict__ dat,
+k_merge(Params p, const uint64_t* __restrict__ states, const int64_t* __restrict__ pops, const double* __restrict__ dat,
         long long nstates, const int* __restrict__ tile_off, const int64_t* __restrict__ ins,
         const double* __restrict__ ins_dat, const int* __restrict__ pnins, uint64_t* __restrict__ ostates,
-        int64_t* __restrict__ opops, double* __restrict__ odat, long long* __restrict__ part_npart, int ntiles) {
+        int64_t* __restrict__ opops, double* __restrict__ odat, long long* __restrict__ part_npart, int ntiles,
+        unsigned long long* __restrict__ tile_state, unsigned* __restrict__ ticket, int* __restrict__ total_kept,
+        int* __restrict__ err) {
     constexpr int E = W + 2;
     const long long nins = *pnins;
     __shared__ int swarp[8];
     __shared__ int skept[TILE + 1];
     __shared__ long long sk[2];
     __shared__ long long sred[8];
+    __shared__ unsigned s_tile;
+    __shared__ long long s_excl;
     const int tid = threadIdx.x;
-    const long long t0 = (long long)blockIdx.x * TILE;
+    unsigned tile = blockIdx.x;
+    if (FUSED) {
+        if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        tile = s_tile;
+    }
+    const long long t0 = (long long)tile * TILE;
     const long long t1 = min(nstates, t0 + TILE);
-    const bool last = (blockIdx.x == ntiles - 1);
+    const bool last = ((int)tile == ntiles - 1);
     if (tid < 2) {
         // inserts with pos in [t0, t1) (last tile: also pos == nstates) are a contiguous range [k_lo, k_hi)
         const long long target = (tid == 0) ? t0 : t1;
@@ -243,15 +259,52 @@ k_merge(const uint64_t* __restrict__ states, const int64_t* __restrict__ pops, c
     const long long m = t0 + tid;
     int keep = 0;
     int64_t pop = 0;
-    if (m < t1) { pop = pops[m]; keep = pop != 0; }
+    if (m < t1) {
+        pop = pops[m];
+        if (FUSED && p.real_amplitudes) {
+            // remove_unoccupied_dets: stochastic rounding of |population| < 1 (src/annihilation.f90:537-598)
+            const int64_t ap = pop < 0 ? -pop : pop;
+            if (pop != 0 && ap < p.real_factor) {
+                uint64_t f[W];
+                load_det<W>(states + m * W, f);
+                PhiloxStream rng;
+                rng.begin(p.seed, p.cycle, RNG_ROUND_MAIN, det_hash64<W>(f, HB_NW(p)), 0);
+                pop = stochastic_round(rng, pop, p.real_factor);
+            }
+        }
+        keep = pop != 0;
+    }
     int tot;
     const int kb = block_excl_scan(keep, swarp, &tot);
     skept[tid] = kb;
     if (tid == 0) skept[TILE] = tot;
+    if (FUSED && tid == 0) {
+        unsigned long long excl = 0;
+        if (tile == 0) {
+            atomicExch(&tile_state[0], LB_PREFIX | (unsigned long long)tot);
+        } else {
+            atomicExch(&tile_state[tile], LB_AGG | (unsigned long long)tot);
+            long long j = (long long)tile - 1;
+            unsigned spins = 0;
+            for (;;) {
+                const unsigned long long v = atomicAdd(&tile_state[j], 0ull);
+                if ((v >> 62) == 0) {
+                    if (++spins > (1u << 28)) { atomicOr(err + 1, 2); break; }      // never in a correct run
+                    continue;
+                }
+                excl += v & LB_MASK;
+                if (v & LB_PREFIX) break;
+                --j;
+            }
+            atomicExch(&tile_state[tile], LB_PREFIX | (excl + (unsigned long long)tot));
+        }
+        s_excl = (long long)excl;
+        if (last) *total_kept = (int)(excl + (unsigned long long)tot);
+    }
     __syncthreads();
     const long long k_lo = sk[0], k_hi = sk[1];
     const long long ns = k_hi - k_lo;
-    const long long out_base = (long long)tile_off[blockIdx.x] + k_lo;
+    const long long out_base = (FUSED ? s_excl : (long long)tile_off[tile]) + k_lo;
     long long npart = 0;
     long long o_out = 0;
     if (keep) {
@@ -304,7 +357,7 @@ k_merge(const uint64_t* __restrict__ states, const int64_t* __restrict__ pops, c
     if (tid == 0) {
         long long t = 0;
         for (int w = 0; w < TILE / 32; ++w) t += sred[w];
-        part_npart[blockIdx.x] = t;
+        part_npart[tile] = t;
     }
 }
 
@@ -405,11 +458,21 @@ static int list_sc0(hb200_engine* e, double H00, const uint64_t* dets, long long
     CK(cudaGetLastError());
     return 0;
 }
+// fused = true: rounding + survivor counts + merge in one pass (k_round_count and the tile scan are not launched)
 template <int W>
-static int list_merge(hb200_engine* e, const int64_t* ins, int ntiles) {
+static int list_merge(hb200_engine* e, const Params& p, const int64_t* ins, int ntiles, bool fused) {
     const int c = e->cur, o = e->alt;
-    k_merge<W><<<ntiles, TILE, 0, e->stream>>>(e->d_states[c], e->d_pops[c], e->d_dat[c], e->nstates, e->d_tile_off, ins, e->d_ins_dat,
-                                                e->d_total, e->d_states[o], e->d_pops[o], e->d_dat[o], e->d_part_ll, ntiles);
+    if (fused) {
+        CK(cudaMemsetAsync(e->d_tile_state, 0, sizeof(unsigned long long) * (size_t)ntiles, e->stream));
+        CK(cudaMemsetAsync(e->d_ticket, 0, sizeof(unsigned), e->stream));
+        k_merge<W, true><<<ntiles, TILE, 0, e->stream>>>(p, e->d_states[c], e->d_pops[c], e->d_dat[c], e->nstates, e->d_tile_off, ins,
+                                                         e->d_ins_dat, e->d_total, e->d_states[o], e->d_pops[o], e->d_dat[o],
+                                                         e->d_part_ll, ntiles, e->d_tile_state, e->d_ticket, e->d_total + 1, e->d_err);
+    } else {
+        k_merge<W, false><<<ntiles, TILE, 0, e->stream>>>(p, e->d_states[c], e->d_pops[c], e->d_dat[c], e->nstates, e->d_tile_off, ins,
+                                                          e->d_ins_dat, e->d_total, e->d_states[o], e->d_pops[o], e->d_dat[o],
+                                                          e->d_part_ll, ntiles, nullptr, nullptr, nullptr, e->d_err);
+    }
     CK(cudaGetLastError());
     return 0;
 }

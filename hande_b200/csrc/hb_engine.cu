@@ -2390,6 +2390,14 @@ int hb200_p2p_export(hb200_engine* e, uint8_t handle[64]) {
     return 0;
 }
 
+// Switch the peer-to-peer exchange off (or back on after a successful hb200_p2p_import): every rank must use the same
+// exchange, so a host whose import failed on one rank (no peer access between two of the GPUs) disables it everywhere.
+int hb200_p2p_enable(hb200_engine* e, int32_t on) {
+    if (on && !e->d_peer_recv) FAIL("p2p_enable: hb200_p2p_import has not succeeded on this rank");
+    e->p2p = on != 0;
+    return 0;
+}
+
 int hb200_set_host_barrier(hb200_engine* e, hb200_barrier_fn fn, void* arg) {
     e->host_barrier = fn;
     e->host_barrier_arg = arg;

@@ -163,6 +163,7 @@ def load_library():
     L.hb200_redistribute_particles.argtypes = [C.c_void_p, C.c_void_p]
     L.hb200_p2p_import.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
     L.hb200_set_host_barrier.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hb200_p2p_enable.argtypes = [C.c_void_p, C.c_int32]
     L.hb200_last_timing.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     _LIB = L
     return L
@@ -176,7 +177,7 @@ ABI_SYMBOLS = [
     "hb200_download_psips", "hb200_nstates", "hb200_iterate", "hb200_spawn_death", "hb200_comm_spawn",
     "hb200_ccmc_spawn", "hb200_ccmc_iterate", "hb200_ccmc_set_hash_shift", "hb200_ccmc_set_full_nc", "hb200_set_pattempt", "hb200_get_ps_stats", "hb200_set_pattempt_parallel", "hb200_get_pattempt_parallel", "hb200_build_power_pitzer_orderN", "hb200_build_power_pitzer", "hb200_set_quasi_newton", "hb200_annihilate_spawn", "hb200_annihilate_main", "hb200_download_spawn", "hb200_upload_spawn", "hb200_spawn_counts",
     "hb200_sc0_batch", "hb200_gen_excit_batch", "hb200_get_unique_id", "hb200_comm_init", "hb200_last_timing",
-    "hb200_p2p_export", "hb200_p2p_import", "hb200_set_host_barrier", "hb200_slot_populations", "hb200_set_propagator_weight",
+    "hb200_p2p_export", "hb200_p2p_import", "hb200_set_host_barrier", "hb200_p2p_enable", "hb200_slot_populations", "hb200_set_propagator_weight",
     "hb200_redistribute_particles",
 ]
 
@@ -502,8 +503,17 @@ class Engine:
             h = np.zeros(64, dtype=np.uint8)
             self._chk(self.L.hb200_p2p_export(self.h, _p(h)))
             allh = np.ascontiguousarray(comm.allgather_bytes(h), dtype=np.uint8)
-            self._chk(self.L.hb200_p2p_import(self.h, _p(allh), comm.size))
-            self.p2p = True
+            ok = self.L.hb200_p2p_import(self.h, _p(allh), comm.size) == 0
+            # every rank must run the same exchange: peer-to-peer only if the import succeeded everywhere
+            nok = int(round(float(comm.allreduce_sum(np.array([1.0 if ok else 0.0]))[0])))
+            if nok == comm.size:
+                self.p2p = True
+            else:
+                if not nccl:
+                    raise EngineError("peer-to-peer import failed and no NCCL communicator to fall back to: " +
+                                      self.L.hb200_last_error().decode())
+                if ok:
+                    self._chk(self.L.hb200_p2p_enable(self.h, 0))
 
     def last_timing(self):
         ms = np.zeros(8)

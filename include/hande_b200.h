@@ -292,6 +292,9 @@ int hb200_comm_init(hb200_engine* e, const uint8_t id[128]);
  * for the collective that ends an exchange).  Without these calls hb200_iterate uses the NCCL send/recv path. */
 int hb200_p2p_export(hb200_engine* e, uint8_t handle[64]);
 int hb200_p2p_import(hb200_engine* e, const uint8_t* handles, int32_t nprocs);
+/* All ranks must run the same exchange: when hb200_p2p_import fails on any rank (GPUs without peer access), the host
+ * calls hb200_p2p_enable(h, 0) on every rank and hb200_iterate falls back to the NCCL send/recv path. */
+int hb200_p2p_enable(hb200_engine* e, int32_t on);
 /* A host without NCCL (plain MPI; or several ranks sharing one GPU, which NCCL refuses) ends an exchange with its own
  * barrier instead: fn(arg) must return once every rank has called it (MPI_Barrier).  With a host barrier set,
  * hb200_comm_init is not needed for hb200_iterate. */

@@ -132,6 +132,9 @@ if os.path.exists(rep) or os.path.exists(rawcsv):
         bl = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_by_line.py"), tmp, lib, "k_spawn_death", "40"],
                             capture_output=True, text=True).stdout
         out.append("## k_spawn_death: instruction / stall-sample share by source line (tools/ncu_by_line.py)\n\n```\n" + bl + "```\n")
+        bf = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_by_function.py"), tmp, lib, "24"],
+                            capture_output=True, text=True).stdout
+        out.append("## k_spawn_death: the same listing summed by source function (tools/ncu_by_function.py)\n\n```\n" + bf + "```\n")
 
 # ---- CCMC cluster kernel (tools/gpu_prof_ccmc.sh): before / after grouping a block's attempts by cluster size
 ccmc_rows = []

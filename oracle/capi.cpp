@@ -295,6 +295,7 @@ void orc_set_psips(void* h, int rank, int64_t n, const uint64_t* states, const i
     }
     r.nstates = n;
     o->recompute_nparticles(r);
+    o->determ.doing = false;   // a deterministic space is built on the list it is given (orc_init_semi_stoch afterwards)
 }
 void orc_set_reference_det(void* h, const uint64_t* f0) {
     Oracle* o = (Oracle*)h;
@@ -711,5 +712,74 @@ int orc_rank_annihilate(void* h, int rank, const int64_t* sdata, int64_t n, doub
     out[0] = r.nparticles; out[1] = (double)r.nstates; out[2] = (r.spawn_error || r.psip_error) ? 1.0 : 0.0;
     return 0;
     ORC_CATCH(-1)
+}
+
+// semi_stoch = { space = "high" | "ci", size, start_iteration, shift_start_iteration, ci_space = { ex_level },
+// separate_annihilation }; pop_real_bits: 31, or 11 for real_amplitude_force_32.  Call before orc_init.
+void orc_set_semi_stoch(void* h, int space, int target_size, int start_iter, int shift_iter, int ci_ex_level, int separate,
+                        int pop_real_bits) {
+    Oracle* o = (Oracle*)h;
+    o->in.ss_space = space; o->in.ss_target_size = target_size; o->in.ss_start_iter = start_iter;
+    o->in.ss_shift_iter = shift_iter; o->in.ss_ci_ex_level = ci_ex_level; o->in.ss_separate_annihilation = separate != 0;
+    o->in.pop_real_bits = pop_real_bits;
+}
+void orc_set_vary_shift(void* h, int on) { ((Oracle*)h)->vary_shift = on != 0; }
+// init_semi_stoch_t on the current lists of all emulated ranks (what do_fciqmc does at iteration semi_stoch_iter)
+int orc_init_semi_stoch(void* h) {
+    ORC_TRY
+    ((Oracle*)h)->init_semi_stoch();
+    return 0;
+    ORC_CATCH(-1)
+}
+// the same with the space given by the caller: dets = every deterministic state, rank by rank (sizes[nprocs])
+int orc_init_semi_stoch_dets(void* h, const uint64_t* dets, const int* sizes) {
+    ORC_TRY
+    Oracle* o = (Oracle*)h;
+    // reuse init_semi_stoch through a "ci"-like hook: temporarily mark the given states as the most populated
+    const int W = o->sys.W;
+    std::vector<std::vector<Det>> mine((size_t)o->in.nprocs);
+    size_t k = 0;
+    for (int r = 0; r < o->in.nprocs; ++r)
+        for (int i = 0; i < sizes[r]; ++i, ++k) {
+            Det f;
+            for (int w = 0; w < W; ++w) f.w[w] = dets[k * W + w];
+            mine[(size_t)r].push_back(f);
+        }
+    o->given_determ = mine;
+    const int keep = o->in.ss_space;
+    o->in.ss_space = 3;
+    o->init_semi_stoch();
+    o->in.ss_space = keep;
+    return 0;
+    ORC_CATCH(-1)
+}
+int orc_determ_sizes(void* h, int* sizes) {
+    Oracle* o = (Oracle*)h;
+    for (size_t r = 0; r < o->determ.sizes.size(); ++r) sizes[r] = o->determ.sizes[r];
+    return o->determ.tot_size;
+}
+void orc_get_determ_dets(void* h, uint64_t* out) {
+    Oracle* o = (Oracle*)h;
+    const int W = o->sys.W;
+    for (size_t i = 0; i < o->determ.dets.size(); ++i)
+        for (int w = 0; w < W; ++w) out[i * W + w] = o->determ.dets[i].w[w];
+}
+// determ%hamil of one rank: returns nnz; row_ptr[tot_size+1] (0-based), col_ind[nnz] (0-based), mat[nnz]
+int64_t orc_get_determ_hamil(void* h, int rank, int* row_ptr, int* col_ind, double* mat) {
+    Oracle* o = (Oracle*)h;
+    RankState& R = o->ranks[rank];
+    if (row_ptr) {
+        std::copy(R.drow_ptr.begin(), R.drow_ptr.end(), row_ptr);
+        std::copy(R.dcol_ind.begin(), R.dcol_ind.end(), col_ind);
+        std::copy(R.dmat.begin(), R.dmat.end(), mat);
+    }
+    return (int64_t)R.dmat.size();
+}
+// determ%vector of one rank (after a cycle: -tau (H - S) v restricted to the rank) and determ%flags (0 = deterministic)
+void orc_get_determ_vector(void* h, int rank, double* vec, uint8_t* flags) {
+    Oracle* o = (Oracle*)h;
+    RankState& R = o->ranks[rank];
+    if (vec) std::copy(R.dvector.begin(), R.dvector.end(), vec);
+    if (flags) std::copy(R.dflag.begin(), R.dflag.end(), flags);
 }
 }

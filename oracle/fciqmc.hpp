@@ -18,6 +18,7 @@
 // np2/np4 golden trajectories can be followed too.
 #pragma once
 #include <memory>
+#include <functional>
 #include <cmath>
 #include "system.hpp"
 #include "rng.hpp"
@@ -58,6 +59,13 @@ struct QmcIn {
     // false = mathematically intended symmetric rule (what the GPU engine implements).
     bool literal_event_int32 = true;
     std::vector<int> ref_det;  // explicit reference determinant (reference = { det = {...} }); empty => Aufbau
+    int pop_real_bits = 31;    // real amplitudes are stored times 2^31 (POP_SIZE=64); real_amplitude_force_32 => 2^11
+    // semi_stoch_in_t (src/qmc_data.f90:305-338)
+    int ss_space = 0;          // 0 empty_determ_space, 1 high_pop_determ_space ("high"), 2 ci_determ_space ("ci")
+    int ss_target_size = 0;    // size: number of most populated determinants wanted (space = "high")
+    int ss_start_iter = 1, ss_shift_iter = -1;
+    int ss_ci_ex_level = -1;   // ci_space = { ex_level = ... }
+    bool ss_separate_annihilation = true;   // projection_mode (src/qmc_data.f90:325)
 };
 
 struct SpawnElem {
@@ -88,6 +96,13 @@ struct RankState {
     int nspawn_events = 0;
     int64_t ndeath = 0;
     int64_t nattempts = 0;
+    // semi_stoch_t, the per-process part (src/semi_stoch.F90:40-108)
+    std::vector<uint8_t> dflag;          // determ%flags: 0 = deterministic state, 1 = not (one per state of the main list)
+    std::vector<double> dvector;         // determ%vector
+    std::vector<int64_t> dindices;       // determ%indices (0-based positions in the main list)
+    std::vector<int> drow_ptr, dcol_ind; // determ%hamil (csrp_t): rows = every deterministic state, columns = this rank's
+    std::vector<double> dmat;
+    std::vector<double> drho_minus_qn;   // determ%rho_minus_qn_weight
 };
 
 struct ReportRow {
@@ -382,7 +397,7 @@ struct Oracle {
         f0 = sys.encode(occ_list0.data(), sys.nel);
         H00 = diag_hmatel(sys, f0);
         ref_ex_level = (in.ex_level < 0) ? sys.nel : in.ex_level;
-        pop_real_factor = in.real_amplitudes ? (1ll << 31) : 1;  // src/particle_t_utils.f90 (POP_SIZE=64)
+        pop_real_factor = in.real_amplitudes ? (1ll << in.pop_real_bits) : 1;  // src/particle_t_utils.f90 (2^31; force_32: 2^11)
         double cutoff = in.real_amplitudes ? in.spawn_cutoff : 0.0;
         spawn_cutoff = (int64_t)std::ceil(cutoff * (double)pop_real_factor);  // src/spawn_data.F90:215
         if (in.spawned_walker_length % in.nprocs != 0)
@@ -429,6 +444,8 @@ struct Oracle {
         initial_distribution();
         for (auto& r : ranks) recompute_nparticles(r);
         mc_cycles_done = 0;
+        determ = Determ();
+        semi_stoch_iter = std::max(in.ss_start_iter, mc_cycles_done + 1);   // src/fciqmc.f90:228
         rows.clear();
         est = Estimators();
     }
@@ -552,11 +569,20 @@ struct Oracle {
         r.nattempts = (int64_t)std::llround(2 * r.nparticles);
         const int64_t block_size = in.spawned_walker_length / in.nprocs;
         DetInfo d;
+        int ideterm = 0;
         for (int64_t idet = 0; idet < r.nstates; ++idet) {
             decode_for(sys, EG(), r.states[idet], d);
             double real_population = (double)r.pops[idet] / (double)pop_real_factor;
-            // set_parent_flag (src/ifciqmc.f90:13-57), nspaces=1, no deterministic space (determ_flag=1)
-            d.initiator_flag = (std::fabs(real_population) > in.initiator_pop) ? 0 : 1;
+            // set_determ_info (src/semi_stoch.F90:826-857)
+            bool determ_parent = false;
+            if (determ.doing && r.dflag[(size_t)idet] == 0) {
+                r.dvector[(size_t)ideterm] = real_population;
+                r.dindices[(size_t)ideterm] = idet;
+                ideterm++;
+                determ_parent = true;
+            }
+            // set_parent_flag (src/ifciqmc.f90:13-57), nspaces=1: deterministic states are always initiators
+            d.initiator_flag = (std::fabs(real_population) > in.initiator_pop || determ_parent) ? 0 : 1;
             update_proj_energy(d, real_population, r.D0_population, r.proj_energy);
             const double dfock = qn ? fock_sum_of(d.occ) : 0.0;
             rng.begin(RNG_NATTEMPTS, d.f, sys.W, 0);
@@ -580,6 +606,8 @@ struct Oracle {
                 int64_t nspawned = attempt_to_spawn(rng, g.hmatel * qn_weight * cheb_weight(), g.pgen, pop);
                 if (nspawned != 0) {
                     Det fnew = sys.create_excited_det(d.f, g.conn);
+                    // spawning from the deterministic space into it is the projection's job (src/fciqmc.f90:726-736)
+                    if (determ_parent && check_if_determ(fnew)) continue;
                     // create_spawned_particle[_initiator][_truncated] (src/spawning.F90:1074-1319)
                     if (in.ex_level >= 0 && sys.excitation_level(f0, fnew) > ref_ex_level) continue;
                     int dest = owner(fnew);
@@ -594,8 +622,8 @@ struct Oracle {
                     }
                 }
             }
-            // stochastic_death (src/death.f90:11-130)
-            {
+            // stochastic_death (src/death.f90:11-130); not for deterministic states (src/fciqmc.f90:368)
+            if (!determ_parent) {
                 rng.begin(RNG_DEATH, d.f, sys.W, 0);
                 double Kii = r.dat[idet];
                 double weight = qn_weighting(dfock);
@@ -750,22 +778,26 @@ struct Oracle {
     void remove_unoccupied_dets(RankState& r) const {
         Rng& rng = *r.rng;
         int64_t nzero = 0;
+        const bool ss = determ.doing;
         for (int64_t i = 0; i < r.nstates; ++i) {
-            if (in.real_amplitudes) {
+            const bool determ_det = ss && r.dflag[(size_t)i] == 0;
+            if (in.real_amplitudes && !determ_det) {
                 int64_t old_pop = r.pops[i];
                 rng.begin(RNG_ROUND_MAIN, r.states[i], sys.W, 0);
                 stochastic_round(rng, r.pops[i], pop_real_factor);
                 r.nparticles = r.nparticles + (double)(std::llabs(r.pops[i]) - std::llabs(old_pop)) / (double)pop_real_factor;
             }
-            if (r.pops[i] == 0) {
+            if (r.pops[i] == 0 && !determ_det) {
                 nzero++;
             } else if (nzero > 0) {
                 int64_t k = i - nzero;
                 r.states[k] = r.states[i]; r.pops[k] = r.pops[i]; r.dat[k] = r.dat[i];
+                if (ss) r.dflag[(size_t)k] = r.dflag[(size_t)i];
             }
         }
         r.nstates -= nzero;
         r.states.resize(r.nstates); r.pops.resize(r.nstates); r.dat.resize(r.nstates);
+        if (ss) r.dflag.resize((size_t)r.nstates);
     }
 
     // round_low_population_spawns (src/annihilation.f90:600-675)
@@ -792,6 +824,8 @@ struct Oracle {
         if (r.psip_error) return;
         int64_t nold = r.nstates;
         r.states.resize(nold + head); r.pops.resize(nold + head); r.dat.resize(nold + head);
+        const bool ss = determ.doing;
+        if (ss) r.dflag.resize((size_t)(nold + head), 1);
         int istart = 1, iend = (int)nold;
         for (int i = head; i >= 1; --i) {
             bool hit; int pos;
@@ -799,8 +833,10 @@ struct Oracle {
             for (int j = iend; j >= pos; --j) {
                 int k = j + i;
                 r.states[k - 1] = r.states[j - 1]; r.pops[k - 1] = r.pops[j - 1]; r.dat[k - 1] = r.dat[j - 1];
+                if (ss) r.dflag[(size_t)k - 1] = r.dflag[(size_t)j - 1];
             }
             int k = pos + i - 1;
+            if (ss) r.dflag[(size_t)k - 1] = 1;   // a deterministic state never leaves the list, so a new state is not one
             // insert_new_walker (src/annihilation.f90:820-901)
             r.states[k - 1] = s[i - 1].f;
             r.pops[k - 1] = s[i - 1].pop;
@@ -815,6 +851,7 @@ struct Oracle {
     // direct_annihilation (src/annihilation.f90:9-79) for one rank, after comm
     void annihilate_rank(RankState& r) {
         std::vector<SpawnElem>& s = r.recv;
+        if (determ.doing && in.ss_separate_annihilation) deterministic_annihilation(r);
         if (!s.empty()) {
             qsort_spawn(s, (int)s.size(), sys.W);
             if (in.initiator_approx) annihilate_spawn_t_initiator(s); else annihilate_spawn_t(s);
@@ -931,8 +968,295 @@ struct Oracle {
         }
     }
 
+
+    // ---------------------------------------------------------------- semi-stochastic projection (src/semi_stoch.F90)
+    struct Determ {
+        bool doing = false;              // determ%doing_semi_stoch
+        int tot_size = 0;
+        std::vector<int> sizes;          // per rank
+        std::vector<Det> dets;           // every deterministic state, rank by rank, each rank's sorted like its main list
+        std::vector<Det> sorted;         // the same set sorted once, for check_if_determ (the reference hashes; membership only)
+        std::vector<double> full_vector; // determ%full_vector
+    } determ;
+    int semi_stoch_iter = 1;
+    std::vector<std::vector<Det>> given_determ;
+
+    // get_hmatel (src/hamiltonian_molecular.f90:12-71, src/hamiltonian_ueg.f90:12-69)
+    double get_hmatel(const Det& f1, const Det& f2) const {
+        Excit ex = sys.get_excitation(f1, f2);
+        if (ex.nexcit == 0) return diag_hmatel(sys, f1);
+        if (sys.kind == SYS_UEG) {
+            if (ex.nexcit == 2) return slater_condon2_ueg(sys, ex.from_orb[0], ex.from_orb[1], ex.to_orb[0], ex.to_orb[1], ex.perm);
+            return 0.0;
+        }
+        if (ex.nexcit <= 2) return offdiag_hmatel(f1, f2);
+        return 0.0;
+    }
+    // check_if_determ (src/semi_stoch.F90:795-824)
+    bool check_if_determ(const Det& f) const {
+        const int W = sys.W;
+        auto it = std::lower_bound(determ.sorted.begin(), determ.sorted.end(), f,
+                                   [W](const Det& a, const Det& b) { return det_less(a, b, W); });
+        return it != determ.sorted.end() && *it == f;
+    }
+    // find_most_populated_dets (src/semi_stoch.F90:1318-1385)
+    static void find_most_populated_dets(const std::vector<Det>& dets_in, const std::vector<int64_t>& pops_in, int ndets_in,
+                                         int ndets_out, std::vector<Det>& dets_out, std::vector<int64_t>& pops_out) {
+        dets_out.assign(dets_in.begin(), dets_in.begin() + ndets_out);
+        pops_out.assign(ndets_out, 0);
+        if (ndets_out == 0) return;
+        pops_out[0] = std::llabs(pops_in[0]);
+        int64_t min_pop = pops_out[0];
+        int min_ind = 0;
+        for (int i = 1; i < ndets_out; ++i) {
+            pops_out[i] = std::llabs(pops_in[i]);
+            if (pops_out[i] < min_pop) { min_pop = pops_out[i]; min_ind = i; }
+        }
+        for (int i = ndets_out; i < ndets_in; ++i) {
+            if (std::llabs(pops_in[i]) > min_pop) {
+                dets_out[min_ind] = dets_in[i];
+                pops_out[min_ind] = std::llabs(pops_in[i]);
+                min_pop = pops_out[0]; min_ind = 0;
+                for (int j = 1; j < ndets_out; ++j)
+                    if (pops_out[j] < min_pop) { min_pop = pops_out[j]; min_ind = j; }
+            }
+        }
+    }
+    // find_indices_of_most_populated_dets (src/semi_stoch.F90:1387-1448); 0-based indices, -1 = unused
+    static void find_indices_of_most_populated_dets(int npops_in, int nind_out, const std::vector<int64_t>& pops,
+                                                    std::vector<int>& indices) {
+        indices.assign(nind_out, -1);
+        if (nind_out == 0 || npops_in == 0) return;
+        indices[0] = 0;
+        int64_t min_pop = std::llabs(pops[0]);
+        int min_ind = 0;
+        for (int i = 1; i < std::min(nind_out, npops_in); ++i) {
+            indices[i] = i;
+            if (std::llabs(pops[i]) < min_pop) { min_pop = std::llabs(pops[i]); min_ind = i; }
+        }
+        for (int i = nind_out; i < npops_in; ++i) {
+            if (std::llabs(pops[i]) > min_pop) {
+                indices[min_ind] = i;
+                min_pop = std::llabs(pops[indices[0]]); min_ind = 0;
+                for (int j = 1; j < nind_out; ++j)
+                    if (std::llabs(pops[indices[j]]) < min_pop) { min_pop = std::llabs(pops[indices[j]]); min_ind = j; }
+            }
+        }
+    }
+    // create_high_pop_space (src/semi_stoch.F90:1198-1316): every rank offers its min(target, nstates) most populated
+    // determinants, the target_size most populated of the offers are kept
+    void create_high_pop_space(std::vector<std::vector<Det>>& dets_this_proc) {
+        const int np = in.nprocs;
+        std::vector<int> all_ndets(np), displs(np + 1, 0);
+        std::vector<std::vector<Det>> determ_dets(np);
+        std::vector<int64_t> all_determ_pops;
+        for (int r = 0; r < np; ++r) {
+            const RankState& R = ranks[r];
+            all_ndets[r] = (int)std::min<int64_t>(in.ss_target_size, R.nstates);
+            std::vector<int64_t> pops;
+            find_most_populated_dets(R.states, R.pops, (int)R.nstates, all_ndets[r], determ_dets[r], pops);
+            displs[r + 1] = displs[r] + all_ndets[r];
+            all_determ_pops.insert(all_determ_pops.end(), pops.begin(), pops.end());
+        }
+        const int ndets_tot = displs[np];
+        const int determ_size = std::min(in.ss_target_size, ndets_tot);
+        std::vector<int> indices;
+        find_indices_of_most_populated_dets(ndets_tot, determ_size, all_determ_pops, indices);
+        for (int r = 0; r < np; ++r) {
+            dets_this_proc[r].clear();
+            for (int i = 0; i < determ_size; ++i)
+                if (indices[i] >= displs[r] && indices[i] < displs[r + 1])
+                    dets_this_proc[r].push_back(determ_dets[r][(size_t)(indices[i] - displs[r])]);
+        }
+    }
+    // create_ci_determ_space (src/semi_stoch.F90:1763-1823): every determinant of the calculation's symmetry and spin
+    // within ci_space.ex_level excitations of the reference (enumerate_determinants); restated by stepping through the
+    // excitations of the reference level by level and keeping those the Hamiltonian can connect to it by symmetry
+    void create_ci_determ_space(std::vector<std::vector<Det>>& dets_this_proc) {
+        std::vector<int> occ0 = occ_list0;
+        const int nel = sys.nel, nb = sys.nbasis;
+        std::vector<Det> out;
+        const int maxl = std::min(in.ss_ci_ex_level, nel);
+        // combinations of `l` occupied orbitals to remove and `l` virtual orbitals to add
+        std::vector<int> virt;
+        for (int o = 1; o <= nb; ++o) if (!det_test(f0, o)) virt.push_back(o);
+        const int ref_sym = det_symmetry(f0);
+        std::vector<int> hole(maxl), part(maxl);
+        for (int l = 0; l <= maxl; ++l) {
+            // choose l holes (ascending) then l particles (ascending)
+            std::function<void(int, int)> holes = [&](int k, int start) {
+                if (k == l) {
+                    std::function<void(int, int)> parts = [&](int k2, int start2) {
+                        if (k2 == l) {
+                            Det f = f0;
+                            int ms = 0;
+                            for (int t = 0; t < l; ++t) { det_clr(f, hole[t]); ms -= sys.bf[hole[t]].ms; }
+                            for (int t = 0; t < l; ++t) { det_set(f, part[t]); ms += sys.bf[part[t]].ms; }
+                            if (ms != 0) return;
+                            if (det_symmetry(f) != ref_sym) return;
+                            out.push_back(f);
+                            return;
+                        }
+                        for (int v = start2; v < (int)virt.size(); ++v) { part[k2] = virt[v]; parts(k2 + 1, v + 1); }
+                    };
+                    parts(0, 0);
+                    return;
+                }
+                for (int o = start; o < nel; ++o) { hole[k] = occ0[o]; holes(k + 1, o + 1); }
+            };
+            holes(0, 0);
+        }
+        for (auto& v : dets_this_proc) v.clear();
+        for (const Det& f : out) dets_this_proc[(size_t)owner(f)].push_back(f);   // add_det_to_determ_space(check_proc=.true.)
+    }
+    // symmetry label of a determinant: the product of its orbitals' symmetries (symmetry_orb_list); for the UEG the
+    // total momentum, packed so that equal labels mean equal momenta
+    int det_symmetry(const Det& f) const {
+        if (sys.kind == SYS_UEG) {
+            int kx = 0, ky = 0, kz = 0;
+            for (int o = 1; o <= sys.nbasis; ++o)
+                if (det_test(f, o)) { kx += sys.ueg.l[3 * o]; ky += sys.ueg.l[3 * o + 1]; kz += sys.ueg.l[3 * o + 2]; }
+            return ((kx + 512) * 1024 + (ky + 512)) * 1024 + (kz + 512);
+        }
+        int sym = sys.gamma_sym;
+        for (int o = 1; o <= sys.nbasis; ++o)
+            if (det_test(f, o)) sym = sys.cross_product(sym, sys.bf[o].sym);
+        return sym;
+    }
+    // init_semi_stoch_t (src/semi_stoch.F90:134-377) for all emulated ranks
+    void init_semi_stoch() {
+        const int np = in.nprocs, W = sys.W;
+        std::vector<std::vector<Det>> dets_this_proc(np);
+        if (in.ss_space == 1) create_high_pop_space(dets_this_proc);
+        else if (in.ss_space == 2) create_ci_determ_space(dets_this_proc);
+        else if (in.ss_space == 3) dets_this_proc = given_determ;   // read_determ_space: the caller's list (SEMI.STOCH file)
+        determ.doing = true;
+        determ.sizes.assign(np, 0);
+        determ.dets.clear();
+        std::vector<int> displs(np, 0);
+        for (int r = 0; r < np; ++r) {
+            std::sort(dets_this_proc[r].begin(), dets_this_proc[r].end(), [W](const Det& a, const Det& b) { return det_less(a, b, W); });
+            determ.sizes[r] = (int)dets_this_proc[r].size();
+            displs[r] = (int)determ.dets.size();
+            determ.dets.insert(determ.dets.end(), dets_this_proc[r].begin(), dets_this_proc[r].end());
+        }
+        determ.tot_size = (int)determ.dets.size();
+        determ.sorted = determ.dets;
+        std::sort(determ.sorted.begin(), determ.sorted.end(), [W](const Det& a, const Det& b) { return det_less(a, b, W); });
+        determ.full_vector.assign((size_t)determ.tot_size, 0.0);
+        for (int r = 0; r < np; ++r) {
+            RankState& R = ranks[r];
+            const std::vector<Det>& mine = dets_this_proc[r];
+            const bool separate = in.ss_separate_annihilation;
+            const int n_spawnees = separate ? determ.sizes[r] : determ.tot_size;
+            R.dvector.assign((size_t)determ.sizes[r], 0.0);
+            R.dindices.assign((size_t)determ.sizes[r], 0);
+            // create_determ_hamil (src/semi_stoch.F90:533-685)
+            R.drho_minus_qn.assign((size_t)n_spawnees, 1.0);
+            if (qn) {
+                for (int j = 0; j < n_spawnees; ++j) {
+                    DetInfo d;
+                    decode_det_occ(sys, separate ? mine[(size_t)j] : determ.dets[(size_t)j], d);
+                    R.drho_minus_qn[(size_t)j] = qn_weighting(fock_sum_of(d.occ));
+                }
+            }
+            R.drow_ptr.assign((size_t)determ.tot_size + 1, 0);
+            R.dcol_ind.clear(); R.dmat.clear();
+            for (int i = 0; i < determ.tot_size; ++i) {
+                R.drow_ptr[(size_t)i] = (int)R.dmat.size();
+                for (int j = 0; j < determ.sizes[r]; ++j) {
+                    double h = get_hmatel(determ.dets[(size_t)i], mine[(size_t)j]);
+                    if (i == j + displs[r]) h = h - H00;
+                    const double weight = separate ? R.drho_minus_qn[(size_t)j] : R.drho_minus_qn[(size_t)i];
+                    h = weight * h;
+                    if (std::fabs(h) > depsilon) { R.dmat.push_back(h); R.dcol_ind.push_back(j); }
+                }
+            }
+            R.drow_ptr[(size_t)determ.tot_size] = (int)R.dmat.size();
+            for (auto& x : R.drho_minus_qn) x = qn_pop_control - x;
+            // add_determ_dets_to_psip_list (src/semi_stoch.F90:728-793)
+            R.dflag.assign((size_t)R.nstates, 1);
+            int istart = 1, iend = (int)R.nstates;
+            for (int i = 0; i < determ.sizes[r]; ++i) {
+                bool hit; int pos;
+                binary_search(R.states, mine[(size_t)i], istart, iend, W, hit, pos);
+                if (!hit) {
+                    R.states.insert(R.states.begin() + (pos - 1), mine[(size_t)i]);
+                    R.pops.insert(R.pops.begin() + (pos - 1), 0);
+                    R.dat.insert(R.dat.begin() + (pos - 1), diag_hmatel(sys, mine[(size_t)i]) - H00);
+                    R.dflag.insert(R.dflag.begin() + (pos - 1), 1);
+                    R.nstates++;
+                }
+                R.dflag[(size_t)pos - 1] = 0;
+                istart = pos + 1;
+                iend = (int)R.nstates;
+            }
+        }
+    }
+    // determ_proj_separate_annihil (src/semi_stoch.F90:1009-1094) for all emulated ranks
+    void determ_proj_separate() {
+        size_t k = 0;
+        for (auto& R : ranks)
+            for (double v : R.dvector) determ.full_vector[k++] = v;   // mpi_allgatherv
+        const double a = -1.0 * tau;
+        for (auto& R : ranks) {
+            for (size_t j = 0; j < R.dvector.size(); ++j)
+                R.dvector[j] = (-tau * (est.proj_energy_old * R.drho_minus_qn[j] - shift * qn_pop_control)) * R.dvector[j];
+            // csrpgemv(.true., .false., -tau, hamil, full_vector, vector) (lib/local/csr.f90:148-204)
+            for (int irow = 0; irow < determ.tot_size; ++irow)
+                for (int iz = R.drow_ptr[(size_t)irow]; iz < R.drow_ptr[(size_t)irow + 1]; ++iz) {
+                    const int icol = R.dcol_ind[(size_t)iz];
+                    R.dvector[(size_t)icol] = R.dvector[(size_t)icol] + a * R.dmat[(size_t)iz] * determ.full_vector[(size_t)irow];
+                }
+        }
+    }
+    // determ_proj_combined_annihil (src/semi_stoch.F90:897-975) + create_spawned_particle_determ (:1096-1146); one rank only
+    // (the np > 1 form also needs compress_determ_repeats, src/spawn_data.F90:1103-1170, which is not restated)
+    void determ_proj_combined(RankState& R) {
+        if (in.nprocs != 1) throw std::runtime_error("semi-stochastic: combined annihilation is restated for one rank only");
+        Rng& rng = *R.rng;
+        const int64_t block_size = in.spawned_walker_length / in.nprocs;
+        for (int row = 0; row < determ.tot_size; ++row) {
+            double out_vec = 0.0;   // csrpgemv_single_row
+            for (int iz = R.drow_ptr[(size_t)row]; iz < R.drow_ptr[(size_t)row + 1]; ++iz)
+                out_vec = out_vec + R.dmat[(size_t)iz] * R.dvector[(size_t)R.dcol_ind[(size_t)iz]];
+            out_vec = -tau * (out_vec + (est.proj_energy_old * R.drho_minus_qn[(size_t)row] - qn_pop_control * shift) * R.dvector[(size_t)row]);
+            const double scaled = out_vec * (double)pop_real_factor;
+            const double sgn = (out_vec < 0.0) ? -1.0 : 1.0;
+            int64_t nspawn = (int64_t)std::fabs(scaled);
+            rng.begin(RNG_DETERM, determ.dets[(size_t)row], sys.W, 0);
+            if (std::fabs(scaled) - (double)nspawn > rng.next()) nspawn++;
+            nspawn = nspawn * (int64_t)std::llround(sgn);
+            if ((int64_t)R.send[0].size() + 1 > block_size) { R.spawn_error = true; continue; }
+            SpawnElem e; e.f = determ.dets[(size_t)row]; e.pop = nspawn; e.flag = 0;
+            R.send[0].push_back(e);
+        }
+        R.nspawn_events = (int)R.send[0].size();   // calc_events_spawn_t runs after the projection (src/annihilation.f90:56)
+    }
+    // deterministic_annihilation (src/annihilation.f90:488-535)
+    void deterministic_annihilation(RankState& R) {
+        Rng& rng = *R.rng;
+        for (size_t i = 0; i < R.dvector.size(); ++i) {
+            const int64_t ind = R.dindices[i];
+            double scaled_amp = R.dvector[i] * (double)pop_real_factor;
+            const int64_t spawn_sign = (scaled_amp < 0.0) ? -1 : 1;
+            scaled_amp = std::fabs(scaled_amp);
+            int64_t nspawn = (int64_t)scaled_amp;
+            scaled_amp = scaled_amp - (double)nspawn;
+            rng.begin(RNG_DETERM, R.states[(size_t)ind], sys.W, 0);
+            if (scaled_amp > rng.next()) nspawn++;
+            const int64_t old_pop = R.pops[(size_t)ind];
+            R.pops[(size_t)ind] = R.pops[(size_t)ind] + spawn_sign * nspawn;
+            R.nparticles = R.nparticles + (double)(std::llabs(R.pops[(size_t)ind]) - std::llabs(old_pop)) / (double)pop_real_factor;
+        }
+    }
+
     void mc_cycle(uint32_t cycle_id) {
         for (auto& r : ranks) spawn_death_rank(r, cycle_id);
+        if (determ.doing) {   // determ_projection (src/semi_stoch.F90:859-895)
+            if (in.ss_separate_annihilation) determ_proj_separate();
+            else for (auto& r : ranks) determ_proj_combined(r);
+        }
         comm_spawn();
         for (auto& r : ranks) {
             annihilate_rank(r);
@@ -985,6 +1309,8 @@ struct Oracle {
             // counter-based stream is keyed by the sub-cycle index
             for (int icheb = 1; icheb <= cheb.order; ++icheb) {
                 cheb.icheb = icheb;
+                // should the semi-stochastic projection start now? (src/fciqmc.f90:300-305)
+                if (iter == semi_stoch_iter && in.ss_space != 0 && !determ.doing) init_semi_stoch();
                 mc_cycle((uint32_t)(cheb.on ? (iter - 1) * cheb.order + icheb : iter));
             }
         }
@@ -1006,6 +1332,8 @@ struct Oracle {
         ntot_particles_old = ntot;
         if (!vary_shift && ntot > in.target_particles) {
             vary_shift = true;
+            // semi-stochastic start relative to the shift start (src/qmc_common.F90:1200-1204)
+            if (in.ss_shift_iter != -1) semi_stoch_iter = in.ss_shift_iter + (mc_cycles_done + ireport * in.ncycles) + 1;
             if (in.vary_shift_from_proje) shift = est.proj_energy / est.D0_population;
             else shift = in.vary_shift_from;
         }

@@ -372,6 +372,60 @@ class Oracle:
         self.L.orc_get_ps_stats(self.h, int(rank), out.ctypes.data_as(C.c_void_p), int(reset))
         return out
 
+    def set_semi_stoch(self, space="high", size=0, start_iteration=1, shift_start_iteration=-1, ci_ex_level=-1,
+                       separate_annihilation=True, pop_real_bits=31):
+        """semi_stoch = { space = "high" | "ci", size, start_iteration, ... } (before init); pop_real_bits = 11 restates
+        real_amplitude_force_32"""
+        self.L.orc_set_semi_stoch.argtypes = [C.c_void_p] + [C.c_int] * 7
+        self.L.orc_set_semi_stoch(self.h, {"none": 0, "high": 1, "ci": 2}[space], int(size), int(start_iteration),
+                                  int(shift_start_iteration), int(ci_ex_level), int(separate_annihilation), int(pop_real_bits))
+
+    def set_vary_shift(self, on=True):
+        """qmc = { vary_shift = true } (after init)"""
+        self.L.orc_set_vary_shift.argtypes = [C.c_void_p, C.c_int]
+        self.L.orc_set_vary_shift(self.h, int(on))
+
+    def init_semi_stoch(self, dets=None, sizes=None):
+        """init_semi_stoch_t on the current lists; with dets (ntot x W, rank by rank) and sizes the space is the caller's"""
+        if dets is None:
+            self._chk(self.L.orc_init_semi_stoch(self.h))
+            return
+        dets = np.ascontiguousarray(dets, dtype=np.uint64)
+        sizes = np.ascontiguousarray(sizes, dtype=np.int32)
+        self.L.orc_init_semi_stoch_dets.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        self._chk(self.L.orc_init_semi_stoch_dets(self.h, _p(dets), _p(sizes)))
+
+    def determ_space(self):
+        """(dets [tot x W], sizes per rank)"""
+        sizes = np.zeros(self.qmc.nprocs, dtype=np.int32)
+        self.L.orc_determ_sizes.argtypes = [C.c_void_p, C.c_void_p]
+        tot = self.L.orc_determ_sizes(self.h, _p(sizes))
+        dets = np.zeros((tot, self.W), dtype=np.uint64)
+        self.L.orc_get_determ_dets.argtypes = [C.c_void_p, C.c_void_p]
+        if tot:
+            self.L.orc_get_determ_dets(self.h, _p(dets))
+        return dets, sizes
+
+    def determ_hamil(self, rank=0):
+        """determ%hamil of one rank as (row_ptr, col_ind, mat), 0-based"""
+        self.L.orc_get_determ_hamil.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        self.L.orc_get_determ_hamil.restype = C.c_int64
+        nnz = self.L.orc_get_determ_hamil(self.h, int(rank), None, None, None)
+        dets, sizes = self.determ_space()
+        rp = np.zeros(len(dets) + 1, dtype=np.int32)
+        ci = np.zeros(max(nnz, 1), dtype=np.int32)
+        mat = np.zeros(max(nnz, 1))
+        self.L.orc_get_determ_hamil(self.h, int(rank), _p(rp), _p(ci), _p(mat))
+        return rp, ci[:nnz], mat[:nnz]
+
+    def determ_vector(self, rank=0):
+        dets, sizes = self.determ_space()
+        v = np.zeros(int(sizes[rank]))
+        fl = np.zeros(int(self.nstates(rank)), dtype=np.uint8)
+        self.L.orc_get_determ_vector.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        self.L.orc_get_determ_vector(self.h, int(rank), _p(v) if len(v) else None, _p(fl) if len(fl) else None)
+        return v, fl
+
     def set_quasi_newton(self, on=True, threshold=-1.0, value=-1.0, pop_control=-1.0):
         """qmc = { quasi_newton = true, ... } (before init)"""
         self.L.orc_set_quasi_newton.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double]

@@ -29,6 +29,7 @@ enum RngPurpose : uint32_t {
     RNG_DEATH = 2,       // stochastic_death
     RNG_ROUND_MAIN = 3,  // remove_unoccupied_dets / stochastic_round
     RNG_ROUND_SPAWN = 4, // round_low_population_spawns
+    RNG_DETERM = 5,      // deterministic_annihilation / create_spawned_particle_determ (semi-stochastic)
 };
 
 struct Rng {

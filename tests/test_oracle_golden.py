@@ -37,7 +37,11 @@ def _run(case, fcidump_path, nrows, wide=False):
         o.set_pattempt_parallel(g["pattempt_parallel"])
     if "quasi_newton" in g:
         o.set_quasi_newton(True, **g["quasi_newton"])
+    if "semi_stoch" in g:
+        o.set_semi_stoch(**g["semi_stoch"])
     o.init()
+    if g.get("vary_shift"):
+        o.set_vary_shift(True)
     if "chebyshev" in g:
         hi, z, w = o.init_chebyshev(order=g["chebyshev"]["order"], harmonic_forcing=g["chebyshev"]["harmonic_forcing"])
         k = g["kat"]        # the spectral range, zeroes and weights the reference prints (9 significant digits)
@@ -96,6 +100,27 @@ def test_h4_wall_chebyshev_np1(fcidump_path):
     sub-cycles per cycle, update_chebyshev) with harmonic forcing of the shift, real amplitudes - every row of the
     reference's table"""
     _run("h4_cheby", fcidump_path, 30)
+
+
+def test_semi_stochastic_projection(fcidump_path):
+    """semi-stochastic projection (src/semi_stoch.F90, deterministic_annihilation of
+    src/annihilation.f90:488-535), every row of both tables of the reference that the container can run:
+      * ueg_ss_np4: CI space of the quadruples (358 determinants over 4 ranks, 83..98 per rank as the reference prints),
+        separate annihilation (the engine's mode): all-gathered vector, transposed CSR product, stochastic rounding of
+        the deterministic amplitudes into the main list, deterministic states kept at zero population;
+      * he2_ss: the 100 most populated determinants picked at iteration 1000 (create_high_pop_space), combined
+        annihilation (the deterministic spawns travel through the spawned list)"""
+    o = _run("ueg_ss_np4", fcidump_path, 200)
+    k = load_golden("ueg_ss_np4")["kat"]
+    dets, sizes = o.determ_space()
+    assert len(dets) == k["determ_size"] and sizes.min() == k["determ_min"] and sizes.max() == k["determ_max"]
+    assert abs(o.reference()["H00"] - k["H00"]) < 5e-9
+    o = _run("he2_ss", fcidump_path, 200)
+    k = load_golden("he2_ss")["kat"]
+    dets, sizes = o.determ_space()
+    assert len(dets) == k["determ_size"] and abs(o.reference()["H00"] - k["H00"]) < 5e-9
+    rp, ci, mat = o.determ_hamil(0)
+    assert rp[-1] == len(mat) and len(mat) > 100
 
 
 def test_ueg_np2_np4(fcidump_path):

@@ -48,6 +48,20 @@ CASES = {
                      qmc=dict(tau=1.0, seed=2004313765, D0_population=200, ncycles=1, nreport=30, target_particles=1e5,
                               real_amplitudes=1, spawn_cutoff=0.01, vary_shift_from_proje=1, shift_damping=0.05,
                               walker_length=71428571 // 64, spawned_walker_length=62500000 // 64)),
+    # semi-stochastic projection: CI space of the quadruples, separate annihilation, 4 ranks
+    "ueg_ss_np4": dict(dir="fciqmc_real_32/np4/ueg_n7_rs1_e1_SS_cisdtq", bench="benchmark.out.9712b5a3.inp=ueg.in",
+                       ueg=dict(nel=7, ms=7, rs=1.0, cutoff=1.0), ref_det=[1, 3, 5, 7, 9, 11, 13], vary_shift=True,
+                       semi_stoch=dict(space="ci", ci_ex_level=4, pop_real_bits=11),
+                       qmc=dict(tau=0.01, seed=7, D0_population=1000, ncycles=10, nreport=200, target_particles=1000,
+                                real_amplitudes=1, spawn_cutoff=0.01, walker_length=178571, spawned_walker_length=31250,
+                                nprocs=4)),
+    # the same projection with the deterministic spawns sent through the spawned list (combined annihilation), the 100
+    # most populated determinants, switched on at iteration 1000
+    "he2_ss": dict(dir="fciqmc_real_32/np1/He2-aug-cc-pVDZ_real_32_SS", bench="benchmark.out.9712b5a3.inp=he2.in",
+                   int_file="INTDUMP", sys=dict(nel=4, ms=0), vary_shift=True,
+                   semi_stoch=dict(space="high", size=100, start_iteration=1000, separate_annihilation=False, pop_real_bits=11),
+                   qmc=dict(tau=0.01, seed=7, D0_population=1000, ncycles=10, nreport=200, target_particles=1000,
+                            real_amplitudes=1, spawn_cutoff=0.01, walker_length=178571, spawned_walker_length=31250)),
     # uniform electron gas: sys = ueg{electrons=6, ms=0, dim=3, cutoff=2, rs=2}, explicit reference
     "ueg_np2": dict(dir="fciqmc/np2/ueg_n10_rs2_e4_fciqmc", bench="benchmark.out.9712b5a3.inp=ueg.fciqmc.in",
                     ueg=dict(nel=6, ms=0, rs=2.0, cutoff=2.0), ref_det=[1, 2, 3, 10, 11, 14],
@@ -166,7 +180,11 @@ def run_case(name, max_rows=None, quiet=False):
         o.set_pattempt_parallel(c["pattempt_parallel"])
     if "quasi_newton" in c:
         o.set_quasi_newton(True, **c["quasi_newton"])
+    if "semi_stoch" in c:
+        o.set_semi_stoch(**c["semi_stoch"])
     o.init()
+    if c.get("vary_shift"):
+        o.set_vary_shift(True)
     t = time.time()
     if c.get("ccmc"):
         o.ccmc_set_full_nc(bool(c.get("full_nc")))

@@ -22,6 +22,7 @@ FCIDUMP_NAME = {"h2o": "h2o", "ne_init": "ne", "ne_ci6_np2": "ne", "ne_ci6_np4":
                 "ccmc_h2o_ccsdt_fullnc_np2": "h2o_vdz"}
 FCIDUMP_NAME.update({k: "nh3_631g" for k in CASES if k.startswith("ccmc_nh3_")})
 FCIDUMP_NAME["h4_cheby"] = "h4_sto3g"
+FCIDUMP_NAME["he2_ss"] = "he2_avdz"
 FCIDUMP_NAME["ccmc_h2o_ccsdt_qn"] = "h2o_vdz"
 FCIDUMP_NAME["ccmc_h2o_ccsdt_qn_fullnc"] = "h2o_vdz"
 
@@ -45,9 +46,13 @@ for name, c in CASES.items():
         rows = parse_table(d + c["bench"]).tolist()
         json.dump({"source": "test_suite/" + c["dir"] + "/" + c["bench"], "ueg": c["ueg"], "ref_det": c["ref_det"],
                    "qmc": c["qmc"], **({"quasi_newton": c["quasi_newton"]} if "quasi_newton" in c else {}),
+                   **({"semi_stoch": c["semi_stoch"], "vary_shift": True} if "semi_stoch" in c else {}),
                    "columns": ["iterations", "shift", "proj_energy", "D0_population", "nparticles", "nstates",
                                "nspawn_events", "rspawn"],
-                   "kat": {"H00": 2.02890441, "L": 5.85836755, "nbasis": 66, "sp_eigv_3": 5.75143889E-01},
+                   # the "H00", box length, basis size and third eigenvalue the reference prints for the system
+                   "kat": ({"H00": 11.13923996, "nbasis": 38, "determ_size": 358, "determ_min": 83, "determ_max": 98}
+                           if name == "ueg_ss_np4" else
+                           {"H00": 2.02890441, "L": 5.85836755, "nbasis": 66, "sp_eigv_3": 5.75143889E-01}),
                    "rows": rows}, open(os.path.join(OUT, name + ".json"), "w"))
         print(name, len(rows), "rows")
         continue
@@ -70,6 +75,8 @@ for name, c in CASES.items():
     json.dump({"source": "test_suite/" + c["dir"] + "/" + c["bench"], "fcidump": FCIDUMP_NAME[name], "sys": c["sys"],
                "qmc": c["qmc"], "ccmc": bool(c.get("ccmc")), "full_nc": bool(c.get("full_nc")),
                **({"quasi_newton": c["quasi_newton"]} if "quasi_newton" in c else {}),
+               **({"semi_stoch": c["semi_stoch"], "vary_shift": True, "kat": {"H00": -5.69708312, "determ_size": 100}}
+                  if "semi_stoch" in c else {}),
                **({"chebyshev": c["chebyshev"],
                    "kat": {"spectral_range": 2.92929139E+00,     # the "Initial estimate of spectral range" and the
                            "zeroes": [2.32507329E-01, 8.56209883E-01, 1.67308651E+00, 2.42378465E+00, 2.86996294E+00],

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libhande_b200.so")
-HEADERS = ["hb_core.cuh", "hb_common.cuh", "hb_spawn.cuh", "hb_ccmc.cuh", "hb_list.cuh", os.path.join("..", "..", "include", "hande_b200.h")]
+HEADERS = ["hb_core.cuh", "hb_common.cuh", "hb_spawn.cuh", "hb_ccmc.cuh", "hb_list.cuh", "hb_semistoch.cuh", os.path.join("..", "..", "include", "hande_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     # no FMA contraction: sums must follow the reference's operation order (bit-exact excitation choice / nspawn)
@@ -33,13 +33,13 @@ def units():
         u.append((f"hb_ccmc_w{w}.o", "hb_ccmc_tu.cu", [f"-DHB_TU_W={w}"],
                   ["hb_core.cuh", "hb_common.cuh", "hb_ccmc.cuh", HEADERS[-1]]))
         u.append((f"hb_list_w{w}.o", "hb_list_tu.cu", [f"-DHB_TU_W={w}"],
-                  ["hb_core.cuh", "hb_common.cuh", "hb_list.cuh", HEADERS[-1]]))
+                  ["hb_core.cuh", "hb_common.cuh", "hb_list.cuh", "hb_semistoch.cuh", HEADERS[-1]]))
     # wide layout (bit strings of 5..32 words, stored as 32): 16-bit occupied lists; the generators without
     # nbasis^3 / nbasis^4 tables only (the UEG's, group 4)
     wide = ["-DHB_TU_W=32", "-DHB_OCC16"]
     u.append(("hb_spawn_w32_g4.o", "hb_spawn_tu.cu", wide + ["-DHB_TU_GROUP=4"], ["hb_core.cuh", "hb_common.cuh", "hb_spawn.cuh", HEADERS[-1]]))
     u.append(("hb_ccmc_w32.o", "hb_ccmc_tu.cu", wide, ["hb_core.cuh", "hb_common.cuh", "hb_ccmc.cuh", HEADERS[-1]]))
-    u.append(("hb_list_w32.o", "hb_list_tu.cu", wide, ["hb_core.cuh", "hb_common.cuh", "hb_list.cuh", HEADERS[-1]]))
+    u.append(("hb_list_w32.o", "hb_list_tu.cu", wide, ["hb_core.cuh", "hb_common.cuh", "hb_list.cuh", "hb_semistoch.cuh", HEADERS[-1]]))
     return u
 
 

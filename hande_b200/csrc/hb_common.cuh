@@ -153,8 +153,31 @@ struct HostOut {
 // ------------------------------------------------------------------------------------------------
 // Engine
 // ------------------------------------------------------------------------------------------------
+// semi_stoch_t (src/semi_stoch.F90:40-108), separate annihilation; see hb_semistoch.cuh
+struct SemiStoch {
+    bool on = false;
+    int tot = 0, nloc = 0, maxsz = 0, displ = 0;   // determ%tot_size, sizes(iproc), max(sizes), displs(iproc)
+    std::vector<int> sizes;
+    uint64_t* d_all = nullptr;      // [tot][W] determ%dets: rank by rank, each rank's part sorted
+    uint64_t* d_local = nullptr;    // = d_all + displ * W
+    uint64_t* d_sorted = nullptr;   // [tot][W] sorted copy (check_if_determ)
+    int* d_pad = nullptr;           // [tot] position of row i in the all-gathered vector (rank * maxsz + local index)
+    long long* d_idx = nullptr;     // [nloc] determ%indices
+    uint32_t* d_bits = nullptr;     // one bit per main-list state: determ%flags == 0
+    double* d_full = nullptr;       // [nprocs * maxsz] determ%full_vector (padded per rank)
+    double* d_vec = nullptr;        // [nloc] determ%vector after the projection
+    double* d_rho = nullptr;        // [nloc] determ%rho_minus_qn_weight
+    long long* d_colptr = nullptr;  // [nloc + 1] determ%hamil by column
+    int* d_row = nullptr;
+    double* d_val = nullptr;
+    long long nnz = 0;
+    int* d_miss = nullptr;
+    std::vector<void*> bufs;        // everything above (freed when the space is replaced)
+};
+
 struct hb200_engine {
     hb200_config cfg;
+    SemiStoch ss;
     int W = 1, E = 3;            // words per determinant / per spawn element on the DEVICE (1..4, or 32 = wide layout)
     int We = 1;                  // words per determinant in the host's layout, ceil(nbasis/64)
     const struct ListOps* ops = nullptr;
@@ -288,6 +311,10 @@ struct ListOps {
     int (*compress)(hb200_engine* e, const int64_t* sp, long long bound, int bits, int kw, int64_t* items);
     int (*gather)(hb200_engine* e, const int64_t* sp, int kw, const int64_t* items, int64_t* out);
     int (*owner_slot_shift)(const hb200_engine* e, const Params& p);
+    // semi-stochastic projection (hb_semistoch.cuh)
+    int (*ss_locate)(hb200_engine* e, int buf, const int* ntot2);
+    int (*ss_hamil)(hb200_engine* e, int pass);
+    int (*ss_project)(hb200_engine* e, const Params& p);
 };
 const ListOps* hb_list_ops_w1();
 const ListOps* hb_list_ops_w2();

@@ -159,6 +159,12 @@ struct Params {
     // wall-Chebyshev propagator (src/propagators.f90): weight 1/(S_i - E_0) of the current sub-cycle on the spawning
     // amplitude (src/spawning.F90:117-118) and the death probability (src/death.f90:89); 1 for the linear projector
     double cheby_weight;
+    // semi-stochastic projection (semi_stoch_t, src/semi_stoch.F90:40-108): one bit per state of the main list (set:
+    // deterministic, i.e. determ%flags == 0) and every deterministic determinant of every rank, sorted, for
+    // check_if_determ; null / 0 while the projection is off
+    const uint32_t* ss_bits;
+    const uint64_t* ss_sorted;
+    int ss_tot;
 };
 // p_single_double_coll_t (src/excit_gens.f90:13-27): sums of |H_ij| pattempt_{single,double} / pgen over the allowed
 // single / double excitations generated, and how many there were
@@ -173,7 +179,7 @@ enum { EXCIT_GEN_RENORM = 0, EXCIT_GEN_RENORM_SPIN = 1, EXCIT_GEN_NO_RENORM = 2,
        EXCIT_GEN_HEAT_BATH = 10, EXCIT_GEN_HEAT_BATH_UNIFORM = 11, EXCIT_GEN_HEAT_BATH_SINGLE = 12 };
 enum { PPN_IS = 0, PPN_IAS = 1, PPN_ID = 2, PPN_IJD = 3, PPN_IAD = 4, PPN_JBD = 5 };
 #define HB_NW(p) ((W > 4) ? (p).we : W)
-enum { RNG_NATTEMPTS = 0, RNG_SPAWN = 1, RNG_DEATH = 2, RNG_ROUND_MAIN = 3, RNG_ROUND_SPAWN = 4 };
+enum { RNG_NATTEMPTS = 0, RNG_SPAWN = 1, RNG_DEATH = 2, RNG_ROUND_MAIN = 3, RNG_ROUND_SPAWN = 4, RNG_DETERM = 5 };
 
 // ------------------------------------------------------------------------------------------------
 // Counter-based random stream: Philox4x32-10 keyed by (seed, cycle); counter
@@ -2280,11 +2286,18 @@ HB_HD int64_t stochastic_round(R& rng, int64_t pop, int64_t cutoff) {
 // Projected-energy contribution of one determinant (get_excitation src/excitations.F90:75-200 +
 // update_proj_energy_mol src/energy_evaluation.F90:906-986).  Returns H_0j (incl. sign) or 0; sets
 // is_ref when f == f0.
+// hmatel_pair: the same between f (whose occupied list is occ) and any determinant f0 (get_hmatel, off-diagonal part).
+template <int W>
+HB_HD double hmatel_pair(const Sys& s, const uint64_t* f, const occ_t* occ, const uint64_t* f0, bool& is_ref);
 template <int W>
 HB_HDN double proj_energy_hmatel(const Sys& s, const Params& p, const uint64_t* f, const occ_t* occ, bool& is_ref) {
+    return hmatel_pair<W>(s, f, occ, p.f0, is_ref);
+}
+template <int W>
+HB_HD double hmatel_pair(const Sys& s, const uint64_t* f, const occ_t* occ, const uint64_t* f0, bool& is_ref) {
     int nx = 0;
 #pragma unroll
-    for (int k = 0; k < W; ++k) nx += popc64(f[k] ^ p.f0[k]);
+    for (int k = 0; k < W; ++k) nx += popc64(f[k] ^ f0[k]);
     is_ref = (nx == 0);
     if (nx == 0 || nx > 4) return 0.0;
     const int nexcit = nx / 2;
@@ -2292,7 +2305,7 @@ HB_HDN double proj_energy_hmatel(const Sys& s, const Params& p, const uint64_t* 
     int from[2] = {0, 0}, to[2] = {0, 0};
     int iexcit1 = 0, iexcit2 = 0, iel1 = 0, iel2 = 0, perm = 0;
     for (int i = 0; i < W; ++i) {
-        uint64_t f1 = f[i], f2 = p.f0[i];
+        uint64_t f1 = f[i], f2 = f0[i];
         if (f1 == f2) {
             if (((iexcit1 - iexcit2) & 1) != 0) {
                 int n = popc64(f1);
@@ -2338,6 +2351,18 @@ HB_HD int excit_level(const uint64_t* f, const uint64_t* f0) {
 #pragma unroll
     for (int k = 0; k < W; ++k) nx += popc64(f[k] ^ f0[k]);
     return nx / 2;
+}
+
+// check_if_determ (src/semi_stoch.F90:795-824): is f one of the deterministic states?  The reference walks a hash
+// bucket; membership is all that matters, so the sorted copy of determ%dets is bisected instead.
+template <int W>
+HB_HDNI bool ss_check_if_determ(const uint64_t* __restrict__ sorted, int n, const uint64_t* f) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (det_less<W>(sorted + (size_t)mid * W, f)) lo = mid + 1; else hi = mid;
+    }
+    return lo < n && det_eq<W>(sorted + (size_t)lo * W, f);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -498,6 +498,8 @@ __global__ void k_hb_alias(int nb, long long nrows, const double* __restrict__ w
 // cudaMemcpy runs on the legacy stream, which is NOT ordered with kernels on a cudaStreamNonBlocking stream, and a
 // pageable H2D copy may return before its DMA has landed.
 static cudaError_t copy_sync(hb200_engine* e, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind);
+static int ss_relocate(hb200_engine* e, int buf, const int* ntot2, bool check);
+static int stage_determ(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, const double* full_host);
 template <class T>
 static int dalloc(hb200_engine* e, T** p, size_t n) {
     void* q = nullptr;
@@ -701,6 +703,7 @@ void hb200_destroy(hb200_engine* e) {
     for (int i = 0; i < 8; ++i) if (e->ev_chunk[i]) cudaEventDestroy(e->ev_chunk[i]);
     if (e->ev_comm) cudaEventDestroy(e->ev_comm);
     if (e->comm_stream) cudaStreamDestroy(e->comm_stream);
+    for (void* q : e->ss.bufs) cudaFree(q);
     for (void* q : e->owned) cudaFree(q);
     for (int i = 0; i < 6; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     for (int i = 0; i < 2; ++i) if (e->evk[i]) cudaEventDestroy(e->evk[i]);
@@ -1319,6 +1322,7 @@ int hb200_upload_psips(hb200_engine* e, const uint64_t* states, const int64_t* p
     }
     e->nstates = n;
     e->nparticles_enc = s;
+    if (e->ss.on && ss_relocate(e, e->cur, nullptr, true)) return 1;   // a new list must still hold the deterministic states
     return 0;
 }
 
@@ -1771,6 +1775,7 @@ static int stage_annihilate_main(hb200_engine* e, uint32_t cycle, CycleStats* hs
     CK(cudaMemcpyAsync(&npart, e->d_ll, sizeof(long long), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     finish_merge(e, hst, h_tot[0], h_tot[1], npart);
+    if (e->ss.on && ss_relocate(e, e->cur, nullptr, true)) return 1;   // determ%indices / determ%flags follow the new list
     return 0;
 }
 
@@ -2304,11 +2309,14 @@ int hb200_iterate(hb200_engine* e, int32_t ncycles, const hb200_iter_in* in, hb2
             bound = e->sp_n;
         }
         CK(cudaEventRecord(e->ev[2], st));
+        // determ_projection + deterministic_annihilation (src/fciqmc.f90:394, src/annihilation.f90:64-65)
+        if (e->ss.on && stage_determ(e, in, cycle, nullptr)) return 1;
         // the sort kernels split the list by its real length whatever their grid is, so the grid follows the length of
         // the previous cycle's list (a hint) rather than the loose upper bound
         if (stage_sort(e, std::min(bound, std::max<long long>(4096, 2 * e->last_spn + 1024)))) return 1;
         CK(cudaEventRecord(e->ev[3], st));
         if (stage_annihilate_launch(e, cycle, bound)) return 1;
+        if (e->ss.on && ss_relocate(e, e->alt, e->d_total, false)) return 1;   // on the merged list, counts still on the device
         CK(cudaEventRecord(e->ev[4], st));
         // the cycle's results: one pinned block, one synchronisation
         CK(cudaMemcpyAsync(&ho->st, e->d_stats, sizeof(CycleStats), cudaMemcpyDeviceToHost, st));
@@ -2521,6 +2529,256 @@ int hb200_gen_excit_batch_rn(hb200_engine* e, const uint64_t* states, const int6
     cudaFree(d_f); cudaFree(d_p); cudaFree(d_rn); cudaFree(d_io); cudaFree(d_do); cudaFree(d_ns); cudaFree(d_nu);
     return 0;
 }
+
+}  // extern "C"
+
+// ---- semi-stochastic projection (src/semi_stoch.F90; separate annihilation, the reference's default) --------------------
+__global__ void __launch_bounds__(256)
+k_ss_gather_pops(const int64_t* __restrict__ pops, const long long* __restrict__ idx, int nloc, double real_factor,
+                 double* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < nloc) out[j] = (double)pops[idx[j]] / real_factor;   // set_determ_info (src/semi_stoch.F90:826-857)
+}
+static void ss_free(hb200_engine* e) {
+    for (void* q : e->ss.bufs) cudaFree(q);
+    e->ss = SemiStoch();
+    e->par.ss_bits = nullptr; e->par.ss_sorted = nullptr; e->par.ss_tot = 0;
+}
+template <class T>
+static int ss_alloc(hb200_engine* e, T** p, size_t n) {
+    void* q = nullptr;
+    CK(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
+    *p = (T*)q;
+    e->ss.bufs.push_back(q);
+    return 0;
+}
+// positions of this rank's deterministic states in the current list + the flag bits; fails if one is missing
+static int ss_relocate(hb200_engine* e, int buf, const int* ntot2, bool check) {
+    if (e->ops->ss_locate(e, buf, ntot2)) return 1;
+    e->launches++;
+    if (check) {
+        int miss = 0;
+        CK(copy_sync(e, &miss, e->ss.d_miss, sizeof(int), cudaMemcpyDeviceToHost));
+        if (miss) FAIL("semi-stochastic: deterministic states of this rank are missing from the main list");
+    }
+    return 0;
+}
+// gather this rank's deterministic amplitudes into its slot of the all-gather buffer (set_determ_info)
+static int ss_gather(hb200_engine* e) {
+    SemiStoch& S = e->ss;
+    if (S.nloc > 0) {
+        k_ss_gather_pops<<<(S.nloc + 255) / 256, 256, 0, e->stream>>>(e->d_pops[e->cur], S.d_idx, S.nloc, (double)e->par.real_factor,
+                                                                      S.d_full + (size_t)e->par.iproc * S.maxsz);
+        CK(cudaGetLastError());
+        e->launches++;
+    }
+    return 0;
+}
+// determ_projection + deterministic_annihilation of one cycle; full == nullptr: the vector is all-gathered with NCCL
+static int stage_determ(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, const double* full_host) {
+    SemiStoch& S = e->ss;
+    Params& p = e->par;
+    p.tau = in->tau; p.shift = in->shift; p.proj_energy_old = in->proj_energy_old; p.cycle = cycle;
+    const int np = p.nprocs;
+    if (full_host) {
+        // the host's own mpi_allgatherv (src/semi_stoch.F90:1061-1063): sizes(r) amplitudes of every rank, rank by rank
+        size_t k = 0;
+        for (int r = 0; r < np; ++r) {
+            if (S.sizes[r])
+                CK(cudaMemcpyAsync(S.d_full + (size_t)r * S.maxsz, full_host + k, sizeof(double) * S.sizes[r], cudaMemcpyHostToDevice,
+                                   e->stream));
+            k += (size_t)S.sizes[r];
+        }
+    } else {
+        if (ss_gather(e)) return 1;
+        if (np > 1) {
+            if (!e->comm) FAIL("semi-stochastic: nprocs > 1 needs hb200_comm_init (or the staged hb200_determ_project call)");
+            NCK(g_nccl.AllGather(S.d_full + (size_t)p.iproc * S.maxsz, S.d_full, (size_t)S.maxsz, ncclDouble, e->comm, e->stream));
+        }
+    }
+    if (e->ops->ss_project(e, p)) return 1;
+    e->launches++;
+    return 0;
+}
+
+extern "C" {
+
+// init_semi_stoch_t (src/semi_stoch.F90:134-377) with the space chosen by the host (create_high_pop_space,
+// create_ci_determ_space and read_determ_from_file are host logic): dets = determ%dets, every deterministic
+// determinant rank by rank in the host's layout (We words each), every rank's part in ascending list order;
+// sizes = determ%sizes.  Builds the hash-free membership table, this rank's slice of the deterministic Hamiltonian (on the
+// device, create_determ_hamil) and adds the rank's deterministic states that are not in its main list with zero
+// population (add_determ_dets_to_psip_list).  tot = 0 switches the projection off.
+int hb200_set_determ_space(hb200_engine* e, const uint64_t* dets, const int32_t* sizes) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (!e->have_sys || !e->have_ref) FAIL("set_determ_space: system / reference not set");
+    CK(cudaStreamSynchronize(e->stream));
+    ss_free(e);
+    const int np = e->par.nprocs, ip = e->par.iproc, We = e->We, W = e->W;
+    long long tot = 0;
+    int maxsz = 0, displ = 0;
+    for (int r = 0; r < np; ++r) {
+        if (sizes[r] < 0) FAIL("set_determ_space: negative size");
+        if (r < ip) displ += sizes[r];
+        tot += sizes[r];
+        maxsz = std::max(maxsz, (int)sizes[r]);
+    }
+    if (tot == 0) return 0;
+    if (tot > (1ll << 30)) FAIL("set_determ_space: deterministic space too large");
+    SemiStoch& S = e->ss;
+    S.tot = (int)tot; S.nloc = sizes[ip]; S.maxsz = maxsz; S.displ = displ;
+    S.sizes.assign(sizes, sizes + np);
+    auto less = [We](const uint64_t* a, const uint64_t* b) {
+        for (int k = We - 1; k >= 0; --k) {
+            if (a[k] < b[k]) return true;
+            if (a[k] > b[k]) return false;
+        }
+        return false;
+    };
+    const uint64_t* mine = dets + (size_t)displ * We;
+    for (int j = 1; j < S.nloc; ++j)
+        if (!less(mine + (size_t)(j - 1) * We, mine + (size_t)j * We)) FAIL("set_determ_space: this rank's determinants are not in ascending order");
+    // --- add_determ_dets_to_psip_list: merge the missing states into the list with zero population
+    {
+        const long long n = e->nstates;
+        std::vector<uint64_t> st((size_t)(n + S.nloc) * We), st2;
+        std::vector<int64_t> po((size_t)(n + S.nloc)), po2;
+        std::vector<double> da((size_t)(n + S.nloc)), da2;
+        int64_t got = 0;
+        if (hb200_download_psips(e, st.data(), po.data(), da.data(), n + S.nloc, &got)) return 1;
+        std::vector<int> missing;
+        {
+            long long i = 0;
+            for (int j = 0; j < S.nloc; ++j) {
+                const uint64_t* f = mine + (size_t)j * We;
+                while (i < n && less(st.data() + (size_t)i * We, f)) ++i;
+                if (i >= n || less(f, st.data() + (size_t)i * We)) missing.push_back(j);
+            }
+        }
+        if (!missing.empty()) {
+            const long long m = (long long)missing.size();
+            if (n + m > e->cfg.walker_length) FAIL("set_determ_space: the deterministic states do not fit the main list");
+            std::vector<uint64_t> mf((size_t)m * We);
+            std::vector<double> md((size_t)m);
+            for (long long k = 0; k < m; ++k) memcpy(mf.data() + (size_t)k * We, mine + (size_t)missing[(size_t)k] * We, (size_t)We * 8);
+            if (hb200_sc0_batch(e, mf.data(), m, md.data())) return 1;
+            st2.resize((size_t)(n + m) * We); po2.resize((size_t)(n + m)); da2.resize((size_t)(n + m));
+            long long i = 0, o = 0;
+            for (long long k = 0; k <= m; ++k) {
+                const uint64_t* f = (k < m) ? mf.data() + (size_t)k * We : nullptr;
+                while (i < n && (!f || less(st.data() + (size_t)i * We, f))) {
+                    memcpy(st2.data() + (size_t)o * We, st.data() + (size_t)i * We, (size_t)We * 8);
+                    po2[(size_t)o] = po[(size_t)i]; da2[(size_t)o] = da[(size_t)i];
+                    ++i; ++o;
+                }
+                if (f) {
+                    memcpy(st2.data() + (size_t)o * We, f, (size_t)We * 8);
+                    po2[(size_t)o] = 0; da2[(size_t)o] = md[(size_t)k] - e->par.H00;   // insert_new_walker: sc0 - H00
+                    ++o;
+                }
+            }
+            int herr[4] = {0, 0, 0, 0};
+            CK(copy_sync(e, herr, e->d_err, 4 * sizeof(int), cudaMemcpyDeviceToHost));
+            if (hb200_upload_psips(e, st2.data(), po2.data(), da2.data(), n + m)) return 1;
+            CK(copy_sync(e, e->d_err, herr, 4 * sizeof(int), cudaMemcpyHostToDevice));   // upload resets the error flags
+        }
+    }
+    // --- device tables
+    if (ss_alloc(e, &S.d_all, (size_t)tot * W) || ss_alloc(e, &S.d_sorted, (size_t)tot * W) || ss_alloc(e, &S.d_pad, (size_t)tot) ||
+        ss_alloc(e, &S.d_idx, (size_t)S.nloc) || ss_alloc(e, &S.d_bits, ((size_t)e->cfg.walker_length + 31) / 32 + 1) ||
+        ss_alloc(e, &S.d_full, (size_t)np * maxsz) || ss_alloc(e, &S.d_vec, (size_t)S.nloc) || ss_alloc(e, &S.d_rho, (size_t)S.nloc) ||
+        ss_alloc(e, &S.d_colptr, (size_t)S.nloc + 1) || ss_alloc(e, &S.d_miss, 1))
+        return 1;
+    S.d_local = S.d_all + (size_t)displ * W;
+    CK(cudaMemsetAsync(S.d_full, 0, sizeof(double) * (size_t)np * maxsz, e->stream));
+    CK(copy_states_h2d(e, S.d_all, dets, tot, e->stream));
+    {
+        std::vector<const uint64_t*> ptr((size_t)tot);
+        for (long long i = 0; i < tot; ++i) ptr[(size_t)i] = dets + (size_t)i * We;
+        std::sort(ptr.begin(), ptr.end(), less);
+        std::vector<uint64_t> sorted((size_t)tot * We);
+        for (long long i = 0; i < tot; ++i) memcpy(sorted.data() + (size_t)i * We, ptr[(size_t)i], (size_t)We * 8);
+        for (long long i = 1; i < tot; ++i)
+            if (!less(sorted.data() + (size_t)(i - 1) * We, sorted.data() + (size_t)i * We)) FAIL("set_determ_space: repeated determinant");
+        CK(copy_states_h2d(e, S.d_sorted, sorted.data(), tot, e->stream));
+        std::vector<int> pad((size_t)tot);
+        long long i = 0;
+        for (int r = 0; r < np; ++r)
+            for (int k = 0; k < sizes[r]; ++k, ++i) pad[(size_t)i] = r * maxsz + k;
+        CK(cudaMemcpyAsync(S.d_pad, pad.data(), sizeof(int) * (size_t)tot, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+    }
+    // --- create_determ_hamil: count, scan, fill
+    if (e->ops->ss_hamil(e, 0)) return 1;
+    {
+        std::vector<long long> cp((size_t)S.nloc + 1, 0);
+        if (S.nloc) CK(copy_sync(e, cp.data(), S.d_colptr, sizeof(long long) * (size_t)S.nloc, cudaMemcpyDeviceToHost));
+        long long run = 0;
+        for (int j = 0; j <= S.nloc; ++j) { const long long c = (j < S.nloc) ? cp[(size_t)j] : 0; cp[(size_t)j] = run; run += c; }
+        S.nnz = run;
+        CK(copy_sync(e, S.d_colptr, cp.data(), sizeof(long long) * ((size_t)S.nloc + 1), cudaMemcpyHostToDevice));
+        if (ss_alloc(e, &S.d_row, (size_t)S.nnz) || ss_alloc(e, &S.d_val, (size_t)S.nnz)) return 1;
+    }
+    if (e->ops->ss_hamil(e, 1)) return 1;
+    CK(cudaStreamSynchronize(e->stream));
+    // --- determ%indices / determ%flags on the current list
+    if (ss_relocate(e, e->cur, nullptr, true)) return 1;
+    S.on = true;
+    e->par.ss_bits = S.d_bits; e->par.ss_sorted = S.d_sorted; e->par.ss_tot = S.tot;
+    return 0;
+}
+
+// determ%hamil of this rank by column (create_determ_hamil): nnz is returned; with non-null arrays col_ptr[sizes(iproc)+1],
+// row[nnz] (row index 0..tot-1 in determ%dets order) and val[nnz] are filled.
+int64_t hb200_determ_hamil(hb200_engine* e, int64_t* col_ptr, int32_t* row, double* val) {
+    SemiStoch& S = e->ss;
+    if (!S.on) return 0;
+    if (col_ptr) {
+        cudaSetDevice(e->cfg.device);
+        if (copy_sync(e, col_ptr, S.d_colptr, sizeof(long long) * ((size_t)S.nloc + 1), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        if (S.nnz) {
+            std::vector<int> pr((size_t)S.nnz);
+            if (copy_sync(e, pr.data(), S.d_row, sizeof(int) * (size_t)S.nnz, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+            if (copy_sync(e, val, S.d_val, sizeof(double) * (size_t)S.nnz, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+            std::vector<int> displs(S.sizes.size(), 0);
+            for (size_t r = 1; r < S.sizes.size(); ++r) displs[r] = displs[r - 1] + S.sizes[r - 1];
+            for (long long z = 0; z < S.nnz; ++z) row[z] = displs[(size_t)(pr[(size_t)z] / S.maxsz)] + pr[(size_t)z] % S.maxsz;
+        }
+    }
+    return S.nnz;
+}
+
+// determ%vector of this rank: which = 0 the amplitudes of its deterministic states now (what set_determ_info collects
+// during the spawning loop; the host all-gathers these for hb200_determ_project), which = 1 the result of the last
+// projection, -tau (H - S) v restricted to the rank.
+int hb200_determ_vector(hb200_engine* e, int32_t which, double* vec) {
+    CK(cudaSetDevice(e->cfg.device));
+    SemiStoch& S = e->ss;
+    if (!S.on) FAIL("determ_vector: no deterministic space");
+    if (S.nloc == 0) return 0;
+    if (which == 0) {
+        if (ss_gather(e)) return 1;
+        CK(copy_sync(e, vec, S.d_full + (size_t)e->par.iproc * S.maxsz, sizeof(double) * (size_t)S.nloc, cudaMemcpyDeviceToHost));
+    } else {
+        CK(copy_sync(e, vec, S.d_vec, sizeof(double) * (size_t)S.nloc, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+// Staged call between hb200_spawn_death and hb200_annihilate_main: determ_projection + deterministic_annihilation
+// (src/semi_stoch.F90:1009-1094, src/annihilation.f90:488-535).  full_vector = determ%full_vector gathered by the host
+// (tot doubles, rank by rank), or NULL to gather on the device (one rank, or NCCL).
+int hb200_determ_project(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, const double* full_vector) {
+    CK(cudaSetDevice(e->cfg.device));
+    if (!e->ss.on) FAIL("determ_project: no deterministic space");
+    if (stage_determ(e, in, cycle, full_vector)) return 1;
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+}  // extern "C"
+
+extern "C" {
 
 int hb200_get_unique_id(uint8_t id[128]) {
     ncclUniqueId uid;

@@ -193,7 +193,9 @@ k_round_count(Params p, const uint64_t* __restrict__ states, int64_t* __restrict
     int keep = 0;
     if (i < nstates) {
         int64_t pop = pops[i];
-        if (p.real_amplitudes) {
+        // deterministic states are neither rounded nor removed (src/annihilation.f90:572-586)
+        const bool determ_det = p.ss_bits != nullptr && ((p.ss_bits[i >> 5] >> (i & 31)) & 1u);
+        if (p.real_amplitudes && !determ_det) {
             const int64_t ap = pop < 0 ? -pop : pop;
             if (pop != 0 && ap < p.real_factor) {
                 uint64_t f[W];
@@ -204,7 +206,7 @@ k_round_count(Params p, const uint64_t* __restrict__ states, int64_t* __restrict
                 pops[i] = pop;
             }
         }
-        keep = pop != 0;
+        keep = pop != 0 || determ_det;
     }
     int tot;
     block_excl_scan(keep, swarp, &tot);
@@ -261,7 +263,8 @@ k_merge(Params p, const uint64_t* __restrict__ states, const int64_t* __restrict
     int64_t pop = 0;
     if (m < t1) {
         pop = pops[m];
-        if (FUSED && p.real_amplitudes) {
+        const bool determ_det = p.ss_bits != nullptr && ((p.ss_bits[m >> 5] >> (m & 31)) & 1u);
+        if (FUSED && p.real_amplitudes && !determ_det) {
             // remove_unoccupied_dets: stochastic rounding of |population| < 1 (src/annihilation.f90:537-598)
             const int64_t ap = pop < 0 ? -pop : pop;
             if (pop != 0 && ap < p.real_factor) {
@@ -272,7 +275,7 @@ k_merge(Params p, const uint64_t* __restrict__ states, const int64_t* __restrict
                 pop = stochastic_round(rng, pop, p.real_factor);
             }
         }
-        keep = pop != 0;
+        keep = pop != 0 || determ_det;
     }
     int tot;
     const int kb = block_excl_scan(keep, swarp, &tot);
@@ -500,9 +503,12 @@ template <int W>
 static int list_owner_slot_shift(const hb200_engine* e, const Params& p) {
     return owner_slot_shift<W>(p.f0, e->sys.nbasis, p.hash_seed, p.ccmc_shift, p.ccmc_freq, p.nprocs, p.nslots);
 }
+#include "hb_semistoch.cuh"
+
 template <int W>
 static const ListOps* list_ops() {
     static const ListOps ops = {list_annihilate<W>, list_compact<W>, list_round_count<W>, list_sc0<W>, list_merge<W>,
-                                list_slot_pop<W>, list_compress<W>, list_gather<W>, list_owner_slot_shift<W>};
+                                list_slot_pop<W>, list_compress<W>, list_gather<W>, list_owner_slot_shift<W>,
+                                ss_locate<W>, ss_hamil<W>, ss_project<W>};
     return &ops;
 }

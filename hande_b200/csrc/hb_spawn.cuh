@@ -162,8 +162,10 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
         const uint64_t h = det_hash64<W>(f, HB_NW(p));
         if (!hb_stage) shash[tid] = h;
         const double real_pop = (double)pop / (double)p.real_factor;
-        // set_parent_flag (src/ifciqmc.f90:13-57)
-        sflag[tid] = (fabs(real_pop) > p.initiator_pop) ? 0 : 1;
+        // set_determ_info (src/semi_stoch.F90:826-857): bit 1 of the staged flag marks a deterministic parent
+        const bool determ_parent = p.ss_bits != nullptr && ((p.ss_bits[idx >> 5] >> (idx & 31)) & 1u);
+        // set_parent_flag (src/ifciqmc.f90:13-57): deterministic states are always initiators
+        sflag[tid] = ((fabs(real_pop) > p.initiator_pop || determ_parent) ? 0 : 1) | (determ_parent ? 2 : 0);
         // update_proj_energy_mol (src/energy_evaluation.F90:906-986)
         bool is_ref;
         double hm = proj_energy_hmatel<W>(s, p, f, occ, is_ref);
@@ -179,7 +181,10 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
             sdf[tid] = dfock;
             death_weight = qn_weighting(p, dfock);
         }
-        const int64_t newpop = stochastic_death(rng, p, Kii, pop, kill_abs, death_weight);
+        // no death step for deterministic states (src/fciqmc.f90:368): the projection carries their diagonal
+        int64_t newpop = pop;
+        kill_abs = 0;
+        if (!determ_parent) newpop = stochastic_death(rng, p, Kii, pop, kill_abs, death_weight);
         pops[idx] = newpop;
         ndeath = kill_abs;
         npart = newpop < 0 ? -newpop : newpop;
@@ -399,10 +404,12 @@ k_spawn_death(Sys s, Params p, const uint64_t* __restrict__ states, int64_t* __r
                 // create_spawned_particle[_initiator]_truncated (src/spawning.F90:1186-1319)
                 if (p.trunc_level >= 0 && excit_level<W>(child, p.f0) > p.trunc_level) {
                     nspawn = 0;
+                } else if ((sflag[lo] & 2) && ss_check_if_determ<W>(p.ss_sorted, p.ss_tot, child)) {
+                    nspawn = 0;   // deterministic -> deterministic: the projection's job (src/fciqmc.f90:726-736)
                 } else {
                     // assign_particle_processor (src/spawning.F90:770-838)
                     dest = (p.nprocs > 1) ? proc_map[owner_slot(child, s.nbasis, p.hash_seed, p.nprocs, p.nslots)] : 0;
-                    pflag = p.initiator ? sflag[lo] : 0;
+                    pflag = p.initiator ? (sflag[lo] & 1) : 0;
                 }
             }
         }

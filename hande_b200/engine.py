@@ -165,6 +165,11 @@ def load_library():
     L.hb200_set_host_barrier.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.hb200_p2p_enable.argtypes = [C.c_void_p, C.c_int32]
     L.hb200_last_timing.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hb200_set_determ_space.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hb200_determ_hamil.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hb200_determ_hamil.restype = C.c_int64
+    L.hb200_determ_vector.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    L.hb200_determ_project.argtypes = [C.c_void_p, C.POINTER(IterIn), C.c_uint32, C.c_void_p]
     _LIB = L
     return L
 
@@ -178,7 +183,8 @@ ABI_SYMBOLS = [
     "hb200_ccmc_spawn", "hb200_ccmc_iterate", "hb200_ccmc_set_hash_shift", "hb200_ccmc_set_full_nc", "hb200_set_pattempt", "hb200_get_ps_stats", "hb200_set_pattempt_parallel", "hb200_get_pattempt_parallel", "hb200_build_power_pitzer_orderN", "hb200_build_power_pitzer", "hb200_set_quasi_newton", "hb200_annihilate_spawn", "hb200_annihilate_main", "hb200_download_spawn", "hb200_upload_spawn", "hb200_spawn_counts",
     "hb200_sc0_batch", "hb200_gen_excit_batch", "hb200_get_unique_id", "hb200_comm_init", "hb200_last_timing",
     "hb200_p2p_export", "hb200_p2p_import", "hb200_set_host_barrier", "hb200_p2p_enable", "hb200_slot_populations", "hb200_set_propagator_weight",
-    "hb200_redistribute_particles",
+    "hb200_redistribute_particles", "hb200_set_determ_space", "hb200_determ_hamil", "hb200_determ_vector",
+    "hb200_determ_project",
 ]
 
 
@@ -366,6 +372,40 @@ class Engine:
         assert len(sp) == self.sys.nbasis + 1
         self._chk(self.L.hb200_set_quasi_newton(self.h, _p(sp), float(ref_fock_sum), float(threshold), float(value),
                                                 float(pop_control)))
+
+    # ---- semi-stochastic projection (src/semi_stoch.F90)
+    def set_determ_space(self, dets, sizes):
+        """init_semi_stoch_t with the host's space: dets = determ%dets (tot x W, rank by rank, each rank's part in list
+        order), sizes = determ%sizes; all sizes zero switches the projection off"""
+        sizes = np.ascontiguousarray(sizes, dtype=np.int32)
+        assert len(sizes) == self.nprocs
+        dets = np.ascontiguousarray(dets, dtype=np.uint64).reshape(-1, self.W)
+        assert len(dets) == int(sizes.sum())
+        self.determ_sizes = sizes.copy()
+        self._chk(self.L.hb200_set_determ_space(self.h, _p(dets) if len(dets) else None, _p(sizes)))
+
+    def determ_hamil(self):
+        """determ%hamil of this rank by column: (col_ptr, row, val)"""
+        nnz = self.L.hb200_determ_hamil(self.h, None, None, None)
+        nloc = int(self.determ_sizes[self.iproc])
+        cp = np.zeros(nloc + 1, dtype=np.int64)
+        row = np.zeros(max(nnz, 1), dtype=np.int32)
+        val = np.zeros(max(nnz, 1))
+        if self.L.hb200_determ_hamil(self.h, _p(cp), _p(row), _p(val)) < 0:
+            raise EngineError("determ_hamil")
+        return cp, row[:nnz], val[:nnz]
+
+    def determ_vector(self, which=0):
+        """determ%vector of this rank: which=0 the deterministic amplitudes now, which=1 the last projection's result"""
+        v = np.zeros(int(self.determ_sizes[self.iproc]))
+        self._chk(self.L.hb200_determ_vector(self.h, int(which), _p(v) if len(v) else None))
+        return v
+
+    def determ_project(self, tau, shift, proj_energy_old, cycle, full_vector=None):
+        """staged determ_projection + deterministic_annihilation (between spawn_death and annihilate_main)"""
+        i = IterIn(tau=tau, shift=shift, proj_energy_old=proj_energy_old, first_cycle=cycle)
+        fv = None if full_vector is None else np.ascontiguousarray(full_vector, dtype=np.float64)
+        self._chk(self.L.hb200_determ_project(self.h, C.byref(i), cycle, None if fv is None else _p(fv)))
 
     def set_propagator_weight(self, weight):
         """wall-Chebyshev: weight 1/(S_i - E_0) of the sub-cycle the next iterate()/spawn_death() calls run"""

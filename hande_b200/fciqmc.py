@@ -20,6 +20,7 @@ from . import read_in as _ri
 from .engine import Engine
 from . import load_balancing as _lb
 from . import propagators as _prop
+from . import semi_stoch as _ss
 
 HUGE = _ri.HUGE
 
@@ -69,6 +70,13 @@ class QmcIn:
     load_balancing_pop: float = 1000.0
     percent_imbal: float = 0.05
     max_load_attempts: int = 2
+    # semi_stoch_in_t (src/qmc_data.f90:305-338): space = "high" (the `size` most populated determinants) with the
+    # reference's default projection mode (separate annihilation); start at start_iteration, or shift_start_iteration
+    # iterations after the shift starts to vary
+    semi_stoch_space: str = "none"
+    semi_stoch_size: int = 0
+    semi_stoch_start_iteration: int = 1
+    semi_stoch_shift_start_iteration: int = -1
     full_non_composite: bool = False  # ccmc = {full_non_composite = true} (CCMC only)
     reference_det: list = None      # reference = {det = {...}}: explicit reference determinant (1-based orbitals)
 
@@ -249,6 +257,19 @@ class TorchDist:
         return np.stack([x.cpu().numpy() for x in out])
 
 
+def _merge_out(o, oc):
+    """accumulate the outputs of consecutive hb200_iterate calls of one report loop"""
+    if o is None:
+        return dict(oc)
+    for key in ("proj_energy", "D0_population", "rspawn", "nattempts_spawn", "walker_iterations"):
+        o[key] = o[key] + oc[key]
+    for key in ("nparticles", "nstates", "nspawn_events", "ndeath", "nattempts"):
+        o[key] = oc[key]
+    o["spawn_error"] = o["spawn_error"] or oc["spawn_error"]
+    o["psip_error"] = o["psip_error"] or oc["psip_error"]
+    return o
+
+
 HEADER = (" #     iterations   Shift                 \\sum H_0j N_j         N_0                   # H psips"
           "                  # states  # spawn_events   R_spawn    time    ")
 
@@ -273,6 +294,7 @@ class FciqmcResult:
     pattempt_log: list = field(default_factory=list)   # pattempt_single after each pattempt_update change
     load_balancing_log: list = field(default_factory=list)   # (first cycle, proc_map) of every load-balancing step
     chebyshev: object = None                                  # propagators.Chebyshev of the run (None: linear projector)
+    determ_space: object = None                               # (determ%dets, determ%sizes) once the semi-stochastic projection is on
 
 
 def do_fciqmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, keep_engine=False, psips=None):
@@ -351,6 +373,13 @@ def do_fciqmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, 
         out.write(HEADER + "\n")
         out.write(format_row(0, shift, proj_energy, D0, ntot_old, tot_nstates, 0, 0.0, 0.0, comment=True) + "\n")
     mc_cycles_done = 0
+    ss_on, ss_done = qmc.semi_stoch_space == "high" and qmc.semi_stoch_size > 0, False
+    if qmc.semi_stoch_space not in ("none", "high"):
+        raise ValueError("semi_stoch: only space = 'high' is chosen by this driver (other spaces: Engine.set_determ_space)")
+    if ss_on and (cheb is not None or qmc.load_balancing):
+        raise ValueError("semi_stoch with the wall-Chebyshev propagator or load balancing is not supported")
+    semi_stoch_iter = max(qmc.semi_stoch_start_iteration, mc_cycles_done + 1)     # src/fciqmc.f90:228
+    res.determ_space = None
     lb_needed, lb_attempts = False, 0
     proc_map = [i % nprocs for i in range(nprocs * qmc.nslots)]      # src/load_balancing.F90:170
     for ireport in range(1, qmc.nreports + 1):
@@ -372,7 +401,17 @@ def do_fciqmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, 
                 res.load_balancing_log.append((first_cycle, list(proc_map)))
             lb_needed = False
         if cheb is None:
-            o = eng.iterate(qmc.mc_cycles, tau, shift, pe_old, first_cycle)
+            ncyc, cyc0, o = qmc.mc_cycles, first_cycle, None
+            if ss_on and not ss_done and cyc0 <= semi_stoch_iter < cyc0 + ncyc:
+                # should the semi-stochastic projection start now? (src/fciqmc.f90:300-305): the cycles before it, then
+                # init_semi_stoch_t on the list as it stands
+                k = semi_stoch_iter - cyc0
+                if k > 0:
+                    o = eng.iterate(k, tau, shift, pe_old, cyc0)
+                    cyc0, ncyc = cyc0 + k, ncyc - k
+                res.determ_space = _ss.init_semi_stoch(eng, comm, qmc.semi_stoch_size)
+                ss_done = True
+            o = _merge_out(o, eng.iterate(ncyc, tau, shift, pe_old, cyc0))
         else:
             # `order` linear projectors per MC cycle (src/fciqmc.f90:298-299), each a full spawn / annihilation cycle
             # with its own weight; the engine's random stream is keyed by the sub-cycle index
@@ -380,16 +419,7 @@ def do_fciqmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, 
             for icycle in range(qmc.mc_cycles):
                 for icheb in range(1, order + 1):
                     eng.set_propagator_weight(cheb.weights[icheb - 1])
-                    oc = eng.iterate(1, tau, shift, pe_old, (first_cycle + icycle - 1) * order + icheb)
-                    if o is None:
-                        o = dict(oc)
-                    else:
-                        for key in ("proj_energy", "D0_population", "rspawn", "nattempts_spawn", "walker_iterations"):
-                            o[key] = o[key] + oc[key]
-                        for key in ("nparticles", "nstates", "nspawn_events", "ndeath", "nattempts"):
-                            o[key] = oc[key]
-                        o["spawn_error"] = o["spawn_error"] or oc["spawn_error"]
-                        o["psip_error"] = o["psip_error"] or oc["psip_error"]
+                    o = _merge_out(o, eng.iterate(1, tau, shift, pe_old, (first_cycle + icycle - 1) * order + icheb))
         res.timings.append(eng.last_timing())
         # local_energy_estimators + MPI_Allreduce + communicated_energy_estimators
         # (src/energy_evaluation.F90:126-201, 320-655)
@@ -416,6 +446,8 @@ def do_fciqmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, 
         if not vary_shift and ntot > qmc.target_population:
             vary_shift = True
             shift = proj_energy / D0 if qmc.vary_shift_from_proje else qmc.vary_shift_from
+            if qmc.semi_stoch_shift_start_iteration != -1:       # src/qmc_common.F90:1200-1204
+                semi_stoch_iter = qmc.semi_stoch_shift_start_iteration + (mc_cycles_done + ireport * qmc.mc_cycles) + 1
         if pupd is not None:
             pupd.end_report_loop(vary_shift)
         if cheb is not None:

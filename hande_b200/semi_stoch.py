@@ -1,0 +1,109 @@
+"""Host side of the semi-stochastic projection (semi_stoch = {...}; src/semi_stoch.F90).
+
+The engine keeps the deterministic space on the device (hb200_set_determ_space: membership table, the rank's slice of the
+deterministic Hamiltonian, the projection and its annihilation every cycle); choosing the space is host logic in the
+reference too and is mirrored here:
+
+  * create_high_pop_space (src/semi_stoch.F90:1198-1316): every rank offers its min(target, nstates) most populated
+    determinants (find_most_populated_dets, :1318-1385), the target_size most populated offers are kept
+    (find_indices_of_most_populated_dets, :1387-1448).  Both walk their input once, replacing the current minimum
+    (first slot among equal minima) by any later entry that is strictly larger - restated with a heap keyed (|pop|, slot),
+    which evicts exactly that entry.
+  * init_semi_stoch_t's bookkeeping (:134-377): sizes all-gathered, each rank's determinants sorted in list order, the
+    ranks' lists concatenated.
+"""
+import heapq
+
+import numpy as np
+
+from . import synthetic
+
+
+def _allgatherv(comm, a):
+    """MPI_Allgatherv of one numpy array per rank over the driver's fixed-record allgather_bytes: [size] arrays"""
+    a = np.ascontiguousarray(a)
+    raw = np.frombuffer(a.tobytes(), dtype=np.uint8)
+    lens = comm.allgather_bytes(np.frombuffer(np.int64(len(raw)).tobytes(), dtype=np.uint8))
+    lens = [int(np.frombuffer(np.ascontiguousarray(x).tobytes(), dtype=np.int64)[0]) for x in lens]
+    m = max(max(lens), 1)
+    buf = np.zeros(m, dtype=np.uint8)
+    buf[:len(raw)] = raw
+    rows = comm.allgather_bytes(buf)
+    return [np.frombuffer(np.ascontiguousarray(rows[r][:lens[r]]).tobytes(), dtype=a.dtype) for r in range(len(lens))]
+
+
+def _most_populated(abs_pops, nout, chunk=1 << 20):
+    """Slots -> input index after one pass of the reference's replace-the-minimum selection (nout <= len(abs_pops))."""
+    n = len(abs_pops)
+    slots = list(range(nout))
+    if nout == 0:
+        return np.zeros(0, dtype=np.int64)
+    heap = [(int(abs_pops[i]), i) for i in range(nout)]      # (|pop|, slot)
+    heapq.heapify(heap)
+    for c0 in range(nout, n, chunk):
+        a = abs_pops[c0:c0 + chunk]
+        cand = np.nonzero(a > heap[0][0])[0]                  # the minimum only grows: a superset of the real candidates
+        for k in cand:
+            v = int(a[k])
+            if v > heap[0][0]:
+                _, slot = heap[0]
+                heapq.heapreplace(heap, (v, slot))
+                slots[slot] = c0 + int(k)
+    return np.asarray(slots, dtype=np.int64)
+
+
+def find_most_populated_dets(states, pops, ndets_out):
+    """find_most_populated_dets (src/semi_stoch.F90:1318-1385): (dets_out, pops_out) in slot order"""
+    ap = np.abs(np.asarray(pops, dtype=np.int64))
+    idx = _most_populated(ap, int(ndets_out))
+    return np.asarray(states)[idx], ap[idx]
+
+
+def find_indices_of_most_populated_dets(pops, nind_out):
+    """find_indices_of_most_populated_dets (src/semi_stoch.F90:1387-1448): 0-based indices, -1 for unused slots"""
+    ap = np.abs(np.asarray(pops, dtype=np.int64))
+    n = len(ap)
+    out = np.full(int(nind_out), -1, dtype=np.int64)
+    k = min(int(nind_out), n)
+    out[:k] = _most_populated(ap, k)
+    return out
+
+
+def create_high_pop_space(comm, states, pops, target_size):
+    """create_high_pop_space (src/semi_stoch.F90:1198-1316) for this rank: its deterministic determinants, unsorted.
+    comm: the driver's communicator (fciqmc.SerialComm / TorchDist) - allgather_bytes is all that is used."""
+    states = np.ascontiguousarray(states, dtype=np.uint64)
+    W = states.shape[1] if states.ndim == 2 else 1
+    nstates = len(states)
+    ndets = min(int(target_size), nstates)
+    determ_dets, determ_pops = find_most_populated_dets(states, pops, ndets)
+    all_pops = _allgatherv(comm, np.ascontiguousarray(determ_pops, dtype=np.int64))
+    all_ndets = [len(a) for a in all_pops]
+    displs = np.concatenate([[0], np.cumsum(all_ndets)])
+    ndets_tot = int(displs[-1])
+    determ_size = min(int(target_size), ndets_tot)
+    indices = find_indices_of_most_populated_dets(np.concatenate(all_pops) if ndets_tot else np.zeros(0, np.int64), determ_size)
+    me = comm.rank
+    mine = [int(i - displs[me]) for i in indices if displs[me] <= i < displs[me + 1]]
+    return determ_dets[mine].reshape(-1, W)
+
+
+def gather_determ_space(comm, dets_this_proc):
+    """init_semi_stoch_t (src/semi_stoch.F90:236-340): sort this rank's determinants in list order, all-gather sizes and
+    determinants.  Returns (determ%dets [tot x W], determ%sizes)."""
+    d = np.ascontiguousarray(dets_this_proc, dtype=np.uint64)
+    W = d.shape[1]
+    d = synthetic.sort_dets(d) if len(d) else d
+    parts = [x.reshape(-1, W) for x in _allgatherv(comm, d)]
+    sizes = np.asarray([len(x) for x in parts], dtype=np.int32)
+    return (np.concatenate(parts) if sizes.sum() else np.zeros((0, W), dtype=np.uint64)), sizes
+
+
+def init_semi_stoch(eng, comm, target_size):
+    """semi_stoch = { space = "high", size = target_size } at the current iteration: choose the space from the engine's
+    list and hand it to hb200_set_determ_space.  Returns (dets, sizes)."""
+    f, p, _ = eng.download_psips()
+    mine = create_high_pop_space(comm, f, p, target_size)
+    dets, sizes = gather_determ_space(comm, mine)
+    eng.set_determ_space(dets, sizes)
+    return dets, sizes

@@ -275,6 +275,37 @@ int hb200_gen_excit_batch_rn(hb200_engine* e, const uint64_t* states, const int6
  * (src/spawning.F90:117-118) and to the death probability (src/death.f90:89) until the next call.  Default 1. */
 int hb200_set_propagator_weight(hb200_engine* e, double weight);
 
+/* Semi-stochastic projection (semi_stoch = {...}; src/semi_stoch.F90, deterministic_annihilation of
+ * src/annihilation.f90:488-535), the reference's default projection mode (separate_annihilation = true).
+ *
+ * hb200_set_determ_space replaces init_semi_stoch_t (src/semi_stoch.F90:134-377) once the host has chosen the space
+ * (create_high_pop_space / create_ci_determ_space / read_determ_from_file are host logic; hande_b200.semi_stoch mirrors the
+ * first): dets = determ%dets, all determ%tot_size determinants rank by rank (ceil(nbasis/64) words each), every rank's
+ * part in ascending list order; sizes = determ%sizes(0:nprocs-1).  It builds the membership table check_if_determ uses
+ * (:795-824), this rank's slice of the deterministic Hamiltonian on the device (create_determ_hamil, :533-685,
+ * <D_i|H|D_j> - H00 delta_ij times the quasi-Newton weight of D_j, elements above depsilon), rho_minus_qn_weight, and
+ * adds the rank's deterministic states that its main list lacks with zero population (add_determ_dets_to_psip_list,
+ * :728-793).  From then on hb200_iterate and the staged calls treat deterministic states as the reference does: always
+ * initiators (set_parent_flag), no death step, spawning onto another deterministic state cancelled
+ * (src/fciqmc.f90:368,726-736), never rounded nor removed (remove_unoccupied_dets), and once per cycle
+ * v <- -tau (H - S) v over the space (determ_proj_separate_annihil, :1009-1094; the amplitudes of all ranks are
+ * all-gathered with NCCL) is rounded stochastically to the amplitude resolution and added to their populations.
+ * All sizes zero switches the projection off.  hb200_upload_psips with a space set requires the new list to hold every
+ * deterministic state of the rank. */
+int hb200_set_determ_space(hb200_engine* e, const uint64_t* dets, const int32_t* sizes);
+/* determ%hamil of this rank, stored by column (column j = deterministic state j of this rank, rows in determ%dets
+ * order - the order csrpgemv's transposed product accumulates in, lib/local/csr.f90:188-194).  Returns nnz; with
+ * non-null arrays fills col_ptr[sizes(iproc)+1], row[nnz], val[nnz]. */
+int64_t hb200_determ_hamil(hb200_engine* e, int64_t* col_ptr, int32_t* row, double* val);
+/* determ%vector of this rank: which = 0 the amplitudes of its deterministic states now (set_determ_info, :826-857);
+ * which = 1 the result of the last projection. */
+int hb200_determ_vector(hb200_engine* e, int32_t which, double* vec);
+/* Staged form of the projection for hosts that drive the cycle themselves (between hb200_spawn_death and
+ * hb200_annihilate_main): full_vector = determ%full_vector as the host's mpi_allgatherv delivers it (tot_size doubles,
+ * rank by rank), or NULL to gather on the device (one rank, or NCCL).  Does determ_proj_separate_annihil and
+ * deterministic_annihilation for MC cycle `cycle`. */
+int hb200_determ_project(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, const double* full_vector);
+
 /* NCCL bootstrap for nprocs > 1: rank 0 calls hb200_get_unique_id, the host broadcasts the 128 bytes
  * (MPI_Bcast in the Fortran host, torch.distributed in this repo's harness), every rank calls
  * hb200_comm_init.  Replaces MPI_COMM_WORLD use in comm_spawn_t. */

@@ -680,6 +680,11 @@ int orc_rank_spawn(void* h, int rank, uint32_t cycle_id, double tau, double shif
     RankState& r = o->ranks[rank];
     r.proj_energy = 0.0; r.D0_population = 0.0;
     o->spawn_death_rank(r, cycle_id);
+    // one rank per process: the deterministic projection needs every rank's amplitudes, so only nprocs == 1 here
+    if (o->determ.doing) {
+        if (o->in.nprocs != 1) throw std::runtime_error("orc_rank_spawn: semi-stochastic projection with one rank per process");
+        o->determ_proj_separate();
+    }
     out[0] = r.proj_energy; out[1] = r.D0_population; out[2] = (double)r.nspawn_events; out[3] = (double)r.ndeath;
     out[4] = (double)r.nattempts;
     return 0;

@@ -421,7 +421,9 @@ class Oracle:
     def determ_vector(self, rank=0):
         dets, sizes = self.determ_space()
         v = np.zeros(int(sizes[rank]))
-        fl = np.zeros(int(self.nstates(rank)), dtype=np.uint8)
+        self.L.orc_nstates.restype = C.c_int64
+        self.L.orc_nstates.argtypes = [C.c_void_p, C.c_int]
+        fl = np.zeros(int(self.L.orc_nstates(self.h, int(rank))), dtype=np.uint8)
         self.L.orc_get_determ_vector.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         self.L.orc_get_determ_vector(self.h, int(rank), _p(v) if len(v) else None, _p(fl) if len(fl) else None)
         return v, fl

@@ -71,6 +71,14 @@ def make_engine_cls(fcidump_path, sys_kw, rng_kind=0, ueg=None, ref_det=None, qu
             self.o.set_psips(np.asarray(states).reshape(-1, self.o.W), pops, dat, rank=self.rank)
             self._nparticles = float(np.abs(np.asarray(pops, dtype=np.int64)).sum()) / self.real_factor
 
+        def download_psips(self):
+            return self.o.get_psips(self.rank)
+
+        def set_determ_space(self, dets, sizes):
+            """init_semi_stoch_t with the driver's space (one rank per process: world == 1 only)"""
+            assert self.world == 1
+            self.o.init_semi_stoch(dets, sizes)
+
         @property
         def nstates(self):
             return int(self.o.L.orc_nstates(self.o.h, self.rank))

@@ -222,3 +222,31 @@ def test_wall_chebyshev_trajectory_matches_oracle_philox():
         assert a[0] == b[0] and a[5] == b[5] and a[6] == b[6], (a, b)
         for k in (1, 2, 3, 4):
             assert abs(a[k] - b[k]) <= 1e-10 * max(1.0, abs(b[k])), (k, a, b)
+
+
+def test_semi_stochastic_trajectory_matches_oracle_philox():
+    """semi_stoch = { space = "high", size = 60, start_iteration = 45 } through do_fciqmc on the GPU engine (the host picks
+    the space from the downloaded list, hb200_set_determ_space, projection inside hb200_iterate) against the oracle's
+    own semi-stochastic run under the same Philox stream: every report row, with the shift varying.  The oracle's semi-stochastic runs reproduce the reference's tables with the dSFMT stream."""
+    path, kw = system_path("h2o")
+    s = R.read_in(path, **kw)
+    qmc = QmcIn(tau=0.003, rng_seed=7, init_pop=300, mc_cycles=10, nreports=30, target_population=2000, real_amplitudes=True,
+                state_size=1 << 17, spawned_state_size=1 << 16, semi_stoch_space="high", semi_stoch_size=60,
+                semi_stoch_start_iteration=45)
+    res = do_fciqmc(s, qmc)
+    o = Oracle()
+    o.read_fcidump(path, **kw)
+    o.set_qmc(rng_kind=1, literal_event_int32=0, tau=0.003, seed=7, D0_population=300, ncycles=10, nreport=30,
+              target_particles=2000, real_amplitudes=1, spawn_cutoff=0.01, walker_length=1 << 17,
+              spawned_walker_length=1 << 16)
+    o.set_semi_stoch(space="high", size=60, start_iteration=45)
+    o.init()
+    rows = o.run()
+    dets_o, sizes_o = o.determ_space()
+    assert len(res.rows) == len(rows) == 31 and not res.error
+    assert (res.determ_space[0] == dets_o).all() and int(res.determ_space[1].sum()) == 60
+    assert res.vary_shift and rows[-1][1] != 0.0
+    for a, b in zip(res.rows, rows):
+        assert a[0] == b[0] and a[5] == b[5] and a[6] == b[6], (a, b)
+        for k in (1, 2, 3, 4):
+            assert abs(a[k] - b[k]) <= 1e-10 * max(1.0, abs(b[k])), (k, a, b)

@@ -1,0 +1,125 @@
+"""Host side of the semi-stochastic projection on the CPU: the choice of the deterministic space
+(hande_b200.semi_stoch, mirror of create_high_pop_space) against the oracle's, on one and on several ranks, and the
+driver's start-iteration logic (do_fciqmc with the oracle-backed test engine) against the oracle's own run."""
+import threading
+
+import numpy as np
+
+from hande_b200 import read_in as R
+from hande_b200 import semi_stoch as SS
+from hande_b200.fciqmc import QmcIn, do_fciqmc, _SingleProcess
+from oracle.pyoracle import HUGE, Oracle
+
+
+class ThreadComm:
+    """allgather_bytes between `size` threads of this process (the collective create_high_pop_space uses)"""
+
+    def __init__(self, rank, size, shared):
+        self.rank, self.size, self.sh = rank, size, shared
+
+    def allgather_bytes(self, arr):
+        self.sh["slot"][self.rank] = np.asarray(arr, dtype=np.uint8).copy()
+        self.sh["bar"].wait()
+        out = np.stack(self.sh["slot"])
+        self.sh["bar"].wait()
+        return out
+
+
+def _grown_oracle(fcidump_path, nprocs):
+    o = Oracle()
+    o.read_fcidump(fcidump_path("ne"), nel=10, ms=0, sym=0, cas=(8, 22))
+    o.set_qmc(tau=0.002, seed=18, D0_population=10, ncycles=10, nreport=40, target_particles=50000, walker_length=50000,
+              spawned_walker_length=5000, ex_level=5, nprocs=nprocs, real_amplitudes=1, spawn_cutoff=0.01)
+    o.init()
+    o.run()
+    return o
+
+
+def test_high_pop_space_matches_oracle_on_four_ranks(fcidump_path):
+    """create_high_pop_space + the sort / all-gather of init_semi_stoch_t (src/semi_stoch.F90:134-377, 1198-1448): the
+    host mirror picks, rank by rank, exactly the determinants the oracle picks (whose semi-stochastic runs reproduce the
+    reference's tables), including the ties among equal populations"""
+    nprocs, size = 4, 120
+    o = _grown_oracle(fcidump_path, nprocs)
+    lists = [o.get_psips(r) for r in range(nprocs)]
+    assert sum(len(x[0]) for x in lists) > 3 * size
+    o.set_semi_stoch(space="high", size=size)
+    o.init_semi_stoch()
+    dets_o, sizes_o = o.determ_space()
+    shared = {"slot": [None] * nprocs, "bar": threading.Barrier(nprocs)}
+    res = [None] * nprocs
+
+    def work(r):
+        comm = ThreadComm(r, nprocs, shared)
+        mine = SS.create_high_pop_space(comm, lists[r][0], lists[r][1], size)
+        res[r] = SS.gather_determ_space(comm, mine)
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(nprocs)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for r in range(nprocs):
+        dets, sizes = res[r]
+        assert (sizes == sizes_o).all() and (dets == dets_o).all()
+    assert sizes_o.sum() == size
+    # the oracle now holds the space: zero-population deterministic states stay in the lists over further cycles
+    o.iterate(5, 1000, 0.002, -0.1, -0.1)
+    for r in range(nprocs):
+        v, flags = o.determ_vector(r)
+        assert int((flags == 0).sum()) == sizes_o[r] and len(v) == sizes_o[r]
+
+
+def test_selection_with_ties_and_short_lists():
+    """find_most_populated_dets / find_indices_of_most_populated_dets (src/semi_stoch.F90:1318-1448) restated literally
+    and compared with the heap form on inputs full of equal populations; a list shorter than the target"""
+    def literal(pops, nout):
+        pops = [abs(int(x)) for x in pops]
+        out = list(range(nout))
+        val = pops[:nout]
+        mi = min(range(nout), key=lambda i: (val[i], i))
+        for i in range(nout, len(pops)):
+            if pops[i] > val[mi]:
+                out[mi], val[mi] = i, pops[i]
+                mi = min(range(nout), key=lambda k: (val[k], k))
+        return out
+    rng = np.random.default_rng(5)
+    for trial in range(20):
+        n, k = int(rng.integers(5, 300)), int(rng.integers(1, 40))
+        pops = rng.integers(-6, 7, n)
+        k = min(k, n)
+        assert list(SS._most_populated(np.abs(pops), k, chunk=17)) == literal(pops, k)
+    idx = SS.find_indices_of_most_populated_dets(np.array([3, -9, 4]), 5)
+    assert list(idx) == [0, 1, 2, -1, -1]
+    st = np.arange(3, dtype=np.uint64).reshape(-1, 1)
+    d = SS.create_high_pop_space(_SingleProcess(), st, np.array([3, -9, 4]), 10)
+    assert sorted(d[:, 0].tolist()) == [0, 1, 2]
+
+
+def test_driver_starts_the_projection_at_the_requested_iteration(fcidump_path):
+    """do_fciqmc with semi_stoch = { space = "high", size = 40, start_iteration = 33 } (mid report loop) against the
+    oracle's own run with the same options: every row of the report table, reference dSFMT stream, one rank"""
+    from tests.oracle_engine import make_engine_cls
+    path = fcidump_path("he2_avdz")
+    kw = dict(nel=4, ms=0, sym=HUGE, cas=(-1, -1))
+    o = Oracle()
+    o.read_fcidump(path, **kw)
+    q = dict(tau=0.01, seed=7, D0_population=200, ncycles=10, nreport=12, target_particles=400, real_amplitudes=1,
+             spawn_cutoff=0.01, walker_length=4000, spawned_walker_length=2000)
+    o.set_qmc(**q)
+    o.set_semi_stoch(space="high", size=12, start_iteration=33)
+    o.init()
+    rows_o = o.run()
+    dets_o, sizes_o = o.determ_space()
+    assert sizes_o.sum() == 12
+    s = R.read_in(path, **kw)
+    qmc = QmcIn(tau=0.01, rng_seed=7, init_pop=200, mc_cycles=10, nreports=12, target_population=400, real_amplitudes=True,
+                spawn_cutoff=0.01, state_size=4000, spawned_state_size=2000, semi_stoch_space="high", semi_stoch_size=12,
+                semi_stoch_start_iteration=33)
+    res = do_fciqmc(s, qmc, engine_cls=make_engine_cls(path, kw, rng_kind=0))
+    dets, sizes = res.determ_space
+    assert (dets == dets_o).all() and (sizes == sizes_o).all()
+    rows = np.array(res.rows)
+    assert len(rows) == len(rows_o) == 13
+    for a, b in zip(rows, rows_o):
+        assert a[0] == b[0] and a[5] == b[5] and a[6] == b[6]
+        for k in (1, 2, 3, 4):
+            assert abs(a[k] - b[k]) <= 1e-11 * max(1.0, abs(b[k])), (a, b)

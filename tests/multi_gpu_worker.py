@@ -147,6 +147,27 @@ def main():
         assert abs(tot[0] - ro["proj_energy"]) <= 1e-12 * max(1.0, abs(ro["proj_energy"]))
         assert abs(tot[1] - ro["D0_population"]) <= 1e-12 * max(1.0, abs(ro["D0_population"]))
         assert tot[2] == ro["nspawn_events"] and tot[3] == ro["ndeath"] and tot[4] == ro["nstates"]
+    nss = int(os.environ.get("HB200_TEST_SEMI_STOCH", "0"))
+    if nss:
+        # semi-stochastic projection across the GPUs: the space is chosen by the host driver code over the real
+        # communicator (create_high_pop_space), the deterministic amplitudes are all-gathered with NCCL inside hb200_iterate
+        from hande_b200 import semi_stoch as SS
+        o.set_semi_stoch(space="high", size=nss)
+        o.init_semi_stoch()
+        dets_o, sizes_o = o.determ_space()
+        dets, sizes = SS.init_semi_stoch(eng, comm, nss)
+        assert (sizes == sizes_o).all() and (dets == dets_o).all() and sizes.sum() == nss and (sizes > 0).all()
+        for block in range(2):
+            ro = o.iterate(4, cyc, tau, -0.05, -0.1)
+            rg = eng.iterate(4, tau, -0.05, -0.1, cyc)
+            cyc += 4
+            fo, po, do_ = o.get_psips(rank)
+            fg, pg, dg = eng.download_psips()
+            assert len(fg) == len(fo), (rank, len(fg), len(fo))
+            assert (fg == fo).all() and (pg == po).all() and (dg == do_).all(), rank
+            assert (eng.determ_vector(1) == o.determ_vector(rank)[0]).all()
+            tot = comm.allreduce_sum(np.array([float(rg["nspawn_events"]), float(rg["ndeath"]), float(rg["nstates"])]))
+            assert tot[0] == ro["nspawn_events"] and tot[1] == ro["ndeath"] and tot[2] == ro["nstates"]
     if ps_on:
         a, b = eng.get_ps_stats(), o.ps_stats(rank)
         assert a[1] == b[1] and a[3] == b[3] and abs(a[0] - b[0]) <= 1e-12 * abs(b[0]) and abs(a[2] - b[2]) <= 1e-12 * abs(b[2])

@@ -35,6 +35,24 @@ def test_two_rank_parity(name, gen, real, init, tau):
     assert res.stdout.count("OK") == nproc
 
 
+@pytest.mark.parametrize("name,gen,real,init,tau", [("h2o", "renorm", 1, 0, 0.003), ("s12", "heat_bath", 1, 1, 0.004)])
+def test_multi_rank_semi_stochastic(name, gen, real, init, tau):
+    """Semi-stochastic projection over NCCL (determ_proj_separate_annihil's all-gather, src/semi_stoch.F90:1056-1066):
+    after the plain cycles the 80 most populated determinants become the deterministic space and every rank's list
+    keeps matching the oracle's emulated rank."""
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    nproc = 4 if n >= 4 else 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", "29539", os.path.join(ROOT, "tests", "multi_gpu_worker.py"),
+           name, gen, str(real), str(init), str(tau)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, HB200_P2P_MIN_TILES="1", HB200_TEST_SEMI_STOCH="80"))
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.stdout.count("OK") == nproc
+
+
 def test_driver_load_balancing():
     """do_fciqmc with load balancing over NCCL: imbalance check, policy, redistribute_particles, direct_annihilation."""
     n = _ngpu()

@@ -176,6 +176,9 @@ def main():
     ap.add_argument("--excips", type=float, default=4e6, help="--calc ccmc: excips per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--semi-stoch", type=int, default=0,
+                    help="side measurement: semi-stochastic projection on, deterministic space = the reference and its first "
+                         "N-1 single and double excitations (a connected space, added to the list with zero population)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -186,6 +189,8 @@ def main():
         sys.argv = [sys.argv[0], "--excips", str(args.excips), "--steps", str(args.steps), "--warmup", str(args.warmup)]
         bench_ccmc.main()
         return
+    if args.semi_stoch > 0:
+        args.no_e2e = True        # the end-to-end legs re-upload the host's list, which lacks the added deterministic states
     if args.scaling == "auto":
         args.scaling = "strong" if (world > 1 and args.walkers == 0.0) else "weak"
     if args.walkers == 0.0:
@@ -280,6 +285,43 @@ def main():
                     break
         tau = float(f"{trial:.3g}")
     upload()
+    ss_info = None
+    if args.semi_stoch > 0:
+        # semi-stochastic projection (src/semi_stoch.F90): a CISD-like deterministic space shared out by the hash-owner rule
+        from hande_b200 import semi_stoch as SS
+        from hande_b200.fciqmc import owner_of
+        t_ss = time.time()
+        occ = list(occ0)
+        virt = [o for o in range(1, s.nbasis + 1) if o not in occ]
+        space = [np.array(f0, dtype=np.uint64).reshape(-1)]
+
+        def excite(frm, to):
+            g = space[0].copy()
+            for o in frm:
+                g[(o - 1) >> 6] &= ~np.uint64(1 << ((o - 1) & 63))
+            for o in to:
+                g[(o - 1) >> 6] |= np.uint64(1 << ((o - 1) & 63))
+            return g
+        for i in occ:
+            for a in virt:
+                if (i - a) % 2 == 0 and len(space) < args.semi_stoch:
+                    space.append(excite((i,), (a,)))
+        for ii, i in enumerate(occ):
+            for j in occ[ii + 1:]:
+                for ia, a in enumerate(virt):
+                    for b in virt[ia + 1:]:
+                        if len(space) >= args.semi_stoch:
+                            break
+                        if (i % 2) + (j % 2) == (a % 2) + (b % 2):
+                            space.append(excite((i, j), (a, b)))
+        space = np.array(space, dtype=np.uint64).reshape(-1, s.W)
+        mine = space[[owner_of(x, s.nbasis, world, 1) == rank for x in space]] if world > 1 else space
+        dets, sizes = SS.gather_determ_space(comm, mine)
+        eng.set_determ_space(dets, sizes)
+        cp, _, _ = eng.determ_hamil()
+        ss_info = {"size": int(sizes.sum()), "sizes": [int(x) for x in sizes], "nnz_this_rank": int(cp[-1]),
+                   "set_space_s": time.time() - t_ss,
+                   "space": "reference + its first single and double excitations (spin-conserving), zero population"}
     setup_s = time.time() - t_setup
 
     def barrier():
@@ -450,6 +492,8 @@ def main():
             "clocks": clocks, "wall_s_timed": wall, "setup_s": setup_s,
             "errors": {"spawn_error": out["spawn_error"], "psip_error": out["psip_error"]},
         }
+        if ss_info is not None:
+            line["semi_stoch"] = ss_info
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:

@@ -2308,9 +2308,10 @@ int hb200_iterate(hb200_engine* e, int32_t ncycles, const hb200_iter_in* in, hb2
             if (stage_comm(e)) return 1;
             bound = e->sp_n;
         }
-        CK(cudaEventRecord(e->ev[2], st));
-        // determ_projection + deterministic_annihilation (src/fciqmc.f90:394, src/annihilation.f90:64-65)
+        // determ_projection + deterministic_annihilation (src/fciqmc.f90:394, src/annihilation.f90:64-65); its all-gather
+        // is ordered after the exchange's collective, and its time is reported with the exchange (comm_ms)
         if (e->ss.on && stage_determ(e, in, cycle, nullptr)) return 1;
+        CK(cudaEventRecord(e->ev[2], st));
         // the sort kernels split the list by its real length whatever their grid is, so the grid follows the length of
         // the previous cycle's list (a hint) rather than the loose upper bound
         if (stage_sort(e, std::min(bound, std::max<long long>(4096, 2 * e->last_spn + 1024)))) return 1;

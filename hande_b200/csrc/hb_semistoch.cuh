@@ -104,18 +104,29 @@ k_ss_hamil(Sys s, Params p, const uint64_t* __restrict__ all, int tot, const int
 // determ_proj_separate_annihil (src/semi_stoch.F90:1009-1094) + deterministic_annihilation (src/annihilation.f90:488-535):
 //   vector_j <- -tau (E_proj rho_j - S pop_control) v_j, then += (-tau H_ij) v_i for the rows i of column j in row order,
 // then the result is stochastically rounded to the amplitude resolution and added to the state's population.
+// One warp per column: 32 elements are loaded (coalesced) and multiplied at a time, then every lane adds the 32 products
+// in row order (shuffles), so the sum is the reference's sequential sum bit for bit while the loads run in parallel.
 template <int W>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_ss_project(Params p, const uint64_t* __restrict__ local, int nloc, const double* __restrict__ full, int self0,
              const long long* __restrict__ colptr, const int* __restrict__ row, const double* __restrict__ val,
              const double* __restrict__ rho, double* __restrict__ vec, const long long* __restrict__ idx,
              int64_t* __restrict__ pops) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (j >= nloc) return;
     const double pc = p.qn ? p.qn_pop_control : 1.0;
     double y = (-p.tau * (p.proj_energy_old * rho[j] - p.shift * pc)) * full[self0 + j];
     const double a = -1.0 * p.tau;
-    for (long long z = colptr[j]; z < colptr[j + 1]; ++z) y = y + a * val[z] * full[row[z]];
+    const long long z1 = colptr[j + 1];
+    for (long long z0 = colptr[j]; z0 < z1; z0 += 32) {
+        const long long z = z0 + lane;
+        double t = 0.0;
+        if (z < z1) t = a * __ldcs(val + z) * full[__ldcs(row + z)];
+        const int n = (int)min((long long)32, z1 - z0);
+        for (int k = 0; k < n; ++k) y = y + __shfl_sync(0xffffffffu, t, k);
+    }
+    if (lane != 0) return;
     vec[j] = y;
     double scaled = y * (double)p.real_factor;
     const int64_t sign = (scaled < 0.0) ? -1 : 1;
@@ -158,7 +169,7 @@ template <int W>
 static int ss_project(hb200_engine* e, const Params& p) {
     SemiStoch& S = e->ss;
     if (S.nloc == 0) return 0;
-    k_ss_project<W><<<(S.nloc + 127) / 128, 128, 0, e->stream>>>(p, S.d_local, S.nloc, S.d_full, p.iproc * S.maxsz, S.d_colptr,
+    k_ss_project<W><<<(unsigned)(((long long)S.nloc * 32 + 255) / 256), 256, 0, e->stream>>>(p, S.d_local, S.nloc, S.d_full, p.iproc * S.maxsz, S.d_colptr,
                                                                  S.d_row, S.d_val, S.d_rho, S.d_vec, S.d_idx, e->d_pops[e->cur]);
     CK(cudaGetLastError());
     return 0;

@@ -88,6 +88,40 @@ def create_high_pop_space(comm, states, pops, target_size):
     return determ_dets[mine].reshape(-1, W)
 
 
+def create_ci_determ_space(sys, occ0, ex_level, owner=None):
+    """create_ci_determ_space (src/semi_stoch.F90:1763-1823): every determinant within ex_level excitations of the
+    reference that has its spin polarisation and its symmetry (enumerate_determinants with ref_sym = sys%symmetry) - the
+    point-group product of the orbitals for read_in systems, the total momentum for the UEG.  owner(f) -> bool keeps
+    the determinants of this rank (add_det_to_determ_space with check_proc); None keeps all."""
+    from itertools import combinations
+    occ0 = [int(o) for o in occ0]
+    nb = int(sys.nbasis)
+    virt = [o for o in range(1, nb + 1) if o not in occ0]
+    ueg = hasattr(sys, "kvec")
+
+    def symmetry(occ):
+        if ueg:
+            return tuple(int(x) for x in np.asarray(sys.kvec)[list(occ)].sum(axis=0))
+        return int(sys.symmetry_orb_list(list(occ)))
+    ref_sym = symmetry(occ0)
+    out = []
+    for level in range(0, min(int(ex_level), len(occ0), len(virt)) + 1):
+        for holes in combinations(occ0, level):
+            nalpha_out = sum(o % 2 for o in holes)
+            kept = [o for o in occ0 if o not in holes]
+            for parts in combinations(virt, level):
+                if sum(o % 2 for o in parts) != nalpha_out:        # odd orbitals are alpha: ms conserved
+                    continue
+                occ = sorted(kept + list(parts))
+                if symmetry(occ) != ref_sym:
+                    continue
+                f = np.asarray(sys.encode(occ), dtype=np.uint64).reshape(-1)
+                if owner is None or owner(f):
+                    out.append(f)
+    W = (nb + 63) // 64
+    return np.asarray(out, dtype=np.uint64).reshape(-1, W)
+
+
 def gather_determ_space(comm, dets_this_proc):
     """init_semi_stoch_t (src/semi_stoch.F90:236-340): sort this rank's determinants in list order, all-gather sizes and
     determinants.  Returns (determ%dets [tot x W], determ%sizes)."""
@@ -99,11 +133,15 @@ def gather_determ_space(comm, dets_this_proc):
     return (np.concatenate(parts) if sizes.sum() else np.zeros((0, W), dtype=np.uint64)), sizes
 
 
-def init_semi_stoch(eng, comm, target_size):
-    """semi_stoch = { space = "high", size = target_size } at the current iteration: choose the space from the engine's
-    list and hand it to hb200_set_determ_space.  Returns (dets, sizes)."""
-    f, p, _ = eng.download_psips()
-    mine = create_high_pop_space(comm, f, p, target_size)
+def init_semi_stoch(eng, comm, target_size, space="high", sys=None, occ0=None, ci_ex_level=-1, owner=None):
+    """semi_stoch = { space = "high", size = target_size } or { space = "ci", ci_space = { ex_level = ... } } at the
+    current iteration: choose the space (from the engine's list, or by enumeration) and hand it to
+    hb200_set_determ_space.  Returns (dets, sizes)."""
+    if space == "ci":
+        mine = create_ci_determ_space(sys, occ0, ci_ex_level, owner)
+    else:
+        f, p, _ = eng.download_psips()
+        mine = create_high_pop_space(comm, f, p, target_size)
     dets, sizes = gather_determ_space(comm, mine)
     eng.set_determ_space(dets, sizes)
     return dets, sizes

@@ -250,3 +250,30 @@ def test_semi_stochastic_trajectory_matches_oracle_philox():
         assert a[0] == b[0] and a[5] == b[5] and a[6] == b[6], (a, b)
         for k in (1, 2, 3, 4):
             assert abs(a[k] - b[k]) <= 1e-10 * max(1.0, abs(b[k])), (k, a, b)
+
+
+def test_semi_stochastic_ci_space_trajectory_matches_oracle_philox():
+    """semi_stoch = { space = "ci", ci_space = { ex_level = 2 } } from the first iteration (the whole CISD space is added
+    to the one-determinant list with zero population, add_determ_dets_to_psip_list) through do_fciqmc on the GPU engine
+    against the oracle's own run under the same Philox stream, initiator approximation on."""
+    path, kw = system_path("h2o")
+    s = R.read_in(path, **kw)
+    qmc = QmcIn(tau=0.003, rng_seed=7, init_pop=100, mc_cycles=10, nreports=15, target_population=1500, real_amplitudes=True,
+                initiator=True, state_size=1 << 17, spawned_state_size=1 << 16, semi_stoch_space="ci", semi_stoch_ci_ex_level=2)
+    res = do_fciqmc(s, qmc)
+    o = Oracle()
+    o.read_fcidump(path, **kw)
+    o.set_qmc(rng_kind=1, literal_event_int32=0, tau=0.003, seed=7, D0_population=100, ncycles=10, nreport=15,
+              target_particles=1500, real_amplitudes=1, spawn_cutoff=0.01, initiator_approx=1, walker_length=1 << 17,
+              spawned_walker_length=1 << 16)
+    o.set_semi_stoch(space="ci", ci_ex_level=2)
+    o.init()
+    rows = o.run()
+    dets_o, sizes_o = o.determ_space()
+    assert len(res.rows) == len(rows) == 16 and not res.error
+    assert (res.determ_space[0] == dets_o).all() and len(dets_o) > 100
+    assert rows[1][5] >= len(dets_o)                  # every deterministic state is in the list from the first cycle on
+    for a, b in zip(res.rows, rows):
+        assert a[0] == b[0] and a[5] == b[5] and a[6] == b[6], (a, b)
+        for k in (1, 2, 3, 4):
+            assert abs(a[k] - b[k]) <= 1e-10 * max(1.0, abs(b[k])), (k, a, b)

@@ -123,3 +123,75 @@ def test_driver_starts_the_projection_at_the_requested_iteration(fcidump_path):
         assert a[0] == b[0] and a[5] == b[5] and a[6] == b[6]
         for k in (1, 2, 3, 4):
             assert abs(a[k] - b[k]) <= 1e-11 * max(1.0, abs(b[k])), (a, b)
+
+
+def test_ci_space_matches_oracle_and_reference_printout(fcidump_path):
+    """create_ci_determ_space (src/semi_stoch.F90:1763-1823): the host enumeration gives, rank by rank, the space the
+    oracle builds for the reference's ueg_n7_rs1_e1_SS_cisdtq run (358 determinants, 83..98 per rank as the reference
+    prints), and the oracle's space for a molecular point group (He2, doubles)"""
+    from hande_b200.fciqmc import owner_of
+    from hande_b200.ueg import UegSystem
+    from tests.conftest import load_golden
+    g = load_golden("ueg_ss_np4")
+    o = Oracle()
+    o.init_ueg(**g["ueg"])
+    o.set_ref_det(g["ref_det"])
+    o.set_qmc(**dict(g["qmc"], nreport=1))
+    o.set_semi_stoch(**g["semi_stoch"])
+    o.init()
+    o.run()                                   # start_iteration = 1: the space is built in the first cycle
+    dets_o, sizes_o = o.determ_space()
+    s = UegSystem(g["ueg"]["nel"], g["ueg"]["ms"], g["ueg"]["rs"], g["ueg"]["cutoff"])
+    parts = []
+    for r in range(4):
+        mine = SS.create_ci_determ_space(s, g["ref_det"], 4, owner=lambda f: owner_of(f, s.nbasis, 4, 1) == r)
+        parts.append(SS.gather_determ_space(_SingleProcess(), mine)[0])
+    assert [len(p) for p in parts] == list(sizes_o) and sum(len(p) for p in parts) == g["kat"]["determ_size"]
+    assert min(len(p) for p in parts) == g["kat"]["determ_min"] and max(len(p) for p in parts) == g["kat"]["determ_max"]
+    assert (np.concatenate(parts) == dets_o).all()
+    # molecular: D2h He2, all symmetry-allowed singles and doubles of the reference
+    path = fcidump_path("he2_avdz")
+    kw = dict(nel=4, ms=0, sym=HUGE, cas=(-1, -1))
+    o = Oracle()
+    o.read_fcidump(path, **kw)
+    o.set_qmc(tau=0.01, seed=7, D0_population=100, ncycles=2, nreport=1, target_particles=1e6, real_amplitudes=1)
+    o.set_semi_stoch(space="ci", ci_ex_level=2)
+    o.init()
+    o.run()
+    dets_o, sizes_o = o.determ_space()
+    sm = R.read_in(path, **kw)
+    mine = SS.create_ci_determ_space(sm, o.reference()["occ"], 2)
+    dets, sizes = SS.gather_determ_space(_SingleProcess(), mine)
+    assert len(dets) == len(dets_o) > 20 and (dets == dets_o).all()
+
+
+def test_driver_with_a_ci_space_on_the_polarised_ueg():
+    """do_fciqmc with semi_stoch = { space = "ci", ci_space = { ex_level = 4 } } on the reference's fully polarised
+    7-electron UEG (one rank, reference dSFMT stream) against the oracle's own run: every row"""
+    from hande_b200.ueg import UegSystem
+    from tests.conftest import load_golden
+    from tests.oracle_engine import make_engine_cls
+    g = load_golden("ueg_ss_np4")
+    u = g["ueg"]
+    o = Oracle()
+    o.init_ueg(**u)
+    o.set_ref_det(g["ref_det"])
+    q = dict(g["qmc"], nreport=15, nprocs=1)
+    o.set_qmc(**q)
+    o.set_semi_stoch(space="ci", ci_ex_level=4, start_iteration=21)
+    o.init()
+    rows_o = o.run()
+    s = UegSystem(u["nel"], u["ms"], u["rs"], u["cutoff"])
+    qmc = QmcIn(tau=q["tau"], rng_seed=q["seed"], init_pop=q["D0_population"], mc_cycles=q["ncycles"], nreports=15,
+                target_population=q["target_particles"], real_amplitudes=True, spawn_cutoff=0.01, excit_gen="no_renorm",
+                state_size=q["walker_length"], spawned_state_size=q["spawned_walker_length"], semi_stoch_space="ci",
+                semi_stoch_ci_ex_level=4, semi_stoch_start_iteration=21, reference_det=g["ref_det"])
+    res = do_fciqmc(s, qmc, engine_cls=make_engine_cls(None, None, rng_kind=0, ueg=(u["nel"], u["ms"], u["rs"], u["cutoff"]),
+                                                       ref_det=g["ref_det"]))
+    assert int(res.determ_space[1].sum()) == 358
+    rows = np.array(res.rows)
+    assert len(rows) == len(rows_o) == 16
+    for a, b in zip(rows, rows_o):
+        assert a[0] == b[0] and a[5] == b[5] and a[6] == b[6], (a, b)
+        for k in (1, 2, 3, 4):
+            assert abs(a[k] - b[k]) <= 1e-11 * max(1.0, abs(b[k])), (a, b)

@@ -119,12 +119,38 @@ k_ss_project(Params p, const uint64_t* __restrict__ local, int nloc, const doubl
     double y = (-p.tau * (p.proj_energy_old * rho[j] - p.shift * pc)) * full[self0 + j];
     const double a = -1.0 * p.tau;
     const long long z1 = colptr[j + 1];
-    for (long long z0 = colptr[j]; z0 < z1; z0 += 32) {
-        const long long z = z0 + lane;
-        double t = 0.0;
-        if (z < z1) t = a * __ldcs(val + z) * full[__ldcs(row + z)];
-        const int n = (int)min((long long)32, z1 - z0);
-        for (int k = 0; k < n; ++k) y = y + __shfl_sync(0xffffffffu, t, k);
+    long long z0 = colptr[j];
+    // 128 rows per step: the four loads of a lane are in flight together, and the products of the next step are fetched
+    // while the current 128 are added (the additions are one dependent chain, the loads are not)
+    constexpr int C = 4;
+    double tn[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const long long z = z0 + 32 * c + lane;
+        tn[c] = (z < z1) ? a * __ldcs(val + z) * full[__ldcs(row + z)] : 0.0;
+    }
+    for (; z0 < z1; z0 += 32 * C) {
+        double t[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) t[c] = tn[c];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const long long z = z0 + 32 * (C + c) + lane;
+            tn[c] = (z < z1) ? a * __ldcs(val + z) * full[__ldcs(row + z)] : 0.0;
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const long long left = z1 - (z0 + 32 * c);
+            if (left >= 32) {
+                double u[32];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) u[k] = __shfl_sync(0xffffffffu, t[c], k);
+#pragma unroll
+                for (int k = 0; k < 32; ++k) y = y + u[k];
+            } else if (left > 0) {
+                for (int k = 0; k < (int)left; ++k) y = y + __shfl_sync(0xffffffffu, t[c], k);
+            }
+        }
     }
     if (lane != 0) return;
     vec[j] = y;

@@ -1822,6 +1822,7 @@ int hb200_ccmc_spawn(hb200_engine* e, const hb200_iter_in* in, uint32_t cycle, i
     if (!e->have_sys) FAIL("ccmc_spawn: system not set");
     if (uses_heat_bath_tables(e) && !e->have_hb) FAIL("ccmc_spawn: heat-bath tables not built");
     if (e->par.cheby_weight != 1.0) FAIL("ccmc_spawn: the wall-Chebyshev propagator is only implemented for FCIQMC");
+    if (e->ss.on) FAIL("ccmc_spawn: the semi-stochastic projection is an FCIQMC feature (clear the deterministic space)");
     if (e->cfg.excit_gen == HB200_EXCIT_GEN_POWER_PITZER_ORDERN && !e->have_ppn) FAIL("ccmc_spawn: power_pitzer_orderN tables not built");
     if (e->cfg.excit_gen == HB200_EXCIT_GEN_POWER_PITZER && !e->have_pp) FAIL("ccmc_spawn: power_pitzer tables not built");
     if (e->par.nprocs > 1 && !e->comm) FAIL("ccmc_spawn: nprocs > 1 but hb200_comm_init was not called");
@@ -2164,6 +2165,9 @@ int hb200_slot_populations(hb200_engine* e, double* slot_pop, int32_t n) {
 // redistribute_load_balancing_dets, src/qmc_common.F90:1332-1390).  nsent: population that left (real units).
 int hb200_redistribute_particles(hb200_engine* e, double* nsent) {
     CK(cudaSetDevice(e->cfg.device));
+    // redistribute_semi_stoch_t (src/semi_stoch.F90:1725-1761) is not restated: switch the projection off
+    // (hb200_set_determ_space with all sizes zero), redistribute, then set the space again from determ%dets
+    if (e->ss.on) FAIL("redistribute_particles: a deterministic space is set (clear it first, set it again afterwards)");
     Params p = e->par;
     p.ccmc_shift = 0; p.ccmc_freq = 0;
     cudaStream_t st = e->stream;

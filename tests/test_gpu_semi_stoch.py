@@ -150,3 +150,30 @@ def test_semi_stochastic_ranks_on_one_device(name, gen, real, init, tau, world):
         assert sum(st["ndeath"] for st in stats) == ro["ndeath"]
     for e in engs:
         e.close()
+
+
+def test_determ_space_error_paths():
+    """hb200_set_determ_space refuses a rank's determinants out of list order or repeated; hb200_upload_psips refuses a
+    new list that lacks a deterministic state; load-balancing redistribution refuses to run with a space set"""
+    from hande_b200.engine import EngineError
+    s, o, eng, ref = make_pair("h2o", excit_gen="renorm", tau=0.003, real=True)
+    rf = 2**31
+    f0 = ref["f0"].reshape(1, -1)
+    eng.upload_psips(f0, [80 * rf], [0.0])
+    eng.iterate(20, 0.003, 0.0, 0.0, 1)
+    f, p, d = eng.download_psips()
+    dets, sizes = SS.gather_determ_space(_SingleProcess(), SS.create_high_pop_space(_SingleProcess(), f, p, 10))
+    with pytest.raises(EngineError):
+        eng.set_determ_space(dets[::-1].copy(), sizes)                      # descending
+    with pytest.raises(EngineError):
+        eng.set_determ_space(np.concatenate([dets[:9], dets[8:9]]), sizes)  # repeated
+    eng.set_determ_space(dets, sizes)
+    with pytest.raises(EngineError):
+        eng.upload_psips(f0, [80 * rf], [0.0])                              # nine deterministic states missing
+    with pytest.raises(EngineError):
+        eng.redistribute_particles()
+    # the engine is still usable: a complete list is accepted and propagates
+    eng.upload_psips(f, p, d)
+    out = eng.iterate(2, 0.003, 0.0, 0.0, 50)
+    assert out["spawn_error"] == 0 and out["nstates"] >= 10
+    eng.close()

@@ -680,11 +680,9 @@ int orc_rank_spawn(void* h, int rank, uint32_t cycle_id, double tau, double shif
     RankState& r = o->ranks[rank];
     r.proj_energy = 0.0; r.D0_population = 0.0;
     o->spawn_death_rank(r, cycle_id);
-    // one rank per process: the deterministic projection needs every rank's amplitudes, so only nprocs == 1 here
-    if (o->determ.doing) {
-        if (o->in.nprocs != 1) throw std::runtime_error("orc_rank_spawn: semi-stochastic projection with one rank per process");
-        o->determ_proj_separate();
-    }
+    // one rank per process: with nprocs > 1 the deterministic projection needs every rank's amplitudes - the caller
+    // gathers them and calls orc_rank_determ_project before orc_rank_annihilate
+    if (o->determ.doing && o->in.nprocs == 1) o->determ_proj_separate();
     out[0] = r.proj_energy; out[1] = r.D0_population; out[2] = (double)r.nspawn_events; out[3] = (double)r.ndeath;
     out[4] = (double)r.nattempts;
     return 0;
@@ -786,5 +784,19 @@ void orc_get_determ_vector(void* h, int rank, double* vec, uint8_t* flags) {
     RankState& R = o->ranks[rank];
     if (vec) std::copy(R.dvector.begin(), R.dvector.end(), vec);
     if (flags) std::copy(R.dflag.begin(), R.dflag.end(), flags);
+}
+// one rank per process (tests/oracle_engine.py): this rank's determ%vector as set_determ_info left it, and the
+// projection of this rank given determ%full_vector gathered by the caller (tot_size doubles, rank by rank)
+void orc_rank_get_dvector(void* h, int rank, double* out) {
+    Oracle* o = (Oracle*)h;
+    std::copy(o->ranks[rank].dvector.begin(), o->ranks[rank].dvector.end(), out);
+}
+int orc_rank_determ_project(void* h, int rank, const double* full) {
+    ORC_TRY
+    Oracle* o = (Oracle*)h;
+    for (size_t i = 0; i < o->determ.full_vector.size(); ++i) o->determ.full_vector[i] = full[i];
+    o->determ_proj_rank(o->ranks[rank]);
+    return 0;
+    ORC_CATCH(-1)
 }
 }

@@ -1198,17 +1198,19 @@ struct Oracle {
         size_t k = 0;
         for (auto& R : ranks)
             for (double v : R.dvector) determ.full_vector[k++] = v;   // mpi_allgatherv
+        for (auto& R : ranks) determ_proj_rank(R);
+    }
+    // one rank's part, determ%full_vector already gathered
+    void determ_proj_rank(RankState& R) {
         const double a = -1.0 * tau;
-        for (auto& R : ranks) {
-            for (size_t j = 0; j < R.dvector.size(); ++j)
-                R.dvector[j] = (-tau * (est.proj_energy_old * R.drho_minus_qn[j] - shift * qn_pop_control)) * R.dvector[j];
-            // csrpgemv(.true., .false., -tau, hamil, full_vector, vector) (lib/local/csr.f90:148-204)
-            for (int irow = 0; irow < determ.tot_size; ++irow)
-                for (int iz = R.drow_ptr[(size_t)irow]; iz < R.drow_ptr[(size_t)irow + 1]; ++iz) {
-                    const int icol = R.dcol_ind[(size_t)iz];
-                    R.dvector[(size_t)icol] = R.dvector[(size_t)icol] + a * R.dmat[(size_t)iz] * determ.full_vector[(size_t)irow];
-                }
-        }
+        for (size_t j = 0; j < R.dvector.size(); ++j)
+            R.dvector[j] = (-tau * (est.proj_energy_old * R.drho_minus_qn[j] - shift * qn_pop_control)) * R.dvector[j];
+        // csrpgemv(.true., .false., -tau, hamil, full_vector, vector) (lib/local/csr.f90:148-204)
+        for (int irow = 0; irow < determ.tot_size; ++irow)
+            for (int iz = R.drow_ptr[(size_t)irow]; iz < R.drow_ptr[(size_t)irow + 1]; ++iz) {
+                const int icol = R.dcol_ind[(size_t)iz];
+                R.dvector[(size_t)icol] = R.dvector[(size_t)icol] + a * R.dmat[(size_t)iz] * determ.full_vector[(size_t)irow];
+            }
     }
     // determ_proj_combined_annihil (src/semi_stoch.F90:897-975) + create_spawned_particle_determ (:1096-1146); one rank only
     // (the np > 1 form also needs compress_determ_repeats, src/spawn_data.F90:1103-1170, which is not restated)

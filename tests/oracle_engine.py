@@ -75,9 +75,13 @@ def make_engine_cls(fcidump_path, sys_kw, rng_kind=0, ueg=None, ref_det=None, qu
             return self.o.get_psips(self.rank)
 
         def set_determ_space(self, dets, sizes):
-            """init_semi_stoch_t with the driver's space (one rank per process: world == 1 only)"""
-            assert self.world == 1
+            """init_semi_stoch_t with the driver's space; with one rank per process the amplitudes of all ranks are
+            all-gathered between the spawning loop and the annihilation (iterate)"""
             self.o.init_semi_stoch(dets, sizes)
+            self.determ_sizes = np.asarray(sizes, dtype=np.int64)
+            L = self.o.L
+            L.orc_rank_get_dvector.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+            L.orc_rank_determ_project.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
 
         @property
         def nstates(self):
@@ -97,6 +101,15 @@ def make_engine_cls(fcidump_path, sys_kw, rng_kind=0, ueg=None, ref_det=None, qu
                     buf = np.zeros((n, self.E), dtype=np.int64)
                     L.orc_rank_get_send(o.h, self.rank, d, buf.ctypes.data_as(C.c_void_p))
                     blocks.append(buf)
+                if self.world > 1 and getattr(self, "determ_sizes", None) is not None and self.determ_sizes.sum() > 0:
+                    # determ_proj_separate_annihil: mpi_allgatherv of determ%vector, then this rank's projection
+                    mine = np.zeros(int(self.determ_sizes[self.rank]))
+                    if len(mine):
+                        L.orc_rank_get_dvector(o.h, self.rank, mine.ctypes.data_as(C.c_void_p))
+                    parts = [None] * self.world
+                    self.dist.all_gather_object(parts, mine)
+                    full = np.ascontiguousarray(np.concatenate(parts))
+                    assert L.orc_rank_determ_project(o.h, self.rank, full.ctypes.data_as(C.c_void_p)) == 0
                 gathered = [None] * self.world
                 if self.world > 1:
                     self.dist.all_gather_object(gathered, blocks)        # comm_spawn_t: personalised all-to-all

@@ -2165,8 +2165,10 @@ int hb200_slot_populations(hb200_engine* e, double* slot_pop, int32_t n) {
 // redistribute_load_balancing_dets, src/qmc_common.F90:1332-1390).  nsent: population that left (real units).
 int hb200_redistribute_particles(hb200_engine* e, double* nsent) {
     CK(cudaSetDevice(e->cfg.device));
-    // redistribute_semi_stoch_t (src/semi_stoch.F90:1725-1761) is not restated: switch the projection off
-    // (hb200_set_determ_space with all sizes zero), redistribute, then set the space again from determ%dets
+    // redistribute_load_balancing_dets annihilates the moved determinants without the deterministic flags and
+    // redistribute_semi_stoch_t (src/qmc_common.F90:597-650) then rebuilds the space under the new proc_map: the host
+    // switches the projection off (hb200_set_determ_space with all sizes zero), redistributes, and sets the space again
+    // from determ%dets (hande_b200/fciqmc.py does)
     if (e->ss.on) FAIL("redistribute_particles: a deterministic space is set (clear it first, set it again afterwards)");
     Params p = e->par;
     p.ccmc_shift = 0; p.ccmc_freq = 0;

@@ -380,8 +380,8 @@ def do_fciqmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, 
     if qmc.semi_stoch_space not in ("none", "high", "ci"):
         raise ValueError("semi_stoch: space = 'high' or 'ci' are chosen by this driver (a space read from a file: "
                          "Engine.set_determ_space)")
-    if ss_on and (cheb is not None or qmc.load_balancing):
-        raise ValueError("semi_stoch with the wall-Chebyshev propagator or load balancing is not supported")
+    if ss_on and cheb is not None:
+        raise ValueError("semi_stoch with the wall-Chebyshev propagator is not supported")
     semi_stoch_iter = max(qmc.semi_stoch_start_iteration, mc_cycles_done + 1)     # src/fciqmc.f90:228
     res.determ_space = None
     lb_needed, lb_attempts = False, 0
@@ -401,7 +401,17 @@ def do_fciqmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, 
                 proc_map = new_map
                 lb_attempts += 1
                 eng.set_proc_map(proc_map)
+                if ss_done:
+                    # redistribute_load_balancing_dets (src/qmc_common.F90:1332-1390): the moved determinants are
+                    # annihilated without the deterministic flags, then redistribute_semi_stoch_t (:597-650) rebuilds the
+                    # space from determ%dets under the new proc_map (recreate_determ_space)
+                    all_dets = res.determ_space[0]
+                    eng.set_determ_space(all_dets[:0], np.zeros(nprocs, dtype=np.int32))
                 eng.redistribute(0x80000000 | first_cycle)
+                if ss_done:
+                    mine = all_dets[[owner_of(f, sys.nbasis, nprocs, qmc.nslots, proc_map) == iproc for f in all_dets]]
+                    res.determ_space = _ss.gather_determ_space(comm, mine.reshape(-1, all_dets.shape[1]))
+                    eng.set_determ_space(*res.determ_space)
                 res.load_balancing_log.append((first_cycle, list(proc_map)))
             lb_needed = False
         if cheb is None:

@@ -946,6 +946,12 @@ struct Oracle {
     // then direct_annihilation of the moved determinants.  The rounding streams of this extra annihilation are keyed
     // by cycle_id (the engine and the tests pass the cycle with the top bit set).
     void redistribute_fciqmc(uint32_t cycle_id) {
+        // redistribute_load_balancing_dets (src/qmc_common.F90:1332-1390): the moved determinants are annihilated WITHOUT
+        // the deterministic flags (direct_annihilation has no determ argument there), then redistribute_semi_stoch_t
+        // (:597-650) rebuilds the semi-stochastic objects from determ%dets under the new proc_map
+        const bool ss = determ.doing;
+        const std::vector<Det> all_dets = determ.dets;
+        determ.doing = false;
         const int64_t block_size = in.spawned_walker_length / in.nprocs;
         for (auto& r : ranks) {
             for (auto& b : r.send) b.clear();
@@ -965,6 +971,14 @@ struct Oracle {
         for (auto& r : ranks) {
             r.rng->set_cycle(cycle_id);
             annihilate_rank(r);
+        }
+        if (ss) {   // recreate_determ_space (src/semi_stoch.F90:1725-1761): every rank keeps the determinants it now owns
+            given_determ.assign((size_t)in.nprocs, {});
+            for (const Det& f : all_dets) given_determ[(size_t)owner(f)].push_back(f);
+            const int keep = in.ss_space;
+            in.ss_space = 3;
+            init_semi_stoch();
+            in.ss_space = keep;
         }
     }
 

@@ -201,6 +201,9 @@ def main_lb():
     qmc = QmcIn(tau=0.003, init_pop=200, mc_cycles=5, nreports=12, target_population=1e9, real_amplitudes=True,
                 excit_gen="renorm", nslots=20, load_balancing=True, load_balancing_pop=500, percent_imbal=0.001,
                 max_load_attempts=2, state_size=1 << 17, spawned_state_size=1 << 16, initial_shift=0.3)
+    nss = int(os.environ.get("HB200_TEST_SEMI_STOCH", "0"))
+    if nss:     # the projection is switched on before the first load-balancing step, which then has to move the space too
+        qmc.semi_stoch_space, qmc.semi_stoch_size, qmc.semi_stoch_start_iteration = "high", nss, 8
     res = do_fciqmc(s, qmc, comm=comm, device=local, keep_engine=True)
     assert not res.error
     assert 1 <= len(res.load_balancing_log) <= 2, res.load_balancing_log
@@ -210,6 +213,16 @@ def main_lb():
     assert all(owner_of(x, s.nbasis, world, 20, proc_map=pmap) == rank for x in f)
     tot = comm.allreduce_sum(np.array([float(np.abs(pops).sum()) / 2**31, float(len(f))]))
     assert abs(tot[0] - res.rows[-1][4]) < 1e-9 * tot[0] and int(tot[1]) == res.rows[-1][5]
+    if nss:
+        dets, sizes = res.determ_space
+        assert 10 < int(sizes.sum()) <= nss                      # min(target, states in the lists at iteration 8)
+        assert res.load_balancing_log[-1][0] > 8                 # a load-balancing step ran with the projection on
+        off = int(sizes[:rank].sum())
+        mine = dets[off:off + int(sizes[rank])]
+        assert all(owner_of(x, s.nbasis, world, 20, proc_map=pmap) == rank for x in mine)   # the space followed the slots
+        keys = {tuple(x) for x in f.tolist()}
+        assert all(tuple(x) in keys for x in mine.tolist())                                  # and is in the list
+        assert len(res.engine.determ_vector(1)) == int(sizes[rank])
     print(f"rank {rank}: OK {len(f)} states after {len(res.load_balancing_log)} load-balancing steps", flush=True)
     res.engine.close()
     dist.destroy_process_group()

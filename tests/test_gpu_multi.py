@@ -65,6 +65,10 @@ def test_driver_load_balancing():
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert res.stdout.count("OK") == nproc
+    # the same run with the semi-stochastic projection on: redistribute_semi_stoch_t in the driver
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, HB200_TEST_SEMI_STOCH="60"))
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.stdout.count("OK") == nproc
 
 
 @pytest.mark.parametrize("name,gen,real,exl,tau,full_nc", [("ne_vdz", "renorm", 0, 2, 0.01, 0), ("s12", "renorm", 1, 3, 0.001, 0),

@@ -177,3 +177,67 @@ def test_determ_space_error_paths():
     out = eng.iterate(2, 0.003, 0.0, 0.0, 50)
     assert out["spawn_error"] == 0 and out["nstates"] >= 10
     eng.close()
+
+
+def test_load_balancing_with_a_deterministic_space():
+    """redistribute_load_balancing_dets + redistribute_semi_stoch_t (src/qmc_common.F90:597-650,1332-1390): with the
+    projection on, slots change owner - the moved determinants are annihilated without the deterministic flags, then the
+    space is rebuilt from determ%dets under the new proc_map (recreate_determ_space) - and the projection carries on;
+    three ranks on one device against the oracle's emulated ranks."""
+    from hande_b200.fciqmc import owner_of
+    name, gen, real, init, tau, world, nslots = "h2o", "renorm", True, False, 0.003, 3, 20
+    s, o, engs = _setup(name, gen, real, init, tau, world, 4000, nslots=nslots)
+    shift, pe_old = -0.05, -0.1
+
+    def cycle_all(cycle):
+        o.iterate(1, cycle, tau, shift, pe_old)
+        for e in engs:
+            e.spawn_death(tau, shift, pe_old, cycle)
+        full = np.concatenate([e.determ_vector(0) for e in engs])
+        for e in engs:
+            e.determ_project(tau, shift, pe_old, cycle, full)
+        _exchange_and_annihilate(s, o, engs, cycle)
+
+    def compare(tag):
+        for d, e in enumerate(engs):
+            fo, po, do_ = o.get_psips(d)
+            fg, pg, dg = e.download_psips()
+            assert len(fg) == len(fo), (tag, d, len(fg), len(fo))
+            assert (fg == fo).all() and (pg == po).all() and (dg == do_).all(), (tag, d)
+
+    o.set_semi_stoch(space="high", size=120)
+    o.init_semi_stoch()
+    dets, sizes = o.determ_space()
+    for e in engs:
+        e.set_determ_space(dets, sizes)
+    for cycle in (1, 2):
+        cycle_all(cycle)
+    compare("before")
+    # a new proc_map: a third of the slots change owner
+    pmap = np.arange(world * nslots) % world
+    rng = np.random.default_rng(3)
+    moved = rng.choice(world * nslots, size=world * nslots // 3, replace=False)
+    pmap[moved] = (pmap[moved] + 1) % world
+    o.set_proc_map(pmap)
+    lb_cycle = 0x80000000 | 3
+    o.redistribute(lb_cycle)
+    for e in engs:
+        e.set_determ_space(dets[:0], np.zeros(world, dtype=np.int32))
+        e.set_proc_map(pmap)
+        e.redistribute_particles()
+    _exchange_and_annihilate(s, o, engs, lb_cycle)
+    own = np.array([owner_of(f, s.nbasis, world, nslots, proc_map=pmap) for f in dets])
+    from hande_b200.synthetic import sort_dets
+    new_dets = np.concatenate([sort_dets(dets[own == r]) for r in range(world)])   # each rank's part in list order
+    new_sizes = np.array([(own == r).sum() for r in range(world)], dtype=np.int32)
+    dets_o, sizes_o = o.determ_space()
+    assert (new_sizes == sizes_o).all() and (new_dets == dets_o).all() and (new_sizes != sizes).any()
+    for e in engs:
+        e.set_determ_space(new_dets, new_sizes)
+    compare("redistributed")
+    for cycle in (3, 4, 5):
+        cycle_all(cycle)
+    compare("after")
+    for d, e in enumerate(engs):
+        assert (e.determ_vector(1) == o.determ_vector(d)[0]).all()
+        e.close()

@@ -1369,6 +1369,7 @@ int hb200_upload_psips_commit(hb200_engine* e) {
     CK(cudaStreamSynchronize(st));
     e->nstates = n;
     e->nparticles_enc = s;
+    if (e->ss.on && ss_relocate(e, e->cur, nullptr, true)) return 1;   // as hb200_upload_psips: the space follows the new list
     return 0;
 }
 

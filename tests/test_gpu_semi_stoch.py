@@ -176,6 +176,17 @@ def test_determ_space_error_paths():
     eng.upload_psips(f, p, d)
     out = eng.iterate(2, 0.003, 0.0, 0.0, 50)
     assert out["spawn_error"] == 0 and out["nstates"] >= 10
+    # the asynchronous upload relocates the deterministic states too (here: the list shifted by one new state in front)
+    f2, p2, d2 = eng.download_psips()
+    import torch
+    hs = torch.from_numpy(f2.view(np.int64).copy()).pin_memory()
+    hp = torch.from_numpy(p2.copy()).pin_memory()
+    hd = torch.from_numpy(d2.copy()).pin_memory()
+    eng.upload_psips_begin_ptr(hs.data_ptr(), hp.data_ptr(), hd.data_ptr(), len(p2))
+    eng.upload_psips_commit()
+    v0 = eng.determ_vector(0)
+    keys = {tuple(x): k for k, x in enumerate(f2.tolist())}
+    assert (v0 == np.array([p2[keys[tuple(x)]] / rf for x in dets.tolist()])).all()
     eng.close()
 
 

@@ -73,7 +73,9 @@ class QmcIn:
     # semi_stoch_in_t (src/qmc_data.f90:305-338): space = "high" (the `size` most populated determinants) with the
     # reference's default projection mode (separate annihilation); start at start_iteration, or shift_start_iteration
     # iterations after the shift starts to vary
-    semi_stoch_space: str = "none"    # "high" | "ci" (ci_space = { ex_level = semi_stoch_ci_ex_level })
+    semi_stoch_space: str = "none"    # "high" | "ci" (ci_space = { ex_level = semi_stoch_ci_ex_level }) | "read"
+    semi_stoch_read_file: str = None  # space = "read": the stored determ%dets (.npy; the reference's SEMI.STOCH.<id>.H5)
+    semi_stoch_write_file: str = None # write_determ_space: rank 0 stores determ%dets once the space is built
     semi_stoch_size: int = 0
     semi_stoch_ci_ex_level: int = -1
     semi_stoch_start_iteration: int = 1
@@ -375,11 +377,11 @@ def do_fciqmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, 
         out.write(format_row(0, shift, proj_energy, D0, ntot_old, tot_nstates, 0, 0.0, 0.0, comment=True) + "\n")
     mc_cycles_done = 0
     ss_on = (qmc.semi_stoch_space == "high" and qmc.semi_stoch_size > 0) or \
-        (qmc.semi_stoch_space == "ci" and qmc.semi_stoch_ci_ex_level >= 0)
+        (qmc.semi_stoch_space == "ci" and qmc.semi_stoch_ci_ex_level >= 0) or \
+        (qmc.semi_stoch_space == "read" and qmc.semi_stoch_read_file is not None)
     ss_done = False
-    if qmc.semi_stoch_space not in ("none", "high", "ci"):
-        raise ValueError("semi_stoch: space = 'high' or 'ci' are chosen by this driver (a space read from a file: "
-                         "Engine.set_determ_space)")
+    if qmc.semi_stoch_space not in ("none", "high", "ci", "read"):
+        raise ValueError("semi_stoch: space must be 'high', 'ci' or 'read'")
     if ss_on and cheb is not None:
         raise ValueError("semi_stoch with the wall-Chebyshev propagator is not supported")
     semi_stoch_iter = max(qmc.semi_stoch_start_iteration, mc_cycles_done + 1)     # src/fciqmc.f90:228
@@ -425,8 +427,10 @@ def do_fciqmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, 
                     cyc0, ncyc = cyc0 + k, ncyc - k
                 res.determ_space = _ss.init_semi_stoch(
                     eng, comm, qmc.semi_stoch_size, space=qmc.semi_stoch_space, sys=sys, occ0=occ0,
-                    ci_ex_level=qmc.semi_stoch_ci_ex_level,
+                    ci_ex_level=qmc.semi_stoch_ci_ex_level, path=qmc.semi_stoch_read_file,
                     owner=lambda f: owner_of(f, sys.nbasis, nprocs, qmc.nslots, proc_map) == iproc)
+                if qmc.semi_stoch_write_file and iproc == 0:
+                    _ss.write_determ_to_file(qmc.semi_stoch_write_file, res.determ_space[0])
                 ss_done = True
             o = _merge_out(o, eng.iterate(ncyc, tau, shift, pe_old, cyc0))
         else:

@@ -133,12 +133,32 @@ def gather_determ_space(comm, dets_this_proc):
     return (np.concatenate(parts) if sizes.sum() else np.zeros((0, W), dtype=np.uint64)), sizes
 
 
-def init_semi_stoch(eng, comm, target_size, space="high", sys=None, occ0=None, ci_ex_level=-1, owner=None):
-    """semi_stoch = { space = "high", size = target_size } or { space = "ci", ci_space = { ex_level = ... } } at the
-    current iteration: choose the space (from the engine's list, or by enumeration) and hand it to
+def read_determ_from_file(path, owner=None):
+    """read_determ_from_file (src/semi_stoch.F90:1450-1645) for this rank: the determinants of a stored space that the
+    rank owns (add_det_to_determ_space with check_proc).  The reference keeps the space in SEMI.STOCH.<id>.H5
+    (dataset `dets`); without HDF5 here the same array is a .npy file (uint64, one row per determinant)."""
+    dets = np.ascontiguousarray(np.load(path), dtype=np.uint64)
+    if dets.ndim == 1:
+        dets = dets.reshape(-1, 1)
+    if owner is None:
+        return dets
+    keep = [bool(owner(f)) for f in dets]
+    return dets[keep].reshape(-1, dets.shape[1])
+
+
+def write_determ_to_file(path, dets):
+    """write_determ_to_file (src/semi_stoch.F90:1647-1723): determ%dets, all ranks' determinants, written by the parent"""
+    np.save(path, np.ascontiguousarray(dets, dtype=np.uint64))
+
+
+def init_semi_stoch(eng, comm, target_size, space="high", sys=None, occ0=None, ci_ex_level=-1, owner=None, path=None):
+    """semi_stoch = { space = "high", size = target_size }, { space = "ci", ci_space = { ex_level = ... } } or
+    { space = "read" } at the current iteration: choose the space (from the engine's list, or by enumeration) and hand it to
     hb200_set_determ_space.  Returns (dets, sizes)."""
     if space == "ci":
         mine = create_ci_determ_space(sys, occ0, ci_ex_level, owner)
+    elif space == "read":
+        mine = read_determ_from_file(path, owner)
     else:
         f, p, _ = eng.download_psips()
         mine = create_high_pop_space(comm, f, p, target_size)

@@ -195,3 +195,35 @@ def test_driver_with_a_ci_space_on_the_polarised_ueg():
         assert a[0] == b[0] and a[5] == b[5] and a[6] == b[6], (a, b)
         for k in (1, 2, 3, 4):
             assert abs(a[k] - b[k]) <= 1e-11 * max(1.0, abs(b[k])), (a, b)
+
+
+def test_driver_writes_and_reads_a_determ_space(fcidump_path, tmp_path):
+    """write_determ_to_file / read_determ_from_file (src/semi_stoch.F90:1450-1723) through do_fciqmc: a run stores the
+    space it picked; a second run that reads it from the first iteration on propagates exactly like the oracle handed
+    the same determinants (init_semi_stoch_t with read_determ_space)"""
+    from tests.oracle_engine import make_engine_cls
+    path = fcidump_path("he2_avdz")
+    kw = dict(nel=4, ms=0, sym=HUGE, cas=(-1, -1))
+    s = R.read_in(path, **kw)
+    store = str(tmp_path / "SEMI.STOCH.0.npy")
+    base = dict(tau=0.01, rng_seed=7, init_pop=200, mc_cycles=10, nreports=6, target_population=400, real_amplitudes=True,
+                spawn_cutoff=0.01, state_size=4000, spawned_state_size=2000)
+    res = do_fciqmc(s, QmcIn(semi_stoch_space="high", semi_stoch_size=15, semi_stoch_start_iteration=31,
+                             semi_stoch_write_file=store, **base), engine_cls=make_engine_cls(path, kw, rng_kind=0))
+    dets = res.determ_space[0]
+    assert len(dets) == 15 and (np.load(store) == dets).all()
+    res2 = do_fciqmc(s, QmcIn(semi_stoch_space="read", semi_stoch_read_file=store, **base),
+                     engine_cls=make_engine_cls(path, kw, rng_kind=0))
+    assert (res2.determ_space[0] == dets).all()
+    o = Oracle()
+    o.read_fcidump(path, **kw)
+    o.set_qmc(tau=0.01, seed=7, D0_population=200, ncycles=10, nreport=6, target_particles=400, real_amplitudes=1,
+              spawn_cutoff=0.01, walker_length=4000, spawned_walker_length=2000)
+    o.init()
+    o.init_semi_stoch(dets, [15])        # before the first cycle, as start_iteration = 1 does (the oracle's iteration-0
+    rows_o = o.run()                     # row therefore already counts the 15 states; the driver's counts the reference)
+    assert len(res2.rows) == len(rows_o) == 7
+    for a, b in zip(np.array(res2.rows), rows_o):
+        assert a[0] == b[0] and (a[5] == b[5] or a[0] == 0) and a[6] == b[6], (a, b)
+        for k in (1, 2, 3, 4):
+            assert abs(a[k] - b[k]) <= 1e-11 * max(1.0, abs(b[k])), (a, b)

@@ -384,7 +384,10 @@ def do_fciqmc(sys, qmc: QmcIn, comm=None, device=0, io=None, engine_cls=Engine, 
         raise ValueError("semi_stoch: space must be 'high', 'ci' or 'read'")
     if ss_on and cheb is not None:
         raise ValueError("semi_stoch with the wall-Chebyshev propagator is not supported")
-    semi_stoch_iter = max(qmc.semi_stoch_start_iteration, mc_cycles_done + 1)     # src/fciqmc.f90:228
+    # shift_start_iteration overrides start_iteration: start_iter = huge(0) until the shift comes on
+    # (read_semi_stoch_in, src/lua_hande_calc.f90:1712-1715)
+    ss_start = qmc.semi_stoch_start_iteration if qmc.semi_stoch_shift_start_iteration == -1 else 2**31 - 1
+    semi_stoch_iter = max(ss_start, mc_cycles_done + 1)                            # src/fciqmc.f90:228
     res.determ_space = None
     lb_needed, lb_attempts = False, 0
     proc_map = [i % nprocs for i in range(nprocs * qmc.nslots)]      # src/load_balancing.F90:170

@@ -376,6 +376,8 @@ class Oracle:
                        separate_annihilation=True, pop_real_bits=31):
         """semi_stoch = { space = "high" | "ci", size, start_iteration, ... } (before init); pop_real_bits = 11 restates
         real_amplitude_force_32"""
+        if shift_start_iteration != -1:          # read_semi_stoch_in (src/lua_hande_calc.f90:1712-1715)
+            start_iteration = 2**31 - 1
         self.L.orc_set_semi_stoch.argtypes = [C.c_void_p] + [C.c_int] * 7
         self.L.orc_set_semi_stoch(self.h, {"none": 0, "high": 1, "ci": 2}[space], int(size), int(start_iteration),
                                   int(shift_start_iteration), int(ci_ex_level), int(separate_annihilation), int(pop_real_bits))

@@ -227,3 +227,31 @@ def test_driver_writes_and_reads_a_determ_space(fcidump_path, tmp_path):
         assert a[0] == b[0] and (a[5] == b[5] or a[0] == 0) and a[6] == b[6], (a, b)
         for k in (1, 2, 3, 4):
             assert abs(a[k] - b[k]) <= 1e-11 * max(1.0, abs(b[k])), (a, b)
+
+
+def test_driver_starts_the_projection_relative_to_the_shift(fcidump_path):
+    """semi_stoch = { shift_start_iteration = 12 }: start_iteration becomes huge(0) until the report loop in which the
+    shift starts to vary fixes it to that iteration + 12 + 1 (src/lua_hande_calc.f90:1712-1715,
+    src/qmc_common.F90:1200-1204); driver against the oracle's own run, every row"""
+    from tests.oracle_engine import make_engine_cls
+    path = fcidump_path("he2_avdz")
+    kw = dict(nel=4, ms=0, sym=HUGE, cas=(-1, -1))
+    o = Oracle()
+    o.read_fcidump(path, **kw)
+    o.set_qmc(tau=0.01, seed=7, D0_population=200, ncycles=10, nreport=14, target_particles=260, real_amplitudes=1,
+              spawn_cutoff=0.01, walker_length=4000, spawned_walker_length=2000)
+    o.set_semi_stoch(space="high", size=12, shift_start_iteration=12)
+    o.init()
+    rows_o = o.run()
+    started = next(i for i, r in enumerate(rows_o) if r[1] != 0.0)        # first row with a varying shift
+    assert 1 < started < 10 and o.determ_space()[1].sum() == 12
+    s = R.read_in(path, **kw)
+    qmc = QmcIn(tau=0.01, rng_seed=7, init_pop=200, mc_cycles=10, nreports=14, target_population=260, real_amplitudes=True,
+                spawn_cutoff=0.01, state_size=4000, spawned_state_size=2000, semi_stoch_space="high", semi_stoch_size=12,
+                semi_stoch_shift_start_iteration=12)
+    res = do_fciqmc(s, qmc, engine_cls=make_engine_cls(path, kw, rng_kind=0))
+    assert (res.determ_space[0] == o.determ_space()[0]).all()
+    for a, b in zip(np.array(res.rows), rows_o):
+        assert a[0] == b[0] and a[5] == b[5] and a[6] == b[6], (a, b)
+        for k in (1, 2, 3, 4):
+            assert abs(a[k] - b[k]) <= 1e-11 * max(1.0, abs(b[k])), (a, b)

@@ -144,6 +144,11 @@ double orc_proj_hmatel(void* h, const uint64_t* f) {
     o->update_proj_energy(d, 1.0, d0, pe);
     return pe;
 }
+// get_hmatel(f1, f2) (src/hamiltonian_molecular.f90:12-71, src/hamiltonian_ueg.f90:12-69), diagonal included
+double orc_get_hmatel(void* h, const uint64_t* f1, const uint64_t* f2) {
+    Oracle* o = (Oracle*)h;
+    return o->get_hmatel(mkdet(o->sys, f1), mkdet(o->sys, f2));
+}
 // Slater-Condon single: matrix element <D|H|D_i^a> incl. permutation sign
 double orc_sc1(void* h, const uint64_t* f, int i, int a) {
     const System& s = ((Oracle*)h)->sys;

@@ -240,6 +240,13 @@ class Oracle:
         f = np.ascontiguousarray(f, dtype=np.uint64)
         return self.L.orc_proj_hmatel(self.h, _p(f))
 
+    def get_hmatel(self, f1, f2):
+        f1 = np.ascontiguousarray(f1, dtype=np.uint64)
+        f2 = np.ascontiguousarray(f2, dtype=np.uint64)
+        self.L.orc_get_hmatel.restype = C.c_double
+        self.L.orc_get_hmatel.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        return self.L.orc_get_hmatel(self.h, _p(f1), _p(f2))
+
     def sc1(self, f, i, a, checked=False):
         f = np.ascontiguousarray(f, dtype=np.uint64)
         fn = self.L.orc_sc1_checked if checked else self.L.orc_sc1

@@ -146,6 +146,19 @@ class HdCheck:
         self.L.hd_philox_stream(seed, cycle, purpose, _p(f), len(f), attempt, n, _p(out))
         return out
 
+    def hmatel_pair(self, f1, f2):
+        f1 = np.ascontiguousarray(f1, dtype=np.uint64)
+        f2 = np.ascontiguousarray(f2, dtype=np.uint64)
+        self.L.hd_hmatel_pair.restype = C.c_double
+        self.L.hd_hmatel_pair.argtypes = [C.c_void_p, C.c_void_p]
+        return self.L.hd_hmatel_pair(_p(f1), _p(f2))
+
+    def check_if_determ(self, sorted_dets, f):
+        sd = np.ascontiguousarray(sorted_dets, dtype=np.uint64)
+        f = np.ascontiguousarray(f, dtype=np.uint64)
+        self.L.hd_check_if_determ.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        return bool(self.L.hd_check_if_determ(_p(sd), len(sd), _p(f)))
+
     def proj_hmatel(self, f):
         f = np.ascontiguousarray(f, dtype=np.uint64)
         r = np.zeros(1, dtype=np.int32)

@@ -2,6 +2,7 @@
 // (hande_b200/csrc/hb_core.cuh) with g++ so that the per-attempt logic - excitation generators,
 // Slater-Condon rules, Philox stream, owner hash, death/spawn arithmetic - can be compared with the
 // oracle on a machine without a GPU.  The product library never uses these host instantiations.
+#include <type_traits>
 #include <cstring>
 #include <vector>
 #include "../../hande_b200/csrc/hb_core.cuh"
@@ -187,6 +188,36 @@ double hd_proj_hmatel(const uint64_t* f, int* is_ref) {
                        default: decode_det<4>(f, occ); h = proj_energy_hmatel<4>(g_sys, g_par, f, occ, r); }
     *is_ref = r;
     return h;
+}
+// <f1|H|f2> - H00 delta as the deterministic Hamiltonian of the semi-stochastic projection uses it (hb_semistoch.cuh
+// ss_hmatel: get_hmatel of src/semi_stoch.F90:620): popcount reject, diagonal from slater_condon0, else hmatel_pair
+double hd_hmatel_pair(const uint64_t* f1, const uint64_t* f2) {
+    uint8_t occ[HB_MAXNEL];
+    bool same;
+    auto run = [&](auto wtag) {
+        constexpr int W = decltype(wtag)::value;
+        int nx = 0;
+        for (int k = 0; k < W; ++k) nx += popc64(f1[k] ^ f2[k]);
+        if (nx > 4) return 0.0;
+        decode_det<W>(f1, occ);
+        if (nx == 0) return ((g_sys.kind == SYS_UEG) ? slater_condon0_ueg(g_sys, occ) : slater_condon0(g_sys, occ)) - g_par.H00;
+        return hmatel_pair<W>(g_sys, f1, occ, f2, same);
+    };
+    switch (g_sys.W) {
+        case 1: return run(std::integral_constant<int, 1>());
+        case 2: return run(std::integral_constant<int, 2>());
+        case 3: return run(std::integral_constant<int, 3>());
+        default: return run(std::integral_constant<int, 4>());
+    }
+}
+// check_if_determ by bisection of the sorted space (hb_core.cuh ss_check_if_determ)
+int hd_check_if_determ(const uint64_t* sorted, int n, const uint64_t* f) {
+    switch (g_sys.W) {
+        case 1: return ss_check_if_determ<1>(sorted, n, f);
+        case 2: return ss_check_if_determ<2>(sorted, n, f);
+        case 3: return ss_check_if_determ<3>(sorted, n, f);
+        default: return ss_check_if_determ<4>(sorted, n, f);
+    }
 }
 // Brute-force check of the guarded prefix-sum alias selection against the reference's table construction
 // (generate_alias_tables + select_weighted_value_precalc).  Returns the number of mismatches; out[0] = calls,

@@ -325,3 +325,59 @@ def test_alias_prefix_sum_selection_equals_table_walk():
     out = np.zeros(2, dtype=np.int64)
     bad = L.hd_alias_selftest(400000, 7, out.ctypes.data)
     assert bad == 0
+
+
+def _neighbours(s, f0_occ, rng, n):
+    """random determinants within two excitations of random starting points (so that pairs are often connected)"""
+    out = []
+    occ0 = list(f0_occ)
+    for _ in range(n):
+        occ = list(occ0)
+        for _k in range(int(rng.integers(0, 3))):
+            spin = int(rng.integers(0, 2))
+            mine = [o for o in occ if o % 2 == spin]
+            free = [v for v in range(1, s.nbasis + 1) if v % 2 == spin and v not in occ]
+            if mine and free:
+                occ.remove(int(rng.choice(mine)))
+                occ.append(int(rng.choice(free)))
+        out.append(np.asarray(s.encode(sorted(occ)), dtype=np.uint64).reshape(-1))
+    return out
+
+
+@pytest.mark.parametrize("system", ["h2o", "ne", "ueg"])
+def test_deterministic_hamiltonian_elements(fcidump_path, system):
+    """The element function of the semi-stochastic projection's Hamiltonian (hb_semistoch.cuh ss_hmatel = hmatel_pair +
+    the diagonal, compiled for the host) against the oracle's get_hmatel (src/hamiltonian_molecular.f90:12-71,
+    src/hamiltonian_ueg.f90:12-69) on pairs of determinants zero to four excitations apart, bit for bit; and
+    check_if_determ's bisection against set membership"""
+    if system == "ueg":
+        from hande_b200.ueg import UegSystem
+        s = UegSystem(6, 0, 2.0, 2.0)
+        o = Oracle()
+        o.init_ueg(6, 0, 2.0, 2.0)
+        o.set_qmc(tau=0.01, seed=11, excit_gen="no_renorm", rng_kind=1)
+        o.init()
+        ref = o.reference()
+        h = HdCheck(s, EXCIT_GEN["no_renorm"], 0.0, 1.0, 0.01, 0.0, 0.0, 1, 0, 11, ref["f0"], ref["H00"])
+    else:
+        kw = dict(nel=10, ms=0, sym=0, cas=(8, 13)) if system == "h2o" else dict(nel=10, ms=0, sym=0, cas=(8, 22))
+        s, o, h = _setup(fcidump_path(system), kw, "renorm")
+        ref = o.reference()
+    rng = np.random.default_rng(7)
+    dets = _neighbours(s, ref["occ"], rng, 120)
+    nz = diag = 0
+    for f1 in dets[:60]:
+        for f2 in dets[60:] + [f1]:
+            a = h.hmatel_pair(f1, f2)
+            b = o.get_hmatel(f1, f2)
+            if (f1 == f2).all():
+                b = b - ref["H00"]
+                diag += 1
+            assert a == b, (f1, f2, a, b)
+            nz += a != 0.0
+    assert nz > (40 if system == "ueg" else 200) and diag >= 60      # the UEG conserves momentum: most pairs vanish
+    uniq = sorted({tuple(int(x) for x in f[::-1]) for f in dets})          # list order: last word most significant
+    sd = np.array([t[::-1] for t in uniq], dtype=np.uint64)
+    members = {tuple(int(x) for x in f) for f in sd}
+    for f in dets + _neighbours(s, ref["occ"], rng, 60):
+        assert h.check_if_determ(sd, f) == (tuple(int(x) for x in f) in members)

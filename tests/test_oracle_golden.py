@@ -39,6 +39,8 @@ def _run(case, fcidump_path, nrows, wide=False):
         o.set_quasi_newton(True, **g["quasi_newton"])
     if "semi_stoch" in g:
         o.set_semi_stoch(**g["semi_stoch"])
+    elif "pop_real_bits" in g:
+        o.set_semi_stoch(space="none", pop_real_bits=g["pop_real_bits"])
     o.init()
     if g.get("vary_shift"):
         o.set_vary_shift(True)
@@ -100,6 +102,14 @@ def test_h4_wall_chebyshev_np1(fcidump_path):
     sub-cycles per cycle, update_chebyshev) with harmonic forcing of the shift, real amplitudes - every row of the
     reference's table"""
     _run("h4_cheby", fcidump_path, 30)
+
+
+def test_real_amplitude_force_32(fcidump_path):
+    """real_amplitude_force_32 (amplitudes stored times 2^11, src/particle_t_utils.f90): the truncated Ne runs of
+    fciqmc_real_32/np{2,4}; the complete 1201-row tables were verified with tools/golden_compare.py
+    (ne_ci6_real32_np2, ne_ci6_real32_np4)"""
+    _run("ne_ci6_real32_np2", fcidump_path, 90)
+    _run("ne_ci6_real32_np4", fcidump_path, 60)
 
 
 def test_semi_stochastic_projection(fcidump_path):

@@ -37,6 +37,19 @@ CASES = {
                               qmc=dict(tau=0.002, seed=18, D0_population=10, ncycles=10, nreport=1200,
                                        target_particles=50000, walker_length=50000, spawned_walker_length=50000,
                                        ex_level=5, nprocs=2, real_amplitudes=1, spawn_cutoff=0.01)),
+    # amplitudes stored times 2^11 (real_amplitude_force_32): the same run as ne_ci6_real64_np2 at the coarser resolution
+    "ne_ci6_real32_np2": dict(dir="fciqmc_real_32/np2/Ne-aug-cc-pVDZ-ci6qmc_real_32",
+                              bench="benchmark.out.9712b5a3.inp=ne.ciqmc.in", int_file="INTDUMP",
+                              sys=dict(nel=10, ms=0, sym=0, cas=(8, 22)), pop_real_bits=11,
+                              qmc=dict(tau=0.002, seed=18, D0_population=10, ncycles=10, nreport=1200,
+                                       target_particles=50000, walker_length=50000, spawned_walker_length=50000,
+                                       ex_level=5, nprocs=2, real_amplitudes=1, spawn_cutoff=0.01)),
+    "ne_ci6_real32_np4": dict(dir="fciqmc_real_32/np4/Ne-aug-cc-pVDZ-ci6qmc_real_32",
+                              bench="benchmark.out.9712b5a3.inp=ne.ciqmc.in", int_file="INTDUMP",
+                              sys=dict(nel=10, ms=0, sym=0, cas=(8, 22)), pop_real_bits=11,
+                              qmc=dict(tau=0.002, seed=18, D0_population=10, ncycles=10, nreport=1200,
+                                       target_particles=50000, walker_length=50000, spawned_walker_length=50000,
+                                       ex_level=5, nprocs=4, real_amplitudes=1, spawn_cutoff=0.01)),
     "ne_ci6_np4": dict(dir="fciqmc/np4/Ne-aug-cc-pVDZ-ci6qmc", bench="benchmark.out.9712b5a3.inp=ne.ciqmc.in",
                        int_file="INTDUMP", sys=dict(nel=10, ms=0, sym=0, cas=(8, 22)),
                        qmc=dict(tau=0.002, seed=18, D0_population=10, ncycles=10, nreport=1200,
@@ -182,6 +195,8 @@ def run_case(name, max_rows=None, quiet=False):
         o.set_quasi_newton(True, **c["quasi_newton"])
     if "semi_stoch" in c:
         o.set_semi_stoch(**c["semi_stoch"])
+    elif "pop_real_bits" in c:
+        o.set_semi_stoch(space="none", pop_real_bits=c["pop_real_bits"])
     o.init()
     if c.get("vary_shift"):
         o.set_vary_shift(True)

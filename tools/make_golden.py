@@ -18,6 +18,7 @@ from tools.golden_compare import CASES, TS, parse_table  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 FCIDUMP_NAME = {"h2o": "h2o", "ne_init": "ne", "ne_ci6_np2": "ne", "ne_ci6_np4": "ne", "ne_ci6_real64_np2": "ne",
+                "ne_ci6_real32_np2": "ne", "ne_ci6_real32_np4": "ne",
                 "ccmc_ne": "ne_vdz", "ccmc_h2o_np2": "h2o_vdz",
                 "ccmc_h2o_ccsdt_fullnc_np2": "h2o_vdz"}
 FCIDUMP_NAME.update({k: "nh3_631g" for k in CASES if k.startswith("ccmc_nh3_")})
@@ -75,6 +76,7 @@ for name, c in CASES.items():
     json.dump({"source": "test_suite/" + c["dir"] + "/" + c["bench"], "fcidump": FCIDUMP_NAME[name], "sys": c["sys"],
                "qmc": c["qmc"], "ccmc": bool(c.get("ccmc")), "full_nc": bool(c.get("full_nc")),
                **({"quasi_newton": c["quasi_newton"]} if "quasi_newton" in c else {}),
+               **({"pop_real_bits": c["pop_real_bits"]} if "pop_real_bits" in c else {}),
                **({"semi_stoch": c["semi_stoch"], "vary_shift": True, "kat": {"H00": -5.69708312, "determ_size": 100}}
                   if "semi_stoch" in c else {}),
                **({"chebyshev": c["chebyshev"],

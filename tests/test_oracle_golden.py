@@ -110,6 +110,9 @@ def test_real_amplitude_force_32(fcidump_path):
     (ne_ci6_real32_np2, ne_ci6_real32_np4)"""
     _run("ne_ci6_real32_np2", fcidump_path, 90)
     _run("ne_ci6_real32_np4", fcidump_path, 60)
+    # and the UEG runs of fciqmc_real_32/np{2,4}/ueg_n10_rs2_e4_fciqmc_real_32 (complete 1001-row tables verified likewise)
+    _run("ueg_real32_np2", fcidump_path, 150)
+    _run("ueg_real32_np4", fcidump_path, 150)
 
 
 def test_semi_stochastic_projection(fcidump_path):

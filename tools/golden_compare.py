@@ -84,6 +84,17 @@ CASES = {
                     ueg=dict(nel=6, ms=0, rs=2.0, cutoff=2.0), ref_det=[1, 2, 3, 10, 11, 14],
                     qmc=dict(tau=0.005, seed=122, D0_population=10, ncycles=10, nreport=1000, target_particles=90000,
                              walker_length=50000, spawned_walker_length=5000, nprocs=4)),
+    # the same UEG with real amplitudes stored times 2^11 (real_amplitude_force_32), two and four ranks
+    "ueg_real32_np2": dict(dir="fciqmc_real_32/np2/ueg_n10_rs2_e4_fciqmc_real_32", bench="benchmark.out.9712b5a3.inp=ueg.fciqmc.in",
+                           ueg=dict(nel=6, ms=0, rs=2.0, cutoff=2.0), ref_det=[1, 2, 3, 10, 11, 14], pop_real_bits=11,
+                           qmc=dict(tau=0.005, seed=122, D0_population=10, ncycles=10, nreport=1000, target_particles=90000,
+                                    walker_length=50000, spawned_walker_length=50000, nprocs=2, real_amplitudes=1,
+                                    spawn_cutoff=0.01)),
+    "ueg_real32_np4": dict(dir="fciqmc_real_32/np4/ueg_n10_rs2_e4_fciqmc_real_32", bench="benchmark.out.9712b5a3.inp=ueg.fciqmc.in",
+                           ueg=dict(nel=6, ms=0, rs=2.0, cutoff=2.0), ref_det=[1, 2, 3, 10, 11, 14], pop_real_bits=11,
+                           qmc=dict(tau=0.005, seed=122, D0_population=10, ncycles=10, nreport=1000, target_particles=90000,
+                                    walker_length=50000, spawned_walker_length=50000, nprocs=4, real_amplitudes=1,
+                                    spawn_cutoff=0.01)),
     # quasi-Newton propagator on the same UEG, real amplitudes
     "ueg_qn_real64_np2": dict(dir="fciqmc_real_64/np2/ueg_qn_n10_rs2_e4_fciqmc_real_64", bench="benchmark.out.9712b5a3.inp=ueg.fciqmc.in",
                               ueg=dict(nel=6, ms=0, rs=2.0, cutoff=2.0), ref_det=[1, 2, 3, 10, 11, 14], quasi_newton=dict(threshold=1.0),

@@ -48,6 +48,7 @@ for name, c in CASES.items():
         json.dump({"source": "test_suite/" + c["dir"] + "/" + c["bench"], "ueg": c["ueg"], "ref_det": c["ref_det"],
                    "qmc": c["qmc"], **({"quasi_newton": c["quasi_newton"]} if "quasi_newton" in c else {}),
                    **({"semi_stoch": c["semi_stoch"], "vary_shift": True} if "semi_stoch" in c else {}),
+                   **({"pop_real_bits": c["pop_real_bits"]} if "pop_real_bits" in c else {}),
                    "columns": ["iterations", "shift", "proj_energy", "D0_population", "nparticles", "nstates",
                                "nspawn_events", "rspawn"],
                    # the "H00", box length, basis size and third eigenvalue the reference prints for the system

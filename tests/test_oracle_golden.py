@@ -134,6 +134,12 @@ def test_semi_stochastic_projection(fcidump_path):
     assert len(dets) == k["determ_size"] and abs(o.reference()["H00"] - k["H00"]) < 5e-9
     rp, ci, mat = o.determ_hamil(0)
     assert rp[-1] == len(mat) and len(mat) > 100
+    # the same He2 run in the reference's default mode, separate annihilation with the most populated determinants (the
+    # engine's mode and the host driver's space, on one rank), and with the CISD space of the reference determinant (69
+    # determinants after the point-group filter, as the reference prints)
+    for case in ("he2_ss_sep", "he2_ss_cisd"):
+        o = _run(case, fcidump_path, 200)
+        assert len(o.determ_space()[0]) == load_golden(case)["kat"]["determ_size"]
 
 
 def test_ueg_np2_np4(fcidump_path):

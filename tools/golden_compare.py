@@ -75,6 +75,18 @@ CASES = {
                    semi_stoch=dict(space="high", size=100, start_iteration=1000, separate_annihilation=False, pop_real_bits=11),
                    qmc=dict(tau=0.01, seed=7, D0_population=1000, ncycles=10, nreport=200, target_particles=1000,
                             real_amplitudes=1, spawn_cutoff=0.01, walker_length=178571, spawned_walker_length=31250)),
+    # the same run with the reference's default projection mode (separate annihilation - what the engine implements)
+    "he2_ss_sep": dict(dir="fciqmc_real_32/np1/He2-aug-cc-pVDZ_real_32_SS_Extra_MPI", bench="benchmark.out.9712b5a3.inp=he2.in",
+                       int_file="INTDUMP", sys=dict(nel=4, ms=0), vary_shift=True,
+                       semi_stoch=dict(space="high", size=100, start_iteration=1000, pop_real_bits=11),
+                       qmc=dict(tau=0.01, seed=7, D0_population=1000, ncycles=10, nreport=200, target_particles=1000,
+                                real_amplitudes=1, spawn_cutoff=0.01, walker_length=178571, spawned_walker_length=31250)),
+    # and with the CISD space of the reference determinant (point-group symmetry filter of enumerate_determinants)
+    "he2_ss_cisd": dict(dir="fciqmc_real_32/np1/He2-aug-cc-pVDZ_real_32_SS_cisd", bench="benchmark.out.9712b5a3.inp=he2.in",
+                        int_file="INTDUMP", sys=dict(nel=4, ms=0), vary_shift=True,
+                        semi_stoch=dict(space="ci", ci_ex_level=2, start_iteration=1000, pop_real_bits=11),
+                        qmc=dict(tau=0.01, seed=7, D0_population=1000, ncycles=10, nreport=200, target_particles=1000,
+                                 real_amplitudes=1, spawn_cutoff=0.01, walker_length=178571, spawned_walker_length=31250)),
     # uniform electron gas: sys = ueg{electrons=6, ms=0, dim=3, cutoff=2, rs=2}, explicit reference
     "ueg_np2": dict(dir="fciqmc/np2/ueg_n10_rs2_e4_fciqmc", bench="benchmark.out.9712b5a3.inp=ueg.fciqmc.in",
                     ueg=dict(nel=6, ms=0, rs=2.0, cutoff=2.0), ref_det=[1, 2, 3, 10, 11, 14],

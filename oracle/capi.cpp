@@ -462,6 +462,8 @@ void orc_get_spawn(void* h, int rank, int64_t* sdata) {
             ++k;
         }
 }
+// qmc = { shift_harmonic_forcing = ... } on its own (src/qmc.F90:195-212); call after orc_init
+void orc_set_harmonic_forcing(void* h, double v) { ((Oracle*)h)->shift_harmonic_forcing = v; }
 // wall-Chebyshev propagator: init_chebyshev (call after orc_init), optional harmonic forcing of the shift
 int orc_init_chebyshev(void* h, int order, double cshift, double cscale, int skip_gershgorin, double harmonic_forcing,
                        double* out) {

@@ -468,6 +468,11 @@ class Oracle:
         self._chk(self.L.orc_stage_annihilate(self.h))
 
     # ---- wall-Chebyshev propagator (src/propagators.f90)
+    def set_harmonic_forcing(self, value):
+        """qmc = { shift_harmonic_forcing = value } (after init)"""
+        self.L.orc_set_harmonic_forcing.argtypes = [C.c_void_p, C.c_double]
+        self.L.orc_set_harmonic_forcing(self.h, float(value))
+
     def init_chebyshev(self, order=5, shift=0.0, scale=1.1, skip_gershgorin=False, harmonic_forcing=0.0):
         """after init(); returns (upper spectral bound, zeroes, weights).  The oracle sets tau itself? no: as in the
         reference the caller passes tau = 1 (lua_hande_calc.f90:1410)."""

@@ -44,6 +44,8 @@ def _run(case, fcidump_path, nrows, wide=False):
     o.init()
     if g.get("vary_shift"):
         o.set_vary_shift(True)
+    if "harmonic_forcing" in g:
+        o.set_harmonic_forcing(g["harmonic_forcing"])
     if "chebyshev" in g:
         hi, z, w = o.init_chebyshev(order=g["chebyshev"]["order"], harmonic_forcing=g["chebyshev"]["harmonic_forcing"])
         k = g["kat"]        # the spectral range, zeroes and weights the reference prints (9 significant digits)
@@ -102,6 +104,14 @@ def test_h4_wall_chebyshev_np1(fcidump_path):
     sub-cycles per cycle, update_chebyshev) with harmonic forcing of the shift, real amplitudes - every row of the
     reference's table"""
     _run("h4_cheby", fcidump_path, 30)
+
+
+def test_no_renorm_fciqmc_and_n2(fcidump_path):
+    """Two more of the reference's FCIQMC tables: the no_renorm generator in an FCIQMC run (Ne CISDTQ, two ranks;
+    complete 751-row table verified with tools/golden_compare.py) and N2 / STO-3G in D2h with nel and ms taken from the
+    FCIDUMP header (two ranks, every one of its 1001 rows)"""
+    _run("ne_cisdtq_no_renorm_np2", fcidump_path, 150)
+    _run("n2_harmonic_np2", fcidump_path, 1000)
 
 
 def test_real_amplitude_force_32(fcidump_path):

@@ -50,6 +50,19 @@ CASES = {
                               qmc=dict(tau=0.002, seed=18, D0_population=10, ncycles=10, nreport=1200,
                                        target_particles=50000, walker_length=50000, spawned_walker_length=50000,
                                        ex_level=5, nprocs=4, real_amplitudes=1, spawn_cutoff=0.01)),
+    # the no_renorm excitation generator in an FCIQMC run (integer walkers, truncation at quadruples, two ranks)
+    "ne_cisdtq_no_renorm_np2": dict(dir="fciqmc/np2/Ne-aug-cc-pVDZ-cisdtq_no_renorm",
+                                    bench="benchmark.out.9712b5a3.inp=ne.no_renorm.in", int_file="INTDUMP",
+                                    sys=dict(nel=10, ms=0, sym=0, cas=(8, 22)),
+                                    qmc=dict(tau=0.003, seed=14373, D0_population=100, ncycles=10, nreport=750,
+                                             target_particles=50000, walker_length=3571428, spawned_walker_length=1562500,
+                                             ex_level=4, nprocs=2, excit_gen="no_renorm")),
+    # harmonic forcing of the shift on its own (qmc = { shift_harmonic_forcing = 0.0004, shift_damping = 0.04 }), two ranks
+    "n2_harmonic_np2": dict(dir="fciqmc/np2/N2-RHF-STO-3G-harmonic_pop_control",
+                            bench="benchmark.out.9712b5a3.inp=n2_sto3g_fciqmc_harmonic_pop_control.in",
+                            int_file="n2_sto3g.fcidump", sys=dict(), harmonic_forcing=0.0004,
+                            qmc=dict(tau=0.001, seed=21, D0_population=100, ncycles=10, nreport=1000, target_particles=5e6,
+                                     shift_damping=0.04, walker_length=35714285, spawned_walker_length=31250000, nprocs=2)),
     "ne_ci6_np4": dict(dir="fciqmc/np4/Ne-aug-cc-pVDZ-ci6qmc", bench="benchmark.out.9712b5a3.inp=ne.ciqmc.in",
                        int_file="INTDUMP", sys=dict(nel=10, ms=0, sym=0, cas=(8, 22)),
                        qmc=dict(tau=0.002, seed=18, D0_population=10, ncycles=10, nreport=1200,
@@ -223,6 +236,8 @@ def run_case(name, max_rows=None, quiet=False):
     o.init()
     if c.get("vary_shift"):
         o.set_vary_shift(True)
+    if "harmonic_forcing" in c:
+        o.set_harmonic_forcing(c["harmonic_forcing"])
     t = time.time()
     if c.get("ccmc"):
         o.ccmc_set_full_nc(bool(c.get("full_nc")))

@@ -23,6 +23,8 @@ FCIDUMP_NAME = {"h2o": "h2o", "ne_init": "ne", "ne_ci6_np2": "ne", "ne_ci6_np4":
                 "ccmc_h2o_ccsdt_fullnc_np2": "h2o_vdz"}
 FCIDUMP_NAME.update({k: "nh3_631g" for k in CASES if k.startswith("ccmc_nh3_")})
 FCIDUMP_NAME["h4_cheby"] = "h4_sto3g"
+FCIDUMP_NAME["ne_cisdtq_no_renorm_np2"] = "ne"
+FCIDUMP_NAME["n2_harmonic_np2"] = "n2_sto3g"
 FCIDUMP_NAME["he2_ss"] = "he2_avdz"
 FCIDUMP_NAME["he2_ss_sep"] = "he2_avdz"
 FCIDUMP_NAME["he2_ss_cisd"] = "he2_avdz"
@@ -80,6 +82,7 @@ for name, c in CASES.items():
                "qmc": c["qmc"], "ccmc": bool(c.get("ccmc")), "full_nc": bool(c.get("full_nc")),
                **({"quasi_newton": c["quasi_newton"]} if "quasi_newton" in c else {}),
                **({"pop_real_bits": c["pop_real_bits"]} if "pop_real_bits" in c else {}),
+               **({"harmonic_forcing": c["harmonic_forcing"]} if "harmonic_forcing" in c else {}),
                **({"semi_stoch": c["semi_stoch"], "vary_shift": True, "kat": {"H00": -5.69708312, "determ_size": 69 if name == "he2_ss_cisd" else 100}}
                   if "semi_stoch" in c else {}),
                **({"chebyshev": c["chebyshev"],
